@@ -1,0 +1,152 @@
+"""ctypes binding of the C ABI in include/dvb.h (libdvb.so, built in-tree by
+__graft_entry__.build()).
+
+The product path has NO CPU fallback: if the CUDA library is missing, `lib()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+DVB_MAX_CHANNELS = 16
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libdvb.so')
+
+
+class DvbPileupParams(C.Structure):
+  _fields_ = [
+      ('width', C.c_int32),
+      ('height', C.c_int32),
+      ('reference_band_height', C.c_int32),
+      ('num_channels', C.c_int32),
+      ('channels', C.c_int32 * DVB_MAX_CHANNELS),
+      ('num_alt_channels', C.c_int32),
+      ('base_color_offset_a_and_g', C.c_int32),
+      ('base_color_offset_t_and_c', C.c_int32),
+      ('base_color_stride', C.c_int32),
+      ('allele_supporting_read_alpha', C.c_float),
+      ('allele_unsupporting_read_alpha', C.c_float),
+      ('other_allele_supporting_read_alpha', C.c_float),
+      ('reference_matching_read_alpha', C.c_float),
+      ('reference_mismatching_read_alpha', C.c_float),
+      ('indel_anchoring_base_char', C.c_int32),
+      ('reference_base_quality', C.c_int32),
+      ('positive_strand_color', C.c_int32),
+      ('negative_strand_color', C.c_int32),
+      ('base_quality_cap', C.c_int32),
+      ('mapping_quality_cap', C.c_int32),
+      ('min_base_quality', C.c_int32),
+      ('min_mapping_quality', C.c_int32),
+      ('sort_by_haplotypes', C.c_int32),
+      ('hp_tag_for_assembly_polishing', C.c_int32),
+      ('sort_by_alt_allele_support', C.c_int32),
+      ('random_seed', C.c_uint32),
+      ('max_reads_per_image', C.c_int32),
+  ]
+
+
+class DvbBatch(C.Structure):
+  _fields_ = [
+      ('n_images', C.c_int32),
+      ('n_reads', C.c_int32),
+      ('n_pairs', C.c_int64),
+      ('n_bases', C.c_int64),
+      ('n_cigar', C.c_int64),
+      ('ref_bases', C.c_void_p),
+      ('ref_stride', C.c_int32),
+      ('image_start_pos', C.c_void_p),
+      ('variant_start', C.c_void_p),
+      ('pair_begin', C.c_void_p),
+      ('pair_read', C.c_void_p),
+      ('pair_support', C.c_void_p),
+      ('pair_allele_group', C.c_void_p),
+      ('read_pos', C.c_void_p),
+      ('read_sort_pos', C.c_void_p),
+      ('read_mapq', C.c_void_p),
+      ('read_flags', C.c_void_p),
+      ('read_fragment_length', C.c_void_p),
+      ('read_hp', C.c_void_p),
+      ('read_name_rank', C.c_void_p),
+      ('read_seq_begin', C.c_void_p),
+      ('read_cigar_begin', C.c_void_p),
+      ('bases', C.c_void_p),
+      ('quals', C.c_void_p),
+      ('cigar', C.c_void_p),
+  ]
+
+
+# name -> (dtype string, per-what) for every array member of DvbBatch, in struct order.
+BATCH_ARRAYS = (
+    ('ref_bases', 'uint8'), ('image_start_pos', 'int32'), ('variant_start', 'int32'),
+    ('pair_begin', 'int64'), ('pair_read', 'int32'), ('pair_support', 'uint8'),
+    ('pair_allele_group', 'uint8'), ('read_pos', 'int32'), ('read_sort_pos', 'int32'),
+    ('read_mapq', 'int32'), ('read_flags', 'uint8'), ('read_fragment_length', 'int32'),
+    ('read_hp', 'int32'), ('read_name_rank', 'uint32'), ('read_seq_begin', 'int64'),
+    ('read_cigar_begin', 'int64'), ('bases', 'uint8'), ('quals', 'uint8'), ('cigar', 'uint32'),
+)
+
+DVB_STATUS_NAMES = {
+    0: 'DVB_OK', 1: 'DVB_ERR_INVALID_ARGUMENT', 2: 'DVB_ERR_UNSUPPORTED_CHANNEL',
+    3: 'DVB_ERR_BAD_CIGAR', 4: 'DVB_ERR_TOO_MANY_READS', 5: 'DVB_ERR_CUDA',
+    6: 'DVB_ERR_NO_DEVICE', 7: 'DVB_ERR_INTERNAL',
+}
+
+
+class DvbError(RuntimeError):
+
+  def __init__(self, status: int, message: str):
+    super().__init__(f'{DVB_STATUS_NAMES.get(status, status)}: {message}')
+    self.status = status
+
+
+_lib: Optional[C.CDLL] = None
+
+# Every symbol include/dvb.h declares: (name, restype, argtypes).
+SYMBOLS = (
+    ('dvb_abi_version', C.c_int, []),
+    ('dvb_last_error', C.c_char_p, []),
+    ('dvb_pileup_params_default', None, [C.POINTER(DvbPileupParams)]),
+    ('dvb_image_bytes', C.c_int64, [C.POINTER(DvbPileupParams)]),
+    ('dvb_shuffle_table', C.c_int, [C.c_int32, C.c_uint32, C.c_void_p]),
+    ('dvb_encoder_create', C.c_int, [C.POINTER(DvbPileupParams), C.c_int, C.POINTER(C.c_void_p)]),
+    ('dvb_encoder_destroy', None, [C.c_void_p]),
+    ('dvb_encode_batch_device', C.c_int, [C.c_void_p, C.POINTER(DvbBatch), C.c_void_p, C.c_void_p, C.c_void_p]),
+    ('dvb_encoder_check', C.c_int, [C.c_void_p, C.c_void_p]),
+    ('dvb_encode_batch_host', C.c_int, [C.c_void_p, C.POINTER(DvbBatch), C.c_void_p, C.c_void_p]),
+    ('dvb_encoder_launch_count', C.c_int64, [C.c_void_p]),
+    ('dvb_cnn_create', C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_int32, C.c_int, C.POINTER(C.c_void_p)]),
+    ('dvb_cnn_destroy', None, [C.c_void_p]),
+    ('dvb_cnn_forward_device', C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    ('dvb_cnn_forward_host', C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    ('dvb_cnn_launch_count', C.c_int64, [C.c_void_p]),
+    ('dvb_cnn_flops_per_image', C.c_double, [C.c_void_p]),
+)
+
+
+def lib() -> C.CDLL:
+  """Loads libdvb.so.  Raises (never falls back) when the CUDA library is absent."""
+  global _lib
+  if _lib is None:
+    if not os.path.exists(LIB_PATH):
+      raise RuntimeError(
+          f'{LIB_PATH} not found: the CUDA extension is not built. Run '
+          '`python -c "import __graft_entry__ as g; g.build()"` at the repo root. '
+          'There is no CPU fallback for the product path.')
+    l = C.CDLL(LIB_PATH)
+    for name, restype, argtypes in SYMBOLS:
+      fn = getattr(l, name)  # AttributeError if the .so does not export a declared symbol
+      fn.restype = restype
+      fn.argtypes = argtypes
+    if l.dvb_abi_version() != 1:
+      raise RuntimeError('libdvb.so ABI version mismatch')
+    _lib = l
+  return _lib
+
+
+def check(status: int) -> None:
+  if status != 0:
+    msg = lib().dvb_last_error()
+    raise DvbError(status, msg.decode() if msg else '')

@@ -1,0 +1,225 @@
+"""Packs candidates + reads into the Structure-of-Arrays batch of include/dvb.h (DvbBatch).
+
+This is host-side glue between the reference-shaped objects (DeepVariantCall, Read) and the
+CUDA encoder.  The string work the reference does per read per image — the read-name search
+in ReadSupportsVariantChannel::ReadSupportsAlt (channels/read_supports_variant_channel.cc:75-104),
+the allele-group map of BuildPileupForOneSample (pileup_image_native.cc:345-360,384-392) and the
+(fragment_name, read_number) tie-break of SortImageRows (pileup_image_native.cc:75-102) — is
+resolved here ONCE into small integers so that the device works on integers only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from deepvariant_b200 import _lib
+from deepvariant_b200.protos import DeepVariantCall, Read
+
+READ_REVERSE_STRAND = 1
+READ_SUPPLEMENTARY = 2
+READ_HAS_HP = 4
+READ_HP_MULTI = 8
+
+
+@dataclasses.dataclass
+class ImageSpec:
+  """One BuildPileupForOneSample call."""
+  ref_bases: str
+  image_start_pos: int
+  variant_start: int
+  reads: List[Read]                 # in InMemoryReader::Query order
+  support: List[int]                # per read: 0 / 1 / 2
+  allele_group: List[int]           # per read (only used with sort_by_alt_allele_support)
+  sort_positions: Optional[List[int]] = None  # alignment positions before trimming
+
+
+def read_supports_alt(dv_call: DeepVariantCall, read_key: str, alt_alleles: Sequence[str]) -> int:
+  """ReadSupportsAlt (channels/read_supports_variant_channel.cc:75-104): iterate ALL alternate
+  bases in order, first name match wins: 1 if that alt is in alt_alleles, else 2; 0 if none."""
+  for alt_allele in dv_call.variant.alternate_bases:
+    names = dv_call.allele_support.get(alt_allele)
+    if names is None:
+      continue
+    if read_key in names:
+      return 1 if alt_allele in alt_alleles else 2
+  return 0
+
+
+def allele_groups(dv_call: DeepVariantCall, reads: Sequence[Read]) -> List[int]:
+  """read_name_to_allele_group_map (pileup_image_native.cc:345-360): later alts overwrite
+  earlier ones; reads in no alt's support list get num_alt_alleles (sorts last)."""
+  n_alt = len(dv_call.variant.alternate_bases)
+  m: Dict[str, int] = {}
+  for i, alt in enumerate(dv_call.variant.alternate_bases):
+    for name in dv_call.allele_support.get(alt, ()):
+      m[name] = i
+  return [m.get(r.key(), n_alt) for r in reads]
+
+
+def image_spec_for(dv_call: DeepVariantCall, ref_bases: str, reads: List[Read], image_start_pos: int,
+                   alt_alleles: List[str], options, sort_positions: Optional[List[int]] = None) -> ImageSpec:
+  support_sets = {alt: set(names) for alt, names in dv_call.allele_support.items()}
+  view = DeepVariantCall(variant=dv_call.variant, allele_support=support_sets)
+  support = [read_supports_alt(view, r.key(), alt_alleles) for r in reads]
+  groups = allele_groups(dv_call, reads) if options.sort_by_alt_allele_support else [0] * len(reads)
+  return ImageSpec(ref_bases=ref_bases, image_start_pos=image_start_pos,
+                   variant_start=dv_call.variant.start, reads=reads, support=support,
+                   allele_group=groups, sort_positions=sort_positions)
+
+
+@dataclasses.dataclass
+class PackedBatch:
+  """Host numpy arrays laid out exactly as DvbBatch expects."""
+  n_images: int
+  n_reads: int
+  n_pairs: int
+  ref_stride: int
+  arrays: Dict[str, np.ndarray]
+
+  def as_ctypes(self) -> _lib.DvbBatch:
+    b = _lib.DvbBatch()
+    b.n_images = self.n_images
+    b.n_reads = self.n_reads
+    b.n_pairs = self.n_pairs
+    b.n_bases = int(self.arrays['read_seq_begin'][-1])
+    b.n_cigar = int(self.arrays['read_cigar_begin'][-1])
+    b.ref_stride = self.ref_stride
+    for name, dtype in _lib.BATCH_ARRAYS:
+      a = self.arrays[name]
+      assert a.dtype == np.dtype(dtype) and a.flags['C_CONTIGUOUS'], name
+      setattr(b, name, a.ctypes.data_as(C.c_void_p))
+    return b
+
+  def input_bytes(self) -> int:
+    return int(sum(a.nbytes for a in self.arrays.values()))
+
+
+class DeviceBatch:
+  """The same batch resident in HBM (torch tensors own the memory)."""
+
+  def __init__(self, packed: PackedBatch, device, stream=None, pinned: Optional[Dict] = None):
+    import torch
+    self.n_images, self.n_reads, self.n_pairs = packed.n_images, packed.n_reads, packed.n_pairs
+    self.ref_stride = packed.ref_stride
+    self.tensors = {}
+    for name, _ in _lib.BATCH_ARRAYS:
+      a = packed.arrays[name]
+      t = torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a)
+      self.tensors[name] = t.to(device, non_blocking=True)
+    self.n_bases = int(packed.arrays['read_seq_begin'][-1])
+    self.n_cigar = int(packed.arrays['read_cigar_begin'][-1])
+
+  def as_ctypes(self) -> _lib.DvbBatch:
+    b = _lib.DvbBatch()
+    b.n_images, b.n_reads, b.n_pairs = self.n_images, self.n_reads, self.n_pairs
+    b.n_bases, b.n_cigar, b.ref_stride = self.n_bases, self.n_cigar, self.ref_stride
+    for name, _ in _lib.BATCH_ARRAYS:
+      setattr(b, name, C.c_void_p(self.tensors[name].data_ptr()))
+    return b
+
+
+def name_ranks(reads: Sequence[Read]) -> np.ndarray:
+  """Dense rank of (fragment_name, read_number) — std::tuple<std::string,int> operator<
+  (pileup_image_native.cc:98-101): byte-wise string compare, then int compare."""
+  keys = [(r.fragment_name.encode(), r.read_number) for r in reads]
+  order = sorted(set(keys))
+  rank = {k: i for i, k in enumerate(order)}
+  return np.array([rank[k] for k in keys], dtype=np.uint32)
+
+
+def pack_images(specs: Sequence[ImageSpec], params: _lib.DvbPileupParams) -> PackedBatch:
+  """Builds a PackedBatch; reads shared between images (same object) are stored once."""
+  width = params.width
+  ref_stride = (width + 15) // 16 * 16
+  n_images = len(specs)
+  ref = np.zeros((n_images, ref_stride), dtype=np.uint8)
+  image_start = np.zeros(n_images, dtype=np.int32)
+  variant_start = np.zeros(n_images, dtype=np.int32)
+  pair_begin = np.zeros(n_images + 1, dtype=np.int64)
+
+  read_index: Dict[int, int] = {}
+  reads: List[Read] = []
+  sort_pos: List[int] = []
+  pair_read: List[int] = []
+  pair_support: List[int] = []
+  pair_group: List[int] = []
+  for i, s in enumerate(specs):
+    rb = s.ref_bases.encode() if isinstance(s.ref_bases, str) else bytes(s.ref_bases)
+    if len(rb) != width:
+      raise ValueError(f'ref_bases has {len(rb)} bases, expected width {width}')
+    ref[i, :width] = np.frombuffer(rb, dtype=np.uint8)
+    image_start[i] = s.image_start_pos
+    variant_start[i] = s.variant_start
+    for j, r in enumerate(s.reads):
+      sp = s.sort_positions[j] if s.sort_positions else r.position
+      key = (id(r), sp)
+      k = read_index.get(key)
+      if k is None:
+        k = len(reads)
+        read_index[key] = k
+        reads.append(r)
+        sort_pos.append(sp)
+      pair_read.append(k)
+      pair_support.append(s.support[j])
+      pair_group.append(s.allele_group[j] if s.allele_group else 0)
+    pair_begin[i + 1] = len(pair_read)
+
+  n_reads = len(reads)
+  seq_begin = np.zeros(n_reads + 1, dtype=np.int64)
+  cig_begin = np.zeros(n_reads + 1, dtype=np.int64)
+  flags = np.zeros(n_reads, dtype=np.uint8)
+  hp = np.zeros(n_reads, dtype=np.int32)
+  for k, r in enumerate(reads):
+    if len(r.aligned_quality) != len(r.aligned_sequence):
+      raise ValueError('aligned_quality and aligned_sequence differ in length')
+    seq_begin[k + 1] = seq_begin[k] + len(r.aligned_sequence)
+    cig_begin[k + 1] = cig_begin[k] + len(r.cigar)
+    f = 0
+    if r.reverse_strand:
+      f |= READ_REVERSE_STRAND
+    if r.supplementary_alignment:
+      f |= READ_SUPPLEMENTARY
+    if r.hp_values:  # info contains "HP" with >= 1 value
+      f |= READ_HAS_HP
+      hp[k] = r.hp_values[0]
+      if len(r.hp_values) > 1:
+        f |= READ_HP_MULTI
+    flags[k] = f
+  bases = np.frombuffer(b''.join(bytes(r.aligned_sequence) for r in reads), dtype=np.uint8).copy() \
+      if n_reads else np.zeros(0, dtype=np.uint8)
+  quals = np.frombuffer(b''.join(bytes(r.aligned_quality) for r in reads), dtype=np.uint8).copy() \
+      if n_reads else np.zeros(0, dtype=np.uint8)
+  cigar = np.array([(ln << 4) | op for r in reads for op, ln in r.cigar], dtype=np.uint32)
+
+  def _pad(a: np.ndarray) -> np.ndarray:
+    # never hand the C side a NULL / zero-length allocation for an empty array
+    return a if a.size else np.zeros(1, dtype=a.dtype)
+
+  arrays = {
+      'ref_bases': ref.reshape(-1),
+      'image_start_pos': image_start,
+      'variant_start': variant_start,
+      'pair_begin': pair_begin,
+      'pair_read': np.array(pair_read, dtype=np.int32),
+      'pair_support': np.array(pair_support, dtype=np.uint8),
+      'pair_allele_group': np.array(pair_group, dtype=np.uint8),
+      'read_pos': np.array([r.position for r in reads], dtype=np.int32),
+      'read_sort_pos': np.array(sort_pos, dtype=np.int32),
+      'read_mapq': np.array([r.mapping_quality for r in reads], dtype=np.int32),
+      'read_flags': flags,
+      'read_fragment_length': np.array([r.fragment_length for r in reads], dtype=np.int32),
+      'read_hp': hp,
+      'read_name_rank': name_ranks(reads),
+      'read_seq_begin': seq_begin,
+      'read_cigar_begin': cig_begin,
+      'bases': bases,
+      'quals': quals,
+      'cigar': cigar,
+  }
+  arrays = {k: np.ascontiguousarray(_pad(v)) for k, v in arrays.items()}
+  pb = PackedBatch(n_images=n_images, n_reads=n_reads, n_pairs=len(pair_read), ref_stride=ref_stride,
+                   arrays=arrays)
+  return pb

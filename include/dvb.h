@@ -1,0 +1,211 @@
+/*
+ * dvb.h — C ABI of the B200-native pileup-encode + CNN path (libdvb.so).
+ *
+ * This is the drop-in boundary for the one hot path of google/deepvariant v1.10.0
+ * that this repository accelerates:
+ *
+ *   encoder  : replaces  PileupImageEncoderNative::BuildPileupForOneSample
+ *              (deepvariant/pileup_image_native.cc:296-447), the per-candidate
+ *              driver loop ExamplesGenerator::CreateAndWriteExamplesForCandidate
+ *              (deepvariant/make_examples_native.cc:632-736) and the planar→HWC
+ *              flatten FillPileupArray (deepvariant/pileup_image_native.h:214-308)
+ *              — a whole batch of candidates per call instead of one.
+ *   cnn      : replaces the SavedModel call in call_variants.predict_step
+ *              (deepvariant/call_variants.py:904-932) = dv_utils.preprocess_images
+ *              (deepvariant/dv_utils.py:356-380) + keras_modeling.inceptionv3
+ *              (deepvariant/keras_modeling.py:246-336).
+ *
+ * Plain C: pointers + sizes, no torch / C++ types.  Every function returns a
+ * DvbStatus (0 = OK) and never aborts the process (the reference CHECK-fails);
+ * dvb_last_error() gives the message of the last failure on the calling thread.
+ * Handles are per-device; calls are stream-ordered; the caller owns all buffers.
+ */
+#ifndef DVB_H_
+#define DVB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVB_ABI_VERSION 1
+#define DVB_MAX_CHANNELS 16
+
+typedef enum DvbStatus {
+  DVB_OK = 0,
+  DVB_ERR_INVALID_ARGUMENT = 1,
+  DVB_ERR_UNSUPPORTED_CHANNEL = 2,
+  DVB_ERR_BAD_CIGAR = 3,          /* reference: LOG(FATAL) "Unrecognized CIGAR op", pileup_channel_lib.cc:251 */
+  DVB_ERR_TOO_MANY_READS = 4,     /* > max_reads_per_image reads overlap one candidate */
+  DVB_ERR_CUDA = 5,
+  DVB_ERR_NO_DEVICE = 6,
+  DVB_ERR_INTERNAL = 7
+} DvbStatus;
+
+/* DeepVariantChannelEnum values (deepvariant/protos/deepvariant.proto:1288-1343)
+ * this library computes per read.  Anything else -> DVB_ERR_UNSUPPORTED_CHANNEL. */
+enum {
+  DVB_CH_READ_BASE = 1,
+  DVB_CH_BASE_QUALITY = 2,
+  DVB_CH_MAPPING_QUALITY = 3,
+  DVB_CH_STRAND = 4,
+  DVB_CH_READ_SUPPORTS_VARIANT = 5,
+  DVB_CH_BASE_DIFFERS_FROM_REF = 6,
+  DVB_CH_HAPLOTYPE_TAG = 7,
+  DVB_CH_BLANK = 18,
+  DVB_CH_INSERT_SIZE = 19,
+  DVB_CH_SUPPLEMENTARY_ALIGNMENT = 26
+};
+
+/* read_flags bits */
+enum {
+  DVB_READ_REVERSE_STRAND = 1,  /* alignment.position.reverse_strand */
+  DVB_READ_SUPPLEMENTARY = 2,   /* supplementary_alignment */
+  DVB_READ_HAS_HP = 4,          /* info["HP"] present with >=1 value; read_hp holds values(0).int_value */
+  DVB_READ_HP_MULTI = 8         /* info["HP"] has >1 value: haplotype channel uses 0 (haplotype_tag_channel.cc:83-86) */
+};
+
+/* CIGAR is packed like BAM: (length << 4) | op, op = M0 I1 D2 N3 S4 H5 P6 =7 X8. */
+
+/* Mirrors the PileupImageOptions fields the hot path reads
+ * (deepvariant/protos/deepvariant.proto PileupImageOptions; defaults in
+ * deepvariant/pileup_image.py:36-74). */
+typedef struct DvbPileupParams {
+  int32_t width;                  /* odd, >= 3 (pileup_image_native.cc:114) */
+  int32_t height;                 /* rows per image (single sample) */
+  int32_t reference_band_height;
+  int32_t num_channels;           /* channels computed per read */
+  int32_t channels[DVB_MAX_CHANNELS];
+  int32_t num_alt_channels;       /* 0, or 2 for alt-aligned diff/base channels appended last (zero-filled here) */
+  int32_t base_color_offset_a_and_g;
+  int32_t base_color_offset_t_and_c;
+  int32_t base_color_stride;
+  float allele_supporting_read_alpha;
+  float allele_unsupporting_read_alpha;
+  float other_allele_supporting_read_alpha;
+  float reference_matching_read_alpha;
+  float reference_mismatching_read_alpha;
+  int32_t indel_anchoring_base_char;   /* '*' */
+  int32_t reference_base_quality;
+  int32_t positive_strand_color;
+  int32_t negative_strand_color;
+  int32_t base_quality_cap;
+  int32_t mapping_quality_cap;
+  int32_t min_base_quality;       /* read_requirements.min_base_quality */
+  int32_t min_mapping_quality;    /* read_requirements.min_mapping_quality */
+  int32_t sort_by_haplotypes;
+  int32_t hp_tag_for_assembly_polishing;
+  int32_t sort_by_alt_allele_support;
+  uint32_t random_seed;           /* 2101079370 */
+  int32_t max_reads_per_image;    /* capacity of the down-sampling tables; 0 -> 2048 */
+} DvbPileupParams;
+
+/* One batch = the images of any number of candidates x alt-allele combinations.
+ * All arrays are Structure-of-Arrays; for the *_device entry point every pointer
+ * is a device pointer, for *_host every pointer is a host pointer.
+ *
+ * An "image" is one call of BuildPileupForOneSample: (dv_call, ref_bases, reads,
+ * image_start_pos, alt_alleles).  Its reads are given as a CSR list of "pairs"
+ * in the order InMemoryReader::Query returns them (make_examples_native.cc:802).
+ * pair_support restates ReadSupportsVariantChannel::ReadSupportsAlt
+ * (channels/read_supports_variant_channel.cc:75-104) as a class per (image, read):
+ * 0 = ref/none, 1 = supports an alt of this image, 2 = supports another alt. */
+typedef struct DvbBatch {
+  int32_t n_images;
+  int32_t n_reads;
+  int64_t n_pairs;
+  int64_t n_bases;   /* length of bases[] / quals[] */
+  int64_t n_cigar;   /* length of cigar[] */
+  /* per image */
+  const uint8_t* ref_bases;        /* [n_images * ref_stride]; first `width` bytes of each record valid */
+  int32_t ref_stride;              /* >= width */
+  const int32_t* image_start_pos;  /* [n_images] variant.start - (width-1)/2 */
+  const int32_t* variant_start;    /* [n_images] dv_call.variant.start */
+  const int64_t* pair_begin;       /* [n_images + 1] */
+  /* per pair */
+  const int32_t* pair_read;        /* [n_pairs] row of the read table */
+  const uint8_t* pair_support;     /* [n_pairs] 0/1/2 */
+  const uint8_t* pair_allele_group;/* [n_pairs] or NULL; only read when sort_by_alt_allele_support */
+  /* per read */
+  const int32_t* read_pos;         /* alignment.position.position (after trimming) */
+  const int32_t* read_sort_pos;    /* alignment position before trimming (pileup_image_native.cc:395-398) */
+  const int32_t* read_mapq;
+  const uint8_t* read_flags;
+  const int32_t* read_fragment_length;
+  const int32_t* read_hp;
+  const uint32_t* read_name_rank;  /* dense rank of (fragment_name, read_number); equal keys share a rank */
+  const int64_t* read_seq_begin;   /* [n_reads + 1] into bases / quals */
+  const int64_t* read_cigar_begin; /* [n_reads + 1] into cigar */
+  const uint8_t* bases;            /* ASCII aligned_sequence */
+  const uint8_t* quals;            /* aligned_quality */
+  const uint32_t* cigar;
+} DvbBatch;
+
+typedef struct DvbEncoder DvbEncoder;
+typedef struct DvbCnn DvbCnn;
+
+int dvb_abi_version(void);
+const char* dvb_last_error(void);
+
+/* Fills *p with pileup_image.default_options() (pileup_image.py:36-74) and the six
+ * default channels (dv_constants.py:45-52). */
+void dvb_pileup_params_default(DvbPileupParams* p);
+
+/* Bytes of one image: height * width * (num_channels + num_alt_channels). */
+int64_t dvb_image_bytes(const DvbPileupParams* p);
+
+/* DownsampleReadIndices (pileup_image_native.cc:153-165): iota(n) shuffled by
+ * libstdc++ std::shuffle with a fresh std::mt19937_64(seed).  Host only. */
+int dvb_shuffle_table(int32_t n, uint32_t seed, int32_t* out);
+
+/* device: CUDA ordinal.  Builds the down-sampling tables and uploads constants. */
+int dvb_encoder_create(const DvbPileupParams* params, int device, DvbEncoder** out);
+void dvb_encoder_destroy(DvbEncoder* enc);
+
+/* All pointers in `batch`, `out` and `rows_kept` are device pointers on the encoder's device.
+ * out: uint8[n_images][height][width][num_channels + num_alt_channels].
+ * rows_kept: int32[n_images] or NULL — number of read rows each image received (reads that
+ *   EncodeRead did not reject, capped at height - reference_band_height).
+ * stream: cudaStream_t (NULL = default stream).  Asynchronous. */
+int dvb_encode_batch_device(DvbEncoder* enc, const DvbBatch* batch, uint8_t* out,
+                            int32_t* rows_kept, void* stream);
+
+/* Device-side error word set by the kernel (bad CIGAR op, too many reads).
+ * Synchronises `stream`, returns the status and clears it. */
+int dvb_encoder_check(DvbEncoder* enc, void* stream);
+
+/* Host buffers in, host buffer out: validates, stages H2D, encodes, copies D2H,
+ * synchronises.  This is the call a reference maintainer would bind. */
+int dvb_encode_batch_host(DvbEncoder* enc, const DvbBatch* batch, uint8_t* out_host,
+                          int32_t* rows_kept_host /* or NULL */);
+
+/* Number of kernel launches issued by this handle so far (bench bookkeeping). */
+int64_t dvb_encoder_launch_count(const DvbEncoder* enc);
+
+/* ---- CNN (Inception-v3 + genotype softmax) ------------------------------- */
+
+/* Weights blob layout: see deepvariant_b200/modeling.py (pack_weights): a flat
+ * little-endian stream of per-layer folded conv weights (fp16, [Cout][KH][KW][Cin_pad])
+ * and fp32 biases in network order, then the dense 2048x3 fp32 head.
+ * precision: 0 = fp16 operands / fp32 accumulate (single pass),
+ *            1 = split-fp16 x3 (fp32-grade products). */
+int dvb_cnn_create(const void* weights, int64_t weights_bytes, int32_t height, int32_t width,
+                   int32_t channels, int32_t max_batch, int32_t precision, int device, DvbCnn** out);
+void dvb_cnn_destroy(DvbCnn* cnn);
+
+/* images: device uint8 [n][H][W][C] (the encoder's output, consumed in place);
+ * probs: device float [n][3].  Asynchronous on `stream`. */
+int dvb_cnn_forward_device(DvbCnn* cnn, const uint8_t* images, int32_t n, float* probs, void* stream);
+
+/* Host in / host out variant. */
+int dvb_cnn_forward_host(DvbCnn* cnn, const uint8_t* images_host, int32_t n, float* probs_host);
+
+int64_t dvb_cnn_launch_count(const DvbCnn* cnn);
+/* FLOPs of one forward for one image (conv MACs x 2). */
+double dvb_cnn_flops_per_image(const DvbCnn* cnn);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* DVB_H_ */
