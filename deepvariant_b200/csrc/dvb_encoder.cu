@@ -1,0 +1,756 @@
+// dvb_encoder.cu — batched pileup-image encoder for sm_100a (B200) + its C ABI.
+//
+// Replaces, for a whole batch of candidate images per launch, the reference's
+//   BuildPileupForOneSample            deepvariant/pileup_image_native.cc:296-447
+//     DownsampleReadIndices            :153-165   (tables built on the host with libstdc++)
+//     EncodeRead / CalculateChannels   :477-510, deepvariant/pileup_channel_lib.cc:91-261
+//     GetHapIndex / SortImageRows      :449-475, :75-102
+//     EncodeReference                  :512-527,  pileup_channel_lib.cc:263-293
+//   FillPileupArray (planar -> HWC)    deepvariant/pileup_image_native.h:214-308
+//
+// Formulation (integer / byte work, HBM-write bound: H*W*C bytes out per image):
+//   one CTA per image (grid-stride), 8 warps.
+//   phase A  thread-per-read acceptance test (mapq, low-quality base at variant.start found by a
+//            scalar CIGAR walk), block scan -> the first (H - band) accepted reads in visit order;
+//   phase S  rank sort of <= (H - band) keys (hap, allele group, position, name rank, visit index);
+//   phase B  warp-per-row: the row is assembled in shared memory at the SAME 16-byte phase as its
+//            global address (CIGAR ops in order, __syncwarp between ops => last-writer-wins is
+//            preserved), then streamed out with 16-byte coalesced stores; blank rows are stored
+//            straight from registers.
+// Colour arithmetic that the reference does in float32 per pixel is tabulated on the host with
+// the identical float expressions (256-entry LUTs) or done once per row with IEEE _rn intrinsics.
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <numeric>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "dvb_common.h"
+
+namespace dvb {
+std::string& last_error() {
+  static thread_local std::string e;
+  return e;
+}
+}  // namespace dvb
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr float kMaxPixelValueAsFloat = 254.0f;  // channels/channel.h:78
+constexpr float kMaxFragmentLength = 1000.0f;    // channels/channel.h:81
+
+enum Kind : uint8_t { K_ZERO = 0, K_BASE = 1, K_QUAL = 2, K_DIFF = 3, K_CONST = 4 };
+
+struct EncDev {
+  int W, H, band, C, Cout, max_rows;
+  int row_bytes;
+  long long image_bytes;
+  int min_bq, min_mq, anchor_char;
+  int sort_by_hap, polish_tag, sort_by_group;
+  float mapq_cap;
+  int pos_strand, neg_strand;
+  uint8_t sup_color[4];     // by support class 0/1/2
+  uint8_t match_color, mismatch_color;
+  uint8_t supp_color[2];    // supplementary_alignment false/true
+  uint8_t kind[DVB_MAX_CHANNELS];
+  uint8_t chan[DVB_MAX_CHANNELS];       // channel enum
+  uint8_t ref_const[DVB_MAX_CHANNELS];  // reference-row value (K_BASE uses base_lut)
+  // A pixel is assembled as up to 4 little-endian words: const + base*mask_base + qual*mask_qual +
+  // diff*mask_diff, where a mask has 0x01 in the byte of every channel of that kind (no carries:
+  // every term is < 256 and the byte positions of different kinds are disjoint).
+  unsigned mask_base[4], mask_qual[4], mask_diff[4], mask_const[4], ref_words[4];
+  int n_words;
+  int perm_cap;             // largest n with a down-sampling table
+  const int* perm;          // tables for n = max_rows+1 .. perm_cap, concatenated
+  uint8_t base_lut[256];    // BaseColor(char)
+  uint8_t qual_lut[256];    // ScaleColor(q, base_quality_cap)
+};
+
+__device__ __forceinline__ long long perm_offset(int n, int max_rows) {
+  // sum_{k=max_rows+1}^{n-1} k
+  return (long long)(n - 1) * n / 2 - (long long)max_rows * (max_rows + 1) / 2;
+}
+
+// ScaleColor (channels/mapping_quality_channel.cc:60-67) with IEEE round-to-nearest ops.
+__device__ __forceinline__ uint8_t scale_color_dev(int value, float max_val) {
+  float v = (float)value;
+  if (v > max_val) { value = (int)max_val; v = (float)value; }
+  return (uint8_t)(int)__fmul_rn(kMaxPixelValueAsFloat, __fdiv_rn(v, max_val));
+}
+
+struct ReadHdr {
+  int pos, mapq, fraglen, hp;
+  unsigned flags;
+  long long seq0, cig0;
+  int n_cig;
+};
+
+__device__ __forceinline__ ReadHdr load_read(const DvbBatch& B, int r) {
+  ReadHdr h;
+  h.pos = B.read_pos[r];
+  h.mapq = B.read_mapq[r];
+  h.fraglen = B.read_fragment_length[r];
+  h.hp = B.read_hp[r];
+  h.flags = B.read_flags[r];
+  h.seq0 = B.read_seq_begin[r];
+  h.cig0 = B.read_cigar_begin[r];
+  h.n_cig = (int)(B.read_cigar_begin[r + 1] - h.cig0);
+  return h;
+}
+
+// EncodeRead's keep/drop decision (pileup_image_native.cc:485-491 + the low-quality-base-at-call-site
+// bail-out of pileup_channel_lib.cc:144-150), evaluated without drawing.  Returns 1 keep, 0 drop,
+// -1 unrecognized CIGAR op.
+__device__ int accept_read(const EncDev& P, const DvbBatch& B, int r, int vstart, int image_start) {
+  const ReadHdr h = load_read(B, r);
+  if (h.mapq < P.min_mq) return 0;
+  const unsigned vcol = (unsigned)(vstart - image_start);
+  const bool v_in_window = vcol < (unsigned)P.W;
+  const uint8_t* bases = B.bases + h.seq0;
+  const uint8_t* quals = B.quals + h.seq0;
+  int ref_i = h.pos, read_i = 0;
+  for (int k = 0; k < h.n_cig; ++k) {
+    const unsigned cw = B.cigar[h.cig0 + k];
+    const int op = cw & 0xF, len = (int)(cw >> 4);
+    switch (op) {
+      case 0: case 7: case 8:
+        if (v_in_window && vstart >= ref_i && vstart < ref_i + len) {
+          const int ri = read_i + (vstart - ref_i);
+          if (bases[ri] != 0 && (int)quals[ri] < P.min_bq) return 0;
+        }
+        ref_i += len; read_i += len;
+        break;
+      case 1:
+        if (ref_i > 0 && P.anchor_char && v_in_window && ref_i - 1 == vstart &&
+            (int)quals[read_i] < P.min_bq) return 0;
+        read_i += len;
+        break;
+      case 4:
+        read_i += len;
+        break;
+      case 2:
+        if (read_i > 0 && P.anchor_char && v_in_window && ref_i - 1 == vstart &&
+            (int)quals[read_i - 1] < P.min_bq) return 0;
+        ref_i += len;
+        break;
+      case 3:
+        ref_i += len;
+        break;
+      case 5: case 6:
+        break;
+      default:
+        return -1;
+    }
+  }
+  return 1;
+}
+
+// GetHapIndex, pileup_image_native.cc:449-475.
+__device__ __forceinline__ int hap_index(const EncDev& P, unsigned flags, int hp) {
+  if (!P.sort_by_hap || !(flags & DVB_READ_HAS_HP)) return 0;
+  if (P.polish_tag > 0 && hp == P.polish_tag) return -1;
+  if (hp < 0) return 0;
+  return hp;
+}
+
+// Per-read constant of a K_CONST channel (channels/*_channel.cc FillReadBase).
+__device__ uint8_t read_const(const EncDev& P, int chan, const ReadHdr& h, int support) {
+  switch (chan) {
+    case DVB_CH_MAPPING_QUALITY:
+      return scale_color_dev(h.mapq, P.mapq_cap);
+    case DVB_CH_STRAND:
+      return (uint8_t)((h.flags & DVB_READ_REVERSE_STRAND) ? P.neg_strand : P.pos_strand);
+    case DVB_CH_READ_SUPPORTS_VARIANT:
+      return P.sup_color[support > 2 ? 2 : support];
+    case DVB_CH_HAPLOTYPE_TAG: {  // haplotype_tag_channel.cc:74-109
+      int v = 0;
+      if ((h.flags & DVB_READ_HAS_HP) && !(h.flags & DVB_READ_HP_MULTI)) {
+        v = h.hp;
+        if (P.polish_tag == 2) { if (v == 1) v = 2; else if (v == 2) v = 1; }
+      }
+      return scale_color_dev(v, 2.0f);
+    }
+    case DVB_CH_INSERT_SIZE: {  // insert_size_channel.cc:80-89
+      int f = h.fraglen < 0 ? -h.fraglen : h.fraglen;
+      if ((float)f > kMaxFragmentLength) f = (int)kMaxFragmentLength;
+      return (uint8_t)(int)__fmul_rn(kMaxPixelValueAsFloat, __fdiv_rn((float)f, kMaxFragmentLength));
+    }
+    case DVB_CH_SUPPLEMENTARY_ALIGNMENT:
+      return P.supp_color[(h.flags & DVB_READ_SUPPLEMENTARY) ? 1 : 0];
+    default:
+      return 0;
+  }
+}
+
+// Streams `row_bytes` bytes of a row to global memory.  `src` (shared) holds the row at the same
+// 16-byte phase as `dst`; src == nullptr stores zeros.
+__device__ __forceinline__ void flush_row(uint8_t* __restrict__ dst, const uint8_t* src, int row_bytes, int lane) {
+  const int phase = (int)((uintptr_t)dst & 15);
+  int head = (16 - phase) & 15;
+  if (head > row_bytes) head = row_bytes;
+  if (lane < head) dst[lane] = src ? src[lane] : (uint8_t)0;
+  const int body = (row_bytes - head) >> 4;
+  uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+  if (src) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+    for (int i = lane; i < body; i += 32) d4[i] = s4[i];
+  } else {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int i = lane; i < body; i += 32) d4[i] = z;
+  }
+  const int done = head + (body << 4);
+  const int tail = row_bytes - done;
+  if (lane < tail) dst[done + lane] = src ? src[done + lane] : (uint8_t)0;
+}
+
+__global__ void __launch_bounds__(kThreads, 4)
+dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, int* __restrict__ rows_kept,
+                  int* __restrict__ err) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  // layout: [base_lut 256][qual_lut 256][ref Wpad][sel arrays 6 x max_rows x 4B][order max_rows x 4B]
+  //         [warp totals][row buffers kWarps x rowbuf_bytes]
+  const int Wpad = (P.W + 15) & ~15;
+  uint8_t* s_base = smem;
+  uint8_t* s_qual = smem + 256;
+  uint8_t* s_ref = smem + 512;
+  int* s_pair = reinterpret_cast<int*>(s_ref + Wpad);
+  int* s_hap = s_pair + P.max_rows;
+  int* s_grp = s_hap + P.max_rows;
+  int* s_pos = s_grp + P.max_rows;
+  unsigned* s_rank = reinterpret_cast<unsigned*>(s_pos + P.max_rows);
+  int* s_visit = reinterpret_cast<int*>(s_rank + P.max_rows);
+  int* s_order = s_visit + P.max_rows;
+  int* s_wtot = s_order + P.max_rows;          // kWarps + 2 ints
+  const int rowbuf_bytes = ((P.row_bytes + 15) & ~15) + 32;
+  uintptr_t rb0 = (reinterpret_cast<uintptr_t>(s_wtot + kWarps + 2) + 15) & ~(uintptr_t)15;
+  uint8_t* s_rows = reinterpret_cast<uint8_t*>(rb0);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  s_base[tid] = P.base_lut[tid];
+  s_qual[tid] = P.qual_lut[tid];
+
+  for (int img = blockIdx.x; img < B.n_images; img += gridDim.x) {
+    __syncthreads();  // previous image fully flushed before smem is reused
+    const int image_start = B.image_start_pos[img];
+    const int vstart = B.variant_start[img];
+    const long long p0 = B.pair_begin[img];
+    const int n = (int)(B.pair_begin[img + 1] - p0);
+    for (int i = tid; i < Wpad; i += kThreads)
+      s_ref[i] = i < P.W ? B.ref_bases[(long long)img * B.ref_stride + i] : (uint8_t)0;
+    if (tid == 0) { s_wtot[kWarps] = 0; }
+
+    // ---- phase A: acceptance + first max_rows accepted in visit order --------------------
+    const bool shuffled = n > P.max_rows;
+    const int* perm = nullptr;
+    if (shuffled) {
+      if (n > P.perm_cap) { if (tid == 0) atomicMax(err, DVB_ERR_TOO_MANY_READS); }
+      else perm = P.perm + perm_offset(n, P.max_rows);
+    }
+    __syncthreads();
+    int n_acc = 0;
+    for (int base = 0; base < n && n_acc < P.max_rows; base += kThreads) {
+      const int i = base + tid;
+      int ok = 0;
+      long long p = 0;
+      if (i < n) {
+        p = p0 + (perm ? perm[i] : i);
+        ok = accept_read(P, B, B.pair_read[p], vstart, image_start);
+        if (ok < 0) { atomicMax(err, DVB_ERR_BAD_CIGAR); ok = 0; }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0) s_wtot[warp] = __popc(m);
+      __syncthreads();
+      int before = n_acc;
+      for (int w = 0; w < warp; ++w) before += s_wtot[w];
+      int total = 0;
+      for (int w = 0; w < kWarps; ++w) total += s_wtot[w];
+      const int slot = before + __popc(m & ((1u << lane) - 1u));
+      if (ok && slot < P.max_rows) {
+        const int r = B.pair_read[p];
+        const unsigned fl = B.read_flags[r];
+        s_pair[slot] = (int)(p - p0);
+        s_hap[slot] = hap_index(P, fl, B.read_hp[r]);
+        s_grp[slot] = (P.sort_by_group && B.pair_allele_group) ? (int)B.pair_allele_group[p] : 0;
+        s_pos[slot] = B.read_sort_pos[r];
+        s_rank[slot] = B.read_name_rank[r];
+        s_visit[slot] = i;
+      }
+      n_acc += total;
+      __syncthreads();
+    }
+    const int n_rows = n_acc < P.max_rows ? n_acc : P.max_rows;
+    if (tid == 0 && rows_kept) rows_kept[img] = n_rows;
+
+    // ---- phase S: stable sort by (hap, group, pos, name rank); visit index breaks ties -----
+    for (int e = tid; e < n_rows; e += kThreads) {
+      const int h = s_hap[e], g = s_grp[e], ps = s_pos[e], v = s_visit[e];
+      const unsigned rk = s_rank[e];
+      int less = 0;
+      for (int f = 0; f < n_rows; ++f) {
+        const int h2 = s_hap[f], g2 = s_grp[f], p2 = s_pos[f], v2 = s_visit[f];
+        const unsigned r2 = s_rank[f];
+        bool lt;
+        if (h2 != h) lt = h2 < h;
+        else if (g2 != g) lt = g2 < g;
+        else if (p2 != ps) lt = p2 < ps;
+        else if (r2 != rk) lt = r2 < rk;
+        else lt = v2 < v;
+        less += lt ? 1 : 0;
+      }
+      s_order[less] = e;
+    }
+    __syncthreads();
+
+    // ---- phase B: one warp per image row ---------------------------------------------------
+    uint8_t* img_out = out + (long long)img * P.image_bytes;
+    for (int row = warp; row < P.H; row += kWarps) {
+      uint8_t* dst = img_out + (long long)row * P.row_bytes;
+      if (row >= P.band + n_rows) {  // blank tail (pileup_image_native.cc:414-421)
+        flush_row(dst, nullptr, P.row_bytes, lane);
+        continue;
+      }
+      uint8_t* buf = s_rows + warp * rowbuf_bytes;
+      const int phase = (int)((uintptr_t)dst & 15);
+      uint8_t* px = buf + phase;  // pixel (col, ch) lives at px[col * Cout + ch]
+      {
+        uint4* b4 = reinterpret_cast<uint4*>(buf);
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (int i = lane; i < (rowbuf_bytes >> 4); i += 32) b4[i] = z;
+      }
+      __syncwarp();
+      if (row < P.band) {
+        // EncodeReference / CalculateRefRows
+        for (int col = lane; col < P.W; col += 32) {
+          const unsigned bc = s_base[s_ref[col]];
+          uint8_t* q = px + col * P.Cout;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            if (w < P.n_words) {
+              const unsigned word = P.ref_words[w] + bc * P.mask_base[w];
+#pragma unroll
+              for (int b = 0; b < 4; ++b)
+                if (w * 4 + b < P.C) q[w * 4 + b] = (uint8_t)(word >> (8 * b));
+            }
+          }
+        }
+      } else {
+        const int e = s_order[row - P.band];
+        const long long p = p0 + s_pair[e];
+        const int r = B.pair_read[p];
+        const int support = B.pair_support[p];
+        const ReadHdr h = load_read(B, r);
+        // per-read constants: lane c computes channel c, then every lane gathers them into words
+        unsigned myc = 0;
+        if (lane < P.C && P.kind[lane] == K_CONST) myc = read_const(P, P.chan[lane], h, support);
+        unsigned tc[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int c = 0; c < DVB_MAX_CHANNELS; ++c) {
+          const unsigned v = __shfl_sync(0xffffffffu, myc, c);
+          tc[c >> 2] |= (v & 0xFFu) << (8 * (c & 3));
+        }
+        const uint8_t* bases = B.bases + h.seq0;
+        const uint8_t* quals = B.quals + h.seq0;
+        int ref_i = h.pos, read_i = 0;
+        for (int k = 0; k < h.n_cig; ++k) {
+          const unsigned cw = B.cigar[h.cig0 + k];
+          const int op = cw & 0xF, len = (int)(cw >> 4);
+          if (op == 0 || op == 7 || op == 8) {
+            const int c0 = ref_i - image_start;
+            const int lo = c0 < 0 ? -c0 : 0;
+            const int hi = P.W - c0 < len ? P.W - c0 : len;
+            for (int j = lo + lane; j < hi; j += 32) {
+              const int col = c0 + j;
+              const unsigned b = bases[read_i + j];
+              if (b != 0) {
+                const unsigned bc = s_base[b];
+                const unsigned ql = s_qual[quals[read_i + j]];
+                const unsigned df = (b == s_ref[col]) ? P.match_color : P.mismatch_color;
+                uint8_t* q = px + col * P.Cout;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                  if (w < P.n_words) {
+                    const unsigned word = tc[w] + bc * P.mask_base[w] + ql * P.mask_qual[w] + df * P.mask_diff[w];
+#pragma unroll
+                    for (int bb = 0; bb < 4; ++bb)
+                      if (w * 4 + bb < P.C) q[w * 4 + bb] = (uint8_t)(word >> (8 * bb));
+                  }
+                }
+              }
+            }
+            ref_i += len; read_i += len;
+          } else if (op == 1 || op == 2) {
+            // INSERT: anchor = ref_i - 1, quality of read_i; DELETE: anchor = ref_i - 1 (after the
+            // reference's own `ref_i -= 1`), quality of read_i - 1.  pileup_channel_lib.cc:129-137,228-245
+            const bool fires = (op == 1) ? (ref_i > 0) : (read_i > 0);
+            const int col = ref_i - 1 - image_start;
+            if (lane == 0 && fires && P.anchor_char && (unsigned)col < (unsigned)P.W) {
+              const unsigned bc = s_base[P.anchor_char & 0xFF];
+              const unsigned ql = s_qual[quals[op == 1 ? read_i : read_i - 1]];
+              const unsigned df = ((unsigned)P.anchor_char == s_ref[col]) ? P.match_color : P.mismatch_color;
+              uint8_t* q = px + col * P.Cout;
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                if (w < P.n_words) {
+                  const unsigned word = tc[w] + bc * P.mask_base[w] + ql * P.mask_qual[w] + df * P.mask_diff[w];
+#pragma unroll
+                  for (int bb = 0; bb < 4; ++bb)
+                    if (w * 4 + bb < P.C) q[w * 4 + bb] = (uint8_t)(word >> (8 * bb));
+                }
+              }
+            }
+            if (op == 1) read_i += len; else ref_i += len;
+          } else if (op == 4) {
+            read_i += len;
+          } else if (op == 3) {
+            ref_i += len;
+          }  // 5, 6 ignored; others were flagged in phase A
+          __syncwarp();  // orders this op's shared-memory writes before the next op's
+        }
+      }
+      __syncwarp();
+      flush_row(dst, buf + phase, P.row_bytes, lane);
+    }
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+
+struct DvbEncoder {
+  DvbPileupParams params;
+  EncDev dev;
+  int device = 0;
+  int num_sms = 148;
+  int smem_bytes = 0;
+  int grid_cap = 0;
+  int* d_perm = nullptr;
+  int* d_err = nullptr;
+  int64_t launches = 0;
+  // staging for the host entry point
+  dvb::DevBuf d_in, d_out, d_rows;
+  dvb::PinBuf h_in, h_out;
+  cudaStream_t stream = nullptr;
+};
+
+namespace {
+
+// ---- host restatement of the float32 colour expressions (exactly the reference's forms) ----
+uint8_t HostScaleColor(int value, float max_val) {  // channels/base_quality_channel.cc:59-66
+  if (static_cast<float>(value) > max_val) value = max_val;
+  return static_cast<int>(kMaxPixelValueAsFloat * (static_cast<float>(value) / max_val));
+}
+int HostAlphaColor(float alpha) { return static_cast<int>(kMaxPixelValueAsFloat * alpha); }
+
+int HostBaseColor(int base, const DvbPileupParams& o) {  // channels/read_base_channel.cc:56-73
+  switch (base) {
+    case 'A': return o.base_color_offset_a_and_g + o.base_color_stride * 3;
+    case 'G': return o.base_color_offset_a_and_g + o.base_color_stride * 2;
+    case 'T': return o.base_color_offset_t_and_c + o.base_color_stride * 1;
+    case 'C': return o.base_color_offset_t_and_c + o.base_color_stride * 0;
+    default: return 0;
+  }
+}
+
+int BuildDev(const DvbPileupParams& o, EncDev* d) {
+  memset(d, 0, sizeof(*d));
+  if (o.width < 1) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "width must be >= 1");
+  if (o.num_channels < 1 || o.num_channels > DVB_MAX_CHANNELS || o.num_alt_channels < 0 ||
+      o.num_channels + o.num_alt_channels > DVB_MAX_CHANNELS)
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "bad channel count %d + %d", o.num_channels, o.num_alt_channels);
+  if (o.reference_band_height < 0 || o.height <= o.reference_band_height)
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "height %d must exceed reference_band_height %d", o.height,
+                     o.reference_band_height);
+  d->W = o.width; d->H = o.height; d->band = o.reference_band_height;
+  d->C = o.num_channels; d->Cout = o.num_channels + o.num_alt_channels;
+  d->max_rows = o.height - o.reference_band_height;
+  d->row_bytes = d->W * d->Cout;
+  d->image_bytes = (long long)d->H * d->row_bytes;
+  d->min_bq = o.min_base_quality; d->min_mq = o.min_mapping_quality;
+  d->anchor_char = o.indel_anchoring_base_char & 0xFF;
+  d->sort_by_hap = o.sort_by_haplotypes; d->polish_tag = o.hp_tag_for_assembly_polishing;
+  d->sort_by_group = o.sort_by_alt_allele_support;
+  d->mapq_cap = (float)o.mapping_quality_cap;
+  d->pos_strand = o.positive_strand_color; d->neg_strand = o.negative_strand_color;
+  d->sup_color[0] = (uint8_t)HostAlphaColor(o.allele_unsupporting_read_alpha);
+  d->sup_color[1] = (uint8_t)HostAlphaColor(o.allele_supporting_read_alpha);
+  d->sup_color[2] = (uint8_t)HostAlphaColor(o.other_allele_supporting_read_alpha);
+  d->match_color = (uint8_t)HostAlphaColor(o.reference_matching_read_alpha);
+  d->mismatch_color = (uint8_t)HostAlphaColor(o.reference_mismatching_read_alpha);
+  d->supp_color[0] = static_cast<unsigned char>(kMaxPixelValueAsFloat * o.allele_unsupporting_read_alpha);
+  d->supp_color[1] = static_cast<unsigned char>(kMaxPixelValueAsFloat * o.allele_supporting_read_alpha);
+  for (int c = 0; c < o.num_channels; ++c) {
+    const int ch = o.channels[c];
+    d->chan[c] = (uint8_t)ch;
+    switch (ch) {
+      case DVB_CH_READ_BASE: d->kind[c] = K_BASE; d->ref_const[c] = 0; break;
+      case DVB_CH_BASE_QUALITY:
+        d->kind[c] = K_QUAL; d->ref_const[c] = HostScaleColor(o.reference_base_quality, o.base_quality_cap); break;
+      case DVB_CH_MAPPING_QUALITY:  // mapping_quality_channel.cc:53-58 scales by base_quality_cap
+        d->kind[c] = K_CONST; d->ref_const[c] = HostScaleColor(o.reference_base_quality, o.base_quality_cap); break;
+      case DVB_CH_STRAND: d->kind[c] = K_CONST; d->ref_const[c] = (uint8_t)o.positive_strand_color; break;
+      case DVB_CH_READ_SUPPORTS_VARIANT: d->kind[c] = K_CONST; d->ref_const[c] = d->sup_color[0]; break;
+      case DVB_CH_BASE_DIFFERS_FROM_REF: d->kind[c] = K_DIFF; d->ref_const[c] = d->match_color; break;
+      case DVB_CH_HAPLOTYPE_TAG: d->kind[c] = K_CONST; d->ref_const[c] = HostScaleColor(0, 2); break;
+      case DVB_CH_INSERT_SIZE: d->kind[c] = K_CONST; d->ref_const[c] = static_cast<uint8_t>(kMaxPixelValueAsFloat); break;
+      case DVB_CH_SUPPLEMENTARY_ALIGNMENT:  // supplementary_alignment_channel.cc:60-63: float -> uchar
+        d->kind[c] = K_CONST; d->ref_const[c] = static_cast<unsigned char>(o.allele_unsupporting_read_alpha); break;
+      case DVB_CH_BLANK: d->kind[c] = K_ZERO; d->ref_const[c] = 0; break;
+      default:
+        return dvb::fail(DVB_ERR_UNSUPPORTED_CHANNEL, "channel enum %d is not implemented", ch);
+    }
+  }
+  d->n_words = (d->C + 3) / 4;
+  for (int c = 0; c < d->C; ++c) {
+    const unsigned one = 1u << (8 * (c & 3));
+    if (d->kind[c] == K_BASE) d->mask_base[c >> 2] |= one;
+    else if (d->kind[c] == K_QUAL) d->mask_qual[c >> 2] |= one;
+    else if (d->kind[c] == K_DIFF) d->mask_diff[c >> 2] |= one;
+    else if (d->kind[c] == K_CONST) d->mask_const[c >> 2] |= one;
+    if (d->kind[c] != K_BASE) d->ref_words[c >> 2] |= (unsigned)d->ref_const[c] << (8 * (c & 3));
+  }
+  for (int i = 0; i < 256; ++i) {
+    d->base_lut[i] = (uint8_t)HostBaseColor(i, o);
+    d->qual_lut[i] = HostScaleColor(i, (float)o.base_quality_cap);
+  }
+  return DVB_OK;
+}
+
+int SmemBytes(const EncDev& d) {
+  const int Wpad = (d.W + 15) & ~15;
+  const int rowbuf = ((d.row_bytes + 15) & ~15) + 32;
+  return 512 + Wpad + 7 * d.max_rows * 4 + (kWarps + 2) * 4 + 16 + kWarps * rowbuf;
+}
+
+int Launch(DvbEncoder* enc, const DvbBatch& b, uint8_t* out, int32_t* rows_kept, cudaStream_t stream) {
+  if (b.n_images <= 0) return DVB_OK;
+  int grid = std::min(b.n_images, enc->grid_cap);
+  dvb_encode_kernel<<<grid, kThreads, enc->smem_bytes, stream>>>(enc->dev, b, out, rows_kept, enc->d_err);
+  enc->launches++;
+  DVB_CUDA(cudaGetLastError());
+  return DVB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dvb_abi_version(void) { return DVB_ABI_VERSION; }
+const char* dvb_last_error(void) { return dvb::last_error().c_str(); }
+
+void dvb_pileup_params_default(DvbPileupParams* p) {
+  memset(p, 0, sizeof(*p));
+  p->width = 221; p->height = 100; p->reference_band_height = 5;
+  p->num_channels = 6;
+  for (int i = 0; i < 6; ++i) p->channels[i] = i + 1;
+  p->base_color_offset_a_and_g = 40; p->base_color_offset_t_and_c = 30; p->base_color_stride = 70;
+  p->allele_supporting_read_alpha = 1.0f; p->allele_unsupporting_read_alpha = 0.6f;
+  p->other_allele_supporting_read_alpha = 0.6f; p->reference_matching_read_alpha = 0.2f;
+  p->reference_mismatching_read_alpha = 1.0f; p->indel_anchoring_base_char = '*';
+  p->reference_base_quality = 60; p->positive_strand_color = 70; p->negative_strand_color = 240;
+  p->base_quality_cap = 40; p->mapping_quality_cap = 60;
+  p->min_base_quality = 10; p->min_mapping_quality = 10;
+  p->random_seed = 2101079370u;
+  p->max_reads_per_image = 0;
+}
+
+int64_t dvb_image_bytes(const DvbPileupParams* p) {
+  return (int64_t)p->height * p->width * (p->num_channels + p->num_alt_channels);
+}
+
+int dvb_shuffle_table(int32_t n, uint32_t seed, int32_t* out) {
+  if (n < 0 || !out) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_shuffle_table: bad arguments");
+  std::vector<int> idx(n);
+  std::iota(idx.begin(), idx.end(), 0);
+  std::mt19937_64 gen(seed);
+  std::shuffle(idx.begin(), idx.end(), gen);
+  for (int i = 0; i < n; ++i) out[i] = idx[i];
+  return DVB_OK;
+}
+
+int dvb_encoder_create(const DvbPileupParams* params, int device, DvbEncoder** out) {
+  if (!params || !out) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  EncDev dev;
+  int st = BuildDev(*params, &dev);
+  if (st) return st;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return dvb::fail(DVB_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "device %d out of range", device);
+  DVB_CUDA(cudaSetDevice(device));
+  DvbEncoder* enc = new DvbEncoder();
+  enc->params = *params;
+  enc->device = device;
+  cudaDeviceProp prop;
+  DVB_CUDA(cudaGetDeviceProperties(&prop, device));
+  enc->num_sms = prop.multiProcessorCount;
+  // down-sampling tables for n = max_rows+1 .. cap
+  const int cap = std::max(params->max_reads_per_image > 0 ? params->max_reads_per_image : 2048, dev.max_rows + 1);
+  std::vector<int> tables;
+  tables.reserve((size_t)cap * cap / 2);
+  for (int n = dev.max_rows + 1; n <= cap; ++n) {
+    std::vector<int> idx(n);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::mt19937_64 gen(params->random_seed);  // fresh generator per call, pileup_image_native.cc:327,343
+    std::shuffle(idx.begin(), idx.end(), gen);
+    tables.insert(tables.end(), idx.begin(), idx.end());
+  }
+  DVB_CUDA(cudaMalloc(&enc->d_perm, std::max<size_t>(tables.size(), 1) * sizeof(int)));
+  DVB_CUDA(cudaMemcpy(enc->d_perm, tables.data(), tables.size() * sizeof(int), cudaMemcpyHostToDevice));
+  DVB_CUDA(cudaMalloc(&enc->d_err, sizeof(int)));
+  DVB_CUDA(cudaMemset(enc->d_err, 0, sizeof(int)));
+  dev.perm = enc->d_perm;
+  dev.perm_cap = cap;
+  enc->dev = dev;
+  enc->smem_bytes = SmemBytes(dev);
+  if (enc->smem_bytes > 227 * 1024) {
+    delete enc;
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "image row too large for shared memory (%d bytes)", enc->smem_bytes);
+  }
+  DVB_CUDA(cudaFuncSetAttribute(dvb_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, enc->smem_bytes));
+  int occ = 1;
+  DVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dvb_encode_kernel, kThreads, enc->smem_bytes));
+  enc->grid_cap = enc->num_sms * std::max(occ, 1);
+  DVB_CUDA(cudaStreamCreateWithFlags(&enc->stream, cudaStreamNonBlocking));
+  *out = enc;
+  return DVB_OK;
+}
+
+void dvb_encoder_destroy(DvbEncoder* enc) {
+  if (!enc) return;
+  cudaSetDevice(enc->device);
+  if (enc->d_perm) cudaFree(enc->d_perm);
+  if (enc->d_err) cudaFree(enc->d_err);
+  enc->d_in.release(); enc->d_out.release(); enc->d_rows.release();
+  enc->h_in.release(); enc->h_out.release();
+  if (enc->stream) cudaStreamDestroy(enc->stream);
+  delete enc;
+}
+
+int dvb_encode_batch_device(DvbEncoder* enc, const DvbBatch* batch, uint8_t* out, int32_t* rows_kept, void* stream) {
+  if (!enc || !batch || (!out && batch->n_images > 0)) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "null argument");
+  if (batch->ref_stride < enc->dev.W) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "ref_stride < width");
+  DVB_CUDA(cudaSetDevice(enc->device));
+  return Launch(enc, *batch, out, rows_kept, static_cast<cudaStream_t>(stream));
+}
+
+int dvb_encoder_check(DvbEncoder* enc, void* stream) {
+  if (!enc) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "null encoder");
+  DVB_CUDA(cudaSetDevice(enc->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int e = 0;
+  DVB_CUDA(cudaMemcpyAsync(&e, enc->d_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  DVB_CUDA(cudaStreamSynchronize(s));
+  if (e) {
+    DVB_CUDA(cudaMemsetAsync(enc->d_err, 0, sizeof(int), s));
+    DVB_CUDA(cudaStreamSynchronize(s));
+    if (e == DVB_ERR_BAD_CIGAR) return dvb::fail(e, "Unrecognized CIGAR op");
+    if (e == DVB_ERR_TOO_MANY_READS)
+      return dvb::fail(e, "more than %d reads overlap one candidate (raise max_reads_per_image)", enc->dev.perm_cap);
+    return dvb::fail(e, "device error %d", e);
+  }
+  return DVB_OK;
+}
+
+int dvb_encode_batch_host(DvbEncoder* enc, const DvbBatch* hb, uint8_t* out_host, int32_t* rows_kept_host) {
+  if (!enc || !hb || (!out_host && hb->n_images > 0)) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "null argument");
+  if (hb->n_images == 0) return DVB_OK;
+  if (hb->ref_stride < enc->dev.W) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "ref_stride < width");
+  DVB_CUDA(cudaSetDevice(enc->device));
+  const int64_t NI = hb->n_images, NR = hb->n_reads, NP = hb->n_pairs, NB = hb->n_bases, NC = hb->n_cigar;
+  // ---- validation the reference leaves to CHECKs / UB ----
+  if (hb->pair_begin[0] != 0 || hb->pair_begin[NI] != NP) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "pair_begin is not a CSR over n_pairs");
+  for (int64_t i = 0; i < NI; ++i)
+    if (hb->pair_begin[i + 1] < hb->pair_begin[i]) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "pair_begin not monotone");
+  for (int64_t p = 0; p < NP; ++p)
+    if (hb->pair_read[p] < 0 || hb->pair_read[p] >= NR) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "pair_read out of range");
+  if (NR > 0 && (hb->read_seq_begin[NR] != NB || hb->read_cigar_begin[NR] != NC))
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "read_seq_begin / read_cigar_begin do not end at n_bases / n_cigar");
+  for (int64_t r = 0; r < NR; ++r) {
+    int64_t consumed = 0;
+    for (int64_t k = hb->read_cigar_begin[r]; k < hb->read_cigar_begin[r + 1]; ++k) {
+      const unsigned op = hb->cigar[k] & 0xF;
+      if (op > 8) return dvb::fail(DVB_ERR_BAD_CIGAR, "Unrecognized CIGAR op");
+      if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) consumed += hb->cigar[k] >> 4;
+    }
+    if (consumed > hb->read_seq_begin[r + 1] - hb->read_seq_begin[r])
+      return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "read %lld: CIGAR consumes %lld bases, sequence has %lld", (long long)r,
+                       (long long)consumed, (long long)(hb->read_seq_begin[r + 1] - hb->read_seq_begin[r]));
+  }
+  // ---- pack every input array into one pinned staging block, one H2D copy ----
+  struct Seg { const void* src; size_t bytes; size_t off; };
+  Seg segs[19];
+  int ns = 0;
+  size_t total = 0;
+  auto add = [&](const void* p, size_t bytes) {
+    segs[ns].src = p; segs[ns].bytes = p ? bytes : 0; segs[ns].off = total;
+    total += (segs[ns].bytes + 255) & ~(size_t)255;
+    return ns++;
+  };
+  const int i_ref = add(hb->ref_bases, (size_t)NI * hb->ref_stride);
+  const int i_isp = add(hb->image_start_pos, NI * 4);
+  const int i_vs = add(hb->variant_start, NI * 4);
+  const int i_pb = add(hb->pair_begin, (NI + 1) * 8);
+  const int i_pr = add(hb->pair_read, NP * 4);
+  const int i_ps = add(hb->pair_support, NP);
+  const int i_pg = add(hb->pair_allele_group, NP);
+  const int i_rp = add(hb->read_pos, NR * 4);
+  const int i_rsp = add(hb->read_sort_pos, NR * 4);
+  const int i_rmq = add(hb->read_mapq, NR * 4);
+  const int i_rfl = add(hb->read_flags, NR);
+  const int i_rfr = add(hb->read_fragment_length, NR * 4);
+  const int i_rhp = add(hb->read_hp, NR * 4);
+  const int i_rnr = add(hb->read_name_rank, NR * 4);
+  const int i_rsb = add(hb->read_seq_begin, (NR + 1) * 8);
+  const int i_rcb = add(hb->read_cigar_begin, (NR + 1) * 8);
+  const int i_ba = add(hb->bases, NB);
+  const int i_qu = add(hb->quals, NB);
+  const int i_ci = add(hb->cigar, NC * 4);
+  total = std::max<size_t>(total, 256);
+  DVB_CUDA(enc->h_in.reserve(total));
+  DVB_CUDA(enc->d_in.reserve(total));
+  for (int i = 0; i < ns; ++i)
+    if (segs[i].bytes) memcpy(static_cast<char*>(enc->h_in.p) + segs[i].off, segs[i].src, segs[i].bytes);
+  cudaStream_t s = enc->stream;
+  DVB_CUDA(cudaMemcpyAsync(enc->d_in.p, enc->h_in.p, total, cudaMemcpyHostToDevice, s));
+  DvbBatch db = *hb;
+  char* base = static_cast<char*>(enc->d_in.p);
+  auto dp = [&](int i) -> const void* { return segs[i].bytes || segs[i].src ? base + segs[i].off : nullptr; };
+  db.ref_bases = (const uint8_t*)dp(i_ref); db.image_start_pos = (const int32_t*)dp(i_isp);
+  db.variant_start = (const int32_t*)dp(i_vs); db.pair_begin = (const int64_t*)dp(i_pb);
+  db.pair_read = (const int32_t*)dp(i_pr); db.pair_support = (const uint8_t*)dp(i_ps);
+  db.pair_allele_group = hb->pair_allele_group ? (const uint8_t*)dp(i_pg) : nullptr;
+  db.read_pos = (const int32_t*)dp(i_rp); db.read_sort_pos = (const int32_t*)dp(i_rsp);
+  db.read_mapq = (const int32_t*)dp(i_rmq); db.read_flags = (const uint8_t*)dp(i_rfl);
+  db.read_fragment_length = (const int32_t*)dp(i_rfr); db.read_hp = (const int32_t*)dp(i_rhp);
+  db.read_name_rank = (const uint32_t*)dp(i_rnr); db.read_seq_begin = (const int64_t*)dp(i_rsb);
+  db.read_cigar_begin = (const int64_t*)dp(i_rcb); db.bases = (const uint8_t*)dp(i_ba);
+  db.quals = (const uint8_t*)dp(i_qu); db.cigar = (const uint32_t*)dp(i_ci);
+
+  const size_t out_bytes = (size_t)NI * enc->dev.image_bytes;
+  DVB_CUDA(enc->d_out.reserve(out_bytes));
+  DVB_CUDA(enc->d_rows.reserve(NI * 4));
+  DVB_CUDA(enc->h_out.reserve(out_bytes + NI * 4));
+  int st = Launch(enc, db, static_cast<uint8_t*>(enc->d_out.p), static_cast<int32_t*>(enc->d_rows.p), s);
+  if (st) return st;
+  DVB_CUDA(cudaMemcpyAsync(enc->h_out.p, enc->d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+  DVB_CUDA(cudaMemcpyAsync(static_cast<char*>(enc->h_out.p) + out_bytes, enc->d_rows.p, NI * 4, cudaMemcpyDeviceToHost, s));
+  st = dvb_encoder_check(enc, s);  // synchronises
+  if (st) return st;
+  memcpy(out_host, enc->h_out.p, out_bytes);
+  if (rows_kept_host) memcpy(rows_kept_host, static_cast<char*>(enc->h_out.p) + out_bytes, NI * 4);
+  return DVB_OK;
+}
+
+int64_t dvb_encoder_launch_count(const DvbEncoder* enc) { return enc ? enc->launches : 0; }
+
+}  // extern "C"
