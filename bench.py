@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — candidate variants/sec of the pileup-encode + CNN hot path on N B200s.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` (torchrun for
+N>1, one rank per GPU); W untimed warm-up steps, then exactly K steps timed with CUDA events
+between barriers; rank 0 prints ONE JSON line.
+
+  step      one pass of the hot path over one batch of `--batch` synthetic candidate windows
+            per GPU (config "HG002 chr20 30x WGS" stand-in: SURVEY.md §8(d) generator, 100x221x7).
+  value     whole-job candidates/s, inputs resident in HBM.
+  e2e       same metric through the host-buffer entry points (pinned host inputs, H2D + D2H
+            inside the timed region).
+  roofline  dominant kernel vs MEASURED_PEAKS.json; `roofline_encoder` is the HBM roofline of
+            the pileup kernel (the "pileup HBM GB/s" half of the metric).
+  cpu_baseline  the CPU oracle (faithful restatement of the reference algorithm) timed on a
+            bounded sample on this box's host cores.
+
+`--impl reference` times the reference-algorithm CPU path (oracle port; the reference itself
+cannot be built here — DESIGN.md) on a bounded sample per step, rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+METRIC = 'candidate variants/sec (encode+CNN)'
+UNIT = 'candidates/s'
+
+
+def parse_args():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=8)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--batch', type=int, default=16384, help='candidate windows per step per GPU')
+  ap.add_argument('--stage', default='auto', choices=['auto', 'encode', 'both'])
+  ap.add_argument('--cpu-sample', type=int, default=2048, help='images in the bounded CPU sample')
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-e2e', action='store_true')
+  return ap.parse_args()
+
+
+def load_peaks():
+  p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(p):
+    d = json.load(open(p))
+    return {'hbm_gbs': d['hbm_gbs'], 'tflops': d['bf16_tflops'], 'tflops_sustained': d.get('bf16_tflops_sustained', d['bf16_tflops']),
+            'source': 'measured (MEASURED_PEAKS.json)'}
+  return {'hbm_gbs': 6650.0, 'tflops': 1590.0, 'tflops_sustained': 1400.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+  Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+       'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+       'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, gpu_index):
+    self.gpu = gpu_index
+    self.lines = []
+    self.proc = None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.gpu}', f'--query-gpu={self.Q}',
+                                    '--format=csv,noheader,nounits', '-lms', '100'],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.t = threading.Thread(target=self._read, daemon=True)
+      self.t.start()
+    except OSError:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.lines.append(line.strip())
+
+  def stop(self):
+    if not self.proc:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    time.sleep(0.15)
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except subprocess.TimeoutExpired:
+      self.proc.kill()
+    sm, mx, reasons = [], [], set()
+    for ln in self.lines:
+      f = [x.strip() for x in ln.split(',')]
+      if len(f) < 8:
+        continue
+      try:
+        sm.append(float(f[1])); mx.append(float(f[2]))
+      except ValueError:
+        continue
+      for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
+        if v.lower().startswith('active'):
+          reasons.add(name)
+    sm.sort()
+    return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+            'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def wgs_options():
+  from deepvariant_b200 import pileup_image as pi
+  o = pi.default_options()
+  o.channels = list(pi.PILEUP_CHANNELS_WITH_INSERT_SIZE)
+  o.num_channels = 7
+  return o
+
+
+def cpu_oracle_rate(tb_cpu, params, n_images, threads):
+  """Oracle images/s on `threads` host threads over the first n_images images (ctypes drops the GIL)."""
+  import numpy as np
+  from concurrent.futures import ThreadPoolExecutor
+  import oracle_lib
+  from subbatch_util import take_images
+  packed = tb_cpu.to_packed()
+  n_images = min(n_images, packed.n_images)
+  parts = [take_images(packed, idx) for idx in np.array_split(np.arange(n_images), threads) if len(idx)]
+  oracle_lib.oracle()
+  t0 = time.perf_counter()
+  with ThreadPoolExecutor(max_workers=threads) as ex:
+    outs = list(ex.map(lambda pb: oracle_lib.encode_batch(params, pb), parts))
+  dt = time.perf_counter() - t0
+  return n_images / dt, dt, outs
+
+
+def run_reference(args):
+  """--impl reference: the reference algorithm's CPU path (oracle port), rank 0 only."""
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  import torch
+  from deepvariant_b200 import pileup_image as pi, synthetic
+  params = pi.to_params(wgs_options())
+  cores = os.cpu_count() or 1
+  sample = args.cpu_sample
+  tb = synthetic.make_batch(sample, 'cpu')
+  cnn = None
+  try:
+    import cnn_oracle  # tests/cnn_oracle.py: torch fp32 Inception-v3 restating the tf_keras topology
+    cnn = cnn_oracle.build_reference_model(7).eval()
+    torch.set_num_threads(cores)
+  except ImportError:
+    pass
+  times = []
+  for it in range(args.warmup + args.steps):
+    t0 = time.perf_counter()
+    _, _, outs = cpu_oracle_rate(tb, params, sample, cores)
+    if cnn is not None:
+      import numpy as np
+      imgs = torch.from_numpy(np.concatenate(outs))
+      with torch.no_grad():
+        for i in range(0, imgs.shape[0], 64):
+          cnn_oracle.predict(cnn, imgs[i:i + 64])
+    dt = time.perf_counter() - t0
+    if it >= args.warmup:
+      times.append(dt)
+  total = sum(times)
+  value = sample * len(times) / total
+  stage = 'encode+cnn' if cnn is not None else 'encode'
+  line = {
+      'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+      'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True, 'scaling': 'weak',
+      'vs_baseline': None, 'dtype': 'u8' if cnn is None else 'u8+f32', 'data': 'synthetic',
+      'config': {'workload': 'HG002 chr20 30x WGS stand-in: synthetic 100x221x7 windows (SURVEY 8d)', 'stage': stage,
+                 'sample_images_per_step': sample},
+      'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                       'sample': f'{sample} synthetic windows per step, oracle C++ port of pileup_image_native'
+                                 + (' + torch fp32 CPU Inception-v3' if cnn is not None else '')},
+      'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+  }
+  print(json.dumps(line), flush=True)
+
+
+def main():
+  args = parse_args()
+  if args.impl == 'reference':
+    run_reference(args)
+    return
+  import torch
+  import torch.distributed as dist
+  from deepvariant_b200 import pileup_image as pi, synthetic
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+  torch.cuda.set_device(local)
+  dev = torch.device('cuda', local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+  peaks = load_peaks()
+
+  o = wgs_options()
+  params = pi.to_params(o)
+  enc = pi.GpuEncoder(params, device=local)
+  B = args.batch
+  # Region sharding: every rank owns its own candidate windows (chunk = rank); no exchange.
+  tb = synthetic.make_batch(B, dev, chunk=rank)
+  images = torch.empty((B,) + enc.shape, dtype=torch.uint8, device=dev)
+
+  cnn = None
+  stage = args.stage
+  if stage in ('auto', 'both'):
+    try:
+      from deepvariant_b200 import call_variants as cv
+      cnn = cv.GpuCnn.random_init(enc.shape, device=local, max_batch=B)
+      stage = 'both'
+    except (ImportError, AttributeError) as e:
+      if stage == 'both':
+        raise
+      stage = 'encode'
+  probs = torch.empty((B, 3), dtype=torch.float32, device=dev) if cnn else None
+  stream = torch.cuda.current_stream()
+
+  def step():
+    enc.encode_device(tb, images, stream=stream)
+    if cnn:
+      cnn.forward_device(images, probs, stream=stream)
+
+  def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  for _ in range(args.warmup):
+    step()
+  enc.check()
+  barrier()
+  l0 = enc.launch_count + (cnn.launch_count if cnn else 0)
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  # per-kernel-group device time of the encoder, on the launching stream
+  enc_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+  e0.record(stream)
+  for k in range(args.steps):
+    enc_ev[k][0].record(stream)
+    enc.encode_device(tb, images, stream=stream)
+    enc_ev[k][1].record(stream)
+    if cnn:
+      cnn.forward_device(images, probs, stream=stream)
+  e1.record(stream)
+  barrier()
+  clocks = sampler.stop() if rank == 0 else None
+  enc.check()
+  ms_total = e0.elapsed_time(e1)
+  launches = enc.launch_count + (cnn.launch_count if cnn else 0) - l0
+  enc_ms = sum(a.elapsed_time(b) for a, b in enc_ev) / args.steps
+  t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms_total = float(t.item())
+  ms_step = ms_total / args.steps
+  value = world * B / (ms_step * 1e-3)
+
+  # ---- e2e: pinned host inputs -> H2D -> hot path -> D2H, through the same entry points ----
+  e2e = None
+  if not args.no_e2e:
+    host = tb.to('cpu').pin()
+    h2d = host.input_bytes()
+    if cnn:
+      out_host = torch.empty((B, 3), dtype=torch.float32).pin_memory()
+      d2h = out_host.numel() * 4
+    else:
+      out_host = torch.empty((B,) + enc.shape, dtype=torch.uint8).pin_memory()
+      d2h = out_host.numel()
+
+    def e2e_step():
+      d = host.to(dev, non_blocking=True)
+      enc.encode_device(d, images, stream=stream)
+      if cnn:
+        cnn.forward_device(images, probs, stream=stream)
+        out_host.copy_(probs, non_blocking=True)
+      else:
+        out_host.copy_(images, non_blocking=True)
+      return d
+
+    keep = [e2e_step() for _ in range(max(1, args.warmup // 2))]
+    barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_e2e = max(2, args.steps // 2)
+    a0.record(stream)
+    for _ in range(n_e2e):
+      keep.append(e2e_step())
+    a1.record(stream)
+    barrier()
+    t2 = torch.tensor([a0.elapsed_time(a1) / n_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e = {'value': world * B / (float(t2.item()) * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+           'd2h_bytes_per_step': d2h, 'steps': n_e2e}
+    del keep
+
+  if rank != 0:
+    if world > 1:
+      dist.destroy_process_group()
+    return
+
+  # ---- rooflines ----
+  alg_bytes = tb.algorithmic_bytes(enc.image_bytes, o.width)
+  enc_gbs = alg_bytes / (enc_ms * 1e-3) / 1e9
+  roof_enc = {'bound': 'hbm', 'kernel': 'dvb_encode_kernel', 'achieved': enc_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+              'frac': enc_gbs / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peaks['source'],
+              'ms_per_launch': enc_ms, 'algorithmic_bytes_per_launch': alg_bytes,
+              'windows_per_s_encode_only': B / (enc_ms * 1e-3)}
+  if cnn:
+    roofline = cnn.roofline(ms_step - enc_ms, B, peaks)
+  else:
+    roofline = roof_enc
+
+  cpu_baseline = None
+  if not args.no_cpu_baseline:
+    cores = os.cpu_count() or 1
+    tb_cpu = synthetic.make_batch(args.cpu_sample, 'cpu')
+    rate, dt, _ = cpu_oracle_rate(tb_cpu, params, args.cpu_sample, cores)
+    cpu_baseline = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                    'sample': f'{args.cpu_sample} synthetic windows, encoder stage only (C++ oracle port of '
+                              f'pileup_image_native.cc), {dt:.1f} s'}
+
+  line = {
+      'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+      'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+      'dtype': 'u8' if not cnn else 'u8 encode + fp16 CNN (fp32 accumulate)', 'data': 'synthetic',
+      'config': {'workload': 'HG002 chr20 30x WGS stand-in: synthetic 100x221x7 candidate windows (SURVEY 8d config 2/5)',
+                 'stage': stage, 'batch_per_gpu': B, 'image_shape': list(enc.shape),
+                 'l2': 'working set per step (inputs %.0f MB, images %.0f MB) exceeds the 126 MB L2' %
+                       (tb.input_bytes() / 1e6, B * enc.image_bytes / 1e6),
+                 'sharding': 'candidates region-sharded across ranks, no collective'},
+      'gpu_launches': launches, 'clocks': clocks, 'e2e': e2e, 'roofline': roofline, 'roofline_encoder': roof_enc,
+      'cpu_baseline': cpu_baseline,
+  }
+  print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+  main()

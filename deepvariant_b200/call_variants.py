@@ -1,0 +1,170 @@
+"""Host-side mirror of the reference's call_variants stage around the CUDA classifier.
+
+  GpuCnn                 the SavedModel call of predict_step (deepvariant/call_variants.py:904-932):
+                         uint8 pileup images in, float32 genotype probabilities (p00, p0x, pxx) out
+  round_gls              deepvariant/call_variants.py:248-285
+  create_cvo             deepvariant/call_variants.py:353-399 (_create_cvo_proto, MID="deepvariant")
+  call_variants          deepvariant/call_variants.py:766-1047 (examples TFRecords -> CVO TFRecords)
+
+There is no CPU path: GpuCnn raises when libdvb.so or a B200 is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import struct
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from deepvariant_b200 import _lib, modeling, protos
+
+DEEP_VARIANT_MODEL_ID = 'deepvariant'  # call_variants.py:85
+_GL_PRECISION = 10                       # call_variants.py:79
+_DEFAULT_BATCH = 1024                    # --batch_size default, call_variants.py:115-117
+
+
+class GpuCnn:
+  """Owns one DvbCnn handle (per device)."""
+
+  def __init__(self, weights: modeling.ModelWeights, image_shape: Sequence[int], device: int = 0,
+               max_batch: int = 2048, precision: int = 0):
+    self._lib = _lib.lib()
+    h, w, c = [int(x) for x in image_shape]
+    if c != weights.in_channels:
+      raise ValueError(f'model expects {weights.in_channels} channels, images have {c}')
+    blob = modeling.pack_weights(weights)
+    self.shape = (h, w, c)
+    self.device = device
+    self.max_batch = max_batch
+    handle = C.c_void_p()
+    buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+    _lib.check(self._lib.dvb_cnn_create(C.cast(buf, C.c_void_p), len(blob), h, w, c, max_batch, precision, device,
+                                        C.byref(handle)))
+    self._h = handle
+    self.flops_per_image = float(self._lib.dvb_cnn_flops_per_image(self._h))
+
+  @classmethod
+  def random_init(cls, image_shape: Sequence[int], device: int = 0, max_batch: int = 2048, seed: int = 0) -> 'GpuCnn':
+    """Random-init weights of the right architecture (no checkpoints ship with the reference)."""
+    return cls(modeling.random_weights(int(image_shape[2]), seed), image_shape, device, min(max_batch, 2048))
+
+  def forward_device(self, images, probs, stream=None) -> None:
+    """images: torch uint8 [n, H, W, C] on the device; probs: torch float32 [n, 3].  Asynchronous."""
+    n = int(images.shape[0])
+    sp = C.c_void_p(stream.cuda_stream) if stream is not None else C.c_void_p(0)
+    _lib.check(self._lib.dvb_cnn_forward_device(self._h, C.c_void_p(images.data_ptr()), n, C.c_void_p(probs.data_ptr()), sp))
+
+  def forward_host(self, images: np.ndarray) -> np.ndarray:
+    images = np.ascontiguousarray(images, dtype=np.uint8)
+    if images.shape[1:] != self.shape:
+      raise ValueError(f'images {images.shape[1:]} != model input {self.shape}')
+    probs = np.empty((images.shape[0], 3), dtype=np.float32)
+    _lib.check(self._lib.dvb_cnn_forward_host(self._h, images.ctypes.data_as(C.c_void_p), images.shape[0],
+                                              probs.ctypes.data_as(C.c_void_p)))
+    return probs
+
+  def debug_tensor(self, name: str, n: int) -> np.ndarray:
+    h, w, c = C.c_int32(), C.c_int32(), C.c_int32()
+    _lib.check(self._lib.dvb_cnn_debug_tensor(self._h, name.encode(), n, None, C.byref(h), C.byref(w), C.byref(c)))
+    out = np.empty((n, h.value, w.value, c.value), dtype=np.float32)
+    _lib.check(self._lib.dvb_cnn_debug_tensor(self._h, name.encode(), n, out.ctypes.data_as(C.c_void_p), C.byref(h),
+                                              C.byref(w), C.byref(c)))
+    return out
+
+  @property
+  def launch_count(self) -> int:
+    return int(self._lib.dvb_cnn_launch_count(self._h))
+
+  def roofline(self, ms_per_step: float, images_per_step: int, peaks: dict) -> dict:
+    """Tensor-core roofline of the classifier: algorithmic conv FLOPs / device time of the CNN part."""
+    tf = images_per_step * self.flops_per_image / (ms_per_step * 1e-3) / 1e12
+    return {'bound': 'tensor', 'kernel': 'conv_gemm_kernel (94 implicit-GEMM launches per forward) + pools + tail',
+            'achieved': tf, 'peak': peaks['tflops_sustained'], 'unit': 'TFLOP/s', 'frac': tf / peaks['tflops_sustained'],
+            'traffic': None, 'peak_source': peaks['source'] + ', sustained cuBLAS bf16',
+            'flops_per_image': self.flops_per_image, 'ms_cnn_per_step': ms_per_step}
+
+  def close(self):
+    if getattr(self, '_h', None):
+      self._lib.dvb_cnn_destroy(self._h)
+      self._h = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pylint: disable=broad-except
+      pass
+
+
+def round_gls(gls: Sequence[float], precision: Optional[int] = None) -> List[float]:
+  """deepvariant/call_variants.py:248-285."""
+  gls = [float(g) for g in gls]
+  if abs(sum(gls) - 1) > 1e-6:
+    raise ValueError('Invalid genotype likelihoods do not sum to one: sum({}) = {}'.format(gls, sum(gls)))
+  if precision is None:
+    return gls
+  min_ix = 0
+  min_gl = gls[0]
+  for ix, gl in enumerate(gls):
+    if gl < min_gl:
+      min_gl = gl
+      min_ix = ix
+  rounded_gls = [round(gl, precision) for gl in gls]
+  rounded_gls[min_ix] = max(0.0, round(1 - sum(rounded_gls[:min_ix] + rounded_gls[min_ix + 1:]), precision))
+  return rounded_gls
+
+
+def _set_model_id(variant_encoded: bytes, model_id: str) -> bytes:
+  """variantcall_utils.set_model_id (third_party/nucleus/util/variantcall_utils.py:235): sets
+  calls[0].info['MID'] = [string_value model_id] inside a serialized Variant.
+  Variant.calls = 11; VariantCall.info = map<string, ListValue> field 2; Value.string_value = 3."""
+  entry = protos.f_bytes(1, b'MID') + protos.f_bytes(2, protos.f_bytes(1, protos.f_bytes(3, model_id.encode())))
+  out = bytearray()
+  done = False
+  for fn, wt, val, raw in protos.iter_fields(variant_encoded):
+    if fn == 11 and not done:
+      call = bytearray()
+      for f2, w2, v2, raw2 in protos.iter_fields(bytes(val)):
+        if f2 == 2:
+          key = b''
+          for f3, w3, v3, _ in protos.iter_fields(bytes(v2)):
+            if f3 == 1:
+              key = bytes(v3)
+          if key == b'MID':
+            continue
+        call += raw2
+      call += protos.f_bytes(2, entry)
+      out += protos.f_bytes(11, bytes(call))
+      done = True
+    else:
+      out += raw
+  if not done:
+    raise IndexError('variant has no calls')  # reference: variant.calls[0] raises
+  return bytes(out)
+
+
+def create_cvo(variant_encoded: bytes, gls: Sequence[float], alt_allele_indices_encoded: bytes) -> bytes:
+  """_create_cvo_proto (call_variants.py:353-399) without debug info -> serialized CallVariantsOutput."""
+  variant = _set_model_id(variant_encoded, DEEP_VARIANT_MODEL_ID)
+  out = bytearray()
+  out += protos.f_bytes(1, variant)
+  out += protos.f_bytes(2, alt_allele_indices_encoded)
+  out += protos.f_bytes(3, struct.pack('<3d', *[float(g) for g in gls]))
+  return bytes(out)
+
+
+def smoke(images) -> None:
+  """Called by __graft_entry__.smoke(): a few encoder images through the CNN, checked against the
+  torch fp32 oracle (tests/cnn_oracle.py)."""
+  import torch
+  import cnn_oracle
+  n = min(8, int(images.shape[0]))
+  shape = tuple(int(x) for x in images.shape[1:])
+  w = modeling.random_weights(shape[2], 0)
+  net = GpuCnn(w, shape, device=0, max_batch=n)
+  probs = torch.empty((n, 3), dtype=torch.float32, device=images.device)
+  net.forward_device(images[:n].contiguous(), probs)
+  torch.cuda.synchronize()
+  want = cnn_oracle.ReferenceModel(w).forward(images[:n].cpu())
+  err = (probs.cpu() - want).abs().max().item()
+  print(f'[smoke] cnn: {n} images, max |p - oracle fp32| = {err:.2e}, launches {net.launch_count}')
+  assert err < 2e-2, 'CNN output far from the fp32 oracle'

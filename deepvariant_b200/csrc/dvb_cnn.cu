@@ -1,0 +1,872 @@
+// dvb_cnn.cu — Inception-v3 genotype classifier for sm_100a (B200) + its C ABI.
+//
+// Replaces the SavedModel call of call_variants.predict_step (deepvariant/call_variants.py:904-932):
+//   dv_utils.preprocess_images   deepvariant/dv_utils.py:356-380      (x - 128) / 128
+//   keras_modeling.inceptionv3   deepvariant/keras_modeling.py:246-336 (tf_keras InceptionV3 backbone,
+//                                                                      pooling='avg')
+//   head                         deepvariant/keras_modeling.py:46-67   Dense(3, softmax, float32)
+//
+// Every convolution (94 of them, BN folded on the host) is an implicit GEMM on the 5th-gen tensor
+// cores, written by hand:
+//   M = output pixels (batch folded in), N = Cout, K = taps x Cin.
+//   A  NHWC fp16 activations, fetched tap by tap with TILED TMA (4-D tensor map {C, W, H, N}): the
+//      M tile is a box of Wt x Ht x Nt output pixels, so one cp.async.bulk.tensor per (tap, Cin
+//      block) lands a [<=128 rows x BLOCK_K] K-major, hardware-swizzled tile in shared memory;
+//      'same' padding and ragged edges are the TMA's out-of-bounds zero fill, stride-2 layers use
+//      the tensor map's element strides.
+//   B  [Cout][taps][Cin] fp16 weights, 3-D tensor map, one [BLOCK_N x BLOCK_K] tile per K block.
+//   D  fp32 accumulators in TMEM (tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16), read back
+//      with tcgen05.ld by 4 epilogue warps that add the folded-BN bias, apply ReLU and store fp16
+//      straight into the consumer's NHWC tensor at the branch's channel offset (concat = no copy).
+//   Warp roles: warp 0 TMA producer, warp 1 TMEM allocator + single-thread MMA issuer, warps 2-5
+//   epilogue; a 4-stage mbarrier ring decouples TMA from MMA.
+// Pools are small CUDA-core kernels; global-average-pool + Dense(3) + softmax is one fused fp32 tail.
+
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "dvb_common.h"
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kConvThreads = 192;  // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr uint32_t kBlobMagic = 0x31424E4E;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a mis-programmed TMA / MMA must surface as an error, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  unsigned long long t0 = 0;
+  for (unsigned it = 0;; ++it) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((it & 1023u) == 1023u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) {  // 2 s
+        printf("dvb_cnn: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, parity);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem];  kind::f16 (fp16 operands, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on `bar` once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major canonical layouts (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+//   [0,14) start>>4  [16,30) LBO>>4  [32,46) SBO>>4  [46,48) version=1  [61,64) layout type
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                          // LBO (unused for swizzled K-major; canonical value 1)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+  d |= (uint64_t)(layout_type & 7) << 61;
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Convolution = implicit GEMM
+// ---------------------------------------------------------------------------------------------
+struct ConvArgs {
+  int kh, kw, pad_h, pad_w, stride;
+  int cin_blocks, block_k;        // K per stage (16 / 32 / 64 fp16 = 32 / 64 / 128-byte swizzle)
+  int Wt, Ht, Nt;                 // output-pixel box of one M tile (Wt*Ht*Nt <= 128)
+  int tiles_w, tiles_h, tiles_n;
+  int Hout, Wout, n_images;
+  int block_n, tmem_cols;
+  int out_cstride, out_coff, relu;
+  uint32_t idesc, layout_type, sbo_bytes;
+  uint32_t a_bytes, b_bytes, a_stage, b_stage;  // TMA bytes and shared-memory footprint per stage
+  __half* out;
+  const float* bias;
+};
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ConvArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * p.a_stage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kStages * p.b_stage);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tw = t % p.tiles_w; t /= p.tiles_w;
+  const int th = t % p.tiles_h; t /= p.tiles_h;
+  const int tn = t;
+  const int w0 = tw * p.Wt, h0 = th * p.Ht, n0 = tn * p.Nt;
+  const int nb = blockIdx.y;
+  const int num_kb = p.kh * p.kw * p.cin_blocks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_b);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  } else if (warp == 1) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int kb = 0;
+      for (int r = 0; r < p.kh; ++r) {
+        for (int s = 0; s < p.kw; ++s) {
+          for (int cb = 0; cb < p.cin_blocks; ++cb, ++kb) {
+            const int st = kb % kStages;
+            const uint32_t ph = (kb / kStages) & 1;
+            mbar_wait(&empty_bar[st], ph ^ 1);
+            mbar_arrive_expect_tx(&full_bar[st], p.a_bytes + p.b_bytes);
+            tma_load_4d(smem_a + st * p.a_stage, &map_a, &full_bar[st], cb * p.block_k, w0 * p.stride + s - p.pad_w,
+                        h0 * p.stride + r - p.pad_h, n0);
+            tma_load_3d(smem_b + st * p.b_stage, &map_b, &full_bar[st], cb * p.block_k, r * p.kw + s, nb * p.block_n);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer (one thread) =====
+      const int mma_per_kb = p.block_k / 16;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int st = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&full_bar[st], ph);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(smem_a + st * p.a_stage);
+        const uint32_t b0 = smem_u32(smem_b + st * p.b_stage);
+        for (int k = 0; k < mma_per_kb; ++k) {
+          const uint64_t ad = make_smem_desc(a0 + k * 32, p.sbo_bytes, p.layout_type);
+          const uint64_t bd = make_smem_desc(b0 + k * 32, p.sbo_bytes, p.layout_type);
+          umma_f16(tmem_base, ad, bd, p.idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[st]);   // frees the stage once these MMAs retire
+      }
+      umma_commit(tmem_full);          // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> bias + ReLU -> fp16 -> NHWC global =====
+    const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;            // accumulator row = pixel index inside the tile
+    const int w = row % p.Wt;
+    const int h = (row / p.Wt) % p.Ht;
+    const int n = row / (p.Wt * p.Ht);
+    const bool valid = (n < p.Nt) && (w0 + w < p.Wout) && (h0 + h < p.Hout) && (n0 + n < p.n_images);
+    __half* dst = p.out + ((size_t)((size_t)(n0 + n) * p.Hout + (h0 + h)) * p.Wout + (w0 + w)) * p.out_cstride + p.out_coff +
+                  nb * p.block_n;
+    const float* bias = p.bias + nb * p.block_n;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c = 0; c < p.block_n; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(taddr + c, v);
+      tmem_ld_wait();
+      if (valid) {
+        uint32_t packed[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float x0 = __uint_as_float(v[2 * j]) + __ldg(bias + c + 2 * j);
+          float x1 = __uint_as_float(v[2 * j + 1]) + __ldg(bias + c + 2 * j + 1);
+          if (p.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+          __half2 hh = __floats2half2_rn(x0, x1);
+          packed[j] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        uint4* d4 = reinterpret_cast<uint4*>(dst + c);
+        d4[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        d4[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small CUDA-core kernels
+// ---------------------------------------------------------------------------------------------
+
+// dv_utils.preprocess_images: uint8 [N,H,W,C] -> fp16 [N,H,W,Cp] = (x - 128) / 128, channels >= C zero.
+// (x - 128) / 128 is exact in fp16 (|x-128| <= 128, power-of-two divisor).
+__global__ void preprocess_kernel(const uint8_t* __restrict__ in, __half* __restrict__ out, long long n_pixels, int C, int Cp) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pixels) return;
+  const uint8_t* src = in + i * C;
+  __half* dst = out + i * Cp;
+  for (int c = 0; c < Cp; c += 8) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c0 = c + 2 * j, c1 = c0 + 1;
+      const float a = c0 < C ? ((float)src[c0] - 128.f) * (1.f / 128.f) : 0.f;
+      const float b = c1 < C ? ((float)src[c1] - 128.f) * (1.f / 128.f) : 0.f;
+      __half2 hh = __floats2half2_rn(a, b);
+      pk[j] = *reinterpret_cast<uint32_t*>(&hh);
+    }
+    *reinterpret_cast<uint4*>(dst + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// 3x3 pooling on NHWC fp16, 8 channels per thread.  mode 0: max, stride 2, valid.  mode 1: average,
+// stride 1, 'same', divisor = number of in-bounds taps (TF AveragePooling2D semantics).
+__global__ void pool3x3_kernel(const __half* __restrict__ in, __half* __restrict__ out, int n_images, int Hin, int Win, int C,
+                               int Hout, int Wout, int out_cstride, int out_coff, int mode) {
+  const int cvec = C / 8;
+  const long long total = (long long)n_images * Hout * Wout * cvec;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cv = (int)(i % cvec);
+  long long pix = i / cvec;
+  const int ow = (int)(pix % Wout); pix /= Wout;
+  const int oh = (int)(pix % Hout);
+  const int n = (int)(pix / Hout);
+  const int stride = mode == 0 ? 2 : 1, pad = mode == 0 ? 0 : 1;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = mode == 0 ? -INFINITY : 0.f;
+  int cnt = 0;
+  for (int r = 0; r < 3; ++r) {
+    const int ih = oh * stride + r - pad;
+    if (ih < 0 || ih >= Hin) continue;
+    for (int s = 0; s < 3; ++s) {
+      const int iw = ow * stride + s - pad;
+      if (iw < 0 || iw >= Win) continue;
+      ++cnt;
+      const uint4 raw = *reinterpret_cast<const uint4*>(in + (((size_t)n * Hin + ih) * Win + iw) * C + cv * 8);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        if (mode == 0) { acc[2 * j] = fmaxf(acc[2 * j], f.x); acc[2 * j + 1] = fmaxf(acc[2 * j + 1], f.y); }
+        else { acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+      }
+    }
+  }
+  uint32_t pk[4];
+  const float inv = mode == 0 ? 1.f : 1.f / (float)cnt;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __half2 hh = __floats2half2_rn(acc[2 * j] * inv, acc[2 * j + 1] * inv);
+    pk[j] = *reinterpret_cast<uint32_t*>(&hh);
+  }
+  *reinterpret_cast<uint4*>(out + (((size_t)n * Hout + oh) * Wout + ow) * out_cstride + out_coff + cv * 8) =
+      make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
+// GlobalAveragePooling2D + Dense(3) + softmax, fp32.  One block per image.
+__global__ void __launch_bounds__(256) tail_kernel(const __half* __restrict__ feat, int hw, int C, const float* __restrict__ dense_w,
+                                                   const float* __restrict__ dense_b, float* __restrict__ probs, float* __restrict__ pooled_out) {
+  const int n = blockIdx.x;
+  const __half* f = feat + (size_t)n * hw * C;
+  float l0 = 0.f, l1 = 0.f, l2 = 0.f;
+  const float inv = 1.f / (float)hw;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < hw; ++p) s += __half2float(f[(size_t)p * C + c]);
+    s *= inv;
+    if (pooled_out) pooled_out[(size_t)n * C + c] = s;
+    l0 += s * dense_w[c * 3 + 0];
+    l1 += s * dense_w[c * 3 + 1];
+    l2 += s * dense_w[c * 3 + 2];
+  }
+  __shared__ float red[3][8];
+  for (int o = 16; o > 0; o >>= 1) {
+    l0 += __shfl_xor_sync(0xffffffffu, l0, o);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+    l2 += __shfl_xor_sync(0xffffffffu, l2, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = l0; red[1][warp] = l1; red[2][warp] = l2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float z[3];
+    for (int k = 0; k < 3; ++k) {
+      float s = dense_b[k];
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[k][w];
+      z[k] = s;
+    }
+    const float m = fmaxf(z[0], fmaxf(z[1], z[2]));
+    const float e0 = expf(z[0] - m), e1 = expf(z[1] - m), e2 = expf(z[2] - m);
+    const float d = e0 + e1 + e2;
+    probs[n * 3 + 0] = e0 / d;
+    probs[n * 3 + 1] = e1 / d;
+    probs[n * 3 + 2] = e2 / d;
+  }
+}
+
+__global__ void half_to_float_kernel(const __half* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __half2float(in[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side: network plan
+// ---------------------------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn GetEncodeTiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct TensorBuf {
+  std::string name;
+  int H = 0, W = 0, C = 0;   // C = stored channels (padded for the input)
+  __half* ptr = nullptr;
+};
+
+struct OpDesc {
+  int kind;  // 0 conv, 1 maxpool, 2 avgpool
+  std::string src, dst;
+  int off, cin, cout, kh, kw, stride, same;
+};
+
+int PadCin(int cin) { return cin < 16 ? 16 : (cin + 7) / 8 * 8; }
+
+// Restates deepvariant_b200/modeling.py inception_v3_graph() (tf_keras InceptionV3 topology).
+void BuildGraph(int in_channels, std::vector<OpDesc>* ops, std::map<std::string, int>* ch) {
+  (*ch)["input"] = in_channels;
+  auto conv = [&](const std::string& s, const std::string& d, int cout, int kh, int kw, int stride = 1, int same = 1, int off = 0,
+                  int total = 0) {
+    if (!ch->count(d)) (*ch)[d] = total ? total : cout;
+    ops->push_back({0, s, d, off, (*ch)[s], cout, kh, kw, stride, same});
+  };
+  auto pool = [&](int kind, const std::string& s, const std::string& d, int off = 0, int total = 0) {
+    if (!ch->count(d)) (*ch)[d] = total ? total : (*ch)[s];
+    ops->push_back({kind, s, d, off, (*ch)[s], (*ch)[s], 3, 3, kind == 1 ? 2 : 1, kind == 2});
+  };
+  conv("input", "s1", 32, 3, 3, 2, 0);
+  conv("s1", "s2", 32, 3, 3, 1, 0);
+  conv("s2", "s3", 64, 3, 3);
+  pool(1, "s3", "p1");
+  conv("p1", "s4", 80, 1, 1, 1, 0);
+  conv("s4", "s5", 192, 3, 3, 1, 0);
+  pool(1, "s5", "p2");
+  std::string x = "p2";
+  const int pool_ch[3] = {32, 64, 64};
+  for (int i = 0; i < 3; ++i) {
+    const std::string m = "mixed" + std::to_string(i);
+    const int total = 64 + 64 + 96 + pool_ch[i];
+    conv(x, m, 64, 1, 1, 1, 1, 0, total);
+    conv(x, m + "_b5a", 48, 1, 1);
+    conv(m + "_b5a", m, 64, 5, 5, 1, 1, 64);
+    conv(x, m + "_d1", 64, 1, 1);
+    conv(m + "_d1", m + "_d2", 96, 3, 3);
+    conv(m + "_d2", m, 96, 3, 3, 1, 1, 128);
+    pool(2, x, m + "_ap");
+    conv(m + "_ap", m, pool_ch[i], 1, 1, 1, 1, 224);
+    x = m;
+  }
+  {
+    const int total = 384 + 96 + (*ch)[x];
+    conv(x, "mixed3", 384, 3, 3, 2, 0, 0, total);
+    conv(x, "mixed3_d1", 64, 1, 1);
+    conv("mixed3_d1", "mixed3_d2", 96, 3, 3);
+    conv("mixed3_d2", "mixed3", 96, 3, 3, 2, 0, 384);
+    pool(1, x, "mixed3", 480);
+    x = "mixed3";
+  }
+  const int c7s[4] = {128, 160, 160, 192};
+  for (int i = 4; i <= 7; ++i) {
+    const std::string m = "mixed" + std::to_string(i);
+    const int c7 = c7s[i - 4];
+    conv(x, m, 192, 1, 1, 1, 1, 0, 768);
+    conv(x, m + "_s1", c7, 1, 1);
+    conv(m + "_s1", m + "_s2", c7, 1, 7);
+    conv(m + "_s2", m, 192, 7, 1, 1, 1, 192);
+    conv(x, m + "_d1", c7, 1, 1);
+    conv(m + "_d1", m + "_d2", c7, 7, 1);
+    conv(m + "_d2", m + "_d3", c7, 1, 7);
+    conv(m + "_d3", m + "_d4", c7, 7, 1);
+    conv(m + "_d4", m, 192, 1, 7, 1, 1, 384);
+    pool(2, x, m + "_ap");
+    conv(m + "_ap", m, 192, 1, 1, 1, 1, 576);
+    x = m;
+  }
+  {
+    const int total = 320 + 192 + (*ch)[x];
+    conv(x, "mixed8_a1", 192, 1, 1);
+    conv("mixed8_a1", "mixed8", 320, 3, 3, 2, 0, 0, total);
+    conv(x, "mixed8_b1", 192, 1, 1);
+    conv("mixed8_b1", "mixed8_b2", 192, 1, 7);
+    conv("mixed8_b2", "mixed8_b3", 192, 7, 1);
+    conv("mixed8_b3", "mixed8", 192, 3, 3, 2, 0, 320);
+    pool(1, x, "mixed8", 512);
+    x = "mixed8";
+  }
+  for (int i = 9; i <= 10; ++i) {
+    const std::string m = "mixed" + std::to_string(i);
+    conv(x, m, 320, 1, 1, 1, 1, 0, 2048);
+    conv(x, m + "_t1", 384, 1, 1);
+    conv(m + "_t1", m, 384, 1, 3, 1, 1, 320);
+    conv(m + "_t1", m, 384, 3, 1, 1, 1, 704);
+    conv(x, m + "_d1", 448, 1, 1);
+    conv(m + "_d1", m + "_d2", 384, 3, 3);
+    conv(m + "_d2", m, 384, 1, 3, 1, 1, 1088);
+    conv(m + "_d2", m, 384, 3, 1, 1, 1, 1472);
+    pool(2, x, m + "_ap");
+    conv(m + "_ap", m, 192, 1, 1, 1, 1, 1856);
+    x = m;
+  }
+}
+
+struct ConvLaunch {
+  CUtensorMap map_a, map_b;
+  ConvArgs args;
+  dim3 grid;
+  int smem;
+  double macs_per_image;
+};
+struct PoolLaunch {
+  const __half* in; __half* out;
+  int Hin, Win, C, Hout, Wout, out_cstride, out_coff, mode;
+};
+struct Step { int kind; int index; };  // 0 conv, 1 pool
+
+}  // namespace
+
+struct DvbCnn {
+  int device = 0, H = 0, W = 0, C = 0, Cp = 16, max_batch = 0, precision = 0;
+  std::vector<TensorBuf> tensors;
+  std::map<std::string, int> tensor_index;
+  std::vector<ConvLaunch> convs;
+  std::vector<PoolLaunch> pools;
+  std::vector<Step> steps;
+  std::vector<void*> allocs;
+  float* d_dense_w = nullptr; float* d_dense_b = nullptr;
+  float* d_pooled = nullptr;
+  int feat_tensor = -1;
+  double flops_per_image = 0;
+  int64_t launches = 0;
+  cudaStream_t stream = nullptr;
+  dvb::DevBuf d_in, d_probs;
+  dvb::PinBuf h_io;
+};
+
+namespace {
+
+struct TileChoice { int Wt, Ht, Nt; };
+
+TileChoice ChooseTile(int Hout, int Wout, int stride) {
+  TileChoice best{1, 1, 1};
+  double best_eff = -1;
+  const int max_box = 256 / stride;  // boxDim <= 256 in input space
+  for (int Wt = 1; Wt <= std::min(std::min(Wout, 128), max_box); ++Wt) {
+    for (int Ht = 1; Ht <= std::min(std::min(Hout, 128 / Wt), max_box); ++Ht) {
+      int Nt = 1;
+      if (Wt == Wout && Ht == Hout) Nt = std::max(1, 128 / (Wt * Ht));
+      const long tiles = (long)((Wout + Wt - 1) / Wt) * ((Hout + Ht - 1) / Ht);
+      const double eff = (double)Wout * Hout * Nt / ((double)tiles * 128.0);
+      if (eff > best_eff + 1e-9 || (std::fabs(eff - best_eff) <= 1e-9 && Wt > best.Wt)) {
+        best_eff = eff;
+        best = {Wt, Ht, Nt};
+      }
+    }
+  }
+  return best;
+}
+
+int ChooseBlockN(int cout) {
+  if (cout <= 256) return cout;
+  for (int d = 256; d >= 16; d -= 16)
+    if (cout % d == 0) return d;
+  return 16;
+}
+
+int TmemCols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
+
+int EnvInt(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+int MakeMap(CUtensorMap* m, void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
+            const cuuint32_t* estr, int block_k) {
+  EncodeTiledFn fn = GetEncodeTiled();
+  if (!fn) return dvb::fail(DVB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  CUtensorMapSwizzle sw = block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, ptr, dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return dvb::fail(DVB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+  return DVB_OK;
+}
+
+int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
+  std::vector<OpDesc> ops;
+  std::map<std::string, int> ch;
+  BuildGraph(net->C, &ops, &ch);
+  // --- header
+  if (blob_bytes < 12) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob too small");
+  const int32_t* hdr = reinterpret_cast<const int32_t*>(blob);
+  if ((uint32_t)hdr[0] != kBlobMagic) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob: bad magic");
+  if (hdr[1] != net->C) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob is for %d input channels, not %d", hdr[1], net->C);
+  int n_conv = 0;
+  for (auto& o : ops) n_conv += o.kind == 0;
+  if (hdr[2] != n_conv) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob has %d convs, expected %d", hdr[2], n_conv);
+  int64_t pos = 12;
+
+  // --- tensors
+  std::map<std::string, std::pair<int, int>> hw;
+  hw["input"] = {net->H, net->W};
+  auto add_tensor = [&](const std::string& name, int H, int W, int C) -> int {
+    if (net->tensor_index.count(name)) return DVB_OK;
+    TensorBuf t;
+    t.name = name; t.H = H; t.W = W; t.C = C;
+    const size_t bytes = (size_t)net->max_batch * H * W * C * sizeof(__half);
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return dvb::fail(DVB_ERR_CUDA, "cudaMalloc of %zu bytes for tensor %s failed", bytes, name.c_str());
+    cudaMemset(p, 0, bytes);
+    net->allocs.push_back(p);
+    t.ptr = static_cast<__half*>(p);
+    net->tensor_index[name] = (int)net->tensors.size();
+    net->tensors.push_back(t);
+    return DVB_OK;
+  };
+  int st = add_tensor("input", net->H, net->W, net->Cp);
+  if (st) return st;
+
+  const int force_bk = EnvInt("DVB_CNN_BLOCK_K", 0);       // 0 = per-layer choice
+  const int stride_mode = EnvInt("DVB_TMA_STRIDE_MODE", 0);  // how boxDim is stated for strided traversal
+  double macs_total = 0;
+  for (auto& o : ops) {
+    const auto [Hin, Win] = hw[o.src];
+    int Hout, Wout;
+    if (o.same) { Hout = Hin; Wout = Win; }
+    else { Hout = (Hin - o.kh) / o.stride + 1; Wout = (Win - o.kw) / o.stride + 1; }
+    if (Hout < 1 || Wout < 1) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "image %dx%d is too small for the network", net->H, net->W);
+    hw[o.dst] = {Hout, Wout};
+    st = add_tensor(o.dst, Hout, Wout, ch[o.dst]);
+    if (st) return st;
+    const TensorBuf& src = net->tensors[net->tensor_index[o.src]];
+    const TensorBuf& dst = net->tensors[net->tensor_index[o.dst]];
+    if (o.kind != 0) {
+      PoolLaunch pl{src.ptr, dst.ptr, Hin, Win, src.C, Hout, Wout, dst.C, o.off, o.kind == 1 ? 0 : 1};
+      net->steps.push_back({1, (int)net->pools.size()});
+      net->pools.push_back(pl);
+      continue;
+    }
+    // --- conv weights from the blob
+    if (pos + 20 > blob_bytes) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob truncated");
+    const int32_t* lh = reinterpret_cast<const int32_t*>(blob + pos);
+    pos += 20;
+    const int cin_store = src.C;  // channels physically present in the source tensor
+    if (lh[0] != o.kh || lh[1] != o.kw || lh[2] != o.cin || lh[3] != PadCin(o.cin) || lh[4] != o.cout || lh[3] != cin_store)
+      return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob: conv %zu header mismatch (%d %d %d %d %d)", net->convs.size(), lh[0], lh[1],
+                       lh[2], lh[3], lh[4]);
+    const size_t wbytes = (size_t)o.cout * o.kh * o.kw * cin_store * sizeof(__half);
+    const size_t bbytes = (size_t)o.cout * sizeof(float);
+    if (pos + (int64_t)(wbytes + bbytes) > blob_bytes) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob truncated");
+    void* dw = nullptr; void* db = nullptr;
+    if (cudaMalloc(&dw, wbytes) != cudaSuccess || cudaMalloc(&db, bbytes) != cudaSuccess) return dvb::fail(DVB_ERR_CUDA, "cudaMalloc (weights) failed");
+    net->allocs.push_back(dw); net->allocs.push_back(db);
+    cudaMemcpy(dw, blob + pos, wbytes, cudaMemcpyHostToDevice);
+    cudaMemcpy(db, blob + pos + wbytes, bbytes, cudaMemcpyHostToDevice);
+    pos += wbytes + bbytes;
+
+    ConvLaunch cl;
+    memset(&cl, 0, sizeof(cl));
+    ConvArgs& a = cl.args;
+    a.kh = o.kh; a.kw = o.kw; a.stride = o.stride;
+    a.pad_h = o.same ? (o.kh - 1) / 2 : 0;
+    a.pad_w = o.same ? (o.kw - 1) / 2 : 0;
+    int bk = force_bk ? force_bk : (cin_store % 64 == 0 ? 64 : cin_store % 32 == 0 ? 32 : 16);
+    if (cin_store < bk) bk = cin_store >= 32 ? 32 : 16;
+    a.block_k = bk;
+    a.cin_blocks = (cin_store + bk - 1) / bk;
+    const TileChoice tc = ChooseTile(Hout, Wout, o.stride);
+    a.Wt = tc.Wt; a.Ht = tc.Ht; a.Nt = tc.Nt;
+    a.tiles_w = (Wout + tc.Wt - 1) / tc.Wt;
+    a.tiles_h = (Hout + tc.Ht - 1) / tc.Ht;
+    a.Hout = Hout; a.Wout = Wout;
+    a.block_n = ChooseBlockN(o.cout);
+    a.tmem_cols = TmemCols(a.block_n);
+    a.out = dst.ptr; a.out_cstride = dst.C; a.out_coff = o.off; a.relu = 1;
+    a.bias = static_cast<const float*>(db);
+    // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=F32, A=B=F16, K-major, M=128
+    a.idesc = (1u << 4) | ((uint32_t)(a.block_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    a.layout_type = bk == 64 ? 2u : bk == 32 ? 4u : 6u;
+    a.sbo_bytes = 8u * (uint32_t)bk * 2u;
+    const int rows = tc.Wt * tc.Ht * tc.Nt;
+    a.a_bytes = (uint32_t)rows * bk * 2;
+    a.b_bytes = (uint32_t)a.block_n * bk * 2;
+    a.a_stage = 128u * bk * 2;
+    a.b_stage = ((uint32_t)a.block_n * bk * 2 + 1023u) & ~1023u;
+    cl.smem = kStages * (a.a_stage + a.b_stage) + 1024 + 256;
+    cl.macs_per_image = (double)Hout * Wout * o.cout * o.kh * o.kw * o.cin;
+    macs_total += cl.macs_per_image;
+    // --- tensor maps
+    {
+      const cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)net->max_batch};
+      const cuuint64_t strides[3] = {(cuuint64_t)src.C * 2, (cuuint64_t)Win * src.C * 2, (cuuint64_t)Hin * Win * src.C * 2};
+      cuuint32_t bw = tc.Wt, bh = tc.Ht;
+      if (o.stride > 1) {
+        if (stride_mode == 0) { bw = tc.Wt * o.stride; bh = tc.Ht * o.stride; }
+        else if (stride_mode == 1) { bw = (tc.Wt - 1) * o.stride + 1; bh = (tc.Ht - 1) * o.stride + 1; }
+      }
+      const cuuint32_t box[4] = {(cuuint32_t)bk, bw, bh, (cuuint32_t)tc.Nt};
+      const cuuint32_t estr[4] = {1, (cuuint32_t)o.stride, (cuuint32_t)o.stride, 1};
+      st = MakeMap(&cl.map_a, src.ptr, 4, dims, strides, box, estr, bk);
+      if (st) return st;
+    }
+    {
+      const cuuint64_t dims[3] = {(cuuint64_t)cin_store, (cuuint64_t)(o.kh * o.kw), (cuuint64_t)o.cout};
+      const cuuint64_t strides[2] = {(cuuint64_t)cin_store * 2, (cuuint64_t)o.kh * o.kw * cin_store * 2};
+      const cuuint32_t box[3] = {(cuuint32_t)bk, 1, (cuuint32_t)a.block_n};
+      const cuuint32_t estr[3] = {1, 1, 1};
+      st = MakeMap(&cl.map_b, dw, 3, dims, strides, box, estr, bk);
+      if (st) return st;
+    }
+    cl.grid = dim3(1, (unsigned)(o.cout / a.block_n), 1);
+    net->steps.push_back({0, (int)net->convs.size()});
+    net->convs.push_back(cl);
+  }
+  // --- head
+  const size_t dwb = 2048 * 3 * sizeof(float), dbb = 3 * sizeof(float);
+  if (pos + (int64_t)(dwb + dbb) != blob_bytes) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob size mismatch (%lld of %lld bytes consumed before the head)", (long long)pos, (long long)blob_bytes);
+  if (ch["mixed10"] != 2048) return dvb::fail(DVB_ERR_INTERNAL, "backbone does not end in 2048 channels");
+  cudaMalloc(&net->d_dense_w, dwb); cudaMalloc(&net->d_dense_b, dbb);
+  cudaMemcpy(net->d_dense_w, blob + pos, dwb, cudaMemcpyHostToDevice);
+  cudaMemcpy(net->d_dense_b, blob + pos + dwb, dbb, cudaMemcpyHostToDevice);
+  cudaMalloc(&net->d_pooled, (size_t)net->max_batch * 2048 * sizeof(float));
+  net->feat_tensor = net->tensor_index["mixed10"];
+  net->flops_per_image = 2.0 * macs_total;
+  int max_smem = 0;
+  for (auto& c : net->convs) max_smem = std::max(max_smem, c.smem);
+  if (cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess)
+    return dvb::fail(DVB_ERR_CUDA, "cannot reserve %d bytes of shared memory", max_smem);
+  if (cudaDeviceSynchronize() != cudaSuccess) return dvb::fail(DVB_ERR_CUDA, "weight upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return DVB_OK;
+}
+
+int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaStream_t s) {
+  const TensorBuf& in = net->tensors[0];
+  const long long npix = (long long)n * net->H * net->W;
+  preprocess_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(images, in.ptr, npix, net->C, net->Cp);
+  net->launches++;
+  for (const Step& stp : net->steps) {
+    if (stp.kind == 0) {
+      ConvLaunch& c = net->convs[stp.index];
+      ConvArgs a = c.args;
+      a.n_images = n;
+      a.tiles_n = (n + a.Nt - 1) / a.Nt;
+      dim3 grid((unsigned)(a.tiles_w * a.tiles_h * a.tiles_n), c.grid.y, 1);
+      conv_gemm_kernel<<<grid, kConvThreads, c.smem, s>>>(c.map_a, c.map_b, a);
+    } else {
+      const PoolLaunch& p = net->pools[stp.index];
+      const long long total = (long long)n * p.Hout * p.Wout * (p.C / 8);
+      pool3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p.in, p.out, n, p.Hin, p.Win, p.C, p.Hout, p.Wout, p.out_cstride,
+                                                                      p.out_coff, p.mode);
+    }
+    net->launches++;
+  }
+  const TensorBuf& f = net->tensors[net->feat_tensor];
+  tail_kernel<<<n, 256, 0, s>>>(f.ptr, f.H * f.W, f.C, net->d_dense_w, net->d_dense_b, probs, net->d_pooled);
+  net->launches++;
+  DVB_CUDA(cudaGetLastError());
+  return DVB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dvb_cnn_create(const void* weights, int64_t weights_bytes, int32_t height, int32_t width, int32_t channels, int32_t max_batch,
+                   int32_t precision, int device, DvbCnn** out) {
+  if (!weights || !out || height < 1 || width < 1 || channels < 1 || channels > 16 || max_batch < 1)
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_cnn_create: bad arguments");
+  *out = nullptr;
+  if (precision != 0) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "precision %d is not implemented (0 = fp16 operands / fp32 accumulate)", precision);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return dvb::fail(DVB_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "device %d out of range", device);
+  DVB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  DVB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return dvb::fail(DVB_ERR_NO_DEVICE, "the CNN kernels are tcgen05 (sm_100a) only; device is sm_%d%d", prop.major, prop.minor);
+  DvbCnn* net = new DvbCnn();
+  net->device = device; net->H = height; net->W = width; net->C = channels; net->Cp = PadCin(channels);
+  net->max_batch = max_batch; net->precision = precision;
+  int st = Plan(net, static_cast<const uint8_t*>(weights), weights_bytes);
+  if (st) { dvb_cnn_destroy(net); return st; }
+  DVB_CUDA(cudaStreamCreateWithFlags(&net->stream, cudaStreamNonBlocking));
+  *out = net;
+  return DVB_OK;
+}
+
+void dvb_cnn_destroy(DvbCnn* net) {
+  if (!net) return;
+  cudaSetDevice(net->device);
+  for (void* p : net->allocs) cudaFree(p);
+  if (net->d_dense_w) cudaFree(net->d_dense_w);
+  if (net->d_dense_b) cudaFree(net->d_dense_b);
+  if (net->d_pooled) cudaFree(net->d_pooled);
+  net->d_in.release(); net->d_probs.release(); net->h_io.release();
+  if (net->stream) cudaStreamDestroy(net->stream);
+  delete net;
+}
+
+int dvb_cnn_forward_device(DvbCnn* net, const uint8_t* images, int32_t n, float* probs, void* stream) {
+  if (!net || (n > 0 && (!images || !probs)) || n < 0) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_cnn_forward_device: bad arguments");
+  DVB_CUDA(cudaSetDevice(net->device));
+  const size_t image_bytes = (size_t)net->H * net->W * net->C;
+  for (int i = 0; i < n; i += net->max_batch) {
+    const int m = std::min(net->max_batch, n - i);
+    int st = ForwardChunk(net, images + (size_t)i * image_bytes, m, probs + (size_t)i * 3, static_cast<cudaStream_t>(stream));
+    if (st) return st;
+  }
+  return DVB_OK;
+}
+
+int dvb_cnn_forward_host(DvbCnn* net, const uint8_t* images_host, int32_t n, float* probs_host) {
+  if (!net || (n > 0 && (!images_host || !probs_host)) || n < 0) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_cnn_forward_host: bad arguments");
+  if (n == 0) return DVB_OK;
+  DVB_CUDA(cudaSetDevice(net->device));
+  const size_t image_bytes = (size_t)net->H * net->W * net->C;
+  DVB_CUDA(net->d_in.reserve((size_t)n * image_bytes));
+  DVB_CUDA(net->d_probs.reserve((size_t)n * 3 * sizeof(float)));
+  DVB_CUDA(cudaMemcpyAsync(net->d_in.p, images_host, (size_t)n * image_bytes, cudaMemcpyHostToDevice, net->stream));
+  int st = dvb_cnn_forward_device(net, static_cast<const uint8_t*>(net->d_in.p), n, static_cast<float*>(net->d_probs.p), net->stream);
+  if (st) return st;
+  DVB_CUDA(cudaMemcpyAsync(probs_host, net->d_probs.p, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, net->stream));
+  DVB_CUDA(cudaStreamSynchronize(net->stream));
+  return DVB_OK;
+}
+
+int64_t dvb_cnn_launch_count(const DvbCnn* net) { return net ? net->launches : 0; }
+double dvb_cnn_flops_per_image(const DvbCnn* net) { return net ? net->flops_per_image : 0.0; }
+
+// Debug / test access to an intermediate activation of the LAST forward (first `n` images):
+// out_host = float[n][H][W][C] (NHWC).  name: "input", "s1".."s5", "p1", "p2", "mixed0".."mixed10", branch tensors.
+// name "pooled" returns float[n][2048].  *h/*w/*c receive the shape.
+int dvb_cnn_debug_tensor(DvbCnn* net, const char* name, int32_t n, float* out_host, int32_t* h, int32_t* w, int32_t* c) {
+  if (!net || !name) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "null argument");
+  DVB_CUDA(cudaSetDevice(net->device));
+  DVB_CUDA(cudaDeviceSynchronize());
+  if (std::string(name) == "pooled") {
+    if (h) *h = 1; if (w) *w = 1; if (c) *c = 2048;
+    if (out_host) DVB_CUDA(cudaMemcpy(out_host, net->d_pooled, (size_t)n * 2048 * sizeof(float), cudaMemcpyDeviceToHost));
+    return DVB_OK;
+  }
+  auto it = net->tensor_index.find(name);
+  if (it == net->tensor_index.end()) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "no tensor named %s", name);
+  const TensorBuf& t = net->tensors[it->second];
+  if (h) *h = t.H; if (w) *w = t.W; if (c) *c = t.C;
+  if (!out_host) return DVB_OK;
+  const long long cnt = (long long)n * t.H * t.W * t.C;
+  float* tmp = nullptr;
+  DVB_CUDA(cudaMalloc(&tmp, cnt * sizeof(float)));
+  half_to_float_kernel<<<(unsigned)((cnt + 255) / 256), 256>>>(t.ptr, tmp, cnt);
+  cudaError_t e = cudaMemcpy(out_host, tmp, cnt * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(tmp);
+  if (e != cudaSuccess) return dvb::fail(DVB_ERR_CUDA, "debug copy failed: %s", cudaGetErrorString(e));
+  return DVB_OK;
+}
+
+}  // extern "C"

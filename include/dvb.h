@@ -205,6 +205,13 @@ int64_t dvb_cnn_launch_count(const DvbCnn* cnn);
 /* FLOPs of one forward for one image (conv MACs x 2). */
 double dvb_cnn_flops_per_image(const DvbCnn* cnn);
 
+/* Debug / test access to an intermediate activation of the LAST forward (first `n` images of the
+ * last chunk), converted to float NHWC: out_host = float[n][H][W][C].  Names follow
+ * deepvariant_b200/modeling.py ("input", "s1".."s5", "p1", "p2", "mixed0".."mixed10", branch
+ * tensors); "pooled" returns the 2048-wide pre-logits.  out_host may be NULL to query the shape. */
+int dvb_cnn_debug_tensor(DvbCnn* cnn, const char* name, int32_t n, float* out_host, int32_t* h,
+                         int32_t* w, int32_t* c);
+
 #ifdef __cplusplus
 }
 #endif
