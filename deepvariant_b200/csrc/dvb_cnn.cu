@@ -633,7 +633,6 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
   if (st) return st;
 
   const int force_bk = EnvInt("DVB_CNN_BLOCK_K", 0);       // 0 = per-layer choice
-  const int stride_mode = EnvInt("DVB_TMA_STRIDE_MODE", 0);  // how boxDim is stated for strided traversal
   double macs_total = 0;
   for (auto& o : ops) {
     const auto [Hin, Win] = hw[o.src];
@@ -705,11 +704,10 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
     {
       const cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)net->max_batch};
       const cuuint64_t strides[3] = {(cuuint64_t)src.C * 2, (cuuint64_t)Win * src.C * 2, (cuuint64_t)Hin * Win * src.C * 2};
-      cuuint32_t bw = tc.Wt, bh = tc.Ht;
-      if (o.stride > 1) {
-        if (stride_mode == 0) { bw = tc.Wt * o.stride; bh = tc.Ht * o.stride; }
-        else if (stride_mode == 1) { bw = (tc.Wt - 1) * o.stride + 1; bh = (tc.Ht - 1) * o.stride + 1; }
-      }
+      // With elementStrides = s the box is stated in UN-strided input elements and the TMA delivers
+      // ceil(box / s) of them (measured on B200: box = Wt loads too few bytes and the mbarrier never
+      // completes; box = Wt * s delivers exactly Wt).
+      const cuuint32_t bw = tc.Wt * o.stride, bh = tc.Ht * o.stride;
       const cuuint32_t box[4] = {(cuuint32_t)bk, bw, bh, (cuuint32_t)tc.Nt};
       const cuuint32_t estr[4] = {1, (cuuint32_t)o.stride, (cuuint32_t)o.stride, 1};
       st = MakeMap(&cl.map_a, src.ptr, 4, dims, strides, box, estr, bk);

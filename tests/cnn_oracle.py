@@ -90,3 +90,47 @@ def build_reference_model(in_channels: int, seed: int = 0, device='cpu') -> Refe
 
 def predict(model: ReferenceModel, images_u8: torch.Tensor) -> torch.Tensor:
   return model.forward(images_u8)
+
+
+class FastCpuModel:
+  """Same arithmetic as ReferenceModel with BN folded and channels_last tensors so that oneDNN's NHWC
+  kernels are used — the fairest stand-in available here for the reference's TF-CPU (oneDNN)
+  call_variants when bench.py times the CPU baseline.  Checked against ReferenceModel in
+  tests/test_cnn_oracle.py."""
+
+  def __init__(self, weights: modeling.ModelWeights):
+    self.ops, _ = modeling.inception_v3_graph(weights.in_channels)
+    self.convs = []
+    for p in weights.convs:
+      k, b = modeling.fold_bn(p)
+      wt = torch.from_numpy(np.ascontiguousarray(np.transpose(k, (3, 2, 0, 1)))).contiguous(memory_format=torch.channels_last)
+      self.convs.append((wt, torch.from_numpy(b)))
+    self.dense_w = torch.from_numpy(weights.dense_kernel)
+    self.dense_b = torch.from_numpy(weights.dense_bias)
+
+  def forward(self, images_u8: torch.Tensor) -> torch.Tensor:
+    with torch.inference_mode():
+      x = ((images_u8.float() - 128.0) / 128.0).permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
+      t = {'input': x}
+      parts = {}
+
+      def get(name):
+        if name not in t:
+          t[name] = torch.cat([parts[name][k] for k in sorted(parts[name])], 1)
+        return t[name]
+
+      ci = 0
+      for o in self.ops:
+        s = get(o.src)
+        if o.kind == 'conv':
+          wt, b = self.convs[ci]
+          ci += 1
+          pad = ((o.kh - 1) // 2, (o.kw - 1) // 2) if o.same else (0, 0)
+          y = F.relu(F.conv2d(s, wt, b, stride=o.stride, padding=pad))
+        elif o.kind == 'maxpool':
+          y = F.max_pool2d(s, 3, 2, 0)
+        else:
+          y = F.avg_pool2d(s, 3, 1, 1, count_include_pad=False)
+        parts.setdefault(o.dst, {})[o.dst_channel_offset] = y
+      f = get('mixed10').mean((2, 3))
+      return torch.softmax(f @ self.dense_w + self.dense_b, 1)

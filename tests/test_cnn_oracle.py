@@ -94,3 +94,11 @@ def test_cvo_carries_model_id_and_probabilities():
   v, idx, probs = protos.parse_call_variants_output(cvo)
   assert idx == [0] and probs == [0.1, 0.2, 0.7]
   assert b'MID' in v and b'deepvariant' in v and protos.parse_variant(v).start == 41
+
+
+def test_fast_cpu_model_matches_reference_model():
+  w = modeling.random_weights(7, 6)
+  x = torch.randint(0, 255, (2, 100, 221, 7), dtype=torch.uint8)
+  a = cnn_oracle.ReferenceModel(w).forward(x)
+  b = cnn_oracle.FastCpuModel(w).forward(x)
+  assert float((a - b).abs().max()) < 1e-5
