@@ -123,6 +123,8 @@ SYMBOLS = (
     ('dvb_cnn_forward_host', C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     ('dvb_cnn_launch_count', C.c_int64, [C.c_void_p]),
     ('dvb_cnn_flops_per_image', C.c_double, [C.c_void_p]),
+    ('dvb_crc32c', C.c_uint32, [C.c_char_p, C.c_size_t]),
+    ('dvb_masked_crc32c', C.c_uint32, [C.c_char_p, C.c_size_t]),
     ('dvb_cnn_debug_tensor', C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32),
                                        C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 )

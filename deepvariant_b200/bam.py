@@ -1,0 +1,131 @@
+"""Minimal BAM reader (BGZF + BAM records via zlib; no htslib) producing the Read fields the pileup
+path uses, with the conversions of nucleus' SamReader (third_party/nucleus/io/sam_reader.cc:760-860):
+  fragment_name = qname, fragment_length = isize, read_number = 0 if (FREAD1 or unpaired) else 1,
+  number_reads = 2 if paired else 1, aligned_sequence upper-case from the 4-bit codes ("=ACMGRSVTWYHKDBN"),
+  aligned_quality raw phred bytes, HP aux tag -> info['HP'] (with parse_sam_aux_fields).
+and its ReadRequirements filter (sam_reader.cc:217-245, utils.cc:261-266).
+This is SURVEY §8(f) "next" row #1 in its simplest form: whole-file decode, in-memory region query.
+"""
+from __future__ import annotations
+
+import gzip
+import struct
+from typing import Dict, Iterable, List, Optional
+
+from deepvariant_b200.protos import Read
+
+_SEQ = '=ACMGRSVTWYHKDBN'
+FPAIRED, FPROPER, FUNMAP, FMUNMAP, FREVERSE, FMREVERSE, FREAD1, FREAD2, FSECONDARY, FQCFAIL, FDUP, FSUPP = (
+    0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40, 0x80, 0x100, 0x200, 0x400, 0x800)
+
+
+class ReadRequirements:
+  """reads.proto ReadRequirements defaults as make_examples sets them (make_examples_options.py:957-964)."""
+
+  def __init__(self, min_mapping_quality=5, keep_duplicates=False, keep_failed_vendor_quality_checks=False,
+               keep_secondary_alignments=False, keep_supplementary_alignments=False, keep_unaligned=False,
+               keep_improperly_placed=False):
+    self.__dict__.update(locals())
+
+
+def _parse_aux_hp(aux: bytes) -> Optional[int]:
+  i = 0
+  sizes = {b'A': 1, b'c': 1, b'C': 1, b's': 2, b'S': 2, b'i': 4, b'I': 4, b'f': 4}
+  fmts = {b'c': '<b', b'C': '<B', b's': '<h', b'S': '<H', b'i': '<i', b'I': '<I'}
+  n = len(aux)
+  while i + 3 <= n:
+    tag, typ = aux[i:i + 2], aux[i + 2:i + 3]
+    i += 3
+    if typ in sizes:
+      if tag == b'HP' and typ in fmts:
+        return struct.unpack_from(fmts[typ], aux, i)[0]
+      i += sizes[typ]
+    elif typ in (b'Z', b'H'):
+      j = aux.index(b'\0', i)
+      i = j + 1
+    elif typ == b'B':
+      sub = aux[i:i + 1]
+      cnt = struct.unpack_from('<i', aux, i + 1)[0]
+      i += 5 + cnt * sizes[sub]
+    else:
+      break
+  return None
+
+
+class BamReader:
+
+  def __init__(self, path: str, read_requirements: Optional[ReadRequirements] = None, parse_aux: bool = False):
+    self.requirements = read_requirements or ReadRequirements()
+    with gzip.open(path, 'rb') as f:   # BGZF is a series of gzip members
+      data = f.read()
+    if data[:4] != b'BAM\1':
+      raise ValueError(f'{path} is not a BAM file')
+    l_text = struct.unpack_from('<i', data, 4)[0]
+    pos = 8 + l_text
+    n_ref = struct.unpack_from('<i', data, pos)[0]
+    pos += 4
+    self.references: List[str] = []
+    for _ in range(n_ref):
+      l_name = struct.unpack_from('<i', data, pos)[0]
+      self.references.append(data[pos + 4:pos + 4 + l_name - 1].decode())
+      pos += 4 + l_name + 4
+    self.reads: List[Read] = []
+    while pos + 4 <= len(data):
+      block_size = struct.unpack_from('<i', data, pos)[0]
+      rec = data[pos + 4:pos + 4 + block_size]
+      pos += 4 + block_size
+      r = self._convert(rec, parse_aux)
+      if r is not None:
+        self.reads.append(r)
+    self._by_contig: Dict[str, List[Read]] = {}
+    for r in self.reads:
+      self._by_contig.setdefault(r.reference_name, []).append(r)
+
+  def _convert(self, rec: bytes, parse_aux: bool) -> Optional[Read]:
+    ref_id, pos_, l_read_name, mapq, _bin, n_cigar, flag, l_seq, next_ref, next_pos, tlen = struct.unpack_from('<iiBBHHHiiii', rec, 0)
+    req = self.requirements
+    if ((flag & FDUP and not req.keep_duplicates) or (flag & FQCFAIL and not req.keep_failed_vendor_quality_checks) or
+        (flag & FSECONDARY and not req.keep_secondary_alignments) or (flag & FSUPP and not req.keep_supplementary_alignments)):
+      return None
+    mapped = not flag & FUNMAP
+    if not mapped and not req.keep_unaligned:
+      return None
+    paired = bool(flag & FPAIRED)
+    off = 32
+    name = rec[off:off + l_read_name - 1].decode()
+    off += l_read_name
+    cigar = []
+    for k in range(n_cigar):
+      v = struct.unpack_from('<I', rec, off + 4 * k)[0]
+      cigar.append((v & 0xF, v >> 4))
+    off += 4 * n_cigar
+    seq_bytes = rec[off:off + (l_seq + 1) // 2]
+    off += (l_seq + 1) // 2
+    seq = ''.join(_SEQ[b >> 4] + _SEQ[b & 0xF] for b in seq_bytes)[:l_seq]
+    qual = rec[off:off + l_seq]
+    off += l_seq
+    contig = self.references[ref_id] if ref_id >= 0 else ''
+    mate_contig = self.references[next_ref] if (paired and not flag & FMUNMAP and next_ref >= 0) else ''
+    number_reads = 2 if paired else 1
+    proper = bool(flag & FPROPER)
+    # IsReadProperlyPlaced (utils.cc:261-266)
+    if not req.keep_improperly_placed and mapped:
+      if not (number_reads < 2 or proper or not mate_contig or contig == mate_contig):
+        return None
+    if mapped and mapq < req.min_mapping_quality:
+      return None
+    r = Read(fragment_name=name, read_number=0 if (flag & FREAD1 or not paired) else 1, reference_name=contig,
+             position=pos_, reverse_strand=bool(flag & FREVERSE), mapping_quality=mapq, cigar=cigar if mapped else [],
+             aligned_sequence=seq.encode(), aligned_quality=bytes(qual), fragment_length=tlen,
+             supplementary_alignment=bool(flag & FSUPP), secondary_alignment=bool(flag & FSECONDARY),
+             duplicate_fragment=bool(flag & FDUP), failed_vendor_quality_checks=bool(flag & FQCFAIL),
+             proper_placement=proper, number_reads=number_reads)
+    if parse_aux:
+      hp = _parse_aux_hp(rec[off:])
+      if hp is not None:
+        r.hp_values = [hp]
+    return r
+
+  def query(self, contig: str, start: int, end: int) -> List[Read]:
+    """Reads overlapping [start, end) in file order (ReadOverlapsRegion, utils.cc:172-188)."""
+    return [r for r in self._by_contig.get(contig, ()) if end > r.position and start < r.end()]

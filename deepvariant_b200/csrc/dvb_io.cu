@@ -1,0 +1,53 @@
+// dvb_io.cu — host-only helpers of libdvb.so for the file boundary between the stages.
+//
+// TFRecord framing (tensorflow/core/lib/io/record_writer.cc, the format behind
+// third_party/nucleus/io/example_writer.cc:99-115 and tfrecord_writer.cc): every record is
+//   uint64 length | uint32 masked_crc32c(length) | data | uint32 masked_crc32c(data)
+// with crc32c = CRC-32C (Castagnoli, reflected 0x82F63B78) and mask(c) = ((c >> 15) | (c << 17)) + 0xa282ead8.
+#include <cstddef>
+#include <cstdint>
+
+#include "dvb_common.h"
+
+namespace {
+struct Crc32cTables {
+  uint32_t t[8][256];
+  Crc32cTables() {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      t[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int s = 1; s < 8; ++s) t[s][i] = (t[s - 1][i] >> 8) ^ t[0][t[s - 1][i] & 0xFF];
+  }
+};
+const Crc32cTables& Tables() {
+  static const Crc32cTables tables;
+  return tables;
+}
+}  // namespace
+
+extern "C" {
+
+uint32_t dvb_crc32c(const void* data, size_t n) {
+  const Crc32cTables& T = Tables();
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint32_t c = 0xFFFFFFFFu;
+  while (n && (reinterpret_cast<uintptr_t>(p) & 7)) { c = T.t[0][(c ^ *p++) & 0xFF] ^ (c >> 8); --n; }
+  while (n >= 8) {  // slicing-by-8
+    uint64_t w = *reinterpret_cast<const uint64_t*>(p) ^ c;
+    c = T.t[7][w & 0xFF] ^ T.t[6][(w >> 8) & 0xFF] ^ T.t[5][(w >> 16) & 0xFF] ^ T.t[4][(w >> 24) & 0xFF] ^
+        T.t[3][(w >> 32) & 0xFF] ^ T.t[2][(w >> 40) & 0xFF] ^ T.t[1][(w >> 48) & 0xFF] ^ T.t[0][(w >> 56) & 0xFF];
+    p += 8; n -= 8;
+  }
+  while (n--) c = T.t[0][(c ^ *p++) & 0xFF] ^ (c >> 8);
+  return c ^ 0xFFFFFFFFu;
+}
+
+uint32_t dvb_masked_crc32c(const void* data, size_t n) {
+  const uint32_t c = dvb_crc32c(data, n);
+  return ((c >> 15) | (c << 17)) + 0xa282ead8u;
+}
+
+}  // extern "C"

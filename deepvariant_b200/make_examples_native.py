@@ -1,0 +1,376 @@
+"""Host-side mirror of deepvariant.python.make_examples_native (the per-region example driver).
+
+  ExamplesGenerator(options, example_filenames, test_mode=False)
+      .write_examples_in_region(candidates, reads_per_sample, sample_order, role,
+                                mean_coverage_per_sample) -> (stats dict, image_shape[3])
+      .signal_shard_finished()
+  (deepvariant/python/make_examples_native_pybind.cc:56-109)
+
+Restated host logic, each citing the reference (deepvariant/make_examples_native.cc):
+  alt_allele_combinations          :191-267   encoded_variant_type            :301-321
+  encode_alt_alleles               :350-374   encode_example                  :388-474
+  get_reference_bases_for_pileup   :514-538   need_alt_alignment              :498-512
+  create_and_write_examples_for_candidate :632-736 (as plan_region + finish_region)
+  InMemoryReader.query             :802-810 + third_party/nucleus/util/utils.cc:172-240
+  trim_cigar / trim_read / trim_reads / calculate_alignment_region
+                                   deepvariant/alt_aligned_pileup_lib.cc:91-266
+
+Where the reference encodes one candidate at a time on the CPU, this driver PLANS a whole region
+(every candidate x alt-allele combination becomes one image spec), encodes all images in ONE CUDA
+launch through libdvb.so, then serialises the tf.Examples.  There is no CPU encoder in this module.
+
+Scope notes: single sample; alt-aligned pileups ('diff_channels' / 'base_channels')
+are produced with zero alt channels — exactly what the reference emits for SNP candidates under
+types_to_alt_align='indels' — and candidates that would need haplotype re-alignment (indels) are
+counted in stats['n_needs_alt_alignment'] (SSW re-alignment is §8(f) "next" #3).  'rows' /
+'single_row' layouts, training labels and the shared-memory stream are not implemented.
+"""
+from __future__ import annotations
+
+import dataclasses
+import json
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from deepvariant_b200 import packing
+from deepvariant_b200 import pileup_image as pi
+from deepvariant_b200 import protos
+from deepvariant_b200 import tfrecord
+from deepvariant_b200.protos import DeepVariantCall, Read, Variant
+
+K_DEFAULT_MINIMUM_READ_OVERLAP = 15  # make_examples_native.cc:75
+VERSION = '1.10.0'
+
+
+@dataclasses.dataclass
+class SampleOptions:
+  role: str = 'main_sample'
+  name: str = ''
+  pileup_height: int = 0
+  order: List[int] = dataclasses.field(default_factory=lambda: [0])
+  keep_only_window_spanning_reads: bool = False
+
+
+@dataclasses.dataclass
+class MakeExamplesOptions:
+  pic_options: pi.PileupImageOptions = dataclasses.field(default_factory=pi.default_options)
+  sample_options: List[SampleOptions] = dataclasses.field(default_factory=lambda: [SampleOptions()])
+  reference_filename: str = ''
+  trim_reads_for_pileup: bool = False
+  stream_examples: bool = False
+
+
+# ---- small pure functions ---------------------------------------------------------------------
+
+def encoded_variant_type(variant: Variant) -> int:
+  """EncodedVariantType (make_examples_native.cc:301-321): 1 = SNP, 2 = indel, 0 = unknown."""
+  if len(variant.reference_bases) == 1 and len(variant.alternate_bases) >= 1:
+    if all(len(a) == 1 for a in variant.alternate_bases):
+      return 1
+  if len(variant.reference_bases) > 1:
+    return 2
+  if any(len(a) > 1 for a in variant.alternate_bases):
+    return 2
+  return 0
+
+
+def alt_allele_combinations(candidate: DeepVariantCall, multi_allelic_mode: str) -> List[List[str]]:
+  """AltAlleleCombinations / AltAlleleCombinationsFromIndices (make_examples_native.cc:191-267)."""
+  variant = candidate.variant
+  if multi_allelic_mode not in ('NO_HET_ALT_IMAGES', 'ADD_HET_ALT_IMAGES'):
+    raise ValueError('multi_allelic_mode cannot be UNSPECIFIED')
+  if candidate.make_examples_alt_allele_indices:
+    alts = list(variant.alternate_bases)
+    out = []
+    for indices in candidate.make_examples_alt_allele_indices:
+      if multi_allelic_mode == 'NO_HET_ALT_IMAGES':
+        if len(indices) == 1:
+          out.append([alts[indices[0]]])
+      else:
+        out.append([alts[i] for i in indices])
+    return out
+  if multi_allelic_mode == 'NO_HET_ALT_IMAGES':
+    return [[alt] for alt in variant.alternate_bases]
+  alts = [variant.reference_bases] + list(variant.alternate_bases)
+  out = []
+  for i in range(len(alts)):
+    for j in range(i + 1, len(alts)):
+      comb = []
+      if i > 0:  # the ref allele is not used in combinations
+        comb.append(alts[i])
+      comb.append(alts[j])
+      out.append(comb)
+  return out
+
+
+def encode_alt_alleles(variant: Variant, alt_combination: Sequence[str]) -> Tuple[bytes, List[int]]:
+  """EncodeAltAlleles (make_examples_native.cc:350-374).  A later duplicate alt overwrites the
+  index of an earlier one (flat_hash_map assignment)."""
+  alt_indices = {}
+  for i, alt in enumerate(variant.alternate_bases):
+    alt_indices[alt] = i
+  indices = [alt_indices.get(alt, 0) for alt in alt_combination]  # operator[] default-inserts 0
+  return protos.encode_alt_allele_indices(indices), indices
+
+
+def need_alt_alignment(variant: Variant, pic: pi.PileupImageOptions) -> bool:
+  """NeedAltAlignment (make_examples_native.cc:498-512)."""
+  if pic.alt_aligned_pileup == 'none' or not pic.alt_aligned_pileup:
+    return False
+  if pic.types_to_alt_align == 'all':
+    return True
+  if pic.types_to_alt_align == 'indels':
+    return len(variant.reference_bases) > 1 or any(len(a) > 1 for a in variant.alternate_bases)
+  return False
+
+
+def read_overlaps_region(read: Read, contig: str, start: int, end: int) -> bool:
+  """nucleus ReadOverlapsRegion (third_party/nucleus/util/utils.cc:172-188)."""
+  return end > read.position and start < read.end() and contig == read.reference_name
+
+
+# ---- trimming (alt_aligned_pileup_lib.cc) -----------------------------------------------------
+
+_REF_ADVANCING = (0, 7, 8, 2, 3)      # M = X D N   (IsOperationRefAdvancing, :60-72)
+_READ_ADVANCING = (0, 7, 1, 4, 8)     # M = I S X   (IsOperationReadAdvancing, :74-88)
+
+
+def trim_cigar(cigar: Sequence[Tuple[int, int]], ref_start: int, ref_length: int):
+  """TrimCigar (alt_aligned_pileup_lib.cc:91-150) -> (new_cigar, read_start, new_read_length)."""
+  trim_remaining = ref_start
+  ref_to_cover_remaining = ref_length
+  read_start = 0
+  new_read_length = 0
+  new_cigar: List[Tuple[int, int]] = []
+  for op, op_len in cigar:
+    c_operation_length = op_len
+    advances_ref = op in _REF_ADVANCING
+    advances_read = op in _READ_ADVANCING
+    ref_step = c_operation_length if advances_ref else 0
+    if trim_remaining > 0:
+      if ref_step <= trim_remaining:
+        trim_remaining -= ref_step
+        read_start += c_operation_length if advances_read else 0
+        continue
+      else:
+        ref_step -= trim_remaining
+        read_start += trim_remaining if advances_read else 0
+        c_operation_length = ref_step
+        trim_remaining = 0
+    if trim_remaining == 0:
+      if ref_step <= ref_to_cover_remaining:
+        new_cigar.append((op, c_operation_length))
+        ref_to_cover_remaining -= ref_step
+        new_read_length += c_operation_length if advances_read else 0
+      else:
+        c_operation_length = ref_to_cover_remaining
+        new_cigar.append((op, c_operation_length))
+        new_read_length += c_operation_length if advances_read else 0
+        ref_to_cover_remaining = 0
+        break
+  return new_cigar, read_start, new_read_length
+
+
+def trim_read(read: Read, region_start: int, region_end: int) -> Read:
+  """TrimRead (alt_aligned_pileup_lib.cc:152-236)."""
+  read_start = read.position
+  trim_left = max(region_start - read_start, 0)
+  ref_length = region_end - max(region_start, read_start)
+  if ref_length <= 0:
+    raise ValueError('CHECK_GT(ref_length, 0) failed')
+  new_cigar, read_trim, new_read_length = trim_cigar(read.cigar, trim_left, ref_length)
+  if not (read_trim >= 0 and read_trim + new_read_length <= len(read.aligned_sequence)):
+    raise ValueError('trimmed read exceeds aligned_sequence')
+  new = dataclasses.replace(read, cigar=new_cigar,
+                            aligned_sequence=read.aligned_sequence[read_trim:read_trim + new_read_length],
+                            aligned_quality=read.aligned_quality[read_trim:read_trim + new_read_length])
+  if trim_left != 0:
+    new.position = region_start
+  return new
+
+
+def calculate_alignment_region(variant: Variant, half_width: int, contig_n_bases: int) -> Tuple[int, int]:
+  """CalculateAlignmentRegion (alt_aligned_pileup_lib.cc:238-252)."""
+  ref_end = variant.start + len(variant.reference_bases)
+  return max(variant.start - half_width, 0), min(contig_n_bases, ref_end + half_width)
+
+
+def trim_reads(reads: Sequence[Read], region_start: int, region_end: int, min_overlap: int):
+  """TrimReads (alt_aligned_pileup_lib.cc:254-276) -> (trimmed reads, original alignment positions)."""
+  out, original = [], []
+  for read in reads:
+    t = trim_read(read, region_start, region_end)
+    cigar_len = sum(ln for op, ln in t.cigar if op in _REF_ADVANCING)
+    if cigar_len >= min_overlap and len(t.aligned_sequence) > 0:
+      original.append(read.position)
+      out.append(t)
+  return out, original
+
+
+# ---- the generator ----------------------------------------------------------------------------
+
+@dataclasses.dataclass
+class ExamplePlan:
+  """One (candidate, alt-allele combination): everything except the pixels."""
+  spec: packing.ImageSpec
+  variant: Variant
+  alt_combination: List[str]
+  variant_type: int
+
+
+class ExamplesGenerator:
+
+  def __init__(self, options: MakeExamplesOptions, example_filenames: Optional[Dict[str, str]] = None,
+               test_mode: bool = False, device: int = 0, ref_reader=None):
+    self.options = options
+    pic = options.pic_options
+    self.half_width = (pic.width - 1) // 2
+    if pic.alt_aligned_pileup in ('rows', 'single_row'):
+      raise NotImplementedError("alt_aligned_pileup 'rows' / 'single_row' is not implemented (SURVEY 8f)")
+    if len(options.sample_options) != 1:
+      raise NotImplementedError('multi-sample pileups are out of scope (SURVEY 8, Appendix A)')
+    sample = options.sample_options[0]
+    # CalculatePileupImageHeight (pileup_image_native.cc:229-250), single sample, no extra rows
+    self.pileup_image_height = sample.pileup_height or pic.height
+    self._device = device
+    self._encoder: Optional[pi.GpuEncoder] = None
+    self.ref_reader = ref_reader
+    self.writers: Dict[str, tfrecord.Writer] = {}
+    self._example_filenames = dict(example_filenames or {})
+    self._wrote_info = False
+    if test_mode:
+      return
+    if self.ref_reader is None:
+      from deepvariant_b200 import fasta
+      self.ref_reader = fasta.IndexedFastaReader(options.reference_filename)
+    for role, path in self._example_filenames.items():
+      self.writers[role] = tfrecord.Writer(path)
+
+  # -- reference window --------------------------------------------------------------------------
+  def get_reference_bases_for_pileup(self, variant: Variant) -> str:
+    """GetReferenceBasesForPileup (make_examples_native.cc:514-538): N-padded at contig edges,
+    '' when the clipped interval is invalid."""
+    n_bases = self.ref_reader.n_bases(variant.reference_name)
+    start = variant.start - self.half_width
+    end = start + self.options.pic_options.width
+    region_start, region_end = max(0, start), min(n_bases, end)
+    if not self.ref_reader.is_valid_interval(variant.reference_name, region_start, region_end):
+      return ''
+    ref_bases = self.ref_reader.query(variant.reference_name, region_start, region_end)
+    if start < 0:
+      ref_bases = 'N' * abs(start) + ref_bases
+    if end > n_bases:
+      ref_bases = ref_bases + 'N' * (end - n_bases)
+    return ref_bases
+
+  # -- planning (host) ---------------------------------------------------------------------------
+  def plan_region(self, candidates: Sequence[DeepVariantCall], reads: Sequence[Read], stats: Dict[str, int]) -> List[ExamplePlan]:
+    """CreateAndWriteExamplesForCandidate (make_examples_native.cc:632-736) for every candidate of the
+    region, up to (not including) the pixel work."""
+    pic = self.options.pic_options
+    sample = self.options.sample_options[0]
+    plans: List[ExamplePlan] = []
+    for candidate in candidates:
+      variant = candidate.variant
+      image_start_pos = variant.start - self.half_width
+      q_start = variant.start - pic.read_overlap_buffer_bp
+      q_end = variant.end + pic.read_overlap_buffer_bp
+      reference_bases = self.get_reference_bases_for_pileup(variant)
+      if not reference_bases:
+        continue  # at the edge of the contig, example cannot be created (:650-653)
+      needs_alt = need_alt_alignment(variant, pic)
+      if needs_alt:
+        stats['n_needs_alt_alignment'] = stats.get('n_needs_alt_alignment', 0) + 1
+      use_trimmed = self.options.trim_reads_for_pileup or needs_alt or sample.keep_only_window_spanning_reads
+      query = [r for r in reads if read_overlaps_region(r, variant.reference_name, q_start, q_end)]
+      sort_positions = None
+      if use_trimmed:
+        min_overlap = pic.width if sample.keep_only_window_spanning_reads else K_DEFAULT_MINIMUM_READ_OVERLAP
+        a_start, a_end = calculate_alignment_region(variant, self.half_width, self.ref_reader.n_bases(variant.reference_name))
+        query, sort_positions = trim_reads(query, a_start, a_end, min_overlap)
+      vtype = encoded_variant_type(variant)
+      for alt_combination in alt_allele_combinations(candidate, pic.multi_allelic_mode):
+        spec = packing.image_spec_for(candidate, reference_bases, query, image_start_pos, alt_combination, pic,
+                                      sort_positions=sort_positions)
+        plans.append(ExamplePlan(spec, variant, list(alt_combination), vtype))
+    return plans
+
+  # -- serialisation (host) ----------------------------------------------------------------------
+  def image_shape(self) -> List[int]:
+    pic = self.options.pic_options
+    return [self.pileup_image_height, pic.width, len(pic.channels)]
+
+  def encode_example(self, plan: ExamplePlan, image: np.ndarray, stats: Dict[str, int]) -> bytes:
+    """EncodeExample (make_examples_native.cc:388-474), calling mode (no label)."""
+    variant = plan.variant
+    shape = self.image_shape()
+    if list(image.shape) != shape:
+      raise ValueError(f'image shape {image.shape} != {shape}')
+    alt_indices_encoded, _ = encode_alt_alleles(variant, plan.alt_combination)
+    locus = f'{variant.reference_name}:{variant.start + 1}-{variant.end}'
+    features = {
+        'alt_allele_indices/encoded': ('bytes', [alt_indices_encoded]),
+        'image/encoded': ('bytes', [image.tobytes()]),
+        'image/shape': ('int64', shape),
+        'locus': ('bytes', [locus.encode()]),
+        'sequencing_type': ('int64', [self.options.pic_options.sequencing_type]),
+        'variant/encoded': ('bytes', [variant.serialize()]),
+        'variant_type': ('int64', [plan.variant_type]),
+    }
+    stats['n_examples'] = stats.get('n_examples', 0) + 1   # UpdateStats (:330-348)
+    if plan.variant_type == 2:
+      stats['n_indels'] = stats.get('n_indels', 0) + 1
+    else:
+      stats['n_snps'] = stats.get('n_snps', 0) + 1
+    return protos.encode_tf_example(features)
+
+  def finish_region(self, plans: Sequence[ExamplePlan], images: np.ndarray, stats: Dict[str, int]) -> List[bytes]:
+    return [self.encode_example(p, images[i], stats) for i, p in enumerate(plans)]
+
+  # -- the pybind entry point --------------------------------------------------------------------
+  def _gpu(self) -> pi.GpuEncoder:
+    if self._encoder is None:
+      self._encoder = pi.GpuEncoder(pi.to_params(self.options.pic_options, height=self.pileup_image_height), self._device)
+    return self._encoder
+
+  def encode_plans(self, plans: Sequence[ExamplePlan]) -> np.ndarray:
+    """All images of the region in one CUDA launch (dvb_encode_batch_host)."""
+    enc = self._gpu()
+    if not plans:
+      return np.zeros((0,) + enc.shape, dtype=np.uint8)
+    return enc.encode_host(packing.pack_images([p.spec for p in plans], enc.params))
+
+  def write_examples_in_region(self, candidates: Sequence[DeepVariantCall], reads_per_sample: Sequence[Sequence[Read]],
+                               sample_order: Sequence[int], role: str,
+                               mean_coverage_per_sample: Optional[Sequence[float]] = None):
+    """WriteExamplesInRegion (make_examples_native.cc:742-793)."""
+    if role not in self.writers:
+      raise KeyError(f'Role {role} does not have a writer.')
+    stats: Dict[str, int] = {}
+    reads = list(reads_per_sample[sample_order[0]]) if reads_per_sample else []
+    plans = self.plan_region(candidates, reads, stats)
+    images = self.encode_plans(plans)
+    for rec in self.finish_region(plans, images, stats):
+      self.writers[role].write(rec)
+    return stats, self.image_shape()
+
+  def signal_shard_finished(self) -> None:
+    for role, w in self.writers.items():
+      w.close()
+      write_example_info_json(self._example_filenames[role], self.image_shape(),
+                              example_info_channels(self.options.pic_options))
+    self.writers = {}
+
+
+def example_info_channels(pic: pi.PileupImageOptions) -> List[int]:
+  """Channel enums for example_info.json (make_examples_core.py:3755-3774): computed channels, then
+  the alt-aligned pseudo channels (9,10 / 20,21)."""
+  return pi.all_channels_enum(pic, pic.alt_aligned_pileup if pic.alt_aligned_pileup in ('diff_channels', 'base_channels') else '')
+
+
+def write_example_info_json(examples_path: str, shape: Sequence[int], channels: Sequence[int]) -> str:
+  path = examples_path + '.example_info.json'
+  with open(path, 'w') as f:
+    json.dump({'version': VERSION, 'shape': list(shape), 'channels': list(channels)}, f)
+  return path

@@ -23,6 +23,7 @@
 #ifndef DVB_H_
 #define DVB_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -204,6 +205,12 @@ int dvb_cnn_forward_host(DvbCnn* cnn, const uint8_t* images_host, int32_t n, flo
 int64_t dvb_cnn_launch_count(const DvbCnn* cnn);
 /* FLOPs of one forward for one image (conv MACs x 2). */
 double dvb_cnn_flops_per_image(const DvbCnn* cnn);
+
+/* ---- file boundary helpers (host only) ------------------------------------- */
+/* CRC-32C (Castagnoli) and TensorFlow's masked variant used by the TFRecord framing
+ * (third_party/nucleus/io/example_writer.cc:99-115 -> tensorflow RecordWriter). */
+uint32_t dvb_crc32c(const void* data, size_t n);
+uint32_t dvb_masked_crc32c(const void* data, size_t n);
 
 /* Debug / test access to an intermediate activation of the LAST forward (first `n` images of the
  * last chunk), converted to float NHWC: out_host = float[n][H][W][C].  Names follow

@@ -1,0 +1,93 @@
+"""Pins against the REFERENCE'S OWN golden outputs (fixtures derived by tools/make_golden_fixtures.py from
+deepvariant/testdata/golden.calling_{candidates,examples}.tfrecord.gz + NA12878_S1.chr20.10_10p1mb.bam):
+the 7 golden pileup images whose reads the (out-of-scope) realigner did not rewrite must be reproduced
+byte-for-byte by the oracle (CPU) and by the CUDA encoder (GPU) from the packed candidate + read inputs."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from deepvariant_b200 import packing, protos, tfrecord
+from deepvariant_b200 import pileup_image as pi
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _fixture():
+  d = np.load(os.path.join(GOLDEN, 'wgs_golden_subset.npz'))
+  arrays = {k[4:]: d[k] for k in d.files if k.startswith('arr_')}
+  pb = packing.PackedBatch(int(d['n_images']), int(d['n_reads']), int(d['n_pairs']), int(d['ref_stride']), arrays)
+  o = pi.default_options(pi.ReadRequirements(min_base_quality=10, min_mapping_quality=5))
+  o.channels = list(pi.PILEUP_CHANNELS_WITH_INSERT_SIZE)
+  return pb, d['golden_images'], pi.to_params(o)
+
+
+def test_oracle_reproduces_reference_golden_images():
+  pb, golden, params = _fixture()
+  assert golden.shape == (7, 100, 221, 7)
+  got = oracle_lib.encode_batch(params, pb)
+  np.testing.assert_array_equal(got, golden)
+
+
+@pytest.mark.gpu
+def test_cuda_encoder_reproduces_reference_golden_images():
+  pb, golden, params = _fixture()
+  enc = pi.GpuEncoder(params, 0)
+  got = enc.encode_host(pb)
+  np.testing.assert_array_equal(got, golden)
+  assert enc.last_rows_kept[:7].tolist() == [int(g[5:].reshape(95, -1).any(1).sum()) for g in golden]
+
+
+def test_golden_report_numbers():
+  """Regression pin of the per-example match report: all 84 reference bands, 7 whole images and >= 80 % of
+  the 4309 golden read rows are reproduced; the rest are reads the reference realigner rewrote."""
+  r = json.load(open(os.path.join(GOLDEN, 'wgs_golden_report.json')))
+  assert r['n_examples'] == 84 and r['n_exact'] == 7
+  assert all(e['ref_band_equal'] for e in r['examples'])
+  assert r['golden_read_rows'] == 4309 and r['golden_read_rows_reproduced'] >= 3467
+
+
+def test_reference_tf_examples_parse_and_reencode():
+  """The 7-feature tf.Example of make_examples (make_examples_native.cc:388-474) through our wire codec."""
+  recs = list(tfrecord.read_records(os.path.join(GOLDEN, 'golden.calling_examples.first3.tfrecord.gz'), check_crc=True))
+  assert len(recs) == 3
+  for rec in recs:
+    ex = protos.parse_tf_example(rec)
+    assert sorted(ex) == ['alt_allele_indices/encoded', 'image/encoded', 'image/shape', 'locus', 'sequencing_type',
+                          'variant/encoded', 'variant_type']
+    assert ex['image/shape'][1] == [100, 221, 7] and len(ex['image/encoded'][1][0]) == 154700
+    v = protos.parse_variant(ex['variant/encoded'][1][0])
+    assert ex['locus'][1][0].decode() == f'{v.reference_name}:{v.start + 1}-{v.end}'
+    assert protos.parse_alt_allele_indices(ex['alt_allele_indices/encoded'][1][0]) == [0]
+    again = protos.parse_tf_example(protos.encode_tf_example(ex))
+    assert again == ex
+  img = np.frombuffer(protos.parse_tf_example(recs[0])['image/encoded'][1][0], np.uint8).reshape(100, 221, 7)
+  assert (img[:5, :, 1:] == np.array([254, 254, 70, 152, 50, 254], np.uint8)).all()
+
+
+def test_reference_candidates_parse():
+  cands = [protos.parse_deepvariant_call(r) for r in
+           tfrecord.read_records(os.path.join(GOLDEN, 'golden.calling_candidates.first8.tfrecord.gz'), check_crc=True)]
+  assert len(cands) == 8
+  c = cands[0]
+  assert (c.variant.reference_name, c.variant.start, c.variant.end, c.variant.reference_bases, c.variant.alternate_bases) == (
+      'chr20', 10000116, 10000117, 'C', ['T'])
+  assert len(c.allele_support['T']) == 30 and all('/' in n for n in c.allele_support['T'])
+
+
+def test_tfrecord_roundtrip_and_sharding(tmp_path):
+  spec = str(tmp_path / 'ex.tfrecord@3.gz')
+  paths = tfrecord.shard_paths(spec)
+  assert [os.path.basename(p) for p in paths] == ['ex.tfrecord-00000-of-00003.gz', 'ex.tfrecord-00001-of-00003.gz',
+                                                   'ex.tfrecord-00002-of-00003.gz']
+  payload = [os.urandom(n) for n in (0, 1, 17, 70000)]
+  with tfrecord.Writer(paths[1]) as w:
+    for p in payload:
+      w.write(p)
+  assert list(tfrecord.read_records(paths[1], check_crc=True)) == payload
+  assert tfrecord.masked_crc32c(b'') == ((0 >> 15 | 0 << 17) + 0xa282ead8) & 0xFFFFFFFF
+  # CRC-32C check value (RFC 3720 appendix B.4)
+  from deepvariant_b200 import _lib
+  assert _lib.lib().dvb_crc32c(b'123456789', 9) == 0xE3069283
