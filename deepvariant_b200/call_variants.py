@@ -168,3 +168,115 @@ def smoke(images) -> None:
   err = (probs.cpu() - want).abs().max().item()
   print(f'[smoke] cnn: {n} images, max |p - oracle fp32| = {err:.2e}, launches {net.launch_count}')
   assert err < 2e-2, 'CNN output far from the fp32 oracle'
+
+
+# ---- the stage driver (deepvariant/call_variants.py:766-1047) -------------------------------------
+
+_MAX_WRITER_THREADS = 16   # call_variants.py:82
+
+
+def load_weights(checkpoint_path: str, in_channels: int) -> modeling.ModelWeights:
+  """Model weights for --checkpoint.  Supported here: a .npz written by modeling.save_npz, or
+  'random[:seed]' (architecture-correct random init; no Inception weights ship with the reference).
+  A TF SavedModel / ckpt (tensor-bundle) importer is not implemented (out of scope this round)."""
+  if checkpoint_path.startswith('random'):
+    seed = int(checkpoint_path.split(':')[1]) if ':' in checkpoint_path else 0
+    return modeling.random_weights(in_channels, seed)
+  if checkpoint_path.endswith('.npz'):
+    w = modeling.load_npz(checkpoint_path)
+    if w.in_channels != in_channels:
+      raise ValueError(f'model has {w.in_channels} input channels, examples have {in_channels}')
+    return w
+  raise NotImplementedError(f'unsupported checkpoint format: {checkpoint_path} (use a .npz from modeling.save_npz)')
+
+
+def output_shard_paths(output_file: str, writer_threads: int = 0) -> List[str]:
+  """Dynamic output sharding (call_variants.py:800-826): with a GPU present K = min(cpu_count, 16) writers
+  unless the name is already sharded; name.tfrecord.gz -> name-0000i-of-0000K.tfrecord.gz."""
+  import os
+  from deepvariant_b200 import tfrecord
+  if tfrecord.is_sharded_spec(output_file) or '-of-' in os.path.basename(output_file):
+    return tfrecord.shard_paths(output_file)
+  k = writer_threads if writer_threads else (os.cpu_count() or 1)
+  k = max(1, min(k, _MAX_WRITER_THREADS))
+  return tfrecord.shard_paths(output_file.replace('.tfrecord.gz', f'@{k}.tfrecord.gz'))
+
+
+def write_empty_output_file(output_file: str) -> List[str]:
+  """write_empty_output_file (call_variants.py:605-619): one empty shard."""
+  from deepvariant_b200 import tfrecord
+  paths = tfrecord.shard_paths(output_file.replace('.tfrecord.gz', '@1.tfrecord.gz'))
+  for p in paths:
+    tfrecord.Writer(p).close()
+  return paths
+
+
+def call_variants(examples_filename: str, checkpoint_path: str, output_file: str, batch_size: int = _DEFAULT_BATCH,
+                  writer_threads: int = 0, device: int = 0, max_batches: Optional[int] = None) -> dict:
+  """examples TFRecords -> CallVariantsOutput TFRecords.  Returns {'n_examples', 'n_batches', 'paths'}."""
+  import json
+  import os
+  import torch
+  from deepvariant_b200 import tfrecord
+  paths_in = tfrecord.resolve_input_paths(examples_filename)
+
+  def records():
+    for p in paths_in:
+      for rec in tfrecord.read_records(p):
+        yield rec
+
+  it = records()
+  first = next(it, None)
+  if first is None:
+    return {'n_examples': 0, 'n_batches': 0, 'paths': write_empty_output_file(output_file)}
+  ex0 = protos.parse_tf_example(first)
+  shape = [int(x) for x in ex0['image/shape'][1]]
+  info_path = paths_in[0] + '.example_info.json'
+  if os.path.exists(info_path):
+    info = json.load(open(info_path))
+    if [int(x) for x in info['shape']] != shape:
+      raise ValueError(f'example_info.json shape {info["shape"]} != example image/shape {shape}')
+  weights = load_weights(checkpoint_path, shape[2])
+  net = GpuCnn(weights, shape, device=device, max_batch=min(batch_size, 2048))
+  out_paths = output_shard_paths(output_file, writer_threads)
+  writers = [tfrecord.Writer(p) for p in out_paths]
+  image_bytes = shape[0] * shape[1] * shape[2]
+  pinned = torch.empty((batch_size, image_bytes), dtype=torch.uint8).pin_memory()
+  dev = torch.device('cuda', device)
+  probs_dev = torch.empty((batch_size, 3), dtype=torch.float32, device=dev)
+  stream = torch.cuda.current_stream(dev)
+
+  n_examples = n_batches = 0
+  batch_meta: List[Tuple[bytes, bytes]] = []
+
+  def flush():
+    nonlocal n_examples, n_batches
+    n = len(batch_meta)
+    if n == 0:
+      return
+    images = pinned[:n].to(dev, non_blocking=True)
+    net.forward_device(images.view((n,) + tuple(shape)), probs_dev[:n], stream=stream)
+    probs = probs_dev[:n].cpu().numpy().astype(np.float64)
+    w = writers[n_batches % len(writers)]
+    for (variant, alt_idx), p in zip(batch_meta, probs):
+      w.write(create_cvo(variant, round_gls(p.tolist(), _GL_PRECISION), alt_idx))
+    n_examples += n
+    n_batches += 1
+    batch_meta.clear()
+
+  import itertools
+  for rec in itertools.chain([first], it):
+    ex = protos.parse_tf_example(rec)
+    img = ex['image/encoded'][1][0]
+    if len(img) != image_bytes:
+      raise ValueError(f'image/encoded has {len(img)} bytes, expected {image_bytes}')
+    pinned[len(batch_meta)].copy_(torch.frombuffer(bytearray(img), dtype=torch.uint8))
+    batch_meta.append((ex['variant/encoded'][1][0], ex['alt_allele_indices/encoded'][1][0]))
+    if len(batch_meta) == batch_size:
+      flush()
+      if max_batches and n_batches >= max_batches:
+        break
+  flush()
+  for w in writers:
+    w.close()
+  return {'n_examples': n_examples, 'n_batches': n_batches, 'paths': out_paths}

@@ -1,0 +1,154 @@
+"""Command-line surface kept from the reference for the two stages this repository replaces
+(scripts/run_deepvariant.py:430-528 builds exactly these commands):
+
+  python -m deepvariant_b200.cli make_examples --mode calling --ref REF --reads BAM --examples X@N.gz
+         --candidates CANDS.tfrecord.gz [--task i --regions chr:start-end --channel_list ... --pileup_image_width W
+         --pileup_image_height H --min_mapping_quality q --min_base_quality q --sort_by_haplotypes
+         --trim_reads_for_pileup --alt_aligned_pileup diff_channels --partition_size 1000]
+  python -m deepvariant_b200.cli call_variants --examples X@N.gz --outfile Y.tfrecord.gz --checkpoint M [--batch_size 1024]
+  python -m deepvariant_b200.cli run_deepvariant --model_type WGS --ref REF --reads BAM --candidates C --output_dir D
+
+Candidate generation (allele counting, realignment, thresholds: make_examples_core.RegionProcessor) is upstream of the
+hot path and out of scope: `--candidates` takes the DeepVariantCall TFRecord the
+reference itself writes with `make_examples --candidates`.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import re
+import sys
+from typing import List
+
+MODEL_DEFAULTS = {   # scripts/run_deepvariant.py + model.example_info.json flags_for_calling
+    'WGS': dict(channel_list='BASE_CHANNELS,insert_size', pileup_image_width=221),
+    'WES': dict(channel_list='BASE_CHANNELS,insert_size', pileup_image_width=221),
+    'PACBIO': dict(channel_list='BASE_CHANNELS,haplotype,supplementary_alignment', pileup_image_width=147, sort_by_haplotypes=True,
+                   trim_reads_for_pileup=True, alt_aligned_pileup='diff_channels', min_mapping_quality=1, partition_size=25000,
+                   parse_sam_aux_fields=True),
+}
+
+
+def _channels(spec: str) -> List[str]:
+  from deepvariant_b200 import pileup_image as pi
+  out: List[str] = []
+  for c in spec.split(','):
+    c = c.strip()
+    if c == 'BASE_CHANNELS':
+      out += pi.PILEUP_DEFAULT_CHANNELS
+    elif c:
+      out.append(c)
+  return out
+
+
+def parse_region(s: str):
+  m = re.match(r'^([^:]+):([\d,]+)-([\d,]+)$', s)
+  if not m:
+    raise ValueError(f'bad region {s}')
+  return m.group(1), int(m.group(2).replace(',', '')) - 1, int(m.group(3).replace(',', ''))
+
+
+def make_examples(argv):
+  ap = argparse.ArgumentParser('make_examples')
+  ap.add_argument('--mode', default='calling', choices=['calling'])
+  ap.add_argument('--ref', required=True)
+  ap.add_argument('--reads', required=True)
+  ap.add_argument('--examples', required=True)
+  ap.add_argument('--candidates', required=True)
+  ap.add_argument('--task', type=int, default=0)
+  ap.add_argument('--regions', default='')
+  ap.add_argument('--channel_list', default='BASE_CHANNELS')
+  ap.add_argument('--pileup_image_width', type=int, default=221)
+  ap.add_argument('--pileup_image_height', type=int, default=100)
+  ap.add_argument('--min_mapping_quality', type=int, default=5)
+  ap.add_argument('--min_base_quality', type=int, default=10)
+  ap.add_argument('--partition_size', type=int, default=1000)
+  ap.add_argument('--sort_by_haplotypes', action='store_true')
+  ap.add_argument('--trim_reads_for_pileup', action='store_true')
+  ap.add_argument('--parse_sam_aux_fields', action='store_true')
+  ap.add_argument('--alt_aligned_pileup', default='none')
+  ap.add_argument('--device', type=int, default=0)
+  a = ap.parse_args(argv)
+  from deepvariant_b200 import bam, make_examples_native as men, pileup_image as pi, protos, tfrecord
+  pic = pi.default_options(pi.ReadRequirements(a.min_base_quality, a.min_mapping_quality))
+  pic.channels = _channels(a.channel_list)
+  if a.alt_aligned_pileup == 'diff_channels':
+    pic.channels += ['diff_channels_alternate_allele_1', 'diff_channels_alternate_allele_2']
+  pic.num_channels = len(pic.channels)
+  pic.width, pic.height = a.pileup_image_width, a.pileup_image_height
+  pic.sort_by_haplotypes = a.sort_by_haplotypes
+  pic.alt_aligned_pileup = a.alt_aligned_pileup
+  opts = men.MakeExamplesOptions(pic_options=pic, reference_filename=a.ref, trim_reads_for_pileup=a.trim_reads_for_pileup)
+  out_path = tfrecord.shard_path(a.examples, a.task)
+  n_shards = len(tfrecord.shard_paths(a.examples))
+  gen = men.ExamplesGenerator(opts, {'main_sample': out_path}, device=a.device)
+  reader = bam.BamReader(a.reads, bam.ReadRequirements(min_mapping_quality=a.min_mapping_quality), parse_aux=a.parse_sam_aux_fields)
+  cands = [protos.parse_deepvariant_call(r) for p in tfrecord.resolve_input_paths(a.candidates) for r in tfrecord.read_records(p)]
+  region = parse_region(a.regions) if a.regions else None
+  totals = {}
+  for (contig, k, origin), cs in men.shard_partitions(men.partition_candidates(cands, a.partition_size, region), n_shards, a.task):
+    p0 = origin + k * a.partition_size
+    p1 = p0 + a.partition_size if not region else min(p0 + a.partition_size, region[2])
+    reads = reader.query(contig, p0, p1)
+    stats, _ = gen.write_examples_in_region(cs, [reads], [0], 'main_sample', [0.0])
+    for key, val in stats.items():
+      totals[key] = totals.get(key, 0) + val
+  gen.signal_shard_finished()
+  print(f'make_examples task {a.task}: {totals}', file=sys.stderr)
+  return 0
+
+
+def call_variants(argv):
+  ap = argparse.ArgumentParser('call_variants')
+  ap.add_argument('--examples', required=True)
+  ap.add_argument('--outfile', required=True)
+  ap.add_argument('--checkpoint', required=True)
+  ap.add_argument('--batch_size', type=int, default=1024)
+  ap.add_argument('--writer_threads', type=int, default=0)
+  ap.add_argument('--device', type=int, default=0)
+  a = ap.parse_args(argv)
+  from deepvariant_b200 import call_variants as cv
+  r = cv.call_variants(a.examples, a.checkpoint, a.outfile, a.batch_size, a.writer_threads, a.device)
+  print(f'call_variants: {r["n_examples"]} examples in {r["n_batches"]} batches -> {len(r["paths"])} shard(s)', file=sys.stderr)
+  return 0
+
+
+def run_deepvariant(argv):
+  ap = argparse.ArgumentParser('run_deepvariant')
+  ap.add_argument('--model_type', required=True, choices=sorted(MODEL_DEFAULTS))
+  ap.add_argument('--ref', required=True)
+  ap.add_argument('--reads', required=True)
+  ap.add_argument('--candidates', required=True)
+  ap.add_argument('--output_dir', required=True)
+  ap.add_argument('--regions', default='')
+  ap.add_argument('--num_shards', type=int, default=1)
+  ap.add_argument('--customized_model', default='random')
+  a = ap.parse_args(argv)
+  os.makedirs(a.output_dir, exist_ok=True)
+  d = MODEL_DEFAULTS[a.model_type]
+  examples = os.path.join(a.output_dir, f'make_examples.tfrecord@{a.num_shards}.gz')
+  for task in range(a.num_shards):
+    args = ['--mode', 'calling', '--ref', a.ref, '--reads', a.reads, '--candidates', a.candidates, '--examples', examples, '--task',
+            str(task), '--channel_list', d['channel_list'], '--pileup_image_width', str(d['pileup_image_width'])]
+    for flag in ('sort_by_haplotypes', 'trim_reads_for_pileup', 'parse_sam_aux_fields'):
+      if d.get(flag):
+        args.append('--' + flag)
+    for flag in ('alt_aligned_pileup', 'min_mapping_quality', 'partition_size'):
+      if flag in d:
+        args += ['--' + flag, str(d[flag])]
+    if a.regions:
+      args += ['--regions', a.regions]
+    make_examples(args)
+  return call_variants(['--examples', examples, '--outfile', os.path.join(a.output_dir, 'call_variants_output.tfrecord.gz'),
+                        '--checkpoint', a.customized_model])
+
+
+def main():
+  if len(sys.argv) < 2 or sys.argv[1] not in ('make_examples', 'call_variants', 'run_deepvariant'):
+    print(__doc__)
+    return 2
+  return {'make_examples': make_examples, 'call_variants': call_variants, 'run_deepvariant': run_deepvariant}[sys.argv[1]](sys.argv[2:])
+
+
+if __name__ == '__main__':
+  sys.exit(main())

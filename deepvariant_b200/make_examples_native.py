@@ -363,6 +363,26 @@ class ExamplesGenerator:
     self.writers = {}
 
 
+def partition_candidates(candidates: Sequence[DeepVariantCall], partition_size: int, region: Optional[Tuple[str, int, int]] = None):
+  """Groups candidates by genomic partition (make_examples' --partition_size regions,
+  make_examples_core.processing_regions_from_options :3341): returns a sorted list of
+  ((contig, partition_index, origin), [candidates])."""
+  by_part = {}
+  for c in candidates:
+    v = c.variant
+    if region and not (v.reference_name == region[0] and region[1] <= v.start < region[2]):
+      continue
+    origin = region[1] if region else 0
+    by_part.setdefault((v.reference_name, (v.start - origin) // partition_size, origin), []).append(c)
+  return sorted(by_part.items())
+
+
+def shard_partitions(partitions, n_shards: int, task: int):
+  """Partition i goes to task i mod N — the region sharding of `make_examples --task i` (scripts/run_deepvariant.py:457-497)
+  and of the per-GPU ranks: disjoint, exhaustive, no exchange between shards."""
+  return [p for i, p in enumerate(partitions) if i % n_shards == task]
+
+
 def example_info_channels(pic: pi.PileupImageOptions) -> List[int]:
   """Channel enums for example_info.json (make_examples_core.py:3755-3774): computed channels, then
   the alt-aligned pseudo channels (9,10 / 20,21)."""
