@@ -39,7 +39,7 @@
 
 namespace {
 
-constexpr int kStages = 4;
+constexpr int kMaxStages = 8;
 constexpr int kConvThreads = 192;  // warp0 TMA, warp1 MMA, warps 2..5 epilogue
 constexpr uint32_t kBlobMagic = 0x31424E4E;
 
@@ -158,7 +158,7 @@ struct ConvArgs {
   int Wt, Ht, Nt;                 // output-pixel box of one M tile (Wt*Ht*Nt <= 128)
   int tiles_w, tiles_h, tiles_n;
   int Hout, Wout, n_images;
-  int block_n, tmem_cols;
+  int block_n, tmem_cols, stages;
   int out_cstride, out_coff, relu;
   uint32_t idesc, layout_type, sbo_bytes;
   uint32_t a_bytes, b_bytes, a_stage, b_stage;  // TMA bytes and shared-memory footprint per stage
@@ -171,12 +171,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStages * p.a_stage;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kStages * p.b_stage);
+  uint8_t* smem_b = smem + p.stages * p.a_stage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.stages * p.b_stage);
   uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + kStages;
-  uint64_t* tmem_full = bars + 2 * kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* tmem_full = bars + 2 * kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // tile coordinates
@@ -191,7 +191,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_b);
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   } else if (warp == 1) {
@@ -205,17 +205,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      int kb = 0;
+      int st = 0;
+      uint32_t ph = 0;
       for (int r = 0; r < p.kh; ++r) {
         for (int s = 0; s < p.kw; ++s) {
-          for (int cb = 0; cb < p.cin_blocks; ++cb, ++kb) {
-            const int st = kb % kStages;
-            const uint32_t ph = (kb / kStages) & 1;
+          for (int cb = 0; cb < p.cin_blocks; ++cb) {
             mbar_wait(&empty_bar[st], ph ^ 1);
             mbar_arrive_expect_tx(&full_bar[st], p.a_bytes + p.b_bytes);
             tma_load_4d(smem_a + st * p.a_stage, &map_a, &full_bar[st], cb * p.block_k, w0 * p.stride + s - p.pad_w,
                         h0 * p.stride + r - p.pad_h, n0);
             tma_load_3d(smem_b + st * p.b_stage, &map_b, &full_bar[st], cb * p.block_k, r * p.kw + s, nb * p.block_n);
+            if (++st == p.stages) { st = 0; ph ^= 1; }
           }
         }
       }
@@ -224,9 +224,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (lane == 0) {
       // ===== MMA issuer (one thread) =====
       const int mma_per_kb = p.block_k / 16;
+      int st = 0;
+      uint32_t ph = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int st = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
         mbar_wait(&full_bar[st], ph);
         tc_fence_after();
         const uint32_t a0 = smem_u32(smem_a + st * p.a_stage);
@@ -237,6 +237,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           umma_f16(tmem_base, ad, bd, p.idesc, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[st]);   // frees the stage once these MMAs retire
+        if (++st == p.stages) { st = 0; ph ^= 1; }
       }
       umma_commit(tmem_full);          // accumulator complete
     }
@@ -283,71 +284,129 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // Small CUDA-core kernels
 // ---------------------------------------------------------------------------------------------
 
-// dv_utils.preprocess_images: uint8 [N,H,W,C] -> fp16 [N,H,W,Cp] = (x - 128) / 128, channels >= C zero.
-// (x - 128) / 128 is exact in fp16 (|x-128| <= 128, power-of-two divisor).
-__global__ void preprocess_kernel(const uint8_t* __restrict__ in, __half* __restrict__ out, long long n_pixels, int C, int Cp) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pixels) return;
-  const uint8_t* src = in + i * C;
-  __half* dst = out + i * Cp;
-  for (int c = 0; c < Cp; c += 8) {
+// dv_utils.preprocess_images fused with the im2col of the first convolution (3x3, stride 2, valid):
+//   out[n][oh][ow][k] = (x[n][2*oh + r][2*ow + s][c] - 128) / 128   with k = (r*3 + s)*C + c,  k >= 9*C -> 0
+// so that conv1 becomes a plain GEMM over K = Kp (64 for the 7-channel WGS image): one contiguous, fully
+// used 128-byte row per output pixel instead of nine strided 32-byte TMA boxes.  (x - 128) / 128 is exact
+// in fp16 (|x - 128| <= 128, power-of-two divisor).  One thread per (output pixel, 8 consecutive k).
+constexpr int kPatchTile = 64;  // output pixels per block
+__global__ void __launch_bounds__(256) stem_patch_kernel(const uint8_t* __restrict__ in, __half* __restrict__ out, int n_images, int H,
+                                                         int W, int C, int Ho, int Wo, int Kp) {
+  // One block = kPatchTile consecutive output pixels of one output row: the three input rows they touch are
+  // staged in shared memory with coalesced byte loads, then every thread emits 16-byte chunks of patches.
+  extern __shared__ uint8_t s_in[];  // [3][(2*kPatchTile + 1) * C] then short koff[Kp]
+  const int tiles_w = (Wo + kPatchTile - 1) / kPatchTile;
+  int b = blockIdx.x;
+  const int tw = b % tiles_w; b /= tiles_w;
+  const int oh = b % Ho;
+  const int n = b / Ho;
+  const int ow0 = tw * kPatchTile;
+  const int npx = min(kPatchTile, Wo - ow0);
+  const int seg = (2 * npx + 1) * C;           // bytes of one input row segment
+  const int seg_pitch = (2 * kPatchTile + 1) * C;
+  short* koff = reinterpret_cast<short*>(s_in + ((3 * seg_pitch + 15) & ~15));
+  for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+    const int r = k / (3 * C);
+    koff[k] = k < 9 * C ? (short)(r * seg_pitch + (k - r * 3 * C)) : (short)-1;   // (s, c) is contiguous in the input row
+  }
+  for (int r = 0; r < 3; ++r) {
+    const uint8_t* src = in + (((size_t)n * H + 2 * oh + r) * W + 2 * ow0) * C;
+    for (int i = threadIdx.x; i < seg; i += blockDim.x) s_in[r * seg_pitch + i] = src[i];
+  }
+  __syncthreads();
+  const int kvec = Kp / 8;
+  __half* dst = out + (((size_t)n * Ho + oh) * Wo + ow0) * Kp;
+  for (int t = threadIdx.x; t < npx * kvec; t += blockDim.x) {
+    const int px = t / kvec, kv = t - px * kvec;
     uint32_t pk[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int c0 = c + 2 * j, c1 = c0 + 1;
-      const float a = c0 < C ? ((float)src[c0] - 128.f) * (1.f / 128.f) : 0.f;
-      const float b = c1 < C ? ((float)src[c1] - 128.f) * (1.f / 128.f) : 0.f;
-      __half2 hh = __floats2half2_rn(a, b);
+      float v[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int o = koff[kv * 8 + 2 * j + e];
+        v[e] = o >= 0 ? ((float)s_in[o + 2 * px * C] - 128.f) * (1.f / 128.f) : 0.f;
+      }
+      __half2 hh = __floats2half2_rn(v[0], v[1]);
       pk[j] = *reinterpret_cast<uint32_t*>(&hh);
     }
-    *reinterpret_cast<uint4*>(dst + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(dst + (size_t)t * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
 
-// 3x3 pooling on NHWC fp16, 8 channels per thread.  mode 0: max, stride 2, valid.  mode 1: average,
-// stride 1, 'same', divisor = number of in-bounds taps (TF AveragePooling2D semantics).
+// 3x3 pooling on NHWC fp16.  mode 0: max, stride 2, valid.  mode 1: average, stride 1, 'same', divisor = number
+// of in-bounds taps (TF AveragePooling2D semantics).  One thread owns (image, output row, 8 channels) and slides
+// along W keeping the per-column partial results of the previous columns in registers, so every input element is
+// loaded once per output row (3 loads per output for the stride-1 average, 6 for the stride-2 max) instead of 9.
+__device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
+  const uint4 raw = *reinterpret_cast<const uint4*>(p);
+  const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h2[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+}
+__device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
+  uint32_t pk[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { __half2 hh = __floats2half2_rn(v[2 * j], v[2 * j + 1]); pk[j] = *reinterpret_cast<uint32_t*>(&hh); }
+  *reinterpret_cast<uint4*>(p) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
 __global__ void pool3x3_kernel(const __half* __restrict__ in, __half* __restrict__ out, int n_images, int Hin, int Win, int C,
                                int Hout, int Wout, int out_cstride, int out_coff, int mode) {
   const int cvec = C / 8;
-  const long long total = (long long)n_images * Hout * Wout * cvec;
+  const long long total = (long long)n_images * Hout * cvec;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int cv = (int)(i % cvec);
-  long long pix = i / cvec;
-  const int ow = (int)(pix % Wout); pix /= Wout;
-  const int oh = (int)(pix % Hout);
-  const int n = (int)(pix / Hout);
-  const int stride = mode == 0 ? 2 : 1, pad = mode == 0 ? 0 : 1;
-  float acc[8];
+  long long t = i / cvec;
+  const int oh = (int)(t % Hout);
+  const int n = (int)(t / Hout);
+  const __half* src = in + (size_t)n * Hin * Win * C + cv * 8;
+  __half* dst = out + ((size_t)n * Hout + oh) * Wout * out_cstride + out_coff + cv * 8;
+  if (mode == 0) {
+    // column maxima over rows 2oh..2oh+2; output ow uses columns 2ow, 2ow+1, 2ow+2
+    const __half* r0 = src + (size_t)(2 * oh) * Win * C;
+    float prev[8], a[8], b[8], c[8];
+    auto colmax = [&](int iw, float (&m)[8]) {
+      load8(r0 + (size_t)iw * C, a); load8(r0 + ((size_t)Win + iw) * C, b); load8(r0 + ((size_t)2 * Win + iw) * C, c);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = mode == 0 ? -INFINITY : 0.f;
-  int cnt = 0;
-  for (int r = 0; r < 3; ++r) {
-    const int ih = oh * stride + r - pad;
-    if (ih < 0 || ih >= Hin) continue;
-    for (int s = 0; s < 3; ++s) {
-      const int iw = ow * stride + s - pad;
-      if (iw < 0 || iw >= Win) continue;
-      ++cnt;
-      const uint4 raw = *reinterpret_cast<const uint4*>(in + (((size_t)n * Hin + ih) * Win + iw) * C + cv * 8);
-      const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+      for (int j = 0; j < 8; ++j) m[j] = fmaxf(a[j], fmaxf(b[j], c[j]));
+    };
+    colmax(0, prev);
+    for (int ow = 0; ow < Wout; ++ow) {
+      float m1[8], m2[8], o[8];
+      colmax(2 * ow + 1, m1);
+      colmax(2 * ow + 2, m2);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(h2[j]);
-        if (mode == 0) { acc[2 * j] = fmaxf(acc[2 * j], f.x); acc[2 * j + 1] = fmaxf(acc[2 * j + 1], f.y); }
-        else { acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+      for (int j = 0; j < 8; ++j) { o[j] = fmaxf(prev[j], fmaxf(m1[j], m2[j])); prev[j] = m2[j]; }
+      store8(dst + (size_t)ow * out_cstride, o);
+    }
+  } else {
+    const int h_lo = oh > 0 ? oh - 1 : 0, h_hi = oh + 1 < Hin ? oh + 1 : Hin - 1;
+    const int nrows = h_hi - h_lo + 1;
+    float s0[8], s1[8], s2[8], v[8];
+    auto colsum = [&](int iw, float (&m)[8]) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m[j] = 0.f;
+      if (iw < 0 || iw >= Win) return;
+      for (int ih = h_lo; ih <= h_hi; ++ih) {
+        load8(src + ((size_t)ih * Win + iw) * C, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] += v[j];
       }
+    };
+    colsum(-1, s0);
+    colsum(0, s1);
+    for (int ow = 0; ow < Wout; ++ow) {
+      colsum(ow + 1, s2);
+      const int ncols = (ow > 0 ? 1 : 0) + 1 + (ow + 1 < Win ? 1 : 0);
+      const float inv = 1.f / (float)(nrows * ncols);
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { o[j] = (s0[j] + s1[j] + s2[j]) * inv; s0[j] = s1[j]; s1[j] = s2[j]; }
+      store8(dst + (size_t)ow * out_cstride, o);
     }
   }
-  uint32_t pk[4];
-  const float inv = mode == 0 ? 1.f : 1.f / (float)cnt;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    __half2 hh = __floats2half2_rn(acc[2 * j] * inv, acc[2 * j + 1] * inv);
-    pk[j] = *reinterpret_cast<uint32_t*>(&hh);
-  }
-  *reinterpret_cast<uint4*>(out + (((size_t)n * Hout + oh) * Wout + ow) * out_cstride + out_coff + cv * 8) =
-      make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
 // GlobalAveragePooling2D + Dense(3) + softmax, fp32.  One block per image.
@@ -523,6 +582,8 @@ struct ConvLaunch {
   dim3 grid;
   int smem;
   double macs_per_image;
+  bool flat;
+  int pixels_per_image;
 };
 struct PoolLaunch {
   const __half* in; __half* out;
@@ -534,6 +595,7 @@ struct Step { int kind; int index; };  // 0 conv, 1 pool
 
 struct DvbCnn {
   int device = 0, H = 0, W = 0, C = 0, Cp = 16, max_batch = 0, precision = 0;
+  int stem_Ho = 0, stem_Wo = 0, stem_Kp = 64, num_sms = 148;
   std::vector<TensorBuf> tensors;
   std::map<std::string, int> tensor_index;
   std::vector<ConvLaunch> convs;
@@ -629,12 +691,25 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
     net->tensors.push_back(t);
     return DVB_OK;
   };
-  int st = add_tensor("input", net->H, net->W, net->Cp);
+  // The first convolution (3x3 stride 2 valid) runs as a GEMM over pre-gathered patches (stem_patch_kernel):
+  // tensor "input" holds [N][Ho][Wo][Kp] with k = (r*3 + s)*C + c.
+  if (ops.empty() || ops[0].kind != 0 || ops[0].kh != 3 || ops[0].kw != 3 || ops[0].stride != 2 || ops[0].same)
+    return dvb::fail(DVB_ERR_INTERNAL, "unexpected stem");
+  if (net->H < 3 || net->W < 3) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "image %dx%d is too small for the network", net->H, net->W);
+  net->stem_Ho = (net->H - 3) / 2 + 1;
+  net->stem_Wo = (net->W - 3) / 2 + 1;
+  net->stem_Kp = 9 * net->C <= 64 ? 64 : (9 * net->C + 31) / 32 * 32;
+  hw["input"] = {net->stem_Ho, net->stem_Wo};
+  int st = add_tensor("input", net->stem_Ho, net->stem_Wo, net->stem_Kp);
   if (st) return st;
 
   const int force_bk = EnvInt("DVB_CNN_BLOCK_K", 0);       // 0 = per-layer choice
   double macs_total = 0;
-  for (auto& o : ops) {
+  for (size_t op_index = 0; op_index < ops.size(); ++op_index) {
+    OpDesc o = ops[op_index];
+    const bool is_stem = op_index == 0;
+    const OpDesc orig = o;
+    if (is_stem) { o.kh = 1; o.kw = 1; o.stride = 1; o.same = 0; }   // GEMM over the patch tensor
     const auto [Hin, Win] = hw[o.src];
     int Hout, Wout;
     if (o.same) { Hout = Hin; Wout = Win; }
@@ -656,18 +731,30 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
     const int32_t* lh = reinterpret_cast<const int32_t*>(blob + pos);
     pos += 20;
     const int cin_store = src.C;  // channels physically present in the source tensor
-    if (lh[0] != o.kh || lh[1] != o.kw || lh[2] != o.cin || lh[3] != PadCin(o.cin) || lh[4] != o.cout || lh[3] != cin_store)
+    const int blob_cin = PadCin(orig.cin);
+    if (lh[0] != orig.kh || lh[1] != orig.kw || lh[2] != orig.cin || lh[3] != blob_cin || lh[4] != o.cout || (!is_stem && blob_cin != cin_store))
       return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob: conv %zu header mismatch (%d %d %d %d %d)", net->convs.size(), lh[0], lh[1],
                        lh[2], lh[3], lh[4]);
+    const size_t blob_wbytes = (size_t)o.cout * orig.kh * orig.kw * blob_cin * sizeof(__half);
     const size_t wbytes = (size_t)o.cout * o.kh * o.kw * cin_store * sizeof(__half);
     const size_t bbytes = (size_t)o.cout * sizeof(float);
-    if (pos + (int64_t)(wbytes + bbytes) > blob_bytes) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob truncated");
+    if (pos + (int64_t)(blob_wbytes + bbytes) > blob_bytes) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob truncated");
     void* dw = nullptr; void* db = nullptr;
     if (cudaMalloc(&dw, wbytes) != cudaSuccess || cudaMalloc(&db, bbytes) != cudaSuccess) return dvb::fail(DVB_ERR_CUDA, "cudaMalloc (weights) failed");
     net->allocs.push_back(dw); net->allocs.push_back(db);
-    cudaMemcpy(dw, blob + pos, wbytes, cudaMemcpyHostToDevice);
-    cudaMemcpy(db, blob + pos + wbytes, bbytes, cudaMemcpyHostToDevice);
-    pos += wbytes + bbytes;
+    if (is_stem) {
+      // [cout][3][3][blob_cin] -> [cout][Kp], k = (r*3 + s)*C + c (the patch order of stem_patch_kernel)
+      std::vector<__half> w2((size_t)o.cout * cin_store, __float2half(0.f));
+      const __half* w = reinterpret_cast<const __half*>(blob + pos);
+      for (int co = 0; co < o.cout; ++co)
+        for (int t = 0; t < 9; ++t)
+          for (int c = 0; c < net->C; ++c) w2[(size_t)co * cin_store + t * net->C + c] = w[((size_t)co * 9 + t) * blob_cin + c];
+      cudaMemcpy(dw, w2.data(), wbytes, cudaMemcpyHostToDevice);
+    } else {
+      cudaMemcpy(dw, blob + pos, wbytes, cudaMemcpyHostToDevice);
+    }
+    cudaMemcpy(db, blob + pos + blob_wbytes, bbytes, cudaMemcpyHostToDevice);
+    pos += blob_wbytes + bbytes;
 
     ConvLaunch cl;
     memset(&cl, 0, sizeof(cl));
@@ -679,12 +766,32 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
     if (cin_store < bk) bk = cin_store >= 32 ? 32 : 16;
     a.block_k = bk;
     a.cin_blocks = (cin_store + bk - 1) / bk;
-    const TileChoice tc = ChooseTile(Hout, Wout, o.stride);
+    // 1x1 stride-1 convolutions have no halo: all N*H*W pixels are flattened into one dimension and every
+    // M tile is a full 128 rows.
+    const bool flat = o.kh == 1 && o.kw == 1 && o.stride == 1;
+    cl.flat = flat;
+    cl.pixels_per_image = Hout * Wout;
+    const TileChoice tc = flat ? TileChoice{128, 1, 1} : ChooseTile(Hout, Wout, o.stride);
     a.Wt = tc.Wt; a.Ht = tc.Ht; a.Nt = tc.Nt;
     a.tiles_w = (Wout + tc.Wt - 1) / tc.Wt;
     a.tiles_h = (Hout + tc.Ht - 1) / tc.Ht;
     a.Hout = Hout; a.Wout = Wout;
-    a.block_n = ChooseBlockN(o.cout);
+    // BLOCK_N: the whole Cout when it fits one instruction (<= 256), except that layers with few M tiles are
+    // split further so that the grid still covers >= 2 CTAs on each of the 148 SMs.
+    {
+      const long m_tiles = flat ? ((long)net->max_batch * Hout * Wout + 127) / 128
+                                : (long)a.tiles_w * a.tiles_h * ((net->max_batch + tc.Nt - 1) / tc.Nt);
+      int bn = ChooseBlockN(o.cout);
+      const long want_ctas = 4L * net->num_sms;
+      while (m_tiles * (o.cout / bn) < want_ctas && bn > 64) {
+        int next = 0;
+        for (int d = bn - 16; d >= 32; d -= 16)
+          if (o.cout % d == 0) { next = d; break; }
+        if (!next) break;
+        bn = next;
+      }
+      a.block_n = bn;
+    }
     a.tmem_cols = TmemCols(a.block_n);
     a.out = dst.ptr; a.out_cstride = dst.C; a.out_coff = o.off; a.relu = 1;
     a.bias = static_cast<const float*>(db);
@@ -697,13 +804,29 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
     a.b_bytes = (uint32_t)a.block_n * bk * 2;
     a.a_stage = 128u * bk * 2;
     a.b_stage = ((uint32_t)a.block_n * bk * 2 + 1023u) & ~1023u;
-    cl.smem = kStages * (a.a_stage + a.b_stage) + 1024 + 256;
-    cl.macs_per_image = (double)Hout * Wout * o.cout * o.kh * o.kw * o.cin;
+    // Pipeline depth: as deep as fits in ~108 KB so that two CTAs (one in its epilogue, one issuing MMAs) share an SM.
+    {
+      const int stage_bytes = (int)(a.a_stage + a.b_stage);
+      const int num_kb = o.kh * o.kw * a.cin_blocks;
+      // Occupancy beats pipeline depth here (measured): aim for ~4 co-resident CTAs of 2-4 stages each.
+      const int target_kb = EnvInt("DVB_CNN_SMEM_KB", 72);
+      const int max_stages = std::min(EnvInt("DVB_CNN_MAX_STAGES", 3), kMaxStages);
+      int stages = (target_kb * 1024 - 1280) / stage_bytes;
+      stages = std::max(2, std::min(stages, max_stages));
+      stages = std::max(1, std::min(stages, num_kb));
+      a.stages = EnvInt("DVB_CNN_STAGES", 0) > 0 ? std::min(EnvInt("DVB_CNN_STAGES", 0), kMaxStages) : stages;
+      cl.smem = a.stages * stage_bytes + 1024 + 256;
+    }
+    cl.macs_per_image = (double)Hout * Wout * o.cout * orig.kh * orig.kw * orig.cin;
     macs_total += cl.macs_per_image;
     // --- tensor maps
     {
-      const cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)net->max_batch};
-      const cuuint64_t strides[3] = {(cuuint64_t)src.C * 2, (cuuint64_t)Win * src.C * 2, (cuuint64_t)Hin * Win * src.C * 2};
+      cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)net->max_batch};
+      cuuint64_t strides[3] = {(cuuint64_t)src.C * 2, (cuuint64_t)Win * src.C * 2, (cuuint64_t)Hin * Win * src.C * 2};
+      if (flat) {
+        dims[1] = (cuuint64_t)Win * Hin * net->max_batch; dims[2] = 1; dims[3] = 1;
+        strides[1] = dims[1] * src.C * 2; strides[2] = strides[1];
+      }
       // With elementStrides = s the box is stated in UN-strided input elements and the TMA delivers
       // ceil(box / s) of them (measured on B200: box = Wt loads too few bytes and the mbarrier never
       // completes; box = Wt * s delivers exactly Wt).
@@ -745,8 +868,12 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
 
 int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaStream_t s) {
   const TensorBuf& in = net->tensors[0];
-  const long long npix = (long long)n * net->H * net->W;
-  preprocess_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, s>>>(images, in.ptr, npix, net->C, net->Cp);
+  {
+    const int tiles_w = (net->stem_Wo + kPatchTile - 1) / kPatchTile;
+    const int smem = ((3 * (2 * kPatchTile + 1) * net->C + 15) & ~15) + 2 * net->stem_Kp;
+    stem_patch_kernel<<<(unsigned)((long long)n * net->stem_Ho * tiles_w), 256, smem, s>>>(images, in.ptr, n, net->H, net->W, net->C,
+                                                                                         net->stem_Ho, net->stem_Wo, net->stem_Kp);
+  }
   net->launches++;
   for (const Step& stp : net->steps) {
     if (stp.kind == 0) {
@@ -754,12 +881,16 @@ int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaSt
       ConvArgs a = c.args;
       a.n_images = n;
       a.tiles_n = (n + a.Nt - 1) / a.Nt;
+      if (c.flat) {  // one long row of n * H * W pixels
+        a.Wout = n * c.pixels_per_image; a.Hout = 1; a.n_images = 1;
+        a.tiles_w = (a.Wout + 127) / 128; a.tiles_h = 1; a.tiles_n = 1;
+      }
       dim3 grid((unsigned)(a.tiles_w * a.tiles_h * a.tiles_n), c.grid.y, 1);
       conv_gemm_kernel<<<grid, kConvThreads, c.smem, s>>>(c.map_a, c.map_b, a);
     } else {
       const PoolLaunch& p = net->pools[stp.index];
-      const long long total = (long long)n * p.Hout * p.Wout * (p.C / 8);
-      pool3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p.in, p.out, n, p.Hin, p.Win, p.C, p.Hout, p.Wout, p.out_cstride,
+      const long long total = (long long)n * p.Hout * (p.C / 8);
+      pool3x3_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(p.in, p.out, n, p.Hin, p.Win, p.C, p.Hout, p.Wout, p.out_cstride,
                                                                       p.out_coff, p.mode);
     }
     net->launches++;
@@ -789,6 +920,7 @@ int dvb_cnn_create(const void* weights, int64_t weights_bytes, int32_t height, i
   DVB_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return dvb::fail(DVB_ERR_NO_DEVICE, "the CNN kernels are tcgen05 (sm_100a) only; device is sm_%d%d", prop.major, prop.minor);
   DvbCnn* net = new DvbCnn();
+  net->num_sms = prop.multiProcessorCount;
   net->device = device; net->H = height; net->W = width; net->C = channels; net->Cp = PadCin(channels);
   net->max_batch = max_batch; net->precision = precision;
   int st = Plan(net, static_cast<const uint8_t*>(weights), weights_bytes);

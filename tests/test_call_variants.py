@@ -63,6 +63,8 @@ def test_stage_clis_make_examples_then_call_variants(tmp_path):
   from test_make_examples_native import _region_fixture
   from deepvariant_b200 import make_examples_native as men
   ref, reads, cands, pic = _region_fixture()
+  for c in cands:   # call_variants sets calls[0].info['MID'] (variantcall_utils.set_model_id): give every variant a call
+    c.variant.raw = c.variant.serialize() + protos.f_bytes(11, protos.f_bytes(9, b'sample'))
   ex_path = str(tmp_path / 'make_examples.tfrecord-00000-of-00001.gz')
   gen = men.ExamplesGenerator(men.MakeExamplesOptions(pic_options=pic), {'main_sample': ex_path}, ref_reader=ref)
   gen.write_examples_in_region(cands, [reads], [0], 'main_sample', [0.0])

@@ -33,8 +33,6 @@ def _check_layers(shape, n, names, seed=0):
   for name in names:
     got = net.debug_tensor(name, n)
     ref = tensors[name].permute(0, 2, 3, 1).numpy()
-    if name == 'input':
-      got = got[..., :shape[2]]
     assert got.shape == ref.shape, (name, got.shape, ref.shape)
     scale = max(float(np.abs(ref).max()), 1e-6)
     err = float(np.abs(got - ref).max()) / scale
@@ -43,15 +41,32 @@ def _check_layers(shape, n, names, seed=0):
   return report, worst, probs.cpu(), want_p, net, pooled
 
 
-STEM = ['input', 's1', 's2', 's3', 'p1', 's4', 's5', 'p2']
+STEM = ['s1', 's2', 's3', 'p1', 's4', 's5', 'p2']
 
 
 def test_stem_layers_match_oracle():
   report, worst, _, _, _, _ = _check_layers((100, 221, 7), 3, STEM)
   print(report)
-  assert dict(report)['input'] == 0.0            # (x - 128) / 128 is exact in fp16
   for name, err in report:
     assert err < 6e-3, report
+
+
+def test_stem_patches_are_exact():
+  """Tensor 'input' = preprocess + im2col of conv1: patch k = (r*3+s)*C + c holds (x[2oh+r, 2ow+s, c] - 128)/128 exactly."""
+  shape = (100, 221, 7)
+  net = cv.GpuCnn(modeling.random_weights(7, 0), shape, device=0, max_batch=2)
+  imgs = _images(2, shape, 9)
+  probs = torch.empty((2, 3), dtype=torch.float32, device='cuda:0')
+  net.forward_device(imgs.to('cuda:0'), probs)
+  torch.cuda.synchronize()
+  got = net.debug_tensor('input', 2)
+  assert got.shape == (2, 49, 110, 64)
+  x = (imgs.numpy().astype(np.float32) - 128.0) / 128.0
+  for r in range(3):
+    for s in range(3):
+      want = x[:, r:r + 2 * 49:2, s:s + 2 * 110:2, :]
+      np.testing.assert_array_equal(got[..., (r * 3 + s) * 7:(r * 3 + s) * 7 + 7], want)
+  assert not got[..., 63:].any()
 
 
 def test_all_block_outputs_match_oracle():
