@@ -81,6 +81,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -149,6 +152,100 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
   return d;
 }
 
+// The MMA-issuing thread is ONE thread: every instruction on its dependent chain costs ~4-6 cycles and nothing
+// hides it (measured with the clock64 timeline below: 190 cycles per MMA with 64-bit descriptor arithmetic and
+// parameter reloads = 3.5k cycles to issue the 18 MMAs of one tile whose tensor work is 0.3k cycles).  So the
+// descriptor is kept as two 32-bit halves: `hi` (SBO, version, swizzle) is loop invariant, `lo` (start address >> 4
+// plus LBO) advances by plain 32-bit adds, and the 64-bit value is only assembled inside the asm block.
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((layout_type & 7u) << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+
+__device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_f16_lohi2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// Epilogue of one accumulator row: TMEM -> registers -> + bias (shared memory, broadcast) -> ReLU -> fp16 -> global.
+// All 32 lanes must call it (tcgen05.ld is warp-collective); `valid` masks the stores only.
+template <int W>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[W], const float* s_bias, __half* dst, bool valid, int relu) {
+  if (!valid) return;
+#pragma unroll
+  for (int g = 0; g < W / 8; ++g) {
+    const float4 b0 = *reinterpret_cast<const float4*>(s_bias + g * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(s_bias + g * 8 + 4);
+    float x[8] = {__uint_as_float(v[g * 8 + 0]) + b0.x, __uint_as_float(v[g * 8 + 1]) + b0.y, __uint_as_float(v[g * 8 + 2]) + b0.z,
+                  __uint_as_float(v[g * 8 + 3]) + b0.w, __uint_as_float(v[g * 8 + 4]) + b1.x, __uint_as_float(v[g * 8 + 5]) + b1.y,
+                  __uint_as_float(v[g * 8 + 6]) + b1.z, __uint_as_float(v[g * 8 + 7]) + b1.w};
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.f);
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __half2 hh = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+      pk[j] = *reinterpret_cast<uint32_t*>(&hh);
+    }
+    *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+__device__ __forceinline__ void epilogue_row(uint32_t taddr, int block_n, const float* s_bias, __half* dst, bool valid, int relu) {
+  int c = 0;
+  for (; c + 32 <= block_n; c += 32) {
+    uint32_t v[32];
+    tmem_ld32(taddr + c, v);
+    tmem_ld_wait();
+    epilogue_chunk<32>(v, s_bias + c, dst + c, valid, relu);
+  }
+  if (c < block_n) {
+    uint32_t v[16];
+    tmem_ld16(taddr + c, v);
+    tmem_ld_wait();
+    epilogue_chunk<16>(v, s_bias + c, dst + c, valid, relu);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Convolution = implicit GEMM
 // ---------------------------------------------------------------------------------------------
@@ -177,8 +274,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* empty_bar = bars + kMaxStages;
   uint64_t* tmem_full = bars + 2 * kMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
+  float* s_bias = reinterpret_cast<float*>(bars + 2 * kMaxStages + 2);   // [block_n]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < p.block_n; i += kConvThreads) s_bias[i] = p.bias[blockIdx.y * p.block_n + i];
   // tile coordinates
   int t = blockIdx.x;
   const int tw = t % p.tiles_w; t /= p.tiles_w;
@@ -224,20 +323,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (lane == 0) {
       // ===== MMA issuer (one thread) =====
       const int mma_per_kb = p.block_k / 16;
+      const uint32_t hi = desc_hi(p.sbo_bytes, p.layout_type), idesc = p.idesc;
+      const uint32_t a_lo0 = desc_lo(smem_u32(smem_a)), b_lo0 = desc_lo(smem_u32(smem_b));
+      const uint32_t a_inc = p.a_stage >> 4, b_inc = p.b_stage >> 4;
+      const int stages = p.stages;
       int st = 0;
-      uint32_t ph = 0;
+      uint32_t ph = 0, a_lo = a_lo0, b_lo = b_lo0, acc = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[st], ph);
         tc_fence_after();
-        const uint32_t a0 = smem_u32(smem_a + st * p.a_stage);
-        const uint32_t b0 = smem_u32(smem_b + st * p.b_stage);
+#pragma unroll 4
         for (int k = 0; k < mma_per_kb; ++k) {
-          const uint64_t ad = make_smem_desc(a0 + k * 32, p.sbo_bytes, p.layout_type);
-          const uint64_t bd = make_smem_desc(b0 + k * 32, p.sbo_bytes, p.layout_type);
-          umma_f16(tmem_base, ad, bd, p.idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_f16_lohi(tmem_base, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, acc);
+          acc = 1;
         }
         umma_commit(&empty_bar[st]);   // frees the stage once these MMAs retire
-        if (++st == p.stages) { st = 0; ph ^= 1; }
+        a_lo += a_inc; b_lo += b_inc;
+        if (++st == stages) { st = 0; ph ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
       }
       umma_commit(tmem_full);          // accumulator complete
     }
@@ -251,28 +353,232 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const bool valid = (n < p.Nt) && (w0 + w < p.Wout) && (h0 + h < p.Hout) && (n0 + n < p.n_images);
     __half* dst = p.out + ((size_t)((size_t)(n0 + n) * p.Hout + (h0 + h)) * p.Wout + (w0 + w)) * p.out_cstride + p.out_coff +
                   nb * p.block_n;
-    const float* bias = p.bias + nb * p.block_n;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c = 0; c < p.block_n; c += 16) {
-      uint32_t v[16];
-      tmem_ld16(taddr + c, v);
-      tmem_ld_wait();
-      if (valid) {
-        uint32_t packed[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float x0 = __uint_as_float(v[2 * j]) + __ldg(bias + c + 2 * j);
-          float x1 = __uint_as_float(v[2 * j + 1]) + __ldg(bias + c + 2 * j + 1);
-          if (p.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-          __half2 hh = __floats2half2_rn(x0, x1);
-          packed[j] = *reinterpret_cast<uint32_t*>(&hh);
+    epilogue_row(tmem_base + ((uint32_t)(q * 32) << 16), p.block_n, s_bias, dst, valid, p.relu);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stride-1 k x k convolution on large feature maps: persistent, weights-resident, halo-reusing variant
+// ---------------------------------------------------------------------------------------------
+// What the tap-by-tap kernel above cannot hide on the wide stem layers (measured, B200):
+//   * every input pixel is fetched kh*kw times and the weights once per M tile: 55-60 % of L2->SM throughput with
+//     the tensor pipe < 35 % busy;
+//   * MMAs that accumulate into the SAME TMEM tile form a dependent chain with ~160-250 cycles per link, far more
+//     than the 16-48 cycles an M=128, N=32..96 MMA occupies the tensor core (clock64 timeline of one CTA).
+// Here one CTA per SM keeps the WHOLE weight slice of its N block in shared memory for its lifetime and walks M
+// tiles persistently in groups of T tiles.  An M tile is Ht output rows x P slots (Ht * P = 128).  Per
+// (tile, Cin block) ONE TMA box brings the (Ht + kh) x P input halo; every tap (r, s) is the same shared-memory
+// block read from a start address shifted by r*P + s pixels (UMMA shared-memory descriptors swizzle on absolute
+// address bits: a shifted start needs no "base offset" — measured: setting it is wrong), so each input pixel is
+// fetched once per Cin block instead of kh*kw times.  The single MMA-issuing thread round-robins the T tiles of
+// a group, i.e. T independent accumulation chains are in flight; two TMEM buffers of T accumulators let the
+// epilogue (8 warps) of group i overlap the MMAs of group i+1.
+constexpr int kHaloEpiWarps = 16;
+constexpr int kHaloThreads = 64 + 32 * kHaloEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
+constexpr int kMaxGroup = 8;
+
+struct HaloArgs {
+  int kh, kw, pad_h, pad_w;
+  int cin_blocks, block_k;
+  int P, Ht, Wv;                  // slots per tile row, tile rows (P * Ht == 128), valid slots per row (P - kw + 1)
+  int tiles_w, tiles_h;           // per image
+  int Hout, Wout, n_images;
+  int block_n, n_blocks, tmem_cols, T, nbuf, stages;
+  int out_cstride, out_coff, relu;
+  uint32_t idesc, layout_type, sbo_bytes;
+  uint32_t a_copy_bytes, a_stage, b_tile, b_total_bytes;
+  __half* out;
+  const float* bias;
+  long long* trace;   // optional timeline of CTA 0: [group][8] clock64 stamps (development aid)
+};
+
+#define HALO_TRACE(grp_i, ev) do { if (p.trace && blockIdx.x == 0 && (grp_i) < 64) p.trace[(grp_i) * 8 + (ev)] = clock64(); } while (0)
+
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const HaloArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int taps = p.kh * p.kw;
+  uint8_t* smem_b = smem;                                           // [cin_blocks][taps][block_n][block_k]
+  uint8_t* smem_a = smem + (size_t)p.cin_blocks * taps * p.b_tile;  // [stages][halo pixels][block_k]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)p.stages * p.a_stage);
+  uint64_t* a_full = bars;                              // [kMaxStages * 2]
+  uint64_t* a_empty = bars + 2 * kMaxStages;
+  uint64_t* b_full = bars + 4 * kMaxStages;
+  uint64_t* tmem_full = bars + 4 * kMaxStages + 1;    // [2]
+  uint64_t* tmem_empty = bars + 4 * kMaxStages + 3;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 5);
+  float* s_bias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 6);   // [block_n]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = blockIdx.x % p.n_blocks;
+  const int g = blockIdx.x / p.n_blocks, G = gridDim.x / p.n_blocks;
+  for (int i = threadIdx.x; i < p.block_n; i += kHaloThreads) s_bias[i] = p.bias[nb * p.block_n + i];
+  const int tiles_per_image = p.tiles_w * p.tiles_h;
+  const int total_tiles = p.n_images * tiles_per_image;
+  const int T = p.T;
+  // CTA g owns tile groups g, g + G, ...; group j holds tiles j*T .. j*T + T-1 (clamped to the last tile: the
+  // duplicates recompute and re-store identical values, which keeps every barrier protocol uniform).
+  const int total_groups = (total_tiles + T - 1) / T;
+  const uint32_t row_bytes = (uint32_t)p.block_k * 2u;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_b);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    mbar_init(b_full, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 32 * kHaloEpiWarps); }
+    fence_barrier_init();
+  } else if (warp == 1) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: weights once, then one halo per (tile, Cin block) =====
+      mbar_arrive_expect_tx(b_full, p.b_total_bytes);
+      for (int cb = 0; cb < p.cin_blocks; ++cb)
+        for (int t = 0; t < taps; ++t)
+          tma_load_3d(smem_b + (size_t)(cb * taps + t) * p.b_tile, &map_b, b_full, cb * p.block_k, nb * p.block_n, t);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int grp = g; grp < total_groups; grp += G) {
+        for (int cb = 0; cb < p.cin_blocks; ++cb) {
+          for (int t = 0; t < T; ++t) {
+            const int tile = min(grp * T + t, total_tiles - 1);
+            const int n = tile / tiles_per_image;
+            const int rem = tile - n * tiles_per_image;
+            const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+            mbar_wait(&a_empty[st], ph ^ 1);
+            mbar_arrive_expect_tx(&a_full[st], p.a_copy_bytes);
+            tma_load_4d(smem_a + (size_t)st * p.a_stage, &map_a, &a_full[st], cb * p.block_k, tw * p.Wv - p.pad_w, th * p.Ht - p.pad_h, n);
+            if (++st == p.stages) { st = 0; ph ^= 1; }
+          }
         }
-        uint4* d4 = reinterpret_cast<uint4*>(dst + c);
-        d4[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-        d4[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+        HALO_TRACE((grp - g) / G, 1);
       }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer: T accumulation chains in flight =====
+      mbar_wait(b_full, 0);
+      tc_fence_after();
+      const int mma_per_kb = p.block_k / 16;
+      const uint32_t hi = desc_hi(p.sbo_bytes, p.layout_type), idesc = p.idesc;
+      const uint32_t a_lo0 = desc_lo(smem_u32(smem_a)), b_lo0 = desc_lo(smem_u32(smem_b));
+      const uint32_t a_stage_inc = p.a_stage >> 4, a_row_inc = ((uint32_t)p.P * row_bytes) >> 4, a_px_inc = row_bytes >> 4;
+      const uint32_t b_tile_inc = p.b_tile >> 4;
+      const int stages = p.stages, kh = p.kh, kw = p.kw, cin_blocks = p.cin_blocks;
+      const uint32_t block_n = (uint32_t)p.block_n;
+      const int nbuf = p.nbuf;
+      int st = 0, buf = 0;
+      uint32_t ph = 0, buf_ph = 0;
+      for (int grp = g; grp < total_groups; grp += G) {
+        mbar_wait(&tmem_empty[buf], buf_ph ^ 1);   // the epilogue has drained this buffer of T accumulators
+        HALO_TRACE((grp - g) / G, 2);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)buf * (uint32_t)T * block_n;
+        const uint32_t d1 = d0 + block_n, d2 = d1 + block_n, d3 = d2 + block_n, d4 = d3 + block_n, d5 = d4 + block_n, d6 = d5 + block_n,
+                       d7 = d6 + block_n;
+        uint32_t accum = 0, b_lo = b_lo0;
+        for (int cb = 0; cb < cin_blocks; ++cb) {
+          uint32_t a_lo_t[kMaxGroup];
+          int st_t = st;
+          uint32_t ph_t = ph;
+#pragma unroll
+          for (int t = 0; t < kMaxGroup; ++t) {
+            a_lo_t[t] = 0;
+            if (t < T) {
+              mbar_wait(&a_full[st_t], ph_t);
+              a_lo_t[t] = a_lo0 + (uint32_t)st_t * a_stage_inc;
+              if (++st_t == stages) { st_t = 0; ph_t ^= 1; }
+            }
+          }
+          if (cb == 0) HALO_TRACE((grp - g) / G, 3);
+          tc_fence_after();
+          uint32_t off_r = 0;
+          for (int r = 0; r < kh; ++r) {
+            uint32_t off = off_r;
+            for (int s = 0; s < kw; ++s) {
+              for (int k = 0; k < mma_per_kb; ++k) {
+                const uint32_t ao = off + 2 * k, bo = b_lo + 2 * k, ac = accum | (uint32_t)(k != 0);
+                // straight-line round-robin over the T accumulators: consecutive MMAs never depend on each other
+                if (T == 8) {
+                  umma_f16_lohi(d0, a_lo_t[0] + ao, bo, hi, idesc, ac);
+                  umma_f16_lohi(d1, a_lo_t[1] + ao, bo, hi, idesc, ac);
+                  umma_f16_lohi(d2, a_lo_t[2] + ao, bo, hi, idesc, ac);
+                  umma_f16_lohi(d3, a_lo_t[3] + ao, bo, hi, idesc, ac);
+                  umma_f16_lohi(d4, a_lo_t[4] + ao, bo, hi, idesc, ac);
+                  umma_f16_lohi(d5, a_lo_t[5] + ao, bo, hi, idesc, ac);
+                  umma_f16_lohi(d6, a_lo_t[6] + ao, bo, hi, idesc, ac);
+                  umma_f16_lohi(d7, a_lo_t[7] + ao, bo, hi, idesc, ac);
+                } else if (T == 4) {
+                  umma_f16_lohi(d0, a_lo_t[0] + ao, bo, hi, idesc, ac);
+                  umma_f16_lohi(d1, a_lo_t[1] + ao, bo, hi, idesc, ac);
+                  umma_f16_lohi(d2, a_lo_t[2] + ao, bo, hi, idesc, ac);
+                  umma_f16_lohi(d3, a_lo_t[3] + ao, bo, hi, idesc, ac);
+                } else {
+#pragma unroll
+                  for (int t = 0; t < kMaxGroup; ++t)
+                    if (t < T) umma_f16_lohi(d0 + (uint32_t)t * block_n, a_lo_t[t] + ao, bo, hi, idesc, ac);
+                }
+              }
+              accum = 1;
+              off += a_px_inc;
+              b_lo += b_tile_inc;
+            }
+            off_r += a_row_inc;
+          }
+          for (int t = 0; t < T; ++t) {
+            umma_commit(&a_empty[st]);
+            if (++st == stages) { st = 0; ph ^= 1; }
+          }
+        }
+        umma_commit(&tmem_full[buf]);
+        HALO_TRACE((grp - g) / G, 4);
+        if (nbuf == 2) { buf ^= 1; if (buf == 0) buf_ph ^= 1; }
+        else buf_ph ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue: 16 warps; a warp may only touch the TMEM lane quarter (warp % 4); the 4 warps of a quarter split the
+    // tiles of the group ((t & 3) == sub).  Many warps because the per-row work is a long dependent chain (TMEM load ->
+    // bias -> ReLU -> pack -> store) that only thread-level parallelism hides.
+    const int e = warp - 2;
+    const int q = warp & 3;
+    const int half = e >> 2;   // 0..3
+    const int row = q * 32 + lane;
+    const int hh = row / p.P, slot = row - hh * p.P;
+    int buf = 0;
+    uint32_t buf_ph = 0;
+    for (int grp = g; grp < total_groups; grp += G) {
+      mbar_wait(&tmem_full[buf], buf_ph);
+      if (threadIdx.x == 64) HALO_TRACE((grp - g) / G, 5);
+      tc_fence_after();
+      for (int t = half; t < T; t += kHaloEpiWarps / 4) {
+        const int tile = min(grp * T + t, total_tiles - 1);
+        const int n = tile / tiles_per_image;
+        const int rem = tile - n * tiles_per_image;
+        const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
+        const int w = tw * p.Wv + slot, h = th * p.Ht + hh;
+        const bool valid = (slot < p.Wv) && (w < p.Wout) && (h < p.Hout);
+        __half* dst = p.out + ((size_t)((size_t)n * p.Hout + h) * p.Wout + w) * p.out_cstride + p.out_coff + nb * p.block_n;
+        epilogue_row(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * T + t) * p.block_n), p.block_n, s_bias, dst, valid, p.relu);
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[buf]);
+      if (threadIdx.x == 64) HALO_TRACE((grp - g) / G, 6);
+      if (p.nbuf == 2) { buf ^= 1; if (buf == 0) buf_ph ^= 1; }
+      else buf_ph ^= 1;
     }
   }
   tc_fence_before();
@@ -289,43 +595,73 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 // so that conv1 becomes a plain GEMM over K = Kp (64 for the 7-channel WGS image): one contiguous, fully
 // used 128-byte row per output pixel instead of nine strided 32-byte TMA boxes.  (x - 128) / 128 is exact
 // in fp16 (|x - 128| <= 128, power-of-two divisor).  One thread per (output pixel, 8 consecutive k).
-constexpr int kPatchTile = 64;  // output pixels per block
+constexpr int kPatchRows = 4;  // output rows per block
 __global__ void __launch_bounds__(256) stem_patch_kernel(const uint8_t* __restrict__ in, __half* __restrict__ out, int n_images, int H,
                                                          int W, int C, int Ho, int Wo, int Kp) {
-  // One block = kPatchTile consecutive output pixels of one output row: the three input rows they touch are
-  // staged in shared memory with coalesced byte loads, then every thread emits 16-byte chunks of patches.
-  extern __shared__ uint8_t s_in[];  // [3][(2*kPatchTile + 1) * C] then short koff[Kp]
-  const int tiles_w = (Wo + kPatchTile - 1) / kPatchTile;
-  int b = blockIdx.x;
-  const int tw = b % tiles_w; b /= tiles_w;
-  const int oh = b % Ho;
-  const int n = b / Ho;
-  const int ow0 = tw * kPatchTile;
-  const int npx = min(kPatchTile, Wo - ow0);
-  const int seg = (2 * npx + 1) * C;           // bytes of one input row segment
-  const int seg_pitch = (2 * kPatchTile + 1) * C;
-  short* koff = reinterpret_cast<short*>(s_in + ((3 * seg_pitch + 15) & ~15));
+  // One block = kPatchRows full output rows of one image: the 2*rows+1 input rows they touch are staged in shared
+  // memory with coalesced 4-byte loads, then every thread emits 16-byte chunks of patches (coalesced stores).
+  extern __shared__ __align__(16) uint8_t s_in[];  // [(2*kPatchRows + 1)][row_pitch] then short koff[Kp]
+  const int groups = (Ho + kPatchRows - 1) / kPatchRows;
+  const int n = blockIdx.x / groups;
+  const int oh0 = (blockIdx.x - n * groups) * kPatchRows;
+  const int rows = min(kPatchRows, Ho - oh0);
+  const int in_rows = 2 * rows + 1;
+  const int row_bytes = W * C;
+  const int row_pitch = (row_bytes + 3 + 15) & ~15;  // +3: the copy below starts at a 4-byte aligned address
+  short* koff = reinterpret_cast<short*>(s_in + (2 * kPatchRows + 1) * row_pitch);
   for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
     const int r = k / (3 * C);
-    koff[k] = k < 9 * C ? (short)(r * seg_pitch + (k - r * 3 * C)) : (short)-1;   // (s, c) is contiguous in the input row
+    koff[k] = k < 9 * C ? (short)(r * row_pitch + (k - r * 3 * C)) : (short)-1;   // (s, c) is contiguous in the input row
   }
-  for (int r = 0; r < 3; ++r) {
-    const uint8_t* src = in + (((size_t)n * H + 2 * oh + r) * W + 2 * ow0) * C;
-    for (int i = threadIdx.x; i < seg; i += blockDim.x) s_in[r * seg_pitch + i] = src[i];
+  // rows are contiguous in global memory: copy [first byte, last byte) with aligned 32-bit loads
+  const size_t g0 = ((size_t)n * H + 2 * oh0) * row_bytes;
+  for (int r = 0; r < in_rows; ++r) {
+    const size_t gb = g0 + (size_t)r * row_bytes;
+    const int mis = (int)(gb & 3);                       // shared copy keeps the same misalignment
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(in + (gb - mis));
+    uint32_t* dstw = reinterpret_cast<uint32_t*>(s_in + r * row_pitch);
+    const int nw = (mis + row_bytes + 3) >> 2;
+    const size_t total_bytes = (size_t)n_images * H * row_bytes;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) {
+      const size_t off = (gb - mis) + 4 * (size_t)i;
+      uint32_t wv;
+      if (off + 4 <= total_bytes) {
+        wv = __ldg(src + i);
+      } else {  // never read past the end of the caller's buffer
+        wv = 0;
+        for (int bb = 0; bb < 4; ++bb)
+          if (off + bb < total_bytes) wv |= (uint32_t)in[off + bb] << (8 * bb);
+      }
+      dstw[i] = wv;
+    }
   }
   __syncthreads();
   const int kvec = Kp / 8;
-  __half* dst = out + (((size_t)n * Ho + oh) * Wo + ow0) * Kp;
-  for (int t = threadIdx.x; t < npx * kvec; t += blockDim.x) {
-    const int px = t / kvec, kv = t - px * kvec;
+  const int per_row = Wo * kvec;
+  __half* dst = out + (((size_t)n * Ho + oh0) * Wo) * Kp;
+  for (int t = threadIdx.x; t < rows * per_row; t += blockDim.x) {
+    const int orow = t / per_row;
+    const int rem = t - orow * per_row;
+    const int px = rem / kvec, kv = rem - px * kvec;
+    const size_t gb = g0 + (size_t)(2 * orow) * row_bytes;
+    const uint8_t* base = s_in + (2 * orow) * row_pitch + (int)(gb & 3) + 2 * px * C;
+    // rows 2*orow+1 and +2 have their own misalignment: fold the difference into the row offset
+    const int mis0 = (int)(gb & 3), mis1 = (int)((gb + row_bytes) & 3), mis2 = (int)((gb + 2 * (size_t)row_bytes) & 3);
     uint32_t pk[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float v[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int o = koff[kv * 8 + 2 * j + e];
-        v[e] = o >= 0 ? ((float)s_in[o + 2 * px * C] - 128.f) * (1.f / 128.f) : 0.f;
+        const int k = kv * 8 + 2 * j + e;
+        const int o = koff[k];
+        float x = 0.f;
+        if (o >= 0) {
+          const int r = o >= 2 * row_pitch ? 2 : (o >= row_pitch ? 1 : 0);
+          const int adj = r == 2 ? mis2 - mis0 : (r == 1 ? mis1 - mis0 : 0);
+          x = ((float)base[o + adj] - 128.f) * (1.f / 128.f);
+        }
+        v[e] = x;
       }
       __half2 hh = __floats2half2_rn(v[0], v[1]);
       pk[j] = *reinterpret_cast<uint32_t*>(&hh);
@@ -585,11 +921,17 @@ struct ConvLaunch {
   bool flat;
   int pixels_per_image;
 };
+struct HaloLaunch {
+  CUtensorMap map_a, map_b;
+  HaloArgs args;
+  int smem, ctas_per_nblock;
+  double macs_per_image;
+};
 struct PoolLaunch {
   const __half* in; __half* out;
   int Hin, Win, C, Hout, Wout, out_cstride, out_coff, mode;
 };
-struct Step { int kind; int index; };  // 0 conv, 1 pool
+struct Step { int kind; int index; };  // 0 conv, 1 pool, 2 halo conv
 
 }  // namespace
 
@@ -599,6 +941,7 @@ struct DvbCnn {
   std::vector<TensorBuf> tensors;
   std::map<std::string, int> tensor_index;
   std::vector<ConvLaunch> convs;
+  std::vector<HaloLaunch> halos;
   std::vector<PoolLaunch> pools;
   std::vector<Step> steps;
   std::vector<void*> allocs;
@@ -756,6 +1099,102 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
     cudaMemcpy(db, blob + pos + blob_wbytes, bbytes, cudaMemcpyHostToDevice);
     pos += blob_wbytes + bbytes;
 
+    // ---- large stride-1 k x k layers: persistent halo-reusing kernel (see conv_halo_kernel)
+    if (!is_stem && o.stride == 1 && o.kh * o.kw > 1 && Hout * Wout >= 1000 && EnvInt("DVB_CNN_HALO", 1)) {
+      HaloLaunch hl;
+      memset(&hl, 0, sizeof(hl));
+      HaloArgs& a = hl.args;
+      const int taps = o.kh * o.kw;
+      const int bk = cin_store % 64 == 0 ? 64 : cin_store % 32 == 0 ? 32 : 16;
+      const int row_bytes = bk * 2;
+      a.kh = o.kh; a.kw = o.kw;
+      a.pad_h = o.same ? (o.kh - 1) / 2 : 0;
+      a.pad_w = o.same ? (o.kw - 1) / 2 : 0;
+      a.block_k = bk;
+      a.cin_blocks = (cin_store + bk - 1) / bk;
+      // slots per tile row: vertical tap offsets (r * P rows) must stay 1024-byte aligned
+      // slots per tile row: the row pitch P * row_bytes keeps vertical taps 1024-byte aligned; P - kw + 1 slots are valid
+      int bestP = 0; double best_eff = -1;
+      for (int P = 1024 / row_bytes; P <= 128; P *= 2) {
+        const int Ht = 128 / P;
+        const int Wv = P - o.kw + 1;
+        if (Wv < 1) continue;
+        const double eff = (double)Hout * Wout / ((double)((Wout + Wv - 1) / Wv) * ((Hout + Ht - 1) / Ht) * 128.0);
+        if (eff > best_eff + 0.04) { best_eff = eff; bestP = P; }   // small P = small halo: a wider row must pay > 4 % in fill
+      }
+      a.P = bestP; a.Ht = 128 / bestP;
+      a.Wv = a.P - o.kw + 1;
+      a.tiles_w = (Wout + a.Wv - 1) / a.Wv;
+      a.tiles_h = (Hout + a.Ht - 1) / a.Ht;
+      a.Hout = Hout; a.Wout = Wout;
+      const int Hh = a.Ht + o.kh;   // Ht + kh - 1 rows are needed; one spare row absorbs the kw-1 pixel overrun of the last tap
+      a.a_copy_bytes = (uint32_t)Hh * a.P * row_bytes;
+      a.a_stage = (a.a_copy_bytes + 1023u) & ~1023u;
+      // N block: the resident weight slice must leave room for the halo ring
+      int bn = ChooseBlockN(o.cout);
+      auto b_total = [&](int n) { return (size_t)a.cin_blocks * taps * (((size_t)n * row_bytes + 1023) & ~(size_t)1023); };
+      while (b_total(bn) + 4 * a.a_stage > 200 * 1024 && bn > 16) {
+        int next = 0;
+        for (int d = bn - 16; d >= 16; d -= 16)
+          if (o.cout % d == 0) { next = d; break; }
+        if (!next) break;
+        bn = next;
+      }
+      a.block_n = bn; a.n_blocks = o.cout / bn;
+      a.b_tile = (uint32_t)((bn * row_bytes + 1023) & ~1023);
+      a.b_total_bytes = (uint32_t)a.cin_blocks * taps * bn * row_bytes;   // bytes the TMA delivers
+      const size_t b_smem = (size_t)a.cin_blocks * taps * a.b_tile;
+      // T tiles in flight = T independent accumulation chains (measured issue interval per MMA, N <= 64: 222 cycles
+      // with 1 chain, 80 with 4, 46 with 8).  Two TMEM buffers of T accumulators when 2*T*bn <= 512 columns, else one.
+      int T = std::min(kMaxGroup, 512 / bn);
+      T = T >= 8 ? 8 : T >= 4 ? 4 : T;
+      T = std::min(T, EnvInt("DVB_HALO_T", 8));
+      while (T > 1 && b_smem + (size_t)(T + 2) * a.a_stage > 216 * 1024) T = T > 4 ? 4 : T - 1;
+      a.T = std::max(1, T);
+      if (2 * a.T * bn > 512 && a.T == 8 && EnvInt("DVB_HALO_PREFER_DB", 1)) a.T = 4;   // measured: T=4 double-buffered beats T=8 single
+      a.nbuf = (2 * a.T * bn <= 512 && EnvInt("DVB_HALO_NBUF", 2) == 2) ? 2 : 1;
+      a.stages = std::min(2 * kMaxStages, std::max(a.T, std::min(2 * a.T, (int)((216 * 1024 - (long)b_smem) / (long)a.a_stage))));
+      a.tmem_cols = TmemCols(a.nbuf * a.T * bn);
+      a.out = dst.ptr; a.out_cstride = dst.C; a.out_coff = o.off; a.relu = 1;
+      a.bias = static_cast<const float*>(db);
+      a.idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      a.layout_type = bk == 64 ? 2u : bk == 32 ? 4u : 6u;
+      a.sbo_bytes = 8u * (uint32_t)row_bytes;
+      hl.smem = (int)(b_smem + (size_t)a.stages * a.a_stage) + 1024 + 512 + bn * 4;
+      hl.macs_per_image = (double)Hout * Wout * o.cout * o.kh * o.kw * o.cin;
+      // Only worth it when >= 4 double-buffered accumulation chains fit in TMEM (N block <= 64); wider layers (conv5,
+      // N = 192) measured slower here than with the tap-by-tap kernel and stay there.
+      if (a.tmem_cols <= 512 && hl.smem <= 227 * 1024 && a.stages >= a.T && a.T >= 4 && a.nbuf == 2 && a.n_blocks == 1) {
+        // weights [Cout][taps][Cin] -> [taps][Cout][Cin] so that one (tap, N block, Cin block) is a canonical K-major tile
+        std::vector<__half> w2((size_t)taps * o.cout * cin_store);
+        const __half* w = reinterpret_cast<const __half*>(blob + pos - blob_wbytes - bbytes);
+        for (int co = 0; co < o.cout; ++co)
+          for (int t = 0; t < taps; ++t)
+            memcpy(&w2[((size_t)t * o.cout + co) * cin_store], &w[((size_t)co * taps + t) * cin_store], (size_t)cin_store * sizeof(__half));
+        cudaMemcpy(dw, w2.data(), wbytes, cudaMemcpyHostToDevice);
+        {
+          const cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)net->max_batch};
+          const cuuint64_t strides[3] = {(cuuint64_t)src.C * 2, (cuuint64_t)Win * src.C * 2, (cuuint64_t)Hin * Win * src.C * 2};
+          const cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)a.P, (cuuint32_t)Hh, 1};
+          const cuuint32_t estr[4] = {1, 1, 1, 1};
+          st = MakeMap(&hl.map_a, src.ptr, 4, dims, strides, box, estr, bk);
+          if (st) return st;
+        }
+        {
+          const cuuint64_t dims[3] = {(cuuint64_t)cin_store, (cuuint64_t)o.cout, (cuuint64_t)taps};
+          const cuuint64_t strides[2] = {(cuuint64_t)cin_store * 2, (cuuint64_t)o.cout * cin_store * 2};
+          const cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)bn, 1};
+          const cuuint32_t estr[3] = {1, 1, 1};
+          st = MakeMap(&hl.map_b, dw, 3, dims, strides, box, estr, bk);
+          if (st) return st;
+        }
+        macs_total += hl.macs_per_image;
+        net->steps.push_back({2, (int)net->halos.size()});
+        net->halos.push_back(hl);
+        continue;
+      }
+    }
+
     ConvLaunch cl;
     memset(&cl, 0, sizeof(cl));
     ConvArgs& a = cl.args;
@@ -815,7 +1254,7 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       stages = std::max(2, std::min(stages, max_stages));
       stages = std::max(1, std::min(stages, num_kb));
       a.stages = EnvInt("DVB_CNN_STAGES", 0) > 0 ? std::min(EnvInt("DVB_CNN_STAGES", 0), kMaxStages) : stages;
-      cl.smem = a.stages * stage_bytes + 1024 + 256;
+      cl.smem = a.stages * stage_bytes + 1024 + 256 + a.block_n * 4;
     }
     cl.macs_per_image = (double)Hout * Wout * o.cout * orig.kh * orig.kw * orig.cin;
     macs_total += cl.macs_per_image;
@@ -862,6 +1301,16 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
   for (auto& c : net->convs) max_smem = std::max(max_smem, c.smem);
   if (cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess)
     return dvb::fail(DVB_ERR_CUDA, "cannot reserve %d bytes of shared memory", max_smem);
+  int max_halo = 0;
+  for (auto& h : net->halos) max_halo = std::max(max_halo, h.smem);
+  if (max_halo && cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_halo) != cudaSuccess)
+    return dvb::fail(DVB_ERR_CUDA, "cannot reserve %d bytes of shared memory (halo kernel)", max_halo);
+  for (auto& h : net->halos) {
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_halo_kernel, kHaloThreads, h.smem);
+    occ = std::max(1, std::min(occ, 512 / h.args.tmem_cols));
+    h.ctas_per_nblock = std::max(1, net->num_sms * occ / h.args.n_blocks);
+  }
   if (cudaDeviceSynchronize() != cudaSuccess) return dvb::fail(DVB_ERR_CUDA, "weight upload failed: %s", cudaGetErrorString(cudaGetLastError()));
   return DVB_OK;
 }
@@ -869,14 +1318,39 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
 int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaStream_t s) {
   const TensorBuf& in = net->tensors[0];
   {
-    const int tiles_w = (net->stem_Wo + kPatchTile - 1) / kPatchTile;
-    const int smem = ((3 * (2 * kPatchTile + 1) * net->C + 15) & ~15) + 2 * net->stem_Kp;
-    stem_patch_kernel<<<(unsigned)((long long)n * net->stem_Ho * tiles_w), 256, smem, s>>>(images, in.ptr, n, net->H, net->W, net->C,
-                                                                                         net->stem_Ho, net->stem_Wo, net->stem_Kp);
+    const int groups = (net->stem_Ho + kPatchRows - 1) / kPatchRows;
+    const int row_pitch = (net->W * net->C + 3 + 15) & ~15;
+    const int smem = (2 * kPatchRows + 1) * row_pitch + 2 * net->stem_Kp;
+    stem_patch_kernel<<<(unsigned)((long long)n * groups), 256, smem, s>>>(images, in.ptr, n, net->H, net->W, net->C, net->stem_Ho,
+                                                                          net->stem_Wo, net->stem_Kp);
   }
   net->launches++;
   for (const Step& stp : net->steps) {
-    if (stp.kind == 0) {
+    if (stp.kind == 2) {
+      HaloLaunch& hl = net->halos[stp.index];
+      HaloArgs a = hl.args;
+      a.n_images = n;
+      const int total_tiles = n * a.tiles_w * a.tiles_h;
+      const int G = std::min(hl.ctas_per_nblock, (total_tiles + a.T - 1) / a.T);
+      static long long* d_trace = nullptr;
+      const bool tracing = EnvInt("DVB_CNN_TRACE", 0) != 0;
+      if (tracing && !d_trace) { cudaMalloc(&d_trace, 64 * 8 * sizeof(long long)); }
+      if (tracing) { cudaMemsetAsync(d_trace, 0, 64 * 8 * sizeof(long long), s); a.trace = d_trace; }
+      conv_halo_kernel<<<(unsigned)(G * a.n_blocks), kHaloThreads, hl.smem, s>>>(hl.map_a, hl.map_b, a);
+      if (tracing) {
+        std::vector<long long> h(64 * 8);
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[halo trace] layer %d P=%d Ht=%d bn=%d stages=%d T=%d kw=%d cinb=%d (cycles rel. to first event)\n", stp.index, a.P, a.Ht,
+                a.block_n, a.stages, a.T * 10 + a.nbuf, a.kw, a.cin_blocks);
+        const long long t0 = h[1];
+        for (int i = 0; i < 12; ++i) {
+          fprintf(stderr, "  group %2d:", i);
+          for (int e = 1; e < 7; ++e) fprintf(stderr, " %8lld", h[i * 8 + e] ? h[i * 8 + e] - t0 : -1);
+          fprintf(stderr, "\n");
+        }
+      }
+    } else if (stp.kind == 0) {
       ConvLaunch& c = net->convs[stp.index];
       ConvArgs a = c.args;
       a.n_images = n;
