@@ -636,37 +636,39 @@ __global__ void __launch_bounds__(256) stem_patch_kernel(const uint8_t* __restri
     }
   }
   __syncthreads();
+  // one thread per output pixel: 3 segments of 3*C contiguous input bytes -> Kp halves = Kp/8 16-byte stores
   const int kvec = Kp / 8;
-  const int per_row = Wo * kvec;
-  __half* dst = out + (((size_t)n * Ho + oh0) * Wo) * Kp;
-  for (int t = threadIdx.x; t < rows * per_row; t += blockDim.x) {
-    const int orow = t / per_row;
-    const int rem = t - orow * per_row;
-    const int px = rem / kvec, kv = rem - px * kvec;
+  const uint4* koff4 = reinterpret_cast<const uint4*>(koff);
+  for (int t = threadIdx.x; t < rows * Wo; t += blockDim.x) {
+    const int orow = t / Wo, px = t - orow * Wo;
     const size_t gb = g0 + (size_t)(2 * orow) * row_bytes;
-    const uint8_t* base = s_in + (2 * orow) * row_pitch + (int)(gb & 3) + 2 * px * C;
-    // rows 2*orow+1 and +2 have their own misalignment: fold the difference into the row offset
     const int mis0 = (int)(gb & 3), mis1 = (int)((gb + row_bytes) & 3), mis2 = (int)((gb + 2 * (size_t)row_bytes) & 3);
-    uint32_t pk[4];
+    // koff[k] = r * row_pitch + j; the three input rows of this pixel start at different 4-byte phases
+    const uint8_t* base = s_in + (2 * orow) * row_pitch + 2 * px * C;
+    const int adj[3] = {mis0, mis1, mis2};
+    __half* dst = out + (((size_t)n * Ho + oh0 + orow) * Wo + px) * Kp;
+    for (int kv = 0; kv < kvec; ++kv) {
+      const uint4 o4 = koff4[kv];
+      const uint32_t ow[4] = {o4.x, o4.y, o4.z, o4.w};
+      uint32_t pk[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float v[2];
+      for (int j = 0; j < 4; ++j) {
+        float v[2];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int k = kv * 8 + 2 * j + e;
-        const int o = koff[k];
-        float x = 0.f;
-        if (o >= 0) {
-          const int r = o >= 2 * row_pitch ? 2 : (o >= row_pitch ? 1 : 0);
-          const int adj = r == 2 ? mis2 - mis0 : (r == 1 ? mis1 - mis0 : 0);
-          x = ((float)base[o + adj] - 128.f) * (1.f / 128.f);
+        for (int e = 0; e < 2; ++e) {
+          const int o = (int)(short)((ow[j] >> (16 * e)) & 0xFFFFu);
+          float x = 0.f;
+          if (o >= 0) {
+            const int r = o >= 2 * row_pitch ? 2 : (o >= row_pitch ? 1 : 0);
+            x = ((float)base[o + adj[r]] - 128.f) * (1.f / 128.f);
+          }
+          v[e] = x;
         }
-        v[e] = x;
+        __half2 hh = __floats2half2_rn(v[0], v[1]);
+        pk[j] = *reinterpret_cast<uint32_t*>(&hh);
       }
-      __half2 hh = __floats2half2_rn(v[0], v[1]);
-      pk[j] = *reinterpret_cast<uint32_t*>(&hh);
+      *reinterpret_cast<uint4*>(dst + kv * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
-    *reinterpret_cast<uint4*>(dst + (size_t)t * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
 

@@ -188,27 +188,47 @@ __device__ uint8_t read_const(const EncDev& P, int chan, const ReadHdr& h, int s
   }
 }
 
-// Streams `row_bytes` bytes of a row to global memory.  `src` (shared) holds the row at the same
-// 16-byte phase as `dst`; src == nullptr stores zeros.
-__device__ __forceinline__ void flush_row(uint8_t* __restrict__ dst, const uint8_t* src, int row_bytes, int lane) {
+// Streams `row_bytes` bytes of a row to global memory with 16-byte stores.
+//   buf == nullptr : blank row, zeros straight from registers.
+//   otherwise      : the row lives in shared memory at px = buf + 16 + 4 * (phase >> 2), phase = dst & 15, i.e. pixel 0 is
+//                    always 4-byte aligned (so that 4-pixel groups can be stored as aligned words) and the 0-3 byte residual
+//                    misalignment s = phase & 3 against the 16-byte global chunks is removed here with one funnel shift per word.
+__device__ __forceinline__ void flush_row(uint8_t* __restrict__ dst, const uint8_t* buf, int row_bytes, int lane) {
   const int phase = (int)((uintptr_t)dst & 15);
   int head = (16 - phase) & 15;
   if (head > row_bytes) head = row_bytes;
-  if (lane < head) dst[lane] = src ? src[lane] : (uint8_t)0;
   const int body = (row_bytes - head) >> 4;
-  uint4* d4 = reinterpret_cast<uint4*>(dst + head);
-  if (src) {
-    const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
-    for (int i = lane; i < body; i += 32) d4[i] = s4[i];
-  } else {
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    for (int i = lane; i < body; i += 32) d4[i] = z;
-  }
   const int done = head + (body << 4);
   const int tail = row_bytes - done;
-  if (lane < tail) dst[done + lane] = src ? src[done + lane] : (uint8_t)0;
+  uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+  if (buf == nullptr) {
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    if (lane < head) dst[lane] = 0;
+    for (int i = lane; i < body; i += 32) d4[i] = z;
+    if (lane < tail) dst[done + lane] = 0;
+    return;
+  }
+  const uint8_t* px = buf + 16 + 4 * (phase >> 2);
+  if (lane < head) dst[lane] = px[lane];
+  const int s = phase & 3;
+  const uint8_t* blk = buf + (phase == 0 ? 16 : 32);     // aligned block holding (most of) body chunk 0
+  if (s == 0) {
+    for (int i = lane; i < body; i += 32) d4[i] = *reinterpret_cast<const uint4*>(blk + 16 * i);
+  } else {
+    const int sh = 32 - 8 * s;
+    for (int i = lane; i < body; i += 32) {
+      const uint4 b = *reinterpret_cast<const uint4*>(blk + 16 * i);
+      const uint32_t wp = *reinterpret_cast<const uint32_t*>(blk + 16 * i - 4);
+      d4[i] = make_uint4(__funnelshift_r(wp, b.x, sh), __funnelshift_r(b.x, b.y, sh), __funnelshift_r(b.y, b.z, sh),
+                         __funnelshift_r(b.z, b.w, sh));
+    }
+  }
+  if (lane < tail) dst[done + lane] = px[done + lane];
 }
 
+// FAST7: 7 computed channels, 7-byte pixels (the WGS layout): runs of 4 pixels whose first column is a multiple of 4 are
+// assembled in registers and stored as 7 aligned 32-bit words instead of 28 byte stores.
+template <bool FAST7>
 __global__ void __launch_bounds__(kThreads, 4)
 dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, int* __restrict__ rows_kept,
                   int* __restrict__ err) {
@@ -227,7 +247,7 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
   int* s_visit = reinterpret_cast<int*>(s_rank + P.max_rows);
   int* s_order = s_visit + P.max_rows;
   int* s_wtot = s_order + P.max_rows;          // kWarps + 2 ints
-  const int rowbuf_bytes = ((P.row_bytes + 15) & ~15) + 32;
+  const int rowbuf_bytes = ((P.row_bytes + 28 + 15) & ~15) + 32;
   uintptr_t rb0 = (reinterpret_cast<uintptr_t>(s_wtot + kWarps + 2) + 15) & ~(uintptr_t)15;
   uint8_t* s_rows = reinterpret_cast<uint8_t*>(rb0);
 
@@ -317,7 +337,7 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
       }
       uint8_t* buf = s_rows + warp * rowbuf_bytes;
       const int phase = (int)((uintptr_t)dst & 15);
-      uint8_t* px = buf + phase;  // pixel (col, ch) lives at px[col * Cout + ch]
+      uint8_t* px = buf + 16 + 4 * (phase >> 2);  // pixel (col, ch) lives at px[col * Cout + ch]; px is 4-byte aligned
       {
         uint4* b4 = reinterpret_cast<uint4*>(buf);
         const uint4 z = make_uint4(0, 0, 0, 0);
@@ -364,7 +384,7 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
             const int c0 = ref_i - image_start;
             const int lo = c0 < 0 ? -c0 : 0;
             const int hi = P.W - c0 < len ? P.W - c0 : len;
-            for (int j = lo + lane; j < hi; j += 32) {
+            auto put_pixel = [&](int j) {      // byte-granular path: one pixel
               const int col = c0 + j;
               const unsigned b = bases[read_i + j];
               if (b != 0) {
@@ -382,6 +402,48 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
                   }
                 }
               }
+            };
+            if (FAST7 && hi > lo) {
+              const int cA = c0 + lo, cB = c0 + hi;            // window columns [cA, cB)
+              const int gA = (cA + 3) >> 2, gB = cB >> 2;      // whole 4-pixel groups [gA, gB)
+              const unsigned mb0 = P.mask_base[0], mq0 = P.mask_qual[0], md0 = P.mask_diff[0];
+              const unsigned mb1 = P.mask_base[1], mq1 = P.mask_qual[1], md1 = P.mask_diff[1];
+              for (int g = gA + lane; g < gB; g += 32) {
+                const int col = 4 * g;
+                const uint8_t* bp = bases + read_i + (col - c0);
+                const uint8_t* qp = quals + read_i + (col - c0);
+                const unsigned b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
+                if (b0 == 0 || b1 == 0 || b2 == 0 || b3 == 0) {   // a zero base is not drawn: rare, take the slow path
+                  for (int j = 0; j < 4; ++j) put_pixel(col - c0 + j);
+                  continue;
+                }
+                const unsigned r4 = *reinterpret_cast<const unsigned*>(s_ref + col);
+                const unsigned q0 = s_qual[qp[0]], q1 = s_qual[qp[1]], q2 = s_qual[qp[2]], q3 = s_qual[qp[3]];
+                const unsigned m = P.match_color, mm = P.mismatch_color;
+                const unsigned f0 = b0 == (r4 & 0xFF) ? m : mm, f1 = b1 == ((r4 >> 8) & 0xFF) ? m : mm;
+                const unsigned f2 = b2 == ((r4 >> 16) & 0xFF) ? m : mm, f3 = b3 == (r4 >> 24) ? m : mm;
+                const unsigned c0c = s_base[b0], c1c = s_base[b1], c2c = s_base[b2], c3c = s_base[b3];
+                const unsigned lo0 = tc[0] + c0c * mb0 + q0 * mq0 + f0 * md0, hi0 = tc[1] + c0c * mb1 + q0 * mq1 + f0 * md1;
+                const unsigned lo1 = tc[0] + c1c * mb0 + q1 * mq0 + f1 * md0, hi1 = tc[1] + c1c * mb1 + q1 * mq1 + f1 * md1;
+                const unsigned lo2 = tc[0] + c2c * mb0 + q2 * mq0 + f2 * md0, hi2 = tc[1] + c2c * mb1 + q2 * mq1 + f2 * md1;
+                const unsigned lo3 = tc[0] + c3c * mb0 + q3 * mq0 + f3 * md0, hi3 = tc[1] + c3c * mb1 + q3 * mq1 + f3 * md1;
+                unsigned* w = reinterpret_cast<unsigned*>(px + 28 * g);   // 4 pixels x 7 bytes = 7 aligned words
+                w[0] = lo0;
+                w[1] = hi0 | (lo1 << 24);
+                w[2] = __funnelshift_r(lo1, hi1, 8);
+                w[3] = (hi1 >> 8) | (lo2 << 16);
+                w[4] = __funnelshift_r(lo2, hi2, 16);
+                w[5] = (hi2 >> 16) | (lo3 << 8);
+                w[6] = __funnelshift_r(lo3, hi3, 24);
+              }
+              // ragged ends: at most 3 + 3 pixels (or the whole run when it holds no whole group)
+              const int head_end = gB > gA ? 4 * gA : cB;
+              const int n_head = head_end - cA;
+              const int tail_begin = gB > gA ? 4 * gB : cB;
+              const int n_tail = cB - tail_begin;
+              for (int i = lane; i < n_head + n_tail; i += 32) put_pixel((i < n_head ? cA + i : tail_begin + (i - n_head)) - c0);
+            } else {
+              for (int j = lo + lane; j < hi; j += 32) put_pixel(j);
             }
             ref_i += len; read_i += len;
           } else if (op == 1 || op == 2) {
@@ -414,7 +476,7 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
         }
       }
       __syncwarp();
-      flush_row(dst, buf + phase, P.row_bytes, lane);
+      flush_row(dst, buf, P.row_bytes, lane);
     }
   }
 }
@@ -432,6 +494,7 @@ struct DvbEncoder {
   int num_sms = 148;
   int smem_bytes = 0;
   int grid_cap = 0;
+  bool fast7 = false;
   int* d_perm = nullptr;
   int* d_err = nullptr;
   int64_t launches = 0;
@@ -526,14 +589,17 @@ int BuildDev(const DvbPileupParams& o, EncDev* d) {
 
 int SmemBytes(const EncDev& d) {
   const int Wpad = (d.W + 15) & ~15;
-  const int rowbuf = ((d.row_bytes + 15) & ~15) + 32;
+  const int rowbuf = ((d.row_bytes + 28 + 15) & ~15) + 32;
   return 512 + Wpad + 7 * d.max_rows * 4 + (kWarps + 2) * 4 + 16 + kWarps * rowbuf;
 }
 
 int Launch(DvbEncoder* enc, const DvbBatch& b, uint8_t* out, int32_t* rows_kept, cudaStream_t stream) {
   if (b.n_images <= 0) return DVB_OK;
   int grid = std::min(b.n_images, enc->grid_cap);
-  dvb_encode_kernel<<<grid, kThreads, enc->smem_bytes, stream>>>(enc->dev, b, out, rows_kept, enc->d_err);
+  if (enc->fast7)
+    dvb_encode_kernel<true><<<grid, kThreads, enc->smem_bytes, stream>>>(enc->dev, b, out, rows_kept, enc->d_err);
+  else
+    dvb_encode_kernel<false><<<grid, kThreads, enc->smem_bytes, stream>>>(enc->dev, b, out, rows_kept, enc->d_err);
   enc->launches++;
   DVB_CUDA(cudaGetLastError());
   return DVB_OK;
@@ -616,9 +682,15 @@ int dvb_encoder_create(const DvbPileupParams* params, int device, DvbEncoder** o
     delete enc;
     return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "image row too large for shared memory (%d bytes)", enc->smem_bytes);
   }
-  DVB_CUDA(cudaFuncSetAttribute(dvb_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, enc->smem_bytes));
+  enc->fast7 = dev.C == 7 && dev.Cout == 7;
   int occ = 1;
-  DVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dvb_encode_kernel, kThreads, enc->smem_bytes));
+  if (enc->fast7) {
+    DVB_CUDA(cudaFuncSetAttribute(dvb_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc->smem_bytes));
+    DVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dvb_encode_kernel<true>, kThreads, enc->smem_bytes));
+  } else {
+    DVB_CUDA(cudaFuncSetAttribute(dvb_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc->smem_bytes));
+    DVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dvb_encode_kernel<false>, kThreads, enc->smem_bytes));
+  }
   enc->grid_cap = enc->num_sms * std::max(occ, 1);
   DVB_CUDA(cudaStreamCreateWithFlags(&enc->stream, cudaStreamNonBlocking));
   *out = enc;
