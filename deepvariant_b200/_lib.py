@@ -121,6 +121,7 @@ SYMBOLS = (
     ('dvb_cnn_destroy', None, [C.c_void_p]),
     ('dvb_cnn_forward_device', C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     ('dvb_cnn_forward_host', C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    ('dvb_encode_classify_host', C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(DvbBatch), C.c_void_p, C.c_void_p]),
     ('dvb_cnn_launch_count', C.c_int64, [C.c_void_p]),
     ('dvb_cnn_flops_per_image', C.c_double, [C.c_void_p]),
     ('dvb_crc32c', C.c_uint32, [C.c_char_p, C.c_size_t]),

@@ -32,7 +32,8 @@ class GpuCnn:
     h, w, c = [int(x) for x in image_shape]
     if c != weights.in_channels:
       raise ValueError(f'model expects {weights.in_channels} channels, images have {c}')
-    blob = modeling.pack_weights(weights)
+    blob = modeling.pack_weights(weights, precision)
+    self.precision = precision
     self.shape = (h, w, c)
     self.device = device
     self.max_batch = max_batch
@@ -44,9 +45,10 @@ class GpuCnn:
     self.flops_per_image = float(self._lib.dvb_cnn_flops_per_image(self._h))
 
   @classmethod
-  def random_init(cls, image_shape: Sequence[int], device: int = 0, max_batch: int = 2048, seed: int = 0) -> 'GpuCnn':
+  def random_init(cls, image_shape: Sequence[int], device: int = 0, max_batch: int = 2048, seed: int = 0,
+                  precision: int = 0) -> 'GpuCnn':
     """Random-init weights of the right architecture (no checkpoints ship with the reference)."""
-    return cls(modeling.random_weights(int(image_shape[2]), seed), image_shape, device, min(max_batch, 2048))
+    return cls(modeling.random_weights(int(image_shape[2]), seed), image_shape, device, min(max_batch, 2048), precision)
 
   def forward_device(self, images, probs, stream=None) -> None:
     """images: torch uint8 [n, H, W, C] on the device; probs: torch float32 [n, 3].  Asynchronous."""

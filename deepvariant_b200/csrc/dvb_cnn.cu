@@ -41,7 +41,8 @@ namespace {
 
 constexpr int kMaxStages = 8;
 constexpr int kConvThreads = 192;  // warp0 TMA, warp1 MMA, warps 2..5 epilogue
-constexpr uint32_t kBlobMagic = 0x31424E4E;
+constexpr uint32_t kBlobMagic = 0x31424E4E;    // 'NNB1': one fp16 plane per kernel
+constexpr uint32_t kBlobMagic2 = 0x32424E4E;   // 'NNB2': main + residual fp16 planes per kernel (precision 1)
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -247,6 +248,52 @@ __device__ __forceinline__ void epilogue_row(uint32_t taddr, int block_n, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// precision = 1: split-fp16 x3 ("fp32-grade" products on the fp16 tensor pipe)
+// ---------------------------------------------------------------------------------------------
+// Every fp32 value x is carried as two fp16 planes:  x = main + res * 2^-11  with  main = fp16(x),
+// res = fp16((x - main) * 2^11).  |x - main| <= 2^-11 |x|, so the scaled residual sits in the same exponent range
+// as main (no fp16 underflow for normal x) and the pair holds ~22 significant bits.  A convolution becomes three
+// tensor-core products into two TMEM accumulators,
+//     D0 += A_main * B_main            D1 += A_main * B_res + A_res * B_main            y = D0 + 2^-11 * D1
+// (fp16 x fp16 products are exact in the fp32 accumulator; the dropped A_res * B_res term is 2^-22 relative).
+constexpr float kSplitScale = 2048.f;
+constexpr float kSplitInv = 1.f / 2048.f;
+
+__device__ __forceinline__ void split_store2(float x0, float x1, uint32_t* main_pk, uint32_t* res_pk) {
+  const __half2 m = __floats2half2_rn(x0, x1);
+  const float2 mf = __half22float2(m);
+  const __half2 r = __floats2half2_rn((x0 - mf.x) * kSplitScale, (x1 - mf.y) * kSplitScale);
+  *main_pk = *reinterpret_cast<const uint32_t*>(&m);
+  *res_pk = *reinterpret_cast<const uint32_t*>(&r);
+}
+
+// Epilogue of one accumulator row in split mode: y = D0 + 2^-11 * D1 + bias -> ReLU -> (main, res) fp16 planes.
+__device__ __forceinline__ void epilogue_row_split(uint32_t taddr, int block_n, const float* s_bias, __half* dst_main, __half* dst_res,
+                                                   bool valid, int relu) {
+  for (int c = 0; c < block_n; c += 16) {
+    uint32_t v0[16], v1[16];
+    tmem_ld16(taddr + c, v0);
+    tmem_ld16(taddr + block_n + c, v1);
+    tmem_ld_wait();
+    if (!valid) continue;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      uint32_t pm[4], pr[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = g * 8 + 2 * j;
+        float x0 = __uint_as_float(v0[i]) + __uint_as_float(v1[i]) * kSplitInv + s_bias[c + i];
+        float x1 = __uint_as_float(v0[i + 1]) + __uint_as_float(v1[i + 1]) * kSplitInv + s_bias[c + i + 1];
+        if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+        split_store2(x0, x1, &pm[j], &pr[j]);
+      }
+      *reinterpret_cast<uint4*>(dst_main + c + g * 8) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
+      *reinterpret_cast<uint4*>(dst_res + c + g * 8) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Convolution = implicit GEMM
 // ---------------------------------------------------------------------------------------------
 struct ConvArgs {
@@ -261,10 +308,16 @@ struct ConvArgs {
   uint32_t a_bytes, b_bytes, a_stage, b_stage;  // TMA bytes and shared-memory footprint per stage
   __half* out;
   const float* bias;
+  // split mode (precision 1): residual planes; a_stage / b_stage then hold {main, res} tiles back to back
+  __half* out_res;
+  uint32_t a_res_off, b_res_off;
+  int skip_a_res;                 // the A residual plane is identically zero (network input): skip its load and MMA
 };
 
+template <bool kSplit>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ConvArgs p) {
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_a_res, const __grid_constant__ CUtensorMap map_b_res, const ConvArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
@@ -304,13 +357,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
+      if constexpr (kSplit) { prefetch_tmap(&map_a_res); prefetch_tmap(&map_b_res); }
       int st = 0;
       uint32_t ph = 0;
       for (int r = 0; r < p.kh; ++r) {
         for (int s = 0; s < p.kw; ++s) {
           for (int cb = 0; cb < p.cin_blocks; ++cb) {
             mbar_wait(&empty_bar[st], ph ^ 1);
-            mbar_arrive_expect_tx(&full_bar[st], p.a_bytes + p.b_bytes);
+            if constexpr (kSplit) {
+              mbar_arrive_expect_tx(&full_bar[st], (p.skip_a_res ? 1u : 2u) * p.a_bytes + 2u * p.b_bytes);
+              if (!p.skip_a_res)
+                tma_load_4d(smem_a + st * p.a_stage + p.a_res_off, &map_a_res, &full_bar[st], cb * p.block_k, w0 * p.stride + s - p.pad_w,
+                            h0 * p.stride + r - p.pad_h, n0);
+              tma_load_3d(smem_b + st * p.b_stage + p.b_res_off, &map_b_res, &full_bar[st], cb * p.block_k, r * p.kw + s, nb * p.block_n);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[st], p.a_bytes + p.b_bytes);
+            }
             tma_load_4d(smem_a + st * p.a_stage, &map_a, &full_bar[st], cb * p.block_k, w0 * p.stride + s - p.pad_w,
                         h0 * p.stride + r - p.pad_h, n0);
             tma_load_3d(smem_b + st * p.b_stage, &map_b, &full_bar[st], cb * p.block_k, r * p.kw + s, nb * p.block_n);
@@ -332,10 +394,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[st], ph);
         tc_fence_after();
+        if constexpr (kSplit) {
+          const uint32_t a_res = a_lo + (p.a_res_off >> 4), b_res = b_lo + (p.b_res_off >> 4), d1 = tmem_base + (uint32_t)p.block_n;
+          const bool with_a_res = !p.skip_a_res;
+          for (int k = 0; k < mma_per_kb; ++k) {
+            umma_f16_lohi(tmem_base, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, acc);   // D0 += A_main * B_main
+            umma_f16_lohi(d1, a_lo + 2 * k, b_res + 2 * k, hi, idesc, acc);         // D1 += A_main * B_res
+            if (with_a_res) umma_f16_lohi(d1, a_res + 2 * k, b_lo + 2 * k, hi, idesc, 1u);   // D1 += A_res * B_main
+            acc = 1;
+          }
+        } else {
 #pragma unroll 4
-        for (int k = 0; k < mma_per_kb; ++k) {
-          umma_f16_lohi(tmem_base, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, acc);
-          acc = 1;
+          for (int k = 0; k < mma_per_kb; ++k) {
+            umma_f16_lohi(tmem_base, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, acc);
+            acc = 1;
+          }
         }
         umma_commit(&empty_bar[st]);   // frees the stage once these MMAs retire
         a_lo += a_inc; b_lo += b_inc;
@@ -355,7 +428,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                   nb * p.block_n;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    epilogue_row(tmem_base + ((uint32_t)(q * 32) << 16), p.block_n, s_bias, dst, valid, p.relu);
+    if constexpr (kSplit)
+      epilogue_row_split(tmem_base + ((uint32_t)(q * 32) << 16), p.block_n, s_bias, dst, p.out_res + (dst - p.out), valid, p.relu);
+    else
+      epilogue_row(tmem_base + ((uint32_t)(q * 32) << 16), p.block_n, s_bias, dst, valid, p.relu);
   }
   tc_fence_before();
   __syncthreads();
@@ -689,8 +765,28 @@ __device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
+// split mode: value = main + res * 2^-11 (see "precision = 1"); `off` is the element offset shared by both planes
+__device__ __forceinline__ void load8s(const __half* main, const __half* res, size_t off, float (&v)[8]) {
+  load8(main + off, v);
+  if (res) {
+    float r[8];
+    load8(res + off, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += r[j] * kSplitInv;
+  }
+}
+__device__ __forceinline__ void store8s(__half* main, __half* res, size_t off, const float (&v)[8]) {
+  if (!res) { store8(main + off, v); return; }
+  uint32_t pm[4], pr[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_store2(v[2 * j], v[2 * j + 1], &pm[j], &pr[j]);
+  *reinterpret_cast<uint4*>(main + off) = make_uint4(pm[0], pm[1], pm[2], pm[3]);
+  *reinterpret_cast<uint4*>(res + off) = make_uint4(pr[0], pr[1], pr[2], pr[3]);
+}
+
 __global__ void pool3x3_kernel(const __half* __restrict__ in, __half* __restrict__ out, int n_images, int Hin, int Win, int C,
-                               int Hout, int Wout, int out_cstride, int out_coff, int mode) {
+                               int Hout, int Wout, int out_cstride, int out_coff, int mode, const __half* __restrict__ in_res,
+                               __half* __restrict__ out_res) {
   const int cvec = C / 8;
   const long long total = (long long)n_images * Hout * cvec;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -699,14 +795,15 @@ __global__ void pool3x3_kernel(const __half* __restrict__ in, __half* __restrict
   long long t = i / cvec;
   const int oh = (int)(t % Hout);
   const int n = (int)(t / Hout);
-  const __half* src = in + (size_t)n * Hin * Win * C + cv * 8;
-  __half* dst = out + ((size_t)n * Hout + oh) * Wout * out_cstride + out_coff + cv * 8;
+  const size_t src = (size_t)n * Hin * Win * C + cv * 8;
+  const size_t dst = ((size_t)n * Hout + oh) * Wout * out_cstride + out_coff + cv * 8;
   if (mode == 0) {
     // column maxima over rows 2oh..2oh+2; output ow uses columns 2ow, 2ow+1, 2ow+2
-    const __half* r0 = src + (size_t)(2 * oh) * Win * C;
+    const size_t r0 = src + (size_t)(2 * oh) * Win * C;
     float prev[8], a[8], b[8], c[8];
     auto colmax = [&](int iw, float (&m)[8]) {
-      load8(r0 + (size_t)iw * C, a); load8(r0 + ((size_t)Win + iw) * C, b); load8(r0 + ((size_t)2 * Win + iw) * C, c);
+      load8s(in, in_res, r0 + (size_t)iw * C, a); load8s(in, in_res, r0 + ((size_t)Win + iw) * C, b);
+      load8s(in, in_res, r0 + ((size_t)2 * Win + iw) * C, c);
 #pragma unroll
       for (int j = 0; j < 8; ++j) m[j] = fmaxf(a[j], fmaxf(b[j], c[j]));
     };
@@ -717,7 +814,7 @@ __global__ void pool3x3_kernel(const __half* __restrict__ in, __half* __restrict
       colmax(2 * ow + 2, m2);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { o[j] = fmaxf(prev[j], fmaxf(m1[j], m2[j])); prev[j] = m2[j]; }
-      store8(dst + (size_t)ow * out_cstride, o);
+      store8s(out, out_res, dst + (size_t)ow * out_cstride, o);
     }
   } else {
     const int h_lo = oh > 0 ? oh - 1 : 0, h_hi = oh + 1 < Hin ? oh + 1 : Hin - 1;
@@ -728,7 +825,7 @@ __global__ void pool3x3_kernel(const __half* __restrict__ in, __half* __restrict
       for (int j = 0; j < 8; ++j) m[j] = 0.f;
       if (iw < 0 || iw >= Win) return;
       for (int ih = h_lo; ih <= h_hi; ++ih) {
-        load8(src + ((size_t)ih * Win + iw) * C, v);
+        load8s(in, in_res, src + ((size_t)ih * Win + iw) * C, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) m[j] += v[j];
       }
@@ -742,21 +839,28 @@ __global__ void pool3x3_kernel(const __half* __restrict__ in, __half* __restrict
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) { o[j] = (s0[j] + s1[j] + s2[j]) * inv; s0[j] = s1[j]; s1[j] = s2[j]; }
-      store8(dst + (size_t)ow * out_cstride, o);
+      store8s(out, out_res, dst + (size_t)ow * out_cstride, o);
     }
   }
 }
 
 // GlobalAveragePooling2D + Dense(3) + softmax, fp32.  One block per image.
 __global__ void __launch_bounds__(256) tail_kernel(const __half* __restrict__ feat, int hw, int C, const float* __restrict__ dense_w,
-                                                   const float* __restrict__ dense_b, float* __restrict__ probs, float* __restrict__ pooled_out) {
+                                                   const float* __restrict__ dense_b, float* __restrict__ probs, float* __restrict__ pooled_out,
+                                                   const __half* __restrict__ feat_res) {
   const int n = blockIdx.x;
   const __half* f = feat + (size_t)n * hw * C;
+  const __half* fr = feat_res ? feat_res + (size_t)n * hw * C : nullptr;
   float l0 = 0.f, l1 = 0.f, l2 = 0.f;
   const float inv = 1.f / (float)hw;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
     for (int p = 0; p < hw; ++p) s += __half2float(f[(size_t)p * C + c]);
+    if (fr) {
+      float sr = 0.f;
+      for (int p = 0; p < hw; ++p) sr += __half2float(fr[(size_t)p * C + c]);
+      s += sr * kSplitInv;
+    }
     s *= inv;
     if (pooled_out) pooled_out[(size_t)n * C + c] = s;
     l0 += s * dense_w[c * 3 + 0];
@@ -788,9 +892,9 @@ __global__ void __launch_bounds__(256) tail_kernel(const __half* __restrict__ fe
   }
 }
 
-__global__ void half_to_float_kernel(const __half* __restrict__ in, float* __restrict__ out, long long n) {
+__global__ void half_to_float_kernel(const __half* __restrict__ in, const __half* __restrict__ in_res, float* __restrict__ out, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = __half2float(in[i]);
+  if (i < n) out[i] = __half2float(in[i]) + (in_res ? __half2float(in_res[i]) * kSplitInv : 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -817,6 +921,7 @@ struct TensorBuf {
   std::string name;
   int H = 0, W = 0, C = 0;   // C = stored channels (padded for the input)
   __half* ptr = nullptr;
+  __half* ptr_res = nullptr;   // residual plane (precision 1), else null
 };
 
 struct OpDesc {
@@ -915,7 +1020,7 @@ void BuildGraph(int in_channels, std::vector<OpDesc>* ops, std::map<std::string,
 }
 
 struct ConvLaunch {
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_a_res, map_b_res;
   ConvArgs args;
   dim3 grid;
   int smem;
@@ -932,6 +1037,7 @@ struct HaloLaunch {
 struct PoolLaunch {
   const __half* in; __half* out;
   int Hin, Win, C, Hout, Wout, out_cstride, out_coff, mode;
+  const __half* in_res; __half* out_res;
 };
 struct Step { int kind; int index; };  // 0 conv, 1 pool, 2 halo conv
 
@@ -961,19 +1067,31 @@ namespace {
 
 struct TileChoice { int Wt, Ht, Nt; };
 
+int EnvInt(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+
+// The M tile is ANY box of Wt x Ht x Nt output pixels (row = (n * Ht + h) * Wt + w): batching images into the tile is
+// not limited to whole feature maps, e.g. the 4x12 maps of mixed3..7 tile as 4 x 4 x 8 = 128 rows (100 % full; a
+// whole-map tile would be 12 x 4 x 2 = 96 rows = 75 %).
 TileChoice ChooseTile(int Hout, int Wout, int stride) {
   TileChoice best{1, 1, 1};
   double best_eff = -1;
   const int max_box = 256 / stride;  // boxDim <= 256 in input space
+  const bool batch_any = EnvInt("DVB_CNN_TILE_ANY_N", 1) != 0;
   for (int Wt = 1; Wt <= std::min(std::min(Wout, 128), max_box); ++Wt) {
     for (int Ht = 1; Ht <= std::min(std::min(Hout, 128 / Wt), max_box); ++Ht) {
-      int Nt = 1;
-      if (Wt == Wout && Ht == Hout) Nt = std::max(1, 128 / (Wt * Ht));
-      const long tiles = (long)((Wout + Wt - 1) / Wt) * ((Hout + Ht - 1) / Ht);
-      const double eff = (double)Wout * Hout * Nt / ((double)tiles * 128.0);
-      if (eff > best_eff + 1e-9 || (std::fabs(eff - best_eff) <= 1e-9 && Wt > best.Wt)) {
-        best_eff = eff;
-        best = {Wt, Ht, Nt};
+      const int nt_max = (batch_any || (Wt == Wout && Ht == Hout)) ? std::max(1, 128 / (Wt * Ht)) : 1;
+      for (int Nt = 1; Nt <= nt_max; ++Nt) {
+        const long tiles = (long)((Wout + Wt - 1) / Wt) * ((Hout + Ht - 1) / Ht);
+        const double eff = (double)Wout * Hout * Nt / ((double)tiles * 128.0);
+        // ties: wider rows first (longer contiguous TMA runs), then fewer images per tile
+        if (eff > best_eff + 1e-9 || (std::fabs(eff - best_eff) <= 1e-9 && (Wt > best.Wt || (Wt == best.Wt && Nt < best.Nt)))) {
+          best_eff = eff;
+          best = {Wt, Ht, Nt};
+        }
       }
     }
   }
@@ -988,11 +1106,6 @@ int ChooseBlockN(int cout) {
 }
 
 int TmemCols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
-
-int EnvInt(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
 
 int MakeMap(CUtensorMap* m, void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
             const cuuint32_t* estr, int block_k) {
@@ -1012,7 +1125,11 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
   // --- header
   if (blob_bytes < 12) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob too small");
   const int32_t* hdr = reinterpret_cast<const int32_t*>(blob);
-  if ((uint32_t)hdr[0] != kBlobMagic) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob: bad magic");
+  if ((uint32_t)hdr[0] != kBlobMagic && (uint32_t)hdr[0] != kBlobMagic2) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob: bad magic");
+  const bool blob_split = (uint32_t)hdr[0] == kBlobMagic2;
+  const bool split = net->precision == 1;
+  if (split && !blob_split)
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "precision 1 needs a weights blob with residual planes (modeling.pack_weights(w, precision=1))");
   if (hdr[1] != net->C) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob is for %d input channels, not %d", hdr[1], net->C);
   int n_conv = 0;
   for (auto& o : ops) n_conv += o.kind == 0;
@@ -1032,6 +1149,13 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
     cudaMemset(p, 0, bytes);
     net->allocs.push_back(p);
     t.ptr = static_cast<__half*>(p);
+    if (split) {
+      void* q = nullptr;
+      if (cudaMalloc(&q, bytes) != cudaSuccess) return dvb::fail(DVB_ERR_CUDA, "cudaMalloc of %zu bytes for tensor %s (residual plane) failed", bytes, name.c_str());
+      cudaMemset(q, 0, bytes);
+      net->allocs.push_back(q);
+      t.ptr_res = static_cast<__half*>(q);
+    }
     net->tensor_index[name] = (int)net->tensors.size();
     net->tensors.push_back(t);
     return DVB_OK;
@@ -1066,7 +1190,7 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
     const TensorBuf& src = net->tensors[net->tensor_index[o.src]];
     const TensorBuf& dst = net->tensors[net->tensor_index[o.dst]];
     if (o.kind != 0) {
-      PoolLaunch pl{src.ptr, dst.ptr, Hin, Win, src.C, Hout, Wout, dst.C, o.off, o.kind == 1 ? 0 : 1};
+      PoolLaunch pl{src.ptr, dst.ptr, Hin, Win, src.C, Hout, Wout, dst.C, o.off, o.kind == 1 ? 0 : 1, src.ptr_res, dst.ptr_res};
       net->steps.push_back({1, (int)net->pools.size()});
       net->pools.push_back(pl);
       continue;
@@ -1083,26 +1207,36 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
     const size_t blob_wbytes = (size_t)o.cout * orig.kh * orig.kw * blob_cin * sizeof(__half);
     const size_t wbytes = (size_t)o.cout * o.kh * o.kw * cin_store * sizeof(__half);
     const size_t bbytes = (size_t)o.cout * sizeof(float);
-    if (pos + (int64_t)(blob_wbytes + bbytes) > blob_bytes) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob truncated");
-    void* dw = nullptr; void* db = nullptr;
+    const size_t blob_planes = blob_split ? 2 : 1;
+    if (pos + (int64_t)(blob_planes * blob_wbytes + bbytes) > blob_bytes) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob truncated");
+    void* dw = nullptr; void* db = nullptr; void* dw_res = nullptr;
     if (cudaMalloc(&dw, wbytes) != cudaSuccess || cudaMalloc(&db, bbytes) != cudaSuccess) return dvb::fail(DVB_ERR_CUDA, "cudaMalloc (weights) failed");
     net->allocs.push_back(dw); net->allocs.push_back(db);
-    if (is_stem) {
-      // [cout][3][3][blob_cin] -> [cout][Kp], k = (r*3 + s)*C + c (the patch order of stem_patch_kernel)
-      std::vector<__half> w2((size_t)o.cout * cin_store, __float2half(0.f));
-      const __half* w = reinterpret_cast<const __half*>(blob + pos);
-      for (int co = 0; co < o.cout; ++co)
-        for (int t = 0; t < 9; ++t)
-          for (int c = 0; c < net->C; ++c) w2[(size_t)co * cin_store + t * net->C + c] = w[((size_t)co * 9 + t) * blob_cin + c];
-      cudaMemcpy(dw, w2.data(), wbytes, cudaMemcpyHostToDevice);
-    } else {
-      cudaMemcpy(dw, blob + pos, wbytes, cudaMemcpyHostToDevice);
+    if (split) {
+      if (cudaMalloc(&dw_res, wbytes) != cudaSuccess) return dvb::fail(DVB_ERR_CUDA, "cudaMalloc (weights) failed");
+      net->allocs.push_back(dw_res);
     }
-    cudaMemcpy(db, blob + pos + blob_wbytes, bbytes, cudaMemcpyHostToDevice);
-    pos += blob_wbytes + bbytes;
+    for (int plane = 0; plane < (split ? 2 : 1); ++plane) {
+      const uint8_t* wsrc = blob + pos + (size_t)plane * blob_wbytes;
+      void* wdst = plane ? dw_res : dw;
+      if (is_stem) {
+        // [cout][3][3][blob_cin] -> [cout][Kp], k = (r*3 + s)*C + c (the patch order of stem_patch_kernel)
+        std::vector<__half> w2((size_t)o.cout * cin_store, __float2half(0.f));
+        const __half* w = reinterpret_cast<const __half*>(wsrc);
+        for (int co = 0; co < o.cout; ++co)
+          for (int t = 0; t < 9; ++t)
+            for (int c = 0; c < net->C; ++c) w2[(size_t)co * cin_store + t * net->C + c] = w[((size_t)co * 9 + t) * blob_cin + c];
+        cudaMemcpy(wdst, w2.data(), wbytes, cudaMemcpyHostToDevice);
+      } else {
+        cudaMemcpy(wdst, wsrc, wbytes, cudaMemcpyHostToDevice);
+      }
+    }
+    cudaMemcpy(db, blob + pos + blob_planes * blob_wbytes, bbytes, cudaMemcpyHostToDevice);
+    const uint8_t* blob_w_main = blob + pos;
+    pos += blob_planes * blob_wbytes + bbytes;
 
     // ---- large stride-1 k x k layers: persistent halo-reusing kernel (see conv_halo_kernel)
-    if (!is_stem && o.stride == 1 && o.kh * o.kw > 1 && Hout * Wout >= 1000 && EnvInt("DVB_CNN_HALO", 1)) {
+    if (!split && !is_stem && o.stride == 1 && o.kh * o.kw > 1 && Hout * Wout >= 1000 && EnvInt("DVB_CNN_HALO", 1)) {
       HaloLaunch hl;
       memset(&hl, 0, sizeof(hl));
       HaloArgs& a = hl.args;
@@ -1169,7 +1303,7 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       if (a.tmem_cols <= 512 && hl.smem <= 227 * 1024 && a.stages >= a.T && a.T >= 4 && a.nbuf == 2 && a.n_blocks == 1) {
         // weights [Cout][taps][Cin] -> [taps][Cout][Cin] so that one (tap, N block, Cin block) is a canonical K-major tile
         std::vector<__half> w2((size_t)taps * o.cout * cin_store);
-        const __half* w = reinterpret_cast<const __half*>(blob + pos - blob_wbytes - bbytes);
+        const __half* w = reinterpret_cast<const __half*>(blob_w_main);
         for (int co = 0; co < o.cout; ++co)
           for (int t = 0; t < taps; ++t)
             memcpy(&w2[((size_t)t * o.cout + co) * cin_store], &w[((size_t)co * taps + t) * cin_store], (size_t)cin_store * sizeof(__half));
@@ -1223,6 +1357,12 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       const long m_tiles = flat ? ((long)net->max_batch * Hout * Wout + 127) / 128
                                 : (long)a.tiles_w * a.tiles_h * ((net->max_batch + tc.Nt - 1) / tc.Nt);
       int bn = ChooseBlockN(o.cout);
+      if (split && bn > 128) {   // two accumulators + {main, res} operand tiles per stage: keep N <= 128
+        int best = 16;
+        for (int d = 128; d >= 16; d -= 16)
+          if (o.cout % d == 0) { best = d; break; }
+        bn = best;
+      }
       const long want_ctas = 4L * net->num_sms;
       while (m_tiles * (o.cout / bn) < want_ctas && bn > 64) {
         int next = 0;
@@ -1233,8 +1373,10 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       }
       a.block_n = bn;
     }
-    a.tmem_cols = TmemCols(a.block_n);
+    a.tmem_cols = TmemCols(split ? 2 * a.block_n : a.block_n);
     a.out = dst.ptr; a.out_cstride = dst.C; a.out_coff = o.off; a.relu = 1;
+    a.out_res = dst.ptr_res;
+    a.skip_a_res = is_stem ? 1 : 0;   // the preprocessed input is exact in fp16: its residual plane is zero
     a.bias = static_cast<const float*>(db);
     // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=F32, A=B=F16, K-major, M=128
     a.idesc = (1u << 4) | ((uint32_t)(a.block_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -1245,12 +1387,13 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
     a.b_bytes = (uint32_t)a.block_n * bk * 2;
     a.a_stage = 128u * bk * 2;
     a.b_stage = ((uint32_t)a.block_n * bk * 2 + 1023u) & ~1023u;
+    if (split) { a.a_res_off = a.a_stage; a.b_res_off = a.b_stage; a.a_stage *= 2; a.b_stage *= 2; }
     // Pipeline depth: as deep as fits in ~108 KB so that two CTAs (one in its epilogue, one issuing MMAs) share an SM.
     {
       const int stage_bytes = (int)(a.a_stage + a.b_stage);
       const int num_kb = o.kh * o.kw * a.cin_blocks;
       // Occupancy beats pipeline depth here (measured): aim for ~4 co-resident CTAs of 2-4 stages each.
-      const int target_kb = EnvInt("DVB_CNN_SMEM_KB", 72);
+      const int target_kb = split ? 200 : EnvInt("DVB_CNN_SMEM_KB", 72);
       const int max_stages = std::min(EnvInt("DVB_CNN_MAX_STAGES", 3), kMaxStages);
       int stages = (target_kb * 1024 - 1280) / stage_bytes;
       stages = std::max(2, std::min(stages, max_stages));
@@ -1276,6 +1419,11 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       const cuuint32_t estr[4] = {1, (cuuint32_t)o.stride, (cuuint32_t)o.stride, 1};
       st = MakeMap(&cl.map_a, src.ptr, 4, dims, strides, box, estr, bk);
       if (st) return st;
+      cl.map_a_res = cl.map_a;
+      if (split) {
+        st = MakeMap(&cl.map_a_res, src.ptr_res, 4, dims, strides, box, estr, bk);
+        if (st) return st;
+      }
     }
     {
       const cuuint64_t dims[3] = {(cuuint64_t)cin_store, (cuuint64_t)(o.kh * o.kw), (cuuint64_t)o.cout};
@@ -1284,6 +1432,11 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       const cuuint32_t estr[3] = {1, 1, 1};
       st = MakeMap(&cl.map_b, dw, 3, dims, strides, box, estr, bk);
       if (st) return st;
+      cl.map_b_res = cl.map_b;
+      if (split) {
+        st = MakeMap(&cl.map_b_res, dw_res, 3, dims, strides, box, estr, bk);
+        if (st) return st;
+      }
     }
     cl.grid = dim3(1, (unsigned)(o.cout / a.block_n), 1);
     net->steps.push_back({0, (int)net->convs.size()});
@@ -1301,7 +1454,8 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
   net->flops_per_image = 2.0 * macs_total;
   int max_smem = 0;
   for (auto& c : net->convs) max_smem = std::max(max_smem, c.smem);
-  if (cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess)
+  if ((split ? cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)
+             : cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess)
     return dvb::fail(DVB_ERR_CUDA, "cannot reserve %d bytes of shared memory", max_smem);
   int max_halo = 0;
   for (auto& h : net->halos) max_halo = std::max(max_halo, h.smem);
@@ -1362,17 +1516,20 @@ int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaSt
         a.tiles_w = (a.Wout + 127) / 128; a.tiles_h = 1; a.tiles_n = 1;
       }
       dim3 grid((unsigned)(a.tiles_w * a.tiles_h * a.tiles_n), c.grid.y, 1);
-      conv_gemm_kernel<<<grid, kConvThreads, c.smem, s>>>(c.map_a, c.map_b, a);
+      if (net->precision == 1)
+        conv_gemm_kernel<true><<<grid, kConvThreads, c.smem, s>>>(c.map_a, c.map_b, c.map_a_res, c.map_b_res, a);
+      else
+        conv_gemm_kernel<false><<<grid, kConvThreads, c.smem, s>>>(c.map_a, c.map_b, c.map_a_res, c.map_b_res, a);
     } else {
       const PoolLaunch& p = net->pools[stp.index];
       const long long total = (long long)n * p.Hout * (p.C / 8);
       pool3x3_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(p.in, p.out, n, p.Hin, p.Win, p.C, p.Hout, p.Wout, p.out_cstride,
-                                                                      p.out_coff, p.mode);
+                                                                      p.out_coff, p.mode, p.in_res, p.out_res);
     }
     net->launches++;
   }
   const TensorBuf& f = net->tensors[net->feat_tensor];
-  tail_kernel<<<n, 256, 0, s>>>(f.ptr, f.H * f.W, f.C, net->d_dense_w, net->d_dense_b, probs, net->d_pooled);
+  tail_kernel<<<n, 256, 0, s>>>(f.ptr, f.H * f.W, f.C, net->d_dense_w, net->d_dense_b, probs, net->d_pooled, f.ptr_res);
   net->launches++;
   DVB_CUDA(cudaGetLastError());
   return DVB_OK;
@@ -1387,7 +1544,8 @@ int dvb_cnn_create(const void* weights, int64_t weights_bytes, int32_t height, i
   if (!weights || !out || height < 1 || width < 1 || channels < 1 || channels > 16 || max_batch < 1)
     return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_cnn_create: bad arguments");
   *out = nullptr;
-  if (precision != 0) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "precision %d is not implemented (0 = fp16 operands / fp32 accumulate)", precision);
+  if (precision != 0 && precision != 1)
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "precision %d is unknown (0 = fp16 operands / fp32 accumulate, 1 = split-fp16 x3)", precision);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return dvb::fail(DVB_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)");
   if (device < 0 || device >= ndev) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "device %d out of range", device);
@@ -1468,7 +1626,7 @@ int dvb_cnn_debug_tensor(DvbCnn* net, const char* name, int32_t n, float* out_ho
   const long long cnt = (long long)n * t.H * t.W * t.C;
   float* tmp = nullptr;
   DVB_CUDA(cudaMalloc(&tmp, cnt * sizeof(float)));
-  half_to_float_kernel<<<(unsigned)((cnt + 255) / 256), 256>>>(t.ptr, tmp, cnt);
+  half_to_float_kernel<<<(unsigned)((cnt + 255) / 256), 256>>>(t.ptr, t.ptr_res, tmp, cnt);
   cudaError_t e = cudaMemcpy(out_host, tmp, cnt * sizeof(float), cudaMemcpyDeviceToHost);
   cudaFree(tmp);
   if (e != cudaSuccess) return dvb::fail(DVB_ERR_CUDA, "debug copy failed: %s", cudaGetErrorString(e));

@@ -605,6 +605,108 @@ int Launch(DvbEncoder* enc, const DvbBatch& b, uint8_t* out, int32_t* rows_kept,
   return DVB_OK;
 }
 
+// Validates a host batch (what the reference leaves to CHECKs / UB), packs every input array into one pinned staging
+// block and issues ONE H2D copy on `s`; *db receives the same batch with device pointers.
+int StageHostBatch(DvbEncoder* enc, const DvbBatch* hb, DvbBatch* out_db, cudaStream_t s) {
+  const int64_t NI = hb->n_images, NR = hb->n_reads, NP = hb->n_pairs, NB = hb->n_bases, NC = hb->n_cigar;
+  // ---- validation the reference leaves to CHECKs / UB ----
+  if (hb->pair_begin[0] != 0 || hb->pair_begin[NI] != NP) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "pair_begin is not a CSR over n_pairs");
+  for (int64_t i = 0; i < NI; ++i)
+    if (hb->pair_begin[i + 1] < hb->pair_begin[i]) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "pair_begin not monotone");
+  for (int64_t p = 0; p < NP; ++p)
+    if (hb->pair_read[p] < 0 || hb->pair_read[p] >= NR) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "pair_read out of range");
+  if (NR > 0 && (hb->read_seq_begin[NR] != NB || hb->read_cigar_begin[NR] != NC))
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "read_seq_begin / read_cigar_begin do not end at n_bases / n_cigar");
+  for (int64_t r = 0; r < NR; ++r) {
+    int64_t consumed = 0;
+    for (int64_t k = hb->read_cigar_begin[r]; k < hb->read_cigar_begin[r + 1]; ++k) {
+      const unsigned op = hb->cigar[k] & 0xF;
+      if (op > 8) return dvb::fail(DVB_ERR_BAD_CIGAR, "Unrecognized CIGAR op");
+      if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) consumed += hb->cigar[k] >> 4;
+    }
+    if (consumed > hb->read_seq_begin[r + 1] - hb->read_seq_begin[r])
+      return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "read %lld: CIGAR consumes %lld bases, sequence has %lld", (long long)r,
+                       (long long)consumed, (long long)(hb->read_seq_begin[r + 1] - hb->read_seq_begin[r]));
+  }
+  // ---- pack every input array into one pinned staging block, one H2D copy ----
+  struct Seg { const void* src; size_t bytes; size_t off; };
+  Seg segs[19];
+  int ns = 0;
+  size_t total = 0;
+  auto add = [&](const void* p, size_t bytes) {
+    segs[ns].src = p; segs[ns].bytes = p ? bytes : 0; segs[ns].off = total;
+    total += (segs[ns].bytes + 255) & ~(size_t)255;
+    return ns++;
+  };
+  const int i_ref = add(hb->ref_bases, (size_t)NI * hb->ref_stride);
+  const int i_isp = add(hb->image_start_pos, NI * 4);
+  const int i_vs = add(hb->variant_start, NI * 4);
+  const int i_pb = add(hb->pair_begin, (NI + 1) * 8);
+  const int i_pr = add(hb->pair_read, NP * 4);
+  const int i_ps = add(hb->pair_support, NP);
+  const int i_pg = add(hb->pair_allele_group, NP);
+  const int i_rp = add(hb->read_pos, NR * 4);
+  const int i_rsp = add(hb->read_sort_pos, NR * 4);
+  const int i_rmq = add(hb->read_mapq, NR * 4);
+  const int i_rfl = add(hb->read_flags, NR);
+  const int i_rfr = add(hb->read_fragment_length, NR * 4);
+  const int i_rhp = add(hb->read_hp, NR * 4);
+  const int i_rnr = add(hb->read_name_rank, NR * 4);
+  const int i_rsb = add(hb->read_seq_begin, (NR + 1) * 8);
+  const int i_rcb = add(hb->read_cigar_begin, (NR + 1) * 8);
+  const int i_ba = add(hb->bases, NB);
+  const int i_qu = add(hb->quals, NB);
+  const int i_ci = add(hb->cigar, NC * 4);
+  total = std::max<size_t>(total, 256);
+  DVB_CUDA(enc->h_in.reserve(total));
+  DVB_CUDA(enc->d_in.reserve(total));
+  // Arrays the caller already keeps in page-locked memory go to the device straight from where they lie; pageable
+  // ones are packed into the pinned staging block first (contiguous pageable runs share one copy).
+  {
+    size_t run_begin = 0, run_end = 0;   // pending staged byte range [run_begin, run_end)
+    auto flush = [&]() -> cudaError_t {
+      if (run_end <= run_begin) return cudaSuccess;
+      cudaError_t e = cudaMemcpyAsync(static_cast<char*>(enc->d_in.p) + run_begin, static_cast<char*>(enc->h_in.p) + run_begin,
+                                      run_end - run_begin, cudaMemcpyHostToDevice, s);
+      run_begin = run_end;
+      return e;
+    };
+    for (int i = 0; i < ns; ++i) {
+      if (!segs[i].bytes) continue;
+      cudaPointerAttributes attr;
+      const bool pinned = segs[i].bytes >= (64u << 10) && cudaPointerGetAttributes(&attr, segs[i].src) == cudaSuccess &&
+                          attr.type == cudaMemoryTypeHost;
+      if (pinned) {
+        DVB_CUDA(flush());
+        DVB_CUDA(cudaMemcpyAsync(static_cast<char*>(enc->d_in.p) + segs[i].off, segs[i].src, segs[i].bytes, cudaMemcpyHostToDevice, s));
+        run_begin = run_end = segs[i].off + ((segs[i].bytes + 255) & ~(size_t)255);
+      } else {
+        if (run_end <= run_begin) run_begin = segs[i].off;
+        memcpy(static_cast<char*>(enc->h_in.p) + segs[i].off, segs[i].src, segs[i].bytes);
+        run_end = segs[i].off + segs[i].bytes;
+      }
+    }
+    DVB_CUDA(flush());
+    cudaGetLastError();   // cudaPointerGetAttributes on plain malloc memory may leave a sticky-free error on old drivers
+  }
+  DvbBatch db = *hb;
+  char* base = static_cast<char*>(enc->d_in.p);
+  auto dp = [&](int i) -> const void* { return segs[i].bytes || segs[i].src ? base + segs[i].off : nullptr; };
+  db.ref_bases = (const uint8_t*)dp(i_ref); db.image_start_pos = (const int32_t*)dp(i_isp);
+  db.variant_start = (const int32_t*)dp(i_vs); db.pair_begin = (const int64_t*)dp(i_pb);
+  db.pair_read = (const int32_t*)dp(i_pr); db.pair_support = (const uint8_t*)dp(i_ps);
+  db.pair_allele_group = hb->pair_allele_group ? (const uint8_t*)dp(i_pg) : nullptr;
+  db.read_pos = (const int32_t*)dp(i_rp); db.read_sort_pos = (const int32_t*)dp(i_rsp);
+  db.read_mapq = (const int32_t*)dp(i_rmq); db.read_flags = (const uint8_t*)dp(i_rfl);
+  db.read_fragment_length = (const int32_t*)dp(i_rfr); db.read_hp = (const int32_t*)dp(i_rhp);
+  db.read_name_rank = (const uint32_t*)dp(i_rnr); db.read_seq_begin = (const int64_t*)dp(i_rsb);
+  db.read_cigar_begin = (const int64_t*)dp(i_rcb); db.bases = (const uint8_t*)dp(i_ba);
+  db.quals = (const uint8_t*)dp(i_qu); db.cigar = (const uint32_t*)dp(i_ci);
+
+  *out_db = db;
+  return DVB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -738,81 +840,16 @@ int dvb_encode_batch_host(DvbEncoder* enc, const DvbBatch* hb, uint8_t* out_host
   if (hb->n_images == 0) return DVB_OK;
   if (hb->ref_stride < enc->dev.W) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "ref_stride < width");
   DVB_CUDA(cudaSetDevice(enc->device));
-  const int64_t NI = hb->n_images, NR = hb->n_reads, NP = hb->n_pairs, NB = hb->n_bases, NC = hb->n_cigar;
-  // ---- validation the reference leaves to CHECKs / UB ----
-  if (hb->pair_begin[0] != 0 || hb->pair_begin[NI] != NP) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "pair_begin is not a CSR over n_pairs");
-  for (int64_t i = 0; i < NI; ++i)
-    if (hb->pair_begin[i + 1] < hb->pair_begin[i]) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "pair_begin not monotone");
-  for (int64_t p = 0; p < NP; ++p)
-    if (hb->pair_read[p] < 0 || hb->pair_read[p] >= NR) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "pair_read out of range");
-  if (NR > 0 && (hb->read_seq_begin[NR] != NB || hb->read_cigar_begin[NR] != NC))
-    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "read_seq_begin / read_cigar_begin do not end at n_bases / n_cigar");
-  for (int64_t r = 0; r < NR; ++r) {
-    int64_t consumed = 0;
-    for (int64_t k = hb->read_cigar_begin[r]; k < hb->read_cigar_begin[r + 1]; ++k) {
-      const unsigned op = hb->cigar[k] & 0xF;
-      if (op > 8) return dvb::fail(DVB_ERR_BAD_CIGAR, "Unrecognized CIGAR op");
-      if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) consumed += hb->cigar[k] >> 4;
-    }
-    if (consumed > hb->read_seq_begin[r + 1] - hb->read_seq_begin[r])
-      return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "read %lld: CIGAR consumes %lld bases, sequence has %lld", (long long)r,
-                       (long long)consumed, (long long)(hb->read_seq_begin[r + 1] - hb->read_seq_begin[r]));
-  }
-  // ---- pack every input array into one pinned staging block, one H2D copy ----
-  struct Seg { const void* src; size_t bytes; size_t off; };
-  Seg segs[19];
-  int ns = 0;
-  size_t total = 0;
-  auto add = [&](const void* p, size_t bytes) {
-    segs[ns].src = p; segs[ns].bytes = p ? bytes : 0; segs[ns].off = total;
-    total += (segs[ns].bytes + 255) & ~(size_t)255;
-    return ns++;
-  };
-  const int i_ref = add(hb->ref_bases, (size_t)NI * hb->ref_stride);
-  const int i_isp = add(hb->image_start_pos, NI * 4);
-  const int i_vs = add(hb->variant_start, NI * 4);
-  const int i_pb = add(hb->pair_begin, (NI + 1) * 8);
-  const int i_pr = add(hb->pair_read, NP * 4);
-  const int i_ps = add(hb->pair_support, NP);
-  const int i_pg = add(hb->pair_allele_group, NP);
-  const int i_rp = add(hb->read_pos, NR * 4);
-  const int i_rsp = add(hb->read_sort_pos, NR * 4);
-  const int i_rmq = add(hb->read_mapq, NR * 4);
-  const int i_rfl = add(hb->read_flags, NR);
-  const int i_rfr = add(hb->read_fragment_length, NR * 4);
-  const int i_rhp = add(hb->read_hp, NR * 4);
-  const int i_rnr = add(hb->read_name_rank, NR * 4);
-  const int i_rsb = add(hb->read_seq_begin, (NR + 1) * 8);
-  const int i_rcb = add(hb->read_cigar_begin, (NR + 1) * 8);
-  const int i_ba = add(hb->bases, NB);
-  const int i_qu = add(hb->quals, NB);
-  const int i_ci = add(hb->cigar, NC * 4);
-  total = std::max<size_t>(total, 256);
-  DVB_CUDA(enc->h_in.reserve(total));
-  DVB_CUDA(enc->d_in.reserve(total));
-  for (int i = 0; i < ns; ++i)
-    if (segs[i].bytes) memcpy(static_cast<char*>(enc->h_in.p) + segs[i].off, segs[i].src, segs[i].bytes);
   cudaStream_t s = enc->stream;
-  DVB_CUDA(cudaMemcpyAsync(enc->d_in.p, enc->h_in.p, total, cudaMemcpyHostToDevice, s));
-  DvbBatch db = *hb;
-  char* base = static_cast<char*>(enc->d_in.p);
-  auto dp = [&](int i) -> const void* { return segs[i].bytes || segs[i].src ? base + segs[i].off : nullptr; };
-  db.ref_bases = (const uint8_t*)dp(i_ref); db.image_start_pos = (const int32_t*)dp(i_isp);
-  db.variant_start = (const int32_t*)dp(i_vs); db.pair_begin = (const int64_t*)dp(i_pb);
-  db.pair_read = (const int32_t*)dp(i_pr); db.pair_support = (const uint8_t*)dp(i_ps);
-  db.pair_allele_group = hb->pair_allele_group ? (const uint8_t*)dp(i_pg) : nullptr;
-  db.read_pos = (const int32_t*)dp(i_rp); db.read_sort_pos = (const int32_t*)dp(i_rsp);
-  db.read_mapq = (const int32_t*)dp(i_rmq); db.read_flags = (const uint8_t*)dp(i_rfl);
-  db.read_fragment_length = (const int32_t*)dp(i_rfr); db.read_hp = (const int32_t*)dp(i_rhp);
-  db.read_name_rank = (const uint32_t*)dp(i_rnr); db.read_seq_begin = (const int64_t*)dp(i_rsb);
-  db.read_cigar_begin = (const int64_t*)dp(i_rcb); db.bases = (const uint8_t*)dp(i_ba);
-  db.quals = (const uint8_t*)dp(i_qu); db.cigar = (const uint32_t*)dp(i_ci);
-
+  DvbBatch db;
+  int st = StageHostBatch(enc, hb, &db, s);
+  if (st) return st;
+  const int64_t NI = hb->n_images;
   const size_t out_bytes = (size_t)NI * enc->dev.image_bytes;
   DVB_CUDA(enc->d_out.reserve(out_bytes));
   DVB_CUDA(enc->d_rows.reserve(NI * 4));
   DVB_CUDA(enc->h_out.reserve(out_bytes + NI * 4));
-  int st = Launch(enc, db, static_cast<uint8_t*>(enc->d_out.p), static_cast<int32_t*>(enc->d_rows.p), s);
+  st = Launch(enc, db, static_cast<uint8_t*>(enc->d_out.p), static_cast<int32_t*>(enc->d_rows.p), s);
   if (st) return st;
   DVB_CUDA(cudaMemcpyAsync(enc->h_out.p, enc->d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
   DVB_CUDA(cudaMemcpyAsync(static_cast<char*>(enc->h_out.p) + out_bytes, enc->d_rows.p, NI * 4, cudaMemcpyDeviceToHost, s));
@@ -820,6 +857,36 @@ int dvb_encode_batch_host(DvbEncoder* enc, const DvbBatch* hb, uint8_t* out_host
   if (st) return st;
   memcpy(out_host, enc->h_out.p, out_bytes);
   if (rows_kept_host) memcpy(rows_kept_host, static_cast<char*>(enc->h_out.p) + out_bytes, NI * 4);
+  return DVB_OK;
+}
+
+
+int dvb_encode_classify_host(DvbEncoder* enc, DvbCnn* cnn, const DvbBatch* hb, float* probs_host, int32_t* rows_kept_host) {
+  if (!enc || !cnn || !hb || (!probs_host && hb->n_images > 0)) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "null argument");
+  if (hb->n_images == 0) return DVB_OK;
+  if (hb->ref_stride < enc->dev.W) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "ref_stride < width");
+  DVB_CUDA(cudaSetDevice(enc->device));
+  cudaStream_t s = enc->stream;
+  DvbBatch db;
+  int st = StageHostBatch(enc, hb, &db, s);
+  if (st) return st;
+  const int64_t NI = hb->n_images;
+  const size_t out_bytes = (size_t)NI * enc->dev.image_bytes;
+  DVB_CUDA(enc->d_out.reserve(out_bytes));
+  DVB_CUDA(enc->d_rows.reserve(NI * 4 + NI * 3 * sizeof(float)));
+  DVB_CUDA(enc->h_out.reserve(NI * 4 + NI * 3 * sizeof(float)));
+  int32_t* d_rows = static_cast<int32_t*>(enc->d_rows.p);
+  float* d_probs = reinterpret_cast<float*>(d_rows + NI);
+  st = Launch(enc, db, static_cast<uint8_t*>(enc->d_out.p), d_rows, s);
+  if (st) return st;
+  // the images never leave HBM: the classifier consumes the encoder's output in place, on the same stream
+  st = dvb_cnn_forward_device(cnn, static_cast<const uint8_t*>(enc->d_out.p), (int32_t)NI, d_probs, s);
+  if (st) return st;
+  DVB_CUDA(cudaMemcpyAsync(enc->h_out.p, d_rows, NI * 4 + NI * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  st = dvb_encoder_check(enc, s);  // synchronises
+  if (st) return st;
+  if (rows_kept_host) memcpy(rows_kept_host, enc->h_out.p, NI * 4);
+  memcpy(probs_host, static_cast<char*>(enc->h_out.p) + NI * 4, NI * 3 * sizeof(float));
   return DVB_OK;
 }
 

@@ -205,22 +205,30 @@ def pad_cin(cin: int) -> int:
   return 16 if cin < 16 else (cin + 7) // 8 * 8
 
 
-def pack_weights(w: ModelWeights) -> bytes:
+BLOB_MAGIC_SPLIT = 0x32424E4E  # 'NNB2': main + residual fp16 planes per kernel
+SPLIT_SCALE = 2048.0           # residual plane = fp16((k - fp16(k)) * 2^11)  (csrc/dvb_cnn.cu "precision = 1")
+
+
+def pack_weights(w: ModelWeights, precision: int = 0) -> bytes:
   """Weights blob for dvb_cnn_create: header {magic, in_channels, n_conv}, then per conv (network
   order) {kh, kw, cin, cin_pad, cout} int32 + fp16 kernel [cout][kh][kw][cin_pad] (BN folded,
-  zero padded) + fp32 bias[cout]; then fp32 dense kernel [2048][3] and bias [3]."""
+  zero padded) [+ the fp16 residual plane of the same shape when precision == 1] + fp32 bias[cout];
+  then fp32 dense kernel [2048][3] and bias [3]."""
   ops, _ = inception_v3_graph(w.in_channels)
   conv_ops = [o for o in ops if o.kind == 'conv']
   assert len(conv_ops) == len(w.convs)
-  out = bytearray(struct.pack('<3i', BLOB_MAGIC, w.in_channels, len(conv_ops)))
+  out = bytearray(struct.pack('<3i', BLOB_MAGIC_SPLIT if precision == 1 else BLOB_MAGIC, w.in_channels, len(conv_ops)))
   for o, p in zip(conv_ops, w.convs):
     assert p.kernel.shape == (o.kh, o.kw, o.cin, o.cout), (o.name, p.kernel.shape)
     k, b = fold_bn(p)
     cp = pad_cin(o.cin)
-    kk = np.zeros((o.cout, o.kh, o.kw, cp), dtype=np.float16)
-    kk[..., :o.cin] = np.transpose(k, (3, 0, 1, 2)).astype(np.float16)
+    k32 = np.zeros((o.cout, o.kh, o.kw, cp), dtype=np.float32)
+    k32[..., :o.cin] = np.transpose(k, (3, 0, 1, 2))
+    kk = k32.astype(np.float16)
     out += struct.pack('<5i', o.kh, o.kw, o.cin, cp, o.cout)
     out += kk.tobytes()
+    if precision == 1:
+      out += ((k32 - kk.astype(np.float32)) * np.float32(SPLIT_SCALE)).astype(np.float16).tobytes()
     out += b.astype(np.float32).tobytes()
   out += w.dense_kernel.astype(np.float32).tobytes()
   out += w.dense_bias.astype(np.float32).tobytes()

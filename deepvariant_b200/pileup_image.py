@@ -204,6 +204,20 @@ class GpuEncoder:
                                                self.last_rows_kept.ctypes.data_as(C.c_void_p)))
     return out
 
+  def encode_classify_host(self, batch, cnn, probs: Optional[np.ndarray] = None) -> np.ndarray:
+    """Host batch in -> float32[n_images, 3] genotype probabilities out (dvb_encode_classify_host):
+    the images stay in HBM between the encoder and the classifier.  `batch` is anything with
+    `.n_images` and `.as_ctypes()` over HOST arrays (packing.PackedBatch, a CPU synthetic.TorchBatch)."""
+    import ctypes as C
+    n = int(batch.n_images)
+    if probs is None:
+      probs = np.empty((n, 3), dtype=np.float32)
+    self.last_rows_kept = np.zeros(max(n, 1), dtype=np.int32)
+    cb = batch.as_ctypes()
+    _lib.check(self._lib.dvb_encode_classify_host(self._h, cnn._h, C.byref(cb), C.c_void_p(probs.ctypes.data),  # pylint: disable=protected-access
+                                                  self.last_rows_kept.ctypes.data_as(C.c_void_p)))
+    return probs
+
   def encode_device(self, dev_batch: 'packing.DeviceBatch', out, rows_kept=None, stream=None) -> None:
     """Device pointers in/out; asynchronous on `stream` (a torch.cuda.Stream or None)."""
     import ctypes as C

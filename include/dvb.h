@@ -202,6 +202,15 @@ int dvb_cnn_forward_device(DvbCnn* cnn, const uint8_t* images, int32_t n, float*
 /* Host in / host out variant. */
 int dvb_cnn_forward_host(DvbCnn* cnn, const uint8_t* images_host, int32_t n, float* probs_host);
 
+/* The fused hot path a reference maintainer binds when make_examples and call_variants run in one process
+ * (the reference's --fast_pipeline mode streams examples through shared memory instead,
+ * deepvariant/fast_pipeline.cc + stream_examples.cc:94-156): host DvbBatch in, genotype probabilities out.
+ * Stages the batch (one H2D copy), encodes on the device, classifies the images where they lie in HBM
+ * (the 155 KB/example image/encoded bytes never cross PCIe), copies float[n_images][3] back, synchronises.
+ * rows_kept_host: int32[n_images] or NULL.  enc and cnn must live on the same device. */
+int dvb_encode_classify_host(DvbEncoder* enc, DvbCnn* cnn, const DvbBatch* batch_host, float* probs_host,
+                             int32_t* rows_kept_host);
+
 int64_t dvb_cnn_launch_count(const DvbCnn* cnn);
 /* FLOPs of one forward for one image (conv MACs x 2). */
 double dvb_cnn_flops_per_image(const DvbCnn* cnn);

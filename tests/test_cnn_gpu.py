@@ -127,3 +127,90 @@ def test_encoder_output_feeds_cnn_in_place():
   torch.cuda.synchronize()
   want = cnn_oracle.ReferenceModel(w).forward(images.cpu())
   assert float((probs.cpu() - want).abs().max()) < 5e-3
+
+
+def test_fused_host_entry_point_matches_two_stage_path():
+  """dvb_encode_classify_host (host DvbBatch in -> probabilities out, images stay in HBM) must give exactly what the
+  two reference-shaped stage calls give (dvb_encode_batch_host, then dvb_cnn_forward_host on the returned images),
+  with pageable and with pinned caller buffers."""
+  from deepvariant_b200 import pileup_image as pi, synthetic
+  o = pi.default_options()
+  o.channels = list(pi.PILEUP_CHANNELS_WITH_INSERT_SIZE)
+  enc = pi.GpuEncoder(pi.to_params(o), 0)
+  host = synthetic.make_batch(40, 'cpu')
+  net = cv.GpuCnn(modeling.random_weights(7, 6), enc.shape, device=0, max_batch=16)   # 40 images -> chunks 16, 16, 8
+  images = enc.encode_host(host.to_packed())
+  rows = enc.last_rows_kept.copy()
+  want = net.forward_host(images)
+  got = enc.encode_classify_host(host, net)
+  np.testing.assert_array_equal(got, want)
+  np.testing.assert_array_equal(enc.last_rows_kept, rows)
+  got_pinned = enc.encode_classify_host(host.pin(), net)
+  np.testing.assert_array_equal(got_pinned, want)
+  oracle = cnn_oracle.ReferenceModel(modeling.random_weights(7, 6)).forward(torch.from_numpy(images))
+  assert float((torch.from_numpy(got) - oracle).abs().max()) < 5e-3
+
+
+# ---- precision = 1 (split-fp16 x3): the north-star tolerance, 1e-5 on the genotype probabilities -------------------
+
+PRECISE_TOL = 1e-5   # BASELINE.json north_star: "outputs within 1e-5 of the reference"
+
+
+def _precise(shape, n, seed):
+  w = modeling.random_weights(shape[2], seed)
+  net = cv.GpuCnn(w, shape, device=0, max_batch=n, precision=1)
+  imgs = _images(n, shape, seed)
+  got = net.forward_host(imgs.numpy())
+  return w, net, imgs, got
+
+
+def test_precise_mode_probabilities_within_1e5_of_fp32_oracle():
+  w, net, imgs, got = _precise((100, 221, 7), 6, seed=11)
+  want32 = cnn_oracle.ReferenceModel(w).forward(imgs).numpy()
+  want64 = cnn_oracle.ReferenceModel(w, dtype=torch.float64).forward(imgs).numpy()
+  e32 = float(np.abs(got - want32).max())
+  e64 = float(np.abs(got - want64).max())
+  o32 = float(np.abs(want32 - want64).max())
+  print(f'precise: |ours - fp32 oracle| {e32:.2e}  |ours - fp64 oracle| {e64:.2e}  |fp32 oracle - fp64 oracle| {o32:.2e}')
+  assert e32 < PRECISE_TOL and e64 < PRECISE_TOL
+  for row in got:
+    cv.round_gls(row.astype(np.float64).tolist(), 10)
+
+
+def test_precise_mode_every_block_output_close_to_fp32_oracle():
+  shape = (100, 221, 7)
+  w = modeling.random_weights(7, 12)
+  n = 2
+  net = cv.GpuCnn(w, shape, device=0, max_batch=n, precision=1)
+  imgs = _images(n, shape, 12)
+  probs = torch.empty((n, 3), dtype=torch.float32, device='cuda:0')
+  net.forward_device(imgs.to('cuda:0'), probs)
+  torch.cuda.synchronize()
+  want_p, tensors, pooled = cnn_oracle.ReferenceModel(w).forward(imgs, return_tensors=True)
+  report = []
+  for name in STEM + [f'mixed{i}' for i in range(11)] + ['mixed0_ap', 'mixed4_d4', 'mixed9_t1']:
+    got = net.debug_tensor(name, n)
+    ref = tensors[name].permute(0, 2, 3, 1).numpy()
+    scale = max(float(np.abs(ref).max()), 1e-6)
+    report.append((name, float(np.abs(got - ref).max()) / scale))
+  print(report)
+  for name, err in report:
+    assert err < 2e-5, report     # fp32-grade: four orders below the single-pass fp16 path
+  assert float((probs.cpu() - want_p).abs().max()) < PRECISE_TOL
+
+
+def test_precise_mode_pacbio_geometry_and_encoder_images():
+  w, net, imgs, got = _precise((100, 147, 10), 3, seed=13)
+  want = cnn_oracle.ReferenceModel(w).forward(imgs).numpy()
+  assert float(np.abs(got - want).max()) < PRECISE_TOL
+  from deepvariant_b200 import pileup_image as pi, synthetic
+  o = pi.default_options()
+  o.channels = list(pi.PILEUP_CHANNELS_WITH_INSERT_SIZE)
+  enc = pi.GpuEncoder(pi.to_params(o), 0)
+  host = synthetic.make_batch(8, 'cpu')
+  w7 = modeling.random_weights(7, 14)
+  net7 = cv.GpuCnn(w7, enc.shape, device=0, max_batch=8, precision=1)
+  images = enc.encode_host(host.to_packed())
+  got7 = enc.encode_classify_host(host, net7)
+  want7 = cnn_oracle.ReferenceModel(w7).forward(torch.from_numpy(images)).numpy()
+  assert float(np.abs(got7 - want7).max()) < PRECISE_TOL

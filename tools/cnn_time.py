@@ -15,9 +15,10 @@ ap.add_argument('--chunk', type=int, default=2048)
 ap.add_argument('--steps', type=int, default=5)
 ap.add_argument('--warmup', type=int, default=2)
 ap.add_argument('--pacbio', action='store_true')
+ap.add_argument('--precision', type=int, default=0)
 a = ap.parse_args()
 shape = (100, 147, 10) if a.pacbio else (100, 221, 7)
-net = cv.GpuCnn(modeling.random_weights(shape[2], 0), shape, device=0, max_batch=a.chunk)
+net = cv.GpuCnn(modeling.random_weights(shape[2], 0), shape, device=0, max_batch=a.chunk, precision=a.precision)
 x = torch.randint(0, 255, (a.batch,) + shape, dtype=torch.uint8, device='cuda:0')
 p = torch.empty((a.batch, 3), dtype=torch.float32, device='cuda:0')
 s = torch.cuda.current_stream()
@@ -31,5 +32,5 @@ for _ in range(a.steps):
 e1.record(s)
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.steps
-print(json.dumps({'batch': a.batch, 'chunk': a.chunk, 'ms_per_forward': ms, 'images_per_s': a.batch / ms * 1e3,
+print(json.dumps({'precision': a.precision, 'batch': a.batch, 'chunk': a.chunk, 'ms_per_forward': ms, 'images_per_s': a.batch / ms * 1e3,
                   'tflops': a.batch * net.flops_per_image / ms / 1e9}))
