@@ -48,6 +48,15 @@ def parse_args():
   return ap.parse_args()
 
 
+def load_traffic():
+  """Measured DRAM traffic per unit (ncu --set full captures; profiles/traffic.json) or {}."""
+  p = os.path.join(ROOT, 'profiles', 'traffic.json')
+  try:
+    return json.load(open(p))
+  except (OSError, ValueError):
+    return {}
+
+
 def load_peaks():
   p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
   if os.path.exists(p):
@@ -330,12 +339,18 @@ def main():
   # ---- rooflines ----
   alg_bytes = tb.algorithmic_bytes(enc.image_bytes, o.width)
   enc_gbs = alg_bytes / (enc_ms * 1e-3) / 1e9
+  traffic = load_traffic()
+  enc_traffic = traffic.get('encoder', {}).get('dram_bytes_per_window')
   roof_enc = {'bound': 'hbm', 'kernel': 'dvb_encode_kernel', 'achieved': enc_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-              'frac': enc_gbs / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peaks['source'],
+              'frac': enc_gbs / peaks['hbm_gbs'], 'traffic': enc_traffic * B if enc_traffic else None,
+              'traffic_source': traffic.get('encoder', {}).get('capture'), 'peak_source': peaks['source'],
               'ms_per_launch': enc_ms, 'algorithmic_bytes_per_launch': alg_bytes,
               'windows_per_s_encode_only': B / (enc_ms * 1e-3)}
   if cnn:
     roofline = cnn.roofline(ms_step - enc_ms, B, peaks)
+    cnn_traffic = traffic.get('cnn', {}).get('dram_bytes_per_image')
+    roofline['traffic'] = cnn_traffic * B if cnn_traffic else None
+    roofline['traffic_source'] = traffic.get('cnn', {}).get('capture')
   else:
     roofline = roof_enc
 

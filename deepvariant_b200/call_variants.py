@@ -48,7 +48,7 @@ class GpuCnn:
   def random_init(cls, image_shape: Sequence[int], device: int = 0, max_batch: int = 2048, seed: int = 0,
                   precision: int = 0) -> 'GpuCnn':
     """Random-init weights of the right architecture (no checkpoints ship with the reference)."""
-    return cls(modeling.random_weights(int(image_shape[2]), seed), image_shape, device, min(max_batch, 2048), precision)
+    return cls(modeling.random_weights(int(image_shape[2]), seed), image_shape, device, min(max_batch, 4096), precision)
 
   def forward_device(self, images, probs, stream=None) -> None:
     """images: torch uint8 [n, H, W, C] on the device; probs: torch float32 [n, 3].  Asynchronous."""

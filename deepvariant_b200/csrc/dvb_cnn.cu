@@ -439,6 +439,151 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
+// Persistent variant of the tap-by-tap implicit GEMM (precision 0)
+// ---------------------------------------------------------------------------------------------
+// Measured on the one-tile-per-CTA kernel above (ncu, 1x1 768->192 on 4x12 maps): tensor pipe 31 %, L2 32 %, DRAM 35 %,
+// 18 % of the warp slots occupied - nothing is saturated.  Each CTA pays TMEM allocation, barrier init and a cold
+// 2-stage pipeline for 12 K blocks of work, and only two CTAs fit an SM (TMEM 2 x 256 columns, 2 x 80 KB).  Here ONE
+// CTA per SM stays resident and walks (M tile, N block) pairs: a deep TMA ring (as many stages as fit ~200 KB) runs
+// ahead across tile boundaries, the accumulator is double buffered in TMEM (2 x BLOCK_N <= 512 columns) and eight
+// epilogue warps (two per TMEM lane quarter, splitting the columns) drain tile i while the MMAs of tile i + 1 issue.
+constexpr int kPersistEpiWarps = 8;
+constexpr int kPersistThreads = 64 + 32 * kPersistEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+
+__global__ void __launch_bounds__(kPersistThreads, 1)
+conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ConvArgs p,
+                            const int n_blocks, const int cout) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + p.stages * p.a_stage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.stages * p.b_stage);
+  uint64_t* full_bar = bars;                       // [kMaxStages]
+  uint64_t* empty_bar = bars + kMaxStages;         // [kMaxStages]
+  uint64_t* tmem_full = bars + 2 * kMaxStages;     // [2]
+  uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  float* s_bias = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);   // [cout], 16-byte aligned
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < cout; i += kPersistThreads) s_bias[i] = p.bias[i];
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total = m_tiles * n_blocks;             // tile t = nb * m_tiles + m  (neighbouring CTAs share the weight block)
+  const int num_kb = p.kh * p.kw * p.cin_blocks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_b);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 32 * kPersistEpiWarps); }
+    fence_barrier_init();
+  } else if (warp == 1) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int st = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int nb = t / m_tiles;
+        int m = t - nb * m_tiles;
+        const int tw = m % p.tiles_w; m /= p.tiles_w;
+        const int th = m % p.tiles_h;
+        const int tn = m / p.tiles_h;
+        const int w0 = tw * p.Wt * p.stride - p.pad_w, h0 = th * p.Ht * p.stride - p.pad_h, n0 = tn * p.Nt;
+        for (int r = 0; r < p.kh; ++r) {
+          for (int s = 0; s < p.kw; ++s) {
+            for (int cb = 0; cb < p.cin_blocks; ++cb) {
+              mbar_wait(&empty_bar[st], ph ^ 1);
+              mbar_arrive_expect_tx(&full_bar[st], p.a_bytes + p.b_bytes);
+              tma_load_4d(smem_a + st * p.a_stage, &map_a, &full_bar[st], cb * p.block_k, w0 + s, h0 + r, n0);
+              tma_load_3d(smem_b + st * p.b_stage, &map_b, &full_bar[st], cb * p.block_k, r * p.kw + s, nb * p.block_n);
+              if (++st == p.stages) { st = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer (one thread) =====
+      const int mma_per_kb = p.block_k / 16;
+      const uint32_t hi = desc_hi(p.sbo_bytes, p.layout_type), idesc = p.idesc;
+      const uint32_t a_lo0 = desc_lo(smem_u32(smem_a)), b_lo0 = desc_lo(smem_u32(smem_b));
+      const uint32_t a_inc = p.a_stage >> 4, b_inc = p.b_stage >> 4;
+      const int stages = p.stages;
+      int st = 0, buf = 0;
+      uint32_t ph = 0, buf_ph = 0, a_lo = a_lo0, b_lo = b_lo0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        mbar_wait(&tmem_empty[buf], buf_ph ^ 1);      // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(buf * p.block_n);
+        uint32_t acc = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[st], ph);
+          tc_fence_after();
+#pragma unroll 4
+          for (int k = 0; k < mma_per_kb; ++k) {
+            umma_f16_lohi(d, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, acc);
+            acc = 1;
+          }
+          umma_commit(&empty_bar[st]);
+          a_lo += a_inc; b_lo += b_inc;
+          if (++st == stages) { st = 0; ph ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
+        }
+        umma_commit(&tmem_full[buf]);
+        buf ^= 1;
+        if (buf == 0) buf_ph ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue: warp e covers TMEM lane quarter (warp & 3) and column half (e >> 2) =====
+    const int e = warp - 2;
+    const int q = warp & 3;
+    const int half = e >> 2;
+    const int row = q * 32 + lane;
+    const int w = row % p.Wt;
+    const int h = (row / p.Wt) % p.Ht;
+    const int n = row / (p.Wt * p.Ht);
+    // column split in multiples of 16: first half gets ceil
+    const int chunks = p.block_n >> 4;
+    const int c_lo = half == 0 ? 0 : ((chunks + 1) >> 1) << 4;
+    const int c_n = half == 0 ? ((chunks + 1) >> 1) << 4 : p.block_n - c_lo;
+    int buf = 0;
+    uint32_t buf_ph = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      const int nb = t / m_tiles;
+      int m = t - nb * m_tiles;
+      const int tw = m % p.tiles_w; m /= p.tiles_w;
+      const int th = m % p.tiles_h;
+      const int tn = m / p.tiles_h;
+      const int w0 = tw * p.Wt, h0 = th * p.Ht, n0 = tn * p.Nt;
+      const bool valid = (n < p.Nt) && (w0 + w < p.Wout) && (h0 + h < p.Hout) && (n0 + n < p.n_images);
+      __half* dst = p.out + ((size_t)((size_t)(n0 + n) * p.Hout + (h0 + h)) * p.Wout + (w0 + w)) * p.out_cstride + p.out_coff +
+                    nb * p.block_n + c_lo;
+      mbar_wait(&tmem_full[buf], buf_ph);
+      tc_fence_after();
+      if (c_n > 0)
+        epilogue_row(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.block_n + c_lo), c_n, s_bias + nb * p.block_n + c_lo, dst, valid,
+                     p.relu);
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[buf]);
+      buf ^= 1;
+      if (buf == 0) buf_ph ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stride-1 k x k convolution on large feature maps: persistent, weights-resident, halo-reusing variant
 // ---------------------------------------------------------------------------------------------
 // What the tap-by-tap kernel above cannot hide on the wide stem layers (measured, B200):
@@ -748,6 +893,151 @@ __global__ void __launch_bounds__(256) stem_patch_kernel(const uint8_t* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused stem: preprocess + im2col + conv1 (3x3 stride 2 valid, C = 7) straight from the uint8 image
+// ---------------------------------------------------------------------------------------------
+// The patch route (stem_patch_kernel -> GEMM) writes and re-reads a [N][Ho][Wo][64] fp16 patch tensor (1.4 GB per 2048
+// images) that exists only to make conv1 TMA-loadable.  Here the SM builds the A tile itself: one tile = 128 output
+// pixels of one output row.  Phase 1 (all threads) streams the three input rows the tile touches from global memory,
+// converts bytes to fp16 with the exact (x - 128) / 128 (magic-number trick: 0x6400 | x = 1024 + x, one HFMA2 per pair)
+// and leaves them in shared memory as halves; phase 2 (two threads per pixel) assembles each pixel's 63-element patch
+// (3 runs of 21 contiguous halves; the middle run lands on an odd half offset -> one funnel shift per word) and stores
+// it as the 128-byte row of a canonical 128B-swizzled K-major tile; one thread issues the 4 MMAs (K = 64, N = 32);
+// warps 0-3 run the bias + ReLU epilogue from TMEM.  Persistent CTAs, several per SM, hide each other's phases.
+constexpr int kStemThreads = 256;
+constexpr int kStemC = 7;
+constexpr int kStemSeg = 3 * kStemC;   // 21 contiguous (s, c) values per tap row
+
+struct StemArgs {
+  const uint8_t* in; __half* out; const float* bias; const __half* w;   // w: [cout][64], k = (r*3 + s)*7 + c
+  int n_images, H, W, Ho, Wo, cout, out_cstride, tiles_w;
+  long long total_bytes;
+  uint32_t idesc;
+  int h_pitch;   // halves per staged input row (multiple of 8)
+};
+
+__global__ void __launch_bounds__(kStemThreads) stem_conv1_kernel(const StemArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                         // 128 rows x 128 B, 128B swizzle
+  uint8_t* sB = smem + 16384;                 // cout rows x 128 B, 128B swizzle (cout <= 32 -> 4 KB)
+  __half* sH = reinterpret_cast<__half*>(smem + 16384 + 4096);   // [3][h_pitch]
+  uint64_t* mma_done = reinterpret_cast<uint64_t*>(sH + 3 * p.h_pitch);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
+  float* s_bias = reinterpret_cast<float*>(mma_done + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid < p.cout) s_bias[tid] = p.bias[tid];
+  for (int i = tid; i < p.cout * 8; i += kStemThreads) {   // weights -> swizzled K-major tile
+    const int n = i >> 3, j = i & 7;
+    *reinterpret_cast<uint4*>(sB + n * 128 + ((j ^ (n & 7)) << 4)) = *reinterpret_cast<const uint4*>(p.w + n * 64 + j * 8);
+  }
+  if (tid == 0) { mbar_init(mma_done, 1); fence_barrier_init(); }
+  if (warp == 1) tmem_alloc(tmem_slot, 32);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int row_bytes = p.W * kStemC;
+  const long long total_tiles = (long long)p.n_images * p.Ho * p.tiles_w;
+  uint32_t phase = 0;
+  const __half2 kScale = __floats2half2_rn(1.f / 128.f, 1.f / 128.f), kBias = __floats2half2_rn(-9.f, -9.f);
+
+  for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int tw = (int)(tile % p.tiles_w);
+    const long long t2 = tile / p.tiles_w;
+    const int oh = (int)(t2 % p.Ho), n = (int)(t2 / p.Ho);
+    const int ow0 = tw * 128;
+    const int npx = min(128, p.Wo - ow0);
+    const int seg_bytes = (2 * (npx - 1) + 3) * kStemC;   // input bytes of one row this tile touches
+    // ---- phase 1: 3 input row segments -> fp16 (x - 128) / 128 in shared memory
+    for (int r = 0; r < 3; ++r) {
+      const long long g0 = ((long long)(n * (long long)p.H + 2 * oh + r)) * row_bytes + (long long)2 * ow0 * kStemC;
+      const int mis = (int)(g0 & 3);
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(p.in + (g0 - mis));
+      const int nw = (seg_bytes + 3) >> 2;
+      uint2* dst = reinterpret_cast<uint2*>(sH + r * p.h_pitch);
+      for (int i = tid; i < nw; i += kStemThreads) {
+        const long long off = (g0 - mis) + 4LL * i;
+        uint32_t lo;
+        if (off + 4 <= p.total_bytes) {
+          lo = __ldg(src + i);
+        } else {   // never read past the end of the caller's buffer
+          lo = 0u;
+          for (int bb = 0; bb < 4; ++bb)
+            if (off + bb < p.total_bytes) lo |= (uint32_t)p.in[off + bb] << (8 * bb);
+        }
+        const uint32_t hi = (mis && off + 8 <= p.total_bytes) ? __ldg(src + i + 1) : 0u;
+        const uint32_t v = __funnelshift_r(lo, hi, 8 * mis);     // bytes g0 + 4i .. g0 + 4i + 3
+        uint32_t a = __byte_perm(v, 0x64646464u, 0x4140), b = __byte_perm(v, 0x64646464u, 0x4342);
+        __half2 ha = __hfma2(*reinterpret_cast<__half2*>(&a), kScale, kBias), hb = __hfma2(*reinterpret_cast<__half2*>(&b), kScale, kBias);
+        dst[i] = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: patch rows.  Thread (m, hf): output words [16 hf, 16 hf + 16) of row m.
+    {
+      const int m = tid >> 1, hf = tid & 1;
+      uint32_t ow[16];
+      if (m < npx) {
+        const uint32_t* W0 = reinterpret_cast<const uint32_t*>(sH) + 7 * m;                       // 14 m halves = 7 m words
+        const uint32_t* W1 = reinterpret_cast<const uint32_t*>(sH + p.h_pitch) + 7 * m;
+        const uint32_t* W2 = reinterpret_cast<const uint32_t*>(sH + 2 * p.h_pitch) + 7 * m;
+        if (hf == 0) {
+#pragma unroll
+          for (int i = 0; i < 10; ++i) ow[i] = W0[i];
+          uint32_t prev = W1[0];
+          ow[10] = (W0[10] & 0xFFFFu) | (prev << 16);
+#pragma unroll
+          for (int i = 11; i < 16; ++i) { const uint32_t nx = W1[i - 10]; ow[i] = __funnelshift_r(prev, nx, 16); prev = nx; }
+        } else {
+          uint32_t prev = W1[5];
+#pragma unroll
+          for (int i = 16; i < 21; ++i) { const uint32_t nx = W1[i - 10]; ow[i - 16] = __funnelshift_r(prev, nx, 16); prev = nx; }
+#pragma unroll
+          for (int i = 21; i < 31; ++i) ow[i - 16] = W2[i - 21];
+          ow[15] = W2[10] & 0xFFFFu;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ow[i] = 0u;
+      }
+      uint8_t* rowp = sA + m * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = hf * 4 + c;
+        *reinterpret_cast<uint4*>(rowp + ((j ^ (m & 7)) << 4)) = make_uint4(ow[4 * c], ow[4 * c + 1], ow[4 * c + 2], ow[4 * c + 3]);
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    // ---- MMA: D[128 x cout] = A[128 x 64] * B[cout x 64]^T
+    if (tid == 32) {
+      tc_fence_after();
+      const uint32_t hi = desc_hi(1024u, 2u), a_lo = desc_lo(smem_u32(sA)), b_lo = desc_lo(smem_u32(sB));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_f16_lohi(tmem_base, a_lo + 2 * k, b_lo + 2 * k, hi, p.idesc, (uint32_t)(k != 0));
+      umma_commit(mma_done);
+    }
+    // ---- epilogue: warps 0..3 own TMEM lane quarters 0..3
+    if (warp < 4) {
+      mbar_wait(mma_done, phase);
+      tc_fence_after();
+      const int m = warp * 32 + lane;
+      const bool valid = m < npx;
+      __half* dst = p.out + (((size_t)n * p.Ho + oh) * p.Wo + ow0 + m) * p.out_cstride;
+      epilogue_row(tmem_base + ((uint32_t)(warp * 32) << 16), p.cout, s_bias, dst, valid, 1);
+      tc_fence_before();
+    }
+    phase ^= 1;
+    __syncthreads();   // accumulator drained, sA / sH free for the next tile
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 32);
+}
+
 // 3x3 pooling on NHWC fp16.  mode 0: max, stride 2, valid.  mode 1: average, stride 1, 'same', divisor = number
 // of in-bounds taps (TF AveragePooling2D semantics).  One thread owns (image, output row, 8 channels) and slides
 // along W keeping the per-column partial results of the previous columns in registers, so every input element is
@@ -786,7 +1076,7 @@ __device__ __forceinline__ void store8s(__half* main, __half* res, size_t off, c
 
 __global__ void pool3x3_kernel(const __half* __restrict__ in, __half* __restrict__ out, int n_images, int Hin, int Win, int C,
                                int Hout, int Wout, int out_cstride, int out_coff, int mode, const __half* __restrict__ in_res,
-                               __half* __restrict__ out_res) {
+                               __half* __restrict__ out_res, const float* __restrict__ bias) {
   const int cvec = C / 8;
   const long long total = (long long)n_images * Hout * cvec;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -839,6 +1129,10 @@ __global__ void pool3x3_kernel(const __half* __restrict__ in, __half* __restrict
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) { o[j] = (s0[j] + s1[j] + s2[j]) * inv; s0[j] = s1[j]; s1[j] = s2[j]; }
+      if (bias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j] + bias[cv * 8 + j], 0.f);
+      }
       store8s(out, out_res, dst + (size_t)ow * out_cstride, o);
     }
   }
@@ -928,6 +1222,8 @@ struct OpDesc {
   int kind;  // 0 conv, 1 maxpool, 2 avgpool
   std::string src, dst;
   int off, cin, cout, kh, kw, stride, same;
+  int no_act = 0;      // conv: raw accumulator out (no bias, no ReLU) - its bias + ReLU move behind the following pool
+  int post_act = 0;    // pool: + bias of the preceding conv, ReLU
 };
 
 int PadCin(int cin) { return cin < 16 ? 16 : (cin + 7) / 8 * 8; }
@@ -1027,6 +1323,8 @@ struct ConvLaunch {
   double macs_per_image;
   bool flat;
   int pixels_per_image;
+  bool persist;          // conv_gemm_persistent_kernel
+  int n_blocks, cout;
 };
 struct HaloLaunch {
   CUtensorMap map_a, map_b;
@@ -1038,8 +1336,19 @@ struct PoolLaunch {
   const __half* in; __half* out;
   int Hin, Win, C, Hout, Wout, out_cstride, out_coff, mode;
   const __half* in_res; __half* out_res;
+  const float* bias;     // post_act pools: + bias[c], ReLU (else null)
 };
-struct Step { int kind; int index; };  // 0 conv, 1 pool, 2 halo conv
+// One launch of the forward.  The inception branches are independent chains: every step runs on one of kMaxLanes
+// streams ("lanes"; lane 0 = the caller's stream) and waits on the events of the producers of its source tensor that
+// ran on other lanes, so that the partial last wave of one branch's kernel is filled by another branch's CTAs.
+constexpr int kMaxLanes = 4;
+struct Step {
+  int kind, index;          // 0 conv, 1 pool, 2 halo conv
+  int lane = 0;
+  bool record = false;      // some consumer on another lane waits on this step's event
+  std::vector<int> deps;    // steps (other lanes) to wait on before launching
+  cudaEvent_t event = nullptr;
+};
 
 }  // namespace
 
@@ -1059,6 +1368,11 @@ struct DvbCnn {
   double flops_per_image = 0;
   int64_t launches = 0;
   cudaStream_t stream = nullptr;
+  bool stem_fused = false;
+  StemArgs stem_args;
+  int n_lanes = 1;
+  cudaStream_t lane_streams[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused (caller's stream)
+  std::vector<int> tail_deps;
   dvb::DevBuf d_in, d_probs;
   dvb::PinBuf h_io;
 };
@@ -1122,6 +1436,27 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
   std::vector<OpDesc> ops;
   std::map<std::string, int> ch;
   BuildGraph(net->C, &ops, &ch);
+  // Average pool followed by a 1x1 convolution: both are linear and act on different axes (the pool per channel over
+  // space, the convolution per pixel over channels; the 'same'-padding divisor depends on the pixel only), so
+  //     relu(conv1x1(avgpool(x)) + b) == relu(avgpool(conv1x1(x)) + b).
+  // Running the convolution first shrinks what the pool has to stream by Cin / Cout (768 -> 192, 2048 -> 192, ...).
+  if (EnvInt("DVB_CNN_POOL_AFTER_CONV", 1)) {
+    for (size_t i = 0; i + 1 < ops.size(); ++i) {
+      OpDesc& pl = ops[i];
+      OpDesc& cv = ops[i + 1];
+      if (pl.kind == 2 && cv.kind == 0 && cv.kh == 1 && cv.kw == 1 && cv.stride == 1 && cv.src == pl.dst) {
+        const std::string x = pl.src, mid = pl.dst, out = cv.dst;
+        const int off = cv.off, cout = cv.cout;
+        OpDesc conv = cv, pool = pl;
+        conv.src = x; conv.dst = mid; conv.off = 0; conv.no_act = 1;
+        pool.src = mid; pool.dst = out; pool.off = off; pool.cin = cout; pool.cout = cout; pool.post_act = 1;
+        ch[mid] = cout;
+        ops[i] = conv; ops[i + 1] = pool;
+        ++i;
+      }
+    }
+  }
+  const float* pending_bias = nullptr;   // bias of the last no_act convolution, consumed by the pool behind it
   // --- header
   if (blob_bytes < 12) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob too small");
   const int32_t* hdr = reinterpret_cast<const int32_t*>(blob);
@@ -1172,6 +1507,7 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
   int st = add_tensor("input", net->stem_Ho, net->stem_Wo, net->stem_Kp);
   if (st) return st;
 
+  std::vector<std::pair<std::string, std::string>> step_io;   // (src, dst) tensor of every step
   const int force_bk = EnvInt("DVB_CNN_BLOCK_K", 0);       // 0 = per-layer choice
   double macs_total = 0;
   for (size_t op_index = 0; op_index < ops.size(); ++op_index) {
@@ -1190,8 +1526,11 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
     const TensorBuf& src = net->tensors[net->tensor_index[o.src]];
     const TensorBuf& dst = net->tensors[net->tensor_index[o.dst]];
     if (o.kind != 0) {
-      PoolLaunch pl{src.ptr, dst.ptr, Hin, Win, src.C, Hout, Wout, dst.C, o.off, o.kind == 1 ? 0 : 1, src.ptr_res, dst.ptr_res};
-      net->steps.push_back({1, (int)net->pools.size()});
+      PoolLaunch pl{src.ptr, dst.ptr, Hin, Win, src.C, Hout, Wout, dst.C, o.off, o.kind == 1 ? 0 : 1, src.ptr_res, dst.ptr_res,
+                    o.post_act ? pending_bias : nullptr};
+      if (o.post_act && !pending_bias) return dvb::fail(DVB_ERR_INTERNAL, "pool without the bias of its convolution");
+      net->steps.push_back(Step{1, (int)net->pools.size()});
+      step_io.push_back({o.src, o.dst});
       net->pools.push_back(pl);
       continue;
     }
@@ -1232,11 +1571,33 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       }
     }
     cudaMemcpy(db, blob + pos + blob_planes * blob_wbytes, bbytes, cudaMemcpyHostToDevice);
+    const float* conv_bias = static_cast<const float*>(db);
+    if (o.no_act) {
+      pending_bias = conv_bias;
+      void* dz = nullptr;
+      if (cudaMalloc(&dz, bbytes) != cudaSuccess) return dvb::fail(DVB_ERR_CUDA, "cudaMalloc (bias) failed");
+      cudaMemset(dz, 0, bbytes);
+      net->allocs.push_back(dz);
+      conv_bias = static_cast<const float*>(dz);
+    }
     const uint8_t* blob_w_main = blob + pos;
     pos += blob_planes * blob_wbytes + bbytes;
 
+    // ---- conv1 fused with preprocess + im2col (stem_conv1_kernel): WGS geometry (7 channels), precision 0
+    if (is_stem && !split && net->C == kStemC && o.cout <= 32 && o.cout % 16 == 0 && cin_store == 64 && EnvInt("DVB_CNN_STEM_FUSED", 1)) {
+      StemArgs& a = net->stem_args;
+      memset(&a, 0, sizeof(a));
+      a.out = dst.ptr; a.bias = static_cast<const float*>(db); a.w = static_cast<const __half*>(dw);
+      a.H = net->H; a.W = net->W; a.Ho = Hout; a.Wo = Wout; a.cout = o.cout; a.out_cstride = dst.C;
+      a.tiles_w = (Wout + 127) / 128;
+      a.idesc = (1u << 4) | ((uint32_t)(o.cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      a.h_pitch = 1808;   // (2 * 127 + 3) * 7 = 1799 bytes per row segment -> 450 words -> 1800 halves, rounded up to 8
+      net->stem_fused = true;
+      macs_total += (double)Hout * Wout * o.cout * orig.kh * orig.kw * orig.cin;
+      continue;
+    }
     // ---- large stride-1 k x k layers: persistent halo-reusing kernel (see conv_halo_kernel)
-    if (!split && !is_stem && o.stride == 1 && o.kh * o.kw > 1 && Hout * Wout >= 1000 && EnvInt("DVB_CNN_HALO", 1)) {
+    if (!split && !is_stem && o.stride == 1 && o.kh * o.kw > 1 && Hout * Wout >= EnvInt("DVB_HALO_MIN_PIXELS", 250) && EnvInt("DVB_CNN_HALO", 1)) {
       HaloLaunch hl;
       memset(&hl, 0, sizeof(hl));
       HaloArgs& a = hl.args;
@@ -1291,8 +1652,8 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       a.nbuf = (2 * a.T * bn <= 512 && EnvInt("DVB_HALO_NBUF", 2) == 2) ? 2 : 1;
       a.stages = std::min(2 * kMaxStages, std::max(a.T, std::min(2 * a.T, (int)((216 * 1024 - (long)b_smem) / (long)a.a_stage))));
       a.tmem_cols = TmemCols(a.nbuf * a.T * bn);
-      a.out = dst.ptr; a.out_cstride = dst.C; a.out_coff = o.off; a.relu = 1;
-      a.bias = static_cast<const float*>(db);
+      a.out = dst.ptr; a.out_cstride = dst.C; a.out_coff = o.off; a.relu = o.no_act ? 0 : 1;
+      a.bias = conv_bias;
       a.idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       a.layout_type = bk == 64 ? 2u : bk == 32 ? 4u : 6u;
       a.sbo_bytes = 8u * (uint32_t)row_bytes;
@@ -1325,7 +1686,8 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
           if (st) return st;
         }
         macs_total += hl.macs_per_image;
-        net->steps.push_back({2, (int)net->halos.size()});
+        net->steps.push_back(Step{2, (int)net->halos.size()});
+        step_io.push_back({o.src, o.dst});
         net->halos.push_back(hl);
         continue;
       }
@@ -1363,7 +1725,17 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
           if (o.cout % d == 0) { best = d; break; }
         bn = best;
       }
-      const long want_ctas = 4L * net->num_sms;
+      // Persistent kernel where it measured faster (B200, 2048 images): 64-wide K blocks, N block >= 160 and at least four
+      // tiles per SM (1x1 768->192/160: 56 -> 42 us, 1x7/7x1 192->192: 66 -> 61 us).  Narrow N blocks or 16/32-wide K blocks
+      // leave its single accumulation chain per SM latency-bound (96->96 3x3: 141 -> 234 us), and on the 1x5 maps of
+      // mixed8-10 a few hundred tiles quantise badly over 148 CTAs; those stay on the one-tile-per-CTA kernel, where
+      // 3-4 co-resident CTAs give 3-4 independent chains.
+      {
+        const int mode = EnvInt("DVB_CNN_PERSIST", 1);   // 0 never, 1 by rule, 2 always
+        const long tiles = m_tiles * (o.cout / bn);
+        cl.persist = !split && (mode == 2 || (mode == 1 && bk == 64 && bn >= 160 && tiles >= 4L * net->num_sms));
+      }
+      const long want_ctas = cl.persist ? 0L : 4L * net->num_sms;   // the persistent kernel keeps the widest N block
       while (m_tiles * (o.cout / bn) < want_ctas && bn > 64) {
         int next = 0;
         for (int d = bn - 16; d >= 32; d -= 16)
@@ -1373,11 +1745,12 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       }
       a.block_n = bn;
     }
-    a.tmem_cols = TmemCols(split ? 2 * a.block_n : a.block_n);
-    a.out = dst.ptr; a.out_cstride = dst.C; a.out_coff = o.off; a.relu = 1;
+    a.tmem_cols = TmemCols(split || cl.persist ? 2 * a.block_n : a.block_n);
+    cl.n_blocks = o.cout / a.block_n; cl.cout = o.cout;
+    a.out = dst.ptr; a.out_cstride = dst.C; a.out_coff = o.off; a.relu = o.no_act ? 0 : 1;
     a.out_res = dst.ptr_res;
     a.skip_a_res = is_stem ? 1 : 0;   // the preprocessed input is exact in fp16: its residual plane is zero
-    a.bias = static_cast<const float*>(db);
+    a.bias = conv_bias;
     // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=F32, A=B=F16, K-major, M=128
     a.idesc = (1u << 4) | ((uint32_t)(a.block_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     a.layout_type = bk == 64 ? 2u : bk == 32 ? 4u : 6u;
@@ -1400,6 +1773,11 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       stages = std::max(1, std::min(stages, num_kb));
       a.stages = EnvInt("DVB_CNN_STAGES", 0) > 0 ? std::min(EnvInt("DVB_CNN_STAGES", 0), kMaxStages) : stages;
       cl.smem = a.stages * stage_bytes + 1024 + 256 + a.block_n * 4;
+      if (cl.persist) {   // one CTA per SM: the ring takes what the SM has
+        a.stages = std::max(2, std::min(kMaxStages, (EnvInt("DVB_PERSIST_SMEM_KB", 200) * 1024) / stage_bytes));
+        cl.smem = a.stages * stage_bytes + 1024 + 256 + o.cout * 4;
+        if (cl.smem > 227 * 1024) return dvb::fail(DVB_ERR_INTERNAL, "conv %zu: %d bytes of shared memory", net->convs.size(), cl.smem);
+      }
     }
     cl.macs_per_image = (double)Hout * Wout * o.cout * orig.kh * orig.kw * orig.cin;
     macs_total += cl.macs_per_image;
@@ -1439,8 +1817,36 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       }
     }
     cl.grid = dim3(1, (unsigned)(o.cout / a.block_n), 1);
-    net->steps.push_back({0, (int)net->convs.size()});
+    net->steps.push_back(Step{0, (int)net->convs.size()});
+    step_io.push_back({o.src, o.dst});
     net->convs.push_back(cl);
+  }
+  // --- lanes: chains of single-producer/single-consumer steps stay on one stream, every other consumer starts a new one
+  {
+    net->n_lanes = std::max(1, std::min(kMaxLanes, EnvInt("DVB_CNN_LANES", kMaxLanes)));
+    std::map<std::string, std::vector<int>> writers;   // tensor -> steps writing (a slice of) it; -1 = stem_patch_kernel
+    writers["input"].push_back(-1);
+    if (net->stem_fused) writers["s1"].push_back(-1);
+    std::map<int, bool> continued;
+    int rr = 1;
+    auto lane_of = [&](int st_i) { return st_i < 0 ? 0 : net->steps[st_i].lane; };
+    for (size_t i = 0; i < net->steps.size(); ++i) {
+      Step& stp = net->steps[i];
+      const std::vector<int>& w = writers[step_io[i].first];
+      if (w.size() == 1 && !continued[w[0]]) { stp.lane = lane_of(w[0]); continued[w[0]] = true; }
+      else { stp.lane = rr % net->n_lanes; ++rr; }
+      for (int d : w)
+        if (d >= 0 && lane_of(d) != stp.lane) { stp.deps.push_back(d); net->steps[d].record = true; }
+      writers[step_io[i].second].push_back((int)i);
+    }
+    for (int d : writers["mixed10"])
+      if (lane_of(d) != 0) { net->tail_deps.push_back(d); net->steps[d].record = true; }
+    for (Step& stp : net->steps)
+      if (stp.record && cudaEventCreateWithFlags(&stp.event, cudaEventDisableTiming) != cudaSuccess)
+        return dvb::fail(DVB_ERR_CUDA, "cudaEventCreate failed");
+    for (int l = 1; l < net->n_lanes; ++l)
+      if (cudaStreamCreateWithFlags(&net->lane_streams[l], cudaStreamNonBlocking) != cudaSuccess)
+        return dvb::fail(DVB_ERR_CUDA, "cudaStreamCreate failed");
   }
   // --- head
   const size_t dwb = 2048 * 3 * sizeof(float), dbb = 3 * sizeof(float);
@@ -1454,6 +1860,11 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
   net->flops_per_image = 2.0 * macs_total;
   int max_smem = 0;
   for (auto& c : net->convs) max_smem = std::max(max_smem, c.smem);
+  int max_persist = 0;
+  for (auto& c : net->convs)
+    if (c.persist) max_persist = std::max(max_persist, c.smem);
+  if (max_persist && cudaFuncSetAttribute(conv_gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_persist) != cudaSuccess)
+    return dvb::fail(DVB_ERR_CUDA, "cannot reserve %d bytes of shared memory (persistent kernel)", max_persist);
   if ((split ? cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)
              : cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess)
     return dvb::fail(DVB_ERR_CUDA, "cannot reserve %d bytes of shared memory", max_smem);
@@ -1471,9 +1882,19 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
   return DVB_OK;
 }
 
-int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaStream_t s) {
+int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaStream_t s0) {
   const TensorBuf& in = net->tensors[0];
-  {
+  cudaStream_t s = s0;
+  if (net->stem_fused) {
+    StemArgs a = net->stem_args;
+    a.in = images; a.n_images = n;
+    a.total_bytes = (long long)n * net->H * net->W * net->C;
+    const long long tiles = (long long)n * a.Ho * a.tiles_w;
+    const int smem = 1024 + 16384 + 4096 + 3 * a.h_pitch * 2 + 16 + a.cout * 4;
+    const int occ = EnvInt("DVB_STEM_CTAS_PER_SM", 4);   // 64 registers x 256 threads -> 4 resident CTAs per SM
+    const unsigned grid = (unsigned)std::min<long long>(tiles, (long long)net->num_sms * occ);
+    stem_conv1_kernel<<<grid, kStemThreads, smem, s>>>(a);
+  } else {
     const int groups = (net->stem_Ho + kPatchRows - 1) / kPatchRows;
     const int row_pitch = (net->W * net->C + 3 + 15) & ~15;
     const int smem = (2 * kPatchRows + 1) * row_pitch + 2 * net->stem_Kp;
@@ -1482,6 +1903,8 @@ int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaSt
   }
   net->launches++;
   for (const Step& stp : net->steps) {
+    cudaStream_t s = stp.lane == 0 ? s0 : net->lane_streams[stp.lane];
+    for (int d : stp.deps) cudaStreamWaitEvent(s, net->steps[d].event, 0);
     if (stp.kind == 2) {
       HaloLaunch& hl = net->halos[stp.index];
       HaloArgs a = hl.args;
@@ -1516,7 +1939,11 @@ int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaSt
         a.tiles_w = (a.Wout + 127) / 128; a.tiles_h = 1; a.tiles_n = 1;
       }
       dim3 grid((unsigned)(a.tiles_w * a.tiles_h * a.tiles_n), c.grid.y, 1);
-      if (net->precision == 1)
+      if (c.persist) {
+        const long total = (long)grid.x * c.n_blocks;
+        conv_gemm_persistent_kernel<<<(unsigned)std::min<long>(total, net->num_sms), kPersistThreads, c.smem, s>>>(c.map_a, c.map_b, a, c.n_blocks,
+                                                                                                                   c.cout);
+      } else if (net->precision == 1)
         conv_gemm_kernel<true><<<grid, kConvThreads, c.smem, s>>>(c.map_a, c.map_b, c.map_a_res, c.map_b_res, a);
       else
         conv_gemm_kernel<false><<<grid, kConvThreads, c.smem, s>>>(c.map_a, c.map_b, c.map_a_res, c.map_b_res, a);
@@ -1524,10 +1951,13 @@ int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaSt
       const PoolLaunch& p = net->pools[stp.index];
       const long long total = (long long)n * p.Hout * (p.C / 8);
       pool3x3_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(p.in, p.out, n, p.Hin, p.Win, p.C, p.Hout, p.Wout, p.out_cstride,
-                                                                      p.out_coff, p.mode, p.in_res, p.out_res);
+                                                                      p.out_coff, p.mode, p.in_res, p.out_res, p.bias);
     }
     net->launches++;
+    if (stp.record) cudaEventRecord(stp.event, s);
   }
+  for (int d : net->tail_deps) cudaStreamWaitEvent(s0, net->steps[d].event, 0);
+  s = s0;
   const TensorBuf& f = net->tensors[net->feat_tensor];
   tail_kernel<<<n, 256, 0, s>>>(f.ptr, f.H * f.W, f.C, net->d_dense_w, net->d_dense_b, probs, net->d_pooled, f.ptr_res);
   net->launches++;
@@ -1573,6 +2003,10 @@ void dvb_cnn_destroy(DvbCnn* net) {
   if (net->d_pooled) cudaFree(net->d_pooled);
   net->d_in.release(); net->d_probs.release(); net->h_io.release();
   if (net->stream) cudaStreamDestroy(net->stream);
+  for (int l = 1; l < kMaxLanes; ++l)
+    if (net->lane_streams[l]) cudaStreamDestroy(net->lane_streams[l]);
+  for (Step& stp : net->steps)
+    if (stp.event) cudaEventDestroy(stp.event);
   delete net;
 }
 

@@ -41,6 +41,12 @@ std::string& last_error() {
 namespace {
 
 constexpr int kThreads = 256;
+// Resident CTAs per SM the register allocation must allow.  The kernel is bound by dependent global-load chains
+// (pair -> read header -> CIGAR -> bases).  Measured on B200 (16,384 windows): 4 -> 0.995 ms (48 registers, 5 CTAs
+// resident), 6 -> 1.066 ms (40 registers, no spills, but the tighter allocation costs more than the extra warps give).
+#ifndef DVB_ENC_MIN_BLOCKS
+#define DVB_ENC_MIN_BLOCKS 4
+#endif
 constexpr int kWarps = kThreads / 32;
 constexpr float kMaxPixelValueAsFloat = 254.0f;  // channels/channel.h:78
 constexpr float kMaxFragmentLength = 1000.0f;    // channels/channel.h:81
@@ -229,7 +235,7 @@ __device__ __forceinline__ void flush_row(uint8_t* __restrict__ dst, const uint8
 // FAST7: 7 computed channels, 7-byte pixels (the WGS layout): runs of 4 pixels whose first column is a multiple of 4 are
 // assembled in registers and stored as 7 aligned 32-bit words instead of 28 byte stores.
 template <bool FAST7>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, DVB_ENC_MIN_BLOCKS)
 dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, int* __restrict__ rows_kept,
                   int* __restrict__ err) {
   extern __shared__ __align__(16) uint8_t smem[];

@@ -51,9 +51,10 @@ def test_stem_layers_match_oracle():
     assert err < 6e-3, report
 
 
-def test_stem_patches_are_exact():
+def test_stem_patches_are_exact(monkeypatch):
   """Tensor 'input' = preprocess + im2col of conv1: patch k = (r*3+s)*C + c holds (x[2oh+r, 2ow+s, c] - 128)/128 exactly."""
   shape = (100, 221, 7)
+  monkeypatch.setenv('DVB_CNN_STEM_FUSED', '0')   # the patch route (PACBIO geometry, precision 1); WGS fuses conv1 into the gather
   net = cv.GpuCnn(modeling.random_weights(7, 0), shape, device=0, max_batch=2)
   imgs = _images(2, shape, 9)
   probs = torch.empty((2, 3), dtype=torch.float32, device='cuda:0')
@@ -82,8 +83,9 @@ def test_all_block_outputs_match_oracle():
 
 
 def test_branch_tensors_match_oracle():
-  names = ['mixed0_b5a', 'mixed0_d2', 'mixed0_ap', 'mixed3_d2', 'mixed4_s2', 'mixed4_d4', 'mixed4_ap', 'mixed8_b3', 'mixed9_t1',
-           'mixed9_d2', 'mixed10_ap']
+  # ('*_ap' tensors are not compared: the engine runs the 1x1 convolution BEFORE the average pool - they commute -
+  # so its '*_ap' buffer holds conv(x), not avgpool(x); the block outputs above cover that branch.)
+  names = ['mixed0_b5a', 'mixed0_d2', 'mixed3_d2', 'mixed4_s2', 'mixed4_d4', 'mixed8_b3', 'mixed9_t1', 'mixed9_d2']
   report, worst, _, _, _, _ = _check_layers((100, 221, 7), 2, names, seed=2)
   print(report)
   for name, err in report:
@@ -188,14 +190,14 @@ def test_precise_mode_every_block_output_close_to_fp32_oracle():
   torch.cuda.synchronize()
   want_p, tensors, pooled = cnn_oracle.ReferenceModel(w).forward(imgs, return_tensors=True)
   report = []
-  for name in STEM + [f'mixed{i}' for i in range(11)] + ['mixed0_ap', 'mixed4_d4', 'mixed9_t1']:
+  for name in STEM + [f'mixed{i}' for i in range(11)] + ['mixed4_d4', 'mixed9_t1']:
     got = net.debug_tensor(name, n)
     ref = tensors[name].permute(0, 2, 3, 1).numpy()
     scale = max(float(np.abs(ref).max()), 1e-6)
     report.append((name, float(np.abs(got - ref).max()) / scale))
   print(report)
   for name, err in report:
-    assert err < 2e-5, report     # fp32-grade: four orders below the single-pass fp16 path
+    assert err < 5e-5, report     # fp32-grade (measured 3e-7 at s1 .. 2e-5 at mixed10 relative to scale): ~1000x below the single-pass fp16 path
   assert float((probs.cpu() - want_p).abs().max()) < PRECISE_TOL
 
 
@@ -214,3 +216,38 @@ def test_precise_mode_pacbio_geometry_and_encoder_images():
   got7 = enc.encode_classify_host(host, net7)
   want7 = cnn_oracle.ReferenceModel(w7).forward(torch.from_numpy(images)).numpy()
   assert float(np.abs(got7 - want7).max()) < PRECISE_TOL
+
+
+def test_fused_stem_equals_patch_route_bit_for_bit(monkeypatch):
+  """stem_conv1_kernel (uint8 image -> s1 in one kernel) and the patch route (stem_patch_kernel + GEMM) feed the tensor
+  cores the same fp16 operands in the same K order, so s1 and everything after it must be identical."""
+  shape = (100, 221, 7)
+  w = modeling.random_weights(7, 15)
+  imgs = _images(5, shape, 15)
+  outs = []
+  for fused in ('1', '0'):
+    monkeypatch.setenv('DVB_CNN_STEM_FUSED', fused)
+    net = cv.GpuCnn(w, shape, device=0, max_batch=5)
+    probs = net.forward_host(imgs.numpy())
+    outs.append((net.debug_tensor('s1', 5), probs))
+    net.close()
+  np.testing.assert_array_equal(outs[0][0], outs[1][0])
+  np.testing.assert_array_equal(outs[0][1], outs[1][1])
+
+
+def test_pool_after_conv_rewrite_matches_original_order(monkeypatch):
+  """relu(conv1x1(avgpool(x)) + b) == relu(avgpool(conv1x1(x)) + b): the engine's reordered graph against the
+  graph in the reference's order, same weights and images (fp16 rounding happens at different points, so close, not equal)."""
+  shape = (100, 221, 7)
+  w = modeling.random_weights(7, 16)
+  imgs = _images(4, shape, 16)
+  outs = []
+  for flag in ('1', '0'):
+    monkeypatch.setenv('DVB_CNN_POOL_AFTER_CONV', flag)
+    net = cv.GpuCnn(w, shape, device=0, max_batch=4)
+    probs = net.forward_host(imgs.numpy())
+    outs.append((net.debug_tensor('mixed10', 4), probs))
+    net.close()
+  scale = float(np.abs(outs[1][0]).max())
+  assert float(np.abs(outs[0][0] - outs[1][0]).max()) / scale < 1e-2
+  assert float(np.abs(outs[0][1] - outs[1][1]).max()) < 2e-3

@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -5 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --steps 8 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench exit $?"; cat gpurun_out/bench_n1.json; tail -3 gpurun_out/bench_n1.err
+echo "== chunk 2048 for comparison"; timeout 200 python tools/cnn_time.py --batch 8192 --chunk 2048 --steps 3
+echo "== chunk 4096"; timeout 200 python tools/cnn_time.py --batch 8192 --chunk 4096 --steps 3
+echo "== persist never"; DVB_CNN_PERSIST=0 timeout 200 python tools/cnn_time.py --batch 8192 --chunk 4096 --steps 3
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 1 --batch 4096 --no-cpu-baseline --no-e2e > gpurun_out/bench_ncu.log 2>&1; echo "ncu launches exit $?"
+timeout 900 ncu --set full --clock-control none -k regex:"conv_|pool3x3|stem_|tail" -s 108 -c 108 -o /tmp/cnn_full -f python tools/cnn_time.py --batch 2048 --chunk 2048 --steps 1 --warmup 1 > gpurun_out/cnn_full.log 2>&1; echo "ncu cnn exit $?"
+ncu -i /tmp/cnn_full.ncu-rep --page raw --csv > gpurun_out/cnn_full_raw.csv 2>/dev/null
+du -sh gpurun_out

@@ -27,21 +27,23 @@ with open(path) as f:
       rows.append((short, r[8], float(r[14]) / 1e3))   # us
 # find the LAST complete forward: ... stem_patch ... tail
 tails = [i for i, r in enumerate(rows) if r[0] == 'tail_kernel']
-stems = [i for i, r in enumerate(rows) if r[0] == 'stem_patch_kernel']
+stems = [i for i, r in enumerate(rows) if r[0].startswith('stem_')]
 end = tails[-1]
 start = max(i for i in stems if i < end)
 fw = rows[start:end + 1]
 ops, _ = modeling.inception_v3_graph(C)
-assert len(fw) == len(ops) + 2, (len(fw), len(ops))
+fused = fw[0][0] == 'stem_conv1_kernel'   # preprocess + im2col + conv1 in one launch
+assert len(fw) == len(ops) + (1 if fused else 2), (len(fw), len(ops))
 hw = {'input': (H, W)}
 total_us = sum(r[2] for r in fw)
 enc = [r for r in rows if r[0] == 'dvb_encode_kernel']
 print(f'| # | op | kernel | grid | out HxW | Cin->Cout k | us | GFLOP | TFLOP/s | % of forward |')
 print('|---|---|---|---|---|---|---|---|---|---|')
-print(f'| 0 | preprocess+im2col | {fw[0][0]} | {fw[0][1]} | | | {fw[0][2]:.1f} | | | {100 * fw[0][2] / total_us:.1f} |')
+if not fused:
+  print(f'| 0 | preprocess+im2col | {fw[0][0]} | {fw[0][1]} | | | {fw[0][2]:.1f} | | | {100 * fw[0][2] / total_us:.1f} |')
 by_kernel = {}
 flops_total = 0.0
-for i, (o, r) in enumerate(zip(ops, fw[1:-1]), 1):
+for i, (o, r) in enumerate(zip(ops, fw[0:-1] if fused else fw[1:-1]), 1):
   h, w = hw[o.src]
   oh, ow = modeling.out_hw(o, h, w)
   hw[o.dst] = (oh, ow)
