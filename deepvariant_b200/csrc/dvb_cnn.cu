@@ -916,13 +916,23 @@ struct StemArgs {
   int h_pitch;   // halves per staged input row (multiple of 8)
 };
 
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kStemRawPitch = 1824;   // bytes per staged raw input row segment (>= 1799 + 3 + 4, multiple of 16)
+
 __global__ void __launch_bounds__(kStemThreads) stem_conv1_kernel(const StemArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                         // 128 rows x 128 B, 128B swizzle
   uint8_t* sB = smem + 16384;                 // cout rows x 128 B, 128B swizzle (cout <= 32 -> 4 KB)
   __half* sH = reinterpret_cast<__half*>(smem + 16384 + 4096);   // [3][h_pitch]
-  uint64_t* mma_done = reinterpret_cast<uint64_t*>(sH + 3 * p.h_pitch);
+  uint8_t* sRaw = reinterpret_cast<uint8_t*>(sH + 3 * p.h_pitch);   // [2][3][kStemRawPitch] raw uint8 row segments (cp.async ring)
+  uint64_t* mma_done = reinterpret_cast<uint64_t*>(sRaw + 2 * 3 * kStemRawPitch);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
   float* s_bias = reinterpret_cast<float*>(mma_done + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -944,32 +954,52 @@ __global__ void __launch_bounds__(kStemThreads) stem_conv1_kernel(const StemArgs
   uint32_t phase = 0;
   const __half2 kScale = __floats2half2_rn(1.f / 128.f, 1.f / 128.f), kBias = __floats2half2_rn(-9.f, -9.f);
 
-  for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  // Asynchronous staging of the raw bytes of one tile (3 row segments) into ring slot `slot`: the loads of tile i + 1 are
+  // in flight while tile i is converted, assembled, multiplied and written out.
+  auto stage = [&](long long tile, int slot) {
+    const int tw = (int)(tile % p.tiles_w);
+    const long long t2 = tile / p.tiles_w;
+    const int oh = (int)(t2 % p.Ho), n = (int)(t2 / p.Ho);
+    const int ow0 = tw * 128;
+    const int npx = min(128, p.Wo - ow0);
+    const int seg_bytes = (2 * (npx - 1) + 3) * kStemC;
+    for (int r = 0; r < 3; ++r) {
+      const long long g0 = ((long long)(n * (long long)p.H + 2 * oh + r)) * row_bytes + (long long)2 * ow0 * kStemC;
+      const int mis = (int)(g0 & 3);
+      const long long base = g0 - mis;
+      const int nwl = ((mis + seg_bytes + 3) >> 2) + 1;   // one spare word for the funnel shift of the last group
+      uint8_t* dst = sRaw + (slot * 3 + r) * kStemRawPitch;
+      for (int i = tid; i < nwl; i += kStemThreads) {
+        const long long off = base + 4LL * i;
+        const long long left = p.total_bytes - off;
+        cp_async4(dst + 4 * i, p.in + (left > 0 ? off : base), left >= 4 ? 4 : (left > 0 ? (int)left : 0));   // never read past the caller's buffer
+      }
+    }
+    cp_async_commit();
+  };
+
+  long long tile = blockIdx.x;
+  int slot = 0;
+  if (tile < total_tiles) stage(tile, 0);
+  for (; tile < total_tiles; tile += gridDim.x, slot ^= 1) {
     const int tw = (int)(tile % p.tiles_w);
     const long long t2 = tile / p.tiles_w;
     const int oh = (int)(t2 % p.Ho), n = (int)(t2 / p.Ho);
     const int ow0 = tw * 128;
     const int npx = min(128, p.Wo - ow0);
     const int seg_bytes = (2 * (npx - 1) + 3) * kStemC;   // input bytes of one row this tile touches
-    // ---- phase 1: 3 input row segments -> fp16 (x - 128) / 128 in shared memory
+    if (tile + gridDim.x < total_tiles) { stage(tile + gridDim.x, slot ^ 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncthreads();
+    // ---- phase 1: raw bytes -> fp16 (x - 128) / 128 in shared memory
     for (int r = 0; r < 3; ++r) {
       const long long g0 = ((long long)(n * (long long)p.H + 2 * oh + r)) * row_bytes + (long long)2 * ow0 * kStemC;
       const int mis = (int)(g0 & 3);
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(p.in + (g0 - mis));
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(sRaw + (slot * 3 + r) * kStemRawPitch);
       const int nw = (seg_bytes + 3) >> 2;
       uint2* dst = reinterpret_cast<uint2*>(sH + r * p.h_pitch);
       for (int i = tid; i < nw; i += kStemThreads) {
-        const long long off = (g0 - mis) + 4LL * i;
-        uint32_t lo;
-        if (off + 4 <= p.total_bytes) {
-          lo = __ldg(src + i);
-        } else {   // never read past the end of the caller's buffer
-          lo = 0u;
-          for (int bb = 0; bb < 4; ++bb)
-            if (off + bb < p.total_bytes) lo |= (uint32_t)p.in[off + bb] << (8 * bb);
-        }
-        const uint32_t hi = (mis && off + 8 <= p.total_bytes) ? __ldg(src + i + 1) : 0u;
-        const uint32_t v = __funnelshift_r(lo, hi, 8 * mis);     // bytes g0 + 4i .. g0 + 4i + 3
+        const uint32_t v = __funnelshift_r(src[i], src[i + 1], 8 * mis);     // bytes g0 + 4i .. g0 + 4i + 3
         uint32_t a = __byte_perm(v, 0x64646464u, 0x4140), b = __byte_perm(v, 0x64646464u, 0x4342);
         __half2 ha = __hfma2(*reinterpret_cast<__half2*>(&a), kScale, kBias), hb = __hfma2(*reinterpret_cast<__half2*>(&b), kScale, kBias);
         dst[i] = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
@@ -1368,6 +1398,11 @@ struct DvbCnn {
   double flops_per_image = 0;
   int64_t launches = 0;
   cudaStream_t stream = nullptr;
+  // Second, independent pipeline (own activation buffers, tensor maps, lanes): odd chunks of a multi-chunk forward run on
+  // it concurrently with the even chunks, so that the bandwidth-bound stem of one chunk overlaps the small-grid,
+  // latency-bound mixed4-10 layers of the other.
+  DvbCnn* twin = nullptr;
+  cudaEvent_t twin_start = nullptr, twin_done = nullptr;
   bool stem_fused = false;
   StemArgs stem_args;
   int n_lanes = 1;
@@ -1890,7 +1925,7 @@ int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaSt
     a.in = images; a.n_images = n;
     a.total_bytes = (long long)n * net->H * net->W * net->C;
     const long long tiles = (long long)n * a.Ho * a.tiles_w;
-    const int smem = 1024 + 16384 + 4096 + 3 * a.h_pitch * 2 + 16 + a.cout * 4;
+    const int smem = 1024 + 16384 + 4096 + 3 * a.h_pitch * 2 + 2 * 3 * kStemRawPitch + 16 + a.cout * 4;
     const int occ = EnvInt("DVB_STEM_CTAS_PER_SM", 4);   // 64 registers x 256 threads -> 4 resident CTAs per SM
     const unsigned grid = (unsigned)std::min<long long>(tiles, (long long)net->num_sms * occ);
     stem_conv1_kernel<<<grid, kStemThreads, smem, s>>>(a);
@@ -1990,6 +2025,18 @@ int dvb_cnn_create(const void* weights, int64_t weights_bytes, int32_t height, i
   int st = Plan(net, static_cast<const uint8_t*>(weights), weights_bytes);
   if (st) { dvb_cnn_destroy(net); return st; }
   DVB_CUDA(cudaStreamCreateWithFlags(&net->stream, cudaStreamNonBlocking));
+  static thread_local bool creating_twin = false;
+  if (!creating_twin && EnvInt("DVB_CNN_TWIN", 1)) {
+    creating_twin = true;
+    st = dvb_cnn_create(weights, weights_bytes, height, width, channels, max_batch, precision, device, &net->twin);
+    creating_twin = false;
+    if (st) { dvb_cnn_destroy(net); return st; }
+    if (cudaEventCreateWithFlags(&net->twin_start, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&net->twin_done, cudaEventDisableTiming) != cudaSuccess) {
+      dvb_cnn_destroy(net);
+      return dvb::fail(DVB_ERR_CUDA, "cudaEventCreate failed");
+    }
+  }
   *out = net;
   return DVB_OK;
 }
@@ -2007,6 +2054,9 @@ void dvb_cnn_destroy(DvbCnn* net) {
     if (net->lane_streams[l]) cudaStreamDestroy(net->lane_streams[l]);
   for (Step& stp : net->steps)
     if (stp.event) cudaEventDestroy(stp.event);
+  if (net->twin) dvb_cnn_destroy(net->twin);
+  if (net->twin_start) cudaEventDestroy(net->twin_start);
+  if (net->twin_done) cudaEventDestroy(net->twin_done);
   delete net;
 }
 
@@ -2014,10 +2064,22 @@ int dvb_cnn_forward_device(DvbCnn* net, const uint8_t* images, int32_t n, float*
   if (!net || (n > 0 && (!images || !probs)) || n < 0) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_cnn_forward_device: bad arguments");
   DVB_CUDA(cudaSetDevice(net->device));
   const size_t image_bytes = (size_t)net->H * net->W * net->C;
-  for (int i = 0; i < n; i += net->max_batch) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool use_twin = net->twin != nullptr && n > net->max_batch;
+  if (use_twin) {   // the twin's stream starts after everything already queued on the caller's stream (the images)
+    DVB_CUDA(cudaEventRecord(net->twin_start, s));
+    DVB_CUDA(cudaStreamWaitEvent(net->twin->stream, net->twin_start, 0));
+  }
+  int k = 0;
+  for (int i = 0; i < n; i += net->max_batch, ++k) {
     const int m = std::min(net->max_batch, n - i);
-    int st = ForwardChunk(net, images + (size_t)i * image_bytes, m, probs + (size_t)i * 3, static_cast<cudaStream_t>(stream));
+    DvbCnn* pipe = (use_twin && (k & 1)) ? net->twin : net;
+    int st = ForwardChunk(pipe, images + (size_t)i * image_bytes, m, probs + (size_t)i * 3, pipe == net ? s : net->twin->stream);
     if (st) return st;
+  }
+  if (use_twin) {
+    DVB_CUDA(cudaEventRecord(net->twin_done, net->twin->stream));
+    DVB_CUDA(cudaStreamWaitEvent(s, net->twin_done, 0));
   }
   return DVB_OK;
 }
@@ -2037,7 +2099,7 @@ int dvb_cnn_forward_host(DvbCnn* net, const uint8_t* images_host, int32_t n, flo
   return DVB_OK;
 }
 
-int64_t dvb_cnn_launch_count(const DvbCnn* net) { return net ? net->launches : 0; }
+int64_t dvb_cnn_launch_count(const DvbCnn* net) { return net ? net->launches + (net->twin ? net->twin->launches : 0) : 0; }
 double dvb_cnn_flops_per_image(const DvbCnn* net) { return net ? net->flops_per_image : 0.0; }
 
 // Debug / test access to an intermediate activation of the LAST forward (first `n` images):
