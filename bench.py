@@ -117,6 +117,28 @@ class ClockSampler:
             'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def effective_cores():
+  """Host cores this process may actually use: the scheduler affinity mask capped by the cgroup CPU quota
+  (os.cpu_count() reports the machine, not the container)."""
+  try:
+    n = len(os.sched_getaffinity(0))
+  except AttributeError:
+    n = os.cpu_count() or 1
+  try:
+    quota, period = open('/sys/fs/cgroup/cpu.max').read().split()[:2]
+    if quota != 'max':
+      n = min(n, max(1, int(float(quota) / float(period) + 0.999)))
+  except (OSError, ValueError):
+    try:   # cgroup v1
+      quota = int(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read())
+      period = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+      if quota > 0 and period > 0:
+        n = min(n, max(1, (quota + period - 1) // period))
+    except (OSError, ValueError):
+      pass
+  return max(1, n)
+
+
 def wgs_options():
   from deepvariant_b200 import pileup_image as pi
   o = pi.default_options()
@@ -136,7 +158,7 @@ class CpuReference:
     from deepvariant_b200 import modeling
     self.params, self.cores = params, cores
     oracle_lib.oracle()
-    torch.set_num_threads(min(cores, 64))
+    torch.set_num_threads(cores)
     self.cnn = cnn_oracle.FastCpuModel(modeling.random_weights(params.num_channels + params.num_alt_channels, 0))
 
   def encode(self, packed, n_images):
@@ -176,7 +198,7 @@ def run_reference(args):
     return
   from deepvariant_b200 import pileup_image as pi, synthetic
   params = pi.to_params(wgs_options())
-  cores = os.cpu_count() or 1
+  cores = effective_cores()
   ref = CpuReference(params, cores)
   packed = synthetic.make_batch(args.cpu_sample, 'cpu').to_packed()
   sample, _, _ = ref.calibrate(packed)
@@ -356,7 +378,7 @@ def main():
 
   cpu_baseline = None
   if not args.no_cpu_baseline:
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     ref = CpuReference(params, cores)
     packed = synthetic.make_batch(args.cpu_sample, 'cpu').to_packed()
     sample, _, _ = ref.calibrate(packed, target_s=6.0)

@@ -101,6 +101,23 @@ class DvbError(RuntimeError):
     self.status = status
 
 
+class DvbReadRequirements(C.Structure):
+  _fields_ = [(n, C.c_int32) for n in (
+      'min_mapping_quality', 'keep_duplicates', 'keep_failed_vendor_quality_checks', 'keep_secondary_alignments',
+      'keep_supplementary_alignments', 'keep_unaligned', 'keep_improperly_placed')]
+
+
+class DvbReadTable(C.Structure):
+  _fields_ = [
+      ('n_reads', C.c_int32), ('n_refs', C.c_int32), ('n_bases', C.c_int64), ('n_cigar', C.c_int64),
+      ('n_name_bytes', C.c_int64), ('n_records_seen', C.c_int64),
+      ('ref_id', C.c_void_p), ('pos', C.c_void_p), ('end', C.c_void_p), ('mapq', C.c_void_p), ('flag', C.c_void_p),
+      ('fragment_length', C.c_void_p), ('hp', C.c_void_p), ('read_number', C.c_void_p), ('number_reads', C.c_void_p),
+      ('seq_begin', C.c_void_p), ('cigar_begin', C.c_void_p), ('name_begin', C.c_void_p),
+      ('bases', C.c_void_p), ('quals', C.c_void_p), ('cigar', C.c_void_p), ('names', C.c_void_p),
+  ]
+
+
 _lib: Optional[C.CDLL] = None
 
 # Every symbol include/dvb.h declares: (name, restype, argtypes).
@@ -124,6 +141,11 @@ SYMBOLS = (
     ('dvb_encode_classify_host', C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(DvbBatch), C.c_void_p, C.c_void_p]),
     ('dvb_cnn_launch_count', C.c_int64, [C.c_void_p]),
     ('dvb_cnn_flops_per_image', C.c_double, [C.c_void_p]),
+    ('dvb_read_requirements_default', None, [C.POINTER(DvbReadRequirements)]),
+    ('dvb_bam_open', C.c_int, [C.c_char_p, C.POINTER(DvbReadRequirements), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    ('dvb_bam_table', C.c_int, [C.c_void_p, C.POINTER(DvbReadTable)]),
+    ('dvb_bam_ref_name', C.c_char_p, [C.c_void_p, C.c_int32]),
+    ('dvb_bam_close', None, [C.c_void_p]),
     ('dvb_crc32c', C.c_uint32, [C.c_char_p, C.c_size_t]),
     ('dvb_masked_crc32c', C.c_uint32, [C.c_char_p, C.c_size_t]),
     ('dvb_cnn_debug_tensor', C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32),

@@ -129,3 +129,99 @@ class BamReader:
   def query(self, contig: str, start: int, end: int) -> List[Read]:
     """Reads overlapping [start, end) in file order (ReadOverlapsRegion, utils.cc:172-188)."""
     return [r for r in self._by_contig.get(contig, ()) if end > r.position and start < r.end()]
+
+
+# ---------------------------------------------------------------------------------------------
+# Native decode (libdvb.so dvb_bam_*, csrc/dvb_bam.cu): BAM -> Structure-of-Arrays read table
+# ---------------------------------------------------------------------------------------------
+
+class NativeBamTable:
+  """Flat numpy arrays of every read that passes the ReadRequirements filter, decoded by the C++ block-parallel
+  BGZF/BAM decoder (include/dvb.h DvbReadTable).  `reads()` materialises the same `Read` objects `BamReader`
+  produces (used by the planner and by the parity tests); `query()` answers region queries on the arrays."""
+
+  def __init__(self, path: str, read_requirements: Optional[ReadRequirements] = None, parse_aux: bool = False,
+               threads: int = 0):
+    import ctypes as C
+    import numpy as np
+    from deepvariant_b200 import _lib
+    lib = _lib.lib()
+    req = read_requirements or ReadRequirements()
+    creq = _lib.DvbReadRequirements(
+        int(req.min_mapping_quality), int(req.keep_duplicates), int(req.keep_failed_vendor_quality_checks),
+        int(req.keep_secondary_alignments), int(req.keep_supplementary_alignments), int(req.keep_unaligned),
+        int(req.keep_improperly_placed))
+    h = C.c_void_p()
+    _lib.check(lib.dvb_bam_open(path.encode(), C.byref(creq), int(parse_aux), threads, C.byref(h)))
+    try:
+      t = _lib.DvbReadTable()
+      _lib.check(lib.dvb_bam_table(h, C.byref(t)))
+      n = t.n_reads
+
+      def arr(ptr, count, dtype):
+        if not count:
+          return np.zeros(0, dtype=dtype)
+        buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=count).copy()   # own the data: the handle is closed below
+
+      self.n_reads = n
+      self.n_records_seen = int(t.n_records_seen)
+      self.references = [lib.dvb_bam_ref_name(h, i).decode() for i in range(t.n_refs)]
+      self.ref_id = arr(t.ref_id, n, np.int32)
+      self.pos = arr(t.pos, n, np.int32)
+      self.end = arr(t.end, n, np.int32)
+      self.mapq = arr(t.mapq, n, np.uint8)
+      self.flag = arr(t.flag, n, np.uint16)
+      self.fragment_length = arr(t.fragment_length, n, np.int32)
+      self.hp = arr(t.hp, n, np.int32)
+      self.read_number = arr(t.read_number, n, np.uint8)
+      self.number_reads = arr(t.number_reads, n, np.uint8)
+      self.seq_begin = arr(t.seq_begin, n + 1, np.int64)
+      self.cigar_begin = arr(t.cigar_begin, n + 1, np.int64)
+      self.name_begin = arr(t.name_begin, n + 1, np.int64)
+      self.bases = arr(t.bases, t.n_bases, np.uint8)
+      self.quals = arr(t.quals, t.n_bases, np.uint8)
+      self.cigar = arr(t.cigar, t.n_cigar, np.uint32)
+      self.names = arr(t.names, t.n_name_bytes, np.uint8).tobytes()
+    finally:
+      lib.dvb_bam_close(h)
+    self.parse_aux = parse_aux
+    self._reads: Optional[List[Read]] = None
+
+  HP_ABSENT = -(1 << 31)
+
+  def read(self, i: int) -> Read:
+    fl = int(self.flag[i])
+    mapped = not fl & FUNMAP
+    c0, c1 = int(self.cigar_begin[i]), int(self.cigar_begin[i + 1])
+    s0, s1 = int(self.seq_begin[i]), int(self.seq_begin[i + 1])
+    rid = int(self.ref_id[i])
+    r = Read(fragment_name=self.names[int(self.name_begin[i]):int(self.name_begin[i + 1])].decode(),
+             read_number=int(self.read_number[i]), reference_name=self.references[rid] if rid >= 0 else '',
+             position=int(self.pos[i]), reverse_strand=bool(fl & FREVERSE), mapping_quality=int(self.mapq[i]),
+             cigar=[(int(v) & 0xF, int(v) >> 4) for v in self.cigar[c0:c1]] if mapped else [],
+             aligned_sequence=self.bases[s0:s1].tobytes(), aligned_quality=self.quals[s0:s1].tobytes(),
+             fragment_length=int(self.fragment_length[i]), supplementary_alignment=bool(fl & FSUPP),
+             secondary_alignment=bool(fl & FSECONDARY), duplicate_fragment=bool(fl & FDUP),
+             failed_vendor_quality_checks=bool(fl & FQCFAIL), proper_placement=bool(fl & FPROPER),
+             number_reads=int(self.number_reads[i]))
+    if self.parse_aux and int(self.hp[i]) != self.HP_ABSENT:
+      r.hp_values = [int(self.hp[i])]
+    return r
+
+  def reads(self) -> List[Read]:
+    if self._reads is None:
+      self._reads = [self.read(i) for i in range(self.n_reads)]
+    return self._reads
+
+  def query_indices(self, contig: str, start: int, end: int):
+    """Indices (file order) of reads overlapping [start, end): ReadOverlapsRegion (utils.cc:172-188)."""
+    import numpy as np
+    if contig not in self.references:
+      return np.zeros(0, dtype=np.int64)
+    rid = self.references.index(contig)
+    return np.nonzero((self.ref_id == rid) & (self.pos < end) & (self.end > start))[0]
+
+  def query(self, contig: str, start: int, end: int) -> List[Read]:
+    rs = self.reads()
+    return [rs[i] for i in self.query_indices(contig, start, end)]

@@ -169,7 +169,14 @@ def smoke(images) -> None:
   want = cnn_oracle.ReferenceModel(w).forward(images[:n].cpu())
   err = (probs.cpu() - want).abs().max().item()
   print(f'[smoke] cnn: {n} images, max |p - oracle fp32| = {err:.2e}, launches {net.launch_count}')
-  assert err < 2e-2, 'CNN output far from the fp32 oracle'
+  assert err < 5e-3, 'CNN output far from the fp32 oracle'
+  net.close()
+  precise = GpuCnn(w, shape, device=0, max_batch=n, precision=1)
+  precise.forward_device(images[:n].contiguous(), probs)
+  torch.cuda.synchronize()
+  err1 = (probs.cpu() - want).abs().max().item()
+  print(f'[smoke] cnn precision 1 (split-fp16 x3): max |p - oracle fp32| = {err1:.2e}')
+  assert err1 < 1e-5, 'precision-1 CNN output is not within 1e-5 of the fp32 oracle'
 
 
 # ---- the stage driver (deepvariant/call_variants.py:766-1047) -------------------------------------

@@ -82,15 +82,20 @@ def make_examples(argv):
   out_path = tfrecord.shard_path(a.examples, a.task)
   n_shards = len(tfrecord.shard_paths(a.examples))
   gen = men.ExamplesGenerator(opts, {'main_sample': out_path}, device=a.device)
-  reader = bam.BamReader(a.reads, bam.ReadRequirements(min_mapping_quality=a.min_mapping_quality), parse_aux=a.parse_sam_aux_fields)
+  # Native block-parallel BAM decode into a Structure-of-Arrays read table (csrc/dvb_bam.cu); untrimmed pileups (WGS/WES)
+  # are planned and packed straight from the table rows, trimmed ones (PACBIO, alt-aligned) from Read objects of table.query().
+  reader = bam.NativeBamTable(a.reads, bam.ReadRequirements(min_mapping_quality=a.min_mapping_quality), parse_aux=a.parse_sam_aux_fields)
+  table_path = not a.trim_reads_for_pileup and a.alt_aligned_pileup == 'none' 
   cands = [protos.parse_deepvariant_call(r) for p in tfrecord.resolve_input_paths(a.candidates) for r in tfrecord.read_records(p)]
   region = parse_region(a.regions) if a.regions else None
   totals = {}
   for (contig, k, origin), cs in men.shard_partitions(men.partition_candidates(cands, a.partition_size, region), n_shards, a.task):
     p0 = origin + k * a.partition_size
     p1 = p0 + a.partition_size if not region else min(p0 + a.partition_size, region[2])
-    reads = reader.query(contig, p0, p1)
-    stats, _ = gen.write_examples_in_region(cs, [reads], [0], 'main_sample', [0.0])
+    if table_path:
+      stats, _ = gen.write_examples_in_region_from_table(cs, reader, 'main_sample', (contig, p0, p1))
+    else:
+      stats, _ = gen.write_examples_in_region(cs, [reader.query(contig, p0, p1)], [0], 'main_sample', [0.0])
     for key, val in stats.items():
       totals[key] = totals.get(key, 0) + val
   gen.signal_shard_finished()

@@ -916,14 +916,14 @@ struct StemArgs {
   int h_pitch;   // halves per staged input row (multiple of 8)
 };
 
-__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src, int src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, int src_bytes) {   // zero-fills past src_bytes
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int kStemRawPitch = 1824;   // bytes per staged raw input row segment (>= 1799 + 3 + 4, multiple of 16)
+constexpr int kStemRawPitch = 1840;   // bytes per staged raw input row segment (>= 15 + 1799 + 4 rounded up to 16)
 
 __global__ void __launch_bounds__(kStemThreads) stem_conv1_kernel(const StemArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -954,61 +954,72 @@ __global__ void __launch_bounds__(kStemThreads) stem_conv1_kernel(const StemArgs
   uint32_t phase = 0;
   const __half2 kScale = __floats2half2_rn(1.f / 128.f, 1.f / 128.f), kBias = __floats2half2_rn(-9.f, -9.f);
 
-  // Asynchronous staging of the raw bytes of one tile (3 row segments) into ring slot `slot`: the loads of tile i + 1 are
-  // in flight while tile i is converted, assembled, multiplied and written out.
-  auto stage = [&](long long tile, int slot) {
-    const int tw = (int)(tile % p.tiles_w);
-    const long long t2 = tile / p.tiles_w;
-    const int oh = (int)(t2 % p.Ho), n = (int)(t2 / p.Ho);
+  // Asynchronous staging of the raw bytes of one tile (3 row segments) into ring slot `slot` with 16-byte cp.async
+  // (source aligned down to 16 bytes; the 0-15 byte misalignment is removed when the bytes are converted): the loads
+  // of tile i + 1 are in flight while tile i is converted, assembled, multiplied and written out.
+  // Tiles are walked with 32-bit (n, oh, tw) counters - no 64-bit divisions in the loop.
+  const int tiles_per_image = p.Ho * p.tiles_w;
+  auto decode = [&](int tile, int& n, int& oh, int& tw) {
+    n = tile / tiles_per_image;
+    const int rem = tile - n * tiles_per_image;
+    oh = rem / p.tiles_w;
+    tw = rem - oh * p.tiles_w;
+  };
+  auto stage = [&](int n, int oh, int tw, int slot) {
     const int ow0 = tw * 128;
     const int npx = min(128, p.Wo - ow0);
     const int seg_bytes = (2 * (npx - 1) + 3) * kStemC;
+    const long long row0 = ((long long)n * p.H + 2 * oh) * row_bytes + (long long)2 * ow0 * kStemC;
     for (int r = 0; r < 3; ++r) {
-      const long long g0 = ((long long)(n * (long long)p.H + 2 * oh + r)) * row_bytes + (long long)2 * ow0 * kStemC;
-      const int mis = (int)(g0 & 3);
-      const long long base = g0 - mis;
-      const int nwl = ((mis + seg_bytes + 3) >> 2) + 1;   // one spare word for the funnel shift of the last group
+      const uint8_t* g = p.in + row0 + (long long)r * row_bytes;
+      const int mis = (int)(reinterpret_cast<uintptr_t>(g) & 15);   // alignment of the ABSOLUTE address
+      const uint8_t* src = g - mis;
+      const int nq = (mis + seg_bytes + 4 + 15) >> 4;            // 16-byte chunks (4 spare bytes for the last funnel shift)
+      const long long left = (p.in + p.total_bytes) - src;       // bytes the caller's buffer still holds from `src`
+      const int full = (int)min((long long)nq, left >> 4);       // chunks that lie completely inside the buffer
       uint8_t* dst = sRaw + (slot * 3 + r) * kStemRawPitch;
-      for (int i = tid; i < nwl; i += kStemThreads) {
-        const long long off = base + 4LL * i;
-        const long long left = p.total_bytes - off;
-        cp_async4(dst + 4 * i, p.in + (left > 0 ? off : base), left >= 4 ? 4 : (left > 0 ? (int)left : 0));   // never read past the caller's buffer
+      for (int i = tid; i < full; i += kStemThreads) cp_async16(dst + 16 * i, src + 16 * i, 16);
+      if (full < nq && tid == 0) {                               // last row of the last image: never read past the buffer
+        const int tail = (int)(left - 16LL * full);
+        cp_async16(dst + 16 * full, tail > 0 ? src + 16 * full : src, tail > 0 ? tail : 0);
       }
     }
     cp_async_commit();
   };
 
-  long long tile = blockIdx.x;
+  const int total = (int)total_tiles;
+  int tile = blockIdx.x;
   int slot = 0;
-  if (tile < total_tiles) stage(tile, 0);
-  for (; tile < total_tiles; tile += gridDim.x, slot ^= 1) {
-    const int tw = (int)(tile % p.tiles_w);
-    const long long t2 = tile / p.tiles_w;
-    const int oh = (int)(t2 % p.Ho), n = (int)(t2 / p.Ho);
+  int n, oh, tw;
+  decode(min(tile, total - 1), n, oh, tw);
+  if (tile < total) stage(n, oh, tw, 0);
+  for (; tile < total; tile += gridDim.x, slot ^= 1) {
     const int ow0 = tw * 128;
     const int npx = min(128, p.Wo - ow0);
     const int seg_bytes = (2 * (npx - 1) + 3) * kStemC;   // input bytes of one row this tile touches
-    if (tile + gridDim.x < total_tiles) { stage(tile + gridDim.x, slot ^ 1); cp_async_wait<1>(); }
+    int n2 = n, oh2 = oh, tw2 = tw;
+    if (tile + (int)gridDim.x < total) { decode(tile + gridDim.x, n2, oh2, tw2); stage(n2, oh2, tw2, slot ^ 1); cp_async_wait<1>(); }
     else cp_async_wait<0>();
     __syncthreads();
     // ---- phase 1: raw bytes -> fp16 (x - 128) / 128 in shared memory
+    const long long row0 = ((long long)n * p.H + 2 * oh) * row_bytes + (long long)2 * ow0 * kStemC;
     for (int r = 0; r < 3; ++r) {
-      const long long g0 = ((long long)(n * (long long)p.H + 2 * oh + r)) * row_bytes + (long long)2 * ow0 * kStemC;
-      const int mis = (int)(g0 & 3);
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(sRaw + (slot * 3 + r) * kStemRawPitch);
+      const int mis = (int)(reinterpret_cast<uintptr_t>(p.in + row0 + (long long)r * row_bytes) & 15);
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(sRaw + (slot * 3 + r) * kStemRawPitch) + (mis >> 2);
+      const int sh = 8 * (mis & 3);
       const int nw = (seg_bytes + 3) >> 2;
       uint2* dst = reinterpret_cast<uint2*>(sH + r * p.h_pitch);
       for (int i = tid; i < nw; i += kStemThreads) {
-        const uint32_t v = __funnelshift_r(src[i], src[i + 1], 8 * mis);     // bytes g0 + 4i .. g0 + 4i + 3
+        const uint32_t v = __funnelshift_r(src[i], src[i + 1], sh);     // bytes g0 + 4i .. g0 + 4i + 3
         uint32_t a = __byte_perm(v, 0x64646464u, 0x4140), b = __byte_perm(v, 0x64646464u, 0x4342);
         __half2 ha = __hfma2(*reinterpret_cast<__half2*>(&a), kScale, kBias), hb = __hfma2(*reinterpret_cast<__half2*>(&b), kScale, kBias);
         dst[i] = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
       }
     }
     __syncthreads();
-    // ---- phase 2: patch rows.  Thread (m, hf): output words [16 hf, 16 hf + 16) of row m.
+    // ---- phase 2: patch rows.  Thread (m, hf): output words [16 hf, 16 hf + 16) of row m (lane stride 7 words: conflict-free).
     {
-      const int m = tid >> 1, hf = tid & 1;
+      const int m = tid & 127, hf = tid >> 7;   // warp-uniform halves: warps 0-3 build words 0..15, warps 4-7 words 16..31
       uint32_t ow[16];
       if (m < npx) {
         const uint32_t* W0 = reinterpret_cast<const uint32_t*>(sH) + 7 * m;                       // 14 m halves = 7 m words
@@ -1061,6 +1072,7 @@ __global__ void __launch_bounds__(kStemThreads) stem_conv1_kernel(const StemArgs
       tc_fence_before();
     }
     phase ^= 1;
+    n = n2; oh = oh2; tw = tw2;
     __syncthreads();   // accumulator drained, sA / sH free for the next tile
   }
   tc_fence_before();
@@ -1398,11 +1410,6 @@ struct DvbCnn {
   double flops_per_image = 0;
   int64_t launches = 0;
   cudaStream_t stream = nullptr;
-  // Second, independent pipeline (own activation buffers, tensor maps, lanes): odd chunks of a multi-chunk forward run on
-  // it concurrently with the even chunks, so that the bandwidth-bound stem of one chunk overlaps the small-grid,
-  // latency-bound mixed4-10 layers of the other.
-  DvbCnn* twin = nullptr;
-  cudaEvent_t twin_start = nullptr, twin_done = nullptr;
   bool stem_fused = false;
   StemArgs stem_args;
   int n_lanes = 1;
@@ -2025,18 +2032,6 @@ int dvb_cnn_create(const void* weights, int64_t weights_bytes, int32_t height, i
   int st = Plan(net, static_cast<const uint8_t*>(weights), weights_bytes);
   if (st) { dvb_cnn_destroy(net); return st; }
   DVB_CUDA(cudaStreamCreateWithFlags(&net->stream, cudaStreamNonBlocking));
-  static thread_local bool creating_twin = false;
-  if (!creating_twin && EnvInt("DVB_CNN_TWIN", 1)) {
-    creating_twin = true;
-    st = dvb_cnn_create(weights, weights_bytes, height, width, channels, max_batch, precision, device, &net->twin);
-    creating_twin = false;
-    if (st) { dvb_cnn_destroy(net); return st; }
-    if (cudaEventCreateWithFlags(&net->twin_start, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&net->twin_done, cudaEventDisableTiming) != cudaSuccess) {
-      dvb_cnn_destroy(net);
-      return dvb::fail(DVB_ERR_CUDA, "cudaEventCreate failed");
-    }
-  }
   *out = net;
   return DVB_OK;
 }
@@ -2054,9 +2049,6 @@ void dvb_cnn_destroy(DvbCnn* net) {
     if (net->lane_streams[l]) cudaStreamDestroy(net->lane_streams[l]);
   for (Step& stp : net->steps)
     if (stp.event) cudaEventDestroy(stp.event);
-  if (net->twin) dvb_cnn_destroy(net->twin);
-  if (net->twin_start) cudaEventDestroy(net->twin_start);
-  if (net->twin_done) cudaEventDestroy(net->twin_done);
   delete net;
 }
 
@@ -2064,22 +2056,10 @@ int dvb_cnn_forward_device(DvbCnn* net, const uint8_t* images, int32_t n, float*
   if (!net || (n > 0 && (!images || !probs)) || n < 0) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_cnn_forward_device: bad arguments");
   DVB_CUDA(cudaSetDevice(net->device));
   const size_t image_bytes = (size_t)net->H * net->W * net->C;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const bool use_twin = net->twin != nullptr && n > net->max_batch;
-  if (use_twin) {   // the twin's stream starts after everything already queued on the caller's stream (the images)
-    DVB_CUDA(cudaEventRecord(net->twin_start, s));
-    DVB_CUDA(cudaStreamWaitEvent(net->twin->stream, net->twin_start, 0));
-  }
-  int k = 0;
-  for (int i = 0; i < n; i += net->max_batch, ++k) {
+  for (int i = 0; i < n; i += net->max_batch) {
     const int m = std::min(net->max_batch, n - i);
-    DvbCnn* pipe = (use_twin && (k & 1)) ? net->twin : net;
-    int st = ForwardChunk(pipe, images + (size_t)i * image_bytes, m, probs + (size_t)i * 3, pipe == net ? s : net->twin->stream);
+    int st = ForwardChunk(net, images + (size_t)i * image_bytes, m, probs + (size_t)i * 3, static_cast<cudaStream_t>(stream));
     if (st) return st;
-  }
-  if (use_twin) {
-    DVB_CUDA(cudaEventRecord(net->twin_done, net->twin->stream));
-    DVB_CUDA(cudaStreamWaitEvent(s, net->twin_done, 0));
   }
   return DVB_OK;
 }
@@ -2099,7 +2079,7 @@ int dvb_cnn_forward_host(DvbCnn* net, const uint8_t* images_host, int32_t n, flo
   return DVB_OK;
 }
 
-int64_t dvb_cnn_launch_count(const DvbCnn* net) { return net ? net->launches + (net->twin ? net->twin->launches : 0) : 0; }
+int64_t dvb_cnn_launch_count(const DvbCnn* net) { return net ? net->launches : 0; }
 double dvb_cnn_flops_per_image(const DvbCnn* net) { return net ? net->flops_per_image : 0.0; }
 
 // Debug / test access to an intermediate activation of the LAST forward (first `n` images):

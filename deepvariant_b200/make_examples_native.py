@@ -296,6 +296,61 @@ class ExamplesGenerator:
         plans.append(ExamplePlan(spec, variant, list(alt_combination), vtype))
     return plans
 
+  def plan_region_from_table(self, candidates: Sequence[DeepVariantCall], table, stats: Dict[str, int],
+                             region: Optional[Tuple[str, int, int]] = None):
+    """plan_region() over a bam.NativeBamTable: the per-candidate read query is an index computation on the table's
+    position arrays and the per-image read lists are row numbers — no Read objects.
+    `region` = (contig, start, end): only reads overlapping it are considered, as when the reference hands
+    WriteExamplesInRegion the reads of one partition.  Returns (plans, table image specs).  Candidates that need
+    trimmed reads (PACBIO / alt-aligned) are not handled here: use plan_region() with table.query()."""
+    pic = self.options.pic_options
+    sample = self.options.sample_options[0]
+    if self.options.trim_reads_for_pileup or sample.keep_only_window_spanning_reads:
+      raise NotImplementedError('the table path covers untrimmed reads; use plan_region() for trimmed pileups')
+    plans: List[ExamplePlan] = []
+    specs: List[packing.TableImageSpec] = []
+    region_rows = table.query_indices(*region) if region is not None else None
+    for candidate in candidates:
+      variant = candidate.variant
+      if need_alt_alignment(variant, pic):
+        raise NotImplementedError('candidate needs alt-aligned (trimmed) reads; use plan_region()')
+      image_start_pos = variant.start - self.half_width
+      reference_bases = self.get_reference_bases_for_pileup(variant)
+      if not reference_bases:
+        continue
+      q_start, q_end = variant.start - pic.read_overlap_buffer_bp, variant.end + pic.read_overlap_buffer_bp
+      if region_rows is None:
+        rows = table.query_indices(variant.reference_name, q_start, q_end)
+      elif region[0] != variant.reference_name:
+        rows = region_rows[:0]
+      else:
+        rows = region_rows[(table.pos[region_rows] < q_end) & (table.end[region_rows] > q_start)]
+      key_to_local = {}
+      for j, r in enumerate(rows):
+        key_to_local.setdefault(table.names[int(table.name_begin[r]):int(table.name_begin[r + 1])].decode() + '/' +
+                                str(int(table.read_number[r])), []).append(j)
+      groups = packing.table_allele_groups(candidate, key_to_local, len(rows)) if pic.sort_by_alt_allele_support else None
+      vtype = encoded_variant_type(variant)
+      for alt_combination in alt_allele_combinations(candidate, pic.multi_allelic_mode):
+        support = packing.table_support(candidate, key_to_local, len(rows), alt_combination)
+        specs.append(packing.TableImageSpec(reference_bases, image_start_pos, variant.start, rows, support, groups))
+        plans.append(ExamplePlan(None, variant, list(alt_combination), vtype))
+    return plans, specs
+
+  def write_examples_in_region_from_table(self, candidates: Sequence[DeepVariantCall], table, role: str,
+                                          region: Optional[Tuple[str, int, int]] = None):
+    """WriteExamplesInRegion with the reads given as a native BAM table (one CUDA launch for the region)."""
+    if role not in self.writers:
+      raise KeyError(f'Role {role} does not have a writer.')
+    stats: Dict[str, int] = {}
+    plans, specs = self.plan_region_from_table(candidates, table, stats, region)
+    enc = self._gpu()
+    images = enc.encode_host(packing.pack_images_from_table(specs, table, enc.params)) if plans else \
+        np.zeros((0,) + enc.shape, dtype=np.uint8)
+    for rec in self.finish_region(plans, images, stats):
+      self.writers[role].write(rec)
+    return stats, self.image_shape()
+
   # -- serialisation (host) ----------------------------------------------------------------------
   def image_shape(self) -> List[int]:
     pic = self.options.pic_options

@@ -223,3 +223,114 @@ def pack_images(specs: Sequence[ImageSpec], params: _lib.DvbPileupParams) -> Pac
   pb = PackedBatch(n_images=n_images, n_reads=n_reads, n_pairs=len(pair_read), ref_stride=ref_stride,
                    arrays=arrays)
   return pb
+
+
+# ---------------------------------------------------------------------------------------------
+# Table path: DvbBatch straight from the native BAM read table (no Read objects)
+# ---------------------------------------------------------------------------------------------
+
+@dataclasses.dataclass
+class TableImageSpec:
+  """One BuildPileupForOneSample call whose reads are rows of a bam.NativeBamTable."""
+  ref_bases: str
+  image_start_pos: int
+  variant_start: int
+  read_rows: np.ndarray            # int64 rows of the table, InMemoryReader::Query order (= file order)
+  support: np.ndarray              # uint8 per read: 0 / 1 / 2
+  allele_group: Optional[np.ndarray] = None
+
+
+def table_support(dv_call: DeepVariantCall, key_to_local: Dict[str, List[int]], n_reads: int, alt_alleles: Sequence[str]) -> np.ndarray:
+  """ReadSupportsAlt for every read of one image at once: walk the alts in order, first name match wins
+  (channels/read_supports_variant_channel.cc:81-103).  key_to_local maps 'fragment_name/read_number' to the
+  positions of the reads with that key in the image's read list."""
+  out = np.zeros(n_reads, dtype=np.uint8)
+  for alt_allele in dv_call.variant.alternate_bases:
+    names = dv_call.allele_support.get(alt_allele)
+    if not names:
+      continue
+    cls = 1 if alt_allele in alt_alleles else 2
+    for name in names:
+      for j in key_to_local.get(name, ()):   # a key can name several rows (same QNAME + read number aligned twice)
+        if out[j] == 0:
+          out[j] = cls
+  return out
+
+
+def table_allele_groups(dv_call: DeepVariantCall, key_to_local: Dict[str, List[int]], n_reads: int) -> np.ndarray:
+  n_alt = len(dv_call.variant.alternate_bases)
+  out = np.full(n_reads, n_alt, dtype=np.uint8)
+  for i, alt in enumerate(dv_call.variant.alternate_bases):
+    for name in dv_call.allele_support.get(alt, ()):
+      for j in key_to_local.get(name, ()):
+        out[j] = i
+  return out
+
+
+def _ragged_gather(values: np.ndarray, begin: np.ndarray, rows: np.ndarray):
+  """Concatenation of values[begin[r]:begin[r+1]] for r in rows, and the new CSR offsets."""
+  lens = (begin[rows + 1] - begin[rows]).astype(np.int64)
+  new_begin = np.zeros(len(rows) + 1, dtype=np.int64)
+  np.cumsum(lens, out=new_begin[1:])
+  total = int(new_begin[-1])
+  if total == 0:
+    return np.zeros(0, dtype=values.dtype), new_begin
+  idx = np.repeat(begin[rows] - new_begin[:-1], lens) + np.arange(total, dtype=np.int64)
+  return values[idx], new_begin
+
+
+def pack_images_from_table(specs: Sequence[TableImageSpec], table, params: _lib.DvbPileupParams) -> PackedBatch:
+  """Same PackedBatch as pack_images() gives for the equivalent Read lists, gathered from the flat table arrays."""
+  width = params.width
+  ref_stride = (width + 15) // 16 * 16
+  n_images = len(specs)
+  ref = np.zeros((n_images, ref_stride), dtype=np.uint8)
+  image_start = np.zeros(n_images, dtype=np.int32)
+  variant_start = np.zeros(n_images, dtype=np.int32)
+  pair_begin = np.zeros(n_images + 1, dtype=np.int64)
+  for i, s in enumerate(specs):
+    rb = s.ref_bases.encode() if isinstance(s.ref_bases, str) else bytes(s.ref_bases)
+    if len(rb) != width:
+      raise ValueError(f'ref_bases has {len(rb)} bases, expected width {width}')
+    ref[i, :width] = np.frombuffer(rb, dtype=np.uint8)
+    image_start[i] = s.image_start_pos
+    variant_start[i] = s.variant_start
+    pair_begin[i + 1] = pair_begin[i] + len(s.read_rows)
+  all_rows = np.concatenate([s.read_rows for s in specs]).astype(np.int64) if n_images else np.zeros(0, dtype=np.int64)
+  # reads are stored once, in order of first use (what pack_images does with its id() map)
+  uniq, first = np.unique(all_rows, return_index=True)
+  order = np.argsort(first, kind='stable')
+  rows = uniq[order]
+  remap = np.empty(len(uniq), dtype=np.int32)
+  remap[order] = np.arange(len(uniq), dtype=np.int32)
+  pair_read = remap[np.searchsorted(uniq, all_rows)] if len(all_rows) else np.zeros(0, dtype=np.int32)
+  pair_support = np.concatenate([s.support for s in specs]).astype(np.uint8) if n_images else np.zeros(0, dtype=np.uint8)
+  pair_group = np.concatenate([s.allele_group if s.allele_group is not None else np.zeros(len(s.read_rows), dtype=np.uint8)
+                               for s in specs]).astype(np.uint8) if n_images else np.zeros(0, dtype=np.uint8)
+  n_reads = len(rows)
+  flag = table.flag[rows]
+  hp_raw = table.hp[rows]
+  has_hp = hp_raw != table.HP_ABSENT
+  flags = (((flag & 0x10) != 0) * READ_REVERSE_STRAND + ((flag & 0x800) != 0) * READ_SUPPLEMENTARY + has_hp * READ_HAS_HP).astype(np.uint8)
+  bases, seq_begin = _ragged_gather(table.bases, table.seq_begin, rows)
+  quals, _ = _ragged_gather(table.quals, table.seq_begin, rows)
+  cigar, cig_begin = _ragged_gather(table.cigar, table.cigar_begin, rows)
+  # dense rank of (fragment_name bytes, read_number) among the reads of this batch
+  keys = [(table.names[int(table.name_begin[r]):int(table.name_begin[r + 1])], int(table.read_number[r])) for r in rows]
+  rank = {k: i for i, k in enumerate(sorted(set(keys)))}
+  name_rank = np.array([rank[k] for k in keys], dtype=np.uint32)
+
+  def _pad(a: np.ndarray) -> np.ndarray:
+    return a if a.size else np.zeros(1, dtype=a.dtype)
+
+  arrays = {
+      'ref_bases': ref.reshape(-1), 'image_start_pos': image_start, 'variant_start': variant_start, 'pair_begin': pair_begin,
+      'pair_read': pair_read.astype(np.int32), 'pair_support': pair_support, 'pair_allele_group': pair_group,
+      'read_pos': table.pos[rows].astype(np.int32), 'read_sort_pos': table.pos[rows].astype(np.int32),
+      'read_mapq': table.mapq[rows].astype(np.int32), 'read_flags': flags,
+      'read_fragment_length': table.fragment_length[rows].astype(np.int32),
+      'read_hp': np.where(has_hp, hp_raw, 0).astype(np.int32), 'read_name_rank': name_rank,
+      'read_seq_begin': seq_begin, 'read_cigar_begin': cig_begin, 'bases': bases, 'quals': quals, 'cigar': cigar.astype(np.uint32),
+  }
+  arrays = {k: np.ascontiguousarray(_pad(v)) for k, v in arrays.items()}
+  return PackedBatch(n_images=n_images, n_reads=n_reads, n_pairs=int(pair_begin[-1]), ref_stride=ref_stride, arrays=arrays)

@@ -381,6 +381,17 @@ def parse_deepvariant_call(buf: bytes) -> DeepVariantCall:
   return c
 
 
+def serialize_deepvariant_call(c: DeepVariantCall) -> bytes:
+  """Inverse of parse_deepvariant_call for the fields modelled here (variant=1, allele_support=2 map entries
+  {key=1, value=2 SupportingReads{read_names=1}}, make_examples_alt_allele_indices=8)."""
+  out = bytearray(f_bytes(1, c.variant.serialize()))
+  for alt, names in c.allele_support.items():
+    out += f_bytes(2, f_bytes(1, alt.encode()) + f_bytes(2, b''.join(f_bytes(1, n.encode()) for n in names)))
+  for idx in c.make_examples_alt_allele_indices:
+    out += f_bytes(8, encode_alt_allele_indices(idx))
+  return bytes(out)
+
+
 def encode_alt_allele_indices(indices: Iterable[int]) -> bytes:
   """CallVariantsOutput.AltAlleleIndices{repeated int32 indices = 1} (proto3 -> packed)."""
   indices = list(indices)

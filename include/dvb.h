@@ -221,6 +221,52 @@ double dvb_cnn_flops_per_image(const DvbCnn* cnn);
 uint32_t dvb_crc32c(const void* data, size_t n);
 uint32_t dvb_masked_crc32c(const void* data, size_t n);
 
+/* ---- BAM -> Structure-of-Arrays read table (host only; SURVEY.md 8(f) "next" row #1) ------------------------
+ * Replaces nucleus SamReader::Iterate + ConvertToPb + ReadSatisfiesRequirements
+ * (third_party/nucleus/io/sam_reader.cc:760-975, 1065-1135, 217-245; third_party/nucleus/util/utils.cc:255-266)
+ * for the pileup path: the file is inflated block-parallel and every record that passes the filter is decoded
+ * once into flat arrays — the layout DvbBatch's per-read arrays are gathered from — instead of one Read proto each. */
+typedef struct DvbReadRequirements {   /* third_party/nucleus/protos/reads.proto ReadRequirements */
+  int32_t min_mapping_quality;         /* make_examples default 5 (make_examples_options.py:957-964) */
+  int32_t keep_duplicates;
+  int32_t keep_failed_vendor_quality_checks;
+  int32_t keep_secondary_alignments;
+  int32_t keep_supplementary_alignments;
+  int32_t keep_unaligned;
+  int32_t keep_improperly_placed;
+} DvbReadRequirements;
+
+typedef struct DvbReadTable {          /* all pointers are owned by the DvbBam handle */
+  int32_t n_reads;
+  int32_t n_refs;
+  int64_t n_bases, n_cigar, n_name_bytes;
+  int64_t n_records_seen;              /* alignment records in the file before filtering */
+  const int32_t* ref_id;               /* [n_reads] index into the header's reference list, -1 unmapped */
+  const int32_t* pos;                  /* alignment.position.position (0-based) */
+  const int32_t* end;                  /* ReadEnd: pos + sum of M/D/N/=/X lengths (utils.cc:222-240) */
+  const uint8_t* mapq;
+  const uint16_t* flag;                /* raw BAM FLAG */
+  const int32_t* fragment_length;      /* isize */
+  const int32_t* hp;                   /* HP aux tag (integer), INT32_MIN when absent or not parsed */
+  const uint8_t* read_number;          /* 0 if FREAD1 or unpaired, else 1 (sam_reader.cc:786-793) */
+  const uint8_t* number_reads;         /* 2 if paired else 1 */
+  const int64_t* seq_begin;            /* [n_reads + 1] into bases / quals */
+  const int64_t* cigar_begin;          /* [n_reads + 1] into cigar (empty for unmapped reads) */
+  const int64_t* name_begin;           /* [n_reads + 1] into names */
+  const uint8_t* bases;                /* ASCII from "=ACMGRSVTWYHKDBN" */
+  const uint8_t* quals;                /* raw phred */
+  const uint32_t* cigar;               /* BAM packing (len << 4 | op) */
+  const char* names;                   /* concatenated QNAMEs, no terminators */
+} DvbReadTable;
+
+typedef struct DvbBam DvbBam;
+void dvb_read_requirements_default(DvbReadRequirements* r);
+/* req may be NULL (defaults).  parse_hp != 0 extracts the HP aux tag.  threads <= 0: hardware concurrency. */
+int dvb_bam_open(const char* path, const DvbReadRequirements* req, int parse_hp, int threads, DvbBam** out);
+int dvb_bam_table(const DvbBam* bam, DvbReadTable* table);
+const char* dvb_bam_ref_name(const DvbBam* bam, int32_t i);   /* NULL when out of range */
+void dvb_bam_close(DvbBam* bam);
+
 /* Debug / test access to an intermediate activation of the LAST forward (first `n` images of the
  * last chunk), converted to float NHWC: out_host = float[n][H][W][C].  Names follow
  * deepvariant_b200/modeling.py ("input", "s1".."s5", "p1", "p2", "mixed0".."mixed10", branch
