@@ -44,6 +44,7 @@ class DvbPileupParams(C.Structure):
       ('sort_by_alt_allele_support', C.c_int32),
       ('random_seed', C.c_uint32),
       ('max_reads_per_image', C.c_int32),
+      ('shuffle_stdlib', C.c_int32),
   ]
 
 
@@ -126,7 +127,7 @@ SYMBOLS = (
     ('dvb_last_error', C.c_char_p, []),
     ('dvb_pileup_params_default', None, [C.POINTER(DvbPileupParams)]),
     ('dvb_image_bytes', C.c_int64, [C.POINTER(DvbPileupParams)]),
-    ('dvb_shuffle_table', C.c_int, [C.c_int32, C.c_uint32, C.c_void_p]),
+    ('dvb_shuffle_table', C.c_int, [C.c_int32, C.c_uint32, C.c_int32, C.c_void_p]),
     ('dvb_encoder_create', C.c_int, [C.POINTER(DvbPileupParams), C.c_int, C.POINTER(C.c_void_p)]),
     ('dvb_encoder_destroy', None, [C.c_void_p]),
     ('dvb_encode_batch_device', C.c_int, [C.c_void_p, C.POINTER(DvbBatch), C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -167,7 +168,7 @@ def lib() -> C.CDLL:
       fn = getattr(l, name)  # AttributeError if the .so does not export a declared symbol
       fn.restype = restype
       fn.argtypes = argtypes
-    if l.dvb_abi_version() != 1:
+    if l.dvb_abi_version() != 2:
       raise RuntimeError('libdvb.so ABI version mismatch')
     _lib = l
   return _lib

@@ -613,6 +613,32 @@ int Launch(DvbEncoder* enc, const DvbBatch& b, uint8_t* out, int32_t* rows_kept,
 
 // Validates a host batch (what the reference leaves to CHECKs / UB), packs every input array into one pinned staging
 // block and issues ONE H2D copy on `s`; *db receives the same batch with device pointers.
+// std::shuffle(iota(n), std::mt19937_64(seed)) as the two standard libraries implement it.  The engine is standardised, the
+// algorithm is not:
+//   libstdc++ (bits/stl_algo.h): Fisher-Yates from the front, two positions per 64-bit draw when the range allows;
+//   libc++    (__algorithm/shuffle.h + __random/uniform_int_distribution.h): for i = 0 .. n-2: j = uniform(0, n-1-i) drawn as the
+//             low ceil(log2(range)) bits of one engine output, rejected while >= range; swap(v[i], v[i+j]).
+// The reference's golden files were produced with the libc++ form (tools/check_downsample_golden.py).
+std::vector<int> ShuffledIndices(int n, uint32_t seed, int shuffle_stdlib) {
+  std::vector<int> idx(std::max(n, 0));
+  std::iota(idx.begin(), idx.end(), 0);
+  std::mt19937_64 gen(seed);
+  if (shuffle_stdlib == DVB_SHUFFLE_LIBSTDCXX) {
+    std::shuffle(idx.begin(), idx.end(), gen);   // this file is compiled with g++/libstdc++
+    return idx;
+  }
+  for (long first = 0, d = (long)n - 1; d >= 1; ++first, --d) {
+    const uint64_t range = (uint64_t)d + 1;           // uniform_int_distribution<ptrdiff_t>(0, d)
+    int w = 64 - __builtin_clzll(range) - 1;
+    if (range & (~uint64_t(0) >> (64 - w))) ++w;      // w = ceil(log2(range)), >= 1 here
+    const uint64_t mask = ~uint64_t(0) >> (64 - w);
+    uint64_t u;
+    do { u = gen() & mask; } while (u >= range);
+    if (u) std::swap(idx[first], idx[first + (long)u]);
+  }
+  return idx;
+}
+
 int StageHostBatch(DvbEncoder* enc, const DvbBatch* hb, DvbBatch* out_db, cudaStream_t s) {
   const int64_t NI = hb->n_images, NR = hb->n_reads, NP = hb->n_pairs, NB = hb->n_bases, NC = hb->n_cigar;
   // ---- validation the reference leaves to CHECKs / UB ----
@@ -740,12 +766,10 @@ int64_t dvb_image_bytes(const DvbPileupParams* p) {
   return (int64_t)p->height * p->width * (p->num_channels + p->num_alt_channels);
 }
 
-int dvb_shuffle_table(int32_t n, uint32_t seed, int32_t* out) {
-  if (n < 0 || !out) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_shuffle_table: bad arguments");
-  std::vector<int> idx(n);
-  std::iota(idx.begin(), idx.end(), 0);
-  std::mt19937_64 gen(seed);
-  std::shuffle(idx.begin(), idx.end(), gen);
+int dvb_shuffle_table(int32_t n, uint32_t seed, int32_t shuffle_stdlib, int32_t* out) {
+  if (n < 0 || !out || (shuffle_stdlib != DVB_SHUFFLE_LIBCXX && shuffle_stdlib != DVB_SHUFFLE_LIBSTDCXX))
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_shuffle_table: bad arguments");
+  std::vector<int> idx = ShuffledIndices(n, seed, shuffle_stdlib);
   for (int i = 0; i < n; ++i) out[i] = idx[i];
   return DVB_OK;
 }
@@ -772,10 +796,7 @@ int dvb_encoder_create(const DvbPileupParams* params, int device, DvbEncoder** o
   std::vector<int> tables;
   tables.reserve((size_t)cap * cap / 2);
   for (int n = dev.max_rows + 1; n <= cap; ++n) {
-    std::vector<int> idx(n);
-    std::iota(idx.begin(), idx.end(), 0);
-    std::mt19937_64 gen(params->random_seed);  // fresh generator per call, pileup_image_native.cc:327,343
-    std::shuffle(idx.begin(), idx.end(), gen);
+    std::vector<int> idx = ShuffledIndices(n, params->random_seed, params->shuffle_stdlib);  // fresh generator per call, pileup_image_native.cc:327,343
     tables.insert(tables.end(), idx.begin(), idx.end());
   }
   DVB_CUDA(cudaMalloc(&enc->d_perm, std::max<size_t>(tables.size(), 1) * sizeof(int)));

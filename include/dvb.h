@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DVB_ABI_VERSION 1
+#define DVB_ABI_VERSION 2
 #define DVB_MAX_CHANNELS 16
 
 typedef enum DvbStatus {
@@ -100,7 +100,13 @@ typedef struct DvbPileupParams {
   int32_t sort_by_alt_allele_support;
   uint32_t random_seed;           /* 2101079370 */
   int32_t max_reads_per_image;    /* capacity of the down-sampling tables; 0 -> 2048 */
+  int32_t shuffle_stdlib;         /* which C++ standard library's std::shuffle DownsampleReadIndices uses (it is
+                                     implementation-defined): DVB_SHUFFLE_LIBCXX (0, default) reproduces the reference's golden
+                                     files (all 51 down-sampled examples of golden.allele_frequency_examples, row for row);
+                                     DVB_SHUFFLE_LIBSTDCXX (1) is what a gcc/libstdc++ build of the reference does */
 } DvbPileupParams;
+
+enum { DVB_SHUFFLE_LIBCXX = 0, DVB_SHUFFLE_LIBSTDCXX = 1 };
 
 /* One batch = the images of any number of candidates x alt-allele combinations.
  * All arrays are Structure-of-Arrays; for the *_device entry point every pointer
@@ -156,9 +162,9 @@ void dvb_pileup_params_default(DvbPileupParams* p);
 /* Bytes of one image: height * width * (num_channels + num_alt_channels). */
 int64_t dvb_image_bytes(const DvbPileupParams* p);
 
-/* DownsampleReadIndices (pileup_image_native.cc:153-165): iota(n) shuffled by
- * libstdc++ std::shuffle with a fresh std::mt19937_64(seed).  Host only. */
-int dvb_shuffle_table(int32_t n, uint32_t seed, int32_t* out);
+/* DownsampleReadIndices (pileup_image_native.cc:153-165): iota(n) shuffled by std::shuffle with a fresh
+ * std::mt19937_64(seed), as the chosen standard library implements it (shuffle_stdlib above).  Host only. */
+int dvb_shuffle_table(int32_t n, uint32_t seed, int32_t shuffle_stdlib, int32_t* out);
 
 /* device: CUDA ordinal.  Builds the down-sampling tables and uploads constants. */
 int dvb_encoder_create(const DvbPileupParams* params, int device, DvbEncoder** out);

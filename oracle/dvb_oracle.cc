@@ -18,8 +18,9 @@
 // pileup_channel_lib_test.cc (transcribed as data), and tests/golden/ holds images of
 // the reference's own golden.calling_examples.tfrecord.gz re-derived through it.
 //
-// Build: see oracle/Makefile (g++ -O2 -shared -fPIC).  libstdc++ is required: the
-// reference is built with gcc and std::shuffle is implementation-defined.
+// Build: see oracle/Makefile (g++ -O2 -shared -fPIC).  std::shuffle is implementation-defined: both
+// forms are restated (DvbPileupParams.shuffle_stdlib) — libc++'s, which the reference's golden files were
+// made with (tests/golden/downsample_golden_*), by hand; libstdc++'s by calling this compiler's own.
 
 #include <algorithm>
 #include <cstdint>
@@ -310,12 +311,38 @@ std::unique_ptr<ImageRow> EncodeReference(const DvbPileupParams& o, const uint8_
   return std::make_unique<ImageRow>(img_row);
 }
 
+// libc++'s std::shuffle (llvm-project libcxx/include/__algorithm/shuffle.h) over libc++'s
+// uniform_int_distribution<ptrdiff_t> (libcxx/include/__random/uniform_int_distribution.h, __independent_bits_engine): walk
+// the range from the front; for the remaining length d + 1 draw j uniformly in [0, d] by keeping the low
+// ceil(log2(d + 1)) bits of ONE 64-bit engine output and rejecting values >= d + 1; swap(first, first + j).
+// Third-party dependency of the reference (the C++ standard library its binaries link), absent from /root/reference;
+// pinned by the reference's golden.allele_frequency_examples (tools/check_downsample_golden.py): all 51 of its
+// down-sampled examples reproduce row for row with this form and none with libstdc++'s.
+template <class Gen>
+void LibcxxShuffle(std::vector<int>& v, Gen& g) {
+  long d = static_cast<long>(v.size());
+  if (d <= 1) return;
+  long first = 0;
+  for (--d; d >= 1; ++first, --d) {
+    const uint64_t rp = static_cast<uint64_t>(d) + 1;
+    size_t w = 64 - static_cast<size_t>(__builtin_clzll(rp)) - 1;
+    if ((rp & (~uint64_t{0} >> (64 - w))) != 0) ++w;
+    const uint64_t mask = w >= 64 ? ~uint64_t{0} : (~uint64_t{0} >> (64 - w));
+    uint64_t u;
+    do {
+      u = g() & mask;
+    } while (u >= rp);
+    if (u != 0) std::swap(v[first], v[first + static_cast<long>(u)]);
+  }
+}
+
 // DownsampleReadIndices, pileup_image_native.cc:153-165 (gen passed BY VALUE).
-std::vector<int> DownsampleReadIndices(size_t n_reads, int max_reads, std::mt19937_64 gen) {
+std::vector<int> DownsampleReadIndices(size_t n_reads, int max_reads, std::mt19937_64 gen, int shuffle_stdlib) {
   std::vector<int> read_indices(n_reads);
   std::iota(read_indices.begin(), read_indices.end(), 0);
   if (n_reads > static_cast<size_t>(max_reads)) {
-    std::shuffle(read_indices.begin(), read_indices.end(), gen);
+    if (shuffle_stdlib == DVB_SHUFFLE_LIBSTDCXX) std::shuffle(read_indices.begin(), read_indices.end(), gen);   // g++ / libstdc++
+    else LibcxxShuffle(read_indices, gen);
   }
   return read_indices;
 }
@@ -361,7 +388,7 @@ int BuildPileupForOneSample(const DvbPileupParams& o, const DvbBatch& b, int32_t
   }
 
   auto gen = std::mt19937_64(o.random_seed);
-  std::vector<int> sampled_indices = DownsampleReadIndices(n_reads, max_reads, gen);
+  std::vector<int> sampled_indices = DownsampleReadIndices(n_reads, max_reads, gen, o.shuffle_stdlib);
 
   std::vector<ReadPileupTuple> pileup_of_reads;
   for (int index : sampled_indices) {
@@ -484,8 +511,8 @@ int dvb_oracle_encode_reference(const DvbPileupParams* params, const uint8_t* re
 }
 
 // DownsampleReadIndices table for n reads (independent of the product's dvb_shuffle_table).
-int dvb_oracle_shuffle_table(int32_t n, uint32_t seed, int32_t max_reads, int32_t* out) {
-  std::vector<int> idx = DownsampleReadIndices(static_cast<size_t>(n), max_reads, std::mt19937_64(seed));
+int dvb_oracle_shuffle_table(int32_t n, uint32_t seed, int32_t max_reads, int32_t shuffle_stdlib, int32_t* out) {
+  std::vector<int> idx = DownsampleReadIndices(static_cast<size_t>(n), max_reads, std::mt19937_64(seed), shuffle_stdlib);
   for (int i = 0; i < n; ++i) out[i] = idx[i];
   return DVB_OK;
 }

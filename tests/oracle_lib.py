@@ -44,7 +44,7 @@ def oracle():
     l.dvb_oracle_encode_reference.restype = C.c_int
     l.dvb_oracle_encode_reference.argtypes = [C.POINTER(_lib.DvbPileupParams), C.c_void_p, C.c_void_p]
     l.dvb_oracle_shuffle_table.restype = C.c_int
-    l.dvb_oracle_shuffle_table.argtypes = [C.c_int32, C.c_uint32, C.c_int32, C.c_void_p]
+    l.dvb_oracle_shuffle_table.argtypes = [C.c_int32, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p]
     _oracle = l
   return _oracle
 
@@ -66,9 +66,9 @@ def encode_batch(params: _lib.DvbPileupParams, batch: packing.PackedBatch) -> np
   return out
 
 
-def shuffle_table(n: int, seed: int, max_reads: int) -> np.ndarray:
+def shuffle_table(n: int, seed: int, max_reads: int, shuffle_stdlib: int = 0) -> np.ndarray:
   out = np.empty(n, dtype=np.int32)
-  oracle().dvb_oracle_shuffle_table(n, seed, max_reads, out.ctypes.data_as(C.c_void_p))
+  oracle().dvb_oracle_shuffle_table(n, seed, max_reads, shuffle_stdlib, out.ctypes.data_as(C.c_void_p))
   return out
 
 

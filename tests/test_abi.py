@@ -55,8 +55,11 @@ def test_defaults_and_host_helpers_without_gpu():
   assert l.dvb_image_bytes(ctypes.byref(p)) == 132600
   import numpy as np
   t = np.zeros(100, dtype=np.int32)
-  assert l.dvb_shuffle_table(100, 2101079370, t.ctypes.data_as(ctypes.c_void_p)) == 0
+  assert l.dvb_shuffle_table(100, 2101079370, 1, t.ctypes.data_as(ctypes.c_void_p)) == 0   # 1 = libstdc++
   assert t[:12].tolist() == [32, 69, 31, 60, 53, 68, 49, 39, 76, 54, 18, 82]
+  assert l.dvb_shuffle_table(100, 2101079370, 0, t.ctypes.data_as(ctypes.c_void_p)) == 0   # 0 = libc++ (golden files)
+  assert sorted(t.tolist()) == list(range(100)) and t[:12].tolist() != [32, 69, 31, 60, 53, 68, 49, 39, 76, 54, 18, 82]
+  assert l.dvb_shuffle_table(100, 2101079370, 7, t.ctypes.data_as(ctypes.c_void_p)) != 0
 
 
 def test_no_device_is_an_error_not_a_fallback():

@@ -91,3 +91,51 @@ def test_tfrecord_roundtrip_and_sharding(tmp_path):
   # CRC-32C check value (RFC 3720 appendix B.4)
   from deepvariant_b200 import _lib
   assert _lib.lib().dvb_crc32c(b'123456789', 9) == 0xE3069283
+
+
+# ---- the down-sampling path (more than 95 reads overlap the candidate) pinned by the reference's golden file -------------
+
+def _downsample_fixture():
+  """tools/check_downsample_golden.py: 12 of the 51 down-sampled examples of the reference's
+  golden.allele_frequency_examples.tfrecord.gz (channels 0-6 of its 100x221x8 images) with the reads of its BAM.  No
+  candidates file ships for that golden, so read support is unknown: channel 4 is not compared."""
+  d = np.load(os.path.join(GOLDEN, 'downsample_golden_subset.npz'))
+  arrays = {k[4:]: d[k] for k in d.files if k.startswith('arr_')}
+  pb = packing.PackedBatch(int(d['n_images']), int(d['n_reads']), int(d['n_pairs']), int(d['ref_stride']), arrays)
+  o = pi.default_options(pi.ReadRequirements(min_base_quality=10, min_mapping_quality=5))
+  o.channels = list(pi.PILEUP_CHANNELS_WITH_INSERT_SIZE)
+  return pb, d['golden_images'], d['channels'].tolist(), o
+
+
+def test_oracle_reproduces_downsampled_golden_rows_in_order():
+  pb, golden, ch, o = _downsample_fixture()
+  assert golden.shape == (12, 100, 221, 7) and ch == [0, 1, 2, 3, 5, 6]
+  n_reads = np.diff(pb.arrays['pair_begin'])
+  assert (n_reads > 95).all() and n_reads.max() >= 190          # every image is down-sampled; some from ~200 reads
+  got = oracle_lib.encode_batch(pi.to_params(o), pb)
+  np.testing.assert_array_equal(got[..., ch], golden[..., ch])  # all 100 rows, in the reference's order
+  # ... and NOT with libstdc++'s std::shuffle (what a gcc build would do): the golden pins the standard library
+  p1 = pi.to_params(o)
+  p1.shuffle_stdlib = 1
+  other = oracle_lib.encode_batch(p1, pb)
+  assert not any(np.array_equal(other[i][..., ch], golden[i][..., ch]) for i in range(12))
+
+
+@pytest.mark.gpu
+def test_cuda_encoder_reproduces_downsampled_golden_rows_in_order():
+  pb, golden, ch, o = _downsample_fixture()
+  enc = pi.GpuEncoder(pi.to_params(o), 0)
+  got = enc.encode_host(pb)
+  np.testing.assert_array_equal(got[..., ch], golden[..., ch])
+  assert enc.last_rows_kept[:12].tolist() == [95] * 12
+  p1 = pi.to_params(o)
+  p1.shuffle_stdlib = 1
+  enc1 = pi.GpuEncoder(p1, 0)
+  np.testing.assert_array_equal(enc1.encode_host(pb), oracle_lib.encode_batch(p1, pb))   # the libstdc++ flavour stays bit-exact vs the oracle
+
+
+def test_downsample_report_numbers():
+  r = json.load(open(os.path.join(GOLDEN, 'downsample_golden_report.json')))
+  assert r['n_examples'] == 78 and r['n_downsampled'] == 51 and r['n_downsampled_exact'] == 51
+  assert r['downsampled_rows'] == r['downsampled_rows_equal_in_place'] == 4845
+  assert all(e['exact_six_channels'] for e in r['examples'])

@@ -341,14 +341,30 @@ def test_sorts_by_haplotype_then_allele_support(backend):
 
 
 def test_downsample_prefix_kat():
-  """SURVEY Appendix A: libstdc++ std::shuffle(iota(n), mt19937_64(2101079370)) prefixes."""
+  """std::shuffle(iota(n), mt19937_64(2101079370)) is implementation-defined: both standard libraries are restated.
+  libstdc++ prefixes: SURVEY Appendix A (g++ 13.3).  libc++ (shuffle_stdlib 0, the default): which reads the reference's
+  golden.allele_frequency_examples drops at n = 96 and n = 103 (tools/check_downsample_golden.py) = the tail of the permutation."""
   import oracle_lib
   exp = {96: [32, 69, 31, 60, 53, 68, 49, 39, 76, 54, 18, 82],
          100: [32, 69, 31, 60, 53, 68, 49, 39, 76, 54, 18, 82],
          150: [32, 69, 31, 60, 53, 68, 107, 39, 76, 54, 113, 122],
          300: [181, 69, 31, 249, 259, 68, 107, 216, 76, 54, 113, 122]}
   for n, prefix in exp.items():
-    t = oracle_lib.shuffle_table(n, 2101079370, 95)
+    t = oracle_lib.shuffle_table(n, 2101079370, 95, shuffle_stdlib=1)
     assert t[:12].tolist() == prefix
     assert sorted(t.tolist()) == list(range(n))
-  assert oracle_lib.shuffle_table(95, 2101079370, 95).tolist() == list(range(95))
+  for flavour in (0, 1):
+    assert oracle_lib.shuffle_table(95, 2101079370, 95, flavour).tolist() == list(range(95))
+  t96 = oracle_lib.shuffle_table(96, 2101079370, 95)
+  assert t96[95] == 91 and sorted(t96.tolist()) == list(range(96))            # the golden image at chr20:61645 lacks query read 91
+  t103 = oracle_lib.shuffle_table(103, 2101079370, 95)
+  assert sorted(t103[95:].tolist()) == [15, 24, 46, 50, 60, 67, 75, 102]      # chr20:61350 lacks exactly these eight
+  assert sorted(t103.tolist()) == list(range(103))
+  # the product's host table (csrc/dvb_encoder.cu) is an independent restatement of both
+  import ctypes
+  from deepvariant_b200 import _lib
+  for flavour in (0, 1):
+    for n in (96, 103, 150, 300, 1000):
+      got = np.zeros(n, dtype=np.int32)
+      assert _lib.lib().dvb_shuffle_table(n, 2101079370, flavour, got.ctypes.data_as(ctypes.c_void_p)) == 0
+      np.testing.assert_array_equal(got, oracle_lib.shuffle_table(n, 2101079370, 95, flavour))
