@@ -296,6 +296,9 @@ __device__ __forceinline__ void epilogue_row_split(uint32_t taddr, int block_n, 
 // ---------------------------------------------------------------------------------------------
 // Convolution = implicit GEMM
 // ---------------------------------------------------------------------------------------------
+constexpr int kMaxSegs = 4;
+struct OutSeg { int col_begin, cstride, coff, relu; __half* out; };   // columns [col_begin, next col_begin) of the GEMM
+
 struct ConvArgs {
   int kh, kw, pad_h, pad_w, stride;
   int cin_blocks, block_k;        // K per stage (16 / 32 / 64 fp16 = 32 / 64 / 128-byte swizzle)
@@ -308,11 +311,33 @@ struct ConvArgs {
   uint32_t a_bytes, b_bytes, a_stage, b_stage;  // TMA bytes and shared-memory footprint per stage
   __half* out;
   const float* bias;
+  // merged 1x1 convolutions (several layers reading the same tensor run as ONE GEMM over the concatenated filters):
+  // column ranges of N go to different tensors.  n_segs == 0: single destination (out / out_cstride / out_coff / relu).
+  int n_segs;
+  OutSeg segs[kMaxSegs];
   // split mode (precision 1): residual planes; a_stage / b_stage then hold {main, res} tiles back to back
   __half* out_res;
   uint32_t a_res_off, b_res_off;
   int skip_a_res;                 // the A residual plane is identically zero (network input): skip its load and MMA
 };
+
+// Epilogue of one accumulator row of a merged GEMM: 16-column chunks, each routed to the tensor that owns its column
+// range (range boundaries are multiples of 16).  `pix` = flat output pixel index, `col0` = first GEMM column of this row piece.
+__device__ __forceinline__ void epilogue_row_segs(uint32_t taddr, int n_cols, int col0, const float* s_bias, const ConvArgs& p, size_t pix,
+                                                  bool valid) {
+  for (int c = 0; c < n_cols; c += 16) {
+    uint32_t v[16];
+    tmem_ld16(taddr + c, v);
+    tmem_ld_wait();
+    const int cg = col0 + c;
+    int k = 0;
+#pragma unroll
+    for (int j = 1; j < kMaxSegs; ++j)
+      if (j < p.n_segs && cg >= p.segs[j].col_begin) k = j;
+    const OutSeg& sg = p.segs[k];
+    epilogue_chunk<16>(v, s_bias + c, sg.out + pix * sg.cstride + sg.coff + (cg - sg.col_begin), valid, sg.relu);
+  }
+}
 
 template <bool kSplit>
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -430,6 +455,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tc_fence_after();
     if constexpr (kSplit)
       epilogue_row_split(tmem_base + ((uint32_t)(q * 32) << 16), p.block_n, s_bias, dst, p.out_res + (dst - p.out), valid, p.relu);
+    else if (p.n_segs)
+      epilogue_row_segs(tmem_base + ((uint32_t)(q * 32) << 16), p.block_n, nb * p.block_n, s_bias, p,
+                        (size_t)((size_t)(n0 + n) * p.Hout + (h0 + h)) * p.Wout + (w0 + w), valid);
     else
       epilogue_row(tmem_base + ((uint32_t)(q * 32) << 16), p.block_n, s_bias, dst, valid, p.relu);
   }
@@ -569,9 +597,14 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
                     nb * p.block_n + c_lo;
       mbar_wait(&tmem_full[buf], buf_ph);
       tc_fence_after();
-      if (c_n > 0)
-        epilogue_row(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.block_n + c_lo), c_n, s_bias + nb * p.block_n + c_lo, dst, valid,
-                     p.relu);
+      if (c_n > 0) {
+        if (p.n_segs)
+          epilogue_row_segs(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.block_n + c_lo), c_n, nb * p.block_n + c_lo,
+                            s_bias + nb * p.block_n + c_lo, p, (size_t)((size_t)(n0 + n) * p.Hout + (h0 + h)) * p.Wout + (w0 + w), valid);
+        else
+          epilogue_row(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.block_n + c_lo), c_n, s_bias + nb * p.block_n + c_lo, dst,
+                       valid, p.relu);
+      }
       tc_fence_before();
       mbar_arrive(&tmem_empty[buf]);
       buf ^= 1;
@@ -1537,7 +1570,6 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       }
     }
   }
-  const float* pending_bias = nullptr;   // bias of the last no_act convolution, consumed by the pool behind it
   // --- header
   if (blob_bytes < 12) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob too small");
   const int32_t* hdr = reinterpret_cast<const int32_t*>(blob);
@@ -1551,6 +1583,44 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
   for (auto& o : ops) n_conv += o.kind == 0;
   if (hdr[2] != n_conv) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob has %d convs, expected %d", hdr[2], n_conv);
   int64_t pos = 12;
+  // blob offset of every convolution (network order), so that layers can be fetched out of order
+  std::vector<int64_t> conv_pos;
+  {
+    int64_t q = 12;
+    for (int ci = 0; ci < n_conv; ++ci) {
+      if (q + 20 > blob_bytes) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob truncated");
+      const int32_t* lh = reinterpret_cast<const int32_t*>(blob + q);
+      if (lh[0] < 1 || lh[1] < 1 || lh[3] < 1 || lh[4] < 1) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob: bad conv header %d", ci);
+      conv_pos.push_back(q);
+      q += 20 + (int64_t)(blob_split ? 2 : 1) * lh[4] * lh[0] * lh[1] * lh[3] * (int64_t)sizeof(__half) + (int64_t)lh[4] * 4;
+    }
+    conv_pos.push_back(q);
+    if (q > blob_bytes) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob truncated");
+  }
+  // 1x1 stride-1 convolutions that read the SAME tensor (the branch heads of an inception block, including the one the
+  // average pool now follows) run as ONE GEMM over their concatenated filters: the input is fetched once instead of 2-4
+  // times and the MMA's N grows from 32-192 to 208-256 (an M=128 SS-mode MMA streams 4 KB of A per instruction whatever
+  // N is, so narrow N wastes the tensor pipe).  leader[i] = ops merged into op i (first of its group); merged_into[i] >= 0
+  // for the others.
+  std::vector<int> conv_index_of(ops.size(), -1);
+  {
+    int ci = 0;
+    for (size_t i = 0; i < ops.size(); ++i)
+      if (ops[i].kind == 0) conv_index_of[i] = ci++;
+  }
+  std::map<size_t, std::vector<size_t>> leader;
+  std::vector<int> merged_into(ops.size(), -1);
+  if (!split && EnvInt("DVB_CNN_MERGE_1X1", 1)) {
+    std::map<std::string, std::vector<size_t>> by_src;
+    for (size_t i = 1; i < ops.size(); ++i)
+      if (ops[i].kind == 0 && ops[i].kh == 1 && ops[i].kw == 1 && ops[i].stride == 1) by_src[ops[i].src].push_back(i);
+    for (auto& kv : by_src) {
+      if (kv.second.size() < 2 || (int)kv.second.size() > kMaxSegs) continue;
+      leader[kv.second[0]] = kv.second;
+      for (size_t k = 1; k < kv.second.size(); ++k) merged_into[kv.second[k]] = (int)kv.second[0];
+    }
+  }
+  std::map<std::string, const float*> pool_bias;   // '*_ap' tensor -> bias its pool adds (bias of the no_act convolution)
 
   // --- tensors
   std::map<std::string, std::pair<int, int>> hw;
@@ -1588,7 +1658,7 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
   int st = add_tensor("input", net->stem_Ho, net->stem_Wo, net->stem_Kp);
   if (st) return st;
 
-  std::vector<std::pair<std::string, std::string>> step_io;   // (src, dst) tensor of every step
+  std::vector<std::pair<std::string, std::vector<std::string>>> step_io;   // (src, dst tensors) of every step
   const int force_bk = EnvInt("DVB_CNN_BLOCK_K", 0);       // 0 = per-layer choice
   double macs_total = 0;
   for (size_t op_index = 0; op_index < ops.size(); ++op_index) {
@@ -1602,33 +1672,35 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
     else { Hout = (Hin - o.kh) / o.stride + 1; Wout = (Win - o.kw) / o.stride + 1; }
     if (Hout < 1 || Wout < 1) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "image %dx%d is too small for the network", net->H, net->W);
     hw[o.dst] = {Hout, Wout};
-    st = add_tensor(o.dst, Hout, Wout, ch[o.dst]);
-    if (st) return st;
+    if (merged_into[op_index] >= 0) continue;     // runs inside its group leader's GEMM
+    std::vector<size_t> members = leader.count(op_index) ? leader[op_index] : std::vector<size_t>{op_index};
+    std::vector<std::string> step_dsts;
+    for (size_t m : members) {                    // all destination tensors exist before any reference is taken
+      hw[ops[m].dst] = {Hout, Wout};
+      st = add_tensor(ops[m].dst, Hout, Wout, ch[ops[m].dst]);
+      if (st) return st;
+      step_dsts.push_back(ops[m].dst);
+    }
     const TensorBuf& src = net->tensors[net->tensor_index[o.src]];
     const TensorBuf& dst = net->tensors[net->tensor_index[o.dst]];
     if (o.kind != 0) {
       PoolLaunch pl{src.ptr, dst.ptr, Hin, Win, src.C, Hout, Wout, dst.C, o.off, o.kind == 1 ? 0 : 1, src.ptr_res, dst.ptr_res,
-                    o.post_act ? pending_bias : nullptr};
-      if (o.post_act && !pending_bias) return dvb::fail(DVB_ERR_INTERNAL, "pool without the bias of its convolution");
+                    o.post_act ? pool_bias[o.src] : nullptr};
+      if (o.post_act && !pl.bias) return dvb::fail(DVB_ERR_INTERNAL, "pool without the bias of its convolution");
       net->steps.push_back(Step{1, (int)net->pools.size()});
-      step_io.push_back({o.src, o.dst});
+      step_io.push_back({o.src, step_dsts});
       net->pools.push_back(pl);
       continue;
     }
-    // --- conv weights from the blob
-    if (pos + 20 > blob_bytes) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob truncated");
-    const int32_t* lh = reinterpret_cast<const int32_t*>(blob + pos);
-    pos += 20;
+    // --- conv weights from the blob (one layer, or the members of a merged group stacked along Cout)
     const int cin_store = src.C;  // channels physically present in the source tensor
     const int blob_cin = PadCin(orig.cin);
-    if (lh[0] != orig.kh || lh[1] != orig.kw || lh[2] != orig.cin || lh[3] != blob_cin || lh[4] != o.cout || (!is_stem && blob_cin != cin_store))
-      return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob: conv %zu header mismatch (%d %d %d %d %d)", net->convs.size(), lh[0], lh[1],
-                       lh[2], lh[3], lh[4]);
-    const size_t blob_wbytes = (size_t)o.cout * orig.kh * orig.kw * blob_cin * sizeof(__half);
-    const size_t wbytes = (size_t)o.cout * o.kh * o.kw * cin_store * sizeof(__half);
-    const size_t bbytes = (size_t)o.cout * sizeof(float);
     const size_t blob_planes = blob_split ? 2 : 1;
-    if (pos + (int64_t)(blob_planes * blob_wbytes + bbytes) > blob_bytes) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob truncated");
+    int cout_total = 0;
+    for (size_t m : members) cout_total += ops[m].cout;
+    const bool merged = members.size() > 1;
+    const size_t wbytes = (size_t)cout_total * o.kh * o.kw * cin_store * sizeof(__half);
+    const size_t bbytes = (size_t)cout_total * sizeof(float);
     void* dw = nullptr; void* db = nullptr; void* dw_res = nullptr;
     if (cudaMalloc(&dw, wbytes) != cudaSuccess || cudaMalloc(&db, bbytes) != cudaSuccess) return dvb::fail(DVB_ERR_CUDA, "cudaMalloc (weights) failed");
     net->allocs.push_back(dw); net->allocs.push_back(db);
@@ -1636,33 +1708,59 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       if (cudaMalloc(&dw_res, wbytes) != cudaSuccess) return dvb::fail(DVB_ERR_CUDA, "cudaMalloc (weights) failed");
       net->allocs.push_back(dw_res);
     }
-    for (int plane = 0; plane < (split ? 2 : 1); ++plane) {
-      const uint8_t* wsrc = blob + pos + (size_t)plane * blob_wbytes;
-      void* wdst = plane ? dw_res : dw;
-      if (is_stem) {
-        // [cout][3][3][blob_cin] -> [cout][Kp], k = (r*3 + s)*C + c (the patch order of stem_patch_kernel)
-        std::vector<__half> w2((size_t)o.cout * cin_store, __float2half(0.f));
-        const __half* w = reinterpret_cast<const __half*>(wsrc);
-        for (int co = 0; co < o.cout; ++co)
-          for (int t = 0; t < 9; ++t)
-            for (int c = 0; c < net->C; ++c) w2[(size_t)co * cin_store + t * net->C + c] = w[((size_t)co * 9 + t) * blob_cin + c];
-        cudaMemcpy(wdst, w2.data(), wbytes, cudaMemcpyHostToDevice);
-      } else {
-        cudaMemcpy(wdst, wsrc, wbytes, cudaMemcpyHostToDevice);
+    std::vector<float> bias_host((size_t)cout_total, 0.f);
+    std::vector<OutSeg> segs;
+    const uint8_t* blob_w_main = nullptr;
+    size_t blob_wbytes = 0;
+    {
+      size_t row0 = 0;   // first output channel of this member inside the stacked filter matrix
+      for (size_t m : members) {
+        const OpDesc& mo = ops[m];
+        pos = conv_pos[conv_index_of[m]];
+        const int32_t* lh = reinterpret_cast<const int32_t*>(blob + pos);
+        pos += 20;
+        if (lh[0] != orig.kh || lh[1] != orig.kw || lh[2] != orig.cin || lh[3] != blob_cin || lh[4] != mo.cout || (!is_stem && blob_cin != cin_store))
+          return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob: conv %d header mismatch (%d %d %d %d %d)", conv_index_of[m], lh[0], lh[1], lh[2],
+                           lh[3], lh[4]);
+        blob_wbytes = (size_t)mo.cout * orig.kh * orig.kw * blob_cin * sizeof(__half);
+        const size_t m_wbytes = (size_t)mo.cout * o.kh * o.kw * cin_store * sizeof(__half);
+        if (pos + (int64_t)(blob_planes * blob_wbytes + (size_t)mo.cout * 4) > blob_bytes) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "weights blob truncated");
+        for (int plane = 0; plane < (split ? 2 : 1); ++plane) {
+          const uint8_t* wsrc = blob + pos + (size_t)plane * blob_wbytes;
+          uint8_t* wdst = static_cast<uint8_t*>(plane ? dw_res : dw) + row0 * o.kh * o.kw * cin_store * sizeof(__half);
+          if (is_stem) {
+            // [cout][3][3][blob_cin] -> [cout][Kp], k = (r*3 + s)*C + c (the patch order of stem_patch_kernel)
+            std::vector<__half> w2((size_t)mo.cout * cin_store, __float2half(0.f));
+            const __half* w = reinterpret_cast<const __half*>(wsrc);
+            for (int co = 0; co < mo.cout; ++co)
+              for (int t = 0; t < 9; ++t)
+                for (int c = 0; c < net->C; ++c) w2[(size_t)co * cin_store + t * net->C + c] = w[((size_t)co * 9 + t) * blob_cin + c];
+            cudaMemcpy(wdst, w2.data(), m_wbytes, cudaMemcpyHostToDevice);
+          } else {
+            cudaMemcpy(wdst, wsrc, m_wbytes, cudaMemcpyHostToDevice);
+          }
+        }
+        const float* b_blob = reinterpret_cast<const float*>(blob + pos + blob_planes * blob_wbytes);
+        if (mo.no_act) {   // raw accumulator out; the pool behind it adds this bias and applies the ReLU
+          void* pb = nullptr;
+          if (cudaMalloc(&pb, (size_t)mo.cout * 4) != cudaSuccess) return dvb::fail(DVB_ERR_CUDA, "cudaMalloc (bias) failed");
+          net->allocs.push_back(pb);
+          cudaMemcpy(pb, b_blob, (size_t)mo.cout * 4, cudaMemcpyHostToDevice);
+          pool_bias[mo.dst] = static_cast<const float*>(pb);
+        } else {
+          memcpy(&bias_host[row0], b_blob, (size_t)mo.cout * 4);
+        }
+        const TensorBuf& md = net->tensors[net->tensor_index[mo.dst]];
+        segs.push_back(OutSeg{(int)row0, md.C, mo.off, mo.no_act ? 0 : 1, md.ptr});
+        blob_w_main = blob + pos;
+        row0 += (size_t)mo.cout;
       }
     }
-    cudaMemcpy(db, blob + pos + blob_planes * blob_wbytes, bbytes, cudaMemcpyHostToDevice);
+    cudaMemcpy(db, bias_host.data(), bbytes, cudaMemcpyHostToDevice);
     const float* conv_bias = static_cast<const float*>(db);
-    if (o.no_act) {
-      pending_bias = conv_bias;
-      void* dz = nullptr;
-      if (cudaMalloc(&dz, bbytes) != cudaSuccess) return dvb::fail(DVB_ERR_CUDA, "cudaMalloc (bias) failed");
-      cudaMemset(dz, 0, bbytes);
-      net->allocs.push_back(dz);
-      conv_bias = static_cast<const float*>(dz);
-    }
-    const uint8_t* blob_w_main = blob + pos;
-    pos += blob_planes * blob_wbytes + bbytes;
+    if (merged) { o.cout = cout_total; o.no_act = 0; }
+    else if (o.no_act) o.no_act = 1;
+    const int relu_single = segs[0].relu;
 
     // ---- conv1 fused with preprocess + im2col (stem_conv1_kernel): WGS geometry (7 channels), precision 0
     if (is_stem && !split && net->C == kStemC && o.cout <= 32 && o.cout % 16 == 0 && cin_store == 64 && EnvInt("DVB_CNN_STEM_FUSED", 1)) {
@@ -1733,7 +1831,7 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       a.nbuf = (2 * a.T * bn <= 512 && EnvInt("DVB_HALO_NBUF", 2) == 2) ? 2 : 1;
       a.stages = std::min(2 * kMaxStages, std::max(a.T, std::min(2 * a.T, (int)((216 * 1024 - (long)b_smem) / (long)a.a_stage))));
       a.tmem_cols = TmemCols(a.nbuf * a.T * bn);
-      a.out = dst.ptr; a.out_cstride = dst.C; a.out_coff = o.off; a.relu = o.no_act ? 0 : 1;
+      a.out = dst.ptr; a.out_cstride = dst.C; a.out_coff = o.off; a.relu = relu_single;
       a.bias = conv_bias;
       a.idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       a.layout_type = bk == 64 ? 2u : bk == 32 ? 4u : 6u;
@@ -1768,7 +1866,7 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
         }
         macs_total += hl.macs_per_image;
         net->steps.push_back(Step{2, (int)net->halos.size()});
-        step_io.push_back({o.src, o.dst});
+        step_io.push_back({o.src, step_dsts});
         net->halos.push_back(hl);
         continue;
       }
@@ -1828,8 +1926,12 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
     }
     a.tmem_cols = TmemCols(split || cl.persist ? 2 * a.block_n : a.block_n);
     cl.n_blocks = o.cout / a.block_n; cl.cout = o.cout;
-    a.out = dst.ptr; a.out_cstride = dst.C; a.out_coff = o.off; a.relu = o.no_act ? 0 : 1;
+    a.out = dst.ptr; a.out_cstride = dst.C; a.out_coff = o.off; a.relu = relu_single;
     a.out_res = dst.ptr_res;
+    if (merged) {
+      a.n_segs = (int)segs.size();
+      for (size_t k = 0; k < segs.size(); ++k) a.segs[k] = segs[k];
+    }
     a.skip_a_res = is_stem ? 1 : 0;   // the preprocessed input is exact in fp16: its residual plane is zero
     a.bias = conv_bias;
     // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=F32, A=B=F16, K-major, M=128
@@ -1899,9 +2001,10 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
     }
     cl.grid = dim3(1, (unsigned)(o.cout / a.block_n), 1);
     net->steps.push_back(Step{0, (int)net->convs.size()});
-    step_io.push_back({o.src, o.dst});
+    step_io.push_back({o.src, step_dsts});
     net->convs.push_back(cl);
   }
+  pos = conv_pos[n_conv];
   // --- lanes: chains of single-producer/single-consumer steps stay on one stream, every other consumer starts a new one
   {
     net->n_lanes = std::max(1, std::min(kMaxLanes, EnvInt("DVB_CNN_LANES", kMaxLanes)));
@@ -1918,7 +2021,7 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       else { stp.lane = rr % net->n_lanes; ++rr; }
       for (int d : w)
         if (d >= 0 && lane_of(d) != stp.lane) { stp.deps.push_back(d); net->steps[d].record = true; }
-      writers[step_io[i].second].push_back((int)i);
+      for (const std::string& d : step_io[i].second) writers[d].push_back((int)i);
     }
     for (int d : writers["mixed10"])
       if (lane_of(d) != 0) { net->tail_deps.push_back(d); net->steps[d].record = true; }

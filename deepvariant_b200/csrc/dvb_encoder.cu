@@ -2,7 +2,7 @@
 //
 // Replaces, for a whole batch of candidate images per launch, the reference's
 //   BuildPileupForOneSample            deepvariant/pileup_image_native.cc:296-447
-//     DownsampleReadIndices            :153-165   (tables built on the host with libstdc++)
+//     DownsampleReadIndices            :153-165   (tables built on the host: libc++ or libstdc++ form, shuffle_stdlib)
 //     EncodeRead / CalculateChannels   :477-510, deepvariant/pileup_channel_lib.cc:91-261
 //     GetHapIndex / SortImageRows      :449-475, :75-102
 //     EncodeReference                  :512-527,  pileup_channel_lib.cc:263-293

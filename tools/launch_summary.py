@@ -33,7 +33,46 @@ start = max(i for i in stems if i < end)
 fw = rows[start:end + 1]
 ops, _ = modeling.inception_v3_graph(C)
 fused = fw[0][0] == 'stem_conv1_kernel'   # preprocess + im2col + conv1 in one launch
-assert len(fw) == len(ops) + (1 if fused else 2), (len(fw), len(ops))
+
+
+def engine_steps(ops):
+  """The engine's launch list (csrc/dvb_cnn.cu Plan): average pool moved behind its 1x1 convolution, 1x1 convolutions that
+  read the same tensor merged into one GEMM at the position of the first.  Returns [(label, kind, [ops])]."""
+  ops = list(ops)
+  i = 0
+  while i + 1 < len(ops):
+    pl, cv = ops[i], ops[i + 1]
+    if pl.kind == 'avgpool' and cv.kind == 'conv' and cv.kh == 1 and cv.kw == 1 and cv.src == pl.dst:
+      ops[i], ops[i + 1] = cv, pl
+      cv._src_override = pl.src if hasattr(cv, '_src_override') is False else cv._src_override
+      i += 1
+    i += 1
+  def src_of(o):
+    return getattr(o, '_src_override', o.src)
+  groups = {}
+  for k, o in enumerate(ops):
+    if k > 0 and o.kind == 'conv' and o.kh == 1 and o.kw == 1 and o.stride == 1:
+      groups.setdefault(src_of(o), []).append(k)
+  merged_into = {}
+  for ks in groups.values():
+    if 2 <= len(ks) <= 4:
+      for k in ks[1:]:
+        merged_into[k] = ks[0]
+  steps = []
+  for k, o in enumerate(ops):
+    if k in merged_into:
+      continue
+    members = [ops[j] for j in groups.get(src_of(o), []) if merged_into.get(j, j) == k] if (o.kind == 'conv' and o.kh == 1 and o.kw == 1 and o.stride == 1 and k > 0) else []
+    members = members if len(members) >= 2 else [o]
+    steps.append(members)
+  return steps, [[o] for o in ops]
+
+
+steps, unmerged = engine_steps(ops)
+n_launch_expected = len(steps) + (1 if fused else 2)
+if len(fw) != n_launch_expected:   # engine built without the graph rewrites: one launch per op
+  steps = unmerged
+assert len(fw) == len(steps) + (1 if fused else 2), (len(fw), len(steps))
 hw = {'input': (H, W)}
 total_us = sum(r[2] for r in fw)
 enc = [r for r in rows if r[0] == 'dvb_encode_kernel']
@@ -43,19 +82,23 @@ if not fused:
   print(f'| 0 | preprocess+im2col | {fw[0][0]} | {fw[0][1]} | | | {fw[0][2]:.1f} | | | {100 * fw[0][2] / total_us:.1f} |')
 by_kernel = {}
 flops_total = 0.0
-for i, (o, r) in enumerate(zip(ops, fw[0:-1] if fused else fw[1:-1]), 1):
-  h, w = hw[o.src]
-  oh, ow = modeling.out_hw(o, h, w)
-  hw[o.dst] = (oh, ow)
-  gf = 2.0 * batch * oh * ow * o.cout * o.kh * o.kw * o.cin / 1e9 if o.kind == 'conv' else 0.0
+for i, (members, r) in enumerate(zip(steps, fw[0:-1] if fused else fw[1:-1]), 1):
+  gf = 0.0
+  for o in members:   # shapes follow the ORIGINAL graph: a pool moved behind its conv does not change H x W
+    h, w = hw[o.src] if o.src in hw else hw[getattr(o, '_src_override', o.src)]
+    oh, ow = modeling.out_hw(o, h, w)
+    hw[o.dst] = (oh, ow)
+    if o.kind == 'conv':
+      gf += 2.0 * batch * oh * ow * o.cout * o.kh * o.kw * o.cin / 1e9
+  o = members[0]
   flops_total += gf
-  tf = gf / r[2] / 1e3 * 1e3 if gf else 0.0   # GFLOP / us = PFLOP/s*1e-3 -> TFLOP/s = gf / us * 1e3 / 1e3
   tf = gf / (r[2] * 1e-6) / 1e3 if gf else 0.0
   by_kernel.setdefault(r[0], [0.0, 0.0])
   by_kernel[r[0]][0] += r[2]
   by_kernel[r[0]][1] += gf
-  print(f'| {i} | {o.name} {o.src}->{o.dst} | {r[0]} | {r[1]} | {oh}x{ow} | {o.cin}->{o.cout} {o.kh}x{o.kw}/{o.stride} | {r[2]:.1f} | '
-        f'{gf:.1f} | {tf:.0f} | {100 * r[2] / total_us:.1f} |')
+  label = ' + '.join(m.name for m in members) if len(members) > 1 else f'{o.name} {o.src}->{o.dst}'
+  shape = f'{o.cin}->{"+".join(str(m.cout) for m in members)} {o.kh}x{o.kw}/{o.stride}'
+  print(f'| {i} | {label} | {r[0]} | {r[1]} | {oh}x{ow} | {shape} | {r[2]:.1f} | {gf:.1f} | {tf:.0f} | {100 * r[2] / total_us:.1f} |')
 print(f'| {len(fw) - 1} | GAP+Dense+softmax | tail_kernel | {fw[-1][1]} | | | {fw[-1][2]:.1f} | | | {100 * fw[-1][2] / total_us:.1f} |')
 print()
 print(f'forward of {batch} images under ncu (serialised, cold caches): {total_us / 1e3:.2f} ms, {flops_total / (total_us * 1e-6) / 1e3:.0f} TFLOP/s overall')
