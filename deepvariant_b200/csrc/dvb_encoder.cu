@@ -194,6 +194,54 @@ __device__ uint8_t read_const(const EncDev& P, int chan, const ReadHdr& h, int s
   }
 }
 
+// ---- pre-pass: everything about a (image, read) pair that does not need the image's other reads --------------------------
+// One record per pair, written by a fully parallel kernel (a warp per image, a lane per pair): EncodeRead's keep/drop
+// decision, the per-read constant channel words, the sort key parts and the read's addresses.  The image kernel then reads
+// ONE 64-byte record per pair (phase A) and per row (phase B) instead of chasing pair -> read header (8 arrays) -> CIGAR
+// -> bases through dependent global loads, and no longer runs the divergent per-channel constant code per row.
+struct __align__(16) PairRec {
+  long long seq0, cig0;     // offsets of the read's bases / quals and CIGAR
+  int pos, n_cig;
+  unsigned tc[4];           // K_CONST channel bytes of this (read, support class), packed like a pixel
+  int sort_pos;
+  unsigned rank;
+  int hap;
+  uint8_t grp, ok, pad0, pad1;
+  int pad2, pad3;           // (tried: first two CIGAR words inline here - 54 registers, one CTA fewer per SM, slower)
+};
+static_assert(sizeof(PairRec) == 64, "PairRec is one 64-byte line");
+
+__global__ void __launch_bounds__(128) dvb_pair_prepass_kernel(const EncDev P, const DvbBatch B, PairRec* __restrict__ recs, int* __restrict__ err) {
+  const int lane = threadIdx.x & 31;
+  const int img = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (img >= B.n_images) return;
+  const int image_start = B.image_start_pos[img];
+  const int vstart = B.variant_start[img];
+  const long long p0 = B.pair_begin[img];
+  const int n = (int)(B.pair_begin[img + 1] - p0);
+  for (int i = lane; i < n; i += 32) {
+    const long long p = p0 + i;
+    const int r = B.pair_read[p];
+    const ReadHdr h = load_read(B, r);
+    int ok = accept_read(P, B, r, vstart, image_start);
+    if (ok < 0) { atomicMax(err, DVB_ERR_BAD_CIGAR); ok = 0; }
+    PairRec rec;
+    rec.seq0 = h.seq0; rec.cig0 = h.cig0; rec.pos = h.pos; rec.n_cig = h.n_cig;
+    rec.tc[0] = rec.tc[1] = rec.tc[2] = rec.tc[3] = 0u;
+    const int support = B.pair_support[p];
+    for (int c = 0; c < P.C; ++c)
+      if (P.kind[c] == K_CONST) rec.tc[c >> 2] |= (unsigned)read_const(P, P.chan[c], h, support) << (8 * (c & 3));
+    rec.sort_pos = B.read_sort_pos[r];
+    rec.rank = B.read_name_rank[r];
+    rec.hap = hap_index(P, h.flags, h.hp);
+    rec.grp = (P.sort_by_group && B.pair_allele_group) ? B.pair_allele_group[p] : (uint8_t)0;
+    rec.ok = (uint8_t)ok; rec.pad0 = rec.pad1 = 0; rec.pad2 = rec.pad3 = 0;
+    uint4* dst = reinterpret_cast<uint4*>(recs + p);
+    const uint4* srcv = reinterpret_cast<const uint4*>(&rec);
+    dst[0] = srcv[0]; dst[1] = srcv[1]; dst[2] = srcv[2]; dst[3] = srcv[3];
+  }
+}
+
 // Streams `row_bytes` bytes of a row to global memory with 16-byte stores.
 //   buf == nullptr : blank row, zeros straight from registers.
 //   otherwise      : the row lives in shared memory at px = buf + 16 + 4 * (phase >> 2), phase = dst & 15, i.e. pixel 0 is
@@ -237,7 +285,7 @@ __device__ __forceinline__ void flush_row(uint8_t* __restrict__ dst, const uint8
 template <bool FAST7>
 __global__ void __launch_bounds__(kThreads, DVB_ENC_MIN_BLOCKS)
 dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, int* __restrict__ rows_kept,
-                  int* __restrict__ err) {
+                  int* __restrict__ err, const PairRec* __restrict__ recs) {
   extern __shared__ __align__(16) uint8_t smem[];
   // layout: [base_lut 256][qual_lut 256][ref Wpad][sel arrays 6 x max_rows x 4B][order max_rows x 4B]
   //         [warp totals][row buffers kWarps x rowbuf_bytes]
@@ -286,8 +334,12 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
       long long p = 0;
       if (i < n) {
         p = p0 + (perm ? perm[i] : i);
-        ok = accept_read(P, B, B.pair_read[p], vstart, image_start);
-        if (ok < 0) { atomicMax(err, DVB_ERR_BAD_CIGAR); ok = 0; }
+        if (recs) {
+          ok = recs[p].ok;
+        } else {
+          ok = accept_read(P, B, B.pair_read[p], vstart, image_start);
+          if (ok < 0) { atomicMax(err, DVB_ERR_BAD_CIGAR); ok = 0; }
+        }
       }
       const unsigned m = __ballot_sync(0xffffffffu, ok);
       if (lane == 0) s_wtot[warp] = __popc(m);
@@ -298,14 +350,19 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
       for (int w = 0; w < kWarps; ++w) total += s_wtot[w];
       const int slot = before + __popc(m & ((1u << lane) - 1u));
       if (ok && slot < P.max_rows) {
-        const int r = B.pair_read[p];
-        const unsigned fl = B.read_flags[r];
         s_pair[slot] = (int)(p - p0);
-        s_hap[slot] = hap_index(P, fl, B.read_hp[r]);
-        s_grp[slot] = (P.sort_by_group && B.pair_allele_group) ? (int)B.pair_allele_group[p] : 0;
-        s_pos[slot] = B.read_sort_pos[r];
-        s_rank[slot] = B.read_name_rank[r];
         s_visit[slot] = i;
+        if (recs) {
+          const PairRec& rc = recs[p];
+          s_hap[slot] = rc.hap; s_grp[slot] = rc.grp; s_pos[slot] = rc.sort_pos; s_rank[slot] = rc.rank;
+        } else {
+          const int r = B.pair_read[p];
+          const unsigned fl = B.read_flags[r];
+          s_hap[slot] = hap_index(P, fl, B.read_hp[r]);
+          s_grp[slot] = (P.sort_by_group && B.pair_allele_group) ? (int)B.pair_allele_group[p] : 0;
+          s_pos[slot] = B.read_sort_pos[r];
+          s_rank[slot] = B.read_name_rank[r];
+        }
       }
       n_acc += total;
       __syncthreads();
@@ -368,17 +425,29 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
       } else {
         const int e = s_order[row - P.band];
         const long long p = p0 + s_pair[e];
-        const int r = B.pair_read[p];
-        const int support = B.pair_support[p];
-        const ReadHdr h = load_read(B, r);
-        // per-read constants: lane c computes channel c, then every lane gathers them into words
-        unsigned myc = 0;
-        if (lane < P.C && P.kind[lane] == K_CONST) myc = read_const(P, P.chan[lane], h, support);
+        ReadHdr h;
         unsigned tc[4] = {0u, 0u, 0u, 0u};
+        if (recs) {   // one 64-byte record (all lanes read the same line)
+          const uint4* rv = reinterpret_cast<const uint4*>(recs + p);
+          const uint4 q0 = rv[0], q1 = rv[1];
+          h.seq0 = (long long)(((unsigned long long)q0.y << 32) | q0.x);
+          h.cig0 = (long long)(((unsigned long long)q0.w << 32) | q0.z);
+          h.pos = (int)q1.x; h.n_cig = (int)q1.y;
+          tc[0] = q1.z; tc[1] = q1.w;
+          if (P.n_words > 2) { const uint4 q2 = rv[2]; tc[2] = q2.x; tc[3] = q2.y; }
+          h.mapq = 0; h.fraglen = 0; h.hp = 0; h.flags = 0;
+        } else {
+          const int r = B.pair_read[p];
+          const int support = B.pair_support[p];
+          h = load_read(B, r);
+          // per-read constants: lane c computes channel c, then every lane gathers them into words
+          unsigned myc = 0;
+          if (lane < P.C && P.kind[lane] == K_CONST) myc = read_const(P, P.chan[lane], h, support);
 #pragma unroll
-        for (int c = 0; c < DVB_MAX_CHANNELS; ++c) {
-          const unsigned v = __shfl_sync(0xffffffffu, myc, c);
-          tc[c >> 2] |= (v & 0xFFu) << (8 * (c & 3));
+          for (int c = 0; c < DVB_MAX_CHANNELS; ++c) {
+            const unsigned v = __shfl_sync(0xffffffffu, myc, c);
+            tc[c >> 2] |= (v & 0xFFu) << (8 * (c & 3));
+          }
         }
         const uint8_t* bases = B.bases + h.seq0;
         const uint8_t* quals = B.quals + h.seq0;
@@ -505,7 +574,8 @@ struct DvbEncoder {
   int* d_err = nullptr;
   int64_t launches = 0;
   // staging for the host entry point
-  dvb::DevBuf d_in, d_out, d_rows;
+  dvb::DevBuf d_in, d_out, d_rows, d_recs;
+  bool prepass = true;
   dvb::PinBuf h_in, h_out;
   cudaStream_t stream = nullptr;
 };
@@ -602,17 +672,22 @@ int SmemBytes(const EncDev& d) {
 int Launch(DvbEncoder* enc, const DvbBatch& b, uint8_t* out, int32_t* rows_kept, cudaStream_t stream) {
   if (b.n_images <= 0) return DVB_OK;
   int grid = std::min(b.n_images, enc->grid_cap);
+  PairRec* recs = nullptr;
+  if (enc->prepass && b.n_pairs > 0) {
+    DVB_CUDA(enc->d_recs.reserve((size_t)b.n_pairs * sizeof(PairRec)));
+    recs = static_cast<PairRec*>(enc->d_recs.p);
+    dvb_pair_prepass_kernel<<<(b.n_images + 3) / 4, 128, 0, stream>>>(enc->dev, b, recs, enc->d_err);
+    enc->launches++;
+  }
   if (enc->fast7)
-    dvb_encode_kernel<true><<<grid, kThreads, enc->smem_bytes, stream>>>(enc->dev, b, out, rows_kept, enc->d_err);
+    dvb_encode_kernel<true><<<grid, kThreads, enc->smem_bytes, stream>>>(enc->dev, b, out, rows_kept, enc->d_err, recs);
   else
-    dvb_encode_kernel<false><<<grid, kThreads, enc->smem_bytes, stream>>>(enc->dev, b, out, rows_kept, enc->d_err);
+    dvb_encode_kernel<false><<<grid, kThreads, enc->smem_bytes, stream>>>(enc->dev, b, out, rows_kept, enc->d_err, recs);
   enc->launches++;
   DVB_CUDA(cudaGetLastError());
   return DVB_OK;
 }
 
-// Validates a host batch (what the reference leaves to CHECKs / UB), packs every input array into one pinned staging
-// block and issues ONE H2D copy on `s`; *db receives the same batch with device pointers.
 // std::shuffle(iota(n), std::mt19937_64(seed)) as the two standard libraries implement it.  The engine is standardised, the
 // algorithm is not:
 //   libstdc++ (bits/stl_algo.h): Fisher-Yates from the front, two positions per 64-bit draw when the range allows;
@@ -639,6 +714,8 @@ std::vector<int> ShuffledIndices(int n, uint32_t seed, int shuffle_stdlib) {
   return idx;
 }
 
+// Validates a host batch (what the reference leaves to CHECKs / UB), packs every input array into one pinned staging
+// block and issues ONE H2D copy on `s`; *db receives the same batch with device pointers.
 int StageHostBatch(DvbEncoder* enc, const DvbBatch* hb, DvbBatch* out_db, cudaStream_t s) {
   const int64_t NI = hb->n_images, NR = hb->n_reads, NP = hb->n_pairs, NB = hb->n_bases, NC = hb->n_cigar;
   // ---- validation the reference leaves to CHECKs / UB ----
@@ -812,6 +889,7 @@ int dvb_encoder_create(const DvbPileupParams* params, int device, DvbEncoder** o
     return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "image row too large for shared memory (%d bytes)", enc->smem_bytes);
   }
   enc->fast7 = dev.C == 7 && dev.Cout == 7;
+  { const char* e = getenv("DVB_ENC_PREPASS"); enc->prepass = !(e && atoi(e) == 0); }
   int occ = 1;
   if (enc->fast7) {
     DVB_CUDA(cudaFuncSetAttribute(dvb_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc->smem_bytes));
@@ -831,7 +909,7 @@ void dvb_encoder_destroy(DvbEncoder* enc) {
   cudaSetDevice(enc->device);
   if (enc->d_perm) cudaFree(enc->d_perm);
   if (enc->d_err) cudaFree(enc->d_err);
-  enc->d_in.release(); enc->d_out.release(); enc->d_rows.release();
+  enc->d_in.release(); enc->d_out.release(); enc->d_rows.release(); enc->d_recs.release();
   enc->h_in.release(); enc->h_out.release();
   if (enc->stream) cudaStreamDestroy(enc->stream);
   delete enc;

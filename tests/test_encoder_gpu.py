@@ -203,3 +203,32 @@ def test_full_size_properties():
   small = take_images(packed, idx)
   want = oracle_lib.encode_batch(params, small)
   _assert_same(out[sample].cpu().numpy(), want)
+
+
+def test_pair_prepass_and_single_kernel_paths_are_identical(monkeypatch):
+  """The encoder runs as pre-pass (one record per (image, read) pair) + image kernel; DVB_ENC_PREPASS=0 keeps everything in
+  the image kernel.  Both must give the oracle's bytes — WGS and PACBIO layouts, down-sampled images included."""
+  import torch
+  from deepvariant_b200 import synthetic
+  for pacbio in (False, True):
+    o = pi.default_options()
+    if pacbio:
+      o.channels = pi.PILEUP_DEFAULT_CHANNELS + ['haplotype', 'supplementary_alignment', 'diff_channels_alternate_allele_1',
+                                                 'diff_channels_alternate_allele_2']
+      o.width = 147
+      o.sort_by_haplotypes = True
+    else:
+      o.channels = list(pi.PILEUP_CHANNELS_WITH_INSERT_SIZE)
+    params = pi.to_params(o)
+    tb = synthetic.make_batch(300, 'cuda:0', width=o.width, hp=pacbio)
+    want = oracle_lib.encode_batch(params, tb.to_packed())
+    for flag in ('1', '0'):
+      monkeypatch.setenv('DVB_ENC_PREPASS', flag)
+      enc = pi.GpuEncoder(params, 0)
+      out = torch.empty((tb.n_images,) + enc.shape, dtype=torch.uint8, device='cuda:0')
+      rows = torch.zeros(tb.n_images, dtype=torch.int32, device='cuda:0')
+      enc.encode_device(tb, out, rows)
+      enc.check()
+      np.testing.assert_array_equal(out.cpu().numpy(), want, err_msg=f'pacbio={pacbio} prepass={flag}')
+      assert enc.launch_count == (2 if flag == '1' else 1)
+      enc.close()
