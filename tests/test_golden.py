@@ -139,3 +139,47 @@ def test_downsample_report_numbers():
   assert r['n_examples'] == 78 and r['n_downsampled'] == 51 and r['n_downsampled_exact'] == 51
   assert r['downsampled_rows'] == r['downsampled_rows_equal_in_place'] == 4845
   assert all(e['exact_six_channels'] for e in r['examples'])
+
+
+# ---- trimmed long reads (PACBIO path: TrimReads / TrimCigar + the window clip) against the reference's PacBio golden ---------
+
+def _pacbio_fixture():
+  """tools/check_pacbio_golden.py: 12 of the 401 examples of the reference's golden.pacbio_examples.tfrecord.gz (first seven of
+  its ten channels) with the TRIMMED reads of its BAM as planned by make_examples_native.trim_reads.  Phasing (upstream) decides
+  the haplotype channel and the row order and no candidates file ships, so rows are compared as multisets on channels 0,1,2,3,5."""
+  d = np.load(os.path.join(GOLDEN, 'pacbio_golden_subset.npz'))
+  arrays = {k[4:]: d[k] for k in d.files if k.startswith('arr_')}
+  pb = packing.PackedBatch(int(d['n_images']), int(d['n_reads']), int(d['n_pairs']), int(d['ref_stride']), arrays)
+  o = pi.default_options(pi.ReadRequirements(min_base_quality=10, min_mapping_quality=1))
+  o.channels = pi.PILEUP_DEFAULT_CHANNELS + ['haplotype']
+  o.width = 147
+  return pb, d['golden_images'], d['channels'].tolist(), pi.to_params(o)
+
+
+def _assert_row_multisets_equal(got, golden, ch):
+  import collections
+  for i in range(golden.shape[0]):
+    np.testing.assert_array_equal(got[i, :5][..., ch], golden[i, :5][..., ch])          # reference band
+    g = collections.Counter(golden[i, r][:, ch].tobytes() for r in range(5, 100) if golden[i, r].any())
+    o = collections.Counter(got[i, r][:, ch].tobytes() for r in range(5, 100) if got[i, r].any())
+    assert g == o, f'example {i}: {sum((g & o).values())} of {sum(g.values())} golden rows reproduced'
+
+
+def test_oracle_reproduces_pacbio_golden_rows():
+  pb, golden, ch, params = _pacbio_fixture()
+  assert golden.shape == (12, 100, 147, 7) and ch == [0, 1, 2, 3, 5]
+  _assert_row_multisets_equal(oracle_lib.encode_batch(params, pb), golden, ch)
+
+
+@pytest.mark.gpu
+def test_cuda_encoder_reproduces_pacbio_golden_rows():
+  pb, golden, ch, params = _pacbio_fixture()
+  got = pi.GpuEncoder(params, 0).encode_host(pb)
+  _assert_row_multisets_equal(got, golden, ch)
+  np.testing.assert_array_equal(got, oracle_lib.encode_batch(params, pb))
+
+
+def test_pacbio_report_numbers():
+  r = json.load(open(os.path.join(GOLDEN, 'pacbio_golden_report.json')))
+  assert r['n_examples'] == 401 and r['ref_band_equal'] == 401 and r['same_row_count'] == 401 and r['all_rows_matched'] == 401
+  assert r['golden_read_rows'] == r['golden_read_rows_matched'] == 13689
