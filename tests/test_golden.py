@@ -183,3 +183,34 @@ def test_pacbio_report_numbers():
   r = json.load(open(os.path.join(GOLDEN, 'pacbio_golden_report.json')))
   assert r['n_examples'] == 401 and r['ref_band_equal'] == 401 and r['same_row_count'] == 401 and r['all_rows_matched'] == 401
   assert r['golden_read_rows'] == r['golden_read_rows_matched'] == 13689
+
+
+# ---- CallVariantsOutput written by the reference's call_variants (a17: _create_cvo_proto + set_model_id) -----------------------
+
+def _proto_fields(buf, nested=()):
+  out = []
+  for fn, wt, val, _ in protos.iter_fields(buf):
+    v = val if isinstance(val, int) else bytes(val)
+    if fn in nested and not isinstance(v, int):
+      v = tuple(sorted(map(repr, _proto_fields(v, (2,)))))   # sub-messages with map fields: entry order is not significant
+    out.append((fn, wt, v))
+  return sorted(map(repr, out))
+
+
+def test_create_cvo_equals_reference_call_variants_output():
+  """10 (example, CallVariantsOutput) pairs of the reference's goldens (all 84 checked by hand in the build container):
+  given the example's variant / alt_allele_indices and the reference's probabilities, create_cvo() emits the same proto —
+  same length, same fields, calls[0].info['MID'] = 'deepvariant' — up to the order of map entries (protobuf maps serialise in
+  hash order; the reference compares parsed protos)."""
+  from deepvariant_b200 import call_variants as cv
+  pairs = json.load(open(os.path.join(GOLDEN, 'cvo_golden_pairs.json')))['pairs']
+  assert len(pairs) == 10
+  for p in pairs:
+    golden = bytes.fromhex(p['cvo'])
+    v, idx, probs = protos.parse_call_variants_output(golden)
+    assert len(probs) == 3 and abs(sum(probs) - 1) < 1e-6
+    mine = cv.create_cvo(bytes.fromhex(p['variant']), probs, bytes.fromhex(p['alt_allele_indices']))
+    v2, idx2, probs2 = protos.parse_call_variants_output(mine)
+    assert len(mine) == len(golden) and idx2 == idx and probs2 == probs
+    assert _proto_fields(v2, (11,)) == _proto_fields(v, (11,))
+    assert protos.encode_call_variants_output(v, idx, probs) == golden     # wire round trip of the golden record itself
