@@ -222,11 +222,43 @@ def run_reference(args):
                                  f'({sample * len(times) / tc_sum:.0f}/s); the reference itself is not buildable here'},
       'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
   }
-  print(json.dumps(line), flush=True)
+  emit(line)
+
+
+def ensure_built():
+  """A fresh checkout has no built library (build artefacts are git-ignored): build in-tree with nvcc (rank 0 first)."""
+  lib = os.path.join(ROOT, 'deepvariant_b200', 'csrc', 'libdvb.so')
+  if os.path.exists(lib):
+    return
+  import __graft_entry__
+  if int(os.environ.get('LOCAL_RANK', '0')) == 0:
+    __graft_entry__.build()
+  else:
+    for _ in range(600):
+      if os.path.exists(lib):
+        time.sleep(2.0)
+        return
+      time.sleep(1.0)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+  """The ONE JSON line of the contract, on the process's real stdout."""
+  out = _REAL_STDOUT or sys.stdout
+  print(json.dumps(line), file=out, flush=True)
 
 
 def main():
+  global _REAL_STDOUT
   args = parse_args()
+  # Libraries write banners to stdout (NCCL prints its version line there): keep the real stdout for the JSON line only
+  # and send everything else to stderr.
+  sys.stdout.flush()
+  _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+  os.dup2(2, 1)
+  ensure_built()
   if args.impl == 'reference':
     run_reference(args)
     return
@@ -406,7 +438,7 @@ def main():
       'gpu_launches': launches, 'clocks': clocks, 'e2e': e2e, 'roofline': roofline, 'roofline_encoder': roof_enc,
       'cpu_baseline': cpu_baseline,
   }
-  print(json.dumps(line), flush=True)
+  emit(line)
   if world > 1:
     dist.destroy_process_group()
 

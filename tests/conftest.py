@@ -11,6 +11,11 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 def pytest_configure(config):
   config.addinivalue_line('markers', 'gpu: test needs a CUDA device (run on the B200 box)')
+  # A fresh checkout has no built library (build artefacts are git-ignored): build it once, in-tree, with nvcc.
+  lib = os.path.join(ROOT, 'deepvariant_b200', 'csrc', 'libdvb.so')
+  if not os.path.exists(lib):
+    import __graft_entry__
+    __graft_entry__.build()
 
 
 def _have_gpu() -> bool:
