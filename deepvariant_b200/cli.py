@@ -48,27 +48,82 @@ def parse_region(s: str):
   return m.group(1), int(m.group(2).replace(',', '')) - 1, int(m.group(3).replace(',', ''))
 
 
+MAKE_EXAMPLES_DEFAULTS = dict(
+    task=0, regions='', channel_list='BASE_CHANNELS', pileup_image_width=221, pileup_image_height=100, min_mapping_quality=5,
+    min_base_quality=10, partition_size=1000, sort_by_haplotypes=False, trim_reads_for_pileup=False, parse_sam_aux_fields=False,
+    alt_aligned_pileup='none', device=0, checkpoint='', checkpoint_json='')
+
+
+def model_example_info_json_path(checkpoint: str, checkpoint_json: str = '') -> str:
+  """get_model_example_info_json_path (deepvariant/make_examples_core.py:3780-3822): --checkpoint_json wins; a saved-model
+  directory holds model.example_info.json (or example_info.json); for a ckpt path the file sits next to the checkpoint."""
+  if checkpoint_json:
+    return checkpoint_json
+  if not checkpoint:
+    return ''
+  dirs = [checkpoint] if os.path.isdir(checkpoint) else [os.path.dirname(checkpoint)]
+  for d in dirs:
+    for name in ('model.example_info.json', 'example_info.json'):
+      if os.path.exists(os.path.join(d, name)):
+        return os.path.join(d, name)
+    if os.path.isdir(d):
+      for name in sorted(os.listdir(d)):
+        if name.endswith('example_info.json'):
+          return os.path.join(d, name)
+  return ''
+
+
+def apply_flags_for_calling(cli_values: dict, checkpoint: str, checkpoint_json: str = '') -> dict:
+  """apply_flags_for_calling (deepvariant/make_examples_core.py:3825-3920): command line > the model's
+  model.example_info.json 'flags_for_calling' > defaults.  Flags this implementation does not know (candidate generation,
+  realigner, small model ...) belong to upstream stages and are reported, not applied."""
+  import json
+  merged = dict(MAKE_EXAMPLES_DEFAULTS)
+  path = model_example_info_json_path(checkpoint, checkpoint_json)
+  ignored = []
+  if path:
+    try:
+      flags_map = json.load(open(path)).get('flags_for_calling', {})
+    except (OSError, ValueError):
+      flags_map = {}
+    for k, v in flags_map.items():
+      if k in MAKE_EXAMPLES_DEFAULTS:
+        want = type(MAKE_EXAMPLES_DEFAULTS[k])
+        merged[k] = (str(v).lower() in ('1', 'true', 'yes')) if want is bool and not isinstance(v, bool) else want(v)
+      else:
+        ignored.append(k)
+  merged.update(cli_values)
+  merged['_ignored_flags_for_calling'] = ignored
+  return merged
+
+
 def make_examples(argv):
-  ap = argparse.ArgumentParser('make_examples')
+  ap = argparse.ArgumentParser('make_examples', argument_default=argparse.SUPPRESS)
   ap.add_argument('--mode', default='calling', choices=['calling'])
   ap.add_argument('--ref', required=True)
   ap.add_argument('--reads', required=True)
   ap.add_argument('--examples', required=True)
   ap.add_argument('--candidates', required=True)
-  ap.add_argument('--task', type=int, default=0)
-  ap.add_argument('--regions', default='')
-  ap.add_argument('--channel_list', default='BASE_CHANNELS')
-  ap.add_argument('--pileup_image_width', type=int, default=221)
-  ap.add_argument('--pileup_image_height', type=int, default=100)
-  ap.add_argument('--min_mapping_quality', type=int, default=5)
-  ap.add_argument('--min_base_quality', type=int, default=10)
-  ap.add_argument('--partition_size', type=int, default=1000)
+  ap.add_argument('--checkpoint')        # model directory / ckpt path: only its example_info.json flags are read here
+  ap.add_argument('--checkpoint_json')
+  ap.add_argument('--task', type=int)
+  ap.add_argument('--regions')
+  ap.add_argument('--channel_list')
+  ap.add_argument('--pileup_image_width', type=int)
+  ap.add_argument('--pileup_image_height', type=int)
+  ap.add_argument('--min_mapping_quality', type=int)
+  ap.add_argument('--min_base_quality', type=int)
+  ap.add_argument('--partition_size', type=int)
   ap.add_argument('--sort_by_haplotypes', action='store_true')
   ap.add_argument('--trim_reads_for_pileup', action='store_true')
   ap.add_argument('--parse_sam_aux_fields', action='store_true')
-  ap.add_argument('--alt_aligned_pileup', default='none')
-  ap.add_argument('--device', type=int, default=0)
-  a = ap.parse_args(argv)
+  ap.add_argument('--alt_aligned_pileup')
+  ap.add_argument('--device', type=int)
+  given = vars(ap.parse_args(argv))
+  merged = apply_flags_for_calling(given, given.get('checkpoint', ''), given.get('checkpoint_json', ''))
+  if merged['_ignored_flags_for_calling']:
+    print('make_examples: flags_for_calling of upstream stages not applied: ' + ', '.join(merged['_ignored_flags_for_calling']), file=sys.stderr)
+  a = argparse.Namespace(**merged)
   from deepvariant_b200 import bam, make_examples_native as men, pileup_image as pi, protos, tfrecord
   pic = pi.default_options(pi.ReadRequirements(a.min_base_quality, a.min_mapping_quality))
   pic.channels = _channels(a.channel_list)
