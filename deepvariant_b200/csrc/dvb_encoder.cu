@@ -72,6 +72,7 @@ struct EncDev {
   // every term is < 256 and the byte positions of different kinds are disjoint).
   unsigned mask_base[4], mask_qual[4], mask_diff[4], mask_const[4], ref_words[4];
   int n_words;
+  int gc_chan;              // index of the gc_content channel (its reference-band value is per image), or -1
   int perm_cap;             // largest n with a down-sampling table
   const int* perm;          // tables for n = max_rows+1 .. perm_cap, concatenated
   uint8_t base_lut[256];    // BaseColor(char)
@@ -95,6 +96,7 @@ struct ReadHdr {
   unsigned flags;
   long long seq0, cig0;
   int n_cig;
+  int len;     // aligned_sequence length
 };
 
 __device__ __forceinline__ ReadHdr load_read(const DvbBatch& B, int r) {
@@ -107,6 +109,7 @@ __device__ __forceinline__ ReadHdr load_read(const DvbBatch& B, int r) {
   h.seq0 = B.read_seq_begin[r];
   h.cig0 = B.read_cigar_begin[r];
   h.n_cig = (int)(B.read_cigar_begin[r + 1] - h.cig0);
+  h.len = (int)(B.read_seq_begin[r + 1] - h.seq0);
   return h;
 }
 
@@ -166,8 +169,45 @@ __device__ __forceinline__ int hap_index(const EncDev& P, unsigned flags, int hp
 }
 
 // Per-read constant of a K_CONST channel (channels/*_channel.cc FillReadBase).
-__device__ uint8_t read_const(const EncDev& P, int chan, const ReadHdr& h, int support) {
+// percent = int(float(a) / float(b) * 100) with the reference's operation order (no FMA contraction)
+__device__ __forceinline__ int percent_dev(int a, int b) { return (int)__fmul_rn(__fdiv_rn((float)a, (float)b), 100.0f); }
+
+__device__ uint8_t read_const(const EncDev& P, const DvbBatch& B, int chan, const ReadHdr& h, int support) {
   switch (chan) {
+    // ---- "Opt Channels": whole-read statistics (channels/{read_mapping_percent,identity,avg_base_quality,
+    //      gap_compressed_identity,gc_content}_channel.cc), one value per read
+    case DVB_CH_READ_MAPPING_PERCENT:
+    case DVB_CH_IDENTITY: {
+      int match_len = 0;
+      for (int k = 0; k < h.n_cig; ++k) {
+        const unsigned cw = B.cigar[h.cig0 + k];
+        const unsigned op = cw & 0xF;
+        if (op == 0 || op == 7) match_len += (int)(cw >> 4);
+      }
+      return scale_color_dev(percent_dev(match_len, h.len), 100.0f);
+    }
+    case DVB_CH_AVG_BASE_QUALITY: {
+      int sum = 0;
+      for (int i = 0; i < h.len; ++i) sum += B.quals[h.seq0 + i];
+      return scale_color_dev((int)__fdiv_rn((float)sum, (float)h.len), 93.0f);
+    }
+    case DVB_CH_GAP_COMPRESSED_IDENTITY: {
+      int match_len = 0, gap_len = 0;
+      for (int k = 0; k < h.n_cig; ++k) {
+        const unsigned cw = B.cigar[h.cig0 + k];
+        const unsigned op = cw & 0xF;
+        const int len = (int)(cw >> 4);
+        if (op == 0 || op == 7) { match_len += len; gap_len += len; }
+        else if (op == 8) gap_len += len;
+        else if (op == 1 || op == 2) gap_len += 1;
+      }
+      return scale_color_dev(percent_dev(match_len, gap_len), 100.0f);
+    }
+    case DVB_CH_GC_CONTENT: {
+      int gc = 0;
+      for (int i = 0; i < h.len; ++i) { const unsigned b = B.bases[h.seq0 + i]; gc += (b == 'G' || b == 'C') ? 1 : 0; }
+      return scale_color_dev(percent_dev(gc, h.len), 100.0f);
+    }
     case DVB_CH_MAPPING_QUALITY:
       return scale_color_dev(h.mapq, P.mapq_cap);
     case DVB_CH_STRAND:
@@ -230,7 +270,7 @@ __global__ void __launch_bounds__(128) dvb_pair_prepass_kernel(const EncDev P, c
     rec.tc[0] = rec.tc[1] = rec.tc[2] = rec.tc[3] = 0u;
     const int support = B.pair_support[p];
     for (int c = 0; c < P.C; ++c)
-      if (P.kind[c] == K_CONST) rec.tc[c >> 2] |= (unsigned)read_const(P, P.chan[c], h, support) << (8 * (c & 3));
+      if (P.kind[c] == K_CONST) rec.tc[c >> 2] |= (unsigned)read_const(P, B, P.chan[c], h, support) << (8 * (c & 3));
     rec.sort_pos = B.read_sort_pos[r];
     rec.rank = B.read_name_rank[r];
     rec.hap = hap_index(P, h.flags, h.hp);
@@ -327,6 +367,12 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
       else perm = P.perm + perm_offset(n, P.max_rows);
     }
     __syncthreads();
+    if (P.gc_chan >= 0 && warp == 0) {   // gc_content reference band: GC content of this image's window (gc_content_channel.cc:64-75)
+      int gc = 0;
+      for (int i = lane; i < P.W; i += 32) gc += (s_ref[i] == 'G' || s_ref[i] == 'C') ? 1 : 0;
+      for (int o = 16; o > 0; o >>= 1) gc += __shfl_xor_sync(0xffffffffu, gc, o);
+      if (lane == 0) s_wtot[kWarps + 1] = (int)scale_color_dev(percent_dev(gc, P.W), 100.0f);
+    }
     int n_acc = 0;
     for (int base = 0; base < n && n_acc < P.max_rows; base += kThreads) {
       const int i = base + tid;
@@ -409,13 +455,14 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
       __syncwarp();
       if (row < P.band) {
         // EncodeReference / CalculateRefRows
+        const unsigned gc_word = P.gc_chan >= 0 ? (unsigned)s_wtot[kWarps + 1] << (8 * (P.gc_chan & 3)) : 0u;
         for (int col = lane; col < P.W; col += 32) {
           const unsigned bc = s_base[s_ref[col]];
           uint8_t* q = px + col * P.Cout;
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             if (w < P.n_words) {
-              const unsigned word = P.ref_words[w] + bc * P.mask_base[w];
+              const unsigned word = P.ref_words[w] + bc * P.mask_base[w] + ((P.gc_chan >> 2) == w ? gc_word : 0u);
 #pragma unroll
               for (int b = 0; b < 4; ++b)
                 if (w * 4 + b < P.C) q[w * 4 + b] = (uint8_t)(word >> (8 * b));
@@ -442,7 +489,7 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
           h = load_read(B, r);
           // per-read constants: lane c computes channel c, then every lane gathers them into words
           unsigned myc = 0;
-          if (lane < P.C && P.kind[lane] == K_CONST) myc = read_const(P, P.chan[lane], h, support);
+          if (lane < P.C && P.kind[lane] == K_CONST) myc = read_const(P, B, P.chan[lane], h, support);
 #pragma unroll
           for (int c = 0; c < DVB_MAX_CHANNELS; ++c) {
             const unsigned v = __shfl_sync(0xffffffffu, myc, c);
@@ -601,6 +648,7 @@ int HostBaseColor(int base, const DvbPileupParams& o) {  // channels/read_base_c
 
 int BuildDev(const DvbPileupParams& o, EncDev* d) {
   memset(d, 0, sizeof(*d));
+  d->gc_chan = -1;
   if (o.width < 1) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "width must be >= 1");
   if (o.num_channels < 1 || o.num_channels > DVB_MAX_CHANNELS || o.num_alt_channels < 0 ||
       o.num_channels + o.num_alt_channels > DVB_MAX_CHANNELS)
@@ -643,6 +691,10 @@ int BuildDev(const DvbPileupParams& o, EncDev* d) {
       case DVB_CH_SUPPLEMENTARY_ALIGNMENT:  // supplementary_alignment_channel.cc:60-63: float -> uchar
         d->kind[c] = K_CONST; d->ref_const[c] = static_cast<unsigned char>(o.allele_unsupporting_read_alpha); break;
       case DVB_CH_BLANK: d->kind[c] = K_ZERO; d->ref_const[c] = 0; break;
+      case DVB_CH_READ_MAPPING_PERCENT: case DVB_CH_AVG_BASE_QUALITY: case DVB_CH_IDENTITY: case DVB_CH_GAP_COMPRESSED_IDENTITY:
+        d->kind[c] = K_CONST; d->ref_const[c] = static_cast<uint8_t>(kMaxPixelValueAsFloat); break;
+      case DVB_CH_GC_CONTENT:   // reference band = GC content of the window: filled per image by the kernel
+        d->kind[c] = K_CONST; d->ref_const[c] = 0; d->gc_chan = c; break;
       default:
         return dvb::fail(DVB_ERR_UNSUPPORTED_CHANNEL, "channel enum %d is not implemented", ch);
     }

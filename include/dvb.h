@@ -54,6 +54,11 @@ enum {
   DVB_CH_READ_SUPPORTS_VARIANT = 5,
   DVB_CH_BASE_DIFFERS_FROM_REF = 6,
   DVB_CH_HAPLOTYPE_TAG = 7,
+  DVB_CH_READ_MAPPING_PERCENT = 11,     /* "Opt Channels" (deepvariant/pileup_channel_lib.h): whole-read statistics, */
+  DVB_CH_AVG_BASE_QUALITY = 12,         /* one constant per read (channels/{read_mapping_percent,avg_base_quality,    */
+  DVB_CH_IDENTITY = 13,                 /* identity,gap_compressed_identity,gc_content}_channel.cc)                    */
+  DVB_CH_GAP_COMPRESSED_IDENTITY = 14,
+  DVB_CH_GC_CONTENT = 15,
   DVB_CH_BLANK = 18,
   DVB_CH_INSERT_SIZE = 19,
   DVB_CH_SUPPLEMENTARY_ALIGNMENT = 26

@@ -142,12 +142,63 @@ int GetHPValueForHPChannel(const ReadView& read, int hp_tag_for_assembly_polishi
   return hp_value;
 }
 
+// ---- "Opt Channels": whole-read statistics (the reference caches them per read in a std::optional) --------------
+// channels/read_mapping_percent_channel.cc:71-90 and channels/identity_channel.cc:65-93 (same arithmetic: matched bases
+// (M, =) over the sequence length, in percent).
+int ReadMappingPercent(const ReadView& read) {
+  int match_len = 0;
+  for (int64_t k = 0; k < read.n_cigar; ++k) {
+    const int op = read.cigar[k] & 0xF;
+    if (op == 0 || op == 7) match_len += static_cast<int>(read.cigar[k] >> 4);   // ALIGNMENT_MATCH, SEQUENCE_MATCH
+  }
+  float mapping_percent = (static_cast<float>(match_len) / static_cast<float>(read.len)) * 100;
+  return static_cast<int>(mapping_percent);
+}
+
+// channels/avg_base_quality_channel.cc:70-86 (the reference LOG(FATAL)s outside [0, 93]; callers validate).
+int AvgBaseQuality(const ReadView& read) {
+  int base_qual_sum = 0;
+  for (int64_t i = 0; i < read.len; ++i) base_qual_sum += read.quals[i];
+  float avg_base_qual = (static_cast<float>(base_qual_sum) / static_cast<float>(read.len));
+  return static_cast<int>(avg_base_qual);
+}
+
+// channels/gap_compressed_identity_channel.cc:67-103: insertions and deletions count as single events.
+int GapCompressedIdentity(const ReadView& read) {
+  int match_len = 0;
+  int gap_compressed_len = 0;
+  for (int64_t k = 0; k < read.n_cigar; ++k) {
+    const int op = read.cigar[k] & 0xF;
+    const int op_len = static_cast<int>(read.cigar[k] >> 4);
+    switch (op) {
+      case 0: case 7: match_len += op_len; gap_compressed_len += op_len; break;
+      case 8: gap_compressed_len += op_len; break;
+      case 1: gap_compressed_len += 1; break;
+      case 2: gap_compressed_len += 1; break;
+      default: break;
+    }
+  }
+  float gap_compressed_identity = static_cast<float>(match_len) / static_cast<float>(gap_compressed_len) * 100;
+  return static_cast<int>(gap_compressed_identity);
+}
+
+// channels/gc_content_channel.cc:77-87
+int GcContent(const uint8_t* seq, int64_t len) {
+  int gc_count{};
+  for (int64_t i = 0; i < len; ++i) {
+    if (seq[i] == 'G' || seq[i] == 'C') gc_count += 1;
+  }
+  return static_cast<int>((static_cast<float>(gc_count) / static_cast<float>(len)) * 100);
+}
+
 bool ChannelSupported(int ch) {
   switch (ch) {
     case DVB_CH_READ_BASE: case DVB_CH_BASE_QUALITY: case DVB_CH_MAPPING_QUALITY:
     case DVB_CH_STRAND: case DVB_CH_READ_SUPPORTS_VARIANT: case DVB_CH_BASE_DIFFERS_FROM_REF:
     case DVB_CH_HAPLOTYPE_TAG: case DVB_CH_BLANK: case DVB_CH_INSERT_SIZE:
     case DVB_CH_SUPPLEMENTARY_ALIGNMENT:
+    case DVB_CH_READ_MAPPING_PERCENT: case DVB_CH_AVG_BASE_QUALITY: case DVB_CH_IDENTITY:
+    case DVB_CH_GAP_COMPRESSED_IDENTITY: case DVB_CH_GC_CONTENT:
       return true;
     default:
       return false;
@@ -177,6 +228,15 @@ unsigned char FillReadBase(int channel_enum, char read_base, char ref_base, int 
       return ScaleColor(GetHPValueForHPChannel(read, o.hp_tag_for_assembly_polishing), 2);
     case DVB_CH_INSERT_SIZE:
       return NormalizeFragmentLength(read.fraglen);
+    case DVB_CH_READ_MAPPING_PERCENT:     // kMaxMappingPercent = 100
+    case DVB_CH_IDENTITY:                 // kMaxIdentity = 100
+      return ScaleColor(ReadMappingPercent(read), 100);
+    case DVB_CH_AVG_BASE_QUALITY:         // kMaxAvgBaseQuality = 93
+      return ScaleColor(AvgBaseQuality(read), 93);
+    case DVB_CH_GAP_COMPRESSED_IDENTITY:
+      return ScaleColor(GapCompressedIdentity(read), 100);
+    case DVB_CH_GC_CONTENT:               // kMaxGcContent = 100
+      return ScaleColor(GcContent(read.bases, read.len), 100);
     case DVB_CH_SUPPLEMENTARY_ALIGNMENT: {  // channels/supplementary_alignment_channel.cc:49-58
       float alpha = (read.flags & DVB_READ_SUPPLEMENTARY) ? o.allele_supporting_read_alpha
                                                           : o.allele_unsupporting_read_alpha;
@@ -189,8 +249,13 @@ unsigned char FillReadBase(int channel_enum, char read_base, char ref_base, int 
 }
 
 // One FillRefBase call (channels/*_channel.cc FillRefBase).
-unsigned char FillRefBase(int channel_enum, char ref_base, const DvbPileupParams& o) {
+unsigned char FillRefBase(int channel_enum, char ref_base, const DvbPileupParams& o, const uint8_t* ref_bases) {
   switch (channel_enum) {
+    case DVB_CH_READ_MAPPING_PERCENT: case DVB_CH_AVG_BASE_QUALITY: case DVB_CH_IDENTITY:
+    case DVB_CH_GAP_COMPRESSED_IDENTITY:   // *_channel.cc FillRefBase: kMaxPixelValueAsFloat
+      return static_cast<std::uint8_t>(kMaxPixelValueAsFloat);
+    case DVB_CH_GC_CONTENT:                // gc_content_channel.cc:64-75: GC content of the reference window itself
+      return ScaleColor(GcContent(ref_bases, o.width), 100);
     case DVB_CH_READ_BASE:
       return BaseColor(ref_base, o);
     case DVB_CH_BASE_QUALITY:      // base_quality_channel.cc:52-57
@@ -305,7 +370,7 @@ std::unique_ptr<ImageRow> EncodeReference(const DvbPileupParams& o, const uint8_
   ImageRow img_row(o.width, o.num_channels);
   for (int c = 0; c < o.num_channels; ++c) {
     for (int i = 0; i < o.width; ++i) {
-      img_row.channel_data[c][i] = FillRefBase(o.channels[c], static_cast<char>(ref_bases[i]), o);
+      img_row.channel_data[c][i] = FillRefBase(o.channels[c], static_cast<char>(ref_bases[i]), o, ref_bases);
     }
   }
   return std::make_unique<ImageRow>(img_row);

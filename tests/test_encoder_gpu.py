@@ -232,3 +232,16 @@ def test_pair_prepass_and_single_kernel_paths_are_identical(monkeypatch):
       np.testing.assert_array_equal(out.cpu().numpy(), want, err_msg=f'pacbio={pacbio} prepass={flag}')
       assert enc.launch_count == (2 if flag == '1' else 1)
       enc.close()
+
+
+def test_opt_channels_random_batch_matches_oracle():
+  """12-channel layout: the six base channels + the five whole-read "Opt Channels" + insert_size, with indels, soft clips,
+  down-sampled images and multi-allelic support classes from the synthetic generator."""
+  chans = pi.PILEUP_DEFAULT_CHANNELS + ['read_mapping_percent', 'avg_base_quality', 'identity', 'gap_compressed_identity', 'gc_content',
+                                        'insert_size']
+  tb = synthetic.make_batch(200, DEV)
+  got, want, rows, _ = _encode_both(_options(chans), tb)
+  assert got.shape[-1] == 12
+  np.testing.assert_array_equal(got, want)
+  assert (got[:, :5, :, 6:10] == 254).all()          # reference band of the four fixed-value statistics
+  assert len(np.unique(got[:, 0, 0, 10])) > 3         # GC content of the window differs from image to image

@@ -368,3 +368,47 @@ def test_downsample_prefix_kat():
       got = np.zeros(n, dtype=np.int32)
       assert _lib.lib().dvb_shuffle_table(n, 2101079370, flavour, got.ctypes.data_as(ctypes.c_void_p)) == 0
       np.testing.assert_array_equal(got, oracle_lib.shuffle_table(n, 2101079370, 95, flavour))
+
+
+# ---- "Opt Channels": whole-read statistics (pileup_channel_lib_test.cc:419-504, 696-832, 851-951) ------------------------
+
+OPT = ['read_mapping_percent', 'avg_base_quality', 'identity', 'gap_compressed_identity', 'gc_content']
+
+
+def _scaled(value, cap):
+  return int(np.float32(254.0) * (np.float32(min(value, cap)) / np.float32(cap)))
+
+
+@pytest.mark.parametrize('channel,bases,cigar,quals,value,cap', [
+    ('read_mapping_percent', 'AAAAATTTTT', '5M5D', [30] * 10, 50, 100),          # ReadMappingPercentTest.BasicCase
+    ('avg_base_quality', 'AAAAATTTTT', '10M', list(range(1, 11)), 5, 93),         # AvgBaseQualityTest.BasicCase
+    ('identity', 'AAAAATTTTT', '5M1I4M', [30] * 10, 90, 100),                     # IdentityTest.BasicCase
+    ('identity', 'AAAAATTTTT', '5=1X4=', [30] * 10, 90, 100),                     # IdentityTest.PacBioStyleCigar
+    ('gap_compressed_identity', 'AAAAATTTTT', '3M4I3M', [30] * 10, 85, 100),      # GapCompressedIdentityTest.InsertionCase
+    ('gap_compressed_identity', 'AAAAATTTTT', '3M4D3M', [30] * 10, 85, 100),      # .DeletionCase
+    ('gap_compressed_identity', 'AAAAATTTTT', '3=2X2I3=', [30] * 10, 66, 100),    # .PacBioStyleCigar
+    ('gc_content', 'GGGGGCCCCC', '10M', [30] * 10, 100, 100),                     # GcContestTest.AllGc
+    ('gc_content', 'GGGGGTTTTT', '10M', [30] * 10, 50, 100),                      # GcContestTest.HalfGc
+])
+def test_opt_channel_read_statistics(backend, channel, bases, cigar, quals, value, cap):
+  """The statistic the reference's unit tests assert, seen through the channel's pixel value ScaleColor(value, cap)."""
+  read = make_read(bases, start=2, cigar=cigar, quals=quals, name='r')
+  got = backend(_options([channel], read_requirements=pi.ReadRequirements(0, 0))).encode_read(_make_dv_call(), 'A' * 21, read, 0, ['C'])
+  drawn = got[0, :, 0][got[0, :, 0] > 0] if value else got[0, :, 0]
+  assert len(drawn) > 0 and set(np.unique(drawn)) == {_scaled(value, cap)}, (np.unique(got), _scaled(value, cap))
+
+
+def test_opt_channels_get_channel_data_kat(backend):
+  """GetChannelDataTest (pileup_channel_lib_test.cc:696-832): read GGGCGCTTTTAT / 11M, every quality 33 ->
+  mapping percent 231, average base quality 90, identity 231, gap-compressed identity 254, GC content 127;
+  GetRefChannelDataTest (:851-951): reference row 254, 254, 254, 254 and the window's own GC content (127)."""
+  read = make_read('GGGCGCTTTTAT', start=1, cigar='11M', quals=[33] * 12, name='r')
+  enc = backend(_options(OPT, read_requirements=pi.ReadRequirements(0, 0)))
+  got = enc.encode_read(_make_dv_call(), 'GGGCGCTTTTAT', read, 1, ['C'])
+  assert got.shape == (1, 12, 5)
+  np.testing.assert_array_equal(got[0, 3], [231, 90, 231, 254, 127])
+  np.testing.assert_array_equal(got[0, :11], np.tile([231, 90, 231, 254, 127], (11, 1)))
+  assert not got[0, 11].any()                                    # 11M covers 11 of the 12 columns
+  ref = enc.encode_reference('GGGCGCTTTTAT')
+  np.testing.assert_array_equal(ref[0], np.tile([254, 254, 254, 254, 127], (12, 1)))
+  assert enc.encode_reference('ATATATATATAT')[0, 0, 4] == 0 and enc.encode_reference('GCGCGCGCGCGC')[0, 5, 4] == 254
