@@ -51,7 +51,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr float kMaxPixelValueAsFloat = 254.0f;  // channels/channel.h:78
 constexpr float kMaxFragmentLength = 1000.0f;    // channels/channel.h:81
 
-enum Kind : uint8_t { K_ZERO = 0, K_BASE = 1, K_QUAL = 2, K_DIFF = 3, K_CONST = 4 };
+enum Kind : uint8_t { K_ZERO = 0, K_BASE = 1, K_QUAL = 2, K_DIFF = 3, K_CONST = 4, K_ISHOMO = 5, K_HOMOW = 6 };
 
 struct EncDev {
   int W, H, band, C, Cout, max_rows;
@@ -71,6 +71,8 @@ struct EncDev {
   // diff*mask_diff, where a mask has 0x01 in the byte of every channel of that kind (no carries:
   // every term is < 256 and the byte positions of different kinds are disjoint).
   unsigned mask_base[4], mask_qual[4], mask_diff[4], mask_const[4], ref_words[4];
+  unsigned mask_ishomo[4], mask_homow[4];   // per-base homopolymer channels (is_homopolymer, homopolymer_weighted)
+  int has_homo;
   int n_words;
   int gc_chan;              // index of the gc_content channel (its reference-band value is per image), or -1
   int perm_cap;             // largest n with a down-sampling table
@@ -169,6 +171,20 @@ __device__ __forceinline__ int hap_index(const EncDev& P, unsigned flags, int hp
 }
 
 // Per-read constant of a K_CONST channel (channels/*_channel.cc FillReadBase).
+// Per-base homopolymer channels at sequence index i of seq[0, len) (channels/is_homopolymer_channel.cc:77-105,
+// channels/homopolymer_weighted_channel.cc:79-115).  *ih = 254 inside a run of >= 3 equal bases else 0;
+// *hw = ScaleColor(uint8(run length), 30).
+__device__ __forceinline__ void homopolymer_at(const uint8_t* seq, int len, int i, bool want_weighted, unsigned* ih, unsigned* hw) {
+  const unsigned b = seq[i];
+  int l = i, r = i;
+  const int reach = want_weighted ? len : 2;          // is_homopolymer only needs to know whether the run reaches 3
+  while (l > 0 && i - l < reach && seq[l - 1] == b) --l;
+  while (r + 1 < len && r - i < reach && seq[r + 1] == b) ++r;
+  const int run = r - l + 1;
+  *ih = run >= 3 ? 254u : 0u;
+  *hw = want_weighted ? (unsigned)scale_color_dev(run & 0xFF, 30.0f) : 0u;
+}
+
 // percent = int(float(a) / float(b) * 100) with the reference's operation order (no FMA contraction)
 __device__ __forceinline__ int percent_dev(int a, int b) { return (int)__fmul_rn(__fdiv_rn((float)a, (float)b), 100.0f); }
 
@@ -247,7 +263,7 @@ struct __align__(16) PairRec {
   unsigned rank;
   int hap;
   uint8_t grp, ok, pad0, pad1;
-  int pad2, pad3;           // (tried: first two CIGAR words inline here - 54 registers, one CTA fewer per SM, slower)
+  int len, pad3;            // sequence length (per-base homopolymer channels); (tried: first two CIGAR words inline here - 54 registers, slower)
 };
 static_assert(sizeof(PairRec) == 64, "PairRec is one 64-byte line");
 
@@ -275,7 +291,7 @@ __global__ void __launch_bounds__(128) dvb_pair_prepass_kernel(const EncDev P, c
     rec.rank = B.read_name_rank[r];
     rec.hap = hap_index(P, h.flags, h.hp);
     rec.grp = (P.sort_by_group && B.pair_allele_group) ? B.pair_allele_group[p] : (uint8_t)0;
-    rec.ok = (uint8_t)ok; rec.pad0 = rec.pad1 = 0; rec.pad2 = rec.pad3 = 0;
+    rec.ok = (uint8_t)ok; rec.pad0 = rec.pad1 = 0; rec.len = h.len; rec.pad3 = 0;
     uint4* dst = reinterpret_cast<uint4*>(recs + p);
     const uint4* srcv = reinterpret_cast<const uint4*>(&rec);
     dst[0] = srcv[0]; dst[1] = srcv[1]; dst[2] = srcv[2]; dst[3] = srcv[3];
@@ -322,7 +338,8 @@ __device__ __forceinline__ void flush_row(uint8_t* __restrict__ dst, const uint8
 
 // FAST7: 7 computed channels, 7-byte pixels (the WGS layout): runs of 4 pixels whose first column is a multiple of 4 are
 // assembled in registers and stored as 7 aligned 32-bit words instead of 28 byte stores.
-template <bool FAST7>
+// HOMO: the per-base homopolymer channels are present (a separate instantiation keeps the common layouts at 48 registers).
+template <bool FAST7, bool HOMO>
 __global__ void __launch_bounds__(kThreads, DVB_ENC_MIN_BLOCKS)
 dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, int* __restrict__ rows_kept,
                   int* __restrict__ err, const PairRec* __restrict__ recs) {
@@ -458,11 +475,14 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
         const unsigned gc_word = P.gc_chan >= 0 ? (unsigned)s_wtot[kWarps + 1] << (8 * (P.gc_chan & 3)) : 0u;
         for (int col = lane; col < P.W; col += 32) {
           const unsigned bc = s_base[s_ref[col]];
+          unsigned ih = 0u, hw = 0u;
+          if constexpr (HOMO) homopolymer_at(s_ref, P.W, col, P.has_homo > 1, &ih, &hw);   // the window treated as a read
           uint8_t* q = px + col * P.Cout;
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             if (w < P.n_words) {
-              const unsigned word = P.ref_words[w] + bc * P.mask_base[w] + ((P.gc_chan >> 2) == w ? gc_word : 0u);
+              const unsigned word = P.ref_words[w] + bc * P.mask_base[w] + ((P.gc_chan >> 2) == w ? gc_word : 0u) +
+                                    (HOMO ? ih * P.mask_ishomo[w] + hw * P.mask_homow[w] : 0u);
 #pragma unroll
               for (int b = 0; b < 4; ++b)
                 if (w * 4 + b < P.C) q[w * 4 + b] = (uint8_t)(word >> (8 * b));
@@ -482,7 +502,8 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
           h.pos = (int)q1.x; h.n_cig = (int)q1.y;
           tc[0] = q1.z; tc[1] = q1.w;
           if (P.n_words > 2) { const uint4 q2 = rv[2]; tc[2] = q2.x; tc[3] = q2.y; }
-          h.mapq = 0; h.fraglen = 0; h.hp = 0; h.flags = 0;
+          h.mapq = 0; h.fraglen = 0; h.hp = 0; h.flags = 0; h.len = 0;
+          if constexpr (HOMO) h.len = (int)rv[3].z;
         } else {
           const int r = B.pair_read[p];
           const int support = B.pair_support[p];
@@ -513,11 +534,14 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
                 const unsigned bc = s_base[b];
                 const unsigned ql = s_qual[quals[read_i + j]];
                 const unsigned df = (b == s_ref[col]) ? P.match_color : P.mismatch_color;
+                unsigned ih = 0u, hw = 0u;
+                if constexpr (HOMO) homopolymer_at(bases, h.len, read_i + j, P.has_homo > 1, &ih, &hw);
                 uint8_t* q = px + col * P.Cout;
 #pragma unroll
                 for (int w = 0; w < 4; ++w) {
                   if (w < P.n_words) {
-                    const unsigned word = tc[w] + bc * P.mask_base[w] + ql * P.mask_qual[w] + df * P.mask_diff[w];
+                    const unsigned word = tc[w] + bc * P.mask_base[w] + ql * P.mask_qual[w] + df * P.mask_diff[w] +
+                                          (HOMO ? ih * P.mask_ishomo[w] + hw * P.mask_homow[w] : 0u);
 #pragma unroll
                     for (int bb = 0; bb < 4; ++bb)
                       if (w * 4 + bb < P.C) q[w * 4 + bb] = (uint8_t)(word >> (8 * bb));
@@ -577,11 +601,14 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
               const unsigned bc = s_base[P.anchor_char & 0xFF];
               const unsigned ql = s_qual[quals[op == 1 ? read_i : read_i - 1]];
               const unsigned df = ((unsigned)P.anchor_char == s_ref[col]) ? P.match_color : P.mismatch_color;
+              unsigned ih = 0u, hw = 0u;
+              if constexpr (HOMO) homopolymer_at(bases, h.len, op == 1 ? read_i : read_i - 1, P.has_homo > 1, &ih, &hw);
               uint8_t* q = px + col * P.Cout;
 #pragma unroll
               for (int w = 0; w < 4; ++w) {
                 if (w < P.n_words) {
-                  const unsigned word = tc[w] + bc * P.mask_base[w] + ql * P.mask_qual[w] + df * P.mask_diff[w];
+                  const unsigned word = tc[w] + bc * P.mask_base[w] + ql * P.mask_qual[w] + df * P.mask_diff[w] +
+                                        (HOMO ? ih * P.mask_ishomo[w] + hw * P.mask_homow[w] : 0u);
 #pragma unroll
                   for (int bb = 0; bb < 4; ++bb)
                     if (w * 4 + bb < P.C) q[w * 4 + bb] = (uint8_t)(word >> (8 * bb));
@@ -693,6 +720,8 @@ int BuildDev(const DvbPileupParams& o, EncDev* d) {
       case DVB_CH_BLANK: d->kind[c] = K_ZERO; d->ref_const[c] = 0; break;
       case DVB_CH_READ_MAPPING_PERCENT: case DVB_CH_AVG_BASE_QUALITY: case DVB_CH_IDENTITY: case DVB_CH_GAP_COMPRESSED_IDENTITY:
         d->kind[c] = K_CONST; d->ref_const[c] = static_cast<uint8_t>(kMaxPixelValueAsFloat); break;
+      case DVB_CH_IS_HOMOPOLYMER: d->kind[c] = K_ISHOMO; d->ref_const[c] = 0; d->has_homo = std::max(d->has_homo, 1); break;
+      case DVB_CH_HOMOPOLYMER_WEIGHTED: d->kind[c] = K_HOMOW; d->ref_const[c] = 0; d->has_homo = 2; break;
       case DVB_CH_GC_CONTENT:   // reference band = GC content of the window: filled per image by the kernel
         d->kind[c] = K_CONST; d->ref_const[c] = 0; d->gc_chan = c; break;
       default:
@@ -706,6 +735,8 @@ int BuildDev(const DvbPileupParams& o, EncDev* d) {
     else if (d->kind[c] == K_QUAL) d->mask_qual[c >> 2] |= one;
     else if (d->kind[c] == K_DIFF) d->mask_diff[c >> 2] |= one;
     else if (d->kind[c] == K_CONST) d->mask_const[c >> 2] |= one;
+    else if (d->kind[c] == K_ISHOMO) d->mask_ishomo[c >> 2] |= one;
+    else if (d->kind[c] == K_HOMOW) d->mask_homow[c >> 2] |= one;
     if (d->kind[c] != K_BASE) d->ref_words[c >> 2] |= (unsigned)d->ref_const[c] << (8 * (c & 3));
   }
   for (int i = 0; i < 256; ++i) {
@@ -732,9 +763,11 @@ int Launch(DvbEncoder* enc, const DvbBatch& b, uint8_t* out, int32_t* rows_kept,
     enc->launches++;
   }
   if (enc->fast7)
-    dvb_encode_kernel<true><<<grid, kThreads, enc->smem_bytes, stream>>>(enc->dev, b, out, rows_kept, enc->d_err, recs);
+    dvb_encode_kernel<true, false><<<grid, kThreads, enc->smem_bytes, stream>>>(enc->dev, b, out, rows_kept, enc->d_err, recs);
+  else if (enc->dev.has_homo)
+    dvb_encode_kernel<false, true><<<grid, kThreads, enc->smem_bytes, stream>>>(enc->dev, b, out, rows_kept, enc->d_err, recs);
   else
-    dvb_encode_kernel<false><<<grid, kThreads, enc->smem_bytes, stream>>>(enc->dev, b, out, rows_kept, enc->d_err, recs);
+    dvb_encode_kernel<false, false><<<grid, kThreads, enc->smem_bytes, stream>>>(enc->dev, b, out, rows_kept, enc->d_err, recs);
   enc->launches++;
   DVB_CUDA(cudaGetLastError());
   return DVB_OK;
@@ -940,15 +973,18 @@ int dvb_encoder_create(const DvbPileupParams* params, int device, DvbEncoder** o
     delete enc;
     return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "image row too large for shared memory (%d bytes)", enc->smem_bytes);
   }
-  enc->fast7 = dev.C == 7 && dev.Cout == 7;
+  enc->fast7 = dev.C == 7 && dev.Cout == 7 && !dev.has_homo;   // the 7-byte fast path knows the four classic pixel terms only
   { const char* e = getenv("DVB_ENC_PREPASS"); enc->prepass = !(e && atoi(e) == 0); }
   int occ = 1;
   if (enc->fast7) {
-    DVB_CUDA(cudaFuncSetAttribute(dvb_encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc->smem_bytes));
-    DVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dvb_encode_kernel<true>, kThreads, enc->smem_bytes));
+    DVB_CUDA(cudaFuncSetAttribute(dvb_encode_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc->smem_bytes));
+    DVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dvb_encode_kernel<true, false>, kThreads, enc->smem_bytes));
+  } else if (dev.has_homo) {
+    DVB_CUDA(cudaFuncSetAttribute(dvb_encode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc->smem_bytes));
+    DVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dvb_encode_kernel<false, true>, kThreads, enc->smem_bytes));
   } else {
-    DVB_CUDA(cudaFuncSetAttribute(dvb_encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc->smem_bytes));
-    DVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dvb_encode_kernel<false>, kThreads, enc->smem_bytes));
+    DVB_CUDA(cudaFuncSetAttribute(dvb_encode_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc->smem_bytes));
+    DVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dvb_encode_kernel<false, false>, kThreads, enc->smem_bytes));
   }
   enc->grid_cap = enc->num_sms * std::max(occ, 1);
   DVB_CUDA(cudaStreamCreateWithFlags(&enc->stream, cudaStreamNonBlocking));

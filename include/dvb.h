@@ -59,6 +59,8 @@ enum {
   DVB_CH_IDENTITY = 13,                 /* identity,gap_compressed_identity,gc_content}_channel.cc)                    */
   DVB_CH_GAP_COMPRESSED_IDENTITY = 14,
   DVB_CH_GC_CONTENT = 15,
+  DVB_CH_IS_HOMOPOLYMER = 16,           /* per base: inside a run of >= 3 equal bases (is_homopolymer_channel.cc:77-91) */
+  DVB_CH_HOMOPOLYMER_WEIGHTED = 17,     /* per base: length of its run, capped at 30 (homopolymer_weighted_channel.cc:79-101) */
   DVB_CH_BLANK = 18,
   DVB_CH_INSERT_SIZE = 19,
   DVB_CH_SUPPLEMENTARY_ALIGNMENT = 26

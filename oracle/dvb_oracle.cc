@@ -191,6 +191,62 @@ int GcContent(const uint8_t* seq, int64_t len) {
   return static_cast<int>((static_cast<float>(gc_count) / static_cast<float>(len)) * 100);
 }
 
+// channels/is_homopolymer_channel.cc:77-91: 1 for every base inside a run of three or more equal bases.
+std::vector<std::uint8_t> IsHomopolymer(const uint8_t* seq, int64_t len) {
+  std::vector<std::uint8_t> homopolymer(static_cast<size_t>(len), 0);
+  for (int64_t i = 2; i < len; i++) {
+    if (seq[i] == seq[i - 1] && seq[i - 1] == seq[i - 2]) {
+      homopolymer[i] = 1;
+      homopolymer[i - 1] = 1;
+      homopolymer[i - 2] = 1;
+    }
+  }
+  return homopolymer;
+}
+
+// channels/homopolymer_weighted_channel.cc:79-101: the length of the run each base belongs to (stored in a uint8).
+std::vector<std::uint8_t> HomopolymerWeighted(const uint8_t* seq, int64_t len) {
+  std::vector<std::uint8_t> homopolymer(static_cast<size_t>(len), 0);
+  if (len == 0) return homopolymer;
+  int current_weight = 1;
+  for (int64_t i = 1; i < len; i++) {
+    if (seq[i] == seq[i - 1]) {
+      current_weight += 1;
+    } else {
+      for (int cw = current_weight; cw >= 1; cw--) homopolymer[i - cw] = current_weight;
+      current_weight = 1;
+    }
+  }
+  for (int cw = current_weight; cw >= 1; cw--) homopolymer[len - cw] = current_weight;
+  return homopolymer;
+}
+
+// ScaleColorVector (is_homopolymer_channel.cc:93-105 / homopolymer_weighted_channel.cc:103-115)
+void ScaleColorVector(std::vector<std::uint8_t>& v, float max_val) {
+  for (auto& x : v) {
+    int value = x;
+    if (static_cast<float>(value) > max_val) value = max_val;
+    x = static_cast<int>(kMaxPixelValueAsFloat * (static_cast<float>(value) / max_val));
+  }
+}
+
+// Per-base channel vectors of one sequence, computed once (the reference caches them in a std::optional per read).
+struct BaseVectors {
+  std::vector<std::uint8_t> is_homopolymer, homopolymer_weighted;
+  BaseVectors(const uint8_t* seq, int64_t len, const DvbPileupParams& o) {
+    for (int c = 0; c < o.num_channels; ++c) {
+      if (o.channels[c] == DVB_CH_IS_HOMOPOLYMER && is_homopolymer.empty()) {
+        is_homopolymer = IsHomopolymer(seq, len);
+        ScaleColorVector(is_homopolymer, 1);      // kMaxIsHomopolymer
+      }
+      if (o.channels[c] == DVB_CH_HOMOPOLYMER_WEIGHTED && homopolymer_weighted.empty()) {
+        homopolymer_weighted = HomopolymerWeighted(seq, len);
+        ScaleColorVector(homopolymer_weighted, 30);   // kMaxHomopolymerWeighted
+      }
+    }
+  }
+};
+
 bool ChannelSupported(int ch) {
   switch (ch) {
     case DVB_CH_READ_BASE: case DVB_CH_BASE_QUALITY: case DVB_CH_MAPPING_QUALITY:
@@ -199,6 +255,7 @@ bool ChannelSupported(int ch) {
     case DVB_CH_SUPPLEMENTARY_ALIGNMENT:
     case DVB_CH_READ_MAPPING_PERCENT: case DVB_CH_AVG_BASE_QUALITY: case DVB_CH_IDENTITY:
     case DVB_CH_GAP_COMPRESSED_IDENTITY: case DVB_CH_GC_CONTENT:
+    case DVB_CH_IS_HOMOPOLYMER: case DVB_CH_HOMOPOLYMER_WEIGHTED:
       return true;
     default:
       return false;
@@ -208,8 +265,13 @@ bool ChannelSupported(int ch) {
 // One FillReadBase call (channels/*_channel.cc FillReadBase), dispatched by enum like
 // Channels::ChannelEnumToObject (pileup_channel_lib.cc:367-447).
 unsigned char FillReadBase(int channel_enum, char read_base, char ref_base, int base_quality,
-                           const ReadView& read, int support_class, const DvbPileupParams& o) {
+                           const ReadView& read, int support_class, const DvbPileupParams& o, int read_index,
+                           const BaseVectors& bv) {
   switch (channel_enum) {
+    case DVB_CH_IS_HOMOPOLYMER:          // data[col] = vector.at(read_index)
+      return bv.is_homopolymer.at(static_cast<size_t>(read_index));
+    case DVB_CH_HOMOPOLYMER_WEIGHTED:
+      return bv.homopolymer_weighted.at(static_cast<size_t>(read_index));
     case DVB_CH_READ_BASE:
       return BaseColor(read_base, o);
     case DVB_CH_BASE_QUALITY:
@@ -249,8 +311,13 @@ unsigned char FillReadBase(int channel_enum, char read_base, char ref_base, int 
 }
 
 // One FillRefBase call (channels/*_channel.cc FillRefBase).
-unsigned char FillRefBase(int channel_enum, char ref_base, const DvbPileupParams& o, const uint8_t* ref_bases) {
+unsigned char FillRefBase(int channel_enum, char ref_base, const DvbPileupParams& o, const uint8_t* ref_bases, int col,
+                          const BaseVectors& ref_bv) {
   switch (channel_enum) {
+    case DVB_CH_IS_HOMOPOLYMER:          // the reference window treated as a read: ref_data[col] = vector.at(col)
+      return ref_bv.is_homopolymer.at(static_cast<size_t>(col));
+    case DVB_CH_HOMOPOLYMER_WEIGHTED:
+      return ref_bv.homopolymer_weighted.at(static_cast<size_t>(col));
     case DVB_CH_READ_MAPPING_PERCENT: case DVB_CH_AVG_BASE_QUALITY: case DVB_CH_IDENTITY:
     case DVB_CH_GAP_COMPRESSED_IDENTITY:   // *_channel.cc FillRefBase: kMaxPixelValueAsFloat
       return static_cast<std::uint8_t>(kMaxPixelValueAsFloat);
@@ -285,6 +352,7 @@ unsigned char FillRefBase(int channel_enum, char ref_base, const DvbPileupParams
 int CalculateChannels(std::vector<std::vector<unsigned char>>& data, const DvbPileupParams& o,
                       const ReadView& read, const uint8_t* ref_bases, int width,
                       int variant_start, int support_class, int image_start_pos) {
+  const BaseVectors bv(read.bases, read.len, o);
   // action_per_cigar_unit, pileup_channel_lib.cc:126-165 (op in BAM numbering here).
   auto action = [&](int ref_i, int read_i, int op) -> bool {
     char read_base = 0;
@@ -305,7 +373,7 @@ int CalculateChannels(std::vector<std::vector<unsigned char>>& data, const DvbPi
       char ref_base = static_cast<char>(ref_bases[col]);
       for (int c = 0; c < o.num_channels; ++c) {
         data[c][col] = FillReadBase(o.channels[c], read_base, ref_base, base_quality, read,
-                                    support_class, o);
+                                    support_class, o, read_i, bv);
       }
     }
     return true;
@@ -368,9 +436,10 @@ int EncodeRead(const DvbPileupParams& o, const ReadView& read, const uint8_t* re
 // pileup_image_native.cc:512-527, pileup_channel_lib.cc:263-293.
 std::unique_ptr<ImageRow> EncodeReference(const DvbPileupParams& o, const uint8_t* ref_bases) {
   ImageRow img_row(o.width, o.num_channels);
+  const BaseVectors ref_bv(ref_bases, o.width, o);
   for (int c = 0; c < o.num_channels; ++c) {
     for (int i = 0; i < o.width; ++i) {
-      img_row.channel_data[c][i] = FillRefBase(o.channels[c], static_cast<char>(ref_bases[i]), o, ref_bases);
+      img_row.channel_data[c][i] = FillRefBase(o.channels[c], static_cast<char>(ref_bases[i]), o, ref_bases, i, ref_bv);
     }
   }
   return std::make_unique<ImageRow>(img_row);

@@ -245,3 +245,17 @@ def test_opt_channels_random_batch_matches_oracle():
   np.testing.assert_array_equal(got, want)
   assert (got[:, :5, :, 6:10] == 254).all()          # reference band of the four fixed-value statistics
   assert len(np.unique(got[:, 0, 0, 10])) > 3         # GC content of the window differs from image to image
+
+
+def test_homopolymer_channels_random_batch_matches_oracle():
+  """The per-base homopolymer channels (separate kernel instantiation) next to the base channels and the whole-read statistics,
+  on the synthetic batch (indels -> anchor pixels, soft clips, down-sampling) and on a PACBIO-width layout with haplotypes."""
+  chans = pi.PILEUP_DEFAULT_CHANNELS + ['is_homopolymer', 'homopolymer_weighted', 'gc_content', 'insert_size']
+  tb = synthetic.make_batch(200, DEV)
+  got, want, _, _ = _encode_both(_options(chans), tb)
+  np.testing.assert_array_equal(got, want)
+  assert set(np.unique(got[..., 6])) == {0, 254} and len(np.unique(got[..., 7])) > 4
+  chans = pi.PILEUP_DEFAULT_CHANNELS + ['haplotype', 'homopolymer_weighted']
+  tb = synthetic.make_batch(120, DEV, width=147, hp=True)
+  got, want, _, _ = _encode_both(_options(chans, width=147, sort_by_haplotypes=True), tb)
+  np.testing.assert_array_equal(got, want)

@@ -412,3 +412,46 @@ def test_opt_channels_get_channel_data_kat(backend):
   ref = enc.encode_reference('GGGCGCTTTTAT')
   np.testing.assert_array_equal(ref[0], np.tile([254, 254, 254, 254, 127], (12, 1)))
   assert enc.encode_reference('ATATATATATAT')[0, 0, 4] == 0 and enc.encode_reference('GCGCGCGCGCGC')[0, 5, 4] == 254
+
+
+# ---- per-base homopolymer channels (pileup_channel_lib_test.cc:506-564, 696-832, 851-951) --------------------------------
+
+@pytest.mark.parametrize('bases,expected', [
+    ('GGGATAATA', [1, 1, 1, 0, 0, 0, 0, 0, 0]),     # IsHomoPolymerTest.IsHomopolymerBeginning
+    ('ATTGGGTTA', [0, 0, 0, 1, 1, 1, 0, 0, 0]),     # .IsHomopolymerMiddle
+    ('ATAATAGGG', [0, 0, 0, 0, 0, 0, 1, 1, 1]),     # .IsHomopolymerEnd
+    ('AAAAAAAAA', [1] * 9),                         # .IsHomopolymerAll
+])
+def test_is_homopolymer(backend, bases, expected):
+  read = make_read(bases, start=3, cigar=f'{len(bases)}M', quals=[30] * len(bases), name='r')
+  got = backend(_options(['is_homopolymer'], read_requirements=pi.ReadRequirements(0, 0))).encode_read(_make_dv_call(), 'C' * 15, read, 0, ['C'])
+  assert got[0, 3:3 + len(bases), 0].tolist() == [254 * e for e in expected]
+  assert not got[0, :3].any() and not got[0, 3 + len(bases):].any()
+
+
+def test_homopolymer_weighted(backend):
+  """HomoPolymerWeightedTest.BasicCase (run lengths 1,1,2,2,3,3,3,4,4,4,4,5,5,5,5,5) and .WeightedHomoPolymerMax (10 G + 20 A)."""
+  enc = backend(_options(['homopolymer_weighted'], read_requirements=pi.ReadRequirements(0, 0)))
+  seq = 'GATTGGGCCCCAAAAA'
+  got = enc.encode_read(_make_dv_call(), 'C' * 20, make_read(seq, start=2, cigar='16M', quals=[30] * 16, name='r'), 0, ['C'])
+  runs = [1, 1, 2, 2, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 5]
+  assert got[0, 2:18, 0].tolist() == [_scaled(r, 30) for r in runs]
+  seq = 'G' * 10 + 'A' * 20 + 'C' * 35          # a 35-long run saturates at 30 -> 254
+  got = enc.encode_read(_make_dv_call(), 'T' * 70, make_read(seq, start=1, cigar='65M', quals=[30] * 65, name='r'), 0, ['C'])
+  assert got[0, 1:66, 0].tolist() == [_scaled(10, 30)] * 10 + [_scaled(20, 30)] * 20 + [254] * 35
+
+
+def test_homopolymer_channels_get_channel_data_kat(backend):
+  """GetChannelDataTest / GetRefChannelDataTest with read = reference window = GGGCGCTTTTAT (11M):
+  is_homopolymer[1] = 254, [4] = 0; homopolymer_weighted[1] = 25 (run 3), [9] = 33 (run 4); same values on the reference row."""
+  chans = ['is_homopolymer', 'homopolymer_weighted']
+  enc = backend(_options(chans, read_requirements=pi.ReadRequirements(0, 0)))
+  read = make_read('GGGCGCTTTTAT', start=1, cigar='11M', quals=[33] * 12, name='r')
+  got = enc.encode_read(_make_dv_call(), 'GGGCGCTTTTAT', read, 1, ['C'])
+  assert got[0, 1, 0] == 254 and got[0, 4, 0] == 0 and got[0, 1, 1] == 25 and got[0, 9, 1] == 33
+  ref = enc.encode_reference('GGGCGCTTTTAT')
+  assert ref[0, 1, 0] == 254 and ref[0, 4, 0] == 0 and ref[0, 1, 1] == 25 and ref[0, 9, 1] == 33
+  # an insertion anchor takes the value at the first inserted base's index, a deletion anchor at the base before it
+  ins = make_read('ACGTTTTGCA', start=2, cigar='3M4I3M', quals=[30] * 10, name='r')
+  got = enc.encode_read(_make_dv_call(), 'A' * 12, ins, 0, ['C'])
+  assert got[0, 4, 0] == 254 and got[0, 4, 1] == _scaled(4, 30)       # anchor column 2+3-1 = 4 <- read index 3 ('T' of TTTT)
