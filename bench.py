@@ -182,6 +182,25 @@ class CpuReference:
       self.cnn.forward(imgs[i:i + batch])
     return time.perf_counter() - t0
 
+  def tfexample_gzip_rate(self, images, n=96):
+    """What the reference's make_examples pays on top of the pixels: one tf.Example per image with the seven
+    features of EncodeExample, written through the gzip TFRecord writer.  One core; returns examples/s per core."""
+    import tempfile
+    from deepvariant_b200 import protos, tfrecord
+    n = min(n, len(images))
+    variant = protos.Variant(reference_name='chr20', start=1000, end=1001, reference_bases='A', alternate_bases=['C']).serialize()
+    idx = protos.encode_alt_allele_indices([0])
+    with tempfile.TemporaryDirectory() as d:
+      t0 = time.perf_counter()
+      with tfrecord.Writer(os.path.join(d, 'ex.tfrecord.gz')) as w:
+        for i in range(n):
+          img = images[i]
+          w.write(protos.encode_tf_example({
+              'alt_allele_indices/encoded': ('bytes', [idx]), 'image/encoded': ('bytes', [img.tobytes()]),
+              'image/shape': ('int64', list(img.shape)), 'locus': ('bytes', [b'chr20:1001-1001']), 'sequencing_type': ('int64', [0]),
+              'variant/encoded': ('bytes', [variant]), 'variant_type': ('int64', [1])}))
+      return n / (time.perf_counter() - t0)
+
   def calibrate(self, packed, target_s=4.0, lo=32, hi=4096):
     """Sample size so that one encode+classify pass takes about target_s seconds."""
     n0 = min(64, packed.n_images)
@@ -421,7 +440,9 @@ def main():
       te += t2; reps += 1
     tc = ref.classify(imgs)
     r_enc, r_cnn = sample * reps / te, sample / tc
+    r_gz = ref.tfexample_gzip_rate(imgs)
     cpu_baseline = {'value': 1.0 / (1.0 / r_enc + 1.0 / r_cnn), 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                    'tfexample_gzip_examples_per_s_per_core': r_gz,
                     'sample': f'{sample} synthetic windows: C++ oracle port of pileup_image_native.cc {r_enc:.0f}/s '
                               f'({te:.1f} s) then torch fp32 CPU Inception-v3 {r_cnn:.0f}/s ({tc:.1f} s) on the same cores',
                     'encode_only': r_enc, 'cnn_only': r_cnn}
