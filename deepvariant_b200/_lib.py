@@ -142,6 +142,7 @@ SYMBOLS = (
     ('dvb_encode_classify_host', C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(DvbBatch), C.c_void_p, C.c_void_p]),
     ('dvb_cnn_launch_count', C.c_int64, [C.c_void_p]),
     ('dvb_cnn_flops_per_image', C.c_double, [C.c_void_p]),
+    ('dvb_cnn_max_batch', C.c_int32, [C.c_void_p]),
     ('dvb_read_requirements_default', None, [C.POINTER(DvbReadRequirements)]),
     ('dvb_bam_open', C.c_int, [C.c_char_p, C.POINTER(DvbReadRequirements), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     ('dvb_bam_table', C.c_int, [C.c_void_p, C.POINTER(DvbReadTable)]),
@@ -149,6 +150,7 @@ SYMBOLS = (
     ('dvb_bam_close', None, [C.c_void_p]),
     ('dvb_crc32c', C.c_uint32, [C.c_char_p, C.c_size_t]),
     ('dvb_masked_crc32c', C.c_uint32, [C.c_char_p, C.c_size_t]),
+    ('dvb_debug_upload_phases', C.c_int, [C.POINTER(DvbBatch), C.c_int64, C.c_void_p, C.c_int32]),
     ('dvb_cnn_debug_tensor', C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32),
                                        C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 )

@@ -2260,6 +2260,7 @@ int dvb_cnn_forward_host(DvbCnn* net, const uint8_t* images_host, int32_t n, flo
 
 int64_t dvb_cnn_launch_count(const DvbCnn* net) { return net ? net->launches : 0; }
 double dvb_cnn_flops_per_image(const DvbCnn* net) { return net ? net->flops_per_image : 0.0; }
+int32_t dvb_cnn_max_batch(const DvbCnn* net) { return net ? net->max_batch : 0; }
 
 // Debug / test access to an intermediate activation of the LAST forward (first `n` images):
 // out_host = float[n][H][W][C] (NHWC).  name: "input", "s1".."s5", "p1", "p2", "mixed0".."mixed10", branch tensors.

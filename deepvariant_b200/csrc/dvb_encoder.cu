@@ -648,6 +648,8 @@ struct DvbEncoder {
   int* d_err = nullptr;
   int64_t launches = 0;
   // staging for the host entry point
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> copy_events;
   dvb::DevBuf d_in, d_out, d_rows, d_recs;
   bool prepass = true;
   dvb::PinBuf h_in, h_out;
@@ -801,7 +803,10 @@ std::vector<int> ShuffledIndices(int n, uint32_t seed, int shuffle_stdlib) {
 
 // Validates a host batch (what the reference leaves to CHECKs / UB), packs every input array into one pinned staging
 // block and issues ONE H2D copy on `s`; *db receives the same batch with device pointers.
-int StageHostBatch(DvbEncoder* enc, const DvbBatch* hb, DvbBatch* out_db, cudaStream_t s) {
+// One phase of a chunked upload: images [i0, i1), their pairs [p0, p1) and the reads [r0, r1) not uploaded by earlier phases.
+struct StagePhase { int64_t i0, i1, p0, p1, r0, r1; cudaEvent_t done; };
+
+int StageHostBatch(DvbEncoder* enc, const DvbBatch* hb, DvbBatch* out_db, cudaStream_t s, std::vector<StagePhase>* phases = nullptr) {
   const int64_t NI = hb->n_images, NR = hb->n_reads, NP = hb->n_pairs, NB = hb->n_bases, NC = hb->n_cigar;
   // ---- validation the reference leaves to CHECKs / UB ----
   if (hb->pair_begin[0] != 0 || hb->pair_begin[NI] != NP) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "pair_begin is not a CSR over n_pairs");
@@ -823,12 +828,17 @@ int StageHostBatch(DvbEncoder* enc, const DvbBatch* hb, DvbBatch* out_db, cudaSt
                        (long long)consumed, (long long)(hb->read_seq_begin[r + 1] - hb->read_seq_begin[r]));
   }
   // ---- pack every input array into one pinned staging block, one H2D copy ----
-  struct Seg { const void* src; size_t bytes; size_t off; };
+  enum Domain { D_IMAGE, D_IMAGE1, D_PAIR, D_READ, D_READ1, D_BASE, D_CIGAR };
+  struct Seg { const void* src; size_t bytes; size_t off; int domain; size_t esz; bool pinned; };
   Seg segs[19];
   int ns = 0;
   size_t total = 0;
+  const Domain kDomains[19] = {D_IMAGE, D_IMAGE, D_IMAGE, D_IMAGE1, D_PAIR, D_PAIR, D_PAIR, D_READ, D_READ, D_READ, D_READ, D_READ, D_READ, D_READ,
+                               D_READ1, D_READ1, D_BASE, D_BASE, D_CIGAR};
+  const size_t kElem[19] = {(size_t)hb->ref_stride, 4, 4, 8, 4, 1, 1, 4, 4, 4, 1, 4, 4, 4, 8, 8, 1, 1, 4};
   auto add = [&](const void* p, size_t bytes) {
     segs[ns].src = p; segs[ns].bytes = p ? bytes : 0; segs[ns].off = total;
+    segs[ns].domain = kDomains[ns]; segs[ns].esz = kElem[ns]; segs[ns].pinned = false;
     total += (segs[ns].bytes + 255) & ~(size_t)255;
     return ns++;
   };
@@ -854,6 +864,42 @@ int StageHostBatch(DvbEncoder* enc, const DvbBatch* hb, DvbBatch* out_db, cudaSt
   total = std::max<size_t>(total, 256);
   DVB_CUDA(enc->h_in.reserve(total));
   DVB_CUDA(enc->d_in.reserve(total));
+  if (phases && phases->size() > 1) {
+    // Chunked upload on `s` (the caller passes its copy stream): phase k brings the per-image and per-pair slices of its
+    // images and the reads no earlier phase brought, then records its event, so that encode + classify of phase k
+    // overlap the upload of phase k + 1.  The device arrays keep the full batch's layout (absolute indices stay valid).
+    for (int i = 0; i < ns; ++i) {
+      cudaPointerAttributes attr;
+      segs[i].pinned = segs[i].bytes > 0 && cudaPointerGetAttributes(&attr, segs[i].src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    }
+    cudaGetLastError();
+    for (StagePhase& ph : *phases) {
+      for (int i = 0; i < ns; ++i) {
+        if (!segs[i].bytes) continue;
+        int64_t lo = 0, hi = 0;
+        switch (segs[i].domain) {
+          case D_IMAGE: lo = ph.i0; hi = ph.i1; break;
+          case D_IMAGE1: lo = ph.i0 + (ph.i0 > 0 ? 1 : 0); hi = ph.i1 + 1; break;   // element i0 came with the previous phase
+          case D_PAIR: lo = ph.p0; hi = ph.p1; break;
+          case D_READ: lo = ph.r0; hi = ph.r1; break;
+          case D_READ1: lo = ph.r0 + (ph.r0 > 0 ? 1 : 0); hi = ph.r1 > ph.r0 ? ph.r1 + 1 : lo; break;   // element r0 came with the previous phase
+          case D_BASE: lo = hb->read_seq_begin[ph.r0]; hi = hb->read_seq_begin[ph.r1]; break;
+          case D_CIGAR: lo = hb->read_cigar_begin[ph.r0]; hi = hb->read_cigar_begin[ph.r1]; break;
+        }
+        if (hi <= lo) continue;
+        const size_t b0 = (size_t)lo * segs[i].esz, nb = (size_t)(hi - lo) * segs[i].esz;
+        const char* src = static_cast<const char*>(segs[i].src) + b0;
+        char* dst = static_cast<char*>(enc->d_in.p) + segs[i].off + b0;
+        if (!segs[i].pinned) {
+          char* stage = static_cast<char*>(enc->h_in.p) + segs[i].off + b0;
+          memcpy(stage, src, nb);
+          src = stage;
+        }
+        DVB_CUDA(cudaMemcpyAsync(dst, src, nb, cudaMemcpyHostToDevice, s));
+      }
+      DVB_CUDA(cudaEventRecord(ph.done, s));
+    }
+  } else
   // Arrays the caller already keeps in page-locked memory go to the device straight from where they lie; pageable
   // ones are packed into the pinned staging block first (contiguous pageable runs share one copy).
   {
@@ -1000,6 +1046,8 @@ void dvb_encoder_destroy(DvbEncoder* enc) {
   enc->d_in.release(); enc->d_out.release(); enc->d_rows.release(); enc->d_recs.release();
   enc->h_in.release(); enc->h_out.release();
   if (enc->stream) cudaStreamDestroy(enc->stream);
+  if (enc->copy_stream) cudaStreamDestroy(enc->copy_stream);
+  for (cudaEvent_t e : enc->copy_events) cudaEventDestroy(e);
   delete enc;
 }
 
@@ -1054,27 +1102,104 @@ int dvb_encode_batch_host(DvbEncoder* enc, const DvbBatch* hb, uint8_t* out_host
 }
 
 
+// Phases of at most `sub` images; phase k uploads the reads [r0, r1) that no earlier phase uploaded (r1 = 1 + the largest
+// read index its pairs reference, never below the previous r1).  Empty when the batch fits one phase.
+static int PlanUploadPhases(const DvbBatch* hb, int64_t sub, std::vector<StagePhase>* phases) {
+  phases->clear();
+  const int64_t NI = hb->n_images;
+  if (NI <= sub || hb->n_pairs <= 0) return DVB_OK;
+  int64_t r_done = 0;
+  for (int64_t i0 = 0; i0 < NI; i0 += sub) {
+    const int64_t i1 = std::min(NI, i0 + sub);
+    StagePhase ph{i0, i1, hb->pair_begin[i0], hb->pair_begin[i1], r_done, r_done, nullptr};
+    if (ph.p0 < 0 || ph.p1 < ph.p0 || ph.p1 > hb->n_pairs) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "pair_begin is not a CSR over n_pairs");
+    int64_t rmax = -1;
+    for (int64_t p = ph.p0; p < ph.p1; ++p) {
+      const int64_t r = hb->pair_read[p];
+      if (r < 0 || r >= hb->n_reads) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "pair_read out of range");
+      rmax = std::max(rmax, r);
+    }
+    ph.r1 = std::max(r_done, rmax + 1);
+    r_done = ph.r1;
+    phases->push_back(ph);
+  }
+  return DVB_OK;
+}
+
+// Test access to the upload plan of dvb_encode_classify_host: out = int64[n][6] = {i0, i1, p0, p1, r0, r1}; returns the
+// number of phases (0 = single upload), or a negative status.
+int dvb_debug_upload_phases(const DvbBatch* hb, int64_t sub, int64_t* out, int32_t cap) {
+  if (!hb || sub < 1) return -DVB_ERR_INVALID_ARGUMENT;
+  std::vector<StagePhase> phases;
+  const int st = PlanUploadPhases(hb, sub, &phases);
+  if (st) return -st;
+  for (size_t k = 0; k < phases.size() && (int32_t)k < cap; ++k) {
+    const StagePhase& ph = phases[k];
+    const int64_t v[6] = {ph.i0, ph.i1, ph.p0, ph.p1, ph.r0, ph.r1};
+    memcpy(out + 6 * k, v, sizeof(v));
+  }
+  return (int)phases.size();
+}
+
 int dvb_encode_classify_host(DvbEncoder* enc, DvbCnn* cnn, const DvbBatch* hb, float* probs_host, int32_t* rows_kept_host) {
   if (!enc || !cnn || !hb || (!probs_host && hb->n_images > 0)) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "null argument");
   if (hb->n_images == 0) return DVB_OK;
   if (hb->ref_stride < enc->dev.W) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "ref_stride < width");
   DVB_CUDA(cudaSetDevice(enc->device));
   cudaStream_t s = enc->stream;
-  DvbBatch db;
-  int st = StageHostBatch(enc, hb, &db, s);
-  if (st) return st;
   const int64_t NI = hb->n_images;
+  // Phases of at most one classifier chunk each: the upload of phase k + 1 (copy stream) overlaps encode + classify of
+  // phase k (compute stream).  Reads are uploaded by the first phase that references them; batches whose images reference
+  // reads in roughly increasing order (position-sorted candidates over position-sorted reads) pipeline fully, any other
+  // order stays correct and simply front-loads the upload.
+  const int64_t sub = std::max<int64_t>(1, dvb_cnn_max_batch(cnn));
+  std::vector<StagePhase> phases;
+  {
+    const char* e = getenv("DVB_E2E_PIPELINE");
+    if (!(e && atoi(e) == 0)) {
+      int st0 = PlanUploadPhases(hb, sub, &phases);
+      if (st0) return st0;
+    }
+    if (!enc->copy_stream) DVB_CUDA(cudaStreamCreateWithFlags(&enc->copy_stream, cudaStreamNonBlocking));
+    while (enc->copy_events.size() < phases.size()) {
+      cudaEvent_t ev;
+      DVB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      enc->copy_events.push_back(ev);
+    }
+    for (size_t k = 0; k < phases.size(); ++k) phases[k].done = enc->copy_events[k];
+  }
+  const bool chunked = phases.size() > 1;
+  DvbBatch db;
+  int st = StageHostBatch(enc, hb, &db, chunked ? enc->copy_stream : s, chunked ? &phases : nullptr);
+  if (st) return st;
   const size_t out_bytes = (size_t)NI * enc->dev.image_bytes;
   DVB_CUDA(enc->d_out.reserve(out_bytes));
   DVB_CUDA(enc->d_rows.reserve(NI * 4 + NI * 3 * sizeof(float)));
   DVB_CUDA(enc->h_out.reserve(NI * 4 + NI * 3 * sizeof(float)));
+  uint8_t* d_images = static_cast<uint8_t*>(enc->d_out.p);
   int32_t* d_rows = static_cast<int32_t*>(enc->d_rows.p);
   float* d_probs = reinterpret_cast<float*>(d_rows + NI);
-  st = Launch(enc, db, static_cast<uint8_t*>(enc->d_out.p), d_rows, s);
-  if (st) return st;
-  // the images never leave HBM: the classifier consumes the encoder's output in place, on the same stream
-  st = dvb_cnn_forward_device(cnn, static_cast<const uint8_t*>(enc->d_out.p), (int32_t)NI, d_probs, s);
-  if (st) return st;
+  if (!chunked) {
+    st = Launch(enc, db, d_images, d_rows, s);
+    if (st) return st;
+    // the images never leave HBM: the classifier consumes the encoder's output in place, on the same stream
+    st = dvb_cnn_forward_device(cnn, d_images, (int32_t)NI, d_probs, s);
+    if (st) return st;
+  } else {
+    for (const StagePhase& ph : phases) {
+      DVB_CUDA(cudaStreamWaitEvent(s, ph.done, 0));
+      DvbBatch sb = db;           // same device arrays; only the per-image views move (pair / read indices are absolute)
+      sb.n_images = (int32_t)(ph.i1 - ph.i0);
+      sb.ref_bases = db.ref_bases + (size_t)ph.i0 * db.ref_stride;
+      sb.image_start_pos = db.image_start_pos + ph.i0;
+      sb.variant_start = db.variant_start + ph.i0;
+      sb.pair_begin = db.pair_begin + ph.i0;
+      st = Launch(enc, sb, d_images + (size_t)ph.i0 * enc->dev.image_bytes, d_rows + ph.i0, s);
+      if (st) return st;
+      st = dvb_cnn_forward_device(cnn, d_images + (size_t)ph.i0 * enc->dev.image_bytes, sb.n_images, d_probs + 3 * ph.i0, s);
+      if (st) return st;
+    }
+  }
   DVB_CUDA(cudaMemcpyAsync(enc->h_out.p, d_rows, NI * 4 + NI * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
   st = dvb_encoder_check(enc, s);  // synchronises
   if (st) return st;

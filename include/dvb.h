@@ -225,6 +225,8 @@ int dvb_encode_classify_host(DvbEncoder* enc, DvbCnn* cnn, const DvbBatch* batch
                              int32_t* rows_kept_host);
 
 int64_t dvb_cnn_launch_count(const DvbCnn* cnn);
+/* Images per internal chunk of a forward (the max_batch the handle was created with). */
+int32_t dvb_cnn_max_batch(const DvbCnn* cnn);
 /* FLOPs of one forward for one image (conv MACs x 2). */
 double dvb_cnn_flops_per_image(const DvbCnn* cnn);
 
@@ -279,6 +281,11 @@ int dvb_bam_open(const char* path, const DvbReadRequirements* req, int parse_hp,
 int dvb_bam_table(const DvbBam* bam, DvbReadTable* table);
 const char* dvb_bam_ref_name(const DvbBam* bam, int32_t i);   /* NULL when out of range */
 void dvb_bam_close(DvbBam* bam);
+
+/* Test access to the chunked-upload plan of dvb_encode_classify_host for phases of `sub` images: out = int64[cap][6] =
+ * {image begin, image end, pair begin, pair end, first read uploaded, one past the last read uploaded}.  Returns the number
+ * of phases (0 = the batch is uploaded in one piece) or -DvbStatus.  Host only, no device needed. */
+int dvb_debug_upload_phases(const DvbBatch* batch_host, int64_t sub, int64_t* out, int32_t cap);
 
 /* Debug / test access to an intermediate activation of the LAST forward (first `n` images of the
  * last chunk), converted to float NHWC: out_host = float[n][H][W][C].  Names follow

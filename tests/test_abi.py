@@ -72,3 +72,33 @@ def test_no_device_is_an_error_not_a_fallback():
   h = ctypes.c_void_p()
   st = l.dvb_encoder_create(ctypes.byref(p), 0, ctypes.byref(h))
   assert st == 6 and b'no CUDA device' in l.dvb_last_error()
+
+
+def test_upload_phase_plan_of_the_fused_host_entry():
+  """dvb_encode_classify_host uploads a large batch in phases of one classifier chunk; the plan is host arithmetic on the
+  CSR arrays (no device): every read is uploaded by the first phase that references it, phases tile the images and pairs."""
+  import numpy as np
+  from deepvariant_b200 import synthetic
+  l = _lib.lib()
+  tb = synthetic.make_batch(100, 'cpu')
+  cb = tb.as_ctypes()
+  out = np.zeros((16, 6), dtype=np.int64)
+  n = l.dvb_debug_upload_phases(ctypes.byref(cb), 32, out.ctypes.data_as(ctypes.c_void_p), 16)
+  assert n == 4
+  ph = out[:n]
+  pair_begin = tb.tensors['pair_begin'].numpy()
+  pair_read = tb.tensors['pair_read'].numpy()
+  assert ph[:, 0].tolist() == [0, 32, 64, 96] and ph[:, 1].tolist() == [32, 64, 96, 100]
+  assert (ph[:, 2] == pair_begin[ph[:, 0]]).all() and (ph[:, 3] == pair_begin[ph[:, 1]]).all()
+  assert ph[0, 4] == 0 and (ph[1:, 4] == ph[:-1, 5]).all()                      # read ranges are contiguous
+  for k in range(n):                                                             # every referenced read is on the device in time
+    assert pair_read[ph[k, 2]:ph[k, 3]].max() < ph[k, 5]
+  assert l.dvb_debug_upload_phases(ctypes.byref(cb), 100, out.ctypes.data_as(ctypes.c_void_p), 16) == 0    # fits one phase
+  # a batch whose FIRST image references the LAST read front-loads the whole read table and stays correct
+  tb.tensors['pair_read'][0] = tb.n_reads - 1
+  cb = tb.as_ctypes()
+  n = l.dvb_debug_upload_phases(ctypes.byref(cb), 32, out.ctypes.data_as(ctypes.c_void_p), 16)
+  assert n == 4 and out[0, 5] == tb.n_reads and (out[1:n, 4] == tb.n_reads).all() and (out[1:n, 5] == tb.n_reads).all()
+  tb.tensors['pair_read'][5] = tb.n_reads + 3                                    # out of range -> status, not a crash
+  cb = tb.as_ctypes()
+  assert l.dvb_debug_upload_phases(ctypes.byref(cb), 32, out.ctypes.data_as(ctypes.c_void_p), 16) == -1
