@@ -119,6 +119,15 @@ class DvbReadTable(C.Structure):
   ]
 
 
+class DvbRegionCandidates(C.Structure):
+  _fields_ = [
+      ('n_images', C.c_int32), ('ref_id', C.c_void_p), ('variant_start', C.c_void_p), ('variant_end', C.c_void_p),
+      ('image_start_pos', C.c_void_p), ('ref_bases', C.c_void_p), ('ref_stride', C.c_int32),
+      ('support_begin', C.c_void_p), ('support_class', C.c_void_p), ('support_group', C.c_void_p),
+      ('support_name_begin', C.c_void_p), ('support_names', C.c_void_p), ('group_default', C.c_void_p),
+  ]
+
+
 _lib: Optional[C.CDLL] = None
 
 # Every symbol include/dvb.h declares: (name, restype, argtypes).
@@ -148,6 +157,10 @@ SYMBOLS = (
     ('dvb_bam_table', C.c_int, [C.c_void_p, C.POINTER(DvbReadTable)]),
     ('dvb_bam_ref_name', C.c_char_p, [C.c_void_p, C.c_int32]),
     ('dvb_bam_close', None, [C.c_void_p]),
+    ('dvb_pack_region_from_bam', C.c_int, [C.c_void_p, C.POINTER(DvbRegionCandidates), C.c_int32, C.c_int32, C.c_int32,
+                                           C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    ('dvb_packed_region_batch', C.c_int, [C.c_void_p, C.POINTER(DvbBatch)]),
+    ('dvb_packed_region_free', None, [C.c_void_p]),
     ('dvb_crc32c', C.c_uint32, [C.c_char_p, C.c_size_t]),
     ('dvb_masked_crc32c', C.c_uint32, [C.c_char_p, C.c_size_t]),
     ('dvb_debug_upload_phases', C.c_int, [C.POINTER(DvbBatch), C.c_int64, C.c_void_p, C.c_int32]),

@@ -162,7 +162,7 @@ class NativeBamTable:
         if not count:
           return np.zeros(0, dtype=dtype)
         buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
-        return np.frombuffer(buf, dtype=dtype, count=count).copy()   # own the data: the handle is closed below
+        return np.frombuffer(buf, dtype=dtype, count=count).copy()   # own the data: valid after close()
 
       self.n_reads = n
       self.n_records_seen = int(t.n_records_seen)
@@ -183,10 +183,27 @@ class NativeBamTable:
       self.quals = arr(t.quals, t.n_bases, np.uint8)
       self.cigar = arr(t.cigar, t.n_cigar, np.uint32)
       self.names = arr(t.names, t.n_name_bytes, np.uint8).tobytes()
-    finally:
+    except BaseException:
       lib.dvb_bam_close(h)
+      raise
+    self._handle = h            # kept open: the native region packer (packing.pack_region_native) reads the C++ table
+    self._close = lib.dvb_bam_close
     self.parse_aux = parse_aux
     self._reads: Optional[List[Read]] = None
+
+  def close(self) -> None:
+    if getattr(self, '_handle', None) is not None:
+      self._close(self._handle)
+      self._handle = None
+
+  def __del__(self):
+    self.close()
+
+  @property
+  def handle(self):
+    if self._handle is None:
+      raise ValueError('NativeBamTable is closed')
+    return self._handle
 
   HP_ABSENT = -(1 << 31)
 

@@ -23,8 +23,11 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <string_view>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "dvb_common.h"
@@ -95,6 +98,12 @@ struct DvbBam {
   std::vector<uint32_t> cigar;
   std::vector<char> names;
   int64_t n_records_seen = 0;
+  // region-packer index, built on first use (EnsureIndex)
+  mutable std::once_flag index_once;
+  mutable bool sorted = false;            // rows ordered by (ref_id, pos): region queries can binary-search
+  mutable int32_t max_span = 0;           // longest end - pos
+  mutable std::unordered_map<uint64_t, int32_t> first_by_key;   // hash(fragment_name, read_number) -> first row with that hash
+  mutable std::vector<int32_t> next_same_hash;                   // chain to the next row with the same hash (file order), -1 ends
 };
 
 extern "C" {
@@ -267,5 +276,200 @@ const char* dvb_bam_ref_name(const DvbBam* bam, int32_t i) {
 }
 
 void dvb_bam_close(DvbBam* bam) { delete bam; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Region packer: candidates + BAM table rows -> DvbBatch arrays, on the host, without per-read objects
+// ---------------------------------------------------------------------------------------------
+// Restates, over the flat read table, what ExamplesGenerator::CreateAndWriteExamplesForCandidate does per candidate before
+// the pixels (deepvariant/make_examples_native.cc:632-736): the InMemoryReader::Query scan (:802-810 with ReadOverlapsRegion,
+// third_party/nucleus/util/utils.cc:172-188) as an index filter on pos / end, ReadSupportsAlt's read-name search
+// (deepvariant/channels/read_supports_variant_channel.cc:75-104) as hash lookups of "fragment_name/read_number" keys, and the
+// gather of the per-read arrays.  Output = exactly the arrays packing.pack_images_from_table builds (tests compare them).
+namespace {
+
+inline std::string_view NameOf(const DvbBam& bam, int32_t r) {
+  return std::string_view(bam.names.data() + bam.name_begin[(size_t)r], (size_t)(bam.name_begin[(size_t)r + 1] - bam.name_begin[(size_t)r]));
+}
+
+inline uint64_t KeyHash(std::string_view name, uint8_t read_number) {
+  uint64_t h = 0xcbf29ce484222325ull ^ read_number;   // FNV-1a over the name bytes
+  for (const char ch : name) h = (h ^ (uint8_t)ch) * 0x100000001b3ull;
+  return h;
+}
+
+void EnsureIndex(const DvbBam& bam) {
+  std::call_once(bam.index_once, [&]() {
+    const int32_t n = (int32_t)bam.pos.size();
+    bool sorted = true;
+    int32_t span = 0;
+    for (int32_t r = 0; r < n; ++r) {
+      span = std::max(span, bam.end[r] - bam.pos[r]);
+      if (r > 0) {   // unmapped reads (ref_id -1) sort last, as in coordinate-sorted BAMs
+        const uint32_t a = (uint32_t)bam.ref_id[r - 1], b = (uint32_t)bam.ref_id[r];
+        if (a > b || (a == b && bam.pos[r - 1] > bam.pos[r])) sorted = false;
+      }
+    }
+    bam.sorted = sorted;
+    bam.max_span = span;
+    bam.next_same_hash.assign((size_t)n, -1);
+    bam.first_by_key.reserve((size_t)n * 2);
+    std::unordered_map<uint64_t, int32_t> last;
+    last.reserve((size_t)n * 2);
+    for (int32_t r = 0; r < n; ++r) {
+      const uint64_t h = KeyHash(NameOf(bam, r), bam.read_number[r]);
+      auto ins = last.emplace(h, r);
+      if (ins.second) bam.first_by_key.emplace(h, r);
+      else { bam.next_same_hash[(size_t)ins.first->second] = r; ins.first->second = r; }
+    }
+  });
+}
+
+}  // namespace
+
+struct DvbPackedRegion {
+  std::vector<uint8_t> ref_bases, pair_support, pair_allele_group, read_flags, bases, quals;
+  std::vector<int32_t> image_start_pos, variant_start, pair_read, read_pos, read_sort_pos, read_mapq, read_fragment_length, read_hp;
+  std::vector<uint32_t> read_name_rank, cigar;
+  std::vector<int64_t> pair_begin, read_seq_begin, read_cigar_begin;
+  int32_t n_images = 0, n_reads = 0, ref_stride = 0;
+};
+
+extern "C" {
+
+int dvb_pack_region_from_bam(const DvbBam* bam, const DvbRegionCandidates* c, int32_t region_ref_id, int32_t region_start,
+                             int32_t region_end, int32_t read_overlap_buffer_bp, int32_t width, DvbPackedRegion** out) {
+  if (!bam || !c || !out || c->n_images < 0 || width < 1 || c->ref_stride < width)
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_pack_region_from_bam: bad arguments");
+  *out = nullptr;
+  EnsureIndex(*bam);
+  const int32_t NR = (int32_t)bam->pos.size();
+  // reads of the region (what the reference hands WriteExamplesInRegion), in file order; rows lie in [row_lo, row_hi)
+  std::vector<int32_t> region_rows;
+  int32_t row_lo = 0, row_hi = NR;
+  if (bam->sorted) {
+    auto before = [&](int32_t r, int32_t rid, int64_t p) { return (uint32_t)bam->ref_id[r] < (uint32_t)rid || (bam->ref_id[r] == rid && bam->pos[r] < p); };
+    int32_t a = 0, b = NR;
+    const int64_t p_lo = (int64_t)region_start - bam->max_span;
+    while (a < b) { const int32_t m = a + (b - a) / 2; if (before(m, region_ref_id, p_lo)) a = m + 1; else b = m; }
+    row_lo = a;
+    b = NR;
+    while (a < b) { const int32_t m = a + (b - a) / 2; if (before(m, region_ref_id, region_end)) a = m + 1; else b = m; }
+    row_hi = a;
+  }
+  for (int32_t r = row_lo; r < row_hi; ++r)
+    if (bam->ref_id[r] == region_ref_id && bam->pos[r] < region_end && bam->end[r] > region_start) region_rows.push_back(r);
+
+  DvbPackedRegion* pr = new DvbPackedRegion();
+  pr->n_images = c->n_images;
+  pr->ref_stride = (width + 15) / 16 * 16;
+  pr->ref_bases.assign((size_t)c->n_images * pr->ref_stride, 0);
+  pr->pair_begin.push_back(0);
+  std::vector<int32_t> table_rows_of_pairs;             // table row per pair, remapped to batch read indices below
+  std::vector<int32_t> local((size_t)(row_hi - row_lo), -1);   // table row - row_lo -> position in the image's read list
+  for (int32_t i = 0; i < c->n_images; ++i) {
+    memcpy(pr->ref_bases.data() + (size_t)i * pr->ref_stride, c->ref_bases + (size_t)i * c->ref_stride, (size_t)width);
+    pr->image_start_pos.push_back(c->image_start_pos[i]);
+    pr->variant_start.push_back(c->variant_start[i]);
+    const int32_t q_start = c->variant_start[i] - read_overlap_buffer_bp, q_end = c->variant_end[i] + read_overlap_buffer_bp;
+    const size_t first_pair = table_rows_of_pairs.size();
+    std::vector<int32_t> members;
+    if (c->ref_id[i] == region_ref_id) {
+      for (const int32_t r : region_rows) {
+        if (bam->pos[r] < q_end && bam->end[r] > q_start) {
+          local[(size_t)(r - row_lo)] = (int32_t)members.size();
+          members.push_back(r);
+          table_rows_of_pairs.push_back(r);
+        }
+      }
+    }
+    const size_t n = members.size();
+    pr->pair_support.resize(first_pair + n, 0);
+    pr->pair_allele_group.resize(first_pair + n, c->group_default ? (uint8_t)c->group_default[i] : (uint8_t)0);
+    // ReadSupportsAlt: entries come in alt order; the first entry that names a read decides its class
+    for (int64_t e = c->support_begin[i]; e < c->support_begin[i + 1]; ++e) {
+      const std::string_view key(c->support_names + c->support_name_begin[e], (size_t)(c->support_name_begin[e + 1] - c->support_name_begin[e]));
+      // table keys are fragment_name + "/" + ("0" | "1"): anything else cannot equal one
+      if (key.size() < 2 || key[key.size() - 2] != '/' || (key.back() != '0' && key.back() != '1')) continue;
+      const std::string_view name = key.substr(0, key.size() - 2);
+      const uint8_t rn = (uint8_t)(key.back() - '0');
+      auto it = bam->first_by_key.find(KeyHash(name, rn));
+      if (it == bam->first_by_key.end()) continue;
+      for (int32_t r = it->second; r >= 0; r = bam->next_same_hash[(size_t)r]) {
+        if (r < row_lo || r >= row_hi) continue;
+        const int32_t j = local[(size_t)(r - row_lo)];
+        if (j < 0 || bam->read_number[r] != rn || NameOf(*bam, r) != name) continue;
+        if (pr->pair_support[first_pair + j] == 0) pr->pair_support[first_pair + j] = c->support_class[e];
+        if (c->support_group) pr->pair_allele_group[first_pair + j] = c->support_group[e];   // later alts overwrite (pileup_image_native.cc:345-360)
+      }
+    }
+    for (const int32_t r : members) local[(size_t)(r - row_lo)] = -1;
+    pr->pair_begin.push_back((int64_t)table_rows_of_pairs.size());
+  }
+  // reads are stored once, in order of first use
+  std::unordered_map<int32_t, int32_t> batch_index;
+  std::vector<int32_t> rows;
+  pr->pair_read.reserve(table_rows_of_pairs.size());
+  for (int32_t r : table_rows_of_pairs) {
+    auto ins = batch_index.emplace(r, (int32_t)rows.size());
+    if (ins.second) rows.push_back(r);
+    pr->pair_read.push_back(ins.first->second);
+  }
+  pr->n_reads = (int32_t)rows.size();
+  pr->read_seq_begin.push_back(0);
+  pr->read_cigar_begin.push_back(0);
+  for (int32_t r : rows) {
+    pr->read_pos.push_back(bam->pos[r]);
+    pr->read_sort_pos.push_back(bam->pos[r]);
+    pr->read_mapq.push_back(bam->mapq[r]);
+    const bool has_hp = bam->hp[r] != INT32_MIN;
+    pr->read_flags.push_back((uint8_t)(((bam->flag[r] & 0x10) ? DVB_READ_REVERSE_STRAND : 0) | ((bam->flag[r] & FSUPP) ? DVB_READ_SUPPLEMENTARY : 0) |
+                                       (has_hp ? DVB_READ_HAS_HP : 0)));
+    pr->read_fragment_length.push_back(bam->fragment_length[r]);
+    pr->read_hp.push_back(has_hp ? bam->hp[r] : 0);
+    pr->bases.insert(pr->bases.end(), bam->bases.begin() + bam->seq_begin[r], bam->bases.begin() + bam->seq_begin[r + 1]);
+    pr->quals.insert(pr->quals.end(), bam->quals.begin() + bam->seq_begin[r], bam->quals.begin() + bam->seq_begin[r + 1]);
+    pr->cigar.insert(pr->cigar.end(), bam->cigar.begin() + bam->cigar_begin[r], bam->cigar.begin() + bam->cigar_begin[r + 1]);
+    pr->read_seq_begin.push_back((int64_t)pr->bases.size());
+    pr->read_cigar_begin.push_back((int64_t)pr->cigar.size());
+  }
+  // dense rank of (fragment_name bytes, read_number): std::tuple<std::string, int> order (pileup_image_native.cc:98-101)
+  {
+    std::vector<int32_t> order(rows.size());
+    for (size_t k = 0; k < rows.size(); ++k) order[k] = (int32_t)k;
+    auto name_of = [&](int32_t r) { return std::string_view(bam->names.data() + bam->name_begin[r], (size_t)(bam->name_begin[r + 1] - bam->name_begin[r])); };
+    auto less = [&](int32_t a, int32_t b) {
+      const std::string_view na = name_of(rows[a]), nb = name_of(rows[b]);
+      if (na != nb) return na < nb;
+      return bam->read_number[rows[a]] < bam->read_number[rows[b]];
+    };
+    std::sort(order.begin(), order.end(), less);
+    pr->read_name_rank.assign(rows.size(), 0);
+    uint32_t rank = 0;
+    for (size_t k = 0; k < order.size(); ++k) {
+      if (k > 0 && less(order[k - 1], order[k])) ++rank;
+      pr->read_name_rank[order[k]] = rank;
+    }
+  }
+  *out = pr;
+  return DVB_OK;
+}
+
+int dvb_packed_region_batch(const DvbPackedRegion* pr, DvbBatch* b) {
+  if (!pr || !b) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_packed_region_batch: null argument");
+  memset(b, 0, sizeof(*b));
+  b->n_images = pr->n_images; b->n_reads = pr->n_reads; b->n_pairs = (int64_t)pr->pair_read.size();
+  b->n_bases = (int64_t)pr->bases.size(); b->n_cigar = (int64_t)pr->cigar.size(); b->ref_stride = pr->ref_stride;
+  b->ref_bases = pr->ref_bases.data(); b->image_start_pos = pr->image_start_pos.data(); b->variant_start = pr->variant_start.data();
+  b->pair_begin = pr->pair_begin.data(); b->pair_read = pr->pair_read.data(); b->pair_support = pr->pair_support.data();
+  b->pair_allele_group = pr->pair_allele_group.data(); b->read_pos = pr->read_pos.data(); b->read_sort_pos = pr->read_sort_pos.data();
+  b->read_mapq = pr->read_mapq.data(); b->read_flags = pr->read_flags.data(); b->read_fragment_length = pr->read_fragment_length.data();
+  b->read_hp = pr->read_hp.data(); b->read_name_rank = pr->read_name_rank.data(); b->read_seq_begin = pr->read_seq_begin.data();
+  b->read_cigar_begin = pr->read_cigar_begin.data(); b->bases = pr->bases.data(); b->quals = pr->quals.data(); b->cigar = pr->cigar.data();
+  return DVB_OK;
+}
+
+void dvb_packed_region_free(DvbPackedRegion* pr) { delete pr; }
 
 }  // extern "C"

@@ -337,15 +337,68 @@ class ExamplesGenerator:
         plans.append(ExamplePlan(None, variant, list(alt_combination), vtype))
     return plans, specs
 
+  def plan_region_native(self, candidates: Sequence[DeepVariantCall], table, region: Tuple[str, int, int]):
+    """plan_region_from_table() with the per-read work left to the C++ region packer: Python enumerates the images
+    (candidate x alt combination), fetches reference windows and flattens allele_support; the read query, the
+    read-name search and the gathers happen in dvb_pack_region_from_bam.  Returns (plans, packing.RegionImage list)."""
+    pic = self.options.pic_options
+    sample = self.options.sample_options[0]
+    if self.options.trim_reads_for_pileup or sample.keep_only_window_spanning_reads:
+      raise NotImplementedError('the table path covers untrimmed reads; use plan_region() for trimmed pileups')
+    plans: List[ExamplePlan] = []
+    images: List[packing.RegionImage] = []
+    ref_index = {name: i for i, name in enumerate(table.references)}
+    for candidate in candidates:
+      variant = candidate.variant
+      if need_alt_alignment(variant, pic):
+        raise NotImplementedError('candidate needs alt-aligned (trimmed) reads; use plan_region()')
+      reference_bases = self.get_reference_bases_for_pileup(variant)
+      if not reference_bases:
+        continue
+      rb = reference_bases.encode() if isinstance(reference_bases, str) else bytes(reference_bases)
+      alts = list(variant.alternate_bases)
+      enc = [[name.encode() for name in (candidate.allele_support.get(alt) or ())] for alt in alts]
+      counts = np.array([len(e) for e in enc], dtype=np.int64)
+      flat = [k for e in enc for k in e]
+      blob = b''.join(flat)
+      key_lens = np.fromiter((len(k) for k in flat), dtype=np.int64, count=len(flat))
+      groups = np.repeat(np.arange(len(alts), dtype=np.uint8), counts) if pic.sort_by_alt_allele_support else None
+      vtype = encoded_variant_type(variant)
+      rid = ref_index.get(variant.reference_name, -2)
+      for alt_combination in alt_allele_combinations(candidate, pic.multi_allelic_mode):
+        classes = np.repeat(np.array([1 if alt in alt_combination else 2 for alt in alts], dtype=np.uint8), counts)
+        images.append(packing.RegionImage(rid, variant.start, variant.end, variant.start - self.half_width, rb, blob, key_lens,
+                                          classes, groups, len(alts)))
+        plans.append(ExamplePlan(None, variant, list(alt_combination), vtype))
+    return plans, images
+
+  def pack_region_native(self, candidates: Sequence[DeepVariantCall], table, region: Tuple[str, int, int]):
+    """(plans, PackedBatch) of a region through the C++ packer."""
+    pic = self.options.pic_options
+    plans, images = self.plan_region_native(candidates, table, region)
+    rid = table.references.index(region[0]) if region[0] in table.references else -3
+    params = pi.to_params(pic, height=self.pileup_image_height)   # host-side struct; no device needed to pack
+    packed = packing.pack_region_native(table, images, rid, region[1], region[2], pic.read_overlap_buffer_bp,
+                                        params, with_groups=bool(pic.sort_by_alt_allele_support))
+    return plans, packed
+
   def write_examples_in_region_from_table(self, candidates: Sequence[DeepVariantCall], table, role: str,
-                                          region: Optional[Tuple[str, int, int]] = None):
-    """WriteExamplesInRegion with the reads given as a native BAM table (one CUDA launch for the region)."""
+                                          region: Optional[Tuple[str, int, int]] = None, native_packer: Optional[bool] = None):
+    """WriteExamplesInRegion with the reads given as a native BAM table (one CUDA launch for the region).  With a
+    region and an open table the C++ region packer builds the batch (native_packer=False forces the numpy packer;
+    both give identical arrays, tests/test_bam_native.py)."""
     if role not in self.writers:
       raise KeyError(f'Role {role} does not have a writer.')
     stats: Dict[str, int] = {}
-    plans, specs = self.plan_region_from_table(candidates, table, stats, region)
     enc = self._gpu()
-    images = enc.encode_host(packing.pack_images_from_table(specs, table, enc.params)) if plans else \
+    if native_packer is None:
+      native_packer = region is not None and getattr(table, '_handle', None) is not None
+    if native_packer:
+      plans, packed = self.pack_region_native(candidates, table, region)
+    else:
+      plans, specs = self.plan_region_from_table(candidates, table, stats, region)
+      packed = packing.pack_images_from_table(specs, table, enc.params) if plans else None
+    images = enc.encode_host(packed) if plans else \
         np.zeros((0,) + enc.shape, dtype=np.uint8)
     for rec in self.finish_region(plans, images, stats):
       self.writers[role].write(rec)

@@ -334,3 +334,76 @@ def pack_images_from_table(specs: Sequence[TableImageSpec], table, params: _lib.
   }
   arrays = {k: np.ascontiguousarray(_pad(v)) for k, v in arrays.items()}
   return PackedBatch(n_images=n_images, n_reads=n_reads, n_pairs=int(pair_begin[-1]), ref_stride=ref_stride, arrays=arrays)
+
+
+@dataclasses.dataclass
+class RegionImage:
+  """One image of a region for pack_region_native: a candidate x alt combination, with allele_support flattened into
+  (key, class, group) entries in alt order.  The key blob / lengths / groups are shared by the images of a candidate."""
+  ref_id: int
+  variant_start: int
+  variant_end: int
+  image_start_pos: int
+  ref_bases: bytes
+  keys_blob: bytes                 # the "fragment_name/read_number" keys of all alts, concatenated
+  key_lens: np.ndarray             # int64 per entry
+  support_class: np.ndarray        # uint8 per entry: 1 = alt of this image, 2 = other alt
+  support_group: Optional[np.ndarray] = None   # uint8 per entry: alt index
+  group_default: int = 0
+
+
+def pack_region_native(table, images: Sequence[RegionImage], region_ref_id: int, region_start: int, region_end: int,
+                       read_overlap_buffer_bp: int, params: _lib.DvbPileupParams, with_groups: bool = False) -> PackedBatch:
+  """pack_images_from_table() done by the C++ region packer (dvb_pack_region_from_bam, csrc/dvb_bam.cu): the read query,
+  the read-name support search and the gathers run over the native table; Python only flattens the candidates."""
+  lib = _lib.lib()
+  width = params.width
+  n = len(images)
+  for im in images:
+    if len(im.ref_bases) != width:
+      raise ValueError(f'ref_bases has {len(im.ref_bases)} bases, expected width {width}')
+  ref = np.frombuffer(b''.join(im.ref_bases for im in images) or bytes(width), dtype=np.uint8)
+  meta = np.array([(im.ref_id, im.variant_start, im.variant_end, im.image_start_pos, len(im.key_lens), im.group_default)
+                   for im in images], dtype=np.int64).reshape(n, 6)
+  ref_id, vstart, vend, istart = (np.ascontiguousarray(meta[:, k], dtype=np.int32) if n else np.zeros(1, np.int32) for k in range(4))
+  support_begin = np.zeros(n + 1, dtype=np.int64)
+  np.cumsum(meta[:, 4], out=support_begin[1:])
+  lens = np.concatenate([im.key_lens for im in images]) if n else np.zeros(0, dtype=np.int64)
+  name_begin = np.zeros(len(lens) + 1, dtype=np.int64)
+  np.cumsum(lens, out=name_begin[1:])
+  names = b''.join(im.keys_blob for im in images) or b'\0'
+  cat8 = lambda parts: np.ascontiguousarray(np.concatenate(parts + [np.zeros(1, np.uint8)]), dtype=np.uint8)
+  classes = cat8([im.support_class for im in images])
+  groups = cat8([im.support_group for im in images]) if with_groups else None
+  gdef = np.ascontiguousarray(np.append(meta[:, 5], 0), dtype=np.uint8) if with_groups else None
+  c = _lib.DvbRegionCandidates()
+  c.n_images = n
+  c.ref_id, c.variant_start, c.variant_end, c.image_start_pos = (a.ctypes.data for a in (ref_id, vstart, vend, istart))
+  c.ref_bases, c.ref_stride = ref.ctypes.data, width
+  c.support_begin, c.support_class = support_begin.ctypes.data, classes.ctypes.data
+  c.support_group = groups.ctypes.data if with_groups else None
+  c.support_name_begin = name_begin.ctypes.data
+  c.support_names = C.cast(C.c_char_p(names), C.c_void_p)
+  c.group_default = gdef.ctypes.data if with_groups else None
+  h = C.c_void_p()
+  _lib.check(lib.dvb_pack_region_from_bam(table.handle, C.byref(c), region_ref_id, region_start, region_end,
+                                          read_overlap_buffer_bp, width, C.byref(h)))
+  try:
+    b = _lib.DvbBatch()
+    _lib.check(lib.dvb_packed_region_batch(h, C.byref(b)))
+    counts = {'ref_bases': b.n_images * b.ref_stride, 'image_start_pos': b.n_images, 'variant_start': b.n_images,
+              'pair_begin': b.n_images + 1, 'pair_read': b.n_pairs, 'pair_support': b.n_pairs, 'pair_allele_group': b.n_pairs,
+              'read_seq_begin': b.n_reads + 1, 'read_cigar_begin': b.n_reads + 1, 'bases': b.n_bases, 'quals': b.n_bases,
+              'cigar': b.n_cigar}
+    arrays = {}
+    for name, dtype in _lib.BATCH_ARRAYS:
+      cnt = int(counts.get(name, b.n_reads))
+      ptr = getattr(b, name)
+      if cnt and ptr:
+        arrays[name] = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(cnt * np.dtype(dtype).itemsize,)).view(dtype).copy()
+      else:
+        arrays[name] = np.zeros(1, dtype=dtype)
+    return PackedBatch(n_images=int(b.n_images), n_reads=int(b.n_reads), n_pairs=int(b.n_pairs), ref_stride=int(b.ref_stride),
+                       arrays=arrays)
+  finally:
+    lib.dvb_packed_region_free(h)

@@ -282,6 +282,37 @@ int dvb_bam_table(const DvbBam* bam, DvbReadTable* table);
 const char* dvb_bam_ref_name(const DvbBam* bam, int32_t i);   /* NULL when out of range */
 void dvb_bam_close(DvbBam* bam);
 
+/* ---- region packer: candidates + BAM table -> DvbBatch on the host (SURVEY.md 8(f) "next" row #1, second half) ---------
+ * Restates what CreateAndWriteExamplesForCandidate does per candidate before the pixels
+ * (deepvariant/make_examples_native.cc:632-736): the InMemoryReader::Query scan over the region's reads (:802-810,
+ * third_party/nucleus/util/utils.cc:172-188), ReadSupportsAlt's read-name search
+ * (deepvariant/channels/read_supports_variant_channel.cc:75-104) and the allele-group map
+ * (deepvariant/pileup_image_native.cc:345-360), over the flat read table of a DvbBam.  The caller enumerates images
+ * (candidate x alt combination), fetches the reference windows (FASTA) and flattens allele_support into entries. */
+typedef struct DvbRegionCandidates {
+  int32_t n_images;
+  const int32_t* ref_id;              /* [n_images] contig of the candidate (index into the BAM header) */
+  const int32_t* variant_start;       /* [n_images] */
+  const int32_t* variant_end;         /* [n_images] */
+  const int32_t* image_start_pos;     /* [n_images] variant.start - (width - 1) / 2 */
+  const uint8_t* ref_bases;           /* [n_images * ref_stride] reference windows */
+  int32_t ref_stride;
+  /* read support, per image: entries in alt order (all names of alt 0, then alt 1, ...); the first entry naming a read
+   * decides its class; keys are "fragment_name/read_number" */
+  const int64_t* support_begin;       /* [n_images + 1] CSR into the entry arrays */
+  const uint8_t* support_class;       /* [n_entries] 1 = this image's alt set, 2 = another alt of the variant */
+  const uint8_t* support_group;       /* [n_entries] allele group (alt index) or NULL when not sorting by allele support */
+  const int64_t* support_name_begin;  /* [n_entries + 1] into support_names */
+  const char* support_names;
+  const uint8_t* group_default;       /* [n_images] group of reads no alt names (= number of alts) or NULL */
+} DvbRegionCandidates;
+
+typedef struct DvbPackedRegion DvbPackedRegion;
+int dvb_pack_region_from_bam(const DvbBam* bam, const DvbRegionCandidates* candidates, int32_t region_ref_id, int32_t region_start,
+                             int32_t region_end, int32_t read_overlap_buffer_bp, int32_t width, DvbPackedRegion** out);
+int dvb_packed_region_batch(const DvbPackedRegion* packed, DvbBatch* batch /* host pointers owned by `packed` */);
+void dvb_packed_region_free(DvbPackedRegion* packed);
+
 /* Test access to the chunked-upload plan of dvb_encode_classify_host for phases of `sub` images: out = int64[cap][6] =
  * {image begin, image end, pair begin, pair end, first read uploaded, one past the last read uploaded}.  Returns the number
  * of phases (0 = the batch is uploaded in one piece) or -DvbStatus.  Host only, no device needed. */

@@ -152,6 +152,9 @@ def test_table_path_packs_the_same_batch_as_the_read_path_on_the_reference_candi
     assert [(p.variant.start, p.alt_combination, p.variant_type) for p in plans] == \
         [(p.variant.start, p.alt_combination, p.variant_type) for p in plans_t]
     _assert_batches_equal(got, want)
+    plans_n, native = gen.pack_region_native(cs, table, region)   # C++ region packer
+    assert [(p.variant.start, p.alt_combination) for p in plans_n] == [(p.variant.start, p.alt_combination) for p in plans]
+    _assert_batches_equal(native, want)
     n_images += got.n_images
   assert n_images == 84   # the reference's golden.calling_examples has 84 examples for these candidates
 
@@ -190,7 +193,95 @@ def test_table_path_on_a_hand_built_bam(tmp_path):
   plans = gen.plan_region(cands, reader.query(*region), {})
   plans_t, specs = gen.plan_region_from_table(cands, table, {}, region)
   assert len(plans) == len(plans_t) == 1 + 3 + 1 + 3
-  _assert_batches_equal(packing.pack_images_from_table(specs, table, params), packing.pack_images([p.spec for p in plans], params))
+  want = packing.pack_images([p.spec for p in plans], params)
+  _assert_batches_equal(packing.pack_images_from_table(specs, table, params), want)
+  plans_n, native = gen.pack_region_native(cands, table, region)
+  assert len(plans_n) == len(plans)
+  _assert_batches_equal(native, want)
+  # allele-support sorting on (pair_allele_group filled), a region that cuts reads off, a candidate on another contig
+  gen.options.pic_options.sort_by_alt_allele_support = True
+  other = protos.DeepVariantCall(variant=protos.Variant(reference_name='chrX', start=500, end=501, reference_bases='A', alternate_bases=['C']),
+                                 allele_support={'C': keys[:3]})
+  for region in (('chr20', 400, 800), ('chr20', 500, 620), ('chr20', 0, 10)):
+    cs = cands + [other]
+    plans = gen.plan_region(cs, reader.query(*region), {})
+    want = packing.pack_images([p.spec for p in plans], params)
+    _, specs = gen.plan_region_from_table(cs, table, {}, region)
+    _assert_batches_equal(packing.pack_images_from_table(specs, table, params), want)
+    _, native = gen.pack_region_native(cs, table, region)
+    _assert_batches_equal(native, want)
+  assert want.arrays['pair_allele_group'].max() >= 0
+  # no candidates at all
+  _, empty = gen.pack_region_native([], table, ('chr20', 400, 800))
+  assert (empty.n_images, empty.n_reads, empty.n_pairs) == (0, 0, 0)
+
+
+@pytest.mark.parametrize('seed,coordinate_sorted', [(1, True), (2, False), (3, True), (4, False)])
+def test_region_packer_equals_numpy_packer_on_random_bams(tmp_path, seed, coordinate_sorted):
+  """C++ region packer == numpy table packer on random files: two contigs, unsorted files (linear scan instead of the
+  binary search), the same QNAME aligned twice, reads with very different spans, support keys that name no read or are
+  not of the "name/0|1" form, regions that clip the read set, sort_by_alt_allele_support on and off."""
+  from deepvariant_b200 import packing, protos
+  rng = np.random.default_rng(seed)
+  recs = []
+  for i in range(300):
+    ref_id = int(rng.integers(0, 2))
+    pos = 1000 + int(rng.integers(0, 1500))
+    ln = int(rng.choice([30, 80, 400]))
+    seq = ''.join(rng.choice(list('ACGT'), ln))
+    paired = i % 4 != 0
+    flag = (0x1 | 0x2 | (0x40 if i % 2 else 0x80)) if paired else 0
+    name = f'q{int(rng.integers(0, 120))}'            # few names: several alignments share a key
+    cigar = [(0, ln)] if i % 5 else [(0, 10), (2, 7), (0, ln - 10)]
+    recs.append(((ref_id, pos), _record(ref_id, pos, name, 10 + i % 50, flag, cigar, seq, rng.integers(5, 41, ln).tolist(),
+                                        ref_id if paired else -1, pos + 50 if paired else -1, 200)))
+  if coordinate_sorted:
+    recs.sort(key=lambda t: t[0])
+  path = str(tmp_path / f'rand{seed}.bam')
+  open(path, 'wb').write(_bam([r for _, r in recs]))
+  table = bam.NativeBamTable(path)
+  keys = [r.key() for r in table.reads()]
+
+  class Ref:
+    def n_bases(self, contig): return 1000000
+    def is_valid_interval(self, contig, s, e): return 0 <= s < e <= 1000000
+    def query(self, contig, s, e): return ('ACGT' * 250001)[s:e]
+  gen, params = _wgs_generator(Ref())
+  cands = []
+  for k in range(12):
+    contig = 'chr20' if k % 3 else 'chr21'
+    start = 1000 + int(rng.integers(0, 1600))
+    alts = ['T', 'TA', 'G'][:1 + k % 3]
+    sup = {a: [keys[int(j)] for j in rng.integers(0, len(keys), 8)] + ['nobody/0', 'noslash', keys[0] + '1', keys[1][:-1] + '2', '']
+           for a in alts}
+    v = protos.Variant(reference_name=contig, start=start, end=start + 1 + k % 2, reference_bases='A' * (1 + k % 2), alternate_bases=alts)
+    cands.append(protos.DeepVariantCall(variant=v, allele_support=sup))
+  for sort_by_support in (False, True):
+    gen.options.pic_options.sort_by_alt_allele_support = sort_by_support
+    for region in (('chr20', 900, 3000), ('chr21', 1500, 1700), ('chr20', 2400, 2401), ('chr21', 0, 5)):
+      plans_t, specs = gen.plan_region_from_table(cands, table, {}, region)
+      want = packing.pack_images_from_table(specs, table, params)
+      plans_n, got = gen.pack_region_native(cands, table, region)
+      assert [(p.variant.start, p.alt_combination) for p in plans_n] == [(p.variant.start, p.alt_combination) for p in plans_t]
+      _assert_batches_equal(got, want)
+  assert want.n_images > 12
+
+
+def test_region_packer_argument_errors(tmp_path):
+  from deepvariant_b200 import _lib, packing, pileup_image as pi
+  path = str(tmp_path / 'one.bam')
+  open(path, 'wb').write(_bam([_record(0, 100, 'a', 60, 0, [(0, 4)], 'ACGT', [40] * 4)]))
+  table = bam.NativeBamTable(path)
+  params = pi.to_params(pi.default_options())
+  im = packing.RegionImage(0, 100, 101, 100 - 110, b'A' * (params.width - 1), b'a/0', np.array([3], np.int64), np.array([1], np.uint8))
+  with pytest.raises(ValueError):
+    packing.pack_region_native(table, [im], 0, 0, 1000, 5, params)
+  im.ref_bases = b'A' * params.width
+  b = packing.pack_region_native(table, [im], 0, 0, 1000, 5, params)
+  assert (b.n_images, b.n_reads, b.n_pairs) == (1, 1, 1) and b.arrays['pair_support'][0] == 1
+  table.close()
+  with pytest.raises(ValueError):
+    packing.pack_region_native(table, [im], 0, 0, 1000, 5, params)
 
 
 @pytest.mark.gpu
