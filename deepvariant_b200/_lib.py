@@ -128,6 +128,10 @@ class DvbRegionCandidates(C.Structure):
   ]
 
 
+class DvbExampleBatchMeta(C.Structure):
+  _fields_ = [('variant_blob', C.c_void_p), ('variant_begin', C.c_void_p), ('alt_blob', C.c_void_p), ('alt_begin', C.c_void_p)]
+
+
 _lib: Optional[C.CDLL] = None
 
 # Every symbol include/dvb.h declares: (name, restype, argtypes).
@@ -163,6 +167,15 @@ SYMBOLS = (
     ('dvb_packed_region_free', None, [C.c_void_p]),
     ('dvb_crc32c', C.c_uint32, [C.c_char_p, C.c_size_t]),
     ('dvb_masked_crc32c', C.c_uint32, [C.c_char_p, C.c_size_t]),
+    ('dvb_crc32c_portable', C.c_uint32, [C.c_char_p, C.c_size_t]),
+    ('dvb_examples_reader_open', C.c_int, [C.POINTER(C.c_char_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    ('dvb_examples_reader_shape', C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ('dvb_examples_reader_next', C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(DvbExampleBatchMeta)]),
+    ('dvb_examples_reader_close', None, [C.c_void_p]),
+    ('dvb_cvo_writer_open', C.c_int, [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]),
+    ('dvb_cvo_writer_write_batch', C.c_int, [C.c_void_p, C.c_int32, C.POINTER(DvbExampleBatchMeta), C.c_void_p]),
+    ('dvb_cvo_writer_close', C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    ('dvb_debug_round_gls', C.c_int, [C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_double)]),
     ('dvb_debug_upload_phases', C.c_int, [C.POINTER(DvbBatch), C.c_int64, C.c_void_p, C.c_int32]),
     ('dvb_cnn_debug_tensor', C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32),
                                        C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

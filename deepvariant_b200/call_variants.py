@@ -221,71 +221,63 @@ def write_empty_output_file(output_file: str) -> List[str]:
 
 
 def call_variants(examples_filename: str, checkpoint_path: str, output_file: str, batch_size: int = _DEFAULT_BATCH,
-                  writer_threads: int = 0, device: int = 0, max_batches: Optional[int] = None) -> dict:
-  """examples TFRecords -> CallVariantsOutput TFRecords.  Returns {'n_examples', 'n_batches', 'paths'}."""
+                  writer_threads: int = 0, device: int = 0, max_batches: Optional[int] = None, reader_threads: int = 0) -> dict:
+  """examples TFRecords -> CallVariantsOutput TFRecords (main loop of deepvariant/call_variants.py:766-1047).  Returns
+  {'n_examples', 'n_batches', 'paths'}.
+
+  The records never become Python objects: records.NativeExamplesReader (C++ threads: gunzip, TFRecord framing + CRC,
+  tf.Example field extraction, tf.data's interleave order) fills a pinned uint8 batch buffer, the classifier runs on it,
+  and records.NativeCvoWriter (one C++ thread per output shard, batches dealt round-robin as the reference deals them
+  to its writer processes, call_variants.py:1037-1047) rounds, builds and compresses the CallVariantsOutput protos.
+  While the GPU works on batch k the reader fills batch k + 1 into the other half of the pinned buffer."""
   import json
   import os
   import torch
-  from deepvariant_b200 import tfrecord
+  from deepvariant_b200 import records, tfrecord
   paths_in = tfrecord.resolve_input_paths(examples_filename)
+  reader = records.NativeExamplesReader(paths_in, threads=reader_threads)
+  try:
+    shape, image_bytes = reader.shape()
+    if image_bytes == 0:
+      return {'n_examples': 0, 'n_batches': 0, 'paths': write_empty_output_file(output_file)}
+    if image_bytes != shape[0] * shape[1] * shape[2]:
+      raise ValueError(f'image/encoded has {image_bytes} bytes, image/shape says {shape}')
+    info_path = paths_in[0] + '.example_info.json'
+    if os.path.exists(info_path):
+      info = json.load(open(info_path))
+      if [int(x) for x in info['shape']] != shape:
+        raise ValueError(f'example_info.json shape {info["shape"]} != example image/shape {shape}')
+    weights = load_weights(checkpoint_path, shape[2])
+    net = GpuCnn(weights, shape, device=device, max_batch=min(batch_size, 2048))
+    out_paths = output_shard_paths(output_file, writer_threads)
+    writers = [records.NativeCvoWriter(p, _GL_PRECISION) for p in out_paths]
+    pinned = torch.empty((2, batch_size, image_bytes), dtype=torch.uint8).pin_memory()
+    staging = pinned.numpy()
+    dev = torch.device('cuda', device)
+    images_dev = torch.empty((batch_size, image_bytes), dtype=torch.uint8, device=dev)
+    probs_dev = torch.empty((batch_size, 3), dtype=torch.float32, device=dev)
+    probs_host = torch.empty((batch_size, 3), dtype=torch.float32).pin_memory()
+    stream = torch.cuda.current_stream(dev)
 
-  def records():
-    for p in paths_in:
-      for rec in tfrecord.read_records(p):
-        yield rec
-
-  it = records()
-  first = next(it, None)
-  if first is None:
-    return {'n_examples': 0, 'n_batches': 0, 'paths': write_empty_output_file(output_file)}
-  ex0 = protos.parse_tf_example(first)
-  shape = [int(x) for x in ex0['image/shape'][1]]
-  info_path = paths_in[0] + '.example_info.json'
-  if os.path.exists(info_path):
-    info = json.load(open(info_path))
-    if [int(x) for x in info['shape']] != shape:
-      raise ValueError(f'example_info.json shape {info["shape"]} != example image/shape {shape}')
-  weights = load_weights(checkpoint_path, shape[2])
-  net = GpuCnn(weights, shape, device=device, max_batch=min(batch_size, 2048))
-  out_paths = output_shard_paths(output_file, writer_threads)
-  writers = [tfrecord.Writer(p) for p in out_paths]
-  image_bytes = shape[0] * shape[1] * shape[2]
-  pinned = torch.empty((batch_size, image_bytes), dtype=torch.uint8).pin_memory()
-  dev = torch.device('cuda', device)
-  probs_dev = torch.empty((batch_size, 3), dtype=torch.float32, device=dev)
-  stream = torch.cuda.current_stream(dev)
-
-  n_examples = n_batches = 0
-  batch_meta: List[Tuple[bytes, bytes]] = []
-
-  def flush():
-    nonlocal n_examples, n_batches
-    n = len(batch_meta)
-    if n == 0:
-      return
-    images = pinned[:n].to(dev, non_blocking=True)
-    net.forward_device(images.view((n,) + tuple(shape)), probs_dev[:n], stream=stream)
-    probs = probs_dev[:n].cpu().numpy().astype(np.float64)
-    w = writers[n_batches % len(writers)]
-    for (variant, alt_idx), p in zip(batch_meta, probs):
-      w.write(create_cvo(variant, round_gls(p.tolist(), _GL_PRECISION), alt_idx))
-    n_examples += n
-    n_batches += 1
-    batch_meta.clear()
-
-  import itertools
-  for rec in itertools.chain([first], it):
-    ex = protos.parse_tf_example(rec)
-    img = ex['image/encoded'][1][0]
-    if len(img) != image_bytes:
-      raise ValueError(f'image/encoded has {len(img)} bytes, expected {image_bytes}')
-    pinned[len(batch_meta)].copy_(torch.frombuffer(bytearray(img), dtype=torch.uint8))
-    batch_meta.append((ex['variant/encoded'][1][0], ex['alt_allele_indices/encoded'][1][0]))
-    if len(batch_meta) == batch_size:
-      flush()
-      if max_batches and n_batches >= max_batches:
-        break
-  flush()
-  for w in writers:
-    w.close()
-  return {'n_examples': n_examples, 'n_batches': n_batches, 'paths': out_paths}
+    n_examples = n_batches = 0
+    half = 0
+    meta = reader.next_into(staging[half])
+    while meta is not None:
+      n = meta.n
+      images_dev[:n].copy_(pinned[half, :n], non_blocking=True)
+      net.forward_device(images_dev[:n].view((n,) + tuple(shape)), probs_dev[:n], stream=stream)
+      probs_host[:n].copy_(probs_dev[:n], non_blocking=True)
+      done = max_batches is not None and n_batches + 1 >= max_batches
+      nxt = None if done else reader.next_into(staging[half ^ 1])   # host work of batch k + 1 under the GPU work of batch k
+      stream.synchronize()
+      writers[n_batches % len(writers)].write_batch(meta, probs_host[:n].numpy())
+      n_examples += n
+      n_batches += 1
+      meta = nxt
+      half ^= 1
+    for w in writers:
+      w.close()
+    net.close()
+    return {'n_examples': n_examples, 'n_batches': n_batches, 'paths': out_paths}
+  finally:
+    reader.close()

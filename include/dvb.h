@@ -233,7 +233,8 @@ double dvb_cnn_flops_per_image(const DvbCnn* cnn);
 /* ---- file boundary helpers (host only) ------------------------------------- */
 /* CRC-32C (Castagnoli) and TensorFlow's masked variant used by the TFRecord framing
  * (third_party/nucleus/io/example_writer.cc:99-115 -> tensorflow RecordWriter). */
-uint32_t dvb_crc32c(const void* data, size_t n);
+uint32_t dvb_crc32c(const void* data, size_t n);            /* SSE4.2 crc32 instruction when the CPU has it */
+uint32_t dvb_crc32c_portable(const void* data, size_t n);   /* slicing-by-8 tables; same value (tests compare the two) */
 uint32_t dvb_masked_crc32c(const void* data, size_t n);
 
 /* ---- BAM -> Structure-of-Arrays read table (host only; SURVEY.md 8(f) "next" row #1) ------------------------
@@ -312,6 +313,42 @@ int dvb_pack_region_from_bam(const DvbBam* bam, const DvbRegionCandidates* candi
                              int32_t region_end, int32_t read_overlap_buffer_bp, int32_t width, DvbPackedRegion** out);
 int dvb_packed_region_batch(const DvbPackedRegion* packed, DvbBatch* batch /* host pointers owned by `packed` */);
 void dvb_packed_region_free(DvbPackedRegion* packed);
+
+/* ---- call_variants record I/O on the host ---------------------------------------------
+ * Reader = call_variants.get_dataset (deepvariant/call_variants.py:449-538): the shards of the examples TFRecord
+ * (gzip or plain) are read by `threads` workers and handed out in tf.data's deterministic interleave order
+ * (cycle_length slots, one record per slot per turn; call_variants.py:83 uses 32).  Each record must hold exactly one
+ * bytes value for image/encoded, variant/encoded and alt_allele_indices/encoded (parse_single_example with
+ * FixedLenFeature((), string)).  Record CRCs are verified when verify_crc != 0 (TensorFlow's reader always does). */
+typedef struct DvbExamplesReader DvbExamplesReader;
+typedef struct DvbExampleBatchMeta {
+  const uint8_t* variant_blob;    /* variant/encoded of the batch, concatenated */
+  const int64_t* variant_begin;   /* [n + 1] */
+  const uint8_t* alt_blob;        /* alt_allele_indices/encoded, concatenated */
+  const int64_t* alt_begin;       /* [n + 1] */
+} DvbExampleBatchMeta;
+int dvb_examples_reader_open(const char* const* paths, int32_t n_paths, int32_t threads /* 0 = all cores */,
+                             int32_t cycle_length /* 0 = 32 */, int32_t verify_crc, DvbExamplesReader** out);
+/* image/shape and the byte size of image/encoded of the first record (all zero when there are no records). */
+int dvb_examples_reader_shape(DvbExamplesReader* reader, int64_t shape[3], int64_t* image_bytes);
+/* Copies the next up-to-max_n images into images_host (n * image_bytes, e.g. a pinned staging buffer); *n_out = 0 at the
+ * end.  `meta` points into reader-owned memory that stays valid until the next call on this reader. */
+int dvb_examples_reader_next(DvbExamplesReader* reader, int32_t max_n, uint8_t* images_host, int64_t image_bytes,
+                             int32_t* n_out, DvbExampleBatchMeta* meta);
+void dvb_examples_reader_close(DvbExamplesReader* reader);
+
+/* Writer = write_variant_call / _create_cvo_proto / round_gls (deepvariant/call_variants.py:248-399): per record
+ * CallVariantsOutput{variant with calls[0].info["MID"] = "deepvariant", alt_allele_indices, genotype_probabilities =
+ * round_gls(float64(probs), gl_precision)} framed as a TFRecord, gzip when the path ends in ".gz".  One writer = one
+ * output shard with its own thread (the reference's writer processes, call_variants.py:541-602); write_batch copies its
+ * arguments and returns.  gl_precision < 0 = no rounding.  Errors (likelihoods not summing to 1 within 1e-6, a variant
+ * without calls, I/O) are reported by the next write_batch or by close. */
+typedef struct DvbCvoWriter DvbCvoWriter;
+int dvb_cvo_writer_open(const char* path, int32_t gl_precision, DvbCvoWriter** out);
+int dvb_cvo_writer_write_batch(DvbCvoWriter* writer, int32_t n, const DvbExampleBatchMeta* meta, const float* probs /* [n, 3] host */);
+int dvb_cvo_writer_close(DvbCvoWriter* writer, int64_t* n_written /* may be NULL */);
+/* Test access to the writer's round_gls (call_variants.py:248-285); precision < 0 = none. */
+int dvb_debug_round_gls(const double gls[3], int32_t precision, double out[3]);
 
 /* Test access to the chunked-upload plan of dvb_encode_classify_host for phases of `sub` images: out = int64[cap][6] =
  * {image begin, image end, pair begin, pair end, first read uploaded, one past the last read uploaded}.  Returns the number
