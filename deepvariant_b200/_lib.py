@@ -128,6 +128,17 @@ class DvbRegionCandidates(C.Structure):
   ]
 
 
+class DvbCandidateOptions(C.Structure):
+  _fields_ = [
+      ('min_mapping_quality', C.c_int32), ('min_base_quality', C.c_int32), ('keep_legacy_behavior', C.c_int32),
+      ('track_ref_reads', C.c_int32), ('min_count_snps', C.c_int32), ('min_count_indels', C.c_int32),
+      ('min_fraction_snps', C.c_float), ('min_fraction_indels', C.c_float), ('min_fraction_multiplier', C.c_float),
+      ('vsc_min_indel_fraction_for_small_indels', C.c_float), ('vsc_min_indel_fraction_for_large_indels', C.c_float),
+      ('vsc_small_indel_threshold', C.c_int32), ('small_model_vaf_context_window_size', C.c_int32),
+      ('sample_name', C.c_char_p),
+  ]
+
+
 class DvbExampleBatchMeta(C.Structure):
   _fields_ = [('variant_blob', C.c_void_p), ('variant_begin', C.c_void_p), ('alt_blob', C.c_void_p), ('alt_begin', C.c_void_p)]
 
@@ -165,6 +176,15 @@ SYMBOLS = (
                                            C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     ('dvb_packed_region_batch', C.c_int, [C.c_void_p, C.POINTER(DvbBatch)]),
     ('dvb_packed_region_free', None, [C.c_void_p]),
+    ('dvb_candidate_options_default', None, [C.POINTER(DvbCandidateOptions)]),
+    ('dvb_candidates_in_region', C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                           C.POINTER(DvbCandidateOptions), C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
+    ('dvb_candidate_positions', C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                          C.POINTER(DvbCandidateOptions), C.POINTER(C.c_void_p)]),
+    ('dvb_candidates_count', C.c_int64, [C.c_void_p]),
+    ('dvb_candidates_protos', C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    ('dvb_candidates_positions', C.c_int64, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    ('dvb_candidates_free', None, [C.c_void_p]),
     ('dvb_crc32c', C.c_uint32, [C.c_char_p, C.c_size_t]),
     ('dvb_masked_crc32c', C.c_uint32, [C.c_char_p, C.c_size_t]),
     ('dvb_crc32c_portable', C.c_uint32, [C.c_char_p, C.c_size_t]),

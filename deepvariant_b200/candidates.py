@@ -1,0 +1,214 @@
+"""Candidate generation for make_examples --mode calling (SURVEY.md 8(f) "next" row #2, host half).
+
+Mirrors how deepvariant/make_examples_core.py drives the allele counter and the very-sensitive caller for ONE sample:
+
+  regions_to_process           make_examples_core.py:799-888 (calling regions cut into --partition_size pieces, piece i -> task i mod N)
+  region_reads                 RegionProcessor.region_reads_norealign (:2408-2477) + utils.reservoir_sample
+                               (third_party/nucleus/util/utils.py:80-124) with np.random.RandomState(random_seed)
+  candidates_in_region         RegionProcessor.candidates_in_region (:2832-2960): [track_ref_reads: first pass for the
+                               candidate positions], AlleleCounter over the region, VariantCaller.calls_from_allele_counts
+  sample_name_from_bam         assign_sample_name / extract_sample_name_from_sam_reader (:190-212, :470-505)
+
+The arithmetic runs in C++ over the rows of the native BAM table (csrc/dvb_candidates.cu, dvb_candidates_in_region); this module
+selects the rows, hands over the contig's bases and parses the DeepVariantCall protos that come back.  The realigner is not
+restated: this is make_examples with --norealign_reads (the default for PACBIO / ONT; for WGS / WES the reference realigns
+reads first, which moves a minority of candidates - see tools/check_candidates_golden.py for the measured agreement).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+import gzip
+import struct
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from deepvariant_b200 import _lib, protos
+
+DEFAULT_SAMPLE_NAME = 'default'          # dv_constants.DEFAULT_SAMPLE_NAME
+MAKE_EXAMPLES_RANDOM_SEED = 609314161    # make_examples_options.py:981
+
+
+@dataclasses.dataclass
+class CandidateOptions:
+  """The make_examples flags that reach AlleleCounterOptions / VariantCallerOptions (make_examples_options.py:293-343, 597-922;
+  make_vc_options make_examples_core.py:214-248)."""
+  min_mapping_quality: int = 5
+  min_base_quality: int = 10
+  keep_legacy_allele_counter_behavior: bool = False
+  track_ref_reads: bool = False
+  vsc_min_count_snps: int = 2
+  vsc_min_count_indels: int = 2
+  vsc_min_fraction_snps: float = 0.12
+  vsc_min_fraction_indels: float = 0.06
+  vsc_min_fraction_multiplier: float = 1.0
+  vsc_min_indel_fraction_for_small_indels: float = 0.0
+  vsc_min_indel_fraction_for_large_indels: float = 0.0
+  vsc_small_indel_threshold: int = 0
+  small_model_vaf_context_window_size: int = 0
+  sample_name: str = ''
+  max_reads_per_partition: int = 1500
+  partition_size: int = 1000
+  random_seed: int = MAKE_EXAMPLES_RANDOM_SEED
+
+  def to_c(self) -> _lib.DvbCandidateOptions:
+    o = _lib.DvbCandidateOptions()
+    _lib.lib().dvb_candidate_options_default(C.byref(o))
+    o.min_mapping_quality = self.min_mapping_quality
+    o.min_base_quality = self.min_base_quality
+    o.keep_legacy_behavior = int(self.keep_legacy_allele_counter_behavior)
+    o.track_ref_reads = int(self.track_ref_reads)
+    o.min_count_snps = self.vsc_min_count_snps
+    o.min_count_indels = self.vsc_min_count_indels
+    o.min_fraction_snps = self.vsc_min_fraction_snps
+    o.min_fraction_indels = self.vsc_min_fraction_indels
+    o.min_fraction_multiplier = self.vsc_min_fraction_multiplier
+    o.vsc_min_indel_fraction_for_small_indels = self.vsc_min_indel_fraction_for_small_indels
+    o.vsc_min_indel_fraction_for_large_indels = self.vsc_min_indel_fraction_for_large_indels
+    o.vsc_small_indel_threshold = self.vsc_small_indel_threshold
+    o.small_model_vaf_context_window_size = self.small_model_vaf_context_window_size
+    o.sample_name = self.sample_name.encode()
+    return o
+
+
+def sample_name_from_bam(path: str) -> str:
+  """SM of the @RG header lines: the only one, or the first when several differ; 'default' when there is none."""
+  with gzip.open(path, 'rb') as f:
+    head = f.read(8)
+    if head[:4] != b'BAM\1':
+      raise ValueError(f'{path} is not a BAM file')
+    text = f.read(struct.unpack('<i', head[4:])[0]).decode(errors='replace')
+  samples = []
+  for line in text.split('\n'):
+    if line.startswith('@RG'):
+      for field in line.rstrip('\r').split('\t')[1:]:
+        if field.startswith('SM:') and field[3:]:
+          samples.append(field[3:])
+  return samples[0] if samples else DEFAULT_SAMPLE_NAME
+
+
+def regions_to_process(contigs: Sequence[Tuple[str, int]], partition_size: int, calling_region: Optional[Tuple[str, int, int]] = None,
+                       task_id: Optional[int] = None, num_shards: Optional[int] = None) -> List[Tuple[str, int, int]]:
+  """contigs = [(name, n_bases)] in reference order; calling_region = (contig, start, end) 0-based half-open or None."""
+  if (task_id is None) != (num_shards is None):
+    raise ValueError('Both task_id and num_shards must be present if either is', task_id, num_shards)
+  if num_shards:
+    if task_id < 0 or task_id >= num_shards:
+      raise ValueError('task_id={} should be >= 0 and < num_shards={}'.format(task_id, num_shards))
+  if partition_size <= 0:
+    raise ValueError('max_size must be > 0: {}'.format(partition_size))
+  pieces = []
+  for name, n_bases in contigs:
+    lo, hi = 0, n_bases
+    if calling_region is not None:
+      if calling_region[0] != name:
+        continue
+      lo, hi = max(lo, calling_region[1]), min(hi, calling_region[2])
+    for pos in range(lo, hi, partition_size):
+      pieces.append((name, pos, min(hi, pos + partition_size)))
+  if num_shards:
+    return [r for i, r in enumerate(pieces) if i % num_shards == task_id]
+  return pieces
+
+
+def reservoir_sample(items: Iterable, k: int, random=None) -> list:
+  """utils.reservoir_sample (Algorithm R): same draws, same order of the retained elements."""
+  if k < 0:
+    raise ValueError('k must be nonnegative, but got {}'.format(k))
+  if random is None:
+    random = np.random
+  sample = []
+  for i, item in enumerate(items):
+    if len(sample) < k:
+      sample.append(item)
+    else:
+      j = random.randint(0, i + 1)
+      if j < k:
+        sample[j] = item
+  return sample
+
+
+def region_reads(table, contig: str, start: int, end: int, max_reads_per_partition: int = 1500,
+                 random_seed: int = MAKE_EXAMPLES_RANDOM_SEED) -> np.ndarray:
+  """Rows of the BAM table that the reference would hold in its InMemorySamReader for this region."""
+  rows = table.query_indices(contig, start, end)
+  if max_reads_per_partition > 0 and len(rows) > max_reads_per_partition:
+    rows = np.asarray(reservoir_sample(rows.tolist(), max_reads_per_partition, np.random.RandomState(random_seed)), dtype=np.int64)
+  return np.ascontiguousarray(rows, dtype=np.int64)
+
+
+class NativeCandidates:
+  """Result of one dvb_candidates_in_region call: raw DeepVariantCall records + parsed objects on demand."""
+
+  def __init__(self, handle, keep: Optional[Tuple[int, int]] = None):
+    lib = _lib.lib()
+    try:
+      n = int(lib.dvb_candidates_count(handle))
+      pos_ptr = C.c_void_p()
+      lib.dvb_candidates_positions(handle, C.byref(pos_ptr))
+      starts = np.frombuffer((C.c_char * (4 * n)).from_address(pos_ptr.value), dtype=np.int32).copy() if n else np.zeros(0, np.int32)
+      data, begin = C.c_void_p(), C.c_void_p()
+      _lib.check(lib.dvb_candidates_protos(handle, C.byref(data), C.byref(begin)))
+      offs = np.frombuffer((C.c_char * (8 * (n + 1))).from_address(begin.value), dtype=np.int64).copy()
+      blob = bytes((C.c_char * int(offs[-1])).from_address(data.value)) if n and offs[-1] else b''
+      self.records: List[bytes] = [blob[int(offs[i]):int(offs[i + 1])] for i in range(n)
+                                   if keep is None or keep[0] <= int(starts[i]) < keep[1]]
+    finally:
+      lib.dvb_candidates_free(handle)
+    self._parsed: Optional[List[protos.DeepVariantCall]] = None
+
+  def calls(self) -> List[protos.DeepVariantCall]:
+    if self._parsed is None:
+      self._parsed = [protos.parse_deepvariant_call(r) for r in self.records]
+    return self._parsed
+
+
+def _contig_buffer(ref_reader, contig: str):
+  seq = ref_reader._contig(contig)   # pylint: disable=protected-access  (upper-cased bytes of the whole contig, cached)
+  return seq, C.cast(C.c_char_p(seq), C.c_void_p)
+
+
+def candidate_positions(table, ref_reader, contig: str, start: int, end: int, rows: np.ndarray, options: CandidateOptions) -> List[int]:
+  """VariantCaller.get_candidate_positions (first pass of track_ref_reads)."""
+  lib = _lib.lib()
+  seq, ptr = _contig_buffer(ref_reader, contig)
+  rows = np.ascontiguousarray(rows, dtype=np.int64)
+  co = options.to_c()
+  co.track_ref_reads = 0
+  h = C.c_void_p()
+  _lib.check(lib.dvb_candidate_positions(table.handle, ptr, len(seq), start, end, rows.ctypes.data_as(C.c_void_p), len(rows),
+                                         C.byref(co), C.byref(h)))
+  try:
+    p = C.c_void_p()
+    n = int(lib.dvb_candidates_positions(h, C.byref(p)))
+    return np.frombuffer((C.c_char * (4 * n)).from_address(p.value), dtype=np.int32).tolist() if n else []
+  finally:
+    lib.dvb_candidates_free(h)
+
+
+def candidates_in_region(table, ref_reader, contig: str, start: int, end: int, options: CandidateOptions,
+                         rows: Optional[np.ndarray] = None, padding_pct: int = 0) -> NativeCandidates:
+  """Candidates of [start, end) on `contig` from the reads `rows` (default: region_reads of the region).
+
+  padding_pct > 0 (--phase_reads: dv_constants.PHASE_READS_REGION_PADDING_PCT = 20) counts alleles over the region expanded
+  by that share of its length on both sides (ranges.expand, make_examples_core.py:2306-2318) - still from the reads that
+  overlap the unpadded region - and keeps the candidates that start inside the region (filter_candidates_by_region)."""
+  lib = _lib.lib()
+  if rows is None:
+    rows = region_reads(table, contig, start, end, options.max_reads_per_partition, options.random_seed)
+  rows = np.ascontiguousarray(rows, dtype=np.int64)
+  seq, ptr = _contig_buffer(ref_reader, contig)
+  end = min(end, len(seq))
+  region = (start, end)
+  if padding_pct > 0:
+    pad = int((end - start) * padding_pct / 100)
+    start, end = max(start - pad, 0), min(end + pad, len(seq))
+  positions = np.zeros(0, dtype=np.int32)
+  if options.track_ref_reads:
+    positions = np.asarray(candidate_positions(table, ref_reader, contig, start, end, rows, options), dtype=np.int32)
+  co = options.to_c()
+  h = C.c_void_p()
+  _lib.check(lib.dvb_candidates_in_region(table.handle, contig.encode(), ptr, len(seq), start, end, rows.ctypes.data_as(C.c_void_p),
+                                          len(rows), C.byref(co), positions.ctypes.data_as(C.c_void_p), len(positions), C.byref(h)))
+  return NativeCandidates(h, keep=region if padding_pct > 0 else None)

@@ -1,0 +1,580 @@
+// Candidate generation on the host (SURVEY.md 8(f) "next" row #2, first half): allele counting over the rows of the native
+// BAM table + the very-sensitive variant caller, producing the DeepVariantCall protos the pileup path consumes.
+//
+// Restates (without copying; the reference keeps protobuf maps of strings, this keeps flat per-position entry lists keyed by
+// table row):
+//   AlleleCounter::Add / MakeIndelReadAllele / AddReadAlleles / CanBasesBeUsed / GetAvgBaseQuality / GetPrevBase / RefBases
+//       deepvariant/allelecounter.cc:195-243, 360-519, 880-978
+//   SumAlleleCounts / TotalAlleleCounts                         deepvariant/allelecounter.cc:78-193
+//   multi_sample::VariantCaller::SelectAltAlleles / AlleleFilter / IsGoodAltAlleleWithReason / CalcRefBases / BuildAlleleMap /
+//       AddReadDepths / CallVariant / CallVariantPosition / AddSupportingReads / AddAdjacentAlleleFractionsAtPosition
+//       deepvariant/variant_calling_multisample.cc:95-290, 610-760, 1000-1330 (single sample, create_complex_alleles = false,
+//       use_rejected_alleles = false, no methylation: the make_examples defaults, make_examples_options.py:597-922)
+// Not restated here: read normalisation (--normalize_reads), complex alleles, rejected alleles, methylation, multi-sample
+// filters, gVCF summaries.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "dvb_common.h"
+
+namespace {
+
+enum AlleleType : uint8_t { kUnspecified = 0, kReference = 1, kSubstitution = 2, kInsertion = 3, kDeletion = 4, kSoftClip = 5 };
+
+inline bool Canonical(char b) { return b == 'A' || b == 'C' || b == 'G' || b == 'T'; }
+
+struct Entry {              // one value of AlleleCount.read_alleles (the key is the read: key_id)
+  int32_t row;              // BAM table row
+  int32_t key_id;           // id of "fragment_name/read_number" among the region's reads (equal ids = equal map keys)
+  uint8_t type, low_quality, mapq, reverse;
+  int32_t avg_base_quality;
+  uint32_t bases_off, bases_len;   // into Counter::arena
+};
+
+struct Site {
+  int32_t ref_supporting_read_count = 0;
+  std::vector<Entry> entries;        // insertion order; a later entry with the same key replaces the earlier one in place
+};
+
+struct ReadAllele {         // allelecounter.h:113-166
+  int position = -1;        // kInvalidPosition = skip
+  uint8_t type = kUnspecified, low_quality = 0;
+  int avg_base_quality = 0;
+  uint32_t bases_off = 0, bases_len = 0;
+};
+
+struct Counter {
+  const DvbReadTable* t;
+  const uint8_t* contig;         // upper-case bases of the whole contig
+  int64_t contig_len;
+  int64_t start, end;            // interval (== reads interval: no normalisation)
+  DvbCandidateOptions opt;
+  std::vector<Site> sites;
+  std::string arena;             // allele bases
+  std::vector<int32_t> candidate_positions;   // relative to start, sorted (track_ref_reads second pass)
+  std::vector<ReadAllele> to_add;
+
+  // AlleleCounter::RefBases (allelecounter.cc:360-373): "" when the region is not inside the contig.
+  bool RefBases(int64_t rel_start, int64_t len, const uint8_t** out) const {
+    int64_t abs_start = start + rel_start;
+    if (abs_start < 0 || abs_start + len > contig_len) return false;
+    *out = contig + abs_start;
+    return true;
+  }
+
+  // CanBasesBeUsed (allelecounter.cc:195-224).
+  bool CanBasesBeUsed(const uint8_t* seq, const uint8_t* qual, int offset, int len, bool* low_quality) const {
+    const int min_bq = opt.min_base_quality;
+    int sum = 0;
+    for (int i = 0; i < len; ++i) {
+      sum += qual[offset + i];
+      if (qual[offset + i] < min_bq && opt.keep_legacy_behavior) return false;
+      if (!Canonical((char)seq[offset + i])) return false;
+    }
+    *low_quality = false;
+    if (!opt.keep_legacy_behavior && sum < min_bq * len) *low_quality = true;
+    return true;
+  }
+
+  uint32_t Intern(const uint8_t* a, size_t na, const uint8_t* b, size_t nb) {
+    uint32_t off = (uint32_t)arena.size();
+    arena.append((const char*)a, na);
+    arena.append((const char*)b, nb);
+    return off;
+  }
+
+  // MakeIndelReadAllele (allelecounter.cc:402-473).
+  ReadAllele MakeIndel(const uint8_t* seq, const uint8_t* qual, int seq_len, int interval_offset, int ref_offset, int read_offset,
+                       int op, int op_len) {
+    ReadAllele none;
+    uint8_t prev;
+    if (read_offset == 0) {       // GetPrevBase: the previous base comes from the reference
+      const uint8_t* p;
+      if (!RefBases((int64_t)ref_offset - 1, 1, &p)) return none;
+      prev = *p;
+    } else {
+      prev = seq[read_offset - 1];
+    }
+    bool low_quality = false;
+    if (!Canonical((char)prev)) return none;
+    if (op != 2 /* D */) {
+      if (read_offset + op_len > seq_len) return none;   // the reference CHECK-fails here; a malformed record is dropped
+      if (!CanBasesBeUsed(seq, qual, read_offset, op_len, &low_quality)) return none;
+    }
+    ReadAllele ra;
+    const uint8_t* bases;
+    int avg_bq;
+    if (op == 2) {
+      if (!RefBases(ref_offset, op_len, &bases)) return none;
+      for (int i = 0; i < op_len; ++i)
+        if (!Canonical((char)bases[i])) return none;
+      ra.type = kDeletion;
+      avg_bq = qual[std::max(0, read_offset - 1)];      // GetAvgBaseQuality, DELETE
+    } else {
+      bases = seq + read_offset;
+      ra.type = op == 1 ? kInsertion : kSoftClip;
+      int sum = 0;
+      for (int i = 0; i < op_len; ++i) sum += qual[read_offset + i];
+      avg_bq = sum / std::max(1, op_len);
+    }
+    ra.position = interval_offset - 1;
+    ra.low_quality = low_quality;
+    ra.avg_base_quality = avg_bq;
+    ra.bases_off = Intern(&prev, 1, bases, (size_t)op_len);
+    ra.bases_len = (uint32_t)op_len + 1;
+    return ra;
+  }
+
+  // AlleleCounter::Add (allelecounter.cc:880-978) + AddReadAlleles (:475-546).
+  void Add(int32_t row, int32_t key_id) {
+    if (t->mapq[row] < opt.min_mapping_quality) return;
+    const int64_t s0 = t->seq_begin[row];
+    const int seq_len = (int)(t->seq_begin[row + 1] - s0);
+    if (seq_len == 0) return;     // a record without SEQ carries no alleles
+    const uint8_t* seq = t->bases + s0;
+    const uint8_t* qual = t->quals + s0;
+    const uint32_t* cig = t->cigar + t->cigar_begin[row];
+    const int n_cig = (int)(t->cigar_begin[row + 1] - t->cigar_begin[row]);
+    const bool reverse = (t->flag[row] & 0x10) != 0;
+    const int64_t len = end - start;
+    to_add.clear();
+    int read_offset = 0;
+    int64_t interval_offset = (int64_t)t->pos[row] - start;   // == ref_interval_offset (reads interval == interval)
+    for (int c = 0; c < n_cig; ++c) {
+      const int op = (int)(cig[c] & 0xF), op_len = (int)(cig[c] >> 4);
+      switch (op) {
+        case 0: case 7: case 8:   // M = X
+          for (int i = 0; i < op_len; ++i) {
+            const int64_t ref_offset = interval_offset + i;
+            const int base_offset = read_offset + i;
+            bool low_quality = false;
+            if (ref_offset >= 0 && ref_offset < len && base_offset < seq_len &&
+                CanBasesBeUsed(seq, qual, base_offset, 1, &low_quality)) {
+              ReadAllele ra;
+              ra.position = (int)ref_offset;
+              ra.type = contig[start + ref_offset] == seq[base_offset] ? kReference : kSubstitution;
+              ra.low_quality = low_quality;
+              ra.avg_base_quality = qual[base_offset];
+              ra.bases_off = (uint32_t)base_offset;     // single read base: materialised when (if) the entry is stored
+              ra.bases_len = 0;                          // 0 marks "read base at bases_off"
+              to_add.push_back(ra);
+            }
+          }
+          read_offset += op_len;
+          interval_offset += op_len;
+          break;
+        case 4: case 1:           // S, I
+          to_add.push_back(MakeIndel(seq, qual, seq_len, (int)interval_offset, (int)interval_offset, read_offset, op, op_len));
+          read_offset += op_len;
+          break;
+        case 2:                   // D
+          to_add.push_back(MakeIndel(seq, qual, seq_len, (int)interval_offset, (int)interval_offset, read_offset, op, op_len));
+          interval_offset += op_len;
+          break;
+        case 6: case 3:           // P, N
+          interval_offset += op_len;
+          break;
+        default:                  // H and unknown codes
+          break;
+      }
+    }
+    const size_t n = to_add.size();
+    for (size_t i = 0; i < n; ++i) {
+      const ReadAllele& a = to_add[i];
+      if (a.position < 0 || a.position >= len) continue;                   // skip() or outside the interval
+      if (i + 1 < n && a.position == to_add[i + 1].position) continue;     // superseded by the indel anchored here
+      Site& site = sites[(size_t)a.position];
+      if (a.type == kReference && !a.low_quality) ++site.ref_supporting_read_count;
+      if (a.type != kReference ||
+          (opt.track_ref_reads && std::binary_search(candidate_positions.begin(), candidate_positions.end(), a.position))) {
+        Entry e;
+        e.row = row;
+        e.key_id = key_id;
+        e.type = a.type;
+        e.low_quality = a.low_quality;
+        e.mapq = t->mapq[row];
+        e.reverse = reverse;
+        e.avg_base_quality = a.avg_base_quality;
+        if (a.bases_len == 0) {
+          e.bases_off = Intern(seq + a.bases_off, 1, nullptr, 0);
+          e.bases_len = 1;
+        } else {
+          e.bases_off = a.bases_off;
+          e.bases_len = a.bases_len;
+        }
+        bool replaced = false;
+        for (Entry& old : site.entries)
+          if (old.key_id == key_id) { old = e; replaced = true; break; }   // (*read_alleles)[key] = allele
+        if (!replaced) site.entries.push_back(e);
+      }
+    }
+  }
+};
+
+struct SummedAllele { uint32_t off, len; uint8_t type; int count; };
+
+struct Caller {
+  const Counter* c;
+  const DvbCandidateOptions* opt;
+
+  std::string Bases(uint32_t off, uint32_t len) const { return c->arena.substr(off, len); }
+
+  // SumAlleleCounts(allele_count) (allelecounter.cc:78-116): non-low-quality entries grouped by (bases, type), in the
+  // order of std::map<pair<string_view, AlleleType>>; the synthetic REFERENCE allele is irrelevant to selection.
+  std::vector<SummedAllele> Sum(const Site& s) const {
+    std::map<std::pair<std::string, uint8_t>, SummedAllele> m;
+    for (const Entry& e : s.entries) {
+      if (e.low_quality) continue;
+      auto key = std::make_pair(Bases(e.bases_off, e.bases_len), e.type);
+      auto it = m.find(key);
+      if (it == m.end()) m.emplace(key, SummedAllele{e.bases_off, e.bases_len, e.type, 1});
+      else ++it->second.count;
+    }
+    std::vector<SummedAllele> out;
+    for (auto& kv : m) out.push_back(kv.second);
+    return out;
+  }
+
+  // TotalAlleleCounts (allelecounter.cc:157-169).
+  int Total(const Site& s) const {
+    int n = s.ref_supporting_read_count;
+    for (const Entry& e : s.entries)
+      if (!e.low_quality && e.type != kReference) ++n;
+    return n;
+  }
+
+  int MinCount(const SummedAllele& a) const { return a.type == kSubstitution ? opt->min_count_snps : opt->min_count_indels; }
+  double MinFraction(const SummedAllele& a) const {      // variant_calling_multisample.h:357-372 (proto fields are float)
+    if (a.type == kSubstitution) return (double)opt->min_fraction_snps;
+    if (opt->vsc_small_indel_threshold > 0 && opt->vsc_min_indel_fraction_for_small_indels > 0.0f &&
+        opt->vsc_min_indel_fraction_for_large_indels > 0.0f) {
+      return (int)a.len <= opt->vsc_small_indel_threshold + 1 ? (double)opt->vsc_min_indel_fraction_for_small_indels
+                                                              : (double)opt->vsc_min_indel_fraction_for_large_indels;
+    }
+    return (double)opt->min_fraction_indels;
+  }
+  // IsGoodAltAlleleWithReason (variant_calling_multisample.cc:175-196): 0 accepted, 1 ref, 2 low support, 3 other, 4 low ratio
+  int Reason(const SummedAllele& a, int total, bool trio) const {
+    if (a.type == kReference) return 1;
+    if (a.count < MinCount(a)) return 2;
+    if (a.type == kSoftClip) return 3;
+    if ((1.0 * a.count) / total < MinFraction(a) * (trio ? (double)opt->min_fraction_multiplier : 1.0)) return 4;
+    return 0;
+  }
+  // AlleleFilter for one sample (:203-260): a low-ratio / low-support allele is re-tested against the all-sample counts
+  // (the same counts here) with the trio coefficient.
+  bool Keep(const SummedAllele& a, int total) const {
+    int r = Reason(a, total, false);
+    if (r == 0) return true;
+    if (r == 4 || r == 2) return Reason(a, total, true) == 0;
+    return false;
+  }
+  std::vector<SummedAllele> SelectAlts(const Site& s) const {
+    std::vector<SummedAllele> alts;
+    const int total = Total(s);
+    for (const SummedAllele& a : Sum(s))
+      if (Keep(a, total)) alts.push_back(a);
+    return alts;
+  }
+};
+
+// ---- protobuf wire helpers ---------------------------------------------------------------------------------------------
+void PutVarint(std::string* o, uint64_t v) {
+  while (v >= 0x80) { o->push_back((char)(v | 0x80)); v >>= 7; }
+  o->push_back((char)v);
+}
+void PutTag(std::string* o, int field, int wt) { PutVarint(o, ((uint64_t)field << 3) | (uint64_t)wt); }
+void PutBytes(std::string* o, int field, const std::string& b) { PutTag(o, field, 2); PutVarint(o, b.size()); o->append(b); }
+void PutInt(std::string* o, int field, int64_t v) { PutTag(o, field, 0); PutVarint(o, (uint64_t)v); }
+void PutDouble(std::string* o, int field, double d) { PutTag(o, field, 1); o->append((const char*)&d, 8); }
+
+std::string InfoEntryInts(const char* key, const std::vector<int>& vals) {    // map<string, ListValue>; Value.int_value = 7
+  std::string lv;
+  for (int v : vals) { std::string val; PutInt(&val, 7, v); PutBytes(&lv, 1, val); }
+  std::string e;
+  PutBytes(&e, 1, key);
+  PutBytes(&e, 2, lv);
+  return e;
+}
+std::string InfoEntryDoubles(const char* key, const std::vector<double>& vals) {   // Value.number_value = 2
+  std::string lv;
+  for (double v : vals) { std::string val; PutDouble(&val, 2, v); PutBytes(&lv, 1, val); }
+  std::string e;
+  PutBytes(&e, 1, key);
+  PutBytes(&e, 2, lv);
+  return e;
+}
+
+}  // namespace
+
+struct DvbCandidates {
+  std::string protos;                 // serialized DeepVariantCall records, concatenated
+  std::vector<int64_t> proto_begin;   // [n + 1]
+  std::vector<int32_t> position;      // [n] variant.start
+  std::vector<int32_t> positions_only;   // dvb_candidate_positions result
+  int64_t n_reads_counted = 0;
+};
+
+namespace {
+
+std::string ReadKey(const DvbReadTable& t, int32_t row) {      // AlleleCounter::ReadKey (allelecounter.cc:980-983)
+  std::string k(t.names + t.name_begin[row], (size_t)(t.name_begin[row + 1] - t.name_begin[row]));
+  k.push_back('/');
+  k += std::to_string((int)t.read_number[row]);
+  return k;
+}
+
+int BuildCounter(const DvbBam* bam, DvbReadTable* table, Counter* c, const uint8_t* contig_bases, int64_t contig_n_bases,
+                 int64_t start, int64_t end, const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* opt,
+                 const int32_t* candidate_positions, int32_t n_candidate_positions, std::vector<std::string>* keys) {
+  if (!bam || !contig_bases || !opt || (n_rows && !rows))
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_candidates: null argument");
+  if (start < 0 || end > contig_n_bases || start >= end)
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_candidates: interval [%lld, %lld) is not inside the contig (%lld bases)",
+                     (long long)start, (long long)end, (long long)contig_n_bases);
+  int st = dvb_bam_table(bam, table);
+  if (st != DVB_OK) return st;
+  c->t = table;
+  c->contig = contig_bases;
+  c->contig_len = contig_n_bases;
+  c->start = start;
+  c->end = end;
+  c->opt = *opt;
+  c->sites.assign((size_t)(end - start), Site());
+  for (int32_t i = 0; i < n_candidate_positions; ++i) c->candidate_positions.push_back(candidate_positions[i] - (int32_t)start);
+  std::sort(c->candidate_positions.begin(), c->candidate_positions.end());
+  std::unordered_map<std::string, int32_t> key_ids;
+  keys->clear();
+  for (int64_t i = 0; i < n_rows; ++i) {
+    const int64_t row = rows[i];
+    if (row < 0 || row >= table->n_reads) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_candidates: read row %lld out of range", (long long)row);
+    std::string key = ReadKey(*table, (int32_t)row);
+    auto it = key_ids.find(key);
+    int32_t id;
+    if (it == key_ids.end()) {
+      id = (int32_t)keys->size();
+      key_ids.emplace(key, id);
+      keys->push_back(std::move(key));
+    } else {
+      id = it->second;
+    }
+    c->Add((int32_t)row, id);
+  }
+  return DVB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void dvb_candidate_options_default(DvbCandidateOptions* o) {
+  memset(o, 0, sizeof(*o));
+  o->min_mapping_quality = 5;      // make_examples_options.py:303-310
+  o->min_base_quality = 10;        // :293-302
+  o->min_count_snps = 2;           // :311-326
+  o->min_count_indels = 2;
+  o->min_fraction_snps = 0.12f;    // :327-343
+  o->min_fraction_indels = 0.06f;
+  o->min_fraction_multiplier = 1.0f;
+  o->sample_name = "";
+}
+
+int dvb_candidate_positions(const DvbBam* bam, const uint8_t* contig_bases, int64_t contig_n_bases, int64_t start, int64_t end,
+                            const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* opt, DvbCandidates** out) {
+  if (!out) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_candidate_positions: null out");
+  *out = nullptr;
+  DvbReadTable table;
+  Counter c;
+  std::vector<std::string> keys;
+  int st = BuildCounter(bam, &table, &c, contig_bases, contig_n_bases, start, end, rows, n_rows, opt, nullptr, 0, &keys);
+  if (st != DVB_OK) return st;
+  Caller caller{&c, &c.opt};
+  auto* res = new DvbCandidates();
+  for (size_t i = 0; i < c.sites.size(); ++i) {
+    if (!Canonical((char)contig_bases[start + (int64_t)i])) continue;     // CallVariantPosition (:1075-1115)
+    if (!caller.SelectAlts(c.sites[i]).empty()) res->positions_only.push_back((int32_t)(start + (int64_t)i));
+  }
+  *out = res;
+  return DVB_OK;
+}
+
+int dvb_candidates_in_region(const DvbBam* bam, const char* reference_name, const uint8_t* contig_bases, int64_t contig_n_bases,
+                             int64_t start, int64_t end, const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* opt,
+                             const int32_t* candidate_positions, int32_t n_candidate_positions, DvbCandidates** out) {
+  if (!out || !reference_name) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_candidates_in_region: null argument");
+  *out = nullptr;
+  DvbReadTable table;
+  Counter c;
+  std::vector<std::string> keys;
+  int st = BuildCounter(bam, &table, &c, contig_bases, contig_n_bases, start, end, rows, n_rows, opt, candidate_positions,
+                        n_candidate_positions, &keys);
+  if (st != DVB_OK) return st;
+  Caller caller{&c, &c.opt};
+  auto* res = new DvbCandidates();
+  res->proto_begin.push_back(0);
+  const std::string sample = opt->sample_name ? opt->sample_name : "";
+  const int n_sites = (int)c.sites.size();
+  for (int i = 0; i < n_sites; ++i) {
+    const Site& site = c.sites[(size_t)i];
+    const char ref_base = (char)contig_bases[start + i];
+    if (!Canonical(ref_base)) continue;                                      // CallVariant (:1117-1130)
+    std::vector<SummedAllele> alts = caller.SelectAlts(site);
+    if (alts.empty()) continue;                                              // fraction_reference_sites_to_emit = 0
+    // CalcRefBases (:95-128): the longest selected deletion extends the reference allele.
+    std::string ref_bases(1, ref_base);
+    {
+      int best = -1;
+      const SummedAllele* del = nullptr;
+      for (const SummedAllele& a : alts) {
+        int sz = a.type == kDeletion ? (int)a.len : -1;
+        if (sz > best) { best = sz; del = a.type == kDeletion ? &a : nullptr; }
+      }
+      if (del) ref_bases += c.arena.substr(del->off + 1, del->len - 1);
+    }
+    // BuildAlleleMap (:560-606), ordered like AlleleMap = std::map<Allele, string, OrderAllele> (type, then bases).
+    struct MapItem { SummedAllele a; std::string bases; std::string alt; };
+    std::vector<MapItem> amap;
+    for (const SummedAllele& a : alts) {
+      MapItem m{a, c.arena.substr(a.off, a.len), ""};
+      if (a.type == kSubstitution) {
+        m.alt = (m.bases.size() > 1 && ref_bases.size() > 1) ? m.bases : m.bases + ref_bases.substr(1);
+      } else if (a.type == kInsertion) {
+        m.alt = m.bases + ref_bases.substr(1);
+      } else if (a.type == kDeletion) {
+        m.alt = m.bases.substr(0, 1) + (m.bases.size() >= ref_bases.size() ? std::string() : ref_bases.substr(m.bases.size()));
+      } else {
+        continue;     // SOFT_CLIP never passes the filter
+      }
+      amap.push_back(std::move(m));
+    }
+    std::sort(amap.begin(), amap.end(), [](const MapItem& x, const MapItem& y) {
+      return x.a.type != y.a.type ? x.a.type < y.a.type : x.bases < y.bases;
+    });
+    std::vector<const MapItem*> by_alt;
+    for (const MapItem& m : amap) by_alt.push_back(&m);
+    std::sort(by_alt.begin(), by_alt.end(), [](const MapItem* x, const MapItem* y) { return x->alt < y->alt; });
+    for (size_t k = 1; k < by_alt.size(); ++k)
+      if (by_alt[k]->alt == by_alt[k - 1]->alt) {
+        delete res;
+        return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_candidates_in_region: non-unique alternative alleles at %lld",
+                         (long long)(start + i));   // the reference CHECK-fails (AddReadDepths)
+      }
+    // AddReadDepths (:608-640)
+    const int dp = caller.Total(site);
+    std::vector<int> ad{site.ref_supporting_read_count};
+    std::vector<double> vaf;
+    for (const MapItem* m : by_alt) { ad.push_back(m->a.count); vaf.push_back(1.0 * m->a.count / dp); }
+
+    // ---- Variant (variants.proto:52-118) ----
+    std::string call;     // VariantCall: info = 2, genotype = 7 (packed), call_set_name = 9
+    PutBytes(&call, 2, InfoEntryInts("AD", ad));
+    PutBytes(&call, 2, InfoEntryInts("DP", std::vector<int>{dp}));
+    PutBytes(&call, 2, InfoEntryDoubles("VAF", vaf));
+    {
+      std::string gt;
+      PutVarint(&gt, (uint64_t)(int64_t)-1);
+      PutVarint(&gt, (uint64_t)(int64_t)-1);
+      PutBytes(&call, 7, gt);
+    }
+    if (!sample.empty()) PutBytes(&call, 9, sample);
+    std::string variant;
+    PutBytes(&variant, 6, ref_bases);
+    for (const MapItem* m : by_alt) PutBytes(&variant, 7, m->alt);
+    PutBytes(&variant, 11, call);
+    PutInt(&variant, 13, start + i + (int64_t)ref_bases.size());
+    PutBytes(&variant, 14, reference_name);
+    if (start + i) PutInt(&variant, 16, start + i);
+
+    // ---- AddSupportingReads (:1235-1290): every read_alleles entry, low quality and soft clips included ----
+    std::string dvc;
+    PutBytes(&dvc, 1, variant);
+    std::vector<std::string> support_key;                       // first-seen order of supported alleles
+    std::vector<std::string> support_names, support_ext;        // per supported allele: SupportingReads / SupportingReadsExt
+    std::string ref_names, ref_ext;
+    auto read_support = [&](const Entry& e) {
+      std::string rs;
+      PutBytes(&rs, 1, keys[(size_t)e.key_id]);
+      if (e.low_quality) PutInt(&rs, 2, 1);
+      if (e.mapq) PutInt(&rs, 3, e.mapq);
+      if (e.avg_base_quality) PutInt(&rs, 4, e.avg_base_quality);
+      if (e.reverse) PutInt(&rs, 5, 1);
+      if (!sample.empty()) PutBytes(&rs, 7, sample);
+      return rs;
+    };
+    for (const Entry& e : site.entries) {
+      if (e.type != kReference) {
+        std::string supported = "UNCALLED_ALLELE";
+        for (const MapItem& m : amap)
+          if (m.a.type == e.type && m.a.len == e.bases_len && c.arena.compare(e.bases_off, e.bases_len, m.bases) == 0) { supported = m.alt; break; }
+        size_t k = 0;
+        while (k < support_key.size() && support_key[k] != supported) ++k;
+        if (k == support_key.size()) { support_key.push_back(supported); support_names.emplace_back(); support_ext.emplace_back(); }
+        PutBytes(&support_names[k], 1, keys[(size_t)e.key_id]);
+        PutBytes(&support_ext[k], 1, read_support(e));
+      } else {
+        PutBytes(&ref_names, 4, keys[(size_t)e.key_id]);          // DeepVariantCall.ref_support = 4
+        PutBytes(&ref_ext, 1, read_support(e));
+      }
+    }
+    for (size_t k = 0; k < support_key.size(); ++k) {
+      std::string entry;
+      PutBytes(&entry, 1, support_key[k]);
+      PutBytes(&entry, 2, support_names[k]);
+      PutBytes(&dvc, 2, entry);                                   // allele_support
+    }
+    dvc += ref_names;
+    for (size_t k = 0; k < support_key.size(); ++k) {
+      std::string entry;
+      PutBytes(&entry, 1, support_key[k]);
+      PutBytes(&entry, 2, support_ext[k]);
+      PutBytes(&dvc, 5, entry);                                   // allele_support_ext
+    }
+    if (!ref_ext.empty()) PutBytes(&dvc, 6, ref_ext);             // ref_support_ext
+    // AddAdjacentAlleleFractionsAtPosition (:1330-1360)
+    if (opt->small_model_vaf_context_window_size > 0) {
+      const int half = opt->small_model_vaf_context_window_size / 2;
+      const int lo = i - std::min(i, half), hi = i + std::min(n_sites - i, half + 1);
+      for (int j = lo; j < hi; ++j) {
+        const Site& s = c.sites[(size_t)j];
+        const int n_alleles = (int)s.entries.size();
+        const int depth = s.ref_supporting_read_count + n_alleles;
+        const int v = depth > 0 ? (100 * n_alleles) / depth : 0;
+        std::string entry;
+        PutInt(&entry, 1, start + j);
+        PutInt(&entry, 2, v);
+        PutBytes(&dvc, 7, entry);
+      }
+    }
+    res->protos += dvc;
+    res->proto_begin.push_back((int64_t)res->protos.size());
+    res->position.push_back((int32_t)(start + i));
+  }
+  *out = res;
+  return DVB_OK;
+}
+
+int64_t dvb_candidates_count(const DvbCandidates* c) { return c ? (int64_t)c->position.size() : 0; }
+
+int dvb_candidates_protos(const DvbCandidates* c, const uint8_t** data, const int64_t** begin) {
+  if (!c || !data || !begin) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_candidates_protos: null argument");
+  *data = (const uint8_t*)c->protos.data();
+  *begin = c->proto_begin.data();
+  return DVB_OK;
+}
+
+int64_t dvb_candidates_positions(const DvbCandidates* c, const int32_t** positions) {
+  if (!c) return 0;
+  const std::vector<int32_t>& v = c->positions_only.empty() ? c->position : c->positions_only;
+  if (positions) *positions = v.data();
+  return (int64_t)v.size();
+}
+
+void dvb_candidates_free(DvbCandidates* c) { delete c; }
+
+}  // extern "C"

@@ -314,6 +314,49 @@ int dvb_pack_region_from_bam(const DvbBam* bam, const DvbRegionCandidates* candi
 int dvb_packed_region_batch(const DvbPackedRegion* packed, DvbBatch* batch /* host pointers owned by `packed` */);
 void dvb_packed_region_free(DvbPackedRegion* packed);
 
+/* ---- candidate generation on the host (SURVEY.md 8(f) "next" row #2): allele counting + very-sensitive caller ------------
+ * Replaces, for one sample and the make_examples defaults (no --normalize_reads, no complex / rejected alleles, no
+ * methylation), the pybind modules deepvariant.python.allelecounter (AlleleCounter(ref, range, candidate_positions,
+ * options).add(read, sample); deepvariant/python/allelecounter_pybind.cc, deepvariant/allelecounter.cc:880-978) and
+ * deepvariant.python.variant_calling_multisample (VariantCaller.calls_from_allele_counts /
+ * call_positions_from_allele_counts; deepvariant/variant_calling_multisample.cc:1000-1330) as make_examples_core.py
+ * candidates_in_region (:2832-2960) drives them.  Reads are rows of a DvbBam table, given in the order the reference
+ * would iterate them (InMemorySamReader.query(region) after reservoir sampling). */
+typedef struct DvbCandidateOptions {
+  int32_t min_mapping_quality;        /* AlleleCounterOptions.read_requirements (make_examples_options.py:293-310): 5 */
+  int32_t min_base_quality;           /* 10 */
+  int32_t keep_legacy_behavior;       /* --keep_legacy_allele_counter_behavior: 0 */
+  int32_t track_ref_reads;            /* --track_ref_reads: 0 (1 for PACBIO / ONT) */
+  int32_t min_count_snps;             /* --vsc_min_count_snps 2 */
+  int32_t min_count_indels;           /* --vsc_min_count_indels 2 */
+  float min_fraction_snps;            /* --vsc_min_fraction_snps 0.12 (float in VariantCallerOptions: compared as (double)0.12f) */
+  float min_fraction_indels;          /* --vsc_min_fraction_indels 0.06 */
+  float min_fraction_multiplier;      /* --vsc_min_fraction_multiplier 1.0 */
+  float vsc_min_indel_fraction_for_small_indels;   /* 0 = unused */
+  float vsc_min_indel_fraction_for_large_indels;
+  int32_t vsc_small_indel_threshold;
+  int32_t small_model_vaf_context_window_size;     /* > 0 fills DeepVariantCall.allele_frequency_at_position */
+  const char* sample_name;            /* call_set_name and ReadSupport.sample_name; may be NULL */
+} DvbCandidateOptions;
+typedef struct DvbCandidates DvbCandidates;
+void dvb_candidate_options_default(DvbCandidateOptions* options);
+/* contig_bases = the whole contig, upper-cased (the reference reads its FASTA with keep_true_case = false); [start, end)
+ * is the allele counter's interval; rows = BAM table rows.  candidate_positions (absolute, may be NULL) are the positions
+ * whose reference-supporting reads are tracked when track_ref_reads is set (second pass of candidates_in_region). */
+int dvb_candidates_in_region(const DvbBam* bam, const char* reference_name, const uint8_t* contig_bases, int64_t contig_n_bases,
+                             int64_t start, int64_t end, const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* options,
+                             const int32_t* candidate_positions, int32_t n_candidate_positions, DvbCandidates** out);
+/* First pass of track_ref_reads: positions with at least one selected alt allele (call_positions_from_allele_counts). */
+int dvb_candidate_positions(const DvbBam* bam, const uint8_t* contig_bases, int64_t contig_n_bases, int64_t start, int64_t end,
+                            const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* options, DvbCandidates** out);
+int64_t dvb_candidates_count(const DvbCandidates* candidates);
+/* Serialized learning.genomics.deepvariant.DeepVariantCall records (deepvariant/protos/deepvariant.proto:262-317),
+ * concatenated in coordinate order; begin = int64[count + 1].  Owned by `candidates`. */
+int dvb_candidates_protos(const DvbCandidates* candidates, const uint8_t** data, const int64_t** begin);
+/* variant.start of every candidate (or the positions of dvb_candidate_positions); returns the count. */
+int64_t dvb_candidates_positions(const DvbCandidates* candidates, const int32_t** positions);
+void dvb_candidates_free(DvbCandidates* candidates);
+
 /* ---- call_variants record I/O on the host ---------------------------------------------
  * Reader = call_variants.get_dataset (deepvariant/call_variants.py:449-538): the shards of the examples TFRecord
  * (gzip or plain) are read by `threads` workers and handed out in tf.data's deterministic interleave order
