@@ -185,6 +185,8 @@ SYMBOLS = (
     ('dvb_candidates_protos', C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     ('dvb_candidates_positions', C.c_int64, [C.c_void_p, C.POINTER(C.c_void_p)]),
     ('dvb_candidates_free', None, [C.c_void_p]),
+    ('dvb_debug_allele_counts', C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                            C.POINTER(DvbCandidateOptions), C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
     ('dvb_crc32c', C.c_uint32, [C.c_char_p, C.c_size_t]),
     ('dvb_masked_crc32c', C.c_uint32, [C.c_char_p, C.c_size_t]),
     ('dvb_crc32c_portable', C.c_uint32, [C.c_char_p, C.c_size_t]),

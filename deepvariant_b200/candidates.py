@@ -212,3 +212,110 @@ def candidates_in_region(table, ref_reader, contig: str, start: int, end: int, o
   _lib.check(lib.dvb_candidates_in_region(table.handle, contig.encode(), ptr, len(seq), start, end, rows.ctypes.data_as(C.c_void_p),
                                           len(rows), C.byref(co), positions.ctypes.data_as(C.c_void_p), len(positions), C.byref(h)))
   return NativeCandidates(h, keep=region if padding_pct > 0 else None)
+
+
+def _value(buf):
+  for fn, wt, val, _ in protos.iter_fields(buf):
+    if fn == 7:
+      return protos._to_signed32(val)   # pylint: disable=protected-access
+    if fn == 2:
+      return struct.unpack('<d', struct.pack('<Q', val))[0] if isinstance(val, int) else struct.unpack('<d', bytes(val))[0]
+    if fn == 3:
+      return bytes(val).decode()
+  return None
+
+
+def _read_support(buf):
+  d = {'read_name': '', 'is_low_quality': 0, 'mapping_quality': 0, 'average_base_quality': 0, 'is_reverse_strand': 0, 'sample_name': ''}
+  names = {1: 'read_name', 2: 'is_low_quality', 3: 'mapping_quality', 4: 'average_base_quality', 5: 'is_reverse_strand', 7: 'sample_name'}
+  for fn, wt, val, _ in protos.iter_fields(buf):
+    if fn in names:
+      d[names[fn]] = bytes(val).decode() if wt == 2 else int(val)
+  return d
+
+
+def canonical_call(record: bytes) -> dict:
+  """Semantic content of a DeepVariantCall, independent of map / field order."""
+  out = {'ref': '', 'alts': [], 'start': 0, 'end': 0, 'contig': '', 'info': {}, 'call_set_name': '', 'genotype': [],
+         'allele_support': {}, 'allele_support_ext': {}, 'ref_support': [], 'ref_support_ext': [], 'af_at_position': {}}
+  for fn, wt, val, _ in protos.iter_fields(record):
+    val = bytes(val) if wt == 2 else val
+    if fn == 1:
+      for f2, w2, v2, _ in protos.iter_fields(val):
+        v2 = bytes(v2) if w2 == 2 else v2
+        if f2 == 6:
+          out['ref'] = v2.decode()
+        elif f2 == 7:
+          out['alts'].append(v2.decode())
+        elif f2 == 13:
+          out['end'] = int(v2)
+        elif f2 == 14:
+          out['contig'] = v2.decode()
+        elif f2 == 16:
+          out['start'] = int(v2)
+        elif f2 == 11:
+          for f3, w3, v3, _ in protos.iter_fields(v2):
+            v3 = bytes(v3) if w3 == 2 else v3
+            if f3 == 2:
+              key, vals = '', []
+              for f4, w4, v4, _ in protos.iter_fields(v3):
+                if f4 == 1:
+                  key = bytes(v4).decode()
+                elif f4 == 2:
+                  vals = [_value(bytes(v5)) for f5, w5, v5, _ in protos.iter_fields(bytes(v4)) if f5 == 1]
+              out['info'][key] = vals
+            elif f3 == 7:
+              out['genotype'] = [protos._to_signed32(x) for x in protos.unpack_varints(v3)] if w3 == 2 else out['genotype'] + [protos._to_signed32(v3)]   # pylint: disable=protected-access
+            elif f3 == 9:
+              out['call_set_name'] = v3.decode()
+    elif fn == 2:
+      key, names = '', []
+      for f2, w2, v2, _ in protos.iter_fields(val):
+        if f2 == 1:
+          key = bytes(v2).decode()
+        elif f2 == 2:
+          names = [bytes(v3).decode() for f3, w3, v3, _ in protos.iter_fields(bytes(v2)) if f3 == 1]
+      out['allele_support'][key] = sorted(names)
+    elif fn == 4:
+      out['ref_support'].append(val.decode())
+    elif fn == 5:
+      key, infos = '', []
+      for f2, w2, v2, _ in protos.iter_fields(val):
+        if f2 == 1:
+          key = bytes(v2).decode()
+        elif f2 == 2:
+          infos = [_read_support(bytes(v3)) for f3, w3, v3, _ in protos.iter_fields(bytes(v2)) if f3 == 1]
+      out['allele_support_ext'][key] = sorted(infos, key=lambda d: d['read_name'])
+    elif fn == 6:
+      out['ref_support_ext'] = sorted((_read_support(bytes(v3)) for f3, w3, v3, _ in protos.iter_fields(val) if f3 == 1),
+                                      key=lambda d: d['read_name'])
+    elif fn == 7:
+      k = v = 0
+      for f2, w2, v2, _ in protos.iter_fields(val):
+        if f2 == 1:
+          k = int(v2)
+        elif f2 == 2:
+          v = int(v2)
+      out['af_at_position'][str(k)] = v
+  out['ref_support'].sort()
+  return out
+
+
+
+def debug_allele_counts(table, ref_reader, contig: str, start: int, end: int, rows, options: CandidateOptions,
+                        candidate_positions: Sequence[int] = ()) -> list:
+  """Test access to AlleleCounter.Counts(): per position {'ref': n, 'alleles': [[bases, type, low_quality, key, mapq, avg_bq, reverse]]}."""
+  import json
+  lib = _lib.lib()
+  seq, ptr = _contig_buffer(ref_reader, contig)
+  rows = np.ascontiguousarray(rows, dtype=np.int64)
+  cp = np.ascontiguousarray(candidate_positions, dtype=np.int32)
+  co = options.to_c()
+  args = (table.handle, ptr, len(seq), start, end, rows.ctypes.data_as(C.c_void_p), len(rows), C.byref(co),
+          cp.ctypes.data_as(C.c_void_p), len(cp))
+  n = int(lib.dvb_debug_allele_counts(*args, None, 0))
+  if n < 0:
+    _lib.check(-n)
+  buf = C.create_string_buffer(n + 1)
+  lib.dvb_debug_allele_counts(*args, buf, n + 1)
+  return json.loads(buf.value.decode())

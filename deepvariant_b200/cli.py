@@ -25,7 +25,8 @@ MODEL_DEFAULTS = {   # scripts/run_deepvariant.py + model.example_info.json flag
     'WES': dict(channel_list='BASE_CHANNELS,insert_size', pileup_image_width=221),
     'PACBIO': dict(channel_list='BASE_CHANNELS,haplotype,supplementary_alignment', pileup_image_width=147, sort_by_haplotypes=True,
                    trim_reads_for_pileup=True, alt_aligned_pileup='diff_channels', min_mapping_quality=1, partition_size=25000,
-                   parse_sam_aux_fields=True),
+                   parse_sam_aux_fields=True, track_ref_reads=True, phase_reads=True, max_reads_per_partition=600,
+                   vsc_min_fraction_indels=0.12),       # flags_for_calling of the released PACBIO model's example_info.json
 }
 
 
@@ -51,7 +52,10 @@ def parse_region(s: str):
 MAKE_EXAMPLES_DEFAULTS = dict(
     task=0, regions='', channel_list='BASE_CHANNELS', pileup_image_width=221, pileup_image_height=100, min_mapping_quality=5,
     min_base_quality=10, partition_size=1000, sort_by_haplotypes=False, trim_reads_for_pileup=False, parse_sam_aux_fields=False,
-    alt_aligned_pileup='none', device=0, checkpoint='', checkpoint_json='')
+    alt_aligned_pileup='none', device=0, checkpoint='', checkpoint_json='', candidates='', candidates_in='', max_reads_per_partition=1500,
+    sample_name='', vsc_min_count_snps=2, vsc_min_count_indels=2, vsc_min_fraction_snps=0.12, vsc_min_fraction_indels=0.06,
+    vsc_min_fraction_multiplier=1.0, small_model_vaf_context_window_size=0, track_ref_reads=False, phase_reads=False,
+    keep_legacy_allele_counter_behavior=False, realign_reads=False)
 
 
 def model_example_info_json_path(checkpoint: str, checkpoint_json: str = '') -> str:
@@ -103,7 +107,8 @@ def make_examples(argv):
   ap.add_argument('--ref', required=True)
   ap.add_argument('--reads', required=True)
   ap.add_argument('--examples', required=True)
-  ap.add_argument('--candidates', required=True)
+  ap.add_argument('--candidates')        # OUTPUT, as in the reference (make_examples_options.py:109): the DeepVariantCalls found
+  ap.add_argument('--candidates_in')     # INPUT (not a reference flag): use these DeepVariantCalls instead of generating them
   ap.add_argument('--checkpoint')        # model directory / ckpt path: only its example_info.json flags are read here
   ap.add_argument('--checkpoint_json')
   ap.add_argument('--task', type=int)
@@ -114,6 +119,19 @@ def make_examples(argv):
   ap.add_argument('--min_mapping_quality', type=int)
   ap.add_argument('--min_base_quality', type=int)
   ap.add_argument('--partition_size', type=int)
+  ap.add_argument('--max_reads_per_partition', type=int)
+  ap.add_argument('--sample_name')
+  ap.add_argument('--vsc_min_count_snps', type=int)
+  ap.add_argument('--vsc_min_count_indels', type=int)
+  ap.add_argument('--vsc_min_fraction_snps', type=float)
+  ap.add_argument('--vsc_min_fraction_indels', type=float)
+  ap.add_argument('--vsc_min_fraction_multiplier', type=float)
+  ap.add_argument('--small_model_vaf_context_window_size', type=int)
+  ap.add_argument('--track_ref_reads', action='store_true')
+  ap.add_argument('--phase_reads', action='store_true')
+  ap.add_argument('--keep_legacy_allele_counter_behavior', action='store_true')
+  ap.add_argument('--realign_reads', dest='realign_reads', action='store_true')
+  ap.add_argument('--norealign_reads', dest='realign_reads', action='store_false')
   ap.add_argument('--sort_by_haplotypes', action='store_true')
   ap.add_argument('--trim_reads_for_pileup', action='store_true')
   ap.add_argument('--parse_sam_aux_fields', action='store_true')
@@ -124,7 +142,7 @@ def make_examples(argv):
   if merged['_ignored_flags_for_calling']:
     print('make_examples: flags_for_calling of upstream stages not applied: ' + ', '.join(merged['_ignored_flags_for_calling']), file=sys.stderr)
   a = argparse.Namespace(**merged)
-  from deepvariant_b200 import bam, make_examples_native as men, pileup_image as pi, protos, tfrecord
+  from deepvariant_b200 import bam, candidates as cand, fasta, make_examples_native as men, pileup_image as pi, protos, tfrecord
   pic = pi.default_options(pi.ReadRequirements(a.min_base_quality, a.min_mapping_quality))
   pic.channels = _channels(a.channel_list)
   if a.alt_aligned_pileup == 'diff_channels':
@@ -140,19 +158,56 @@ def make_examples(argv):
   # Native block-parallel BAM decode into a Structure-of-Arrays read table (csrc/dvb_bam.cu); untrimmed pileups (WGS/WES)
   # are planned and packed straight from the table rows, trimmed ones (PACBIO, alt-aligned) from Read objects of table.query().
   reader = bam.NativeBamTable(a.reads, bam.ReadRequirements(min_mapping_quality=a.min_mapping_quality), parse_aux=a.parse_sam_aux_fields)
-  table_path = not a.trim_reads_for_pileup and a.alt_aligned_pileup == 'none' 
-  cands = [protos.parse_deepvariant_call(r) for p in tfrecord.resolve_input_paths(a.candidates) for r in tfrecord.read_records(p)]
+  table_path = not a.trim_reads_for_pileup and a.alt_aligned_pileup == 'none'
   region = parse_region(a.regions) if a.regions else None
   totals = {}
-  for (contig, k, origin), cs in men.shard_partitions(men.partition_candidates(cands, a.partition_size, region), n_shards, a.task):
-    p0 = origin + k * a.partition_size
-    p1 = p0 + a.partition_size if not region else min(p0 + a.partition_size, region[2])
+
+  def examples_in(cs, contig, p0, p1):
     if table_path:
       stats, _ = gen.write_examples_in_region_from_table(cs, reader, 'main_sample', (contig, p0, p1))
     else:
       stats, _ = gen.write_examples_in_region(cs, [reader.query(contig, p0, p1)], [0], 'main_sample', [0.0])
     for key, val in stats.items():
       totals[key] = totals.get(key, 0) + val
+
+  if a.candidates_in:
+    cands = [protos.parse_deepvariant_call(r) for p in tfrecord.resolve_input_paths(a.candidates_in) for r in tfrecord.read_records(p)]
+    for (contig, k, origin), cs in men.shard_partitions(men.partition_candidates(cands, a.partition_size, region), n_shards, a.task):
+      p0 = origin + k * a.partition_size
+      examples_in(cs, contig, p0, p0 + a.partition_size if not region else min(p0 + a.partition_size, region[2]))
+  else:
+    # Candidate generation (csrc/dvb_candidates.cu): allele counter + very-sensitive caller over each region of this task,
+    # exactly the regions `--task i` of N gets in the reference (regions_to_process, make_examples_core.py:799-888).
+    if a.realign_reads:
+      print('make_examples: the local realigner is not implemented; candidates come from the reads as aligned '
+            '(--norealign_reads)', file=sys.stderr)
+    if a.phase_reads:
+      print('make_examples: read phasing is not implemented; the HP tag of the input is used when --parse_sam_aux_fields is set', file=sys.stderr)
+    ref = fasta.IndexedFastaReader(a.ref)
+    copts = cand.CandidateOptions(
+        min_mapping_quality=a.min_mapping_quality, min_base_quality=a.min_base_quality,
+        keep_legacy_allele_counter_behavior=a.keep_legacy_allele_counter_behavior, track_ref_reads=a.track_ref_reads,
+        vsc_min_count_snps=a.vsc_min_count_snps, vsc_min_count_indels=a.vsc_min_count_indels, vsc_min_fraction_snps=a.vsc_min_fraction_snps,
+        vsc_min_fraction_indels=a.vsc_min_fraction_indels, vsc_min_fraction_multiplier=a.vsc_min_fraction_multiplier,
+        small_model_vaf_context_window_size=a.small_model_vaf_context_window_size,
+        sample_name=a.sample_name or cand.sample_name_from_bam(a.reads), max_reads_per_partition=a.max_reads_per_partition,
+        partition_size=a.partition_size)
+    cand_writer = tfrecord.Writer(tfrecord.shard_path(a.candidates, a.task) if tfrecord.is_sharded_spec(a.candidates) else a.candidates) \
+        if a.candidates else None
+    contigs = [(c, ref.n_bases(c)) for c in ref.contig_order if c in reader.references]
+    for contig, p0, p1 in cand.regions_to_process(contigs, a.partition_size, region, a.task, n_shards):
+      rows = cand.region_reads(reader, contig, p0, p1, copts.max_reads_per_partition, copts.random_seed)
+      if not len(rows):
+        continue
+      found = cand.candidates_in_region(reader, ref, contig, p0, p1, copts, rows=rows, padding_pct=20 if a.phase_reads else 0)
+      totals['n_candidates'] = totals.get('n_candidates', 0) + len(found.records)
+      if cand_writer is not None:
+        for rec in found.records:
+          cand_writer.write(rec)
+      if found.records:
+        examples_in(found.calls(), contig, p0, p1)
+    if cand_writer is not None:
+      cand_writer.close()
   gen.signal_shard_finished()
   print(f'make_examples task {a.task}: {totals}', file=sys.stderr)
   return 0
@@ -178,7 +233,7 @@ def run_deepvariant(argv):
   ap.add_argument('--model_type', required=True, choices=sorted(MODEL_DEFAULTS))
   ap.add_argument('--ref', required=True)
   ap.add_argument('--reads', required=True)
-  ap.add_argument('--candidates', required=True)
+  ap.add_argument('--candidates_in', default='')   # optional: DeepVariantCalls exported by another make_examples
   ap.add_argument('--output_dir', required=True)
   ap.add_argument('--regions', default='')
   ap.add_argument('--num_shards', type=int, default=1)
@@ -188,12 +243,14 @@ def run_deepvariant(argv):
   d = MODEL_DEFAULTS[a.model_type]
   examples = os.path.join(a.output_dir, f'make_examples.tfrecord@{a.num_shards}.gz')
   for task in range(a.num_shards):
-    args = ['--mode', 'calling', '--ref', a.ref, '--reads', a.reads, '--candidates', a.candidates, '--examples', examples, '--task',
+    args = ['--mode', 'calling', '--ref', a.ref, '--reads', a.reads, '--examples', examples, '--task',
             str(task), '--channel_list', d['channel_list'], '--pileup_image_width', str(d['pileup_image_width'])]
-    for flag in ('sort_by_haplotypes', 'trim_reads_for_pileup', 'parse_sam_aux_fields'):
+    if a.candidates_in:
+      args += ['--candidates_in', a.candidates_in]
+    for flag in ('sort_by_haplotypes', 'trim_reads_for_pileup', 'parse_sam_aux_fields', 'track_ref_reads', 'phase_reads'):
       if d.get(flag):
         args.append('--' + flag)
-    for flag in ('alt_aligned_pileup', 'min_mapping_quality', 'partition_size'):
+    for flag in ('alt_aligned_pileup', 'min_mapping_quality', 'partition_size', 'max_reads_per_partition', 'vsc_min_fraction_indels'):
       if flag in d:
         args += ['--' + flag, str(d[flag])]
     if a.regions:

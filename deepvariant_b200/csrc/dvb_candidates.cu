@@ -559,6 +559,33 @@ int dvb_candidates_in_region(const DvbBam* bam, const char* reference_name, cons
   return DVB_OK;
 }
 
+int64_t dvb_debug_allele_counts(const DvbBam* bam, const uint8_t* contig_bases, int64_t contig_n_bases, int64_t start, int64_t end,
+                                const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* opt,
+                                const int32_t* candidate_positions, int32_t n_candidate_positions, char* out, int64_t cap) {
+  DvbReadTable table;
+  Counter c;
+  std::vector<std::string> keys;
+  int st = BuildCounter(bam, &table, &c, contig_bases, contig_n_bases, start, end, rows, n_rows, opt, candidate_positions,
+                        n_candidate_positions, &keys);
+  if (st != DVB_OK) return -(int64_t)st;
+  std::string js = "[";
+  for (size_t i = 0; i < c.sites.size(); ++i) {
+    if (i) js += ",";
+    js += "{\"ref\":" + std::to_string(c.sites[i].ref_supporting_read_count) + ",\"alleles\":[";
+    for (size_t k = 0; k < c.sites[i].entries.size(); ++k) {
+      const Entry& e = c.sites[i].entries[k];
+      if (k) js += ",";
+      js += "[\"" + c.arena.substr(e.bases_off, e.bases_len) + "\"," + std::to_string((int)e.type) + "," +
+            std::to_string((int)e.low_quality) + ",\"" + keys[(size_t)e.key_id] + "\"," + std::to_string((int)e.mapq) + "," +
+            std::to_string(e.avg_base_quality) + "," + std::to_string((int)e.reverse) + "]";
+    }
+    js += "]}";
+  }
+  js += "]";
+  if (out && cap > (int64_t)js.size()) memcpy(out, js.c_str(), js.size() + 1);
+  return (int64_t)js.size();
+}
+
 int64_t dvb_candidates_count(const DvbCandidates* c) { return c ? (int64_t)c->position.size() : 0; }
 
 int dvb_candidates_protos(const DvbCandidates* c, const uint8_t** data, const int64_t** begin) {

@@ -356,6 +356,13 @@ int dvb_candidates_protos(const DvbCandidates* candidates, const uint8_t** data,
 /* variant.start of every candidate (or the positions of dvb_candidate_positions); returns the count. */
 int64_t dvb_candidates_positions(const DvbCandidates* candidates, const int32_t** positions);
 void dvb_candidates_free(DvbCandidates* candidates);
+/* Test access to the allele counter (AlleleCounter::Counts()): JSON text, one object per position of [start, end):
+ * {"ref": ref_supporting_read_count, "alleles": [[bases, AlleleType, is_low_quality, read key, mapping quality,
+ * avg base quality, reverse strand], ...]} = the entries of AlleleCount.read_alleles in insertion order.  Returns the text
+ * length (written, NUL-terminated, when cap is larger) or -DvbStatus. */
+int64_t dvb_debug_allele_counts(const DvbBam* bam, const uint8_t* contig_bases, int64_t contig_n_bases, int64_t start, int64_t end,
+                                const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* options,
+                                const int32_t* candidate_positions, int32_t n_candidate_positions, char* out, int64_t cap);
 
 /* ---- call_variants record I/O on the host ---------------------------------------------
  * Reader = call_variants.get_dataset (deepvariant/call_variants.py:449-538): the shards of the examples TFRecord

@@ -324,7 +324,7 @@ def test_make_examples_cli_from_bam_file_matches_oracle(tmp_path):
     w.write(protos.serialize_deepvariant_call(c))
   w.close()
   ex = str(tmp_path / 'make_examples.tfrecord@1.gz')
-  assert cli.make_examples(['--mode', 'calling', '--ref', str(fa), '--reads', bam_path, '--candidates', cpath, '--examples', ex,
+  assert cli.make_examples(['--mode', 'calling', '--ref', str(fa), '--reads', bam_path, '--candidates_in', cpath, '--examples', ex,
                             '--channel_list', 'BASE_CHANNELS,insert_size', '--regions', 'chr20:1001-3000']) == 0
   got = [protos.parse_tf_example(r) for r in tfrecord.read_records(str(tmp_path / 'make_examples.tfrecord-00000-of-00001.gz'))]
   # expected: Read-object planner + CPU oracle, partition by partition (1000-bp partitions from the region start)

@@ -89,13 +89,15 @@ def test_flags_for_calling_precedence(tmp_path):
       'version': '1.10.0', 'shape': [100, 147, 10], 'channels': [1, 2, 3, 4, 5, 6, 7, 9, 10],
       'flags_for_calling': {'pileup_image_width': 147, 'sort_by_haplotypes': True, 'trim_reads_for_pileup': 'true', 'min_mapping_quality': 1,
                             'partition_size': 25000, 'alt_aligned_pileup': 'diff_channels', 'vsc_min_fraction_indels': 0.12,
-                            'phase_reads': True, 'channel_list': 'BASE_CHANNELS,haplotype'}}))
+                            'phase_reads': True, 'channel_list': 'BASE_CHANNELS,haplotype', 'track_ref_reads': 'true',
+                            'call_small_model_examples': True, 'trained_small_model_path': '/x'}}))
   m = cli.apply_flags_for_calling({'min_mapping_quality': 7, 'task': 2}, str(model))
   assert m['pileup_image_width'] == 147 and m['sort_by_haplotypes'] is True and m['trim_reads_for_pileup'] is True
   assert m['partition_size'] == 25000 and m['alt_aligned_pileup'] == 'diff_channels' and m['channel_list'] == 'BASE_CHANNELS,haplotype'
   assert m['min_mapping_quality'] == 7 and m['task'] == 2                       # the command line wins
   assert m['pileup_image_height'] == 100 and m['min_base_quality'] == 10        # defaults
-  assert sorted(m['_ignored_flags_for_calling']) == ['phase_reads', 'vsc_min_fraction_indels']   # upstream stages
+  assert m['phase_reads'] is True and m['track_ref_reads'] is True and abs(m['vsc_min_fraction_indels'] - 0.12) < 1e-12   # candidate generation
+  assert sorted(m['_ignored_flags_for_calling']) == ['call_small_model_examples', 'trained_small_model_path']   # stages not built here
   assert cli.model_example_info_json_path(str(model / 'model.ckpt')) == str(model / 'model.example_info.json')   # json next to a ckpt
   ck = tmp_path / 'ckpt_dir'
   ck.mkdir()

@@ -17,95 +17,9 @@ sys.path.insert(0, ROOT)
 
 from deepvariant_b200 import bam, candidates as cand, fasta, protos, tfrecord  # noqa: E402
 
+canonical = cand.canonical_call
+
 TESTDATA = '/root/reference/deepvariant/testdata'
-
-
-def _value(buf):
-  for fn, wt, val, _ in protos.iter_fields(buf):
-    if fn == 7:
-      return protos._to_signed32(val)   # pylint: disable=protected-access
-    if fn == 2:
-      import struct
-      return struct.unpack('<d', struct.pack('<Q', val))[0] if isinstance(val, int) else struct.unpack('<d', bytes(val))[0]
-    if fn == 3:
-      return bytes(val).decode()
-  return None
-
-
-def _read_support(buf):
-  d = {'read_name': '', 'is_low_quality': 0, 'mapping_quality': 0, 'average_base_quality': 0, 'is_reverse_strand': 0, 'sample_name': ''}
-  names = {1: 'read_name', 2: 'is_low_quality', 3: 'mapping_quality', 4: 'average_base_quality', 5: 'is_reverse_strand', 7: 'sample_name'}
-  for fn, wt, val, _ in protos.iter_fields(buf):
-    if fn in names:
-      d[names[fn]] = bytes(val).decode() if wt == 2 else int(val)
-  return d
-
-
-def canonical(record: bytes) -> dict:
-  """Semantic content of a DeepVariantCall, independent of map / field order."""
-  out = {'ref': '', 'alts': [], 'start': 0, 'end': 0, 'contig': '', 'info': {}, 'call_set_name': '', 'genotype': [],
-         'allele_support': {}, 'allele_support_ext': {}, 'ref_support': [], 'ref_support_ext': [], 'af_at_position': {}}
-  for fn, wt, val, _ in protos.iter_fields(record):
-    val = bytes(val) if wt == 2 else val
-    if fn == 1:
-      for f2, w2, v2, _ in protos.iter_fields(val):
-        v2 = bytes(v2) if w2 == 2 else v2
-        if f2 == 6:
-          out['ref'] = v2.decode()
-        elif f2 == 7:
-          out['alts'].append(v2.decode())
-        elif f2 == 13:
-          out['end'] = int(v2)
-        elif f2 == 14:
-          out['contig'] = v2.decode()
-        elif f2 == 16:
-          out['start'] = int(v2)
-        elif f2 == 11:
-          for f3, w3, v3, _ in protos.iter_fields(v2):
-            v3 = bytes(v3) if w3 == 2 else v3
-            if f3 == 2:
-              key, vals = '', []
-              for f4, w4, v4, _ in protos.iter_fields(v3):
-                if f4 == 1:
-                  key = bytes(v4).decode()
-                elif f4 == 2:
-                  vals = [_value(bytes(v5)) for f5, w5, v5, _ in protos.iter_fields(bytes(v4)) if f5 == 1]
-              out['info'][key] = vals
-            elif f3 == 7:
-              out['genotype'] = [protos._to_signed32(x) for x in protos.unpack_varints(v3)] if w3 == 2 else out['genotype'] + [protos._to_signed32(v3)]   # pylint: disable=protected-access
-            elif f3 == 9:
-              out['call_set_name'] = v3.decode()
-    elif fn == 2:
-      key, names = '', []
-      for f2, w2, v2, _ in protos.iter_fields(val):
-        if f2 == 1:
-          key = bytes(v2).decode()
-        elif f2 == 2:
-          names = [bytes(v3).decode() for f3, w3, v3, _ in protos.iter_fields(bytes(v2)) if f3 == 1]
-      out['allele_support'][key] = sorted(names)
-    elif fn == 4:
-      out['ref_support'].append(val.decode())
-    elif fn == 5:
-      key, infos = '', []
-      for f2, w2, v2, _ in protos.iter_fields(val):
-        if f2 == 1:
-          key = bytes(v2).decode()
-        elif f2 == 2:
-          infos = [_read_support(bytes(v3)) for f3, w3, v3, _ in protos.iter_fields(bytes(v2)) if f3 == 1]
-      out['allele_support_ext'][key] = sorted(infos, key=lambda d: d['read_name'])
-    elif fn == 6:
-      out['ref_support_ext'] = sorted((_read_support(bytes(v3)) for f3, w3, v3, _ in protos.iter_fields(val) if f3 == 1),
-                                      key=lambda d: d['read_name'])
-    elif fn == 7:
-      k = v = 0
-      for f2, w2, v2, _ in protos.iter_fields(val):
-        if f2 == 1:
-          k = int(v2)
-        elif f2 == 2:
-          v = int(v2)
-      out['af_at_position'][str(k)] = v
-  out['ref_support'].sort()
-  return out
 
 
 def diff_fields(a: dict, b: dict):
@@ -142,11 +56,75 @@ def main():
       'golden_only': sorted(k[0] for k in g_by if k not in o_by), 'ours_only': sorted(k[0] for k in o_by if k not in g_by),
       'note': 'golden made with --realign_reads (default); ours = no realigner',
   }
+  report['pacbio'] = pacbio_pin()
   os.makedirs(os.path.join(ROOT, 'tests/golden'), exist_ok=True)
   with open(os.path.join(ROOT, 'tests/golden/candidates_golden_report.json'), 'w') as f:
     json.dump(report, f, indent=1)
   print(json.dumps({k: v for k, v in report.items() if not isinstance(v, list) or len(v) < 30}, indent=1))
-  return fixture, table, ref, opts
+  write_fixture(fixture, g_by, o_by, table, ref, opts)
+
+
+def pacbio_pin():
+  """golden.pacbio_examples.tfrecord.gz (make_examples_test.py:792-831: realigner off, --track_ref_reads, --phase_reads region
+  padding, --vsc_min_fraction_indels 0.12, --partition_size 25000): every variant/encoded of the 401 examples against ours."""
+  examples = [protos.parse_tf_example(r) for r in tfrecord.read_records(os.path.join(TESTDATA, 'golden.pacbio_examples.tfrecord.gz'))]
+  gold = {}
+  for e in examples:
+    c = canonical(protos.f_bytes(1, e['variant/encoded'][1][0]))
+    gold[(c['start'], c['ref'], tuple(c['alts']))] = c
+  bam_path = os.path.join(TESTDATA, 'input/test_pacbio.chr20_100kbp_at_9mb.bam')
+  ref = fasta.IndexedFastaReader(os.path.join(TESTDATA, 'input/grch38.chr20_and_21_10M.fa.gz'))
+  table = bam.NativeBamTable(bam_path, bam.ReadRequirements(min_mapping_quality=1), parse_aux=True)
+  opts = cand.CandidateOptions(sample_name=cand.sample_name_from_bam(bam_path), min_mapping_quality=1, track_ref_reads=True,
+                               vsc_min_fraction_indels=0.12, partition_size=25000)
+  ours = {}
+  for contig, s, e in cand.regions_to_process([(c, ref.n_bases(c)) for c in ref.contig_order], 25000, ('chr20', 8999999, 9100000)):
+    for rec in cand.candidates_in_region(table, ref, contig, s, e, opts, padding_pct=20).records:
+      c = canonical(rec)
+      ours[(c['start'], c['ref'], tuple(c['alts']))] = c
+  same = [k for k in gold if k in ours and all(gold[k][f] == ours[k][f] for f in ('info', 'call_set_name', 'genotype', 'end', 'contig'))]
+  return {'golden_examples': len(examples), 'golden_variants': len(gold), 'ours_candidates': len(ours),
+          'identical_site_alleles_AD_DP_VAF': len(same), 'golden_only': len(set(gold) - set(ours)), 'ours_only': len(set(ours) - set(gold))}
+
+
+def write_fixture(exact, g_by, o_by, table, ref, opts, n_partitions=3):
+  """Portable fixture: the reads (as a small BAM) and reference slice of the partitions whose golden candidates are all
+  reproduced field for field, with those golden candidates as the expected output."""
+  sys.path.insert(0, os.path.join(ROOT, 'tests'))
+  import test_bam_native as tb
+  origin, size = 9999999, opts.partition_size
+  by_part = {}
+  for key, g in g_by.items():
+    by_part.setdefault((key[0] - origin) // size, []).append(key)
+  ours_by_part = {}
+  for key in o_by:
+    ours_by_part.setdefault((key[0] - origin) // size, []).append(key)
+  good = [p for p, keys in sorted(by_part.items())
+          if sorted(keys) == sorted(ours_by_part.get(p, [])) and
+          all(diff_fields(g_by[k], o_by[k]) in ([], ['af_at_position']) for k in keys)]
+  good = sorted(good, key=lambda p: -len(by_part[p]))[:n_partitions]
+  parts, rows_all = [], []
+  for p in sorted(good):
+    s, e = origin + p * size, origin + (p + 1) * size
+    rows = cand.region_reads(table, 'chr20', s, e)
+    rows_all += [int(r) for r in rows if int(r) not in rows_all]
+    # 'af_exact': the +-25 bp allele-fraction context also matches (it does not where the realigner rewrote a nearby read)
+    parts.append({'start': s, 'end': e, 'expected': [dict(g_by[k], af_exact=not diff_fields(g_by[k], o_by[k])) for k in sorted(by_part[p])]})
+  rows_all.sort()
+  lo = min(int(table.pos[r]) for r in rows_all) - 2
+  hi = max(int(table.end[r]) for r in rows_all) + 64
+  recs = []
+  for r in rows_all:
+    rd = table.read(r)
+    recs.append(tb._record(0, rd.position, rd.fragment_name, rd.mapping_quality, int(table.flag[r]), rd.cigar,
+                           rd.aligned_sequence.decode(), rd.aligned_quality, tlen=rd.fragment_length))
+  with open(os.path.join(ROOT, 'tests/golden/candidates_golden_subset.bam'), 'wb') as f:
+    f.write(tb._bam(recs, refs=(('chr20', ref.n_bases('chr20')),)))
+  with open(os.path.join(ROOT, 'tests/golden/candidates_golden_subset.json'), 'w') as f:
+    json.dump({'source': 'deepvariant/testdata/golden.calling_candidates.tfrecord.gz + input/NA12878_S1.chr20.10_10p1mb.bam',
+               'contig': 'chr20', 'n_bases': ref.n_bases('chr20'), 'slice_start': lo, 'slice': ref.query('chr20', lo, hi),
+               'sample_name': opts.sample_name, 'small_model_vaf_context_window_size': 51, 'partitions': parts}, f)
+  print('fixture:', len(rows_all), 'reads,', sum(len(p['expected']) for p in parts), 'golden candidates in partitions', sorted(good))
 
 
 if __name__ == '__main__':
