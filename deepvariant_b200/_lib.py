@@ -185,6 +185,17 @@ SYMBOLS = (
     ('dvb_candidates_protos', C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     ('dvb_candidates_positions', C.c_int64, [C.c_void_p, C.POINTER(C.c_void_p)]),
     ('dvb_candidates_free', None, [C.c_void_p]),
+    ('dvb_device_reads_create', C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    ('dvb_device_reads_destroy', None, [C.c_void_p]),
+    ('dvb_device_reads_launch_count', C.c_int64, [C.c_void_p]),
+    ('dvb_allele_count_device', C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                          C.POINTER(DvbCandidateOptions), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ('dvb_allele_count_host', C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                        C.POINTER(DvbCandidateOptions), C.c_void_p, C.c_void_p]),
+    ('dvb_candidates_at_positions', C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                              C.POINTER(DvbCandidateOptions), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
+    ('dvb_debug_allele_count_dense_host', C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                                    C.POINTER(DvbCandidateOptions), C.c_int, C.c_void_p, C.c_void_p]),
     ('dvb_debug_allele_counts', C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                             C.POINTER(DvbCandidateOptions), C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
     ('dvb_crc32c', C.c_uint32, [C.c_char_p, C.c_size_t]),

@@ -319,3 +319,101 @@ def debug_allele_counts(table, ref_reader, contig: str, start: int, end: int, ro
   buf = C.create_string_buffer(n + 1)
   lib.dvb_debug_allele_counts(*args, buf, n + 1)
   return json.loads(buf.value.decode())
+
+
+# ---- allele counting on the device + exact calls on the flagged sites ---------------------------------------------------------------
+def _dense_arrays(n: int):
+  return np.zeros(6 * n, dtype=np.int32), np.zeros(n, dtype=np.uint8)
+
+
+def split_dense_counts(counts: np.ndarray, n: int):
+  """int32[6 n] -> (ref_count[n], subst[n, 4] by read base A, C, G, T, other[n])."""
+  return counts[:n], counts[n:5 * n].reshape(n, 4), counts[5 * n:]
+
+
+def debug_dense_counts_host(table, ref_reader, contig: str, start: int, end: int, rows, options: CandidateOptions, windowed: bool = True):
+  """Test access: the device pass (walk + dense sink + flags) instantiated on the host."""
+  lib = _lib.lib()
+  seq, ptr = _contig_buffer(ref_reader, contig)
+  rows = np.ascontiguousarray(rows, dtype=np.int64)
+  counts, flags = _dense_arrays(end - start)
+  co = options.to_c()
+  _lib.check(lib.dvb_debug_allele_count_dense_host(table.handle, ptr, len(seq), start, end, rows.ctypes.data_as(C.c_void_p), len(rows),
+                                                   C.byref(co), int(windowed), counts.ctypes.data_as(C.c_void_p), flags.ctypes.data_as(C.c_void_p)))
+  return counts, flags
+
+
+class GpuAlleleCounter:
+  """The reads of a NativeBamTable resident in HBM (dvb_device_reads_create) + the allele-count / flag kernels.  Raises when no
+  CUDA device is present: there is no CPU path behind this class (candidates_in_region is the host implementation)."""
+
+  def __init__(self, table, device: int = 0):
+    self._lib = _lib.lib()
+    self.table = table
+    h = C.c_void_p()
+    _lib.check(self._lib.dvb_device_reads_create(table.handle, device, C.byref(h)))
+    self._h = h
+
+  def count_region(self, ref_reader, contig: str, start: int, end: int, rows, options: CandidateOptions):
+    """-> (counts int32[6 len], flags uint8[len]); host arrays in and out (dvb_allele_count_host)."""
+    seq, ptr = _contig_buffer(ref_reader, contig)
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    counts, flags = _dense_arrays(end - start)
+    co = options.to_c()
+    _lib.check(self._lib.dvb_allele_count_host(self._h, self.table.handle, ptr, len(seq), start, end, rows.ctypes.data_as(C.c_void_p),
+                                               len(rows), C.byref(co), counts.ctypes.data_as(C.c_void_p), flags.ctypes.data_as(C.c_void_p)))
+    return counts, flags
+
+  @property
+  def launch_count(self) -> int:
+    return int(self._lib.dvb_device_reads_launch_count(self._h))
+
+  def close(self):
+    if getattr(self, '_h', None):
+      self._lib.dvb_device_reads_destroy(self._h)
+      self._h = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pylint: disable=broad-except
+      pass
+
+
+def candidates_at_flagged_positions(table, ref_reader, contig: str, start: int, end: int, options: CandidateOptions, rows: np.ndarray,
+                                    flags: np.ndarray) -> NativeCandidates:
+  """The exact caller on the sites the device pass flagged: only the reads that overlap a flagged site (by one base on either
+  side, or the allele-frequency context when requested) are walked on the host.  Equals candidates_in_region(rows) whenever
+  `flags` is a superset of its sites (tests/test_candidates.py)."""
+  if options.track_ref_reads:
+    raise NotImplementedError('track_ref_reads needs the two-pass host counter (candidates_in_region)')
+  lib = _lib.lib()
+  seq, ptr = _contig_buffer(ref_reader, contig)
+  emit = (np.nonzero(flags)[0] + start).astype(np.int32)
+  rows = np.ascontiguousarray(rows, dtype=np.int64)
+  if len(emit):
+    margin = 1 + (options.small_model_vaf_context_window_size // 2 + 1 if options.small_model_vaf_context_window_size > 0 else 0)
+    pos, rend = table.pos[rows].astype(np.int64), table.end[rows].astype(np.int64)
+    # reads overlapping [p - margin, p + margin] for some flagged p: first flagged p >= pos - margin must be <= end - 1 + margin
+    k = np.searchsorted(emit, pos - margin, side='left')
+    keep = (k < len(emit)) & (emit[np.minimum(k, len(emit) - 1)] <= rend - 1 + margin)
+    rows = np.ascontiguousarray(rows[keep])
+  else:
+    rows = rows[:0]
+  co = options.to_c()
+  h = C.c_void_p()
+  _lib.check(lib.dvb_candidates_at_positions(table.handle, contig.encode(), ptr, len(seq), start, end, rows.ctypes.data_as(C.c_void_p),
+                                             len(rows), C.byref(co), None, 0, emit.ctypes.data_as(C.c_void_p), len(emit), C.byref(h)))
+  return NativeCandidates(h)
+
+
+def candidates_in_region_gpu(counter: GpuAlleleCounter, ref_reader, contig: str, start: int, end: int, options: CandidateOptions,
+                             rows: Optional[np.ndarray] = None) -> NativeCandidates:
+  """candidates_in_region with the allele counting on the device: count + flag kernels over the region's reads, then the exact
+  calls on the flagged sites."""
+  table = counter.table
+  if rows is None:
+    rows = region_reads(table, contig, start, end, options.max_reads_per_partition, options.random_seed)
+  end = min(end, ref_reader.n_bases(contig))
+  _, flags = counter.count_region(ref_reader, contig, start, end, rows, options)
+  return candidates_at_flagged_positions(table, ref_reader, contig, start, end, options, rows, flags)

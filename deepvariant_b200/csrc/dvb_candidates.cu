@@ -21,13 +21,18 @@
 #include <utility>
 #include <vector>
 
+#include "dvb_allele_walk.h"
 #include "dvb_common.h"
 
 namespace {
 
-enum AlleleType : uint8_t { kUnspecified = 0, kReference = 1, kSubstitution = 2, kInsertion = 3, kDeletion = 4, kSoftClip = 5 };
-
-inline bool Canonical(char b) { return b == 'A' || b == 'C' || b == 'G' || b == 'T'; }
+using dvb_allele::Canonical;
+using dvb_allele::Element;
+using dvb_allele::kDeletion;
+using dvb_allele::kInsertion;
+using dvb_allele::kReference;
+using dvb_allele::kSoftClip;
+using dvb_allele::kSubstitution;
 
 struct Entry {              // one value of AlleleCount.read_alleles (the key is the read: key_id)
   int32_t row;              // BAM table row
@@ -42,13 +47,6 @@ struct Site {
   std::vector<Entry> entries;        // insertion order; a later entry with the same key replaces the earlier one in place
 };
 
-struct ReadAllele {         // allelecounter.h:113-166
-  int position = -1;        // kInvalidPosition = skip
-  uint8_t type = kUnspecified, low_quality = 0;
-  int avg_base_quality = 0;
-  uint32_t bases_off = 0, bases_len = 0;
-};
-
 struct Counter {
   const DvbReadTable* t;
   const uint8_t* contig;         // upper-case bases of the whole contig
@@ -58,162 +56,68 @@ struct Counter {
   std::vector<Site> sites;
   std::string arena;             // allele bases
   std::vector<int32_t> candidate_positions;   // relative to start, sorted (track_ref_reads second pass)
-  std::vector<ReadAllele> to_add;
 
-  // AlleleCounter::RefBases (allelecounter.cc:360-373): "" when the region is not inside the contig.
-  bool RefBases(int64_t rel_start, int64_t len, const uint8_t** out) const {
-    int64_t abs_start = start + rel_start;
-    if (abs_start < 0 || abs_start + len > contig_len) return false;
-    *out = contig + abs_start;
-    return true;
+  // AddReadAlleles (allelecounter.cc:475-546) for one surviving element of dvb_allele::WalkRead.
+  struct Sink {
+    Counter* c;
+    int32_t row, key_id;
+    const uint8_t* seq;
+    void Commit(const Element& a) {
+      Site& site = c->sites[(size_t)a.position];
+      if (a.type == kReference && !a.low_quality) ++site.ref_supporting_read_count;
+      if (a.type == kReference &&
+          !(c->opt.track_ref_reads && std::binary_search(c->candidate_positions.begin(), c->candidate_positions.end(), a.position)))
+        return;
+      Entry e;
+      e.row = row;
+      e.key_id = key_id;
+      e.type = a.type;
+      e.low_quality = a.low_quality;
+      e.mapq = c->t->mapq[row];
+      e.reverse = (c->t->flag[row] & 0x10) != 0;
+      e.avg_base_quality = a.avg_base_quality;
+      e.bases_off = (uint32_t)c->arena.size();
+      if (a.len == 0) {
+        c->arena.push_back((char)seq[a.read_offset]);
+        e.bases_len = 1;
+      } else {
+        c->arena.push_back((char)a.prev);
+        if (a.type == kDeletion) c->arena.append((const char*)c->contig + a.ref_abs, (size_t)a.len);
+        else c->arena.append((const char*)seq + a.read_offset, (size_t)a.len);
+        e.bases_len = (uint32_t)a.len + 1;
+      }
+      for (Entry& old : site.entries)
+        if (old.key_id == key_id) { old = e; return; }     // (*read_alleles)[key] = allele
+      site.entries.push_back(e);
+    }
+  };
+
+  dvb_allele::WalkParams Params() const {
+    dvb_allele::WalkParams p;
+    p.start = start;
+    p.end = end;
+    p.contig = contig;
+    p.contig_origin = 0;
+    p.contig_avail = contig_len;
+    p.contig_len = contig_len;
+    p.min_base_quality = opt.min_base_quality;
+    p.keep_legacy_behavior = opt.keep_legacy_behavior;
+    return p;
   }
 
-  // CanBasesBeUsed (allelecounter.cc:195-224).
-  bool CanBasesBeUsed(const uint8_t* seq, const uint8_t* qual, int offset, int len, bool* low_quality) const {
-    const int min_bq = opt.min_base_quality;
-    int sum = 0;
-    for (int i = 0; i < len; ++i) {
-      sum += qual[offset + i];
-      if (qual[offset + i] < min_bq && opt.keep_legacy_behavior) return false;
-      if (!Canonical((char)seq[offset + i])) return false;
-    }
-    *low_quality = false;
-    if (!opt.keep_legacy_behavior && sum < min_bq * len) *low_quality = true;
-    return true;
-  }
-
-  uint32_t Intern(const uint8_t* a, size_t na, const uint8_t* b, size_t nb) {
-    uint32_t off = (uint32_t)arena.size();
-    arena.append((const char*)a, na);
-    arena.append((const char*)b, nb);
-    return off;
-  }
-
-  // MakeIndelReadAllele (allelecounter.cc:402-473).
-  ReadAllele MakeIndel(const uint8_t* seq, const uint8_t* qual, int seq_len, int interval_offset, int ref_offset, int read_offset,
-                       int op, int op_len) {
-    ReadAllele none;
-    uint8_t prev;
-    if (read_offset == 0) {       // GetPrevBase: the previous base comes from the reference
-      const uint8_t* p;
-      if (!RefBases((int64_t)ref_offset - 1, 1, &p)) return none;
-      prev = *p;
-    } else {
-      prev = seq[read_offset - 1];
-    }
-    bool low_quality = false;
-    if (!Canonical((char)prev)) return none;
-    if (op != 2 /* D */) {
-      if (read_offset + op_len > seq_len) return none;   // the reference CHECK-fails here; a malformed record is dropped
-      if (!CanBasesBeUsed(seq, qual, read_offset, op_len, &low_quality)) return none;
-    }
-    ReadAllele ra;
-    const uint8_t* bases;
-    int avg_bq;
-    if (op == 2) {
-      if (!RefBases(ref_offset, op_len, &bases)) return none;
-      for (int i = 0; i < op_len; ++i)
-        if (!Canonical((char)bases[i])) return none;
-      ra.type = kDeletion;
-      avg_bq = qual[std::max(0, read_offset - 1)];      // GetAvgBaseQuality, DELETE
-    } else {
-      bases = seq + read_offset;
-      ra.type = op == 1 ? kInsertion : kSoftClip;
-      int sum = 0;
-      for (int i = 0; i < op_len; ++i) sum += qual[read_offset + i];
-      avg_bq = sum / std::max(1, op_len);
-    }
-    ra.position = interval_offset - 1;
-    ra.low_quality = low_quality;
-    ra.avg_base_quality = avg_bq;
-    ra.bases_off = Intern(&prev, 1, bases, (size_t)op_len);
-    ra.bases_len = (uint32_t)op_len + 1;
-    return ra;
-  }
-
-  // AlleleCounter::Add (allelecounter.cc:880-978) + AddReadAlleles (:475-546).
+  // AlleleCounter::Add (allelecounter.cc:880-978).
   void Add(int32_t row, int32_t key_id) {
     if (t->mapq[row] < opt.min_mapping_quality) return;
     const int64_t s0 = t->seq_begin[row];
-    const int seq_len = (int)(t->seq_begin[row + 1] - s0);
-    if (seq_len == 0) return;     // a record without SEQ carries no alleles
-    const uint8_t* seq = t->bases + s0;
-    const uint8_t* qual = t->quals + s0;
-    const uint32_t* cig = t->cigar + t->cigar_begin[row];
-    const int n_cig = (int)(t->cigar_begin[row + 1] - t->cigar_begin[row]);
-    const bool reverse = (t->flag[row] & 0x10) != 0;
-    const int64_t len = end - start;
-    to_add.clear();
-    int read_offset = 0;
-    int64_t interval_offset = (int64_t)t->pos[row] - start;   // == ref_interval_offset (reads interval == interval)
-    for (int c = 0; c < n_cig; ++c) {
-      const int op = (int)(cig[c] & 0xF), op_len = (int)(cig[c] >> 4);
-      switch (op) {
-        case 0: case 7: case 8:   // M = X
-          for (int i = 0; i < op_len; ++i) {
-            const int64_t ref_offset = interval_offset + i;
-            const int base_offset = read_offset + i;
-            bool low_quality = false;
-            if (ref_offset >= 0 && ref_offset < len && base_offset < seq_len &&
-                CanBasesBeUsed(seq, qual, base_offset, 1, &low_quality)) {
-              ReadAllele ra;
-              ra.position = (int)ref_offset;
-              ra.type = contig[start + ref_offset] == seq[base_offset] ? kReference : kSubstitution;
-              ra.low_quality = low_quality;
-              ra.avg_base_quality = qual[base_offset];
-              ra.bases_off = (uint32_t)base_offset;     // single read base: materialised when (if) the entry is stored
-              ra.bases_len = 0;                          // 0 marks "read base at bases_off"
-              to_add.push_back(ra);
-            }
-          }
-          read_offset += op_len;
-          interval_offset += op_len;
-          break;
-        case 4: case 1:           // S, I
-          to_add.push_back(MakeIndel(seq, qual, seq_len, (int)interval_offset, (int)interval_offset, read_offset, op, op_len));
-          read_offset += op_len;
-          break;
-        case 2:                   // D
-          to_add.push_back(MakeIndel(seq, qual, seq_len, (int)interval_offset, (int)interval_offset, read_offset, op, op_len));
-          interval_offset += op_len;
-          break;
-        case 6: case 3:           // P, N
-          interval_offset += op_len;
-          break;
-        default:                  // H and unknown codes
-          break;
-      }
-    }
-    const size_t n = to_add.size();
-    for (size_t i = 0; i < n; ++i) {
-      const ReadAllele& a = to_add[i];
-      if (a.position < 0 || a.position >= len) continue;                   // skip() or outside the interval
-      if (i + 1 < n && a.position == to_add[i + 1].position) continue;     // superseded by the indel anchored here
-      Site& site = sites[(size_t)a.position];
-      if (a.type == kReference && !a.low_quality) ++site.ref_supporting_read_count;
-      if (a.type != kReference ||
-          (opt.track_ref_reads && std::binary_search(candidate_positions.begin(), candidate_positions.end(), a.position))) {
-        Entry e;
-        e.row = row;
-        e.key_id = key_id;
-        e.type = a.type;
-        e.low_quality = a.low_quality;
-        e.mapq = t->mapq[row];
-        e.reverse = reverse;
-        e.avg_base_quality = a.avg_base_quality;
-        if (a.bases_len == 0) {
-          e.bases_off = Intern(seq + a.bases_off, 1, nullptr, 0);
-          e.bases_len = 1;
-        } else {
-          e.bases_off = a.bases_off;
-          e.bases_len = a.bases_len;
-        }
-        bool replaced = false;
-        for (Entry& old : site.entries)
-          if (old.key_id == key_id) { old = e; replaced = true; break; }   // (*read_alleles)[key] = allele
-        if (!replaced) site.entries.push_back(e);
-      }
-    }
+    dvb_allele::ReadView r;
+    r.seq = t->bases + s0;
+    r.qual = t->quals + s0;
+    r.seq_len = (int)(t->seq_begin[row + 1] - s0);
+    r.cigar = t->cigar + t->cigar_begin[row];
+    r.n_cigar = (int)(t->cigar_begin[row + 1] - t->cigar_begin[row]);
+    r.pos = t->pos[row];
+    Sink sink{this, row, key_id, r.seq};
+    dvb_allele::WalkRead(r, Params(), sink);
   }
 };
 
@@ -407,7 +311,16 @@ int dvb_candidate_positions(const DvbBam* bam, const uint8_t* contig_bases, int6
 int dvb_candidates_in_region(const DvbBam* bam, const char* reference_name, const uint8_t* contig_bases, int64_t contig_n_bases,
                              int64_t start, int64_t end, const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* opt,
                              const int32_t* candidate_positions, int32_t n_candidate_positions, DvbCandidates** out) {
+  return dvb_candidates_at_positions(bam, reference_name, contig_bases, contig_n_bases, start, end, rows, n_rows, opt, candidate_positions,
+                                     n_candidate_positions, nullptr, -1, out);
+}
+
+int dvb_candidates_at_positions(const DvbBam* bam, const char* reference_name, const uint8_t* contig_bases, int64_t contig_n_bases,
+                                int64_t start, int64_t end, const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* opt,
+                                const int32_t* candidate_positions, int32_t n_candidate_positions, const int32_t* emit_positions,
+                                int32_t n_emit_positions, DvbCandidates** out) {
   if (!out || !reference_name) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_candidates_in_region: null argument");
+  if (n_emit_positions > 0 && !emit_positions) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_candidates_at_positions: null emit_positions");
   *out = nullptr;
   DvbReadTable table;
   Counter c;
@@ -423,6 +336,7 @@ int dvb_candidates_in_region(const DvbBam* bam, const char* reference_name, cons
   for (int i = 0; i < n_sites; ++i) {
     const Site& site = c.sites[(size_t)i];
     const char ref_base = (char)contig_bases[start + i];
+    if (n_emit_positions >= 0 && !std::binary_search(emit_positions, emit_positions + n_emit_positions, (int32_t)(start + i))) continue;
     if (!Canonical(ref_base)) continue;                                      // CallVariant (:1117-1130)
     std::vector<SummedAllele> alts = caller.SelectAlts(site);
     if (alts.empty()) continue;                                              // fraction_reference_sites_to_emit = 0
@@ -603,5 +517,259 @@ int64_t dvb_candidates_positions(const DvbCandidates* c, const int32_t** positio
 }
 
 void dvb_candidates_free(DvbCandidates* c) { delete c; }
+
+}  // extern "C"
+
+// ================================================================================================================================
+// CUDA allele counting (SURVEY.md 8(f) "next" row #2, device half): the reads of the BAM table live in HBM; one pass with a
+// thread per read runs dvb_allele::WalkRead and adds into dense per-position counters with atomics, a second pass flags the
+// positions that can carry a candidate.  HBM-bound integer work: per read 2 L + 4 n_cigar + 24 bytes in, per position 25
+// bytes of counters (memset + atomics + one read by the flag pass) + 1 flag byte out.
+// ================================================================================================================================
+struct DvbDeviceReads {
+  int device = 0;
+  int64_t n_reads = 0;
+  int32_t* pos = nullptr;
+  uint8_t* mapq = nullptr;
+  int64_t* seq_begin = nullptr;
+  int64_t* cigar_begin = nullptr;
+  uint8_t* bases = nullptr;
+  uint8_t* quals = nullptr;
+  uint32_t* cigar = nullptr;
+  // per-call scratch (grow-only)
+  dvb::DevBuf rows, ref, counts, flags;
+  int64_t launches = 0;
+};
+
+namespace {
+
+struct DeviceTable {
+  const int32_t* pos;
+  const uint8_t* mapq;
+  const int64_t* seq_begin;
+  const int64_t* cigar_begin;
+  const uint8_t* bases;
+  const uint8_t* quals;
+  const uint32_t* cigar;
+};
+
+__global__ void dvb_allele_count_kernel(DeviceTable t, const int64_t* __restrict__ rows, int64_t n_rows, dvb_allele::WalkParams p,
+                                        int min_mapping_quality, dvb_allele::DenseCounts out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  const int64_t row = rows[i];
+  if (t.mapq[row] < min_mapping_quality) return;
+  const int64_t s0 = t.seq_begin[row];
+  dvb_allele::ReadView r;
+  r.seq = t.bases + s0;
+  r.qual = t.quals + s0;
+  r.seq_len = (int)(t.seq_begin[row + 1] - s0);
+  r.cigar = t.cigar + t.cigar_begin[row];
+  r.n_cigar = (int)(t.cigar_begin[row + 1] - t.cigar_begin[row]);
+  r.pos = t.pos[row];
+  dvb_allele::DenseSink sink{out, r.seq};
+  dvb_allele::WalkRead(r, p, sink);
+}
+
+__global__ void dvb_allele_flag_kernel(dvb_allele::DenseCounts c, const uint8_t* __restrict__ ref /* ref[0] = position start */,
+                                       int64_t len, dvb_allele::FlagParams f, uint8_t* __restrict__ flags) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < len) flags[p] = dvb_allele::FlagPosition(c, p, ref[p], f);
+}
+
+dvb_allele::FlagParams MakeFlagParams(const DvbCandidateOptions& o) {
+  dvb_allele::FlagParams f;
+  f.min_count_snps = o.min_count_snps;
+  f.min_fraction_snps = (double)o.min_fraction_snps * std::min(1.0, (double)o.min_fraction_multiplier);
+  return f;
+}
+
+// Window of the contig a set of reads can touch: [min(start, first read) - 1, max(end, last read end) + 1) inside the contig.
+void RefWindow(const DvbReadTable& t, const int64_t* rows, int64_t n_rows, int64_t start, int64_t end, int64_t contig_len,
+               int64_t* w0, int64_t* w1) {
+  int64_t lo = start, hi = end;
+  for (int64_t i = 0; i < n_rows; ++i) {
+    lo = std::min<int64_t>(lo, t.pos[rows[i]]);
+    hi = std::max<int64_t>(hi, t.end[rows[i]]);
+  }
+  *w0 = std::max<int64_t>(0, lo - 1);
+  *w1 = std::min<int64_t>(contig_len, hi + 1);
+}
+
+int CheckCountArgs(const void* reads, const uint8_t* contig_bases, int64_t contig_n_bases, int64_t start, int64_t end,
+                   const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* opt) {
+  if (!reads || !contig_bases || !opt || (n_rows && !rows) || n_rows < 0)
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_allele_count: null argument");
+  if (start < 0 || end > contig_n_bases || start >= end || end - start > (int64_t)1 << 30)
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_allele_count: bad interval [%lld, %lld)", (long long)start, (long long)end);
+  return DVB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dvb_device_reads_create(const DvbBam* bam, int device, DvbDeviceReads** out) {
+  if (!bam || !out) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_device_reads_create: null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return dvb::fail(DVB_ERR_NO_DEVICE, "no CUDA device (allele counting on the device has no CPU path)");
+  if (device < 0 || device >= ndev) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "device %d out of range", device);
+  DVB_CUDA(cudaSetDevice(device));
+  DvbReadTable t;
+  int st = dvb_bam_table(bam, &t);
+  if (st != DVB_OK) return st;
+  auto* d = new DvbDeviceReads();
+  d->device = device;
+  d->n_reads = t.n_reads;
+  auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, std::max<size_t>(bytes, 16));
+    if (e != cudaSuccess) return e;
+    return bytes ? cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) : cudaSuccess;
+  };
+  const size_t n = (size_t)t.n_reads;
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = up((void**)&d->pos, t.pos, n * 4);
+  if (e == cudaSuccess) e = up((void**)&d->mapq, t.mapq, n);
+  if (e == cudaSuccess) e = up((void**)&d->seq_begin, t.seq_begin, (n + 1) * 8);
+  if (e == cudaSuccess) e = up((void**)&d->cigar_begin, t.cigar_begin, (n + 1) * 8);
+  if (e == cudaSuccess) e = up((void**)&d->bases, t.bases, (size_t)t.n_bases);
+  if (e == cudaSuccess) e = up((void**)&d->quals, t.quals, (size_t)t.n_bases);
+  if (e == cudaSuccess) e = up((void**)&d->cigar, t.cigar, (size_t)t.n_cigar * 4);
+  if (e != cudaSuccess) {
+    dvb_device_reads_destroy(d);
+    return dvb::fail(DVB_ERR_CUDA, "dvb_device_reads_create: %s", cudaGetErrorString(e));
+  }
+  *out = d;
+  return DVB_OK;
+}
+
+void dvb_device_reads_destroy(DvbDeviceReads* d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  cudaFree(d->pos); cudaFree(d->mapq); cudaFree(d->seq_begin); cudaFree(d->cigar_begin);
+  cudaFree(d->bases); cudaFree(d->quals); cudaFree(d->cigar);
+  d->rows.release(); d->ref.release(); d->counts.release(); d->flags.release();
+  delete d;
+}
+
+int64_t dvb_device_reads_launch_count(const DvbDeviceReads* d) { return d ? d->launches : 0; }
+
+// Device pointers in and out; asynchronous on `stream`.  ref_dev[0] is absolute position ref_origin and must cover the window
+// the rows touch (RefWindow).  counts_dev = int32[6 * len] laid out as ref_count[len], subst[4 * len], other[len];
+// indel_dev / flags_dev = uint8[len].
+int dvb_allele_count_device(DvbDeviceReads* d, const uint8_t* ref_dev, int64_t ref_origin, int64_t ref_avail, int64_t contig_n_bases,
+                            int64_t start, int64_t end, const int64_t* rows_dev, int64_t n_rows, const DvbCandidateOptions* opt,
+                            int32_t* counts_dev, uint8_t* indel_dev, uint8_t* flags_dev, void* stream) {
+  if (!d || !ref_dev || !opt || !counts_dev || !indel_dev || !flags_dev || (n_rows && !rows_dev))
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_allele_count_device: null argument");
+  if (start < ref_origin || end > ref_origin + ref_avail || start >= end)
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_allele_count_device: interval outside the resident reference window");
+  DVB_CUDA(cudaSetDevice(d->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t len = end - start;
+  DVB_CUDA(cudaMemsetAsync(counts_dev, 0, (size_t)len * 24, s));
+  DVB_CUDA(cudaMemsetAsync(indel_dev, 0, (size_t)len, s));
+  dvb_allele::WalkParams p;
+  p.start = start;
+  p.end = end;
+  p.contig = ref_dev;
+  p.contig_origin = ref_origin;
+  p.contig_avail = ref_avail;
+  p.contig_len = contig_n_bases;
+  p.min_base_quality = opt->min_base_quality;
+  p.keep_legacy_behavior = opt->keep_legacy_behavior;
+  dvb_allele::DenseCounts c{counts_dev, counts_dev + len, counts_dev + 5 * len, indel_dev};
+  DeviceTable t{d->pos, d->mapq, d->seq_begin, d->cigar_begin, d->bases, d->quals, d->cigar};
+  if (n_rows) {
+    dvb_allele_count_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, s>>>(t, rows_dev, n_rows, p, opt->min_mapping_quality, c);
+    ++d->launches;
+  }
+  dvb_allele_flag_kernel<<<(unsigned)((len + 255) / 256), 256, 0, s>>>(c, ref_dev + (start - ref_origin), len, MakeFlagParams(*opt), flags_dev);
+  ++d->launches;
+  DVB_CUDA(cudaGetLastError());
+  return DVB_OK;
+}
+
+// Host pointers in and out (synchronous): uploads the rows and the reference window, counts, flags, copies back.
+// counts_host = int32[6 * len] (ref_count, subst[4 * len], other), flags_host = uint8[len].
+int dvb_allele_count_host(DvbDeviceReads* d, const DvbBam* bam, const uint8_t* contig_bases, int64_t contig_n_bases, int64_t start,
+                          int64_t end, const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* opt, int32_t* counts_host,
+                          uint8_t* flags_host) {
+  int st = CheckCountArgs(d, contig_bases, contig_n_bases, start, end, rows, n_rows, opt);
+  if (st != DVB_OK) return st;
+  if (!bam || !counts_host || !flags_host) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_allele_count_host: null argument");
+  DvbReadTable t;
+  st = dvb_bam_table(bam, &t);
+  if (st != DVB_OK) return st;
+  if (t.n_reads != d->n_reads) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_allele_count_host: device table was made from another BAM");
+  for (int64_t i = 0; i < n_rows; ++i)
+    if (rows[i] < 0 || rows[i] >= t.n_reads) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_allele_count_host: read row out of range");
+  int64_t w0, w1;
+  RefWindow(t, rows, n_rows, start, end, contig_n_bases, &w0, &w1);
+  const int64_t len = end - start;
+  DVB_CUDA(cudaSetDevice(d->device));
+  DVB_CUDA(d->rows.reserve((size_t)std::max<int64_t>(n_rows, 1) * 8));
+  DVB_CUDA(d->ref.reserve((size_t)(w1 - w0)));
+  DVB_CUDA(d->counts.reserve((size_t)len * 25));
+  DVB_CUDA(d->flags.reserve((size_t)len));
+  if (n_rows) DVB_CUDA(cudaMemcpyAsync(d->rows.p, rows, (size_t)n_rows * 8, cudaMemcpyHostToDevice, 0));
+  DVB_CUDA(cudaMemcpyAsync(d->ref.p, contig_bases + w0, (size_t)(w1 - w0), cudaMemcpyHostToDevice, 0));
+  int32_t* counts_dev = (int32_t*)d->counts.p;
+  uint8_t* indel_dev = (uint8_t*)d->counts.p + (size_t)len * 24;
+  st = dvb_allele_count_device(d, (const uint8_t*)d->ref.p, w0, w1 - w0, contig_n_bases, start, end, (const int64_t*)d->rows.p, n_rows,
+                               opt, counts_dev, indel_dev, (uint8_t*)d->flags.p, nullptr);
+  if (st != DVB_OK) return st;
+  DVB_CUDA(cudaMemcpyAsync(counts_host, counts_dev, (size_t)len * 24, cudaMemcpyDeviceToHost, 0));
+  DVB_CUDA(cudaMemcpyAsync(flags_host, d->flags.p, (size_t)len, cudaMemcpyDeviceToHost, 0));
+  DVB_CUDA(cudaStreamSynchronize(0));
+  return DVB_OK;
+}
+
+// Test access: the same walk, sink and flag function instantiated on the host (what the kernels must reproduce).
+int dvb_debug_allele_count_dense_host(const DvbBam* bam, const uint8_t* contig_bases, int64_t contig_n_bases, int64_t start, int64_t end,
+                                      const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* opt, int windowed,
+                                      int32_t* counts_host, uint8_t* flags_host) {
+  int st = CheckCountArgs(bam, contig_bases, contig_n_bases, start, end, rows, n_rows, opt);
+  if (st != DVB_OK) return st;
+  if (!counts_host || !flags_host) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_debug_allele_count_dense_host: null argument");
+  DvbReadTable t;
+  st = dvb_bam_table(bam, &t);
+  if (st != DVB_OK) return st;
+  const int64_t len = end - start;
+  memset(counts_host, 0, (size_t)len * 24);
+  std::vector<uint8_t> indel((size_t)len, 0);
+  dvb_allele::WalkParams p;
+  p.start = start;
+  p.end = end;
+  int64_t w0 = 0, w1 = contig_n_bases;
+  if (windowed) RefWindow(t, rows, n_rows, start, end, contig_n_bases, &w0, &w1);   // the window the device path uploads
+  p.contig = contig_bases + w0;
+  p.contig_origin = w0;
+  p.contig_avail = w1 - w0;
+  p.contig_len = contig_n_bases;
+  p.min_base_quality = opt->min_base_quality;
+  p.keep_legacy_behavior = opt->keep_legacy_behavior;
+  dvb_allele::DenseCounts c{counts_host, counts_host + len, counts_host + 5 * len, indel.data()};
+  for (int64_t i = 0; i < n_rows; ++i) {
+    const int64_t row = rows[i];
+    if (row < 0 || row >= t.n_reads) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "read row out of range");
+    if (t.mapq[row] < opt->min_mapping_quality) continue;
+    const int64_t s0 = t.seq_begin[row];
+    dvb_allele::ReadView r;
+    r.seq = t.bases + s0;
+    r.qual = t.quals + s0;
+    r.seq_len = (int)(t.seq_begin[row + 1] - s0);
+    r.cigar = t.cigar + t.cigar_begin[row];
+    r.n_cigar = (int)(t.cigar_begin[row + 1] - t.cigar_begin[row]);
+    r.pos = t.pos[row];
+    dvb_allele::DenseSink sink{c, r.seq};
+    dvb_allele::WalkRead(r, p, sink);
+  }
+  const dvb_allele::FlagParams f = MakeFlagParams(*opt);
+  for (int64_t q = 0; q < len; ++q) flags_host[q] = dvb_allele::FlagPosition(c, q, contig_bases[start + q], f);
+  return DVB_OK;
+}
 
 }  // extern "C"

@@ -364,6 +364,40 @@ int64_t dvb_debug_allele_counts(const DvbBam* bam, const uint8_t* contig_bases, 
                                 const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* options,
                                 const int32_t* candidate_positions, int32_t n_candidate_positions, char* out, int64_t cap);
 
+/* ---- allele counting on the device (SURVEY.md 8(f) "next" row #2, device half) ------------------------------------------------
+ * The reads of a DvbBam table are uploaded once (Structure of Arrays in HBM); dvb_allele_count_* runs AlleleCounter::Add
+ * (deepvariant/allelecounter.cc:880-978) with one thread per read and atomics into dense per-position counters, then flags the
+ * positions that can carry a candidate: bit 0 = a substitution allele passes the count / ratio tests of
+ * IsGoodAltAlleleWithReason (variant_calling_multisample.cc:175-196; 10 % slack on the ratio), bit 1 = an insertion or
+ * deletion is anchored there.  The flags are a superset of CallVariant's positions; dvb_candidates_at_positions takes the exact
+ * decision on the flagged sites from the reads that overlap them.
+ *   counts = int32[6 * len]: ref_supporting_read_count[len], substitution counts [4 * len] by read base A, C, G, T
+ *            (non-low-quality), other[len] = non-low-quality insertion / deletion / soft-clip entries;  flags = uint8[len]. */
+typedef struct DvbDeviceReads DvbDeviceReads;
+int dvb_device_reads_create(const DvbBam* bam, int device, DvbDeviceReads** out);     /* DVB_ERR_NO_DEVICE without a GPU */
+void dvb_device_reads_destroy(DvbDeviceReads* reads);
+int64_t dvb_device_reads_launch_count(const DvbDeviceReads* reads);
+/* Device pointers, asynchronous on `stream`: ref_dev[0] is absolute position ref_origin, ref_avail bases resident (must cover
+ * every read of rows_dev by one base on either side); indel_dev = uint8[len] scratch. */
+int dvb_allele_count_device(DvbDeviceReads* reads, const uint8_t* ref_dev, int64_t ref_origin, int64_t ref_avail, int64_t contig_n_bases,
+                            int64_t start, int64_t end, const int64_t* rows_dev, int64_t n_rows, const DvbCandidateOptions* options,
+                            int32_t* counts_dev, uint8_t* indel_dev, uint8_t* flags_dev, void* stream);
+/* Host pointers, synchronous: uploads the rows and the reference window, counts, flags, copies the results back. */
+int dvb_allele_count_host(DvbDeviceReads* reads, const DvbBam* bam, const uint8_t* contig_bases, int64_t contig_n_bases, int64_t start,
+                          int64_t end, const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* options, int32_t* counts_host,
+                          uint8_t* flags_host);
+/* dvb_candidates_in_region restricted to `emit_positions` (absolute, sorted): rows need only hold the reads that overlap
+ * those positions (by one base on either side, plus the allele-frequency context when it is requested). */
+int dvb_candidates_at_positions(const DvbBam* bam, const char* reference_name, const uint8_t* contig_bases, int64_t contig_n_bases,
+                                int64_t start, int64_t end, const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* options,
+                                const int32_t* candidate_positions, int32_t n_candidate_positions, const int32_t* emit_positions,
+                                int32_t n_emit_positions, DvbCandidates** out);
+/* Test access: the kernels' walk, sink and flag function instantiated on the host (windowed != 0: with the reference window
+ * the device path uploads instead of the whole contig). */
+int dvb_debug_allele_count_dense_host(const DvbBam* bam, const uint8_t* contig_bases, int64_t contig_n_bases, int64_t start, int64_t end,
+                                      const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* options, int windowed,
+                                      int32_t* counts_host, uint8_t* flags_host);
+
 /* ---- call_variants record I/O on the host ---------------------------------------------
  * Reader = call_variants.get_dataset (deepvariant/call_variants.py:449-538): the shards of the examples TFRecord
  * (gzip or plain) are read by `threads` workers and handed out in tf.data's deterministic interleave order

@@ -576,3 +576,86 @@ def test_make_examples_cli_generates_candidates_on_gpu(tmp_path, monkeypatch):
   monkeypatch.setattr(men.ExamplesGenerator, '_gpu', lambda self: OracleEncoder(pi.to_params(self.options.pic_options, height=self.pileup_image_height)))
   want_examples, want_cands = _run_cli(tmp_path, fa, bam_path, 'oracle')
   assert cands == want_cands and examples == want_examples          # CUDA encoder == CPU oracle, record for record
+
+
+# ---- the device pass, host-instantiated: dense counters, flags, exact calls on the flagged sites --------------------------------------
+def _dense_from_counter(sites):
+  """ref_count / substitution counts by base / other, derived from the host allele counter's entries (dvb_debug_allele_counts)."""
+  n = len(sites)
+  ref, subst, other, indel = np.zeros(n, np.int32), np.zeros((n, 4), np.int32), np.zeros(n, np.int32), np.zeros(n, np.uint8)
+  for i, s in enumerate(sites):
+    ref[i] = s['ref']
+    for bases, typ, low, *_ in s['alleles']:
+      if low:
+        continue
+      if typ == S:
+        subst[i, 'ACGT'.index(bases)] += 1
+      elif typ != R:
+        other[i] += 1
+        indel[i] |= typ in (I, D)
+  return ref, subst, other, indel
+
+
+def _check_device_pass_host_instantiation(table, ref, contig, start, end, rows, o):
+  sites = cand.debug_allele_counts(table, ref, contig, start, end, rows, o)
+  keys = [a[3] for s in sites for a in s['alleles']]
+  unique_keys = all(len({a[3] for a in s['alleles']}) == len(s['alleles']) for s in sites) and len(set(
+      table.names[int(table.name_begin[r]):int(table.name_begin[r + 1])] + bytes([table.read_number[r]]) for r in rows)) == len(rows)
+  want_ref, want_subst, want_other, want_indel = _dense_from_counter(sites)
+  for windowed in (False, True):
+    counts, flags = cand.debug_dense_counts_host(table, ref, contig, start, end, rows, o, windowed=windowed)
+    got_ref, got_subst, got_other = cand.split_dense_counts(counts, end - start)
+    np.testing.assert_array_equal(got_ref, want_ref)          # ref_supporting_read_count is a plain counter in the reference too
+    if unique_keys:                                           # a repeated read key is one map entry there, two counts here
+      np.testing.assert_array_equal(got_subst, want_subst)
+      np.testing.assert_array_equal(got_other, want_other)
+      canon = np.frombuffer(ref._contig(contig)[start:end], np.uint8)
+      canon = np.isin(canon, np.frombuffer(b'ACGT', np.uint8))
+      np.testing.assert_array_equal((flags & 2) != 0, (want_indel != 0) & canon)      # no candidate on a non-ACGT reference base
+  full = cand.candidates_in_region(table, ref, contig, start, end, o, rows=rows)
+  starts = {cand.canonical_call(r)['start'] for r in full.records}
+  flagged = set((np.nonzero(flags)[0] + start).tolist())
+  if unique_keys:
+    assert starts <= flagged                                  # the flags are a superset of the candidate sites
+  if starts <= flagged:
+    assert cand.candidates_at_flagged_positions(table, ref, contig, start, end, o, rows, flags).records == full.records
+  return len(starts), len(flagged), len(keys)
+
+
+@pytest.mark.parametrize('seed', range(8))
+def test_device_pass_on_the_host_equals_the_allele_counter_random(tmp_path, seed):
+  rng = random.Random(2000 + seed)
+  contig, reads = _random_case(rng, rng.choice([120, 300]))
+  if seed % 2 == 0:
+    for i, r in enumerate(reads):
+      r.fragment_name = f'u{i}'                               # unique keys: exact equality of every counter
+  ref = FakeRef([('chr1', contig)])
+  table = _table(tmp_path, reads, [('chr1', contig)])
+  o = cand.CandidateOptions(min_mapping_quality=rng.choice([0, 5]), vsc_min_count_snps=rng.choice([1, 2]), vsc_min_count_indels=rng.choice([1, 2]),
+                            small_model_vaf_context_window_size=rng.choice([0, 11]), keep_legacy_allele_counter_behavior=seed == 5, sample_name='s')
+  n_c, n_f, _ = _check_device_pass_host_instantiation(table, ref, 'chr1', rng.randrange(0, 50), rng.randrange(150, len(contig) + 1),
+                                                      np.arange(len(reads)), o)
+  assert n_c > 0 and n_f >= n_c
+
+
+def test_device_pass_on_the_host_on_the_golden_fixture():
+  fx = json.load(open(os.path.join(GOLDEN, 'candidates_golden_subset.json')))
+  contig = b'N' * fx['slice_start'] + fx['slice'].encode()
+  contig += b'N' * (fx['n_bases'] - len(contig))
+  ref = FakeRef([(fx['contig'], contig)])
+  table = bam.NativeBamTable(os.path.join(GOLDEN, 'candidates_golden_subset.bam'), bam.ReadRequirements(min_mapping_quality=5))
+  o = cand.CandidateOptions(sample_name=fx['sample_name'], small_model_vaf_context_window_size=51)
+  for part in fx['partitions']:
+    rows = cand.region_reads(table, fx['contig'], part['start'], part['end'])
+    n_c, n_f, _ = _check_device_pass_host_instantiation(table, ref, fx['contig'], part['start'], part['end'], rows, o)
+    assert n_c == len(part['expected']) and n_f < 0.1 * (part['end'] - part['start'])      # the pre-filter is selective
+
+
+def test_gpu_allele_counter_needs_a_device(tmp_path):
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip('a CUDA device is present')
+  from deepvariant_b200 import _lib
+  table = _table(tmp_path, [_read('r', 10, 'TCCGT', '5M')], [('chr1', CHR1)])
+  with pytest.raises(_lib.DvbError, match='no CUDA device'):
+    cand.GpuAlleleCounter(table)
