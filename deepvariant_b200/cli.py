@@ -1,16 +1,17 @@
-"""Command-line surface kept from the reference for the two stages this repository replaces
-(scripts/run_deepvariant.py:430-528 builds exactly these commands):
+"""Command-line surface kept from the reference (scripts/run_deepvariant.py:430-528 builds exactly these commands):
 
   python -m deepvariant_b200.cli make_examples --mode calling --ref REF --reads BAM --examples X@N.gz
-         --candidates CANDS.tfrecord.gz [--task i --regions chr:start-end --channel_list ... --pileup_image_width W
-         --pileup_image_height H --min_mapping_quality q --min_base_quality q --sort_by_haplotypes
-         --trim_reads_for_pileup --alt_aligned_pileup diff_channels --partition_size 1000]
+         [--candidates CANDS.tfrecord.gz (output) --task i --regions chr:start-end --channel_list ... --pileup_image_width W
+         --pileup_image_height H --min_mapping_quality q --min_base_quality q --partition_size 1000 --vsc_min_count_snps 2
+         --vsc_min_fraction_snps 0.12 --vsc_min_count_indels 2 --vsc_min_fraction_indels 0.06 --track_ref_reads --phase_reads
+         --sort_by_haplotypes --trim_reads_for_pileup --alt_aligned_pileup diff_channels --norealign_reads]
   python -m deepvariant_b200.cli call_variants --examples X@N.gz --outfile Y.tfrecord.gz --checkpoint M [--batch_size 1024]
-  python -m deepvariant_b200.cli run_deepvariant --model_type WGS --ref REF --reads BAM --candidates C --output_dir D
+  python -m deepvariant_b200.cli postprocess_variants --ref REF --infile Y.tfrecord.gz --outfile OUT.vcf[.gz]
+  python -m deepvariant_b200.cli run_deepvariant --model_type WGS --ref REF --reads BAM --output_dir D [--output_vcf OUT.vcf.gz]
 
-Candidate generation (allele counting, realignment, thresholds: make_examples_core.RegionProcessor) is upstream of the
-hot path and out of scope: `--candidates` takes the DeepVariantCall TFRecord the
-reference itself writes with `make_examples --candidates`.
+make_examples finds its candidates itself (allele counter + very-sensitive caller, deepvariant_b200/candidates.py; the local
+realigner is not implemented, i.e. --norealign_reads); `--candidates_in` (not a reference flag) imports a DeepVariantCall
+TFRecord written by another make_examples instead.
 """
 from __future__ import annotations
 
@@ -228,13 +229,39 @@ def call_variants(argv):
   return 0
 
 
+def postprocess_variants(argv):
+  """postprocess_variants --ref R.fa --infile call_variants_output.tfrecord.gz --outfile out.vcf[.gz] (deepvariant/postprocess_variants.py
+  flags :60-330; the single-sample VCF path - no gVCF)."""
+  ap = argparse.ArgumentParser('postprocess_variants')
+  ap.add_argument('--ref', required=True)
+  ap.add_argument('--infile', required=True)
+  ap.add_argument('--outfile', required=True)
+  ap.add_argument('--sample_name', default='')
+  ap.add_argument('--qual_filter', type=float, default=1.0)
+  ap.add_argument('--multi_allelic_qual_filter', type=float, default=1.0)
+  ap.add_argument('--multiallelic_mode', default='product', choices=['min', 'product'])
+  ap.add_argument('--only_keep_pass', action='store_true')
+  ap.add_argument('--disable_haplotype_resolution', action='store_true')
+  ap.add_argument('--group_variants', dest='group_variants', action='store_true', default=True)
+  ap.add_argument('--nogroup_variants', dest='group_variants', action='store_false')
+  a = ap.parse_args(argv)
+  from deepvariant_b200 import fasta, postprocess_variants as pp
+  ref = fasta.IndexedFastaReader(a.ref)
+  r = pp.postprocess_variants(a.infile, a.outfile, [(c, ref.n_bases(c)) for c in ref.contig_order], a.sample_name, a.qual_filter,
+                              a.multi_allelic_qual_filter, a.multiallelic_mode, a.only_keep_pass, a.disable_haplotype_resolution, a.group_variants)
+  print(f'postprocess_variants: {r}', file=sys.stderr)
+  return 0
+
+
 def run_deepvariant(argv):
   ap = argparse.ArgumentParser('run_deepvariant')
   ap.add_argument('--model_type', required=True, choices=sorted(MODEL_DEFAULTS))
   ap.add_argument('--ref', required=True)
   ap.add_argument('--reads', required=True)
   ap.add_argument('--candidates_in', default='')   # optional: DeepVariantCalls exported by another make_examples
-  ap.add_argument('--output_dir', required=True)
+  ap.add_argument('--output_dir', required=True)   # the reference's --intermediate_results_dir
+  ap.add_argument('--output_vcf', default='')       # scripts/run_deepvariant.py:84: when given, postprocess_variants runs too
+  ap.add_argument('--sample_name', default='')
   ap.add_argument('--regions', default='')
   ap.add_argument('--num_shards', type=int, default=1)
   ap.add_argument('--customized_model', default='random')
@@ -255,16 +282,26 @@ def run_deepvariant(argv):
         args += ['--' + flag, str(d[flag])]
     if a.regions:
       args += ['--regions', a.regions]
+    if a.sample_name:
+      args += ['--sample_name', a.sample_name]
     make_examples(args)
-  return call_variants(['--examples', examples, '--outfile', os.path.join(a.output_dir, 'call_variants_output.tfrecord.gz'),
-                        '--checkpoint', a.customized_model])
+  cvo = os.path.join(a.output_dir, 'call_variants_output.tfrecord.gz')
+  rc = call_variants(['--examples', examples, '--outfile', cvo, '--checkpoint', a.customized_model])
+  if rc or not a.output_vcf:
+    return rc
+  args = ['--ref', a.ref, '--infile', cvo, '--outfile', a.output_vcf]     # the shards call_variants wrote are found by name
+  if a.sample_name:
+    args += ['--sample_name', a.sample_name]
+  return postprocess_variants(args)
 
 
 def main():
-  if len(sys.argv) < 2 or sys.argv[1] not in ('make_examples', 'call_variants', 'run_deepvariant'):
+  stages = {'make_examples': make_examples, 'call_variants': call_variants, 'postprocess_variants': postprocess_variants,
+            'run_deepvariant': run_deepvariant}
+  if len(sys.argv) < 2 or sys.argv[1] not in stages:
     print(__doc__)
     return 2
-  return {'make_examples': make_examples, 'call_variants': call_variants, 'run_deepvariant': run_deepvariant}[sys.argv[1]](sys.argv[2:])
+  return stages[sys.argv[1]](sys.argv[2:])
 
 
 if __name__ == '__main__':

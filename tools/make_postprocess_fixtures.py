@@ -1,0 +1,22 @@
+"""Copies the reference's postprocess_variants golden pairs (CVO TFRecord in, VCF out) into tests/golden/ so that
+tests/test_postprocess.py runs where /root/reference is absent.  Run in the build container."""
+import gzip
+import os
+import shutil
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+T = '/root/reference/deepvariant/testdata/'
+OUT = os.path.join(ROOT, 'tests', 'golden')
+PAIRS = [
+    ('golden.postprocess_single_site_input-00000-of-00001.tfrecord.gz', 'golden.postprocess_single_site_output.vcf'),
+    ('golden.postprocess_single_site_input-00000-of-00001.tfrecord.gz', 'golden.postprocess_single_site_output.pass_only.vcf'),
+    ('golden.vcf_candidate_importer_postprocess_single_site_input-00000-of-00001.tfrecord.gz',
+     'golden.vcf_candidate_importer_postprocess_single_site_output.vcf'),
+    ('golden.postprocess_pacbio_input-00000-of-00001.tfrecord.gz', 'golden.postprocess_single_site_output_pacbio.vcf.gz'),
+]
+for src, vcf in PAIRS:
+  shutil.copy(T + src, os.path.join(OUT, src))
+  dst = os.path.join(OUT, vcf[:-3] if vcf.endswith('.gz') else vcf)
+  with (gzip.open if vcf.endswith('.gz') else open)(T + vcf, 'rt') as f, open(dst, 'w') as g:
+    g.write(f.read())
+  print(src, '->', os.path.basename(dst))
