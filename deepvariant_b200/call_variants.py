@@ -185,9 +185,9 @@ _MAX_WRITER_THREADS = 16   # call_variants.py:82
 
 
 def load_weights(checkpoint_path: str, in_channels: int) -> modeling.ModelWeights:
-  """Model weights for --checkpoint.  Supported here: a .npz written by modeling.save_npz, or
-  'random[:seed]' (architecture-correct random init; no Inception weights ship with the reference).
-  A TF SavedModel / ckpt (tensor-bundle) importer is not implemented (out of scope this round)."""
+  """Model weights for --checkpoint: a TensorFlow SavedModel directory or checkpoint prefix (tf_checkpoint.py reads the tensor
+  bundle without TensorFlow), a .npz written by modeling.save_npz, or 'random[:seed]' (architecture-correct random init; no
+  Inception weights ship with the reference)."""
   if checkpoint_path.startswith('random'):
     seed = int(checkpoint_path.split(':')[1]) if ':' in checkpoint_path else 0
     return modeling.random_weights(in_channels, seed)
@@ -196,7 +196,11 @@ def load_weights(checkpoint_path: str, in_channels: int) -> modeling.ModelWeight
     if w.in_channels != in_channels:
       raise ValueError(f'model has {w.in_channels} input channels, examples have {in_channels}')
     return w
-  raise NotImplementedError(f'unsupported checkpoint format: {checkpoint_path} (use a .npz from modeling.save_npz)')
+  from deepvariant_b200 import tf_checkpoint
+  if tf_checkpoint.is_tf_checkpoint(checkpoint_path):      # a released SavedModel directory or a model.ckpt / ckpt-N prefix
+    return tf_checkpoint.load_inception_weights(checkpoint_path, in_channels)
+  raise NotImplementedError(f'unsupported checkpoint format: {checkpoint_path} (a TensorFlow SavedModel directory / checkpoint prefix, '
+                            'a .npz from modeling.save_npz, or random[:seed])')
 
 
 def output_shard_paths(output_file: str, writer_threads: int = 0) -> List[str]:
