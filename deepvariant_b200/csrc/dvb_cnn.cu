@@ -617,6 +617,235 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair variant of the persistent kernel (tcgen05 cta_group::2, M = 256): DVB_CNN_PAIR=1, off by default until measured
+// ---------------------------------------------------------------------------------------------
+// Two CTAs of a 2-CTA cluster (one TPC) work on TWO neighbouring M tiles against the SAME N block.  Each CTA stages its own
+// 128-row A tile and only HALF of the weight block (block_n / 2 filter rows); the leader CTA (cluster rank 0) issues one
+// tcgen05.mma.cta_group::2 per K step with M = 256, N = block_n, which reads both CTAs' shared memory at the same offsets and
+// writes rows 0-127 of the accumulator into the leader's TMEM and rows 128-255 into the peer's.  Per SM the operand stream per MMA
+// drops from 4 KB + 32 N to 4 KB + 16 N bytes (the SS-mode ceiling N / (128 + N) becomes N / (128 + N / 2)).
+// Barriers: both CTAs' TMA loads complete on the LEADER's full barrier (cp.async.bulk.tensor ... cta_group::2 with the barrier
+// address of the even CTA); tcgen05.commit ... multicast::cluster releases the stage / publishes the accumulator in BOTH CTAs;
+// the epilogue threads of both CTAs arrive on the leader's tmem_empty barrier (mapa + remote arrive).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;    // cute::Sm100MmaPeerBitMask: shared::cluster address of the even CTA of a pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_smem, uint32_t ncols) {   // one warp in EACH CTA, same warp id, same offset
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_lohi_2cta(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once the issued MMAs have completed
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .b16 mask;\n"
+      "mov.b16 mask, 3;\n"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], mask;\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+// arrive on the barrier at this offset in the cluster's rank-0 CTA
+__device__ __forceinline__ void mbar_arrive_rank0(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
+struct PairArgs {
+  uint32_t idesc;        // M = 256
+  uint32_t b_half_bytes, b_half_stage;
+  int stages;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersistThreads, 1)
+conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_half, const ConvArgs p,
+                      const PairArgs q2, const int n_blocks, const int cout) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + q2.stages * p.a_stage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + q2.stages * q2.b_half_stage);
+  uint64_t* full_bar = bars;                       // [kMaxStages]   used in the leader
+  uint64_t* empty_bar = bars + kMaxStages;         // [kMaxStages]   both CTAs (multicast commit)
+  uint64_t* tmem_full = bars + 2 * kMaxStages;     // [2]            both CTAs (multicast commit)
+  uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;   // [2]         used in the leader: epilogue threads of both CTAs arrive
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  float* s_bias = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  for (int i = threadIdx.x; i < cout; i += kPersistThreads) s_bias[i] = p.bias[i];
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int m_pairs = (m_tiles + 1) >> 1;
+  const int total = m_pairs * n_blocks;             // pair tile t = nb * m_pairs + mp; CTA `rank` takes M tile 2 mp + rank
+  const int num_kb = p.kh * p.kw * p.cin_blocks;
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_b_half);
+    for (int s = 0; s < q2.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 2 * 32 * kPersistEpiWarps); }
+    fence_barrier_init();
+  } else if (warp == 1) {
+    tmem_alloc_2cta(tmem_slot, (uint32_t)p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();        // the peer's barriers and TMEM exist before anything remote touches them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs): own A tile + own half of the weight block, completing on the leader's barrier =====
+      int st = 0;
+      uint32_t ph = 0;
+      for (int t = pair_id; t < total; t += num_pairs) {
+        const int nb = t / m_pairs;
+        int m = 2 * (t - nb * m_pairs) + (int)rank;       // m >= m_tiles (odd tile count): every coordinate is out of bounds -> zeros
+        const int tw = m % p.tiles_w; m /= p.tiles_w;
+        const int th = m % p.tiles_h;
+        const int tn = m / p.tiles_h;
+        const int w0 = tw * p.Wt * p.stride - p.pad_w, h0 = th * p.Ht * p.stride - p.pad_h, n0 = tn * p.Nt;
+        for (int r = 0; r < p.kh; ++r) {
+          for (int s = 0; s < p.kw; ++s) {
+            for (int cb = 0; cb < p.cin_blocks; ++cb) {
+              mbar_wait(&empty_bar[st], ph ^ 1);
+              if (leader) mbar_arrive_expect_tx(&full_bar[st], 2u * (p.a_bytes + q2.b_half_bytes));
+              tma_load_4d_2sm(smem_a + st * p.a_stage, &map_a, &full_bar[st], cb * p.block_k, w0 + s, h0 + r, n0);
+              tma_load_3d_2sm(smem_b + st * q2.b_half_stage, &map_b_half, &full_bar[st], cb * p.block_k, r * p.kw + s,
+                              nb * p.block_n + (int)rank * (p.block_n >> 1));
+              if (++st == q2.stages) { st = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ===== MMA issuer: one thread of the leader CTA =====
+      const int mma_per_kb = p.block_k / 16;
+      const uint32_t hi = desc_hi(p.sbo_bytes, p.layout_type), idesc = q2.idesc;
+      const uint32_t a_lo0 = desc_lo(smem_u32(smem_a)), b_lo0 = desc_lo(smem_u32(smem_b));
+      const uint32_t a_inc = p.a_stage >> 4, b_inc = q2.b_half_stage >> 4;
+      const int stages = q2.stages;
+      int st = 0, buf = 0;
+      uint32_t ph = 0, buf_ph = 0, a_lo = a_lo0, b_lo = b_lo0;
+      for (int t = pair_id; t < total; t += num_pairs) {
+        mbar_wait(&tmem_empty[buf], buf_ph ^ 1);      // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(buf * p.block_n);
+        uint32_t acc = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[st], ph);
+          tc_fence_after();
+#pragma unroll 4
+          for (int k = 0; k < mma_per_kb; ++k) {
+            umma_f16_lohi_2cta(d, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, acc);
+            acc = 1;
+          }
+          umma_commit_2cta(&empty_bar[st]);
+          a_lo += a_inc; b_lo += b_inc;
+          if (++st == stages) { st = 0; ph ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
+        }
+        umma_commit_2cta(&tmem_full[buf]);
+        buf ^= 1;
+        if (buf == 0) buf_ph ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs): rows of this CTA's own M tile from its own TMEM =====
+    const int e = warp - 2;
+    const int q = warp & 3;
+    const int half = e >> 2;
+    const int row = q * 32 + lane;
+    const int w = row % p.Wt;
+    const int h = (row / p.Wt) % p.Ht;
+    const int n = row / (p.Wt * p.Ht);
+    const int chunks = p.block_n >> 4;
+    const int c_lo = half == 0 ? 0 : ((chunks + 1) >> 1) << 4;
+    const int c_n = half == 0 ? ((chunks + 1) >> 1) << 4 : p.block_n - c_lo;
+    int buf = 0;
+    uint32_t buf_ph = 0;
+    for (int t = pair_id; t < total; t += num_pairs) {
+      const int nb = t / m_pairs;
+      int m = 2 * (t - nb * m_pairs) + (int)rank;
+      const bool tile_exists = m < m_tiles;
+      const int tw = m % p.tiles_w; m /= p.tiles_w;
+      const int th = m % p.tiles_h;
+      const int tn = m / p.tiles_h;
+      const int w0 = tw * p.Wt, h0 = th * p.Ht, n0 = tn * p.Nt;
+      const bool valid = tile_exists && (n < p.Nt) && (w0 + w < p.Wout) && (h0 + h < p.Hout) && (n0 + n < p.n_images);
+      const size_t pix = (size_t)((size_t)(n0 + n) * p.Hout + (h0 + h)) * p.Wout + (w0 + w);
+      __half* dst = p.out + pix * p.out_cstride + p.out_coff + nb * p.block_n + c_lo;
+      mbar_wait(&tmem_full[buf], buf_ph);
+      tc_fence_after();
+      if (c_n > 0) {
+        if (p.n_segs)
+          epilogue_row_segs(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.block_n + c_lo), c_n, nb * p.block_n + c_lo,
+                            s_bias + nb * p.block_n + c_lo, p, pix, valid);
+        else
+          epilogue_row(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.block_n + c_lo), c_n, s_bias + nb * p.block_n + c_lo, dst,
+                       valid, p.relu);
+      }
+      tc_fence_before();
+      mbar_arrive_rank0(&tmem_empty[buf]);
+      buf ^= 1;
+      if (buf == 0) buf_ph ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();        // no CTA leaves (or frees TMEM) while its partner may still read its shared memory
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stride-1 k x k convolution on large feature maps: persistent, weights-resident, halo-reusing variant
 // ---------------------------------------------------------------------------------------------
 // What the tap-by-tap kernel above cannot hide on the wide stem layers (measured, B200):
@@ -1439,6 +1668,10 @@ struct ConvLaunch {
   bool flat;
   int pixels_per_image;
   bool persist;          // conv_gemm_persistent_kernel
+  bool pair;             // conv_gemm_pair_kernel (cta_group::2) instead of the persistent kernel
+  CUtensorMap map_b_half;
+  PairArgs pair_args;
+  int pair_smem;
   int n_blocks, cout;
 };
 struct HaloLaunch {
@@ -2024,6 +2257,23 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
         if (st) return st;
       }
     }
+    // CTA-pair variant (cta_group::2): same layers as the persistent kernel, when asked for
+    cl.pair = cl.persist && EnvInt("DVB_CNN_PAIR", 0) != 0 && a.block_n % 16 == 0;
+    if (cl.pair) {
+      PairArgs& q2 = cl.pair_args;
+      q2.idesc = (1u << 4) | ((uint32_t)(a.block_n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      q2.b_half_bytes = (uint32_t)(a.block_n / 2) * bk * 2;
+      q2.b_half_stage = (q2.b_half_bytes + 1023u) & ~1023u;
+      const int stage_bytes = (int)(a.a_stage + q2.b_half_stage);
+      q2.stages = std::max(2, std::min(kMaxStages, (EnvInt("DVB_PERSIST_SMEM_KB", 200) * 1024) / stage_bytes));
+      cl.pair_smem = q2.stages * stage_bytes + 1024 + 256 + o.cout * 4;
+      const cuuint64_t dims[3] = {(cuuint64_t)cin_store, (cuuint64_t)(o.kh * o.kw), (cuuint64_t)o.cout};
+      const cuuint64_t strides[2] = {(cuuint64_t)cin_store * 2, (cuuint64_t)o.kh * o.kw * cin_store * 2};
+      const cuuint32_t box[3] = {(cuuint32_t)bk, 1, (cuuint32_t)(a.block_n / 2)};
+      const cuuint32_t estr[3] = {1, 1, 1};
+      st = MakeMap(&cl.map_b_half, dw, 3, dims, strides, box, estr, bk);
+      if (st) return st;
+    }
     cl.grid = dim3(1, (unsigned)(o.cout / a.block_n), 1);
     net->steps.push_back(Step{0, (int)net->convs.size()});
     step_io.push_back({o.src, step_dsts});
@@ -2069,6 +2319,11 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
   net->flops_per_image = 2.0 * macs_total;
   int max_smem = 0;
   for (auto& c : net->convs) max_smem = std::max(max_smem, c.smem);
+  int max_pair = 0;
+  for (const ConvLaunch& c : net->convs)
+    if (c.pair) max_pair = std::max(max_pair, c.pair_smem);
+  if (max_pair && cudaFuncSetAttribute(conv_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_pair) != cudaSuccess)
+    return dvb::fail(DVB_ERR_CUDA, "cannot reserve %d bytes of shared memory (pair kernel)", max_pair);
   int max_persist = 0;
   for (auto& c : net->convs)
     if (c.persist) max_persist = std::max(max_persist, c.smem);
@@ -2148,7 +2403,11 @@ int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaSt
         a.tiles_w = (a.Wout + 127) / 128; a.tiles_h = 1; a.tiles_n = 1;
       }
       dim3 grid((unsigned)(a.tiles_w * a.tiles_h * a.tiles_n), c.grid.y, 1);
-      if (c.persist) {
+      if (c.pair) {
+        const long pairs = (((long)grid.x + 1) / 2) * c.n_blocks;
+        const unsigned ctas = 2u * (unsigned)std::min<long>(pairs, net->num_sms / 2);
+        conv_gemm_pair_kernel<<<ctas, kPersistThreads, c.pair_smem, s>>>(c.map_a, c.map_b_half, a, c.pair_args, c.n_blocks, c.cout);
+      } else if (c.persist) {
         const long total = (long)grid.x * c.n_blocks;
         conv_gemm_persistent_kernel<<<(unsigned)std::min<long>(total, net->num_sms), kPersistThreads, c.smem, s>>>(c.map_a, c.map_b, a, c.n_blocks,
                                                                                                                    c.cout);

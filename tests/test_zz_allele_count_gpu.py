@@ -99,3 +99,32 @@ def test_run_deepvariant_from_bam_to_vcf(tmp_path):
     fields = dict(zip(r[8].split(':'), r[9].split(':')))
     assert len(fields['PL'].split(',')) == 3 and 0 in [int(x) for x in fields['PL'].split(',')]
     assert int(fields['DP']) >= sum(int(x) for x in fields['AD'].split(',')) > 0
+
+
+def test_cta_pair_kernel_equals_persistent_kernel(monkeypatch):
+  """conv_gemm_pair_kernel (tcgen05 cta_group::2, M = 256; DVB_CNN_PAIR=1, off by default) against the persistent one-CTA
+  kernel on the same layers (DVB_CNN_PERSIST=2 routes every eligible layer through them): same operands, same K order, fp32
+  accumulation -> the same activations and probabilities.  An odd and an even number of M tiles are both exercised."""
+  import torch
+  from deepvariant_b200 import call_variants as cv, modeling
+  shape = (100, 221, 7)
+  w = modeling.random_weights(7, 11)
+  names = ['s4', 'mixed0', 'mixed3', 'mixed5', 'mixed8', 'mixed10']
+  for n in (5, 8):
+    g = torch.Generator().manual_seed(n)
+    imgs = torch.randint(0, 255, (n,) + shape, dtype=torch.uint8, generator=g).to('cuda:0')
+    outs = []
+    for pair in ('0', '1'):
+      monkeypatch.setenv('DVB_CNN_PERSIST', '2')
+      monkeypatch.setenv('DVB_CNN_PAIR', pair)
+      net = cv.GpuCnn(w, shape, device=0, max_batch=n)
+      probs = torch.empty((n, 3), dtype=torch.float32, device='cuda:0')
+      net.forward_device(imgs, probs)
+      torch.cuda.synchronize()
+      outs.append((probs.cpu().numpy(), {k: net.debug_tensor(k, n) for k in names}))
+      net.close()
+    (p0, t0), (p1, t1) = outs
+    for k in names:
+      scale = max(float(np.abs(t0[k]).max()), 1e-6)
+      assert float(np.abs(t0[k] - t1[k]).max()) / scale < 2e-3, k
+    assert float(np.abs(p0 - p1).max()) < 1e-3
