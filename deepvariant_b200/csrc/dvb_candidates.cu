@@ -132,16 +132,21 @@ struct Caller {
   // SumAlleleCounts(allele_count) (allelecounter.cc:78-116): non-low-quality entries grouped by (bases, type), in the
   // order of std::map<pair<string_view, AlleleType>>; the synthetic REFERENCE allele is irrelevant to selection.
   std::vector<SummedAllele> Sum(const Site& s) const {
-    std::map<std::pair<std::string, uint8_t>, SummedAllele> m;
+    std::vector<SummedAllele> out;        // a handful of distinct alleles per site: linear grouping, then one sort
+    const char* a = c->arena.data();
     for (const Entry& e : s.entries) {
       if (e.low_quality) continue;
-      auto key = std::make_pair(Bases(e.bases_off, e.bases_len), e.type);
-      auto it = m.find(key);
-      if (it == m.end()) m.emplace(key, SummedAllele{e.bases_off, e.bases_len, e.type, 1});
-      else ++it->second.count;
+      bool found = false;
+      for (SummedAllele& o : out)
+        if (o.type == e.type && o.len == e.bases_len && memcmp(a + o.off, a + e.bases_off, e.bases_len) == 0) { ++o.count; found = true; break; }
+      if (!found) out.push_back(SummedAllele{e.bases_off, e.bases_len, e.type, 1});
     }
-    std::vector<SummedAllele> out;
-    for (auto& kv : m) out.push_back(kv.second);
+    std::sort(out.begin(), out.end(), [a](const SummedAllele& x, const SummedAllele& y) {   // (bases, type) as std::map orders them
+      const int c = memcmp(a + x.off, a + y.off, std::min(x.len, y.len));
+      if (c != 0) return c < 0;
+      if (x.len != y.len) return x.len < y.len;
+      return x.type < y.type;
+    });
     return out;
   }
 
@@ -301,6 +306,7 @@ int dvb_candidate_positions(const DvbBam* bam, const uint8_t* contig_bases, int6
   Caller caller{&c, &c.opt};
   auto* res = new DvbCandidates();
   for (size_t i = 0; i < c.sites.size(); ++i) {
+    if (c.sites[i].entries.empty()) continue;                              // no read allele, no alt allele
     if (!Canonical((char)contig_bases[start + (int64_t)i])) continue;     // CallVariantPosition (:1075-1115)
     if (!caller.SelectAlts(c.sites[i]).empty()) res->positions_only.push_back((int32_t)(start + (int64_t)i));
   }
@@ -335,6 +341,7 @@ int dvb_candidates_at_positions(const DvbBam* bam, const char* reference_name, c
   const int n_sites = (int)c.sites.size();
   for (int i = 0; i < n_sites; ++i) {
     const Site& site = c.sites[(size_t)i];
+    if (site.entries.empty()) continue;                                     // no read allele, no alt allele
     const char ref_base = (char)contig_bases[start + i];
     if (n_emit_positions >= 0 && !std::binary_search(emit_positions, emit_positions + n_emit_positions, (int32_t)(start + i))) continue;
     if (!Canonical(ref_base)) continue;                                      // CallVariant (:1117-1130)
