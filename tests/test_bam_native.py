@@ -284,8 +284,7 @@ def test_region_packer_argument_errors(tmp_path):
     packing.pack_region_native(table, [im], 0, 0, 1000, 5, params)
 
 
-@pytest.mark.gpu
-def test_make_examples_cli_from_bam_file_matches_oracle(tmp_path):
+def _cli_from_bam_file_matches_oracle(tmp_path):
   """The make_examples stage CLI end to end on files: BAM (native decode -> table path) + indexed FASTA + candidates TFRecord
   -> examples TFRecord; every image/encoded equals the CPU oracle's encoding of the same candidate planned from the
   pure-Python reader's Read objects."""
@@ -344,3 +343,26 @@ def test_make_examples_cli_from_bam_file_matches_oracle(tmp_path):
     assert e['alt_allele_indices/encoded'][1][0] == alt_enc
     assert e['image/shape'][1] == [100, 221, 7]
     np.testing.assert_array_equal(np.frombuffer(e['image/encoded'][1][0], np.uint8).reshape(100, 221, 7), img)
+
+
+@pytest.mark.gpu
+def test_make_examples_cli_from_bam_file_matches_oracle(tmp_path):
+  _cli_from_bam_file_matches_oracle(tmp_path)
+
+
+def test_make_examples_cli_from_bam_file_cpu_plumbing(tmp_path, monkeypatch):
+  """The same flow with the encoder replaced by the CPU oracle: everything around the CUDA call (flags, --candidates_in,
+  partitions, native table path, serialisation) runs on the CPU suite too."""
+  import oracle_lib
+  from deepvariant_b200 import make_examples_native as men, pileup_image as pi
+
+  class OracleEncoder:
+    def __init__(self, params):
+      self.params = params
+      self.shape = (params.height, params.width, params.num_channels + params.num_alt_channels)
+
+    def encode_host(self, batch):
+      return oracle_lib.encode_batch(self.params, batch)
+
+  monkeypatch.setattr(men.ExamplesGenerator, '_gpu', lambda self: OracleEncoder(pi.to_params(self.options.pic_options, height=self.pileup_image_height)))
+  _cli_from_bam_file_matches_oracle(tmp_path)

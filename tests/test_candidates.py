@@ -567,17 +567,6 @@ def test_make_examples_cli_generates_candidates_cpu_plumbing(tmp_path, monkeypat
   _check_planted(examples, cands, genome, sites)
 
 
-@pytest.mark.gpu
-def test_make_examples_cli_generates_candidates_on_gpu(tmp_path, monkeypatch):
-  from deepvariant_b200 import make_examples_native as men, pileup_image as pi
-  fa, bam_path, genome, sites = _planted_case(tmp_path)
-  examples, cands = _run_cli(tmp_path, fa, bam_path, 'gpu')
-  _check_planted(examples, cands, genome, sites)
-  monkeypatch.setattr(men.ExamplesGenerator, '_gpu', lambda self: OracleEncoder(pi.to_params(self.options.pic_options, height=self.pileup_image_height)))
-  want_examples, want_cands = _run_cli(tmp_path, fa, bam_path, 'oracle')
-  assert cands == want_cands and examples == want_examples          # CUDA encoder == CPU oracle, record for record
-
-
 # ---- the device pass, host-instantiated: dense counters, flags, exact calls on the flagged sites --------------------------------------
 def _dense_from_counter(sites):
   """ref_count / substitution counts by base / other, derived from the host allele counter's entries (dvb_debug_allele_counts)."""

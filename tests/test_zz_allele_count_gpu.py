@@ -23,6 +23,35 @@ def _compare(counter, table, ref, contig, start, end, rows, o):
   return got_flags
 
 
+def test_make_examples_cli_generates_candidates_on_gpu(tmp_path, monkeypatch):
+  from deepvariant_b200 import make_examples_native as men, pileup_image as pi
+  fa, bam_path, genome, sites = tc._planted_case(tmp_path)
+  examples, cands = tc._run_cli(tmp_path, fa, bam_path, 'gpu')
+  tc._check_planted(examples, cands, genome, sites)
+  monkeypatch.setattr(men.ExamplesGenerator, '_gpu', lambda self: tc.OracleEncoder(pi.to_params(self.options.pic_options, height=self.pileup_image_height)))
+  want_examples, want_cands = tc._run_cli(tmp_path, fa, bam_path, 'oracle')
+  assert cands == want_cands and examples == want_examples          # CUDA encoder == CPU oracle, record for record
+
+
+def test_run_deepvariant_from_bam_to_vcf(tmp_path):
+  """run_deepvariant --ref --reads --output_vcf on the planted genome: candidates (host counter + caller), pileups (CUDA encoder),
+  genotype likelihoods (tcgen05 classifier, random-init weights), CallVariantsOutput shards, VCF."""
+  from deepvariant_b200 import cli
+  fa, bam_path, genome, sites = tc._planted_case(tmp_path)
+  out_dir, vcf = str(tmp_path / 'work'), str(tmp_path / 'out.vcf')
+  assert cli.run_deepvariant(['--model_type', 'WGS', '--ref', fa, '--reads', bam_path, '--output_dir', out_dir, '--output_vcf', vcf,
+                              '--regions', 'chr20:1001-5000', '--customized_model', 'random:3']) == 0
+  lines = [line.split('\t') for line in open(vcf).read().split('\n') if line and not line.startswith('##')]
+  assert lines[0][-1] == 'planted'
+  records = lines[1:]
+  assert [int(r[1]) - 1 for r in records] == sorted(sites.values())
+  for r in records:
+    assert r[8] == 'GT:GQ:DP:AD:VAF:PL' and r[6] in ('PASS', 'RefCall', 'NoCall', 'LowQual')
+    fields = dict(zip(r[8].split(':'), r[9].split(':')))
+    assert len(fields['PL'].split(',')) == 3 and 0 in [int(x) for x in fields['PL'].split(',')]
+    assert int(fields['DP']) >= sum(int(x) for x in fields['AD'].split(',')) > 0
+
+
 @pytest.mark.parametrize('seed', range(6))
 def test_device_counts_and_flags_equal_the_host_instantiation_random(tmp_path, seed):
   rng = random.Random(3000 + seed)
@@ -80,25 +109,6 @@ def test_one_launch_over_a_long_interval(tmp_path):
   flags = _compare(counter, table, ref, 'chr1', 0, n, np.arange(table.n_reads), cand.CandidateOptions())
   assert 0 < int((flags != 0).sum()) < n // 20
   counter.close()
-
-
-def test_run_deepvariant_from_bam_to_vcf(tmp_path):
-  """run_deepvariant --ref --reads --output_vcf on the planted genome: candidates (host counter + caller), pileups (CUDA encoder),
-  genotype likelihoods (tcgen05 classifier, random-init weights), CallVariantsOutput shards, VCF."""
-  from deepvariant_b200 import cli
-  fa, bam_path, genome, sites = tc._planted_case(tmp_path)
-  out_dir, vcf = str(tmp_path / 'work'), str(tmp_path / 'out.vcf')
-  assert cli.run_deepvariant(['--model_type', 'WGS', '--ref', fa, '--reads', bam_path, '--output_dir', out_dir, '--output_vcf', vcf,
-                              '--regions', 'chr20:1001-5000', '--customized_model', 'random:3']) == 0
-  lines = [line.split('\t') for line in open(vcf).read().split('\n') if line and not line.startswith('##')]
-  assert lines[0][-1] == 'planted'
-  records = lines[1:]
-  assert [int(r[1]) - 1 for r in records] == sorted(sites.values())
-  for r in records:
-    assert r[8] == 'GT:GQ:DP:AD:VAF:PL' and r[6] in ('PASS', 'RefCall', 'NoCall', 'LowQual')
-    fields = dict(zip(r[8].split(':'), r[9].split(':')))
-    assert len(fields['PL'].split(',')) == 3 and 0 in [int(x) for x in fields['PL'].split(',')]
-    assert int(fields['DP']) >= sum(int(x) for x in fields['AD'].split(',')) > 0
 
 
 def test_cta_pair_kernel_equals_persistent_kernel(monkeypatch):
