@@ -152,8 +152,8 @@ class NativeCandidates:
       _lib.check(lib.dvb_candidates_protos(handle, C.byref(data), C.byref(begin)))
       offs = np.frombuffer((C.c_char * (8 * (n + 1))).from_address(begin.value), dtype=np.int64).copy()
       blob = bytes((C.c_char * int(offs[-1])).from_address(data.value)) if n and offs[-1] else b''
-      self.records: List[bytes] = [blob[int(offs[i]):int(offs[i + 1])] for i in range(n)
-                                   if keep is None or keep[0] <= int(starts[i]) < keep[1]]
+      self.all_records: List[bytes] = [blob[int(offs[i]):int(offs[i + 1])] for i in range(n)]     # incl. the padding (phasing sees them)
+      self.records: List[bytes] = [r for i, r in enumerate(self.all_records) if keep is None or keep[0] <= int(starts[i]) < keep[1]]
     finally:
       lib.dvb_candidates_free(handle)
     self._parsed: Optional[List[protos.DeepVariantCall]] = None

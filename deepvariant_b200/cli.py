@@ -9,8 +9,8 @@
   python -m deepvariant_b200.cli postprocess_variants --ref REF --infile Y.tfrecord.gz --outfile OUT.vcf[.gz]
   python -m deepvariant_b200.cli run_deepvariant --model_type WGS --ref REF --reads BAM --output_dir D [--output_vcf OUT.vcf.gz]
 
-make_examples finds its candidates itself (allele counter + very-sensitive caller, deepvariant_b200/candidates.py; the local
-realigner is not implemented, i.e. --norealign_reads); `--candidates_in` (not a reference flag) imports a DeepVariantCall
+make_examples finds its candidates itself (allele counter + very-sensitive caller, deepvariant_b200/candidates.py) and phases the
+reads when --phase_reads is set (deepvariant_b200/direct_phasing.py); the local realigner is not implemented, i.e. --norealign_reads; `--candidates_in` (not a reference flag) imports a DeepVariantCall
 TFRecord written by another make_examples instead.
 """
 from __future__ import annotations
@@ -182,8 +182,6 @@ def make_examples(argv):
     if a.realign_reads:
       print('make_examples: the local realigner is not implemented; candidates come from the reads as aligned '
             '(--norealign_reads)', file=sys.stderr)
-    if a.phase_reads:
-      print('make_examples: read phasing is not implemented; the HP tag of the input is used when --parse_sam_aux_fields is set', file=sys.stderr)
     ref = fasta.IndexedFastaReader(a.ref)
     copts = cand.CandidateOptions(
         min_mapping_quality=a.min_mapping_quality, min_base_quality=a.min_base_quality,
@@ -206,7 +204,19 @@ def make_examples(argv):
         for rec in found.records:
           cand_writer.write(rec)
       if found.records:
-        examples_in(found.calls(), contig, p0, p1)
+        if a.phase_reads:
+          # direct phasing over the padded region's candidates (deepvariant/direct_phasing.cc); HP of every region read is
+          # replaced, as make_examples_core.py:2998-3111 does; the pileups then come from these Read objects.
+          from deepvariant_b200 import direct_phasing
+          reads = [reader.read(int(r)) for r in rows]
+          phases = direct_phasing.phase_reads([cand.canonical_call(r) for r in found.all_records], [r.key() for r in reads])
+          for r, ph in zip(reads, phases):
+            r.hp_values = [ph]
+          stats, _ = gen.write_examples_in_region(found.calls(), [reads], [0], 'main_sample', [0.0])
+          for key, val in stats.items():
+            totals[key] = totals.get(key, 0) + val
+        else:
+          examples_in(found.calls(), contig, p0, p1)
     if cand_writer is not None:
       cand_writer.close()
   gen.signal_shard_finished()
