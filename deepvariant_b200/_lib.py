@@ -139,6 +139,10 @@ class DvbCandidateOptions(C.Structure):
   ]
 
 
+class DvbSswAlignment(C.Structure):
+  _fields_ = [(n, C.c_int32) for n in ('sw_score', 'ref_begin', 'ref_end', 'query_begin', 'query_end', 'mismatches', 'cigar_len')]
+
+
 class DvbExampleBatchMeta(C.Structure):
   _fields_ = [('variant_blob', C.c_void_p), ('variant_begin', C.c_void_p), ('alt_blob', C.c_void_p), ('alt_begin', C.c_void_p)]
 
@@ -198,6 +202,8 @@ SYMBOLS = (
                                                     C.POINTER(DvbCandidateOptions), C.c_int, C.c_void_p, C.c_void_p]),
     ('dvb_debug_allele_counts', C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                             C.POINTER(DvbCandidateOptions), C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
+    ('dvb_ssw_align', C.c_int, [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                C.POINTER(DvbSswAlignment), C.c_char_p, C.c_int64]),
     ('dvb_crc32c', C.c_uint32, [C.c_char_p, C.c_size_t]),
     ('dvb_masked_crc32c', C.c_uint32, [C.c_char_p, C.c_size_t]),
     ('dvb_crc32c_portable', C.c_uint32, [C.c_char_p, C.c_size_t]),

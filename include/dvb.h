@@ -398,6 +398,16 @@ int dvb_debug_allele_count_dense_host(const DvbBam* bam, const uint8_t* contig_b
                                       const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* options, int windowed,
                                       int32_t* counts_host, uint8_t* flags_host);
 
+/* ---- Smith-Waterman with libssw's tie-breaking (deepvariant/realigner/ssw.h: Aligner(match, mismatch, gap_open, gap_extend),
+ * SetReferenceSequence, Align(query, Filter(), maskLen, &alignment)) - the aligner behind alt-aligned pileups and the realigner
+ * (SURVEY.md 8(f) "next" row #3).  Host code.  cigar_out receives the ssw_cpp cigar_string ("8S4=1X4=1D5=17S"), NUL-terminated,
+ * when cigar_cap > cigar_len. */
+typedef struct DvbSswAlignment {
+  int32_t sw_score, ref_begin, ref_end, query_begin, query_end, mismatches, cigar_len;
+} DvbSswAlignment;
+int dvb_ssw_align(const char* ref, int64_t ref_len, const char* query, int64_t query_len, int32_t match, int32_t mismatch, int32_t gap_open,
+                  int32_t gap_extend, DvbSswAlignment* out, char* cigar_out, int64_t cigar_cap);
+
 /* ---- call_variants record I/O on the host ---------------------------------------------
  * Reader = call_variants.get_dataset (deepvariant/call_variants.py:449-538): the shards of the examples TFRecord
  * (gzip or plain) are read by `threads` workers and handed out in tf.data's deterministic interleave order
