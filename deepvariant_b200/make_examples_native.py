@@ -59,6 +59,9 @@ class MakeExamplesOptions:
   reference_filename: str = ''
   trim_reads_for_pileup: bool = False
   stream_examples: bool = False
+  # realigner_options.aln_config (deepvariant/realigner/realigner.py:168-243 flag defaults): the aligner of the alt-aligned pileups
+  aln_config: Dict[str, float] = dataclasses.field(default_factory=lambda: dict(
+      match=4, mismatch=6, gap_open=8, gap_extend=2, kmer_size=32, max_num_of_mismatches=2, realignment_similarity_threshold=0.16934))
 
 
 # ---- small pure functions ---------------------------------------------------------------------
@@ -217,6 +220,7 @@ class ExamplePlan:
   variant: Variant
   alt_combination: List[str]
   variant_type: int
+  alt_specs: List[packing.ImageSpec] = dataclasses.field(default_factory=list)   # alt-aligned pileups: one per alt allele (<= 2)
 
 
 class ExamplesGenerator:
@@ -293,8 +297,53 @@ class ExamplesGenerator:
       for alt_combination in alt_allele_combinations(candidate, pic.multi_allelic_mode):
         spec = packing.image_spec_for(candidate, reference_bases, query, image_start_pos, alt_combination, pic,
                                       sort_positions=sort_positions)
-        plans.append(ExamplePlan(spec, variant, list(alt_combination), vtype))
+        plan = ExamplePlan(spec, variant, list(alt_combination), vtype)
+        if needs_alt:
+          plan.alt_specs = self.alt_aligned_specs(candidate, alt_combination, query, sort_positions, image_start_pos)
+        plans.append(plan)
     return plans
+
+  # -- alt-aligned pileups (CreateAltAlignedImages, make_examples_native.cc:553-626) -------------------------------------------
+  def create_haplotype(self, variant: Variant, alt: str) -> Tuple[str, int, int]:
+    """CreateHaplotype (:269-297): the reference window around the variant with `alt` in place of the reference allele."""
+    n_bases = self.ref_reader.n_bases(variant.reference_name)
+    var_end = variant.start + len(variant.reference_bases)
+    ref_start = max(variant.start - self.half_width, 0)
+    ref_end = min(n_bases, var_end + self.half_width)
+    prefix = self.ref_reader.query(variant.reference_name, ref_start, variant.start) if ref_start < variant.start else ''
+    suffix = self.ref_reader.query(variant.reference_name, var_end, ref_end) if ref_end > var_end else ''
+    return prefix + alt + suffix, ref_start, ref_end
+
+  def realign_reads_to_haplotype(self, haplotype: str, reads: Sequence[Read], contig: str, ref_start: int) -> List[Read]:
+    """RealignReadsToHaplotype (alt_aligned_pileup_lib.cc:278-313; kRefAlignMargin = 0, so the aligner's reference IS the haplotype):
+    forced alignment of every trimmed read; reads that cannot be placed come back empty."""
+    from deepvariant_b200 import fast_pass_aligner
+    aligner = fast_pass_aligner.FastPassAligner()
+    a = self.options.aln_config
+    aligner.set_options(kmer_size=a['kmer_size'], read_size=len(reads[0].aligned_sequence) if reads and len(reads[0].aligned_sequence) > 15 else 200,
+                        max_num_of_mismatches=a['max_num_of_mismatches'], realignment_similarity_threshold=a['realignment_similarity_threshold'],
+                        match=a['match'], mismatch=a['mismatch'], gap_open=a['gap_open'], gap_extend=a['gap_extend'], force_alignment=True)
+    aligner.reference = haplotype
+    aligner.region_position_in_chr = ref_start
+    aligner.ref_prefix_len = aligner.ref_suffix_len = 0
+    aligner.haplotypes = [haplotype]
+    return aligner.align_reads(reads)
+
+  def alt_aligned_specs(self, candidate: DeepVariantCall, alt_combination: Sequence[str], trimmed_reads: Sequence[Read],
+                        original_start_positions: Optional[Sequence[int]], image_start_pos: int) -> List[packing.ImageSpec]:
+    pic = self.options.pic_options
+    specs: List[packing.ImageSpec] = []
+    if len(alt_combination) > 2:
+      raise ValueError('an alt combination has at most two alleles')
+    for alt in alt_combination:
+      haplotype, ref_start, _ = self.create_haplotype(candidate.variant, alt)
+      if len(haplotype) < pic.width:
+        break
+      realigned = self.realign_reads_to_haplotype(haplotype, trimmed_reads, candidate.variant.reference_name, ref_start)
+      keep = [i for i, r in enumerate(realigned) if r.aligned_sequence]
+      specs.append(packing.image_spec_for(candidate, haplotype[:pic.width], [realigned[i] for i in keep], image_start_pos, alt_combination, pic,
+                                          sort_positions=[original_start_positions[i] for i in keep]))
+    return specs
 
   def plan_region_from_table(self, candidates: Sequence[DeepVariantCall], table, stats: Dict[str, int],
                              region: Optional[Tuple[str, int, int]] = None):
@@ -447,7 +496,13 @@ class ExamplesGenerator:
     enc = self._gpu()
     if not plans:
       return np.zeros((0,) + enc.shape, dtype=np.uint8)
-    return enc.encode_host(packing.pack_images([p.spec for p in plans], enc.params))
+    specs = [p.spec for p in plans]
+    alt_at = []                       # per plan: indices of its alt-aligned images in the batch
+    for p in plans:
+      alt_at.append(list(range(len(specs), len(specs) + len(p.alt_specs))))
+      specs += p.alt_specs
+    images = enc.encode_host(packing.pack_images(specs, enc.params))
+    return compose_alt_aligned(images, len(plans), alt_at, self.options.pic_options)
 
   def write_examples_in_region(self, candidates: Sequence[DeepVariantCall], reads_per_sample: Sequence[Sequence[Read]],
                                sample_order: Sequence[int], role: str,
@@ -469,6 +524,24 @@ class ExamplesGenerator:
       write_example_info_json(self._example_filenames[role], self.image_shape(),
                               example_info_channels(self.options.pic_options))
     self.writers = {}
+
+
+def compose_alt_aligned(images: np.ndarray, n_plans: int, alt_at: Sequence[Sequence[int]], pic) -> np.ndarray:
+  """FillPileupArray for diff_channels / base_channels (pileup_image_native.h:214-262): the two extra channels of an example are
+  channel 5 (base_differs_from_ref; 0 = read_base for base_channels) of its first and second alt-aligned pileup, row by row; with a
+  single alt-aligned pileup both channels carry it; without any they stay zero."""
+  out = images[:n_plans]
+  n_alt = sum(1 for c in pic.channels if c in pi.ALT_ALIGNED_PSEUDO_CHANNELS)
+  if n_alt != 2 or not any(alt_at):
+    return out
+  c0 = images.shape[-1] - 2
+  src = 5 if pic.alt_aligned_pileup == 'diff_channels' else 0
+  for i, idx in enumerate(alt_at):
+    if not idx:
+      continue
+    out[i, ..., c0] = images[idx[0], ..., src]
+    out[i, ..., c0 + 1] = images[idx[1] if len(idx) > 1 else idx[0], ..., src]
+  return out
 
 
 def partition_candidates(candidates: Sequence[DeepVariantCall], partition_size: int, region: Optional[Tuple[str, int, int]] = None):

@@ -85,15 +85,18 @@ def test_candidate_filter_and_low_quality_support():
 @pytest.mark.skipif(not os.path.isdir('/root/reference/deepvariant/testdata'), reason='reference testdata is only present in the build container')
 def test_pacbio_golden_examples_end_to_end():
   """candidates -> direct phasing -> trimmed, haplotype-sorted pileups == the reference's golden.pacbio_examples on the seven
-  computed channels, row order included, for all 401 examples (270 SNP examples are complete: their alt-aligned channels are zero)."""
+  computed channels, row order included, AND on the two alt-aligned diff channels, for all 401 examples (the golden's base_methylation
+  channel is all zero): the whole golden set is reproduced."""
   sys.path.insert(0, os.path.join(ROOT, 'tools'))
   import check_pacbio_end_to_end
   check_pacbio_end_to_end.main()
   s = json.load(open(os.path.join(ROOT, 'tests/golden/pacbio_end_to_end_report.json')))['stats']
   assert s['examples'] == s['golden_examples'] == s['images_equal_7_channels'] == s['haplotype_channel_equal'] == 401
   assert s['snp_examples'] == s['snp_alt_aligned_channels_zero_in_golden'] == 270 and s['methylation_channel_zero'] == 401
+  # alt-aligned pileups (FastPassAligner + Smith-Waterman against each alt haplotype): every indel example's two diff channels
+  assert s['indel_examples'] == s['indel_alt_aligned_channels_equal'] == 131 and s['whole_image_equal'] == 401
 
 
 def test_end_to_end_report_is_committed():
   s = json.load(open(os.path.join(ROOT, 'tests/golden/pacbio_end_to_end_report.json')))['stats']
-  assert s['images_equal_7_channels'] == s['golden_examples'] == 401
+  assert s['images_equal_7_channels'] == s['whole_image_equal'] == s['golden_examples'] == 401

@@ -6,7 +6,7 @@ For every 25-kb partition: region reads -> candidates over the padded region (cs
 (deepvariant_b200/direct_phasing.py) -> HP on the reads -> trimmed pileups through the planner + CPU oracle, compared with the golden
 images on the seven computed channels (read_base, base_quality, mapping_quality, strand, read_supports_variant,
 base_differs_from_ref, haplotype): whole image, row order included.  base_methylation (channel 7) is all zero in the golden; the two
-alt-aligned channels need the haplotype realigner and are compared only where the candidate needs none (SNPs).
+alt-aligned channels (haplotype realignment: FastPassAligner + Smith-Waterman) are compared too.
 Writes tests/golden/pacbio_end_to_end_report.json."""
 import json
 import os
@@ -38,8 +38,9 @@ def main():
   copts = cand.CandidateOptions(sample_name=cand.sample_name_from_bam(bam_path), min_mapping_quality=1, track_ref_reads=True,
                                 vsc_min_fraction_indels=0.12, partition_size=25000)
   pic = pi.default_options(pi.ReadRequirements(min_base_quality=10, min_mapping_quality=1))
-  pic.channels = pi.PILEUP_DEFAULT_CHANNELS + ['haplotype']
-  pic.num_channels = 7
+  pic.channels = pi.PILEUP_DEFAULT_CHANNELS + ['haplotype', 'diff_channels_alternate_allele_1', 'diff_channels_alternate_allele_2']   # the golden's base_methylation channel (all zero) is left out
+  pic.num_channels = len(pic.channels)
+  pic.alt_aligned_pileup = 'diff_channels'
   pic.width = 147
   pic.sort_by_haplotypes = True
   gen = men.ExamplesGenerator(men.MakeExamplesOptions(pic_options=pic, trim_reads_for_pileup=True), test_mode=True, ref_reader=ref)
@@ -59,7 +60,11 @@ def main():
     plans = gen.plan_region(found.calls(), reads, {})
     if not plans:
       continue
-    ours = oracle_lib.encode_batch(params, packing.pack_images([p.spec for p in plans], params))
+    specs, alt_at = [p.spec for p in plans], []
+    for p in plans:
+      alt_at.append(list(range(len(specs), len(specs) + len(p.alt_specs))))
+      specs += p.alt_specs
+    ours = men.compose_alt_aligned(oracle_lib.encode_batch(params, packing.pack_images(specs, params)), len(plans), alt_at, pic)
     for p, img in zip(plans, ours):
       idx = tuple(p.variant.alternate_bases.index(a) for a in p.alt_combination)
       g = golden.get((p.variant.start, idx))
@@ -72,6 +77,16 @@ def main():
       stats['haplotype_channel_equal'] += bool(np.array_equal(img[..., 6], g[..., 6]))
       stats['row_order_equal'] += bool(np.array_equal(img[..., :4], g[..., :4]))
       stats['methylation_channel_zero'] += bool(not g[..., 7].any())
+      alt_eq = bool(np.array_equal(img[..., 7:9], g[..., 8:10]))
+      stats['alt_aligned_channels_equal'] = stats.get('alt_aligned_channels_equal', 0) + alt_eq
+      stats['whole_image_equal'] = stats.get('whole_image_equal', 0) + (eq7 and alt_eq)
+      if p.variant_type != 1:
+        stats['indel_examples'] = stats.get('indel_examples', 0) + 1
+        stats['indel_alt_aligned_channels_equal'] = stats.get('indel_alt_aligned_channels_equal', 0) + alt_eq
+        if not alt_eq and len(mismatches) < 40:
+          d = (img[..., 7:9] != g[..., 8:10])
+          mismatches.append({'start': p.variant.start, 'alts': p.alt_combination, 'alt_channel_pixels_differ': int(d.sum()),
+                             'rows_differ': int(d.any(axis=(1, 2)).sum()), 'rows': int(sum(1 for r in range(5, 100) if g[r].any()))})
       if p.variant_type == 1:
         stats['snp_examples'] += 1
         stats['snp_alt_aligned_channels_zero_in_golden'] += bool(not g[..., 8:].any())
