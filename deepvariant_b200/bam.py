@@ -242,3 +242,49 @@ class NativeBamTable:
   def query(self, contig: str, start: int, end: int) -> List[Read]:
     rs = self.reads()
     return [rs[i] for i in self.query_indices(contig, start, end)]
+
+
+# ---- writer: reads that exist only in memory (realigned reads) become a BAM so that the native table / packer can take them ---------
+_SEQ_CODE = {c: i for i, c in enumerate('=ACMGRSVTWYHKDBN')}
+
+
+def _bgzf(payload: bytes, block: int = 0xff00) -> bytes:
+  import zlib
+  out = bytearray()
+  for i in list(range(0, len(payload), block)) + [None]:
+    ch = b'' if i is None else payload[i:i + block]
+    co = zlib.compressobj(1, zlib.DEFLATED, -15)
+    body = co.compress(ch) + co.flush()
+    out += struct.pack('<4BI2BH2BHH', 0x1f, 0x8b, 8, 4, 0, 0, 0xff, 6, ord('B'), ord('C'), 2, len(body) + 25)
+    out += body + struct.pack('<II', zlib.crc32(ch) & 0xffffffff, len(ch))
+  return bytes(out)
+
+
+def write_bam(path: str, reads, references, sample_name: str = '') -> None:
+  """references = [(name, length)].  Flags are rebuilt from the Read fields the reader fills (same decisions under
+  ReadRequirements); mate fields are written so that IsReadProperlyPlaced still passes; HP is kept as an aux tag."""
+  ref_index = {name: i for i, (name, _) in enumerate(references)}
+  text = ('@HD\tVN:1.6\n' + (f'@RG\tID:rg\tSM:{sample_name}\n' if sample_name else '')).encode()
+  out = bytearray(b'BAM\1' + struct.pack('<i', len(text)) + text + struct.pack('<i', len(references)))
+  for name, length in references:
+    out += struct.pack('<i', len(name) + 1) + name.encode() + b'\0' + struct.pack('<i', length)
+  for r in reads:
+    paired = r.number_reads == 2
+    flag = ((FPAIRED | (FREAD1 if r.read_number == 0 else 0x80)) if paired else 0) | (FPROPER if r.proper_placement else 0) | \
+        (FREVERSE if r.reverse_strand else 0) | (FSECONDARY if r.secondary_alignment else 0) | (FQCFAIL if r.failed_vendor_quality_checks else 0) | \
+        (FDUP if r.duplicate_fragment else 0) | (FSUPP if r.supplementary_alignment else 0)
+    rid = ref_index.get(r.reference_name, -1)
+    seq = r.aligned_sequence.decode()
+    packed = bytearray((len(seq) + 1) // 2)
+    for i, ch in enumerate(seq):
+      packed[i >> 1] |= _SEQ_CODE.get(ch, 15) << (4 if i % 2 == 0 else 0)
+    aux = b''
+    if r.hp_values:
+      aux = b'HPi' + struct.pack('<i', int(r.hp_values[0]))
+    body = struct.pack('<iiBBHHHiiii', rid, r.position, len(r.fragment_name) + 1, r.mapping_quality, 0, len(r.cigar), flag, len(seq),
+                       rid if paired else -1, r.position if paired else -1, r.fragment_length)
+    body += r.fragment_name.encode() + b'\0' + b''.join(struct.pack('<I', (ln << 4) | op) for op, ln in r.cigar) + bytes(packed) + \
+        bytes(r.aligned_quality) + aux
+    out += struct.pack('<i', len(body)) + body
+  with open(path, 'wb') as f:
+    f.write(_bgzf(bytes(out)))

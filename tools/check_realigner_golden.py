@@ -1,0 +1,87 @@
+"""Pins the local realigner (deepvariant_b200/realigner.py + fast_pass_aligner.py + csrc/dvb_ssw.cu) end to end against the reference's
+WGS goldens, which were made with --realign_reads (scripts/create_golden.sh:165-176): for every 1-kb partition of
+chr20:10,000,000-10,010,000 - region reads -> realigner -> candidates (golden.calling_candidates.tfrecord.gz, 78 DeepVariantCalls,
+every field) -> pileups (golden.calling_examples.tfrecord.gz, 84 images of 100 x 221 x 7 through the planner + CPU oracle).
+Writes tests/golden/realigner_golden_report.json."""
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import oracle_lib  # noqa: E402
+from deepvariant_b200 import bam, candidates as cand, fasta, packing, protos, realigner, tfrecord  # noqa: E402
+from deepvariant_b200 import make_examples_native as men  # noqa: E402
+from deepvariant_b200 import pileup_image as pi  # noqa: E402
+
+T = '/root/reference/deepvariant/testdata/'
+
+
+def main():
+  golden_c = [cand.canonical_call(r) for r in tfrecord.read_records(T + 'golden.calling_candidates.tfrecord.gz')]
+  golden_e = {}
+  for r in tfrecord.read_records(T + 'golden.calling_examples.tfrecord.gz'):
+    e = protos.parse_tf_example(r)
+    v = protos.parse_variant(e['variant/encoded'][1][0])
+    idx = tuple(protos.parse_alt_allele_indices(e['alt_allele_indices/encoded'][1][0]))
+    golden_e[(v.start, idx)] = np.frombuffer(e['image/encoded'][1][0], dtype=np.uint8).reshape(e['image/shape'][1])
+  bam_path = T + 'input/NA12878_S1.chr20.10_10p1mb.bam'
+  ref = fasta.IndexedFastaReader(T + 'input/ucsc.hg19.chr20.unittest.fasta.gz')
+  table = bam.NativeBamTable(bam_path, bam.ReadRequirements(min_mapping_quality=5))
+  copts = cand.CandidateOptions(sample_name=cand.sample_name_from_bam(bam_path), small_model_vaf_context_window_size=51)
+  pic = pi.default_options(pi.ReadRequirements(min_base_quality=10, min_mapping_quality=5))
+  pic.channels = list(pi.PILEUP_CHANNELS_WITH_INSERT_SIZE)
+  pic.num_channels = 7
+  gen = men.ExamplesGenerator(men.MakeExamplesOptions(pic_options=pic), test_mode=True, ref_reader=ref)
+  params = pi.to_params(pic)
+  rl = realigner.Realigner(ref)
+  refs = [(c, ref.n_bases(c)) for c in ref.contig_order]
+  ours_c, images, n_windows = [], {}, 0
+  with tempfile.TemporaryDirectory() as tmp:
+    for contig, s, e in cand.regions_to_process(refs, 1000, ('chr20', 9999999, 10010000)):
+      rows = cand.region_reads(table, contig, s, e)
+      reads = rl.realign_reads(table, contig, rows, (s, e))
+      path = os.path.join(tmp, f'r{s}.bam')
+      bam.write_bam(path, reads, refs)
+      t2 = bam.NativeBamTable(path, bam.ReadRequirements(min_mapping_quality=5))
+      assert t2.n_reads == len(reads), (t2.n_reads, len(reads))
+      rows2 = t2.query_indices(contig, s, e)
+      found = cand.candidates_in_region(t2, ref, contig, s, e, copts, rows=rows2)
+      ours_c += [cand.canonical_call(r) for r in found.records]
+      plans = gen.plan_region(found.calls(), [t2.read(int(i)) for i in rows2], {})
+      if plans:
+        imgs = oracle_lib.encode_batch(params, packing.pack_images([p.spec for p in plans], params))
+        for p, img in zip(plans, imgs):
+          images[(p.variant.start, tuple(p.variant.alternate_bases.index(a) for a in p.alt_combination))] = img
+      t2.close()
+  g_by = {(c['start'], c['ref'], tuple(c['alts'])): c for c in golden_c}
+  o_by = {(c['start'], c['ref'], tuple(c['alts'])): c for c in ours_c}
+  both = [k for k in g_by if k in o_by]
+  exact = [k for k in both if g_by[k] == o_by[k]]
+  partial = [{'start': k[0], 'differs_in': [f for f in g_by[k] if g_by[k][f] != o_by[k][f]]} for k in both if g_by[k] != o_by[k]]
+  img_eq = [k for k in golden_e if k in images and np.array_equal(images[k], golden_e[k])]
+  rows_total = rows_hit = 0
+  for k, g in golden_e.items():
+    if k in images:
+      g_rows = [g[r].tobytes() for r in range(5, 100) if g[r].any()]
+      o_rows = set(images[k][r].tobytes() for r in range(5, 100) if images[k][r].any())
+      rows_total += len(g_rows)
+      rows_hit += sum(1 for r in g_rows if r in o_rows)
+  report = {'golden_candidates': len(golden_c), 'ours_candidates': len(ours_c), 'same_site_and_alleles': len(both),
+            'candidates_identical_in_every_field': len(exact), 'candidates_partial': partial,
+            'golden_only': sorted(k[0] for k in g_by if k not in o_by), 'ours_only': sorted(k[0] for k in o_by if k not in g_by),
+            'golden_examples': len(golden_e), 'examples_planned': len(images), 'images_identical': len(img_eq),
+            'golden_read_rows': rows_total, 'golden_read_rows_reproduced': rows_hit}
+  with open(os.path.join(ROOT, 'tests/golden/realigner_golden_report.json'), 'w') as f:
+    json.dump(report, f, indent=1)
+  print(json.dumps({k: v for k, v in report.items() if not isinstance(v, list) or len(v) < 20}, indent=1))
+  for p in partial[:10]:
+    print(p)
+
+
+if __name__ == '__main__':
+  main()
