@@ -205,7 +205,10 @@ class FastPassAligner:
     coverage = [0] * len(haplotype)
     k = self.kmer_size
     for i in range(len(haplotype) - k + 1):
-      for read_id, read_pos in self.kmer_index.get(haplotype[i:i + k], ()):
+      hits = self.kmer_index.get(haplotype[i:i + k])
+      if hits is None:
+        continue                      # ... which also skips the zero-coverage test below (:181-184)
+      for read_id, read_pos in hits:
         target_start = max(0, i - read_pos)
         read = self.reads[read_id]
         if target_start + len(read) > len(haplotype):
