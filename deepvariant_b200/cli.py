@@ -9,8 +9,8 @@
   python -m deepvariant_b200.cli postprocess_variants --ref REF --infile Y.tfrecord.gz --outfile OUT.vcf[.gz]
   python -m deepvariant_b200.cli run_deepvariant --model_type WGS --ref REF --reads BAM --output_dir D [--output_vcf OUT.vcf.gz]
 
-make_examples finds its candidates itself (allele counter + very-sensitive caller, deepvariant_b200/candidates.py) and phases the
-reads when --phase_reads is set (deepvariant_b200/direct_phasing.py); the local realigner is not implemented, i.e. --norealign_reads; `--candidates_in` (not a reference flag) imports a DeepVariantCall
+make_examples realigns the reads (deepvariant_b200/realigner.py; --norealign_reads turns it off), finds its candidates itself (allele
+counter + very-sensitive caller, deepvariant_b200/candidates.py) and phases the reads when --phase_reads is set (direct_phasing.py); `--candidates_in` (not a reference flag) imports a DeepVariantCall
 TFRecord written by another make_examples instead.
 """
 from __future__ import annotations
@@ -26,7 +26,7 @@ MODEL_DEFAULTS = {   # scripts/run_deepvariant.py + model.example_info.json flag
     'WES': dict(channel_list='BASE_CHANNELS,insert_size', pileup_image_width=221),
     'PACBIO': dict(channel_list='BASE_CHANNELS,haplotype,supplementary_alignment', pileup_image_width=147, sort_by_haplotypes=True,
                    trim_reads_for_pileup=True, alt_aligned_pileup='diff_channels', min_mapping_quality=1, partition_size=25000,
-                   parse_sam_aux_fields=True, track_ref_reads=True, phase_reads=True, max_reads_per_partition=600,
+                   parse_sam_aux_fields=True, track_ref_reads=True, phase_reads=True, max_reads_per_partition=600, norealign_reads=True,
                    vsc_min_fraction_indels=0.12),       # flags_for_calling of the released PACBIO model's example_info.json
 }
 
@@ -56,7 +56,7 @@ MAKE_EXAMPLES_DEFAULTS = dict(
     alt_aligned_pileup='none', device=0, checkpoint='', checkpoint_json='', candidates='', candidates_in='', max_reads_per_partition=1500,
     sample_name='', vsc_min_count_snps=2, vsc_min_count_indels=2, vsc_min_fraction_snps=0.12, vsc_min_fraction_indels=0.06,
     vsc_min_fraction_multiplier=1.0, small_model_vaf_context_window_size=0, track_ref_reads=False, phase_reads=False,
-    keep_legacy_allele_counter_behavior=False, realign_reads=False)
+    keep_legacy_allele_counter_behavior=False, realign_reads=True)      # --realign_reads defaults to true (make_examples_options.py:229)
 
 
 def model_example_info_json_path(checkpoint: str, checkpoint_json: str = '') -> str:
@@ -179,9 +179,12 @@ def make_examples(argv):
   else:
     # Candidate generation (csrc/dvb_candidates.cu): allele counter + very-sensitive caller over each region of this task,
     # exactly the regions `--task i` of N gets in the reference (regions_to_process, make_examples_core.py:799-888).
+    rl = None
+    if a.realign_reads and a.phase_reads:
+      raise NotImplementedError('--realign_reads together with --phase_reads (the PACBIO / ONT models run with --norealign_reads)')
     if a.realign_reads:
-      print('make_examples: the local realigner is not implemented; candidates come from the reads as aligned '
-            '(--norealign_reads)', file=sys.stderr)
+      from deepvariant_b200 import realigner
+      rl = realigner.Realigner(fasta.IndexedFastaReader(a.ref))
     ref = fasta.IndexedFastaReader(a.ref)
     copts = cand.CandidateOptions(
         min_mapping_quality=a.min_mapping_quality, min_base_quality=a.min_base_quality,
@@ -197,6 +200,31 @@ def make_examples(argv):
     for contig, p0, p1 in cand.regions_to_process(contigs, a.partition_size, region, a.task, n_shards):
       rows = cand.region_reads(reader, contig, p0, p1, copts.max_reads_per_partition, copts.random_seed)
       if not len(rows):
+        continue
+      if rl is not None:
+        # --realign_reads: window selection, de Bruijn assembly, FastPassAligner (deepvariant_b200/realigner.py); the realigned reads
+        # replace the region's reads for candidate generation AND pileups, as in_memory_sam_reader.replace_reads does
+        # (make_examples_core.py:2290-2300).  They go through a scratch BAM so that the native table / packer can take them.
+        import tempfile
+        realigned = rl.realign_reads(reader, contig, rows, (p0, p1))
+        with tempfile.TemporaryDirectory() as tmp:
+          scratch = os.path.join(tmp, 'realigned.bam')
+          bam.write_bam(scratch, realigned, [(c, ref.n_bases(c)) for c in ref.contig_order])
+          region_table = bam.NativeBamTable(scratch, bam.ReadRequirements(min_mapping_quality=a.min_mapping_quality), parse_aux=a.parse_sam_aux_fields)
+        region_rows = region_table.query_indices(contig, p0, p1)
+        found = cand.candidates_in_region(region_table, ref, contig, p0, p1, copts, rows=region_rows, padding_pct=20 if a.phase_reads else 0)
+        totals['n_candidates'] = totals.get('n_candidates', 0) + len(found.records)
+        if cand_writer is not None:
+          for rec in found.records:
+            cand_writer.write(rec)
+        if found.records:
+          if table_path and not a.phase_reads:
+            stats, _ = gen.write_examples_in_region_from_table(found.calls(), region_table, 'main_sample', (contig, p0, p1))
+          else:
+            stats, _ = gen.write_examples_in_region(found.calls(), [[region_table.read(int(i)) for i in region_rows]], [0], 'main_sample', [0.0])
+          for key, val in stats.items():
+            totals[key] = totals.get(key, 0) + val
+        region_table.close()
         continue
       found = cand.candidates_in_region(reader, ref, contig, p0, p1, copts, rows=rows, padding_pct=20 if a.phase_reads else 0)
       totals['n_candidates'] = totals.get('n_candidates', 0) + len(found.records)
@@ -284,7 +312,7 @@ def run_deepvariant(argv):
             str(task), '--channel_list', d['channel_list'], '--pileup_image_width', str(d['pileup_image_width'])]
     if a.candidates_in:
       args += ['--candidates_in', a.candidates_in]
-    for flag in ('sort_by_haplotypes', 'trim_reads_for_pileup', 'parse_sam_aux_fields', 'track_ref_reads', 'phase_reads'):
+    for flag in ('sort_by_haplotypes', 'trim_reads_for_pileup', 'parse_sam_aux_fields', 'track_ref_reads', 'phase_reads', 'norealign_reads'):
       if d.get(flag):
         args.append('--' + flag)
     for flag in ('alt_aligned_pileup', 'min_mapping_quality', 'partition_size', 'max_reads_per_partition', 'vsc_min_fraction_indels'):
