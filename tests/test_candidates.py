@@ -527,12 +527,13 @@ def _planted_case(tmp_path):
   return str(fa), bam_path, genome, dict(snp_het=snp_het, snp_hom=snp_hom, ins=ins, dele=dele)
 
 
-def _run_cli(tmp_path, fa, bam_path, tag):
+def _run_cli(tmp_path, fa, bam_path, tag, realign=False):
   from deepvariant_b200 import cli
   ex = str(tmp_path / f'{tag}.examples.tfrecord@1.gz')
   cands = str(tmp_path / f'{tag}.candidates.tfrecord.gz')
   assert cli.make_examples(['--mode', 'calling', '--ref', fa, '--reads', bam_path, '--examples', ex, '--candidates', cands,
-                            '--channel_list', 'BASE_CHANNELS,insert_size', '--regions', 'chr20:1001-5000', '--norealign_reads']) == 0
+                            '--channel_list', 'BASE_CHANNELS,insert_size', '--regions', 'chr20:1001-5000',
+                            '--realign_reads' if realign else '--norealign_reads']) == 0
   from deepvariant_b200 import tfrecord
   return (list(tfrecord.read_records(str(tmp_path / f'{tag}.examples.tfrecord-00000-of-00001.gz'))), list(tfrecord.read_records(cands)))
 
@@ -564,6 +565,10 @@ def test_make_examples_cli_generates_candidates_cpu_plumbing(tmp_path, monkeypat
   monkeypatch.setattr(men.ExamplesGenerator, '_gpu', lambda self: OracleEncoder(pi.to_params(self.options.pic_options, height=self.pileup_image_height)))
   fa, bam_path, genome, sites = _planted_case(tmp_path)
   examples, cands = _run_cli(tmp_path, fa, bam_path, 'cpu')
+  _check_planted(examples, cands, genome, sites)
+  # with the realigner (the default): windows around the planted indels are assembled and their reads realigned; the planted
+  # variants are clean, so the same four candidates come out, through the scratch-BAM / region-table path
+  examples, cands = _run_cli(tmp_path, fa, bam_path, 'cpu_realigned', realign=True)
   _check_planted(examples, cands, genome, sites)
 
 
