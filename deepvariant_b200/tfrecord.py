@@ -88,8 +88,16 @@ class Writer:
     self.close()
 
 
+def _open_for_reading(path: str):
+  """gzip by content, not by name: the reference's sharded files are called name.tfrecord.gz-0000i-of-0000N (nucleus reads them
+  with compression_type GZIP because '.gz' occurs in the name, third_party/nucleus/io/tfrecord.py:88-93)."""
+  with open(path, 'rb') as f:
+    magic = f.read(2)
+  return gzip.open(path, 'rb') if magic == b'\x1f\x8b' else open(path, 'rb')
+
+
 def read_records(path: str, check_crc: bool = False) -> Iterator[bytes]:
-  with _open(path, 'rb') as f:
+  with _open_for_reading(path) as f:
     while True:
       header = f.read(12)
       if not header:

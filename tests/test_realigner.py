@@ -78,6 +78,8 @@ def test_wgs_goldens_made_with_the_realigner_are_reproduced_end_to_end():
   assert r['golden_candidates'] == r['ours_candidates'] == r['candidates_identical_in_every_field'] == 78
   assert r['golden_examples'] == r['examples_planned'] == r['images_identical'] == 84
   assert r['golden_read_rows'] == r['golden_read_rows_reproduced'] == 4309
+  # the tf.Examples themselves (assertDeepVariantExamplesEqual: every feature decoded), their order, and --task i of 3 sharding
+  assert r['tf_examples_equal_feature_by_feature'] == 84 and r['example_order_equal'] and r['sharded_goldens_equal_task_by_task'] == [True] * 3
 
 
 def test_realigner_report_is_committed():

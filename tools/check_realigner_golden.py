@@ -21,14 +21,40 @@ from deepvariant_b200 import pileup_image as pi  # noqa: E402
 T = '/root/reference/deepvariant/testdata/'
 
 
+def decoded_features(e: dict) -> dict:
+  """The comparison of assertDeepVariantExamplesEqual (deepvariant/make_examples_test.py:1047-1066): every feature decoded, the two
+  serialized protos compared as parsed messages."""
+  out = {}
+  for k, (kind, vals) in e.items():
+    if k == 'variant/encoded':
+      c = cand.canonical_call(protos.f_bytes(1, vals[0]))
+      out[k] = {f: c[f] for f in ('ref', 'alts', 'start', 'end', 'contig', 'info', 'call_set_name', 'genotype')}
+    elif k == 'alt_allele_indices/encoded':
+      out[k] = protos.parse_alt_allele_indices(vals[0])
+    elif kind == 'bytes':
+      out[k] = [bytes(v) for v in vals]
+    else:
+      out[k] = list(vals)
+  return out
+
+
 def main():
   golden_c = [cand.canonical_call(r) for r in tfrecord.read_records(T + 'golden.calling_candidates.tfrecord.gz')]
-  golden_e = {}
+  golden_e, golden_features, golden_order = {}, {}, []
   for r in tfrecord.read_records(T + 'golden.calling_examples.tfrecord.gz'):
     e = protos.parse_tf_example(r)
     v = protos.parse_variant(e['variant/encoded'][1][0])
     idx = tuple(protos.parse_alt_allele_indices(e['alt_allele_indices/encoded'][1][0]))
     golden_e[(v.start, idx)] = np.frombuffer(e['image/encoded'][1][0], dtype=np.uint8).reshape(e['image/shape'][1])
+    golden_features[(v.start, idx)] = decoded_features(e)
+    golden_order.append((v.start, idx))
+  golden_shards = []
+  for i in range(3):
+    keys = []
+    for r in tfrecord.read_records(T + f'golden.calling_examples.tfrecord.gz-0000{i}-of-00003'):
+      e = protos.parse_tf_example(r)
+      keys.append((protos.parse_variant(e['variant/encoded'][1][0]).start, tuple(protos.parse_alt_allele_indices(e['alt_allele_indices/encoded'][1][0]))))
+    golden_shards.append(keys)
   bam_path = T + 'input/NA12878_S1.chr20.10_10p1mb.bam'
   ref = fasta.IndexedFastaReader(T + 'input/ucsc.hg19.chr20.unittest.fasta.gz')
   table = bam.NativeBamTable(bam_path, bam.ReadRequirements(min_mapping_quality=5))
@@ -41,6 +67,7 @@ def main():
   rl = realigner.Realigner(ref)
   refs = [(c, ref.n_bases(c)) for c in ref.contig_order]
   ours_c, images, n_windows = [], {}, 0
+  ours_features, ours_order, region_keys = {}, [], []
   with tempfile.TemporaryDirectory() as tmp:
     for contig, s, e in cand.regions_to_process(refs, 1000, ('chr20', 9999999, 10010000)):
       rows = cand.region_reads(table, contig, s, e)
@@ -55,8 +82,16 @@ def main():
       plans = gen.plan_region(found.calls(), [t2.read(int(i)) for i in rows2], {})
       if plans:
         imgs = oracle_lib.encode_batch(params, packing.pack_images([p.spec for p in plans], params))
+        keys = []
         for p, img in zip(plans, imgs):
-          images[(p.variant.start, tuple(p.variant.alternate_bases.index(a) for a in p.alt_combination))] = img
+          key = (p.variant.start, tuple(p.variant.alternate_bases.index(a) for a in p.alt_combination))
+          images[key] = img
+          ours_features[key] = decoded_features(protos.parse_tf_example(gen.encode_example(p, img, {})))
+          ours_order.append(key)
+          keys.append(key)
+        region_keys.append(keys)
+      else:
+        region_keys.append([])
       t2.close()
   g_by = {(c['start'], c['ref'], tuple(c['alts'])): c for c in golden_c}
   o_by = {(c['start'], c['ref'], tuple(c['alts'])): c for c in ours_c}
@@ -71,7 +106,11 @@ def main():
       o_rows = set(images[k][r].tobytes() for r in range(5, 100) if images[k][r].any())
       rows_total += len(g_rows)
       rows_hit += sum(1 for r in g_rows if r in o_rows)
-  report = {'golden_candidates': len(golden_c), 'ours_candidates': len(ours_c), 'same_site_and_alleles': len(both),
+  # --task i of 3: region j goes to task j mod 3 (regions_to_process), records in region order within a shard
+  shards_equal = [sum((region_keys[j] for j in range(i, len(region_keys), 3)), []) == golden_shards[i] for i in range(3)]
+  features_equal = sum(1 for k in golden_features if ours_features.get(k) == golden_features[k])
+  report = {'tf_examples_equal_feature_by_feature': features_equal, 'example_order_equal': ours_order == golden_order,
+            'sharded_goldens_equal_task_by_task': shards_equal, 'golden_candidates': len(golden_c), 'ours_candidates': len(ours_c), 'same_site_and_alleles': len(both),
             'candidates_identical_in_every_field': len(exact), 'candidates_partial': partial,
             'golden_only': sorted(k[0] for k in g_by if k not in o_by), 'ours_only': sorted(k[0] for k in o_by if k not in g_by),
             'golden_examples': len(golden_e), 'examples_planned': len(images), 'images_identical': len(img_eq),
