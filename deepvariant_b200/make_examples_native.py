@@ -230,8 +230,6 @@ class ExamplesGenerator:
     self.options = options
     pic = options.pic_options
     self.half_width = (pic.width - 1) // 2
-    if pic.alt_aligned_pileup in ('rows', 'single_row'):
-      raise NotImplementedError("alt_aligned_pileup 'rows' / 'single_row' is not implemented (SURVEY 8f)")
     if len(options.sample_options) != 1:
       raise NotImplementedError('multi-sample pileups are out of scope (SURVEY 8, Appendix A)')
     sample = options.sample_options[0]
@@ -456,7 +454,9 @@ class ExamplesGenerator:
   # -- serialisation (host) ----------------------------------------------------------------------
   def image_shape(self) -> List[int]:
     pic = self.options.pic_options
-    return [self.pileup_image_height, pic.width, len(pic.channels)]
+    # CalculatePileupImageHeight (pileup_image_native.cc:218-240): 'rows' stacks the two alt-aligned pileups under the main one
+    sections = {'rows': 3, 'single_row': 2}.get(pic.alt_aligned_pileup, 1)
+    return [self.pileup_image_height * sections, pic.width, len(pic.channels)]
 
   def encode_example(self, plan: ExamplePlan, image: np.ndarray, stats: Dict[str, int]) -> bytes:
     """EncodeExample (make_examples_native.cc:388-474), calling mode (no label)."""
@@ -502,7 +502,7 @@ class ExamplesGenerator:
       alt_at.append(list(range(len(specs), len(specs) + len(p.alt_specs))))
       specs += p.alt_specs
     images = enc.encode_host(packing.pack_images(specs, enc.params))
-    return compose_alt_aligned(images, len(plans), alt_at, self.options.pic_options)
+    return compose_alt_aligned(images, len(plans), alt_at, self.options.pic_options, [p.alt_combination for p in plans])
 
   def write_examples_in_region(self, candidates: Sequence[DeepVariantCall], reads_per_sample: Sequence[Sequence[Read]],
                                sample_order: Sequence[int], role: str,
@@ -526,11 +526,29 @@ class ExamplesGenerator:
     self.writers = {}
 
 
-def compose_alt_aligned(images: np.ndarray, n_plans: int, alt_at: Sequence[Sequence[int]], pic) -> np.ndarray:
-  """FillPileupArray for diff_channels / base_channels (pileup_image_native.h:214-262): the two extra channels of an example are
+def compose_alt_aligned(images: np.ndarray, n_plans: int, alt_at: Sequence[Sequence[int]], pic,
+                        alt_combinations: Optional[Sequence[Sequence[str]]] = None) -> np.ndarray:
+  """FillPileupArray (pileup_image_native.h:214-308).  diff_channels / base_channels: the two extra channels of an example are
   channel 5 (base_differs_from_ref; 0 = read_base for base_channels) of its first and second alt-aligned pileup, row by row; with a
-  single alt-aligned pileup both channels carry it; without any they stay zero."""
+  single alt-aligned pileup both channels carry it; without any they stay zero.  rows / single_row: the alt-aligned pileups
+  (GetAltImageRowIndices, pileup_image_native.cc:192-208: both; or the one of the longer alt) are stacked under the main pileup,
+  zeros where there is none."""
   out = images[:n_plans]
+  if pic.alt_aligned_pileup in ('rows', 'single_row'):
+    h = images.shape[1]
+    sections = 3 if pic.alt_aligned_pileup == 'rows' else 2
+    stacked = np.zeros((n_plans, h * sections) + images.shape[2:], dtype=images.dtype)
+    stacked[:, :h] = out
+    for i, idx in enumerate(alt_at):
+      if pic.alt_aligned_pileup == 'rows':
+        wanted = [0, 1]
+      else:
+        combo = alt_combinations[i] if alt_combinations is not None else []
+        wanted = [1] if len(combo) == 2 and len(combo[1]) > len(combo[0]) else [0]
+      for j, w in enumerate(wanted):
+        if w < len(idx):
+          stacked[i, h * (j + 1):h * (j + 2)] = images[idx[w]]
+    return stacked
   n_alt = sum(1 for c in pic.channels if c in pi.ALT_ALIGNED_PSEUDO_CHANNELS)
   if n_alt != 2 or not any(alt_at):
     return out

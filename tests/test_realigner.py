@@ -85,3 +85,30 @@ def test_wgs_goldens_made_with_the_realigner_are_reproduced_end_to_end():
 def test_realigner_report_is_committed():
   r = json.load(open(os.path.join(ROOT, 'tests/golden/realigner_golden_report.json')))
   assert r['candidates_identical_in_every_field'] == 78 and r['images_identical'] == 84
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/deepvariant/testdata'), reason='reference testdata is only present in the build container')
+def test_wgs_alt_aligned_goldens_diff_channels_and_rows():
+  """golden.alt_aligned_pileup_{diff_channels,rows}_examples: 49 of 49 images each (100 x 221 x 8 / 300 x 221 x 6), realigner on."""
+  sys.path.insert(0, os.path.join(ROOT, 'tools'))
+  import check_alt_aligned_wgs_golden
+  check_alt_aligned_wgs_golden.main()
+  for r in json.load(open(os.path.join(ROOT, 'tests/golden/alt_aligned_wgs_report.json'))):
+    assert r['compared'] == r['images_identical'] == r['golden_examples'] == 49 and r['of_those_identical'] == r['examples_with_alt_aligned_pileups'] == 4
+
+
+def test_rows_and_single_row_composition():
+  import numpy as np
+  from deepvariant_b200 import make_examples_native as men, pileup_image as pi
+  pic = pi.default_options()
+  imgs = np.arange(5 * 4 * 3 * 2, dtype=np.uint8).reshape(5, 4, 3, 2)       # 2 plans + 3 alt-aligned pileups, H = 4
+  pic.alt_aligned_pileup = 'rows'
+  out = men.compose_alt_aligned(imgs, 2, [[2, 3], [4]], pic, [['A', 'AT'], ['G']])
+  assert out.shape == (2, 12, 3, 2)
+  assert np.array_equal(out[0, :4], imgs[0]) and np.array_equal(out[0, 4:8], imgs[2]) and np.array_equal(out[0, 8:], imgs[3])
+  assert np.array_equal(out[1, 4:8], imgs[4]) and not out[1, 8:].any()       # a single alt: the third section stays blank
+  pic.alt_aligned_pileup = 'single_row'
+  out = men.compose_alt_aligned(imgs, 2, [[2, 3], [4]], pic, [['A', 'AT'], ['G']])
+  assert out.shape == (2, 8, 3, 2) and np.array_equal(out[0, 4:], imgs[3]) and np.array_equal(out[1, 4:], imgs[4])   # the longer alt's pileup
+  out = men.compose_alt_aligned(imgs, 2, [[2, 3], []], pic, [['AT', 'A'], ['G']])
+  assert np.array_equal(out[0, 4:], imgs[2]) and not out[1, 4:].any()
