@@ -228,3 +228,74 @@ int dvb_ssw_align(const char* ref, int64_t ref_len, const char* query, int64_t q
 }
 
 }  // extern "C"
+
+// ---- FastPassAligner::FastAlignReadsToHaplotypes (deepvariant/realigner/fast_pass_aligner.cc:165-279): the exact k-mer pass -------------
+// For every haplotype: each k-mer of the haplotype is looked up in the index of read k-mers; a read whose k-mer matches is compared
+// base by base at the implied offset and accepted with at most max_mismatches mismatches (N matches anything); the haplotype's score
+// is the sum of its reads' best scores, or 0 as soon as an indexed k-mer position inside [prefix, len - suffix) is covered by no
+// accepted read (never for the reference haplotype).  Outputs, per haplotype h and read r: position[h * n_reads + r] (65535 = not
+// aligned) and score[h * n_reads + r]; hap_score[h].  The CIGAR of an accepted read is always "<len>=".
+#include <unordered_map>
+
+extern "C" int dvb_fast_pass_scores(const char* reference, int64_t ref_len, const char* const* haplotypes, const int64_t* hap_lens, int32_t n_haps,
+                                    const char* const* reads, const int64_t* read_lens, int32_t n_reads, int32_t kmer_size,
+                                    int32_t max_mismatches, int32_t match, int32_t mismatch, int32_t ref_prefix_len, int32_t ref_suffix_len,
+                                    int32_t* hap_score, int32_t* position, int32_t* score) {
+  if (!reference || !haplotypes || !hap_lens || !reads || !read_lens || !hap_score || !position || !score || kmer_size < 1)
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_fast_pass_scores: bad argument");
+  const size_t k = (size_t)kmer_size;
+  std::unordered_map<std::string, std::vector<std::pair<int32_t, int32_t>>> index;     // k-mer -> (read, offset), in insertion order
+  for (int32_t r = 0; r < n_reads; ++r) {
+    const size_t n = (size_t)read_lens[r];
+    if (n <= k) continue;
+    for (size_t i = 0; i + k <= n; ++i) index[std::string(reads[r] + i, k)].emplace_back(r, (int32_t)i);
+  }
+  std::string kmer;
+  for (int32_t h = 0; h < n_haps; ++h) {
+    const char* hap = haplotypes[h];
+    const int64_t hl = hap_lens[h];
+    int32_t* pos = position + (size_t)h * n_reads;
+    int32_t* sc = score + (size_t)h * n_reads;
+    for (int32_t r = 0; r < n_reads; ++r) { pos[r] = 65535; sc[r] = 0; }
+    const bool is_ref = hl == ref_len && memcmp(hap, reference, (size_t)hl) == 0;
+    std::vector<int32_t> coverage((size_t)std::max<int64_t>(hl, 1), 0);
+    int64_t total = 0;
+    bool zeroed = false;
+    for (int64_t i = 0; i + (int64_t)k <= hl && !zeroed; ++i) {
+      kmer.assign(hap + i, k);
+      auto it = index.find(kmer);
+      if (it == index.end()) continue;
+      for (const auto& occ : it->second) {
+        const int32_t r = occ.first;
+        const int64_t start = std::max<int64_t>(0, i - occ.second), n = read_lens[r];
+        if (start + n > hl) continue;
+        if (pos[r] != 65535 && pos[r] == start) continue;
+        int matches = 0, mism = 0;
+        bool rejected = false;
+        const char* a = hap + start;
+        const char* b = reads[r];
+        for (int64_t j = 0; j < n; ++j) {
+          if (a[j] != b[j] && a[j] != 'N' && b[j] != 'N') {
+            if (++mism == max_mismatches + 1) { rejected = true; break; }
+          } else {
+            ++matches;
+          }
+        }
+        if (rejected || mism > max_mismatches) continue;
+        const int32_t new_score = matches * match - mism * mismatch;
+        for (int64_t p = start; p < start + n; ++p) ++coverage[(size_t)p];
+        if (sc[r] < new_score) {
+          total += new_score - sc[r];
+          sc[r] = new_score;
+          pos[r] = (int32_t)start;
+        }
+      }
+      if (coverage[(size_t)i] == 0 && i >= ref_prefix_len && i < hl - ref_suffix_len && !is_ref) zeroed = true;
+    }
+    if (zeroed) total = 0;
+    hap_score[h] = (int32_t)total;
+    if (total == 0)
+      for (int32_t r = 0; r < n_reads; ++r) { pos[r] = 65535; sc[r] = 0; }
+  }
+  return DVB_OK;
+}

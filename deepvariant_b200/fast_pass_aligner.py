@@ -231,6 +231,36 @@ class FastPassAligner:
     return haplotype_score
 
   def fast_align_reads_to_haplotypes(self) -> None:
+    """All haplotypes in one native call (dvb_fast_pass_scores); fast_align_reads_to_haplotype below is the same pass in Python, kept for
+    the known-answer tests and as the cross-check of tests/test_fast_pass_aligner.py."""
+    import ctypes as C
+    import numpy as np
+    from deepvariant_b200 import _lib
+    n_h, n_r = len(self.haplotypes), len(self.reads)
+    if n_h and n_r:
+      haps = [h.encode() for h in self.haplotypes]
+      reads = [r.encode() for r in self.reads]
+      hap_arr, read_arr = (C.c_char_p * n_h)(*haps), (C.c_char_p * n_r)(*reads)
+      hap_lens = np.array([len(h) for h in haps], dtype=np.int64)
+      read_lens = np.array([len(r) for r in reads], dtype=np.int64)
+      hap_score = np.zeros(n_h, dtype=np.int32)
+      position = np.zeros(n_h * n_r, dtype=np.int32)
+      score = np.zeros(n_h * n_r, dtype=np.int32)
+      ref = self.reference.encode()
+      _lib.check(_lib.lib().dvb_fast_pass_scores(ref, len(ref), hap_arr, hap_lens.ctypes.data_as(C.c_void_p), n_h, read_arr,
+                                                 read_lens.ctypes.data_as(C.c_void_p), n_r, self.kmer_size, self.max_num_of_mismatches,
+                                                 self.match_score, self.mismatch_penalty, self.ref_prefix_len, self.ref_suffix_len,
+                                                 hap_score.ctypes.data_as(C.c_void_p), position.ctypes.data_as(C.c_void_p),
+                                                 score.ctypes.data_as(C.c_void_p)))
+      position, score = position.reshape(n_h, n_r), score.reshape(n_h, n_r)
+      for i in range(n_h):
+        scores = [ReadAlignment(int(position[i, r]), f'{len(self.reads[r])}=' if score[i, r] > 0 or position[i, r] != K_NOT_ALIGNED else '',
+                                int(score[i, r])) for r in range(n_r)]
+        self.read_to_haplotype_alignments.append(HaplotypeReadsAlignment(i, int(hap_score[i]), scores))
+      return
+    self.fast_align_reads_to_haplotypes_py()
+
+  def fast_align_reads_to_haplotypes_py(self) -> None:
     for i, haplotype in enumerate(self.haplotypes):
       scores = [ReadAlignment() for _ in self.reads]
       hap_score = self.fast_align_reads_to_haplotype(haplotype, scores)

@@ -408,6 +408,13 @@ typedef struct DvbSswAlignment {
 int dvb_ssw_align(const char* ref, int64_t ref_len, const char* query, int64_t query_len, int32_t match, int32_t mismatch, int32_t gap_open,
                   int32_t gap_extend, DvbSswAlignment* out, char* cigar_out, int64_t cigar_cap);
 
+/* FastPassAligner's exact k-mer pass (deepvariant/realigner/fast_pass_aligner.cc:165-279) for all haplotypes in one call:
+ * hap_score = int32[n_haps]; position / score = int32[n_haps * n_reads] (position 65535 = read not placed on that haplotype). */
+int dvb_fast_pass_scores(const char* reference, int64_t ref_len, const char* const* haplotypes, const int64_t* hap_lens, int32_t n_haps,
+                         const char* const* reads, const int64_t* read_lens, int32_t n_reads, int32_t kmer_size, int32_t max_mismatches,
+                         int32_t match, int32_t mismatch, int32_t ref_prefix_len, int32_t ref_suffix_len, int32_t* hap_score,
+                         int32_t* position, int32_t* score);
+
 /* ---- call_variants record I/O on the host ---------------------------------------------
  * Reader = call_variants.get_dataset (deepvariant/call_variants.py:449-538): the shards of the examples TFRecord
  * (gzip or plain) are read by `threads` workers and handed out in tf.data's deterministic interleave order

@@ -141,3 +141,48 @@ def test_score_threshold_and_normalisation():
   assert a.is_alignment_normalized([(M, 5), (D, 2), (M, 13)], 0, 'AAAAACCCGGGGGTTTTT')
   assert not a.is_alignment_normalized([(M, 7), (I, 1), (M, 13)], 0, 'AAAAACCCCCCGGGGGTTTTT')
   assert a.is_alignment_normalized([(M, 5), (I, 1), (M, 15)], 0, 'AAAAACCCCCCGGGGGTTTTT')
+
+
+@pytest.mark.parametrize('seed', range(4))
+def test_native_fast_pass_equals_the_python_pass(seed):
+  """dvb_fast_pass_scores (all haplotypes in one call) == fast_align_reads_to_haplotype per haplotype, incl. the zero-coverage rule."""
+  import random
+  rng = random.Random(seed)
+  ref = ''.join(rng.choice('ACGT') for _ in range(300))
+  haps = [ref]
+  for _ in range(4):
+    h = list(ref)
+    for _ in range(rng.randrange(1, 4)):
+      p = rng.randrange(60, 240)
+      kind = rng.random()
+      if kind < 0.4:
+        h[p] = rng.choice('ACGT')
+      elif kind < 0.7:
+        h[p] = h[p] + rng.choice('ACGT') * rng.randrange(1, 4)
+      else:
+        h[p] = ''
+    haps.append(''.join(h))
+  reads = []
+  for _ in range(80):
+    src = rng.choice(haps)
+    p = rng.randrange(0, len(src) - 60)
+    r = list(src[p:p + rng.randrange(40, 60)])
+    for _ in range(rng.choice([0, 0, 1, 2, 4])):
+      r[rng.randrange(len(r))] = rng.choice('ACGTN')
+    reads.append(''.join(r))
+  def make():
+    a = fpa.FastPassAligner()
+    a.reference, a.haplotypes, a.reads = ref, haps, list(reads)
+    a.set_options(kmer_size=rng.choice([8, 12, 32]))
+    a.ref_prefix_len, a.ref_suffix_len = 20, 20
+    a.build_index()
+    return a
+  state = rng.getstate()
+  a = make()
+  rng.setstate(state)
+  b = make()
+  a.fast_align_reads_to_haplotypes()
+  b.fast_align_reads_to_haplotypes_py()
+  assert [(h.haplotype_index, h.haplotype_score, [(r.position, r.cigar, r.score) for r in h.read_alignment_scores]) for h in a.read_to_haplotype_alignments] == \
+         [(h.haplotype_index, h.haplotype_score, [(r.position, r.cigar, r.score) for r in h.read_alignment_scores]) for h in b.read_to_haplotype_alignments]
+  assert any(h.haplotype_score > 0 for h in a.read_to_haplotype_alignments)
