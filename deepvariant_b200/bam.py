@@ -9,6 +9,7 @@ This is SURVEY §8(f) "next" row #1 in its simplest form: whole-file decode, in-
 from __future__ import annotations
 
 import gzip
+import os
 import struct
 from typing import Dict, Iterable, List, Optional
 
@@ -288,3 +289,13 @@ def write_bam(path: str, reads, references, sample_name: str = '') -> None:
     out += struct.pack('<i', len(body)) + body
   with open(path, 'wb') as f:
     f.write(_bgzf(bytes(out)))
+
+
+def scratch_table(reads, references, read_requirements: Optional[ReadRequirements] = None, parse_aux: bool = False) -> 'NativeBamTable':
+  """Read objects -> NativeBamTable through a temporary BAM (the table is fully resident once constructed): how realigned /
+  normalised reads reach the native candidate generator and the region packer."""
+  import tempfile
+  with tempfile.TemporaryDirectory() as tmp:
+    path = os.path.join(tmp, 'reads.bam')
+    write_bam(path, reads, references)
+    return NativeBamTable(path, read_requirements, parse_aux=parse_aux)

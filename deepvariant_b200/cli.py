@@ -56,7 +56,7 @@ MAKE_EXAMPLES_DEFAULTS = dict(
     alt_aligned_pileup='none', device=0, checkpoint='', checkpoint_json='', candidates='', candidates_in='', max_reads_per_partition=1500,
     sample_name='', vsc_min_count_snps=2, vsc_min_count_indels=2, vsc_min_fraction_snps=0.12, vsc_min_fraction_indels=0.06,
     vsc_min_fraction_multiplier=1.0, small_model_vaf_context_window_size=0, track_ref_reads=False, phase_reads=False,
-    keep_legacy_allele_counter_behavior=False, realign_reads=True)      # --realign_reads defaults to true (make_examples_options.py:229)
+    keep_legacy_allele_counter_behavior=False, normalize_reads=False, realign_reads=True)      # --realign_reads defaults to true (make_examples_options.py:229)
 
 
 def model_example_info_json_path(checkpoint: str, checkpoint_json: str = '') -> str:
@@ -131,6 +131,7 @@ def make_examples(argv):
   ap.add_argument('--track_ref_reads', action='store_true')
   ap.add_argument('--phase_reads', action='store_true')
   ap.add_argument('--keep_legacy_allele_counter_behavior', action='store_true')
+  ap.add_argument('--normalize_reads', action='store_true')
   ap.add_argument('--realign_reads', dest='realign_reads', action='store_true')
   ap.add_argument('--norealign_reads', dest='realign_reads', action='store_false')
   ap.add_argument('--sort_by_haplotypes', action='store_true')
@@ -182,9 +183,13 @@ def make_examples(argv):
     rl = None
     if a.realign_reads and a.phase_reads:
       raise NotImplementedError('--realign_reads together with --phase_reads (the PACBIO / ONT models run with --norealign_reads)')
+    if a.normalize_reads and a.phase_reads:
+      raise NotImplementedError('--normalize_reads together with --phase_reads')
     if a.realign_reads:
       from deepvariant_b200 import realigner
-      rl = realigner.Realigner(fasta.IndexedFastaReader(a.ref))
+      ropts = realigner.RealignerOptions(normalize_reads=a.normalize_reads)                 # realigner.py:414-429
+      ropts.ws.keep_legacy_behavior = a.keep_legacy_allele_counter_behavior                 # realigner.py:345-360
+      rl = realigner.Realigner(fasta.IndexedFastaReader(a.ref), ropts)
     ref = fasta.IndexedFastaReader(a.ref)
     copts = cand.CandidateOptions(
         min_mapping_quality=a.min_mapping_quality, min_base_quality=a.min_base_quality,
@@ -201,18 +206,30 @@ def make_examples(argv):
       rows = cand.region_reads(reader, contig, p0, p1, copts.max_reads_per_partition, copts.random_seed)
       if not len(rows):
         continue
-      if rl is not None:
+      if rl is not None or a.normalize_reads:
         # --realign_reads: window selection, de Bruijn assembly, FastPassAligner (deepvariant_b200/realigner.py); the realigned reads
         # replace the region's reads for candidate generation AND pileups, as in_memory_sam_reader.replace_reads does
-        # (make_examples_core.py:2290-2300).  They go through a scratch BAM so that the native table / packer can take them.
-        import tempfile
-        realigned = rl.realign_reads(reader, contig, rows, (p0, p1))
-        with tempfile.TemporaryDirectory() as tmp:
-          scratch = os.path.join(tmp, 'realigned.bam')
-          bam.write_bam(scratch, realigned, [(c, ref.n_bases(c)) for c in ref.contig_order])
-          region_table = bam.NativeBamTable(scratch, bam.ReadRequirements(min_mapping_quality=a.min_mapping_quality), parse_aux=a.parse_sam_aux_fields)
+        # (make_examples_core.py:2290-2300).  --normalize_reads then left-normalises the indels of the region's reads
+        # (deepvariant_b200/normalize_reads.py; make_examples_core.py:2900-2953).  The rewritten reads go through a scratch BAM so
+        # that the native table / packer can take them.
+        region_read_list = rl.realign_reads(reader, contig, rows, (p0, p1)) if rl is not None else [reader.read(int(i)) for i in rows]
+        count_reads = None
+        if a.normalize_reads:
+          from deepvariant_b200 import normalize_reads
+          region_read_list, count_reads = normalize_reads.normalize_region_reads(
+              region_read_list, lambda s, e, contig=contig: ref.query(contig, s, e).encode(), p0, p1, ref.n_bases(contig), a.min_mapping_quality)
+        reqs = bam.ReadRequirements(min_mapping_quality=a.min_mapping_quality)
+        refs = [(c, ref.n_bases(c)) for c in ref.contig_order]
+        region_table = bam.scratch_table(region_read_list, refs, reqs, parse_aux=a.parse_sam_aux_fields)
         region_rows = region_table.query_indices(contig, p0, p1)
-        found = cand.candidates_in_region(region_table, ref, contig, p0, p1, copts, rows=region_rows, padding_pct=20 if a.phase_reads else 0)
+        if count_reads is None:
+          found = cand.candidates_in_region(region_table, ref, contig, p0, p1, copts, rows=region_rows, padding_pct=20 if a.phase_reads else 0)
+        else:
+          # a read whose only change is its heading indel is counted with the rewritten alignment but keeps its own in memory
+          # (NormalizeAndAdd, allelecounter.cc:865-870): count from a second table
+          count_table = bam.scratch_table(count_reads, refs, reqs)
+          found = cand.candidates_in_region(count_table, ref, contig, p0, p1, copts, rows=count_table.query_indices(contig, p0, p1))
+          count_table.close()
         totals['n_candidates'] = totals.get('n_candidates', 0) + len(found.records)
         if cand_writer is not None:
           for rec in found.records:

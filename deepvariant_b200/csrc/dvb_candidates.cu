@@ -10,7 +10,8 @@
 //       AddReadDepths / CallVariant / CallVariantPosition / AddSupportingReads / AddAdjacentAlleleFractionsAtPosition
 //       deepvariant/variant_calling_multisample.cc:95-290, 610-760, 1000-1330 (single sample, create_complex_alleles = false,
 //       use_rejected_alleles = false, no methylation: the make_examples defaults, make_examples_options.py:597-922)
-// Not restated here: read normalisation (--normalize_reads), complex alleles, rejected alleles, methylation, multi-sample
+// Read normalisation (--normalize_reads) happens before this counter, on the reads (deepvariant_b200/normalize_reads.py).
+// Not restated here: complex alleles, rejected alleles, methylation, multi-sample
 // filters, gVCF summaries.
 #include <algorithm>
 #include <cstdint>

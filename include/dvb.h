@@ -315,7 +315,7 @@ int dvb_packed_region_batch(const DvbPackedRegion* packed, DvbBatch* batch /* ho
 void dvb_packed_region_free(DvbPackedRegion* packed);
 
 /* ---- candidate generation on the host (SURVEY.md 8(f) "next" row #2): allele counting + very-sensitive caller ------------
- * Replaces, for one sample and the make_examples defaults (no --normalize_reads, no complex / rejected alleles, no
+ * Replaces, for one sample and the make_examples defaults (--normalize_reads rewrites the reads before this call, normalize_reads.py; no complex / rejected alleles, no
  * methylation), the pybind modules deepvariant.python.allelecounter (AlleleCounter(ref, range, candidate_positions,
  * options).add(read, sample); deepvariant/python/allelecounter_pybind.cc, deepvariant/allelecounter.cc:880-978) and
  * deepvariant.python.variant_calling_multisample (VariantCaller.calls_from_allele_counts /

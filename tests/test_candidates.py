@@ -527,13 +527,13 @@ def _planted_case(tmp_path):
   return str(fa), bam_path, genome, dict(snp_het=snp_het, snp_hom=snp_hom, ins=ins, dele=dele)
 
 
-def _run_cli(tmp_path, fa, bam_path, tag, realign=False):
+def _run_cli(tmp_path, fa, bam_path, tag, realign=False, extra=()):
   from deepvariant_b200 import cli
   ex = str(tmp_path / f'{tag}.examples.tfrecord@1.gz')
   cands = str(tmp_path / f'{tag}.candidates.tfrecord.gz')
   assert cli.make_examples(['--mode', 'calling', '--ref', fa, '--reads', bam_path, '--examples', ex, '--candidates', cands,
                             '--channel_list', 'BASE_CHANNELS,insert_size', '--regions', 'chr20:1001-5000',
-                            '--realign_reads' if realign else '--norealign_reads']) == 0
+                            '--realign_reads' if realign else '--norealign_reads', *extra]) == 0
   from deepvariant_b200 import tfrecord
   return (list(tfrecord.read_records(str(tmp_path / f'{tag}.examples.tfrecord-00000-of-00001.gz'))), list(tfrecord.read_records(cands)))
 
@@ -569,6 +569,12 @@ def test_make_examples_cli_generates_candidates_cpu_plumbing(tmp_path, monkeypat
   # with the realigner (the default): windows around the planted indels are assembled and their reads realigned; the planted
   # variants are clean, so the same four candidates come out, through the scratch-BAM / region-table path
   examples, cands = _run_cli(tmp_path, fa, bam_path, 'cpu_realigned', realign=True)
+  _check_planted(examples, cands, genome, sites)
+  # the VG Giraffe flag set (scripts/create_golden.sh:472-487): reads normalised after the realigner, legacy counter
+  giraffe = ('--normalize_reads', '--keep_legacy_allele_counter_behavior', '--min_mapping_quality', '1')
+  examples, cands = _run_cli(tmp_path, fa, bam_path, 'cpu_normalized', realign=True, extra=giraffe)
+  _check_planted(examples, cands, genome, sites)
+  examples, cands = _run_cli(tmp_path, fa, bam_path, 'cpu_normalized_only', realign=False, extra=giraffe)
   _check_planted(examples, cands, genome, sites)
 
 
