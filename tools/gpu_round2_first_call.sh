@@ -5,6 +5,7 @@
 #   2. allele-count timing against the HBM roofline + its ncu launch list and one full-set capture;
 #   3. the classifier with and without DVB_CNN_PAIR=1 (A/B on the same box), and an ncu launch list of the pair run.
 mkdir -p gpurun_out
+export DVB_TEST_PAIR=1      # the CTA-pair GEMM check is opt-in (experimental kernel, child process under a timeout)
 T=tests/test_zz_allele_count_gpu.py
 for k in test_make_examples_cli_generates_candidates_on_gpu test_run_deepvariant_from_bam_to_vcf test_device_counts_and_flags \
          test_gpu_candidates_equal_host test_one_launch_over_a_long_interval test_cta_pair_kernel; do
