@@ -188,6 +188,7 @@ SYMBOLS = (
     ('dvb_candidates_count', C.c_int64, [C.c_void_p]),
     ('dvb_candidates_protos', C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     ('dvb_candidates_positions', C.c_int64, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    ('dvb_candidates_summary_counts', C.c_int64, [C.c_void_p, C.POINTER(C.c_void_p)]),
     ('dvb_candidates_free', None, [C.c_void_p]),
     ('dvb_device_reads_create', C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     ('dvb_device_reads_destroy', None, [C.c_void_p]),

@@ -141,9 +141,15 @@ def region_reads(table, contig: str, start: int, end: int, max_reads_per_partiti
 class NativeCandidates:
   """Result of one dvb_candidates_in_region call: raw DeepVariantCall records + parsed objects on demand."""
 
-  def __init__(self, handle, keep: Optional[Tuple[int, int]] = None):
+  def __init__(self, handle, keep: Optional[Tuple[int, int]] = None, interval: Optional[Tuple[int, int]] = None):
     lib = _lib.lib()
     try:
+      sp = C.c_void_p()
+      n_sites = int(lib.dvb_candidates_summary_counts(handle, C.byref(sp)))
+      # AlleleCounter::SummaryCounts of the counted interval: [n_sites, 2] = (ref_supporting_read_count, total_read_count)
+      self.summary_counts = np.frombuffer((C.c_char * (8 * n_sites)).from_address(sp.value), dtype=np.int32).reshape(n_sites, 2).copy() \
+          if n_sites else np.zeros((0, 2), np.int32)
+      self.interval = interval
       n = int(lib.dvb_candidates_count(handle))
       pos_ptr = C.c_void_p()
       lib.dvb_candidates_positions(handle, C.byref(pos_ptr))
@@ -211,7 +217,7 @@ def candidates_in_region(table, ref_reader, contig: str, start: int, end: int, o
   h = C.c_void_p()
   _lib.check(lib.dvb_candidates_in_region(table.handle, contig.encode(), ptr, len(seq), start, end, rows.ctypes.data_as(C.c_void_p),
                                           len(rows), C.byref(co), positions.ctypes.data_as(C.c_void_p), len(positions), C.byref(h)))
-  return NativeCandidates(h, keep=region if padding_pct > 0 else None)
+  return NativeCandidates(h, keep=region if padding_pct > 0 else None, interval=(start, end))
 
 
 def _value(buf):

@@ -56,7 +56,8 @@ MAKE_EXAMPLES_DEFAULTS = dict(
     alt_aligned_pileup='none', device=0, checkpoint='', checkpoint_json='', candidates='', candidates_in='', max_reads_per_partition=1500,
     sample_name='', vsc_min_count_snps=2, vsc_min_count_indels=2, vsc_min_fraction_snps=0.12, vsc_min_fraction_indels=0.06,
     vsc_min_fraction_multiplier=1.0, small_model_vaf_context_window_size=0, track_ref_reads=False, phase_reads=False,
-    keep_legacy_allele_counter_behavior=False, normalize_reads=False, realign_reads=True)      # --realign_reads defaults to true (make_examples_options.py:229)
+    keep_legacy_allele_counter_behavior=False, normalize_reads=False, realign_reads=True, gvcf='', gvcf_gq_binsize=5, p_error=0.001,
+    include_med_dp=False, haploid_contigs='')      # --realign_reads defaults to true (make_examples_options.py:229)
 
 
 def model_example_info_json_path(checkpoint: str, checkpoint_json: str = '') -> str:
@@ -132,6 +133,11 @@ def make_examples(argv):
   ap.add_argument('--phase_reads', action='store_true')
   ap.add_argument('--keep_legacy_allele_counter_behavior', action='store_true')
   ap.add_argument('--normalize_reads', action='store_true')
+  ap.add_argument('--gvcf')                       # non-variant site records (Variant protos), sharded like --examples
+  ap.add_argument('--gvcf_gq_binsize', type=int)
+  ap.add_argument('--p_error', type=float)
+  ap.add_argument('--include_med_dp', action='store_true')
+  ap.add_argument('--haploid_contigs')
   ap.add_argument('--realign_reads', dest='realign_reads', action='store_true')
   ap.add_argument('--norealign_reads', dest='realign_reads', action='store_false')
   ap.add_argument('--sort_by_haplotypes', action='store_true')
@@ -172,6 +178,8 @@ def make_examples(argv):
     for key, val in stats.items():
       totals[key] = totals.get(key, 0) + val
 
+  if a.candidates_in and a.gvcf:
+    raise ValueError('--gvcf needs the allele counter: not available with --candidates_in')
   if a.candidates_in:
     cands = [protos.parse_deepvariant_call(r) for p in tfrecord.resolve_input_paths(a.candidates_in) for r in tfrecord.read_records(p)]
     for (contig, k, origin), cs in men.shard_partitions(men.partition_candidates(cands, a.partition_size, region), n_shards, a.task):
@@ -202,9 +210,32 @@ def make_examples(argv):
     cand_writer = tfrecord.Writer(tfrecord.shard_path(a.candidates, a.task) if tfrecord.is_sharded_spec(a.candidates) else a.candidates) \
         if a.candidates else None
     contigs = [(c, ref.n_bases(c)) for c in ref.contig_order if c in reader.references]
+    gvcf_writer = gvcf_options = gvcf_confidence = None
+    if a.gvcf:
+      # --gvcf: reference-confidence blocks of every region from the same allele counter (deepvariant_b200/gvcf.py;
+      # variant_caller.py:256-468), one TFRecord of Variant protos per task
+      from deepvariant_b200 import gvcf
+      if a.gvcf_gq_binsize < 1:
+        raise ValueError('--gvcf_gq_binsize must be a positive integer')
+      gvcf_writer = tfrecord.Writer(tfrecord.shard_path(a.gvcf, a.task) if tfrecord.is_sharded_spec(a.gvcf) else a.gvcf)
+      gvcf_options = gvcf.GvcfOptions(sample_name=copts.sample_name, p_error=a.p_error, gq_resolution=a.gvcf_gq_binsize, include_med_dp=a.include_med_dp,
+                                      haploid_contigs=tuple(c for c in a.haploid_contigs.split(',') if c))
+      gvcf_confidence = gvcf.ReferenceConfidence(gvcf_options)
+
+    def write_gvcfs(found, contig, p0, p1):
+      if gvcf_writer is None:
+        return
+      p1 = min(p1, ref.n_bases(contig))
+      lo = p0 - found.interval[0]                 # summary_counts(left_padding, right_padding): without the phasing padding
+      for block in gvcf.make_gvcfs(contig, p0, ref.query(contig, p0, p1), found.summary_counts[lo:lo + (p1 - p0)], gvcf_options, gvcf_confidence):
+        gvcf_writer.write(gvcf.serialize_gvcf_record(block))
+        totals['n_gvcf_records'] = totals.get('n_gvcf_records', 0) + 1
+
     for contig, p0, p1 in cand.regions_to_process(contigs, a.partition_size, region, a.task, n_shards):
       rows = cand.region_reads(reader, contig, p0, p1, copts.max_reads_per_partition, copts.random_seed)
       if not len(rows):
+        if gvcf_writer is not None:               # no early exit with --gvcf: the region still gets its blocks (make_examples_core.py:2872-2875)
+          write_gvcfs(cand.candidates_in_region(reader, ref, contig, p0, p1, copts, rows=rows, padding_pct=20 if a.phase_reads else 0), contig, p0, p1)
         continue
       if rl is not None or a.normalize_reads:
         # --realign_reads: window selection, de Bruijn assembly, FastPassAligner (deepvariant_b200/realigner.py); the realigned reads
@@ -230,6 +261,7 @@ def make_examples(argv):
           count_table = bam.scratch_table(count_reads, refs, reqs)
           found = cand.candidates_in_region(count_table, ref, contig, p0, p1, copts, rows=count_table.query_indices(contig, p0, p1))
           count_table.close()
+        write_gvcfs(found, contig, p0, p1)
         totals['n_candidates'] = totals.get('n_candidates', 0) + len(found.records)
         if cand_writer is not None:
           for rec in found.records:
@@ -244,6 +276,7 @@ def make_examples(argv):
         region_table.close()
         continue
       found = cand.candidates_in_region(reader, ref, contig, p0, p1, copts, rows=rows, padding_pct=20 if a.phase_reads else 0)
+      write_gvcfs(found, contig, p0, p1)
       totals['n_candidates'] = totals.get('n_candidates', 0) + len(found.records)
       if cand_writer is not None:
         for rec in found.records:
@@ -264,6 +297,8 @@ def make_examples(argv):
           examples_in(found.calls(), contig, p0, p1)
     if cand_writer is not None:
       cand_writer.close()
+    if gvcf_writer is not None:
+      gvcf_writer.close()
   gen.signal_shard_finished()
   print(f'make_examples task {a.task}: {totals}', file=sys.stderr)
   return 0
@@ -299,11 +334,14 @@ def postprocess_variants(argv):
   ap.add_argument('--disable_haplotype_resolution', action='store_true')
   ap.add_argument('--group_variants', dest='group_variants', action='store_true', default=True)
   ap.add_argument('--nogroup_variants', dest='group_variants', action='store_false')
+  ap.add_argument('--nonvariant_site_tfrecord_path', default='')     # make_examples --gvcf output, every shard
+  ap.add_argument('--gvcf_outfile', default='')
   a = ap.parse_args(argv)
   from deepvariant_b200 import fasta, postprocess_variants as pp
   ref = fasta.IndexedFastaReader(a.ref)
   r = pp.postprocess_variants(a.infile, a.outfile, [(c, ref.n_bases(c)) for c in ref.contig_order], a.sample_name, a.qual_filter,
-                              a.multi_allelic_qual_filter, a.multiallelic_mode, a.only_keep_pass, a.disable_haplotype_resolution, a.group_variants)
+                              a.multi_allelic_qual_filter, a.multiallelic_mode, a.only_keep_pass, a.disable_haplotype_resolution, a.group_variants,
+                              a.nonvariant_site_tfrecord_path, a.gvcf_outfile, lambda c, p: ref.query(c, p, p + 1))
   print(f'postprocess_variants: {r}', file=sys.stderr)
   return 0
 
@@ -316,6 +354,7 @@ def run_deepvariant(argv):
   ap.add_argument('--candidates_in', default='')   # optional: DeepVariantCalls exported by another make_examples
   ap.add_argument('--output_dir', required=True)   # the reference's --intermediate_results_dir
   ap.add_argument('--output_vcf', default='')       # scripts/run_deepvariant.py:84: when given, postprocess_variants runs too
+  ap.add_argument('--output_gvcf', default='')      # scripts/run_deepvariant.py:90: make_examples --gvcf + the postprocess merge
   ap.add_argument('--sample_name', default='')
   ap.add_argument('--regions', default='')
   ap.add_argument('--num_shards', type=int, default=1)
@@ -324,6 +363,9 @@ def run_deepvariant(argv):
   os.makedirs(a.output_dir, exist_ok=True)
   d = MODEL_DEFAULTS[a.model_type]
   examples = os.path.join(a.output_dir, f'make_examples.tfrecord@{a.num_shards}.gz')
+  nonvariants = os.path.join(a.output_dir, f'gvcf.tfrecord@{a.num_shards}.gz')
+  if a.output_gvcf and not a.output_vcf:
+    raise ValueError('--output_gvcf needs --output_vcf')
   for task in range(a.num_shards):
     args = ['--mode', 'calling', '--ref', a.ref, '--reads', a.reads, '--examples', examples, '--task',
             str(task), '--channel_list', d['channel_list'], '--pileup_image_width', str(d['pileup_image_width'])]
@@ -339,6 +381,8 @@ def run_deepvariant(argv):
       args += ['--regions', a.regions]
     if a.sample_name:
       args += ['--sample_name', a.sample_name]
+    if a.output_gvcf:
+      args += ['--gvcf', nonvariants]
     make_examples(args)
   cvo = os.path.join(a.output_dir, 'call_variants_output.tfrecord.gz')
   rc = call_variants(['--examples', examples, '--outfile', cvo, '--checkpoint', a.customized_model])
@@ -347,6 +391,8 @@ def run_deepvariant(argv):
   args = ['--ref', a.ref, '--infile', cvo, '--outfile', a.output_vcf]     # the shards call_variants wrote are found by name
   if a.sample_name:
     args += ['--sample_name', a.sample_name]
+  if a.output_gvcf:
+    args += ['--nonvariant_site_tfrecord_path', nonvariants, '--gvcf_outfile', a.output_gvcf]
   return postprocess_variants(args)
 
 

@@ -228,6 +228,7 @@ struct DvbCandidates {
   std::vector<int64_t> proto_begin;   // [n + 1]
   std::vector<int32_t> position;      // [n] variant.start
   std::vector<int32_t> positions_only;   // dvb_candidate_positions result
+  std::vector<int32_t> summary;          // [2 n_sites]: ref_supporting_read_count, total_read_count (AlleleCounter::SummaryCounts)
   int64_t n_reads_counted = 0;
 };
 
@@ -340,6 +341,11 @@ int dvb_candidates_at_positions(const DvbBam* bam, const char* reference_name, c
   res->proto_begin.push_back(0);
   const std::string sample = opt->sample_name ? opt->sample_name : "";
   const int n_sites = (int)c.sites.size();
+  res->summary.resize(2 * (size_t)n_sites);          // AlleleCounter::SummaryCounts (allelecounter.cc:986-1007), for the gVCF records
+  for (int i = 0; i < n_sites; ++i) {
+    res->summary[2 * (size_t)i] = c.sites[(size_t)i].ref_supporting_read_count;
+    res->summary[2 * (size_t)i + 1] = caller.Total(c.sites[(size_t)i]);
+  }
   for (int i = 0; i < n_sites; ++i) {
     const Site& site = c.sites[(size_t)i];
     if (site.entries.empty()) continue;                                     // no read allele, no alt allele
@@ -522,6 +528,12 @@ int64_t dvb_candidates_positions(const DvbCandidates* c, const int32_t** positio
   const std::vector<int32_t>& v = c->positions_only.empty() ? c->position : c->positions_only;
   if (positions) *positions = v.data();
   return (int64_t)v.size();
+}
+
+int64_t dvb_candidates_summary_counts(const DvbCandidates* c, const int32_t** counts) {
+  if (!c) return 0;
+  if (counts) *counts = c->summary.data();
+  return (int64_t)(c->summary.size() / 2);
 }
 
 void dvb_candidates_free(DvbCandidates* c) { delete c; }

@@ -486,17 +486,30 @@ def get_sample_name(cvos: Sequence[Cvo], flag: str = '') -> str:
 
 def postprocess_variants(infile: str, outfile: str, contigs: Sequence[Tuple[str, int]], sample_name: str = '', qual_filter: float = 1.0,
                          multi_allelic_qual_filter: float = 1.0, multiallelic_mode: str = 'product', only_keep_pass: bool = False,
-                         disable_haplotype_resolution: bool = False, group_variants: bool = True) -> dict:
-  """CVO TFRecord shards (`infile` may be a sharded spec or a glob) -> VCF text (`outfile`, gzip when it ends in .gz)."""
+                         disable_haplotype_resolution: bool = False, group_variants: bool = True, nonvariant_site_tfrecord_path: str = '',
+                         gvcf_outfile: str = '', base_at=None) -> dict:
+  """CVO TFRecord shards (`infile` may be a sharded spec or a glob) -> VCF text (`outfile`, gzip when it ends in .gz).  With
+  nonvariant_site_tfrecord_path (the --gvcf output of make_examples, every shard) and gvcf_outfile also the gVCF: the variants merged
+  with the reference blocks (deepvariant_b200/gvcf.py; `base_at(contig, position)` supplies the reference base where a block is split)."""
   import gzip
+  if bool(nonvariant_site_tfrecord_path) != bool(gvcf_outfile):
+    raise ValueError('gVCF creation requires both nonvariant_site_tfrecord_path and gvcf_outfile')          # postprocess_variants.py:2245-2251
   cvos = [parse_cvo(r) for p in tfrecord.resolve_input_paths(infile) for r in tfrecord.read_records(p)]
+  blocks = []
+  if gvcf_outfile:
+    from deepvariant_b200 import gvcf
+    blocks = [gvcf.parse_variant_record(r) for p in tfrecord.resolve_input_paths(nonvariant_site_tfrecord_path) for r in tfrecord.read_records(p)]
   sample = get_sample_name(cvos, sample_name)
+  if not sample_name and not cvos and blocks and blocks[0].call_set_name:
+    sample = blocks[0].call_set_name                # get_sample_name (postprocess_variants.py:1651-1676): the gVCF records name the sample
   cvos = sort_cvos(cvos, [c for c, _ in contigs])
   variants = call_variants_outputs_to_variants(cvos, sample, qual_filter, multi_allelic_qual_filter, multiallelic_mode, group_variants)
   if not disable_haplotype_resolution:
     variants = maybe_resolve_conflicting_variants(variants, qual_filter)
   n = 0
   opener = gzip.open if outfile.endswith('.gz') else open
+  if gvcf_outfile:
+    variants = list(variants)
   with opener(outfile, 'wt') as f:
     f.write('\n'.join(vcf_header_lines(contigs, sample)) + '\n')
     for v in variants:
@@ -504,4 +517,16 @@ def postprocess_variants(infile: str, outfile: str, contigs: Sequence[Tuple[str,
         continue
       f.write(vcf_line(v) + '\n')
       n += 1
-  return {'n_cvo_records': len(cvos), 'n_variants_written': n, 'sample_name': sample}
+  out = {'n_cvo_records': len(cvos), 'n_variants_written': n, 'sample_name': sample}
+  if gvcf_outfile:
+    order = {c: i for i, (c, _) in enumerate(contigs)}
+    # ShardedVariantReader: the shards are each sorted, merged by (contig index, start)
+    blocks.sort(key=lambda b: (order[b.reference_name], b.start, b.end))
+    m = 0
+    with (gzip.open if gvcf_outfile.endswith('.gz') else open)(gvcf_outfile, 'wt') as f:
+      f.write('\n'.join(vcf_header_lines(contigs, sample)) + '\n')
+      for rec in gvcf.merge_variants_and_nonvariants(variants, blocks, [c for c, _ in contigs], base_at):
+        f.write(gvcf.gvcf_line(rec) + '\n')
+        m += 1
+    out['n_gvcf_records_written'] = m
+  return out

@@ -355,6 +355,10 @@ int64_t dvb_candidates_count(const DvbCandidates* candidates);
 int dvb_candidates_protos(const DvbCandidates* candidates, const uint8_t** data, const int64_t** begin);
 /* variant.start of every candidate (or the positions of dvb_candidate_positions); returns the count. */
 int64_t dvb_candidates_positions(const DvbCandidates* candidates, const int32_t** positions);
+/* AlleleCounter::SummaryCounts (deepvariant/allelecounter.cc:986-1007) of the counter the candidates came from: int32
+ * [2 * n] = (ref_supporting_read_count, total_read_count) of every position of [start, end), what VariantCaller.make_gvcfs
+ * (deepvariant/variant_caller.py:256-413) turns into gVCF reference blocks.  Returns n.  Owned by `candidates`. */
+int64_t dvb_candidates_summary_counts(const DvbCandidates* candidates, const int32_t** counts);
 void dvb_candidates_free(DvbCandidates* candidates);
 /* Test access to the allele counter (AlleleCounter::Counts()): JSON text, one object per position of [start, end):
  * {"ref": ref_supporting_read_count, "alleles": [[bases, AlleleType, is_low_quality, read key, mapping quality,

@@ -38,9 +38,15 @@ def test_run_deepvariant_from_bam_to_vcf(tmp_path):
   genotype likelihoods (tcgen05 classifier, random-init weights), CallVariantsOutput shards, VCF."""
   from deepvariant_b200 import cli
   fa, bam_path, genome, sites = tc._planted_case(tmp_path)
-  out_dir, vcf = str(tmp_path / 'work'), str(tmp_path / 'out.vcf')
+  out_dir, vcf, gvcf_path = str(tmp_path / 'work'), str(tmp_path / 'out.vcf'), str(tmp_path / 'out.g.vcf')
   assert cli.run_deepvariant(['--model_type', 'WGS', '--ref', fa, '--reads', bam_path, '--output_dir', out_dir, '--output_vcf', vcf,
-                              '--regions', 'chr20:1001-5000', '--customized_model', 'random:3']) == 0
+                              '--output_gvcf', gvcf_path, '--regions', 'chr20:1001-5000', '--customized_model', 'random:3']) == 0
+  # the gVCF tiles the calling region: reference blocks and the four variants, every position in exactly one record
+  nxt = 1001
+  for r in (line.split('\t') for line in open(gvcf_path) if not line.startswith('#')):
+    assert int(r[1]) == nxt and r[4].endswith('<*>')
+    nxt = int(r[7][4:]) + 1 if r[7].startswith('END=') else int(r[1]) + len(r[3])
+  assert nxt == 5001
   lines = [line.split('\t') for line in open(vcf).read().split('\n') if line and not line.startswith('##')]
   assert lines[0][-1] == 'planted'
   records = lines[1:]

@@ -20,3 +20,11 @@ for src, vcf in PAIRS:
   with (gzip.open if vcf.endswith('.gz') else open)(T + vcf, 'rt') as f, open(dst, 'w') as g:
     g.write(f.read())
   print(src, '->', os.path.basename(dst))
+
+# gVCF: make_examples --gvcf records (non-variant blocks) and the merged g.vcf postprocess_variants writes from them
+for src in ['golden.postprocess_gvcf_input.tfrecord.gz', 'golden.postprocess_pacbio_gvcf_input.tfrecord.gz']:
+  shutil.copy(T + src, os.path.join(OUT, src))
+for vcf in ['golden.postprocess_gvcf_output.g.vcf', 'golden.postprocess_gvcf_output_pacbio.g.vcf']:
+  with open(T + vcf, 'rb') as f, gzip.open(os.path.join(OUT, vcf + '.gz'), 'wb') as g:
+    g.write(f.read())
+  print(vcf, '-> .gz')
