@@ -207,7 +207,47 @@ def is_valid_call_variants_outputs(cvos: Sequence[Cvo]) -> bool:
              for c in cvos[1:])
 
 
-def merge_predictions(cvos: Sequence[Cvo], qual_filter: float = 1.0, multiallelic_mode: str = 'product') -> Tuple[OutVariant, List[float]]:
+def correct_nonautosome_probabilities(probabilities: List[float], n_alts: int) -> List[float]:
+  """postprocess_variants.py:1070-1091: every heterozygous genotype of a haploid site gets probability zero, the rest renormalised."""
+  probabilities = list(probabilities)
+  index = 0
+  for h1 in range(n_alts + 1):
+    for h2 in range(h1 + 1):
+      if h2 != h1:
+        if len(probabilities) <= index:
+          raise ValueError("Probabilties array doesn't match alt alleles.")
+        probabilities[index] = 0
+      index += 1
+  total = sum(probabilities) or 1.0
+  return [p / total for p in probabilities]
+
+
+def read_bed(path: str) -> List[Tuple[str, int, int]]:
+  out = []
+  with open(path) as f:
+    for line in f:
+      parts = line.split()
+      if len(parts) >= 3 and not line.startswith(('#', 'track', 'browser')):
+        out.append((parts[0], int(parts[1]), int(parts[2])))
+  return out
+
+
+def _is_haploid_site(v: OutVariant, haploid_contigs: Sequence[str], par_regions: Sequence[Tuple[str, int, int]]) -> bool:
+  """is_non_autosome and not is_in_regions(variant, par_regions) (postprocess_variants.py:1094-1112)."""
+  if not haploid_contigs or v.reference_name not in haploid_contigs:
+    return False
+  return not any(c == v.reference_name and s < v.end and v.start < e for c, s, e in par_regions)
+
+
+def merge_predictions(cvos: Sequence[Cvo], qual_filter: float = 1.0, multiallelic_mode: str = 'product', haploid_contigs: Sequence[str] = (),
+                      par_regions: Sequence[Tuple[str, int, int]] = ()) -> Tuple[OutVariant, List[float]]:
+  canonical, predictions = _merge_predictions(cvos, qual_filter, multiallelic_mode)
+  if _is_haploid_site(canonical, haploid_contigs, par_regions):
+    predictions = correct_nonautosome_probabilities(predictions, len(canonical.alternate_bases))
+  return canonical, predictions
+
+
+def _merge_predictions(cvos: Sequence[Cvo], qual_filter: float = 1.0, multiallelic_mode: str = 'product') -> Tuple[OutVariant, List[float]]:
   if not cvos:
     raise ValueError('Expected 1 or more call_variants_outputs.')
   if not is_valid_call_variants_outputs(cvos):
@@ -407,13 +447,14 @@ def sort_cvos(cvos: List[Cvo], contig_order: Sequence[str]) -> List[Cvo]:
 
 def call_variants_outputs_to_variants(cvos: Sequence[Cvo], sample_name: str, qual_filter: float = 1.0,
                                       multi_allelic_qual_filter: float = 1.0, multiallelic_mode: str = 'product',
-                                      group_variants: bool = True) -> Iterator[OutVariant]:
+                                      group_variants: bool = True, haploid_contigs: Sequence[str] = (),
+                                      par_regions: Sequence[Tuple[str, int, int]] = ()) -> Iterator[OutVariant]:
   """group_call_variants_outputs (:1467-1488): --group_variants groups by the variant's range; without it itertools.groupby
   falls back to equality of consecutive records (the vcf_candidate_importer flow, where one range can hold several variants)."""
   key = (lambda c: (c.variant.reference_name, c.variant.start, c.variant.end)) if group_variants else (lambda c: c.raw)
   for _, group in itertools.groupby(cvos, key=key):
     outputs = sorted(group, key=lambda c: sorted(c.alt_allele_indices))
-    canonical, predictions = merge_predictions(outputs, multi_allelic_qual_filter, multiallelic_mode)
+    canonical, predictions = merge_predictions(outputs, multi_allelic_qual_filter, multiallelic_mode, haploid_contigs, par_regions)
     yield add_call_to_variant(canonical, predictions, qual_filter=qual_filter, sample_name=sample_name)
 
 
@@ -487,7 +528,7 @@ def get_sample_name(cvos: Sequence[Cvo], flag: str = '') -> str:
 def postprocess_variants(infile: str, outfile: str, contigs: Sequence[Tuple[str, int]], sample_name: str = '', qual_filter: float = 1.0,
                          multi_allelic_qual_filter: float = 1.0, multiallelic_mode: str = 'product', only_keep_pass: bool = False,
                          disable_haplotype_resolution: bool = False, group_variants: bool = True, nonvariant_site_tfrecord_path: str = '',
-                         gvcf_outfile: str = '', base_at=None) -> dict:
+                         gvcf_outfile: str = '', base_at=None, haploid_contigs: str = '', par_regions_bed: str = '') -> dict:
   """CVO TFRecord shards (`infile` may be a sharded spec or a glob) -> VCF text (`outfile`, gzip when it ends in .gz).  With
   nonvariant_site_tfrecord_path (the --gvcf output of make_examples, every shard) and gvcf_outfile also the gVCF: the variants merged
   with the reference blocks (deepvariant_b200/gvcf.py; `base_at(contig, position)` supplies the reference base where a block is split)."""
@@ -503,7 +544,9 @@ def postprocess_variants(infile: str, outfile: str, contigs: Sequence[Tuple[str,
   if not sample_name and not cvos and blocks and blocks[0].call_set_name:
     sample = blocks[0].call_set_name                # get_sample_name (postprocess_variants.py:1651-1676): the gVCF records name the sample
   cvos = sort_cvos(cvos, [c for c, _ in contigs])
-  variants = call_variants_outputs_to_variants(cvos, sample, qual_filter, multi_allelic_qual_filter, multiallelic_mode, group_variants)
+  haploid = tuple(item for part in (haploid_contigs or '').split(',') for item in part.split())          # is_non_autosome (:1094-1101)
+  par = read_bed(par_regions_bed) if par_regions_bed else ()
+  variants = call_variants_outputs_to_variants(cvos, sample, qual_filter, multi_allelic_qual_filter, multiallelic_mode, group_variants, haploid, par)
   if not disable_haplotype_resolution:
     variants = maybe_resolve_conflicting_variants(variants, qual_filter)
   n = 0

@@ -229,3 +229,38 @@ def test_cli_bam_to_gvcf_cpu_plumbing(tmp_path, monkeypatch):
   # the regions without reads (first and last kilobase) are blocks of GQ 1, depth 0 (no early exit with --gvcf)
   assert recs[0][9].split(':')[:3] == ['0/0', '1', '0'] and recs[-1][9].split(':')[:3] == ['0/0', '1', '0']
   assert all(l.split('\t')[9].strip() for l in open(gout) if l.startswith('#CHROM')) and '\tplanted\n' in open(gout).read()
+
+
+# ---- --haploid_contigs / --par_regions_bed (postprocess_variants.py:1070-1112) ------------------------------------------------------------
+@pytest.mark.parametrize('probabilities,n_alts,want', [
+    ([0.98, 0.02, 0], 1, [1.0, 0, 0]),
+    ([0.2, 0.5, 0.3], 1, [0.4, 0, 0.6]),
+    ([0.0, 1.0, 0.0], 1, [0, 0, 0]),
+    ([0.02, 0.03, 0.45, 0.07, 0.3, 0.13], 2, [0.033, 0, 0.75, 0, 0, 0.216]),
+])
+def test_correct_nonautosome_probabilities(probabilities, n_alts, want):
+  # postprocess_variants_test.py:2140-2184
+  np.testing.assert_allclose(pp.correct_nonautosome_probabilities(probabilities, n_alts), want, atol=1e-3)
+
+
+def test_haploid_goldens_byte_for_byte(tmp_path):
+  """golden.haploid_chr20.*: the WGS golden CVOs + blocks with --haploid_contigs chr20 (scripts/create_golden.sh:293-305)."""
+  want_g = gzip.open(os.path.join(GOLDEN, 'golden.haploid_chr20.postprocess_gvcf_output.g.vcf.gz'), 'rt').read().splitlines()
+  want_v = gzip.open(os.path.join(GOLDEN, 'golden.haploid_chr20.postprocess_single_site_output.vcf.gz'), 'rt').read().splitlines()
+  contigs = [(l.split('ID=')[1].split(',')[0], int(l.split('length=')[1].rstrip('>'))) for l in want_g if l.startswith('##contig')]
+  bases = {(l.split('\t')[0], int(l.split('\t')[1]) - 1): l.split('\t')[3][0] for l in want_g if not l.startswith('#')}
+  kw = dict(nonvariant_site_tfrecord_path=os.path.join(GOLDEN, 'golden.postprocess_gvcf_input.tfrecord.gz'), gvcf_outfile=str(tmp_path / 'o.g.vcf'),
+            base_at=lambda c, p: bases[(c, p)])
+  cvo = os.path.join(GOLDEN, 'golden.postprocess_single_site_input-00000-of-00001.tfrecord.gz')
+  pp.postprocess_variants(cvo, str(tmp_path / 'o.vcf'), contigs, haploid_contigs='chr20', **kw)
+  assert open(tmp_path / 'o.vcf').read().splitlines() == want_v
+  assert open(tmp_path / 'o.g.vcf').read().splitlines() == want_g
+  # no heterozygous genotype survives on a haploid contig ...
+  gts = [l.split('\t')[9].split(':')[0] for l in want_v if not l.startswith('#')]
+  assert not any(g in ('0/1', '1/2', '0/2') for g in gts)
+  # ... unless the site lies in a pseudo-autosomal region: with all of chr20 declared PAR the diploid output comes back
+  bed = tmp_path / 'par.bed'
+  bed.write_text('chr20\t0\t63025520\n')
+  pp.postprocess_variants(cvo, str(tmp_path / 'p.vcf'), contigs, haploid_contigs='chr20', par_regions_bed=str(bed), **kw)
+  diploid = open(os.path.join(GOLDEN, 'golden.postprocess_single_site_output.vcf')).read().splitlines()
+  assert open(tmp_path / 'p.vcf').read().splitlines() == diploid

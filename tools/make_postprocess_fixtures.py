@@ -24,7 +24,8 @@ for src, vcf in PAIRS:
 # gVCF: make_examples --gvcf records (non-variant blocks) and the merged g.vcf postprocess_variants writes from them
 for src in ['golden.postprocess_gvcf_input.tfrecord.gz', 'golden.postprocess_pacbio_gvcf_input.tfrecord.gz']:
   shutil.copy(T + src, os.path.join(OUT, src))
-for vcf in ['golden.postprocess_gvcf_output.g.vcf', 'golden.postprocess_gvcf_output_pacbio.g.vcf']:
+for vcf in ['golden.postprocess_gvcf_output.g.vcf', 'golden.postprocess_gvcf_output_pacbio.g.vcf', 'golden.haploid_chr20.postprocess_gvcf_output.g.vcf',
+            'golden.haploid_chr20.postprocess_single_site_output.vcf']:      # the last two: --haploid_contigs chr20
   with open(T + vcf, 'rb') as f, gzip.open(os.path.join(OUT, vcf + '.gz'), 'wb') as g:
     g.write(f.read())
   print(vcf, '-> .gz')
