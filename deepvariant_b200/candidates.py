@@ -88,9 +88,92 @@ def sample_name_from_bam(path: str) -> str:
   return samples[0] if samples else DEFAULT_SAMPLE_NAME
 
 
+END_OF_REGION = -1              # make_examples_core.py:125
+END_OF_PARTITION = -2           # :129
+MAX_PARTITION_LEN = 1000000     # :134
+MAX_CANDIDATES_PER_PARTITION = 200   # regions_to_process, :874
+
+
+def partition_by_candidates(regions: Sequence[Tuple[str, int, int]], candidate_positions: Sequence[int], max_size: int) -> List[Tuple[str, int, int]]:
+  """make_examples_core.py:714-796: cuts the calling intervals so that none holds more than max_size candidates (nor spans more than
+  MAX_PARTITION_LEN without one).  candidate_positions = the sorted positions of every interval in turn, each interval's run closed
+  by END_OF_REGION (the merged output of the candidate_sweep shards)."""
+  if max_size <= 0:
+    raise ValueError('max_size must be > 0: {}'.format(max_size))
+  out = []
+  it = 0
+  n = len(candidate_positions)
+  for name, start, end in regions:
+    count = 0
+    p_start = p_end = start
+    while it < n and candidate_positions[it] != END_OF_REGION and start <= candidate_positions[it] < end:
+      if count == max_size or p_end - p_start >= MAX_PARTITION_LEN:
+        for pos in range(p_start, p_end, MAX_PARTITION_LEN):
+          out.append((name, pos, min(p_end, pos + MAX_PARTITION_LEN)))
+        p_start = p_end
+        p_end = p_start + 1
+        count = 0
+      else:
+        p_end = int(candidate_positions[it]) + 1
+        count += 1
+      it += 1
+    if it < n and candidate_positions[it] == END_OF_REGION:
+      for pos in range(p_start, end, MAX_PARTITION_LEN):
+        out.append((name, pos, min(end, pos + MAX_PARTITION_LEN)))
+      it += 1
+    else:
+      raise ValueError('Terminating item is missing in candidates list')
+  return out
+
+
+def merge_ranges_from_files_sequential(position_arrays: Sequence[Sequence[int]]) -> List[int]:
+  """make_examples_core.py:3247-3325: the candidate_sweep shards hold the positions of partitions i, i + N, i + 2N ... each closed
+  by END_OF_PARTITION (and END_OF_REGION after the last partition of a calling region); reading one partition from every shard
+  in turn restores genome order.  Raises AssertionError when the result is not increasing."""
+  merged: List[int] = []
+  index = [0] * len(position_arrays)
+  shard = 0
+  left = len(position_arrays)
+  while left > 0:
+    arr = position_arrays[shard]
+    while index[shard] < len(arr):
+      if arr[index[shard]] == END_OF_PARTITION:
+        index[shard] += 1
+        if index[shard] < len(arr) and arr[index[shard]] == END_OF_REGION:
+          merged.append(END_OF_REGION)
+          index[shard] += 1
+        break
+      if merged:
+        assert arr[index[shard]] > merged[-1]
+      merged.append(int(arr[index[shard]]))
+      index[shard] += 1
+    if index[shard] == len(arr):
+      left -= 1
+    for _ in range(len(position_arrays)):                      # move_to_the_next_non_exhausted_shard (:3222-3244)
+      shard = (shard + 1) % len(position_arrays)
+      if index[shard] < len(position_arrays[shard]):
+        break
+  return merged
+
+
+def load_candidate_positions(path_spec: str) -> List[int]:
+  """make_examples_core.py:3328-3339: every shard of `path@N` (or the one file); unreadable shards are skipped as there."""
+  from deepvariant_b200 import tfrecord
+  arrays = []
+  for path in (tfrecord.shard_paths(path_spec) if tfrecord.is_sharded_spec(path_spec) else [path_spec]):
+    try:
+      arrays.append(np.fromfile(path, dtype=np.int32))
+    except IOError:
+      continue
+  return merge_ranges_from_files_sequential(arrays)
+
+
 def regions_to_process(contigs: Sequence[Tuple[str, int]], partition_size: int, calling_region: Optional[Tuple[str, int, int]] = None,
-                       task_id: Optional[int] = None, num_shards: Optional[int] = None) -> List[Tuple[str, int, int]]:
-  """contigs = [(name, n_bases)] in reference order; calling_region = (contig, start, end) 0-based half-open or None."""
+                       task_id: Optional[int] = None, num_shards: Optional[int] = None,
+                       candidates: Optional[Sequence[int]] = None) -> List[Tuple[str, int, int]]:
+  """contigs = [(name, n_bases)] in reference order; calling_region = (contig, start, end) 0-based half-open or None.
+  make_examples_core.py:799-888; with `candidates` (load_candidate_positions) the partitions are cut by candidate count instead of
+  by length.  Shards take partitions round robin (the TFRecord case, :3439)."""
   if (task_id is None) != (num_shards is None):
     raise ValueError('Both task_id and num_shards must be present if either is', task_id, num_shards)
   if num_shards:
@@ -98,15 +181,19 @@ def regions_to_process(contigs: Sequence[Tuple[str, int]], partition_size: int, 
       raise ValueError('task_id={} should be >= 0 and < num_shards={}'.format(task_id, num_shards))
   if partition_size <= 0:
     raise ValueError('max_size must be > 0: {}'.format(partition_size))
-  pieces = []
+  intervals = []
   for name, n_bases in contigs:
     lo, hi = 0, n_bases
     if calling_region is not None:
       if calling_region[0] != name:
         continue
       lo, hi = max(lo, calling_region[1]), min(hi, calling_region[2])
-    for pos in range(lo, hi, partition_size):
-      pieces.append((name, pos, min(hi, pos + partition_size)))
+    if lo < hi:
+      intervals.append((name, lo, hi))
+  if candidates is not None:
+    pieces = partition_by_candidates(intervals, candidates, MAX_CANDIDATES_PER_PARTITION)
+  else:
+    pieces = [(name, pos, min(hi, pos + partition_size)) for name, lo, hi in intervals for pos in range(lo, hi, partition_size)]
   if num_shards:
     return [r for i, r in enumerate(pieces) if i % num_shards == task_id]
   return pieces

@@ -57,7 +57,7 @@ MAKE_EXAMPLES_DEFAULTS = dict(
     sample_name='', vsc_min_count_snps=2, vsc_min_count_indels=2, vsc_min_fraction_snps=0.12, vsc_min_fraction_indels=0.06,
     vsc_min_fraction_multiplier=1.0, small_model_vaf_context_window_size=0, track_ref_reads=False, phase_reads=False,
     keep_legacy_allele_counter_behavior=False, normalize_reads=False, realign_reads=True, gvcf='', gvcf_gq_binsize=5, p_error=0.001,
-    include_med_dp=False, haploid_contigs='')      # --realign_reads defaults to true (make_examples_options.py:229)
+    include_med_dp=False, haploid_contigs='', candidate_positions='')      # --realign_reads defaults to true (make_examples_options.py:229)
 
 
 def model_example_info_json_path(checkpoint: str, checkpoint_json: str = '') -> str:
@@ -105,7 +105,8 @@ def apply_flags_for_calling(cli_values: dict, checkpoint: str, checkpoint_json: 
 
 def make_examples(argv):
   ap = argparse.ArgumentParser('make_examples', argument_default=argparse.SUPPRESS)
-  ap.add_argument('--mode', default='calling', choices=['calling'])
+  ap.add_argument('--mode', default='calling', choices=['calling', 'candidate_sweep'])
+  ap.add_argument('--candidate_positions')       # candidate_sweep: int32 positions out (sharded like --examples); calling: partitions cut by them
   ap.add_argument('--ref', required=True)
   ap.add_argument('--reads', required=True)
   ap.add_argument('--examples', required=True)
@@ -231,7 +232,28 @@ def make_examples(argv):
         gvcf_writer.write(gvcf.serialize_gvcf_record(block))
         totals['n_gvcf_records'] = totals.get('n_gvcf_records', 0) + 1
 
-    for contig, p0, p1 in cand.regions_to_process(contigs, a.partition_size, region, a.task, n_shards):
+    if a.mode == 'candidate_sweep':
+      # --mode candidate_sweep (make_examples_core.py:2117-2189, 3592-3605): the candidate positions of every partition of this task
+      # (no realigner, one counter pass), each partition closed by END_OF_PARTITION and a calling region by END_OF_REGION; a later
+      # calling run cuts its partitions by candidate count from the merged shards (--candidate_positions).
+      if not a.candidate_positions:
+        raise ValueError('--mode candidate_sweep needs --candidate_positions')
+      import numpy as np
+      path = tfrecord.shard_path(a.candidate_positions, a.task) if tfrecord.is_sharded_spec(a.candidate_positions) else a.candidate_positions
+      region_ends = {(c, min(n, region[2]) if region and region[0] == c else n) for c, n in contigs}
+      with open(path, 'wb') as f:
+        for contig, p0, p1 in cand.regions_to_process(contigs, a.partition_size, region, a.task, n_shards):
+          rows = cand.region_reads(reader, contig, p0, p1, copts.max_reads_per_partition, copts.random_seed)
+          positions = cand.candidate_positions(reader, ref, contig, p0, p1, rows, copts) + [cand.END_OF_PARTITION]
+          if (contig, p1) in region_ends:
+            positions.append(cand.END_OF_REGION)
+          f.write(np.asarray(positions, dtype=np.int32).tobytes())
+          totals['n_candidate_positions'] = totals.get('n_candidate_positions', 0) + sum(1 for x in positions if x >= 0)
+      gen.signal_shard_finished()
+      print(f'make_examples task {a.task}: {totals}', file=sys.stderr)
+      return 0
+    sweep = cand.load_candidate_positions(a.candidate_positions) if a.candidate_positions else None
+    for contig, p0, p1 in cand.regions_to_process(contigs, a.partition_size, region, a.task, n_shards, candidates=sweep):
       rows = cand.region_reads(reader, contig, p0, p1, copts.max_reads_per_partition, copts.random_seed)
       if not len(rows):
         if gvcf_writer is not None:               # no early exit with --gvcf: the region still gets its blocks (make_examples_core.py:2872-2875)
