@@ -50,6 +50,9 @@ def parse_region(s: str):
   return m.group(1), int(m.group(2).replace(',', '')) - 1, int(m.group(3).replace(',', ''))
 
 
+RUNTIME_BY_REGION_COLUMNS = ('region', 'get reads', 'find candidates', 'make pileup images', 'write outputs', 'num reads', 'num candidates', 'num examples',
+                             'small model generate examples', 'small model call examples', 'small model write variants', 'small model total')
+
 MAKE_EXAMPLES_DEFAULTS = dict(
     task=0, regions='', channel_list='BASE_CHANNELS', pileup_image_width=221, pileup_image_height=100, min_mapping_quality=5,
     min_base_quality=10, partition_size=1000, sort_by_haplotypes=False, trim_reads_for_pileup=False, parse_sam_aux_fields=False,
@@ -57,7 +60,7 @@ MAKE_EXAMPLES_DEFAULTS = dict(
     sample_name='', vsc_min_count_snps=2, vsc_min_count_indels=2, vsc_min_fraction_snps=0.12, vsc_min_fraction_indels=0.06,
     vsc_min_fraction_multiplier=1.0, small_model_vaf_context_window_size=0, track_ref_reads=False, phase_reads=False,
     keep_legacy_allele_counter_behavior=False, normalize_reads=False, realign_reads=True, gvcf='', gvcf_gq_binsize=5, p_error=0.001,
-    include_med_dp=False, haploid_contigs='', candidate_positions='')      # --realign_reads defaults to true (make_examples_options.py:229)
+    include_med_dp=False, haploid_contigs='', candidate_positions='', runtime_by_region='')      # --realign_reads defaults to true (make_examples_options.py:229)
 
 
 def model_example_info_json_path(checkpoint: str, checkpoint_json: str = '') -> str:
@@ -106,6 +109,7 @@ def apply_flags_for_calling(cli_values: dict, checkpoint: str, checkpoint_json: 
 def make_examples(argv):
   ap = argparse.ArgumentParser('make_examples', argument_default=argparse.SUPPRESS)
   ap.add_argument('--mode', default='calling', choices=['calling', 'candidate_sweep'])
+  ap.add_argument('--runtime_by_region')          # TSV: seconds per stage and counts, one line per region (sharded like --examples)
   ap.add_argument('--candidate_positions')       # candidate_sweep: int32 positions out (sharded like --examples); calling: partitions cut by them
   ap.add_argument('--ref', required=True)
   ap.add_argument('--reads', required=True)
@@ -253,12 +257,28 @@ def make_examples(argv):
       print(f'make_examples task {a.task}: {totals}', file=sys.stderr)
       return 0
     sweep = cand.load_candidate_positions(a.candidate_positions) if a.candidate_positions else None
-    for contig, p0, p1 in cand.regions_to_process(contigs, a.partition_size, region, a.task, n_shards, candidates=sweep):
+    # --runtime_by_region: one TSV line per region with the seconds of each stage and its counts (make_examples_core.py:95-108,
+    # 1348-1353, 3678-3707; docs/runtime-by-region.md).  Pileup encoding and the example writes are one fused step here
+    # (pack -> CUDA encode -> tf.Example), so 'make pileup images' holds both and 'write outputs' the candidate / gVCF records.
+    import time
+    runtime_writer = None
+    if a.runtime_by_region:
+      runtime_path = tfrecord.shard_path(a.runtime_by_region, a.task) if tfrecord.is_sharded_spec(a.runtime_by_region) else a.runtime_by_region
+      runtime_writer = open(runtime_path, 'w')
+      runtime_writer.write('\t'.join(RUNTIME_BY_REGION_COLUMNS) + '\n')
+
+    def mark(rt, stage):
+      now = time.time()
+      rt[stage] = round(rt.get(stage, 0) + now - rt['_t'], 3)        # trim_runtime: milliseconds
+      rt['_t'] = now
+
+    def region_body(contig, p0, p1, rt):
       rows = cand.region_reads(reader, contig, p0, p1, copts.max_reads_per_partition, copts.random_seed)
+      rt['num reads'] = len(rows)
       if not len(rows):
         if gvcf_writer is not None:               # no early exit with --gvcf: the region still gets its blocks (make_examples_core.py:2872-2875)
           write_gvcfs(cand.candidates_in_region(reader, ref, contig, p0, p1, copts, rows=rows, padding_pct=20 if a.phase_reads else 0), contig, p0, p1)
-        continue
+        return
       if rl is not None or a.normalize_reads:
         # --realign_reads: window selection, de Bruijn assembly, FastPassAligner (deepvariant_b200/realigner.py); the realigned reads
         # replace the region's reads for candidate generation AND pileups, as in_memory_sam_reader.replace_reads does
@@ -275,6 +295,7 @@ def make_examples(argv):
         refs = [(c, ref.n_bases(c)) for c in ref.contig_order]
         region_table = bam.scratch_table(region_read_list, refs, reqs, parse_aux=a.parse_sam_aux_fields)
         region_rows = region_table.query_indices(contig, p0, p1)
+        mark(rt, 'get reads')
         if count_reads is None:
           found = cand.candidates_in_region(region_table, ref, contig, p0, p1, copts, rows=region_rows, padding_pct=20 if a.phase_reads else 0)
         else:
@@ -283,11 +304,14 @@ def make_examples(argv):
           count_table = bam.scratch_table(count_reads, refs, reqs)
           found = cand.candidates_in_region(count_table, ref, contig, p0, p1, copts, rows=count_table.query_indices(contig, p0, p1))
           count_table.close()
+        mark(rt, 'find candidates')
         write_gvcfs(found, contig, p0, p1)
         totals['n_candidates'] = totals.get('n_candidates', 0) + len(found.records)
+        rt['num candidates'] = len(found.records)
         if cand_writer is not None:
           for rec in found.records:
             cand_writer.write(rec)
+        mark(rt, 'write outputs')
         if found.records:
           if table_path and not a.phase_reads:
             stats, _ = gen.write_examples_in_region_from_table(found.calls(), region_table, 'main_sample', (contig, p0, p1))
@@ -295,14 +319,21 @@ def make_examples(argv):
             stats, _ = gen.write_examples_in_region(found.calls(), [[region_table.read(int(i)) for i in region_rows]], [0], 'main_sample', [0.0])
           for key, val in stats.items():
             totals[key] = totals.get(key, 0) + val
+          rt['num examples'] = stats.get('n_examples', 0)
+        mark(rt, 'make pileup images')
         region_table.close()
-        continue
+        return
+      mark(rt, 'get reads')
       found = cand.candidates_in_region(reader, ref, contig, p0, p1, copts, rows=rows, padding_pct=20 if a.phase_reads else 0)
+      mark(rt, 'find candidates')
       write_gvcfs(found, contig, p0, p1)
+      rt['num candidates'] = len(found.records)
       totals['n_candidates'] = totals.get('n_candidates', 0) + len(found.records)
       if cand_writer is not None:
         for rec in found.records:
           cand_writer.write(rec)
+      mark(rt, 'write outputs')
+      before = totals.get('n_examples', 0)
       if found.records:
         if a.phase_reads:
           # direct phasing over the padded region's candidates (deepvariant/direct_phasing.cc); HP of every region read is
@@ -317,6 +348,16 @@ def make_examples(argv):
             totals[key] = totals.get(key, 0) + val
         else:
           examples_in(found.calls(), contig, p0, p1)
+      rt['num examples'] = totals.get('n_examples', 0) - before
+      mark(rt, 'make pileup images')
+
+    for contig, p0, p1 in cand.regions_to_process(contigs, a.partition_size, region, a.task, n_shards, candidates=sweep):
+      rt = {'_t': time.time(), 'region': f'{contig}:{p0 + 1}-{p1}', 'num reads': 0, 'num candidates': 0, 'num examples': 0}
+      region_body(contig, p0, p1, rt)
+      if runtime_writer is not None:
+        runtime_writer.write('\t'.join(str(rt.get(k, 'NA')) for k in RUNTIME_BY_REGION_COLUMNS) + '\n')
+    if runtime_writer is not None:
+      runtime_writer.close()
     if cand_writer is not None:
       cand_writer.close()
     if gvcf_writer is not None:

@@ -206,7 +206,17 @@ def test_cli_bam_to_gvcf_cpu_plumbing(tmp_path, monkeypatch):
   blocks = str(tmp_path / 'gvcf.tfrecord@2.gz')
   for task in (0, 1):
     assert cli.make_examples(['--mode', 'calling', '--ref', fa, '--reads', bam_path, '--examples', ex, '--gvcf', blocks, '--task', str(task),
-                              '--channel_list', 'BASE_CHANNELS,insert_size', '--regions', 'chr20:1-6000', '--norealign_reads']) == 0
+                              '--channel_list', 'BASE_CHANNELS,insert_size', '--regions', 'chr20:1-6000', '--norealign_reads',
+                              '--runtime_by_region', str(tmp_path / 'runtime.tsv@2')]) == 0
+  # --runtime_by_region: the reference's columns, one line per region of the task, counts that add up
+  rows = []
+  for task in (0, 1):
+    lines = open(tmp_path / f'runtime.tsv-0000{task}-of-00002').read().splitlines()
+    assert lines[0].split('\t') == list(cli.RUNTIME_BY_REGION_COLUMNS) and len(lines) == 1 + 3
+    rows += [dict(zip(cli.RUNTIME_BY_REGION_COLUMNS, l.split('\t'))) for l in lines[1:]]
+  assert sorted(r['region'] for r in rows) == sorted(f'chr20:{s + 1}-{s + 1000}' for s in range(0, 6000, 1000))
+  assert sum(int(r['num candidates']) for r in rows) == 4 == sum(int(r['num examples']) for r in rows)
+  assert all(float(r['find candidates']) >= 0 for r in rows if int(r['num reads'])) and rows[0]['small model total'] == 'NA'
   cvo_path = str(tmp_path / 'cvo.tfrecord.gz')
   with tfrecord.Writer(cvo_path) as w:
     for p in tfrecord.resolve_input_paths(ex):
