@@ -525,6 +525,35 @@ def get_sample_name(cvos: Sequence[Cvo], flag: str = '') -> str:
   return 'default'
 
 
+class _VcfTextWriter:
+  """Plain text, or - for *.gz - BGZF with a tabix index beside it, as the reference leaves it (deepvariant_b200/bgzf_tabix.py)."""
+
+  def __init__(self, path: str, header: str):
+    from deepvariant_b200 import bgzf_tabix
+    self._bgzf = bgzf_tabix.BgzfVcfWriter(path) if path.endswith('.gz') else None
+    self._f = None if self._bgzf else open(path, 'w')
+    if self._bgzf:
+      self._bgzf.write_header(header)
+    else:
+      self._f.write(header)
+
+  def write(self, line: str, v: 'OutVariant') -> None:
+    if self._bgzf:
+      self._bgzf.write_record(line, v.reference_name, v.start, v.end)
+    else:
+      self._f.write(line)
+
+  def __enter__(self):
+    return self
+
+  def __exit__(self, *exc):
+    if self._bgzf:
+      self._bgzf.close()
+    else:
+      self._f.close()
+    return False
+
+
 def postprocess_variants(infile: str, outfile: str, contigs: Sequence[Tuple[str, int]], sample_name: str = '', qual_filter: float = 1.0,
                          multi_allelic_qual_filter: float = 1.0, multiallelic_mode: str = 'product', only_keep_pass: bool = False,
                          disable_haplotype_resolution: bool = False, group_variants: bool = True, nonvariant_site_tfrecord_path: str = '',
@@ -550,15 +579,14 @@ def postprocess_variants(infile: str, outfile: str, contigs: Sequence[Tuple[str,
   if not disable_haplotype_resolution:
     variants = maybe_resolve_conflicting_variants(variants, qual_filter)
   n = 0
-  opener = gzip.open if outfile.endswith('.gz') else open
   if gvcf_outfile:
     variants = list(variants)
-  with opener(outfile, 'wt') as f:
-    f.write('\n'.join(vcf_header_lines(contigs, sample)) + '\n')
+  header = '\n'.join(vcf_header_lines(contigs, sample)) + '\n'
+  with _VcfTextWriter(outfile, header) as w:
     for v in variants:
       if only_keep_pass and v.filter != [PASS]:
         continue
-      f.write(vcf_line(v) + '\n')
+      w.write(vcf_line(v) + '\n', v)
       n += 1
   out = {'n_cvo_records': len(cvos), 'n_variants_written': n, 'sample_name': sample}
   if gvcf_outfile:
@@ -566,10 +594,9 @@ def postprocess_variants(infile: str, outfile: str, contigs: Sequence[Tuple[str,
     # ShardedVariantReader: the shards are each sorted, merged by (contig index, start)
     blocks.sort(key=lambda b: (order[b.reference_name], b.start, b.end))
     m = 0
-    with (gzip.open if gvcf_outfile.endswith('.gz') else open)(gvcf_outfile, 'wt') as f:
-      f.write('\n'.join(vcf_header_lines(contigs, sample)) + '\n')
+    with _VcfTextWriter(gvcf_outfile, header) as w:
       for rec in gvcf.merge_variants_and_nonvariants(variants, blocks, [c for c, _ in contigs], base_at):
-        f.write(gvcf.gvcf_line(rec) + '\n')
+        w.write(gvcf.gvcf_line(rec) + '\n', rec)
         m += 1
     out['n_gvcf_records_written'] = m
   return out
