@@ -168,10 +168,32 @@ def load_candidate_positions(path_spec: str) -> List[int]:
   return merge_ranges_from_files_sequential(arrays)
 
 
+def calling_intervals(contigs: Sequence[Tuple[str, int]], calling_regions=None) -> List[Tuple[str, int, int]]:
+  """RangeSet.from_contigs(contigs).intersection(calling_regions) (make_examples_core.py:868-870): the calling regions - one
+  (contig, start, end) or a list of them, in any order, overlapping ones merged - clipped to the contigs, in contig order."""
+  if calling_regions is None:
+    return [(name, 0, n) for name, n in contigs if n > 0]
+  if calling_regions and isinstance(calling_regions[0], str):
+    calling_regions = [calling_regions]
+  out = []
+  for name, n_bases in contigs:
+    own = sorted((max(0, s), min(n_bases, e)) for c, s, e in calling_regions if c == name)
+    merged: List[List[int]] = []
+    for s, e in own:
+      if s >= e:
+        continue
+      if merged and s < merged[-1][1]:
+        merged[-1][1] = max(merged[-1][1], e)
+      else:
+        merged.append([s, e])
+    out += [(name, s, e) for s, e in merged]
+  return out
+
+
 def regions_to_process(contigs: Sequence[Tuple[str, int]], partition_size: int, calling_region: Optional[Tuple[str, int, int]] = None,
                        task_id: Optional[int] = None, num_shards: Optional[int] = None,
                        candidates: Optional[Sequence[int]] = None) -> List[Tuple[str, int, int]]:
-  """contigs = [(name, n_bases)] in reference order; calling_region = (contig, start, end) 0-based half-open or None.
+  """contigs = [(name, n_bases)] in reference order; calling_region = (contig, start, end) 0-based half-open, a list of them, or None.
   make_examples_core.py:799-888; with `candidates` (load_candidate_positions) the partitions are cut by candidate count instead of
   by length.  Shards take partitions round robin (the TFRecord case, :3439)."""
   if (task_id is None) != (num_shards is None):
@@ -181,15 +203,7 @@ def regions_to_process(contigs: Sequence[Tuple[str, int]], partition_size: int, 
       raise ValueError('task_id={} should be >= 0 and < num_shards={}'.format(task_id, num_shards))
   if partition_size <= 0:
     raise ValueError('max_size must be > 0: {}'.format(partition_size))
-  intervals = []
-  for name, n_bases in contigs:
-    lo, hi = 0, n_bases
-    if calling_region is not None:
-      if calling_region[0] != name:
-        continue
-      lo, hi = max(lo, calling_region[1]), min(hi, calling_region[2])
-    if lo < hi:
-      intervals.append((name, lo, hi))
+  intervals = calling_intervals(contigs, calling_region)
   if candidates is not None:
     pieces = partition_by_candidates(intervals, candidates, MAX_CANDIDATES_PER_PARTITION)
   else:

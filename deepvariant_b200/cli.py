@@ -50,6 +50,25 @@ def parse_region(s: str):
   return m.group(1), int(m.group(2).replace(',', '')) - 1, int(m.group(3).replace(',', ''))
 
 
+def parse_regions(text: str):
+  """--regions as the reference takes it (make_examples_options.py: space-separated literals `chr20:10,000-20,000`, whole contigs
+  `chr20`, and BED files): a list of 0-based half-open (contig, start, end)."""
+  from deepvariant_b200 import postprocess_variants as pp
+  out = []
+  for token in text.split():
+    if token.endswith(('.bed', '.bed.gz')) or os.path.exists(token):
+      if token.endswith('.gz'):
+        import gzip
+        out += [(p[0], int(p[1]), int(p[2])) for p in (l.split() for l in gzip.open(token, 'rt')) if len(p) >= 3 and not p[0].startswith(('#', 'track', 'browser'))]
+      else:
+        out += pp.read_bed(token)
+    elif ':' in token:
+      out.append(parse_region(token))
+    else:
+      out.append((token, 0, 1 << 40))
+  return out
+
+
 RUNTIME_BY_REGION_COLUMNS = ('region', 'get reads', 'find candidates', 'make pileup images', 'write outputs', 'num reads', 'num candidates', 'num examples',
                              'small model generate examples', 'small model call examples', 'small model write variants', 'small model total')
 
@@ -172,7 +191,10 @@ def make_examples(argv):
   # are planned and packed straight from the table rows, trimmed ones (PACBIO, alt-aligned) from Read objects of table.query().
   reader = bam.NativeBamTable(a.reads, bam.ReadRequirements(min_mapping_quality=a.min_mapping_quality), parse_aux=a.parse_sam_aux_fields)
   table_path = not a.trim_reads_for_pileup and a.alt_aligned_pileup == 'none'
-  region = parse_region(a.regions) if a.regions else None
+  regions = parse_regions(a.regions) if a.regions else None
+  if regions is not None and len(regions) > 1 and (a.candidates_in or a.mode == 'candidate_sweep'):
+    raise NotImplementedError('several --regions together with --candidates_in / --mode candidate_sweep')
+  region = regions[0] if regions else None
   totals = {}
 
   def examples_in(cs, contig, p0, p1):
@@ -351,7 +373,7 @@ def make_examples(argv):
       rt['num examples'] = totals.get('n_examples', 0) - before
       mark(rt, 'make pileup images')
 
-    for contig, p0, p1 in cand.regions_to_process(contigs, a.partition_size, region, a.task, n_shards, candidates=sweep):
+    for contig, p0, p1 in cand.regions_to_process(contigs, a.partition_size, regions, a.task, n_shards, candidates=sweep):
       rt = {'_t': time.time(), 'region': f'{contig}:{p0 + 1}-{p1}', 'num reads': 0, 'num candidates': 0, 'num examples': 0}
       region_body(contig, p0, p1, rt)
       if runtime_writer is not None:

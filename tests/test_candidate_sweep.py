@@ -87,3 +87,26 @@ def test_two_pass_flow_through_the_cli(tmp_path, monkeypatch):
     assert cli.make_examples(['--mode', 'calling', '--examples', ex, '--candidates', cs] + extra + common) == 0
     outs.append((len(list(tfrecord.read_records(ex))), [cand.canonical_call(r)['start'] for r in tfrecord.read_records(cs)]))
   assert outs[0] == outs[1] == (4, sorted(sites.values()))
+
+
+def test_calling_intervals_and_several_regions(tmp_path, monkeypatch):
+  contigs = [('chr1', 1000), ('chr2', 500)]
+  assert cand.calling_intervals(contigs) == [('chr1', 0, 1000), ('chr2', 0, 500)]
+  assert cand.calling_intervals(contigs, ('chr2', 100, 9999)) == [('chr2', 100, 500)]
+  # any order, overlaps merged, empty and unknown-contig regions dropped, output in contig order
+  assert cand.calling_intervals(contigs, [('chr2', 100, 200), ('chr1', 50, 80), ('chr1', 70, 120), ('chr1', 300, 300), ('chrX', 0, 5)]) == \
+      [('chr1', 50, 120), ('chr2', 100, 200)]
+  assert cand.regions_to_process(contigs, 100, [('chr2', 100, 250), ('chr1', 950, 2000)]) == [('chr1', 950, 1000), ('chr2', 100, 200), ('chr2', 200, 250)]
+  # the stage CLI: two literals and a BED file; the planted variants inside them come out, the others do not
+  import test_candidates as tc
+  from deepvariant_b200 import cli, make_examples_native as men, pileup_image as pi, tfrecord
+  monkeypatch.setattr(men.ExamplesGenerator, '_gpu', lambda self: tc.OracleEncoder(pi.to_params(self.options.pic_options, height=self.pileup_image_height)))
+  fa, bam_path, genome, sites = tc._planted_case(tmp_path)
+  bed = tmp_path / 'r.bed'
+  bed.write_text(f'chr20\t{sites["dele"] - 100}\t{sites["dele"] + 100}\n')
+  assert cli.parse_regions(f'chr20:1,401-1,600 chr20 {bed}') == [('chr20', 1400, 1600), ('chr20', 0, 1 << 40), ('chr20', sites['dele'] - 100, sites['dele'] + 100)]
+  cs = str(tmp_path / 'c.tfrecord.gz')
+  assert cli.make_examples(['--mode', 'calling', '--ref', fa, '--reads', bam_path, '--examples', str(tmp_path / 'e.tfrecord.gz'), '--candidates', cs,
+                            '--channel_list', 'BASE_CHANNELS,insert_size', '--norealign_reads',
+                            '--regions', f'chr20:{sites["snp_het"] - 50}-{sites["snp_het"] + 50} {bed}']) == 0
+  assert [cand.canonical_call(r)['start'] for r in tfrecord.read_records(cs)] == [sites['snp_het'], sites['dele']]
