@@ -45,6 +45,9 @@ def parse_args():
   ap.add_argument('--cpu-sample', type=int, default=2048, help='images in the bounded CPU sample')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-e2e', action='store_true')
+  ap.add_argument('--no-extras', action='store_true', help='skip the parity / precision1 / config4 / config5 blocks')
+  ap.add_argument('--parity-sample', type=int, default=48, help='windows of the last timed step re-derived on the CPU oracle')
+  ap.add_argument('--config5-windows', type=int, default=10_000_000)
   return ap.parse_args()
 
 
@@ -260,6 +263,70 @@ def ensure_built():
       time.sleep(1.0)
 
 
+
+def pacbio_options():
+  """Config 4 (BASELINE.json: HG003 PacBio HiFi, --model_type=PACBIO): 100 x 147 x 10 (8 computed channels + 2 alt-aligned)."""
+  from deepvariant_b200 import pileup_image as pi
+  o = pi.default_options()
+  o.channels = pi.PILEUP_DEFAULT_CHANNELS + ['haplotype', 'supplementary_alignment',
+                                             'diff_channels_alternate_allele_1', 'diff_channels_alternate_allele_2']
+  o.width = 147
+  o.sort_by_haplotypes = True
+  return o
+
+
+def device_time_ms(stream, fn, steps, barrier):
+  """CUDA-event time of `steps` calls of fn on `stream`, bracketed by barriers; returns ms per call."""
+  import torch
+  barrier()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record(stream)
+  for _ in range(steps):
+    fn()
+  e1.record(stream)
+  barrier()
+  return e0.elapsed_time(e1) / steps
+
+
+def max_over_ranks(x, dev, world):
+  import torch
+  import torch.distributed as dist
+  t = torch.tensor([x], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  return float(t.item())
+
+
+def parity_block(params, tb, images, probs, weights_seed, n_sample, probs_p1=None):
+  """Untimed, after the timed loop: a spread of the LAST step's windows re-derived on the CPU oracle (tests/oracle_lib: C++
+  restatement of pileup_image_native; tests/cnn_oracle: torch fp32 Inception-v3).  Images must be bit-exact."""
+  import numpy as np
+  import torch
+  import cnn_oracle
+  import oracle_lib
+  from subbatch_util import take_images
+  from deepvariant_b200 import modeling
+  B = tb.n_images
+  n_sample = max(3, min(n_sample, B))
+  third = n_sample // 3
+  idx = np.unique(np.r_[0:third, B // 2:B // 2 + third, B - (n_sample - 2 * third):B])
+  packed = tb.to_packed()
+  want_img = oracle_lib.encode_batch(params, take_images(packed, idx))
+  got_img = images[torch.from_numpy(idx).to(images.device)].cpu().numpy()
+  equal = int(sum(np.array_equal(got_img[i], want_img[i]) for i in range(len(idx))))
+  out = {'images_checked': int(len(idx)), 'images_equal': equal, 'checker': 'oracle/dvb_oracle.cc (encoder, bit-exact) + tests/cnn_oracle.py (torch fp32)'}
+  if probs is not None:
+    w = modeling.random_weights(int(want_img.shape[3]), weights_seed)
+    want_p = cnn_oracle.ReferenceModel(w).forward(torch.from_numpy(want_img)).numpy()
+    got_p = probs[torch.from_numpy(idx).to(probs.device)].cpu().numpy()
+    out.update({'precision': 0, 'max_abs_dp': float(np.abs(got_p - want_p).max()), 'tolerance_fp16_mode': 5e-3})
+    if probs_p1 is not None:
+      got1 = probs_p1[torch.from_numpy(idx).to(probs_p1.device)].cpu().numpy()
+      out['max_abs_dp_precision1'] = float(np.abs(got1 - want_p).max())
+      out['tolerance_precision1'] = 1e-5
+  return out
+
+
 _REAL_STDOUT = None
 
 
@@ -283,7 +350,8 @@ def main():
     return
   import torch
   import torch.distributed as dist
-  from deepvariant_b200 import pileup_image as pi, synthetic
+  import numpy as np
+  from deepvariant_b200 import call_variants as cv, pileup_image as pi, synthetic
 
   world = int(os.environ.get('WORLD_SIZE', '1'))
   rank = int(os.environ.get('RANK', '0'))
@@ -307,7 +375,6 @@ def main():
   stage = args.stage
   if stage in ('auto', 'both'):
     try:
-      from deepvariant_b200 import call_variants as cv
       cnn = cv.GpuCnn.random_init(enc.shape, device=local, max_batch=B)
       stage = 'both'
     except (ImportError, AttributeError) as e:
@@ -365,7 +432,6 @@ def main():
   if not args.no_e2e:
     host = tb.to('cpu').pin()       # the caller's batch, in pinned host memory
     h2d = host.input_bytes()
-    import numpy as np
     if cnn:
       out_host = torch.empty((B, 3), dtype=torch.float32).pin_memory()
       out_np = out_host.numpy()
@@ -403,6 +469,96 @@ def main():
            'd2h_bytes_per_step': d2h, 'steps': n_e2e,
            'api': 'dvb_encode_classify_host (C ABI, pinned host DvbBatch in, host probabilities out, synchronous)' if cnn else 'device entry points + torch copies'}
     del keep
+
+  # ---- extras (all ranks take part in the timed parts; rank 0 reports): precision 1, config 4, config 5, parity ----
+  extras = {}
+  if not args.no_extras:
+    k_x = max(2, args.steps // 4)
+    if cnn:
+      # (1) precision 1 = split-fp16 x3, the mode that meets the north star's 1e-5: same step, same windows
+      cnn1 = cv.GpuCnn.random_init(enc.shape, device=local, max_batch=min(B, 2048), precision=1)
+      probs1 = torch.empty((B, 3), dtype=torch.float32, device=dev)
+
+      def step1():
+        enc.encode_device(tb, images, stream=stream)
+        cnn1.forward_device(images, probs1, stream=stream)
+      step1()
+      ms1 = max_over_ranks(device_time_ms(stream, step1, k_x, barrier), dev, world)
+      p1 = {'value': world * B / (ms1 * 1e-3), 'unit': UNIT, 'ms_per_step': ms1, 'steps': k_x,
+            'dtype': 'u8 encode + split-fp16 x3 CNN (fp32-grade products, fp32 accumulate)'}
+      if e2e is not None:
+        out1 = np.empty((B, 3), dtype=np.float32)
+        enc.encode_classify_host(host, cnn1, out1)
+        barrier()
+        t_a = time.perf_counter()
+        for _ in range(k_x):
+          enc.encode_classify_host(host, cnn1, out1)
+        torch.cuda.synchronize()
+        t_e = max_over_ranks((time.perf_counter() - t_a) * 1e3 / k_x, dev, world)
+        barrier()
+        p1['e2e'] = {'value': world * B / (t_e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': k_x}
+      extras['precision1'] = p1
+    # (2) config 5: encode-only sweep over --config5-windows candidate windows (several distinct chunks, cycled)
+    n_launch = max(1, (args.config5_windows + B - 1) // B)
+    chunks = [tb] + [synthetic.make_batch(B, dev, chunk=world * (1 + j) + rank) for j in range(2)]
+    it = [0]
+
+    def enc_only():
+      enc.encode_device(chunks[it[0] % len(chunks)], images, stream=stream)
+      it[0] += 1
+    enc_only()
+    ms5 = max_over_ranks(device_time_ms(stream, enc_only, n_launch, barrier), dev, world)
+    enc.check()
+    ab5 = sum(c.algorithmic_bytes(enc.image_bytes, o.width) for c in chunks) / len(chunks)
+    extras['config5_encode_only'] = {
+        'n_windows': world * n_launch * B, 'windows_per_s': world * B / (ms5 * 1e-3), 'ms_per_launch': ms5, 'launches_per_gpu': n_launch,
+        'gbs_per_gpu': ab5 / (ms5 * 1e-3) / 1e9, 'frac': ab5 / (ms5 * 1e-3) / 1e9 / peaks['hbm_gbs'], 'peak': peaks['hbm_gbs'],
+        'workload': 'synthetic 30x reads, 100x221x7 windows, %d distinct chunks of %d cycled' % (len(chunks), B)}
+    del chunks
+    # (3) config 4: PACBIO layout (100 x 147 x 10), encode + classify on long-read-shaped synthetic windows
+    if cnn:
+      o4 = pacbio_options()
+      params4 = pi.to_params(o4)
+      enc4 = pi.GpuEncoder(params4, device=local)
+      tb4 = synthetic.make_batch(B, dev, chunk=rank, width=o4.width, hp=True)
+      images4 = torch.empty((B,) + enc4.shape, dtype=torch.uint8, device=dev)
+      cnn4 = cv.GpuCnn.random_init(enc4.shape, device=local, max_batch=B)
+      probs4 = torch.empty((B, 3), dtype=torch.float32, device=dev)
+
+      def enc4_only():
+        enc4.encode_device(tb4, images4, stream=stream)
+
+      def step4():
+        enc4.encode_device(tb4, images4, stream=stream)
+        cnn4.forward_device(images4, probs4, stream=stream)
+      step4()
+      ms4 = max_over_ranks(device_time_ms(stream, step4, k_x, barrier), dev, world)
+      ms4e = max_over_ranks(device_time_ms(stream, enc4_only, 4 * k_x, barrier), dev, world)
+      enc4.check()
+      ab4 = tb4.algorithmic_bytes(enc4.image_bytes, o4.width)
+      r4 = cnn4.roofline(ms4 - ms4e, B, peaks)
+      extras['config4_pacbio'] = {
+          'value': world * B / (ms4 * 1e-3), 'unit': UNIT, 'ms_per_step': ms4, 'steps': k_x, 'image_shape': list(enc4.shape),
+          'roofline': {k: r4[k] for k in ('bound', 'achieved', 'peak', 'unit', 'frac', 'flops_per_image', 'ms_cnn_per_step')},
+          'roofline_encoder': {'bound': 'hbm', 'achieved': ab4 / (ms4e * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                               'frac': ab4 / (ms4e * 1e-3) / 1e9 / peaks['hbm_gbs'], 'ms_per_launch': ms4e,
+                               'windows_per_s_encode_only': B / (ms4e * 1e-3)}}
+      if rank == 0:
+        extras['config4_pacbio']['parity'] = parity_block(params4, tb4, images4, probs4, 0, min(args.parity_sample, 24))
+      cnn4.close(); enc4.close()
+      del images4, tb4
+    # (4) parity of what was just timed: the last step's images / probabilities against the CPU oracle
+    if rank == 0:
+      step()
+      if cnn:
+        cnn1.forward_device(images, probs1, stream=stream)
+      torch.cuda.synchronize()
+      extras['parity'] = parity_block(params, tb, images, probs, 0, args.parity_sample, probs1 if cnn else None)
+      if cnn and 'precision1' in extras:
+        extras['precision1']['max_abs_dp'] = extras['parity'].get('max_abs_dp_precision1')
+    if cnn:
+      cnn1.close()
+    barrier()
 
   if rank != 0:
     if world > 1:
@@ -459,6 +615,7 @@ def main():
       'gpu_launches': launches, 'clocks': clocks, 'e2e': e2e, 'roofline': roofline, 'roofline_encoder': roof_enc,
       'cpu_baseline': cpu_baseline,
   }
+  line.update(extras)
   emit(line)
   if world > 1:
     dist.destroy_process_group()

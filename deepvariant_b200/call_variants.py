@@ -154,31 +154,6 @@ def create_cvo(variant_encoded: bytes, gls: Sequence[float], alt_allele_indices_
   return bytes(out)
 
 
-def smoke(images) -> None:
-  """Called by __graft_entry__.smoke(): a few encoder images through the CNN, checked against the
-  torch fp32 oracle (tests/cnn_oracle.py)."""
-  import torch
-  import cnn_oracle
-  n = min(8, int(images.shape[0]))
-  shape = tuple(int(x) for x in images.shape[1:])
-  w = modeling.random_weights(shape[2], 0)
-  net = GpuCnn(w, shape, device=0, max_batch=n)
-  probs = torch.empty((n, 3), dtype=torch.float32, device=images.device)
-  net.forward_device(images[:n].contiguous(), probs)
-  torch.cuda.synchronize()
-  want = cnn_oracle.ReferenceModel(w).forward(images[:n].cpu())
-  err = (probs.cpu() - want).abs().max().item()
-  print(f'[smoke] cnn: {n} images, max |p - oracle fp32| = {err:.2e}, launches {net.launch_count}')
-  assert err < 5e-3, 'CNN output far from the fp32 oracle'
-  net.close()
-  precise = GpuCnn(w, shape, device=0, max_batch=n, precision=1)
-  precise.forward_device(images[:n].contiguous(), probs)
-  torch.cuda.synchronize()
-  err1 = (probs.cpu() - want).abs().max().item()
-  print(f'[smoke] cnn precision 1 (split-fp16 x3): max |p - oracle fp32| = {err1:.2e}')
-  assert err1 < 1e-5, 'precision-1 CNN output is not within 1e-5 of the fp32 oracle'
-
-
 # ---- the stage driver (deepvariant/call_variants.py:766-1047) -------------------------------------
 
 _MAX_WRITER_THREADS = 16   # call_variants.py:82
@@ -188,9 +163,13 @@ def load_weights(checkpoint_path: str, in_channels: int) -> modeling.ModelWeight
   """Model weights for --checkpoint: a TensorFlow SavedModel directory or checkpoint prefix (tf_checkpoint.py reads the tensor
   bundle without TensorFlow), a .npz written by modeling.save_npz, or 'random[:seed]' (architecture-correct random init; no
   Inception weights ship with the reference)."""
-  if checkpoint_path.startswith('random'):
-    seed = int(checkpoint_path.split(':')[1]) if ':' in checkpoint_path else 0
-    return modeling.random_weights(in_channels, seed)
+  import re
+  import sys
+  m = re.fullmatch(r'random(?::(\d+))?', checkpoint_path)   # the exact token only: 'random_forest_model/' is a path, not a request for noise
+  if m:
+    print('call_variants: WARNING - --checkpoint random: architecture-correct RANDOM weights; the genotype calls are noise '
+          '(smoke runs and benchmarks only)', file=sys.stderr)
+    return modeling.random_weights(in_channels, int(m.group(1) or 0))
   if checkpoint_path.endswith('.npz'):
     w = modeling.load_npz(checkpoint_path)
     if w.in_channels != in_channels:
@@ -224,10 +203,35 @@ def write_empty_output_file(output_file: str) -> List[str]:
   return paths
 
 
+def check_example_info(examples_info: dict, model_info: Optional[dict]) -> None:
+  """The reference refuses to classify examples whose shape or channel list differs from the model's
+  model.example_info.json (deepvariant/call_variants.py:724-763)."""
+  if not model_info:
+    return
+  if [int(x) for x in model_info.get('shape', examples_info['shape'])] != [int(x) for x in examples_info['shape']]:
+    raise ValueError(f'examples have shape {examples_info["shape"]}, the model was trained on {model_info["shape"]}')
+  if 'channels' in model_info and 'channels' in examples_info and \
+      [int(x) for x in model_info['channels']] != [int(x) for x in examples_info['channels']]:
+    raise ValueError(f'examples have channels {examples_info["channels"]}, the model was trained on {model_info["channels"]}')
+
+
+def model_example_info(checkpoint_path: str) -> Optional[dict]:
+  """model.example_info.json beside a checkpoint / inside a SavedModel directory, or None."""
+  import json
+  import os
+  for cand in (os.path.join(checkpoint_path, 'example_info.json'), os.path.join(checkpoint_path, 'model.example_info.json'),
+               os.path.join(os.path.dirname(checkpoint_path), 'example_info.json'),
+               os.path.join(os.path.dirname(checkpoint_path), 'model.example_info.json'), checkpoint_path + '.example_info.json'):
+    if os.path.isfile(cand):
+      return json.load(open(cand))
+  return None
+
+
 def call_variants(examples_filename: str, checkpoint_path: str, output_file: str, batch_size: int = _DEFAULT_BATCH,
-                  writer_threads: int = 0, device: int = 0, max_batches: Optional[int] = None, reader_threads: int = 0) -> dict:
+                  writer_threads: int = 0, device: int = 0, max_batches: Optional[int] = None, reader_threads: int = 0,
+                  precision: int = 1) -> dict:
   """examples TFRecords -> CallVariantsOutput TFRecords (main loop of deepvariant/call_variants.py:766-1047).  Returns
-  {'n_examples', 'n_batches', 'paths'}.
+  {'n_examples', 'n_batches', 'paths'}.  precision: 1 = split-fp16 x3 (1e-5 of fp32, default), 0 = fp16 operands (3x faster).
 
   The records never become Python objects: records.NativeExamplesReader (C++ threads: gunzip, TFRecord framing + CRC,
   tf.Example field extraction, tf.data's interleave order) fills a pinned uint8 batch buffer, the classifier runs on it,
@@ -251,8 +255,11 @@ def call_variants(examples_filename: str, checkpoint_path: str, output_file: str
       info = json.load(open(info_path))
       if [int(x) for x in info['shape']] != shape:
         raise ValueError(f'example_info.json shape {info["shape"]} != example image/shape {shape}')
+      check_example_info(info, model_example_info(checkpoint_path))
     weights = load_weights(checkpoint_path, shape[2])
-    net = GpuCnn(weights, shape, device=device, max_batch=min(batch_size, 2048))
+    # precision 1 (split-fp16 x3, within 1e-5 of fp32) is the default of the VCF-producing path: the probabilities are rounded
+    # to 10 decimals and feed GQ / QUAL / PL; precision 0 (fp16 operands, 3e-4) is the throughput mode bench.py headlines.
+    net = GpuCnn(weights, shape, device=device, max_batch=min(batch_size, 2048), precision=precision)
     out_paths = output_shard_paths(output_file, writer_threads)
     writers = [records.NativeCvoWriter(p, _GL_PRECISION) for p in out_paths]
     pinned = torch.empty((2, batch_size, image_bytes), dtype=torch.uint8).pin_memory()

@@ -397,9 +397,10 @@ def call_variants(argv):
   ap.add_argument('--batch_size', type=int, default=1024)
   ap.add_argument('--writer_threads', type=int, default=0)
   ap.add_argument('--device', type=int, default=0)
+  ap.add_argument('--precision', type=int, default=1, choices=[0, 1])   # 1: split-fp16 x3, 1e-5 of fp32 (default); 0: fp16 operands
   a = ap.parse_args(argv)
   from deepvariant_b200 import call_variants as cv
-  r = cv.call_variants(a.examples, a.checkpoint, a.outfile, a.batch_size, a.writer_threads, a.device)
+  r = cv.call_variants(a.examples, a.checkpoint, a.outfile, a.batch_size, a.writer_threads, a.device, precision=a.precision)
   print(f'call_variants: {r["n_examples"]} examples in {r["n_batches"]} batches -> {len(r["paths"])} shard(s)', file=sys.stderr)
   return 0
 
@@ -445,7 +446,8 @@ def run_deepvariant(argv):
   ap.add_argument('--sample_name', default='')
   ap.add_argument('--regions', default='')
   ap.add_argument('--num_shards', type=int, default=1)
-  ap.add_argument('--customized_model', default='random')
+  ap.add_argument('--customized_model', required=True)   # SavedModel dir / checkpoint prefix / .npz; the exact token random[:seed] = noise weights (loud warning)
+  ap.add_argument('--precision', type=int, default=1, choices=[0, 1])
   a = ap.parse_args(argv)
   os.makedirs(a.output_dir, exist_ok=True)
   d = MODEL_DEFAULTS[a.model_type]
@@ -472,7 +474,7 @@ def run_deepvariant(argv):
       args += ['--gvcf', nonvariants]
     make_examples(args)
   cvo = os.path.join(a.output_dir, 'call_variants_output.tfrecord.gz')
-  rc = call_variants(['--examples', examples, '--outfile', cvo, '--checkpoint', a.customized_model])
+  rc = call_variants(['--examples', examples, '--outfile', cvo, '--checkpoint', a.customized_model, '--precision', str(a.precision)])
   if rc or not a.output_vcf:
     return rc
   args = ['--ref', a.ref, '--infile', cvo, '--outfile', a.output_vcf]     # the shards call_variants wrote are found by name

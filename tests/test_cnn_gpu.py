@@ -251,3 +251,64 @@ def test_pool_after_conv_rewrite_matches_original_order(monkeypatch):
   scale = float(np.abs(outs[1][0]).max())
   assert float(np.abs(outs[0][0] - outs[1][0]).max()) / scale < 1e-2
   assert float(np.abs(outs[0][1] - outs[1][1]).max()) < 2e-3
+
+
+# ---- every convolution kernel the bench runs, against the oracle ---------------------------------
+# bench.py runs chunks of 4096 images: the plan then routes 26 layers through conv_gemm_persistent_kernel (rule: K block 64,
+# N block >= 160, >= 4 tiles per SM) including the merged-1x1 multi-destination epilogue.  At test-sized batches that rule
+# never fires, so these tests (a) force it (DVB_CNN_PERSIST=2: every GEMM-shaped layer on the persistent kernel) at small
+# batch and compare every block output with the oracle, both geometries, and (b) run the DEFAULT rule at 2,048 images and
+# compare a spread of images with the oracle and all of them with the same engine at chunk 8 (one-tile-per-CTA kernels).
+
+ALL_BLOCKS = STEM + [f'mixed{i}' for i in range(11)]
+BRANCHES = ['mixed0_b5a', 'mixed0_d2', 'mixed3_d2', 'mixed4_s2', 'mixed4_d4', 'mixed8_b3', 'mixed9_t1', 'mixed9_d2']
+
+
+@pytest.mark.parametrize('shape,n', [((100, 221, 7), 5), ((100, 147, 10), 4)])
+def test_persistent_kernel_forced_every_block_matches_oracle(monkeypatch, shape, n):
+  monkeypatch.setenv('DVB_CNN_PERSIST', '2')
+  report, worst, got_p, want_p, net, pooled = _check_layers(shape, n, ALL_BLOCKS + BRANCHES, seed=21)
+  print(report)
+  for name, err in report:
+    assert err < 2e-2, report
+  assert float((got_p - want_p).abs().max()) < 5e-3
+  net.close()
+
+
+def test_persistent_kernel_forced_equals_default_plan(monkeypatch):
+  """Same operands, same K order, fp32 accumulation in TMEM: the persistent kernel and the one-tile-per-CTA kernel must give
+  the same activations wherever both can run the layer (tolerance: 1e-5 of scale; fp16 storage makes any real difference >= 5e-4)."""
+  shape = (100, 221, 7)
+  w = modeling.random_weights(7, 22)
+  imgs = _images(6, shape, 22)
+  outs = []
+  for mode in ('0', '2'):
+    monkeypatch.setenv('DVB_CNN_PERSIST', mode)
+    net = cv.GpuCnn(w, shape, device=0, max_batch=6)
+    probs = net.forward_host(imgs.numpy())
+    outs.append((probs, {k: net.debug_tensor(k, 6) for k in ('mixed0', 'mixed4', 'mixed7', 'mixed10')}))
+    net.close()
+  for k in outs[0][1]:
+    scale = float(np.abs(outs[0][1][k]).max())
+    assert float(np.abs(outs[0][1][k] - outs[1][1][k]).max()) <= 1e-5 * scale, k   # measured: identical
+  assert float(np.abs(outs[0][0] - outs[1][0]).max()) <= 1e-6
+
+
+def test_default_plan_at_bench_scale_matches_oracle_and_small_chunks():
+  """2,048 images in ONE chunk: the plan bench.py times (persistent kernel by rule, halo kernels, fused stem).  A spread of the
+  images is checked against the fp32 oracle; every image against the same engine run in chunks of 8."""
+  shape = (100, 221, 7)
+  n = 2048
+  w = modeling.random_weights(7, 23)
+  imgs = _images(n, shape, 23)
+  big = cv.GpuCnn(w, shape, device=0, max_batch=n)
+  got = big.forward_host(imgs.numpy())
+  big.close()
+  small = cv.GpuCnn(w, shape, device=0, max_batch=8)
+  ref8 = small.forward_host(imgs.numpy())
+  small.close()
+  assert float(np.abs(got - ref8).max()) < 1e-6, 'bench-scale plan differs from the small-chunk plan'
+  idx = np.r_[0:8, 1020:1028, n - 8:n]
+  want = cnn_oracle.ReferenceModel(w).forward(imgs[idx]).numpy()
+  assert float(np.abs(got[idx] - want).max()) < 5e-3
+  assert np.all(np.abs(got.sum(1) - 1) < 1e-6)
