@@ -141,6 +141,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__host__ __device__ __forceinline__ int TmemColsDev(int n) { int c = 32; while (c < n) c <<= 1; return c; }
+
+__device__ __forceinline__ uint4 hmax2x4(const uint4 a, const uint4 b) {
+  uint4 r;
+  const __half2* x = reinterpret_cast<const __half2*>(&a);
+  const __half2* y = reinterpret_cast<const __half2*>(&b);
+  __half2* z = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) z[j] = __hmax2(x[j], y[j]);
+  return r;
+}
+
 // UMMA shared-memory descriptor, K-major canonical layouts (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 //   [0,14) start>>4  [16,30) LBO>>4  [32,46) SBO>>4  [46,48) version=1  [61,64) layout type
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
@@ -319,6 +331,7 @@ struct ConvArgs {
   __half* out_res;
   uint32_t a_res_off, b_res_off;
   int skip_a_res;                 // the A residual plane is identically zero (network input): skip its load and MMA
+  int dbg;                        // timing probes (DVB_CNN_DBG; results are garbage): 1 = no TMA loads, MMAs do not wait; 2 = TMA loads, no MMAs
 };
 
 // Epilogue of one accumulator row of a merged GEMM: 16-column chunks, each routed to the tensor that owns its column
@@ -385,7 +398,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if constexpr (kSplit) { prefetch_tmap(&map_a_res); prefetch_tmap(&map_b_res); }
       int st = 0;
       uint32_t ph = 0;
-      for (int r = 0; r < p.kh; ++r) {
+      for (int r = 0; r < p.kh && !(p.dbg & 1); ++r) {
         for (int s = 0; s < p.kw; ++s) {
           for (int cb = 0; cb < p.cin_blocks; ++cb) {
             mbar_wait(&empty_bar[st], ph ^ 1);
@@ -417,9 +430,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       int st = 0;
       uint32_t ph = 0, a_lo = a_lo0, b_lo = b_lo0, acc = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[st], ph);
+        if (!(p.dbg & 1)) mbar_wait(&full_bar[st], ph);
         tc_fence_after();
-        if constexpr (kSplit) {
+        if (p.dbg & 2) {
+        } else if constexpr (kSplit) {
           const uint32_t a_res = a_lo + (p.a_res_off >> 4), b_res = b_lo + (p.b_res_off >> 4), d1 = tmem_base + (uint32_t)p.block_n;
           const bool with_a_res = !p.skip_a_res;
           for (int k = 0; k < mma_per_kb; ++k) {
@@ -518,7 +532,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
       // ===== TMA producer =====
       int st = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      for (int t = blockIdx.x; t < total && !(p.dbg & 1); t += gridDim.x) {
         const int nb = t / m_tiles;
         int m = t - nb * m_tiles;
         const int tw = m % p.tiles_w; m /= p.tiles_w;
@@ -554,12 +568,14 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
         const uint32_t d = tmem_base + (uint32_t)(buf * p.block_n);
         uint32_t acc = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[st], ph);
+          if (!(p.dbg & 1)) mbar_wait(&full_bar[st], ph);
           tc_fence_after();
+          if (!(p.dbg & 2)) {
 #pragma unroll 4
-          for (int k = 0; k < mma_per_kb; ++k) {
-            umma_f16_lohi(d, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, acc);
-            acc = 1;
+            for (int k = 0; k < mma_per_kb; ++k) {
+              umma_f16_lohi(d, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, acc);
+              acc = 1;
+            }
           }
           umma_commit(&empty_bar[st]);
           a_lo += a_inc; b_lo += b_inc;
@@ -1070,6 +1086,267 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row-streaming 3x3 convolution with the kernel rows stacked along N  (conv2, conv3 [+ max pool p1] of the stem)
+// ---------------------------------------------------------------------------------------------
+// What bounds the narrow stem layers on the kernels above: an M = 128 SS-mode MMA keeps the tensor pipe busy for about
+// 64 + N/2 clocks (the 4 KB A tile is read from shared memory at 64 B per clock whatever N is), so N = 32 / 64 runs at
+// 20 / 33 % of the pipe's rate (measured: conv2 61 % pipe-busy at 12 % of the math rate).  Here N is made 3x wider without
+// any extra arithmetic: ONE input row (128 pixel slots x Cin, one TMA box, fetched exactly once) is multiplied by the filters
+// of all three kernel rows at once, B = [3 kw taps x Cin] x [3 kernel rows x Cout], and the three column blocks of the result
+// accumulate into the TMEM accumulators of three DIFFERENT output rows (input row j adds to output rows j, j-1, j-2).  The
+// accumulators of a stream of rows live in a ring of three column slots; which kernel row lands in which slot rotates with
+// the step, and the rotation is free: the filter tile is stored as five row blocks [r2 r1 r0 r2 r1] and the B descriptor
+// starts at block 2 - (step mod 3).  Per input row: 3 x (Cin / 16) MMAs of N = 3 Cout (conv2: 6 x (64 + 48) = 672 clocks instead
+// of 18 x 80 = 1440; conv3: 960 instead of 1728).  An accumulator slot is complete two steps after it was opened; the epilogue
+// drains it, stores zeros back (every MMA accumulates) and hands it back.  MMA(t + 1) depends on drain(t), so a CTA runs TWO
+// independent streams (two images) that fill each other's bubbles.  One CTA per SM; each stream walks whole images, so rows
+// never cross CTAs and the 3x3 / stride-2 max pool that follows conv3 is fused: the epilogue thread that owns pixel column w
+// keeps the running vertical maximum in registers (fp16 max is exact), every second row goes through a shared-memory row
+// for the horizontal 3-max and leaves as coalesced 16-byte stores - conv3's output (2.7 GB per 4096 images) is never written.
+constexpr int kRowsThreads = 320;        // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue of stream 0, warps 6-9 of stream 1
+constexpr int kRowsRing = 4;             // input-row buffers per stream
+
+struct RowsArgs {
+  int cin, cout;                 // stored input channels (32 or 64), output channels (3 * cout <= 256)
+  int J;                         // input rows streamed per image = Hin + 2 * pad
+  int pad, Hout, Wout, n_images;
+  int pool;                      // 1: out = maxpool3x3/2(relu(conv + b)), [n][Hp][Wp][out_cstride]; 0: [n][Hout][Wout][out_cstride]
+  int Hp, Wp;
+  int out_cstride, out_coff;
+  uint32_t idesc, layout_type, sbo_bytes, row_bytes;
+  uint32_t b_blk_bytes, b_tap_bytes, a_buf_bytes;
+  __half* out;
+  const float* bias;
+};
+
+__device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+__global__ void __launch_bounds__(kRowsThreads, 1)
+conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const RowsArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem;                                                  // [3 taps][5 blocks][cout rows][cin]
+  uint8_t* smem_a = smem_b + 3 * p.b_tap_bytes;                            // [2 streams][kRowsRing][128 slots][cin]
+  uint8_t* smem_row = smem_a + 2 * kRowsRing * p.a_buf_bytes;              // [2 streams][128 pixels][cout] fp16, 16-byte chunks XOR-swizzled
+  const uint32_t row_stage_bytes = 128u * (uint32_t)p.cout * 2u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_row + 2 * row_stage_bytes);
+  uint64_t* in_full = bars;                          // [2][kRowsRing]
+  uint64_t* in_empty = bars + 2 * kRowsRing;         // [2][kRowsRing]
+  uint64_t* acc_done = bars + 4 * kRowsRing;         // [2]
+  uint64_t* acc_free = bars + 4 * kRowsRing + 2;     // [2]
+  uint64_t* b_full = bars + 4 * kRowsRing + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kRowsRing + 5);
+  float* s_bias = reinterpret_cast<float*>(bars + 4 * kRowsRing + 6);      // [cout]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < p.cout; i += kRowsThreads) s_bias[i] = p.bias[i];
+  // images of this CTA: blockIdx.x, + gridDim.x, ...; stream st takes every second one of them
+  const int G = gridDim.x;
+  const int cnt = (p.n_images - (int)blockIdx.x + G - 1) / G;
+  const int cnt_st[2] = {(cnt + 1) >> 1, cnt >> 1};
+  const int steps_st[2] = {cnt_st[0] * p.J, cnt_st[1] * p.J};
+  const int steps_max = steps_st[0];                 // stream 0 never has fewer images than stream 1
+  const int ncol = 3 * p.cout;                       // accumulator columns of one stream (ring of three slots)
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_b);
+    for (int i = 0; i < 2 * kRowsRing; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); }
+    for (int st = 0; st < 2; ++st) { mbar_init(&acc_done[st], 1); mbar_init(&acc_free[st], 128); }
+    mbar_init(b_full, 1);
+    fence_barrier_init();
+  } else if (warp == 1) {
+    tmem_alloc(tmem_slot, (uint32_t)TmemColsDev(2 * ncol));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: the filter tile once, then one input row per (stream, step) =====
+      mbar_arrive_expect_tx(b_full, 15u * p.b_blk_bytes);
+      for (int s = 0; s < 3; ++s)
+        for (int blk = 0; blk < 5; ++blk)
+          tma_load_3d(smem_b + s * p.b_tap_bytes + blk * p.b_blk_bytes, &map_b, b_full, 0, blk * p.cout, s);
+      int rb[2] = {0, 0}, j[2] = {0, 0}, img[2] = {(int)blockIdx.x, (int)blockIdx.x + G};
+      uint32_t rph[2] = {0, 0};
+      for (int t = 0; t < steps_max; ++t) {
+#pragma unroll
+        for (int st = 0; st < 2; ++st) {
+          if (t >= steps_st[st]) continue;
+          uint64_t* full = &in_full[st * kRowsRing + rb[st]];
+          mbar_wait(&in_empty[st * kRowsRing + rb[st]], rph[st] ^ 1);
+          mbar_arrive_expect_tx(full, 128u * p.row_bytes);
+          tma_load_4d(smem_a + (size_t)(st * kRowsRing + rb[st]) * p.a_buf_bytes, &map_a, full, 0, -p.pad, j[st] - p.pad, img[st]);
+          if (++rb[st] == kRowsRing) { rb[st] = 0; rph[st] ^= 1; }
+          if (++j[st] == p.J) { j[st] = 0; img[st] += 2 * G; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer: per (stream, step) 3 taps x cin/16 MMAs of N = 3 cout into the stream's ring of three accumulators =====
+      mbar_wait(b_full, 0);
+      tc_fence_after();
+      const int kper = p.cin >> 4;
+      const uint32_t hi = desc_hi(p.sbo_bytes, p.layout_type), idesc = p.idesc;
+      const uint32_t a_lo0 = desc_lo(smem_u32(smem_a)), b_lo0 = desc_lo(smem_u32(smem_b));
+      const uint32_t a_buf_inc = p.a_buf_bytes >> 4, a_px_inc = p.row_bytes >> 4, b_blk_inc = p.b_blk_bytes >> 4, b_tap_inc = p.b_tap_bytes >> 4;
+      int rb[2] = {0, 0};
+      uint32_t rph[2] = {0, 0};
+      int t3 = 0;                                    // t mod 3
+      for (int t = 0; t < steps_max; ++t) {
+#pragma unroll
+        for (int st = 0; st < 2; ++st) {
+          if (t >= steps_st[st]) continue;
+          mbar_wait(&acc_free[st], (uint32_t)t & 1u);               // the slot this step opens has been drained and zeroed
+          mbar_wait(&in_full[st * kRowsRing + rb[st]], rph[st]);
+          tc_fence_after();
+          const uint32_t d = tmem_base + (uint32_t)(st * ncol);
+          const uint32_t a_lo = a_lo0 + (uint32_t)(st * kRowsRing + rb[st]) * a_buf_inc;
+          const uint32_t b_lo = b_lo0 + (uint32_t)(2 - t3) * b_blk_inc;
+          for (int s = 0; s < 3; ++s)
+            for (int k = 0; k < kper; ++k)
+              umma_f16_lohi(d, a_lo + (uint32_t)s * a_px_inc + 2u * k, b_lo + (uint32_t)s * b_tap_inc + 2u * k, hi, idesc, 1u);
+          umma_commit(&in_empty[st * kRowsRing + rb[st]]);
+          umma_commit(&acc_done[st]);
+          if (++rb[st] == kRowsRing) { rb[st] = 0; rph[st] ^= 1; }
+        }
+        if (++t3 == 3) t3 = 0;
+      }
+    }
+  } else {
+    // ===== epilogue of stream st: 4 warps = 4 TMEM lane quarters; thread = pixel column w of every row of the stream =====
+    const int st = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int w = q * 32 + lane;
+    const int tid = ((warp - 2) & 3) * 32 + lane;     // 0..127 inside the stream's epilogue group
+    const int bar_id = 1 + st;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(st * ncol);
+    uint8_t* stage = smem_row + st * row_stage_bytes;
+    const int nch = p.cout >> 3;                      // 16-byte chunks per pixel
+    const int rows_per_128 = 128 / (p.cout * 2);      // pixels per 128 bytes of the staging row (1 or 2)
+    const int my_sw = (w / rows_per_128) & (nch - 1);
+    // every accumulator column starts at zero
+    for (int c = 0; c < ncol; c += 32) tmem_st32_zero(t_lane + c);
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(&acc_free[st]);
+    uint32_t cur[32];                                 // running vertical maximum (pool mode), packed half2, cout <= 64
+#pragma unroll
+    for (int i = 0; i < 32; ++i) cur[i] = 0u;
+    int j = 0, img = (int)blockIdx.x + st * G, slot = 1;   // slot drained at step t = (t + 1) mod 3
+    for (int t = 0; t < steps_st[st]; ++t) {
+      mbar_wait(&acc_done[st], (uint32_t)t & 1u);
+      tc_fence_after();
+      const bool row_valid = j >= 2;
+      const int o = j - 2;
+      uint32_t hv[32];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        if (cc * 32 < p.cout) {
+          uint32_t v[32];
+          tmem_ld32(t_lane + slot * p.cout + cc * 32, v);
+          tmem_ld_wait();
+          tmem_st32_zero(t_lane + slot * p.cout + cc * 32);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float x0 = fmaxf(__uint_as_float(v[2 * i]) + s_bias[cc * 32 + 2 * i], 0.f);
+            const float x1 = fmaxf(__uint_as_float(v[2 * i + 1]) + s_bias[cc * 32 + 2 * i + 1], 0.f);
+            const __half2 h = __floats2half2_rn(x0, x1);
+            hv[cc * 16 + i] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&acc_free[st]);                      // the MMAs of step t + 1 may go ahead while this row is stored
+      if (row_valid) {
+        const int nh = p.cout >> 1;                    // half2 words per pixel
+        if (!p.pool) {
+          named_bar_sync(bar_id, 128);                 // the previous row has left the staging buffer
+          if (w < p.Wout) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (c < nch)
+                *reinterpret_cast<uint4*>(stage + (size_t)w * (p.cout * 2) + ((c ^ my_sw) << 4)) =
+                    make_uint4(hv[4 * c], hv[4 * c + 1], hv[4 * c + 2], hv[4 * c + 3]);
+          }
+          named_bar_sync(bar_id, 128);
+          __half* dst = p.out + ((size_t)img * p.Hout + o) * p.Wout * p.out_cstride + p.out_coff;
+          for (int i = tid; i < p.Wout * nch; i += 128) {
+            const int px = i / nch, cv = i - px * nch;
+            const uint4 val = *reinterpret_cast<const uint4*>(stage + (size_t)px * (p.cout * 2) + ((cv ^ ((px / rows_per_128) & (nch - 1))) << 4));
+            *reinterpret_cast<uint4*>(dst + (size_t)px * p.out_cstride + cv * 8) = val;
+          }
+        } else {
+          // vertical 3-max over rows 2 ph, 2 ph + 1, 2 ph + 2: an even row closes window ph - 1 and opens window ph
+          const bool even = (o & 1) == 0;
+          const bool emit = even && o >= 2;
+          if (emit) {
+            named_bar_sync(bar_id, 128);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              if (c < nch) {
+                uint32_t m[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const __half2 a = *reinterpret_cast<const __half2*>(&cur[4 * c + e]), b = *reinterpret_cast<const __half2*>(&hv[4 * c + e]);
+                  const __half2 r = __hmax2(a, b);
+                  m[e] = *reinterpret_cast<const uint32_t*>(&r);
+                }
+                if (w < p.Wout)
+                  *reinterpret_cast<uint4*>(stage + (size_t)w * (p.cout * 2) + ((c ^ my_sw) << 4)) = make_uint4(m[0], m[1], m[2], m[3]);
+              }
+            }
+            named_bar_sync(bar_id, 128);
+            const int ph = (o >> 1) - 1;
+            __half* dst = p.out + ((size_t)img * p.Hp + ph) * p.Wp * p.out_cstride + p.out_coff;
+            for (int i = tid; i < p.Wp * nch; i += 128) {
+              const int px = i / nch, cv = i - px * nch;
+              uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                const int pw = 2 * px + dx;
+                const uint4 val = *reinterpret_cast<const uint4*>(stage + (size_t)pw * (p.cout * 2) + ((cv ^ ((pw / rows_per_128) & (nch - 1))) << 4));
+                acc = hmax2x4(acc, val);               // post-ReLU values are >= 0: zero is the identity
+              }
+              *reinterpret_cast<uint4*>(dst + (size_t)px * p.out_cstride + cv * 8) = acc;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i < nh) {
+              if (even) cur[i] = hv[i];
+              else {
+                const __half2 a = *reinterpret_cast<const __half2*>(&cur[i]), b = *reinterpret_cast<const __half2*>(&hv[i]);
+                const __half2 r = __hmax2(a, b);
+                cur[i] = *reinterpret_cast<const uint32_t*>(&r);
+              }
+            }
+          }
+        }
+      }
+      if (++slot == 3) slot = 0;
+      if (++j == p.J) { j = 0; img += 2 * G; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)TmemColsDev(2 * ncol));
+}
+
+// ---------------------------------------------------------------------------------------------
 // Small CUDA-core kernels
 // ---------------------------------------------------------------------------------------------
 
@@ -1445,16 +1722,6 @@ __global__ void pool3x3_kernel(const __half* __restrict__ in, __half* __restrict
 // 3x3 stride-2 'valid' max pool, precision 0: the maximum of fp16 values is exact in fp16, so the whole pool runs on packed
 // half2 (__hmax2) without a single conversion - a third of the instructions and half the registers of the fp32 form above.
 // One thread = (image, output row, segment of the row, 8 channels); segments shorten the serial sliding chain.
-__device__ __forceinline__ uint4 hmax2x4(const uint4 a, const uint4 b) {
-  uint4 r;
-  const __half2* x = reinterpret_cast<const __half2*>(&a);
-  const __half2* y = reinterpret_cast<const __half2*>(&b);
-  __half2* z = reinterpret_cast<__half2*>(&r);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) z[j] = __hmax2(x[j], y[j]);
-  return r;
-}
-
 __global__ void __launch_bounds__(256) maxpool3x3s2_h2_kernel(const __half* __restrict__ in, __half* __restrict__ out, int n_images, int Hin, int Win,
                                                               int C, int Hout, int Wout, int out_cstride, int out_coff, int segs, int seg_len) {
   const int cvec = C / 8;
@@ -1680,6 +1947,12 @@ struct HaloLaunch {
   int smem, ctas_per_nblock;
   double macs_per_image;
 };
+struct RowsLaunch {
+  CUtensorMap map_a, map_b;
+  RowsArgs args;
+  int smem;
+  double macs_per_image;
+};
 struct PoolLaunch {
   const __half* in; __half* out;
   int Hin, Win, C, Hout, Wout, out_cstride, out_coff, mode;
@@ -1691,7 +1964,7 @@ struct PoolLaunch {
 // ran on other lanes, so that the partial last wave of one branch's kernel is filled by another branch's CTAs.
 constexpr int kMaxLanes = 4;
 struct Step {
-  int kind, index;          // 0 conv, 1 pool, 2 halo conv
+  int kind, index;          // 0 conv, 1 pool, 2 halo conv, 3 row-streaming conv (+ fused max pool)
   int lane = 0;
   bool record = false;      // some consumer on another lane waits on this step's event
   std::vector<int> deps;    // steps (other lanes) to wait on before launching
@@ -1707,6 +1980,7 @@ struct DvbCnn {
   std::map<std::string, int> tensor_index;
   std::vector<ConvLaunch> convs;
   std::vector<HaloLaunch> halos;
+  std::vector<RowsLaunch> rows;
   std::vector<PoolLaunch> pools;
   std::vector<Step> steps;
   std::vector<void*> allocs;
@@ -1910,6 +2184,9 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
   if (st) return st;
 
   std::vector<std::pair<std::string, std::vector<std::string>>> step_io;   // (src, dst tensors) of every step
+  std::vector<char> fused_pool(ops.size(), 0);
+  std::map<std::string, int> n_consumers;
+  for (auto& oo : ops) n_consumers[oo.src]++;
   const int force_bk = EnvInt("DVB_CNN_BLOCK_K", 0);       // 0 = per-layer choice
   double macs_total = 0;
   for (size_t op_index = 0; op_index < ops.size(); ++op_index) {
@@ -1924,16 +2201,39 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
     if (Hout < 1 || Wout < 1) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "image %dx%d is too small for the network", net->H, net->W);
     hw[o.dst] = {Hout, Wout};
     if (merged_into[op_index] >= 0) continue;     // runs inside its group leader's GEMM
+    if (fused_pool[op_index]) continue;           // this max pool runs in the epilogue of the convolution before it (conv_rows_kernel)
     std::vector<size_t> members = leader.count(op_index) ? leader[op_index] : std::vector<size_t>{op_index};
+    // Row-streaming kernel (conv_rows_kernel): 3x3 stride-1 layers with <= 64 filters on maps up to 126 pixels wide - conv2 and
+    // conv3 of the stem.  A 3x3 / stride-2 'valid' max pool that is the layer's only consumer runs in its epilogue.
+    bool use_rows = false, rows_pool = false;
+    if (o.kind == 0 && !split && !is_stem && members.size() == 1 && o.stride == 1 && o.kh == 3 && o.kw == 3 && !o.no_act &&
+        (o.cout == 32 || o.cout == 64) && Wout <= 126 && EnvInt("DVB_CNN_ROWS", 1)) {
+      const int cs = net->tensors[net->tensor_index[o.src]].C;
+      use_rows = (cs == 32 || cs == 64) && o.off == 0 && stored(o.dst) == o.cout;
+      if (use_rows && op_index + 1 < ops.size() && EnvInt("DVB_CNN_FUSE_POOL", 1)) {
+        const OpDesc& nx = ops[op_index + 1];
+        rows_pool = nx.kind == 1 && nx.src == o.dst && n_consumers[o.dst] == 1 && Hout >= 3 && Wout >= 3;
+      }
+    }
     std::vector<std::string> step_dsts;
-    for (size_t m : members) {                    // all destination tensors exist before any reference is taken
-      hw[ops[m].dst] = {Hout, Wout};
-      st = add_tensor(ops[m].dst, Hout, Wout, stored(ops[m].dst));
+    if (rows_pool) {
+      const OpDesc& nx = ops[op_index + 1];
+      fused_pool[op_index + 1] = 1;
+      const int Hp = (Hout - 3) / 2 + 1, Wp = (Wout - 3) / 2 + 1;
+      hw[nx.dst] = {Hp, Wp};
+      st = add_tensor(nx.dst, Hp, Wp, stored(nx.dst));
       if (st) return st;
-      step_dsts.push_back(ops[m].dst);
+      step_dsts.push_back(nx.dst);
+    } else {
+      for (size_t m : members) {                    // all destination tensors exist before any reference is taken
+        hw[ops[m].dst] = {Hout, Wout};
+        st = add_tensor(ops[m].dst, Hout, Wout, stored(ops[m].dst));
+        if (st) return st;
+        step_dsts.push_back(ops[m].dst);
+      }
     }
     const TensorBuf& src = net->tensors[net->tensor_index[o.src]];
-    const TensorBuf& dst = net->tensors[net->tensor_index[o.dst]];
+    const TensorBuf& dst = net->tensors[net->tensor_index[rows_pool ? ops[op_index + 1].dst : o.dst]];
     if (o.kind != 0) {
       PoolLaunch pl{src.ptr, dst.ptr, Hin, Win, src.C, Hout, Wout, dst.C, o.off, o.kind == 1 ? 0 : 1, src.ptr_res, dst.ptr_res,
                     o.post_act ? pool_bias[o.src] : nullptr};
@@ -2008,7 +2308,7 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
         } else {
           memcpy(&bias_host[row0], b_blob, (size_t)mo.cout * 4);
         }
-        const TensorBuf& md = net->tensors[net->tensor_index[mo.dst]];
+        const TensorBuf& md = rows_pool ? dst : net->tensors[net->tensor_index[mo.dst]];
         segs.push_back(OutSeg{(int)row0, md.C, mo.off, mo.no_act ? 0 : 1, md.ptr});
         blob_w_main = blob + pos;
         row0 += (size_t)mo.cout;
@@ -2032,6 +2332,67 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       net->stem_fused = true;
       macs_total += (double)Hout * Wout * o.cout * orig.kh * orig.kw * orig.cin;
       continue;
+    }
+    // ---- conv2 / conv3 (+ max pool): row-streaming kernel with the kernel rows stacked along N (see conv_rows_kernel)
+    if (use_rows) {
+      RowsLaunch rl;
+      memset(&rl, 0, sizeof(rl));
+      RowsArgs& a = rl.args;
+      a.cin = cin_store; a.cout = o.cout;
+      a.pad = o.same ? 1 : 0;
+      a.J = Hin + 2 * a.pad;
+      a.Hout = Hout; a.Wout = Wout;
+      a.pool = rows_pool ? 1 : 0;
+      a.Hp = rows_pool ? dst.H : 0; a.Wp = rows_pool ? dst.W : 0;
+      a.out = dst.ptr; a.out_cstride = dst.C; a.out_coff = rows_pool ? ops[op_index + 1].off : o.off;
+      a.bias = conv_bias;
+      a.row_bytes = (uint32_t)cin_store * 2u;
+      a.layout_type = cin_store == 64 ? 2u : 4u;
+      a.sbo_bytes = 8u * a.row_bytes;
+      a.idesc = (1u << 4) | ((uint32_t)((3 * o.cout) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      a.b_blk_bytes = (uint32_t)o.cout * a.row_bytes;
+      a.b_tap_bytes = 5u * a.b_blk_bytes;
+      a.a_buf_bytes = 128u * a.row_bytes;
+      rl.smem = 1024 + (int)(3 * a.b_tap_bytes + 2 * kRowsRing * a.a_buf_bytes + 2 * 128 * o.cout * 2) + (4 * kRowsRing + 6) * 8 + o.cout * 4 + 64;
+      rl.macs_per_image = (double)Hout * Wout * o.cout * 9 * orig.cin;
+      if (rl.smem <= 227 * 1024) {
+        // filters [Cout][3][3][Cin] -> [kw tap s][block: kernel row 2, 1, 0, 2, 1][Cout][Cin]: three consecutive blocks starting at
+        // block b are the kernel rows (2 - b, 1 - b, -b) mod 3 - the rotation the accumulator ring needs at step t = 2 - b (mod 3)
+        std::vector<__half> w2((size_t)3 * 5 * o.cout * cin_store, __float2half(0.f));
+        const __half* w = reinterpret_cast<const __half*>(blob_w_main);
+        const int blk_r[5] = {2, 1, 0, 2, 1};
+        for (int sx = 0; sx < 3; ++sx)
+          for (int blk = 0; blk < 5; ++blk)
+            for (int co = 0; co < o.cout; ++co)
+              memcpy(&w2[(((size_t)sx * 5 + blk) * o.cout + co) * cin_store], &w[(((size_t)co * 3 + blk_r[blk]) * 3 + sx) * blob_cin],
+                     (size_t)blob_cin * sizeof(__half));
+        void* dw5 = nullptr;
+        if (cudaMalloc(&dw5, w2.size() * sizeof(__half)) != cudaSuccess) return dvb::fail(DVB_ERR_CUDA, "cudaMalloc (weights) failed");
+        net->allocs.push_back(dw5);
+        cudaMemcpy(dw5, w2.data(), w2.size() * sizeof(__half), cudaMemcpyHostToDevice);
+        {
+          const cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)net->max_batch};
+          const cuuint64_t strides[3] = {(cuuint64_t)src.C * 2, (cuuint64_t)Win * src.C * 2, (cuuint64_t)Hin * Win * src.C * 2};
+          const cuuint32_t box[4] = {(cuuint32_t)cin_store, 128, 1, 1};
+          const cuuint32_t estr[4] = {1, 1, 1, 1};
+          st = MakeMap(&rl.map_a, src.ptr, 4, dims, strides, box, estr, cin_store);
+          if (st) return st;
+        }
+        {
+          const cuuint64_t dims[3] = {(cuuint64_t)cin_store, (cuuint64_t)(5 * o.cout), 3};
+          const cuuint64_t strides[2] = {(cuuint64_t)cin_store * 2, (cuuint64_t)5 * o.cout * cin_store * 2};
+          const cuuint32_t box[3] = {(cuuint32_t)cin_store, (cuuint32_t)o.cout, 1};
+          const cuuint32_t estr[3] = {1, 1, 1};
+          st = MakeMap(&rl.map_b, dw5, 3, dims, strides, box, estr, cin_store);
+          if (st) return st;
+        }
+        macs_total += rl.macs_per_image;
+        net->steps.push_back(Step{3, (int)net->rows.size()});
+        step_io.push_back({o.src, step_dsts});
+        net->rows.push_back(rl);
+        continue;
+      }
+      if (rows_pool) return dvb::fail(DVB_ERR_INTERNAL, "conv_rows_kernel: %d bytes of shared memory", rl.smem);
     }
     // ---- large stride-1 k x k layers: persistent halo-reusing kernel (see conv_halo_kernel)
     if (!split && !is_stem && o.stride == 1 && o.kh * o.kw > 1 && Hout * Wout >= EnvInt("DVB_HALO_MIN_PIXELS", 250) && EnvInt("DVB_CNN_HALO", 1)) {
@@ -2191,6 +2552,7 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       for (size_t k = 0; k < segs.size(); ++k) a.segs[k] = segs[k];
     }
     a.skip_a_res = is_stem ? 1 : 0;   // the preprocessed input is exact in fp16: its residual plane is zero
+    a.dbg = EnvInt("DVB_CNN_DBG", 0);
     a.bias = conv_bias;
     // instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): D=F32, A=B=F16, K-major, M=128
     a.idesc = (1u << 4) | ((uint32_t)(a.block_n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -2332,6 +2694,10 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
   if ((split ? cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)
              : cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess)
     return dvb::fail(DVB_ERR_CUDA, "cannot reserve %d bytes of shared memory", max_smem);
+  int max_rows = 0;
+  for (auto& r : net->rows) max_rows = std::max(max_rows, r.smem);
+  if (max_rows && cudaFuncSetAttribute(conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_rows) != cudaSuccess)
+    return dvb::fail(DVB_ERR_CUDA, "cannot reserve %d bytes of shared memory (rows kernel)", max_rows);
   int max_halo = 0;
   for (auto& h : net->halos) max_halo = std::max(max_halo, h.smem);
   if (max_halo && cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_halo) != cudaSuccess)
@@ -2369,7 +2735,12 @@ int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaSt
   for (const Step& stp : net->steps) {
     cudaStream_t s = stp.lane == 0 ? s0 : net->lane_streams[stp.lane];
     for (int d : stp.deps) cudaStreamWaitEvent(s, net->steps[d].event, 0);
-    if (stp.kind == 2) {
+    if (stp.kind == 3) {
+      RowsLaunch& rl = net->rows[stp.index];
+      RowsArgs a = rl.args;
+      a.n_images = n;
+      conv_rows_kernel<<<(unsigned)std::min(net->num_sms, n), kRowsThreads, rl.smem, s>>>(rl.map_a, rl.map_b, a);
+    } else if (stp.kind == 2) {
       HaloLaunch& hl = net->halos[stp.index];
       HaloArgs a = hl.args;
       a.n_images = n;

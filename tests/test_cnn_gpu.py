@@ -41,7 +41,9 @@ def _check_layers(shape, n, names, seed=0):
   return report, worst, probs.cpu(), want_p, net, pooled
 
 
-STEM = ['s1', 's2', 's3', 'p1', 's4', 's5', 'p2']
+# 's3' is not materialised by default: conv3's epilogue applies the max pool that follows it (conv_rows_kernel); the test
+# below that sets DVB_CNN_FUSE_POOL=0 checks it.
+STEM = ['s1', 's2', 'p1', 's4', 's5', 'p2']
 
 
 def test_stem_layers_match_oracle():
@@ -49,6 +51,35 @@ def test_stem_layers_match_oracle():
   print(report)
   for name, err in report:
     assert err < 6e-3, report
+
+
+def test_unfused_conv3_output_and_pool_match_oracle(monkeypatch):
+  monkeypatch.setenv('DVB_CNN_FUSE_POOL', '0')
+  report, worst, _, _, net, _ = _check_layers((100, 221, 7), 3, ['s2', 's3', 'p1'], seed=5)
+  print(report)
+  for name, err in report:
+    assert err < 6e-3, report
+  net.close()
+
+
+def test_row_streaming_stem_kernels_equal_halo_kernels(monkeypatch):
+  """conv_rows_kernel (kernel rows stacked along N, accumulator ring, max pool in the epilogue) against conv_halo_kernel + the
+  stand-alone pool on the same layers: same products, same accumulation order -> the same fp16 activations.  Both geometries; an
+  image count that gives some CTAs one stream and others two, and one that leaves a CTA's second stream one image short."""
+  for shape, n in (((100, 221, 7), 5), ((100, 147, 10), 3), ((100, 221, 7), 150)):
+    w = modeling.random_weights(shape[2], 31)
+    imgs = _images(n, shape, 31)
+    outs = []
+    for rows in ('1', '0'):
+      monkeypatch.setenv('DVB_CNN_ROWS', rows)
+      net = cv.GpuCnn(w, shape, device=0, max_batch=n)
+      probs = net.forward_host(imgs.numpy())
+      outs.append((probs, net.debug_tensor('s2', n), net.debug_tensor('p1', n)))
+      net.close()
+    for k in (1, 2):
+      scale = float(np.abs(outs[1][k]).max())
+      assert float(np.abs(outs[0][k] - outs[1][k]).max()) <= 1e-3 * scale, (shape, n, k)
+    assert float(np.abs(outs[0][0] - outs[1][0]).max()) < 2e-3
 
 
 def test_stem_patches_are_exact(monkeypatch):
