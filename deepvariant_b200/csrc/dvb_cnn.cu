@@ -113,6 +113,17 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// One lane of a CONVERGED warp.  The single-thread instructions of this file (tcgen05.mma / commit, cp.async.bulk.tensor) take their
+// operands from uniform registers; when they sit in a branch that ptxas cannot prove single-lane (`if (lane == 0)`), every one of them
+// is wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~100-150 clocks per instruction on the issuing thread - measured: 6 MMAs +
+// 2 commits took 1000 clocks).  With the whole warp running the loop on uniform values and only the instruction itself under
+// elect.sync, ptxas keeps the operands in uniform registers and emits the bare instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .pred px;\nelect.sync _|px, 0xffffffff;\n@px mov.s32 %0, 1;\n}\n" : "+r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -393,35 +404,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
-      if constexpr (kSplit) { prefetch_tmap(&map_a_res); prefetch_tmap(&map_b_res); }
+    {
+      // ===== TMA producer (the whole warp walks the loop, one elected lane issues) =====
+      if constexpr (kSplit) { if (elect_one()) { prefetch_tmap(&map_a_res); prefetch_tmap(&map_b_res); } __syncwarp(); }
       int st = 0;
       uint32_t ph = 0;
       for (int r = 0; r < p.kh && !(p.dbg & 1); ++r) {
         for (int s = 0; s < p.kw; ++s) {
           for (int cb = 0; cb < p.cin_blocks; ++cb) {
             mbar_wait(&empty_bar[st], ph ^ 1);
-            if constexpr (kSplit) {
-              mbar_arrive_expect_tx(&full_bar[st], (p.skip_a_res ? 1u : 2u) * p.a_bytes + 2u * p.b_bytes);
-              if (!p.skip_a_res)
-                tma_load_4d(smem_a + st * p.a_stage + p.a_res_off, &map_a_res, &full_bar[st], cb * p.block_k, w0 * p.stride + s - p.pad_w,
-                            h0 * p.stride + r - p.pad_h, n0);
-              tma_load_3d(smem_b + st * p.b_stage + p.b_res_off, &map_b_res, &full_bar[st], cb * p.block_k, r * p.kw + s, nb * p.block_n);
-            } else {
-              mbar_arrive_expect_tx(&full_bar[st], p.a_bytes + p.b_bytes);
+            if (elect_one()) {
+              if constexpr (kSplit) {
+                mbar_arrive_expect_tx(&full_bar[st], (p.skip_a_res ? 1u : 2u) * p.a_bytes + 2u * p.b_bytes);
+                if (!p.skip_a_res)
+                  tma_load_4d(smem_a + st * p.a_stage + p.a_res_off, &map_a_res, &full_bar[st], cb * p.block_k, w0 * p.stride + s - p.pad_w,
+                              h0 * p.stride + r - p.pad_h, n0);
+                tma_load_3d(smem_b + st * p.b_stage + p.b_res_off, &map_b_res, &full_bar[st], cb * p.block_k, r * p.kw + s, nb * p.block_n);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[st], p.a_bytes + p.b_bytes);
+              }
+              tma_load_4d(smem_a + st * p.a_stage, &map_a, &full_bar[st], cb * p.block_k, w0 * p.stride + s - p.pad_w,
+                          h0 * p.stride + r - p.pad_h, n0);
+              tma_load_3d(smem_b + st * p.b_stage, &map_b, &full_bar[st], cb * p.block_k, r * p.kw + s, nb * p.block_n);
             }
-            tma_load_4d(smem_a + st * p.a_stage, &map_a, &full_bar[st], cb * p.block_k, w0 * p.stride + s - p.pad_w,
-                        h0 * p.stride + r - p.pad_h, n0);
-            tma_load_3d(smem_b + st * p.b_stage, &map_b, &full_bar[st], cb * p.block_k, r * p.kw + s, nb * p.block_n);
+            __syncwarp();
             if (++st == p.stages) { st = 0; ph ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer (one thread) =====
+    {
+      // ===== MMA issuer (the whole warp walks the loop, one elected lane issues) =====
       const int mma_per_kb = p.block_k / 16;
       const uint32_t hi = desc_hi(p.sbo_bytes, p.layout_type), idesc = p.idesc;
       const uint32_t a_lo0 = desc_lo(smem_u32(smem_a)), b_lo0 = desc_lo(smem_u32(smem_b));
@@ -432,28 +446,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       for (int kb = 0; kb < num_kb; ++kb) {
         if (!(p.dbg & 1)) mbar_wait(&full_bar[st], ph);
         tc_fence_after();
-        if (p.dbg & 2) {
-        } else if constexpr (kSplit) {
-          const uint32_t a_res = a_lo + (p.a_res_off >> 4), b_res = b_lo + (p.b_res_off >> 4), d1 = tmem_base + (uint32_t)p.block_n;
-          const bool with_a_res = !p.skip_a_res;
-          for (int k = 0; k < mma_per_kb; ++k) {
-            umma_f16_lohi(tmem_base, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, acc);   // D0 += A_main * B_main
-            umma_f16_lohi(d1, a_lo + 2 * k, b_res + 2 * k, hi, idesc, acc);         // D1 += A_main * B_res
-            if (with_a_res) umma_f16_lohi(d1, a_res + 2 * k, b_lo + 2 * k, hi, idesc, 1u);   // D1 += A_res * B_main
-            acc = 1;
-          }
-        } else {
+        if (elect_one()) {
+          if (p.dbg & 2) {
+          } else if constexpr (kSplit) {
+            const uint32_t a_res = a_lo + (p.a_res_off >> 4), b_res = b_lo + (p.b_res_off >> 4), d1 = tmem_base + (uint32_t)p.block_n;
+            const bool with_a_res = !p.skip_a_res;
+            for (int k = 0; k < mma_per_kb; ++k) {
+              const uint32_t ac = acc | (uint32_t)(k != 0);
+              umma_f16_lohi(tmem_base, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, ac);   // D0 += A_main * B_main
+              umma_f16_lohi(d1, a_lo + 2 * k, b_res + 2 * k, hi, idesc, ac);         // D1 += A_main * B_res
+              if (with_a_res) umma_f16_lohi(d1, a_res + 2 * k, b_lo + 2 * k, hi, idesc, 1u);   // D1 += A_res * B_main
+            }
+          } else {
 #pragma unroll 4
-          for (int k = 0; k < mma_per_kb; ++k) {
-            umma_f16_lohi(tmem_base, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, acc);
-            acc = 1;
+            for (int k = 0; k < mma_per_kb; ++k) umma_f16_lohi(tmem_base, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, acc | (uint32_t)(k != 0));
           }
+          umma_commit(&empty_bar[st]);   // frees the stage once these MMAs retire
         }
-        umma_commit(&empty_bar[st]);   // frees the stage once these MMAs retire
+        __syncwarp();
+        acc = 1;
         a_lo += a_inc; b_lo += b_inc;
         if (++st == stages) { st = 0; ph ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
       }
-      umma_commit(tmem_full);          // accumulator complete
+      if (elect_one()) umma_commit(tmem_full);          // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===== epilogue: TMEM -> registers -> bias + ReLU -> fp16 -> NHWC global =====
@@ -528,8 +544,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer =====
+    {
+      // ===== TMA producer (whole warp, one elected lane issues) =====
       int st = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < total && !(p.dbg & 1); t += gridDim.x) {
@@ -543,9 +559,12 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
           for (int s = 0; s < p.kw; ++s) {
             for (int cb = 0; cb < p.cin_blocks; ++cb) {
               mbar_wait(&empty_bar[st], ph ^ 1);
-              mbar_arrive_expect_tx(&full_bar[st], p.a_bytes + p.b_bytes);
-              tma_load_4d(smem_a + st * p.a_stage, &map_a, &full_bar[st], cb * p.block_k, w0 + s, h0 + r, n0);
-              tma_load_3d(smem_b + st * p.b_stage, &map_b, &full_bar[st], cb * p.block_k, r * p.kw + s, nb * p.block_n);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(&full_bar[st], p.a_bytes + p.b_bytes);
+                tma_load_4d(smem_a + st * p.a_stage, &map_a, &full_bar[st], cb * p.block_k, w0 + s, h0 + r, n0);
+                tma_load_3d(smem_b + st * p.b_stage, &map_b, &full_bar[st], cb * p.block_k, r * p.kw + s, nb * p.block_n);
+              }
+              __syncwarp();
               if (++st == p.stages) { st = 0; ph ^= 1; }
             }
           }
@@ -553,8 +572,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer (one thread) =====
+    {
+      // ===== MMA issuer (whole warp, one elected lane issues) =====
       const int mma_per_kb = p.block_k / 16;
       const uint32_t hi = desc_hi(p.sbo_bytes, p.layout_type), idesc = p.idesc;
       const uint32_t a_lo0 = desc_lo(smem_u32(smem_a)), b_lo0 = desc_lo(smem_u32(smem_b));
@@ -570,18 +589,20 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
         for (int kb = 0; kb < num_kb; ++kb) {
           if (!(p.dbg & 1)) mbar_wait(&full_bar[st], ph);
           tc_fence_after();
-          if (!(p.dbg & 2)) {
+          if (elect_one()) {
+            if (!(p.dbg & 2)) {
 #pragma unroll 4
-            for (int k = 0; k < mma_per_kb; ++k) {
-              umma_f16_lohi(d, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, acc);
-              acc = 1;
+              for (int k = 0; k < mma_per_kb; ++k) umma_f16_lohi(d, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, acc | (uint32_t)(k != 0));
             }
+            umma_commit(&empty_bar[st]);
           }
-          umma_commit(&empty_bar[st]);
+          __syncwarp();
+          acc = 1;
           a_lo += a_inc; b_lo += b_inc;
           if (++st == stages) { st = 0; ph ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
         }
-        umma_commit(&tmem_full[buf]);
+        if (elect_one()) umma_commit(&tmem_full[buf]);
+        __syncwarp();
         buf ^= 1;
         if (buf == 0) buf_ph ^= 1;
       }
@@ -757,8 +778,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer (both CTAs): own A tile + own half of the weight block, completing on the leader's barrier =====
+    {
+      // ===== TMA producer (both CTAs; whole warp, one elected lane issues): own A tile + own half of the weight block, completing on the leader's barrier =====
       int st = 0;
       uint32_t ph = 0;
       for (int t = pair_id; t < total; t += num_pairs) {
@@ -772,10 +793,13 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           for (int s = 0; s < p.kw; ++s) {
             for (int cb = 0; cb < p.cin_blocks; ++cb) {
               mbar_wait(&empty_bar[st], ph ^ 1);
-              if (leader) mbar_arrive_expect_tx(&full_bar[st], 2u * (p.a_bytes + q2.b_half_bytes));
-              tma_load_4d_2sm(smem_a + st * p.a_stage, &map_a, &full_bar[st], cb * p.block_k, w0 + s, h0 + r, n0);
-              tma_load_3d_2sm(smem_b + st * q2.b_half_stage, &map_b_half, &full_bar[st], cb * p.block_k, r * p.kw + s,
-                              nb * p.block_n + (int)rank * (p.block_n >> 1));
+              if (elect_one()) {
+                if (leader) mbar_arrive_expect_tx(&full_bar[st], 2u * (p.a_bytes + q2.b_half_bytes));
+                tma_load_4d_2sm(smem_a + st * p.a_stage, &map_a, &full_bar[st], cb * p.block_k, w0 + s, h0 + r, n0);
+                tma_load_3d_2sm(smem_b + st * q2.b_half_stage, &map_b_half, &full_bar[st], cb * p.block_k, r * p.kw + s,
+                                nb * p.block_n + (int)rank * (p.block_n >> 1));
+              }
+              __syncwarp();
               if (++st == q2.stages) { st = 0; ph ^= 1; }
             }
           }
@@ -783,8 +807,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ===== MMA issuer: one thread of the leader CTA =====
+    if (leader) {
+      // ===== MMA issuer: warp 1 of the leader CTA, one elected lane issues =====
       const int mma_per_kb = p.block_k / 16;
       const uint32_t hi = desc_hi(p.sbo_bytes, p.layout_type), idesc = q2.idesc;
       const uint32_t a_lo0 = desc_lo(smem_u32(smem_a)), b_lo0 = desc_lo(smem_u32(smem_b));
@@ -800,16 +824,18 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[st], ph);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll 4
-          for (int k = 0; k < mma_per_kb; ++k) {
-            umma_f16_lohi_2cta(d, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, acc);
-            acc = 1;
+            for (int k = 0; k < mma_per_kb; ++k) umma_f16_lohi_2cta(d, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, acc | (uint32_t)(k != 0));
+            umma_commit_2cta(&empty_bar[st]);
           }
-          umma_commit_2cta(&empty_bar[st]);
+          __syncwarp();
+          acc = 1;
           a_lo += a_inc; b_lo += b_inc;
           if (++st == stages) { st = 0; ph ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
         }
-        umma_commit_2cta(&tmem_full[buf]);
+        if (elect_one()) umma_commit_2cta(&tmem_full[buf]);
+        __syncwarp();
         buf ^= 1;
         if (buf == 0) buf_ph ^= 1;
       }
@@ -942,12 +968,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer: weights once, then one halo per (tile, Cin block) =====
-      mbar_arrive_expect_tx(b_full, p.b_total_bytes);
-      for (int cb = 0; cb < p.cin_blocks; ++cb)
-        for (int t = 0; t < taps; ++t)
-          tma_load_3d(smem_b + (size_t)(cb * taps + t) * p.b_tile, &map_b, b_full, cb * p.block_k, nb * p.block_n, t);
+    {
+      // ===== TMA producer (whole warp, one elected lane issues): weights once, then one halo per (tile, Cin block) =====
+      if (elect_one()) {
+        mbar_arrive_expect_tx(b_full, p.b_total_bytes);
+        for (int cb = 0; cb < p.cin_blocks; ++cb)
+          for (int t = 0; t < taps; ++t)
+            tma_load_3d(smem_b + (size_t)(cb * taps + t) * p.b_tile, &map_b, b_full, cb * p.block_k, nb * p.block_n, t);
+      }
+      __syncwarp();
       int st = 0;
       uint32_t ph = 0;
       for (int grp = g; grp < total_groups; grp += G) {
@@ -958,17 +987,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int rem = tile - n * tiles_per_image;
             const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
             mbar_wait(&a_empty[st], ph ^ 1);
-            mbar_arrive_expect_tx(&a_full[st], p.a_copy_bytes);
-            tma_load_4d(smem_a + (size_t)st * p.a_stage, &map_a, &a_full[st], cb * p.block_k, tw * p.Wv - p.pad_w, th * p.Ht - p.pad_h, n);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&a_full[st], p.a_copy_bytes);
+              tma_load_4d(smem_a + (size_t)st * p.a_stage, &map_a, &a_full[st], cb * p.block_k, tw * p.Wv - p.pad_w, th * p.Ht - p.pad_h, n);
+            }
+            __syncwarp();
             if (++st == p.stages) { st = 0; ph ^= 1; }
           }
         }
-        HALO_TRACE((grp - g) / G, 1);
+        if (lane == 0) HALO_TRACE((grp - g) / G, 1);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer: T accumulation chains in flight =====
+    {
+      // ===== MMA issuer (whole warp, one elected lane issues): T accumulation chains in flight =====
       mbar_wait(b_full, 0);
       tc_fence_after();
       const int mma_per_kb = p.block_k / 16;
@@ -983,7 +1015,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       uint32_t ph = 0, buf_ph = 0;
       for (int grp = g; grp < total_groups; grp += G) {
         mbar_wait(&tmem_empty[buf], buf_ph ^ 1);   // the epilogue has drained this buffer of T accumulators
-        HALO_TRACE((grp - g) / G, 2);
+        if (lane == 0) HALO_TRACE((grp - g) / G, 2);
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)buf * (uint32_t)T * block_n;
         const uint32_t d1 = d0 + block_n, d2 = d1 + block_n, d3 = d2 + block_n, d4 = d3 + block_n, d5 = d4 + block_n, d6 = d5 + block_n,
@@ -1002,14 +1034,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               if (++st_t == stages) { st_t = 0; ph_t ^= 1; }
             }
           }
-          if (cb == 0) HALO_TRACE((grp - g) / G, 3);
+          if (cb == 0 && lane == 0) HALO_TRACE((grp - g) / G, 3);
           tc_fence_after();
-          uint32_t off_r = 0;
+          if (elect_one()) {
+          uint32_t off_r = 0, bl = b_lo, acm = accum;     // the elected lane's working copies: the warp's loop state changes below, for all lanes
           for (int r = 0; r < kh; ++r) {
             uint32_t off = off_r;
             for (int s = 0; s < kw; ++s) {
               for (int k = 0; k < mma_per_kb; ++k) {
-                const uint32_t ao = off + 2 * k, bo = b_lo + 2 * k, ac = accum | (uint32_t)(k != 0);
+                const uint32_t ao = off + 2 * k, bo = bl + 2 * k, ac = acm | (uint32_t)(k != 0);
                 // straight-line round-robin over the T accumulators: consecutive MMAs never depend on each other
                 if (T == 8) {
                   umma_f16_lohi(d0, a_lo_t[0] + ao, bo, hi, idesc, ac);
@@ -1031,19 +1064,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     if (t < T) umma_f16_lohi(d0 + (uint32_t)t * block_n, a_lo_t[t] + ao, bo, hi, idesc, ac);
                 }
               }
-              accum = 1;
+              acm = 1;
               off += a_px_inc;
-              b_lo += b_tile_inc;
+              bl += b_tile_inc;
             }
             off_r += a_row_inc;
           }
-          for (int t = 0; t < T; ++t) {
-            umma_commit(&a_empty[st]);
-            if (++st == stages) { st = 0; ph ^= 1; }
+          {
+            int st_c = st;
+            for (int t = 0; t < T; ++t) {
+              umma_commit(&a_empty[st_c]);
+              if (++st_c == stages) st_c = 0;
+            }
           }
+          }
+          __syncwarp();
+          accum = 1;
+          b_lo += (uint32_t)(kh * kw) * b_tile_inc;
+          for (int t = 0; t < T; ++t)
+            if (++st == stages) { st = 0; ph ^= 1; }
         }
-        umma_commit(&tmem_full[buf]);
-        HALO_TRACE((grp - g) / G, 4);
+        if (elect_one()) umma_commit(&tmem_full[buf]);
+        __syncwarp();
+        if (lane == 0) HALO_TRACE((grp - g) / G, 4);
         if (nbuf == 2) { buf ^= 1; if (buf == 0) buf_ph ^= 1; }
         else buf_ph ^= 1;
       }
@@ -1117,7 +1160,9 @@ struct RowsArgs {
   uint32_t b_blk_bytes, b_tap_bytes, a_buf_bytes;
   __half* out;
   const float* bias;
+  long long* trace;              // optional clock64 timeline of CTA 0, stream 0: [step][8] (DVB_CNN_TRACE; development aid)
 };
+#define ROWS_TRACE(step, ev) do { if (p.trace && blockIdx.x == 0 && (step) < 48) p.trace[(step) * 8 + (ev)] = clock64(); } while (0)
 
 __device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
   const uint32_t z = 0u;
@@ -1172,12 +1217,15 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===== TMA producer: the filter tile once, then one input row per (stream, step) =====
-      mbar_arrive_expect_tx(b_full, 15u * p.b_blk_bytes);
-      for (int s = 0; s < 3; ++s)
-        for (int blk = 0; blk < 5; ++blk)
-          tma_load_3d(smem_b + s * p.b_tap_bytes + blk * p.b_blk_bytes, &map_b, b_full, 0, blk * p.cout, s);
+    {
+      // ===== TMA producer (whole warp, one elected lane issues): the filter tile once, then one input row per (stream, step) =====
+      if (elect_one()) {
+        mbar_arrive_expect_tx(b_full, 15u * p.b_blk_bytes);
+        for (int s = 0; s < 3; ++s)
+          for (int blk = 0; blk < 5; ++blk)
+            tma_load_3d(smem_b + s * p.b_tap_bytes + blk * p.b_blk_bytes, &map_b, b_full, 0, blk * p.cout, s);
+      }
+      __syncwarp();
       int rb[2] = {0, 0}, j[2] = {0, 0}, img[2] = {(int)blockIdx.x, (int)blockIdx.x + G};
       uint32_t rph[2] = {0, 0};
       for (int t = 0; t < steps_max; ++t) {
@@ -1186,16 +1234,19 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (t >= steps_st[st]) continue;
           uint64_t* full = &in_full[st * kRowsRing + rb[st]];
           mbar_wait(&in_empty[st * kRowsRing + rb[st]], rph[st] ^ 1);
-          mbar_arrive_expect_tx(full, 128u * p.row_bytes);
-          tma_load_4d(smem_a + (size_t)(st * kRowsRing + rb[st]) * p.a_buf_bytes, &map_a, full, 0, -p.pad, j[st] - p.pad, img[st]);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(full, 128u * p.row_bytes);
+            tma_load_4d(smem_a + (size_t)(st * kRowsRing + rb[st]) * p.a_buf_bytes, &map_a, full, 0, -p.pad, j[st] - p.pad, img[st]);
+          }
+          __syncwarp();
           if (++rb[st] == kRowsRing) { rb[st] = 0; rph[st] ^= 1; }
           if (++j[st] == p.J) { j[st] = 0; img[st] += 2 * G; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer: per (stream, step) 3 taps x cin/16 MMAs of N = 3 cout into the stream's ring of three accumulators =====
+    {
+      // ===== MMA issuer (whole warp, one elected lane issues): per (stream, step) 3 taps x cin/16 MMAs of N = 3 cout into the stream's ring =====
       mbar_wait(b_full, 0);
       tc_fence_after();
       const int kper = p.cin >> 4;
@@ -1212,14 +1263,19 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mbar_wait(&acc_free[st], (uint32_t)t & 1u);               // the slot this step opens has been drained and zeroed
           mbar_wait(&in_full[st * kRowsRing + rb[st]], rph[st]);
           tc_fence_after();
+          if (st == 0 && lane == 0) ROWS_TRACE(t, 0);
           const uint32_t d = tmem_base + (uint32_t)(st * ncol);
           const uint32_t a_lo = a_lo0 + (uint32_t)(st * kRowsRing + rb[st]) * a_buf_inc;
           const uint32_t b_lo = b_lo0 + (uint32_t)(2 - t3) * b_blk_inc;
-          for (int s = 0; s < 3; ++s)
-            for (int k = 0; k < kper; ++k)
-              umma_f16_lohi(d, a_lo + (uint32_t)s * a_px_inc + 2u * k, b_lo + (uint32_t)s * b_tap_inc + 2u * k, hi, idesc, 1u);
-          umma_commit(&in_empty[st * kRowsRing + rb[st]]);
-          umma_commit(&acc_done[st]);
+          if (elect_one()) {
+            for (int s = 0; s < 3; ++s)
+              for (int k = 0; k < kper; ++k)
+                umma_f16_lohi(d, a_lo + (uint32_t)s * a_px_inc + 2u * k, b_lo + (uint32_t)s * b_tap_inc + 2u * k, hi, idesc, 1u);
+            umma_commit(&in_empty[st * kRowsRing + rb[st]]);
+            umma_commit(&acc_done[st]);
+          }
+          __syncwarp();
+          if (st == 0 && lane == 0) ROWS_TRACE(t, 1);
           if (++rb[st] == kRowsRing) { rb[st] = 0; rph[st] ^= 1; }
         }
         if (++t3 == 3) t3 = 0;
@@ -1249,6 +1305,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     for (int t = 0; t < steps_st[st]; ++t) {
       mbar_wait(&acc_done[st], (uint32_t)t & 1u);
       tc_fence_after();
+      if (st == 0 && tid == 0) ROWS_TRACE(t, 2);
       const bool row_valid = j >= 2;
       const int o = j - 2;
       uint32_t hv[32];
@@ -1270,6 +1327,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       tmem_st_wait();
       tc_fence_before();
+      if (st == 0 && tid == 0) ROWS_TRACE(t, 3);
       mbar_arrive(&acc_free[st]);                      // the MMAs of step t + 1 may go ahead while this row is stored
       if (row_valid) {
         const int nh = p.cout >> 1;                    // half2 words per pixel
@@ -1337,6 +1395,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
       }
+      if (st == 0 && tid == 0) ROWS_TRACE(t, 4);
       if (++slot == 3) slot = 0;
       if (++j == p.J) { j = 0; img += 2 * G; }
     }
@@ -1593,12 +1652,15 @@ __global__ void __launch_bounds__(kStemThreads) stem_conv1_kernel(const StemArgs
     fence_proxy_async();
     __syncthreads();
     // ---- MMA: D[128 x cout] = A[128 x 64] * B[cout x 64]^T
-    if (tid == 32) {
+    if (warp == 1) {
       tc_fence_after();
       const uint32_t hi = desc_hi(1024u, 2u), a_lo = desc_lo(smem_u32(sA)), b_lo = desc_lo(smem_u32(sB));
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_f16_lohi(tmem_base, a_lo + 2 * k, b_lo + 2 * k, hi, p.idesc, (uint32_t)(k != 0));
-      umma_commit(mma_done);
+        for (int k = 0; k < 4; ++k) umma_f16_lohi(tmem_base, a_lo + 2 * k, b_lo + 2 * k, hi, p.idesc, (uint32_t)(k != 0));
+        umma_commit(mma_done);
+      }
+      __syncwarp();
     }
     // ---- epilogue: warps 0..3 own TMEM lane quarters 0..3
     if (warp < 4) {
@@ -2739,7 +2801,22 @@ int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaSt
       RowsLaunch& rl = net->rows[stp.index];
       RowsArgs a = rl.args;
       a.n_images = n;
+      static long long* d_rtrace = nullptr;
+      const bool tracing = EnvInt("DVB_CNN_TRACE", 0) != 0;
+      if (tracing && !d_rtrace) cudaMalloc(&d_rtrace, 48 * 8 * sizeof(long long));
+      if (tracing) { cudaMemsetAsync(d_rtrace, 0, 48 * 8 * sizeof(long long), s); a.trace = d_rtrace; }
       conv_rows_kernel<<<(unsigned)std::min(net->num_sms, n), kRowsThreads, rl.smem, s>>>(rl.map_a, rl.map_b, a);
+      if (tracing) {
+        std::vector<long long> h(48 * 8);
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h.data(), d_rtrace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[rows trace] layer %d cout=%d pool=%d: step: mma_ready mma_committed acc_done_seen drained stored (cycles rel. to step 0)\n", stp.index, a.cout, a.pool);
+        for (int i = 0; i < 40; ++i) {
+          fprintf(stderr, "  step %2d:", i);
+          for (int e = 0; e < 5; ++e) fprintf(stderr, " %8lld", h[i * 8 + e] ? h[i * 8 + e] - h[0] : -1);
+          fprintf(stderr, "\n");
+        }
+      }
     } else if (stp.kind == 2) {
       HaloLaunch& hl = net->halos[stp.index];
       HaloArgs a = hl.args;

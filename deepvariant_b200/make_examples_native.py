@@ -226,8 +226,12 @@ class ExamplePlan:
 class ExamplesGenerator:
 
   def __init__(self, options: MakeExamplesOptions, example_filenames: Optional[Dict[str, str]] = None,
-               test_mode: bool = False, device: int = 0, ref_reader=None):
+               test_mode: bool = False, device: int = 0, ref_reader=None, sink=None):
     self.options = options
+    # Fused mode (deepvariant_b200/fused.py; the reference's counterpart is fast_pipeline, where make_examples streams to
+    # call_variants without tf.Example files): the planned images go to `sink` (packed reads, or finished images for the
+    # trimmed / alt-aligned route) instead of a TFRecord writer.
+    self.sink = sink
     pic = options.pic_options
     self.half_width = (pic.width - 1) // 2
     if len(options.sample_options) != 1:
@@ -434,7 +438,7 @@ class ExamplesGenerator:
     """WriteExamplesInRegion with the reads given as a native BAM table (one CUDA launch for the region).  With a
     region and an open table the C++ region packer builds the batch (native_packer=False forces the numpy packer;
     both give identical arrays, tests/test_bam_native.py)."""
-    if role not in self.writers:
+    if role not in self.writers and self.sink is None:
       raise KeyError(f'Role {role} does not have a writer.')
     stats: Dict[str, int] = {}
     enc = self._gpu()
@@ -445,6 +449,11 @@ class ExamplesGenerator:
     else:
       plans, specs = self.plan_region_from_table(candidates, table, stats, region)
       packed = packing.pack_images_from_table(specs, table, enc.params) if plans else None
+    if self.sink is not None:
+      self._count_examples(plans, stats)
+      if plans:
+        self.sink.add_packed(plans, packed)
+      return stats, self.image_shape()
     images = enc.encode_host(packed) if plans else \
         np.zeros((0,) + enc.shape, dtype=np.uint8)
     for rec in self.finish_region(plans, images, stats):
@@ -482,6 +491,14 @@ class ExamplesGenerator:
       stats['n_snps'] = stats.get('n_snps', 0) + 1
     return protos.encode_tf_example(features)
 
+  @staticmethod
+  def _count_examples(plans: Sequence[ExamplePlan], stats: Dict[str, int]) -> None:
+    """UpdateStats (make_examples_native.cc:330-348) for plans that go to the fused sink instead of encode_example()."""
+    for p in plans:
+      stats['n_examples'] = stats.get('n_examples', 0) + 1
+      key = 'n_indels' if p.variant_type == 2 else 'n_snps'
+      stats[key] = stats.get(key, 0) + 1
+
   def finish_region(self, plans: Sequence[ExamplePlan], images: np.ndarray, stats: Dict[str, int]) -> List[bytes]:
     return [self.encode_example(p, images[i], stats) for i, p in enumerate(plans)]
 
@@ -508,12 +525,17 @@ class ExamplesGenerator:
                                sample_order: Sequence[int], role: str,
                                mean_coverage_per_sample: Optional[Sequence[float]] = None):
     """WriteExamplesInRegion (make_examples_native.cc:742-793)."""
-    if role not in self.writers:
+    if role not in self.writers and self.sink is None:
       raise KeyError(f'Role {role} does not have a writer.')
     stats: Dict[str, int] = {}
     reads = list(reads_per_sample[sample_order[0]]) if reads_per_sample else []
     plans = self.plan_region(candidates, reads, stats)
     images = self.encode_plans(plans)
+    if self.sink is not None:
+      self._count_examples(plans, stats)
+      if plans:
+        self.sink.add_images(plans, images)
+      return stats, self.image_shape()
     for rec in self.finish_region(plans, images, stats):
       self.writers[role].write(rec)
     return stats, self.image_shape()
