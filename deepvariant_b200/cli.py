@@ -79,7 +79,8 @@ MAKE_EXAMPLES_DEFAULTS = dict(
     sample_name='', vsc_min_count_snps=2, vsc_min_count_indels=2, vsc_min_fraction_snps=0.12, vsc_min_fraction_indels=0.06,
     vsc_min_fraction_multiplier=1.0, small_model_vaf_context_window_size=0, track_ref_reads=False, phase_reads=False,
     keep_legacy_allele_counter_behavior=False, normalize_reads=False, realign_reads=True, gvcf='', gvcf_gq_binsize=5, p_error=0.001,
-    include_med_dp=False, haploid_contigs='', candidate_positions='', runtime_by_region='')      # --realign_reads defaults to true (make_examples_options.py:229)
+    include_med_dp=False, haploid_contigs='', candidate_positions='', runtime_by_region='', examples='', call_variants_outfile='', precision=1,
+    call_batch_size=2048)      # --realign_reads defaults to true (make_examples_options.py:229)
 
 
 def model_example_info_json_path(checkpoint: str, checkpoint_json: str = '') -> str:
@@ -132,7 +133,11 @@ def make_examples(argv):
   ap.add_argument('--candidate_positions')       # candidate_sweep: int32 positions out (sharded like --examples); calling: partitions cut by them
   ap.add_argument('--ref', required=True)
   ap.add_argument('--reads', required=True)
-  ap.add_argument('--examples', required=True)
+  ap.add_argument('--examples')                   # tf.Example shards out (the staged flow); optional with --call_variants_outfile
+  ap.add_argument('--call_variants_outfile')      # FUSED flow (deepvariant_b200/fused.py; cf. the reference's fast_pipeline): pileups are encoded AND classified
+                                                  # here, CallVariantsOutput shards out (name@N.tfrecord.gz), no tf.Example files; needs --checkpoint
+  ap.add_argument('--precision', type=int, choices=[0, 1])
+  ap.add_argument('--call_batch_size', type=int)
   ap.add_argument('--candidates')        # OUTPUT, as in the reference (make_examples_options.py:109): the DeepVariantCalls found
   ap.add_argument('--candidates_in')     # INPUT (not a reference flag): use these DeepVariantCalls instead of generating them
   ap.add_argument('--checkpoint')        # model directory / ckpt path: only its example_info.json flags are read here
@@ -184,9 +189,23 @@ def make_examples(argv):
   pic.sort_by_haplotypes = a.sort_by_haplotypes
   pic.alt_aligned_pileup = a.alt_aligned_pileup
   opts = men.MakeExamplesOptions(pic_options=pic, reference_filename=a.ref, trim_reads_for_pileup=a.trim_reads_for_pileup)
-  out_path = tfrecord.shard_path(a.examples, a.task)
-  n_shards = len(tfrecord.shard_paths(a.examples))
-  gen = men.ExamplesGenerator(opts, {'main_sample': out_path}, device=a.device)
+  fused = bool(a.call_variants_outfile)
+  if not fused and not a.examples:
+    raise ValueError('make_examples needs --examples (staged flow) or --call_variants_outfile (fused flow)')
+  shard_spec = a.call_variants_outfile if fused else a.examples
+  n_shards = len(tfrecord.shard_paths(shard_spec))
+  gen = men.ExamplesGenerator(opts, {'main_sample': tfrecord.shard_path(a.examples, a.task)} if a.examples and not fused else {}, device=a.device)
+  fused_cnn = None
+  if fused:
+    # encoder -> classifier in one call per batch of regions; the CallVariantsOutput shard of this task is what call_variants
+    # would have written for it (same records, same rounding; postprocess_variants sorts across shards either way)
+    from deepvariant_b200 import call_variants as cv, fused as fz
+    if not a.checkpoint:
+      raise ValueError('--call_variants_outfile needs --checkpoint (SavedModel directory / checkpoint prefix / .npz / random[:seed])')
+    shape = gen.image_shape()
+    cv.check_example_info({'shape': shape, 'channels': men.example_info_channels(pic)}, cv.model_example_info(a.checkpoint))
+    fused_cnn = cv.GpuCnn(cv.load_weights(a.checkpoint, shape[2]), shape, device=a.device, max_batch=min(a.call_batch_size, 2048), precision=a.precision)
+    gen.sink = fz.FusedCaller(gen._gpu(), fused_cnn, tfrecord.shard_path(a.call_variants_outfile, a.task), batch_images=a.call_batch_size)  # pylint: disable=protected-access
   # Native block-parallel BAM decode into a Structure-of-Arrays read table (csrc/dvb_bam.cu); untrimmed pileups (WGS/WES)
   # are planned and packed straight from the table rows, trimmed ones (PACBIO, alt-aligned) from Read objects of table.query().
   reader = bam.NativeBamTable(a.reads, bam.ReadRequirements(min_mapping_quality=a.min_mapping_quality), parse_aux=a.parse_sam_aux_fields)
@@ -385,6 +404,10 @@ def make_examples(argv):
     if gvcf_writer is not None:
       gvcf_writer.close()
   gen.signal_shard_finished()
+  if fused:
+    totals['n_call_variants_outputs'] = gen.sink.close()
+    totals['n_classifier_batches'] = gen.sink.n_batches
+    fused_cnn.close()
   print(f'make_examples task {a.task}: {totals}', file=sys.stderr)
   return 0
 
@@ -448,16 +471,36 @@ def run_deepvariant(argv):
   ap.add_argument('--num_shards', type=int, default=1)
   ap.add_argument('--customized_model', required=True)   # SavedModel dir / checkpoint prefix / .npz; the exact token random[:seed] = noise weights (loud warning)
   ap.add_argument('--precision', type=int, default=1, choices=[0, 1])
+  ap.add_argument('--staged', action='store_true')         # the reference's three stages with tf.Example files in between; default = fused
+  ap.add_argument('--num_gpus', type=int, default=0)        # 0 = every visible device; task i runs on device i mod num_gpus
+  ap.add_argument('--jobs', type=int, default=0)            # tasks in flight; 0 = all of them, as `parallel -j num_shards` (scripts/run_deepvariant.py:457-462)
   a = ap.parse_args(argv)
   os.makedirs(a.output_dir, exist_ok=True)
   d = MODEL_DEFAULTS[a.model_type]
   examples = os.path.join(a.output_dir, f'make_examples.tfrecord@{a.num_shards}.gz')
   nonvariants = os.path.join(a.output_dir, f'gvcf.tfrecord@{a.num_shards}.gz')
+  cvo = os.path.join(a.output_dir, 'call_variants_output.tfrecord.gz')
   if a.output_gvcf and not a.output_vcf:
     raise ValueError('--output_gvcf needs --output_vcf')
+  import glob
+  for stale in glob.glob(os.path.join(a.output_dir, 'call_variants_output-?????-of-?????.tfrecord.gz')):
+    os.remove(stale)          # shards of an earlier run with another shard count would be read by postprocess_variants as well
+  n_gpus = a.num_gpus
+  if n_gpus <= 0:
+    try:
+      import torch
+      n_gpus = max(1, torch.cuda.device_count())
+    except ImportError:
+      n_gpus = 1
+  task_args = []
   for task in range(a.num_shards):
-    args = ['--mode', 'calling', '--ref', a.ref, '--reads', a.reads, '--examples', examples, '--task',
-            str(task), '--channel_list', d['channel_list'], '--pileup_image_width', str(d['pileup_image_width'])]
+    args = ['--mode', 'calling', '--ref', a.ref, '--reads', a.reads, '--task',
+            str(task), '--channel_list', d['channel_list'], '--pileup_image_width', str(d['pileup_image_width']), '--device', str(task % n_gpus)]
+    if a.staged:
+      args += ['--examples', examples]
+    else:
+      args += ['--call_variants_outfile', os.path.join(a.output_dir, f'call_variants_output@{a.num_shards}.tfrecord.gz'),
+               '--checkpoint', a.customized_model, '--precision', str(a.precision)]
     if a.candidates_in:
       args += ['--candidates_in', a.candidates_in]
     for flag in ('sort_by_haplotypes', 'trim_reads_for_pileup', 'parse_sam_aux_fields', 'track_ref_reads', 'phase_reads', 'norealign_reads'):
@@ -472,9 +515,28 @@ def run_deepvariant(argv):
       args += ['--sample_name', a.sample_name]
     if a.output_gvcf:
       args += ['--gvcf', nonvariants]
-    make_examples(args)
-  cvo = os.path.join(a.output_dir, 'call_variants_output.tfrecord.gz')
-  rc = call_variants(['--examples', examples, '--outfile', cvo, '--checkpoint', a.customized_model, '--precision', str(a.precision)])
+    task_args.append(args)
+  # One process per task, task i on GPU i mod num_gpus, started together as the reference starts its make_examples shards
+  # (scripts/run_deepvariant.py:457-462, 497); a single task runs in this process.
+  if len(task_args) == 1:
+    make_examples(task_args[0])
+  else:
+    import subprocess
+    jobs = a.jobs if a.jobs > 0 else len(task_args)
+    running, failed, queue = [], [], list(enumerate(task_args))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.environ.get('PYTHONPATH', '')]))
+    while queue or running:
+      while queue and len(running) < jobs:
+        task, args = queue.pop(0)
+        running.append((task, subprocess.Popen([sys.executable, '-m', 'deepvariant_b200.cli', 'make_examples'] + args, env=env)))
+      task, proc = running.pop(0)
+      if proc.wait() != 0:
+        failed.append(task)
+    if failed:
+      raise RuntimeError(f'make_examples tasks {failed} failed')
+  rc = 0
+  if a.staged:
+    rc = call_variants(['--examples', examples, '--outfile', cvo, '--checkpoint', a.customized_model, '--precision', str(a.precision)])
   if rc or not a.output_vcf:
     return rc
   args = ['--ref', a.ref, '--infile', cvo, '--outfile', a.output_vcf]     # the shards call_variants wrote are found by name

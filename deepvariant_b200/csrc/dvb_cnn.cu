@@ -343,7 +343,9 @@ struct ConvArgs {
   uint32_t a_res_off, b_res_off;
   int skip_a_res;                 // the A residual plane is identically zero (network input): skip its load and MMA
   int dbg;                        // timing probes (DVB_CNN_DBG; results are garbage): 1 = no TMA loads, MMAs do not wait; 2 = TMA loads, no MMAs
+  long long* trace;               // optional clock64 timeline of CTA 0's MMA warp: [k block][4] = stage full seen, MMAs issued, commit issued
 };
+#define GEMM_TRACE(i, ev) do { if (p.trace && blockIdx.x == 0 && lane == 0 && (i) < 96) p.trace[(i) * 4 + (ev)] = clock64(); } while (0)
 
 // Epilogue of one accumulator row of a merged GEMM: 16-column chunks, each routed to the tensor that owns its column
 // range (range boundaries are multiples of 16).  `pix` = flat output pixel index, `col0` = first GEMM column of this row piece.
@@ -579,7 +581,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
       const uint32_t a_lo0 = desc_lo(smem_u32(smem_a)), b_lo0 = desc_lo(smem_u32(smem_b));
       const uint32_t a_inc = p.a_stage >> 4, b_inc = p.b_stage >> 4;
       const int stages = p.stages;
-      int st = 0, buf = 0;
+      int st = 0, buf = 0, tr_i = 0;
       uint32_t ph = 0, buf_ph = 0, a_lo = a_lo0, b_lo = b_lo0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         mbar_wait(&tmem_empty[buf], buf_ph ^ 1);      // the epilogue has drained this accumulator
@@ -589,14 +591,18 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
         for (int kb = 0; kb < num_kb; ++kb) {
           if (!(p.dbg & 1)) mbar_wait(&full_bar[st], ph);
           tc_fence_after();
+          GEMM_TRACE(tr_i, 0);
           if (elect_one()) {
             if (!(p.dbg & 2)) {
 #pragma unroll 4
               for (int k = 0; k < mma_per_kb; ++k) umma_f16_lohi(d, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, acc | (uint32_t)(k != 0));
             }
+            GEMM_TRACE(tr_i, 1);
             umma_commit(&empty_bar[st]);
+            GEMM_TRACE(tr_i, 2);
           }
           __syncwarp();
+          ++tr_i;
           acc = 1;
           a_lo += a_inc; b_lo += b_inc;
           if (++st == stages) { st = 0; ph ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
@@ -1172,7 +1178,11 @@ __device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {   // immediate barrier ids: a register id makes ptxas reserve all 16 barriers
+  (void)nthreads;
+  if (id == 1) asm volatile("bar.sync 1, 128;" ::: "memory");
+  else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
 
 __global__ void __launch_bounds__(kRowsThreads, 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const RowsArgs p) {
@@ -1333,6 +1343,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int nh = p.cout >> 1;                    // half2 words per pixel
         if (!p.pool) {
           named_bar_sync(bar_id, 128);                 // the previous row has left the staging buffer
+          if (st == 0 && tid == 0) ROWS_TRACE(t, 5);
           if (w < p.Wout) {
 #pragma unroll
             for (int c = 0; c < 8; ++c)
@@ -1341,6 +1352,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     make_uint4(hv[4 * c], hv[4 * c + 1], hv[4 * c + 2], hv[4 * c + 3]);
           }
           named_bar_sync(bar_id, 128);
+          if (st == 0 && tid == 0) ROWS_TRACE(t, 6);
           __half* dst = p.out + ((size_t)img * p.Hout + o) * p.Wout * p.out_cstride + p.out_coff;
           for (int i = tid; i < p.Wout * nch; i += 128) {
             const int px = i / nch, cv = i - px * nch;
@@ -2770,6 +2782,12 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
     occ = std::max(1, std::min(occ, 512 / h.args.tmem_cols));
     h.ctas_per_nblock = std::max(1, net->num_sms * occ / h.args.n_blocks);
   }
+  if (EnvInt("DVB_CNN_LIST", 0))
+    for (size_t i = 0; i < net->convs.size(); ++i) {
+      const ConvLaunch& c = net->convs[i];
+      fprintf(stderr, "[conv %zu] %dx%d cin_blocks=%d bk=%d N=%d n_blocks=%d persist=%d pair=%d stages=%d\n", i, c.args.kh, c.args.kw, c.args.cin_blocks, c.args.block_k,
+              c.args.block_n, c.n_blocks, (int)c.persist, (int)c.pair, c.args.stages);
+    }
   if (cudaDeviceSynchronize() != cudaSuccess) return dvb::fail(DVB_ERR_CUDA, "weight upload failed: %s", cudaGetErrorString(cudaGetLastError()));
   return DVB_OK;
 }
@@ -2813,7 +2831,7 @@ int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaSt
         fprintf(stderr, "[rows trace] layer %d cout=%d pool=%d: step: mma_ready mma_committed acc_done_seen drained stored (cycles rel. to step 0)\n", stp.index, a.cout, a.pool);
         for (int i = 0; i < 40; ++i) {
           fprintf(stderr, "  step %2d:", i);
-          for (int e = 0; e < 5; ++e) fprintf(stderr, " %8lld", h[i * 8 + e] ? h[i * 8 + e] - h[0] : -1);
+          for (int e = 0; e < 7; ++e) fprintf(stderr, " %8lld", h[i * 8 + e] ? h[i * 8 + e] - h[0] : -1);
           fprintf(stderr, "\n");
         }
       }
@@ -2857,8 +2875,20 @@ int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaSt
         conv_gemm_pair_kernel<<<ctas, kPersistThreads, c.pair_smem, s>>>(c.map_a, c.map_b_half, a, c.pair_args, c.n_blocks, c.cout);
       } else if (c.persist) {
         const long total = (long)grid.x * c.n_blocks;
+        static long long* d_gtrace = nullptr;
+        const bool tracing = EnvInt("DVB_CNN_TRACE", 0) == 2 && stp.index == EnvInt("DVB_CNN_TRACE_LAYER", -1);
+        if (tracing && !d_gtrace) cudaMalloc(&d_gtrace, 96 * 4 * sizeof(long long));
+        if (tracing) { cudaMemsetAsync(d_gtrace, 0, 96 * 4 * sizeof(long long), s); a.trace = d_gtrace; }
         conv_gemm_persistent_kernel<<<(unsigned)std::min<long>(total, net->num_sms), kPersistThreads, c.smem, s>>>(c.map_a, c.map_b, a, c.n_blocks,
                                                                                                                    c.cout);
+        if (tracing) {
+          std::vector<long long> h(96 * 4);
+          cudaStreamSynchronize(s);
+          cudaMemcpy(h.data(), d_gtrace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+          fprintf(stderr, "[gemm trace] conv %d: kh=%d kw=%d cin_blocks=%d block_k=%d block_n=%d stages=%d: k block: full_seen mmas_issued commit_issued (cycles)\n", stp.index, a.kh,
+                  a.kw, a.cin_blocks, a.block_k, a.block_n, a.stages);
+          for (int i = 0; i < 90; ++i) fprintf(stderr, "  kb %2d: %8lld %8lld %8lld\n", i, h[i * 4] - h[0], h[i * 4 + 1] - h[0], h[i * 4 + 2] - h[0]);
+        }
       } else if (net->precision == 1)
         conv_gemm_kernel<true><<<grid, kConvThreads, c.smem, s>>>(c.map_a, c.map_b, c.map_a_res, c.map_b_res, a);
       else

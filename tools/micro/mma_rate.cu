@@ -71,7 +71,32 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(Args a, long long* out) {
   uint64_t* scratch = bar + 1;     // second barrier: the per-k-block commits of the `commit_every` variant land here
   if (threadIdx.x == 0) mbar_init(scratch, (1 << 20) - 1);
   __syncthreads();
-  if (a.elect) {
+  if (a.elect == 2) {
+    // burst: ONE elected lane issues all the MMAs back to back (no per-instruction warp synchronisation): the hardware's own interval
+    if (threadIdx.x < 32 && rank == 0) {
+      t0 = clock64();
+      if (elect_one()) {
+        int acc_i = 0, ks = 0;
+        for (int i = 0; i < a.iters; ++i) {
+          umma<CG>(tmem + (uint32_t)(acc_i * a.n), a_lo + 2 * ks, b_lo + 2 * ks, hi, idesc, 1u);
+          if (++acc_i == a.nacc) acc_i = 0;
+          if (++ks == a.kslices) {
+            ks = 0;
+            if (a.commit_every) {
+              if (CG == 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(scratch)) : "memory");
+              else asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(scratch)) : "memory");
+            }
+          }
+        }
+        if (CG == 1) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+        else asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+      }
+      __syncwarp();
+      mbar_wait(bar, 0);
+      t1 = clock64();
+      if (blockIdx.x < 2 && threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+    }
+  } else if (a.elect) {
     // the form the classifier uses now: the whole warp walks the loop on uniform values, one elected lane issues
     if (threadIdx.x < 32 && rank == 0) {
       t0 = clock64();
@@ -129,17 +154,17 @@ int main() {
   cudaFuncSetAttribute(rate_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   printf("issue cg  M   N  nacc swz kslices commit/kblock  clk/MMA  floor(N/2*M/128/cg)  MAC/clk/SM\n");
   const int iters = 4096;
-  for (int el = 1; el >= 0; --el)
-  for (int ce = 0; ce <= el; ++ce)
+  for (int el = 2; el >= 0; --el)
+  for (int ce = 0; ce <= (el ? 1 : 0); ++ce)
   for (int cg = 1; cg <= 2; ++cg)
-    for (int m64 = 0; m64 <= (cg == 1 && el == 1 && ce == 0 ? 1 : 0); ++m64)
+    for (int m64 = 0; m64 <= (cg == 1 && el == 2 && ce == 0 ? 1 : 0); ++m64)
       for (int n : {32, 64, 96, 128, 192, 256})
         for (int nacc : {1, 2, 4})
           for (int lt : {2, 4}) {       // 2 = 128B swizzle (64-wide K block), 4 = 64B swizzle (32-wide)
             if (nacc * n > 512) continue;
             if (m64 && (n % 8)) continue;
-            if (lt == 4 && (el == 0 || ce == 1 || nacc == 4)) continue;
-            if (el == 0 && nacc == 4) continue;
+            if (lt == 4 && (el != 2 || ce == 1 || nacc == 4)) continue;
+            if (el != 2 && nacc != 1) continue;
             Args a{n, iters, nacc, lt, lt == 2 ? 128 : 64, lt == 2 ? 4 : 2, m64, el, ce};
             long long h[2] = {0, 0};
             cudaMemset(d_out, 0, 16);
@@ -157,7 +182,7 @@ int main() {
             cudaMemcpy(h, d_out, 16, cudaMemcpyDeviceToHost);
             const int M = cg == 2 ? 256 : (m64 ? 64 : 128);
             const double clk = (double)h[0] / iters;
-            printf("%s %d  %3d %3d  %d    %s  %d   %d     %7.1f   %6.1f   %8.0f\n", el ? "elect" : "lane0", cg, M, n, nacc, lt == 2 ? "128B" : " 64B", a.kslices, ce, clk,
+            printf("%s %d  %3d %3d  %d    %s  %d   %d     %7.1f   %6.1f   %8.0f\n", el == 2 ? "burst" : el ? "elect" : "lane0", cg, M, n, nacc, lt == 2 ? "128B" : " 64B", a.kslices, ce, clk,
                    n / 2.0 * (M / 128.0) / cg * (m64 ? 2 : 1), (double)M * n * 16 / clk / cg);
           }
   return 0;
