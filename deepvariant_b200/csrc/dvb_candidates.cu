@@ -618,20 +618,31 @@ constexpr int kAlleleTileThreads = 256;
 
 __global__ void dvb_allele_tile_ranges_kernel(const int64_t* __restrict__ rows, int64_t n_rows, const int32_t* __restrict__ pos,
                                               int64_t start, int64_t len, int64_t max_span, int2* __restrict__ ranges) {
-  const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // one WARP per tile: a 33-ary search (32 probes per step, ~4 steps for a million rows) instead of 20 dependent binary steps
+  const int lane = threadIdx.x & 31;
+  const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_tiles = (len + kAlleleTile - 1) / kAlleleTile;
   if (tile >= n_tiles) return;
   const int64_t p0 = start + tile * kAlleleTile;
   auto lower_bound = [&](int64_t key) {       // first i with pos[rows[i]] >= key
-    int64_t lo = 0, hi = n_rows;
-    while (lo < hi) {
-      const int64_t mid = (lo + hi) >> 1;
-      if ((int64_t)pos[rows[mid]] < key) lo = mid + 1; else hi = mid;
+    int64_t lo = 0, hi = n_rows;              // invariant: every i < lo has pos < key, every i >= hi has pos >= key
+    while (hi - lo > 32) {
+      const int64_t step = (hi - lo + 32) / 33;
+      const int64_t probe = lo + (int64_t)(lane + 1) * step - 1;              // lane 0 .. 31: increasing probes inside [lo, hi)
+      const bool less = probe < hi && (int64_t)pos[rows[probe]] < key;
+      const unsigned m = __ballot_sync(0xffffffffu, less);                   // monotone: the lanes with pos < key form a prefix
+      const int k = __popc(m);
+      const int64_t new_lo = k ? lo + (int64_t)k * step : lo;                // probe of lane k-1 is < key -> lo = that probe + 1
+      const int64_t new_hi = k < 32 ? min(hi, lo + (int64_t)(k + 1) * step - 1) : hi;
+      lo = new_lo; hi = new_hi;
     }
-    return lo;
+    const int64_t i = lo + lane;
+    const bool less = i < hi && (int64_t)pos[rows[i]] < key;
+    return lo + __popc(__ballot_sync(0xffffffffu, less));
   };
   // reads with end > p0 (end <= pos + max_span) and pos <= p0 + tile (a leading insertion / soft clip is anchored at pos - 1)
-  ranges[tile] = make_int2((int)lower_bound(p0 - max_span + 1), (int)lower_bound(p0 + kAlleleTile + 1));
+  const int64_t a = lower_bound(p0 - max_span + 1), b = lower_bound(p0 + kAlleleTile + 1);
+  if (lane == 0) ranges[tile] = make_int2((int)a, (int)b);
 }
 
 struct TileShared {
@@ -717,16 +728,30 @@ dvb_allele_count_tile_kernel(DeviceTable t, const int32_t* __restrict__ read_end
             if (have && lane == 0) TileCommit(sm, tile_lo, tile_n, pending, seq);     // positions differ: every run element lies after it
             // bulk: the run's elements inside the tile, except `last`
             const int64_t b0 = max(i0, (int64_t)tile_lo - interval_offset), b1 = min((int64_t)last, (int64_t)tile_lo + tile_n - interval_offset);
-            for (int64_t i = b0 + lane; i < b1; i += 32) {
-              const int base_offset = read_offset + (int)i;
-              bool lq = false;
-              if (!usable(base_offset, &lq)) continue;
-              const int idx = (int)(interval_offset + i) - tile_lo;
-              const uint8_t b = seq[base_offset];
-              if (dvb_allele::RefAt(p, p.start + interval_offset + i) == b) {
-                if (!lq) atomicAdd(&sm.ref_count[idx], 1);
-              } else if (!lq) {
-                atomicAdd(&sm.subst[4 * idx + (b == 'A' ? 0 : b == 'C' ? 1 : b == 'G' ? 2 : 3)], 1);
+            // 8 x 32 bases per trip with all loads issued before the first use (memory-level parallelism: the kernel is bound by the
+            // latency of dependent global loads, not by bandwidth - measured: the scalar form of this loop ran as slowly as the scatter kernel)
+            for (int64_t base = b0; base < b1; base += 8 * 32) {
+              uint8_t bb[8], qq[8], rr[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int64_t i = base + u * 32 + lane;
+                if (i < b1) {
+                  bb[u] = seq[read_offset + (int)i];
+                  qq[u] = qual[read_offset + (int)i];
+                  rr[u] = dvb_allele::RefAt(p, p.start + interval_offset + i);
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int64_t i = base + u * 32 + lane;
+                if (i >= b1) continue;
+                const uint8_t b = bb[u];
+                const int q = qq[u];
+                if ((q < p.min_base_quality && p.keep_legacy_behavior) || !dvb_allele::Canonical(b)) continue;     // CanBasesBeUsed(offset, 1)
+                if (!p.keep_legacy_behavior && q < p.min_base_quality) continue;                                  // low quality: counted nowhere
+                const int idx = (int)(interval_offset + i) - tile_lo;
+                if (rr[u] == b) atomicAdd(&sm.ref_count[idx], 1);
+                else atomicAdd(&sm.subst[4 * idx + (b == 'A' ? 0 : b == 'C' ? 1 : b == 'G' ? 2 : 3)], 1);
               }
             }
             bool lq = false;
@@ -947,7 +972,7 @@ int dvb_allele_count_device(DvbDeviceReads* d, const uint8_t* ref_dev, int64_t r
       DVB_CUDA(cudaFuncSetAttribute(dvb_allele_count_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)));
       attr_set = true;
     }
-    dvb_allele_tile_ranges_kernel<<<(unsigned)((n_tiles + 127) / 128), 128, 0, s>>>(rows_dev, n_rows, d->pos, start, len, d->max_span, (int2*)d->tiles.p);
+    dvb_allele_tile_ranges_kernel<<<(unsigned)((n_tiles * 32 + 127) / 128), 128, 0, s>>>(rows_dev, n_rows, d->pos, start, len, d->max_span, (int2*)d->tiles.p);
     dvb_allele_count_tile_kernel<<<(unsigned)n_tiles, kAlleleTileThreads, sizeof(TileShared), s>>>(t, d->end, rows_dev, (const int2*)d->tiles.p, p,
                                                                                                    opt->min_mapping_quality, c, MakeFlagParams(*opt), flags_dev);
     d->launches += 2;

@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_a_res, const __grid_constant__ CUtensorMap map_b_res, const ConvArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic (not an integer round trip): ptxas keeps the shared address space -> LDS / STS, not generic LD / ST
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + p.stages * p.a_stage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.stages * p.b_stage);
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1)
 conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const ConvArgs p,
                             const int n_blocks, const int cout) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic (not an integer round trip): ptxas keeps the shared address space -> LDS / STS, not generic LD / ST
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + p.stages * p.a_stage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.stages * p.b_stage);
@@ -747,7 +747,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPersistThreads, 1)
 conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b_half, const ConvArgs p,
                       const PairArgs q2, const int n_blocks, const int cout) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic (not an integer round trip): ptxas keeps the shared address space -> LDS / STS, not generic LD / ST
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + q2.stages * p.a_stage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + q2.stages * q2.b_half_stage);
@@ -933,7 +933,7 @@ struct HaloArgs {
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const HaloArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic (not an integer round trip): ptxas keeps the shared address space -> LDS / STS, not generic LD / ST
   const int taps = p.kh * p.kw;
   uint8_t* smem_b = smem;                                           // [cin_blocks][taps][block_n][block_k]
   uint8_t* smem_a = smem + (size_t)p.cin_blocks * taps * p.b_tile;  // [stages][halo pixels][block_k]
@@ -1187,7 +1187,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {   // imme
 __global__ void __launch_bounds__(kRowsThreads, 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const RowsArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic (not an integer round trip): ptxas keeps the shared address space -> LDS / STS, not generic LD / ST
   uint8_t* smem_b = smem;                                                  // [3 taps][5 blocks][cout rows][cin]
   uint8_t* smem_a = smem_b + 3 * p.b_tap_bytes;                            // [2 streams][kRowsRing][128 slots][cin]
   uint8_t* smem_row = smem_a + 2 * kRowsRing * p.a_buf_bytes;              // [2 streams][128 pixels][cout] fp16, 16-byte chunks XOR-swizzled
@@ -1278,9 +1278,17 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint32_t a_lo = a_lo0 + (uint32_t)(st * kRowsRing + rb[st]) * a_buf_inc;
           const uint32_t b_lo = b_lo0 + (uint32_t)(2 - t3) * b_blk_inc;
           if (elect_one()) {
-            for (int s = 0; s < 3; ++s)
-              for (int k = 0; k < kper; ++k)
-                umma_f16_lohi(d, a_lo + (uint32_t)s * a_px_inc + 2u * k, b_lo + (uint32_t)s * b_tap_inc + 2u * k, hi, idesc, 1u);
+            if (kper == 2) {
+#pragma unroll
+              for (int s = 0; s < 3; ++s) {
+                umma_f16_lohi(d, a_lo + (uint32_t)s * a_px_inc, b_lo + (uint32_t)s * b_tap_inc, hi, idesc, 1u);
+                umma_f16_lohi(d, a_lo + (uint32_t)s * a_px_inc + 2u, b_lo + (uint32_t)s * b_tap_inc + 2u, hi, idesc, 1u);
+              }
+            } else {
+              for (int s = 0; s < 3; ++s)
+                for (int k = 0; k < kper; ++k)
+                  umma_f16_lohi(d, a_lo + (uint32_t)s * a_px_inc + 2u * k, b_lo + (uint32_t)s * b_tap_inc + 2u * k, hi, idesc, 1u);
+            }
             umma_commit(&in_empty[st * kRowsRing + rb[st]]);
             umma_commit(&acc_done[st]);
           }
@@ -1300,9 +1308,13 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int bar_id = 1 + st;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(st * ncol);
     uint8_t* stage = smem_row + st * row_stage_bytes;
-    const int nch = p.cout >> 3;                      // 16-byte chunks per pixel
-    const int rows_per_128 = 128 / (p.cout * 2);      // pixels per 128 bytes of the staging row (1 or 2)
-    const int my_sw = (w / rows_per_128) & (nch - 1);
+    // (all shifts: a run-time integer division costs ~150 clocks, and the copy-out loops below had three per iteration - measured:
+    //  1400 clocks for 3.4 iterations of one shared load + one global store)
+    const int nch = p.cout >> 3;                      // 16-byte chunks per pixel: 4 (cout 32) or 8 (cout 64)
+    const int nch_log2 = p.cout == 64 ? 3 : 2;
+    const int rp_log2 = p.cout == 64 ? 0 : 1;         // log2(pixels per 128 bytes of the staging row)
+    const int px_shift = p.cout == 64 ? 7 : 6;        // log2(bytes per staged pixel)
+    const int my_sw = (w >> rp_log2) & (nch - 1);
     // every accumulator column starts at zero
     for (int c = 0; c < ncol; c += 32) tmem_st32_zero(t_lane + c);
     tmem_st_wait();
@@ -1348,15 +1360,15 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
             for (int c = 0; c < 8; ++c)
               if (c < nch)
-                *reinterpret_cast<uint4*>(stage + (size_t)w * (p.cout * 2) + ((c ^ my_sw) << 4)) =
+                *reinterpret_cast<uint4*>(stage + (w << px_shift) + ((c ^ my_sw) << 4)) =
                     make_uint4(hv[4 * c], hv[4 * c + 1], hv[4 * c + 2], hv[4 * c + 3]);
           }
           named_bar_sync(bar_id, 128);
           if (st == 0 && tid == 0) ROWS_TRACE(t, 6);
           __half* dst = p.out + ((size_t)img * p.Hout + o) * p.Wout * p.out_cstride + p.out_coff;
-          for (int i = tid; i < p.Wout * nch; i += 128) {
-            const int px = i / nch, cv = i - px * nch;
-            const uint4 val = *reinterpret_cast<const uint4*>(stage + (size_t)px * (p.cout * 2) + ((cv ^ ((px / rows_per_128) & (nch - 1))) << 4));
+          for (int i = tid; i < (p.Wout << nch_log2); i += 128) {
+            const int px = i >> nch_log2, cv = i & (nch - 1);
+            const uint4 val = *reinterpret_cast<const uint4*>(stage + (px << px_shift) + ((cv ^ ((px >> rp_log2) & (nch - 1))) << 4));
             *reinterpret_cast<uint4*>(dst + (size_t)px * p.out_cstride + cv * 8) = val;
           }
         } else {
@@ -1376,19 +1388,19 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                   m[e] = *reinterpret_cast<const uint32_t*>(&r);
                 }
                 if (w < p.Wout)
-                  *reinterpret_cast<uint4*>(stage + (size_t)w * (p.cout * 2) + ((c ^ my_sw) << 4)) = make_uint4(m[0], m[1], m[2], m[3]);
+                  *reinterpret_cast<uint4*>(stage + (w << px_shift) + ((c ^ my_sw) << 4)) = make_uint4(m[0], m[1], m[2], m[3]);
               }
             }
             named_bar_sync(bar_id, 128);
             const int ph = (o >> 1) - 1;
             __half* dst = p.out + ((size_t)img * p.Hp + ph) * p.Wp * p.out_cstride + p.out_coff;
-            for (int i = tid; i < p.Wp * nch; i += 128) {
-              const int px = i / nch, cv = i - px * nch;
+            for (int i = tid; i < (p.Wp << nch_log2); i += 128) {
+              const int px = i >> nch_log2, cv = i & (nch - 1);
               uint4 acc = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
               for (int dx = 0; dx < 3; ++dx) {
                 const int pw = 2 * px + dx;
-                const uint4 val = *reinterpret_cast<const uint4*>(stage + (size_t)pw * (p.cout * 2) + ((cv ^ ((pw / rows_per_128) & (nch - 1))) << 4));
+                const uint4 val = *reinterpret_cast<const uint4*>(stage + (pw << px_shift) + ((cv ^ ((pw >> rp_log2) & (nch - 1))) << 4));
                 acc = hmax2x4(acc, val);               // post-ReLU values are >= 0: zero is the identity
               }
               *reinterpret_cast<uint4*>(dst + (size_t)px * p.out_cstride + cv * 8) = acc;
@@ -1537,7 +1549,7 @@ constexpr int kStemRawPitch = 1840;   // bytes per staged raw input row segment 
 
 __global__ void __launch_bounds__(kStemThreads) stem_conv1_kernel(const StemArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic (not an integer round trip): ptxas keeps the shared address space -> LDS / STS, not generic LD / ST
   uint8_t* sA = smem;                         // 128 rows x 128 B, 128B swizzle
   uint8_t* sB = smem + 16384;                 // cout rows x 128 B, 128B swizzle (cout <= 32 -> 4 KB)
   __half* sH = reinterpret_cast<__half*>(smem + 16384 + 4096);   // [3][h_pitch]
