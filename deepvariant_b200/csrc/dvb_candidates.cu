@@ -614,7 +614,7 @@ __global__ void dvb_allele_flag_kernel(dvb_allele::DenseCounts c, const uint8_t*
 // run have distinct, increasing positions - so the run's elements commit independently except the last one, which is held
 // as the pending element exactly as the sequential walk holds it.
 constexpr int kAlleleTile = 2048;
-constexpr int kAlleleTileThreads = 256;
+constexpr int kAlleleTileThreads = 512;   // 16 warps walk reads; 2 CTAs per SM (see the carveout note at the launch)
 
 __global__ void dvb_allele_tile_ranges_kernel(const int64_t* __restrict__ rows, int64_t n_rows, const int32_t* __restrict__ pos,
                                               int64_t start, int64_t len, int64_t max_span, int2* __restrict__ ranges) {
@@ -671,7 +671,7 @@ __device__ __forceinline__ void TileCommit(TileShared& sm, int tile_lo, int tile
   }
 }
 
-__global__ void __launch_bounds__(kAlleleTileThreads)
+__global__ void __launch_bounds__(kAlleleTileThreads, 2)
 dvb_allele_count_tile_kernel(DeviceTable t, const int32_t* __restrict__ read_end, const int64_t* __restrict__ rows, const int2* __restrict__ ranges,
                              dvb_allele::WalkParams p, int min_mapping_quality, dvb_allele::DenseCounts out, dvb_allele::FlagParams fp,
                              uint8_t* __restrict__ flags) {
@@ -970,6 +970,9 @@ int dvb_allele_count_device(DvbDeviceReads* d, const uint8_t* ref_dev, int64_t r
     static bool attr_set = false;
     if (!attr_set) {
       DVB_CUDA(cudaFuncSetAttribute(dvb_allele_count_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)));
+      // Without this the driver picks the smallest shared-memory carveout that fits ONE block: the first version ran one 8-warp CTA per
+      // SM and was bound by the latency of its dependent loads (633 us per 2 Mb, no faster than the scatter kernel).
+      DVB_CUDA(cudaFuncSetAttribute(dvb_allele_count_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
       attr_set = true;
     }
     dvb_allele_tile_ranges_kernel<<<(unsigned)((n_tiles * 32 + 127) / 128), 128, 0, s>>>(rows_dev, n_rows, d->pos, start, len, d->max_span, (int2*)d->tiles.p);

@@ -342,6 +342,7 @@ struct ConvArgs {
   __half* out_res;
   uint32_t a_res_off, b_res_off;
   int skip_a_res;                 // the A residual plane is identically zero (network input): skip its load and MMA
+  uint32_t idesc_cat;             // split mode: N = 2 * block_n over [B_main ; B_res] when the two tiles are contiguous in a stage, else 0
   int dbg;                        // timing probes (DVB_CNN_DBG; results are garbage): 1 = no TMA loads, MMAs do not wait; 2 = TMA loads, no MMAs
   long long* trace;               // optional clock64 timeline of CTA 0's MMA warp: [k block][4] = stage full seen, MMAs issued, commit issued
 };
@@ -453,11 +454,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           } else if constexpr (kSplit) {
             const uint32_t a_res = a_lo + (p.a_res_off >> 4), b_res = b_lo + (p.b_res_off >> 4), d1 = tmem_base + (uint32_t)p.block_n;
             const bool with_a_res = !p.skip_a_res;
-            for (int k = 0; k < mma_per_kb; ++k) {
-              const uint32_t ac = acc | (uint32_t)(k != 0);
-              umma_f16_lohi(tmem_base, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, ac);   // D0 += A_main * B_main
-              umma_f16_lohi(d1, a_lo + 2 * k, b_res + 2 * k, hi, idesc, ac);         // D1 += A_main * B_res
-              if (with_a_res) umma_f16_lohi(d1, a_res + 2 * k, b_lo + 2 * k, hi, idesc, 1u);   // D1 += A_res * B_main
+            if (p.idesc_cat) {
+              // [D0 | D1] += A_main * [B_main ; B_res] as ONE instruction of N = 2 block_n (the two filter tiles are adjacent rows of the
+              // stage and the two accumulators adjacent TMEM columns): 2 MMAs per K step instead of 3, same products, same order
+              for (int k = 0; k < mma_per_kb; ++k) {
+                umma_f16_lohi(tmem_base, a_lo + 2 * k, b_lo + 2 * k, hi, p.idesc_cat, acc | (uint32_t)(k != 0));
+                if (with_a_res) umma_f16_lohi(d1, a_res + 2 * k, b_lo + 2 * k, hi, idesc, 1u);   // D1 += A_res * B_main
+              }
+            } else {
+              for (int k = 0; k < mma_per_kb; ++k) {
+                const uint32_t ac = acc | (uint32_t)(k != 0);
+                umma_f16_lohi(tmem_base, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, ac);   // D0 += A_main * B_main
+                umma_f16_lohi(d1, a_lo + 2 * k, b_res + 2 * k, hi, idesc, ac);         // D1 += A_main * B_res
+                if (with_a_res) umma_f16_lohi(d1, a_res + 2 * k, b_lo + 2 * k, hi, idesc, 1u);   // D1 += A_res * B_main
+              }
             }
           } else {
 #pragma unroll 4
@@ -1308,13 +1318,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int bar_id = 1 + st;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(st * ncol);
     uint8_t* stage = smem_row + st * row_stage_bytes;
-    // (all shifts: a run-time integer division costs ~150 clocks, and the copy-out loops below had three per iteration - measured:
-    //  1400 clocks for 3.4 iterations of one shared load + one global store)
     const int nch = p.cout >> 3;                      // 16-byte chunks per pixel: 4 (cout 32) or 8 (cout 64)
-    const int nch_log2 = p.cout == 64 ? 3 : 2;
-    const int rp_log2 = p.cout == 64 ? 0 : 1;         // log2(pixels per 128 bytes of the staging row)
-    const int px_shift = p.cout == 64 ? 7 : 6;        // log2(bytes per staged pixel)
-    const int my_sw = (w >> rp_log2) & (nch - 1);
     // every accumulator column starts at zero
     for (int c = 0; c < ncol; c += 32) tmem_st32_zero(t_lane + c);
     tmem_st_wait();
@@ -1354,56 +1358,58 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (row_valid) {
         const int nh = p.cout >> 1;                    // half2 words per pixel
         if (!p.pool) {
-          named_bar_sync(bar_id, 128);                 // the previous row has left the staging buffer
-          if (st == 0 && tid == 0) ROWS_TRACE(t, 5);
+          // every thread owns one pixel: cout * 2 contiguous bytes, written straight from its registers (the staging row + two
+          // block barriers + copy-out loop this replaces cost ~1600 clocks per row on the critical path - timeline in profiles/)
           if (w < p.Wout) {
+            __half* dst = p.out + (((size_t)img * p.Hout + o) * p.Wout + w) * p.out_cstride + p.out_coff;
 #pragma unroll
             for (int c = 0; c < 8; ++c)
-              if (c < nch)
-                *reinterpret_cast<uint4*>(stage + (w << px_shift) + ((c ^ my_sw) << 4)) =
-                    make_uint4(hv[4 * c], hv[4 * c + 1], hv[4 * c + 2], hv[4 * c + 3]);
-          }
-          named_bar_sync(bar_id, 128);
-          if (st == 0 && tid == 0) ROWS_TRACE(t, 6);
-          __half* dst = p.out + ((size_t)img * p.Hout + o) * p.Wout * p.out_cstride + p.out_coff;
-          for (int i = tid; i < (p.Wout << nch_log2); i += 128) {
-            const int px = i >> nch_log2, cv = i & (nch - 1);
-            const uint4 val = *reinterpret_cast<const uint4*>(stage + (px << px_shift) + ((cv ^ ((px >> rp_log2) & (nch - 1))) << 4));
-            *reinterpret_cast<uint4*>(dst + (size_t)px * p.out_cstride + cv * 8) = val;
+              if (c < nch) *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(hv[4 * c], hv[4 * c + 1], hv[4 * c + 2], hv[4 * c + 3]);
           }
         } else {
           // vertical 3-max over rows 2 ph, 2 ph + 1, 2 ph + 2: an even row closes window ph - 1 and opens window ph
           const bool even = (o & 1) == 0;
           const bool emit = even && o >= 2;
           if (emit) {
-            named_bar_sync(bar_id, 128);
+            // horizontal 3-max over pixels 2 pw, 2 pw + 1, 2 pw + 2 by the thread of pixel 2 pw: its two right-hand neighbours are
+            // lanes + 1 and + 2 (shuffles); lane 30's second neighbour is lane 0 of the NEXT warp, handed over through a 128-byte
+            // shared-memory slot (double-buffered by emit parity: one block barrier per pooled row)
+            const int par = (o >> 1) & 1;
+            uint32_t* exch = reinterpret_cast<uint32_t*>(stage) + (par * 4) * 32;     // [parity][warp quarter][32 words]
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              if (c < nch) {
-                uint32_t m[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const __half2 a = *reinterpret_cast<const __half2*>(&cur[4 * c + e]), b = *reinterpret_cast<const __half2*>(&hv[4 * c + e]);
-                  const __half2 r = __hmax2(a, b);
-                  m[e] = *reinterpret_cast<const uint32_t*>(&r);
-                }
-                if (w < p.Wout)
-                  *reinterpret_cast<uint4*>(stage + (w << px_shift) + ((c ^ my_sw) << 4)) = make_uint4(m[0], m[1], m[2], m[3]);
+            for (int i = 0; i < 32; ++i) {
+              if (i < nh) {
+                const __half2 a = *reinterpret_cast<const __half2*>(&cur[i]), b = *reinterpret_cast<const __half2*>(&hv[i]);
+                const __half2 r = __hmax2(a, b);
+                cur[i] = *reinterpret_cast<const uint32_t*>(&r);      // cur = the finished vertical maximum of pixel w (re-opened from hv below)
               }
+            }
+            if (lane == 0 && q > 0) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4)
+                if (i < nh) *reinterpret_cast<uint4*>(exch + (q - 1) * 32 + i) = make_uint4(cur[i], cur[i + 1], cur[i + 2], cur[i + 3]);
             }
             named_bar_sync(bar_id, 128);
             const int ph = (o >> 1) - 1;
-            __half* dst = p.out + ((size_t)img * p.Hp + ph) * p.Wp * p.out_cstride + p.out_coff;
-            for (int i = tid; i < (p.Wp << nch_log2); i += 128) {
-              const int px = i >> nch_log2, cv = i & (nch - 1);
-              uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+            const int pw = w >> 1;
+            const bool writer = (lane & 1) == 0 && pw < p.Wp;
+            __half* dst = p.out + (((size_t)img * p.Hp + ph) * p.Wp + pw) * p.out_cstride + p.out_coff;
 #pragma unroll
-              for (int dx = 0; dx < 3; ++dx) {
-                const int pw = 2 * px + dx;
-                const uint4 val = *reinterpret_cast<const uint4*>(stage + (pw << px_shift) + ((cv ^ ((pw >> rp_log2) & (nch - 1))) << 4));
-                acc = hmax2x4(acc, val);               // post-ReLU values are >= 0: zero is the identity
+            for (int c = 0; c < 8; ++c) {
+              if (c < nch) {
+                uint32_t mx[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const uint32_t v0 = cur[4 * c + e];
+                  const uint32_t v1 = __shfl_down_sync(0xffffffffu, v0, 1);
+                  uint32_t v2 = __shfl_down_sync(0xffffffffu, v0, 2);
+                  if (lane == 30) v2 = q < 3 ? exch[q * 32 + 4 * c + e] : 0u;        // post-ReLU values are >= 0: zero is the identity
+                  const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&v0),
+                                            __hmax2(*reinterpret_cast<const __half2*>(&v1), *reinterpret_cast<const __half2*>(&v2)));
+                  mx[e] = *reinterpret_cast<const uint32_t*>(&r);
+                }
+                if (writer) *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(mx[0], mx[1], mx[2], mx[3]);
               }
-              *reinterpret_cast<uint4*>(dst + (size_t)px * p.out_cstride + cv * 8) = acc;
             }
           }
 #pragma unroll
@@ -2226,7 +2232,9 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       if (o.kind != 0 || o.kh * o.kw == 1) continue;
       const int c = ch[o.src];
       if (c < min_c || c % 16 != 0) continue;
-      const int target = c % 32 ? (c + 31) / 32 * 32 : c;   // (padding further to multiples of 64 measured slower: 65.4 -> 66.0-66.4 ms)
+      const int pad64_min = EnvInt("DVB_CNN_PAD_CIN64_MIN", 0);   // > 0: tensors with at least this many channels are padded to multiples of 64 (128-byte TMA rows)
+      const int target = (pad64_min > 0 && c >= pad64_min && c % 64) ? (c + 63) / 64 * 64
+                                                                     : (c % 32 ? (c + 31) / 32 * 32 : c);   // (padding everything to 64 measured slower in round 1: 65.4 -> 66.0-66.4 ms)
       if (target != c) store_ch[o.src] = target;
     }
   }
@@ -2649,7 +2657,11 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
     a.b_bytes = (uint32_t)a.block_n * bk * 2;
     a.a_stage = 128u * bk * 2;
     a.b_stage = ((uint32_t)a.block_n * bk * 2 + 1023u) & ~1023u;
-    if (split) { a.a_res_off = a.a_stage; a.b_res_off = a.b_stage; a.a_stage *= 2; a.b_stage *= 2; }
+    if (split) {
+      a.idesc_cat = (a.b_bytes == a.b_stage && 2 * a.block_n <= 256 && EnvInt("DVB_CNN_SPLIT_CAT", 1))
+                        ? ((1u << 4) | ((uint32_t)((2 * a.block_n) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24)) : 0u;
+      a.a_res_off = a.a_stage; a.b_res_off = a.b_stage; a.a_stage *= 2; a.b_stage *= 2;
+    }
     // Pipeline depth: as deep as fits in ~108 KB so that two CTAs (one in its epilogue, one issuing MMAs) share an SM.
     {
       const int stage_bytes = (int)(a.a_stage + a.b_stage);
@@ -2780,6 +2792,11 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
   if ((split ? cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)
              : cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)) != cudaSuccess)
     return dvb::fail(DVB_ERR_CUDA, "cannot reserve %d bytes of shared memory", max_smem);
+  // several CTAs per SM are the point of these two kernels: ask for the largest shared-memory carveout (the default heuristic may
+  // settle for one that fits fewer blocks)
+  cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(stem_conv1_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   int max_rows = 0;
   for (auto& r : net->rows) max_rows = std::max(max_rows, r.smem);
   if (max_rows && cudaFuncSetAttribute(conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_rows) != cudaSuccess)

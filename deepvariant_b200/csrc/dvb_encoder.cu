@@ -359,8 +359,10 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
   int* s_order = s_visit + P.max_rows;
   int* s_wtot = s_order + P.max_rows;          // kWarps + 2 ints
   const int rowbuf_bytes = ((P.row_bytes + 28 + 15) & ~15) + 32;
-  uintptr_t rb0 = (reinterpret_cast<uintptr_t>(s_wtot + kWarps + 2) + 15) & ~(uintptr_t)15;
-  uint8_t* s_rows = reinterpret_cast<uint8_t*>(rb0);
+  // aligned up to 16 bytes by POINTER arithmetic: an integer round trip loses the shared address space and every pixel store below
+  // becomes a generic ST instead of STS
+  uint8_t* s_rows_raw = reinterpret_cast<uint8_t*>(s_wtot + kWarps + 2);
+  uint8_t* s_rows = s_rows_raw + ((16u - ((unsigned)__cvta_generic_to_shared(s_rows_raw) & 15u)) & 15u);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   s_base[tid] = P.base_lut[tid];
