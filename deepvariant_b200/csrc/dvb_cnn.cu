@@ -56,6 +56,11 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // Bounded wait: a mis-programmed TMA / MMA must surface as an error, never hang the GPU.
+// suspendTimeHint: without it try_wait comes back after a very short system-defined time and the loop below POLLS - ncu's source
+// view showed 3.4 M iterations of it in the four epilogue warps of every one-tile-per-CTA kernel (29 % of all stall samples), issue
+// slots taken from the MMA / TMA warps of the co-resident CTAs.  With the hint the warp is suspended in hardware until the phase
+// completes (wake-up ~60 clocks after the arrive).
+constexpr uint32_t kSuspendHintNs = 1000000u;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
@@ -64,11 +69,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, P1;\n"
         "}\n"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(kSuspendHintNs)
         : "memory");
     if (done) return;
     if ((it & 1023u) == 1023u) {
@@ -448,6 +453,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       uint32_t ph = 0, a_lo = a_lo0, b_lo = b_lo0, acc = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         if (!(p.dbg & 1)) mbar_wait(&full_bar[st], ph);
+        // (non-split mode: a second K block rides in the same elected round when its stage has landed as well - see the persistent kernel)
+        int st2 = st + 1;
+        uint32_t ph2 = ph, a_lo2 = a_lo + a_inc, b_lo2 = b_lo + b_inc;
+        if (st2 == stages) { st2 = 0; ph2 ^= 1; a_lo2 = a_lo0; b_lo2 = b_lo0; }
+        const bool two = !kSplit && kb + 1 < num_kb && stages > 1;
+        if (two && !(p.dbg & 1)) mbar_wait(&full_bar[st2], ph2);
         tc_fence_after();
         if (elect_one()) {
           if (p.dbg & 2) {
@@ -474,9 +485,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             for (int k = 0; k < mma_per_kb; ++k) umma_f16_lohi(tmem_base, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, acc | (uint32_t)(k != 0));
           }
           umma_commit(&empty_bar[st]);   // frees the stage once these MMAs retire
+          if (two) {
+            if (!(p.dbg & 2)) {
+#pragma unroll 4
+              for (int k = 0; k < mma_per_kb; ++k) umma_f16_lohi(tmem_base, a_lo2 + 2 * k, b_lo2 + 2 * k, hi, idesc, 1u);
+            }
+            umma_commit(&empty_bar[st2]);
+          }
         }
         __syncwarp();
         acc = 1;
+        if (two) { st = st2; ph = ph2; a_lo = a_lo2; b_lo = b_lo2; ++kb; }
         a_lo += a_inc; b_lo += b_inc;
         if (++st == stages) { st = 0; ph ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
       }
@@ -598,8 +617,17 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(buf * p.block_n);
         uint32_t acc = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          if (!(p.dbg & 1)) mbar_wait(&full_bar[st], ph);
+        // two K blocks per elected round: the per-round cost on the issuing warp (barrier observation ~90 clocks, elect + warp
+        // synchronisation, loop state: ~280 clocks measured between a commit and the next MMA) is paid once per 8 MMAs instead of per 4
+        for (int kb = 0; kb < num_kb; kb += 2) {
+          const bool two = kb + 1 < num_kb;
+          int st2 = st + 1;
+          uint32_t ph2 = ph, a_lo2 = a_lo + a_inc, b_lo2 = b_lo + b_inc;
+          if (st2 == stages) { st2 = 0; ph2 ^= 1; a_lo2 = a_lo0; b_lo2 = b_lo0; }
+          if (!(p.dbg & 1)) {
+            mbar_wait(&full_bar[st], ph);
+            if (two) mbar_wait(&full_bar[st2], ph2);
+          }
           tc_fence_after();
           GEMM_TRACE(tr_i, 0);
           if (elect_one()) {
@@ -607,13 +635,21 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __g
 #pragma unroll 4
               for (int k = 0; k < mma_per_kb; ++k) umma_f16_lohi(d, a_lo + 2 * k, b_lo + 2 * k, hi, idesc, acc | (uint32_t)(k != 0));
             }
-            GEMM_TRACE(tr_i, 1);
             umma_commit(&empty_bar[st]);
+            GEMM_TRACE(tr_i, 1);
+            if (two) {
+              if (!(p.dbg & 2)) {
+#pragma unroll 4
+                for (int k = 0; k < mma_per_kb; ++k) umma_f16_lohi(d, a_lo2 + 2 * k, b_lo2 + 2 * k, hi, idesc, 1u);
+              }
+              umma_commit(&empty_bar[st2]);
+            }
             GEMM_TRACE(tr_i, 2);
           }
           __syncwarp();
           ++tr_i;
           acc = 1;
+          if (two) { st = st2; ph = ph2; a_lo = a_lo2; b_lo = b_lo2; }
           a_lo += a_inc; b_lo += b_inc;
           if (++st == stages) { st = 0; ph ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
         }
@@ -1394,18 +1430,24 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int pw = w >> 1;
             const bool writer = (lane & 1) == 0 && pw < p.Wp;
             __half* dst = p.out + (((size_t)img * p.Hp + ph) * p.Wp + pw) * p.out_cstride + p.out_coff;
+            // (all 8 shuffles of a 16-byte group are issued before the first one is consumed: the first version consumed each shuffle
+            //  right away and ran 64 of them back to back at their full latency - 3000 clocks per pooled row in the timeline)
+            const bool edge = lane == 30;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               if (c < nch) {
-                uint32_t mx[4];
+                uint4 nb = make_uint4(0u, 0u, 0u, 0u);                               // post-ReLU values are >= 0: zero is the identity
+                if (edge && q < 3) nb = *reinterpret_cast<const uint4*>(exch + q * 32 + 4 * c);
+                uint32_t v1[4], v2[4], mx[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v1[e] = __shfl_down_sync(0xffffffffu, cur[4 * c + e], 1);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v2[e] = __shfl_down_sync(0xffffffffu, cur[4 * c + e], 2);
+                if (edge) { v2[0] = nb.x; v2[1] = nb.y; v2[2] = nb.z; v2[3] = nb.w; }
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const uint32_t v0 = cur[4 * c + e];
-                  const uint32_t v1 = __shfl_down_sync(0xffffffffu, v0, 1);
-                  uint32_t v2 = __shfl_down_sync(0xffffffffu, v0, 2);
-                  if (lane == 30) v2 = q < 3 ? exch[q * 32 + 4 * c + e] : 0u;        // post-ReLU values are >= 0: zero is the identity
-                  const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&v0),
-                                            __hmax2(*reinterpret_cast<const __half2*>(&v1), *reinterpret_cast<const __half2*>(&v2)));
+                  const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&cur[4 * c + e]),
+                                            __hmax2(*reinterpret_cast<const __half2*>(&v1[e]), *reinterpret_cast<const __half2*>(&v2[e])));
                   mx[e] = *reinterpret_cast<const uint32_t*>(&r);
                 }
                 if (writer) *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(mx[0], mx[1], mx[2], mx[3]);
