@@ -457,7 +457,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         int st2 = st + 1;
         uint32_t ph2 = ph, a_lo2 = a_lo + a_inc, b_lo2 = b_lo + b_inc;
         if (st2 == stages) { st2 = 0; ph2 ^= 1; a_lo2 = a_lo0; b_lo2 = b_lo0; }
-        const bool two = !kSplit && kb + 1 < num_kb && stages > 1;
+        const bool two = !kSplit && (p.dbg & 4) && kb + 1 < num_kb && stages > 1;   // off: measured 10 % slower here (2-3 stages: the producer loses its lead)
         if (two && !(p.dbg & 1)) mbar_wait(&full_bar[st2], ph2);
         tc_fence_after();
         if (elect_one()) {
@@ -1407,50 +1407,50 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const bool even = (o & 1) == 0;
           const bool emit = even && o >= 2;
           if (emit) {
-            // horizontal 3-max over pixels 2 pw, 2 pw + 1, 2 pw + 2 by the thread of pixel 2 pw: its two right-hand neighbours are
-            // lanes + 1 and + 2 (shuffles); lane 30's second neighbour is lane 0 of the NEXT warp, handed over through a 128-byte
-            // shared-memory slot (double-buffered by emit parity: one block barrier per pooled row)
+            // horizontal 3-max over pixels 2 pw, 2 pw + 1, 2 pw + 2 through a shared-memory row (16-byte chunks XOR-swizzled, double-buffered
+            // by emit parity: ONE block barrier per pooled row); every thread then produces 16-byte pieces of the pooled row with all its
+            // shared loads issued before the first use, and the row leaves as fully coalesced 16-byte stores.
+            // (tried: neighbours by warp shuffles - 64 dependent shuffles per thread, 3000 clocks per pooled row against 2000 here)
             const int par = (o >> 1) & 1;
-            uint32_t* exch = reinterpret_cast<uint32_t*>(stage) + (par * 4) * 32;     // [parity][warp quarter][32 words]
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (i < nh) {
-                const __half2 a = *reinterpret_cast<const __half2*>(&cur[i]), b = *reinterpret_cast<const __half2*>(&hv[i]);
-                const __half2 r = __hmax2(a, b);
-                cur[i] = *reinterpret_cast<const uint32_t*>(&r);      // cur = the finished vertical maximum of pixel w (re-opened from hv below)
-              }
-            }
-            if (lane == 0 && q > 0) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4)
-                if (i < nh) *reinterpret_cast<uint4*>(exch + (q - 1) * 32 + i) = make_uint4(cur[i], cur[i + 1], cur[i + 2], cur[i + 3]);
-            }
-            named_bar_sync(bar_id, 128);
-            const int ph = (o >> 1) - 1;
-            const int pw = w >> 1;
-            const bool writer = (lane & 1) == 0 && pw < p.Wp;
-            __half* dst = p.out + (((size_t)img * p.Hp + ph) * p.Wp + pw) * p.out_cstride + p.out_coff;
-            // (all 8 shuffles of a 16-byte group are issued before the first one is consumed: the first version consumed each shuffle
-            //  right away and ran 64 of them back to back at their full latency - 3000 clocks per pooled row in the timeline)
-            const bool edge = lane == 30;
+            uint8_t* row_s = stage + par * (128 * 64);                                // cout = 64 -> 128 B per pixel, half of the stream's staging area
+            const int px_shift = p.cout == 64 ? 7 : 6, rp_log2 = p.cout == 64 ? 0 : 1, nch_log2 = p.cout == 64 ? 3 : 2;
+            const int my_sw = (w >> rp_log2) & (nch - 1);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
               if (c < nch) {
-                uint4 nb = make_uint4(0u, 0u, 0u, 0u);                               // post-ReLU values are >= 0: zero is the identity
-                if (edge && q < 3) nb = *reinterpret_cast<const uint4*>(exch + q * 32 + 4 * c);
-                uint32_t v1[4], v2[4], mx[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) v1[e] = __shfl_down_sync(0xffffffffu, cur[4 * c + e], 1);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) v2[e] = __shfl_down_sync(0xffffffffu, cur[4 * c + e], 2);
-                if (edge) { v2[0] = nb.x; v2[1] = nb.y; v2[2] = nb.z; v2[3] = nb.w; }
+                uint32_t m[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&cur[4 * c + e]),
-                                            __hmax2(*reinterpret_cast<const __half2*>(&v1[e]), *reinterpret_cast<const __half2*>(&v2[e])));
-                  mx[e] = *reinterpret_cast<const uint32_t*>(&r);
+                  const __half2 a = *reinterpret_cast<const __half2*>(&cur[4 * c + e]), b = *reinterpret_cast<const __half2*>(&hv[4 * c + e]);
+                  const __half2 r = __hmax2(a, b);
+                  m[e] = *reinterpret_cast<const uint32_t*>(&r);
                 }
-                if (writer) *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(mx[0], mx[1], mx[2], mx[3]);
+                if (w < p.Wout) *reinterpret_cast<uint4*>(row_s + (w << px_shift) + ((c ^ my_sw) << 4)) = make_uint4(m[0], m[1], m[2], m[3]);
+              }
+            }
+            named_bar_sync(bar_id, 128);
+            const int ph = (o >> 1) - 1;
+            __half* dst = p.out + ((size_t)img * p.Hp + ph) * p.Wp * p.out_cstride + p.out_coff;
+            const int n_items = p.Wp << nch_log2;
+            uint4 v[4][3];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int i = tid + u * 128;
+              if (i < n_items) {
+                const int px = i >> nch_log2, cv = i & (nch - 1);
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                  const int pw = 2 * px + dx;
+                  v[u][dx] = *reinterpret_cast<const uint4*>(row_s + (pw << px_shift) + ((cv ^ ((pw >> rp_log2) & (nch - 1))) << 4));
+                }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int i = tid + u * 128;
+              if (i < n_items) {
+                const int px = i >> nch_log2, cv = i & (nch - 1);
+                *reinterpret_cast<uint4*>(dst + (size_t)px * p.out_cstride + cv * 8) = hmax2x4(v[u][0], hmax2x4(v[u][1], v[u][2]));
               }
             }
           }
@@ -1751,6 +1751,202 @@ __global__ void __launch_bounds__(kStemThreads) stem_conv1_kernel(const StemArgs
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 32);
+}
+
+// ---------------------------------------------------------------------------------------------
+// conv1 as a row-streaming, warp-specialised kernel (WGS geometry: 7 channels, 3x3 stride 2 valid, 32 filters)
+// ---------------------------------------------------------------------------------------------
+// stem_conv1_kernel above is a bulk-synchronous design: four block barriers per 128-pixel tile (26 % of its stall samples) and
+// every input row converted 1.5 times.  Here one CTA per SM streams whole images row by row through a pipeline of warp roles:
+//   converters (4 warps, a thread per output pixel)  raw uint8 row (cp.async ring) -> exact (x - 128) / 128 in fp16 -> the K-major
+//       A tile of THAT input row: pixel w holds the 21 values (3 kw taps x 7 channels) at bytes [14 w, 14 w + 21) of the row, padded
+//       to K = 32 (the three bytes that follow ride along against zero weights); each input row is converted exactly once;
+//   MMA warp   input row r adds kernel row r - 2 o to output row o: an even row 2 o' feeds kernel row 0 of output row o' AND kernel
+//       row 2 of output row o' - 1 - one MMA pair of N = 64 over both accumulator slots (the filter tile is stored [W0 W2 W0 W1], so the
+//       slot order flips with the parity of o' by starting 32 rows later); an odd row feeds kernel row 1 of one slot (N = 32);
+//   epilogue (4 warps)  after every even row the finished slot is drained (bias + ReLU -> fp16, 64 contiguous bytes per pixel
+//       straight from registers), zeroed and handed back; the odd row in between touches only the other slot, so draining overlaps it.
+constexpr int kS1Threads = 32 + 128 + 128;   // warp 0 MMA, warps 1-4 converters, warps 5-8 epilogue
+constexpr int kS1RawSlots = 4, kS1RawPitch = 1840, kS1ARing = 4;
+
+struct Stem2Args {
+  const uint8_t* in; __half* out; const float* bias; const __half* w;   // w: [128][32] = filter tile rows [W0 | W2 | W0 | W1] x K (s * 7 + c, zero from 21)
+  int n_images, H, W, Ho, Wo, out_cstride;
+  long long total_bytes;
+};
+
+__global__ void __launch_bounds__(kS1Threads, 1) stem_rows_kernel(const Stem2Args p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                                  // [kS1ARing][128 rows x 64 B], 64B swizzle
+  uint8_t* sB = smem + kS1ARing * 8192;                // 128 rows x 64 B, 64B swizzle
+  uint8_t* sRaw = sB + 8192;                           // [kS1RawSlots][kS1RawPitch]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + kS1RawSlots * kS1RawPitch);
+  uint64_t* a_full = bars;                             // [kS1ARing]  128 converter arrivals
+  uint64_t* a_empty = bars + kS1ARing;                 // [kS1ARing]  tcgen05.commit
+  uint64_t* acc_done = bars + 2 * kS1ARing;            // commit after every even input row
+  uint64_t* acc_free = bars + 2 * kS1ARing + 1;        // 128 epilogue arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kS1ARing + 2);
+  float* s_bias = reinterpret_cast<float*>(bars + 2 * kS1ARing + 3);   // [32]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid < 32) s_bias[tid] = p.bias[tid];
+  for (int i = tid; i < 128 * 4; i += kS1Threads) {    // filter tile -> 64B-swizzled K-major rows
+    const int n = i >> 2, j = i & 3;
+    *reinterpret_cast<uint4*>(sB + n * 64 + ((j ^ ((n >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(p.w + n * 32 + j * 8);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < kS1ARing; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+    mbar_init(acc_done, 1);
+    mbar_init(acc_free, 128);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 64);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int G = gridDim.x;
+  const int n_img = (p.n_images - (int)blockIdx.x + G - 1) / G;      // images blockIdx.x, + G, ...
+  const int rows_per_image = 2 * p.Ho + 1;                           // input rows 0 .. 2 Ho: the last one closes output row Ho - 1
+  const int total_rows = n_img * rows_per_image;
+  const int row_bytes = p.W * kStemC;
+
+  if (warp == 0) {
+    // ===== MMA issuer =====
+    const uint32_t hi = desc_hi(512u, 4u);
+    const uint32_t a_lo0 = desc_lo(smem_u32(sA)), b_lo0 = desc_lo(smem_u32(sB));
+    const uint32_t idesc64 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc32 = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int slot = 0, r = 0;
+    uint32_t ph = 0, even_count = 0;
+    for (int R = 0; R < total_rows; ++R) {
+      const bool even = (r & 1) == 0;
+      const int op = r >> 1;                                        // o' (even rows) / the output row an odd row feeds
+      if (even) mbar_wait(acc_free, even_count & 1u);               // completion #even_count: the slot this row opens is drained and zero
+      mbar_wait(&a_full[slot], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_lo = a_lo0 + (uint32_t)slot * (8192u >> 4);
+        if (even) {
+          const uint32_t b_lo = b_lo0 + ((op & 1) ? (32u * 64u >> 4) : 0u);            // [W0 W2] or [W2 W0] over slots (0, 1)
+          umma_f16_lohi(tmem_base, a_lo, b_lo, hi, idesc64, 1u);
+          umma_f16_lohi(tmem_base, a_lo + 2u, b_lo + 2u, hi, idesc64, 1u);
+        } else {
+          const uint32_t b_lo = b_lo0 + (96u * 64u >> 4);                              // W1
+          const uint32_t d = tmem_base + (uint32_t)((op & 1) * 32);
+          umma_f16_lohi(d, a_lo, b_lo, hi, idesc32, 1u);
+          umma_f16_lohi(d, a_lo + 2u, b_lo + 2u, hi, idesc32, 1u);
+        }
+        umma_commit(&a_empty[slot]);
+        if (even) umma_commit(acc_done);
+      }
+      __syncwarp();
+      if (even) ++even_count;
+      if (++slot == kS1ARing) { slot = 0; ph ^= 1; }
+      if (++r == rows_per_image) r = 0;
+    }
+  } else if (warp <= 4) {
+    // ===== converters: thread = output pixel w of every input row =====
+    const int w = tid - 32;
+    const int ctid = w;                                             // 0 .. 127
+    const __half2 kScale = __floats2half2_rn(1.f / 128.f, 1.f / 128.f), kBias = __floats2half2_rn(-9.f, -9.f);
+    auto stage = [&](int Rr) {                                      // cp.async of input row Rr of this CTA's stream into raw slot Rr & 3
+      if (Rr < total_rows) {
+        const int li = Rr / rows_per_image, rr = Rr - li * rows_per_image;
+        const long long img = (long long)blockIdx.x + (long long)li * G;
+        const uint8_t* g = p.in + (img * p.H + rr) * row_bytes;
+        const int mis = (int)(reinterpret_cast<uintptr_t>(g) & 15);
+        const uint8_t* src = g - mis;
+        const int nq = (mis + row_bytes + 15) >> 4;
+        const long long left = (p.in + p.total_bytes) - src;
+        const int full = (int)min((long long)nq, left >> 4);
+        uint8_t* dst = sRaw + (Rr & (kS1RawSlots - 1)) * kS1RawPitch;
+        if (ctid < full) cp_async16(dst + 16 * ctid, src + 16 * ctid, 16);
+        else if (ctid == full && full < nq) {                       // never read past the caller's buffer
+          const int tail = (int)(left - 16LL * full);
+          cp_async16(dst + 16 * full, tail > 0 ? src + 16 * full : src, tail > 0 ? tail : 0);
+        }
+      }
+      cp_async_commit();
+    };
+    stage(0);
+    stage(1);
+    int slot = 0, r = 0, li = 0;
+    uint32_t ph = 0;
+    for (int R = 0; R < total_rows; ++R) {
+      stage(R + 2);
+      cp_async_wait<2>();
+      asm volatile("bar.sync 3, 128;" ::: "memory");                // every converter's chunks of row R have landed
+      const long long img = (long long)blockIdx.x + (long long)li * G;
+      const uint8_t* g = p.in + (img * p.H + r) * row_bytes;
+      const int mis = (int)(reinterpret_cast<uintptr_t>(g) & 15);
+      const uint8_t* raw = sRaw + (R & (kS1RawSlots - 1)) * kS1RawPitch;
+      const int base = mis + 2 * kStemC * w;                       // first byte of pixel w's 21-byte run
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(raw + (base & ~3));
+      const int sh = 8 * (base & 3);
+      uint32_t wd[7];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) wd[i] = wp[i];
+      uint32_t hw[16];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const uint32_t v = __funnelshift_r(wd[i], wd[i + 1], sh);
+        uint32_t a = __byte_perm(v, 0x64646464u, 0x4140), b = __byte_perm(v, 0x64646464u, 0x4342);
+        const __half2 ha = __hfma2(*reinterpret_cast<__half2*>(&a), kScale, kBias), hb = __hfma2(*reinterpret_cast<__half2*>(&b), kScale, kBias);
+        hw[2 * i] = *reinterpret_cast<const uint32_t*>(&ha);
+        hw[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&hb);
+      }
+      hw[10] &= 0x0000FFFFu;                                        // k = 21: zero weight, but keep it a clean zero
+      hw[11] = 0u;
+      hw[12] = hw[13] = hw[14] = hw[15] = 0u;
+      mbar_wait(&a_empty[slot], ph ^ 1);
+      uint8_t* rowp = sA + slot * 8192 + w * 64;
+      const int sw = (w >> 1) & 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(hw[4 * j], hw[4 * j + 1], hw[4 * j + 2], hw[4 * j + 3]);
+      fence_proxy_async();
+      mbar_arrive(&a_full[slot]);
+      if (++slot == kS1ARing) { slot = 0; ph ^= 1; }
+      if (++r == rows_per_image) { r = 0; ++li; }
+    }
+  } else {
+    // ===== epilogue: after every even input row the slot of output row o' - 1 is complete =====
+    const int q = warp & 3;
+    const int w = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    tmem_st32_zero(t_lane);
+    tmem_st32_zero(t_lane + 32);
+    tmem_st_wait();
+    tc_fence_before();
+    mbar_arrive(acc_free);                                          // completion #0
+    uint32_t n_even = 0;
+    for (int li = 0; li < n_img; ++li) {
+      const long long img = (long long)blockIdx.x + (long long)li * G;
+      for (int op = 0; op <= p.Ho; ++op) {                          // even input row 2 op closes output row op - 1
+        mbar_wait(acc_done, n_even & 1u);
+        tc_fence_after();
+        ++n_even;
+        const int sl = (op + 1) & 1;                                // slot of output row op - 1
+        uint32_t v[32];
+        tmem_ld32(t_lane + sl * 32, v);
+        tmem_ld_wait();
+        tmem_st32_zero(t_lane + sl * 32);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(acc_free);
+        if (op >= 1 && w < p.Wo) {
+          __half* dst = p.out + (((size_t)img * p.Ho + (op - 1)) * p.Wo + w) * p.out_cstride;
+          epilogue_chunk<32>(v, s_bias, dst, true, 1);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 64);
 }
 
 // 3x3 pooling on NHWC fp16.  mode 0: max, stride 2, valid.  mode 1: average, stride 1, 'same', divisor = number
@@ -2126,6 +2322,8 @@ struct DvbCnn {
   cudaStream_t stream = nullptr;
   bool stem_fused = false;
   StemArgs stem_args;
+  bool stem_rows = false;          // stem_rows_kernel instead of stem_conv1_kernel
+  Stem2Args stem2_args;
   int n_lanes = 1;
   cudaStream_t lane_streams[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused (caller's stream)
   std::vector<int> tail_deps;
@@ -2466,6 +2664,26 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       a.idesc = (1u << 4) | ((uint32_t)(o.cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       a.h_pitch = 1808;   // (2 * 127 + 3) * 7 = 1799 bytes per row segment -> 450 words -> 1800 halves, rounded up to 8
       net->stem_fused = true;
+      if (o.cout == 32 && Wout <= 128 && EnvInt("DVB_CNN_STEM_ROWS", 1)) {
+        // filter tile of stem_rows_kernel: rows [W0 | W2 | W0 | W1] (kernel rows; 32 filters each) x K = 32 (k = s * 7 + c, zero from 21)
+        std::vector<__half> wt((size_t)128 * 32, __float2half(0.f));
+        const __half* w = reinterpret_cast<const __half*>(blob_w_main);
+        const int blk_r[4] = {0, 2, 0, 1};
+        for (int blk = 0; blk < 4; ++blk)
+          for (int co = 0; co < 32; ++co)
+            for (int sx = 0; sx < 3; ++sx)
+              for (int c = 0; c < net->C; ++c)
+                wt[((size_t)blk * 32 + co) * 32 + sx * net->C + c] = w[(((size_t)co * 3 + blk_r[blk]) * 3 + sx) * blob_cin + c];
+        void* dwt = nullptr;
+        if (cudaMalloc(&dwt, wt.size() * sizeof(__half)) != cudaSuccess) return dvb::fail(DVB_ERR_CUDA, "cudaMalloc (weights) failed");
+        net->allocs.push_back(dwt);
+        cudaMemcpy(dwt, wt.data(), wt.size() * sizeof(__half), cudaMemcpyHostToDevice);
+        Stem2Args& b = net->stem2_args;
+        memset(&b, 0, sizeof(b));
+        b.out = dst.ptr; b.bias = static_cast<const float*>(db); b.w = static_cast<const __half*>(dwt);
+        b.H = net->H; b.W = net->W; b.Ho = Hout; b.Wo = Wout; b.out_cstride = dst.C;
+        net->stem_rows = true;
+      }
       macs_total += (double)Hout * Wout * o.cout * orig.kh * orig.kw * orig.cin;
       continue;
     }
@@ -2839,6 +3057,9 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
   cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(stem_conv1_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  if (net->stem_rows && cudaFuncSetAttribute(stem_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             1024 + kS1ARing * 8192 + 8192 + kS1RawSlots * kS1RawPitch + (2 * kS1ARing + 3) * 8 + 32 * 4 + 64) != cudaSuccess)
+    return dvb::fail(DVB_ERR_CUDA, "cannot reserve shared memory (stem rows kernel)");
   int max_rows = 0;
   for (auto& r : net->rows) max_rows = std::max(max_rows, r.smem);
   if (max_rows && cudaFuncSetAttribute(conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_rows) != cudaSuccess)
@@ -2866,7 +3087,13 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
 int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaStream_t s0) {
   const TensorBuf& in = net->tensors[0];
   cudaStream_t s = s0;
-  if (net->stem_fused) {
+  if (net->stem_rows) {
+    Stem2Args a = net->stem2_args;
+    a.in = images; a.n_images = n;
+    a.total_bytes = (long long)n * net->H * net->W * net->C;
+    const int smem = 1024 + kS1ARing * 8192 + 8192 + kS1RawSlots * kS1RawPitch + (2 * kS1ARing + 3) * 8 + 32 * 4 + 64;
+    stem_rows_kernel<<<(unsigned)std::min(net->num_sms, n), kS1Threads, smem, s>>>(a);
+  } else if (net->stem_fused) {
     StemArgs a = net->stem_args;
     a.in = images; a.n_images = n;
     a.total_bytes = (long long)n * net->H * net->W * net->C;
