@@ -205,6 +205,8 @@ SYMBOLS = (
                                             C.POINTER(DvbCandidateOptions), C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
     ('dvb_ssw_align', C.c_int, [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                 C.POINTER(DvbSswAlignment), C.c_char_p, C.c_int64]),
+    ('dvb_ssw_align_batch', C.c_int, [C.POINTER(C.c_char_p), C.c_void_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_int32, C.POINTER(DvbSswAlignment), C.c_char_p, C.c_int64]),
     ('dvb_fast_pass_scores', C.c_int, [C.c_char_p, C.c_int64, C.POINTER(C.c_char_p), C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.c_void_p,
                                        C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     ('dvb_crc32c', C.c_uint32, [C.c_char_p, C.c_size_t]),

@@ -1237,7 +1237,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint8_t* smem_b = smem;                                                  // [3 taps][5 blocks][cout rows][cin]
   uint8_t* smem_a = smem_b + 3 * p.b_tap_bytes;                            // [2 streams][kRowsRing][128 slots][cin]
   uint8_t* smem_row = smem_a + 2 * kRowsRing * p.a_buf_bytes;              // [2 streams][128 pixels][cout] fp16, 16-byte chunks XOR-swizzled
-  const uint32_t row_stage_bytes = 128u * (uint32_t)p.cout * 2u;
+  const uint32_t row_stage_bytes = 2u * 128u * (uint32_t)p.cout * 2u;       // two parities of one pooled-row staging buffer per stream
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_row + 2 * row_stage_bytes);
   uint64_t* in_full = bars;                          // [2][kRowsRing]
   uint64_t* in_empty = bars + 2 * kRowsRing;         // [2][kRowsRing]
@@ -1412,7 +1412,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             // shared loads issued before the first use, and the row leaves as fully coalesced 16-byte stores.
             // (tried: neighbours by warp shuffles - 64 dependent shuffles per thread, 3000 clocks per pooled row against 2000 here)
             const int par = (o >> 1) & 1;
-            uint8_t* row_s = stage + par * (128 * 64);                                // cout = 64 -> 128 B per pixel, half of the stream's staging area
+            uint8_t* row_s = stage + par * (128 * p.cout * 2);
             const int px_shift = p.cout == 64 ? 7 : 6, rp_log2 = p.cout == 64 ? 0 : 1, nch_log2 = p.cout == 64 ? 3 : 2;
             const int my_sw = (w >> rp_log2) & (nch - 1);
 #pragma unroll
@@ -1432,25 +1432,28 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int ph = (o >> 1) - 1;
             __half* dst = p.out + ((size_t)img * p.Hp + ph) * p.Wp * p.out_cstride + p.out_coff;
             const int n_items = p.Wp << nch_log2;
-            uint4 v[4][3];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int i = tid + u * 128;
-              if (i < n_items) {
-                const int px = i >> nch_log2, cv = i & (nch - 1);
+            for (int u0 = 0; u0 < 4; u0 += 2) {
+              uint4 v[2][3];
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                  const int pw = 2 * px + dx;
-                  v[u][dx] = *reinterpret_cast<const uint4*>(row_s + (pw << px_shift) + ((cv ^ ((pw >> rp_log2) & (nch - 1))) << 4));
+              for (int u = 0; u < 2; ++u) {
+                const int i = tid + (u0 + u) * 128;
+                if (i < n_items) {
+                  const int px = i >> nch_log2, cv = i & (nch - 1);
+#pragma unroll
+                  for (int dx = 0; dx < 3; ++dx) {
+                    const int pw = 2 * px + dx;
+                    v[u][dx] = *reinterpret_cast<const uint4*>(row_s + (pw << px_shift) + ((cv ^ ((pw >> rp_log2) & (nch - 1))) << 4));
+                  }
                 }
               }
-            }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int i = tid + u * 128;
-              if (i < n_items) {
-                const int px = i >> nch_log2, cv = i & (nch - 1);
-                *reinterpret_cast<uint4*>(dst + (size_t)px * p.out_cstride + cv * 8) = hmax2x4(v[u][0], hmax2x4(v[u][1], v[u][2]));
+              for (int u = 0; u < 2; ++u) {
+                const int i = tid + (u0 + u) * 128;
+                if (i < n_items) {
+                  const int px = i >> nch_log2, cv = i & (nch - 1);
+                  *reinterpret_cast<uint4*>(dst + (size_t)px * p.out_cstride + cv * 8) = hmax2x4(v[u][0], hmax2x4(v[u][1], v[u][2]));
+                }
               }
             }
           }
@@ -1787,7 +1790,7 @@ __global__ void __launch_bounds__(kS1Threads, 1) stem_rows_kernel(const Stem2Arg
   uint64_t* acc_done = bars + 2 * kS1ARing;            // commit after every even input row
   uint64_t* acc_free = bars + 2 * kS1ARing + 1;        // 128 epilogue arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kS1ARing + 2);
-  float* s_bias = reinterpret_cast<float*>(bars + 2 * kS1ARing + 3);   // [32]
+  float* s_bias = reinterpret_cast<float*>(bars + 2 * kS1ARing + 4);   // [32], 16-byte aligned (read as float4)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid < 32) s_bias[tid] = p.bias[tid];
@@ -2707,7 +2710,7 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       a.b_blk_bytes = (uint32_t)o.cout * a.row_bytes;
       a.b_tap_bytes = 5u * a.b_blk_bytes;
       a.a_buf_bytes = 128u * a.row_bytes;
-      rl.smem = 1024 + (int)(3 * a.b_tap_bytes + 2 * kRowsRing * a.a_buf_bytes + 2 * 128 * o.cout * 2) + (4 * kRowsRing + 6) * 8 + o.cout * 4 + 64;
+      rl.smem = 1024 + (int)(3 * a.b_tap_bytes + 2 * kRowsRing * a.a_buf_bytes + 2 * 2 * 128 * o.cout * 2) + (4 * kRowsRing + 6) * 8 + o.cout * 4 + 64;
       rl.macs_per_image = (double)Hout * Wout * o.cout * 9 * orig.cin;
       if (rl.smem <= 227 * 1024) {
         // filters [Cout][3][3][Cin] -> [kw tap s][block: kernel row 2, 1, 0, 2, 1][Cout][Cin]: three consecutive blocks starting at
@@ -3058,7 +3061,7 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
   cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(stem_conv1_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   if (net->stem_rows && cudaFuncSetAttribute(stem_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             1024 + kS1ARing * 8192 + 8192 + kS1RawSlots * kS1RawPitch + (2 * kS1ARing + 3) * 8 + 32 * 4 + 64) != cudaSuccess)
+                                             1024 + kS1ARing * 8192 + 8192 + kS1RawSlots * kS1RawPitch + (2 * kS1ARing + 4) * 8 + 32 * 4 + 64) != cudaSuccess)
     return dvb::fail(DVB_ERR_CUDA, "cannot reserve shared memory (stem rows kernel)");
   int max_rows = 0;
   for (auto& r : net->rows) max_rows = std::max(max_rows, r.smem);
@@ -3091,7 +3094,7 @@ int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaSt
     Stem2Args a = net->stem2_args;
     a.in = images; a.n_images = n;
     a.total_bytes = (long long)n * net->H * net->W * net->C;
-    const int smem = 1024 + kS1ARing * 8192 + 8192 + kS1RawSlots * kS1RawPitch + (2 * kS1ARing + 3) * 8 + 32 * 4 + 64;
+    const int smem = 1024 + kS1ARing * 8192 + 8192 + kS1RawSlots * kS1RawPitch + (2 * kS1ARing + 4) * 8 + 32 * 4 + 64;
     stem_rows_kernel<<<(unsigned)std::min(net->num_sms, n), kS1Threads, smem, s>>>(a);
   } else if (net->stem_fused) {
     StemArgs a = net->stem_args;

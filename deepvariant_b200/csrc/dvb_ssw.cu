@@ -166,6 +166,54 @@ bool BandedSw(const int8_t* ref, const int8_t* read, int ref_len, int read_len, 
 
 }  // namespace
 
+
+namespace dvb_ssw_internal {
+
+// Second half of the alignment: out->{sw_score, ref_begin, ref_end, query_begin, query_end} are known (from the two scans - host
+// Scan() above or the CUDA wavefront kernel in dvb_ssw_gpu.cu); banded traceback inside that window, then ssw_cpp's
+// ConvertAlignment + CalculateNumberMismatch (soft clips, '=' / 'X' runs).  r / q = base codes 0..4.
+int FinishFromEnds(const int8_t* r, const int8_t* q, int query_len, const int8_t* mat, int gap_open, int gap_extend, DvbSswAlignment* out,
+                   char* cigar_out, int64_t cigar_cap) {
+  const int sub_ref = out->ref_end - out->ref_begin + 1, sub_read = out->query_end - out->query_begin + 1;
+  std::vector<std::pair<int, char>> cigar;
+  if (!BandedSw(r + out->ref_begin, q + out->query_begin, sub_ref, sub_read, out->sw_score, gap_open, gap_extend,
+                std::abs(sub_ref - sub_read) + 1, mat, &cigar))
+    return dvb::fail(DVB_ERR_INTERNAL, "dvb_ssw_align: banded traceback failed");
+  std::string s;
+  if (out->query_begin > 0) s += std::to_string(out->query_begin) + "S";
+  const int8_t* rp = r + out->ref_begin;
+  const int8_t* qp = q + out->query_begin;
+  int mism = 0, len_m = 0, len_x = 0;
+  auto flush = [&]() {
+    if (len_m) s += std::to_string(len_m) + "=";
+    if (len_x) s += std::to_string(len_x) + "X";
+    len_m = len_x = 0;
+  };
+  for (const auto& c : cigar) {
+    if (c.second == 'M') {
+      for (int k = 0; k < c.first; ++k, ++rp, ++qp) {
+        if (*rp != *qp) { ++mism; if (len_m) flush(); ++len_x; }
+        else { if (len_x) flush(); ++len_m; }
+      }
+    } else if (c.second == 'I') {
+      qp += c.first; mism += c.first; flush(); s += std::to_string(c.first) + "I";
+    } else {
+      rp += c.first; mism += c.first; flush(); s += std::to_string(c.first) + "D";
+    }
+  }
+  flush();
+  const int tail = query_len - out->query_end - 1;
+  if (tail > 0) s += std::to_string(tail) + "S";
+  out->mismatches = mism;
+  out->cigar_len = (int32_t)s.size();
+  if (cigar_cap > (int64_t)s.size()) memcpy(cigar_out, s.c_str(), s.size() + 1);
+  return DVB_OK;
+}
+
+int8_t BaseCode(char c) { return Code(c); }
+
+}  // namespace dvb_ssw_internal
+
 extern "C" {
 
 int dvb_ssw_align(const char* ref, int64_t ref_len, const char* query, int64_t query_len, int32_t match, int32_t mismatch, int32_t gap_open,
@@ -190,41 +238,7 @@ int dvb_ssw_align(const char* ref, int64_t ref_len, const char* query, int64_t q
   const Best rev = Scan(r.data(), fwd.ref, -1, -1, rq.data(), fwd.read + 1, mat, gap_open, gap_extend, fwd.score);
   out->ref_begin = rev.ref;
   out->query_begin = fwd.read - rev.read;
-  const int sub_ref = out->ref_end - out->ref_begin + 1, sub_read = out->query_end - out->query_begin + 1;
-  std::vector<std::pair<int, char>> cigar;
-  if (!BandedSw(r.data() + out->ref_begin, q.data() + out->query_begin, sub_ref, sub_read, fwd.score, gap_open, gap_extend,
-                std::abs(sub_ref - sub_read) + 1, mat, &cigar))
-    return dvb::fail(DVB_ERR_INTERNAL, "dvb_ssw_align: banded traceback failed");
-  // ConvertAlignment + CalculateNumberMismatch: soft clips, '=' / 'X' runs
-  std::string s;
-  if (out->query_begin > 0) s += std::to_string(out->query_begin) + "S";
-  const int8_t* rp = r.data() + out->ref_begin;
-  const int8_t* qp = q.data() + out->query_begin;
-  int mism = 0, len_m = 0, len_x = 0;
-  auto flush = [&]() {
-    if (len_m) s += std::to_string(len_m) + "=";
-    if (len_x) s += std::to_string(len_x) + "X";
-    len_m = len_x = 0;
-  };
-  for (const auto& c : cigar) {
-    if (c.second == 'M') {
-      for (int k = 0; k < c.first; ++k, ++rp, ++qp) {
-        if (*rp != *qp) { ++mism; if (len_m) flush(); ++len_x; }
-        else { if (len_x) flush(); ++len_m; }
-      }
-    } else if (c.second == 'I') {
-      qp += c.first; mism += c.first; flush(); s += std::to_string(c.first) + "I";
-    } else {
-      rp += c.first; mism += c.first; flush(); s += std::to_string(c.first) + "D";
-    }
-  }
-  flush();
-  const int tail = (int)query_len - out->query_end - 1;
-  if (tail > 0) s += std::to_string(tail) + "S";
-  out->mismatches = mism;
-  out->cigar_len = (int32_t)s.size();
-  if (cigar_cap > (int64_t)s.size()) memcpy(cigar_out, s.c_str(), s.size() + 1);
-  return DVB_OK;
+  return dvb_ssw_internal::FinishFromEnds(r.data(), q.data(), (int)query_len, mat, gap_open, gap_extend, out, cigar_out, cigar_cap);
 }
 
 }  // extern "C"

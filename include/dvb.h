@@ -411,6 +411,15 @@ typedef struct DvbSswAlignment {
 } DvbSswAlignment;
 int dvb_ssw_align(const char* ref, int64_t ref_len, const char* query, int64_t query_len, int32_t match, int32_t mismatch, int32_t gap_open,
                   int32_t gap_extend, DvbSswAlignment* out, char* cigar_out, int64_t cigar_cap);
+/* n alignments in one launch on `device` (csrc/dvb_ssw_gpu.cu): the two full-matrix Smith-Waterman scans of every (reference, query) pair
+ * run on the GPU, a warp per alignment as an anti-diagonal wavefront; the banded traceback inside the window they delimit runs on the
+ * host.  The reference side is FastPassAligner::SswAlignReadsToHaplotypes (deepvariant/realigner/fast_pass_aligner.cc:281-322) and
+ * RealignReadsToHaplotype (deepvariant/alt_aligned_pileup_lib.cc:278-313), which call ssw once per (haplotype, read).  Results equal
+ * dvb_ssw_align's field for field.  cigars = char[n][cigar_stride] (NUL-terminated; empty when the string does not fit - cigar_len says
+ * how long it is). */
+int dvb_ssw_align_batch(const char* const* refs, const int64_t* ref_lens, const char* const* queries, const int64_t* query_lens, int32_t n,
+                        int32_t match, int32_t mismatch, int32_t gap_open, int32_t gap_extend, int32_t device, DvbSswAlignment* out,
+                        char* cigars, int64_t cigar_stride);
 
 /* FastPassAligner's exact k-mer pass (deepvariant/realigner/fast_pass_aligner.cc:165-279) for all haplotypes in one call:
  * hap_score = int32[n_haps]; position / score = int32[n_haps * n_reads] (position 65535 = read not placed on that haplotype). */

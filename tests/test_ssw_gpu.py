@@ -1,0 +1,71 @@
+"""Batched Smith-Waterman on the device (csrc/dvb_ssw_gpu.cu: a warp per alignment, anti-diagonal wavefront over strips of 32 query
+rows) against the host implementation (csrc/dvb_ssw.cu, pinned by the reference's ssw / fast_pass_aligner known answers in
+tests/test_fast_pass_aligner.py): every field and the CIGAR string, pair by pair.  `-m gpu`."""
+import random
+
+import pytest
+
+from deepvariant_b200 import ssw
+
+pytestmark = pytest.mark.gpu
+
+KATS = [   # deepvariant/realigner/ssw_test.cc:47-58, python/ssw_misc_test.py:44-84, python/ssw_wrap_test.py:37-72
+    ((4, 2, 4, 2), 'tttt', 'ttAtt', dict(cigar_string='2=1I2=')),
+    ((4, 2, 4, 2), 'TTTTGGGGGGGGGGGGG', 'TTATTGGGGGGGGGGGGG', dict(cigar_string='2=1I15=')),
+    ((2, 2, 3, 1), 'CAGCCTTTCTGACCCGGAAATCAAAATAGGCACAACAAA', 'CTGAGCCGGTAAATC',
+     dict(sw_score=21, ref_begin=8, ref_end=21, query_begin=0, query_end=14, mismatches=2, cigar_string='4=1X4=1I5=')),
+    ((2, 2, 3, 1), 'CTGAGCCGGTAAATC', 'CAGCCTTTCTGACCCGGAAATCAAAATAGGCACAACAAA',
+     dict(sw_score=21, query_begin=8, query_end=21, ref_begin=0, ref_end=14, mismatches=2, cigar_string='8S4=1X4=1D5=17S')),
+    ((4, 6, 8, 1), 'TTTGCCGAAGTTAAACCC', 'GCCGAAGTTA', dict(cigar_string='10=', ref_begin=3)),
+]
+
+
+def test_reference_known_answers_through_the_batch_entry_point():
+  for params, ref, query, expected in KATS:
+    al = ssw.align_batch([(ref, query)], *params)[0]
+    for k, v in expected.items():
+      assert getattr(al, k) == v, (k, al)
+
+
+def _mutate(rng, s, n_sub, n_indel):
+  s = list(s)
+  for _ in range(n_sub):
+    s[rng.randrange(len(s))] = rng.choice('ACGT')
+  for _ in range(n_indel):
+    at = rng.randrange(1, len(s) - 1)
+    if rng.random() < 0.5:
+      del s[at:at + rng.randint(1, 6)]
+    else:
+      s[at:at] = [rng.choice('ACGT') for _ in range(rng.randint(1, 6))]
+  return ''.join(s)
+
+
+def test_batch_equals_host_alignments_on_read_to_haplotype_shaped_pairs():
+  """Trimmed long reads against haplotype windows (the alt-aligned pileup's workload), short reads against realigner windows, queries
+  longer than one 32-row strip and than the reference, N bases, a pair with nothing to align, an empty query, a reference longer than
+  the kernel's shared-memory window (host scans take over), ties between equally good placements (repeats)."""
+  rng = random.Random(7)
+  pairs = []
+  for k in range(160):
+    ref_len = rng.choice([40, 147, 221, 300, 420])
+    ref = ''.join(rng.choice('ACGT') for _ in range(ref_len))
+    lo = rng.randrange(0, max(1, ref_len - 30))
+    hi = min(ref_len, lo + rng.choice([20, 33, 64, 100, 150, 260]))
+    q = _mutate(rng, ref[lo:hi], rng.randint(0, 6), rng.randint(0, 3))
+    if k % 9 == 0:
+      q = ''.join(rng.choice('ACGT') for _ in range(rng.randint(3, 12))) + q + ''.join(rng.choice('ACGT') for _ in range(rng.randint(3, 30)))   # soft clips
+    if k % 13 == 0:
+      q = q[:len(q) // 2] + 'N' + q[len(q) // 2 + 1:]
+    pairs.append((ref, q))
+  pairs.append(('ACGT' * 30, 'ACGTACGTACGT'))                     # a repeat: many equally good placements
+  pairs.append(('A' * 50, 'C' * 20))                             # nothing aligns
+  pairs.append(('ACGTACGT', ''))                                 # empty query
+  pairs.append((''.join(rng.choice('ACGT') for _ in range(2500)), ''.join(rng.choice('ACGT') for _ in range(90))))   # beyond the shared-memory window
+  long_ref = ''.join(rng.choice('ACGT') for _ in range(900))
+  pairs.append((long_ref, _mutate(rng, long_ref[100:700], 20, 8)))                                                     # 19 strips
+  for params in ((2, 2, 3, 1), (4, 6, 8, 2)):
+    got = ssw.align_batch(pairs, *params)
+    host = ssw.Aligner(*params)
+    for (ref, q), g in zip(pairs, got):
+      host.set_reference_sequence(ref)
+      assert g == host.align(q), (ref[:30], q[:30], params)
