@@ -80,7 +80,7 @@ class GpuCnn:
   def roofline(self, ms_per_step: float, images_per_step: int, peaks: dict) -> dict:
     """Tensor-core roofline of the classifier: algorithmic conv FLOPs / device time of the CNN part."""
     tf = images_per_step * self.flops_per_image / (ms_per_step * 1e-3) / 1e12
-    return {'bound': 'tensor', 'kernel': 'classifier forward = 94 tcgen05 implicit-GEMM convolutions (stem_conv1 / conv_halo / conv_gemm_persistent / conv_gemm kernels) + 13 pools + tail',
+    return {'bound': 'tensor', 'kernel': 'classifier forward = 94 tcgen05 implicit-GEMM convolutions (stem_conv1 / conv_rows / conv_gemm_persistent / conv_gemm_pair / conv_gemm kernels) + 12 pools + tail',
             'achieved': tf, 'peak': peaks['tflops_sustained'], 'unit': 'TFLOP/s', 'frac': tf / peaks['tflops_sustained'],
             'traffic': None, 'peak_source': peaks['source'] + ', sustained cuBLAS bf16',
             'flops_per_image': self.flops_per_image, 'ms_cnn_per_step': ms_per_step}

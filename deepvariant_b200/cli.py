@@ -195,6 +195,12 @@ def make_examples(argv):
   shard_spec = a.call_variants_outfile if fused else a.examples
   n_shards = len(tfrecord.shard_paths(shard_spec))
   gen = men.ExamplesGenerator(opts, {'main_sample': tfrecord.shard_path(a.examples, a.task)} if a.examples and not fused else {}, device=a.device)
+  try:
+    import torch
+    if torch.cuda.is_available():
+      gen.ssw_device = a.device      # read-to-haplotype Smith-Waterman of alt-aligned pileups: one batched launch per candidate haplotype
+  except ImportError:
+    pass
   fused_cnn = None
   if fused:
     # encoder -> classifier in one call per batch of regions; the CallVariantsOutput shard of this task is what call_variants

@@ -1230,6 +1230,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {   // imme
   else asm volatile("bar.sync 2, 128;" ::: "memory");
 }
 
+template <bool kPool>      // two instantiations: the plain one (conv2) does not carry the pooling state's registers
 __global__ void __launch_bounds__(kRowsThreads, 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const RowsArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -1237,7 +1238,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint8_t* smem_b = smem;                                                  // [3 taps][5 blocks][cout rows][cin]
   uint8_t* smem_a = smem_b + 3 * p.b_tap_bytes;                            // [2 streams][kRowsRing][128 slots][cin]
   uint8_t* smem_row = smem_a + 2 * kRowsRing * p.a_buf_bytes;              // [2 streams][128 pixels][cout] fp16, 16-byte chunks XOR-swizzled
-  const uint32_t row_stage_bytes = 2u * 128u * (uint32_t)p.cout * 2u;       // two parities of one pooled-row staging buffer per stream
+  const uint32_t row_stage_bytes = 128u * (uint32_t)p.cout * 2u;            // exchange slots of the pooled-row emit live here
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_row + 2 * row_stage_bytes);
   uint64_t* in_full = bars;                          // [2][kRowsRing]
   uint64_t* in_empty = bars + 2 * kRowsRing;         // [2][kRowsRing]
@@ -1360,9 +1361,9 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tmem_st_wait();
     tc_fence_before();
     mbar_arrive(&acc_free[st]);
-    uint32_t cur[32];                                 // running vertical maximum (pool mode), packed half2, cout <= 64
+    uint32_t cur[kPool ? 32 : 1];                     // running vertical maximum (pool mode), packed half2, cout <= 64
 #pragma unroll
-    for (int i = 0; i < 32; ++i) cur[i] = 0u;
+    for (int i = 0; i < (kPool ? 32 : 1); ++i) cur[i] = 0u;
     int j = 0, img = (int)blockIdx.x + st * G, slot = 1;   // slot drained at step t = (t + 1) mod 3
     for (int t = 0; t < steps_st[st]; ++t) {
       mbar_wait(&acc_done[st], (uint32_t)t & 1u);
@@ -1393,7 +1394,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_arrive(&acc_free[st]);                      // the MMAs of step t + 1 may go ahead while this row is stored
       if (row_valid) {
         const int nh = p.cout >> 1;                    // half2 words per pixel
-        if (!p.pool) {
+        if constexpr (!kPool) {
           // every thread owns one pixel: cout * 2 contiguous bytes, written straight from its registers (the staging row + two
           // block barriers + copy-out loop this replaces cost ~1600 clocks per row on the critical path - timeline in profiles/)
           if (w < p.Wout) {
@@ -1412,7 +1413,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             // shared loads issued before the first use, and the row leaves as fully coalesced 16-byte stores.
             // (tried: neighbours by warp shuffles - 64 dependent shuffles per thread, 3000 clocks per pooled row against 2000 here)
             const int par = (o >> 1) & 1;
-            uint8_t* row_s = stage + par * (128 * p.cout * 2);
+            uint8_t* row_s = stage + par * (128 * 64);                                // cout = 64 -> 128 B per pixel, half of the stream's staging area
             const int px_shift = p.cout == 64 ? 7 : 6, rp_log2 = p.cout == 64 ? 0 : 1, nch_log2 = p.cout == 64 ? 3 : 2;
             const int my_sw = (w >> rp_log2) & (nch - 1);
 #pragma unroll
@@ -1432,28 +1433,25 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int ph = (o >> 1) - 1;
             __half* dst = p.out + ((size_t)img * p.Hp + ph) * p.Wp * p.out_cstride + p.out_coff;
             const int n_items = p.Wp << nch_log2;
+            uint4 v[4][3];
 #pragma unroll
-            for (int u0 = 0; u0 < 4; u0 += 2) {
-              uint4 v[2][3];
+            for (int u = 0; u < 4; ++u) {
+              const int i = tid + u * 128;
+              if (i < n_items) {
+                const int px = i >> nch_log2, cv = i & (nch - 1);
 #pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const int i = tid + (u0 + u) * 128;
-                if (i < n_items) {
-                  const int px = i >> nch_log2, cv = i & (nch - 1);
-#pragma unroll
-                  for (int dx = 0; dx < 3; ++dx) {
-                    const int pw = 2 * px + dx;
-                    v[u][dx] = *reinterpret_cast<const uint4*>(row_s + (pw << px_shift) + ((cv ^ ((pw >> rp_log2) & (nch - 1))) << 4));
-                  }
+                for (int dx = 0; dx < 3; ++dx) {
+                  const int pw = 2 * px + dx;
+                  v[u][dx] = *reinterpret_cast<const uint4*>(row_s + (pw << px_shift) + ((cv ^ ((pw >> rp_log2) & (nch - 1))) << 4));
                 }
               }
+            }
 #pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const int i = tid + (u0 + u) * 128;
-                if (i < n_items) {
-                  const int px = i >> nch_log2, cv = i & (nch - 1);
-                  *reinterpret_cast<uint4*>(dst + (size_t)px * p.out_cstride + cv * 8) = hmax2x4(v[u][0], hmax2x4(v[u][1], v[u][2]));
-                }
+            for (int u = 0; u < 4; ++u) {
+              const int i = tid + u * 128;
+              if (i < n_items) {
+                const int px = i >> nch_log2, cv = i & (nch - 1);
+                *reinterpret_cast<uint4*>(dst + (size_t)px * p.out_cstride + cv * 8) = hmax2x4(v[u][0], hmax2x4(v[u][1], v[u][2]));
               }
             }
           }
@@ -2667,7 +2665,7 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       a.idesc = (1u << 4) | ((uint32_t)(o.cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       a.h_pitch = 1808;   // (2 * 127 + 3) * 7 = 1799 bytes per row segment -> 450 words -> 1800 halves, rounded up to 8
       net->stem_fused = true;
-      if (o.cout == 32 && Wout <= 128 && EnvInt("DVB_CNN_STEM_ROWS", 1)) {
+      if (o.cout == 32 && Wout <= 128 && EnvInt("DVB_CNN_STEM_ROWS", 0)) {
         // filter tile of stem_rows_kernel: rows [W0 | W2 | W0 | W1] (kernel rows; 32 filters each) x K = 32 (k = s * 7 + c, zero from 21)
         std::vector<__half> wt((size_t)128 * 32, __float2half(0.f));
         const __half* w = reinterpret_cast<const __half*>(blob_w_main);
@@ -2710,7 +2708,7 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       a.b_blk_bytes = (uint32_t)o.cout * a.row_bytes;
       a.b_tap_bytes = 5u * a.b_blk_bytes;
       a.a_buf_bytes = 128u * a.row_bytes;
-      rl.smem = 1024 + (int)(3 * a.b_tap_bytes + 2 * kRowsRing * a.a_buf_bytes + 2 * 2 * 128 * o.cout * 2) + (4 * kRowsRing + 6) * 8 + o.cout * 4 + 64;
+      rl.smem = 1024 + (int)(3 * a.b_tap_bytes + 2 * kRowsRing * a.a_buf_bytes + 2 * 128 * o.cout * 2) + (4 * kRowsRing + 6) * 8 + o.cout * 4 + 64;
       rl.macs_per_image = (double)Hout * Wout * o.cout * 9 * orig.cin;
       if (rl.smem <= 227 * 1024) {
         // filters [Cout][3][3][Cin] -> [kw tap s][block: kernel row 2, 1, 0, 2, 1][Cout][Cin]: three consecutive blocks starting at
@@ -2981,7 +2979,14 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       }
     }
     // CTA-pair variant (cta_group::2): same layers as the persistent kernel, when asked for
-    cl.pair = cl.persist && EnvInt("DVB_CNN_PAIR", 0) != 0 && a.block_n % 16 == 0;
+    // CTA pairs (cta_group::2, M = 256): DVB_CNN_PAIR = 0 never, 1 every persistent layer, 2 (default) by the measured rule - the
+    // single-destination k x k layers with a 192-wide N block (1x7 / 7x1 192->192: 93 -> 84 us per 4096 images; the merged 1x1 GEMMs with
+    // their multi-destination epilogue measured 8 % slower as pairs, 128->192 the same).
+    {
+      const int pair_mode = EnvInt("DVB_CNN_PAIR", 2);
+      cl.pair = cl.persist && a.block_n % 16 == 0 &&
+                (pair_mode == 1 || (pair_mode == 2 && !merged && a.block_n == 192 && o.kh * o.kw > 1 && a.cin_blocks >= 3));
+    }
     if (cl.pair) {
       PairArgs& q2 = cl.pair_args;
       q2.idesc = (1u << 4) | ((uint32_t)(a.block_n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
@@ -3065,7 +3070,8 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
     return dvb::fail(DVB_ERR_CUDA, "cannot reserve shared memory (stem rows kernel)");
   int max_rows = 0;
   for (auto& r : net->rows) max_rows = std::max(max_rows, r.smem);
-  if (max_rows && cudaFuncSetAttribute(conv_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_rows) != cudaSuccess)
+  if (max_rows && (cudaFuncSetAttribute(conv_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_rows) != cudaSuccess ||
+                   cudaFuncSetAttribute(conv_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_rows) != cudaSuccess))
     return dvb::fail(DVB_ERR_CUDA, "cannot reserve %d bytes of shared memory (rows kernel)", max_rows);
   int max_halo = 0;
   for (auto& h : net->halos) max_halo = std::max(max_halo, h.smem);
@@ -3124,7 +3130,8 @@ int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaSt
       const bool tracing = EnvInt("DVB_CNN_TRACE", 0) != 0;
       if (tracing && !d_rtrace) cudaMalloc(&d_rtrace, 48 * 8 * sizeof(long long));
       if (tracing) { cudaMemsetAsync(d_rtrace, 0, 48 * 8 * sizeof(long long), s); a.trace = d_rtrace; }
-      conv_rows_kernel<<<(unsigned)std::min(net->num_sms, n), kRowsThreads, rl.smem, s>>>(rl.map_a, rl.map_b, a);
+      if (a.pool) conv_rows_kernel<true><<<(unsigned)std::min(net->num_sms, n), kRowsThreads, rl.smem, s>>>(rl.map_a, rl.map_b, a);
+      else conv_rows_kernel<false><<<(unsigned)std::min(net->num_sms, n), kRowsThreads, rl.smem, s>>>(rl.map_a, rl.map_b, a);
       if (tracing) {
         std::vector<long long> h(48 * 8);
         cudaStreamSynchronize(s);

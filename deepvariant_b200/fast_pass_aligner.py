@@ -128,6 +128,7 @@ def _merge_one_base(read_op: int, hap_op: int, read_len: int, out: List[List[int
 
 
 class FastPassAligner:
+  ssw_batch_min = 4      # fewer (haplotype, read) pairs than this are aligned on the host even when ssw_device is set
 
   def __init__(self):
     self.kmer_size = 32
@@ -146,6 +147,7 @@ class FastPassAligner:
     self.read_to_haplotype_alignments: List[HaplotypeReadsAlignment] = []
     self.ssw_alignment_score_threshold = 0
     self._ssw: Optional[ssw.Aligner] = None
+    self.ssw_device: Optional[int] = None      # CUDA device for batched Smith-Waterman (None: host dvb_ssw_align per pair)
 
   # -- configuration (set_options :81-109: zero / unset fields keep the defaults) ----------------------------------------------
   def set_options(self, kmer_size=0, read_size=0, max_num_of_mismatches=0, realignment_similarity_threshold=0.0, match=0, mismatch=0,
@@ -297,6 +299,9 @@ class FastPassAligner:
       ha.hap_to_ref_positions_map = set_positions_map(len(self.haplotypes[ha.haplotype_index]), ha.cigar)
 
   def ssw_align_reads_to_haplotypes(self, score_threshold: int) -> None:
+    """SswAlignReadsToHaplotypes (fast_pass_aligner.cc:281-322).  With `ssw_device` set, all (haplotype, read) pairs of the call go
+    through ONE dvb_ssw_align_batch launch (the Smith-Waterman scans on the GPU, csrc/dvb_ssw_gpu.cu); same results either way."""
+    jobs = []
     for i, read in enumerate(self.reads):
       if any(ha.read_alignment_scores[i].score > 0 for ha in self.read_to_haplotype_alignments):
         continue
@@ -304,10 +309,18 @@ class FastPassAligner:
         forced = self.force_alignment and ha.is_reference
         if ha.haplotype_score == 0 and not forced:
           continue
-        al = self._ssw_align(self.haplotypes[ha.haplotype_index], read)
-        if al.sw_score > 0 and (al.sw_score >= score_threshold or forced):
-          ra = ha.read_alignment_scores[i]
-          ra.score, ra.cigar, ra.position = al.sw_score, al.cigar_string, al.ref_begin
+        jobs.append((i, ha, forced))
+    if not jobs:
+      return
+    if self.ssw_device is not None and len(jobs) >= self.ssw_batch_min:
+      als = ssw.align_batch([(self.haplotypes[ha.haplotype_index], self.reads[i]) for i, ha, _ in jobs], self.match_score, self.mismatch_penalty,
+                            self.gap_opening_penalty, self.gap_extending_penalty, device=self.ssw_device)
+    else:
+      als = [self._ssw_align(self.haplotypes[ha.haplotype_index], self.reads[i]) for i, ha, _ in jobs]
+    for (i, ha, forced), al in zip(jobs, als):
+      if al.sw_score > 0 and (al.sw_score >= score_threshold or forced):
+        ra = ha.read_alignment_scores[i]
+        ra.score, ra.cigar, ra.position = al.sw_score, al.cigar_string, al.ref_begin
 
   def get_best_read_alignment(self, read_id: int) -> Optional[int]:
     best_score, best = 0, None

@@ -232,6 +232,7 @@ class ExamplesGenerator:
     # call_variants without tf.Example files): the planned images go to `sink` (packed reads, or finished images for the
     # trimmed / alt-aligned route) instead of a TFRecord writer.
     self.sink = sink
+    self.ssw_device: Optional[int] = None    # CUDA device for the read-to-haplotype Smith-Waterman of alt-aligned pileups (None = host)
     pic = options.pic_options
     self.half_width = (pic.width - 1) // 2
     if len(options.sample_options) != 1:
@@ -325,6 +326,7 @@ class ExamplesGenerator:
     aligner.set_options(kmer_size=a['kmer_size'], read_size=len(reads[0].aligned_sequence) if reads and len(reads[0].aligned_sequence) > 15 else 200,
                         max_num_of_mismatches=a['max_num_of_mismatches'], realignment_similarity_threshold=a['realignment_similarity_threshold'],
                         match=a['match'], mismatch=a['mismatch'], gap_open=a['gap_open'], gap_extend=a['gap_extend'], force_alignment=True)
+    aligner.ssw_device = self.ssw_device     # batched Smith-Waterman on the GPU when the stage runs on one (cli.make_examples sets it)
     aligner.reference = haplotype
     aligner.region_position_in_chr = ref_start
     aligner.ref_prefix_len = aligner.ref_suffix_len = 0

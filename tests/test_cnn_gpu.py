@@ -350,3 +350,28 @@ def test_default_plan_at_bench_scale_matches_oracle_and_small_chunks():
   want = cnn_oracle.ReferenceModel(w).forward(imgs[idx]).numpy()
   assert float(np.abs(got[idx] - want).max()) < 5e-3
   assert np.all(np.abs(got.sum(1) - 1) < 1e-6)
+
+
+def test_cta_pair_kernel_equals_persistent_kernel(monkeypatch):
+  """conv_gemm_pair_kernel (tcgen05 cta_group::2, M = 256: two CTAs of a cluster share one N block, each stages half of the weights)
+  against the one-CTA persistent kernel on the same layers (DVB_CNN_PERSIST=2 routes every eligible layer through them, DVB_CNN_PAIR=1
+  makes all of those pairs; the default, DVB_CNN_PAIR=2, pairs the 192-wide k x k layers at bench-sized batches): same operands, same K
+  order, fp32 accumulation -> the same activations and probabilities.  An odd and an even number of M tiles."""
+  shape = (100, 221, 7)
+  w = modeling.random_weights(7, 11)
+  names = ['s4', 'mixed0', 'mixed3', 'mixed5', 'mixed8', 'mixed10']
+  monkeypatch.setenv('DVB_CNN_PERSIST', '2')
+  for n in (5, 8):
+    imgs = _images(n, shape, n)
+    outs = []
+    for pair in ('0', '1'):
+      monkeypatch.setenv('DVB_CNN_PAIR', pair)
+      net = cv.GpuCnn(w, shape, device=0, max_batch=n)
+      probs = net.forward_host(imgs.numpy())
+      outs.append((probs, {k: net.debug_tensor(k, n) for k in names}))
+      net.close()
+    (p0, t0), (p1, t1) = outs
+    for k in names:
+      scale = max(float(np.abs(t0[k]).max()), 1e-6)
+      assert float(np.abs(t0[k] - t1[k]).max()) / scale < 2e-3, k
+    assert float(np.abs(p0 - p1).max()) < 1e-3

@@ -69,3 +69,32 @@ def test_batch_equals_host_alignments_on_read_to_haplotype_shaped_pairs():
     for (ref, q), g in zip(pairs, got):
       host.set_reference_sequence(ref)
       assert g == host.align(q), (ref[:30], q[:30], params)
+
+
+def test_alt_aligned_pileups_through_the_gpu_flow_equal_the_host_flow(tmp_path, monkeypatch):
+  """make_examples --alt_aligned_pileup diff_channels on the planted genome (a 2-bp insertion and a 3-bp deletion among the candidates):
+  CUDA encoder + batched GPU Smith-Waterman for the read-to-haplotype alignments against the CPU oracle encoder + host Smith-Waterman
+  (the flow tools/check_pacbio_end_to_end.py pins on all 131 indel examples of the reference's golden.pacbio_examples): the tf.Examples
+  must be the same, record for record - images 100 x 221 x 9 with both alt-aligned diff channels."""
+  import test_candidates as tc
+  from deepvariant_b200 import fast_pass_aligner as fpa, make_examples_native as men, pileup_image as pi, protos
+  fa, bam_path, genome, sites = tc._planted_case(tmp_path)
+  calls = {'batch': 0}
+  real_batch = ssw.align_batch
+
+  def counting_batch(pairs, *a, **k):
+    calls['batch'] += len(pairs)
+    return real_batch(pairs, *a, **k)
+  monkeypatch.setattr(ssw, 'align_batch', counting_batch)
+  monkeypatch.setattr(fpa.ssw, 'align_batch', counting_batch)
+  extra = ('--alt_aligned_pileup', 'diff_channels')
+  gpu_examples, gpu_cands = tc._run_cli(tmp_path, fa, bam_path, 'alt_gpu', extra=extra)
+  assert calls['batch'] > 0, 'the GPU flow never used the batched Smith-Waterman'
+  monkeypatch.setattr(men.ExamplesGenerator, '_gpu', lambda self: tc.OracleEncoder(pi.to_params(self.options.pic_options, height=self.pileup_image_height)))
+  monkeypatch.setattr(fpa.FastPassAligner, 'ssw_batch_min', 1 << 30, raising=False)       # host dvb_ssw_align per pair
+  before = calls['batch']
+  cpu_examples, cpu_cands = tc._run_cli(tmp_path, fa, bam_path, 'alt_cpu', extra=extra)
+  assert calls['batch'] == before
+  assert gpu_cands == cpu_cands and gpu_examples == cpu_examples
+  shapes = [protos.parse_tf_example(r)['image/shape'][1] for r in gpu_examples]
+  assert shapes and all(s == [100, 221, 9] for s in shapes)

@@ -115,48 +115,3 @@ def test_one_launch_over_a_long_interval(tmp_path):
   flags = _compare(counter, table, ref, 'chr1', 0, n, np.arange(table.n_reads), cand.CandidateOptions())
   assert 0 < int((flags != 0).sum()) < n // 20
   counter.close()
-
-
-_PAIR_CHECK = r"""
-import os, sys
-import numpy as np, torch
-from deepvariant_b200 import call_variants as cv, modeling
-shape = (100, 221, 7)
-w = modeling.random_weights(7, 11)
-names = ['s4', 'mixed0', 'mixed3', 'mixed5', 'mixed8', 'mixed10']
-for n in (5, 8):
-  g = torch.Generator().manual_seed(n)
-  imgs = torch.randint(0, 255, (n,) + shape, dtype=torch.uint8, generator=g).to('cuda:0')
-  outs = []
-  for pair in ('0', '1'):
-    os.environ['DVB_CNN_PERSIST'] = '2'
-    os.environ['DVB_CNN_PAIR'] = pair
-    net = cv.GpuCnn(w, shape, device=0, max_batch=n)
-    probs = torch.empty((n, 3), dtype=torch.float32, device='cuda:0')
-    net.forward_device(imgs, probs)
-    torch.cuda.synchronize()
-    outs.append((probs.cpu().numpy(), {k: net.debug_tensor(k, n) for k in names}))
-    net.close()
-  (p0, t0), (p1, t1) = outs
-  for k in names:
-    scale = max(float(np.abs(t0[k]).max()), 1e-6)
-    assert float(np.abs(t0[k] - t1[k]).max()) / scale < 2e-3, k
-  assert float(np.abs(p0 - p1).max()) < 1e-3
-print('pair kernel == persistent kernel')
-"""
-
-
-@pytest.mark.skipif(os.environ.get('DVB_TEST_PAIR') != '1',
-                    reason='conv_gemm_pair_kernel is experimental, off by default (DVB_CNN_PAIR=0) and not yet run on hardware: '
-                           'DVB_TEST_PAIR=1 (tools/gpu_round2_first_call.sh) runs this check')
-def test_cta_pair_kernel_equals_persistent_kernel():
-  """conv_gemm_pair_kernel (tcgen05 cta_group::2, M = 256; DVB_CNN_PAIR=1, off by default) against the persistent one-CTA
-  kernel on the same layers (DVB_CNN_PERSIST=2 routes every eligible layer through them): same operands, same K order, fp32
-  accumulation -> the same activations and probabilities.  An odd and an even number of M tiles are both exercised.  Runs in
-  a child process under a hard timeout: a cluster kernel that was never executed may wait on a barrier for ever, and that
-  must cost this one test, not the session."""
-  import subprocess
-  import sys
-  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-  r = subprocess.run([sys.executable, '-c', _PAIR_CHECK], cwd=root, capture_output=True, text=True, timeout=240)
-  assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
