@@ -173,6 +173,8 @@ SYMBOLS = (
     ('dvb_cnn_max_batch', C.c_int32, [C.c_void_p]),
     ('dvb_read_requirements_default', None, [C.POINTER(DvbReadRequirements)]),
     ('dvb_bam_open', C.c_int, [C.c_char_p, C.POINTER(DvbReadRequirements), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    ('dvb_bam_open_regions', C.c_int, [C.c_char_p, C.POINTER(DvbReadRequirements), C.c_int, C.c_int, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p,
+                                       C.c_int32, C.POINTER(C.c_void_p)]),
     ('dvb_bam_table', C.c_int, [C.c_void_p, C.POINTER(DvbReadTable)]),
     ('dvb_bam_ref_name', C.c_char_p, [C.c_void_p, C.c_int32]),
     ('dvb_bam_close', None, [C.c_void_p]),

@@ -142,7 +142,9 @@ class NativeBamTable:
   produces (used by the planner and by the parity tests); `query()` answers region queries on the arrays."""
 
   def __init__(self, path: str, read_requirements: Optional[ReadRequirements] = None, parse_aux: bool = False,
-               threads: int = 0):
+               threads: int = 0, regions=None):
+    """regions: optional [(contig, start, end), ...] (0-based, half-open) - only reads overlapping one of them are decoded
+    (dvb_bam_open_regions: the .bai linear index is used when they lie on one contig and the index is beside the file)."""
     import ctypes as C
     import numpy as np
     from deepvariant_b200 import _lib
@@ -153,7 +155,14 @@ class NativeBamTable:
         int(req.keep_secondary_alignments), int(req.keep_supplementary_alignments), int(req.keep_unaligned),
         int(req.keep_improperly_placed))
     h = C.c_void_p()
-    _lib.check(lib.dvb_bam_open(path.encode(), C.byref(creq), int(parse_aux), threads, C.byref(h)))
+    if regions:
+      names = (C.c_char_p * len(regions))(*[r[0].encode() for r in regions])
+      starts = np.array([r[1] for r in regions], dtype=np.int64)
+      ends = np.array([min(int(r[2]), (1 << 62)) for r in regions], dtype=np.int64)
+      _lib.check(lib.dvb_bam_open_regions(path.encode(), C.byref(creq), int(parse_aux), threads, names, starts.ctypes.data_as(C.c_void_p),
+                                          ends.ctypes.data_as(C.c_void_p), len(regions), C.byref(h)))
+    else:
+      _lib.check(lib.dvb_bam_open(path.encode(), C.byref(creq), int(parse_aux), threads, C.byref(h)))
     try:
       t = _lib.DvbReadTable()
       _lib.check(lib.dvb_bam_table(h, C.byref(t)))
@@ -187,6 +196,16 @@ class NativeBamTable:
     except BaseException:
       lib.dvb_bam_close(h)
       raise
+    # region queries: a coordinate-sorted table answers them with two binary searches (rows with pos < end form a prefix; the running
+    # maximum of `end` is monotone, so rows that can reach `start` form a suffix of it) instead of a scan of every read per partition
+    key = self.ref_id.astype(np.int64) * (1 << 32) + self.pos.astype(np.int64)
+    mapped = self.ref_id >= 0
+    self._sorted = bool(np.all(np.diff(key[mapped]) >= 0)) and (not mapped.any() or not (~mapped)[:int(np.nonzero(mapped)[0][-1]) + 1].any())
+    self._key = key if self._sorted else None
+    self._cummax_end = None
+    if self._sorted and n:
+      # per contig running maximum: encode (ref_id, end) so that the maximum restarts with every contig
+      self._cummax_end = np.maximum.accumulate(self.ref_id.astype(np.int64) * (1 << 32) + self.end.astype(np.int64))
     self._handle = h            # kept open: the native region packer (packing.pack_region_native) reads the C++ table
     self._close = lib.dvb_bam_close
     self.parse_aux = parse_aux
@@ -238,6 +257,13 @@ class NativeBamTable:
     if contig not in self.references:
       return np.zeros(0, dtype=np.int64)
     rid = self.references.index(contig)
+    if self._sorted and self.n_reads:
+      hi = int(np.searchsorted(self._key, rid * (1 << 32) + end, side='left'))            # first row with pos >= end (or a later contig)
+      lo = int(np.searchsorted(self._cummax_end, rid * (1 << 32) + start, side='right'))  # first row whose running max(end) exceeds start
+      if lo >= hi:
+        return np.zeros(0, dtype=np.int64)
+      sel = np.nonzero((self.end[lo:hi] > start) & (self.ref_id[lo:hi] == rid))[0]
+      return sel + lo
     return np.nonzero((self.ref_id == rid) & (self.pos < end) & (self.end > start))[0]
 
   def query(self, contig: str, start: int, end: int) -> List[Read]:

@@ -214,9 +214,16 @@ def make_examples(argv):
     gen.sink = fz.FusedCaller(gen._gpu(), fused_cnn, tfrecord.shard_path(a.call_variants_outfile, a.task), batch_images=a.call_batch_size)  # pylint: disable=protected-access
   # Native block-parallel BAM decode into a Structure-of-Arrays read table (csrc/dvb_bam.cu); untrimmed pileups (WGS/WES)
   # are planned and packed straight from the table rows, trimmed ones (PACBIO, alt-aligned) from Read objects of table.query().
-  reader = bam.NativeBamTable(a.reads, bam.ReadRequirements(min_mapping_quality=a.min_mapping_quality), parse_aux=a.parse_sam_aux_fields)
-  table_path = not a.trim_reads_for_pileup and a.alt_aligned_pileup == 'none'
   regions = parse_regions(a.regions) if a.regions else None
+  # Only the reads this task can touch are decoded (dvb_bam_open_regions; with a .bai beside the file and one contig, the decoder
+  # seeks): --regions widened by what the stages reach beyond a partition - the phasing padding (20 % of a partition), the realigner's
+  # windows and the pileup's read-overlap buffer.
+  read_regions = None
+  if regions and not a.candidates_in:
+    margin = (a.partition_size // 5 if a.phase_reads else 0) + 1000
+    read_regions = [(c, max(0, s - margin), e + margin) for c, s, e in regions]
+  reader = bam.NativeBamTable(a.reads, bam.ReadRequirements(min_mapping_quality=a.min_mapping_quality), parse_aux=a.parse_sam_aux_fields, regions=read_regions)
+  table_path = not a.trim_reads_for_pileup and a.alt_aligned_pileup == 'none'
   if regions is not None and len(regions) > 1 and (a.candidates_in or a.mode == 'candidate_sweep'):
     raise NotImplementedError('several --regions together with --candidates_in / --mode candidate_sweep')
   region = regions[0] if regions else None

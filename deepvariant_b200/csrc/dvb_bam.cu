@@ -23,6 +23,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <string_view>
@@ -98,6 +99,7 @@ struct DvbBam {
   std::vector<uint32_t> cigar;
   std::vector<char> names;
   int64_t n_records_seen = 0;
+  bool seeked = false;                    // opened through the .bai linear index (dvb_bam_open_regions): only part of the file was read
   // region-packer index, built on first use (EnsureIndex)
   mutable std::once_flag index_once;
   mutable bool sorted = false;            // rows ordered by (ref_id, pos): region queries can binary-search
@@ -106,138 +108,185 @@ struct DvbBam {
   mutable std::vector<int32_t> next_same_hash;                   // chain to the next row with the same hash (file order), -1 ends
 };
 
-extern "C" {
+namespace {
 
-void dvb_read_requirements_default(DvbReadRequirements* r) {
-  memset(r, 0, sizeof(*r));
-  r->min_mapping_quality = 5;   // make_examples_options.py:957-964
+struct Region { int32_t ref_id; int64_t start, end; };
+
+// BGZF members of `buf` (complete ones only): appends to `blocks` with out_off relative to `out_base`; returns the number of
+// compressed bytes consumed, or (size_t)-1 on a malformed member.  A member is: gzip header with the 'BC' extra subfield
+// (BSIZE = member size - 1), raw deflate data, CRC32, ISIZE.
+size_t IndexBgzf(const uint8_t* buf, size_t n, size_t in_base, size_t* out_total, std::vector<BgzfBlock>* blocks) {
+  size_t off = 0;
+  while (off + 18 <= n) {
+    const uint8_t* h = buf + off;
+    if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return (size_t)-1;
+    const size_t xlen = rd16(h + 10);
+    if (off + 12 + xlen > n) break;                       // extra field not complete in this buffer
+    size_t x = 12, bsize = 0;
+    while (x + 4 <= 12 + xlen) {
+      const size_t slen = rd16(h + x + 2);
+      if (h[x] == 'B' && h[x + 1] == 'C' && slen == 2 && x + 6 <= 12 + xlen) bsize = (size_t)rd16(h + x + 4) + 1;
+      x += 4 + slen;
+    }
+    if (!bsize || bsize < 12 + xlen + 8) return (size_t)-1;   // no BC subfield / a size that cannot hold header + trailer (would underflow below)
+    if (off + bsize > n) break;                           // member not complete in this buffer
+    const size_t isize = rd32(h + bsize - 4);
+    blocks->push_back({in_base + off + 12 + xlen, bsize - 12 - xlen - 8, *out_total, isize});
+    *out_total += isize;
+    off += bsize;
+  }
+  return off;
 }
 
-int dvb_bam_open(const char* path, const DvbReadRequirements* req_in, int parse_hp, int threads, DvbBam** out) {
-  if (!path || !out) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_bam_open: null argument");
+// Inflates blocks[b0 ..) from `comp` (in_off relative to comp_base) into out (out_off relative to out_base), in parallel.
+bool InflateBlocks(const std::vector<BgzfBlock>& blocks, size_t b0, const uint8_t* comp, size_t comp_base, uint8_t* out, size_t out_base, int threads) {
+  int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+  nt = std::max(1, std::min(nt, (int)std::max<size_t>(1, (blocks.size() - b0) / 4)));
+  std::atomic<size_t> next{b0};
+  std::atomic<int> bad{0};
+  auto work = [&]() {
+    for (;;) {
+      const size_t b = next.fetch_add(1);
+      if (b >= blocks.size()) return;
+      const BgzfBlock& k = blocks[b];
+      if (!k.out_len) continue;
+      z_stream zs;
+      memset(&zs, 0, sizeof(zs));
+      if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
+      zs.next_in = const_cast<uint8_t*>(comp + (k.in_off - comp_base)); zs.avail_in = (uInt)k.in_len;
+      zs.next_out = out + (k.out_off - out_base); zs.avail_out = (uInt)k.out_len;
+      const int rc = inflate(&zs, Z_FINISH);
+      inflateEnd(&zs);
+      if (rc != Z_STREAM_END || zs.avail_out != 0) { bad = 1; return; }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+  return !bad;
+}
+
+// Smallest virtual file offset at which a read overlapping [start, ...) of reference `ref_id` can begin, from the .bai linear index
+// (SAM spec 5.2: ioffset[w] = offset of the first alignment overlapping the 16-kb window w); 0 = not known (scan from the beginning).
+uint64_t BaiLinearOffset(const std::string& bai_path, int32_t ref_id, int64_t start) {
+  FILE* f = fopen(bai_path.c_str(), "rb");
+  if (!f) return 0;
+  std::vector<uint8_t> b;
+  fseek(f, 0, SEEK_END);
+  const long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  b.resize((size_t)std::max(0L, n));
+  const bool ok = n > 8 && fread(b.data(), 1, b.size(), f) == b.size();
+  fclose(f);
+  if (!ok || memcmp(b.data(), "BAI\1", 4) != 0) return 0;
+  size_t p = 8;
+  const int32_t n_ref = rdi32(b.data() + 4);
+  for (int32_t r = 0; r < n_ref; ++r) {
+    if (p + 4 > b.size()) return 0;
+    const int32_t n_bin = rdi32(b.data() + p); p += 4;
+    for (int32_t k = 0; k < n_bin; ++k) {
+      if (p + 8 > b.size()) return 0;
+      const int32_t n_chunk = rdi32(b.data() + p + 4);
+      p += 8 + 16 * (size_t)std::max(0, n_chunk);
+    }
+    if (p + 4 > b.size()) return 0;
+    const int32_t n_intv = rdi32(b.data() + p); p += 4;
+    if (p + 8 * (size_t)std::max(0, n_intv) > b.size()) return 0;
+    if (r == ref_id) {
+      int64_t w = start >> 14;
+      if (n_intv <= 0) return 0;
+      if (w >= n_intv) w = n_intv - 1;
+      for (; w >= 0; --w) {                                   // an empty window has offset 0: an earlier one is a valid (earlier) start
+        uint64_t v;
+        memcpy(&v, b.data() + p + 8 * (size_t)w, 8);
+        if (v) return v;
+      }
+      return 0;
+    }
+    p += 8 * (size_t)std::max(0, n_intv);
+  }
+  return 0;
+}
+
+int OpenImpl(const char* path, const DvbReadRequirements* req_in, int parse_hp, int threads, const char* const* contigs, const int64_t* starts,
+             const int64_t* ends, int32_t n_regions, DvbBam** out) {
+  if (!path || !out || (n_regions > 0 && (!contigs || !starts || !ends)) || n_regions < 0) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_bam_open: bad arguments");
   *out = nullptr;
   DvbReadRequirements req;
   if (req_in) req = *req_in; else dvb_read_requirements_default(&req);
   FILE* f = fopen(path, "rb");
   if (!f) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "cannot open %s", path);
+  struct Closer { FILE* f; ~Closer() { if (f) fclose(f); } } closer{f};
   fseek(f, 0, SEEK_END);
-  const long fsz = ftell(f);
+  const size_t fsz = (size_t)std::max(0L, ftell(f));
   fseek(f, 0, SEEK_SET);
-  std::vector<uint8_t> file((size_t)std::max(0L, fsz));
-  if (fsz > 0 && fread(file.data(), 1, file.size(), f) != file.size()) { fclose(f); return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "short read on %s", path); }
-  fclose(f);
+  constexpr size_t kChunk = 32u << 20;      // compressed bytes read, indexed and inflated per round
 
-  // ---- BGZF block index: gzip member with the 'BC' extra subfield (BSIZE), ISIZE in the last 4 bytes
-  std::vector<BgzfBlock> blocks;
-  size_t off = 0, total_out = 0;
-  while (off + 18 <= file.size()) {
-    const uint8_t* h = file.data() + off;
-    if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: not a BGZF block at offset %zu", path, off);
-    const uint16_t xlen = rd16(h + 10);
-    size_t x = 12, bsize = 0;
-    while (x + 4 <= 12 + (size_t)xlen) {
-      const uint16_t slen = rd16(h + x + 2);
-      if (h[x] == 'B' && h[x + 1] == 'C' && slen == 2) bsize = (size_t)rd16(h + x + 4) + 1;
-      x += 4 + slen;
-    }
-    if (!bsize || off + bsize > file.size()) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: truncated BGZF block at offset %zu", path, off);
-    const size_t isize = rd32(h + bsize - 4);
-    blocks.push_back({off + 12 + xlen, bsize - 12 - xlen - 8, total_out, isize});
-    total_out += isize;
-    off += bsize;
-  }
-  // ---- block-parallel inflate
-  std::vector<uint8_t> data(total_out);
-  {
-    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
-    nt = std::max(1, std::min(nt, (int)std::max<size_t>(1, blocks.size() / 4)));
-    std::atomic<size_t> next{0};
-    std::atomic<int> bad{0};
-    auto work = [&]() {
-      for (;;) {
-        const size_t b = next.fetch_add(1);
-        if (b >= blocks.size()) return;
-        const BgzfBlock& k = blocks[b];
-        if (!k.out_len) continue;
-        z_stream zs;
-        memset(&zs, 0, sizeof(zs));
-        if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
-        zs.next_in = file.data() + k.in_off; zs.avail_in = (uInt)k.in_len;
-        zs.next_out = data.data() + k.out_off; zs.avail_out = (uInt)k.out_len;
-        const int rc = inflate(&zs, Z_FINISH);
-        inflateEnd(&zs);
-        if (rc != Z_STREAM_END || zs.avail_out != 0) { bad = 1; return; }
-      }
-    };
-    std::vector<std::thread> pool;
-    for (int t = 1; t < nt; ++t) pool.emplace_back(work);
-    work();
-    for (auto& t : pool) t.join();
-    if (bad) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: BGZF inflate failed", path);
-  }
-  std::vector<uint8_t>().swap(file);
-
-  // ---- header
-  if (data.size() < 12 || memcmp(data.data(), "BAM\1", 4) != 0) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s is not a BAM file", path);
-  DvbBam* bam = new DvbBam();
-  size_t p = 8 + (size_t)rdi32(data.data() + 4);
-  if (p + 4 > data.size()) { delete bam; return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: truncated header", path); }
-  const int32_t n_ref = rdi32(data.data() + p);
-  p += 4;
-  for (int32_t i = 0; i < n_ref; ++i) {
-    if (p + 4 > data.size()) { delete bam; return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: truncated reference list", path); }
-    const int32_t l_name = rdi32(data.data() + p);
-    if (l_name < 1 || p + 8 + (size_t)l_name > data.size()) { delete bam; return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: bad reference record", path); }
-    bam->refs.emplace_back(reinterpret_cast<const char*>(data.data() + p + 4), (size_t)l_name - 1);
-    bam->ref_len.push_back(rdi32(data.data() + p + 4 + l_name));
-    p += 8 + (size_t)l_name;
-  }
-  // ---- records
+  std::unique_ptr<DvbBam> bam(new DvbBam());
+  std::vector<Region> regions;
+  std::vector<uint8_t> comp, data;          // compressed chunk; inflated bytes not yet consumed
+  size_t comp_off = 0;                      // file offset of the next byte to read
+  size_t skip_first = 0;                    // uncompressed bytes of the first inflated block to drop (after a seek by the index)
+  bool header_done = false, stop = false;
+  int32_t span_ref = -1;
+  int64_t span_lo = 0, span_hi = 0;
   static const char kSeq[] = "=ACMGRSVTWYHKDBN";
   bam->seq_begin.push_back(0); bam->cigar_begin.push_back(0); bam->name_begin.push_back(0);
-  while (p + 4 <= data.size()) {
-    const int32_t block_size = rdi32(data.data() + p);
-    if (block_size < 32 || p + 4 + (size_t)block_size > data.size()) { delete bam; return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: truncated alignment record", path); }
-    const uint8_t* r = data.data() + p + 4;
-    p += 4 + (size_t)block_size;
+
+  // one alignment record (after its 4-byte block_size); returns false on a malformed record
+  auto take_record = [&](const uint8_t* r, int32_t block_size) -> bool {
     bam->n_records_seen++;
     const int32_t ref_id = rdi32(r), pos = rdi32(r + 4);
     const uint8_t l_read_name = r[8], mapq = r[9];
     const uint16_t n_cigar = rd16(r + 12), flag = rd16(r + 14);
     const int32_t l_seq = rdi32(r + 16), next_ref = rdi32(r + 20), tlen = rdi32(r + 28);
     const size_t need = 32 + (size_t)l_read_name + 4 * (size_t)n_cigar + ((size_t)l_seq + 1) / 2 + (size_t)l_seq;
-    if (l_seq < 0 || need > (size_t)block_size) { delete bam; return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: malformed alignment record", path); }
+    if (l_seq < 0 || need > (size_t)block_size) return false;
+    if (span_ref >= 0 && ((uint32_t)ref_id > (uint32_t)span_ref || (ref_id == span_ref && pos >= span_hi))) { stop = true; return true; }   // sorted file: nothing later can overlap
     // ReadSatisfiesRequirements (sam_reader.cc:217-245)
     if (((flag & FDUP) && !req.keep_duplicates) || ((flag & FQCFAIL) && !req.keep_failed_vendor_quality_checks) ||
         ((flag & FSECONDARY) && !req.keep_secondary_alignments) || ((flag & FSUPP) && !req.keep_supplementary_alignments))
-      continue;
+      return true;
     const bool mapped = !(flag & FUNMAP);
-    if (!mapped && !req.keep_unaligned) continue;
+    if (!mapped && !req.keep_unaligned) return true;
     const bool paired = flag & FPAIRED;
     if (!req.keep_improperly_placed && mapped) {   // IsReadProperlyPlaced (utils.cc:261-266)
       const bool mate_has_contig = paired && !(flag & FMUNMAP) && next_ref >= 0;
-      if (!(!paired || (flag & FPROPER) || !mate_has_contig || next_ref == ref_id)) continue;
+      if (!(!paired || (flag & FPROPER) || !mate_has_contig || next_ref == ref_id)) return true;
     }
-    if (mapped && (int)mapq < req.min_mapping_quality) continue;
-    // ---- decode
+    if (mapped && (int)mapq < req.min_mapping_quality) return true;
     const uint8_t* name = r + 32;
     const uint8_t* cig = name + l_read_name;
     const uint8_t* seq = cig + 4 * (size_t)n_cigar;
     const uint8_t* qual = seq + ((size_t)l_seq + 1) / 2;
     const uint8_t* aux = qual + l_seq;
+    int32_t e = pos;
+    if (mapped)
+      for (uint16_t k = 0; k < n_cigar; ++k) {
+        const uint32_t c = rd32(cig + 4 * (size_t)k);
+        const uint32_t op = c & 0xF;
+        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) e += (int32_t)(c >> 4);
+      }
+    if (!regions.empty()) {                      // --regions: only reads that overlap one of them are kept (ReadOverlapsRegion, utils.cc:172-188)
+      // regions are sorted and merged: the first one that ends behind the read's start decides (binary search; records of a
+      // coordinate-sorted file move the answer forward monotonically, but nothing here depends on the order)
+      const int32_t rend = std::max(e, pos + 1);
+      size_t lo = 0, hi = regions.size();
+      while (lo < hi) {
+        const size_t mid = (lo + hi) >> 1;
+        const Region& g = regions[mid];
+        if (g.ref_id < ref_id || (g.ref_id == ref_id && g.end <= pos)) lo = mid + 1; else hi = mid;
+      }
+      if (lo == regions.size() || regions[lo].ref_id != ref_id || regions[lo].start >= rend) return true;
+    }
+    // ---- decode
     bam->ref_id.push_back(ref_id); bam->pos.push_back(pos); bam->mapq.push_back(mapq); bam->flag.push_back(flag);
     bam->fragment_length.push_back(tlen);
     bam->read_number.push_back(((flag & FREAD1) || !paired) ? 0 : 1);
     bam->number_reads.push_back(paired ? 2 : 1);
-    int32_t e = pos;
-    if (mapped) {
-      for (uint16_t k = 0; k < n_cigar; ++k) {
-        const uint32_t c = rd32(cig + 4 * (size_t)k);
-        bam->cigar.push_back(c);
-        const uint32_t op = c & 0xF;
-        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) e += (int32_t)(c >> 4);
-      }
-    }
+    if (mapped)
+      for (uint16_t k = 0; k < n_cigar; ++k) bam->cigar.push_back(rd32(cig + 4 * (size_t)k));
     bam->end.push_back(e);
     bam->cigar_begin.push_back((int64_t)bam->cigar.size());
     const size_t b0 = bam->bases.size();
@@ -248,9 +297,154 @@ int dvb_bam_open(const char* path, const DvbReadRequirements* req_in, int parse_
     bam->names.insert(bam->names.end(), name, name + (l_read_name ? l_read_name - 1 : 0));
     bam->name_begin.push_back((int64_t)bam->names.size());
     bam->hp.push_back(parse_hp ? ParseHp(aux, (size_t)block_size - need) : INT32_MIN);
+    return true;
+  };
+
+  // header + reference list from the front of `data`; returns bytes consumed, 0 = need more data, (size_t)-1 = malformed
+  auto take_header = [&]() -> size_t {
+    if (data.size() < 12) return 0;
+    if (memcmp(data.data(), "BAM\1", 4) != 0) return (size_t)-1;
+    size_t p = 8 + (size_t)rdi32(data.data() + 4);
+    if (p + 4 > data.size()) return 0;
+    const int32_t n_ref = rdi32(data.data() + p);
+    p += 4;
+    std::vector<std::string> refs;
+    std::vector<int32_t> lens;
+    for (int32_t i = 0; i < n_ref; ++i) {
+      if (p + 4 > data.size()) return 0;
+      const int32_t l_name = rdi32(data.data() + p);
+      if (l_name < 1) return (size_t)-1;
+      if (p + 8 + (size_t)l_name > data.size()) return 0;
+      refs.emplace_back(reinterpret_cast<const char*>(data.data() + p + 4), (size_t)l_name - 1);
+      lens.push_back(rdi32(data.data() + p + 4 + l_name));
+      p += 8 + (size_t)l_name;
+    }
+    bam->refs = refs;
+    bam->ref_len = lens;
+    return p;
+  };
+
+  while (!stop) {
+    // ---- read the next chunk of compressed bytes, index its complete BGZF members, inflate them behind the unconsumed bytes
+    if (comp_off >= fsz && comp.empty()) break;
+    const size_t have = comp.size();
+    // (the first rounds are small: the header is at the front and an index seek should not be preceded by 32 MB of inflating)
+    const size_t want = std::min(header_done ? kChunk : (size_t)(256u << 10), fsz - std::min(fsz, comp_off));
+    comp.resize(have + want);
+    if (want) {
+      if (fseek(f, (long)comp_off, SEEK_SET) != 0 || fread(comp.data() + have, 1, want, f) != want) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "short read on %s", path);
+      comp_off += want;
+    }
+    std::vector<BgzfBlock> blocks;
+    size_t out_total = data.size();
+    const size_t used = IndexBgzf(comp.data(), comp.size(), 0, &out_total, &blocks);
+    if (used == (size_t)-1) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: not a BGZF block (or a malformed one) near offset %zu", path, comp_off - comp.size());
+    if (blocks.empty()) {
+      if (!want) {
+        if (!comp.empty()) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: truncated BGZF block at the end of the file", path);
+        break;
+      }
+      continue;                                  // a member larger than what is buffered so far: read on
+    }
+    const size_t data0 = data.size();
+    data.resize(out_total);
+    if (!InflateBlocks(blocks, 0, comp.data(), 0, data.data(), 0, threads)) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: BGZF inflate failed", path);
+    comp.erase(comp.begin(), comp.begin() + (long)used);
+    if (skip_first) {                            // first block after a seek: drop the bytes before the indexed record
+      const size_t drop = std::min(skip_first, data.size() - data0);
+      data.erase(data.begin() + (long)data0, data.begin() + (long)(data0 + drop));
+      skip_first = 0;
+    }
+    // ---- consume
+    size_t p = 0;
+    if (!header_done) {
+      const size_t h = take_header();
+      if (h == (size_t)-1) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s is not a BAM file", path);
+      if (h == 0) { if (!want && comp.empty()) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: truncated header", path); continue; }
+      p = h;
+      header_done = true;
+      // regions -> reference ids; when they all lie on one contig and a .bai sits beside the file, jump to the first block that can
+      // hold an overlapping read and stop at the first read behind the last region (coordinate-sorted files only - the index implies it)
+      for (int32_t i = 0; i < n_regions; ++i) {
+        int32_t id = -1;
+        for (size_t k = 0; k < bam->refs.size(); ++k)
+          if (bam->refs[k] == contigs[i]) { id = (int32_t)k; break; }
+        if (id < 0) continue;                    // a contig the file does not know: no reads
+        regions.push_back({id, std::max<int64_t>(0, starts[i]), ends[i]});
+      }
+      if (n_regions > 0 && regions.empty()) { stop = true; break; }
+      if (!regions.empty()) {                    // sort by (contig, start) and merge what overlaps or touches
+        std::sort(regions.begin(), regions.end(), [](const Region& a, const Region& b) { return a.ref_id != b.ref_id ? a.ref_id < b.ref_id : a.start < b.start; });
+        std::vector<Region> merged;
+        for (const Region& g : regions) {
+          if (g.end <= g.start) continue;
+          if (!merged.empty() && merged.back().ref_id == g.ref_id && g.start <= merged.back().end) merged.back().end = std::max(merged.back().end, g.end);
+          else merged.push_back(g);
+        }
+        regions.swap(merged);
+        if (regions.empty()) { stop = true; break; }
+      }
+      if (!regions.empty()) {
+        bool one = true;
+        span_lo = regions[0].start; span_hi = regions[0].end;
+        for (const Region& g : regions) { one = one && g.ref_id == regions[0].ref_id; span_lo = std::min(span_lo, g.start); span_hi = std::max(span_hi, g.end); }
+        std::string bai = std::string(path) + ".bai";
+        FILE* t = fopen(bai.c_str(), "rb");
+        if (!t) {
+          const std::string ps(path);
+          const size_t dot = ps.rfind('.');
+          if (dot != std::string::npos) { bai = ps.substr(0, dot) + ".bai"; t = fopen(bai.c_str(), "rb"); }
+        }
+        if (t) fclose(t);
+        if (one && t) {
+          span_ref = regions[0].ref_id;
+          const uint64_t v = BaiLinearOffset(bai, span_ref, span_lo);
+          const size_t coff = (size_t)(v >> 16);
+          if (v && coff < fsz && coff >= comp_off - comp.size()) {   // seek only forward of what has been read and inflated
+            comp.clear();
+            data.clear();
+            comp_off = coff;
+            skip_first = (size_t)(v & 0xFFFF);
+            bam->seeked = true;
+            continue;
+          }
+        }
+      }
+    }
+    while (p + 4 <= data.size() && !stop) {
+      const int32_t block_size = rdi32(data.data() + p);
+      if (block_size < 32) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: truncated alignment record", path);
+      if (p + 4 + (size_t)block_size > data.size()) break;      // the record continues in the next chunk
+      if (!take_record(data.data() + p + 4, block_size)) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: malformed alignment record", path);
+      p += 4 + (size_t)block_size;
+    }
+    data.erase(data.begin(), data.begin() + (long)p);
+    if (!want && comp.empty()) {
+      if (!data.empty() && !stop) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: truncated alignment record", path);
+      break;
+    }
   }
-  *out = bam;
+  if (!header_done) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s is not a BAM file", path);
+  *out = bam.release();
   return DVB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void dvb_read_requirements_default(DvbReadRequirements* r) {
+  memset(r, 0, sizeof(*r));
+  r->min_mapping_quality = 5;   // make_examples_options.py:957-964
+}
+
+int dvb_bam_open(const char* path, const DvbReadRequirements* req_in, int parse_hp, int threads, DvbBam** out) {
+  return OpenImpl(path, req_in, parse_hp, threads, nullptr, nullptr, nullptr, 0, out);
+}
+
+int dvb_bam_open_regions(const char* path, const DvbReadRequirements* req_in, int parse_hp, int threads, const char* const* contigs,
+                         const int64_t* starts, const int64_t* ends, int32_t n_regions, DvbBam** out) {
+  return OpenImpl(path, req_in, parse_hp, threads, contigs, starts, ends, n_regions, out);
 }
 
 int dvb_bam_table(const DvbBam* bam, DvbReadTable* t) {

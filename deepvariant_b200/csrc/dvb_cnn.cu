@@ -1408,50 +1408,50 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const bool even = (o & 1) == 0;
           const bool emit = even && o >= 2;
           if (emit) {
-            // horizontal 3-max over pixels 2 pw, 2 pw + 1, 2 pw + 2 through a shared-memory row (16-byte chunks XOR-swizzled, double-buffered
-            // by emit parity: ONE block barrier per pooled row); every thread then produces 16-byte pieces of the pooled row with all its
-            // shared loads issued before the first use, and the row leaves as fully coalesced 16-byte stores.
-            // (tried: neighbours by warp shuffles - 64 dependent shuffles per thread, 3000 clocks per pooled row against 2000 here)
+            // horizontal 3-max over pixels 2 pw, 2 pw + 1, 2 pw + 2 by the thread of pixel 2 pw: its two right-hand neighbours are
+            // lanes + 1 and + 2 (shuffles); lane 30's second neighbour is lane 0 of the NEXT warp, handed over through a 128-byte
+            // shared-memory slot (double-buffered by emit parity: one block barrier per pooled row)
             const int par = (o >> 1) & 1;
-            uint8_t* row_s = stage + par * (128 * 64);                                // cout = 64 -> 128 B per pixel, half of the stream's staging area
-            const int px_shift = p.cout == 64 ? 7 : 6, rp_log2 = p.cout == 64 ? 0 : 1, nch_log2 = p.cout == 64 ? 3 : 2;
-            const int my_sw = (w >> rp_log2) & (nch - 1);
+            uint32_t* exch = reinterpret_cast<uint32_t*>(stage) + (par * 4) * 32;     // [parity][warp quarter][32 words]
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              if (c < nch) {
-                uint32_t m[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const __half2 a = *reinterpret_cast<const __half2*>(&cur[4 * c + e]), b = *reinterpret_cast<const __half2*>(&hv[4 * c + e]);
-                  const __half2 r = __hmax2(a, b);
-                  m[e] = *reinterpret_cast<const uint32_t*>(&r);
-                }
-                if (w < p.Wout) *reinterpret_cast<uint4*>(row_s + (w << px_shift) + ((c ^ my_sw) << 4)) = make_uint4(m[0], m[1], m[2], m[3]);
+            for (int i = 0; i < 32; ++i) {
+              if (i < nh) {
+                const __half2 a = *reinterpret_cast<const __half2*>(&cur[i]), b = *reinterpret_cast<const __half2*>(&hv[i]);
+                const __half2 r = __hmax2(a, b);
+                cur[i] = *reinterpret_cast<const uint32_t*>(&r);      // cur = the finished vertical maximum of pixel w (re-opened from hv below)
               }
+            }
+            if (lane == 0 && q > 0) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4)
+                if (i < nh) *reinterpret_cast<uint4*>(exch + (q - 1) * 32 + i) = make_uint4(cur[i], cur[i + 1], cur[i + 2], cur[i + 3]);
             }
             named_bar_sync(bar_id, 128);
             const int ph = (o >> 1) - 1;
-            __half* dst = p.out + ((size_t)img * p.Hp + ph) * p.Wp * p.out_cstride + p.out_coff;
-            const int n_items = p.Wp << nch_log2;
-            uint4 v[4][3];
+            const int pw = w >> 1;
+            const bool writer = (lane & 1) == 0 && pw < p.Wp;
+            __half* dst = p.out + (((size_t)img * p.Hp + ph) * p.Wp + pw) * p.out_cstride + p.out_coff;
+            // (all 8 shuffles of a 16-byte group are issued before the first one is consumed: the first version consumed each shuffle
+            //  right away and ran 64 of them back to back at their full latency - 3000 clocks per pooled row in the timeline)
+            const bool edge = lane == 30;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int i = tid + u * 128;
-              if (i < n_items) {
-                const int px = i >> nch_log2, cv = i & (nch - 1);
+            for (int c = 0; c < 8; ++c) {
+              if (c < nch) {
+                uint4 nb = make_uint4(0u, 0u, 0u, 0u);                               // post-ReLU values are >= 0: zero is the identity
+                if (edge && q < 3) nb = *reinterpret_cast<const uint4*>(exch + q * 32 + 4 * c);
+                uint32_t v1[4], v2[4], mx[4];
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                  const int pw = 2 * px + dx;
-                  v[u][dx] = *reinterpret_cast<const uint4*>(row_s + (pw << px_shift) + ((cv ^ ((pw >> rp_log2) & (nch - 1))) << 4));
+                for (int e = 0; e < 4; ++e) v1[e] = __shfl_down_sync(0xffffffffu, cur[4 * c + e], 1);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v2[e] = __shfl_down_sync(0xffffffffu, cur[4 * c + e], 2);
+                if (edge) { v2[0] = nb.x; v2[1] = nb.y; v2[2] = nb.z; v2[3] = nb.w; }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&cur[4 * c + e]),
+                                            __hmax2(*reinterpret_cast<const __half2*>(&v1[e]), *reinterpret_cast<const __half2*>(&v2[e])));
+                  mx[e] = *reinterpret_cast<const uint32_t*>(&r);
                 }
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int i = tid + u * 128;
-              if (i < n_items) {
-                const int px = i >> nch_log2, cv = i & (nch - 1);
-                *reinterpret_cast<uint4*>(dst + (size_t)px * p.out_cstride + cv * 8) = hmax2x4(v[u][0], hmax2x4(v[u][1], v[u][2]));
+                if (writer) *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(mx[0], mx[1], mx[2], mx[3]);
               }
             }
           }

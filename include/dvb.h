@@ -279,6 +279,13 @@ typedef struct DvbBam DvbBam;
 void dvb_read_requirements_default(DvbReadRequirements* r);
 /* req may be NULL (defaults).  parse_hp != 0 extracts the HP aux tag.  threads <= 0: hardware concurrency. */
 int dvb_bam_open(const char* path, const DvbReadRequirements* req, int parse_hp, int threads, DvbBam** out);
+/* The same, restricted to the reads that overlap one of n_regions half-open [start, end) intervals (ReadOverlapsRegion,
+ * third_party/nucleus/util/utils.cc:172-188) - what sam_reader.cc:Query returns for make_examples --regions.  When all intervals lie on
+ * one contig and `path`.bai (or path with .bai for .bam) exists, decoding starts at the block the linear index gives for the first
+ * interval and stops at the first read behind the last one (coordinate-sorted file); otherwise the file is scanned and filtered.
+ * The file is read, inflated and parsed in 32-MB rounds either way (bounded memory besides the table itself). */
+int dvb_bam_open_regions(const char* path, const DvbReadRequirements* req, int parse_hp, int threads, const char* const* contigs,
+                         const int64_t* starts, const int64_t* ends, int32_t n_regions, DvbBam** out);
 int dvb_bam_table(const DvbBam* bam, DvbReadTable* table);
 const char* dvb_bam_ref_name(const DvbBam* bam, int32_t i);   /* NULL when out of range */
 void dvb_bam_close(DvbBam* bam);

@@ -366,3 +366,68 @@ def test_make_examples_cli_from_bam_file_cpu_plumbing(tmp_path, monkeypatch):
 
   monkeypatch.setattr(men.ExamplesGenerator, '_gpu', lambda self: OracleEncoder(pi.to_params(self.options.pic_options, height=self.pileup_image_height)))
   _cli_from_bam_file_matches_oracle(tmp_path)
+
+
+def _assert_same_rows(sub, full, keep):
+  import numpy as np
+  assert sub.n_reads == int(keep.sum())
+  for name in ('ref_id', 'pos', 'end', 'mapq', 'flag', 'fragment_length', 'read_number'):
+    np.testing.assert_array_equal(getattr(sub, name), getattr(full, name)[keep], err_msg=name)
+  idx = np.nonzero(keep)[0]
+  for k in (0, len(idx) // 2, len(idx) - 1):
+    if len(idx):
+      assert sub.read(k).key() == full.read(int(idx[k])).key() and sub.read(k).aligned_sequence == full.read(int(idx[k])).aligned_sequence
+
+
+def test_region_restricted_open_equals_the_filtered_full_table(tmp_path):
+  """dvb_bam_open_regions: (a) an un-indexed synthetic file (scan + filter, several regions on two contigs, a contig the file does not
+  know), (b) the reference's indexed chr20 test BAM through its .bai linear index (one region: decoding starts at the indexed block and
+  stops behind the region) - both against the full table filtered with ReadOverlapsRegion; sorted-table region queries (two binary
+  searches) against the scan."""
+  import numpy as np
+  from deepvariant_b200 import bam
+  rng = np.random.default_rng(3)
+  recs = []
+  for ref, n in ((0, 900), (1, 400)):
+    for pos in np.sort(rng.integers(0, 20000, n)).tolist():
+      L = int(rng.integers(30, 151))
+      recs.append(_record(ref, pos, f'r{len(recs)}', 60, 0, [(0, L)], ''.join(rng.choice(list('ACGT'), L)), rng.integers(5, 41, L).tolist()))
+  path = str(tmp_path / 'two.bam')
+  open(path, 'wb').write(_bam(recs, refs=(('chr1', 30000), ('chr2', 30000))))
+  reqs = bam.ReadRequirements(min_mapping_quality=5)
+  full = bam.NativeBamTable(path, reqs)
+  regions = [('chr1', 1000, 1500), ('chr2', 300, 320), ('chr1', 15000, 15010), ('chrUn', 0, 100)]
+  keep = np.zeros(full.n_reads, dtype=bool)
+  for c, s, e in regions[:3]:
+    rid = full.references.index(c)
+    keep |= (full.ref_id == rid) & (full.pos < e) & (full.end > s)
+  _assert_same_rows(bam.NativeBamTable(path, reqs, regions=regions), full, keep)
+  assert bam.NativeBamTable(path, reqs, regions=[('chrUn', 0, 100)]).n_reads == 0
+  for c, s, e in (('chr1', 0, 1), ('chr1', 1000, 1500), ('chr2', 19990, 30000), ('chr2', 5000, 5001), ('chr1', 29999, 30000)):
+    rid = full.references.index(c)
+    np.testing.assert_array_equal(full.query_indices(c, s, e), np.nonzero((full.ref_id == rid) & (full.pos < e) & (full.end > s))[0])
+  real = '/root/reference/deepvariant/testdata/input/NA12878_S1.chr20.10_10p1mb.bam'
+  if os.path.exists(real) and os.path.exists(real + '.bai'):
+    full = bam.NativeBamTable(real, reqs)
+    for s, e in ((10_000_000, 10_010_000), (10_050_123, 10_050_124), (10_099_000, 10_100_000), (9_000_000, 9_500_000)):
+      rid = full.references.index('chr20')
+      keep = (full.ref_id == rid) & (full.pos < e) & (full.end > s)
+      sub = bam.NativeBamTable(real, reqs, regions=[('chr20', s, e)])
+      _assert_same_rows(sub, full, keep)
+      if keep.any() and s > 10_020_000:
+        assert sub.n_records_seen < full.n_records_seen // 2, 'the index was not used: the whole file was parsed'
+
+
+def test_malformed_bgzf_headers_are_rejected_not_overrun(tmp_path):
+  """BSIZE smaller than header + trailer (the subtraction would wrap), an extra field running past the block, a missing BC subfield."""
+  from deepvariant_b200 import _lib, bam
+  good = _bam([_record(0, 5, 'a', 60, 0, [(0, 10)], 'ACGTACGTAC', [30] * 10)])
+  for name, blob in (
+      ('tiny_bsize', good[:16] + (5).to_bytes(2, 'little') + good[18:]),
+      ('xlen_overrun', good[:10] + (60000).to_bytes(2, 'little') + good[12:]),
+      ('no_bc', good[:12] + b'XY' + good[14:]),
+  ):
+    p = tmp_path / f'{name}.bam'
+    p.write_bytes(blob)
+    with pytest.raises(_lib.DvbError):
+      bam.NativeBamTable(str(p))
