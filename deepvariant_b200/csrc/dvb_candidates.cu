@@ -686,21 +686,36 @@ dvb_allele_count_tile_kernel(DeviceTable t, const int32_t* __restrict__ read_end
   const int2 range = ranges[blockIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t abs_lo = p.start + tile_lo;
-  for (int ri = range.x + warp; ri < range.y; ri += kAlleleTileThreads / 32) {
-    const int64_t row = rows[ri];
-    if (t.mapq[row] < min_mapping_quality) continue;
-    if ((int64_t)read_end[row] <= abs_lo && (int64_t)t.pos[row] < abs_lo) continue;     // ends before the tile (a zero-span read is kept: its clip is anchored at pos - 1)
-    const int64_t s0 = t.seq_begin[row];
+  // Reads are taken 32 at a time per warp: every lane fetches the header of one read (row -> mapping quality, position, end, sequence
+  // and CIGAR offsets: two dependent levels of global loads, 32 reads in flight), then the warp walks the 32 reads one after the other
+  // with the header fields broadcast by shuffle - the header latency is paid once per 32 reads instead of once per read.
+  constexpr int kWarps = kAlleleTileThreads / 32;
+  for (int rb = range.x + warp * 32; rb < range.y; rb += kWarps * 32) {
+    const int my = rb + lane;
+    long long h_row = -1, h_s0 = 0, h_s1 = 0, h_c0 = 0, h_c1 = 0;
+    int h_pos = 0, h_ok = 0;
+    if (my < range.y) {
+      h_row = rows[my];
+      h_pos = t.pos[h_row];
+      h_ok = t.mapq[h_row] >= min_mapping_quality && !((int64_t)read_end[h_row] <= abs_lo && (int64_t)h_pos < abs_lo);   // ends before the tile (a zero-span read is kept: its clip is anchored at pos - 1)
+      if (h_ok) { h_s0 = t.seq_begin[h_row]; h_s1 = t.seq_begin[h_row + 1]; h_c0 = t.cigar_begin[h_row]; h_c1 = t.cigar_begin[h_row + 1]; }
+    }
+    const unsigned ok_mask = __ballot_sync(0xffffffffu, h_ok);
+    for (unsigned rest = ok_mask; rest; rest &= rest - 1) {
+    const int src = __ffs(rest) - 1;
+    const int64_t s0 = __shfl_sync(0xffffffffu, h_s0, src);
+    const int seq_len = (int)(__shfl_sync(0xffffffffu, h_s1, src) - s0);
+    const int64_t c0g = __shfl_sync(0xffffffffu, h_c0, src);
+    const int n_cigar = (int)(__shfl_sync(0xffffffffu, h_c1, src) - c0g);
+    const int read_pos = __shfl_sync(0xffffffffu, h_pos, src);
     const uint8_t* seq = t.bases + s0;
     const uint8_t* qual = t.quals + s0;
-    const int seq_len = (int)(t.seq_begin[row + 1] - s0);
     if (seq_len == 0) continue;
-    const uint32_t* cigar = t.cigar + t.cigar_begin[row];
-    const int n_cigar = (int)(t.cigar_begin[row + 1] - t.cigar_begin[row]);
+    const uint32_t* cigar = t.cigar + c0g;
     bool have = false;
     PendingElement pending{-1, 0, 0, 0};
     int read_offset = 0;
-    int64_t interval_offset = (int64_t)t.pos[row] - p.start;
+    int64_t interval_offset = (int64_t)read_pos - p.start;
     auto usable = [&](int base_offset, bool* low_quality) {        // CanBasesBeUsed(offset, 1)
       const int q = qual[base_offset];
       if (q < p.min_base_quality && p.keep_legacy_behavior) return false;
@@ -823,6 +838,7 @@ dvb_allele_count_tile_kernel(DeviceTable t, const int32_t* __restrict__ read_end
       }
     }
     if (have && lane == 0) TileCommit(sm, tile_lo, tile_n, pending, seq);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < tile_n; i += kAlleleTileThreads) {
