@@ -75,8 +75,28 @@ class DvbBatch(C.Structure):
       ('bases', C.c_void_p),
       ('quals', C.c_void_p),
       ('cigar', C.c_void_p),
+      ('allele_begin', C.c_void_p),
+      ('allele_type', C.c_void_p),
+      ('allele_class', C.c_void_p),
+      ('allele_group', C.c_void_p),
+      ('allele_bases_begin', C.c_void_p),
+      ('allele_bases', C.c_void_p),
+      ('image_ref_run', C.c_void_p),
+      ('image_group_default', C.c_void_p),
+      ('n_alleles', C.c_int64),
+      ('n_allele_bases', C.c_int64),
+      ('support_min_mapping_quality', C.c_int32),
+      ('support_min_base_quality', C.c_int32),
+      ('support_flags', C.c_int32),
   ]
 
+
+# Optional members (device-side pair support): absent from PackedBatch.arrays = NULL.
+ALLELE_ARRAYS = (
+    ('allele_begin', 'int64'), ('allele_type', 'uint8'), ('allele_class', 'uint8'), ('allele_group', 'uint8'),
+    ('allele_bases_begin', 'int64'), ('allele_bases', 'uint8'), ('image_ref_run', 'int32'), ('image_group_default', 'uint8'),
+)
+SUPPORT_KEEP_LEGACY, SUPPORT_TRACK_REF_READS, SUPPORT_REPEATED_KEYS = 1, 2, 4
 
 # name -> (dtype string, per-what) for every array member of DvbBatch, in struct order.
 BATCH_ARRAYS = (
@@ -205,6 +225,9 @@ SYMBOLS = (
                                                     C.POINTER(DvbCandidateOptions), C.c_int, C.c_void_p, C.c_void_p]),
     ('dvb_debug_allele_counts', C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                             C.POINTER(DvbCandidateOptions), C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
+    ('dvb_debug_read_allele_at', C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+                                           C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    ('dvb_encoder_last_pair_support', C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     ('dvb_ssw_align', C.c_int, [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                 C.POINTER(DvbSswAlignment), C.c_char_p, C.c_int64]),
     ('dvb_ssw_align_batch', C.c_int, [C.POINTER(C.c_char_p), C.c_void_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
@@ -242,7 +265,7 @@ def lib() -> C.CDLL:
       fn = getattr(l, name)  # AttributeError if the .so does not export a declared symbol
       fn.restype = restype
       fn.argtypes = argtypes
-    if l.dvb_abi_version() != 2:
+    if l.dvb_abi_version() != 3:
       raise RuntimeError('libdvb.so ABI version mismatch')
     _lib = l
   return _lib

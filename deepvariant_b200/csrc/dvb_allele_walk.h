@@ -170,6 +170,87 @@ DVB_HD void WalkRead(const ReadView& r, const WalkParams& p, Sink& sink) {
   if (have && pending.position >= 0 && pending.position < len) sink.Commit(pending);
 }
 
+// ---- the read allele of ONE position (the (candidate, read) support kernel) ------------------------------------------------------
+// What AlleleCount.read_alleles of position `target` holds for this read once WalkRead has run: elements come in non-decreasing
+// position order, only an element followed by one of a different position is committed, and a later commit of the same read at
+// the same site replaces the earlier one - so the entry is the LAST generated element whose position is `target`.  This walk visits
+// the CIGAR only (O(n_cigar)), looks at the one base that can land on `target` and at the indel operations anchored on it, and
+// needs three facts about the reference instead of the contig: the base at `target`, and how many canonical in-contig bases follow
+// it (`ref_run`: a deletion of op_len bases anchored here is usable iff op_len <= ref_run; allelecounter.cc:449-456).
+// tests/test_pair_support.py checks it against WalkRead on random reads (host instantiation, whole contig resident).
+struct TargetParams {
+  int64_t target;            // absolute position
+  uint8_t ref_base;          // contig[target], upper case
+  int ref_run;               // canonical bases in [target + 1, contig end) before the first non-canonical one (capped by the caller)
+  int min_base_quality;
+  int keep_legacy_behavior;
+};
+
+struct TargetElement {
+  uint8_t type, low_quality, prev;
+  int read_offset, len;
+};
+
+DVB_HD bool BasesUsable(const ReadView& r, int min_base_quality, int keep_legacy, int offset, int len, bool* low_quality) {
+  int sum = 0;
+  for (int i = 0; i < len; ++i) {
+    const int q = r.qual[offset + i];
+    sum += q;
+    if (q < min_base_quality && keep_legacy) return false;
+    if (!Canonical(r.seq[offset + i])) return false;
+  }
+  *low_quality = !keep_legacy && sum < min_base_quality * len;
+  return true;
+}
+
+DVB_HD bool ElementAt(const ReadView& r, const TargetParams& p, TargetElement* out) {
+  if (r.seq_len == 0) return false;
+  bool found = false;
+  int read_offset = 0;
+  int64_t ref_pos = r.pos;                              // absolute position the next reference-consuming operation starts at
+  for (int c = 0; c < r.n_cigar; ++c) {
+    if (ref_pos - 1 > p.target) break;                  // every later element lies right of the target
+    const int op = (int)(r.cigar[c] & 0xF), op_len = (int)(r.cigar[c] >> 4);
+    if (op == 0 || op == 7 || op == 8) {
+      const int64_t i = p.target - ref_pos;
+      if (i >= 0 && i < op_len && read_offset + i < r.seq_len) {
+        const int base_offset = read_offset + (int)i;
+        bool low_quality = false;
+        if (BasesUsable(r, p.min_base_quality, p.keep_legacy_behavior, base_offset, 1, &low_quality)) {
+          out->type = r.seq[base_offset] == p.ref_base ? kReference : kSubstitution;
+          out->low_quality = low_quality;
+          out->prev = 0;
+          out->read_offset = base_offset;
+          out->len = 0;
+          found = true;
+        }
+      }
+      read_offset += op_len;
+      ref_pos += op_len;
+    } else if (op == 4 || op == 1 || op == 2) {
+      if (ref_pos - 1 == p.target) {
+        // MakeIndelReadAllele: the anchor is the previous read base, or the reference base when the read starts here
+        const uint8_t prev = read_offset == 0 ? p.ref_base : r.seq[read_offset - 1];
+        bool ok = Canonical(prev), low_quality = false;
+        if (ok && op != 2) ok = read_offset + op_len <= r.seq_len && BasesUsable(r, p.min_base_quality, p.keep_legacy_behavior, read_offset, op_len, &low_quality);
+        if (ok && op == 2) ok = op_len <= p.ref_run;
+        if (ok) {
+          out->type = op == 2 ? kDeletion : op == 1 ? kInsertion : kSoftClip;
+          out->low_quality = low_quality;
+          out->prev = prev;
+          out->read_offset = read_offset;
+          out->len = op_len;
+          found = true;
+        }
+      }
+      if (op == 2) ref_pos += op_len; else read_offset += op_len;
+    } else if (op == 6 || op == 3) {
+      ref_pos += op_len;
+    }
+  }
+  return found;
+}
+
 // ---- dense per-position counters (the CUDA allele-count pass; also instantiated on the host for the tests) ---------------------
 // What SumAlleleCounts / TotalAlleleCounts (allelecounter.cc:78-169) need for substitutions, without read identities:
 //   ref_count[p]      AlleleCount.ref_supporting_read_count

@@ -514,6 +514,44 @@ int64_t dvb_debug_allele_counts(const DvbBam* bam, const uint8_t* contig_bases, 
   return (int64_t)js.size();
 }
 
+// Test access to dvb_allele::ElementAt (the (candidate, read) support walk of the encoder's pre-pass): the read allele of one
+// read at `target` found (a) by the full WalkRead over [start, end) with the whole contig resident - the last commit at that
+// position, which is what the read's map entry ends up holding - and (b) by ElementAt from the three reference facts.
+// each out: {found, type, low_quality, prev, read_offset, len}.
+int dvb_debug_read_allele_at(const uint8_t* seq, const uint8_t* qual, int32_t seq_len, const uint32_t* cigar, int32_t n_cigar, int64_t pos,
+                             const uint8_t* contig, int64_t contig_len, int64_t start, int64_t end, int64_t target, int32_t min_base_quality,
+                             int32_t keep_legacy, int32_t* walk_out, int32_t* at_out) {
+  if (!seq || !qual || !cigar || !contig || !walk_out || !at_out || target < start || target >= end || start < 0 || end > contig_len)
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_debug_read_allele_at: bad arguments");
+  dvb_allele::ReadView r{seq, qual, seq_len, cigar, n_cigar, pos};
+  dvb_allele::WalkParams wp;
+  wp.start = start; wp.end = end; wp.contig = contig; wp.contig_origin = 0; wp.contig_avail = contig_len; wp.contig_len = contig_len;
+  wp.min_base_quality = min_base_quality; wp.keep_legacy_behavior = keep_legacy;
+  struct LastAt {
+    int want;
+    int32_t* o;
+    void Commit(const Element& e) {
+      if (e.position != want) return;
+      o[0] = 1; o[1] = e.type; o[2] = e.low_quality; o[3] = e.len ? e.prev : 0; o[4] = e.read_offset; o[5] = e.len;
+    }
+  } sink{(int)(target - start), walk_out};
+  for (int k = 0; k < 6; ++k) walk_out[k] = at_out[k] = 0;
+  dvb_allele::WalkRead(r, wp, sink);
+  dvb_allele::TargetParams tp;
+  tp.target = target;
+  tp.ref_base = contig[target];
+  int64_t run = 0;
+  while (target + 1 + run < contig_len && Canonical(contig[target + 1 + run])) ++run;
+  tp.ref_run = (int)std::min<int64_t>(run, 0x7fffffff);
+  tp.min_base_quality = min_base_quality;
+  tp.keep_legacy_behavior = keep_legacy;
+  dvb_allele::TargetElement e;
+  if (dvb_allele::ElementAt(r, tp, &e)) {
+    at_out[0] = 1; at_out[1] = e.type; at_out[2] = e.low_quality; at_out[3] = e.len ? e.prev : 0; at_out[4] = e.read_offset; at_out[5] = e.len;
+  }
+  return DVB_OK;
+}
+
 int64_t dvb_candidates_count(const DvbCandidates* c) { return c ? (int64_t)c->position.size() : 0; }
 
 int dvb_candidates_protos(const DvbCandidates* c, const uint8_t** data, const int64_t** begin) {

@@ -29,6 +29,7 @@
 #include <string>
 #include <vector>
 
+#include "dvb_allele_walk.h"
 #include "dvb_common.h"
 
 namespace dvb {
@@ -267,7 +268,51 @@ struct __align__(16) PairRec {
 };
 static_assert(sizeof(PairRec) == 64, "PairRec is one 64-byte line");
 
-__global__ void __launch_bounds__(128) dvb_pair_prepass_kernel(const EncDev P, const DvbBatch B, PairRec* __restrict__ recs, int* __restrict__ err) {
+// ---- (candidate, read) support on the device ---------------------------------------------------------------------------------
+// The read allele AlleleCounter::Add records for read `h` at the image's variant_start (dvb_allele::ElementAt), matched against the
+// image's alt-allele keys.  Returns bit 7 = the read holds an entry in AlleleCount.read_alleles at that site, bits 0-1 = the
+// ReadSupportsAlt class of that entry; *group = the matched alt's index.
+constexpr unsigned kSupportHasEntry = 0x80u;
+
+__device__ __forceinline__ unsigned pair_read_allele(const DvbBatch& B, const ReadHdr& h, int img, int vstart, uint8_t ref_base, int ref_run,
+                                                     long long a0, int n_alleles, uint8_t* group) {
+  if (h.mapq < B.support_min_mapping_quality) return 0u;             // AlleleCounter::Add's first test
+  dvb_allele::ReadView r;
+  r.seq = B.bases + h.seq0; r.qual = B.quals + h.seq0; r.seq_len = h.len;
+  r.cigar = B.cigar + h.cig0; r.n_cigar = h.n_cig; r.pos = h.pos;
+  dvb_allele::TargetParams tp;
+  tp.target = vstart; tp.ref_base = ref_base; tp.ref_run = ref_run;
+  tp.min_base_quality = B.support_min_base_quality;
+  tp.keep_legacy_behavior = (B.support_flags & DVB_SUPPORT_KEEP_LEGACY) ? 1 : 0;
+  dvb_allele::TargetElement e;
+  if (!dvb_allele::ElementAt(r, tp, &e)) return 0u;
+  if (e.type == dvb_allele::kReference) return (B.support_flags & DVB_SUPPORT_TRACK_REF_READS) ? kSupportHasEntry : 0u;
+  if (e.type == dvb_allele::kSoftClip) return kSupportHasEntry;       // never an alt allele (IsGoodAltAlleleWithReason)
+  const int key_len = e.len + 1;
+  for (int a = 0; a < n_alleles; ++a) {
+    if (B.allele_type[a0 + a] != e.type) continue;
+    const long long b0 = B.allele_bases_begin[a0 + a];
+    if ((int)(B.allele_bases_begin[a0 + a + 1] - b0) != key_len) continue;
+    const uint8_t* key = B.allele_bases + b0;
+    bool same;
+    if (e.type == dvb_allele::kSubstitution) {
+      same = key[0] == r.seq[e.read_offset];
+    } else {
+      same = key[0] == e.prev;
+      if (e.type == dvb_allele::kInsertion)                           // deleted bases are the reference's: equal lengths, equal bases
+        for (int k = 0; same && k < e.len; ++k) same = key[1 + k] == r.seq[e.read_offset + k];
+    }
+    if (same) {
+      if (B.allele_group) *group = B.allele_group[a0 + a];
+      return kSupportHasEntry | B.allele_class[a0 + a];
+    }
+  }
+  return kSupportHasEntry;                                            // "UNCALLED_ALLELE"
+}
+
+// sup (when the batch carries allele keys): uint8[4][n_pairs] = raw class byte, raw group, final class, final group.
+__global__ void __launch_bounds__(128) dvb_pair_prepass_kernel(const EncDev P, const DvbBatch B, PairRec* __restrict__ recs, int* __restrict__ err,
+                                                                uint8_t* __restrict__ sup) {
   const int lane = threadIdx.x & 31;
   const int img = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (img >= B.n_images) return;
@@ -275,6 +320,25 @@ __global__ void __launch_bounds__(128) dvb_pair_prepass_kernel(const EncDev P, c
   const int vstart = B.variant_start[img];
   const long long p0 = B.pair_begin[img];
   const int n = (int)(B.pair_begin[img + 1] - p0);
+  const bool derive = B.allele_begin != nullptr;
+  const bool repeated = derive && (B.support_flags & DVB_SUPPORT_REPEATED_KEYS);
+  const uint8_t group_default = derive && B.image_group_default ? B.image_group_default[img] : (uint8_t)0;
+  if (derive) {
+    const long long a0 = B.allele_begin[img];
+    const int n_alleles = (int)(B.allele_begin[img + 1] - a0);
+    const int off = vstart - image_start;
+    const uint8_t ref_base = (off >= 0 && off < P.W) ? B.ref_bases[(size_t)img * B.ref_stride + off] : (uint8_t)0;
+    const int ref_run = B.image_ref_run[img];
+    for (int i = lane; i < n; i += 32) {
+      const long long p = p0 + i;
+      const ReadHdr h = load_read(B, B.pair_read[p]);
+      uint8_t g = group_default;
+      const unsigned raw = pair_read_allele(B, h, img, vstart, ref_base, ref_run, a0, n_alleles, &g);
+      sup[p] = (uint8_t)raw;
+      sup[B.n_pairs + p] = g;
+    }
+    __syncwarp();
+  }
   for (int i = lane; i < n; i += 32) {
     const long long p = p0 + i;
     const int r = B.pair_read[p];
@@ -284,13 +348,33 @@ __global__ void __launch_bounds__(128) dvb_pair_prepass_kernel(const EncDev P, c
     PairRec rec;
     rec.seq0 = h.seq0; rec.cig0 = h.cig0; rec.pos = h.pos; rec.n_cig = h.n_cig;
     rec.tc[0] = rec.tc[1] = rec.tc[2] = rec.tc[3] = 0u;
-    const int support = B.pair_support[p];
+    int support;
+    uint8_t grp;
+    if (derive) {
+      // AlleleCount.read_alleles is a map keyed by (fragment_name, read_number): of the image's reads that share this one's key,
+      // the last one that holds an entry decides for all of them
+      long long q = p;
+      if (repeated) {
+        const unsigned rank = B.read_name_rank[r];
+        q = -1;
+        for (int k = n - 1; k >= 0; --k)
+          if ((sup[p0 + k] & kSupportHasEntry) && B.read_name_rank[B.pair_read[p0 + k]] == rank) { q = p0 + k; break; }
+      }
+      support = q >= 0 ? (int)(sup[q] & 3u) : 0;
+      grp = q >= 0 ? sup[B.n_pairs + q] : group_default;
+      if (q >= 0 && !(sup[q] & kSupportHasEntry)) grp = group_default;
+      sup[2 * B.n_pairs + p] = (uint8_t)support;
+      sup[3 * B.n_pairs + p] = grp;
+    } else {
+      support = B.pair_support[p];
+      grp = B.pair_allele_group ? B.pair_allele_group[p] : (uint8_t)0;
+    }
     for (int c = 0; c < P.C; ++c)
       if (P.kind[c] == K_CONST) rec.tc[c >> 2] |= (unsigned)read_const(P, B, P.chan[c], h, support) << (8 * (c & 3));
     rec.sort_pos = B.read_sort_pos[r];
     rec.rank = B.read_name_rank[r];
     rec.hap = hap_index(P, h.flags, h.hp);
-    rec.grp = (P.sort_by_group && B.pair_allele_group) ? B.pair_allele_group[p] : (uint8_t)0;
+    rec.grp = P.sort_by_group ? grp : (uint8_t)0;
     rec.ok = (uint8_t)ok; rec.pad0 = rec.pad1 = 0; rec.len = h.len; rec.pad3 = 0;
     uint4* dst = reinterpret_cast<uint4*>(recs + p);
     const uint4* srcv = reinterpret_cast<const uint4*>(&rec);
@@ -652,8 +736,9 @@ struct DvbEncoder {
   // staging for the host entry point
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> copy_events;
-  dvb::DevBuf d_in, d_out, d_rows, d_recs;
+  dvb::DevBuf d_in, d_out, d_rows, d_recs, d_support;
   bool prepass = true;
+  int64_t last_support_pairs = -1;   // pairs of the last batch whose support was derived on the device
   dvb::PinBuf h_in, h_out;
   cudaStream_t stream = nullptr;
 };
@@ -760,10 +845,19 @@ int Launch(DvbEncoder* enc, const DvbBatch& b, uint8_t* out, int32_t* rows_kept,
   if (b.n_images <= 0) return DVB_OK;
   int grid = std::min(b.n_images, enc->grid_cap);
   PairRec* recs = nullptr;
-  if (enc->prepass && b.n_pairs > 0) {
+  const bool derive = b.allele_begin != nullptr;     // pair_support comes from the allele keys: the pre-pass is where it is derived
+  if ((enc->prepass || derive) && b.n_pairs > 0) {
     DVB_CUDA(enc->d_recs.reserve((size_t)b.n_pairs * sizeof(PairRec)));
     recs = static_cast<PairRec*>(enc->d_recs.p);
-    dvb_pair_prepass_kernel<<<(b.n_images + 3) / 4, 128, 0, stream>>>(enc->dev, b, recs, enc->d_err);
+    uint8_t* sup = nullptr;
+    if (derive) {
+      if (!b.allele_bases_begin || !b.image_ref_run || (b.n_alleles > 0 && (!b.allele_type || !b.allele_class || !b.allele_bases)))
+        return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "allele_begin without the other allele arrays");
+      DVB_CUDA(enc->d_support.reserve((size_t)b.n_pairs * 4));
+      sup = static_cast<uint8_t*>(enc->d_support.p);
+      enc->last_support_pairs = b.n_pairs;
+    }
+    dvb_pair_prepass_kernel<<<(b.n_images + 3) / 4, 128, 0, stream>>>(enc->dev, b, recs, enc->d_err, sup);
     enc->launches++;
   }
   if (enc->fast7)
@@ -830,14 +924,27 @@ int StageHostBatch(DvbEncoder* enc, const DvbBatch* hb, DvbBatch* out_db, cudaSt
                        (long long)consumed, (long long)(hb->read_seq_begin[r + 1] - hb->read_seq_begin[r]));
   }
   // ---- pack every input array into one pinned staging block, one H2D copy ----
-  enum Domain { D_IMAGE, D_IMAGE1, D_PAIR, D_READ, D_READ1, D_BASE, D_CIGAR };
+  enum Domain { D_IMAGE, D_IMAGE1, D_PAIR, D_READ, D_READ1, D_BASE, D_CIGAR, D_ALLELE, D_ALLELE1, D_ABASE };
   struct Seg { const void* src; size_t bytes; size_t off; int domain; size_t esz; bool pinned; };
-  Seg segs[19];
+  constexpr int kSegs = 27;
+  Seg segs[kSegs];
   int ns = 0;
   size_t total = 0;
-  const Domain kDomains[19] = {D_IMAGE, D_IMAGE, D_IMAGE, D_IMAGE1, D_PAIR, D_PAIR, D_PAIR, D_READ, D_READ, D_READ, D_READ, D_READ, D_READ, D_READ,
-                               D_READ1, D_READ1, D_BASE, D_BASE, D_CIGAR};
-  const size_t kElem[19] = {(size_t)hb->ref_stride, 4, 4, 8, 4, 1, 1, 4, 4, 4, 1, 4, 4, 4, 8, 8, 1, 1, 4};
+  const Domain kDomains[kSegs] = {D_IMAGE, D_IMAGE, D_IMAGE, D_IMAGE1, D_PAIR, D_PAIR, D_PAIR, D_READ, D_READ, D_READ, D_READ, D_READ, D_READ, D_READ,
+                                  D_READ1, D_READ1, D_BASE, D_BASE, D_CIGAR, D_IMAGE1, D_IMAGE, D_IMAGE, D_ALLELE, D_ALLELE, D_ALLELE, D_ALLELE1, D_ABASE};
+  const size_t kElem[kSegs] = {(size_t)hb->ref_stride, 4, 4, 8, 4, 1, 1, 4, 4, 4, 1, 4, 4, 4, 8, 8, 1, 1, 4, 8, 4, 1, 1, 1, 1, 8, 1};
+  const bool derive = hb->allele_begin != nullptr;
+  const int64_t NA = derive ? hb->n_alleles : 0, NAB = derive ? hb->n_allele_bases : 0;
+  if (derive) {
+    if (!hb->allele_bases_begin || !hb->image_ref_run || (NA > 0 && (!hb->allele_type || !hb->allele_class)) || (NAB > 0 && !hb->allele_bases))
+      return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "allele_begin without the other allele arrays");
+    if (hb->allele_begin[0] != 0 || hb->allele_begin[NI] != NA || hb->allele_bases_begin[0] != 0 || hb->allele_bases_begin[NA] != NAB)
+      return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "allele_begin / allele_bases_begin are not CSR arrays over n_alleles / n_allele_bases");
+    for (int64_t i = 0; i < NI; ++i)
+      if (hb->allele_begin[i + 1] < hb->allele_begin[i]) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "allele_begin not monotone");
+    for (int64_t a = 0; a < NA; ++a)
+      if (hb->allele_bases_begin[a + 1] <= hb->allele_bases_begin[a]) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "empty or negative allele key");
+  }
   auto add = [&](const void* p, size_t bytes) {
     segs[ns].src = p; segs[ns].bytes = p ? bytes : 0; segs[ns].off = total;
     segs[ns].domain = kDomains[ns]; segs[ns].esz = kElem[ns]; segs[ns].pinned = false;
@@ -863,6 +970,14 @@ int StageHostBatch(DvbEncoder* enc, const DvbBatch* hb, DvbBatch* out_db, cudaSt
   const int i_ba = add(hb->bases, NB);
   const int i_qu = add(hb->quals, NB);
   const int i_ci = add(hb->cigar, NC * 4);
+  const int i_ab = add(derive ? hb->allele_begin : nullptr, (NI + 1) * 8);
+  const int i_irr = add(derive ? hb->image_ref_run : nullptr, NI * 4);
+  const int i_igd = add(derive ? hb->image_group_default : nullptr, NI);
+  const int i_at = add(derive ? hb->allele_type : nullptr, NA);
+  const int i_ac = add(derive ? hb->allele_class : nullptr, NA);
+  const int i_ag = add(derive ? hb->allele_group : nullptr, NA);
+  const int i_abb = add(derive ? hb->allele_bases_begin : nullptr, (NA + 1) * 8);
+  const int i_aba = add(derive ? hb->allele_bases : nullptr, NAB);
   total = std::max<size_t>(total, 256);
   DVB_CUDA(enc->h_in.reserve(total));
   DVB_CUDA(enc->d_in.reserve(total));
@@ -887,6 +1002,9 @@ int StageHostBatch(DvbEncoder* enc, const DvbBatch* hb, DvbBatch* out_db, cudaSt
           case D_READ1: lo = ph.r0 + (ph.r0 > 0 ? 1 : 0); hi = ph.r1 > ph.r0 ? ph.r1 + 1 : lo; break;   // element r0 came with the previous phase
           case D_BASE: lo = hb->read_seq_begin[ph.r0]; hi = hb->read_seq_begin[ph.r1]; break;
           case D_CIGAR: lo = hb->read_cigar_begin[ph.r0]; hi = hb->read_cigar_begin[ph.r1]; break;
+          case D_ALLELE: lo = hb->allele_begin[ph.i0]; hi = hb->allele_begin[ph.i1]; break;
+          case D_ALLELE1: lo = hb->allele_begin[ph.i0] + (ph.i0 > 0 ? 1 : 0); hi = hb->allele_begin[ph.i1] + 1; break;
+          case D_ABASE: lo = hb->allele_bases_begin[hb->allele_begin[ph.i0]]; hi = hb->allele_bases_begin[hb->allele_begin[ph.i1]]; break;
         }
         if (hi <= lo) continue;
         const size_t b0 = (size_t)lo * segs[i].esz, nb = (size_t)(hi - lo) * segs[i].esz;
@@ -944,6 +1062,13 @@ int StageHostBatch(DvbEncoder* enc, const DvbBatch* hb, DvbBatch* out_db, cudaSt
   db.read_name_rank = (const uint32_t*)dp(i_rnr); db.read_seq_begin = (const int64_t*)dp(i_rsb);
   db.read_cigar_begin = (const int64_t*)dp(i_rcb); db.bases = (const uint8_t*)dp(i_ba);
   db.quals = (const uint8_t*)dp(i_qu); db.cigar = (const uint32_t*)dp(i_ci);
+  if (derive) {
+    db.allele_begin = (const int64_t*)dp(i_ab); db.image_ref_run = (const int32_t*)dp(i_irr);
+    db.image_group_default = hb->image_group_default ? (const uint8_t*)dp(i_igd) : nullptr;
+    db.allele_type = (const uint8_t*)dp(i_at); db.allele_class = (const uint8_t*)dp(i_ac);
+    db.allele_group = hb->allele_group ? (const uint8_t*)dp(i_ag) : nullptr;
+    db.allele_bases_begin = (const int64_t*)dp(i_abb); db.allele_bases = (const uint8_t*)dp(i_aba);
+  }
 
   *out_db = db;
   return DVB_OK;
@@ -1045,7 +1170,7 @@ void dvb_encoder_destroy(DvbEncoder* enc) {
   cudaSetDevice(enc->device);
   if (enc->d_perm) cudaFree(enc->d_perm);
   if (enc->d_err) cudaFree(enc->d_err);
-  enc->d_in.release(); enc->d_out.release(); enc->d_rows.release(); enc->d_recs.release();
+  enc->d_in.release(); enc->d_out.release(); enc->d_rows.release(); enc->d_recs.release(); enc->d_support.release();
   enc->h_in.release(); enc->h_out.release();
   if (enc->stream) cudaStreamDestroy(enc->stream);
   if (enc->copy_stream) cudaStreamDestroy(enc->copy_stream);
@@ -1190,12 +1315,17 @@ int dvb_encode_classify_host(DvbEncoder* enc, DvbCnn* cnn, const DvbBatch* hb, f
   } else {
     for (const StagePhase& ph : phases) {
       DVB_CUDA(cudaStreamWaitEvent(s, ph.done, 0));
-      DvbBatch sb = db;           // same device arrays; only the per-image views move (pair / read indices are absolute)
+      DvbBatch sb = db;           // same device arrays; only the per-image views move (pair / read / allele indices are absolute)
       sb.n_images = (int32_t)(ph.i1 - ph.i0);
       sb.ref_bases = db.ref_bases + (size_t)ph.i0 * db.ref_stride;
       sb.image_start_pos = db.image_start_pos + ph.i0;
       sb.variant_start = db.variant_start + ph.i0;
       sb.pair_begin = db.pair_begin + ph.i0;
+      if (db.allele_begin) {
+        sb.allele_begin = db.allele_begin + ph.i0;
+        sb.image_ref_run = db.image_ref_run + ph.i0;
+        if (db.image_group_default) sb.image_group_default = db.image_group_default + ph.i0;
+      }
       st = Launch(enc, sb, d_images + (size_t)ph.i0 * enc->dev.image_bytes, d_rows + ph.i0, s);
       if (st) return st;
       st = dvb_cnn_forward_device(cnn, d_images + (size_t)ph.i0 * enc->dev.image_bytes, sb.n_images, d_probs + 3 * ph.i0, s);
@@ -1211,5 +1341,19 @@ int dvb_encode_classify_host(DvbEncoder* enc, DvbCnn* cnn, const DvbBatch* hb, f
 }
 
 int64_t dvb_encoder_launch_count(const DvbEncoder* enc) { return enc ? enc->launches : 0; }
+
+int dvb_encoder_last_pair_support(DvbEncoder* enc, int64_t n_pairs, uint8_t* support, uint8_t* group) {
+  if (!enc || n_pairs < 0 || (n_pairs > 0 && !support)) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_encoder_last_pair_support: bad arguments");
+  if (enc->last_support_pairs != n_pairs)
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_encoder_last_pair_support: the last batch derived support for %lld pairs, not %lld",
+                     (long long)enc->last_support_pairs, (long long)n_pairs);
+  if (n_pairs == 0) return DVB_OK;
+  DVB_CUDA(cudaSetDevice(enc->device));
+  DVB_CUDA(cudaDeviceSynchronize());
+  const uint8_t* sup = static_cast<const uint8_t*>(enc->d_support.p);
+  DVB_CUDA(cudaMemcpy(support, sup + 2 * n_pairs, (size_t)n_pairs, cudaMemcpyDeviceToHost));
+  if (group) DVB_CUDA(cudaMemcpy(group, sup + 3 * n_pairs, (size_t)n_pairs, cudaMemcpyDeviceToHost));
+  return DVB_OK;
+}
 
 }  // extern "C"

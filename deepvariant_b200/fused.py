@@ -55,7 +55,41 @@ def concat_packed(batches: Sequence[packing.PackedBatch]) -> packing.PackedBatch
   for name, dtype in _lib.BATCH_ARRAYS:
     v = np.ascontiguousarray(np.concatenate(out[name]).astype(np.dtype(dtype), copy=False))
     arrays[name] = v if v.size else np.zeros(1, dtype=np.dtype(dtype))
-  return packing.PackedBatch(sum(b.n_images for b in batches), reads, pairs, ref_stride, arrays)
+  merged = packing.PackedBatch(sum(b.n_images for b in batches), reads, pairs, ref_stride, arrays)
+  # allele keys (device-side pair support): all batches carry them, under the same allele-counter options, or none does
+  with_keys = [b.support is not None for b in batches]
+  if any(with_keys):
+    if not all(with_keys) or len({b.support[:2] + (b.support[2] & ~_lib.SUPPORT_REPEATED_KEYS,) for b in batches}) != 1:
+      raise ValueError('batches with and without allele keys (or of different allele-counter options) cannot be concatenated')
+    groups = ['allele_group' in b.arrays for b in batches]
+    if any(groups) != all(groups):
+      raise ValueError('allele_group present in some batches only')
+    alleles = abases = 0
+    parts = {name: [] for name, _ in _lib.ALLELE_ARRAYS}
+    for b in batches:
+      a = b.arrays
+      na = int(a['allele_begin'][b.n_images])
+      nab = int(a['allele_bases_begin'][na])
+      parts['allele_begin'].append(a['allele_begin'][:b.n_images] + alleles)
+      parts['allele_bases_begin'].append(a['allele_bases_begin'][:na] + abases)
+      for k in ('allele_type', 'allele_class') + (('allele_group',) if groups[0] else ()):
+        parts[k].append(a[k][:na])
+      parts['allele_bases'].append(a['allele_bases'][:nab])
+      parts['image_ref_run'].append(a['image_ref_run'][:b.n_images])
+      if groups[0]:
+        parts['image_group_default'].append(a['image_group_default'][:b.n_images])
+      alleles += na; abases += nab
+    parts['allele_begin'].append(np.array([alleles], dtype=np.int64))
+    parts['allele_bases_begin'].append(np.array([abases], dtype=np.int64))
+    for name, dtype in _lib.ALLELE_ARRAYS:
+      if parts[name]:
+        v = np.ascontiguousarray(np.concatenate(parts[name]).astype(np.dtype(dtype), copy=False))
+        arrays[name] = v if v.size else np.zeros(1, dtype=np.dtype(dtype))
+    flags = 0
+    for b in batches:
+      flags |= b.support[2]
+    merged.support = batches[0].support[:2] + (flags,)
+  return merged
 
 
 class FusedCaller:

@@ -29,6 +29,7 @@ from __future__ import annotations
 
 import dataclasses
 import json
+import re
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -65,6 +66,9 @@ class MakeExamplesOptions:
 
 
 # ---- small pure functions ---------------------------------------------------------------------
+
+_NON_CANONICAL = re.compile('[^ACGT]')
+
 
 def encoded_variant_type(variant: Variant) -> int:
   """EncodedVariantType (make_examples_native.cc:301-321): 1 = SNP, 2 = indel, 0 = unknown."""
@@ -233,6 +237,11 @@ class ExamplesGenerator:
     # trimmed / alt-aligned route) instead of a TFRecord writer.
     self.sink = sink
     self.ssw_device: Optional[int] = None    # CUDA device for the read-to-haplotype Smith-Waterman of alt-aligned pileups (None = host)
+    # (min_mapping_quality, min_base_quality, keep_legacy_allele_counter_behavior, track_ref_reads) of the allele counter that
+    # produced the candidates, when they come from the very-sensitive caller over the same reads the pileups show: the table path
+    # then lets the encoder derive pair_support on the device (DvbBatch.allele_begin) instead of searching read names on the host.
+    self.support_options: Optional[Tuple[int, int, bool, bool]] = None
+    self.last_region_derived_support = False
     pic = options.pic_options
     self.half_width = (pic.width - 1) // 2
     if len(options.sample_options) != 1:
@@ -401,7 +410,13 @@ class ExamplesGenerator:
     plans: List[ExamplePlan] = []
     images: List[packing.RegionImage] = []
     ref_index = {name: i for i, name in enumerate(table.references)}
-    for candidate in candidates:
+    # device-side support: the alt alleles go to the encoder as read-allele keys and the read names stay on the host unread
+    derive = self.support_options is not None
+    if derive:
+      keys_of = [[packing.read_allele_key(c.variant.reference_bases, alt) for alt in c.variant.alternate_bases] for c in candidates]
+      derive = all(k is not None for ks in keys_of for k in ks)
+    self.last_region_derived_support = derive
+    for ci, candidate in enumerate(candidates):
       variant = candidate.variant
       if need_alt_alignment(variant, pic):
         raise NotImplementedError('candidate needs alt-aligned (trimmed) reads; use plan_region()')
@@ -410,7 +425,8 @@ class ExamplesGenerator:
         continue
       rb = reference_bases.encode() if isinstance(reference_bases, str) else bytes(reference_bases)
       alts = list(variant.alternate_bases)
-      enc = [[name.encode() for name in (candidate.allele_support.get(alt) or ())] for alt in alts]
+      enc = [[] if derive else [name.encode() for name in (candidate.allele_support.get(alt) or ())] for alt in alts]
+      ref_run = self.canonical_run_after(variant.reference_name, variant.start) if derive else 0
       counts = np.array([len(e) for e in enc], dtype=np.int64)
       flat = [k for e in enc for k in e]
       blob = b''.join(flat)
@@ -422,8 +438,28 @@ class ExamplesGenerator:
         classes = np.repeat(np.array([1 if alt in alt_combination else 2 for alt in alts], dtype=np.uint8), counts)
         images.append(packing.RegionImage(rid, variant.start, variant.end, variant.start - self.half_width, rb, blob, key_lens,
                                           classes, groups, len(alts)))
+        if derive:
+          images[-1].alleles = [(k[0], k[1], 1 if alt in alt_combination else 2, j) for j, (alt, k) in enumerate(zip(alts, keys_of[ci]))]
+          images[-1].ref_run = ref_run
         plans.append(ExamplePlan(None, variant, list(alt_combination), vtype))
     return plans, images
+
+  def canonical_run_after(self, contig: str, position: int) -> int:
+    """Number of consecutive canonical (ACGT) in-contig reference bases after `position`: a deletion anchored there is a usable
+    read allele iff it is not longer (MakeIndelReadAllele, allelecounter.cc:449-456).  Capped at 2^20."""
+    n_bases = self.ref_reader.n_bases(contig)
+    run, span = 0, 1024
+    while run < (1 << 20):
+      lo = position + 1 + run
+      hi = min(n_bases, lo + span)
+      if hi <= lo:
+        break
+      m = _NON_CANONICAL.search(self.ref_reader.query(contig, lo, hi).upper())
+      if m is not None:
+        return run + m.start()
+      run += hi - lo
+      span *= 8
+    return run
 
   def pack_region_native(self, candidates: Sequence[DeepVariantCall], table, region: Tuple[str, int, int]):
     """(plans, PackedBatch) of a region through the C++ packer."""
@@ -433,6 +469,9 @@ class ExamplesGenerator:
     params = pi.to_params(pic, height=self.pileup_image_height)   # host-side struct; no device needed to pack
     packed = packing.pack_region_native(table, images, rid, region[1], region[2], pic.read_overlap_buffer_bp,
                                         params, with_groups=bool(pic.sort_by_alt_allele_support))
+    if self.last_region_derived_support:
+      mq, bq, legacy, track = self.support_options
+      packing.attach_alleles(packed, images, mq, bq, legacy, track, with_groups=bool(pic.sort_by_alt_allele_support))
     return plans, packed
 
   def write_examples_in_region_from_table(self, candidates: Sequence[DeepVariantCall], table, role: str,

@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import dataclasses
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -78,6 +78,9 @@ class PackedBatch:
   n_pairs: int
   ref_stride: int
   arrays: Dict[str, np.ndarray]
+  # (min_mapping_quality, min_base_quality, DVB_SUPPORT_* flags) of the allele counter when the batch carries allele keys
+  # (arrays['allele_begin'] ...): pair_support / pair_allele_group are then derived on the device (attach_alleles below)
+  support: Optional[Tuple[int, int, int]] = None
 
   def as_ctypes(self) -> _lib.DvbBatch:
     b = _lib.DvbBatch()
@@ -91,6 +94,16 @@ class PackedBatch:
       a = self.arrays[name]
       assert a.dtype == np.dtype(dtype) and a.flags['C_CONTIGUOUS'], name
       setattr(b, name, a.ctypes.data_as(C.c_void_p))
+    if self.support is not None:
+      for name, dtype in _lib.ALLELE_ARRAYS:
+        a = self.arrays.get(name)
+        if a is None:
+          continue
+        assert a.dtype == np.dtype(dtype) and a.flags['C_CONTIGUOUS'], name
+        setattr(b, name, a.ctypes.data_as(C.c_void_p))
+      b.n_alleles = int(self.arrays['allele_begin'][self.n_images])
+      b.n_allele_bases = int(self.arrays['allele_bases_begin'][b.n_alleles])
+      b.support_min_mapping_quality, b.support_min_base_quality, b.support_flags = self.support
     return b
 
   def input_bytes(self) -> int:
@@ -336,6 +349,51 @@ def pack_images_from_table(specs: Sequence[TableImageSpec], table, params: _lib.
   return PackedBatch(n_images=n_images, n_reads=n_reads, n_pairs=int(pair_begin[-1]), ref_stride=ref_stride, arrays=arrays)
 
 
+def read_allele_key(ref: str, alt: str) -> Optional[Tuple[int, bytes]]:
+  """The (AlleleType, bases) key AlleleCount.read_alleles holds for reads that support `alt` of a candidate whose reference
+  allele is `ref` - the inverse of BuildAlleleMap (variant_calling_multisample.cc:560-606): a substitution's alt is its read
+  base + ref[1:], an insertion's is anchor + inserted bases + ref[1:], a deletion's is anchor + ref[1 + deleted:].
+  None when (ref, alt) is not of that form (not a candidate of the very-sensitive caller)."""
+  if not ref or not alt:
+    return None
+  if len(alt) == len(ref):
+    return (2, alt[:1].encode()) if alt[1:] == ref[1:] and alt[0] != ref[0] else None
+  if len(alt) > len(ref):
+    return (3, alt[:len(alt) - len(ref) + 1].encode()) if alt.endswith(ref[1:]) else None
+  n = len(ref) - len(alt) + 1
+  return (4, (alt[:1] + ref[1:n]).encode()) if alt[1:] == ref[n:] else None
+
+
+def attach_alleles(packed: 'PackedBatch', images: Sequence['RegionImage'], min_mapping_quality: int, min_base_quality: int,
+                   keep_legacy: bool, track_ref_reads: bool, with_groups: bool) -> 'PackedBatch':
+  """Adds the allele keys of `images` (RegionImage.alleles / ref_run) to a packed batch: the encoder's pre-pass then derives
+  pair_support / pair_allele_group on the device (DvbBatch.allele_begin, include/dvb.h) and the arrays of the same name are ignored."""
+  n = len(images)
+  assert n == packed.n_images
+  counts = np.fromiter((len(im.alleles) for im in images), dtype=np.int64, count=n)
+  begin = np.zeros(n + 1, dtype=np.int64)
+  np.cumsum(counts, out=begin[1:])
+  flat = [a for im in images for a in im.alleles]
+  lens = np.fromiter((len(a[1]) for a in flat), dtype=np.int64, count=len(flat))
+  bases_begin = np.zeros(len(flat) + 1, dtype=np.int64)
+  np.cumsum(lens, out=bases_begin[1:])
+  u8 = lambda k: np.ascontiguousarray(np.fromiter((a[k] for a in flat), dtype=np.uint8, count=len(flat))) if flat else np.zeros(1, np.uint8)
+  a = packed.arrays
+  a['allele_begin'] = begin
+  a['allele_type'], a['allele_class'] = u8(0), u8(2)
+  if with_groups:
+    a['allele_group'] = u8(3)
+    a['image_group_default'] = np.ascontiguousarray(np.fromiter((im.group_default for im in images), dtype=np.uint8, count=n)) if n else np.zeros(1, np.uint8)
+  a['allele_bases_begin'] = bases_begin
+  a['allele_bases'] = np.frombuffer(b''.join(x[1] for x in flat) or b'\0', dtype=np.uint8).copy()
+  a['image_ref_run'] = np.ascontiguousarray(np.fromiter((im.ref_run for im in images), dtype=np.int32, count=n)) if n else np.zeros(1, np.int32)
+  repeated = packed.n_reads > 0 and int(a['read_name_rank'][:packed.n_reads].max()) + 1 < packed.n_reads
+  packed.support = (int(min_mapping_quality), int(min_base_quality),
+                    (_lib.SUPPORT_KEEP_LEGACY if keep_legacy else 0) | (_lib.SUPPORT_TRACK_REF_READS if track_ref_reads else 0) |
+                    (_lib.SUPPORT_REPEATED_KEYS if repeated else 0))
+  return packed
+
+
 @dataclasses.dataclass
 class RegionImage:
   """One image of a region for pack_region_native: a candidate x alt combination, with allele_support flattened into
@@ -350,6 +408,9 @@ class RegionImage:
   support_class: np.ndarray        # uint8 per entry: 1 = alt of this image, 2 = other alt
   support_group: Optional[np.ndarray] = None   # uint8 per entry: alt index
   group_default: int = 0
+  # device-side support (attach_alleles): (AlleleType, key bases, class, group) per alt, and the canonical reference run after variant_start
+  alleles: Optional[List[Tuple[int, bytes, int, int]]] = None
+  ref_run: int = 0
 
 
 def pack_region_native(table, images: Sequence[RegionImage], region_ref_id: int, region_start: int, region_end: int,

@@ -204,6 +204,15 @@ class GpuEncoder:
                                                self.last_rows_kept.ctypes.data_as(C.c_void_p)))
     return out
 
+  def last_pair_support(self, n_pairs: int):
+    """(pair_support, pair_allele_group) the device derived for the last batch that carried allele keys
+    (packing.attach_alleles; dvb_encoder_last_pair_support)."""
+    import ctypes as C
+    support = np.zeros(max(n_pairs, 1), dtype=np.uint8)
+    group = np.zeros(max(n_pairs, 1), dtype=np.uint8)
+    _lib.check(self._lib.dvb_encoder_last_pair_support(self._h, n_pairs, C.c_void_p(support.ctypes.data), C.c_void_p(group.ctypes.data)))
+    return support[:n_pairs], group[:n_pairs]
+
   def encode_classify_host(self, batch, cnn, probs: Optional[np.ndarray] = None) -> np.ndarray:
     """Host batch in -> float32[n_images, 3] genotype probabilities out (dvb_encode_classify_host):
     the images stay in HBM between the encoder and the classifier.  `batch` is anything with

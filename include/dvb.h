@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DVB_ABI_VERSION 2
+#define DVB_ABI_VERSION 3
 #define DVB_MAX_CHANNELS 16
 
 typedef enum DvbStatus {
@@ -154,7 +154,34 @@ typedef struct DvbBatch {
   const uint8_t* bases;            /* ASCII aligned_sequence */
   const uint8_t* quals;            /* aligned_quality */
   const uint32_t* cigar;
+  /* Optional (allele_begin == NULL: pair_support / pair_allele_group above are used as given).  The alt alleles of each
+   * image in the allele counter's read-allele form (AlleleCount.read_alleles values, deepvariant.proto: a substitution is
+   * its one read base; an insertion / deletion is the anchor base followed by the inserted / deleted bases).  The encoder
+   * then derives pair_support and pair_allele_group on the device: each (image, read) pair is walked over the read's CIGAR
+   * to the read allele AlleleCounter::Add (allelecounter.cc:880-978) records at variant_start, which is matched against
+   * these keys - what DeepVariantCall.allele_support + ReadSupportsAlt (read_supports_variant_channel.cc:75-104) express
+   * through read names.  Holds for candidates of the very-sensitive caller over the same reads (dvb_candidates_in_region). */
+  const int64_t* allele_begin;       /* [n_images + 1] CSR into the allele arrays */
+  const uint8_t* allele_type;        /* [n_alleles] 2 substitution, 3 insertion, 4 deletion (AlleleType) */
+  const uint8_t* allele_class;       /* [n_alleles] 1 = an alt allele of this image, 2 = another alt of the candidate */
+  const uint8_t* allele_group;       /* [n_alleles] alt index (sort_by_alt_allele_support), or NULL */
+  const int64_t* allele_bases_begin; /* [n_alleles + 1] into allele_bases */
+  const uint8_t* allele_bases;
+  const int32_t* image_ref_run;      /* [n_images] canonical in-contig reference bases after variant_start (a deletion
+                                        anchored there is usable iff it is not longer; allelecounter.cc:449-456) */
+  const uint8_t* image_group_default;/* [n_images] pair_allele_group of reads that support no alt, or NULL (0) */
+  int64_t n_alleles, n_allele_bases;
+  int32_t support_min_mapping_quality;  /* AlleleCounterOptions.read_requirements.min_mapping_quality */
+  int32_t support_min_base_quality;     /* ... min_base_quality */
+  int32_t support_flags;                /* DVB_SUPPORT_* */
 } DvbBatch;
+
+enum {
+  DVB_SUPPORT_KEEP_LEGACY = 1,     /* keep_legacy_allele_counter_behavior */
+  DVB_SUPPORT_TRACK_REF_READS = 2, /* reference-matching reads also hold an entry at candidate positions */
+  DVB_SUPPORT_REPEATED_KEYS = 4    /* some (fragment_name, read_number) occurs on more than one read of the batch: the later
+                                      read's entry replaces the earlier one's (a std::map keyed by read name) */
+};
 
 typedef struct DvbEncoder DvbEncoder;
 typedef struct DvbCnn DvbCnn;
@@ -196,6 +223,10 @@ int dvb_encode_batch_host(DvbEncoder* enc, const DvbBatch* batch, uint8_t* out_h
 
 /* Number of kernel launches issued by this handle so far (bench bookkeeping). */
 int64_t dvb_encoder_launch_count(const DvbEncoder* enc);
+
+/* After a batch with allele keys (DvbBatch.allele_begin): the pair_support / pair_allele_group arrays the device derived for it
+ * (host buffers of n_pairs bytes; group may be NULL).  Synchronises the device.  For tests and for callers that want the classes. */
+int dvb_encoder_last_pair_support(DvbEncoder* enc, int64_t n_pairs, uint8_t* support, uint8_t* group);
 
 /* ---- CNN (Inception-v3 + genotype softmax) ------------------------------- */
 
@@ -374,6 +405,13 @@ void dvb_candidates_free(DvbCandidates* candidates);
 int64_t dvb_debug_allele_counts(const DvbBam* bam, const uint8_t* contig_bases, int64_t contig_n_bases, int64_t start, int64_t end,
                                 const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* options,
                                 const int32_t* candidate_positions, int32_t n_candidate_positions, char* out, int64_t cap);
+
+/* Test access to the (candidate, read) support walk of the encoder's pre-pass (DvbBatch.allele_begin): the read allele of one read
+ * at `target`, (a) walk_out: the last commit of the full allele-counter walk over [start, end) at that position, (b) at_out: what the
+ * CIGAR-only walk used on the device finds.  Each int32[6] = {found, AlleleType, is_low_quality, anchor base, read offset, length}. */
+int dvb_debug_read_allele_at(const uint8_t* seq, const uint8_t* qual, int32_t seq_len, const uint32_t* cigar, int32_t n_cigar, int64_t pos,
+                             const uint8_t* contig, int64_t contig_len, int64_t start, int64_t end, int64_t target, int32_t min_base_quality,
+                             int32_t keep_legacy, int32_t* walk_out, int32_t* at_out);
 
 /* ---- allele counting on the device (SURVEY.md 8(f) "next" row #2, device half) ------------------------------------------------
  * The reads of a DvbBam table are uploaded once (Structure of Arrays in HBM); dvb_allele_count_* runs AlleleCounter::Add
