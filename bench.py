@@ -575,6 +575,23 @@ def main():
               'traffic_source': traffic.get('encoder', {}).get('capture'), 'peak_source': peaks['source'],
               'ms_per_launch': enc_ms, 'algorithmic_bytes_per_launch': alg_bytes,
               'windows_per_s_encode_only': B / (enc_ms * 1e-3)}
+  # The kernel writes 36 bytes for every byte it reads, and HBM3e takes a pure write stream at about 60 % of its copy rate: the
+  # write-only ceiling is measured here, on this GPU, with cudaMemset over the image buffer (reported beside `peak`, not instead of it).
+  try:
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    flat = images.view(-1)
+    for _ in range(2):
+      flat.zero_()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+      flat.zero_()
+    e1.record()
+    torch.cuda.synchronize()
+    wc = 5 * flat.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    roof_enc['write_only_ceiling'] = {'gbs': wc, 'frac_of_it': enc_gbs / wc, 'how': f'cudaMemset of the {flat.numel() >> 20} MiB image buffer, 5 runs, CUDA events'}
+  except Exception as e:   # pylint: disable=broad-except
+    roof_enc['write_only_ceiling'] = {'error': str(e)[:120]}
   if cnn:
     roofline = cnn.roofline(ms_step - enc_ms, B, peaks)
     cnn_traffic = traffic.get('cnn', {}).get('dram_bytes_per_image')

@@ -492,8 +492,14 @@ def run_deepvariant(argv):
   ap.add_argument('--staged', action='store_true')         # the reference's three stages with tf.Example files in between; default = fused
   ap.add_argument('--num_gpus', type=int, default=0)        # 0 = every visible device; task i runs on device i mod num_gpus
   ap.add_argument('--jobs', type=int, default=0)            # tasks in flight; 0 = all of them, as `parallel -j num_shards` (scripts/run_deepvariant.py:457-462)
+  ap.add_argument('--logging_dir', default='')              # scripts/run_deepvariant.py:141
+  ap.add_argument('--runtime_report', action='store_true')  # scripts/run_deepvariant.py:149,744-758: make_examples --runtime_by_region into logging_dir
   a = ap.parse_args(argv)
   os.makedirs(a.output_dir, exist_ok=True)
+  runtime_by_region = ''
+  if a.logging_dir and a.runtime_report:
+    os.makedirs(os.path.join(a.logging_dir, 'make_examples_runtime_by_region'), exist_ok=True)
+    runtime_by_region = os.path.join(a.logging_dir, 'make_examples_runtime_by_region', f'make_examples_runtime@{a.num_shards}.tsv')
   d = MODEL_DEFAULTS[a.model_type]
   examples = os.path.join(a.output_dir, f'make_examples.tfrecord@{a.num_shards}.gz')
   nonvariants = os.path.join(a.output_dir, f'gvcf.tfrecord@{a.num_shards}.gz')
@@ -533,6 +539,8 @@ def run_deepvariant(argv):
       args += ['--sample_name', a.sample_name]
     if a.output_gvcf:
       args += ['--gvcf', nonvariants]
+    if runtime_by_region:
+      args += ['--runtime_by_region', runtime_by_region]
     task_args.append(args)
   # One process per task, task i on GPU i mod num_gpus, started together as the reference starts its make_examples shards
   # (scripts/run_deepvariant.py:457-462, 497); a single task runs in this process.

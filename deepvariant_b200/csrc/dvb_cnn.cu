@@ -966,6 +966,7 @@ struct HaloArgs {
   int tiles_w, tiles_h;           // per image
   int Hout, Wout, n_images;
   int block_n, n_blocks, tmem_cols, T, nbuf, stages;
+  int n_split;                    // epilogue: column ranges per tile (block_n / n_split columns each, a multiple of 16)
   int out_cstride, out_coff, relu;
   uint32_t idesc, layout_type, sbo_bytes;
   uint32_t a_copy_bytes, a_stage, b_tile, b_total_bytes;
@@ -1158,15 +1159,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_wait(&tmem_full[buf], buf_ph);
       if (threadIdx.x == 64) HALO_TRACE((grp - g) / G, 5);
       tc_fence_after();
-      for (int t = half; t < T; t += kHaloEpiWarps / 4) {
+      const int n_split = p.n_split, cols = p.block_n / n_split;
+      for (int u = half; u < T * n_split; u += kHaloEpiWarps / 4) {
+        const int t = u / n_split, c0 = (u - t * n_split) * cols;
         const int tile = min(grp * T + t, total_tiles - 1);
         const int n = tile / tiles_per_image;
         const int rem = tile - n * tiles_per_image;
         const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
         const int w = tw * p.Wv + slot, h = th * p.Ht + hh;
         const bool valid = (slot < p.Wv) && (w < p.Wout) && (h < p.Hout);
-        __half* dst = p.out + ((size_t)((size_t)n * p.Hout + h) * p.Wout + w) * p.out_cstride + p.out_coff + nb * p.block_n;
-        epilogue_row(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * T + t) * p.block_n), p.block_n, s_bias, dst, valid, p.relu);
+        __half* dst = p.out + ((size_t)((size_t)n * p.Hout + h) * p.Wout + w) * p.out_cstride + p.out_coff + nb * p.block_n + c0;
+        epilogue_row(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * T + t) * p.block_n + c0), cols, s_bias + c0, dst, valid, p.relu);
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[buf]);
@@ -2079,6 +2082,71 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_h2_kernel(const __half* __re
   }
 }
 
+// 3x3 stride-1 'same' average pool (count excludes the padding) [+ bias + ReLU when it stands behind its 1x1 convolution], precision 0.
+// One thread = one output pixel x 8 channels: its nine 16-byte loads are independent (the sliding form of pool3x3_kernel above chains
+// Wout dependent load groups per thread: 1 TB/s on maps that should stream at 5), neighbours meet in L1.  The sums are taken in the
+// order of pool3x3_kernel (per column top to bottom, then left + centre + right): results are bit-identical.
+__global__ void __launch_bounds__(256) avgpool3x3s1_kernel(const __half* __restrict__ in, __half* __restrict__ out, int n_images, int H, int W, int C,
+                                                           int out_cstride, int out_coff, const float* __restrict__ bias) {
+  const int cvec = C / 8;
+  const long long total = (long long)n_images * H * W * cvec;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int cv = (int)(i % cvec);
+  long long t = i / cvec;
+  const int ow = (int)(t % W); t /= W;
+  const int oh = (int)(t % H);
+  const int n = (int)(t / H);
+  const int h_lo = oh > 0 ? oh - 1 : 0, h_hi = oh + 1 < H ? oh + 1 : H - 1;
+  const int w_lo = ow > 0 ? ow - 1 : 0, w_hi = ow + 1 < W ? ow + 1 : W - 1;
+  const uint4* src = reinterpret_cast<const uint4*>(in + (size_t)n * H * W * C + cv * 8);
+  const size_t pitch = (size_t)C / 8;
+  uint4 v[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const int ih = h_lo + a, iw = w_lo + b;
+      v[a][b] = (ih <= h_hi && iw <= w_hi) ? src[((size_t)ih * W + iw) * pitch] : make_uint4(0, 0, 0, 0);
+    }
+  // columns left of / right of the map contribute an exact 0.f first or last, as colsum(-1) / colsum(W) do above
+  float col[3][8];
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) col[b][j] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (h_lo + a > h_hi || w_lo + b > w_hi) continue;
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v[a][b]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h2[j]);
+        col[b][2 * j] += f.x; col[b][2 * j + 1] += f.y;
+      }
+    }
+  }
+  const int ncols = w_hi - w_lo + 1;
+  const float inv = 1.f / (float)((h_hi - h_lo + 1) * ncols);
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    // pool3x3_kernel adds s0 + s1 + s2 = (column ow-1) + (column ow) + (column ow+1), absent columns as 0.f
+    const float s0 = ow > 0 ? col[0][j] : 0.f;
+    const float s1 = ow > 0 ? col[1][j] : col[0][j];
+    const float s2 = ow > 0 ? (ncols == 3 ? col[2][j] : 0.f) : (ncols >= 2 ? col[1][j] : 0.f);
+    o[j] = __fmul_rn(s0 + s1 + s2, inv);                                    // no FMA contraction with the bias: pool3x3_kernel rounds the mean first
+    if (bias) o[j] = fmaxf(__fadd_rn(o[j], bias[cv * 8 + j]), 0.f);
+  }
+  uint32_t pk[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __half2 h = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
+    pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(out + (((size_t)n * H + oh) * W + ow) * out_cstride + out_coff + cv * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
 // GlobalAveragePooling2D + Dense(3) + softmax, fp32.  One block per image.
 __global__ void __launch_bounds__(256) tail_kernel(const __half* __restrict__ feat, int hw, int C, const float* __restrict__ dense_w,
                                                    const float* __restrict__ dense_b, float* __restrict__ probs, float* __restrict__ pooled_out,
@@ -2783,7 +2851,8 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       // N block: the resident weight slice must leave room for the halo ring
       int bn = ChooseBlockN(o.cout);
       auto b_total = [&](int n) { return (size_t)a.cin_blocks * taps * (((size_t)n * row_bytes + 1023) & ~(size_t)1023); };
-      while (b_total(bn) + 4 * a.a_stage > 200 * 1024 && bn > 16) {
+      const int halo_rule = EnvInt("DVB_HALO_RULE", 1);
+      while ((halo_rule == 2 ? b_total(bn) + 2 * a.a_stage > 216 * 1024 : b_total(bn) + 4 * a.a_stage > 200 * 1024) && bn > 16) {
         int next = 0;
         for (int d = bn - 16; d >= 16; d -= 16)
           if (o.cout % d == 0) { next = d; break; }
@@ -2796,7 +2865,20 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       const size_t b_smem = (size_t)a.cin_blocks * taps * a.b_tile;
       // T tiles in flight = T independent accumulation chains (measured issue interval per MMA, N <= 64: 222 cycles
       // with 1 chain, 80 with 4, 46 with 8).  Two TMEM buffers of T accumulators when 2*T*bn <= 512 columns, else one.
-      int T = std::min(kMaxGroup, 512 / bn);
+      // Rule 2 (round 2, after the issue path was fixed - one accumulation chain now runs at the tensor pipe's own interval, see
+      // DESIGN.md 4.0): what bounds the tap-by-tap kernels on these layers is the SM's ingest from L2 (about 36-40 B per clock:
+      // 9 taps x (A tile + weight tile) per 128 pixels), so the halo kernel pays whenever its weights fit, with T = 1 or 2 tiles in
+      // flight (2 when TMEM holds two double-buffered accumulators and the halo ring has 4 slots) - any N block count.
+      const int avail_stages = (int)((216 * 1024 - (long)b_smem) / (long)a.a_stage);
+      int T;
+      if (halo_rule == 2) {
+        T = (4 * bn <= 512 && avail_stages >= 4) ? 2 : 1;
+        T = std::max(1, std::min(T, EnvInt("DVB_HALO_T", 8)));
+        a.T = T;
+        a.nbuf = 2 * a.T * bn <= 512 ? 2 : 1;
+        a.stages = std::max(1, std::min(std::min(2 * kMaxStages, std::max(4, 2 * a.T)), avail_stages));
+      } else {
+      T = std::min(kMaxGroup, 512 / bn);
       T = T >= 8 ? 8 : T >= 4 ? 4 : T;
       T = std::min(T, EnvInt("DVB_HALO_T", 8));
       while (T > 1 && b_smem + (size_t)(T + 2) * a.a_stage > 216 * 1024) T = T > 4 ? 4 : T - 1;
@@ -2804,6 +2886,11 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       if (2 * a.T * bn > 512 && a.T == 8 && EnvInt("DVB_HALO_PREFER_DB", 1)) a.T = 4;   // measured: T=4 double-buffered beats T=8 single
       a.nbuf = (2 * a.T * bn <= 512 && EnvInt("DVB_HALO_NBUF", 2) == 2) ? 2 : 1;
       a.stages = std::min(2 * kMaxStages, std::max(a.T, std::min(2 * a.T, (int)((216 * 1024 - (long)b_smem) / (long)a.a_stage))));
+      }
+      // epilogue work units: T tiles x n_split column ranges over the 4 warp groups of a TMEM lane quarter
+      a.n_split = 1;
+      for (int ns = std::max(1, 4 / a.T); ns >= 1; --ns)
+        if (bn % ns == 0 && (bn / ns) % 16 == 0) { a.n_split = ns; break; }
       a.tmem_cols = TmemCols(a.nbuf * a.T * bn);
       a.out = dst.ptr; a.out_cstride = dst.C; a.out_coff = o.off; a.relu = relu_single;
       a.bias = conv_bias;
@@ -2814,7 +2901,9 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       hl.macs_per_image = (double)Hout * Wout * o.cout * o.kh * o.kw * o.cin;
       // Only worth it when >= 4 double-buffered accumulation chains fit in TMEM (N block <= 64); wider layers (conv5,
       // N = 192) measured slower here than with the tap-by-tap kernel and stay there.
-      if (a.tmem_cols <= 512 && hl.smem <= 227 * 1024 && a.stages >= a.T && a.T >= 4 && a.nbuf == 2 && a.n_blocks == 1) {
+      const bool halo_ok = halo_rule == 2 ? (a.stages >= std::max(2, a.T) && a.nbuf == 2 && bn >= 64 && a.b_tile == (uint32_t)(bn * row_bytes))
+                                           : (a.stages >= a.T && a.T >= 4 && a.nbuf == 2 && a.n_blocks == 1);
+      if (a.tmem_cols <= 512 && hl.smem <= 227 * 1024 && halo_ok) {
         // weights [Cout][taps][Cin] -> [taps][Cout][Cin] so that one (tap, N block, Cin block) is a canonical K-major tile
         std::vector<__half> w2((size_t)taps * o.cout * cin_store, __float2half(0.f));
         const __half* w = reinterpret_cast<const __half*>(blob_w_main);
@@ -2886,7 +2975,7 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       {
         const int mode = EnvInt("DVB_CNN_PERSIST", 1);   // 0 never, 1 by rule, 2 always
         const long tiles = m_tiles * (o.cout / bn);
-        cl.persist = !split && (mode == 2 || (mode == 1 && bk == 64 && bn >= 160 && tiles >= 4L * net->num_sms));
+        cl.persist = !split && (mode == 2 || (mode == 1 && bk == 64 && bn >= EnvInt("DVB_PERSIST_MIN_N", 160) && tiles >= 4L * net->num_sms));
       }
       const long want_ctas = cl.persist ? 0L : 4L * net->num_sms;   // the persistent kernel keeps the widest N block
       while (m_tiles * (o.cout / bn) < want_ctas && bn > 64) {
@@ -2985,7 +3074,8 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
     {
       const int pair_mode = EnvInt("DVB_CNN_PAIR", 2);
       cl.pair = cl.persist && a.block_n % 16 == 0 &&
-                (pair_mode == 1 || (pair_mode == 2 && !merged && a.block_n == 192 && o.kh * o.kw > 1 && a.cin_blocks >= 3));
+                (pair_mode == 1 || (pair_mode == 2 && !merged && a.block_n == 192 && o.kh * o.kw > 1 && a.cin_blocks >= 3) ||
+                 (pair_mode == 3 && !merged && a.block_n >= 128 && o.kh * o.kw > 1 && a.cin_blocks >= 2));
     }
     if (cl.pair) {
       PairArgs& q2 = cl.pair_args;
@@ -3088,6 +3178,12 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       const ConvLaunch& c = net->convs[i];
       fprintf(stderr, "[conv %zu] %dx%d cin_blocks=%d bk=%d N=%d n_blocks=%d persist=%d pair=%d stages=%d\n", i, c.args.kh, c.args.kw, c.args.cin_blocks, c.args.block_k,
               c.args.block_n, c.n_blocks, (int)c.persist, (int)c.pair, c.args.stages);
+    }
+  if (EnvInt("DVB_CNN_LIST", 0))
+    for (size_t i = 0; i < net->halos.size(); ++i) {
+      const HaloArgs& h = net->halos[i].args;
+      fprintf(stderr, "[halo %zu] %dx%d %dx%d cin_blocks=%d bk=%d N=%d n_blocks=%d P=%d Ht=%d T=%d nbuf=%d stages=%d n_split=%d smem=%d\n", i, h.kh, h.kw, h.Hout, h.Wout,
+              h.cin_blocks, h.block_k, h.block_n, h.n_blocks, h.P, h.Ht, h.T, h.nbuf, h.stages, h.n_split, net->halos[i].smem);
     }
   if (cudaDeviceSynchronize() != cudaSuccess) return dvb::fail(DVB_ERR_CUDA, "weight upload failed: %s", cudaGetErrorString(cudaGetLastError()));
   return DVB_OK;
@@ -3211,6 +3307,13 @@ int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaSt
         const long long total = (long long)n * p.Hout * segs * (p.C / 8);
         maxpool3x3s2_h2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p.in, p.out, n, p.Hin, p.Win, p.C, p.Hout, p.Wout, p.out_cstride,
                                                                                p.out_coff, segs, seg_len);
+        net->launches++;
+        if (stp.record) cudaEventRecord(stp.event, s);
+        continue;
+      }
+      if (p.mode == 1 && !p.in_res && p.Hout == p.Hin && p.Wout == p.Win && EnvInt("DVB_CNN_AVGPOOL_FLAT", 1)) {
+        const long long total = (long long)n * p.Hout * p.Wout * (p.C / 8);
+        avgpool3x3s1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(p.in, p.out, n, p.Hin, p.Win, p.C, p.out_cstride, p.out_coff, p.bias);
         net->launches++;
         if (stp.record) cudaEventRecord(stp.event, s);
         continue;

@@ -375,3 +375,83 @@ def test_cta_pair_kernel_equals_persistent_kernel(monkeypatch):
       scale = max(float(np.abs(t0[k]).max()), 1e-6)
       assert float(np.abs(t0[k] - t1[k]).max()) / scale < 2e-3, k
     assert float(np.abs(p0 - p1).max()) < 1e-3
+
+
+# ---- round 2: the halo kernel under rule 2, the wider CTA-pair rule, the flat average pool ------------------------------------
+@pytest.mark.parametrize('shape,n', [((100, 221, 7), 5), ((100, 147, 10), 4)])
+def test_halo_kernel_rule2_every_block_matches_oracle(monkeypatch, shape, n):
+  """DVB_HALO_RULE=2: conv5 and the 3x3 layers of the 35x35 blocks on conv_halo_kernel (weights resident, one halo box per Cin block,
+  T = 1 or 2 accumulation chains, several N blocks, epilogue split over column ranges) against the fp32 oracle, every block."""
+  monkeypatch.setenv('DVB_HALO_RULE', '2')
+  report, worst, got_p, want_p, net, pooled = _check_layers(shape, n, ALL_BLOCKS + BRANCHES, seed=31)
+  print(report)
+  for name, err in report:
+    assert err < 2e-2, report
+  assert float((got_p - want_p).abs().max()) < 5e-3
+  net.close()
+
+
+@pytest.mark.parametrize('extra', [{}, {'DVB_HALO_T': '1'}])
+def test_halo_kernel_rule2_equals_tap_by_tap_kernels(monkeypatch, extra):
+  """Same operands and fp32 accumulation; the K order differs (Cin block outermost instead of tap outermost), so the fp32 sums
+  differ in their last bits and a stored fp16 activation can land one ulp apart: close, not equal."""
+  shape = (100, 221, 7)
+  w = modeling.random_weights(7, 32)
+  imgs = _images(7, shape, 32)
+  outs = []
+  for rule in ('1', '2'):
+    monkeypatch.setenv('DVB_HALO_RULE', rule)
+    for k, v in extra.items():
+      monkeypatch.setenv(k, v)
+    net = cv.GpuCnn(w, shape, device=0, max_batch=7)
+    probs = net.forward_host(imgs.numpy())
+    outs.append((probs, {k: net.debug_tensor(k, 7) for k in ('s5', 'mixed0', 'mixed2', 'mixed3', 'mixed10')}))
+    net.close()
+  for k in outs[0][1]:
+    scale = float(np.abs(outs[0][1][k]).max())
+    assert float(np.abs(outs[0][1][k] - outs[1][1][k]).max()) <= 5e-3 * scale, k     # one fp16 ulp where an fp32 sum rounds the other way, carried on
+  assert float(np.abs(outs[0][0] - outs[1][0]).max()) <= 5e-4
+
+
+def test_wider_cta_pair_rule_equals_default_plan(monkeypatch):
+  """DVB_CNN_PAIR=3 + DVB_PERSIST_MIN_N=128 (+ 160-channel tensors stored 192 wide): the 128- and 160-wide 1x7 / 7x1 layers as CTA
+  pairs.  Forced onto small batches with DVB_CNN_PERSIST=2; against the default plan."""
+  shape = (100, 221, 7)
+  w = modeling.random_weights(7, 33)
+  imgs = _images(6, shape, 33)
+  outs = []
+  for env in ({}, {'DVB_CNN_PERSIST': '2', 'DVB_CNN_PAIR': '3', 'DVB_PERSIST_MIN_N': '128'},
+              {'DVB_CNN_PERSIST': '2', 'DVB_CNN_PAIR': '3', 'DVB_PERSIST_MIN_N': '128', 'DVB_CNN_PAD_CIN64_MIN': '160'}):
+    for k in ('DVB_CNN_PERSIST', 'DVB_CNN_PAIR', 'DVB_PERSIST_MIN_N', 'DVB_CNN_PAD_CIN64_MIN'):
+      monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+      monkeypatch.setenv(k, v)
+    net = cv.GpuCnn(w, shape, device=0, max_batch=6)
+    probs = net.forward_host(imgs.numpy())
+    outs.append((probs, {k: net.debug_tensor(k, 6) for k in ('mixed4', 'mixed5', 'mixed6', 'mixed7', 'mixed10')}))
+    net.close()
+  for other in outs[1:]:
+    for k in outs[0][1]:
+      scale = float(np.abs(outs[0][1][k]).max())
+      assert float(np.abs(outs[0][1][k] - other[1][k]).max()) <= 1e-5 * scale, k
+    assert float(np.abs(outs[0][0] - other[0]).max()) <= 1e-6
+
+
+@pytest.mark.parametrize('pool_after_conv', ['1', '0'])
+def test_flat_average_pool_equals_sliding_form_bit_for_bit(monkeypatch, pool_after_conv):
+  """avgpool3x3s1_kernel (one thread per output pixel x 8 channels, nine independent loads) keeps the summation order of
+  pool3x3_kernel: identical activations, with the bias + ReLU of the pool-behind-conv rewrite and without."""
+  monkeypatch.setenv('DVB_CNN_POOL_AFTER_CONV', pool_after_conv)
+  for shape in ((100, 221, 7), (100, 147, 10)):
+    w = modeling.random_weights(shape[2], 34)
+    imgs = _images(5, shape, 34)
+    net = cv.GpuCnn(w, shape, device=0, max_batch=5)
+    outs = []
+    for flat in ('0', '1'):
+      monkeypatch.setenv('DVB_CNN_AVGPOOL_FLAT', flat)
+      probs = net.forward_host(imgs.numpy())
+      outs.append((probs, {k: net.debug_tensor(k, 5) for k in ('mixed0', 'mixed3', 'mixed5', 'mixed9', 'mixed10')}))
+    net.close()
+    for k in outs[0][1]:
+      np.testing.assert_array_equal(outs[0][1][k], outs[1][1][k])
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])

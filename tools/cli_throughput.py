@@ -49,11 +49,18 @@ def run(name, fa, bam_path, regions, extra, out_dir):
   d = os.path.join(out_dir, name)
   t0 = time.time()
   rc = cli.run_deepvariant(['--model_type', 'WGS', '--ref', fa, '--reads', bam_path, '--regions', regions, '--customized_model', 'random:1',
-                            '--output_dir', d, '--output_vcf', os.path.join(d, 'out.vcf')] + extra)
+                            '--output_dir', d, '--output_vcf', os.path.join(d, 'out.vcf'), '--logging_dir', os.path.join(d, 'logs'), '--runtime_report'] + extra)
   dt = time.time() - t0
   assert rc == 0
+  stages = {}
+  import glob
+  for path in glob.glob(os.path.join(d, 'logs', 'make_examples_runtime_by_region', '*.tsv')):
+    rows = [line.rstrip('\n').split('\t') for line in open(path)]
+    for row in rows[1:]:
+      for k, v in zip(rows[0][1:8], row[1:8]):
+        stages[k] = round(stages.get(k, 0) + float(v), 3)
   n = sum(1 for p in tfrecord.resolve_input_paths(os.path.join(d, 'call_variants_output.tfrecord.gz')) for _ in tfrecord.read_records(p))
-  return {'seconds': round(dt, 2), 'call_variants_outputs': n, 'candidates_per_s': round(n / dt, 1),
+  return {'seconds': round(dt, 2), 'make_examples_stage_seconds_summed_over_regions': stages, 'call_variants_outputs': n, 'candidates_per_s': round(n / dt, 1),
           'vcf_records': sum(1 for line in open(os.path.join(d, 'out.vcf')) if not line.startswith('#'))}
 
 
