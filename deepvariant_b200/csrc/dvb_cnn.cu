@@ -2823,13 +2823,26 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       memset(&hl, 0, sizeof(hl));
       HaloArgs& a = hl.args;
       const int taps = o.kh * o.kw;
-      const int bk = cin_store % 64 == 0 ? 64 : cin_store % 32 == 0 ? 32 : 16;
+      const int halo_rule = EnvInt("DVB_HALO_RULE", 1);
+      int bk = cin_store % 64 == 0 ? 64 : cin_store % 32 == 0 ? 32 : 16;
+      int k_channels = cin_store;
+      if (halo_rule == 2) {
+        // K block: the fewest 16-wide K steps over the layer's REAL input channels - a tensor stored wider than the layer's Cin carries
+        // zero channels (48 stored as 64, 80 as 96) that the tap-by-tap kernels multiply along; narrow blocks also shrink the resident weights
+        int best_units = 1 << 30;
+        for (int cand = 64; cand >= 16; cand >>= 1) {
+          if (cin_store % cand) continue;
+          const int units = ((blob_cin + cand - 1) / cand) * (cand / 16);
+          if (units < best_units) { best_units = units; bk = cand; }
+        }
+        k_channels = blob_cin;
+      }
       const int row_bytes = bk * 2;
       a.kh = o.kh; a.kw = o.kw;
       a.pad_h = o.same ? (o.kh - 1) / 2 : 0;
       a.pad_w = o.same ? (o.kw - 1) / 2 : 0;
       a.block_k = bk;
-      a.cin_blocks = (cin_store + bk - 1) / bk;
+      a.cin_blocks = (k_channels + bk - 1) / bk;
       // slots per tile row: vertical tap offsets (r * P rows) must stay 1024-byte aligned
       // slots per tile row: the row pitch P * row_bytes keeps vertical taps 1024-byte aligned; P - kw + 1 slots are valid
       int bestP = 0; double best_eff = -1;
@@ -2851,7 +2864,6 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       // N block: the resident weight slice must leave room for the halo ring
       int bn = ChooseBlockN(o.cout);
       auto b_total = [&](int n) { return (size_t)a.cin_blocks * taps * (((size_t)n * row_bytes + 1023) & ~(size_t)1023); };
-      const int halo_rule = EnvInt("DVB_HALO_RULE", 1);
       while ((halo_rule == 2 ? b_total(bn) + 2 * a.a_stage > 216 * 1024 : b_total(bn) + 4 * a.a_stage > 200 * 1024) && bn > 16) {
         int next = 0;
         for (int d = bn - 16; d >= 16; d -= 16)

@@ -127,6 +127,22 @@ def _merge_one_base(read_op: int, hap_op: int, read_len: int, out: List[List[int
       break
 
 
+def _merge_bases(read_op: int, hap_op: int, count: int, read_len: int, out: List[List[int]]) -> None:
+  """`count` calls of _merge_one_base(read_op, hap_op) (the reference merges base by base, fast_pass_aligner.cc:760-800): only a
+  call that meets the I-after-D / D-after-I rewrite of MergeCigarOp depends on being a single base; once the last operation is
+  anything else, the remaining calls just extend it (clamped to the read length, deletions unclamped) - one call does that."""
+  assert (read_op, hap_op) not in ((D, I), (I, D))
+  op = next(o for o in (S, D, I, M) if read_op == o or hap_op == o)
+  while count > 0:
+    last_op = out[-1][0] if out else None
+    if (op == I and last_op == D) or (op == D and last_op == I):
+      merge_cigar_op(op, 1, read_len, out)
+      count -= 1
+      continue
+    merge_cigar_op(op, count, read_len, out)
+    return
+
+
 class FastPassAligner:
   ssw_batch_min = 4      # fewer (haplotype, read) pairs than this are aligned on the host even when ssw_device is set
 
@@ -363,18 +379,21 @@ class FastPassAligner:
             h2r.insert(0, [M, 1])
             r2h.insert(0, [M, 1])
           continue
-        _merge_one_base(cur_r[0], cur_h[0], read_len, out)
+        # the pair of operations stays the same until one of them runs out: merge the whole run
         if cur_r[0] == I:
-          cur_r[1] -= 1
+          _merge_bases(cur_r[0], cur_h[0], cur_r[1], read_len, out)
+          cur_r[1] = 0
         elif cur_h[0] == D:
-          cur_h[1] -= 1
+          _merge_bases(cur_r[0], cur_h[0], cur_h[1], read_len, out)
+          cur_h[1] = 0
         else:
-          cur_h[1] -= 1
-          cur_r[1] -= 1
+          k = min(cur_r[1], cur_h[1])
+          _merge_bases(cur_r[0], cur_h[0], k, read_len, out)
+          cur_h[1] -= k
+          cur_r[1] -= k
     if cur_r[1] > 0 and cur_r[0] == S:
-      while cur_r[1] > 0:
-        _merge_one_base(cur_r[0], cur_h[0], read_len, out)
-        cur_r[1] -= 1
+      _merge_bases(cur_r[0], cur_h[0], cur_r[1], read_len, out)
+      cur_r[1] = 0
     if r2h or cur_r[1] > 0:
       out = []
     return out

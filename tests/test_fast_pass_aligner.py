@@ -186,3 +186,30 @@ def test_native_fast_pass_equals_the_python_pass(seed):
   assert [(h.haplotype_index, h.haplotype_score, [(r.position, r.cigar, r.score) for r in h.read_alignment_scores]) for h in a.read_to_haplotype_alignments] == \
          [(h.haplotype_index, h.haplotype_score, [(r.position, r.cigar, r.score) for r in h.read_alignment_scores]) for h in b.read_to_haplotype_alignments]
   assert any(h.haplotype_score > 0 for h in a.read_to_haplotype_alignments)
+
+
+def test_run_merge_equals_base_by_base_merge():
+  """_merge_bases (one call per run of equal operation pairs) against `count` calls of _merge_one_base, the reference's
+  base-by-base form (fast_pass_aligner.cc:760-800), from every kind of preceding CIGAR - incl. the I-after-D / D-after-I rewrite
+  of MergeCigarOp and the clamp at the read length."""
+  import copy
+  import numpy as np
+  from deepvariant_b200 import fast_pass_aligner as fpa
+  rng = np.random.default_rng(3)
+  ops = [fpa.M, fpa.I, fpa.D, fpa.S]
+  n = 0
+  for _ in range(4000):
+    read_len = int(rng.integers(1, 40))
+    start = [[ops[int(rng.integers(0, 4))], int(rng.integers(1, 6))] for _ in range(int(rng.integers(0, 4)))]
+    start = [o for i, o in enumerate(start) if i == 0 or o[0] != start[i - 1][0]]
+    read_op, hap_op = ops[int(rng.integers(0, 4))], ops[int(rng.integers(0, 4))]
+    if (read_op, hap_op) in ((fpa.D, fpa.I), (fpa.I, fpa.D)):
+      continue
+    count = int(rng.integers(1, 30))
+    a, b = copy.deepcopy(start), copy.deepcopy(start)
+    for _ in range(count):
+      fpa._merge_one_base(read_op, hap_op, read_len, a)
+    fpa._merge_bases(read_op, hap_op, count, read_len, b)
+    assert a == b, (start, read_op, hap_op, count, read_len, a, b)
+    n += 1
+  assert n > 3000
