@@ -492,10 +492,15 @@ def run_deepvariant(argv):
   ap.add_argument('--staged', action='store_true')         # the reference's three stages with tf.Example files in between; default = fused
   ap.add_argument('--num_gpus', type=int, default=0)        # 0 = every visible device; task i runs on device i mod num_gpus
   ap.add_argument('--jobs', type=int, default=0)            # tasks in flight; 0 = all of them, as `parallel -j num_shards` (scripts/run_deepvariant.py:457-462)
+  ap.add_argument('--call_variants_extra_args', default='')  # scripts/run_deepvariant.py:112-118: "flag=value,..." - batch_size is honoured (classifier chunk, device memory)
   ap.add_argument('--logging_dir', default='')              # scripts/run_deepvariant.py:141
   ap.add_argument('--runtime_report', action='store_true')  # scripts/run_deepvariant.py:149,744-758: make_examples --runtime_by_region into logging_dir
   a = ap.parse_args(argv)
   os.makedirs(a.output_dir, exist_ok=True)
+  cv_extra = dict(kv.split('=', 1) for kv in a.call_variants_extra_args.split(',') if '=' in kv)
+  unknown = sorted(set(cv_extra) - {'batch_size'})
+  if unknown:
+    raise ValueError(f'--call_variants_extra_args: unsupported flags {unknown} (batch_size is)')
   runtime_by_region = ''
   if a.logging_dir and a.runtime_report:
     os.makedirs(os.path.join(a.logging_dir, 'make_examples_runtime_by_region'), exist_ok=True)
@@ -525,6 +530,8 @@ def run_deepvariant(argv):
     else:
       args += ['--call_variants_outfile', os.path.join(a.output_dir, f'call_variants_output@{a.num_shards}.tfrecord.gz'),
                '--checkpoint', a.customized_model, '--precision', str(a.precision)]
+      if 'batch_size' in cv_extra:
+        args += ['--call_batch_size', str(int(cv_extra['batch_size']))]
     if a.candidates_in:
       args += ['--candidates_in', a.candidates_in]
     for flag in ('sort_by_haplotypes', 'trim_reads_for_pileup', 'parse_sam_aux_fields', 'track_ref_reads', 'phase_reads', 'norealign_reads'):
@@ -562,7 +569,8 @@ def run_deepvariant(argv):
       raise RuntimeError(f'make_examples tasks {failed} failed')
   rc = 0
   if a.staged:
-    rc = call_variants(['--examples', examples, '--outfile', cvo, '--checkpoint', a.customized_model, '--precision', str(a.precision)])
+    rc = call_variants(['--examples', examples, '--outfile', cvo, '--checkpoint', a.customized_model, '--precision', str(a.precision)] +
+                       (['--batch_size', str(int(cv_extra['batch_size']))] if 'batch_size' in cv_extra else []))
   if rc or not a.output_vcf:
     return rc
   args = ['--ref', a.ref, '--infile', cvo, '--outfile', a.output_vcf]     # the shards call_variants wrote are found by name

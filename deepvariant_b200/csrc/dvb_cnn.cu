@@ -2987,7 +2987,7 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       {
         const int mode = EnvInt("DVB_CNN_PERSIST", 1);   // 0 never, 1 by rule, 2 always
         const long tiles = m_tiles * (o.cout / bn);
-        cl.persist = !split && (mode == 2 || (mode == 1 && bk == 64 && bn >= EnvInt("DVB_PERSIST_MIN_N", 160) && tiles >= 4L * net->num_sms));
+        cl.persist = !split && (mode == 2 || (mode == 1 && bk == 64 && bn >= EnvInt("DVB_PERSIST_MIN_N", 160) && tiles >= (long)EnvInt("DVB_PERSIST_MIN_TILES_PER_SM", 4) * net->num_sms));
       }
       const long want_ctas = cl.persist ? 0L : 4L * net->num_sms;   // the persistent kernel keeps the widest N block
       while (m_tiles * (o.cout / bn) < want_ctas && bn > 64) {

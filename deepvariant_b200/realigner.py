@@ -153,6 +153,10 @@ def select_windows(table, ref_reader, contig: str, rows: np.ndarray, region: Tup
   return candidates_to_windows(candidate_positions_from_counts(sites, start, o), o)
 
 
+_NOT_ACGT = np.ones(256, dtype=bool)
+_NOT_ACGT[[65, 67, 71, 84]] = False
+
+
 # ---- de Bruijn graph ----------------------------------------------------------------------------------------------------------------------
 class DeBruijnGraph:
 
@@ -184,16 +188,20 @@ class DeBruijnGraph:
 
   def _add_read(self, read: Read) -> None:
     bases = read.aligned_sequence.decode().upper()
-    quals = read.aligned_quality
     n, k = len(bases), self.k
     stop = n - k
-    i = 0
+    # positions that break a run of usable bases (non-ACGT or below the base-quality floor), found once per read
+    seq = np.frombuffer(bases.encode(), dtype=np.uint8)
+    quals = np.frombuffer(bytes(read.aligned_quality), dtype=np.uint8)
+    breaks = np.flatnonzero((_NOT_ACGT[seq]) | (quals[:n] < self.o.min_base_quality)).tolist() if len(quals) >= n else None
+    if breaks is None:
+      raise ValueError('read with fewer qualities than bases')
+    breaks.append(n)
+    i, b = 0, 0
     while i < stop:
-      bad = n
-      for j in range(i, n):
-        if bases[j] not in 'ACGT' or quals[j] < self.o.min_base_quality:
-          bad = j
-          break
+      while breaks[b] < i:
+        b += 1
+      bad = breaks[b]
       self._add(bases, i, bad - k, False)
       i = bad + 1
 

@@ -70,11 +70,12 @@ def main():
   ap.add_argument('--shards', type=int, default=1)
   ap.add_argument('--gpus', type=int, default=1)
   ap.add_argument('--precision', type=int, default=0)
+  ap.add_argument('--batch_size', type=int, default=512)     # classifier chunk per task (device memory per process)
   ap.add_argument('--out', default='')
   a = ap.parse_args()
   res = {'what': 'run_deepvariant (fused flow) wall clock, random-init weights', 'shards': a.shards, 'gpus': a.gpus, 'precision': a.precision,
          'host_cores': len(os.sched_getaffinity(0))}
-  extra = ['--num_shards', str(a.shards), '--num_gpus', str(a.gpus), '--precision', str(a.precision)]
+  extra = ['--num_shards', str(a.shards), '--num_gpus', str(a.gpus), '--precision', str(a.precision), '--call_variants_extra_args', f'batch_size={a.batch_size}']
   with tempfile.TemporaryDirectory() as d:
     g = os.path.join(ROOT, 'tests', 'golden')
     if os.path.exists(os.path.join(g, 'quickstart.chr20_10mb.bam')):

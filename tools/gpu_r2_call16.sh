@@ -11,3 +11,4 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 DVB_CNN_PAIR=3 DVB_PERSIST_MIN_N=128 timeout 200 python tools/cnn_time.py --batch 8192 --chunk 4096 > gpurun_out/c16_time_pair3.json 2>/dev/null; echo "pair3 exit $?"; cat gpurun_out/c16_time_pair3.json
 DVB_CNN_PAD_CIN64_MIN=160 DVB_CNN_PAIR=3 DVB_PERSIST_MIN_N=128 DVB_CNN_LIST=1 timeout 200 python tools/cnn_time.py --batch 8192 --chunk 4096 > gpurun_out/c16_time_pair3_pad.json 2> gpurun_out/c16_list_pair3_pad.txt; echo "pair3+pad exit $?"; cat gpurun_out/c16_time_pair3_pad.json
 DVB_HALO_RULE=2 DVB_CNN_PAD_CIN64_MIN=160 DVB_CNN_PAIR=3 DVB_PERSIST_MIN_N=128 timeout 200 python tools/cnn_time.py --batch 8192 --chunk 4096 > gpurun_out/c16_time_all.json 2>/dev/null; echo "all exit $?"; cat gpurun_out/c16_time_all.json
+DVB_CNN_PAIR=3 DVB_PERSIST_MIN_N=128 DVB_PERSIST_MIN_TILES_PER_SM=2 timeout 200 python tools/cnn_time.py --batch 8192 --chunk 4096 > gpurun_out/c16_time_pair3_tiles2.json 2>/dev/null; echo "pair3 tiles2 exit $?"; cat gpurun_out/c16_time_pair3_tiles2.json
