@@ -296,12 +296,19 @@ __device__ __forceinline__ void split_store2(float x0, float x1, uint32_t* main_
 }
 
 // Epilogue of one accumulator row in split mode: y = D0 + 2^-11 * D1 + bias -> ReLU -> (main, res) fp16 planes.
+__device__ __forceinline__ void epilogue_row_split2(uint32_t taddr, uint32_t taddr1, int block_n, const float* s_bias, __half* dst_main,
+                                                    __half* dst_res, bool valid, int relu);
 __device__ __forceinline__ void epilogue_row_split(uint32_t taddr, int block_n, const float* s_bias, __half* dst_main, __half* dst_res,
                                                    bool valid, int relu) {
+  epilogue_row_split2(taddr, taddr + (uint32_t)block_n, block_n, s_bias, dst_main, dst_res, valid, relu);
+}
+// D0 columns at taddr, D1 columns at taddr1 (a column range of a wider accumulator pair)
+__device__ __forceinline__ void epilogue_row_split2(uint32_t taddr, uint32_t taddr1, int block_n, const float* s_bias, __half* dst_main,
+                                                    __half* dst_res, bool valid, int relu) {
   for (int c = 0; c < block_n; c += 16) {
     uint32_t v0[16], v1[16];
     tmem_ld16(taddr + c, v0);
-    tmem_ld16(taddr + block_n + c, v1);
+    tmem_ld16(taddr1 + c, v1);
     tmem_ld_wait();
     if (!valid) continue;
 #pragma unroll
@@ -970,20 +977,29 @@ struct HaloArgs {
   int out_cstride, out_coff, relu;
   uint32_t idesc, layout_type, sbo_bytes;
   uint32_t a_copy_bytes, a_stage, b_tile, b_total_bytes;
+  uint32_t a_res_off, idesc_cat;  // precision 1: residual plane of a halo stage; instruction descriptor of N = 2 block_n
   __half* out;
+  __half* out_res;
   const float* bias;
   long long* trace;   // optional timeline of CTA 0: [group][8] clock64 stamps (development aid)
 };
 
 #define HALO_TRACE(grp_i, ev) do { if (p.trace && blockIdx.x == 0 && (grp_i) < 64) p.trace[(grp_i) * 8 + (ev)] = clock64(); } while (0)
 
+// kSplit (precision 1, split-fp16 x3): every weight tile is followed by its residual tile, every halo stage holds the main and the
+// residual plane, a tile's accumulators are the column pair [D0 | D1]:  [D0 | D1] += A_main * [B_main ; B_res]  (one instruction,
+// N = 2 block_n) and  D1 += A_res * B_main.
+template <bool kSplit>
 __global__ void __launch_bounds__(kHaloThreads, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const HaloArgs p) {
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_a_res,
+                 const __grid_constant__ CUtensorMap map_b_res, const HaloArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic (not an integer round trip): ptxas keeps the shared address space -> LDS / STS, not generic LD / ST
   const int taps = p.kh * p.kw;
-  uint8_t* smem_b = smem;                                           // [cin_blocks][taps][block_n][block_k]
-  uint8_t* smem_a = smem + (size_t)p.cin_blocks * taps * p.b_tile;  // [stages][halo pixels][block_k]
+  constexpr uint32_t kPlanes = kSplit ? 2u : 1u;
+  const uint32_t b_slot = kPlanes * p.b_tile;                       // one (Cin block, tap): the filter tile [+ its residual tile]
+  uint8_t* smem_b = smem;                                           // [cin_blocks][taps][planes][block_n][block_k]
+  uint8_t* smem_a = smem + (size_t)p.cin_blocks * taps * b_slot;    // [stages][planes][halo pixels][block_k]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)p.stages * p.a_stage);
   uint64_t* a_full = bars;                              // [kMaxStages * 2]
   uint64_t* a_empty = bars + 2 * kMaxStages;
@@ -1008,6 +1024,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_b);
+    if constexpr (kSplit) { prefetch_tmap(&map_a_res); prefetch_tmap(&map_b_res); }
     for (int s = 0; s < p.stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     mbar_init(b_full, 1);
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 32 * kHaloEpiWarps); }
@@ -1024,10 +1041,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     {
       // ===== TMA producer (whole warp, one elected lane issues): weights once, then one halo per (tile, Cin block) =====
       if (elect_one()) {
-        mbar_arrive_expect_tx(b_full, p.b_total_bytes);
+        mbar_arrive_expect_tx(b_full, kPlanes * p.b_total_bytes);
         for (int cb = 0; cb < p.cin_blocks; ++cb)
-          for (int t = 0; t < taps; ++t)
-            tma_load_3d(smem_b + (size_t)(cb * taps + t) * p.b_tile, &map_b, b_full, cb * p.block_k, nb * p.block_n, t);
+          for (int t = 0; t < taps; ++t) {
+            tma_load_3d(smem_b + (size_t)(cb * taps + t) * b_slot, &map_b, b_full, cb * p.block_k, nb * p.block_n, t);
+            if constexpr (kSplit) tma_load_3d(smem_b + (size_t)(cb * taps + t) * b_slot + p.b_tile, &map_b_res, b_full, cb * p.block_k, nb * p.block_n, t);
+          }
       }
       __syncwarp();
       int st = 0;
@@ -1041,8 +1060,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int th = rem / p.tiles_w, tw = rem - th * p.tiles_w;
             mbar_wait(&a_empty[st], ph ^ 1);
             if (elect_one()) {
-              mbar_arrive_expect_tx(&a_full[st], p.a_copy_bytes);
+              mbar_arrive_expect_tx(&a_full[st], kPlanes * p.a_copy_bytes);
               tma_load_4d(smem_a + (size_t)st * p.a_stage, &map_a, &a_full[st], cb * p.block_k, tw * p.Wv - p.pad_w, th * p.Ht - p.pad_h, n);
+              if constexpr (kSplit)
+                tma_load_4d(smem_a + (size_t)st * p.a_stage + p.a_res_off, &map_a_res, &a_full[st], cb * p.block_k, tw * p.Wv - p.pad_w, th * p.Ht - p.pad_h, n);
             }
             __syncwarp();
             if (++st == p.stages) { st = 0; ph ^= 1; }
@@ -1060,9 +1081,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t hi = desc_hi(p.sbo_bytes, p.layout_type), idesc = p.idesc;
       const uint32_t a_lo0 = desc_lo(smem_u32(smem_a)), b_lo0 = desc_lo(smem_u32(smem_b));
       const uint32_t a_stage_inc = p.a_stage >> 4, a_row_inc = ((uint32_t)p.P * row_bytes) >> 4, a_px_inc = row_bytes >> 4;
-      const uint32_t b_tile_inc = p.b_tile >> 4;
+      const uint32_t b_tile_inc = b_slot >> 4, a_res_inc = p.a_res_off >> 4;
       const int stages = p.stages, kh = p.kh, kw = p.kw, cin_blocks = p.cin_blocks;
-      const uint32_t block_n = (uint32_t)p.block_n;
+      const uint32_t block_n = kPlanes * (uint32_t)p.block_n;     // TMEM columns of one tile's accumulator(s)
       const int nbuf = p.nbuf;
       int st = 0, buf = 0;
       uint32_t ph = 0, buf_ph = 0;
@@ -1097,7 +1118,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               for (int k = 0; k < mma_per_kb; ++k) {
                 const uint32_t ao = off + 2 * k, bo = bl + 2 * k, ac = acm | (uint32_t)(k != 0);
                 // straight-line round-robin over the T accumulators: consecutive MMAs never depend on each other
-                if (T == 8) {
+                if constexpr (kSplit) {
+#pragma unroll
+                  for (int t = 0; t < kMaxGroup; ++t)
+                    if (t < T) {
+                      umma_f16_lohi(d0 + (uint32_t)t * block_n, a_lo_t[t] + ao, bo, hi, p.idesc_cat, ac);                            // [D0 | D1] += A_main * [B_main ; B_res]
+                      umma_f16_lohi(d0 + (uint32_t)t * block_n + (uint32_t)p.block_n, a_lo_t[t] + a_res_inc + ao, bo, hi, idesc, 1u);   // D1 += A_res * B_main
+                    }
+                } else if (T == 8) {
                   umma_f16_lohi(d0, a_lo_t[0] + ao, bo, hi, idesc, ac);
                   umma_f16_lohi(d1, a_lo_t[1] + ao, bo, hi, idesc, ac);
                   umma_f16_lohi(d2, a_lo_t[2] + ao, bo, hi, idesc, ac);
@@ -1169,7 +1197,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int w = tw * p.Wv + slot, h = th * p.Ht + hh;
         const bool valid = (slot < p.Wv) && (w < p.Wout) && (h < p.Hout);
         __half* dst = p.out + ((size_t)((size_t)n * p.Hout + h) * p.Wout + w) * p.out_cstride + p.out_coff + nb * p.block_n + c0;
-        epilogue_row(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * T + t) * p.block_n + c0), cols, s_bias + c0, dst, valid, p.relu);
+        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * T + t) * (int)kPlanes * p.block_n + c0);
+        if constexpr (kSplit) epilogue_row_split2(tacc, tacc + (uint32_t)p.block_n, cols, s_bias + c0, dst, p.out_res + (dst - p.out), valid, p.relu);
+        else epilogue_row(tacc, cols, s_bias + c0, dst, valid, p.relu);
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[buf]);
@@ -2341,7 +2371,7 @@ struct ConvLaunch {
   int n_blocks, cout;
 };
 struct HaloLaunch {
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_a_res, map_b_res;
   HaloArgs args;
   int smem, ctas_per_nblock;
   double macs_per_image;
@@ -2818,7 +2848,8 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       if (rows_pool) return dvb::fail(DVB_ERR_INTERNAL, "conv_rows_kernel: %d bytes of shared memory", rl.smem);
     }
     // ---- large stride-1 k x k layers: persistent halo-reusing kernel (see conv_halo_kernel)
-    if (!split && !is_stem && o.stride == 1 && o.kh * o.kw > 1 && Hout * Wout >= EnvInt("DVB_HALO_MIN_PIXELS", 250) && EnvInt("DVB_CNN_HALO", 1)) {
+    const bool halo_split = split && EnvInt("DVB_HALO_RULE", 1) == 2 && EnvInt("DVB_HALO_SPLIT", 1);   // precision 1 runs the halo kernel only under rule 2
+    if ((!split || halo_split) && !is_stem && o.stride == 1 && o.kh * o.kw > 1 && Hout * Wout >= EnvInt("DVB_HALO_MIN_PIXELS", 250) && EnvInt("DVB_CNN_HALO", 1)) {
       HaloLaunch hl;
       memset(&hl, 0, sizeof(hl));
       HaloArgs& a = hl.args;
@@ -2859,11 +2890,17 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       a.tiles_h = (Hout + a.Ht - 1) / a.Ht;
       a.Hout = Hout; a.Wout = Wout;
       const int Hh = a.Ht + o.kh;   // Ht + kh - 1 rows are needed; one spare row absorbs the kw-1 pixel overrun of the last tap
+      const int planes = split ? 2 : 1;
       a.a_copy_bytes = (uint32_t)Hh * a.P * row_bytes;
-      a.a_stage = (a.a_copy_bytes + 1023u) & ~1023u;
+      a.a_res_off = (a.a_copy_bytes + 1023u) & ~1023u;
+      a.a_stage = (uint32_t)planes * a.a_res_off;
       // N block: the resident weight slice must leave room for the halo ring
       int bn = ChooseBlockN(o.cout);
-      auto b_total = [&](int n) { return (size_t)a.cin_blocks * taps * (((size_t)n * row_bytes + 1023) & ~(size_t)1023); };
+      if (split && bn > 128) {   // [D0 | D1] in one instruction: N = 2 block_n <= 256
+        for (int d = 128; d >= 16; d -= 16)
+          if (o.cout % d == 0) { bn = d; break; }
+      }
+      auto b_total = [&](int n) { return (size_t)planes * a.cin_blocks * taps * (((size_t)n * row_bytes + 1023) & ~(size_t)1023); };
       while ((halo_rule == 2 ? b_total(bn) + 2 * a.a_stage > 216 * 1024 : b_total(bn) + 4 * a.a_stage > 200 * 1024) && bn > 16) {
         int next = 0;
         for (int d = bn - 16; d >= 16; d -= 16)
@@ -2873,8 +2910,9 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       }
       a.block_n = bn; a.n_blocks = o.cout / bn;
       a.b_tile = (uint32_t)((bn * row_bytes + 1023) & ~1023);
-      a.b_total_bytes = (uint32_t)a.cin_blocks * taps * bn * row_bytes;   // bytes the TMA delivers
-      const size_t b_smem = (size_t)a.cin_blocks * taps * a.b_tile;
+      a.b_total_bytes = (uint32_t)a.cin_blocks * taps * bn * row_bytes;   // bytes the TMA delivers (per plane)
+      const size_t b_smem = (size_t)planes * a.cin_blocks * taps * a.b_tile;
+      const int acc_cols = planes * bn;                                   // TMEM columns of one tile
       // T tiles in flight = T independent accumulation chains (measured issue interval per MMA, N <= 64: 222 cycles
       // with 1 chain, 80 with 4, 46 with 8).  Two TMEM buffers of T accumulators when 2*T*bn <= 512 columns, else one.
       // Rule 2 (round 2, after the issue path was fixed - one accumulation chain now runs at the tensor pipe's own interval, see
@@ -2884,10 +2922,10 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       const int avail_stages = (int)((216 * 1024 - (long)b_smem) / (long)a.a_stage);
       int T;
       if (halo_rule == 2) {
-        T = (4 * bn <= 512 && avail_stages >= 4) ? 2 : 1;
+        T = (4 * acc_cols <= 512 && avail_stages >= 4) ? 2 : 1;
         T = std::max(1, std::min(T, EnvInt("DVB_HALO_T", 8)));
         a.T = T;
-        a.nbuf = 2 * a.T * bn <= 512 ? 2 : 1;
+        a.nbuf = 2 * a.T * acc_cols <= 512 ? 2 : 1;
         a.stages = std::max(1, std::min(std::min(2 * kMaxStages, std::max(4, 2 * a.T)), avail_stages));
       } else {
       T = std::min(kMaxGroup, 512 / bn);
@@ -2903,17 +2941,19 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       a.n_split = 1;
       for (int ns = std::max(1, 4 / a.T); ns >= 1; --ns)
         if (bn % ns == 0 && (bn / ns) % 16 == 0) { a.n_split = ns; break; }
-      a.tmem_cols = TmemCols(a.nbuf * a.T * bn);
-      a.out = dst.ptr; a.out_cstride = dst.C; a.out_coff = o.off; a.relu = relu_single;
+      a.tmem_cols = TmemCols(a.nbuf * a.T * acc_cols);
+      a.out = dst.ptr; a.out_res = dst.ptr_res; a.out_cstride = dst.C; a.out_coff = o.off; a.relu = relu_single;
       a.bias = conv_bias;
       a.idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      a.idesc_cat = (1u << 4) | ((uint32_t)((2 * bn) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       a.layout_type = bk == 64 ? 2u : bk == 32 ? 4u : 6u;
       a.sbo_bytes = 8u * (uint32_t)row_bytes;
       hl.smem = (int)(b_smem + (size_t)a.stages * a.a_stage) + 1024 + 512 + bn * 4;
       hl.macs_per_image = (double)Hout * Wout * o.cout * o.kh * o.kw * o.cin;
       // Only worth it when >= 4 double-buffered accumulation chains fit in TMEM (N block <= 64); wider layers (conv5,
       // N = 192) measured slower here than with the tap-by-tap kernel and stay there.
-      const bool halo_ok = halo_rule == 2 ? (a.stages >= std::max(2, a.T) && a.nbuf == 2 && bn >= 64 && a.b_tile == (uint32_t)(bn * row_bytes))
+      const bool halo_ok = halo_rule == 2 ? (a.stages >= std::max(2, a.T) && a.nbuf == 2 && (bn >= 64 || bn == o.cout || split) && bn >= 32 &&
+                                             a.b_tile == (uint32_t)(bn * row_bytes) && (!split || 2 * bn <= 256))
                                            : (a.stages >= a.T && a.T >= 4 && a.nbuf == 2 && a.n_blocks == 1);
       if (a.tmem_cols <= 512 && hl.smem <= 227 * 1024 && halo_ok) {
         // weights [Cout][taps][Cin] -> [taps][Cout][Cin] so that one (tap, N block, Cin block) is a canonical K-major tile
@@ -2923,6 +2963,13 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
           for (int t = 0; t < taps; ++t)
             memcpy(&w2[((size_t)t * o.cout + co) * cin_store], &w[((size_t)co * taps + t) * blob_cin], (size_t)blob_cin * sizeof(__half));
         cudaMemcpy(dw, w2.data(), wbytes, cudaMemcpyHostToDevice);
+        if (split) {   // the residual plane of the filters, same re-layout
+          const __half* wr = reinterpret_cast<const __half*>(blob_w_main + blob_wbytes);
+          for (int co = 0; co < o.cout; ++co)
+            for (int t = 0; t < taps; ++t)
+              memcpy(&w2[((size_t)t * o.cout + co) * cin_store], &wr[((size_t)co * taps + t) * blob_cin], (size_t)blob_cin * sizeof(__half));
+          cudaMemcpy(dw_res, w2.data(), wbytes, cudaMemcpyHostToDevice);
+        }
         {
           const cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)net->max_batch};
           const cuuint64_t strides[3] = {(cuuint64_t)src.C * 2, (cuuint64_t)Win * src.C * 2, (cuuint64_t)Hin * Win * src.C * 2};
@@ -2930,6 +2977,11 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
           const cuuint32_t estr[4] = {1, 1, 1, 1};
           st = MakeMap(&hl.map_a, src.ptr, 4, dims, strides, box, estr, bk);
           if (st) return st;
+          hl.map_a_res = hl.map_a;
+          if (split) {
+            st = MakeMap(&hl.map_a_res, src.ptr_res, 4, dims, strides, box, estr, bk);
+            if (st) return st;
+          }
         }
         {
           const cuuint64_t dims[3] = {(cuuint64_t)cin_store, (cuuint64_t)o.cout, (cuuint64_t)taps};
@@ -2938,6 +2990,11 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
           const cuuint32_t estr[3] = {1, 1, 1};
           st = MakeMap(&hl.map_b, dw, 3, dims, strides, box, estr, bk);
           if (st) return st;
+          hl.map_b_res = hl.map_b;
+          if (split) {
+            st = MakeMap(&hl.map_b_res, dw_res, 3, dims, strides, box, estr, bk);
+            if (st) return st;
+          }
         }
         macs_total += hl.macs_per_image;
         net->steps.push_back(Step{2, (int)net->halos.size()});
@@ -3177,11 +3234,13 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
     return dvb::fail(DVB_ERR_CUDA, "cannot reserve %d bytes of shared memory (rows kernel)", max_rows);
   int max_halo = 0;
   for (auto& h : net->halos) max_halo = std::max(max_halo, h.smem);
-  if (max_halo && cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_halo) != cudaSuccess)
+  if (max_halo && (cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_halo) != cudaSuccess ||
+                   cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_halo) != cudaSuccess))
     return dvb::fail(DVB_ERR_CUDA, "cannot reserve %d bytes of shared memory (halo kernel)", max_halo);
   for (auto& h : net->halos) {
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_halo_kernel, kHaloThreads, h.smem);
+    if (net->precision == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_halo_kernel<true>, kHaloThreads, h.smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_halo_kernel<false>, kHaloThreads, h.smem);
     occ = std::max(1, std::min(occ, 512 / h.args.tmem_cols));
     h.ctas_per_nblock = std::max(1, net->num_sms * occ / h.args.n_blocks);
   }
@@ -3261,7 +3320,10 @@ int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaSt
       const bool tracing = EnvInt("DVB_CNN_TRACE", 0) != 0;
       if (tracing && !d_trace) { cudaMalloc(&d_trace, 64 * 8 * sizeof(long long)); }
       if (tracing) { cudaMemsetAsync(d_trace, 0, 64 * 8 * sizeof(long long), s); a.trace = d_trace; }
-      conv_halo_kernel<<<(unsigned)(G * a.n_blocks), kHaloThreads, hl.smem, s>>>(hl.map_a, hl.map_b, a);
+      if (net->precision == 1)
+        conv_halo_kernel<true><<<(unsigned)(G * a.n_blocks), kHaloThreads, hl.smem, s>>>(hl.map_a, hl.map_b, hl.map_a_res, hl.map_b_res, a);
+      else
+        conv_halo_kernel<false><<<(unsigned)(G * a.n_blocks), kHaloThreads, hl.smem, s>>>(hl.map_a, hl.map_b, hl.map_a_res, hl.map_b_res, a);
       if (tracing) {
         std::vector<long long> h(64 * 8);
         cudaStreamSynchronize(s);
