@@ -1629,16 +1629,20 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 constexpr int kStemRawPitch = 1840;   // bytes per staged raw input row segment (>= 15 + 1799 + 4 rounded up to 16)
 
-__global__ void __launch_bounds__(kStemThreads) stem_conv1_kernel(const StemArgs p) {
+// kPipe: the tile loop as a software pipeline - the MMAs of tile i run while tile i + 1 is converted, and the epilogue of tile i (all
+// eight warps, two per TMEM lane quarter) sits between the conversion and the patch assembly of tile i + 1: two accumulators in TMEM,
+// three block barriers per tile instead of four, no warp waits for the tensor pipe's latency.
+template <bool kPipe>
+__global__ void __launch_bounds__(kStemThreads, 4) stem_conv1_kernel(const StemArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic (not an integer round trip): ptxas keeps the shared address space -> LDS / STS, not generic LD / ST
   uint8_t* sA = smem;                         // 128 rows x 128 B, 128B swizzle
   uint8_t* sB = smem + 16384;                 // cout rows x 128 B, 128B swizzle (cout <= 32 -> 4 KB)
   __half* sH = reinterpret_cast<__half*>(smem + 16384 + 4096);   // [3][h_pitch]
   uint8_t* sRaw = reinterpret_cast<uint8_t*>(sH + 3 * p.h_pitch);   // [2][3][kStemRawPitch] raw uint8 row segments (cp.async ring)
-  uint64_t* mma_done = reinterpret_cast<uint64_t*>(sRaw + 2 * 3 * kStemRawPitch);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
-  float* s_bias = reinterpret_cast<float*>(mma_done + 2);
+  uint64_t* mma_done = reinterpret_cast<uint64_t*>(sRaw + 2 * 3 * kStemRawPitch);   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 2);
+  float* s_bias = reinterpret_cast<float*>(mma_done + 3);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid < p.cout) s_bias[tid] = p.bias[tid];
@@ -1646,8 +1650,8 @@ __global__ void __launch_bounds__(kStemThreads) stem_conv1_kernel(const StemArgs
     const int n = i >> 3, j = i & 7;
     *reinterpret_cast<uint4*>(sB + n * 128 + ((j ^ (n & 7)) << 4)) = *reinterpret_cast<const uint4*>(p.w + n * 64 + j * 8);
   }
-  if (tid == 0) { mbar_init(mma_done, 1); fence_barrier_init(); }
-  if (warp == 1) tmem_alloc(tmem_slot, 32);
+  if (tid == 0) { mbar_init(&mma_done[0], 1); mbar_init(&mma_done[1], 1); fence_barrier_init(); }
+  if (warp == 1) tmem_alloc(tmem_slot, kPipe ? 64 : 32);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -1691,10 +1695,24 @@ __global__ void __launch_bounds__(kStemThreads) stem_conv1_kernel(const StemArgs
     cp_async_commit();
   };
 
+  // epilogue of one tile: kPipe - all eight warps, two per TMEM lane quarter, half of the filters each (cout = 32) or the first four (cout = 16)
+  auto drain = [&](int en, int eoh, int etw, int buf) {
+    const int q = warp & 3, hf = warp >> 2;
+    const int cw = p.cout >= 32 ? p.cout / 2 : p.cout;
+    if (hf == 1 && p.cout < 32) return;
+    const int eow0 = etw * 128;
+    const int m = q * 32 + lane;
+    const bool valid = m < min(128, p.Wo - eow0);
+    __half* dst = p.out + (((size_t)en * p.Ho + eoh) * p.Wo + eow0 + m) * p.out_cstride + hf * cw;
+    epilogue_row(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 32 + hf * cw), cw, s_bias + hf * cw, dst, valid, 1);
+  };
   const int total = (int)total_tiles;
   int tile = blockIdx.x;
   int slot = 0;
   int n, oh, tw;
+  int pn = 0, poh = 0, ptw = 0, pbuf = 0, buf = 0;   // kPipe: the tile whose MMAs are in flight
+  bool have_prev = false;
+  uint32_t done_ph0 = 0u, done_ph1 = 0u;
   decode(min(tile, total - 1), n, oh, tw);
   if (tile < total) stage(n, oh, tw, 0);
   for (; tile < total; tile += gridDim.x, slot ^= 1) {
@@ -1720,7 +1738,16 @@ __global__ void __launch_bounds__(kStemThreads) stem_conv1_kernel(const StemArgs
         dst[i] = make_uint2(*reinterpret_cast<uint32_t*>(&ha), *reinterpret_cast<uint32_t*>(&hb));
       }
     }
-    __syncthreads();
+    if constexpr (kPipe) {
+      if (have_prev) {   // the previous tile's MMAs were issued a whole conversion ago: its accumulator is (all but always) complete
+        mbar_wait(&mma_done[pbuf], pbuf ? done_ph1 : done_ph0);
+        if (pbuf) done_ph1 ^= 1u; else done_ph0 ^= 1u;
+        tc_fence_after();
+        drain(pn, poh, ptw, pbuf);
+        tc_fence_before();
+      }
+    }
+    __syncthreads();   // (kPipe: every warp has seen the previous tile's MMAs retire -> sA may be rewritten)
     // ---- phase 2: patch rows.  Thread (m, hf): output words [16 hf, 16 hf + 16) of row m (lane stride 7 words: conflict-free).
     {
       const int m = tid & 127, hf = tid >> 7;   // warp-uniform halves: warps 0-3 build words 0..15, warps 4-7 words 16..31
@@ -1763,14 +1790,20 @@ __global__ void __launch_bounds__(kStemThreads) stem_conv1_kernel(const StemArgs
       const uint32_t hi = desc_hi(1024u, 2u), a_lo = desc_lo(smem_u32(sA)), b_lo = desc_lo(smem_u32(sB));
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_lohi(tmem_base, a_lo + 2 * k, b_lo + 2 * k, hi, p.idesc, (uint32_t)(k != 0));
-        umma_commit(mma_done);
+        for (int k = 0; k < 4; ++k) umma_f16_lohi(tmem_base + (uint32_t)(buf * 32), a_lo + 2 * k, b_lo + 2 * k, hi, p.idesc, (uint32_t)(k != 0));
+        umma_commit(&mma_done[buf]);
       }
       __syncwarp();
     }
+    if constexpr (kPipe) {
+      pn = n; poh = oh; ptw = tw; pbuf = buf; have_prev = true;
+      buf ^= 1;
+      n = n2; oh = oh2; tw = tw2;
+      continue;   // no closing barrier: the next iteration's first barrier orders the ring slot, the barrier before its patch assembly orders sA
+    }
     // ---- epilogue: warps 0..3 own TMEM lane quarters 0..3
     if (warp < 4) {
-      mbar_wait(mma_done, phase);
+      mbar_wait(&mma_done[0], phase);
       tc_fence_after();
       const int m = warp * 32 + lane;
       const bool valid = m < npx;
@@ -1782,9 +1815,16 @@ __global__ void __launch_bounds__(kStemThreads) stem_conv1_kernel(const StemArgs
     n = n2; oh = oh2; tw = tw2;
     __syncthreads();   // accumulator drained, sA / sH free for the next tile
   }
+  if constexpr (kPipe) {
+    if (have_prev) {
+      mbar_wait(&mma_done[pbuf], pbuf ? done_ph1 : done_ph0);
+      tc_fence_after();
+      drain(pn, poh, ptw, pbuf);
+    }
+  }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 32);
+  if (warp == 1) tmem_dealloc(tmem_base, kPipe ? 64 : 32);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -3223,7 +3263,8 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
   // settle for one that fits fewer blocks)
   cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-  cudaFuncSetAttribute(stem_conv1_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(stem_conv1_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(stem_conv1_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   if (net->stem_rows && cudaFuncSetAttribute(stem_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              1024 + kS1ARing * 8192 + 8192 + kS1RawSlots * kS1RawPitch + (2 * kS1ARing + 4) * 8 + 32 * 4 + 64) != cudaSuccess)
     return dvb::fail(DVB_ERR_CUDA, "cannot reserve shared memory (stem rows kernel)");
@@ -3274,10 +3315,11 @@ int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaSt
     a.in = images; a.n_images = n;
     a.total_bytes = (long long)n * net->H * net->W * net->C;
     const long long tiles = (long long)n * a.Ho * a.tiles_w;
-    const int smem = 1024 + 16384 + 4096 + 3 * a.h_pitch * 2 + 2 * 3 * kStemRawPitch + 16 + a.cout * 4;
+    const int smem = 1024 + 16384 + 4096 + 3 * a.h_pitch * 2 + 2 * 3 * kStemRawPitch + 32 + a.cout * 4;
     const int occ = EnvInt("DVB_STEM_CTAS_PER_SM", 4);   // 64 registers x 256 threads -> 4 resident CTAs per SM
     const unsigned grid = (unsigned)std::min<long long>(tiles, (long long)net->num_sms * occ);
-    stem_conv1_kernel<<<grid, kStemThreads, smem, s>>>(a);
+    if (EnvInt("DVB_STEM_PIPE", 0)) stem_conv1_kernel<true><<<grid, kStemThreads, smem, s>>>(a);
+    else stem_conv1_kernel<false><<<grid, kStemThreads, smem, s>>>(a);
   } else {
     const int groups = (net->stem_Ho + kPatchRows - 1) / kPatchRows;
     const int row_pitch = (net->W * net->C + 3 + 15) & ~15;

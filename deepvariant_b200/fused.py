@@ -114,6 +114,8 @@ class FusedCaller:
       return
     if packed.n_images != len(plans):
       raise ValueError('one packed image per plan expected')
+    if self._packed and (self._packed[-1].support is None) != (packed.support is None):
+      self.flush()       # batches with allele keys (device-side support) and batches with name-searched support do not share a launch
     self._packed.append(packed)
     self._order.append(('p', len(plans), list(plans)))
     self._pending += len(plans)

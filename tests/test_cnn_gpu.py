@@ -455,3 +455,21 @@ def test_flat_average_pool_equals_sliding_form_bit_for_bit(monkeypatch, pool_aft
     for k in outs[0][1]:
       np.testing.assert_array_equal(outs[0][1][k], outs[1][1][k])
     np.testing.assert_array_equal(outs[0][0], outs[1][0])
+
+
+def test_pipelined_stem_conv1_equals_bulk_synchronous_form(monkeypatch):
+  """stem_conv1_kernel<kPipe> (MMAs of tile i under the conversion of tile i + 1, epilogue on all eight warps from two TMEM
+  accumulators) against the bulk-synchronous form: same operands, same instructions -> identical s1 and probabilities; several
+  tiles per CTA (48 images) so that both accumulators and both barrier phases cycle."""
+  shape = (100, 221, 7)
+  w = modeling.random_weights(7, 35)
+  imgs = _images(48, shape, 35)
+  outs = []
+  for pipe in ('0', '1'):
+    monkeypatch.setenv('DVB_STEM_PIPE', pipe)
+    net = cv.GpuCnn(w, shape, device=0, max_batch=48)
+    probs = net.forward_host(imgs.numpy())
+    outs.append((net.debug_tensor('s1', 48), probs))
+    net.close()
+  np.testing.assert_array_equal(outs[0][0], outs[1][0])
+  np.testing.assert_array_equal(outs[0][1], outs[1][1])

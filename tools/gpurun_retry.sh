@@ -4,7 +4,7 @@ log=$1; shift
 for attempt in $(seq 1 60); do
   /usr/local/graft/bin/gpurun "$@" > "$log" 2>&1
   rc=$?
-  if ! grep -q "status=transient" "$log" && [ $rc -ne 3 ]; then exit $rc; fi
+  if ! grep -q "status=transient\|already running" "$log" && [ $rc -ne 3 ]; then exit $rc; fi
   sleep 90
 done
 exit 3
