@@ -225,6 +225,8 @@ SYMBOLS = (
                                                     C.POINTER(DvbCandidateOptions), C.c_int, C.c_void_p, C.c_void_p]),
     ('dvb_debug_allele_counts', C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                             C.POINTER(DvbCandidateOptions), C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
+    ('dvb_dbg_candidate_haplotypes', C.c_int64, [C.c_char_p, C.c_int64, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                                 C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     ('dvb_debug_read_allele_at', C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
                                            C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     ('dvb_encoder_last_pair_support', C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -257,6 +257,7 @@ def make_examples(argv):
       ropts = realigner.RealignerOptions(normalize_reads=a.normalize_reads)                 # realigner.py:414-429
       ropts.ws.keep_legacy_behavior = a.keep_legacy_allele_counter_behavior                 # realigner.py:345-360
       rl = realigner.Realigner(fasta.IndexedFastaReader(a.ref), ropts)
+      rl.ssw_device = gen.ssw_device     # read-to-haplotype / haplotype-to-reference Smith-Waterman in batched launches when the stage runs on a GPU
     ref = fasta.IndexedFastaReader(a.ref)
     copts = cand.CandidateOptions(
         min_mapping_quality=a.min_mapping_quality, min_base_quality=a.min_base_quality,

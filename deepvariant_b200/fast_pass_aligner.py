@@ -298,13 +298,20 @@ class FastPassAligner:
     if not self.read_to_haplotype_alignments:
       self.read_to_haplotype_alignments = [HaplotypeReadsAlignment(i, -1, [ReadAlignment() for _ in self.reads])
                                            for i in range(len(self.haplotypes))]
+    # with `ssw_device` set the haplotype-to-reference alignments of the call share one dvb_ssw_align_batch launch
+    todo = [ha for ha in self.read_to_haplotype_alignments if self.haplotypes[ha.haplotype_index] != self.reference]
+    batched = {}
+    if self.ssw_device is not None and len(todo) >= 2:
+      als = ssw.align_batch([(self.reference, self.haplotypes[ha.haplotype_index]) for ha in todo], self.match_score, self.mismatch_penalty,
+                            self.gap_opening_penalty, self.gap_extending_penalty, device=self.ssw_device)
+      batched = {id(ha): al for ha, al in zip(todo, als)}
     for ha in self.read_to_haplotype_alignments:
       hap = self.haplotypes[ha.haplotype_index]
       if hap == self.reference:
         ha.is_reference, ha.cigar, ha.ref_pos = True, f'{len(hap)}=', 0
         ha.cigar_ops = cigar_string_to_ops(ha.cigar)
       else:
-        al = self._ssw_align(self.reference, hap)
+        al = batched[id(ha)] if batched else self._ssw_align(self.reference, hap)
         if al.sw_score > 0:
           ha.is_reference = al.cigar_string == f'{len(hap)}='
           ha.cigar, ha.ref_pos = al.cigar_string, al.ref_begin

@@ -284,6 +284,36 @@ def build_graph(ref: str, reads: Sequence[Read], o: DeBruijnGraphOptions) -> Opt
   return None
 
 
+def candidate_haplotypes_native(ref: str, reads: Sequence[Read], o: DeBruijnGraphOptions) -> Optional[List[str]]:
+  """build_graph(...).candidate_haplotypes() in native code (csrc/dvb_dbg.cu, dvb_dbg_candidate_haplotypes): None when no k gives
+  an acyclic graph, else the sorted haplotypes (possibly none).  The Python DeBruijnGraph above is its cross-check in the tests."""
+  import ctypes as C
+  from deepvariant_b200 import _lib
+  lib = _lib.lib()
+  seqs = [bytes(r.aligned_sequence) for r in reads]
+  begin = np.zeros(len(reads) + 1, dtype=np.int64)
+  if reads:
+    np.cumsum([len(x) for x in seqs], out=begin[1:])
+  bases = b''.join(seqs)
+  quals = np.frombuffer(b''.join(bytes(r.aligned_quality) for r in reads), dtype=np.uint8) if reads else np.zeros(1, np.uint8)
+  if len(quals) < int(begin[-1]):
+    raise ValueError('read with fewer qualities than bases')
+  mapq = np.fromiter((r.mapping_quality for r in reads), dtype=np.int32, count=len(reads)) if reads else np.zeros(1, np.int32)
+  ref_b = ref.encode()
+  cap = 64 * (len(ref_b) + 64)
+  while True:
+    out = C.create_string_buffer(cap)
+    need = lib.dvb_dbg_candidate_haplotypes(ref_b, len(ref_b), bases, quals.ctypes.data, begin.ctypes.data, mapq.ctypes.data, len(reads), o.min_k, o.max_k,
+                                            o.step_k, o.min_mapq, o.min_base_quality, o.min_edge_weight, o.max_num_paths, out, cap, None)
+    if need < 0:
+      _lib.check(int(-need))
+    if need == 0:
+      return None
+    if need <= cap:
+      return out.value.decode().split('\n')[:-1] if need > 1 else []
+    cap = int(need)
+
+
 # ---- the realigner ----------------------------------------------------------------------------------------------------------------------------
 def _overlap(a0: int, a1: int, b0: int, b1: int) -> int:
   return max(0, min(a1, b1) - max(a0, b0))
@@ -294,6 +324,8 @@ class Realigner:
   def __init__(self, ref_reader, options: Optional[RealignerOptions] = None):
     self.ref_reader = ref_reader
     self.o = options or RealignerOptions()
+    self.native_graph = True      # de Bruijn graph in native code (csrc/dvb_dbg.cu); False = the Python restatement (the tests' cross-check)
+    self.ssw_device: Optional[int] = None   # CUDA device for the Smith-Waterman alignments of FastPassAligner (batched launches); None = host
 
   def call_debruijn_graph(self, contig: str, windows: Sequence[Tuple[int, int]], reads: Sequence[Read]) -> List[Tuple[Tuple[int, int], List[str]]]:
     out = []
@@ -302,8 +334,12 @@ class Realigner:
         continue
       ref = self.ref_reader.query(contig, w0, w1)
       window_reads = [r for r in reads if w1 > r.position and w0 < r.end()]
-      g = build_graph(ref, window_reads, self.o.dbg)
-      haplotypes = [ref] if g is None else g.candidate_haplotypes()
+      if self.native_graph:
+        haplotypes = candidate_haplotypes_native(ref, window_reads, self.o.dbg)
+        haplotypes = [ref] if haplotypes is None else haplotypes
+      else:
+        g = build_graph(ref, window_reads, self.o.dbg)
+        haplotypes = [ref] if g is None else g.candidate_haplotypes()
       if haplotypes and haplotypes != [ref]:
         out.append(((w0, w1), haplotypes))
     return out
@@ -320,6 +356,7 @@ class Realigner:
       return reads
     suffix = self.ref_reader.query(contig, region[1], ref_end)
     a = fast_pass_aligner.FastPassAligner()
+    a.ssw_device = self.ssw_device
     a.normalize_reads = self.o.normalize_reads
     c = self.o.aln
     a.set_options(kmer_size=c['kmer_size'], read_size=len(reads[0].aligned_sequence), max_num_of_mismatches=c['max_num_of_mismatches'],

@@ -406,6 +406,16 @@ int64_t dvb_debug_allele_counts(const DvbBam* bam, const uint8_t* contig_bases, 
                                 const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* options,
                                 const int32_t* candidate_positions, int32_t n_candidate_positions, char* out, int64_t cap);
 
+/* ---- local realigner, host side (the graph in native code) ----------------------------------
+ * Candidate haplotypes of one window from the de Bruijn graph of its reference and reads (deepvariant/realigner/debruijn_graph.cc:
+ * Build :224-248, AddEdges :250-300, Prune :302-345, CandidateHaplotypes :347-391): sorted, '\n'-separated, written to `out` when
+ * they fit `cap`.  Returns the bytes needed (>= 1; 1 = a graph without a path), 0 when no k gives an acyclic graph (the caller
+ * keeps the reference alone), or -DvbStatus.  reads: bases / qualities concatenated, read i at [read_begin[i], read_begin[i + 1]). */
+int64_t dvb_dbg_candidate_haplotypes(const char* ref, int64_t ref_len, const char* bases, const uint8_t* quals, const int64_t* read_begin,
+                                     const int32_t* mapq, int32_t n_reads, int32_t min_k, int32_t max_k, int32_t step_k, int32_t min_mapq,
+                                     int32_t min_base_quality, int32_t min_edge_weight, int32_t max_num_paths, char* out, int64_t cap,
+                                     int32_t* k_used);
+
 /* Test access to the (candidate, read) support walk of the encoder's pre-pass (DvbBatch.allele_begin): the read allele of one read
  * at `target`, (a) walk_out: the last commit of the full allele-counter walk over [start, end) at that position, (b) at_out: what the
  * CIGAR-only walk used on the device finds.  Each int32[6] = {found, AlleleType, is_low_quality, anchor base, read offset, length}. */

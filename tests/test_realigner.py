@@ -112,3 +112,47 @@ def test_rows_and_single_row_composition():
   assert out.shape == (2, 8, 3, 2) and np.array_equal(out[0, 4:], imgs[3]) and np.array_equal(out[1, 4:], imgs[4])   # the longer alt's pileup
   out = men.compose_alt_aligned(imgs, 2, [[2, 3], []], pic, [['AT', 'A'], ['G']])
   assert np.array_equal(out[0, 4:], imgs[2]) and not out[1, 4:].any()
+
+
+def test_native_de_bruijn_graph_equals_python_restatement():
+  """csrc/dvb_dbg.cu (dvb_dbg_candidate_haplotypes) against DeBruijnGraph / build_graph on random windows: repeats in the
+  reference (k search, cycles), reads with substitutions / insertions / N / low qualities / low mapping quality / lower case,
+  path-count overflow; the three outcomes (no graph, a graph without a path, haplotypes) all occur."""
+  import numpy as np
+  rng = np.random.default_rng(1)
+  outcomes = {'none': 0, 'empty': 0, 'ref_only': 0, 'several': 0}
+  for trial in range(400):
+    n = int(rng.integers(30, 300))
+    ref = ''.join(rng.choice(list('ACGT'), n))
+    if trial % 5 == 0:
+      ref = ref[:n // 2] + ref[:n // 2]
+      n = len(ref)
+    snps = sorted(set(int(x) for x in rng.integers(5, n - 5, int(rng.integers(0, 6)))))       # planted on haplotype 1
+    ins_at = int(rng.integers(5, n - 5))                                                       # planted on haplotype 2
+    reads = []
+    for i in range(int(rng.integers(0, 80))):
+      s, length = int(rng.integers(0, max(1, n - 20))), int(rng.integers(25, 120))
+      seq = []
+      for pos in range(s, min(n, s + length)):
+        b = ref[pos]
+        if i % 3 == 1 and pos in snps:
+          b = 'ACGT'[('ACGT'.index(b) + 1) % 4]
+        seq.append(b)
+        if i % 3 == 2 and pos == ins_at:
+          seq += list('GATTACA')
+      for j in range(len(seq)):
+        if rng.random() < 0.004:
+          seq[j] = 'N'
+      seq = ''.join(seq)
+      if rng.random() < 0.1:
+        seq = seq.lower()
+      quals = bytes(rng.choice([5, 20, 30, 40, 40, 40, 40, 40, 40, 40, 40, 40], len(seq)).astype(np.uint8))
+      reads.append(Read(fragment_name=f'r{i}', aligned_sequence=seq.encode(), aligned_quality=quals, mapping_quality=int(rng.choice([5, 20, 60, 60]))))
+    o = rl.DeBruijnGraphOptions(min_k=int(rng.choice([3, 6, 10])), max_k=int(rng.choice([12, 30, 101])), step_k=int(rng.choice([1, 2])),
+                                max_num_paths=int(rng.choice([4, 256])))
+    g = rl.build_graph(ref, reads, o)
+    want = None if g is None else g.candidate_haplotypes()
+    got = rl.candidate_haplotypes_native(ref, reads, o)
+    assert got == want, (trial, o)
+    outcomes['none' if want is None else 'empty' if not want else 'ref_only' if want == [ref] else 'several'] += 1
+  assert all(v > 5 for v in outcomes.values()), outcomes

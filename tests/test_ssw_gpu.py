@@ -1,6 +1,7 @@
 """Batched Smith-Waterman on the device (csrc/dvb_ssw_gpu.cu: a warp per alignment, anti-diagonal wavefront over strips of 32 query
 rows) against the host implementation (csrc/dvb_ssw.cu, pinned by the reference's ssw / fast_pass_aligner known answers in
 tests/test_fast_pass_aligner.py): every field and the CIGAR string, pair by pair.  `-m gpu`."""
+import os
 import random
 
 import pytest
@@ -98,3 +99,24 @@ def test_alt_aligned_pileups_through_the_gpu_flow_equal_the_host_flow(tmp_path, 
   assert gpu_cands == cpu_cands and gpu_examples == cpu_examples
   shapes = [protos.parse_tf_example(r)['image/shape'][1] for r in gpu_examples]
   assert shapes and all(s == [100, 221, 9] for s in shapes)
+
+
+@pytest.mark.gpu
+def test_realigner_with_device_smith_waterman_equals_host():
+  """The local realigner over BASELINE config 1's reads (NA12878 chr20:10,000,000-10,004,000): with `ssw_device` set, FastPassAligner
+  sends its read-to-haplotype and haplotype-to-reference alignments through dvb_ssw_align_batch; every realigned read (position,
+  CIGAR) equals the host flow's."""
+  from deepvariant_b200 import bam, candidates as cand, fasta, realigner
+  g = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+  table = bam.NativeBamTable(os.path.join(g, 'quickstart.chr20_10mb.bam'), bam.ReadRequirements(min_mapping_quality=5))
+  ref = fasta.IndexedFastaReader(os.path.join(g, 'quickstart.chr20_10mb.fa.gz'))
+  outs = []
+  for device in (None, 0):
+    rl = realigner.Realigner(ref, realigner.RealignerOptions())
+    rl.ssw_device = device
+    rows_out = []
+    for p0 in range(10_000_000, 10_004_000, 1000):
+      rows = cand.region_reads(table, 'chr20', p0, p0 + 1000, 1500, 609314161)
+      rows_out += [(r.fragment_name, r.read_number, r.position, tuple(r.cigar)) for r in rl.realign_reads(table, 'chr20', rows, (p0, p0 + 1000))]
+    outs.append(rows_out)
+  assert len(outs[0]) > 1000 and outs[0] == outs[1]
