@@ -2906,6 +2906,8 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
           const int units = ((blob_cin + cand - 1) / cand) * (cand / 16);
           if (units < best_units) { best_units = units; bk = cand; }
         }
+        const int force_halo_bk = EnvInt("DVB_HALO_FORCE_BK", 0);     // experiment switch
+        if (force_halo_bk && cin_store % force_halo_bk == 0) bk = force_halo_bk;
         k_channels = blob_cin;
       }
       const int row_bytes = bk * 2;
@@ -2923,6 +2925,10 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
         if (Wv < 1) continue;
         const double eff = (double)Hout * Wout / ((double)((Wout + Wv - 1) / Wv) * ((Hout + Ht - 1) / Ht) * 128.0);
         if (eff > best_eff + 0.04) { best_eff = eff; bestP = P; }   // small P = small halo: a wider row must pay > 4 % in fill
+      }
+      {
+        const int force_p = EnvInt("DVB_HALO_FORCE_P", 0);            // experiment switch: slots per tile row (power of two)
+        if (force_p >= 1024 / row_bytes && force_p <= 128 && (force_p & (force_p - 1)) == 0 && force_p - o.kw + 1 >= 1 && Hout * Wout > 1000) bestP = force_p;
       }
       a.P = bestP; a.Ht = 128 / bestP;
       a.Wv = a.P - o.kw + 1;
