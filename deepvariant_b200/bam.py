@@ -13,6 +13,8 @@ import os
 import struct
 from typing import Dict, Iterable, List, Optional
 
+import numpy as np
+
 from deepvariant_b200.protos import Read
 
 _SEQ = '=ACMGRSVTWYHKDBN'
@@ -287,6 +289,11 @@ def _bgzf(payload: bytes, block: int = 0xff00) -> bytes:
   return bytes(out)
 
 
+_SEQ_CODE_LUT = np.full(256, 15, dtype=np.uint8)
+for _ch, _code in _SEQ_CODE.items():
+  _SEQ_CODE_LUT[ord(_ch)] = _code
+
+
 def write_bam(path: str, reads, references, sample_name: str = '') -> None:
   """references = [(name, length)].  Flags are rebuilt from the Read fields the reader fills (same decisions under
   ReadRequirements); mate fields are written so that IsReadProperlyPlaced still passes; HP is kept as an aux tag."""
@@ -301,10 +308,11 @@ def write_bam(path: str, reads, references, sample_name: str = '') -> None:
         (FREVERSE if r.reverse_strand else 0) | (FSECONDARY if r.secondary_alignment else 0) | (FQCFAIL if r.failed_vendor_quality_checks else 0) | \
         (FDUP if r.duplicate_fragment else 0) | (FSUPP if r.supplementary_alignment else 0)
     rid = ref_index.get(r.reference_name, -1)
-    seq = r.aligned_sequence.decode()
-    packed = bytearray((len(seq) + 1) // 2)
-    for i, ch in enumerate(seq):
-      packed[i >> 1] |= _SEQ_CODE.get(ch, 15) << (4 if i % 2 == 0 else 0)
+    seq = r.aligned_sequence
+    codes = _SEQ_CODE_LUT[np.frombuffer(bytes(seq), dtype=np.uint8)]
+    if len(codes) & 1:
+      codes = np.append(codes, np.uint8(0))
+    packed = ((codes[0::2] << 4) | codes[1::2]).astype(np.uint8).tobytes()
     aux = b''
     if r.hp_values:
       aux = b'HPi' + struct.pack('<i', int(r.hp_values[0]))
