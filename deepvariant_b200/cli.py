@@ -267,7 +267,8 @@ def make_examples(argv):
         small_model_vaf_context_window_size=a.small_model_vaf_context_window_size,
         sample_name=a.sample_name or cand.sample_name_from_bam(a.reads), max_reads_per_partition=a.max_reads_per_partition,
         partition_size=a.partition_size)
-    if table_path and not a.normalize_reads and not a.phase_reads and os.environ.get('DVB_DEVICE_SUPPORT', '1') != '0':
+    if table_path and not a.normalize_reads and not a.phase_reads and os.environ.get('DVB_DEVICE_SUPPORT', '1') != '0' and \
+        isinstance(gen._gpu(), pi.GpuEncoder):   # pylint: disable=protected-access  (a stand-in encoder, as in the CPU tests, cannot derive: names then)
       # the candidates come from the allele counter over the very reads the pileups show: the encoder's pre-pass derives the
       # (candidate, read) support classes on the device from the alt alleles instead of a read-name search on the host
       # (--normalize_reads counts from rewritten alignments that the pileups do not show: names stay authoritative there)

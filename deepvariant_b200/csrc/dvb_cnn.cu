@@ -1642,7 +1642,7 @@ __global__ void __launch_bounds__(kStemThreads, 4) stem_conv1_kernel(const StemA
   uint8_t* sRaw = reinterpret_cast<uint8_t*>(sH + 3 * p.h_pitch);   // [2][3][kStemRawPitch] raw uint8 row segments (cp.async ring)
   uint64_t* mma_done = reinterpret_cast<uint64_t*>(sRaw + 2 * 3 * kStemRawPitch);   // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 2);
-  float* s_bias = reinterpret_cast<float*>(mma_done + 3);
+  float* s_bias = reinterpret_cast<float*>(mma_done + 4);   // 32 bytes on: the epilogue reads the bias as float4
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid < p.cout) s_bias[tid] = p.bias[tid];
@@ -2888,7 +2888,7 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
       if (rows_pool) return dvb::fail(DVB_ERR_INTERNAL, "conv_rows_kernel: %d bytes of shared memory", rl.smem);
     }
     // ---- large stride-1 k x k layers: persistent halo-reusing kernel (see conv_halo_kernel)
-    const bool halo_split = split && EnvInt("DVB_HALO_RULE", 1) == 2 && EnvInt("DVB_HALO_SPLIT", 1);   // precision 1 runs the halo kernel only under rule 2
+    const bool halo_split = split && EnvInt("DVB_HALO_RULE", 1) == 2 && EnvInt("DVB_HALO_SPLIT", 0);   // precision 1 runs the halo kernel only under rule 2
     if ((!split || halo_split) && !is_stem && o.stride == 1 && o.kh * o.kw > 1 && Hout * Wout >= EnvInt("DVB_HALO_MIN_PIXELS", 250) && EnvInt("DVB_CNN_HALO", 1)) {
       HaloLaunch hl;
       memset(&hl, 0, sizeof(hl));
@@ -3321,7 +3321,7 @@ int ForwardChunk(DvbCnn* net, const uint8_t* images, int n, float* probs, cudaSt
     a.in = images; a.n_images = n;
     a.total_bytes = (long long)n * net->H * net->W * net->C;
     const long long tiles = (long long)n * a.Ho * a.tiles_w;
-    const int smem = 1024 + 16384 + 4096 + 3 * a.h_pitch * 2 + 2 * 3 * kStemRawPitch + 32 + a.cout * 4;
+    const int smem = 1024 + 16384 + 4096 + 3 * a.h_pitch * 2 + 2 * 3 * kStemRawPitch + 48 + a.cout * 4;
     const int occ = EnvInt("DVB_STEM_CTAS_PER_SM", 4);   // 64 registers x 256 threads -> 4 resident CTAs per SM
     const unsigned grid = (unsigned)std::min<long long>(tiles, (long long)net->num_sms * occ);
     if (EnvInt("DVB_STEM_PIPE", 0)) stem_conv1_kernel<true><<<grid, kStemThreads, smem, s>>>(a);

@@ -266,7 +266,7 @@ def test_device_derives_the_support_classes_of_the_read_name_search(track_ref, s
   table, ref = _quickstart()
   opts = cand.CandidateOptions(min_mapping_quality=5, min_base_quality=10, track_ref_reads=track_ref)
   gen, params = _generator(ref, sort_by_support)
-  enc = pi.GpuEncoder(gen.options.pic_options, device=0)
+  enc = pi.GpuEncoder(params, device=0)
   by_name, by_key = [], []
   for region, calls in _regions_with_candidates(table, ref, opts):
     gen.support_options = None
@@ -366,8 +366,8 @@ def test_device_resolves_repeated_read_keys(tmp_path, track_ref):
   from deepvariant_b200 import candidates as cand, pileup_image as pi
   table, ref = _repeated_keys_case(tmp_path)
   opts = cand.CandidateOptions(min_mapping_quality=5, min_base_quality=10, track_ref_reads=track_ref)
-  gen, _ = _generator(ref)
-  enc = pi.GpuEncoder(gen.options.pic_options, device=0)
+  gen, params = _generator(ref)
+  enc = pi.GpuEncoder(params, device=0)
   calls = cand.candidates_in_region(table, ref, 'chr20', 0, 3000, opts).calls()
   gen.support_options = None
   _, by_name = gen.pack_region_native(calls, table, ('chr20', 0, 3000))
