@@ -45,6 +45,7 @@ class DvbPileupParams(C.Structure):
       ('random_seed', C.c_uint32),
       ('max_reads_per_image', C.c_int32),
       ('shuffle_stdlib', C.c_int32),
+      ('mean_coverage', C.c_float),
   ]
 
 
@@ -88,6 +89,8 @@ class DvbBatch(C.Structure):
       ('support_min_mapping_quality', C.c_int32),
       ('support_min_base_quality', C.c_int32),
       ('support_flags', C.c_int32),
+      ('pair_channel', C.c_void_p * 3),
+      ('base_channel', C.c_void_p * 5),
   ]
 
 
@@ -96,6 +99,11 @@ ALLELE_ARRAYS = (
     ('allele_begin', 'int64'), ('allele_type', 'uint8'), ('allele_class', 'uint8'), ('allele_group', 'uint8'),
     ('allele_bases_begin', 'int64'), ('allele_bases', 'uint8'), ('image_ref_run', 'int32'), ('image_group_default', 'uint8'),
 )
+# Optional channel planes (include/dvb.h DVB_PAIR_PLANE_* / DVB_BASE_PLANE_*): PackedBatch.arrays['pair_channel_<k>'] uint8[n_pairs],
+# ['base_channel_<k>'] uint8[n_bases]; channel enum -> (member, slot).
+PLANE_OF_CHANNEL = {8: ('pair_channel', 0), 25: ('pair_channel', 1), 27: ('pair_channel', 2),
+                    23: ('base_channel', 0), 24: ('base_channel', 1), 28: ('base_channel', 2), 29: ('base_channel', 3), 30: ('base_channel', 4)}
+PLANE_ARRAYS = tuple(('pair_channel', k) for k in range(3)) + tuple(('base_channel', k) for k in range(5))
 SUPPORT_KEEP_LEGACY, SUPPORT_TRACK_REF_READS, SUPPORT_REPEATED_KEYS = 1, 2, 4
 
 # name -> (dtype string, per-what) for every array member of DvbBatch, in struct order.
@@ -182,6 +190,11 @@ SYMBOLS = (
     ('dvb_encoder_check', C.c_int, [C.c_void_p, C.c_void_p]),
     ('dvb_encode_batch_host', C.c_int, [C.c_void_p, C.POINTER(DvbBatch), C.c_void_p, C.c_void_p]),
     ('dvb_encoder_launch_count', C.c_int64, [C.c_void_p]),
+    ('dvb_channel_base_modification_plane', C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    ('dvb_channel_hmer_quality_plane', C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    ('dvb_channel_t0_plane', C.c_int, [C.c_int64, C.c_char_p, C.c_int64, C.c_void_p]),
+    ('dvb_channel_allele_frequency_color', C.c_int32, [C.c_float, C.c_float]),
+    ('dvb_channel_allele_sample_probability_color', C.c_int32, [C.c_int32, C.c_float]),
     ('dvb_cnn_create', C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_int32, C.c_int, C.POINTER(C.c_void_p)]),
     ('dvb_cnn_destroy', None, [C.c_void_p]),
@@ -267,7 +280,7 @@ def lib() -> C.CDLL:
       fn = getattr(l, name)  # AttributeError if the .so does not export a declared symbol
       fn.restype = restype
       fn.argtypes = argtypes
-    if l.dvb_abi_version() != 3:
+    if l.dvb_abi_version() != 4:
       raise RuntimeError('libdvb.so ABI version mismatch')
     _lib = l
   return _lib

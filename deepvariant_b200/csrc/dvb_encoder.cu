@@ -52,7 +52,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr float kMaxPixelValueAsFloat = 254.0f;  // channels/channel.h:78
 constexpr float kMaxFragmentLength = 1000.0f;    // channels/channel.h:81
 
-enum Kind : uint8_t { K_ZERO = 0, K_BASE = 1, K_QUAL = 2, K_DIFF = 3, K_CONST = 4, K_ISHOMO = 5, K_HOMOW = 6 };
+enum Kind : uint8_t { K_ZERO = 0, K_BASE = 1, K_QUAL = 2, K_DIFF = 3, K_CONST = 4, K_ISHOMO = 5, K_HOMOW = 6, K_PLANE = 7 };
 
 struct EncDev {
   int W, H, band, C, Cout, max_rows;
@@ -74,6 +74,13 @@ struct EncDev {
   unsigned mask_base[4], mask_qual[4], mask_diff[4], mask_const[4], ref_words[4];
   unsigned mask_ishomo[4], mask_homow[4];   // per-base homopolymer channels (is_homopolymer, homopolymer_weighted)
   int has_homo;
+  // per-base channel planes (DvbBatch.base_channel): channel index and plane slot of each K_PLANE channel
+  int n_planes;
+  uint8_t plane_chan[DVB_N_BASE_PLANES], plane_slot[DVB_N_BASE_PLANES];
+  int n_pair_planes;        // per-pair channel planes (DvbBatch.pair_channel), kind K_ZERO in the pixel loop: their bytes ride in tc[]
+  uint8_t pair_plane_chan[DVB_N_PAIR_PLANES], pair_plane_slot[DVB_N_PAIR_PLANES];
+  // mean_coverage overlay (pileup_image_native.cc:422-444): channel index or -1; rows [0, cov_rows) are painted
+  int cov_chan, cov_rows;
   int n_words;
   int gc_chan;              // index of the gc_content channel (its reference-band value is per image), or -1
   int perm_cap;             // largest n with a down-sampling table
@@ -188,6 +195,24 @@ __device__ __forceinline__ void homopolymer_at(const uint8_t* seq, int len, int 
 
 // percent = int(float(a) / float(b) * 100) with the reference's operation order (no FMA contraction)
 __device__ __forceinline__ int percent_dev(int a, int b) { return (int)__fmul_rn(__fdiv_rn((float)a, (float)b), 100.0f); }
+
+// Bytes of the per-base channel planes at base `idx` (absolute index into bases[]), placed at their channels' byte positions.
+__device__ __forceinline__ void plane_words(const EncDev& P, const DvbBatch& B, long long idx, unsigned ex[4]) {
+  for (int k = 0; k < P.n_planes; ++k) {
+    const int c = P.plane_chan[k];
+    ex[c >> 2] += (unsigned)B.base_channel[P.plane_slot[k]][idx] << (8 * (c & 3));
+  }
+}
+
+// Bytes of the per-pair channel planes of pair p - values the caller computed per (image, read): allele_frequency_channel.cc:57-68,
+// read_supports_variant_fuzzy_channel.cc:99-110, allele_sample_probability_channel.cc:48-79 (functions of DeepVariantCall's
+// string-keyed maps) - placed like the K_CONST bytes.
+__device__ __forceinline__ void pair_plane_words(const EncDev& P, const DvbBatch& B, long long p, unsigned tc[4]) {
+  for (int k = 0; k < P.n_pair_planes; ++k) {
+    const int c = P.pair_plane_chan[k];
+    tc[c >> 2] |= (unsigned)B.pair_channel[P.pair_plane_slot[k]][p] << (8 * (c & 3));
+  }
+}
 
 __device__ uint8_t read_const(const EncDev& P, const DvbBatch& B, int chan, const ReadHdr& h, int support) {
   switch (chan) {
@@ -311,6 +336,7 @@ __device__ __forceinline__ unsigned pair_read_allele(const DvbBatch& B, const Re
 }
 
 // sup (when the batch carries allele keys): uint8[4][n_pairs] = raw class byte, raw group, final class, final group.
+template <bool kPairPlanes>   // the batch carries per-pair channel planes (a separate instantiation keeps the common layouts' registers)
 __global__ void __launch_bounds__(128) dvb_pair_prepass_kernel(const EncDev P, const DvbBatch B, PairRec* __restrict__ recs, int* __restrict__ err,
                                                                 uint8_t* __restrict__ sup) {
   const int lane = threadIdx.x & 31;
@@ -371,6 +397,7 @@ __global__ void __launch_bounds__(128) dvb_pair_prepass_kernel(const EncDev P, c
     }
     for (int c = 0; c < P.C; ++c)
       if (P.kind[c] == K_CONST) rec.tc[c >> 2] |= (unsigned)read_const(P, B, P.chan[c], h, support) << (8 * (c & 3));
+    if constexpr (kPairPlanes) pair_plane_words(P, B, p, rec.tc);
     rec.sort_pos = B.read_sort_pos[r];
     rec.rank = B.read_name_rank[r];
     rec.hap = hap_index(P, h.flags, h.hp);
@@ -422,7 +449,8 @@ __device__ __forceinline__ void flush_row(uint8_t* __restrict__ dst, const uint8
 
 // FAST7: 7 computed channels, 7-byte pixels (the WGS layout): runs of 4 pixels whose first column is a multiple of 4 are
 // assembled in registers and stored as 7 aligned 32-bit words instead of 28 byte stores.
-// HOMO: the per-base homopolymer channels are present (a separate instantiation keeps the common layouts at 48 registers).
+// HOMO: per-base extra channels are present - the homopolymer channels and / or channel planes (a separate instantiation keeps the
+// common layouts at 48 registers).
 template <bool FAST7, bool HOMO>
 __global__ void __launch_bounds__(kThreads, DVB_ENC_MIN_BLOCKS)
 dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, int* __restrict__ rows_kept,
@@ -543,7 +571,8 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
     uint8_t* img_out = out + (long long)img * P.image_bytes;
     for (int row = warp; row < P.H; row += kWarps) {
       uint8_t* dst = img_out + (long long)row * P.row_bytes;
-      if (row >= P.band + n_rows) {  // blank tail (pileup_image_native.cc:414-421)
+      const bool cov_row = P.cov_chan >= 0 && row < P.cov_rows;   // mean_coverage is painted over finished rows, blank ones included
+      if (row >= P.band + n_rows && !cov_row) {  // blank tail (pileup_image_native.cc:414-421)
         flush_row(dst, nullptr, P.row_bytes, lane);
         continue;
       }
@@ -562,7 +591,7 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
         for (int col = lane; col < P.W; col += 32) {
           const unsigned bc = s_base[s_ref[col]];
           unsigned ih = 0u, hw = 0u;
-          if constexpr (HOMO) homopolymer_at(s_ref, P.W, col, P.has_homo > 1, &ih, &hw);   // the window treated as a read
+          if constexpr (HOMO) { if (P.has_homo) homopolymer_at(s_ref, P.W, col, P.has_homo > 1, &ih, &hw); }   // the window treated as a read
           uint8_t* q = px + col * P.Cout;
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
@@ -575,7 +604,7 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
             }
           }
         }
-      } else {
+      } else if (row < P.band + n_rows) {
         const int e = s_order[row - P.band];
         const long long p = p0 + s_pair[e];
         ReadHdr h;
@@ -589,7 +618,7 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
           tc[0] = q1.z; tc[1] = q1.w;
           if (P.n_words > 2) { const uint4 q2 = rv[2]; tc[2] = q2.x; tc[3] = q2.y; }
           h.mapq = 0; h.fraglen = 0; h.hp = 0; h.flags = 0; h.len = 0;
-          if constexpr (HOMO) h.len = (int)rv[3].z;
+          if constexpr (HOMO) h.len = (int)rv[3].z;   // (seq0 above is what the channel planes are indexed from)
         } else {
           const int r = B.pair_read[p];
           const int support = B.pair_support[p];
@@ -602,6 +631,7 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
             const unsigned v = __shfl_sync(0xffffffffu, myc, c);
             tc[c >> 2] |= (v & 0xFFu) << (8 * (c & 3));
           }
+          if (P.n_pair_planes) pair_plane_words(P, B, p, tc);
         }
         const uint8_t* bases = B.bases + h.seq0;
         const uint8_t* quals = B.quals + h.seq0;
@@ -621,13 +651,17 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
                 const unsigned ql = s_qual[quals[read_i + j]];
                 const unsigned df = (b == s_ref[col]) ? P.match_color : P.mismatch_color;
                 unsigned ih = 0u, hw = 0u;
-                if constexpr (HOMO) homopolymer_at(bases, h.len, read_i + j, P.has_homo > 1, &ih, &hw);
+                unsigned ex[4] = {0u, 0u, 0u, 0u};
+                if constexpr (HOMO) {
+                  if (P.has_homo) homopolymer_at(bases, h.len, read_i + j, P.has_homo > 1, &ih, &hw);
+                  plane_words(P, B, h.seq0 + read_i + j, ex);
+                }
                 uint8_t* q = px + col * P.Cout;
 #pragma unroll
                 for (int w = 0; w < 4; ++w) {
                   if (w < P.n_words) {
                     const unsigned word = tc[w] + bc * P.mask_base[w] + ql * P.mask_qual[w] + df * P.mask_diff[w] +
-                                          (HOMO ? ih * P.mask_ishomo[w] + hw * P.mask_homow[w] : 0u);
+                                          (HOMO ? ih * P.mask_ishomo[w] + hw * P.mask_homow[w] + ex[w] : 0u);
 #pragma unroll
                     for (int bb = 0; bb < 4; ++bb)
                       if (w * 4 + bb < P.C) q[w * 4 + bb] = (uint8_t)(word >> (8 * bb));
@@ -688,13 +722,17 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
               const unsigned ql = s_qual[quals[op == 1 ? read_i : read_i - 1]];
               const unsigned df = ((unsigned)P.anchor_char == s_ref[col]) ? P.match_color : P.mismatch_color;
               unsigned ih = 0u, hw = 0u;
-              if constexpr (HOMO) homopolymer_at(bases, h.len, op == 1 ? read_i : read_i - 1, P.has_homo > 1, &ih, &hw);
+              unsigned ex[4] = {0u, 0u, 0u, 0u};
+              if constexpr (HOMO) {
+                if (P.has_homo) homopolymer_at(bases, h.len, op == 1 ? read_i : read_i - 1, P.has_homo > 1, &ih, &hw);
+                plane_words(P, B, h.seq0 + (op == 1 ? read_i : read_i - 1), ex);
+              }
               uint8_t* q = px + col * P.Cout;
 #pragma unroll
               for (int w = 0; w < 4; ++w) {
                 if (w < P.n_words) {
                   const unsigned word = tc[w] + bc * P.mask_base[w] + ql * P.mask_qual[w] + df * P.mask_diff[w] +
-                                        (HOMO ? ih * P.mask_ishomo[w] + hw * P.mask_homow[w] : 0u);
+                                        (HOMO ? ih * P.mask_ishomo[w] + hw * P.mask_homow[w] + ex[w] : 0u);
 #pragma unroll
                   for (int bb = 0; bb < 4; ++bb)
                     if (w * 4 + bb < P.C) q[w * 4 + bb] = (uint8_t)(word >> (8 * bb));
@@ -711,6 +749,11 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
         }
       }
       __syncwarp();
+      if (cov_row) {   // kChannelValue255 on the reference band, kChannelValue200 below it (pileup_image_native.cc:433-441)
+        const uint8_t v = row < P.band ? (uint8_t)255 : (uint8_t)200;
+        for (int col = lane; col < P.W; col += 32) px[col * P.Cout + P.cov_chan] = v;
+        __syncwarp();
+      }
       flush_row(dst, buf, P.row_bytes, lane);
     }
   }
@@ -765,6 +808,7 @@ int HostBaseColor(int base, const DvbPileupParams& o) {  // channels/read_base_c
 int BuildDev(const DvbPileupParams& o, EncDev* d) {
   memset(d, 0, sizeof(*d));
   d->gc_chan = -1;
+  d->cov_chan = -1;
   if (o.width < 1) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "width must be >= 1");
   if (o.num_channels < 1 || o.num_channels > DVB_MAX_CHANNELS || o.num_alt_channels < 0 ||
       o.num_channels + o.num_alt_channels > DVB_MAX_CHANNELS)
@@ -813,6 +857,34 @@ int BuildDev(const DvbPileupParams& o, EncDev* d) {
       case DVB_CH_HOMOPOLYMER_WEIGHTED: d->kind[c] = K_HOMOW; d->ref_const[c] = 0; d->has_homo = 2; break;
       case DVB_CH_GC_CONTENT:   // reference band = GC content of the window: filled per image by the kernel
         d->kind[c] = K_CONST; d->ref_const[c] = 0; d->gc_chan = c; break;
+      case DVB_CH_ALLELE_FREQUENCY: case DVB_CH_ALLELE_SAMPLE_PROBABILITY: case DVB_CH_READ_SUPPORTS_VARIANT_FUZZY: {
+        // per pair from the caller's plane; reference band 0 (AlleleFrequencyColor(0) = 0, allele_frequency_channel.cc:70-82) or
+        // SupportsAltColor(0) (read_supports_variant_fuzzy_channel.cc:112-116)
+        d->kind[c] = K_ZERO; d->ref_const[c] = ch == DVB_CH_READ_SUPPORTS_VARIANT_FUZZY ? d->sup_color[0] : (uint8_t)0;
+        if (d->n_pair_planes >= DVB_N_PAIR_PLANES) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "a per-pair plane channel is listed twice");
+        d->pair_plane_chan[d->n_pair_planes] = (uint8_t)c;
+        d->pair_plane_slot[d->n_pair_planes++] = (uint8_t)(ch == DVB_CH_ALLELE_FREQUENCY ? DVB_PAIR_PLANE_ALLELE_FREQUENCY
+                                                           : ch == DVB_CH_READ_SUPPORTS_VARIANT_FUZZY ? DVB_PAIR_PLANE_FUZZY_SUPPORT
+                                                                                                       : DVB_PAIR_PLANE_ALLELE_SAMPLE_PROBABILITY);
+        break;
+      }
+      case DVB_CH_BASE_METHYLATION: case DVB_CH_BASE_6MA: case DVB_CH_HOMOPOLYMER_INSERTION_QUALITY:
+      case DVB_CH_HOMOPOLYMER_DELETION_QUALITY: case DVB_CH_INTER_HOMOPOLYMER_INSERTION_QUALITY: {   // per base from the caller's plane; band 0
+        static const int kSlot[] = {DVB_BASE_PLANE_5MC, DVB_BASE_PLANE_6MA, -1, -1, -1, DVB_BASE_PLANE_HMER_INSERTION,
+                                    DVB_BASE_PLANE_HMER_DELETION, DVB_BASE_PLANE_INTER_HMER_INSERTION};
+        d->kind[c] = K_PLANE; d->ref_const[c] = 0;
+        if (d->n_planes >= DVB_N_BASE_PLANES) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "a per-base plane channel is listed twice");
+        d->plane_chan[d->n_planes] = (uint8_t)c; d->plane_slot[d->n_planes] = (uint8_t)kSlot[ch - DVB_CH_BASE_METHYLATION];
+        ++d->n_planes;
+        break;
+      }
+      case DVB_CH_MEAN_COVERAGE:   // a BlankChannel per read (pileup_channel_lib.cc:418-421); the overlay is painted by the kernel
+        d->kind[c] = K_ZERO; d->ref_const[c] = 0;
+        if (d->cov_chan < 0) {     // std::find: the first such channel
+          d->cov_chan = c;
+          d->cov_rows = std::max(0, std::min(static_cast<int>(o.mean_coverage) + o.reference_band_height, o.height));
+        }
+        break;
       default:
         return dvb::fail(DVB_ERR_UNSUPPORTED_CHANNEL, "channel enum %d is not implemented", ch);
     }
@@ -843,6 +915,13 @@ int SmemBytes(const EncDev& d) {
 
 int Launch(DvbEncoder* enc, const DvbBatch& b, uint8_t* out, int32_t* rows_kept, cudaStream_t stream) {
   if (b.n_images <= 0) return DVB_OK;
+  for (int k = 0; k < enc->dev.n_pair_planes; ++k)   // a plane-backed channel needs its plane
+    if (b.n_pairs > 0 && !b.pair_channel[enc->dev.pair_plane_slot[k]])
+      return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "channel enum %d needs DvbBatch.pair_channel[%d]", (int)enc->dev.chan[enc->dev.pair_plane_chan[k]],
+                       (int)enc->dev.pair_plane_slot[k]);
+  for (int k = 0; k < enc->dev.n_planes; ++k)
+    if (b.n_bases > 0 && !b.base_channel[enc->dev.plane_slot[k]])
+      return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "channel enum %d needs DvbBatch.base_channel[%d]", (int)enc->dev.chan[enc->dev.plane_chan[k]], (int)enc->dev.plane_slot[k]);
   int grid = std::min(b.n_images, enc->grid_cap);
   PairRec* recs = nullptr;
   const bool derive = b.allele_begin != nullptr;     // pair_support comes from the allele keys: the pre-pass is where it is derived
@@ -857,12 +936,13 @@ int Launch(DvbEncoder* enc, const DvbBatch& b, uint8_t* out, int32_t* rows_kept,
       sup = static_cast<uint8_t*>(enc->d_support.p);
       enc->last_support_pairs = b.n_pairs;
     }
-    dvb_pair_prepass_kernel<<<(b.n_images + 3) / 4, 128, 0, stream>>>(enc->dev, b, recs, enc->d_err, sup);
+    if (enc->dev.n_pair_planes) dvb_pair_prepass_kernel<true><<<(b.n_images + 3) / 4, 128, 0, stream>>>(enc->dev, b, recs, enc->d_err, sup);
+    else dvb_pair_prepass_kernel<false><<<(b.n_images + 3) / 4, 128, 0, stream>>>(enc->dev, b, recs, enc->d_err, sup);
     enc->launches++;
   }
   if (enc->fast7)
     dvb_encode_kernel<true, false><<<grid, kThreads, enc->smem_bytes, stream>>>(enc->dev, b, out, rows_kept, enc->d_err, recs);
-  else if (enc->dev.has_homo)
+  else if (enc->dev.has_homo || enc->dev.n_planes)
     dvb_encode_kernel<false, true><<<grid, kThreads, enc->smem_bytes, stream>>>(enc->dev, b, out, rows_kept, enc->d_err, recs);
   else
     dvb_encode_kernel<false, false><<<grid, kThreads, enc->smem_bytes, stream>>>(enc->dev, b, out, rows_kept, enc->d_err, recs);
@@ -926,13 +1006,15 @@ int StageHostBatch(DvbEncoder* enc, const DvbBatch* hb, DvbBatch* out_db, cudaSt
   // ---- pack every input array into one pinned staging block, one H2D copy ----
   enum Domain { D_IMAGE, D_IMAGE1, D_PAIR, D_READ, D_READ1, D_BASE, D_CIGAR, D_ALLELE, D_ALLELE1, D_ABASE };
   struct Seg { const void* src; size_t bytes; size_t off; int domain; size_t esz; bool pinned; };
-  constexpr int kSegs = 27;
+  constexpr int kSegs = 27 + DVB_N_PAIR_PLANES + DVB_N_BASE_PLANES;
   Seg segs[kSegs];
   int ns = 0;
   size_t total = 0;
   const Domain kDomains[kSegs] = {D_IMAGE, D_IMAGE, D_IMAGE, D_IMAGE1, D_PAIR, D_PAIR, D_PAIR, D_READ, D_READ, D_READ, D_READ, D_READ, D_READ, D_READ,
-                                  D_READ1, D_READ1, D_BASE, D_BASE, D_CIGAR, D_IMAGE1, D_IMAGE, D_IMAGE, D_ALLELE, D_ALLELE, D_ALLELE, D_ALLELE1, D_ABASE};
-  const size_t kElem[kSegs] = {(size_t)hb->ref_stride, 4, 4, 8, 4, 1, 1, 4, 4, 4, 1, 4, 4, 4, 8, 8, 1, 1, 4, 8, 4, 1, 1, 1, 1, 8, 1};
+                                  D_READ1, D_READ1, D_BASE, D_BASE, D_CIGAR, D_IMAGE1, D_IMAGE, D_IMAGE, D_ALLELE, D_ALLELE, D_ALLELE, D_ALLELE1, D_ABASE,
+                                  D_PAIR, D_PAIR, D_PAIR, D_BASE, D_BASE, D_BASE, D_BASE, D_BASE};
+  const size_t kElem[kSegs] = {(size_t)hb->ref_stride, 4, 4, 8, 4, 1, 1, 4, 4, 4, 1, 4, 4, 4, 8, 8, 1, 1, 4, 8, 4, 1, 1, 1, 1, 8, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+  static_assert(DVB_N_PAIR_PLANES == 3 && DVB_N_BASE_PLANES == 5, "segment tables above list 3 + 5 planes");
   const bool derive = hb->allele_begin != nullptr;
   const int64_t NA = derive ? hb->n_alleles : 0, NAB = derive ? hb->n_allele_bases : 0;
   if (derive) {
@@ -978,6 +1060,9 @@ int StageHostBatch(DvbEncoder* enc, const DvbBatch* hb, DvbBatch* out_db, cudaSt
   const int i_ag = add(derive ? hb->allele_group : nullptr, NA);
   const int i_abb = add(derive ? hb->allele_bases_begin : nullptr, (NA + 1) * 8);
   const int i_aba = add(derive ? hb->allele_bases : nullptr, NAB);
+  int i_pch[DVB_N_PAIR_PLANES], i_bch[DVB_N_BASE_PLANES];
+  for (int k = 0; k < DVB_N_PAIR_PLANES; ++k) i_pch[k] = add(hb->pair_channel[k], NP);
+  for (int k = 0; k < DVB_N_BASE_PLANES; ++k) i_bch[k] = add(hb->base_channel[k], NB);
   total = std::max<size_t>(total, 256);
   DVB_CUDA(enc->h_in.reserve(total));
   DVB_CUDA(enc->d_in.reserve(total));
@@ -1069,6 +1154,8 @@ int StageHostBatch(DvbEncoder* enc, const DvbBatch* hb, DvbBatch* out_db, cudaSt
     db.allele_group = hb->allele_group ? (const uint8_t*)dp(i_ag) : nullptr;
     db.allele_bases_begin = (const int64_t*)dp(i_abb); db.allele_bases = (const uint8_t*)dp(i_aba);
   }
+  for (int k = 0; k < DVB_N_PAIR_PLANES; ++k) db.pair_channel[k] = hb->pair_channel[k] ? (const uint8_t*)dp(i_pch[k]) : nullptr;
+  for (int k = 0; k < DVB_N_BASE_PLANES; ++k) db.base_channel[k] = hb->base_channel[k] ? (const uint8_t*)dp(i_bch[k]) : nullptr;
 
   *out_db = db;
   return DVB_OK;
@@ -1146,13 +1233,13 @@ int dvb_encoder_create(const DvbPileupParams* params, int device, DvbEncoder** o
     delete enc;
     return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "image row too large for shared memory (%d bytes)", enc->smem_bytes);
   }
-  enc->fast7 = dev.C == 7 && dev.Cout == 7 && !dev.has_homo;   // the 7-byte fast path knows the four classic pixel terms only
+  enc->fast7 = dev.C == 7 && dev.Cout == 7 && !dev.has_homo && !dev.n_planes;   // the 7-byte fast path knows the four classic pixel terms only
   { const char* e = getenv("DVB_ENC_PREPASS"); enc->prepass = !(e && atoi(e) == 0); }
   int occ = 1;
   if (enc->fast7) {
     DVB_CUDA(cudaFuncSetAttribute(dvb_encode_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc->smem_bytes));
     DVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dvb_encode_kernel<true, false>, kThreads, enc->smem_bytes));
-  } else if (dev.has_homo) {
+  } else if (dev.has_homo || dev.n_planes) {
     DVB_CUDA(cudaFuncSetAttribute(dvb_encode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc->smem_bytes));
     DVB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dvb_encode_kernel<false, true>, kThreads, enc->smem_bytes));
   } else {

@@ -104,6 +104,12 @@ class PackedBatch:
       b.n_alleles = int(self.arrays['allele_begin'][self.n_images])
       b.n_allele_bases = int(self.arrays['allele_bases_begin'][b.n_alleles])
       b.support_min_mapping_quality, b.support_min_base_quality, b.support_flags = self.support
+    for member, k in _lib.PLANE_ARRAYS:
+      a = self.arrays.get(f'{member}_{k}')
+      if a is not None:
+        want = self.n_pairs if member == 'pair_channel' else b.n_bases
+        assert a.dtype == np.uint8 and a.flags['C_CONTIGUOUS'] and a.size == want, (member, k, a.size, want)
+        getattr(b, member)[k] = a.ctypes.data
     return b
 
   def input_bytes(self) -> int:
@@ -122,6 +128,10 @@ class DeviceBatch:
       a = packed.arrays[name]
       t = torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a)
       self.tensors[name] = t.to(device, non_blocking=True)
+    for member, k in _lib.PLANE_ARRAYS:
+      a = packed.arrays.get(f'{member}_{k}')
+      if a is not None:
+        self.tensors[f'{member}_{k}'] = torch.from_numpy(a).to(device, non_blocking=True)
     self.n_bases = int(packed.arrays['read_seq_begin'][-1])
     self.n_cigar = int(packed.arrays['read_cigar_begin'][-1])
 
@@ -131,6 +141,10 @@ class DeviceBatch:
     b.n_bases, b.n_cigar, b.ref_stride = self.n_bases, self.n_cigar, self.ref_stride
     for name, _ in _lib.BATCH_ARRAYS:
       setattr(b, name, C.c_void_p(self.tensors[name].data_ptr()))
+    for member, k in _lib.PLANE_ARRAYS:
+      t = self.tensors.get(f'{member}_{k}')
+      if t is not None:
+        getattr(b, member)[k] = t.data_ptr()
     return b
 
 

@@ -153,6 +153,10 @@ class Read:
   proper_placement: bool = False
   number_reads: int = 0
   hp_values: Optional[List[int]] = None  # info['HP'] int values (None = tag absent)
+  # per-base aux data of the optional channels (deepvariant_b200/channels.py); None / empty = absent
+  base_modifications: Optional[Dict[str, bytes]] = None   # Read.base_modifications: '5mC' / '6mA' -> one ML byte per base
+  tp_values: Optional[List[int]] = None                   # info['tp'] int values (Ultima)
+  t0_value: Optional[bytes] = None                        # info['t0'] string value (phred + 33 text)
 
   def key(self) -> str:
     # read_supports_variant_channel.cc:78-79
@@ -308,6 +312,10 @@ class Variant:
   reference_bases: str = ''
   alternate_bases: List[str] = dataclasses.field(default_factory=list)
   raw: Optional[bytes] = None
+  # only read by the fuzzy read-support channel (channels.py); not parsed from / written to the wire here
+  alternate_bases_rejected: List[str] = dataclasses.field(default_factory=list)   # variants.proto:75
+  alt_ps: Optional[List[int]] = None       # info['ALT_PS'] int values
+  alt_ps_ext: Optional[List[int]] = None   # info['ALT_PS_EXT'] int values
 
   def serialize(self) -> bytes:
     if self.raw is not None:
@@ -350,6 +358,10 @@ class DeepVariantCall:
   variant: Variant = dataclasses.field(default_factory=Variant)
   allele_support: Dict[str, List[str]] = dataclasses.field(default_factory=dict)
   make_examples_alt_allele_indices: List[List[int]] = dataclasses.field(default_factory=list)
+  # fields only the optional channels read (deepvariant.proto:280-287): rejected_allele_support=10, allele_frequency=3, ref_support=4
+  rejected_allele_support: Dict[str, List[str]] = dataclasses.field(default_factory=dict)
+  allele_frequency: Dict[str, float] = dataclasses.field(default_factory=dict)
+  ref_support: List[str] = dataclasses.field(default_factory=list)
 
 
 def _parse_indices(buf: bytes) -> List[int]:
@@ -376,6 +388,24 @@ def parse_deepvariant_call(buf: bytes) -> DeepVariantCall:
         elif fn2 == 2:
           names = [bytes(v3).decode() for f3, w3, v3, _ in iter_fields(bytes(val2)) if f3 == 1]
       c.allele_support[k] = names
+    elif fn == 10:
+      k, names = '', []
+      for fn2, wt2, val2, _ in iter_fields(bytes(val)):
+        if fn2 == 1:
+          k = bytes(val2).decode()
+        elif fn2 == 2:
+          names = [bytes(v3).decode() for f3, w3, v3, _ in iter_fields(bytes(val2)) if f3 == 1]
+      c.rejected_allele_support[k] = names
+    elif fn == 3:
+      k, f = '', 0.0
+      for fn2, wt2, val2, _ in iter_fields(bytes(val)):
+        if fn2 == 1:
+          k = bytes(val2).decode()
+        elif fn2 == 2:
+          f = struct.unpack('<f', struct.pack('<I', val2))[0] if isinstance(val2, int) else struct.unpack('<f', bytes(val2))[0]
+      c.allele_frequency[k] = f
+    elif fn == 4:
+      c.ref_support.append(bytes(val).decode())
     elif fn == 8:
       c.make_examples_alt_allele_indices.append(_parse_indices(bytes(val)))
   return c

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DVB_ABI_VERSION 3
+#define DVB_ABI_VERSION 4
 #define DVB_MAX_CHANNELS 16
 
 typedef enum DvbStatus {
@@ -54,6 +54,7 @@ enum {
   DVB_CH_READ_SUPPORTS_VARIANT = 5,
   DVB_CH_BASE_DIFFERS_FROM_REF = 6,
   DVB_CH_HAPLOTYPE_TAG = 7,
+  DVB_CH_ALLELE_FREQUENCY = 8,          /* one value per (image, read): DvbBatch.pair_channel[DVB_PAIR_PLANE_ALLELE_FREQUENCY] (allele_frequency_channel.cc:57-118) */
   DVB_CH_READ_MAPPING_PERCENT = 11,     /* "Opt Channels" (deepvariant/pileup_channel_lib.h): whole-read statistics, */
   DVB_CH_AVG_BASE_QUALITY = 12,         /* one constant per read (channels/{read_mapping_percent,avg_base_quality,    */
   DVB_CH_IDENTITY = 13,                 /* identity,gap_compressed_identity,gc_content}_channel.cc)                    */
@@ -63,8 +64,27 @@ enum {
   DVB_CH_HOMOPOLYMER_WEIGHTED = 17,     /* per base: length of its run, capped at 30 (homopolymer_weighted_channel.cc:79-101) */
   DVB_CH_BLANK = 18,
   DVB_CH_INSERT_SIZE = 19,
-  DVB_CH_SUPPLEMENTARY_ALIGNMENT = 26
+  DVB_CH_MEAN_COVERAGE = 22,            /* blank per read; rows [0, band) = 255 and [band, band + int(mean_coverage)) = 200 painted over the finished
+                                           image (pileup_image_native.cc:422-444) */
+  DVB_CH_BASE_METHYLATION = 23,         /* per base: DvbBatch.base_channel[DVB_BASE_PLANE_5MC] (base_methylation_channel.cc:54-99) */
+  DVB_CH_BASE_6MA = 24,                 /* per base: base_channel[DVB_BASE_PLANE_6MA] (base_6ma_channel.cc:54-99) */
+  DVB_CH_READ_SUPPORTS_VARIANT_FUZZY = 25,   /* per (image, read): pair_channel[DVB_PAIR_PLANE_FUZZY_SUPPORT] (read_supports_variant_fuzzy_channel.cc:99-310) */
+  DVB_CH_SUPPLEMENTARY_ALIGNMENT = 26,
+  DVB_CH_ALLELE_SAMPLE_PROBABILITY = 27,     /* per (image, read): pair_channel[DVB_PAIR_PLANE_ALLELE_SAMPLE_PROBABILITY] (allele_sample_probability_channel.cc:48-101) */
+  DVB_CH_HOMOPOLYMER_INSERTION_QUALITY = 28, /* per base, from the reads' tp tag: base_channel[DVB_BASE_PLANE_HMER_INSERTION] (homopolymer_indel_quality_channel.cc:127-183) */
+  DVB_CH_HOMOPOLYMER_DELETION_QUALITY = 29,  /* base_channel[DVB_BASE_PLANE_HMER_DELETION] */
+  DVB_CH_INTER_HOMOPOLYMER_INSERTION_QUALITY = 30   /* from the t0 tag: base_channel[DVB_BASE_PLANE_INTER_HMER_INSERTION] (inter_homopolymer_insertion_quality_channel.cc:75-127) */
 };
+
+/* Channel planes (DvbBatch.pair_channel / base_channel).  These channels are functions of data the pileup loop does not hold -
+ * DeepVariantCall maps keyed by read-name strings (allele_frequency, allele_support sizes, ALT_PS phases) or per-base aux tags of
+ * the alignment records (MM/ML base modifications, Ultima's tp / t0) - so the caller that owns that data hands the encoder the
+ * channel's PIXEL VALUES: one byte per (image, read) pair, or one byte per base parallel to `bases` (0 where a read has no such
+ * data: the reference leaves those pixels unwritten).  deepvariant_b200/channels.py restates the reference's value functions;
+ * the encoder places the bytes exactly where FillReadBase would (same CIGAR walk, same last-writer-wins order). */
+enum { DVB_PAIR_PLANE_ALLELE_FREQUENCY = 0, DVB_PAIR_PLANE_FUZZY_SUPPORT = 1, DVB_PAIR_PLANE_ALLELE_SAMPLE_PROBABILITY = 2, DVB_N_PAIR_PLANES = 3 };
+enum { DVB_BASE_PLANE_5MC = 0, DVB_BASE_PLANE_6MA = 1, DVB_BASE_PLANE_HMER_INSERTION = 2, DVB_BASE_PLANE_HMER_DELETION = 3,
+       DVB_BASE_PLANE_INTER_HMER_INSERTION = 4, DVB_N_BASE_PLANES = 5 };
 
 /* read_flags bits */
 enum {
@@ -111,6 +131,7 @@ typedef struct DvbPileupParams {
                                      implementation-defined): DVB_SHUFFLE_LIBCXX (0, default) reproduces the reference's golden
                                      files (all 51 down-sampled examples of golden.allele_frequency_examples, row for row);
                                      DVB_SHUFFLE_LIBSTDCXX (1) is what a gcc/libstdc++ build of the reference does */
+  float mean_coverage;            /* SampleOptions.mean_coverage (--mean_coverage_per_sample); only read with DVB_CH_MEAN_COVERAGE */
 } DvbPileupParams;
 
 enum { DVB_SHUFFLE_LIBCXX = 0, DVB_SHUFFLE_LIBSTDCXX = 1 };
@@ -174,6 +195,10 @@ typedef struct DvbBatch {
   int32_t support_min_mapping_quality;  /* AlleleCounterOptions.read_requirements.min_mapping_quality */
   int32_t support_min_base_quality;     /* ... min_base_quality */
   int32_t support_flags;                /* DVB_SUPPORT_* */
+  /* Optional channel planes (see DVB_PAIR_PLANE_* / DVB_BASE_PLANE_* above); a plane is required exactly when params.channels names
+   * its channel (else DVB_ERR_INVALID_ARGUMENT) and ignored otherwise. */
+  const uint8_t* pair_channel[DVB_N_PAIR_PLANES];   /* each [n_pairs] */
+  const uint8_t* base_channel[DVB_N_BASE_PLANES];   /* each [n_bases], parallel to bases / quals */
 } DvbBatch;
 
 enum {
@@ -227,6 +252,21 @@ int64_t dvb_encoder_launch_count(const DvbEncoder* enc);
 /* After a batch with allele keys (DvbBatch.allele_begin): the pair_support / pair_allele_group arrays the device derived for it
  * (host buffers of n_pairs bytes; group may be NULL).  Synchronises the device.  For tests and for callers that want the classes. */
 int dvb_encoder_last_pair_support(DvbEncoder* enc, int64_t n_pairs, uint8_t* support, uint8_t* group);
+
+/* ---- value functions of the plane-backed channels (host only; csrc/dvb_channels.cu) ---------------------------------------
+ * What the caller puts into DvbBatch.base_channel / pair_channel, with the reference's float arithmetic. */
+/* base_methylation_channel.cc:87-99 / base_6ma_channel.cc:87-99 ScaleColorVector(values, 255): values = the modification's ML bytes
+ * per base of the aligned sequence (nucleus Read.base_modifications["5mC" | "6mA"]). */
+int dvb_channel_base_modification_plane(const uint8_t* values, int64_t len, uint8_t* out);
+/* homopolymer_indel_quality_channel.cc:127-183 HomoPolymerInDelQuality: tp = the read's tp tag as int8 per base (NULL = no tag),
+ * is_deletion 0 = homopolymer_insertion_quality, 1 = homopolymer_deletion_quality. */
+int dvb_channel_hmer_quality_plane(const uint8_t* seq, const uint8_t* qual, int64_t len, const int8_t* tp, int32_t is_deletion, uint8_t* out);
+/* inter_homopolymer_insertion_quality_channel.cc:75-127 GetT0QualityValues: t0 = the t0 tag's text (phred + 33), t0_len 0 = no tag. */
+int dvb_channel_t0_plane(int64_t len, const char* t0, int64_t t0_len, uint8_t* out);
+/* allele_frequency_channel.cc:76-87 AlleleFrequencyColor. */
+int32_t dvb_channel_allele_frequency_color(float allele_frequency, float min_non_zero_allele_frequency);
+/* allele_sample_probability_channel.cc:87-101 ScaleColor(reads supporting the read's allele, all reads). */
+int32_t dvb_channel_allele_sample_probability_color(int32_t value, float max_val);
 
 /* ---- CNN (Inception-v3 + genotype softmax) ------------------------------- */
 

@@ -59,6 +59,7 @@ struct ReadView {  // the fields of nucleus Read the path touches
   int64_t len;
   const uint32_t* cigar;
   int64_t n_cigar;
+  const uint8_t* base_plane[DVB_N_BASE_PLANES];   // per-base channel values of this read (nullptr: plane absent)
 };
 
 ReadView GetRead(const DvbBatch& b, int32_t r) {
@@ -75,6 +76,7 @@ ReadView GetRead(const DvbBatch& b, int32_t r) {
   v.len = b.read_seq_begin[r + 1] - b.read_seq_begin[r];
   v.cigar = b.cigar + b.read_cigar_begin[r];
   v.n_cigar = b.read_cigar_begin[r + 1] - b.read_cigar_begin[r];
+  for (int k = 0; k < DVB_N_BASE_PLANES; ++k) v.base_plane[k] = b.base_channel[k] ? b.base_channel[k] + b.read_seq_begin[r] : nullptr;
   return v;
 }
 
@@ -256,6 +258,10 @@ bool ChannelSupported(int ch) {
     case DVB_CH_READ_MAPPING_PERCENT: case DVB_CH_AVG_BASE_QUALITY: case DVB_CH_IDENTITY:
     case DVB_CH_GAP_COMPRESSED_IDENTITY: case DVB_CH_GC_CONTENT:
     case DVB_CH_IS_HOMOPOLYMER: case DVB_CH_HOMOPOLYMER_WEIGHTED:
+    case DVB_CH_ALLELE_FREQUENCY: case DVB_CH_READ_SUPPORTS_VARIANT_FUZZY: case DVB_CH_ALLELE_SAMPLE_PROBABILITY:
+    case DVB_CH_BASE_METHYLATION: case DVB_CH_BASE_6MA: case DVB_CH_HOMOPOLYMER_INSERTION_QUALITY:
+    case DVB_CH_HOMOPOLYMER_DELETION_QUALITY: case DVB_CH_INTER_HOMOPOLYMER_INSERTION_QUALITY:
+    case DVB_CH_MEAN_COVERAGE:
       return true;
     default:
       return false;
@@ -264,10 +270,40 @@ bool ChannelSupported(int ch) {
 
 // One FillReadBase call (channels/*_channel.cc FillReadBase), dispatched by enum like
 // Channels::ChannelEnumToObject (pileup_channel_lib.cc:367-447).
+// Plane slot of a plane-backed channel (include/dvb.h), or -1.
+int PairPlaneOf(int channel_enum) {
+  switch (channel_enum) {
+    case DVB_CH_ALLELE_FREQUENCY: return DVB_PAIR_PLANE_ALLELE_FREQUENCY;
+    case DVB_CH_READ_SUPPORTS_VARIANT_FUZZY: return DVB_PAIR_PLANE_FUZZY_SUPPORT;
+    case DVB_CH_ALLELE_SAMPLE_PROBABILITY: return DVB_PAIR_PLANE_ALLELE_SAMPLE_PROBABILITY;
+    default: return -1;
+  }
+}
+int BasePlaneOf(int channel_enum) {
+  switch (channel_enum) {
+    case DVB_CH_BASE_METHYLATION: return DVB_BASE_PLANE_5MC;
+    case DVB_CH_BASE_6MA: return DVB_BASE_PLANE_6MA;
+    case DVB_CH_HOMOPOLYMER_INSERTION_QUALITY: return DVB_BASE_PLANE_HMER_INSERTION;
+    case DVB_CH_HOMOPOLYMER_DELETION_QUALITY: return DVB_BASE_PLANE_HMER_DELETION;
+    case DVB_CH_INTER_HOMOPOLYMER_INSERTION_QUALITY: return DVB_BASE_PLANE_INTER_HMER_INSERTION;
+    default: return -1;
+  }
+}
+
+// pair_values: the (image, read) pair's bytes of DvbBatch.pair_channel (the value the reference caches per read in a std::optional:
+// allele_frequency_channel.cc:57-68, read_supports_variant_fuzzy_channel.cc:99-110; allele_sample_probability_channel.cc:48-79).
 unsigned char FillReadBase(int channel_enum, char read_base, char ref_base, int base_quality,
                            const ReadView& read, int support_class, const DvbPileupParams& o, int read_index,
-                           const BaseVectors& bv) {
+                           const BaseVectors& bv, const uint8_t* pair_values) {
   switch (channel_enum) {
+    case DVB_CH_ALLELE_FREQUENCY: case DVB_CH_READ_SUPPORTS_VARIANT_FUZZY: case DVB_CH_ALLELE_SAMPLE_PROBABILITY:
+      return pair_values[PairPlaneOf(channel_enum)];
+    case DVB_CH_BASE_METHYLATION: case DVB_CH_BASE_6MA:                       // data[col] = vector.at(read_index) when the read has one
+    case DVB_CH_HOMOPOLYMER_INSERTION_QUALITY: case DVB_CH_HOMOPOLYMER_DELETION_QUALITY:
+    case DVB_CH_INTER_HOMOPOLYMER_INSERTION_QUALITY:                          // data[col] = vector[read_index]
+      return read.base_plane[BasePlaneOf(channel_enum)][read_index];
+    case DVB_CH_MEAN_COVERAGE:           // a BlankChannel per read (pileup_channel_lib.cc:418-421); painted in BuildPileupForOneSample
+      return 0;
     case DVB_CH_IS_HOMOPOLYMER:          // data[col] = vector.at(read_index)
       return bv.is_homopolymer.at(static_cast<size_t>(read_index));
     case DVB_CH_HOMOPOLYMER_WEIGHTED:
@@ -331,7 +367,13 @@ unsigned char FillRefBase(int channel_enum, char ref_base, const DvbPileupParams
     case DVB_CH_STRAND:
       return static_cast<std::uint8_t>(o.positive_strand_color);
     case DVB_CH_READ_SUPPORTS_VARIANT:
+    case DVB_CH_READ_SUPPORTS_VARIANT_FUZZY:   // read_supports_variant_fuzzy_channel.cc:112-116
       return SupportsAltColor(0, o);
+    case DVB_CH_ALLELE_FREQUENCY:              // AlleleFrequencyColor(0) = 0 (allele_frequency_channel.cc:70-74, 79-82)
+    case DVB_CH_ALLELE_SAMPLE_PROBABILITY: case DVB_CH_BASE_METHYLATION: case DVB_CH_BASE_6MA:
+    case DVB_CH_HOMOPOLYMER_INSERTION_QUALITY: case DVB_CH_HOMOPOLYMER_DELETION_QUALITY:
+    case DVB_CH_INTER_HOMOPOLYMER_INSERTION_QUALITY: case DVB_CH_MEAN_COVERAGE:
+      return 0;
     case DVB_CH_BASE_DIFFERS_FROM_REF:
       return MatchesRefColor(true, o);
     case DVB_CH_HAPLOTYPE_TAG:
@@ -351,7 +393,7 @@ unsigned char FillRefBase(int channel_enum, char ref_base, const DvbPileupParams
 // site), -1 unrecognized CIGAR op (the reference LOG(FATAL)s).
 int CalculateChannels(std::vector<std::vector<unsigned char>>& data, const DvbPileupParams& o,
                       const ReadView& read, const uint8_t* ref_bases, int width,
-                      int variant_start, int support_class, int image_start_pos) {
+                      int variant_start, int support_class, int image_start_pos, const uint8_t* pair_values) {
   const BaseVectors bv(read.bases, read.len, o);
   // action_per_cigar_unit, pileup_channel_lib.cc:126-165 (op in BAM numbering here).
   auto action = [&](int ref_i, int read_i, int op) -> bool {
@@ -373,7 +415,7 @@ int CalculateChannels(std::vector<std::vector<unsigned char>>& data, const DvbPi
       char ref_base = static_cast<char>(ref_bases[col]);
       for (int c = 0; c < o.num_channels; ++c) {
         data[c][col] = FillReadBase(o.channels[c], read_base, ref_base, base_quality, read,
-                                    support_class, o, read_i, bv);
+                                    support_class, o, read_i, bv, pair_values);
       }
     }
     return true;
@@ -419,14 +461,14 @@ int CalculateChannels(std::vector<std::vector<unsigned char>>& data, const DvbPi
 // PileupImageEncoderNative::EncodeRead, pileup_image_native.cc:477-510.
 // status: 1 row produced, 0 nullptr, -1 bad cigar.
 int EncodeRead(const DvbPileupParams& o, const ReadView& read, const uint8_t* ref_bases,
-               int variant_start, int support_class, int image_start_pos,
+               int variant_start, int support_class, int image_start_pos, const uint8_t* pair_values,
                std::unique_ptr<ImageRow>* out) {
   ImageRow img_row(o.width, o.num_channels);
   if (read.mapq < o.min_mapping_quality) {
     return 0;
   }
   int st = CalculateChannels(img_row.channel_data, o, read, ref_bases, o.width, variant_start,
-                             support_class, image_start_pos);
+                             support_class, image_start_pos, pair_values);
   if (st != 1) return st;
   *out = std::make_unique<ImageRow>(img_row);
   return 1;
@@ -505,8 +547,7 @@ bool SortImageRows(const ReadPileupTuple& a, const ReadPileupTuple& b) {
   return std::get<3>(a) < std::get<3>(b);
 }
 
-// BuildPileupForOneSample, pileup_image_native.cc:296-447 (uniform down-sampling branch;
-// mean-coverage overlay omitted: mean_coverage is always 0.0, make_examples_core.py:1996).
+// BuildPileupForOneSample, pileup_image_native.cc:296-447 (uniform down-sampling branch).
 int BuildPileupForOneSample(const DvbPileupParams& o, const DvbBatch& b, int32_t img,
                             std::vector<std::unique_ptr<ImageRow>>* rows_out) {
   const uint8_t* ref_bases = b.ref_bases + static_cast<int64_t>(img) * b.ref_stride;
@@ -530,8 +571,10 @@ int BuildPileupForOneSample(const DvbPileupParams& o, const DvbBatch& b, int32_t
     const int64_t p = p0 + index;
     const ReadView read = GetRead(b, b.pair_read[p]);
     std::unique_ptr<ImageRow> image_row;
+    uint8_t pair_values[DVB_N_PAIR_PLANES];
+    for (int k = 0; k < DVB_N_PAIR_PLANES; ++k) pair_values[k] = b.pair_channel[k] ? b.pair_channel[k][p] : 0;
     int st = EncodeRead(o, read, ref_bases, b.variant_start[img], b.pair_support[p],
-                        b.image_start_pos[img], &image_row);
+                        b.image_start_pos[img], pair_values, &image_row);
     if (st < 0) return DVB_ERR_BAD_CIGAR;
     if (st == 0) continue;
     int hap_idx = GetHapIndex(o, read);
@@ -549,6 +592,15 @@ int BuildPileupForOneSample(const DvbPileupParams& o, const DvbBatch& b, int32_t
   int empty_rows = pileup_height - static_cast<int>(rows.size());
   for (int i = 0; i < empty_rows; i++) {
     rows.push_back(std::make_unique<ImageRow>(o.width, o.num_channels));
+  }
+
+  // "Add average coverage information after reads are added and sorted", pileup_image_native.cc:422-444.
+  for (int c = 0; c < o.num_channels; ++c) {
+    if (o.channels[c] != DVB_CH_MEAN_COVERAGE) continue;
+    for (int i = 0; i < std::min(static_cast<int>(o.mean_coverage) + o.reference_band_height, pileup_height); i++) {
+      rows[i]->channel_data[c].assign(o.width, i < o.reference_band_height ? 255 : 200);   // kChannelValue255 / kChannelValue200
+    }
+    break;   // std::find: the first such channel
   }
   return DVB_OK;
 }
@@ -576,6 +628,18 @@ int64_t FillPileupArray(const std::vector<std::unique_ptr<ImageRow>>& image, int
   return buffer_pos;
 }
 
+// A plane-backed channel needs its plane (include/dvb.h: DVB_ERR_INVALID_ARGUMENT otherwise).
+int ValidatePlanes(const DvbPileupParams& o, const DvbBatch& b) {
+  for (int c = 0; c < o.num_channels; ++c) {
+    const int pp = PairPlaneOf(o.channels[c]), bp = BasePlaneOf(o.channels[c]);
+    if ((pp >= 0 && b.n_pairs > 0 && !b.pair_channel[pp]) || (bp >= 0 && b.n_bases > 0 && !b.base_channel[bp])) {
+      g_err = "channel enum " + std::to_string(o.channels[c]) + " needs its channel plane";
+      return DVB_ERR_INVALID_ARGUMENT;
+    }
+  }
+  return DVB_OK;
+}
+
 int ValidateParams(const DvbPileupParams& o) {
   if (o.width < 1) { g_err = "width must be >= 1"; return DVB_ERR_INVALID_ARGUMENT; }
   if (o.num_channels < 1 || o.num_channels > DVB_MAX_CHANNELS) { g_err = "bad num_channels"; return DVB_ERR_INVALID_ARGUMENT; }
@@ -596,6 +660,8 @@ const char* dvb_oracle_last_error(void) { return g_err.c_str(); }
 int dvb_oracle_encode_batch(const DvbPileupParams* params, const DvbBatch* batch, uint8_t* out) {
   if (!params || !batch || (!out && batch->n_images > 0)) { g_err = "null argument"; return DVB_ERR_INVALID_ARGUMENT; }
   int st = ValidateParams(*params);
+  if (st) return st;
+  st = ValidatePlanes(*params, *batch);
   if (st) return st;
   const int64_t image_bytes = static_cast<int64_t>(params->height) * params->width *
                               (params->num_channels + params->num_alt_channels);
@@ -620,11 +686,15 @@ int dvb_oracle_encode_read(const DvbPileupParams* params, const DvbBatch* batch,
   int st = ValidateParams(*params);
   if (st) return st;
   const DvbPileupParams& o = *params;
+  st = ValidatePlanes(o, *batch);
+  if (st) return st;
   const ReadView read = GetRead(*batch, batch->pair_read[pair]);
   std::unique_ptr<ImageRow> row;
+  uint8_t pair_values[DVB_N_PAIR_PLANES];
+  for (int k = 0; k < DVB_N_PAIR_PLANES; ++k) pair_values[k] = batch->pair_channel[k] ? batch->pair_channel[k][pair] : 0;
   int r = EncodeRead(o, read, batch->ref_bases + static_cast<int64_t>(img) * batch->ref_stride,
                      batch->variant_start[img], batch->pair_support[pair],
-                     batch->image_start_pos[img], &row);
+                     batch->image_start_pos[img], pair_values, &row);
   if (r < 0) { g_err = "Unrecognized CIGAR op"; return DVB_ERR_BAD_CIGAR; }
   *kept = r;
   if (r == 1) {
