@@ -135,10 +135,12 @@ def fuzzy_supports_alt_color(read_supports_alt: int, options) -> int:
 
 def allele_sample_probability_color(dv_call: DeepVariantCall, read_key: str) -> int:
   """AlleleSampleProbabilityChannel::FillReadBase (:48-79): sqrt-scaled share of the reads that support the read's allele; the
-  reference walks the allele_support MAP (key order) and stops at the first allele listing the read."""
+  reference walks the allele_support protobuf MAP and stops at the first allele listing the read, so with several alleles its total
+  depends on the map's (unspecified, hash-seeded) iteration order; here the order is fixed: the variant's alts, then other keys sorted."""
   total_reads = 0
   supporting = None
-  for allele in sorted(dv_call.allele_support):   # protobuf map iteration order is unspecified; the sum up to the hit is what is used
+  alts = [a for a in dv_call.variant.alternate_bases if a in dv_call.allele_support]
+  for allele in alts + sorted(k for k in dv_call.allele_support if k not in alts):
     names = dv_call.allele_support[allele]
     total_reads += len(names)
     if read_key in names:

@@ -34,6 +34,10 @@ class ImageSpec:
   support: List[int]                # per read: 0 / 1 / 2
   allele_group: List[int]           # per read (only used with sort_by_alt_allele_support)
   sort_positions: Optional[List[int]] = None  # alignment positions before trimming
+  pair_channels: Optional[Dict[int, List[int]]] = None   # per-pair channel planes: slot -> one pixel value per read (channels.pair_planes)
+
+
+PAIR_PLANE_CHANNELS = ('allele_frequency', 'read_supports_variant_fuzzy', 'allele_sample_probability')
 
 
 def read_supports_alt(dv_call: DeepVariantCall, read_key: str, alt_alleles: Sequence[str]) -> int:
@@ -65,9 +69,13 @@ def image_spec_for(dv_call: DeepVariantCall, ref_bases: str, reads: List[Read], 
   view = DeepVariantCall(variant=dv_call.variant, allele_support=support_sets)
   support = [read_supports_alt(view, r.key(), alt_alleles) for r in reads]
   groups = allele_groups(dv_call, reads) if options.sort_by_alt_allele_support else [0] * len(reads)
+  pair_channels = None
+  if any(c in PAIR_PLANE_CHANNELS for c in options.channels):
+    from deepvariant_b200 import channels   # the value functions call into libdvb
+    pair_channels = channels.pair_planes(dv_call, reads, alt_alleles, options)
   return ImageSpec(ref_bases=ref_bases, image_start_pos=image_start_pos,
                    variant_start=dv_call.variant.start, reads=reads, support=support,
-                   allele_group=groups, sort_positions=sort_positions)
+                   allele_group=groups, sort_positions=sort_positions, pair_channels=pair_channels)
 
 
 @dataclasses.dataclass
@@ -108,7 +116,7 @@ class PackedBatch:
       a = self.arrays.get(f'{member}_{k}')
       if a is not None:
         want = self.n_pairs if member == 'pair_channel' else b.n_bases
-        assert a.dtype == np.uint8 and a.flags['C_CONTIGUOUS'] and a.size == want, (member, k, a.size, want)
+        assert a.dtype == np.uint8 and a.flags['C_CONTIGUOUS'] and a.size >= want, (member, k, a.size, want)
         getattr(b, member)[k] = a.ctypes.data
     return b
 
@@ -173,6 +181,10 @@ def pack_images(specs: Sequence[ImageSpec], params: _lib.DvbPileupParams) -> Pac
   pair_read: List[int] = []
   pair_support: List[int] = []
   pair_group: List[int] = []
+  enums = [params.channels[c] for c in range(params.num_channels)]
+  pair_slots = sorted(k for e, (member, k) in _lib.PLANE_OF_CHANNEL.items() if member == 'pair_channel' and e in enums)
+  base_slots = sorted(k for e, (member, k) in _lib.PLANE_OF_CHANNEL.items() if member == 'base_channel' and e in enums)
+  pair_planes: Dict[int, List[int]] = {k: [] for k in pair_slots}
   for i, s in enumerate(specs):
     rb = s.ref_bases.encode() if isinstance(s.ref_bases, str) else bytes(s.ref_bases)
     if len(rb) != width:
@@ -192,6 +204,10 @@ def pack_images(specs: Sequence[ImageSpec], params: _lib.DvbPileupParams) -> Pac
       pair_read.append(k)
       pair_support.append(s.support[j])
       pair_group.append(s.allele_group[j] if s.allele_group else 0)
+    for k in pair_slots:
+      if s.pair_channels is None or k not in s.pair_channels:
+        raise ValueError(f'the channel list names a per-pair plane channel (slot {k}) but the ImageSpec carries no values for it')
+      pair_planes[k].extend(s.pair_channels[k])
     pair_begin[i + 1] = len(pair_read)
 
   n_reads = len(reads)
@@ -246,6 +262,12 @@ def pack_images(specs: Sequence[ImageSpec], params: _lib.DvbPileupParams) -> Pac
       'quals': quals,
       'cigar': cigar,
   }
+  for k in pair_slots:
+    arrays[f'pair_channel_{k}'] = np.array(pair_planes[k], dtype=np.uint8)
+  if base_slots:
+    from deepvariant_b200 import channels   # one native pass per read
+    for k in base_slots:
+      arrays[f'base_channel_{k}'] = np.concatenate([channels.base_plane(r, k) for r in reads]) if n_reads else np.zeros(0, dtype=np.uint8)
   arrays = {k: np.ascontiguousarray(_pad(v)) for k, v in arrays.items()}
   pb = PackedBatch(n_images=n_images, n_reads=n_reads, n_pairs=len(pair_read), ref_stride=ref_stride,
                    arrays=arrays)

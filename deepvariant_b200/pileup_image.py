@@ -44,12 +44,13 @@ CHANNEL_ENUM: Dict[str, int] = {
     'is_homopolymer': 16, 'homopolymer_weighted': 17, 'blank': 18, 'insert_size': 19,
     'base_channels_alternate_allele_1': 20, 'base_channels_alternate_allele_2': 21,
     'mean_coverage': 22, 'base_methylation': 23, 'base_6ma': 24,
-    'supplementary_alignment': 26,
+    'read_supports_variant_fuzzy': 25, 'supplementary_alignment': 26, 'allele_sample_probability': 27,
+    'homopolymer_insertion_quality': 28, 'homopolymer_deletion_quality': 29, 'inter_homopolymer_insertion_quality': 30,
 }
 ALT_ALIGNED_PSEUDO_CHANNELS = (
     'diff_channels_alternate_allele_1', 'diff_channels_alternate_allele_2',
     'base_channels_alternate_allele_1', 'base_channels_alternate_allele_2')
-SUPPORTED_ENUMS = (1, 2, 3, 4, 5, 6, 7, 18, 19, 26)
+SUPPORTED_ENUMS = (1, 2, 3, 4, 5, 6, 7, 8, 11, 12, 13, 14, 15, 16, 17, 18, 19, 22, 23, 24, 25, 26, 27, 28, 29, 30)
 
 
 @dataclasses.dataclass
@@ -91,6 +92,8 @@ class PileupImageOptions:
   sort_by_haplotypes: bool = False
   hp_tag_for_assembly_polishing: int = 0
   sort_by_alt_allele_support: bool = False
+  min_non_zero_allele_frequency: float = 0.0   # PileupImageOptions field 33 (allele_frequency channel)
+  mean_coverage: float = 0.0                   # SampleOptions.mean_coverage of the one sample (mean_coverage channel)
 
 
 def default_options(read_requirements: Optional[ReadRequirements] = None) -> PileupImageOptions:
@@ -123,6 +126,7 @@ def default_options(read_requirements: Optional[ReadRequirements] = None) -> Pil
       sequencing_type=0,
       alt_aligned_pileup='none',
       types_to_alt_align='indels',
+      min_non_zero_allele_frequency=0.00001,
   )
 
 
@@ -177,6 +181,7 @@ def to_params(options: PileupImageOptions, height: Optional[int] = None) -> _lib
   p.sort_by_alt_allele_support = int(options.sort_by_alt_allele_support)
   p.random_seed = options.random_seed & 0xFFFFFFFF
   p.max_reads_per_image = 0
+  p.mean_coverage = options.mean_coverage
   return p
 
 

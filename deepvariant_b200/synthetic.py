@@ -48,6 +48,10 @@ class TorchBatch:
     b.n_bases, b.n_cigar, b.ref_stride = self.n_bases, self.n_cigar, self.ref_stride
     for name, _ in _lib.BATCH_ARRAYS:
       setattr(b, name, C.c_void_p(self.tensors[name].data_ptr()))
+    for member, k in _lib.PLANE_ARRAYS:   # optional channel planes (tensors['pair_channel_<k>'] / ['base_channel_<k>'])
+      t = self.tensors.get(f'{member}_{k}')
+      if t is not None:
+        getattr(b, member)[k] = t.data_ptr()
     return b
 
   def to(self, device, non_blocking=False) -> 'TorchBatch':
@@ -76,6 +80,11 @@ class TorchBatch:
         a = a.view(np.uint32)
       a = np.ascontiguousarray(a)
       arrays[name] = a if a.size else np.zeros(1, dtype=a.dtype)
+    for member, k in _lib.PLANE_ARRAYS:
+      t = self.tensors.get(f'{member}_{k}')
+      if t is not None:
+        a = np.ascontiguousarray(t.cpu().numpy())
+        arrays[f'{member}_{k}'] = a if a.size else np.zeros(1, dtype=np.uint8)
     pb = packing.PackedBatch(self.n_images, self.n_reads, self.n_pairs, self.ref_stride, arrays)
     return pb
 
