@@ -69,13 +69,18 @@ def parse_regions(text: str):
   return out
 
 
+def _lib_plane_enums():
+  from deepvariant_b200 import _lib
+  return set(_lib.PLANE_OF_CHANNEL)
+
+
 RUNTIME_BY_REGION_COLUMNS = ('region', 'get reads', 'find candidates', 'make pileup images', 'write outputs', 'num reads', 'num candidates', 'num examples',
                              'small model generate examples', 'small model call examples', 'small model write variants', 'small model total')
 
 MAKE_EXAMPLES_DEFAULTS = dict(
     task=0, regions='', channel_list='BASE_CHANNELS', pileup_image_width=221, pileup_image_height=100, min_mapping_quality=5,
     min_base_quality=10, partition_size=1000, sort_by_haplotypes=False, trim_reads_for_pileup=False, parse_sam_aux_fields=False,
-    alt_aligned_pileup='none', device=0, checkpoint='', checkpoint_json='', candidates='', candidates_in='', max_reads_per_partition=1500,
+    alt_aligned_pileup='none', population_vcfs='', mean_coverage_per_sample='', device=0, checkpoint='', checkpoint_json='', candidates='', candidates_in='', max_reads_per_partition=1500,
     sample_name='', vsc_min_count_snps=2, vsc_min_count_indels=2, vsc_min_fraction_snps=0.12, vsc_min_fraction_indels=0.06,
     vsc_min_fraction_multiplier=1.0, small_model_vaf_context_window_size=0, track_ref_reads=False, phase_reads=False,
     keep_legacy_allele_counter_behavior=False, normalize_reads=False, realign_reads=True, gvcf='', gvcf_gq_binsize=5, p_error=0.001,
@@ -173,6 +178,8 @@ def make_examples(argv):
   ap.add_argument('--trim_reads_for_pileup', action='store_true')
   ap.add_argument('--parse_sam_aux_fields', action='store_true')
   ap.add_argument('--alt_aligned_pileup')
+  ap.add_argument('--population_vcfs')            # allele_frequency channel: one VCF for all contigs, or one per contig (space / comma separated)
+  ap.add_argument('--mean_coverage_per_sample')   # mean_coverage channel (make_examples_options.py:573-580); the first value is this sample's
   ap.add_argument('--device', type=int)
   given = vars(ap.parse_args(argv))
   merged = apply_flags_for_calling(given, given.get('checkpoint', ''), given.get('checkpoint_json', ''))
@@ -188,6 +195,17 @@ def make_examples(argv):
   pic.width, pic.height = a.pileup_image_width, a.pileup_image_height
   pic.sort_by_haplotypes = a.sort_by_haplotypes
   pic.alt_aligned_pileup = a.alt_aligned_pileup
+  if a.mean_coverage_per_sample:
+    pic.mean_coverage = float(str(a.mean_coverage_per_sample).replace(',', ' ').split()[0])
+  # Channels whose values come from DeepVariantCall maps or per-base aux data (deepvariant_b200/channels.py) are planned from Read
+  # objects, where that data lives; the table packers carry the classic per-read fields only.
+  plane_channels = [c for c in pic.channels if pi.CHANNEL_ENUM.get(c) in _lib_plane_enums()]
+  population = None
+  if 'allele_frequency' in pic.channels:
+    if not a.population_vcfs:
+      raise ValueError('the allele_frequency channel needs --population_vcfs')
+    from deepvariant_b200 import allele_frequency as af
+    population = af.make_population_vcf_readers(str(a.population_vcfs).replace(',', ' ').split())
   opts = men.MakeExamplesOptions(pic_options=pic, reference_filename=a.ref, trim_reads_for_pileup=a.trim_reads_for_pileup)
   fused = bool(a.call_variants_outfile)
   if not fused and not a.examples:
@@ -223,13 +241,22 @@ def make_examples(argv):
     margin = (a.partition_size // 5 if a.phase_reads else 0) + 1000
     read_regions = [(c, max(0, s - margin), e + margin) for c, s, e in regions]
   reader = bam.NativeBamTable(a.reads, bam.ReadRequirements(min_mapping_quality=a.min_mapping_quality), parse_aux=a.parse_sam_aux_fields, regions=read_regions)
-  table_path = not a.trim_reads_for_pileup and a.alt_aligned_pileup == 'none'
+  table_path = not a.trim_reads_for_pileup and a.alt_aligned_pileup == 'none' and not plane_channels
+
+  def annotated(calls, contig):
+    # make_examples_core.py:2380-2388: population allele frequencies of the candidates' alleles
+    if population is None:
+      return calls
+    return af.add_allele_frequencies_to_candidates(calls, population.get(contig, population.get('*')), ref_for_af)
   if regions is not None and len(regions) > 1 and (a.candidates_in or a.mode == 'candidate_sweep'):
     raise NotImplementedError('several --regions together with --candidates_in / --mode candidate_sweep')
   region = regions[0] if regions else None
   totals = {}
 
+  ref_for_af = fasta.IndexedFastaReader(a.ref) if population is not None else None
+
   def examples_in(cs, contig, p0, p1):
+    cs = annotated(cs, contig)
     if table_path:
       stats, _ = gen.write_examples_in_region_from_table(cs, reader, 'main_sample', (contig, p0, p1))
     else:
@@ -377,7 +404,7 @@ def make_examples(argv):
           if table_path and not a.phase_reads:
             stats, _ = gen.write_examples_in_region_from_table(found.calls(), region_table, 'main_sample', (contig, p0, p1))
           else:
-            stats, _ = gen.write_examples_in_region(found.calls(), [[region_table.read(int(i)) for i in region_rows]], [0], 'main_sample', [0.0])
+            stats, _ = gen.write_examples_in_region(annotated(found.calls(), contig), [[region_table.read(int(i)) for i in region_rows]], [0], 'main_sample', [0.0])
           for key, val in stats.items():
             totals[key] = totals.get(key, 0) + val
           rt['num examples'] = stats.get('n_examples', 0)
@@ -404,7 +431,7 @@ def make_examples(argv):
           phases = direct_phasing.phase_reads([cand.canonical_call(r) for r in found.all_records], [r.key() for r in reads])
           for r, ph in zip(reads, phases):
             r.hp_values = [ph]
-          stats, _ = gen.write_examples_in_region(found.calls(), [reads], [0], 'main_sample', [0.0])
+          stats, _ = gen.write_examples_in_region(annotated(found.calls(), contig), [reads], [0], 'main_sample', [0.0])
           for key, val in stats.items():
             totals[key] = totals.get(key, 0) + val
         else:

@@ -214,3 +214,30 @@ def test_create_cvo_equals_reference_call_variants_output():
     assert len(mine) == len(golden) and idx2 == idx and probs2 == probs
     assert _proto_fields(v2, (11,)) == _proto_fields(v, (11,))
     assert protos.encode_call_variants_output(v, idx, probs) == golden     # wire round trip of the golden record itself
+
+
+def _allele_frequency_fixture():
+  """tools/check_allele_frequency_golden.py: examples of the reference's golden.allele_frequency_examples.tfrecord.gz (100 x 221 x 8:
+  the 7 WGS channels + allele_frequency), all 8 channels, with the batches the product flow packed for them from BAM + FASTA +
+  population VCF (realigned reads, candidates, read support, the allele_frequency pair plane)."""
+  d = np.load(os.path.join(GOLDEN, 'allele_frequency_golden_subset.npz'))
+  arrays = {k[4:]: d[k] for k in d.files if k.startswith('arr_')}
+  pb = packing.PackedBatch(int(d['n_images']), int(d['n_reads']), int(d['n_pairs']), int(d['ref_stride']), arrays)
+  o = pi.default_options(pi.ReadRequirements(min_base_quality=10, min_mapping_quality=5))
+  o.channels = list(pi.PILEUP_CHANNELS_WITH_INSERT_SIZE) + ['allele_frequency']
+  return pb, d['golden_images'], o
+
+
+def test_oracle_reproduces_allele_frequency_golden_images():
+  pb, golden, o = _allele_frequency_fixture()
+  assert golden.shape[1:] == (100, 221, 8) and golden.shape[0] >= 6
+  assert sum(1 for g in golden if g[5:, :, 7].any()) >= 6               # images whose reads carry a population frequency
+  assert 'pair_channel_0' in pb.arrays
+  np.testing.assert_array_equal(oracle_lib.encode_batch(pi.to_params(o), pb), golden)
+
+
+@pytest.mark.gpu
+def test_cuda_encoder_reproduces_allele_frequency_golden_images():
+  pb, golden, o = _allele_frequency_fixture()
+  enc = pi.GpuEncoder(pi.to_params(o), 0)
+  np.testing.assert_array_equal(enc.encode_host(pb), golden)
