@@ -46,6 +46,7 @@ class DvbPileupParams(C.Structure):
       ('max_reads_per_image', C.c_int32),
       ('shuffle_stdlib', C.c_int32),
       ('mean_coverage', C.c_float),
+      ('blank_channel_mask', C.c_uint32),
   ]
 
 

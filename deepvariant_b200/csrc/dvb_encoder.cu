@@ -73,6 +73,8 @@ struct EncDev {
   // every term is < 256 and the byte positions of different kinds are disjoint).
   unsigned mask_base[4], mask_qual[4], mask_diff[4], mask_const[4], ref_words[4];
   unsigned mask_ishomo[4], mask_homow[4];   // per-base homopolymer channels (is_homopolymer, homopolymer_weighted)
+  // the same masks as the reference band uses them: channels_enum_to_blank (blank_channel_mask) clears a channel from the READ masks only
+  unsigned ref_mask_base[4], ref_mask_ishomo[4], ref_mask_homow[4];
   int has_homo;
   // per-base channel planes (DvbBatch.base_channel): channel index and plane slot of each K_PLANE channel
   int n_planes;
@@ -596,8 +598,8 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             if (w < P.n_words) {
-              const unsigned word = P.ref_words[w] + bc * P.mask_base[w] + ((P.gc_chan >> 2) == w ? gc_word : 0u) +
-                                    (HOMO ? ih * P.mask_ishomo[w] + hw * P.mask_homow[w] : 0u);
+              const unsigned word = P.ref_words[w] + bc * P.ref_mask_base[w] + ((P.gc_chan >> 2) == w ? gc_word : 0u) +
+                                    (HOMO ? ih * P.ref_mask_ishomo[w] + hw * P.ref_mask_homow[w] : 0u);
 #pragma unroll
               for (int b = 0; b < 4; ++b)
                 if (w * 4 + b < P.C) q[w * 4 + b] = (uint8_t)(word >> (8 * b));
@@ -899,6 +901,24 @@ int BuildDev(const DvbPileupParams& o, EncDev* d) {
     else if (d->kind[c] == K_ISHOMO) d->mask_ishomo[c >> 2] |= one;
     else if (d->kind[c] == K_HOMOW) d->mask_homow[c >> 2] |= one;
     if (d->kind[c] != K_BASE) d->ref_words[c >> 2] |= (unsigned)d->ref_const[c] << (8 * (c & 3));
+  }
+  // channels_enum_to_blank: FillReadBase is skipped for these channels (pileup_channel_lib.cc:152-161) while CalculateRefRows still
+  // draws them - keep the reference band's masks, then take the channel out of everything the read rows use
+  for (int w = 0; w < 4; ++w) { d->ref_mask_base[w] = d->mask_base[w]; d->ref_mask_ishomo[w] = d->mask_ishomo[w]; d->ref_mask_homow[w] = d->mask_homow[w]; }
+  for (int c = 0; c < d->C; ++c) {
+    if (!(o.blank_channel_mask & (1u << c))) continue;
+    const unsigned keep = ~(0xFFu << (8 * (c & 3)));
+    d->mask_base[c >> 2] &= keep; d->mask_qual[c >> 2] &= keep; d->mask_diff[c >> 2] &= keep; d->mask_const[c >> 2] &= keep;
+    d->mask_ishomo[c >> 2] &= keep; d->mask_homow[c >> 2] &= keep;
+    d->kind[c] = K_ZERO;
+    int n = 0;
+    for (int k = 0; k < d->n_planes; ++k)
+      if (d->plane_chan[k] != c) { d->plane_chan[n] = d->plane_chan[k]; d->plane_slot[n++] = d->plane_slot[k]; }
+    d->n_planes = n;
+    n = 0;
+    for (int k = 0; k < d->n_pair_planes; ++k)
+      if (d->pair_plane_chan[k] != c) { d->pair_plane_chan[n] = d->pair_plane_chan[k]; d->pair_plane_slot[n++] = d->pair_plane_slot[k]; }
+    d->n_pair_planes = n;
   }
   for (int i = 0; i < 256; ++i) {
     d->base_lut[i] = (uint8_t)HostBaseColor(i, o);

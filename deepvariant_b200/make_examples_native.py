@@ -51,6 +51,7 @@ class SampleOptions:
   pileup_height: int = 0
   order: List[int] = dataclasses.field(default_factory=lambda: [0])
   keep_only_window_spanning_reads: bool = False
+  channels_enum_to_blank: List[int] = dataclasses.field(default_factory=list)   # deepvariant.proto SampleOptions: channel enums left blank in this sample's read rows
 
 
 @dataclasses.dataclass
@@ -244,13 +245,18 @@ class ExamplesGenerator:
     self.last_region_derived_support = False
     pic = options.pic_options
     self.half_width = (pic.width - 1) // 2
-    if len(options.sample_options) != 1:
-      raise NotImplementedError('multi-sample pileups are out of scope (SURVEY 8, Appendix A)')
+    if not options.sample_options:
+      raise ValueError('MakeExamplesOptions.sample_options is empty')
+    if len(options.sample_options) > 1 and pic.alt_aligned_pileup not in ('', 'none'):
+      raise NotImplementedError('alt-aligned pileups of multi-sample images')
     sample = options.sample_options[0]
-    # CalculatePileupImageHeight (pileup_image_native.cc:229-250), single sample, no extra rows
-    self.pileup_image_height = sample.pileup_height or pic.height
+    # CalculatePileupImageHeight (pileup_image_native.cc:219-240): the samples' blocks are stacked (FillPileupArrayBySample,
+    # pileup_image_native.h:313-336); pileup_image_height is ONE sample's block (the first sample's in multi-sample runs)
+    self.sample_heights = [s.pileup_height or pic.height for s in options.sample_options]
+    self.pileup_image_height = self.sample_heights[0]
     self._device = device
     self._encoder: Optional[pi.GpuEncoder] = None
+    self._sample_encoders: Dict[tuple, pi.GpuEncoder] = {}
     self.ref_reader = ref_reader
     self.writers: Dict[str, tfrecord.Writer] = {}
     self._example_filenames = dict(example_filenames or {})
@@ -506,6 +512,8 @@ class ExamplesGenerator:
     pic = self.options.pic_options
     # CalculatePileupImageHeight (pileup_image_native.cc:218-240): 'rows' stacks the two alt-aligned pileups under the main one
     sections = {'rows': 3, 'single_row': 2}.get(pic.alt_aligned_pileup, 1)
+    if len(self.options.sample_options) > 1:
+      return [sum(self.sample_heights), pic.width, len(pic.channels)]
     return [self.pileup_image_height * sections, pic.width, len(pic.channels)]
 
   def encode_example(self, plan: ExamplePlan, image: np.ndarray, stats: Dict[str, int]) -> bytes:
@@ -562,6 +570,79 @@ class ExamplesGenerator:
     images = enc.encode_host(packing.pack_images(specs, enc.params))
     return compose_alt_aligned(images, len(plans), alt_at, self.options.pic_options, [p.alt_combination for p in plans])
 
+  # -- multi-sample images (DeepTrio / DeepSomatic layouts) -------------------------------------------------------------------
+  def _sample_encoder(self, sample_index: int, mean_coverage: float):
+    """The encoder handle of one sample's block: its own height, channels_enum_to_blank and mean coverage
+    (BuildPileupForOneSample's sample_options / mean_coverage / channels_enum_to_blank arguments, pileup_image_native.cc:296-304)."""
+    sample = self.options.sample_options[sample_index]
+    key = (self.sample_heights[sample_index], tuple(sorted(sample.channels_enum_to_blank)), float(mean_coverage))
+    if key not in self._sample_encoders:
+      pic = dataclasses.replace(self.options.pic_options, channels_enum_to_blank=key[1], mean_coverage=key[2])
+      self._sample_encoders[key] = self._make_encoder(pi.to_params(pic, height=key[0]))
+    return key, self._sample_encoders[key]
+
+  def _make_encoder(self, params):
+    return pi.GpuEncoder(params, self._device)
+
+  def plan_region_by_sample(self, candidates: Sequence[DeepVariantCall], reads_per_sample: Sequence[Sequence[Read]], sample_order: Sequence[int],
+                            stats: Dict[str, int]):
+    """CreateAndWriteExamplesForCandidate (make_examples_native.cc:632-736) with several samples: for every candidate and alt
+    combination one BuildPileupForOneSample per sample of `sample_order`, all from the same DeepVariantCall.  Returns (plans,
+    specs_of) with specs_of[i] = [(sample index, ImageSpec), ...] in stacking order."""
+    pic = self.options.pic_options
+    plans: List[ExamplePlan] = []
+    specs_of: List[List[Tuple[int, packing.ImageSpec]]] = []
+    for candidate in candidates:
+      variant = candidate.variant
+      image_start_pos = variant.start - self.half_width
+      q_start = variant.start - pic.read_overlap_buffer_bp
+      q_end = variant.end + pic.read_overlap_buffer_bp
+      reference_bases = self.get_reference_bases_for_pileup(variant)
+      if not reference_bases:
+        continue
+      vtype = encoded_variant_type(variant)
+      queries = {}
+      for alt_combination in alt_allele_combinations(candidate, pic.multi_allelic_mode):
+        per_sample = []
+        for this_sample in sample_order:
+          sample = self.options.sample_options[this_sample]
+          if this_sample not in queries:
+            query = [r for r in reads_per_sample[this_sample] if read_overlaps_region(r, variant.reference_name, q_start, q_end)]
+            sort_positions = None
+            if self.options.trim_reads_for_pileup or sample.keep_only_window_spanning_reads:
+              min_overlap = pic.width if sample.keep_only_window_spanning_reads else K_DEFAULT_MINIMUM_READ_OVERLAP
+              a_start, a_end = calculate_alignment_region(variant, self.half_width, self.ref_reader.n_bases(variant.reference_name))
+              query, sort_positions = trim_reads(query, a_start, a_end, min_overlap)
+            queries[this_sample] = (query, sort_positions)
+          query, sort_positions = queries[this_sample]
+          per_sample.append((this_sample, packing.image_spec_for(candidate, reference_bases, query, image_start_pos, alt_combination, pic,
+                                                                 sort_positions=sort_positions)))
+        plans.append(ExamplePlan(None, variant, list(alt_combination), vtype))
+        specs_of.append(per_sample)
+    return plans, specs_of
+
+  def encode_plans_by_sample(self, specs_of, mean_coverage_per_sample: Optional[Sequence[float]] = None) -> np.ndarray:
+    """FillPileupArrayBySample (pileup_image_native.h:313-336): each sample's block from its own encoder handle (one CUDA launch per
+    distinct (height, blanked channels, mean coverage)), stacked in sample order."""
+    shape = self.image_shape()
+    out = np.zeros((len(specs_of),) + tuple(shape), dtype=np.uint8)
+    groups: Dict[tuple, list] = {}
+    for i, per_sample in enumerate(specs_of):
+      row0 = 0
+      for this_sample, spec in per_sample:
+        cov = mean_coverage_per_sample[this_sample] if mean_coverage_per_sample else 0.0
+        key, _ = self._sample_encoder(this_sample, cov)
+        groups.setdefault(key, []).append((i, row0, spec))
+        row0 += self.sample_heights[this_sample]
+      if row0 != shape[0]:
+        raise ValueError(f'the samples of sample_order stack to {row0} rows, the image has {shape[0]}')
+    for key, items in groups.items():
+      enc = self._sample_encoders[key]
+      images = enc.encode_host(packing.pack_images([spec for _, _, spec in items], enc.params))
+      for (i, row0, _), img in zip(items, images):
+        out[i, row0:row0 + key[0]] = img
+    return out
+
   def write_examples_in_region(self, candidates: Sequence[DeepVariantCall], reads_per_sample: Sequence[Sequence[Read]],
                                sample_order: Sequence[int], role: str,
                                mean_coverage_per_sample: Optional[Sequence[float]] = None):
@@ -569,9 +650,13 @@ class ExamplesGenerator:
     if role not in self.writers and self.sink is None:
       raise KeyError(f'Role {role} does not have a writer.')
     stats: Dict[str, int] = {}
-    reads = list(reads_per_sample[sample_order[0]]) if reads_per_sample else []
-    plans = self.plan_region(candidates, reads, stats)
-    images = self.encode_plans(plans)
+    if len(self.options.sample_options) > 1:
+      plans, specs_of = self.plan_region_by_sample(candidates, reads_per_sample, sample_order, stats)
+      images = self.encode_plans_by_sample(specs_of, mean_coverage_per_sample)
+    else:
+      reads = list(reads_per_sample[sample_order[0]]) if reads_per_sample else []
+      plans = self.plan_region(candidates, reads, stats)
+      images = self.encode_plans(plans)
     if self.sink is not None:
       self._count_examples(plans, stats)
       if plans:

@@ -94,6 +94,7 @@ class PileupImageOptions:
   sort_by_alt_allele_support: bool = False
   min_non_zero_allele_frequency: float = 0.0   # PileupImageOptions field 33 (allele_frequency channel)
   mean_coverage: float = 0.0                   # SampleOptions.mean_coverage of the one sample (mean_coverage channel)
+  channels_enum_to_blank: Sequence[int] = ()   # SampleOptions.channels_enum_to_blank of the sample: channel enums whose read pixels stay 0
 
 
 def default_options(read_requirements: Optional[ReadRequirements] = None) -> PileupImageOptions:
@@ -182,6 +183,8 @@ def to_params(options: PileupImageOptions, height: Optional[int] = None) -> _lib
   p.random_seed = options.random_seed & 0xFFFFFFFF
   p.max_reads_per_image = 0
   p.mean_coverage = options.mean_coverage
+  blank = set(getattr(options, 'channels_enum_to_blank', ()) or ())
+  p.blank_channel_mask = sum(1 << i for i, e in enumerate(enums) if e in blank)
   return p
 
 

@@ -132,6 +132,8 @@ typedef struct DvbPileupParams {
                                      files (all 51 down-sampled examples of golden.allele_frequency_examples, row for row);
                                      DVB_SHUFFLE_LIBSTDCXX (1) is what a gcc/libstdc++ build of the reference does */
   float mean_coverage;            /* SampleOptions.mean_coverage (--mean_coverage_per_sample); only read with DVB_CH_MEAN_COVERAGE */
+  uint32_t blank_channel_mask;    /* bit c set: channels[c] is in the sample's channels_enum_to_blank - its read pixels stay 0, the
+                                     reference band is drawn as usual (pileup_channel_lib.cc:152-161; make_examples_native.cc:696-706) */
 } DvbPileupParams;
 
 enum { DVB_SHUFFLE_LIBCXX = 0, DVB_SHUFFLE_LIBSTDCXX = 1 };

@@ -414,6 +414,7 @@ int CalculateChannels(std::vector<std::vector<unsigned char>>& data, const DvbPi
       }
       char ref_base = static_cast<char>(ref_bases[col]);
       for (int c = 0; c < o.num_channels; ++c) {
+        if (o.blank_channel_mask & (1u << c)) continue;   // channels_enum_to_blank.contains(channel_enum), pileup_channel_lib.cc:154
         data[c][col] = FillReadBase(o.channels[c], read_base, ref_base, base_quality, read,
                                     support_class, o, read_i, bv, pair_values);
       }

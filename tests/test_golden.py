@@ -241,3 +241,40 @@ def test_cuda_encoder_reproduces_allele_frequency_golden_images():
   pb, golden, o = _allele_frequency_fixture()
   enc = pi.GpuEncoder(pi.to_params(o), 0)
   np.testing.assert_array_equal(enc.encode_host(pb), golden)
+
+
+def _deeptrio_fixture():
+  """tools/check_deeptrio_golden.py: examples of the reference's DeepTrio golden (deeptrio/testdata/golden_child.calling_examples,
+  140 x 221 x 7 = parent1 (40 rows) | child (60) | parent2 (40), every block down-sampled) with the three per-sample batches the
+  multi-sample planner packed for them (each sample's realigned reads against the same DeepVariantCall)."""
+  d = np.load(os.path.join(GOLDEN, 'deeptrio_golden_subset.npz'))
+  o = pi.default_options(pi.ReadRequirements(min_base_quality=10, min_mapping_quality=5))
+  o.channels = list(pi.PILEUP_CHANNELS_WITH_INSERT_SIZE)
+  blocks = []
+  for b, h in enumerate((40, 60, 40)):
+    n = d[f's{b}_n']
+    arrays = {k[len(f's{b}_arr_'):]: d[k] for k in d.files if k.startswith(f's{b}_arr_')}
+    blocks.append((packing.PackedBatch(int(n[0]), int(n[1]), int(n[2]), int(n[3]), arrays), pi.to_params(o, height=h)))
+  return blocks, d['golden_images']
+
+
+def test_oracle_reproduces_deeptrio_golden_images():
+  blocks, golden = _deeptrio_fixture()
+  assert golden.shape[1:] == (140, 221, 7)
+  got = np.concatenate([oracle_lib.encode_batch(params, pb) for pb, params in blocks], axis=1)   # FillPileupArrayBySample: blocks stacked
+  np.testing.assert_array_equal(got, golden)
+  assert any((np.diff(pb.arrays['pair_begin'])[:pb.n_images] > params.height - 5).any() for pb, params in blocks)   # down-sampled blocks
+
+
+@pytest.mark.gpu
+def test_cuda_encoder_reproduces_deeptrio_golden_images():
+  blocks, golden = _deeptrio_fixture()
+  got = np.concatenate([pi.GpuEncoder(params, 0).encode_host(pb) for pb, params in blocks], axis=1)
+  np.testing.assert_array_equal(got, golden)
+
+
+def test_multi_sample_golden_report_says_every_example_is_reproduced():
+  import json
+  r = json.load(open(os.path.join(GOLDEN, 'deeptrio_golden_report.json')))
+  assert r['golden_examples'] == r['images_identical'] == 88 and r['same_examples_in_same_order']
+  assert r['blocks_identical_parent1_child_parent2'] == [88, 88, 88]

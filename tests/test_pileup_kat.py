@@ -455,3 +455,44 @@ def test_homopolymer_channels_get_channel_data_kat(backend):
   ins = make_read('ACGTTTTGCA', start=2, cigar='3M4I3M', quals=[30] * 10, name='r')
   got = enc.encode_read(_make_dv_call(), 'A' * 12, ins, 0, ['C'])
   assert got[0, 4, 0] == 254 and got[0, 4, 1] == _scaled(4, 30)       # anchor column 2+3-1 = 4 <- read index 3 ('T' of TTTT)
+
+
+# ---- channels_enum_to_blank: GetChannelDataTest with its three parameter sets (pileup_channel_lib_test.cc:696-849) ---------------
+
+GET_CHANNEL_DATA_CHANNELS = ['read_base', 'base_quality', 'mapping_quality', 'strand', 'read_supports_variant', 'base_differs_from_ref',
+                             'read_mapping_percent', 'avg_base_quality', 'identity', 'gap_compressed_identity', 'gc_content', 'is_homopolymer',
+                             'homopolymer_weighted', 'blank', 'insert_size', 'supplementary_alignment']
+
+
+@pytest.mark.parametrize('to_blank', [(), (1,), (1, 3)])      # {}, {CH_READ_BASE}, {CH_READ_BASE, CH_MAPPING_QUALITY}
+def test_get_channel_data_with_channels_enum_to_blank(backend, to_blank):
+  """All 16 channels of the reference's test in one read row, its options (mapping_quality_cap 1, positive_strand_color 20,
+  allele_unsupporting_read_alpha 1, base colour offsets / stride 1, base_quality_cap 20, matching alpha 1, mismatching alpha 0), read =
+  window = GGGCGCTTTTAT / 11M at position 1, qualities 33, fragment length 1000.  A blanked channel's read pixels are 0; the rest and
+  the reference row are what they are without blanking."""
+  o = pi.PileupImageOptions(reference_band_height=5, mapping_quality_cap=1, positive_strand_color=20, allele_unsupporting_read_alpha=1.0,
+                            base_color_offset_a_and_g=1, base_color_offset_t_and_c=1, base_color_stride=1, base_quality_cap=20,
+                            reference_matching_read_alpha=1.0, reference_mismatching_read_alpha=0.0, width=13, height=100,
+                            channels=list(GET_CHANNEL_DATA_CHANNELS), num_channels=16, channels_enum_to_blank=tuple(to_blank))
+  read = Read(fragment_name='r', read_number=0, aligned_sequence=b'GGGCGCTTTTAT', aligned_quality=bytes([33] * 12), position=1, mapping_quality=90,
+              cigar=parse_cigar_string('11M'), fragment_length=1000)
+  enc = backend(o)
+  got = enc.encode_read(DeepVariantCall(variant=Variant(start=-100)), 'NGGGCGCTTTTAT', read, 0, [])[0]   # columns = reference positions (image_start_pos 0)
+  ch = {n: i for i, n in enumerate(GET_CHANNEL_DATA_CHANNELS)}
+  if 1 not in to_blank:
+    assert [got[c, ch['read_base']] for c in (11, 9, 1, 4)] == [4, 2, 3, 1]
+  else:
+    assert not got[:, ch['read_base']].any()
+  assert got[1, ch['base_quality']] == 254
+  assert got[1, ch['mapping_quality']] == (0 if 3 in to_blank else 254)
+  assert got[1, ch['strand']] == 20 and got[1, ch['read_supports_variant']] == 254 and got[1, ch['base_differs_from_ref']] == 254
+  assert got[3, ch['read_mapping_percent']] == 231 and got[3, ch['avg_base_quality']] == 90 and got[9, ch['identity']] == 231
+  assert got[9, ch['gap_compressed_identity']] == 254 and got[3, ch['gc_content']] == 127
+  assert got[1, ch['is_homopolymer']] == 254 and got[4, ch['is_homopolymer']] == 0
+  assert got[1, ch['homopolymer_weighted']] == 25 and got[9, ch['homopolymer_weighted']] == 33
+  assert got[1, ch['blank']] == 0 and got[1, ch['insert_size']] == 254
+  # the reference band ignores the blank set (CalculateRefRows draws every channel): same row with and without it
+  ref_row = enc.encode_reference('NGGGCGCTTTTAT')
+  plain = backend(dataclasses.replace(o, channels_enum_to_blank=())).encode_reference('NGGGCGCTTTTAT')
+  np.testing.assert_array_equal(ref_row, plain)
+  assert ref_row[0, 1, ch['read_base']] == 3 and ref_row[0, 1, ch['strand']] == 20
