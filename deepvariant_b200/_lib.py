@@ -260,6 +260,17 @@ SYMBOLS = (
     ('dvb_cvo_writer_open', C.c_int, [C.c_char_p, C.c_int32, C.POINTER(C.c_void_p)]),
     ('dvb_cvo_writer_write_batch', C.c_int, [C.c_void_p, C.c_int32, C.POINTER(DvbExampleBatchMeta), C.c_void_p]),
     ('dvb_cvo_writer_close', C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    ('dvb_stream_open', C.c_int, [C.c_char_p, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_void_p)]),
+    ('dvb_stream_close', None, [C.c_void_p]),
+    ('dvb_stream_remove', C.c_int, [C.c_char_p, C.c_int32]),
+    ('dvb_stream_buffer_size', C.c_int64, [C.c_void_p]),
+    ('dvb_stream_start', C.c_int, [C.c_void_p]),
+    ('dvb_stream_put', C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_void_p, C.c_int32]),
+    ('dvb_stream_end', C.c_int, [C.c_void_p, C.c_int32]),
+    ('dvb_stream_shard_finished', C.c_int, [C.c_void_p]),
+    ('dvb_stream_wait_attached', C.c_int, [C.c_void_p, C.c_int64]),
+    ('dvb_stream_next', C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                  C.POINTER(DvbExampleBatchMeta), C.POINTER(C.c_int32)]),
     ('dvb_debug_round_gls', C.c_int, [C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_double)]),
     ('dvb_debug_upload_phases', C.c_int, [C.POINTER(DvbBatch), C.c_int64, C.c_void_p, C.c_int32]),
     ('dvb_cnn_debug_tensor', C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, C.c_void_p, C.POINTER(C.c_int32),

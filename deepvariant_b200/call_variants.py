@@ -227,6 +227,45 @@ def model_example_info(checkpoint_path: str) -> Optional[dict]:
   return None
 
 
+def call_variants_from_stream(shm_prefix: str, num_input_shards: int, checkpoint_path: str, output_file: str, image_shape: Optional[Sequence[int]] = None,
+                              writer_threads: int = 0, device: int = 0, precision: int = 1, net=None) -> dict:
+  """call_variants --stream_examples (deepvariant/call_variants.py:504-538 + stream_examples_kernel.cc): the examples come from the
+  make_examples processes' shared-memory buffers (stream_examples.StreamConsumer) instead of TFRecord files; one classifier batch per
+  drained buffer.  The image shape is the model's (model.example_info.json) unless given.  `net` (anything with forward_host(images) ->
+  float32[n, 3]) replaces the GPU classifier in tests."""
+  from deepvariant_b200 import records, stream_examples
+  if image_shape is None:
+    info = model_example_info(checkpoint_path)
+    if not info:
+      raise ValueError('--stream_examples needs the image shape: no example_info.json beside the checkpoint')
+    image_shape = info['shape']
+  shape = [int(x) for x in image_shape]
+  own = net is None
+  if own:
+    net = GpuCnn(load_weights(checkpoint_path, shape[2]), shape, device=device, max_batch=2048, precision=precision)
+  consumer = stream_examples.StreamConsumer(shm_prefix, num_input_shards, tuple(shape))
+  out_paths = output_shard_paths(output_file, writer_threads)
+  writers = [records.NativeCvoWriter(p, _GL_PRECISION) for p in out_paths]
+  n_examples = n_batches = 0
+  try:
+    while True:
+      batch = consumer.next()
+      if batch is None:
+        break
+      images, variants, alts = batch
+      probs = net.forward_host(images)
+      writers[n_batches % len(writers)].write_batch(records.BatchMeta.from_lists(variants, alts), probs)
+      n_examples += len(variants)
+      n_batches += 1
+  finally:
+    for w in writers:
+      w.close()
+    consumer.close()
+    if own:
+      net.close()
+  return {'n_examples': n_examples, 'n_batches': n_batches, 'paths': out_paths}
+
+
 def call_variants(examples_filename: str, checkpoint_path: str, output_file: str, batch_size: int = _DEFAULT_BATCH,
                   writer_threads: int = 0, device: int = 0, max_batches: Optional[int] = None, reader_threads: int = 0,
                   precision: int = 1) -> dict:

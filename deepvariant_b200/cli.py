@@ -69,6 +69,16 @@ def parse_regions(text: str):
   return out
 
 
+class _NullWriter:
+  """--stream_examples: finish_region hands the examples to the stream and returns no records."""
+
+  def write(self, rec):
+    raise AssertionError('a streamed example reached the TFRecord writer')
+
+  def close(self):
+    pass
+
+
 def _lib_plane_enums():
   from deepvariant_b200 import _lib
   return set(_lib.PLANE_OF_CHANNEL)
@@ -80,7 +90,7 @@ RUNTIME_BY_REGION_COLUMNS = ('region', 'get reads', 'find candidates', 'make pil
 MAKE_EXAMPLES_DEFAULTS = dict(
     task=0, regions='', channel_list='BASE_CHANNELS', pileup_image_width=221, pileup_image_height=100, min_mapping_quality=5,
     min_base_quality=10, partition_size=1000, sort_by_haplotypes=False, trim_reads_for_pileup=False, parse_sam_aux_fields=False,
-    alt_aligned_pileup='none', population_vcfs='', mean_coverage_per_sample='', device=0, checkpoint='', checkpoint_json='', candidates='', candidates_in='', max_reads_per_partition=1500,
+    alt_aligned_pileup='none', stream_examples=False, shm_prefix='', population_vcfs='', mean_coverage_per_sample='', device=0, checkpoint='', checkpoint_json='', candidates='', candidates_in='', max_reads_per_partition=1500,
     sample_name='', vsc_min_count_snps=2, vsc_min_count_indels=2, vsc_min_fraction_snps=0.12, vsc_min_fraction_indels=0.06,
     vsc_min_fraction_multiplier=1.0, small_model_vaf_context_window_size=0, track_ref_reads=False, phase_reads=False,
     keep_legacy_allele_counter_behavior=False, normalize_reads=False, realign_reads=True, gvcf='', gvcf_gq_binsize=5, p_error=0.001,
@@ -178,6 +188,8 @@ def make_examples(argv):
   ap.add_argument('--trim_reads_for_pileup', action='store_true')
   ap.add_argument('--parse_sam_aux_fields', action='store_true')
   ap.add_argument('--alt_aligned_pileup')
+  ap.add_argument('--stream_examples', action='store_true')   # examples go to the shard's shared-memory buffer (the reference's fast_pipeline boundary)
+  ap.add_argument('--shm_prefix')
   ap.add_argument('--population_vcfs')            # allele_frequency channel: one VCF for all contigs, or one per contig (space / comma separated)
   ap.add_argument('--mean_coverage_per_sample')   # mean_coverage channel (make_examples_options.py:573-580); the first value is this sample's
   ap.add_argument('--device', type=int)
@@ -208,11 +220,18 @@ def make_examples(argv):
     population = af.make_population_vcf_readers(str(a.population_vcfs).replace(',', ' ').split())
   opts = men.MakeExamplesOptions(pic_options=pic, reference_filename=a.ref, trim_reads_for_pileup=a.trim_reads_for_pileup)
   fused = bool(a.call_variants_outfile)
+  if a.stream_examples and (fused or not a.shm_prefix or not a.examples):
+    raise ValueError('--stream_examples needs --shm_prefix and --examples (its @N gives the shard count), and excludes --call_variants_outfile')
   if not fused and not a.examples:
     raise ValueError('make_examples needs --examples (staged flow) or --call_variants_outfile (fused flow)')
   shard_spec = a.call_variants_outfile if fused else a.examples
   n_shards = len(tfrecord.shard_paths(shard_spec))
-  gen = men.ExamplesGenerator(opts, {'main_sample': tfrecord.shard_path(a.examples, a.task)} if a.examples and not fused else {}, device=a.device)
+  gen = men.ExamplesGenerator(opts, {'main_sample': tfrecord.shard_path(a.examples, a.task)} if a.examples and not fused and not a.stream_examples else {},
+                              device=a.device)
+  if a.stream_examples:
+    from deepvariant_b200 import stream_examples
+    gen.stream = stream_examples.StreamProducer(a.shm_prefix, a.task)
+    gen.writers = {'main_sample': _NullWriter()}
   try:
     import torch
     if torch.cuda.is_available():
@@ -461,7 +480,10 @@ def make_examples(argv):
 
 def call_variants(argv):
   ap = argparse.ArgumentParser('call_variants')
-  ap.add_argument('--examples', required=True)
+  ap.add_argument('--examples', default='')
+  ap.add_argument('--stream_examples', action='store_true')   # examples from the make_examples processes' shared-memory buffers
+  ap.add_argument('--shm_prefix', default='')
+  ap.add_argument('--num_input_shards', type=int, default=0)
   ap.add_argument('--outfile', required=True)
   ap.add_argument('--checkpoint', required=True)
   ap.add_argument('--batch_size', type=int, default=1024)
@@ -470,7 +492,15 @@ def call_variants(argv):
   ap.add_argument('--precision', type=int, default=1, choices=[0, 1])   # 1: split-fp16 x3, 1e-5 of fp32 (default); 0: fp16 operands
   a = ap.parse_args(argv)
   from deepvariant_b200 import call_variants as cv
-  r = cv.call_variants(a.examples, a.checkpoint, a.outfile, a.batch_size, a.writer_threads, a.device, precision=a.precision)
+  if a.stream_examples:
+    if not a.shm_prefix or a.num_input_shards < 1:
+      raise ValueError('--stream_examples needs --shm_prefix and --num_input_shards')
+    r = cv.call_variants_from_stream(a.shm_prefix, a.num_input_shards, a.checkpoint, a.outfile, writer_threads=a.writer_threads, device=a.device,
+                                     precision=a.precision)
+  else:
+    if not a.examples:
+      raise ValueError('call_variants needs --examples (or --stream_examples)')
+    r = cv.call_variants(a.examples, a.checkpoint, a.outfile, a.batch_size, a.writer_threads, a.device, precision=a.precision)
   print(f'call_variants: {r["n_examples"]} examples in {r["n_batches"]} batches -> {len(r["paths"])} shard(s)', file=sys.stderr)
   return 0
 

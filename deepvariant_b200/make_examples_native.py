@@ -237,6 +237,9 @@ class ExamplesGenerator:
     # call_variants without tf.Example files): the planned images go to `sink` (packed reads, or finished images for the
     # trimmed / alt-aligned route) instead of a TFRecord writer.
     self.sink = sink
+    # --stream_examples (make_examples_native.cc:724-731, stream_examples.cc): a stream_examples.StreamProducer; the examples of a region
+    # go into the shard's shared-memory buffer instead of a TFRecord
+    self.stream = None
     self.ssw_device: Optional[int] = None    # CUDA device for the read-to-haplotype Smith-Waterman of alt-aligned pileups (None = host)
     # (min_mapping_quality, min_base_quality, keep_legacy_allele_counter_behavior, track_ref_reads) of the allele counter that
     # produced the candidates, when they come from the very-sensitive caller over the same reads the pileups show: the table path
@@ -549,6 +552,15 @@ class ExamplesGenerator:
       stats[key] = stats.get(key, 0) + 1
 
   def finish_region(self, plans: Sequence[ExamplePlan], images: np.ndarray, stats: Dict[str, int]) -> List[bytes]:
+    if self.stream is not None:
+      # WriteExamplesInRegion with stream_examples (make_examples_native.cc:757-790): StartStreaming, one StreamExample per example
+      # (alt_allele_indices, variant, image), EndStreaming(data_written)
+      self.stream.start_streaming()
+      for i, p in enumerate(plans):
+        self.stream.stream_example(encode_alt_alleles(p.variant, p.alt_combination)[0], p.variant.serialize(), images[i])
+      self.stream.end_streaming(bool(plans))
+      self._count_examples(plans, stats)
+      return []
     return [self.encode_example(p, images[i], stats) for i, p in enumerate(plans)]
 
   # -- the pybind entry point --------------------------------------------------------------------
@@ -667,8 +679,12 @@ class ExamplesGenerator:
     return stats, self.image_shape()
 
   def signal_shard_finished(self) -> None:
+    if self.stream is not None:
+      self.stream.signal_shard_finished()   # StreamExamples::SignalShardFinished
     for role, w in self.writers.items():
       w.close()
+      if role not in self._example_filenames:
+        continue              # streamed examples: no file, no example_info.json beside it
       write_example_info_json(self._example_filenames[role], self.image_shape(),
                               example_info_channels(self.options.pic_options))
     self.writers = {}

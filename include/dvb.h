@@ -561,6 +561,34 @@ int dvb_cvo_writer_close(DvbCvoWriter* writer, int64_t* n_written /* may be NULL
 /* Test access to the writer's round_gls (call_variants.py:248-285); precision < 0 = none. */
 int dvb_debug_round_gls(const double gls[3], int32_t precision, double out[3]);
 
+/* ---- the reference's shared-memory example stream, both ends (SURVEY.md 8(b) optional row; csrc/dvb_stream.cu) ----------------------
+ * make_examples --stream_examples writes { int32 len, alt_allele_indices, int32 len, variant, int32 len, image } records, closed by
+ * int32 0, into one POSIX shared-memory buffer per shard ("<prefix>_shm_<shard>") and hands it over through three named mutexes
+ * ("<prefix>_buffer_empty_<shard>", "_items_available_", "_shard_finished_"; boost::interprocess named_mutex = a named semaphore of
+ * count 1): deepvariant/stream_examples.cc:60-176, stream_examples_kernel.cc:166-240, fast_pipeline.cc:125-165,
+ * fast_pipeline_utils.h:44-64.  A producer handle here can feed the reference's call_variants, a consumer handle can be fed by the
+ * reference's make_examples; the orchestrator role creates (and dvb_stream_remove deletes) the objects as fast_pipeline does. */
+enum { DVB_STREAM_ORCHESTRATOR = 0, DVB_STREAM_PRODUCER = 1, DVB_STREAM_CONSUMER = 2 };
+typedef struct DvbStream DvbStream;
+int dvb_stream_open(const char* shm_prefix, int32_t shard, int32_t role, int64_t buffer_size /* orchestrator only */, DvbStream** out);
+void dvb_stream_close(DvbStream* stream);
+int dvb_stream_remove(const char* shm_prefix, int32_t shard);
+int64_t dvb_stream_buffer_size(const DvbStream* stream);
+/* producer: StartStreaming / StreamExample / EndStreaming once per region, SignalShardFinished at the end of the shard */
+int dvb_stream_start(DvbStream* stream);
+int dvb_stream_put(DvbStream* stream, const void* alt_indices, int32_t alt_len, const void* variant, int32_t variant_len, const uint8_t* image,
+                   int32_t image_len);
+int dvb_stream_end(DvbStream* stream, int32_t data_written);
+int dvb_stream_shard_finished(DvbStream* stream);
+/* consumer, before its first dvb_stream_next: wait until the shard's producer has attached (it holds items_available and shard_finished,
+ * or buffer_empty).  The reference relies on call_variants starting slowly instead. */
+int dvb_stream_wait_attached(DvbStream* stream, int64_t timeout_ms);
+/* consumer: StreamExamplesResource::Next over n shard handles, polling from shard index % n: the first ready buffer is drained - images
+ * copied to images_host (images_cap bytes), records readable through *meta until the next call that drains the same shard.
+ * *n_out = 0 with *all_finished = 1: every shard is done; *n_out = 0 with *all_finished = 0: a shard has just finished, call again. */
+int dvb_stream_next(DvbStream* const* shards, int32_t n, int64_t index, uint8_t* images_host, int64_t images_cap, int64_t image_bytes,
+                    int32_t* n_out, int32_t* shard_out, DvbExampleBatchMeta* meta, int32_t* all_finished);
+
 /* Test access to the chunked-upload plan of dvb_encode_classify_host for phases of `sub` images: out = int64[cap][6] =
  * {image begin, image end, pair begin, pair end, first read uploaded, one past the last read uploaded}.  Returns the number
  * of phases (0 = the batch is uploaded in one piece) or -DvbStatus.  Host only, no device needed. */
