@@ -524,12 +524,14 @@ def postprocess_variants(argv):
   ap.add_argument('--gvcf_outfile', default='')
   ap.add_argument('--haploid_contigs', default='')                   # e.g. chrX,chrY: heterozygous genotypes are ruled out there ...
   ap.add_argument('--par_regions_bed', default='')                   # ... except inside these pseudo-autosomal regions
+  ap.add_argument('--cpus', type=int, default=min(os.cpu_count() or 1, 16))   # worker processes of the CVO -> Variant conversion (the reference's --cpus)
   a = ap.parse_args(argv)
   from deepvariant_b200 import fasta, postprocess_variants as pp
   ref = fasta.IndexedFastaReader(a.ref)
   r = pp.postprocess_variants(a.infile, a.outfile, [(c, ref.n_bases(c)) for c in ref.contig_order], a.sample_name, a.qual_filter,
                               a.multi_allelic_qual_filter, a.multiallelic_mode, a.only_keep_pass, a.disable_haplotype_resolution, a.group_variants,
-                              a.nonvariant_site_tfrecord_path, a.gvcf_outfile, lambda c, p: ref.query(c, p, p + 1), a.haploid_contigs, a.par_regions_bed)
+                              a.nonvariant_site_tfrecord_path, a.gvcf_outfile, lambda c, p: ref.query(c, p, p + 1), a.haploid_contigs, a.par_regions_bed,
+                              cpus=a.cpus)
   print(f'postprocess_variants: {r}', file=sys.stderr)
   return 0
 

@@ -525,6 +525,51 @@ def get_sample_name(cvos: Sequence[Cvo], flag: str = '') -> str:
   return 'default'
 
 
+# ---- --cpus: the CVO -> Variant conversion over worker processes (deepvariant/postprocess_variants.py --cpus, :160-172, 1998-2087) --------
+def cvo_range_key(record: bytes) -> Tuple[str, int, int]:
+  """(reference_name, start, end) of a serialized CallVariantsOutput without building the variant: CallVariantsOutput.variant = 1,
+  Variant.reference_name = 14 / start = 16 / end = 13 - all the parent process needs to sort the records and cut them into chunks."""
+  name, start, end = '', 0, 0
+  for fn, wt, val, _ in protos.iter_fields(record):
+    if fn == 1:
+      for f2, w2, v2, _ in protos.iter_fields(bytes(val)):
+        if f2 == 14:
+          name = bytes(v2).decode()
+        elif f2 == 16:
+          start = v2 if v2 < (1 << 63) else v2 - (1 << 64)
+        elif f2 == 13:
+          end = v2 if v2 < (1 << 63) else v2 - (1 << 64)
+      break
+  return name, start, end
+
+
+def independent_chunks(keys: Sequence[Tuple[str, int, int]], target: int) -> List[Tuple[int, int]]:
+  """Cuts SORTED (contig, start, end) keys into [begin, end) chunks of about `target` records such that no variant range of one chunk
+  overlaps a range of another - grouping by range, multi-allelic merging and the resolution of overlapping variants never look across
+  such a cut, so the chunks can be converted independently and concatenated."""
+  chunks, begin, reach, contig = [], 0, -1, None
+  for i, (c, s, e) in enumerate(keys):
+    if i - begin >= target and (c != contig or s >= reach):
+      chunks.append((begin, i))
+      begin = i
+    if c != contig:
+      contig, reach = c, e
+    else:
+      reach = max(reach, e)
+  if begin < len(keys):
+    chunks.append((begin, len(keys)))
+  return chunks
+
+
+def _convert_chunk(args):
+  records, sample, qual_filter, multi_allelic_qual_filter, multiallelic_mode, group_variants, haploid, par, disable_haplotype_resolution = args
+  cvos = [parse_cvo(r) for r in records]                      # already in sorted order
+  variants = call_variants_outputs_to_variants(cvos, sample, qual_filter, multi_allelic_qual_filter, multiallelic_mode, group_variants, haploid, par)
+  if not disable_haplotype_resolution:
+    variants = maybe_resolve_conflicting_variants(variants, qual_filter)
+  return list(variants)
+
+
 class _VcfTextWriter:
   """Plain text, or - for *.gz - BGZF with a tabix index beside it, as the reference leaves it (deepvariant_b200/bgzf_tabix.py)."""
 
@@ -557,14 +602,20 @@ class _VcfTextWriter:
 def postprocess_variants(infile: str, outfile: str, contigs: Sequence[Tuple[str, int]], sample_name: str = '', qual_filter: float = 1.0,
                          multi_allelic_qual_filter: float = 1.0, multiallelic_mode: str = 'product', only_keep_pass: bool = False,
                          disable_haplotype_resolution: bool = False, group_variants: bool = True, nonvariant_site_tfrecord_path: str = '',
-                         gvcf_outfile: str = '', base_at=None, haploid_contigs: str = '', par_regions_bed: str = '') -> dict:
+                         gvcf_outfile: str = '', base_at=None, haploid_contigs: str = '', par_regions_bed: str = '', cpus: int = 0,
+                         chunk_records: int = 5000) -> dict:
   """CVO TFRecord shards (`infile` may be a sharded spec or a glob) -> VCF text (`outfile`, gzip when it ends in .gz).  With
   nonvariant_site_tfrecord_path (the --gvcf output of make_examples, every shard) and gvcf_outfile also the gVCF: the variants merged
   with the reference blocks (deepvariant_b200/gvcf.py; `base_at(contig, position)` supplies the reference base where a block is split)."""
   import gzip
   if bool(nonvariant_site_tfrecord_path) != bool(gvcf_outfile):
     raise ValueError('gVCF creation requires both nonvariant_site_tfrecord_path and gvcf_outfile')          # postprocess_variants.py:2245-2251
-  cvos = [parse_cvo(r) for p in tfrecord.resolve_input_paths(infile) for r in tfrecord.read_records(p)]
+  records = [r for p in tfrecord.resolve_input_paths(infile) for r in tfrecord.read_records(p)]
+  if cpus > 1 and len(records) > chunk_records:
+    return _postprocess_variants_parallel(records, outfile, contigs, sample_name, qual_filter, multi_allelic_qual_filter, multiallelic_mode, only_keep_pass,
+                                          disable_haplotype_resolution, group_variants, nonvariant_site_tfrecord_path, gvcf_outfile, base_at, haploid_contigs,
+                                          par_regions_bed, cpus, chunk_records)
+  cvos = [parse_cvo(r) for r in records]
   blocks = []
   if gvcf_outfile:
     from deepvariant_b200 import gvcf
@@ -578,8 +629,38 @@ def postprocess_variants(infile: str, outfile: str, contigs: Sequence[Tuple[str,
   variants = call_variants_outputs_to_variants(cvos, sample, qual_filter, multi_allelic_qual_filter, multiallelic_mode, group_variants, haploid, par)
   if not disable_haplotype_resolution:
     variants = maybe_resolve_conflicting_variants(variants, qual_filter)
+  return _write_outputs(variants, len(cvos), blocks, outfile, gvcf_outfile, contigs, sample, only_keep_pass, base_at)
+
+
+def _postprocess_variants_parallel(records, outfile, contigs, sample_name, qual_filter, multi_allelic_qual_filter, multiallelic_mode, only_keep_pass,
+                                   disable_haplotype_resolution, group_variants, nonvariant_site_tfrecord_path, gvcf_outfile, base_at, haploid_contigs,
+                                   par_regions_bed, cpus, chunk_records) -> dict:
+  """The same result with the per-record work (proto parsing, merge_predictions, genotype / GQ / QUAL, haplotype resolution) spread over
+  `cpus` worker processes: the parent only extracts the range keys, sorts, cuts independent chunks and writes."""
+  import multiprocessing
+  keys = [cvo_range_key(r) for r in records]
+  pos = {c: i for i, (c, _) in enumerate(contigs)}
+  order = sorted(range(len(records)), key=lambda i: (pos.get(keys[i][0], len(pos)), keys[i][1], keys[i][2]))      # stable, like sort_cvos
+  records = [records[i] for i in order]
+  keys = [keys[i] for i in order]
+  blocks = []
+  if gvcf_outfile:
+    from deepvariant_b200 import gvcf
+    blocks = [gvcf.parse_variant_record(r) for p in tfrecord.resolve_input_paths(nonvariant_site_tfrecord_path) for r in tfrecord.read_records(p)]
+  sample = get_sample_name([parse_cvo(records[0])] if records else [], sample_name)
+  haploid = tuple(item for part in (haploid_contigs or '').split(',') for item in part.split())
+  par = read_bed(par_regions_bed) if par_regions_bed else ()
+  jobs = [(records[b:e], sample, qual_filter, multi_allelic_qual_filter, multiallelic_mode, group_variants, haploid, par, disable_haplotype_resolution)
+          for b, e in independent_chunks(keys, chunk_records)]
+  with multiprocessing.get_context('fork').Pool(min(cpus, len(jobs))) as pool:
+    variants = (v for chunk in pool.imap(_convert_chunk, jobs) for v in chunk)          # in chunk order = genome order
+    return _write_outputs(variants, len(records), blocks, outfile, gvcf_outfile, contigs, sample, only_keep_pass, base_at)
+
+
+def _write_outputs(variants, n_cvos, blocks, outfile, gvcf_outfile, contigs, sample, only_keep_pass, base_at) -> dict:
   n = 0
   if gvcf_outfile:
+    from deepvariant_b200 import gvcf
     variants = list(variants)
   header = '\n'.join(vcf_header_lines(contigs, sample)) + '\n'
   with _VcfTextWriter(outfile, header) as w:
@@ -588,7 +669,7 @@ def postprocess_variants(infile: str, outfile: str, contigs: Sequence[Tuple[str,
         continue
       w.write(vcf_line(v) + '\n', v)
       n += 1
-  out = {'n_cvo_records': len(cvos), 'n_variants_written': n, 'sample_name': sample}
+  out = {'n_cvo_records': n_cvos, 'n_variants_written': n, 'sample_name': sample}
   if gvcf_outfile:
     order = {c: i for i, (c, _) in enumerate(contigs)}
     # ShardedVariantReader: the shards are each sorted, merged by (contig index, start)

@@ -145,3 +145,40 @@ def test_vcf_number_formatting():
   assert pp.vcf_line(v).split('\t')[5] == '0.1' and pp.vcf_line(v).split('\t')[9].startswith('1|0:')
   v.quality = 0.04
   assert pp.vcf_line(v).split('\t')[5] == '0'
+
+
+# ---- --cpus: the conversion over worker processes gives the same bytes --------------------------------------------------------------
+
+def test_independent_chunks_never_cut_through_overlapping_ranges():
+  keys = [('a', 0, 5), ('a', 3, 4), ('a', 4, 9), ('a', 9, 10), ('a', 9, 10), ('a', 12, 13), ('b', 1, 2), ('b', 1, 8), ('b', 8, 9)]
+  chunks = pp.independent_chunks(keys, 1)
+  assert chunks == [(0, 3), (3, 5), (5, 6), (6, 8), (8, 9)]      # [0,5) [3,4) [4,9) overlap; the two equal ranges stay together; contig change cuts
+  assert pp.independent_chunks(keys, 100) == [(0, 9)] and pp.independent_chunks([], 3) == []
+  rng = np.random.RandomState(1)
+  starts = np.sort(rng.randint(0, 3000, 500))
+  keys = [('c', int(s), int(s + rng.randint(1, 30))) for s in starts]
+  chunks = pp.independent_chunks(keys, 7)
+  assert chunks[0][0] == 0 and chunks[-1][1] == 500 and all(a[1] == b[0] for a, b in zip(chunks, chunks[1:]))
+  for b, e in chunks[1:]:
+    assert keys[b][1] >= max(k[2] for k in keys[:b])               # nothing before the cut reaches past it
+
+
+def test_cvo_range_key_equals_the_parsed_variant_range():
+  for name in ('golden.postprocess_single_site_input-00000-of-00001.tfrecord.gz', 'golden.postprocess_pacbio_input-00000-of-00001.tfrecord.gz'):
+    from deepvariant_b200 import tfrecord
+    for r in tfrecord.read_records(os.path.join(GOLDEN, name)):
+      v = pp.parse_cvo(r).variant
+      assert pp.cvo_range_key(r) == (v.reference_name, v.start, v.end)
+
+
+@pytest.mark.parametrize('name,vcf', [('golden.postprocess_single_site_input-00000-of-00001.tfrecord.gz', 'golden.postprocess_single_site_output.vcf'),
+                                      ('golden.postprocess_pacbio_input-00000-of-00001.tfrecord.gz', None)])
+def test_worker_processes_give_the_serial_output_byte_for_byte(tmp_path, name, vcf):
+  contigs = CHR20
+  serial, parallel = str(tmp_path / 'serial.vcf'), str(tmp_path / 'parallel.vcf')
+  a = pp.postprocess_variants(os.path.join(GOLDEN, name), serial, contigs)
+  b = pp.postprocess_variants(os.path.join(GOLDEN, name), parallel, contigs, cpus=3, chunk_records=9)     # many small chunks
+  assert a == b and a['n_variants_written'] > 50
+  assert open(serial).read() == open(parallel).read()
+  if vcf:
+    assert open(parallel).read() == open(os.path.join(GOLDEN, vcf)).read()                               # ... which is the reference's golden VCF
