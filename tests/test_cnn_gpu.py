@@ -430,11 +430,11 @@ def test_wider_cta_pair_rule_equals_default_plan(monkeypatch):
     probs = net.forward_host(imgs.numpy())
     outs.append((probs, {k: net.debug_tensor(k, 6) for k in ('mixed4', 'mixed5', 'mixed6', 'mixed7', 'mixed10')}))
     net.close()
-  for other in outs[1:]:
+  for i, other in enumerate(outs[1:]):
     for k in outs[0][1]:
       scale = float(np.abs(outs[0][1][k]).max())
-      assert float(np.abs(outs[0][1][k] - other[1][k]).max()) <= 1e-5 * scale, k
-    assert float(np.abs(outs[0][0] - other[0]).max()) <= 1e-6
+      assert float(np.abs(outs[0][1][k] - other[1][k]).max()) <= 1e-5 * scale, (k, 'plan', i + 1)
+    assert float(np.abs(outs[0][0] - other[0]).max()) <= 1e-6, ('plan', i + 1)
 
 
 @pytest.mark.parametrize('pool_after_conv', ['1', '0'])
