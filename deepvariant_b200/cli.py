@@ -56,7 +56,9 @@ def parse_regions(text: str):
   from deepvariant_b200 import postprocess_variants as pp
   out = []
   for token in text.split():
-    if token.endswith(('.bed', '.bed.gz')) or os.path.exists(token):
+    # a region literal or a contig name first: a contig that happens to be called like a local file or directory is not a BED
+    is_literal = re.fullmatch(r'[^:\s]+:[\d,]+(-[\d,]+)?', token) is not None
+    if token.endswith(('.bed', '.bed.gz')) or (not is_literal and os.path.isfile(token)):
       if token.endswith('.gz'):
         import gzip
         out += [(p[0], int(p[1]), int(p[2])) for p in (l.split() for l in gzip.open(token, 'rt')) if len(p) >= 3 and not p[0].startswith(('#', 'track', 'browser'))]

@@ -55,6 +55,16 @@ def resolve_input_paths(spec: str) -> List[str]:
   found = sorted(glob.glob(spec + '-?????-of-?????')) or sorted(glob.glob(re.sub(r'(\.[^.]+(\.gz)?)$', r'-?????-of-?????\1', spec)))
   if not found:
     raise FileNotFoundError(spec)
+  # one consistent -of-N set: shards left behind by an earlier run with another shard count would otherwise be read twice
+  totals = {}
+  for f in found:
+    m = re.search(r'-(\d{5})-of-(\d{5})', f)
+    totals.setdefault(int(m.group(2)), []).append(int(m.group(1)))
+  if len(totals) != 1:
+    raise ValueError(f'{spec}: shards of several runs are mixed ({sorted(totals)} shard counts): delete the stale ones')
+  (n, have), = totals.items()
+  if sorted(have) != list(range(n)):
+    raise ValueError(f'{spec}: expected shards 0..{n - 1} of {n}, found {sorted(have)}')
   return found
 
 
