@@ -2616,6 +2616,11 @@ int Plan(DvbCnn* net, const uint8_t* blob, int64_t blob_bytes) {
                                                                      : (c % 32 ? (c + 31) / 32 * 32 : c);   // (padding everything to 64 measured slower in round 1: 65.4 -> 66.0-66.4 ms)
       if (target != c) store_ch[o.src] = target;
     }
+    // A pool copies its source's STORED channel count into its slice of the block tensor, so a padded source would spill into the
+    // next pixel's first channels (seen with DVB_CNN_PAD_CIN64_MIN=160: mixed2, 288 -> 320, feeds conv27 AND the block's max pool;
+    // the default rule only pads s4 and the 48-channel 5x5 inputs, which no pool reads).  Such tensors keep their own width.
+    for (auto& o : ops)
+      if (o.kind != 0) store_ch.erase(o.src);
   }
   auto stored = [&](const std::string& name) { return store_ch.count(name) ? store_ch[name] : ch[name]; };
 

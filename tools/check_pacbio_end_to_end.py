@@ -38,7 +38,7 @@ def main():
   copts = cand.CandidateOptions(sample_name=cand.sample_name_from_bam(bam_path), min_mapping_quality=1, track_ref_reads=True,
                                 vsc_min_fraction_indels=0.12, partition_size=25000)
   pic = pi.default_options(pi.ReadRequirements(min_base_quality=10, min_mapping_quality=1))
-  pic.channels = pi.PILEUP_DEFAULT_CHANNELS + ['haplotype', 'diff_channels_alternate_allele_1', 'diff_channels_alternate_allele_2']   # the golden's base_methylation channel (all zero) is left out
+  pic.channels = pi.PILEUP_DEFAULT_CHANNELS + ['haplotype', 'base_methylation', 'diff_channels_alternate_allele_1', 'diff_channels_alternate_allele_2']   # the golden's own ten channels [1-7, 23, 9, 10]; the test BAM has no MM / ML tags, so base_methylation is all zero
   pic.num_channels = len(pic.channels)
   pic.alt_aligned_pileup = 'diff_channels'
   pic.width = 147
@@ -77,14 +77,14 @@ def main():
       stats['haplotype_channel_equal'] += bool(np.array_equal(img[..., 6], g[..., 6]))
       stats['row_order_equal'] += bool(np.array_equal(img[..., :4], g[..., :4]))
       stats['methylation_channel_zero'] += bool(not g[..., 7].any())
-      alt_eq = bool(np.array_equal(img[..., 7:9], g[..., 8:10]))
+      alt_eq = bool(np.array_equal(img[..., 8:10], g[..., 8:10]))
       stats['alt_aligned_channels_equal'] = stats.get('alt_aligned_channels_equal', 0) + alt_eq
-      stats['whole_image_equal'] = stats.get('whole_image_equal', 0) + (eq7 and alt_eq)
+      stats['whole_image_equal'] = stats.get('whole_image_equal', 0) + bool(np.array_equal(img, g))   # all ten channels, the golden's own layout
       if p.variant_type != 1:
         stats['indel_examples'] = stats.get('indel_examples', 0) + 1
         stats['indel_alt_aligned_channels_equal'] = stats.get('indel_alt_aligned_channels_equal', 0) + alt_eq
         if not alt_eq and len(mismatches) < 40:
-          d = (img[..., 7:9] != g[..., 8:10])
+          d = (img[..., 8:10] != g[..., 8:10])
           mismatches.append({'start': p.variant.start, 'alts': p.alt_combination, 'alt_channel_pixels_differ': int(d.sum()),
                              'rows_differ': int(d.any(axis=(1, 2)).sum()), 'rows': int(sum(1 for r in range(5, 100) if g[r].any()))})
       if p.variant_type == 1:
