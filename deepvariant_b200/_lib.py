@@ -145,6 +145,7 @@ class DvbReadTable(C.Structure):
       ('fragment_length', C.c_void_p), ('hp', C.c_void_p), ('read_number', C.c_void_p), ('number_reads', C.c_void_p),
       ('seq_begin', C.c_void_p), ('cigar_begin', C.c_void_p), ('name_begin', C.c_void_p),
       ('bases', C.c_void_p), ('quals', C.c_void_p), ('cigar', C.c_void_p), ('names', C.c_void_p),
+      ('n_aux_bytes', C.c_int64), ('aux_begin', C.c_void_p), ('aux', C.c_void_p),
   ]
 
 

@@ -10,8 +10,9 @@ from __future__ import annotations
 
 import gzip
 import os
+import re
 import struct
-from typing import Dict, Iterable, List, Optional
+from typing import Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
 
@@ -53,6 +54,119 @@ def _parse_aux_hp(aux: bytes) -> Optional[int]:
     else:
       break
   return None
+
+
+_AUX_SIZES = {b'A': 1, b'c': 1, b'C': 1, b's': 2, b'S': 2, b'i': 4, b'I': 4, b'f': 4}
+_AUX_FMTS = {b'c': 'b', b'C': 'B', b's': 'h', b'S': 'H', b'i': 'i', b'I': 'I', b'f': 'f'}
+
+
+def parse_aux_tags(aux: bytes, wanted=(b'MM', b'ML', b'MN', b'tp', b't0', b'X5', b'X6')) -> dict:
+  """The wanted tags of one record's aux bytes (BAM encoding): integers as int, Z as bytes, B arrays as lists."""
+  out, i, n = {}, 0, len(aux)
+  while i + 3 <= n:
+    tag, typ = aux[i:i + 2], aux[i + 2:i + 3]
+    i += 3
+    if typ in _AUX_SIZES:
+      if tag in wanted and typ in _AUX_FMTS:
+        out[tag] = struct.unpack_from('<' + _AUX_FMTS[typ], aux, i)[0]
+      i += _AUX_SIZES[typ]
+    elif typ in (b'Z', b'H'):
+      j = aux.index(b'\0', i)
+      if tag in wanted:
+        out[tag] = bytes(aux[i:j])
+      i = j + 1
+    elif typ == b'B':
+      sub = aux[i:i + 1]
+      cnt = struct.unpack_from('<i', aux, i + 1)[0]
+      if tag in wanted:
+        out[tag] = list(struct.unpack_from(f'<{cnt}{_AUX_FMTS[sub]}', aux, i + 5))
+      i += 5 + cnt * _AUX_SIZES[sub]
+    else:
+      break
+  return out
+
+
+_COMPLEMENT = bytes.maketrans(b'ACGTNacgtn', b'TGCANtgcan')
+_BASE_MODIFICATION = re.compile(r'([ACGTUN])([-+])([a-z]+|[0-9]+)([.?]?)')       # kBaseModificationRegexp, sam_reader.cc:518-519
+
+
+def parse_base_modifications(aligned_sequence: bytes, reverse_strand: bool, mm: Optional[str], ml: Optional[Sequence[int]],
+                             mn: Optional[int] = None) -> dict:
+  """ParseBaseModifications (third_party/nucleus/io/sam_reader.cc:521-716): the MM / ML (/ MN) aux tags -> {'5mC' | '6mA': one
+  probability byte per base of the aligned sequence}.  MM counts occurrences of the modified base along the ORIGINAL read (the
+  reverse complement of a reverse-strand alignment), skipping mm_delta of them before each modified one; ML concatenates the
+  probabilities of all modifications; a second entry for the same modification (6mA on A+ and T-) is merged by maximum; an MN that
+  differs from the sequence length, or ML running out, voids everything (hard-clipped records)."""
+  result: dict = {}
+  if mm is None or ml is None:
+    return result
+  n = len(aligned_sequence)
+  if (mn if mn is not None else n) != n:
+    return result
+  seq = bytes(aligned_sequence).translate(_COMPLEMENT)[::-1] if reverse_strand else bytes(aligned_sequence)
+  ml_offset = 0
+  body = mm[:-1] if mm.endswith(';') else mm
+  for entry in body.split(';'):
+    parts = entry.split(',')
+    if len(parts) <= 1:
+      continue
+    m = _BASE_MODIFICATION.fullmatch(parts[0])
+    if m is None:
+      raise ValueError(f'bad MM entry {parts[0]!r}')      # the reference dereferences an empty capture here
+    base, strand, modification = m.group(1), m.group(2), m.group(3)
+    if base == 'C' and strand == '+' and modification == 'm':
+      spec = '5mC'
+    elif (base == 'A' and strand == '+' and modification == 'a') or (base == 'T' and strand == '-' and modification == 'a'):
+      spec = '6mA'
+    else:
+      ml_offset += len(parts) - 1
+      continue
+    deltas = parts[1:]
+    values = bytearray(n)
+    base_count, k = 0, 0
+    mm_delta = int(deltas[0])
+    target = ord(base)
+    for pos in range(n):
+      if seq[pos] != target:
+        continue
+      if base_count != mm_delta:
+        base_count += 1
+        continue
+      if ml_offset + k >= len(ml):
+        return {}
+      values[pos] = ml[k + ml_offset] & 0xFF
+      base_count = 0
+      k += 1
+      if k >= len(deltas):
+        ml_offset += k
+        out = bytes(values[::-1]) if reverse_strand else bytes(values)
+        if spec in result:
+          # std::max over the chars of two std::strings (:697-701): a SIGNED comparison on the reference's platforms, so a probability
+          # byte >= 128 loses against the other entry's 0 - kept as it is, the pixels must equal the reference's
+          signed = lambda b: b - 256 if b >= 128 else b
+          out = bytes(a if signed(a) >= signed(b) else b for a, b in zip(result[spec], out))
+        result[spec] = out
+        break
+      mm_delta = int(deltas[k])
+  return result
+
+
+def apply_aux_tags(read: Read, aux: bytes) -> None:
+  """Fills the per-base aux data of the optional channels (Read.base_modifications, tp_values, t0_value) from a record's aux bytes.
+  X5 / X6 are this package's own scratch tags: the already-parsed 5mC / 6mA bytes of a read that went through a scratch BAM."""
+  tags = parse_aux_tags(aux)
+  mods = {}
+  if b'MM' in tags and b'ML' in tags and isinstance(tags[b'ML'], list):
+    mods = parse_base_modifications(read.aligned_sequence, read.reverse_strand, tags[b'MM'].decode(), tags[b'ML'], tags.get(b'MN'))
+  for tag, key in ((b'X5', '5mC'), (b'X6', '6mA')):
+    if isinstance(tags.get(tag), list):
+      mods[key] = bytes(tags[tag])
+  if mods:
+    read.base_modifications = mods
+  if isinstance(tags.get(b'tp'), list):
+    read.tp_values = tags[b'tp']
+  if isinstance(tags.get(b't0'), bytes):
+    read.t0_value = tags[b't0']
 
 
 class BamReader:
@@ -124,6 +238,7 @@ class BamReader:
              duplicate_fragment=bool(flag & FDUP), failed_vendor_quality_checks=bool(flag & FQCFAIL),
              proper_placement=proper, number_reads=number_reads)
     if parse_aux:
+      apply_aux_tags(r, rec[off:])
       hp = _parse_aux_hp(rec[off:])
       if hp is not None:
         r.hp_values = [hp]
@@ -161,10 +276,10 @@ class NativeBamTable:
       names = (C.c_char_p * len(regions))(*[r[0].encode() for r in regions])
       starts = np.array([r[1] for r in regions], dtype=np.int64)
       ends = np.array([min(int(r[2]), (1 << 62)) for r in regions], dtype=np.int64)
-      _lib.check(lib.dvb_bam_open_regions(path.encode(), C.byref(creq), int(parse_aux), threads, names, starts.ctypes.data_as(C.c_void_p),
+      _lib.check(lib.dvb_bam_open_regions(path.encode(), C.byref(creq), 3 if parse_aux else 0, threads, names, starts.ctypes.data_as(C.c_void_p),
                                           ends.ctypes.data_as(C.c_void_p), len(regions), C.byref(h)))
     else:
-      _lib.check(lib.dvb_bam_open(path.encode(), C.byref(creq), int(parse_aux), threads, C.byref(h)))
+      _lib.check(lib.dvb_bam_open(path.encode(), C.byref(creq), 3 if parse_aux else 0, threads, C.byref(h)))   # HP + the raw aux bytes
     try:
       t = _lib.DvbReadTable()
       _lib.check(lib.dvb_bam_table(h, C.byref(t)))
@@ -195,6 +310,8 @@ class NativeBamTable:
       self.quals = arr(t.quals, t.n_bases, np.uint8)
       self.cigar = arr(t.cigar, t.n_cigar, np.uint32)
       self.names = arr(t.names, t.n_name_bytes, np.uint8).tobytes()
+      self.aux_begin = arr(t.aux_begin, n + 1, np.int64) if t.n_aux_bytes else None
+      self.aux = arr(t.aux, t.n_aux_bytes, np.uint8).tobytes() if t.n_aux_bytes else b''
     except BaseException:
       lib.dvb_bam_close(h)
       raise
@@ -246,6 +363,8 @@ class NativeBamTable:
              number_reads=int(self.number_reads[i]))
     if self.parse_aux and int(self.hp[i]) != self.HP_ABSENT:
       r.hp_values = [int(self.hp[i])]
+    if self.parse_aux and self.aux_begin is not None and self.aux_begin[i + 1] > self.aux_begin[i]:
+      apply_aux_tags(r, self.aux[int(self.aux_begin[i]):int(self.aux_begin[i + 1])])   # MM / ML / MN, tp, t0 (the optional channels' per-base data)
     return r
 
   def reads(self) -> List[Read]:
@@ -316,6 +435,14 @@ def write_bam(path: str, reads, references, sample_name: str = '') -> None:
     aux = b''
     if r.hp_values:
       aux = b'HPi' + struct.pack('<i', int(r.hp_values[0]))
+    for tag, key in ((b'X5', '5mC'), (b'X6', '6mA')):          # parsed base modifications travel as this package's own byte-array tags
+      v = (r.base_modifications or {}).get(key)
+      if v:
+        aux += tag + b'BC' + struct.pack('<i', len(v)) + bytes(v)
+    if r.tp_values:
+      aux += b'tpBc' + struct.pack('<i', len(r.tp_values)) + struct.pack(f'<{len(r.tp_values)}b', *[max(-128, min(127, int(x))) for x in r.tp_values])
+    if r.t0_value:
+      aux += b't0Z' + bytes(r.t0_value) + b'\0'
     body = struct.pack('<iiBBHHHiiii', rid, r.position, len(r.fragment_name) + 1, r.mapping_quality, 0, len(r.cigar), flag, len(seq),
                        rid if paired else -1, r.position if paired else -1, r.fragment_length)
     body += r.fragment_name.encode() + b'\0' + b''.join(struct.pack('<I', (ln << 4) | op) for op, ln in r.cigar) + bytes(packed) + \

@@ -261,6 +261,10 @@ def make_examples(argv):
   if regions and not a.candidates_in:
     margin = (a.partition_size // 5 if a.phase_reads else 0) + 1000
     read_regions = [(c, max(0, s - margin), e + margin) for c, s, e in regions]
+  # MM / ML / MN (and Ultima's tp / t0) are parsed when a channel that needs them is requested, or with --parse_sam_aux_fields
+  # (make_examples_options.py:445-452)
+  if any(pi.CHANNEL_ENUM.get(c) in (23, 24, 28, 29, 30) for c in pic.channels):
+    a.parse_sam_aux_fields = True
   reader = bam.NativeBamTable(a.reads, bam.ReadRequirements(min_mapping_quality=a.min_mapping_quality), parse_aux=a.parse_sam_aux_fields, regions=read_regions)
   table_path = not a.trim_reads_for_pileup and a.alt_aligned_pileup == 'none' and not plane_channels
 

@@ -98,6 +98,8 @@ struct DvbBam {
   std::vector<uint8_t> bases, quals;
   std::vector<uint32_t> cigar;
   std::vector<char> names;
+  std::vector<int64_t> aux_begin;         // parse_hp & 2: the raw aux bytes of every kept record (MM / ML / MN, tp, t0 ... are parsed by the caller)
+  std::vector<uint8_t> aux;
   int64_t n_records_seen = 0;
   bool seeked = false;                    // opened through the .bai linear index (dvb_bam_open_regions): only part of the file was read
   // region-packer index, built on first use (EnsureIndex)
@@ -232,7 +234,7 @@ int OpenImpl(const char* path, const DvbReadRequirements* req_in, int parse_hp, 
   int32_t span_ref = -1;
   int64_t span_lo = 0, span_hi = 0;
   static const char kSeq[] = "=ACMGRSVTWYHKDBN";
-  bam->seq_begin.push_back(0); bam->cigar_begin.push_back(0); bam->name_begin.push_back(0);
+  bam->seq_begin.push_back(0); bam->cigar_begin.push_back(0); bam->name_begin.push_back(0); bam->aux_begin.push_back(0);
 
   // one alignment record (after its 4-byte block_size); returns false on a malformed record
   auto take_record = [&](const uint8_t* r, int32_t block_size) -> bool {
@@ -296,7 +298,9 @@ int OpenImpl(const char* path, const DvbReadRequirements* req_in, int parse_hp, 
     bam->seq_begin.push_back((int64_t)bam->bases.size());
     bam->names.insert(bam->names.end(), name, name + (l_read_name ? l_read_name - 1 : 0));
     bam->name_begin.push_back((int64_t)bam->names.size());
-    bam->hp.push_back(parse_hp ? ParseHp(aux, (size_t)block_size - need) : INT32_MIN);
+    bam->hp.push_back((parse_hp & 1) ? ParseHp(aux, (size_t)block_size - need) : INT32_MIN);
+    if (parse_hp & 2) bam->aux.insert(bam->aux.end(), aux, aux + ((size_t)block_size - need));
+    bam->aux_begin.push_back((int64_t)bam->aux.size());
     return true;
   };
 
@@ -461,6 +465,7 @@ int dvb_bam_table(const DvbBam* bam, DvbReadTable* t) {
   t->read_number = bam->read_number.data(); t->number_reads = bam->number_reads.data();
   t->seq_begin = bam->seq_begin.data(); t->cigar_begin = bam->cigar_begin.data(); t->name_begin = bam->name_begin.data();
   t->bases = bam->bases.data(); t->quals = bam->quals.data(); t->cigar = bam->cigar.data(); t->names = bam->names.data();
+  t->n_aux_bytes = (int64_t)bam->aux.size(); t->aux_begin = bam->aux_begin.data(); t->aux = bam->aux.data();
   return DVB_OK;
 }
 

@@ -346,11 +346,15 @@ typedef struct DvbReadTable {          /* all pointers are owned by the DvbBam h
   const uint8_t* quals;                /* raw phred */
   const uint32_t* cigar;               /* BAM packing (len << 4 | op) */
   const char* names;                   /* concatenated QNAMEs, no terminators */
+  int64_t n_aux_bytes;                 /* parse_hp & 2: the records' raw aux fields (BAM encoding), for tags the caller parses itself - */
+  const int64_t* aux_begin;            /* [n_reads + 1] MM / ML / MN -> Read.base_modifications (sam_reader.cc:521-716), Ultima's tp / t0 */
+  const uint8_t* aux;
 } DvbReadTable;
 
 typedef struct DvbBam DvbBam;
 void dvb_read_requirements_default(DvbReadRequirements* r);
-/* req may be NULL (defaults).  parse_hp != 0 extracts the HP aux tag.  threads <= 0: hardware concurrency. */
+/* req may be NULL (defaults).  parse_hp: bit 0 extracts the HP aux tag, bit 1 keeps every record's raw aux bytes (DvbReadTable.aux).
+ * threads <= 0: hardware concurrency. */
 int dvb_bam_open(const char* path, const DvbReadRequirements* req, int parse_hp, int threads, DvbBam** out);
 /* The same, restricted to the reads that overlap one of n_regions half-open [start, end) intervals (ReadOverlapsRegion,
  * third_party/nucleus/util/utils.cc:172-188) - what sam_reader.cc:Query returns for make_examples --regions.  When all intervals lie on
