@@ -21,7 +21,8 @@ shape = (100, 147, 10) if a.pacbio else (100, 221, 7)
 net = cv.GpuCnn(modeling.random_weights(shape[2], 0), shape, device=0, max_batch=a.chunk, precision=a.precision)
 x = torch.randint(0, 255, (a.batch,) + shape, dtype=torch.uint8, device='cuda:0')
 p = torch.empty((a.batch, 3), dtype=torch.float32, device='cuda:0')
-s = torch.cuda.current_stream()
+s = torch.cuda.Stream(device='cuda:0') if os.environ.get('DVB_CNN_SIDE_STREAM') or os.environ.get('DVB_CNN_GRAPH') else torch.cuda.current_stream()   # graphs cannot be captured on the legacy default stream
+torch.cuda.synchronize()
 for _ in range(a.warmup):
   net.forward_device(x, p, stream=s)
 torch.cuda.synchronize()
