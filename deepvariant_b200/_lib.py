@@ -212,6 +212,7 @@ SYMBOLS = (
                                        C.c_int32, C.POINTER(C.c_void_p)]),
     ('dvb_bam_table', C.c_int, [C.c_void_p, C.POINTER(DvbReadTable)]),
     ('dvb_bam_ref_name', C.c_char_p, [C.c_void_p, C.c_int32]),
+    ('dvb_bam_ref_length', C.c_int32, [C.c_void_p, C.c_int32]),
     ('dvb_bam_close', None, [C.c_void_p]),
     ('dvb_pack_region_from_bam', C.c_int, [C.c_void_p, C.POINTER(DvbRegionCandidates), C.c_int32, C.c_int32, C.c_int32,
                                            C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),

@@ -294,6 +294,7 @@ class NativeBamTable:
       self.n_reads = n
       self.n_records_seen = int(t.n_records_seen)
       self.references = [lib.dvb_bam_ref_name(h, i).decode() for i in range(t.n_refs)]
+      self.reference_lengths = [int(lib.dvb_bam_ref_length(h, i)) for i in range(t.n_refs)]
       self.ref_id = arr(t.ref_id, n, np.int32)
       self.pos = arr(t.pos, n, np.int32)
       self.end = arr(t.end, n, np.int32)

@@ -71,6 +71,27 @@ def parse_regions(text: str):
   return out
 
 
+# The reference skips the decoys, alternate loci, unplaced / unlocalised scaffolds, EBV and HLA contigs of the common human references
+# (deepvariant/exclude_contigs.py EXCLUDED_HUMAN_CONTIGS: 3402 names of hs37d5 and the GRCh38 analysis set).  Every one of those names
+# has one of these shapes; the shapes are used instead of the table.
+_EXCLUDED_CONTIG = re.compile(r'^(GL000\d{3}\.1|NC_007605|hs37d5|chrEBV|HLA-.*|chrUn_.*|chr(\d+|X|Y)_[A-Z]{2}\d+v\d+_(alt|random)|.*_decoy)$')
+
+
+def shared_contigs(ref_contigs, reads_contigs, min_coverage_fraction: float = 0.9):
+  """_ensure_consistent_contigs / common_contigs / validate_reference_contig_coverage (deepvariant/make_examples_core.py:540-640): the
+  reference contigs (minus the excluded ones) that the reads' header has too, with the same length; an error when they cover less than
+  `min_coverage_fraction` of the non-excluded reference bases (reads aligned to another build)."""
+  ref_contigs = [(c, n) for c, n in ref_contigs if not _EXCLUDED_CONTIG.match(c)]
+  shared = [(c, n) for c, n in ref_contigs if reads_contigs.get(c) == n]
+  ref_bp, common_bp = sum(n for _, n in ref_contigs), sum(n for _, n in shared)
+  coverage = common_bp / ref_bp if ref_bp else 0.0
+  if not shared or coverage < min_coverage_fraction:
+    raise ValueError(f'Reference contigs span {ref_bp} bases but only {common_bp} bases ({100 * coverage:.2f}%) were found in common among our input '
+                     f'files. Check that the sources were created on a common genome reference build. Contig matches were: '
+                     + ', '.join(f'"{c}" is {n} bp and {"matches" if reads_contigs.get(c) == n else "IS MISSING" if c not in reads_contigs else "has another length"}' for c, n in ref_contigs[:30]))
+  return shared
+
+
 class _NullWriter:
   """--stream_examples: finish_region hands the examples to the stream and returns no records."""
 
@@ -92,7 +113,7 @@ RUNTIME_BY_REGION_COLUMNS = ('region', 'get reads', 'find candidates', 'make pil
 MAKE_EXAMPLES_DEFAULTS = dict(
     task=0, regions='', channel_list='BASE_CHANNELS', pileup_image_width=221, pileup_image_height=100, min_mapping_quality=5,
     min_base_quality=10, partition_size=1000, sort_by_haplotypes=False, trim_reads_for_pileup=False, parse_sam_aux_fields=False,
-    alt_aligned_pileup='none', stream_examples=False, shm_prefix='', population_vcfs='', mean_coverage_per_sample='', device=0, checkpoint='', checkpoint_json='', candidates='', candidates_in='', max_reads_per_partition=1500,
+    alt_aligned_pileup='none', min_shared_contigs_basepairs=0.9, stream_examples=False, shm_prefix='', population_vcfs='', mean_coverage_per_sample='', device=0, checkpoint='', checkpoint_json='', candidates='', candidates_in='', max_reads_per_partition=1500,
     sample_name='', vsc_min_count_snps=2, vsc_min_count_indels=2, vsc_min_fraction_snps=0.12, vsc_min_fraction_indels=0.06,
     vsc_min_fraction_multiplier=1.0, small_model_vaf_context_window_size=0, track_ref_reads=False, phase_reads=False,
     keep_legacy_allele_counter_behavior=False, normalize_reads=False, realign_reads=True, gvcf='', gvcf_gq_binsize=5, p_error=0.001,
@@ -192,6 +213,7 @@ def make_examples(argv):
   ap.add_argument('--alt_aligned_pileup')
   ap.add_argument('--stream_examples', action='store_true')   # examples go to the shard's shared-memory buffer (the reference's fast_pipeline boundary)
   ap.add_argument('--shm_prefix')
+  ap.add_argument('--min_shared_contigs_basepairs', type=float)   # make_examples_options.py: 0.9
   ap.add_argument('--population_vcfs')            # allele_frequency channel: one VCF for all contigs, or one per contig (space / comma separated)
   ap.add_argument('--mean_coverage_per_sample')   # mean_coverage channel (make_examples_options.py:573-580); the first value is this sample's
   ap.add_argument('--device', type=int)
@@ -327,7 +349,8 @@ def make_examples(argv):
       gen.support_options = (a.min_mapping_quality, a.min_base_quality, bool(a.keep_legacy_allele_counter_behavior), bool(a.track_ref_reads))
     cand_writer = tfrecord.Writer(tfrecord.shard_path(a.candidates, a.task) if tfrecord.is_sharded_spec(a.candidates) else a.candidates) \
         if a.candidates else None
-    contigs = [(c, ref.n_bases(c)) for c in ref.contig_order if c in reader.references]
+    contigs = shared_contigs([(c, ref.n_bases(c)) for c in ref.contig_order], dict(zip(reader.references, reader.reference_lengths)),
+                             a.min_shared_contigs_basepairs)
     gvcf_writer = gvcf_options = gvcf_confidence = None
     if a.gvcf:
       # --gvcf: reference-confidence blocks of every region from the same allele counter (deepvariant_b200/gvcf.py;

@@ -474,6 +474,11 @@ const char* dvb_bam_ref_name(const DvbBam* bam, int32_t i) {
   return bam->refs[(size_t)i].c_str();
 }
 
+int32_t dvb_bam_ref_length(const DvbBam* bam, int32_t i) {
+  if (!bam || i < 0 || i >= (int32_t)bam->ref_len.size()) return -1;
+  return bam->ref_len[(size_t)i];
+}
+
 void dvb_bam_close(DvbBam* bam) { delete bam; }
 
 }  // extern "C"

@@ -365,6 +365,7 @@ int dvb_bam_open_regions(const char* path, const DvbReadRequirements* req, int p
                          const int64_t* starts, const int64_t* ends, int32_t n_regions, DvbBam** out);
 int dvb_bam_table(const DvbBam* bam, DvbReadTable* table);
 const char* dvb_bam_ref_name(const DvbBam* bam, int32_t i);   /* NULL when out of range */
+int32_t dvb_bam_ref_length(const DvbBam* bam, int32_t i);     /* l_ref of the header's reference i (-1 when out of range) */
 void dvb_bam_close(DvbBam* bam);
 
 /* ---- region packer: candidates + BAM table -> DvbBatch on the host (SURVEY.md 8(f) "next" row #1, second half) ---------

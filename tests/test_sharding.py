@@ -66,3 +66,20 @@ def test_two_rank_gloo_sharding():
     assert total == 97 and abs(tmax - 0.002) < 1e-12
     assert not set(gathered[0]) & set(gathered[1])
     assert sorted(gathered[0] + gathered[1]) == sorted(c.variant.start for c in _cands())
+
+
+def test_shared_contigs_excludes_decoys_and_checks_the_build():
+  """_ensure_consistent_contigs (make_examples_core.py:540-640): excluded names are dropped from the reference side, a contig is shared when
+  name AND length agree, and less than 90 % shared bases is an error."""
+  from deepvariant_b200 import cli
+  ref = [('chr1', 1000), ('chr2', 800), ('chr1_KI270706v1_random', 50), ('chrUn_GL000195v1', 60), ('chrEBV', 70), ('HLA-A*01:01:01:01', 3), ('chrUn_KN707606v1_decoy', 9),
+         ('chr6_GL000250v2_alt', 10)]
+  reads = {'chr1': 1000, 'chr2': 800, 'chrEBV': 70, 'chr1_KI270706v1_random': 50}
+  assert cli.shared_contigs(ref, reads) == [('chr1', 1000), ('chr2', 800)]
+  assert cli.shared_contigs([('20', 100), ('GL000207.1', 5), ('hs37d5', 9), ('NC_007605', 3)], {'20': 100, 'hs37d5': 9}) == [('20', 100)]
+  import pytest
+  with pytest.raises(ValueError, match='common genome reference build'):
+    cli.shared_contigs(ref, {'chr1': 999, 'chr2': 800})                       # chr1 has another length: 800 of 1800 bases shared
+  assert cli.shared_contigs(ref, {'chr1': 1000}, min_coverage_fraction=0.5) == [('chr1', 1000)]
+  with pytest.raises(ValueError):
+    cli.shared_contigs(ref, {})
