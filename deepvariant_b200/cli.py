@@ -117,7 +117,7 @@ MAKE_EXAMPLES_DEFAULTS = dict(
     sample_name='', vsc_min_count_snps=2, vsc_min_count_indels=2, vsc_min_fraction_snps=0.12, vsc_min_fraction_indels=0.06,
     vsc_min_fraction_multiplier=1.0, small_model_vaf_context_window_size=0, track_ref_reads=False, phase_reads=False,
     keep_legacy_allele_counter_behavior=False, normalize_reads=False, realign_reads=True, gvcf='', gvcf_gq_binsize=5, p_error=0.001,
-    include_med_dp=False, haploid_contigs='', candidate_positions='', runtime_by_region='', examples='', call_variants_outfile='', precision=1,
+    include_med_dp=False, haploid_contigs='', par_regions_bed='', candidate_positions='', runtime_by_region='', examples='', call_variants_outfile='', precision=1,
     call_batch_size=2048)      # --realign_reads defaults to true (make_examples_options.py:229)
 
 
@@ -205,6 +205,7 @@ def make_examples(argv):
   ap.add_argument('--p_error', type=float)
   ap.add_argument('--include_med_dp', action='store_true')
   ap.add_argument('--haploid_contigs')
+  ap.add_argument('--par_regions_bed')           # pseudo-autosomal regions of the haploid contigs: diploid reference confidence there
   ap.add_argument('--realign_reads', dest='realign_reads', action='store_true')
   ap.add_argument('--norealign_reads', dest='realign_reads', action='store_false')
   ap.add_argument('--sort_by_haplotypes', action='store_true')
@@ -360,7 +361,9 @@ def make_examples(argv):
         raise ValueError('--gvcf_gq_binsize must be a positive integer')
       gvcf_writer = tfrecord.Writer(tfrecord.shard_path(a.gvcf, a.task) if tfrecord.is_sharded_spec(a.gvcf) else a.gvcf)
       gvcf_options = gvcf.GvcfOptions(sample_name=copts.sample_name, p_error=a.p_error, gq_resolution=a.gvcf_gq_binsize, include_med_dp=a.include_med_dp,
-                                      haploid_contigs=tuple(c for c in a.haploid_contigs.split(',') if c))
+                                      haploid_contigs=tuple(c for c in a.haploid_contigs.split(',') if c),
+                                      par_regions=tuple(__import__('deepvariant_b200.postprocess_variants', fromlist=['read_bed']).read_bed(a.par_regions_bed))
+                                      if a.par_regions_bed else ())
       gvcf_confidence = gvcf.ReferenceConfidence(gvcf_options)
 
     def write_gvcfs(found, contig, p0, p1):
