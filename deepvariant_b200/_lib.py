@@ -12,7 +12,7 @@ from typing import Optional
 DVB_MAX_CHANNELS = 16
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libdvb.so')
+LIB_PATH = os.environ.get('DVB_LIB_PATH') or os.path.join(_HERE, 'csrc', 'libdvb.so')   # DVB_LIB_PATH: a differently compiled build of the same sources (A/B of compile-time choices)
 
 
 class DvbPileupParams(C.Structure):

@@ -43,11 +43,20 @@ namespace {
 
 constexpr int kThreads = 256;
 // Resident CTAs per SM the register allocation must allow.  The kernel is bound by dependent global-load chains
-// (pair -> read header -> CIGAR -> bases).  Measured on B200 (16,384 windows): 4 -> 0.995 ms (48 registers, 5 CTAs
-// resident), 6 -> 1.066 ms (40 registers, no spills, but the tighter allocation costs more than the extra warps give).
+// (record -> CIGAR -> bases).  Measured on B200, 16,384 windows per launch pair (profiles/r02e_encoder_variants.json; A/B of prebuilt
+// libraries of the same sources through DVB_LIB_PATH): 1 -> 1.447 ms (96 registers, 2 CTAs resident), 2 -> 0.924 (62 registers, 4 CTAs),
+// 3 -> 0.941 (56), 4 -> 0.967 (56: the same count, a more constrained schedule), 5 -> 0.957 (46, 5 CTAs).  The freer allocation wins at
+// the same occupancy.  The instantiation with the per-base extra channels keeps 4 (72 registers would drop it to 3 CTAs).
 #ifndef DVB_ENC_MIN_BLOCKS
-#define DVB_ENC_MIN_BLOCKS 4
+#define DVB_ENC_MIN_BLOCKS 2
 #endif
+// The 4 bases / 4 qualities of a 4-pixel group as aligned word loads + a funnel shift instead of 8 byte loads: 0.924 -> 0.877 ms.
+#ifndef DVB_ENC_WORD_LOADS
+#define DVB_ENC_WORD_LOADS 1
+#endif
+// Measured and dropped in the same series: the blank tail of an image zeroed as one contiguous span before the read rows (0.931 ms:
+// the early burst of stores competes with the rows' loads), the row's record and first CIGAR word requested before its buffer is
+// cleared (0.895), a grid-stride pre-pass that fills the resident slots once (0.895: fewer, longer-lived warps lose to more CTAs).
 constexpr int kWarps = kThreads / 32;
 constexpr float kMaxPixelValueAsFloat = 254.0f;  // channels/channel.h:78
 constexpr float kMaxFragmentLength = 1000.0f;    // channels/channel.h:81
@@ -454,7 +463,7 @@ __device__ __forceinline__ void flush_row(uint8_t* __restrict__ dst, const uint8
 // HOMO: per-base extra channels are present - the homopolymer channels and / or channel planes (a separate instantiation keeps the
 // common layouts at 48 registers).
 template <bool FAST7, bool HOMO>
-__global__ void __launch_bounds__(kThreads, DVB_ENC_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, HOMO ? 4 : DVB_ENC_MIN_BLOCKS)
 dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, int* __restrict__ rows_kept,
                   int* __restrict__ err, const PairRec* __restrict__ recs) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -680,6 +689,28 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
                 const int col = 4 * g;
                 const uint8_t* bp = bases + read_i + (col - c0);
                 const uint8_t* qp = quals + read_i + (col - c0);
+#if DVB_ENC_WORD_LOADS
+                // the 4 bases / 4 qualities of a group as two aligned words each and a funnel shift (the misalignment is the same for
+                // every group of the run) instead of 8 byte loads; the last groups of the arrays keep the byte loads (no read past the end)
+                unsigned bw, qw;
+                if (h.seq0 + read_i + (col - c0) + 8 <= B.n_bases) {
+                  const unsigned sb = (unsigned)((uintptr_t)bp & 3u), sq = (unsigned)((uintptr_t)qp & 3u);
+                  const unsigned* bpw = reinterpret_cast<const unsigned*>(bp - sb);
+                  const unsigned* qpw = reinterpret_cast<const unsigned*>(qp - sq);
+                  bw = __funnelshift_r(bpw[0], bpw[1], 8 * sb);
+                  qw = __funnelshift_r(qpw[0], qpw[1], 8 * sq);
+                } else {
+                  bw = bp[0] | (bp[1] << 8) | (bp[2] << 16) | ((unsigned)bp[3] << 24);
+                  qw = qp[0] | (qp[1] << 8) | (qp[2] << 16) | ((unsigned)qp[3] << 24);
+                }
+                const unsigned b0 = bw & 0xFF, b1 = (bw >> 8) & 0xFF, b2 = (bw >> 16) & 0xFF, b3 = bw >> 24;
+                if (((bw - 0x01010101u) & ~bw & 0x80808080u) != 0) {   // a zero base is not drawn: rare, take the slow path
+                  for (int j = 0; j < 4; ++j) put_pixel(col - c0 + j);
+                  continue;
+                }
+                const unsigned r4 = *reinterpret_cast<const unsigned*>(s_ref + col);
+                const unsigned q0 = s_qual[qw & 0xFF], q1 = s_qual[(qw >> 8) & 0xFF], q2 = s_qual[(qw >> 16) & 0xFF], q3 = s_qual[qw >> 24];
+#else
                 const unsigned b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
                 if (b0 == 0 || b1 == 0 || b2 == 0 || b3 == 0) {   // a zero base is not drawn: rare, take the slow path
                   for (int j = 0; j < 4; ++j) put_pixel(col - c0 + j);
@@ -687,6 +718,7 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
                 }
                 const unsigned r4 = *reinterpret_cast<const unsigned*>(s_ref + col);
                 const unsigned q0 = s_qual[qp[0]], q1 = s_qual[qp[1]], q2 = s_qual[qp[2]], q3 = s_qual[qp[3]];
+#endif
                 const unsigned m = P.match_color, mm = P.mismatch_color;
                 const unsigned f0 = b0 == (r4 & 0xFF) ? m : mm, f1 = b1 == ((r4 >> 8) & 0xFF) ? m : mm;
                 const unsigned f2 = b2 == ((r4 >> 16) & 0xFF) ? m : mm, f3 = b3 == (r4 >> 24) ? m : mm;
