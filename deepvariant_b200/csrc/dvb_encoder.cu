@@ -41,14 +41,20 @@ std::string& last_error() {
 
 namespace {
 
-constexpr int kThreads = 256;
+#ifndef DVB_ENC_THREADS
+#define DVB_ENC_THREADS 128
+#endif
+constexpr int kThreads = DVB_ENC_THREADS;   // threads per image CTA
 // Resident CTAs per SM the register allocation must allow.  The kernel is bound by dependent global-load chains
 // (record -> CIGAR -> bases).  Measured on B200, 16,384 windows per launch pair (profiles/r02e_encoder_variants.json; A/B of prebuilt
 // libraries of the same sources through DVB_LIB_PATH): 1 -> 1.447 ms (96 registers, 2 CTAs resident), 2 -> 0.924 (62 registers, 4 CTAs),
 // 3 -> 0.941 (56), 4 -> 0.967 (56: the same count, a more constrained schedule), 5 -> 0.957 (46, 5 CTAs).  The freer allocation wins at
-// the same occupancy.  The instantiation with the per-base extra channels keeps 4 (72 registers would drop it to 3 CTAs).
+// the same occupancy (256-thread CTAs; minimum blocks counted for that size).
+// Then the CTA size (calls 36-37, same harness): 128 threads with at least 8 resident CTAs (56 registers, 9 CTAs = 36 warps) 0.846 ms
+// against 0.873 for 256 threads x 2; 64 threads 0.930, 512 threads 1.100, 128 x 10 (46 registers) 0.918, 128 x 12 (40, spills) 0.874,
+// two 4-pixel groups per lane and iteration 0.901.  Smaller CTAs = more images in flight per SM and cheaper block barriers.
 #ifndef DVB_ENC_MIN_BLOCKS
-#define DVB_ENC_MIN_BLOCKS 2
+#define DVB_ENC_MIN_BLOCKS 8
 #endif
 // The 4 bases / 4 qualities of a 4-pixel group as aligned word loads + a funnel shift instead of 8 byte loads: 0.924 -> 0.877 ms.
 #ifndef DVB_ENC_WORD_LOADS
@@ -463,7 +469,7 @@ __device__ __forceinline__ void flush_row(uint8_t* __restrict__ dst, const uint8
 // HOMO: per-base extra channels are present - the homopolymer channels and / or channel planes (a separate instantiation keeps the
 // common layouts at 48 registers).
 template <bool FAST7, bool HOMO>
-__global__ void __launch_bounds__(kThreads, HOMO ? 4 : DVB_ENC_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, DVB_ENC_MIN_BLOCKS)
 dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, int* __restrict__ rows_kept,
                   int* __restrict__ err, const PairRec* __restrict__ recs) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -488,8 +494,10 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
   uint8_t* s_rows = s_rows_raw + ((16u - ((unsigned)__cvta_generic_to_shared(s_rows_raw) & 15u)) & 15u);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  s_base[tid] = P.base_lut[tid];
-  s_qual[tid] = P.qual_lut[tid];
+  for (int i = tid; i < 256; i += kThreads) {
+    s_base[i] = P.base_lut[i];
+    s_qual[i] = P.qual_lut[i];
+  }
 
   for (int img = blockIdx.x; img < B.n_images; img += gridDim.x) {
     __syncthreads();  // previous image fully flushed before smem is reused
