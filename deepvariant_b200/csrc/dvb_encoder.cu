@@ -353,11 +353,15 @@ __device__ __forceinline__ unsigned pair_read_allele(const DvbBatch& B, const Re
 }
 
 // sup (when the batch carries allele keys): uint8[4][n_pairs] = raw class byte, raw group, final class, final group.
+#ifndef DVB_ENC_PREPASS_THREADS
+#define DVB_ENC_PREPASS_THREADS 128
+#endif
+constexpr int kPreThreads = DVB_ENC_PREPASS_THREADS, kPreWarps = kPreThreads / 32;   // a warp per image
 template <bool kPairPlanes>   // the batch carries per-pair channel planes (a separate instantiation keeps the common layouts' registers)
-__global__ void __launch_bounds__(128) dvb_pair_prepass_kernel(const EncDev P, const DvbBatch B, PairRec* __restrict__ recs, int* __restrict__ err,
+__global__ void __launch_bounds__(kPreThreads) dvb_pair_prepass_kernel(const EncDev P, const DvbBatch B, PairRec* __restrict__ recs, int* __restrict__ err,
                                                                 uint8_t* __restrict__ sup) {
   const int lane = threadIdx.x & 31;
-  const int img = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int img = blockIdx.x * kPreWarps + (threadIdx.x >> 5);
   if (img >= B.n_images) return;
   const int image_start = B.image_start_pos[img];
   const int vstart = B.variant_start[img];
@@ -996,8 +1000,9 @@ int Launch(DvbEncoder* enc, const DvbBatch& b, uint8_t* out, int32_t* rows_kept,
       sup = static_cast<uint8_t*>(enc->d_support.p);
       enc->last_support_pairs = b.n_pairs;
     }
-    if (enc->dev.n_pair_planes) dvb_pair_prepass_kernel<true><<<(b.n_images + 3) / 4, 128, 0, stream>>>(enc->dev, b, recs, enc->d_err, sup);
-    else dvb_pair_prepass_kernel<false><<<(b.n_images + 3) / 4, 128, 0, stream>>>(enc->dev, b, recs, enc->d_err, sup);
+    const int pre_grid = (b.n_images + kPreWarps - 1) / kPreWarps;
+    if (enc->dev.n_pair_planes) dvb_pair_prepass_kernel<true><<<pre_grid, kPreThreads, 0, stream>>>(enc->dev, b, recs, enc->d_err, sup);
+    else dvb_pair_prepass_kernel<false><<<pre_grid, kPreThreads, 0, stream>>>(enc->dev, b, recs, enc->d_err, sup);
     enc->launches++;
   }
   if (enc->fast7)
