@@ -52,6 +52,8 @@ class SampleOptions:
   order: List[int] = dataclasses.field(default_factory=lambda: [0])
   keep_only_window_spanning_reads: bool = False
   channels_enum_to_blank: List[int] = dataclasses.field(default_factory=list)   # deepvariant.proto SampleOptions: channel enums left blank in this sample's read rows
+  use_non_uniform_downsampling: bool = False        # SampleOptions 19 / 20 (make_examples_somatic.py:189-202): keep at least `threshold` reads
+  non_uniform_downsampling_threshold: int = 0       # of every allele's supporters when a pileup has more reads than rows
 
 
 @dataclasses.dataclass
@@ -289,6 +291,22 @@ class ExamplesGenerator:
       ref_bases = ref_bases + 'N' * (end - n_bases)
     return ref_bases
 
+  def _non_uniform_subset(self, sample_index: int, candidate: DeepVariantCall, query, sort_positions):
+    """BuildPileupForOneSample's non-uniform branch (pileup_image_native.cc:326-341): the reads DownsampleReadIndicesWithMinsPerAllele
+    keeps, in index order - a host-side filter, after which the encoder has nothing left to down-sample; when the thresholds cannot be
+    met the reads go on unfiltered and the encoder's uniform shuffle decides, as in the reference."""
+    sample = self.options.sample_options[sample_index]
+    if not sample.use_non_uniform_downsampling:
+      return query, sort_positions
+    from deepvariant_b200 import sampling_util
+    pic = self.options.pic_options
+    max_reads = self.sample_heights[sample_index] - pic.reference_band_height
+    keep = sampling_util.downsample_read_indices_with_mins_per_allele([r.key() for r in query], max_reads, candidate.allele_support,
+                                                                     sample.non_uniform_downsampling_threshold, pic.random_seed)
+    if keep is None:
+      return query, sort_positions
+    return [query[i] for i in keep], ([sort_positions[i] for i in keep] if sort_positions else sort_positions)
+
   # -- planning (host) ---------------------------------------------------------------------------
   def plan_region(self, candidates: Sequence[DeepVariantCall], reads: Sequence[Read], stats: Dict[str, int]) -> List[ExamplePlan]:
     """CreateAndWriteExamplesForCandidate (make_examples_native.cc:632-736) for every candidate of the
@@ -314,6 +332,7 @@ class ExamplesGenerator:
         min_overlap = pic.width if sample.keep_only_window_spanning_reads else K_DEFAULT_MINIMUM_READ_OVERLAP
         a_start, a_end = calculate_alignment_region(variant, self.half_width, self.ref_reader.n_bases(variant.reference_name))
         query, sort_positions = trim_reads(query, a_start, a_end, min_overlap)
+      query, sort_positions = self._non_uniform_subset(0, candidate, query, sort_positions)
       vtype = encoded_variant_type(variant)
       for alt_combination in alt_allele_combinations(candidate, pic.multi_allelic_mode):
         spec = packing.image_spec_for(candidate, reference_bases, query, image_start_pos, alt_combination, pic,
@@ -625,7 +644,7 @@ class ExamplesGenerator:
               min_overlap = pic.width if sample.keep_only_window_spanning_reads else K_DEFAULT_MINIMUM_READ_OVERLAP
               a_start, a_end = calculate_alignment_region(variant, self.half_width, self.ref_reader.n_bases(variant.reference_name))
               query, sort_positions = trim_reads(query, a_start, a_end, min_overlap)
-            queries[this_sample] = (query, sort_positions)
+            queries[this_sample] = self._non_uniform_subset(this_sample, candidate, query, sort_positions)
           query, sort_positions = queries[this_sample]
           per_sample.append((this_sample, packing.image_spec_for(candidate, reference_bases, query, image_start_pos, alt_combination, pic,
                                                                  sort_positions=sort_positions)))
