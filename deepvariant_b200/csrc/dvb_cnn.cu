@@ -1633,7 +1633,10 @@ constexpr int kStemRawPitch = 1840;   // bytes per staged raw input row segment 
 // eight warps, two per TMEM lane quarter) sits between the conversion and the patch assembly of tile i + 1: two accumulators in TMEM,
 // three block barriers per tile instead of four, no warp waits for the tensor pipe's latency.
 template <bool kPipe>
-__global__ void __launch_bounds__(kStemThreads, 4) stem_conv1_kernel(const StemArgs p) {
+#ifndef DVB_STEM_MIN_BLOCKS
+#define DVB_STEM_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(kStemThreads, DVB_STEM_MIN_BLOCKS) stem_conv1_kernel(const StemArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic (not an integer round trip): ptxas keeps the shared address space -> LDS / STS, not generic LD / ST
   uint8_t* sA = smem;                         // 128 rows x 128 B, 128B swizzle
