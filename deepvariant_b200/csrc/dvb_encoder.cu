@@ -60,6 +60,14 @@ constexpr int kThreads = DVB_ENC_THREADS;   // threads per image CTA
 #ifndef DVB_ENC_WORD_LOADS
 #define DVB_ENC_WORD_LOADS 1
 #endif
+// L2 prefetch of every accepted row's CIGAR and window part of its bases / qualities in phase A: 0.847 -> 0.834 ms (WGS), 0.971 -> 0.934
+// (PACBIO layout) per 16,384 windows (call 43).
+#ifndef DVB_ENC_PREFETCH
+#define DVB_ENC_PREFETCH 1
+#endif
+#ifndef DVB_ENC_PREFETCH_NEXT
+#define DVB_ENC_PREFETCH_NEXT 0
+#endif
 // Measured and dropped in the same series: the blank tail of an image zeroed as one contiguous span before the read rows (0.931 ms:
 // the early burst of stores competes with the rows' loads), the row's record and first CIGAR word requested before its buffer is
 // cleared (0.895), a grid-stride pre-pass that fills the resident slots once (0.895: fewer, longer-lived warps lose to more CTAs).
@@ -555,6 +563,20 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
         if (recs) {
           const PairRec& rc = recs[p];
           s_hap[slot] = rc.hap; s_grp[slot] = rc.grp; s_pos[slot] = rc.sort_pos; s_rank[slot] = rc.rank;
+#if DVB_ENC_PREFETCH
+          // the row's CIGAR and the part of its bases / qualities that can land in the window are asked into L2 now, a sort and several
+          // rows before phase B reads them (the row's dependent chain record -> CIGAR -> bases then runs on L2 hits)
+          {
+            const long long off = image_start > rc.pos ? (long long)(image_start - rc.pos) : 0;
+            long long a = rc.seq0 + (off > 32 ? off - 32 : 0);
+            const long long a_end = a + P.W + 96 < B.n_bases ? a + P.W + 96 : B.n_bases;
+            for (; a < a_end; a += 128) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(B.bases + a));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(B.quals + a));
+            }
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(B.cigar + rc.cig0));
+          }
+#endif
         } else {
           const int r = B.pair_read[p];
           const unsigned fl = B.read_flags[r];
@@ -590,6 +612,14 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
     }
     __syncthreads();
 
+#if DVB_ENC_PREFETCH_NEXT
+    // the pair records of the image this CTA takes next are asked into L2 while this one's rows are drawn (phase A then starts on hits)
+    if (recs && img + (int)gridDim.x < B.n_images) {
+      const long long q0 = B.pair_begin[img + gridDim.x];
+      const int nn = (int)(B.pair_begin[img + gridDim.x + 1] - q0);
+      for (int i = 2 * tid; i < nn; i += 2 * kThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(recs + q0 + i));
+    }
+#endif
     // ---- phase B: one warp per image row ---------------------------------------------------
     uint8_t* img_out = out + (long long)img * P.image_bytes;
     for (int row = warp; row < P.H; row += kWarps) {
