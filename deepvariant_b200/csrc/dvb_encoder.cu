@@ -65,9 +65,7 @@ constexpr int kThreads = DVB_ENC_THREADS;   // threads per image CTA
 #ifndef DVB_ENC_PREFETCH
 #define DVB_ENC_PREFETCH 1
 #endif
-#ifndef DVB_ENC_PREFETCH_NEXT
-#define DVB_ENC_PREFETCH_NEXT 0
-#endif
+// (measured and dropped: asking the NEXT image's pair records into L2 during phase B - 0.867 ms against 0.836)
 // Measured and dropped in the same series: the blank tail of an image zeroed as one contiguous span before the read rows (0.931 ms:
 // the early burst of stores competes with the rows' loads), the row's record and first CIGAR word requested before its buffer is
 // cleared (0.895), a grid-stride pre-pass that fills the resident slots once (0.895: fewer, longer-lived warps lose to more CTAs).
@@ -612,14 +610,6 @@ dvb_encode_kernel(const EncDev P, const DvbBatch B, uint8_t* __restrict__ out, i
     }
     __syncthreads();
 
-#if DVB_ENC_PREFETCH_NEXT
-    // the pair records of the image this CTA takes next are asked into L2 while this one's rows are drawn (phase A then starts on hits)
-    if (recs && img + (int)gridDim.x < B.n_images) {
-      const long long q0 = B.pair_begin[img + gridDim.x];
-      const int nn = (int)(B.pair_begin[img + gridDim.x + 1] - q0);
-      for (int i = 2 * tid; i < nn; i += 2 * kThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(recs + q0 + i));
-    }
-#endif
     // ---- phase B: one warp per image row ---------------------------------------------------
     uint8_t* img_out = out + (long long)img * P.image_bytes;
     for (int row = warp; row < P.H; row += kWarps) {
