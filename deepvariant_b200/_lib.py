@@ -237,6 +237,9 @@ SYMBOLS = (
                                         C.POINTER(DvbCandidateOptions), C.c_void_p, C.c_void_p]),
     ('dvb_candidates_at_positions', C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                               C.POINTER(DvbCandidateOptions), C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
+    ('dvb_candidates_from_proposed', C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
+                                               C.POINTER(DvbCandidateOptions), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
     ('dvb_debug_allele_count_dense_host', C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,
                                                     C.POINTER(DvbCandidateOptions), C.c_int, C.c_void_p, C.c_void_p]),
     ('dvb_debug_allele_counts', C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64,

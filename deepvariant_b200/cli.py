@@ -118,7 +118,7 @@ MAKE_EXAMPLES_DEFAULTS = dict(
     vsc_min_fraction_multiplier=1.0, small_model_vaf_context_window_size=0, track_ref_reads=False, phase_reads=False,
     keep_legacy_allele_counter_behavior=False, normalize_reads=False, realign_reads=True, gvcf='', gvcf_gq_binsize=5, p_error=0.001,
     include_med_dp=False, haploid_contigs='', par_regions_bed='', candidate_positions='', runtime_by_region='', examples='', call_variants_outfile='', precision=1,
-    call_batch_size=2048)      # --realign_reads defaults to true (make_examples_options.py:229)
+    call_batch_size=2048, variant_caller='very_sensitive_caller', proposed_variants='')      # --realign_reads defaults to true (make_examples_options.py:229)
 
 
 def model_example_info_json_path(checkpoint: str, checkpoint_json: str = '') -> str:
@@ -178,6 +178,9 @@ def make_examples(argv):
   ap.add_argument('--call_batch_size', type=int)
   ap.add_argument('--candidates')        # OUTPUT, as in the reference (make_examples_options.py:109): the DeepVariantCalls found
   ap.add_argument('--candidates_in')     # INPUT (not a reference flag): use these DeepVariantCalls instead of generating them
+  # make_examples_options.py:1420-1490: 'very_sensitive_caller' (default) or 'vcf_candidate_importer' with --proposed_variants
+  ap.add_argument('--variant_caller', choices=['very_sensitive_caller', 'vcf_candidate_importer'])
+  ap.add_argument('--proposed_variants')
   ap.add_argument('--checkpoint')        # model directory / ckpt path: only its example_info.json flags are read here
   ap.add_argument('--checkpoint_json')
   ap.add_argument('--task', type=int)
@@ -342,7 +345,8 @@ def make_examples(argv):
         small_model_vaf_context_window_size=a.small_model_vaf_context_window_size,
         sample_name=a.sample_name or cand.sample_name_from_bam(a.reads), max_reads_per_partition=a.max_reads_per_partition,
         partition_size=a.partition_size)
-    if table_path and not a.normalize_reads and not a.phase_reads and os.environ.get('DVB_DEVICE_SUPPORT', '1') != '0' and \
+    if table_path and not a.normalize_reads and not a.phase_reads and a.variant_caller == 'very_sensitive_caller' and \
+        os.environ.get('DVB_DEVICE_SUPPORT', '1') != '0' and \
         isinstance(gen._gpu(), pi.GpuEncoder):   # pylint: disable=protected-access  (a stand-in encoder, as in the CPU tests, cannot derive: names then)
       # the candidates come from the allele counter over the very reads the pileups show: the encoder's pre-pass derives the
       # (candidate, read) support classes on the device from the alt alleles instead of a read-name search on the host
@@ -395,6 +399,20 @@ def make_examples(argv):
       gen.signal_shard_finished()
       print(f'make_examples task {a.task}: {totals}', file=sys.stderr)
       return 0
+    proposed = None
+    if a.variant_caller == 'vcf_candidate_importer':
+      if not a.proposed_variants:
+        raise SystemExit('--proposed_variants is required with --variant_caller vcf_candidate_importer')   # make_examples_options.py:1478-1486
+      from deepvariant_b200 import vcf_candidate_importer
+      proposed = vcf_candidate_importer.ProposedVcfReader(a.proposed_variants)
+    elif a.proposed_variants:
+      raise SystemExit('--proposed_variants needs --variant_caller vcf_candidate_importer')
+
+    def find_candidates(table_, contig, p0, p1, rows_, padding_pct=0):
+      if proposed is not None:
+        return vcf_candidate_importer.calls_from_vcf(table_, ref, contig, p0, p1, copts, proposed, rows=rows_, padding_pct=padding_pct)
+      return cand.candidates_in_region(table_, ref, contig, p0, p1, copts, rows=rows_, padding_pct=padding_pct)
+
     sweep = cand.load_candidate_positions(a.candidate_positions) if a.candidate_positions else None
     # --runtime_by_region: one TSV line per region with the seconds of each stage and its counts (make_examples_core.py:95-108,
     # 1348-1353, 3678-3707; docs/runtime-by-region.md).  Pileup encoding and the example writes are one fused step here
@@ -412,13 +430,15 @@ def make_examples(argv):
       rt['_t'] = now
 
     def region_body(contig, p0, p1, rt):
+      if proposed is not None and gvcf_writer is None and not vcf_candidate_importer.region_has_proposed_variant(proposed, contig, p0, p1):
+        return       # filter_regions_by_vcf (make_examples_core.py:3443-3478): nothing proposed here and no gVCF blocks to write
       rows = cand.region_reads(reader, contig, p0, p1, copts.max_reads_per_partition, copts.random_seed)
       rt['num reads'] = len(rows)
-      if not len(rows):
-        if gvcf_writer is not None:               # no early exit with --gvcf: the region still gets its blocks (make_examples_core.py:2872-2875)
-          write_gvcfs(cand.candidates_in_region(reader, ref, contig, p0, p1, copts, rows=rows, padding_pct=20 if a.phase_reads else 0), contig, p0, p1)
+      if not len(rows) and proposed is None:      # (the importer still proposes its records, with no evidence: the reference's own early exit,
+        if gvcf_writer is not None:               #  make_examples_core.py:2871-2875, tests a generator and never fires)               # no early exit with --gvcf: the region still gets its blocks (make_examples_core.py:2872-2875)
+          write_gvcfs(find_candidates(reader, contig, p0, p1, rows, 20 if a.phase_reads else 0), contig, p0, p1)
         return
-      if rl is not None or a.normalize_reads:
+      if (rl is not None or a.normalize_reads) and len(rows):
         # --realign_reads: window selection, de Bruijn assembly, FastPassAligner (deepvariant_b200/realigner.py); the realigned reads
         # replace the region's reads for candidate generation AND pileups, as in_memory_sam_reader.replace_reads does
         # (make_examples_core.py:2290-2300).  --normalize_reads then left-normalises the indels of the region's reads
@@ -436,12 +456,12 @@ def make_examples(argv):
         region_rows = region_table.query_indices(contig, p0, p1)
         mark(rt, 'get reads')
         if count_reads is None:
-          found = cand.candidates_in_region(region_table, ref, contig, p0, p1, copts, rows=region_rows, padding_pct=20 if a.phase_reads else 0)
+          found = find_candidates(region_table, contig, p0, p1, region_rows, 20 if a.phase_reads else 0)
         else:
           # a read whose only change is its heading indel is counted with the rewritten alignment but keeps its own in memory
           # (NormalizeAndAdd, allelecounter.cc:865-870): count from a second table
           count_table = bam.scratch_table(count_reads, refs, reqs)
-          found = cand.candidates_in_region(count_table, ref, contig, p0, p1, copts, rows=count_table.query_indices(contig, p0, p1))
+          found = find_candidates(count_table, contig, p0, p1, count_table.query_indices(contig, p0, p1))
           count_table.close()
         mark(rt, 'find candidates')
         write_gvcfs(found, contig, p0, p1)
@@ -463,7 +483,7 @@ def make_examples(argv):
         region_table.close()
         return
       mark(rt, 'get reads')
-      found = cand.candidates_in_region(reader, ref, contig, p0, p1, copts, rows=rows, padding_pct=20 if a.phase_reads else 0)
+      found = find_candidates(reader, contig, p0, p1, rows, 20 if a.phase_reads else 0)
       mark(rt, 'find candidates')
       write_gvcfs(found, contig, p0, p1)
       rt['num candidates'] = len(found.records)

@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <utility>
@@ -484,6 +485,200 @@ int dvb_candidates_at_positions(const DvbBam* bam, const char* reference_name, c
     res->position.push_back((int32_t)(start + i));
   }
   *out = res;
+  return DVB_OK;
+}
+
+// VcfCandidateImporter: candidates PROPOSED by a VCF, with the evidence of this region's reads attached.  Restates
+//   VariantCaller::CallsFromVcf / CallsFromVariantsInRegion / ComputeVariant      deepvariant/variant_calling.cc:393-435, 493-541
+//   SelectAltAlleles / IsGoodAltAllele (the single-sample rule, no trio re-test)   :226-252
+//   CalcRefBases :176-203, MakeVariantConsistentWithRefAndAlts :118-143, BuildAlleleMap :254-291 (a substitution is always
+//   bases + ref[1:] here), AddReadDepths :300-345 (alleles matched through SimplifyRefAlt, utils.cc:63-84),
+//   AddSupportingReads :675-712 (read name + is_low_quality only; the suffix when the proposed reference allele is longer).
+// The caller passes the records that START inside [start, end) (CallsFromVcf keeps variant->start() >= range.start() of the
+// records that overlap the range) after the uncalled-genotype filter; allele 0 of each record is its reference allele.
+int dvb_candidates_from_proposed(const DvbBam* bam, const char* reference_name, const uint8_t* contig_bases, int64_t contig_n_bases,
+                                 int64_t start, int64_t end, const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* opt,
+                                 const int32_t* candidate_positions, int32_t n_candidate_positions, int32_t n_proposed,
+                                 const int64_t* proposed_start, const int32_t* allele_first, const int64_t* allele_begin,
+                                 const char* allele_chars, DvbCandidates** out) {
+  if (!out || !reference_name) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_candidates_from_proposed: null argument");
+  if (n_proposed < 0 || (n_proposed > 0 && (!proposed_start || !allele_first || !allele_begin || !allele_chars)))
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_candidates_from_proposed: null proposed-variant arrays");
+  *out = nullptr;
+  DvbReadTable table;
+  Counter c;
+  std::vector<std::string> keys;
+  int st = BuildCounter(bam, &table, &c, contig_bases, contig_n_bases, start, end, rows, n_rows, opt, candidate_positions,
+                        n_candidate_positions, &keys);
+  if (st != DVB_OK) return st;
+  Caller caller{&c, &c.opt};
+  std::unique_ptr<DvbCandidates> res(new DvbCandidates());
+  res->proto_begin.push_back(0);
+  const std::string sample = opt->sample_name ? opt->sample_name : "";
+  const int n_sites = (int)c.sites.size();
+  res->summary.resize(2 * (size_t)n_sites);
+  for (int i = 0; i < n_sites; ++i) {
+    res->summary[2 * (size_t)i] = c.sites[(size_t)i].ref_supporting_read_count;
+    res->summary[2 * (size_t)i + 1] = caller.Total(c.sites[(size_t)i]);
+  }
+  auto simplify = [](const std::string& ref, const std::string& alt) {          // SimplifyRefAlt
+    const size_t shortest = std::min(ref.size(), alt.size());
+    size_t common = 0;
+    for (size_t k = 1; k < shortest; ++k) {
+      if (ref[ref.size() - k] != alt[alt.size() - k]) break;
+      common = k;
+    }
+    return ref.substr(0, ref.size() - common) + "->" + alt.substr(0, alt.size() - common);
+  };
+  const Site empty_site;
+  for (int32_t v = 0; v < n_proposed; ++v) {
+    const int32_t a0 = allele_first[v], a1 = allele_first[v + 1];
+    if (a1 <= a0) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_candidates_from_proposed: variant %d has no reference allele", v);
+    auto allele = [&](int32_t a) { return std::string(allele_chars + allele_begin[a], (size_t)(allele_begin[a + 1] - allele_begin[a])); };
+    std::string var_ref = allele(a0);
+    std::vector<std::string> var_alts;
+    for (int32_t a = a0 + 1; a < a1; ++a) var_alts.push_back(allele(a));
+    const int64_t pos = proposed_start[v];
+    // AlleleIndex: no AlleleCount at the position = a call with no evidence (missing genotype downstream)
+    const bool inside = pos >= start && pos < end;
+    const Site& site = inside ? c.sites[(size_t)(pos - start)] : empty_site;
+    std::string ref_base;
+    if (inside) {
+      ref_base.assign(1, (char)contig_bases[pos]);
+      if (!Canonical(ref_base[0])) continue;
+    }
+    // SelectAltAlleles, single-sample rule
+    std::vector<SummedAllele> alts;
+    const int total = caller.Total(site);
+    for (const SummedAllele& a : caller.Sum(site))
+      if (a.type != kReference && a.type != kSoftClip && a.count >= caller.MinCount(a) &&
+          (1.0 * a.count) / total >= (a.type == kSubstitution ? (double)opt->min_fraction_snps : (double)opt->min_fraction_indels))
+        alts.push_back(a);
+    std::string ref_bases = ref_base;               // CalcRefBases
+    {
+      int best = -1;
+      const SummedAllele* del = nullptr;
+      for (const SummedAllele& a : alts) {
+        const int sz = a.type == kDeletion ? (int)a.len : -1;
+        if (sz > best) { best = sz; del = a.type == kDeletion ? &a : nullptr; }
+      }
+      if (del) ref_bases += c.arena.substr(del->off + 1, del->len - 1);
+    }
+    int64_t var_end = pos + (int64_t)var_ref.size();
+    if (var_ref != ref_bases) {                     // MakeVariantConsistentWithRefAndAlts
+      if (var_ref.size() == ref_bases.size() || (var_ref.size() < ref_bases.size() && ref_bases.compare(0, var_ref.size(), var_ref) != 0))
+        return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_candidates_from_proposed: proposed variant at %s:%lld has incorrect ref bases (%s, the reads say %s)",
+                         reference_name, (long long)(pos + 1), var_ref.c_str(), ref_bases.c_str());      // the reference QCHECK-fails
+      if (var_ref.size() < ref_bases.size()) {
+        const std::string suffix = ref_bases.substr(var_ref.size());
+        var_ref += suffix;
+        for (std::string& a : var_alts) a += suffix;
+        var_end += (int64_t)suffix.size();
+      }
+    }
+    struct MapItem { SummedAllele a; std::string bases; std::string alt; };
+    std::vector<MapItem> amap;                      // BuildAlleleMap
+    for (const SummedAllele& a : alts) {
+      MapItem m{a, c.arena.substr(a.off, a.len), ""};
+      const std::string tail1 = ref_bases.size() > 1 ? ref_bases.substr(1) : std::string();
+      if (a.type == kSubstitution || a.type == kInsertion) m.alt = m.bases + tail1;
+      else if (a.type == kDeletion) m.alt = m.bases.substr(0, 1) + (m.bases.size() >= ref_bases.size() ? std::string() : ref_bases.substr(m.bases.size()));
+      else continue;
+      amap.push_back(std::move(m));
+    }
+    // AddReadDepths
+    const int dp = total;
+    std::string call;
+    const bool only_dp = var_alts.size() == 1 && (var_alts[0] == "." || var_alts[0] == "<*>");
+    if (!only_dp) {
+      std::vector<std::pair<std::string, const MapItem*>> by_key;
+      for (const MapItem& m : amap) by_key.emplace_back(simplify(ref_bases, m.alt), &m);
+      for (size_t x = 0; x < by_key.size(); ++x)
+        for (size_t y = x + 1; y < by_key.size(); ++y)
+          if (by_key[x].first == by_key[y].first)
+            return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_candidates_from_proposed: non-unique alternative alleles at %lld", (long long)pos);
+      std::vector<int> ad{site.ref_supporting_read_count};
+      std::vector<double> vaf;
+      for (const std::string& alt : var_alts) {
+        const std::string key = simplify(var_ref, alt);
+        int count = 0;
+        for (const auto& kv : by_key)
+          if (kv.first == key) count = kv.second->a.count;
+        ad.push_back(count);
+        vaf.push_back(dp > 0 ? 1.0 * count / dp : 0.0);
+      }
+      PutBytes(&call, 2, InfoEntryInts("AD", ad));
+      PutBytes(&call, 2, InfoEntryInts("DP", std::vector<int>{dp}));
+      PutBytes(&call, 2, InfoEntryDoubles("VAF", vaf));
+    } else {
+      PutBytes(&call, 2, InfoEntryInts("DP", std::vector<int>{dp}));
+    }
+    {
+      std::string gt;
+      PutVarint(&gt, (uint64_t)(int64_t)-1);
+      PutVarint(&gt, (uint64_t)(int64_t)-1);
+      PutBytes(&call, 7, gt);
+    }
+    if (!sample.empty()) PutBytes(&call, 9, sample);
+    std::string variant;
+    PutBytes(&variant, 6, var_ref);
+    for (const std::string& a : var_alts) PutBytes(&variant, 7, a);
+    PutBytes(&variant, 11, call);
+    PutInt(&variant, 13, var_end);
+    PutBytes(&variant, 14, reference_name);
+    if (pos) PutInt(&variant, 16, pos);
+    // AddSupportingReads
+    std::string suffix;
+    if (var_ref.size() > ref_bases.size()) {
+      if (var_ref.compare(0, ref_bases.size(), ref_bases) != 0)
+        return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_candidates_from_proposed: %s has to be a prefix of %s (%s:%lld)", ref_bases.c_str(),
+                         var_ref.c_str(), reference_name, (long long)(pos + 1));
+      suffix = var_ref.substr(ref_bases.size());
+    }
+    std::string dvc;
+    PutBytes(&dvc, 1, variant);
+    std::vector<std::string> support_key, support_names, support_ext;
+    std::string ref_names, ref_ext;
+    auto read_support = [&](const Entry& e) {
+      std::string rs;
+      PutBytes(&rs, 1, keys[(size_t)e.key_id]);
+      if (e.low_quality) PutInt(&rs, 2, 1);
+      return rs;
+    };
+    for (const Entry& e : site.entries) {
+      if (e.type != kReference) {
+        std::string supported = "UNCALLED_ALLELE";
+        for (const MapItem& m : amap)
+          if (m.a.type == e.type && m.a.len == e.bases_len && c.arena.compare(e.bases_off, e.bases_len, m.bases) == 0) { supported = m.alt + suffix; break; }
+        size_t k = 0;
+        while (k < support_key.size() && support_key[k] != supported) ++k;
+        if (k == support_key.size()) { support_key.push_back(supported); support_names.emplace_back(); support_ext.emplace_back(); }
+        PutBytes(&support_names[k], 1, keys[(size_t)e.key_id]);
+        PutBytes(&support_ext[k], 1, read_support(e));
+      } else if (opt->track_ref_reads) {
+        PutBytes(&ref_names, 4, keys[(size_t)e.key_id]);
+        PutBytes(&ref_ext, 1, read_support(e));
+      }
+    }
+    for (size_t k = 0; k < support_key.size(); ++k) {
+      std::string entry;
+      PutBytes(&entry, 1, support_key[k]);
+      PutBytes(&entry, 2, support_names[k]);
+      PutBytes(&dvc, 2, entry);
+    }
+    dvc += ref_names;
+    for (size_t k = 0; k < support_key.size(); ++k) {
+      std::string entry;
+      PutBytes(&entry, 1, support_key[k]);
+      PutBytes(&entry, 2, support_ext[k]);
+      PutBytes(&dvc, 5, entry);
+    }
+    if (!ref_ext.empty()) PutBytes(&dvc, 6, ref_ext);
+    res->protos += dvc;
+    res->proto_begin.push_back((int64_t)res->protos.size());
+    res->position.push_back((int32_t)pos);
+  }
+  *out = res.release();
   return DVB_OK;
 }
 

@@ -11,7 +11,11 @@
 //   3. CIGAR: banded_sw over [begin, end] x [begin, end] (band |ref_len - query_len| + 1, doubled until the score is reached) with
 //      its direction codes: a diagonal step wins ties against a gap, between gaps "e1 > f1 ? E : F", gap extension vs opening by
 //      "temp1 > temp2 ? open : extend"; traceback from the end cell while the query index is positive;
-//   4. ssw_cpp's ConvertAlignment / CalculateNumberMismatch: leading / trailing soft clips, M runs split into '=' / 'X'.
+//   4. ssw_cpp's ConvertAlignment / CalculateNumberMismatch: leading / trailing soft clips, M runs split into '=' / 'X';
+//   5. the score matrix of ssw_cpp's BuildSwScoreMatrix (1.2.5): N against anything, N included, costs a mismatch (older releases
+//      and ssw.c's own example score it 0).  Pinned by the reference's importer golden: the one read of 223 images that tells the two
+//      apart (59 N-ridden bases in front of 42 clean ones) keeps its 59S42M there and becomes 4S97M with N scored 0
+//      (tests/test_vcf_candidate_importer.py::test_libssw_penalises_n_like_a_mismatch).
 // Pinned by the known answers of the reference's ssw tests (deepvariant/realigner/ssw_test.cc:47-58,
 // deepvariant/realigner/python/ssw_misc_test.py:44-84, ssw_wrap_test.py:37-72) and of fast_pass_aligner_test.cc
 // (tests/test_ssw.py, tests/test_fast_pass_aligner.py).
@@ -224,7 +228,7 @@ int dvb_ssw_align(const char* ref, int64_t ref_len, const char* query, int64_t q
   if (ref_len <= 0 || query_len <= 0) return DVB_OK;           // ssw_cpp's Align returns false: empty alignment, score 0
   int8_t mat[25];
   for (int i = 0; i < 5; ++i)
-    for (int j = 0; j < 5; ++j) mat[i * 5 + j] = (i == 4 || j == 4) ? 0 : (i == j ? (int8_t)match : (int8_t)-mismatch);
+    for (int j = 0; j < 5; ++j) mat[i * 5 + j] = (i == 4 || j == 4) ? (int8_t)-mismatch : (i == j ? (int8_t)match : (int8_t)-mismatch);
   std::vector<int8_t> r((size_t)ref_len), q((size_t)query_len);
   for (int64_t i = 0; i < ref_len; ++i) r[(size_t)i] = Code(ref[i]);
   for (int64_t i = 0; i < query_len; ++i) q[(size_t)i] = Code(query[i]);

@@ -77,7 +77,7 @@ __device__ Best3 WarpScan(WarpSmem& sm, int ref0, int rstep, int ncols, const in
           f_in = up_f;
         }
         const int rc = sm.ref[ref0 + c * rstep];
-        const int sc = (rc == 4 || qc == 4) ? 0 : (rc == qc ? match : -mismatch);
+        const int sc = (rc == 4 || qc == 4) ? -mismatch : (rc == qc ? match : -mismatch);
         int hv = diag + sc;
         hv = max(hv, e);
         hv = max(hv, f_in);
@@ -187,7 +187,7 @@ int dvb_ssw_align_batch(const char* const* refs, const int64_t* ref_lens, const 
   if (ce != cudaSuccess) return dvb::fail(DVB_ERR_CUDA, "dvb_ssw_align_batch: %s", cudaGetErrorString(ce));
   int8_t mat[25];
   for (int i = 0; i < 5; ++i)
-    for (int j = 0; j < 5; ++j) mat[i * 5 + j] = (i == 4 || j == 4) ? 0 : (i == j ? (int8_t)match : (int8_t)-mismatch);
+    for (int j = 0; j < 5; ++j) mat[i * 5 + j] = (i == 4 || j == 4) ? (int8_t)-mismatch : (i == j ? (int8_t)match : (int8_t)-mismatch);
   for (int i = 0; i < n; ++i) {
     char* cg = cigar_stride > 0 ? cigars + (size_t)i * cigar_stride : nullptr;
     memset(&out[i], 0, sizeof(out[i]));

@@ -498,6 +498,17 @@ int dvb_candidates_at_positions(const DvbBam* bam, const char* reference_name, c
                                 int64_t start, int64_t end, const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* options,
                                 const int32_t* candidate_positions, int32_t n_candidate_positions, const int32_t* emit_positions,
                                 int32_t n_emit_positions, DvbCandidates** out);
+/* --variant_caller vcf_candidate_importer: one DeepVariantCall per PROPOSED variant, with this region's read evidence attached
+ * (replaces VariantCaller::CallsFromVcf -> ComputeVariant, deepvariant/variant_calling.cc:393-435, 493-541, bound by
+ * deepvariant/vcf_candidate_importer.py:62-70).  The caller passes the VCF records that start inside [start, end), in file order:
+ * variant v has the alleles allele_first[v] .. allele_first[v + 1] - 1 (the first one is its reference allele), allele a is
+ * allele_chars[allele_begin[a] .. allele_begin[a + 1]).  A record whose reference allele contradicts the reads' is an error
+ * (the reference QCHECK-fails); a non-canonical reference base drops the record. */
+int dvb_candidates_from_proposed(const DvbBam* bam, const char* reference_name, const uint8_t* contig_bases, int64_t contig_n_bases,
+                                 int64_t start, int64_t end, const int64_t* rows, int64_t n_rows, const DvbCandidateOptions* options,
+                                 const int32_t* candidate_positions, int32_t n_candidate_positions, int32_t n_proposed,
+                                 const int64_t* proposed_start, const int32_t* allele_first, const int64_t* allele_begin,
+                                 const char* allele_chars, DvbCandidates** out);
 /* Test access: the kernels' walk, sink and flag function instantiated on the host (windowed != 0: with the reference window
  * the device path uploads instead of the whole contig). */
 int dvb_debug_allele_count_dense_host(const DvbBam* bam, const uint8_t* contig_bases, int64_t contig_n_bases, int64_t start, int64_t end,
