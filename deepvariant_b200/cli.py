@@ -588,6 +588,54 @@ def postprocess_variants(argv):
   return 0
 
 
+def extra_args_to_dict(extra_args: str) -> dict:
+  """scripts/run_deepvariant.py:343-357: "flag=value,flag2=true" -> {flag: value}; true / false become booleans.  A comma inside a
+  value is kept when the piece after it has no '=' (split_extra_args, :330-340: `regions=chr1 chr2,other=x`)."""
+  out, pieces = {}, []
+  for piece in (extra_args or '').split(','):
+    if '=' in piece or not pieces:
+      pieces.append(piece)
+    else:
+      pieces[-1] += ',' + piece
+  for piece in pieces:
+    if not piece.strip():
+      continue
+    if '=' not in piece:
+      raise ValueError(f'extra args: "{piece}" is not flag=value')
+    name, value = piece.split('=', 1)
+    name = name.strip().strip('-')
+    out[name] = True if value.lower() == 'true' else False if value.lower() == 'false' else value
+  return out
+
+
+def _value_flags(args: List[str]) -> set:
+  return {x[2:] for i, x in enumerate(args) if x.startswith('--') and i + 1 < len(args) and not args[i + 1].startswith('--')}
+
+
+def apply_extra_args(args: List[str], extra: dict, value_flags) -> List[str]:
+  """_update_kwargs_with_warning + _extend_command_by_args_dict (scripts/run_deepvariant.py:360-386) on an argv list: an extra flag
+  replaces the one the wrapper set (with the reference's warning); booleans become --flag / --noflag."""
+  args = list(args)
+  for key in sorted(extra):
+    value = extra[key]
+    for name in ('--' + key, '--no' + key):
+      while name in args:
+        i = args.index(name)
+        takes_value = name == '--' + key and key in value_flags
+        old = args[i + 1] if takes_value else name == '--' + key
+        if old != value:
+          print(f'\nWarning: --{key} is previously set to {old}, now to {value}.', file=sys.stderr)
+        del args[i:i + (2 if takes_value else 1)]
+    if isinstance(value, bool):
+      if value:
+        args.append('--' + key)
+      elif key in ('realign_reads', 'group_variants'):     # the two switches that default to true have a --no form; false is the default of the rest
+        args.append('--no' + key)
+    else:
+      args += ['--' + key, str(value)]
+  return args
+
+
 def run_deepvariant(argv):
   ap = argparse.ArgumentParser('run_deepvariant')
   ap.add_argument('--model_type', required=True, choices=sorted(MODEL_DEFAULTS))
@@ -606,6 +654,8 @@ def run_deepvariant(argv):
   ap.add_argument('--num_gpus', type=int, default=0)        # 0 = every visible device; task i runs on device i mod num_gpus
   ap.add_argument('--jobs', type=int, default=0)            # tasks in flight; 0 = all of them, as `parallel -j num_shards` (scripts/run_deepvariant.py:457-462)
   ap.add_argument('--call_variants_extra_args', default='')  # scripts/run_deepvariant.py:112-118: "flag=value,..." - batch_size is honoured (classifier chunk, device memory)
+  ap.add_argument('--make_examples_extra_args', default='')          # scripts/run_deepvariant.py:105-111, e.g. "variant_caller=vcf_candidate_importer,proposed_variants=X.vcf.gz"
+  ap.add_argument('--postprocess_variants_extra_args', default='')   # :119-125
   ap.add_argument('--logging_dir', default='')              # scripts/run_deepvariant.py:141
   ap.add_argument('--runtime_report', action='store_true')  # scripts/run_deepvariant.py:149,744-758: make_examples --runtime_by_region into logging_dir
   a = ap.parse_args(argv)
@@ -614,6 +664,8 @@ def run_deepvariant(argv):
   unknown = sorted(set(cv_extra) - {'batch_size'})
   if unknown:
     raise ValueError(f'--call_variants_extra_args: unsupported flags {unknown} (batch_size is)')
+  me_extra = extra_args_to_dict(a.make_examples_extra_args)
+  pp_extra = extra_args_to_dict(a.postprocess_variants_extra_args)
   runtime_by_region = ''
   if a.logging_dir and a.runtime_report:
     os.makedirs(os.path.join(a.logging_dir, 'make_examples_runtime_by_region'), exist_ok=True)
@@ -661,6 +713,8 @@ def run_deepvariant(argv):
       args += ['--gvcf', nonvariants]
     if runtime_by_region:
       args += ['--runtime_by_region', runtime_by_region]
+    if me_extra:
+      args = apply_extra_args(args, me_extra, _value_flags(args))
     task_args.append(args)
   # One process per task, task i on GPU i mod num_gpus, started together as the reference starts its make_examples shards
   # (scripts/run_deepvariant.py:457-462, 497); a single task runs in this process.
@@ -691,6 +745,8 @@ def run_deepvariant(argv):
     args += ['--sample_name', a.sample_name]
   if a.output_gvcf:
     args += ['--nonvariant_site_tfrecord_path', nonvariants, '--gvcf_outfile', a.output_gvcf]
+  if pp_extra:
+    args = apply_extra_args(args, pp_extra, _value_flags(args))
   return postprocess_variants(args)
 
 

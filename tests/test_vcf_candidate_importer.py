@@ -200,3 +200,73 @@ def test_golden_report_is_current():
   t = r['training_golden']
   assert t['golden_examples'] == t['images_identical'] == t['variants_identical_fields_but_genotype'] == t['golden_images_with_read_rows'] == 223
   assert t['same_examples_in_same_order'] and t['extra_examples'] == []
+
+
+def _proposed_for_planted(tmp_path, genome, sites):
+  """The four planted variants as a proposed VCF, plus a SNP nobody carries, a record in a partition without reads and a ./. record."""
+  g = genome
+  rows = [(sites['snp_het'], g[sites['snp_het']], ['ACGT'[('ACGT'.index(g[sites['snp_het']]) + 1) % 4]], '0/1'),
+          (1800, g[1800], ['ACGT'[('ACGT'.index(g[1800]) + 2) % 4]], '0/1'),                        # no read shows it: AD [n, 0]
+          (sites['snp_hom'], g[sites['snp_hom']], ['ACGT'[('ACGT'.index(g[sites['snp_hom']]) + 1) % 4]], '1/1'),
+          (sites['ins'], g[sites['ins']], [g[sites['ins']] + 'GT'], '0/1'),
+          (sites['dele'], g[sites['dele']:sites['dele'] + 4], [g[sites['dele']]], './.'),
+          (5500, g[5500], ['ACGT'[('ACGT'.index(g[5500]) + 1) % 4]], '0/1')]                        # outside --regions
+  path = str(tmp_path / 'proposed.vcf')
+  with open(path, 'w') as f:
+    f.write(_records('chr20', rows))
+  return path, rows
+
+
+def test_make_examples_cli_with_proposed_variants_cpu_plumbing(tmp_path, monkeypatch):
+  """make_examples --variant_caller vcf_candidate_importer --proposed_variants: one candidate per proposed record of the regions, in
+  file order, evidence from the reads (with and without the realigner), pileups through the same planner.  The encoder is the CPU
+  oracle here; test_cuda_encoder_reproduces_importer_golden_images covers the kernel on the reference's own golden."""
+  from deepvariant_b200 import make_examples_native as men, protos
+  monkeypatch.setattr(men.ExamplesGenerator, '_gpu', lambda self: tc.OracleEncoder(pi.to_params(self.options.pic_options, height=self.pileup_image_height)))
+  fa, bam_path, genome, sites = tc._planted_case(tmp_path)
+  vcf, rows = _proposed_for_planted(tmp_path, genome, sites)
+  in_regions = [r for r in rows if r[0] < 5000]
+  for tag, realign in (('plain', False), ('realigned', True)):
+    examples, cands = tc._run_cli(tmp_path, fa, bam_path, 'vci_' + tag, realign=realign,
+                                  extra=('--variant_caller', 'vcf_candidate_importer', '--proposed_variants', vcf))
+    calls = [cand.canonical_call(r) for r in cands]
+    assert [(c['start'], c['ref'], c['alts']) for c in calls] == [(p, ref, alts) for p, ref, alts, _ in in_regions]
+    by = {c['start']: c for c in calls}
+    assert by[1800]['info']['AD'][1] == 0 and by[1800]['info']['AD'][0] > 10 and by[1800]['info']['VAF'] == [0.0]
+    assert by[sites['snp_hom']]['info']['AD'][0] == 0 and by[sites['snp_hom']]['info']['AD'][1] > 10
+    assert 0.3 < by[sites['snp_het']]['info']['VAF'][0] < 0.7
+    assert by[sites['ins']]['info']['AD'][1] > 5 and by[sites['dele']]['info']['AD'][1] > 5       # ./. is only skipped in training mode
+    assert all(c['call_set_name'] == 'planted' and c['genotype'] == [-1, -1] and c['af_at_position'] == {} for c in calls)
+    ex = [protos.parse_tf_example(r) for r in examples]
+    assert [protos.parse_variant(e['variant/encoded'][1][0]).start for e in ex] == [r[0] for r in in_regions]
+    # the proposed SNP without support: no read row carries the supports-variant mark (channel 4 is 152 = "does not support" under reads)
+    img = np.frombuffer(ex[1]['image/encoded'][1][0], np.uint8).reshape(100, 221, 7)
+    assert img[5:, :, 0].any() and not (img[5:, :, 4] == 254).any()
+    img = np.frombuffer(ex[2]['image/encoded'][1][0], np.uint8).reshape(100, 221, 7)
+    assert (img[5:, :, 4] == 254).any()
+  # flag errors of make_examples_options.py:1440-1490
+  from deepvariant_b200 import cli
+  base = ['--mode', 'calling', '--ref', fa, '--reads', bam_path, '--examples', str(tmp_path / 'x.tfrecord.gz'), '--regions', 'chr20:1001-2000']
+  with pytest.raises(SystemExit, match='--proposed_variants is required'):
+    cli.make_examples(base + ['--variant_caller', 'vcf_candidate_importer'])
+  with pytest.raises(SystemExit, match='needs --variant_caller'):
+    cli.make_examples(base + ['--proposed_variants', vcf])
+
+
+def test_run_deepvariant_extra_args_helpers(capsys):
+  """scripts/run_deepvariant.py:330-386: --make_examples_extra_args / --postprocess_variants_extra_args."""
+  from deepvariant_b200 import cli
+  d = cli.extra_args_to_dict('variant_caller=vcf_candidate_importer,proposed_variants=X.vcf.gz,regions=chr1:1-2,chr2,--realign_reads=false,sort_by_haplotypes=TRUE')
+  assert d == {'variant_caller': 'vcf_candidate_importer', 'proposed_variants': 'X.vcf.gz', 'regions': 'chr1:1-2,chr2', 'realign_reads': False,
+               'sort_by_haplotypes': True}
+  assert cli.extra_args_to_dict('') == {} and cli.extra_args_to_dict(None) == {}
+  with pytest.raises(ValueError):
+    cli.extra_args_to_dict('just_a_flag')
+  args = ['--mode', 'calling', '--partition_size', '25000', '--norealign_reads', '--phase_reads']
+  out = cli.apply_extra_args(args, cli.extra_args_to_dict('partition_size=1000,realign_reads=true,phase_reads=false,variant_caller=vcf_candidate_importer'),
+                             cli._value_flags(args))
+  assert out == ['--mode', 'calling', '--partition_size', '1000', '--realign_reads', '--variant_caller', 'vcf_candidate_importer']
+  err = capsys.readouterr().err
+  assert 'Warning: --partition_size is previously set to 25000, now to 1000.' in err and '--phase_reads is previously set to True, now to False' in err
+  assert args == ['--mode', 'calling', '--partition_size', '25000', '--norealign_reads', '--phase_reads']       # the input list is not touched
+  assert cli.apply_extra_args(['--a', '1'], {'realign_reads': False, 'group_variants': False, 'other': False}, {'a'}) == ['--a', '1', '--nogroup_variants', '--norealign_reads']
