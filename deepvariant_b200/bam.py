@@ -397,12 +397,13 @@ class NativeBamTable:
 _SEQ_CODE = {c: i for i, c in enumerate('=ACMGRSVTWYHKDBN')}
 
 
-def _bgzf(payload: bytes, block: int = 0xff00) -> bytes:
+def _bgzf(payload: bytes, block: int = 0xff00, level: int = 1) -> bytes:
+  """BGZF blocks of `block` payload bytes; level 0 = stored deflate blocks (5 bytes of framing per block, still under the 64 KiB limit)."""
   import zlib
   out = bytearray()
   for i in list(range(0, len(payload), block)) + [None]:
     ch = b'' if i is None else payload[i:i + block]
-    co = zlib.compressobj(1, zlib.DEFLATED, -15)
+    co = zlib.compressobj(level, zlib.DEFLATED, -15)
     body = co.compress(ch) + co.flush()
     out += struct.pack('<4BI2BH2BHH', 0x1f, 0x8b, 8, 4, 0, 0, 0xff, 6, ord('B'), ord('C'), 2, len(body) + 25)
     out += body + struct.pack('<II', zlib.crc32(ch) & 0xffffffff, len(ch))
@@ -414,7 +415,7 @@ for _ch, _code in _SEQ_CODE.items():
   _SEQ_CODE_LUT[ord(_ch)] = _code
 
 
-def write_bam(path: str, reads, references, sample_name: str = '') -> None:
+def write_bam(path: str, reads, references, sample_name: str = '', level: int = 1) -> None:
   """references = [(name, length)].  Flags are rebuilt from the Read fields the reader fills (same decisions under
   ReadRequirements); mate fields are written so that IsReadProperlyPlaced still passes; HP is kept as an aux tag."""
   ref_index = {name: i for i, (name, _) in enumerate(references)}
@@ -450,7 +451,7 @@ def write_bam(path: str, reads, references, sample_name: str = '') -> None:
         bytes(r.aligned_quality) + aux
     out += struct.pack('<i', len(body)) + body
   with open(path, 'wb') as f:
-    f.write(_bgzf(bytes(out)))
+    f.write(_bgzf(bytes(out), level=level))
 
 
 def scratch_table(reads, references, read_requirements: Optional[ReadRequirements] = None, parse_aux: bool = False) -> 'NativeBamTable':
@@ -459,5 +460,5 @@ def scratch_table(reads, references, read_requirements: Optional[ReadRequirement
   import tempfile
   with tempfile.TemporaryDirectory() as tmp:
     path = os.path.join(tmp, 'reads.bam')
-    write_bam(path, reads, references)
+    write_bam(path, reads, references, level=0)       # a scratch file read back at once: stored blocks, no deflate work
     return NativeBamTable(path, read_requirements, parse_aux=parse_aux)

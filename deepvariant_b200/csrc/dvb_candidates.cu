@@ -533,7 +533,11 @@ int dvb_candidates_from_proposed(const DvbBam* bam, const char* reference_name, 
   const Site empty_site;
   for (int32_t v = 0; v < n_proposed; ++v) {
     const int32_t a0 = allele_first[v], a1 = allele_first[v + 1];
-    if (a1 <= a0) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_candidates_from_proposed: variant %d has no reference allele", v);
+    if (a0 < 0 || a1 <= a0) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_candidates_from_proposed: variant %d has no reference allele", v);
+    for (int32_t a = a0; a < a1; ++a)
+      if (allele_begin[a] < 0 || allele_begin[a + 1] < allele_begin[a])
+        return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_candidates_from_proposed: allele_begin is not ascending at allele %d", a);
+    if (allele_begin[a0 + 1] == allele_begin[a0]) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_candidates_from_proposed: variant %d has an empty reference allele", v);
     auto allele = [&](int32_t a) { return std::string(allele_chars + allele_begin[a], (size_t)(allele_begin[a + 1] - allele_begin[a])); };
     std::string var_ref = allele(a0);
     std::vector<std::string> var_alts;
