@@ -280,6 +280,14 @@ class NativeBamTable:
                                           ends.ctypes.data_as(C.c_void_p), len(regions), C.byref(h)))
     else:
       _lib.check(lib.dvb_bam_open(path.encode(), C.byref(creq), 3 if parse_aux else 0, threads, C.byref(h)))   # HP + the raw aux bytes
+    self._load(h, parse_aux)
+
+  def _load(self, h, parse_aux: bool) -> None:
+    """The arrays of an open DvbBam handle (owned by this object from here on)."""
+    import ctypes as C
+    import numpy as np
+    from deepvariant_b200 import _lib
+    lib = _lib.lib()
     try:
       t = _lib.DvbReadTable()
       _lib.check(lib.dvb_bam_table(h, C.byref(t)))
@@ -331,6 +339,36 @@ class NativeBamTable:
     self.parse_aux = parse_aux
     self._reads: Optional[List[Read]] = None
 
+  @classmethod
+  def derived(cls, source: 'NativeBamTable', rows, alignments=None) -> 'NativeBamTable':
+    """The reads `rows` of `source` (in that order) as a table of their own; alignments[i] = (position, [(op, length), ...]) replaces
+    the alignment of rows[i], None keeps it (dvb_bam_derive): realigned / normalised reads without a BAM file in between."""
+    import ctypes as C
+    import numpy as np
+    from deepvariant_b200 import _lib
+    lib = _lib.lib()
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    h = C.c_void_p()
+    if alignments is None:
+      _lib.check(lib.dvb_bam_derive(source.handle, rows.ctypes.data_as(C.c_void_p), len(rows), None, None, None, C.byref(h)))
+    else:
+      if len(alignments) != len(rows):
+        raise ValueError('one alignment (or None) per row')
+      pos = np.zeros(len(rows), dtype=np.int32)
+      begin = np.zeros(len(rows) + 1, dtype=np.int64)
+      ops: list = []
+      for i, a in enumerate(alignments):
+        if a is not None:
+          pos[i] = a[0]
+          ops.extend((int(n) << 4) | int(op) for op, n in a[1])
+        begin[i + 1] = len(ops)
+      cig = np.asarray(ops, dtype=np.uint32)
+      _lib.check(lib.dvb_bam_derive(source.handle, rows.ctypes.data_as(C.c_void_p), len(rows), pos.ctypes.data_as(C.c_void_p),
+                                    begin.ctypes.data_as(C.c_void_p), cig.ctypes.data_as(C.c_void_p), C.byref(h)))
+    self = cls.__new__(cls)
+    self._load(h, source.parse_aux)
+    return self
+
   def close(self) -> None:
     if getattr(self, '_handle', None) is not None:
       self._close(self._handle)
@@ -366,6 +404,7 @@ class NativeBamTable:
       r.hp_values = [int(self.hp[i])]
     if self.parse_aux and self.aux_begin is not None and self.aux_begin[i + 1] > self.aux_begin[i]:
       apply_aux_tags(r, self.aux[int(self.aux_begin[i]):int(self.aux_begin[i + 1])])   # MM / ML / MN, tp, t0 (the optional channels' per-base data)
+    r._table, r._row = self, i        # where the record lives natively (scratch_table derives from it; copy.copy keeps the tags)
     return r
 
   def reads(self) -> List[Read]:
@@ -455,8 +494,13 @@ def write_bam(path: str, reads, references, sample_name: str = '', level: int = 
 
 
 def scratch_table(reads, references, read_requirements: Optional[ReadRequirements] = None, parse_aux: bool = False) -> 'NativeBamTable':
-  """Read objects -> NativeBamTable through a temporary BAM (the table is fully resident once constructed): how realigned /
-  normalised reads reach the native candidate generator and the region packer."""
+  """Read objects -> NativeBamTable: how realigned / normalised reads reach the native candidate generator and the region packer
+  (in_memory_sam_reader.replace_reads, make_examples_core.py:2290-2300).  Reads that came out of one open NativeBamTable (read() tags
+  them; the realigner and the normaliser hand on shallow copies with a new position / cigar) become a table derived natively from
+  that one - only position and cigar are taken from the objects (dvb_bam_derive).  Anything else goes through a temporary BAM."""
+  source = getattr(reads[0], '_table', None) if len(reads) else None
+  if source is not None and getattr(source, '_handle', None) is not None and all(getattr(r, '_table', None) is source for r in reads):
+    return NativeBamTable.derived(source, [r._row for r in reads], [(r.position, r.cigar) if r.cigar else None for r in reads])
   import tempfile
   with tempfile.TemporaryDirectory() as tmp:
     path = os.path.join(tmp, 'reads.bam')

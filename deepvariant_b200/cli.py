@@ -442,8 +442,8 @@ def make_examples(argv):
         # --realign_reads: window selection, de Bruijn assembly, FastPassAligner (deepvariant_b200/realigner.py); the realigned reads
         # replace the region's reads for candidate generation AND pileups, as in_memory_sam_reader.replace_reads does
         # (make_examples_core.py:2290-2300).  --normalize_reads then left-normalises the indels of the region's reads
-        # (deepvariant_b200/normalize_reads.py; make_examples_core.py:2900-2953).  The rewritten reads go through a scratch BAM so
-        # that the native table / packer can take them.
+        # (deepvariant_b200/normalize_reads.py; make_examples_core.py:2900-2953).  The rewritten reads become a table derived natively from
+        # the source table's rows (bam.scratch_table -> dvb_bam_derive) so that the candidate generator / packer can take them.
         region_read_list = rl.realign_reads(reader, contig, rows, (p0, p1)) if rl is not None else [reader.read(int(i)) for i in rows]
         count_reads = None
         if a.normalize_reads:

@@ -481,6 +481,67 @@ int32_t dvb_bam_ref_length(const DvbBam* bam, int32_t i) {
 
 void dvb_bam_close(DvbBam* bam) { delete bam; }
 
+// A table of `n_rows` reads of `src` in the given order, row i with the alignment (new_pos[i], new_cigar[new_cigar_begin[i] ..
+// new_cigar_begin[i + 1])) when that range is not empty and with its own otherwise; everything else of the record (name, flag,
+// bases, qualities, mate fields, HP, raw aux bytes) is copied.  This is how realigned / normalised reads reach the candidate
+// generator and the region packer: what in_memory_sam_reader.replace_reads does in the reference (make_examples_core.py:2290-2300),
+// without a BAM file in between.
+int dvb_bam_derive(const DvbBam* src, const int64_t* rows, int64_t n_rows, const int32_t* new_pos, const int64_t* new_cigar_begin,
+                   const uint32_t* new_cigar, DvbBam** out) {
+  if (!src || !out || n_rows < 0 || (n_rows > 0 && !rows)) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_bam_derive: null argument");
+  *out = nullptr;
+  const bool replace = new_cigar_begin != nullptr;
+  if (replace && (!new_pos || (new_cigar_begin[n_rows] > new_cigar_begin[0] && !new_cigar)))
+    return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_bam_derive: new_cigar_begin without new_pos / new_cigar");
+  const int64_t n_src = (int64_t)src->pos.size();
+  std::unique_ptr<DvbBam> d(new DvbBam());
+  d->refs = src->refs;
+  d->ref_len = src->ref_len;
+  d->n_records_seen = n_rows;
+  const bool has_aux = (int64_t)src->aux_begin.size() == n_src + 1 && n_src > 0;      // the source kept its records' raw aux bytes (parse_hp & 2)
+  d->seq_begin.push_back(0); d->cigar_begin.push_back(0); d->name_begin.push_back(0); d->aux_begin.push_back(0);
+  for (int64_t i = 0; i < n_rows; ++i) {
+    const int64_t r = rows[i];
+    if (r < 0 || r >= n_src) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_bam_derive: row %lld out of range (%lld reads)", (long long)r, (long long)n_src);
+    d->ref_id.push_back(src->ref_id[r]); d->mapq.push_back(src->mapq[r]); d->flag.push_back(src->flag[r]);
+    d->fragment_length.push_back(src->fragment_length[r]); d->hp.push_back(src->hp[r]);
+    d->read_number.push_back(src->read_number[r]); d->number_reads.push_back(src->number_reads[r]);
+    const bool swap = replace && new_cigar_begin[i + 1] > new_cigar_begin[i];
+    if (replace && new_cigar_begin[i + 1] < new_cigar_begin[i]) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_bam_derive: new_cigar_begin is not ascending at %lld", (long long)i);
+    if (swap) {
+      int64_t query = 0, e = new_pos[i];
+      for (int64_t k = new_cigar_begin[i]; k < new_cigar_begin[i + 1]; ++k) {
+        const uint32_t c = new_cigar[k], op = c & 0xF;
+        if (op > 8) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_bam_derive: CIGAR operation %u of read %lld", op, (long long)i);
+        if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) query += (int64_t)(c >> 4);
+        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) e += (int64_t)(c >> 4);
+        d->cigar.push_back(c);
+      }
+      if (query != src->seq_begin[r + 1] - src->seq_begin[r] || new_pos[i] < 0)
+        return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_bam_derive: the new CIGAR of read %lld consumes %lld bases, the read has %lld", (long long)i,
+                         (long long)query, (long long)(src->seq_begin[r + 1] - src->seq_begin[r]));
+      d->pos.push_back(new_pos[i]);
+      d->end.push_back((int32_t)e);
+    } else {
+      d->cigar.insert(d->cigar.end(), src->cigar.begin() + src->cigar_begin[r], src->cigar.begin() + src->cigar_begin[r + 1]);
+      d->pos.push_back(src->pos[r]);
+      d->end.push_back(src->end[r]);
+    }
+    d->cigar_begin.push_back((int64_t)d->cigar.size());
+    d->bases.insert(d->bases.end(), src->bases.begin() + src->seq_begin[r], src->bases.begin() + src->seq_begin[r + 1]);
+    d->quals.insert(d->quals.end(), src->quals.begin() + src->seq_begin[r], src->quals.begin() + src->seq_begin[r + 1]);
+    d->seq_begin.push_back((int64_t)d->bases.size());
+    d->names.insert(d->names.end(), src->names.begin() + src->name_begin[r], src->names.begin() + src->name_begin[r + 1]);
+    d->name_begin.push_back((int64_t)d->names.size());
+    if (has_aux) {
+      d->aux.insert(d->aux.end(), src->aux.begin() + src->aux_begin[r], src->aux.begin() + src->aux_begin[r + 1]);
+      d->aux_begin.push_back((int64_t)d->aux.size());
+    }
+  }
+  *out = d.release();
+  return DVB_OK;
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------

@@ -364,6 +364,12 @@ int dvb_bam_open(const char* path, const DvbReadRequirements* req, int parse_hp,
 int dvb_bam_open_regions(const char* path, const DvbReadRequirements* req, int parse_hp, int threads, const char* const* contigs,
                          const int64_t* starts, const int64_t* ends, int32_t n_regions, DvbBam** out);
 int dvb_bam_table(const DvbBam* bam, DvbReadTable* table);
+/* A new table holding rows[0 .. n_rows) of `src` in that order; row i takes the alignment new_pos[i] + new_cigar[new_cigar_begin[i] ..
+ * new_cigar_begin[i + 1]) (BAM packing) when that range is not empty and keeps its own otherwise (new_cigar_begin NULL: all kept).
+ * Replaces in_memory_sam_reader.replace_reads (deepvariant/make_examples_core.py:2290-2300; third_party/nucleus/io/sam.py:357-361):
+ * realigned / normalised reads as a table the candidate generator and the region packer take.  Close with dvb_bam_close. */
+int dvb_bam_derive(const DvbBam* src, const int64_t* rows, int64_t n_rows, const int32_t* new_pos, const int64_t* new_cigar_begin,
+                   const uint32_t* new_cigar, DvbBam** out);
 const char* dvb_bam_ref_name(const DvbBam* bam, int32_t i);   /* NULL when out of range */
 int32_t dvb_bam_ref_length(const DvbBam* bam, int32_t i);     /* l_ref of the header's reference i (-1 when out of range) */
 void dvb_bam_close(DvbBam* bam);

@@ -7,7 +7,7 @@ import zlib
 import numpy as np
 import pytest
 
-from deepvariant_b200 import bam
+from deepvariant_b200 import _lib, bam
 
 REF_INPUT = '/root/reference/deepvariant/testdata/input'
 
@@ -431,3 +431,58 @@ def test_malformed_bgzf_headers_are_rejected_not_overrun(tmp_path):
     p.write_bytes(blob)
     with pytest.raises(_lib.DvbError):
       bam.NativeBamTable(str(p))
+
+
+@pytest.mark.parametrize('seed', [1, 2])
+def test_derived_table_equals_the_scratch_bam_table(tmp_path, seed):
+  """dvb_bam_derive (realigned / normalised reads as a table of their own) against the path through a temporary BAM: the same reads in the
+  same order, new alignments applied, everything else of the records copied; a region query, the native packer's view and the errors."""
+  import copy
+  rng = np.random.default_rng(seed)
+  recs = []
+  for i in range(200):
+    pos = 1000 + int(rng.integers(0, 1500))
+    ln = int(rng.choice([30, 80, 150]))
+    paired = i % 4 != 0
+    flag = (0x1 | 0x2 | (0x40 if i % 2 else 0x80) | (0x20 if i % 3 == 0 else 0)) if paired else (0x10 if i % 2 else 0)
+    cigar = [(0, ln)] if i % 5 else [(4, 3), (0, 7), (2, 7), (0, ln - 10)]
+    aux = b'HPi' + (1 + i % 2).to_bytes(4, 'little') if i % 3 == 0 else b''
+    recs.append((pos, _record(0, pos, f'q{i // 2}', 10 + i % 50, flag, cigar, ''.join(rng.choice(list('ACGTN'), ln)), rng.integers(5, 41, ln).tolist(),
+                              0 if paired else -1, pos + 50 if paired else -1, 200, aux)))
+  recs.sort(key=lambda t: t[0])
+  path = str(tmp_path / f'derive{seed}.bam')
+  open(path, 'wb').write(_bam([r for _, r in recs]))
+  table = bam.NativeBamTable(path, bam.ReadRequirements(min_mapping_quality=12), parse_aux=True)
+  rows = rng.permutation(table.query_indices('chr20', 1200, 2300))          # the realigner reorders reads
+  reads = [copy.copy(table.read(int(i))) for i in rows]
+  changed = 0
+  for k, r in enumerate(reads):
+    if k % 3 == 0 and len(r.aligned_sequence) > 20:
+      n = len(r.aligned_sequence)
+      r.position += int(rng.integers(-5, 20))
+      r.cigar = [(4, 2), (0, 8), (1, 3), (0, n - 16), (2, 4), (0, 3)]
+      changed += 1
+  assert changed > 10
+  refs = list(zip(table.references, table.reference_lengths))
+  derived = bam.scratch_table(reads, refs, bam.ReadRequirements(min_mapping_quality=12), parse_aux=True)     # every read carries its source row
+  for r in reads:
+    del r._table, r._row
+  scratch = bam.scratch_table(reads, refs, bam.ReadRequirements(min_mapping_quality=12), parse_aux=True)     # ... and now none does: temporary BAM
+  assert derived.n_reads == scratch.n_reads == len(reads)
+  assert derived.reads() == scratch.reads() == reads
+  for name in ('ref_id', 'pos', 'end', 'mapq', 'fragment_length', 'hp', 'read_number', 'number_reads', 'seq_begin', 'cigar_begin', 'name_begin',
+               'bases', 'quals', 'cigar'):
+    np.testing.assert_array_equal(getattr(derived, name), getattr(scratch, name), err_msg=name)
+  assert derived.names == scratch.names and derived.references == scratch.references and derived.reference_lengths == scratch.reference_lengths
+  np.testing.assert_array_equal(derived.query_indices('chr20', 1500, 1600), scratch.query_indices('chr20', 1500, 1600))
+  same = bam.NativeBamTable.derived(table, rows)                                     # no new alignments: a plain sub-table
+  assert same.reads() == [table.read(int(i)) for i in rows]
+  assert bam.NativeBamTable.derived(table, []).n_reads == 0
+  with pytest.raises(_lib.DvbError, match='out of range'):
+    bam.NativeBamTable.derived(table, [table.n_reads])
+  with pytest.raises(_lib.DvbError, match='consumes'):
+    bam.NativeBamTable.derived(table, rows[:1], [(5, [(0, 7)])])
+  with pytest.raises(_lib.DvbError, match='CIGAR operation'):
+    bam.NativeBamTable.derived(table, rows[:1], [(5, [(9, len(reads[0].aligned_sequence))])])
+  with pytest.raises(ValueError):
+    bam.NativeBamTable.derived(table, rows[:2], [None])
