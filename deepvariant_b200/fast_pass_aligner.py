@@ -279,6 +279,8 @@ class FastPassAligner:
     self.fast_align_reads_to_haplotypes_py()
 
   def fast_align_reads_to_haplotypes_py(self) -> None:
+    if not self.kmer_index:
+      self.build_index()
     for i, haplotype in enumerate(self.haplotypes):
       scores = [ReadAlignment() for _ in self.reads]
       hap_score = self.fast_align_reads_to_haplotype(haplotype, scores)
@@ -454,8 +456,7 @@ class FastPassAligner:
   def align_reads(self, reads: Sequence[Read]) -> List[Read]:
     self.reads += [r.aligned_sequence.decode().upper() for r in reads]
     self.calculate_ssw_alignment_score_threshold()
-    self.build_index()
-    self.fast_align_reads_to_haplotypes()
+    self.fast_align_reads_to_haplotypes()      # the native pass indexes the reads' k-mers itself; build_index() serves the Python cross-check
     self.align_haplotypes_to_reference()
     self.calculate_position_maps()
     self.ssw_align_reads_to_haplotypes(self.ssw_alignment_score_threshold)
