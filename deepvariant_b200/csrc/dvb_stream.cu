@@ -81,6 +81,9 @@ void CloseAll(DvbStream* s) {
   if (s->shard_finished != SEM_FAILED) sem_close(s->shard_finished);
 }
 
+// named_mutex::lock: a signal that interrupts the wait must not be taken for the lock
+inline void Lock(sem_t* m) { while (sem_wait(m) != 0 && errno == EINTR) {} }
+
 inline void WriteLen(DvbStream* s, int len) { memcpy(s->buf + s->pos, &len, sizeof len); s->pos += sizeof len; }
 inline void WriteBytes(DvbStream* s, const void* p, int len) { WriteLen(s, len); memcpy(s->buf + s->pos, p, (size_t)len); s->pos += len; }
 
@@ -97,8 +100,8 @@ int dvb_stream_open(const char* shm_prefix, int32_t shard, int32_t role, int64_t
   const int st = OpenAll(s, role == DVB_STREAM_ORCHESTRATOR);
   if (st) { CloseAll(s); delete s; return st; }
   if (role == DVB_STREAM_PRODUCER) {   // stream_examples.cc:83-91: nothing is available and the shard is not finished yet
-    sem_wait(s->items_available);
-    sem_wait(s->shard_finished);
+    Lock(s->items_available);
+    Lock(s->shard_finished);
   }
   *out = s;
   return DVB_OK;
@@ -126,7 +129,7 @@ int64_t dvb_stream_buffer_size(const DvbStream* s) { return s ? s->size : 0; }
 // ---- producer (make_examples side) ---------------------------------------------------------------------------------------
 int dvb_stream_start(DvbStream* s) {   // StartStreaming: once per region
   if (!s || s->role != DVB_STREAM_PRODUCER) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_stream_start: not a producer");
-  sem_wait(s->buffer_empty);
+  Lock(s->buffer_empty);
   s->pos = 0;
   return DVB_OK;
 }
@@ -148,7 +151,7 @@ int dvb_stream_put(DvbStream* s, const void* alt_indices, int32_t alt_len, const
     }
     if (s->size - s->pos > 0) WriteLen(s, 0);   // end of this buffer's batch (the reference writes it when any byte is left)
     sem_post(s->items_available);
-    sem_wait(s->buffer_empty);
+    Lock(s->buffer_empty);
     s->pos = 0;
   }
 }
@@ -166,7 +169,7 @@ int dvb_stream_end(DvbStream* s, int32_t data_written) {   // EndStreaming: once
 
 int dvb_stream_shard_finished(DvbStream* s) {   // SignalShardFinished
   if (!s || s->role != DVB_STREAM_PRODUCER) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "dvb_stream_shard_finished: not a producer");
-  sem_wait(s->buffer_empty);
+  Lock(s->buffer_empty);
   sem_post(s->shard_finished);
   return DVB_OK;
 }
@@ -210,9 +213,13 @@ int dvb_stream_next(DvbStream* const* shards, int32_t n, int64_t index, uint8_t*
       s->alt_begin.assign(1, 0); s->variant_begin.assign(1, 0);
       int64_t pos = 0, used = 0;
       int count = 0, len = 0;
-      auto read_len = [&]() { memcpy(&len, s->buf + pos, sizeof len); pos += sizeof len; };
+      auto read_len = [&]() {       // a length that would lie past the buffer reads as -1 (malformed: every branch below rejects it)
+        if (pos + (int64_t)sizeof len > s->size) { len = -1; return; }
+        memcpy(&len, s->buf + pos, sizeof len); pos += sizeof len;
+      };
       int st = DVB_OK;
       read_len();
+      if (len < 0) st = dvb::fail(DVB_ERR_INTERNAL, "stream shard %d: bad record length", shard);
       while (len > 0) {
         if (pos + len > s->size) { st = dvb::fail(DVB_ERR_INTERNAL, "stream shard %d: record runs past the buffer", shard); break; }
         s->alt_blob.insert(s->alt_blob.end(), s->buf + pos, s->buf + pos + len); pos += len;
