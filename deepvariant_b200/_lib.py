@@ -210,6 +210,8 @@ SYMBOLS = (
     ('dvb_bam_open', C.c_int, [C.c_char_p, C.POINTER(DvbReadRequirements), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     ('dvb_bam_open_regions', C.c_int, [C.c_char_p, C.POINTER(DvbReadRequirements), C.c_int, C.c_int, C.POINTER(C.c_char_p), C.c_void_p, C.c_void_p,
                                        C.c_int32, C.POINTER(C.c_void_p)]),
+    ('dvb_cram_to_bam', C.c_int, [C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.POINTER(C.c_int64)]),
     ('dvb_bam_derive', C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     ('dvb_bam_table', C.c_int, [C.c_void_p, C.POINTER(DvbReadTable)]),
     ('dvb_bam_ref_name', C.c_char_p, [C.c_void_p, C.c_int32]),

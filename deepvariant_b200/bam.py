@@ -259,7 +259,7 @@ class NativeBamTable:
   produces (used by the planner and by the parity tests); `query()` answers region queries on the arrays."""
 
   def __init__(self, path: str, read_requirements: Optional[ReadRequirements] = None, parse_aux: bool = False,
-               threads: int = 0, regions=None):
+               threads: int = 0, regions=None, ref_reader=None):
     """regions: optional [(contig, start, end), ...] (0-based, half-open) - only reads overlapping one of them are decoded
     (dvb_bam_open_regions: the .bai linear index is used when they lie on one contig and the index is beside the file)."""
     import ctypes as C
@@ -272,6 +272,16 @@ class NativeBamTable:
         int(req.keep_secondary_alignments), int(req.keep_supplementary_alignments), int(req.keep_unaligned),
         int(req.keep_improperly_placed))
     h = C.c_void_p()
+    scratch = None
+    if is_cram(path):
+      # CRAM: the wanted containers become an uncompressed BAM in a scratch directory, which the decoder below reads (sam_reader.cc
+      # hands CRAM to htslib with the FASTA; here that FASTA is `ref_reader`)
+      import tempfile
+      if ref_reader is None:
+        raise ValueError(f'{path} is a CRAM file: the reference FASTA is needed to decode it (ref_reader=)')
+      scratch = tempfile.TemporaryDirectory()
+      cram_to_bam(path, os.path.join(scratch.name, 'reads.bam'), ref_reader, regions)
+      path = os.path.join(scratch.name, 'reads.bam')
     if regions:
       names = (C.c_char_p * len(regions))(*[r[0].encode() for r in regions])
       starts = np.array([r[1] for r in regions], dtype=np.int64)
@@ -280,6 +290,8 @@ class NativeBamTable:
                                           ends.ctypes.data_as(C.c_void_p), len(regions), C.byref(h)))
     else:
       _lib.check(lib.dvb_bam_open(path.encode(), C.byref(creq), 3 if parse_aux else 0, threads, C.byref(h)))   # HP + the raw aux bytes
+    if scratch is not None:
+      scratch.cleanup()
     self._load(h, parse_aux)
 
   def _load(self, h, parse_aux: bool) -> None:
@@ -430,6 +442,90 @@ class NativeBamTable:
   def query(self, contig: str, start: int, end: int) -> List[Read]:
     rs = self.reads()
     return [rs[i] for i in self.query_indices(contig, start, end)]
+
+
+def is_cram(path: str) -> bool:
+  with open(path, 'rb') as f:
+    return f.read(4) == b'CRAM'
+
+
+def sam_header_text(path: str) -> str:
+  """The SAM header of a BAM or CRAM file (CRAM: the block of the first container, raw or gzip as htslib / htsjdk write it)."""
+  import gzip
+  import zlib
+  if not is_cram(path):
+    with gzip.open(path, 'rb') as f:
+      head = f.read(8)
+      if head[:4] != b'BAM\1':
+        raise ValueError(f'{path} is not a BAM file')
+      return f.read(struct.unpack('<i', head[4:])[0]).decode(errors='replace')
+
+  def itf8(b, o):
+    v = b[o]
+    if v < 0x80:
+      return v, o + 1
+    if v < 0xC0:
+      return ((v & 0x3f) << 8) | b[o + 1], o + 2
+    if v < 0xE0:
+      return ((v & 0x1f) << 16) | (b[o + 1] << 8) | b[o + 2], o + 3
+    if v < 0xF0:
+      return ((v & 0x0f) << 24) | (b[o + 1] << 16) | (b[o + 2] << 8) | b[o + 3], o + 4
+    return ((v & 0x0f) << 28) | (b[o + 1] << 20) | (b[o + 2] << 12) | (b[o + 3] << 4) | (b[o + 4] & 0x0f), o + 5
+
+  with open(path, 'rb') as f:
+    f.seek(26)
+    length = struct.unpack('<i', f.read(4))[0]
+    b = f.read(length + 256)
+  o = 0
+  for _ in range(4):                      # ref id, start, span, number of records
+    _, o = itf8(b, o)
+  for _ in range(2):                      # record counter, bases (LTF8)
+    n = 0
+    while n < 8 and b[o] & (0x80 >> n):
+      n += 1
+    o += 1 + n
+  _, o = itf8(b, o)                       # number of blocks
+  n_land, o = itf8(b, o)
+  for _ in range(n_land):
+    _, o = itf8(b, o)
+  o += 4                                  # CRC32
+  method = b[o]
+  o += 2
+  _, o = itf8(b, o)
+  csz, o = itf8(b, o)
+  _, o = itf8(b, o)
+  data = b[o:o + csz]
+  if method == 1:
+    data = zlib.decompress(data, 31)
+  elif method != 0:
+    raise ValueError(f'{path}: header block compression method {method}')
+  return data[4:4 + struct.unpack('<i', data[:4])[0]].decode(errors='replace')
+
+
+def cram_to_bam(cram_path: str, bam_path: str, ref_reader, regions=None) -> int:
+  """CRAM 3.0 -> uncompressed BAM (dvb_cram_to_bam, csrc/dvb_cram.cu); `ref_reader` supplies the contigs the file was compressed
+  against (fasta.IndexedFastaReader: `contig_order`, `_contig(name)` = the whole sequence).  regions: [(contig, start, end)] - only the
+  containers overlapping them are decoded, and only their contigs are handed over.  Returns the number of records written."""
+  import ctypes as C
+  import numpy as np
+  from deepvariant_b200 import _lib
+  wanted = None if not regions else {r[0] for r in regions}
+  names = [c for c in (ref_reader.contig_order if ref_reader is not None else []) if wanted is None or c in wanted]
+  seqs = [ref_reader._contig(c) for c in names]   # pylint: disable=protected-access
+  name_arr = (C.c_char_p * max(1, len(names)))(*[n.encode() for n in names])
+  seq_arr = (C.c_char_p * max(1, len(names)))(*seqs)
+  lens = np.asarray([len(s) for s in seqs], dtype=np.int64)
+  n = C.c_int64(0)
+  if regions:
+    rc = (C.c_char_p * len(regions))(*[r[0].encode() for r in regions])
+    rs = np.asarray([r[1] for r in regions], dtype=np.int64)
+    re_ = np.asarray([min(int(r[2]), 1 << 62) for r in regions], dtype=np.int64)
+    _lib.check(_lib.lib().dvb_cram_to_bam(cram_path.encode(), bam_path.encode(), name_arr, seq_arr, lens.ctypes.data_as(C.c_void_p), len(names),
+                                          rc, rs.ctypes.data_as(C.c_void_p), re_.ctypes.data_as(C.c_void_p), len(regions), C.byref(n)))
+  else:
+    _lib.check(_lib.lib().dvb_cram_to_bam(cram_path.encode(), bam_path.encode(), name_arr, seq_arr, lens.ctypes.data_as(C.c_void_p), len(names),
+                                          None, None, None, 0, C.byref(n)))
+  return int(n.value)
 
 
 # ---- writer: reads that exist only in memory (realigned reads) become a BAM so that the native table / packer can take them ---------

@@ -74,11 +74,8 @@ class CandidateOptions:
 
 def sample_name_from_bam(path: str) -> str:
   """SM of the @RG header lines: the only one, or the first when several differ; 'default' when there is none."""
-  with gzip.open(path, 'rb') as f:
-    head = f.read(8)
-    if head[:4] != b'BAM\1':
-      raise ValueError(f'{path} is not a BAM file')
-    text = f.read(struct.unpack('<i', head[4:])[0]).decode(errors='replace')
+  from deepvariant_b200 import bam
+  text = bam.sam_header_text(path)      # BAM or CRAM
   samples = []
   for line in text.split('\n'):
     if line.startswith('@RG'):

@@ -291,7 +291,9 @@ def make_examples(argv):
   # (make_examples_options.py:445-452)
   if any(pi.CHANNEL_ENUM.get(c) in (23, 24, 28, 29, 30) for c in pic.channels):
     a.parse_sam_aux_fields = True
-  reader = bam.NativeBamTable(a.reads, bam.ReadRequirements(min_mapping_quality=a.min_mapping_quality), parse_aux=a.parse_sam_aux_fields, regions=read_regions)
+  # --reads may be a CRAM (decoded against --ref: csrc/dvb_cram.cu), as sam_reader.cc takes one with the FASTA
+  reader = bam.NativeBamTable(a.reads, bam.ReadRequirements(min_mapping_quality=a.min_mapping_quality), parse_aux=a.parse_sam_aux_fields, regions=read_regions,
+                              ref_reader=fasta.IndexedFastaReader(a.ref) if bam.is_cram(a.reads) else None)
   table_path = not a.trim_reads_for_pileup and a.alt_aligned_pileup == 'none' and not plane_channels
 
   def annotated(calls, contig):

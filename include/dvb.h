@@ -364,6 +364,15 @@ int dvb_bam_open(const char* path, const DvbReadRequirements* req, int parse_hp,
 int dvb_bam_open_regions(const char* path, const DvbReadRequirements* req, int parse_hp, int threads, const char* const* contigs,
                          const int64_t* starts, const int64_t* ends, int32_t n_regions, DvbBam** out);
 int dvb_bam_table(const DvbBam* bam, DvbReadTable* table);
+/* CRAM 3.0 input: decodes `cram_path` (all of it, or with n_regions > 0 only the containers that overlap one of the half-open
+ * intervals) into an uncompressed BAM at `bam_path`, which dvb_bam_open / dvb_bam_open_regions then read - what hts_open + sam_read1
+ * give the reference for a CRAM (third_party/nucleus/io/sam_reader.cc:325-399, which also wants the FASTA there).  The reference
+ * contigs the reads were compressed against come as whole upper- or lower-case sequences by name (only contigs the wanted containers
+ * touch need to be present; a missing one is an error when a read needs it).  gzip and rANS 4x8 blocks; bzip2 / lzma blocks and the
+ * 3.1 codecs are reported as errors.  *n_records_out = alignment records written. */
+int dvb_cram_to_bam(const char* cram_path, const char* bam_path, const char* const* ref_names, const uint8_t* const* ref_bases,
+                    const int64_t* ref_lens, int32_t n_refs, const char* const* region_contigs, const int64_t* region_starts,
+                    const int64_t* region_ends, int32_t n_regions, int64_t* n_records_out);
 /* A new table holding rows[0 .. n_rows) of `src` in that order; row i takes the alignment new_pos[i] + new_cigar[new_cigar_begin[i] ..
  * new_cigar_begin[i + 1]) (BAM packing) when that range is not empty and keeps its own otherwise (new_cigar_begin NULL: all kept).
  * Replaces in_memory_sam_reader.replace_reads (deepvariant/make_examples_core.py:2290-2300; third_party/nucleus/io/sam.py:357-361):
