@@ -445,8 +445,11 @@ class NativeBamTable:
 
 
 def is_cram(path: str) -> bool:
-  with open(path, 'rb') as f:
-    return f.read(4) == b'CRAM'
+  try:
+    with open(path, 'rb') as f:
+      return f.read(4) == b'CRAM'
+  except OSError:
+    return False          # the native open reports the missing / unreadable file
 
 
 def sam_header_text(path: str) -> str:
