@@ -675,6 +675,7 @@ int dvb_cram_to_bam(const char* cram_path, const char* bam_path, const char* con
           c.name = head < ri ? recs[(size_t)head].name : "cram." + std::to_string(name_counter++);
         }
         if (c.name.size() > 254) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: read name of %zu bytes", cram_path, c.name.size());
+        if (c.cigar.size() > 65535) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: a read with %zu CIGAR operations (BAM holds 65535; the CG-tag form is not written)", cram_path, c.cigar.size());
         const int32_t pos0 = (c.ref >= 0 || c.ap > 0) ? c.ap - 1 : -1;
         const int64_t end0 = (c.bf & 4) || c.end <= pos0 ? (int64_t)pos0 + 1 : c.end;
         const int32_t l_seq = (int32_t)c.seq.size();
