@@ -292,8 +292,34 @@ def make_examples(argv):
   if any(pi.CHANNEL_ENUM.get(c) in (23, 24, 28, 29, 30) for c in pic.channels):
     a.parse_sam_aux_fields = True
   # --reads may be a CRAM (decoded against --ref: csrc/dvb_cram.cu), as sam_reader.cc takes one with the FASTA
-  reader = bam.NativeBamTable(a.reads, bam.ReadRequirements(min_mapping_quality=a.min_mapping_quality), parse_aux=a.parse_sam_aux_fields, regions=read_regions,
-                              ref_reader=fasta.IndexedFastaReader(a.ref) if bam.is_cram(a.reads) else None)
+  cram_ref = fasta.IndexedFastaReader(a.ref) if bam.is_cram(a.reads) else None
+
+  def open_reads(read_regions_):
+    return bam.NativeBamTable(a.reads, bam.ReadRequirements(min_mapping_quality=a.min_mapping_quality), parse_aux=a.parse_sam_aux_fields, regions=read_regions_,
+                              ref_reader=cram_ref)
+  # Without --regions a task walks its partitions over the whole genome (the reference queries its indexed reader once per partition,
+  # make_examples_core.py:2262-2288).  Holding every read of a 30x genome is not an option, so the table then covers one
+  # window of the genome at a time: DVB_READ_WINDOW_BP bases (default 10 Mb, rounded to whole partitions), widened by the same margin
+  # as --regions, re-opened through the .bai / the CRAM container headers when the walk leaves it.  Memory is one window's reads; each
+  # task decodes each window it has a partition in once.
+  window_bp = int(os.environ.get('DVB_READ_WINDOW_BP', '0'))
+  indexed = cram_ref is not None or any(os.path.exists(p) for p in (a.reads + '.bai', os.path.splitext(a.reads)[0] + '.bai'))
+  windowed = not regions and not a.candidates_in and (window_bp > 0 or indexed)
+  if windowed:
+    window_bp = max(a.partition_size, (window_bp or 10_000_000) // a.partition_size * a.partition_size)
+  loaded = [None]            # (contig, first base, last base + 1) of the window `reader` holds
+  reader = open_reads([(fasta.IndexedFastaReader(a.ref).contig_order[0], 0, 1)] if windowed else read_regions)
+
+  def ensure_reads(contig, p0, p1):
+    nonlocal reader
+    if not windowed or (loaded[0] is not None and loaded[0][0] == contig and loaded[0][1] <= p0 and p1 <= loaded[0][2]):
+      return
+    lo = p0 // window_bp * window_bp
+    hi = max(lo + window_bp, p1)          # a partition cut by candidate count (--candidate_positions) may be longer than a window
+    margin = (max(a.partition_size, p1 - p0) // 5 if a.phase_reads else 0) + 1000
+    reader.close()
+    reader = open_reads([(contig, max(0, lo - margin), hi + margin)])
+    loaded[0] = (contig, lo, hi)
   table_path = not a.trim_reads_for_pileup and a.alt_aligned_pileup == 'none' and not plane_channels
 
   def annotated(calls, contig):
@@ -392,6 +418,7 @@ def make_examples(argv):
       region_ends = {(c, min(n, region[2]) if region and region[0] == c else n) for c, n in contigs}
       with open(path, 'wb') as f:
         for contig, p0, p1 in cand.regions_to_process(contigs, a.partition_size, region, a.task, n_shards):
+          ensure_reads(contig, p0, p1)
           rows = cand.region_reads(reader, contig, p0, p1, copts.max_reads_per_partition, copts.random_seed)
           positions = cand.candidate_positions(reader, ref, contig, p0, p1, rows, copts) + [cand.END_OF_PARTITION]
           if (contig, p1) in region_ends:
@@ -432,6 +459,7 @@ def make_examples(argv):
       rt['_t'] = now
 
     def region_body(contig, p0, p1, rt):
+      ensure_reads(contig, p0, p1)
       if proposed is not None and gvcf_writer is None and not vcf_candidate_importer.region_has_proposed_variant(proposed, contig, p0, p1):
         return       # filter_regions_by_vcf (make_examples_core.py:3443-3478): nothing proposed here and no gVCF blocks to write
       rows = cand.region_reads(reader, contig, p0, p1, copts.max_reads_per_partition, copts.random_seed)

@@ -659,3 +659,40 @@ def test_gpu_allele_counter_needs_a_device(tmp_path):
   table = _table(tmp_path, [_read('r', 10, 'TCCGT', '5M')], [('chr1', CHR1)])
   with pytest.raises(_lib.DvbError, match='no CUDA device'):
     cand.GpuAlleleCounter(table)
+
+
+def test_make_examples_cli_windowed_reads_equal_the_whole_table(tmp_path, monkeypatch):
+  """Without --regions the reads are held one genome window at a time (DVB_READ_WINDOW_BP; the default when the file has an index):
+  the same examples and candidates as with every read resident, windows smaller than the spacing of the planted variants, with and
+  without the realigner, and for two tasks of a sharded run."""
+  from deepvariant_b200 import cli, make_examples_native as men, pileup_image as pi, tfrecord
+  monkeypatch.setattr(men.ExamplesGenerator, '_gpu', lambda self: OracleEncoder(pi.to_params(self.options.pic_options, height=self.pileup_image_height)))
+  fa, bam_path, genome, sites = _planted_case(tmp_path)
+
+  def run(tag, window, extra=()):
+    if window:
+      monkeypatch.setenv('DVB_READ_WINDOW_BP', str(window))
+    else:
+      monkeypatch.delenv('DVB_READ_WINDOW_BP', raising=False)
+    ex = str(tmp_path / f'{tag}.examples.tfrecord.gz')
+    cands = str(tmp_path / f'{tag}.candidates.tfrecord.gz')
+    assert cli.make_examples(['--mode', 'calling', '--ref', fa, '--reads', bam_path, '--examples', ex, '--candidates', cands,
+                              '--channel_list', 'BASE_CHANNELS,insert_size', *extra]) == 0
+    return list(tfrecord.read_records(ex)), list(tfrecord.read_records(cands))
+  for extra in (('--norealign_reads',), ('--realign_reads',), ('--norealign_reads', '--gvcf', str(tmp_path / 'g.tfrecord.gz'))):
+    whole = run('whole', 0, extra)
+    assert len(whole[0]) == 4
+    for window in (1000, 1700, 100000):
+      assert run(f'w{window}', window, extra) == whole
+  # two tasks of a sharded run: each walks its own partitions (every second kilobase) across the windows
+  shards = {}
+  for window in (0, 1000):
+    if window:
+      monkeypatch.setenv('DVB_READ_WINDOW_BP', str(window))
+    else:
+      monkeypatch.delenv('DVB_READ_WINDOW_BP', raising=False)
+    for task in range(2):
+      assert cli.make_examples(['--mode', 'calling', '--ref', fa, '--reads', bam_path, '--examples', str(tmp_path / f's{window}.tfrecord@2.gz'),
+                                '--channel_list', 'BASE_CHANNELS,insert_size', '--norealign_reads', '--task', str(task)]) == 0
+    shards[window] = [list(tfrecord.read_records(str(tmp_path / f's{window}.tfrecord-0000{t}-of-00002.gz'))) for t in range(2)]
+  assert shards[0] == shards[1000] and sum(len(x) for x in shards[0]) == 4
