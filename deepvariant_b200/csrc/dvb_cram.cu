@@ -16,6 +16,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <climits>
 #include <cstdint>
 #include <cstdio>
@@ -23,6 +24,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "dvb_common.h"
@@ -32,7 +34,6 @@ namespace {
 struct Rd {                          // bounds-checked cursor
   const uint8_t* p; const uint8_t* e; bool bad = false;
   uint8_t u8() { if (p >= e) { bad = true; return 0; } return *p++; }
-  int32_t i32() { if (e - p < 4) { bad = true; p = e; return 0; } int32_t v; memcpy(&v, p, 4); p += 4; return v; }
   int32_t itf8() {
     const uint8_t v = u8();
     if (v < 0x80) return v;
@@ -380,6 +381,258 @@ int ParseCompressionHeader(const Block& b, CompressionHeader* h) {
   return r.bad ? dvb::fail(DVB_ERR_INVALID_ARGUMENT, "CRAM: truncated compression header") : DVB_OK;
 }
 
+// One data container -> BAM records (appended to `w`).  Containers are independent of each other: dvb_cram_to_bam decodes a batch of
+// them on several threads and writes the results in file order.
+struct Out {
+  std::vector<uint8_t> buf;
+  void Put(const void* p, size_t n) { buf.insert(buf.end(), (const uint8_t*)p, (const uint8_t*)p + n); }
+  void I32(int32_t v) { Put(&v, 4); }
+};
+
+struct Ctx {
+  const char* cram_path;
+  const std::vector<std::string>* sq_names;
+  const std::vector<int>* sq_to_given;
+  const uint8_t* const* ref_bases;
+  const int64_t* ref_lens;
+};
+
+int DecodeContainer(const Ctx& cx, const std::vector<uint8_t>& cbuf, const std::vector<int32_t>& landmarks, const std::string& name_prefix, Out& w,
+                    int64_t* n_written) {
+  const char* cram_path = cx.cram_path;
+  const std::vector<std::string>& sq_names = *cx.sq_names;
+  const std::vector<int>& sq_to_given = *cx.sq_to_given;
+  const uint8_t* const* ref_bases = cx.ref_bases;
+  const int64_t* ref_lens = cx.ref_lens;
+  int64_t name_count = 0;
+  int64_t* name_counter = &name_count;
+  Rd cr{cbuf.data(), cbuf.data() + cbuf.size()};
+  // ---- a data container: compression header, then slices at the landmarks
+  Block chb;
+  int st = ReadBlock(cr, &chb);
+  if (st) return st;
+  if (chb.ctype != 1) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: container without a compression header", cram_path);
+  CompressionHeader ch;
+  if ((st = ParseCompressionHeader(chb, &ch))) return st;
+  auto enc = [&](const char* key) -> const Enc& { static const Enc none; auto it = ch.ds.find(key); return it == ch.ds.end() ? none : it->second; };
+  for (size_t li = 0; li < landmarks.size(); ++li) {
+    if (landmarks[li] < 0 || (size_t)landmarks[li] >= cbuf.size()) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: landmark outside its container", cram_path);
+    Rd sr{cbuf.data() + landmarks[li], cbuf.data() + cbuf.size()};
+    Block shb;
+    if ((st = ReadBlock(sr, &shb))) return st;
+    if (shb.ctype != 2) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: landmark does not point at a slice header", cram_path);
+    Rd hs{shb.data.data(), shb.data.data() + shb.data.size()};
+    const int32_t s_ref = hs.itf8(), s_start = hs.itf8();
+    hs.itf8();
+    const int32_t s_nrec = hs.itf8();
+    hs.ltf8();
+    const int32_t s_nblocks = hs.itf8(), n_ids = hs.itf8();
+    for (int32_t i = 0; i < n_ids; ++i) hs.itf8();
+    const int32_t embedded = hs.itf8();
+    if (hs.bad || s_nrec < 0 || s_nblocks < 0) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: malformed slice header", cram_path);
+    std::vector<std::unique_ptr<Block>> blocks;
+    Slice sl;
+    for (int32_t i = 0; i < s_nblocks; ++i) {
+      blocks.emplace_back(new Block());
+      if ((st = ReadBlock(sr, blocks.back().get()))) return st;
+      if (blocks.back()->ctype == 5) sl.core = blocks.back().get(); else sl.ext[blocks.back()->id] = blocks.back().get();
+    }
+    std::vector<Rec> recs((size_t)s_nrec);
+    int32_t prev_ap = s_start;
+    for (int32_t ri = 0; ri < s_nrec; ++ri) {
+      Rec& c = recs[(size_t)ri];
+      c.bf = sl.Int(enc("BF")); c.cf = sl.Int(enc("CF"));
+      c.ref = s_ref == -2 ? sl.Int(enc("RI")) : s_ref;
+      c.rl = sl.Int(enc("RL"));
+      c.ap = sl.Int(enc("AP"));
+      if (ch.ap_delta) { c.ap += prev_ap; prev_ap = c.ap; }
+      sl.Int(enc("RG"));
+      if (ch.rn) sl.Bytes(enc("RN"), &c.name);
+      if (c.cf & 2) {                                    // detached: the mate fields are stored
+        c.mf = sl.Int(enc("MF"));
+        if (!ch.rn) sl.Bytes(enc("RN"), &c.name);
+        c.ns = sl.Int(enc("NS")); c.np = sl.Int(enc("NP")); c.tlen = sl.Int(enc("TS"));
+      } else if (c.cf & 4) {
+        c.mate_line = ri + sl.Int(enc("NF")) + 1;
+      }
+      const int32_t tl = sl.Int(enc("TL"));
+      if (sl.bad || c.rl < 0 || tl < 0 || (size_t)tl >= ch.td.size()) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: malformed record %d of a slice", cram_path, ri);
+      for (const std::string& t : ch.td[(size_t)tl]) {
+        const int32_t key = ((uint8_t)t[0] << 16) | ((uint8_t)t[1] << 8) | (uint8_t)t[2];
+        auto it = ch.tags.find(key);
+        if (it == ch.tags.end()) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: tag %c%c without an encoding", cram_path, t[0], t[1]);
+        c.aux.append(t);
+        const size_t v0 = c.aux.size();
+        sl.Bytes(it->second, &c.aux);
+        if ((t[2] == 'Z' || t[2] == 'H') && (c.aux.size() == v0 || c.aux.back() != 0)) c.aux.push_back(0);
+      }
+      c.seq.assign((size_t)c.rl, 'N');
+      c.qual.assign((size_t)c.rl, (char)0xff);
+      c.end = c.ap;
+      if (!(c.bf & 4)) {
+        RefSeq ref;
+        if (embedded >= 0) {
+          Block* eb = sl.Ext(embedded);
+          if (eb) { ref.bases = eb->data.data(); ref.len = (int64_t)eb->data.size(); ref.origin = (int64_t)s_start - 1; }
+        } else if (c.ref >= 0 && (size_t)c.ref < sq_to_given.size() && sq_to_given[(size_t)c.ref] >= 0) {
+          ref.bases = ref_bases[sq_to_given[(size_t)c.ref]]; ref.len = ref_lens[sq_to_given[(size_t)c.ref]];
+        }
+        bool ref_missing = false;
+        auto ref_at = [&](int64_t pos0) -> char {
+          const int64_t i = pos0 - ref.origin;
+          if (!ref.bases || i < 0 || i >= ref.len) { ref_missing = true; return 'N'; }
+          const char b = (char)ref.bases[i];
+          return (b >= 'a' && b <= 'z') ? (char)(b - 32) : b;
+        };
+        const int32_t fn = sl.Int(enc("FN"));
+        int64_t read_pos = 0, ref_pos = (int64_t)c.ap - 1;
+        int32_t fpos = 0;
+        auto fill = [&](int64_t upto) {                   // reference matches up to read index `upto` (exclusive)
+          const int64_t gap = std::min<int64_t>(upto, c.rl) - read_pos;
+          if (gap <= 0) return;
+          for (int64_t k = 0; k < gap; ++k) c.seq[(size_t)(read_pos + k)] = ref_at(ref_pos + k);
+          PushCigar(&c.cigar, 0, gap); read_pos += gap; ref_pos += gap;
+        };
+        for (int32_t f = 0; f < fn && !sl.bad; ++f) {
+          const char code = (char)sl.Byte(enc("FC"));
+          fpos += sl.Int(enc("FP"));
+          fill((int64_t)fpos - 1);
+          std::string bytes;
+          switch (code) {
+            case 'X': {
+              const int bs = sl.Byte(enc("BS")) & 3;
+              const char rb = ref_at(ref_pos);
+              const int ri5 = rb == 'A' ? 0 : rb == 'C' ? 1 : rb == 'G' ? 2 : rb == 'T' ? 3 : 4;
+              if (read_pos < c.rl) c.seq[(size_t)read_pos] = (char)ch.sub[ri5][bs];
+              PushCigar(&c.cigar, 0, 1); ++read_pos; ++ref_pos; break;
+            }
+            case 'B': {
+              const int b = sl.Byte(enc("BA")), q = sl.Byte(enc("QS"));
+              if (read_pos < c.rl) { c.seq[(size_t)read_pos] = (char)b; c.qual[(size_t)read_pos] = (char)q; }
+              PushCigar(&c.cigar, 0, 1); ++read_pos; ++ref_pos; break;
+            }
+            case 'b':
+              sl.Bytes(enc("BB"), &bytes);
+              for (size_t k = 0; k < bytes.size() && read_pos + (int64_t)k < c.rl; ++k) c.seq[(size_t)read_pos + k] = bytes[k];
+              PushCigar(&c.cigar, 0, (int64_t)bytes.size()); read_pos += (int64_t)bytes.size(); ref_pos += (int64_t)bytes.size(); break;
+            case 'I':
+              sl.Bytes(enc("IN"), &bytes);
+              for (size_t k = 0; k < bytes.size() && read_pos + (int64_t)k < c.rl; ++k) c.seq[(size_t)read_pos + k] = bytes[k];
+              PushCigar(&c.cigar, 1, (int64_t)bytes.size()); read_pos += (int64_t)bytes.size(); break;
+            case 'i': {
+              const int b = sl.Byte(enc("BA"));
+              if (read_pos < c.rl) c.seq[(size_t)read_pos] = (char)b;
+              PushCigar(&c.cigar, 1, 1); ++read_pos; break;
+            }
+            case 'S':
+              sl.Bytes(enc("SC"), &bytes);
+              for (size_t k = 0; k < bytes.size() && read_pos + (int64_t)k < c.rl; ++k) c.seq[(size_t)read_pos + k] = bytes[k];
+              PushCigar(&c.cigar, 4, (int64_t)bytes.size()); read_pos += (int64_t)bytes.size(); break;
+            case 'D': { const int32_t n = sl.Int(enc("DL")); PushCigar(&c.cigar, 2, n); ref_pos += n; break; }
+            case 'N': { const int32_t n = sl.Int(enc("RS")); PushCigar(&c.cigar, 3, n); ref_pos += n; break; }
+            case 'H': PushCigar(&c.cigar, 5, sl.Int(enc("HC"))); break;
+            case 'P': PushCigar(&c.cigar, 6, sl.Int(enc("PD"))); break;
+            case 'Q': { const int q = sl.Byte(enc("QS")); if (fpos >= 1 && fpos <= c.rl) c.qual[(size_t)fpos - 1] = (char)q; break; }
+            case 'q':
+              sl.Bytes(enc("QQ"), &bytes);
+              for (size_t k = 0; k < bytes.size() && (int64_t)fpos - 1 + (int64_t)k < c.rl; ++k) c.qual[(size_t)fpos - 1 + k] = bytes[k];
+              break;
+            default: return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: read feature '%c'", cram_path, code);
+          }
+        }
+        fill(c.rl);
+        if (ref_missing && ch.rr)
+          return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: the reference bases of %s are needed to decode its reads (pass the FASTA the file was written against)", cram_path,
+                           c.ref >= 0 && (size_t)c.ref < sq_names.size() ? sq_names[(size_t)c.ref].c_str() : "?");
+        c.end = ref_pos;                                  // 1-based inclusive end = 0-based exclusive end
+        c.mq = sl.Int(enc("MQ"));
+        if (c.cf & 1) for (int32_t k = 0; k < c.rl; ++k) c.qual[(size_t)k] = (char)sl.Byte(enc("QS"));
+      } else {
+        for (int32_t k = 0; k < c.rl; ++k) c.seq[(size_t)k] = (char)sl.Byte(enc("BA"));
+        if (c.cf & 1) for (int32_t k = 0; k < c.rl; ++k) c.qual[(size_t)k] = (char)sl.Byte(enc("QS"));
+      }
+      if (c.cf & 8) { c.seq.clear(); c.qual.clear(); }      // sequence unknown ('*')
+      if (sl.bad) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: a data series ran out inside record %d of a slice", cram_path, ri);
+    }
+    // ---- mates (cram_decode_slice_xref)
+    std::vector<int32_t> mate_ref((size_t)s_nrec, -1), mate_pos((size_t)s_nrec, 0);
+    for (int32_t ri = 0; ri < s_nrec; ++ri) {
+      Rec& c = recs[(size_t)ri];
+      if (c.mate_line >= 0) {
+        if (c.mate_line >= s_nrec) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: mate line outside its slice", cram_path);
+        if (c.tlen == INT_MIN) {
+          int id2 = ri; int64_t aleft = c.ap, aright = c.end; int ref = c.ref, left_cnt = 0;
+          do {
+            Rec& m = recs[(size_t)id2];
+            if (aleft > m.ap) { aleft = m.ap; left_cnt = 1; } else if (aleft == m.ap) ++left_cnt;
+            if (aright < m.end) aright = m.end;
+            if (m.mate_line == -1) { m.mate_line = ri; break; }
+            if (m.mate_line <= id2 || m.mate_line >= s_nrec) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: mate chain does not move forward", cram_path);
+            id2 = m.mate_line;
+            if (recs[(size_t)id2].ref != ref) ref = -1;
+          } while (id2 != ri);
+          const int64_t tlen = aright - aleft + 1;
+          id2 = ri;
+          do {
+            Rec& m = recs[(size_t)id2];
+            m.tlen = ref == -1 ? 0 : (m.ap == aleft && (left_cnt == 1 || (m.bf & 0x40))) ? (int32_t)tlen : (int32_t)-tlen;
+            id2 = m.mate_line;
+          } while (id2 != ri && id2 >= 0);
+        }
+        const Rec& m = recs[(size_t)c.mate_line];
+        mate_pos[(size_t)ri] = m.ap; mate_ref[(size_t)ri] = m.ref;
+        c.bf |= 1;
+        if (m.bf & 4) { c.bf |= 8; c.tlen = 0; }
+        if (c.bf & 4) c.tlen = 0;
+        if (m.bf & 0x10) c.bf |= 0x20;
+      } else {
+        if (c.mf & 1) c.bf |= 1 | 0x20;
+        if (c.mf & 2) c.bf |= 8;
+        mate_ref[(size_t)ri] = (c.bf & 1) ? c.ns : -1;
+        mate_pos[(size_t)ri] = c.np;
+      }
+      if (c.tlen == INT_MIN) c.tlen = 0;
+    }
+    // ---- BAM records
+    for (int32_t ri = 0; ri < s_nrec; ++ri) {
+      Rec& c = recs[(size_t)ri];
+      if (c.name.empty()) {                                  // names not preserved: mates share a generated one
+        int head = ri;
+        for (int32_t k = 0; k < ri; ++k) if (recs[(size_t)k].mate_line == ri && k < head) head = k;
+        c.name = head < ri ? recs[(size_t)head].name : name_prefix + std::to_string((*name_counter)++);
+      }
+      if (c.name.size() > 254) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: read name of %zu bytes", cram_path, c.name.size());
+      if (c.cigar.size() > 65535) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: a read with %zu CIGAR operations (BAM holds 65535; the CG-tag form is not written)", cram_path, c.cigar.size());
+      const int32_t pos0 = (c.ref >= 0 || c.ap > 0) ? c.ap - 1 : -1;
+      const int64_t end0 = (c.bf & 4) || c.end <= pos0 ? (int64_t)pos0 + 1 : c.end;
+      const int32_t l_seq = (int32_t)c.seq.size();
+      const size_t body = 32 + c.name.size() + 1 + 4 * c.cigar.size() + ((size_t)l_seq + 1) / 2 + (size_t)l_seq + c.aux.size();
+      w.I32((int32_t)body);
+      w.I32(c.ref); w.I32(pos0);
+      const uint8_t lname = (uint8_t)(c.name.size() + 1), mapq = (uint8_t)c.mq;
+      w.Put(&lname, 1); w.Put(&mapq, 1);
+      const uint16_t bin = (uint16_t)Reg2Bin(std::max(pos0, 0), std::max<int64_t>(end0, 1)), ncig = (uint16_t)c.cigar.size(), flag = (uint16_t)c.bf;
+      w.Put(&bin, 2); w.Put(&ncig, 2); w.Put(&flag, 2);
+      w.I32(l_seq); w.I32(mate_ref[(size_t)ri]); w.I32(mate_pos[(size_t)ri] - 1); w.I32(c.tlen);
+      w.Put(c.name.c_str(), c.name.size() + 1);
+      if (!c.cigar.empty()) w.Put(c.cigar.data(), 4 * c.cigar.size());
+      std::vector<uint8_t> packed(((size_t)l_seq + 1) / 2, 0);
+      for (int32_t k = 0; k < l_seq; ++k) {
+        const char* tbl = "=ACMGRSVTWYHKDBN";
+        const char b = c.seq[(size_t)k] >= 'a' && c.seq[(size_t)k] <= 'z' ? (char)(c.seq[(size_t)k] - 32) : c.seq[(size_t)k];
+        const char* at = strchr(tbl, b);
+        const uint8_t code = (at && b) ? (uint8_t)(at - tbl) : 15;
+        packed[(size_t)k >> 1] |= (k & 1) ? code : (uint8_t)(code << 4);
+      }
+      if (!packed.empty()) w.Put(packed.data(), packed.size());
+      if (l_seq) w.Put(c.qual.data(), (size_t)l_seq);
+      if (!c.aux.empty()) w.Put(c.aux.data(), c.aux.size());
+      ++*n_written;
+    }
+  }
+  return DVB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -407,8 +660,38 @@ int dvb_cram_to_bam(const char* cram_path, const char* bam_path, const char* con
   std::vector<int> sq_to_given;               // -> index into ref_names, -1 when the caller did not supply that contig
   std::vector<std::pair<int, std::pair<int64_t, int64_t>>> regions;   // by CRAM ref id
   bool header_done = false;
-  int64_t n_written = 0, name_counter = 0;
+  int64_t n_written = 0;
   std::vector<uint8_t> cbuf;
+  struct Job { std::vector<uint8_t> cbuf; std::vector<int32_t> landmarks; std::string name_prefix, error; Out out; int64_t n = 0; int status = DVB_OK; };
+  std::vector<Job> jobs;
+  int64_t container_no = 0;
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int n_threads = (int)std::max(1u, std::min(16u, hw ? hw : 1u));
+  const int batch = 4 * n_threads;
+  const Ctx cx{cram_path, &sq_names, &sq_to_given, ref_bases, ref_lens};
+  auto run_jobs = [&]() -> int {
+    if (jobs.empty()) return DVB_OK;
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+      for (size_t k; (k = next.fetch_add(1)) < jobs.size();) {
+        Job& j = jobs[k];
+        j.status = DecodeContainer(cx, j.cbuf, j.landmarks, j.name_prefix, j.out, &j.n);
+        if (j.status) j.error = dvb::last_error();        // the message is thread-local: carry it to the caller's thread
+        std::vector<uint8_t>().swap(j.cbuf);
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads && (size_t)t < jobs.size(); ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    for (Job& j : jobs) {
+      if (j.status) return dvb::fail(j.status, "%s", j.error.c_str());
+      if (!j.out.buf.empty()) w.Put(j.out.buf.data(), j.out.buf.size());
+      n_written += j.n;
+    }
+    jobs.clear();
+    return DVB_OK;
+  };
   for (;;) {
     uint8_t lenb[4];
     if (fread(lenb, 1, 4, in) != 4) break;              // no EOF container: accept the end of the file
@@ -480,230 +763,14 @@ int dvb_cram_to_bam(const char* cram_path, const char* bam_path, const char* con
       header_done = true;
       continue;
     }
-    // ---- a data container: compression header, then slices at the landmarks
-    Block chb;
-    int st = ReadBlock(cr, &chb);
-    if (st) return st;
-    if (chb.ctype != 1) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: container without a compression header", cram_path);
-    CompressionHeader ch;
-    if ((st = ParseCompressionHeader(chb, &ch))) return st;
-    auto enc = [&](const char* key) -> const Enc& { static const Enc none; auto it = ch.ds.find(key); return it == ch.ds.end() ? none : it->second; };
-    for (size_t li = 0; li < landmarks.size(); ++li) {
-      if (landmarks[li] < 0 || (size_t)landmarks[li] >= cbuf.size()) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: landmark outside its container", cram_path);
-      Rd sr{cbuf.data() + landmarks[li], cbuf.data() + cbuf.size()};
-      Block shb;
-      if ((st = ReadBlock(sr, &shb))) return st;
-      if (shb.ctype != 2) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: landmark does not point at a slice header", cram_path);
-      Rd hs{shb.data.data(), shb.data.data() + shb.data.size()};
-      const int32_t s_ref = hs.itf8(), s_start = hs.itf8();
-      hs.itf8();
-      const int32_t s_nrec = hs.itf8();
-      hs.ltf8();
-      const int32_t s_nblocks = hs.itf8(), n_ids = hs.itf8();
-      for (int32_t i = 0; i < n_ids; ++i) hs.itf8();
-      const int32_t embedded = hs.itf8();
-      if (hs.bad || s_nrec < 0 || s_nblocks < 0) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: malformed slice header", cram_path);
-      std::vector<std::unique_ptr<Block>> blocks;
-      Slice sl;
-      for (int32_t i = 0; i < s_nblocks; ++i) {
-        blocks.emplace_back(new Block());
-        if ((st = ReadBlock(sr, blocks.back().get()))) return st;
-        if (blocks.back()->ctype == 5) sl.core = blocks.back().get(); else sl.ext[blocks.back()->id] = blocks.back().get();
-      }
-      std::vector<Rec> recs((size_t)s_nrec);
-      int32_t prev_ap = s_start;
-      for (int32_t ri = 0; ri < s_nrec; ++ri) {
-        Rec& c = recs[(size_t)ri];
-        c.bf = sl.Int(enc("BF")); c.cf = sl.Int(enc("CF"));
-        c.ref = s_ref == -2 ? sl.Int(enc("RI")) : s_ref;
-        c.rl = sl.Int(enc("RL"));
-        c.ap = sl.Int(enc("AP"));
-        if (ch.ap_delta) { c.ap += prev_ap; prev_ap = c.ap; }
-        sl.Int(enc("RG"));
-        if (ch.rn) sl.Bytes(enc("RN"), &c.name);
-        if (c.cf & 2) {                                    // detached: the mate fields are stored
-          c.mf = sl.Int(enc("MF"));
-          if (!ch.rn) sl.Bytes(enc("RN"), &c.name);
-          c.ns = sl.Int(enc("NS")); c.np = sl.Int(enc("NP")); c.tlen = sl.Int(enc("TS"));
-        } else if (c.cf & 4) {
-          c.mate_line = ri + sl.Int(enc("NF")) + 1;
-        }
-        const int32_t tl = sl.Int(enc("TL"));
-        if (sl.bad || c.rl < 0 || tl < 0 || (size_t)tl >= ch.td.size()) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: malformed record %d of a slice", cram_path, ri);
-        for (const std::string& t : ch.td[(size_t)tl]) {
-          const int32_t key = ((uint8_t)t[0] << 16) | ((uint8_t)t[1] << 8) | (uint8_t)t[2];
-          auto it = ch.tags.find(key);
-          if (it == ch.tags.end()) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: tag %c%c without an encoding", cram_path, t[0], t[1]);
-          c.aux.append(t);
-          const size_t v0 = c.aux.size();
-          sl.Bytes(it->second, &c.aux);
-          if ((t[2] == 'Z' || t[2] == 'H') && (c.aux.size() == v0 || c.aux.back() != 0)) c.aux.push_back(0);
-        }
-        c.seq.assign((size_t)c.rl, 'N');
-        c.qual.assign((size_t)c.rl, (char)0xff);
-        c.end = c.ap;
-        if (!(c.bf & 4)) {
-          RefSeq ref;
-          if (embedded >= 0) {
-            Block* eb = sl.Ext(embedded);
-            if (eb) { ref.bases = eb->data.data(); ref.len = (int64_t)eb->data.size(); ref.origin = (int64_t)s_start - 1; }
-          } else if (c.ref >= 0 && (size_t)c.ref < sq_to_given.size() && sq_to_given[(size_t)c.ref] >= 0) {
-            ref.bases = ref_bases[sq_to_given[(size_t)c.ref]]; ref.len = ref_lens[sq_to_given[(size_t)c.ref]];
-          }
-          bool ref_missing = false;
-          auto ref_at = [&](int64_t pos0) -> char {
-            const int64_t i = pos0 - ref.origin;
-            if (!ref.bases || i < 0 || i >= ref.len) { ref_missing = true; return 'N'; }
-            const char b = (char)ref.bases[i];
-            return (b >= 'a' && b <= 'z') ? (char)(b - 32) : b;
-          };
-          const int32_t fn = sl.Int(enc("FN"));
-          int64_t read_pos = 0, ref_pos = (int64_t)c.ap - 1;
-          int32_t fpos = 0;
-          auto fill = [&](int64_t upto) {                   // reference matches up to read index `upto` (exclusive)
-            const int64_t gap = std::min<int64_t>(upto, c.rl) - read_pos;
-            if (gap <= 0) return;
-            for (int64_t k = 0; k < gap; ++k) c.seq[(size_t)(read_pos + k)] = ref_at(ref_pos + k);
-            PushCigar(&c.cigar, 0, gap); read_pos += gap; ref_pos += gap;
-          };
-          for (int32_t f = 0; f < fn && !sl.bad; ++f) {
-            const char code = (char)sl.Byte(enc("FC"));
-            fpos += sl.Int(enc("FP"));
-            fill((int64_t)fpos - 1);
-            std::string bytes;
-            switch (code) {
-              case 'X': {
-                const int bs = sl.Byte(enc("BS")) & 3;
-                const char rb = ref_at(ref_pos);
-                const int ri5 = rb == 'A' ? 0 : rb == 'C' ? 1 : rb == 'G' ? 2 : rb == 'T' ? 3 : 4;
-                if (read_pos < c.rl) c.seq[(size_t)read_pos] = (char)ch.sub[ri5][bs];
-                PushCigar(&c.cigar, 0, 1); ++read_pos; ++ref_pos; break;
-              }
-              case 'B': {
-                const int b = sl.Byte(enc("BA")), q = sl.Byte(enc("QS"));
-                if (read_pos < c.rl) { c.seq[(size_t)read_pos] = (char)b; c.qual[(size_t)read_pos] = (char)q; }
-                PushCigar(&c.cigar, 0, 1); ++read_pos; ++ref_pos; break;
-              }
-              case 'b':
-                sl.Bytes(enc("BB"), &bytes);
-                for (size_t k = 0; k < bytes.size() && read_pos + (int64_t)k < c.rl; ++k) c.seq[(size_t)read_pos + k] = bytes[k];
-                PushCigar(&c.cigar, 0, (int64_t)bytes.size()); read_pos += (int64_t)bytes.size(); ref_pos += (int64_t)bytes.size(); break;
-              case 'I':
-                sl.Bytes(enc("IN"), &bytes);
-                for (size_t k = 0; k < bytes.size() && read_pos + (int64_t)k < c.rl; ++k) c.seq[(size_t)read_pos + k] = bytes[k];
-                PushCigar(&c.cigar, 1, (int64_t)bytes.size()); read_pos += (int64_t)bytes.size(); break;
-              case 'i': {
-                const int b = sl.Byte(enc("BA"));
-                if (read_pos < c.rl) c.seq[(size_t)read_pos] = (char)b;
-                PushCigar(&c.cigar, 1, 1); ++read_pos; break;
-              }
-              case 'S':
-                sl.Bytes(enc("SC"), &bytes);
-                for (size_t k = 0; k < bytes.size() && read_pos + (int64_t)k < c.rl; ++k) c.seq[(size_t)read_pos + k] = bytes[k];
-                PushCigar(&c.cigar, 4, (int64_t)bytes.size()); read_pos += (int64_t)bytes.size(); break;
-              case 'D': { const int32_t n = sl.Int(enc("DL")); PushCigar(&c.cigar, 2, n); ref_pos += n; break; }
-              case 'N': { const int32_t n = sl.Int(enc("RS")); PushCigar(&c.cigar, 3, n); ref_pos += n; break; }
-              case 'H': PushCigar(&c.cigar, 5, sl.Int(enc("HC"))); break;
-              case 'P': PushCigar(&c.cigar, 6, sl.Int(enc("PD"))); break;
-              case 'Q': { const int q = sl.Byte(enc("QS")); if (fpos >= 1 && fpos <= c.rl) c.qual[(size_t)fpos - 1] = (char)q; break; }
-              case 'q':
-                sl.Bytes(enc("QQ"), &bytes);
-                for (size_t k = 0; k < bytes.size() && (int64_t)fpos - 1 + (int64_t)k < c.rl; ++k) c.qual[(size_t)fpos - 1 + k] = bytes[k];
-                break;
-              default: return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: read feature '%c'", cram_path, code);
-            }
-          }
-          fill(c.rl);
-          if (ref_missing && ch.rr)
-            return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: the reference bases of %s are needed to decode its reads (pass the FASTA the file was written against)", cram_path,
-                             c.ref >= 0 && (size_t)c.ref < sq_names.size() ? sq_names[(size_t)c.ref].c_str() : "?");
-          c.end = ref_pos;                                  // 1-based inclusive end = 0-based exclusive end
-          c.mq = sl.Int(enc("MQ"));
-          if (c.cf & 1) for (int32_t k = 0; k < c.rl; ++k) c.qual[(size_t)k] = (char)sl.Byte(enc("QS"));
-        } else {
-          for (int32_t k = 0; k < c.rl; ++k) c.seq[(size_t)k] = (char)sl.Byte(enc("BA"));
-          if (c.cf & 1) for (int32_t k = 0; k < c.rl; ++k) c.qual[(size_t)k] = (char)sl.Byte(enc("QS"));
-        }
-        if (c.cf & 8) { c.seq.clear(); c.qual.clear(); }      // sequence unknown ('*')
-        if (sl.bad) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: a data series ran out inside record %d of a slice", cram_path, ri);
-      }
-      // ---- mates (cram_decode_slice_xref)
-      std::vector<int32_t> mate_ref((size_t)s_nrec, -1), mate_pos((size_t)s_nrec, 0);
-      for (int32_t ri = 0; ri < s_nrec; ++ri) {
-        Rec& c = recs[(size_t)ri];
-        if (c.mate_line >= 0) {
-          if (c.mate_line >= s_nrec) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: mate line outside its slice", cram_path);
-          if (c.tlen == INT_MIN) {
-            int id2 = ri; int64_t aleft = c.ap, aright = c.end; int ref = c.ref, left_cnt = 0;
-            do {
-              Rec& m = recs[(size_t)id2];
-              if (aleft > m.ap) { aleft = m.ap; left_cnt = 1; } else if (aleft == m.ap) ++left_cnt;
-              if (aright < m.end) aright = m.end;
-              if (m.mate_line == -1) { m.mate_line = ri; break; }
-              if (m.mate_line <= id2 || m.mate_line >= s_nrec) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: mate chain does not move forward", cram_path);
-              id2 = m.mate_line;
-              if (recs[(size_t)id2].ref != ref) ref = -1;
-            } while (id2 != ri);
-            const int64_t tlen = aright - aleft + 1;
-            id2 = ri;
-            do {
-              Rec& m = recs[(size_t)id2];
-              m.tlen = ref == -1 ? 0 : (m.ap == aleft && (left_cnt == 1 || (m.bf & 0x40))) ? (int32_t)tlen : (int32_t)-tlen;
-              id2 = m.mate_line;
-            } while (id2 != ri && id2 >= 0);
-          }
-          const Rec& m = recs[(size_t)c.mate_line];
-          mate_pos[(size_t)ri] = m.ap; mate_ref[(size_t)ri] = m.ref;
-          c.bf |= 1;
-          if (m.bf & 4) { c.bf |= 8; c.tlen = 0; }
-          if (c.bf & 4) c.tlen = 0;
-          if (m.bf & 0x10) c.bf |= 0x20;
-        } else {
-          if (c.mf & 1) c.bf |= 1 | 0x20;
-          if (c.mf & 2) c.bf |= 8;
-          mate_ref[(size_t)ri] = (c.bf & 1) ? c.ns : -1;
-          mate_pos[(size_t)ri] = c.np;
-        }
-        if (c.tlen == INT_MIN) c.tlen = 0;
-      }
-      // ---- BAM records
-      for (int32_t ri = 0; ri < s_nrec; ++ri) {
-        Rec& c = recs[(size_t)ri];
-        if (c.name.empty()) {                                  // names not preserved: mates share a generated one
-          int head = ri;
-          for (int32_t k = 0; k < ri; ++k) if (recs[(size_t)k].mate_line == ri && k < head) head = k;
-          c.name = head < ri ? recs[(size_t)head].name : "cram." + std::to_string(name_counter++);
-        }
-        if (c.name.size() > 254) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: read name of %zu bytes", cram_path, c.name.size());
-        if (c.cigar.size() > 65535) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: a read with %zu CIGAR operations (BAM holds 65535; the CG-tag form is not written)", cram_path, c.cigar.size());
-        const int32_t pos0 = (c.ref >= 0 || c.ap > 0) ? c.ap - 1 : -1;
-        const int64_t end0 = (c.bf & 4) || c.end <= pos0 ? (int64_t)pos0 + 1 : c.end;
-        const int32_t l_seq = (int32_t)c.seq.size();
-        const size_t body = 32 + c.name.size() + 1 + 4 * c.cigar.size() + ((size_t)l_seq + 1) / 2 + (size_t)l_seq + c.aux.size();
-        w.I32((int32_t)body);
-        w.I32(c.ref); w.I32(pos0);
-        const uint8_t lname = (uint8_t)(c.name.size() + 1), mapq = (uint8_t)c.mq;
-        w.Put(&lname, 1); w.Put(&mapq, 1);
-        const uint16_t bin = (uint16_t)Reg2Bin(std::max(pos0, 0), std::max<int64_t>(end0, 1)), ncig = (uint16_t)c.cigar.size(), flag = (uint16_t)c.bf;
-        w.Put(&bin, 2); w.Put(&ncig, 2); w.Put(&flag, 2);
-        w.I32(l_seq); w.I32(mate_ref[(size_t)ri]); w.I32(mate_pos[(size_t)ri] - 1); w.I32(c.tlen);
-        w.Put(c.name.c_str(), c.name.size() + 1);
-        if (!c.cigar.empty()) w.Put(c.cigar.data(), 4 * c.cigar.size());
-        std::vector<uint8_t> packed(((size_t)l_seq + 1) / 2, 0);
-        for (int32_t k = 0; k < l_seq; ++k) {
-          const char* tbl = "=ACMGRSVTWYHKDBN";
-          const char b = c.seq[(size_t)k] >= 'a' && c.seq[(size_t)k] <= 'z' ? (char)(c.seq[(size_t)k] - 32) : c.seq[(size_t)k];
-          const char* at = strchr(tbl, b);
-          const uint8_t code = (at && b) ? (uint8_t)(at - tbl) : 15;
-          packed[(size_t)k >> 1] |= (k & 1) ? code : (uint8_t)(code << 4);
-        }
-        if (!packed.empty()) w.Put(packed.data(), packed.size());
-        if (l_seq) w.Put(c.qual.data(), (size_t)l_seq);
-        if (!c.aux.empty()) w.Put(c.aux.data(), c.aux.size());
-        ++n_written;
-      }
-    }
+    // ---- a data container: queued; a batch is decoded on several threads and written in file order
+    jobs.emplace_back();
+    jobs.back().cbuf.swap(cbuf);
+    jobs.back().landmarks = landmarks;
+    jobs.back().name_prefix = "cram." + std::to_string(container_no++) + ".";
+    if (jobs.size() >= (size_t)batch) { const int st = run_jobs(); if (st) return st; }
   }
+  { const int st = run_jobs(); if (st) return st; }
   if (!header_done) return dvb::fail(DVB_ERR_INVALID_ARGUMENT, "%s: no header container", cram_path);
   w.Eof();
   if (w.failed) return dvb::fail(DVB_ERR_INTERNAL, "writing %s failed", bam_path);
