@@ -652,7 +652,9 @@ def _postprocess_variants_parallel(records, outfile, contigs, sample_name, qual_
   par = read_bed(par_regions_bed) if par_regions_bed else ()
   jobs = [(records[b:e], sample, qual_filter, multi_allelic_qual_filter, multiallelic_mode, group_variants, haploid, par, disable_haplotype_resolution)
           for b, e in independent_chunks(keys, chunk_records)]
-  with multiprocessing.get_context('fork').Pool(min(cpus, len(jobs))) as pool:
+  # forkserver: the workers start from a clean single-threaded process (this one may already run BLAS / CUDA / decoder threads, and a
+  # fork() of a multi-threaded process can inherit a held lock); the jobs are plain tuples of bytes
+  with multiprocessing.get_context('forkserver').Pool(min(cpus, len(jobs))) as pool:
     variants = (v for chunk in pool.imap(_convert_chunk, jobs) for v in chunk)          # in chunk order = genome order
     return _write_outputs(variants, len(records), blocks, outfile, gvcf_outfile, contigs, sample, only_keep_pass, base_at)
 
