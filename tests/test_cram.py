@@ -115,3 +115,23 @@ def test_reference_chr20_cram_equals_its_bam_read_for_read():
   br = bam.NativeBamTable(os.path.join(REF_INPUT, 'NA12878_S1.chr20.10_10p1mb.bam'), _keep_all(), regions=regions)
   assert cr.n_reads == br.n_reads > 100 and cr.reads() == br.reads()
   assert cand.sample_name_from_bam(os.path.join(REF_INPUT, 'NA12878_S1.chr20.10_10p1mb.cram')) == 'NA12878'
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_INPUT), reason='reference testdata is only present in the build container')
+def test_make_examples_over_the_cram_writes_the_goldens_of_the_bam(tmp_path, monkeypatch):
+  """make_examples_test.py:330-372 (TestConditions.USE_CRAM): --reads NA12878_S1.chr20.10_10p1mb.cram must give golden.calling_examples.
+  The encoder is the CPU oracle here (no GPU in the build container); reads, realigner, candidates and planning are the product flow."""
+  sys.path.insert(0, os.path.join(ROOT, 'tests'))
+  import test_candidates as tc
+  from deepvariant_b200 import cli, make_examples_native as men, pileup_image as pi, protos, tfrecord
+  monkeypatch.setattr(men.ExamplesGenerator, '_gpu', lambda self: tc.OracleEncoder(pi.to_params(self.options.pic_options, height=self.pileup_image_height)))
+  out = str(tmp_path / 'examples.tfrecord.gz')
+  assert cli.make_examples(['--mode', 'calling', '--ref', os.path.join(REF_INPUT, 'ucsc.hg19.chr20.unittest.fasta.gz'),
+                            '--reads', os.path.join(REF_INPUT, 'NA12878_S1.chr20.10_10p1mb.cram'), '--regions', 'chr20:10,000,000-10,010,000',
+                            '--examples', out, '--channel_list', 'BASE_CHANNELS,insert_size']) == 0
+  golden = [protos.parse_tf_example(r) for r in tfrecord.read_records(os.path.join(os.path.dirname(REF_INPUT), 'golden.calling_examples.tfrecord.gz'))]
+  ours = [protos.parse_tf_example(r) for r in tfrecord.read_records(out)]
+  assert len(ours) == len(golden) == 84
+  for g, o in zip(golden, ours):
+    for key in ('image/encoded', 'image/shape', 'alt_allele_indices/encoded', 'locus'):
+      assert g[key] == o[key], key
